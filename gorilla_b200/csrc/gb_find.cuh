@@ -1,0 +1,202 @@
+// gb_find.cuh -- initial localisation of a particle in the tetrahedral mesh + coordinate-domain check.
+//
+// Replaces (reference file:line):
+//   find_tetra                 SRC/find_tetra_mod.f90:283-600  (boole_grid_for_find_tetra = .false.)
+//   isinside                   SRC/tetra_physics_mod.f90:1038-1072
+//   check_coordinate_domain    SRC/orbit_timestep_gorilla.f90:278-358
+//   and the RK-module pieces find_tetra uses for starts that lie on a face:
+//   initialize_pusher_tetra_rk_mod (ODE coefficients only) SRC/pusher_tetra_rk.f90:50-134,
+//   rk4_step :840-896, normal_distances_func :2422, normal_velocity_func :2451.
+//
+// The reference scans the tetrahedra of one phi-slice in index order and takes the FIRST one that
+// contains the point (tolerance eps*|dist_ref|).  The scan order is part of the result, so it is kept:
+// one lane walks the slice; all lanes of a warp that sit in the same slice read the same 128-byte
+// geometry records, which the L1/L2 serve as broadcasts.
+#pragma once
+#include "gb_poly.cuh"
+
+namespace gb {
+
+#define GB_EPS 1.e-10
+
+// Fortran modulo(a,p) for p > 0
+GB_HD double f_modulo(double a, double p) { return a - floor(a / p) * p; }
+
+// returns 0 ok, 1 outside the computation domain (reference: print + stop)
+GB_HD int check_coordinate_domain(const MeshDev &m, double *x, int boole_periodic_relocation)
+{
+  if (m.coord_system == 1) {
+    if (boole_periodic_relocation) x[1] = f_modulo(x[1], m.period_phi);
+    else if (x[1] < 0.0 || x[1] > m.period_phi) return 1;
+  } else {
+    if (x[0] < m.sfc_s_min || x[0] > 1.0) return 1;
+    if (boole_periodic_relocation) {
+      x[1] = f_modulo(x[1], m.period_theta);
+      x[2] = f_modulo(x[2], m.period_phi);
+    } else if (x[1] < 0.0 || x[1] > m.period_theta || x[2] < 0.0 || x[2] > m.period_phi) {
+      return 1;
+    }
+  }
+  return 0;
+}
+
+GB_HD bool isinside(const MeshDev &m, int64_t ind_tetr, const double *x, double *dist, double &dist_ref)
+{
+  const double *g = m.geom + (ind_tetr - 1) * GEOM_ND;
+  double v[GEOM_ND];
+#pragma unroll
+  for (int i = 0; i < GEOM_ND; i += 2) ld2(g + i, v[i], v[i + 1]);
+  dist_ref = v[3];
+  const double dist_min = GB_EPS * fabs(dist_ref);
+  const double d[3] = {x[0] - v[0], x[1] - v[1], x[2] - v[2]};
+  bool all_ok = true;
+#pragma unroll
+  for (int f = 0; f < 4; f++) {
+    double s = dot3(&v[4 + 3 * f], d);
+    if (f == 0) s = s + dist_ref;
+    dist[f] = s;
+    if (!(s >= -dist_min)) all_ok = false;
+  }
+  return all_ok;
+}
+
+// dz/dtau = b + A z of the RK module (rhs_pusher_tetra_rk4, pusher_tetra_rk.f90:810-836):
+//   (b + matmul(amat, z(1:3))) + Bvec*z(4) ; b4 + spamat*z4
+template <class PP>
+GB_HD void bm_vec_rk(double *o, const PP &P, const double *z)
+{
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    double mv = (P.A.m[i][0] * z[0] + P.A.m[i][1] * z[1]) + P.A.m[i][2] * z[2];
+    o[i] = P.b[i] + mv + P.A.c[i] * z[3];
+  }
+  o[3] = P.b[3] + P.A.s * z[3];
+}
+
+// Start point lies (within tolerance) on >= 1 face: hop through the neighbours until every converged
+// face has inward normal velocity (find_tetra_mod.f90:478-581).
+template <bool PHI>
+GB_HD_NOINLINE void find_tetra_on_face(const MeshDev *mp, double *x, double vpar, double vperp, int32_t &ind_tetr_out,
+                                       int32_t &iface, int sign_t_step, const double *dist0, int n_plane_conv)
+{
+  const MeshDev &m = *mp;
+  PolyPusher<1, PHI> P; // reuse record loader + ODE coefficient builder (same formulas, :104-116 vs poly :1504-1517)
+  P.mp = mp;
+  int iface_new = 1;
+  for (int f = 1; f < 4; f++)
+    if (fabs(dist0[f]) < fabs(dist0[iface_new - 1])) iface_new = f + 1;
+  int32_t tried[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  {
+    Rec<PHI> r0;
+    r0.load(m, ind_tetr_out);
+    double z[3] = {x[0] - r0.x1[0], x[1] - r0.x1[1], x[2] - r0.x1[2]};
+    P.perpinv = -0.5 * (vperp * vperp) / (r0.bmod1 + dot3(r0.gB, z));
+  }
+  for (int i_try = 1; i_try <= 2 * n_plane_conv; i_try++) {
+    if (ind_tetr_out == -1) break;
+    tried[i_try - 1] = ind_tetr_out;
+    // ODE coefficients of this tetrahedron (b, amat, Bvec, spamat) for t_remain = sign_t_step
+    P.init(ind_tetr_out, x, iface_new, vpar, (double)sign_t_step);
+    P.build_ode();
+    double z[4] = {P.z_init[0], P.z_init[1], P.z_init[2], vpar};
+    double dist[4];
+    bool conv[4];
+    for (int f = 0; f < 4; f++) {
+      dist[f] = P.normal_distance(z, f + 1);
+      conv[f] = fabs(dist[f]) <= (GB_EPS * fabs(P.r.dist_ref));
+    }
+    // rk4_step(z, 0.d0, dzdtau): all stages collapse onto z; dzdtau = rhs at the last stage point
+    double dydx[4], yt[4], dyt[4], dym[4];
+    bm_vec_rk(dydx, P, z);
+    for (int i = 0; i < 4; i++) yt[i] = z[i] + 0.0 * dydx[i];
+    bm_vec_rk(dyt, P, yt);
+    for (int i = 0; i < 4; i++) yt[i] = z[i] + 0.0 * dyt[i];
+    bm_vec_rk(dym, P, yt);
+    for (int i = 0; i < 4; i++) yt[i] = z[i] + 0.0 * dym[i];
+    bm_vec_rk(dyt, P, yt);
+    int counter_vnorm_pos = 0;
+    double vn[4];
+    for (int l = 0; l < 4; l++) {
+      vn[l] = dot3(dyt, P.r.an[l]);
+      if (conv[l] && vn[l] > 0.0) counter_vnorm_pos++;
+    }
+    if (counter_vnorm_pos == n_plane_conv) {
+      iface = iface_new;
+      break;
+    }
+    const int ind_tetr_save = ind_tetr_out, iface_new_save = iface_new;
+    const double xs[3] = {x[0], x[1], x[2]};
+    for (int l = 1; l <= 4; l++) {
+      if (!conv[l - 1]) continue;
+      if (vn[l - 1] > 0.0) continue;
+      int32_t out, fout;
+      P.handover(l, x, out, fout);
+      ind_tetr_out = out;
+      iface_new = fout;
+      bool was_tried = false;
+      for (int t = 0; t < 2 * n_plane_conv; t++)
+        if (tried[t] == out) was_tried = true;
+      if (was_tried || out == -1) {
+        x[0] = xs[0]; x[1] = xs[1]; x[2] = xs[2];
+        iface_new = iface_new_save;
+      } else {
+        break;
+      }
+    }
+    (void)ind_tetr_save;
+  }
+}
+
+template <bool PHI>
+GB_HD void find_tetra(const MeshDev *mp, double *x, double vpar, double vperp, int32_t &ind_tetr_out, int32_t &iface,
+                      int sign_t_step)
+{
+  const MeshDev &m = *mp;
+  const double PI = 3.141592653589793238462643383;
+  int64_t indtetr_start, ntetr_searched;
+  const int64_t ntetr = m.ntetr;
+  int corr_plus = 0, corr_minus = 0;
+  const int nphi = m.grid_size2;
+  ind_tetr_out = -1;
+  iface = -1;
+  if (m.grid_kind == 1 || m.grid_kind == 5) {
+    const int nr = m.grid_size1, nz = m.grid_size3;
+    const double hr = (m.Rmax - m.Rmin) / nr, hphi = (2.0 * PI) / nphi, hz = (m.Zmax - m.Zmin) / nz;
+    const int ir = (int)((x[0] - m.Rmin) / hr) + 1, iphi = (int)(x[1] / hphi) + 1, iz = (int)((x[2] - m.Zmin) / hz) + 1;
+    if (ir < 1 || ir > nr || iphi < 1 || iphi > nphi || iz < 1 || iz > nz) return;
+    indtetr_start = (int64_t)(((double)iz - 1.0) * 6.0 + 6.0 * (double)nz * ((double)ir - 1.0) +
+                              6.0 * ((double)iphi - 1.0) * (double)nr * (double)nz + 1.0);
+    ntetr_searched = 6;
+  } else {
+    const int ind_b = (m.coord_system == 2) ? 2 : 1;
+    const int64_t ntetr_in_plane = ntetr / nphi;
+    const double q = x[ind_b] * nphi / (2.0 * PI / m.n_field_periods);
+    const int ind_plane = (int)q;
+    if (fabs(q - (double)ind_plane) > (1.0 - GB_EPS)) corr_plus = 1;
+    if (fabs(q - (double)ind_plane) < GB_EPS) corr_minus = 1;
+    indtetr_start = (int64_t)ind_plane * ntetr_in_plane + 1;
+    ntetr_searched = ntetr_in_plane * (1 + corr_plus + corr_minus);
+  }
+  for (int64_t i = 1; i <= ntetr_searched; i++) {
+    int64_t ind = indtetr_start + i - 1 - (int64_t)corr_minus * (ntetr / nphi);
+    if (ind > ntetr) ind -= ntetr;
+    if (ind <= 0) ind += ntetr;
+    double dist[4], dist_ref;
+    if (isinside(m, ind, x, dist, dist_ref)) {
+      ind_tetr_out = (int32_t)ind;
+      iface = 0;
+      int n_plane_conv = 0;
+#pragma unroll
+      for (int f = 0; f < 4; f++)
+        if (fabs(dist[f]) <= (GB_EPS * fabs(dist_ref))) n_plane_conv++;
+      if (n_plane_conv > 0)
+        find_tetra_on_face<PHI>(mp, x, vpar, vperp, ind_tetr_out, iface, sign_t_step, dist, n_plane_conv);
+      if (ind_tetr_out == -1)
+        iface = -1;
+      else
+        break;
+    }
+  }
+}
+
+} // namespace gb

@@ -1,0 +1,140 @@
+// gb_mesh.cuh -- device-resident mesh: the reference's per-tetrahedron AoS records repacked as a
+// structure of arrays of 32-byte-aligned SUB-RECORDS (one array per access group).
+//
+// Reference types being repacked:
+//   type tetrahedron_physics  (142 doubles, SRC/tetra_physics_mod.f90:9-83)
+//   type tetrahedron_grid     (20 int32,   SRC/tetra_grid_mod.f90:6-15)
+//   type tetrahedron_physics_precomp_poly1 (SRC/tetra_physics_poly_precomp_mod.f90:8-15) is NOT
+//   stored: n.alpha, n.beta, n.curlA are re-formed on the fly in the (rare) paths that use them.
+//
+// Why sub-records and not 60 scalar arrays: one crossing gathers the whole record of ONE random
+// tetrahedron per lane.  A sector is 32 B, so a scalar SoA would move 60 sectors (1920 B) per
+// crossing; sub-records move 4 + 7 (+5) sectors = 352 B (512 B with the electrostatic part),
+// against 344 / 488 algorithmic bytes.  Groups are separate arrays so that the
+// eps_Phi = 0 specialisation never touches the Phi group and the cold group is only read by the
+// fall-back / diagnostic paths.
+//
+//   geom  [ntetr][16] : x1(3) dist_ref anorm(3,4)                                         128 B
+//   bpart [ntetr][28] : bmod1 gB(3) curlA(3) curlh(3) gBxh1(3) gBxcurlA alpmat(3,3) spalpmat
+//                       dt_dtau_const | neighbour_tetr(4) int32 | packed face/periodic flags  224 B
+//   phi   [ntetr][20] : Phi1 gPhi(3) gPhixh1(3) gPhixcurlA betmat(3,3) spbetmat (2 pad)        160 B
+//   cold  [ntetr][12] : tetra_dist_ref R1 Er_mod h_phi1 gh_phi(3) Aphi1 gAphi(3) (1 pad)        96 B
+// Matrices keep the Fortran column-major order: alpmat(i,j) -> [i + 3*j].
+#pragma once
+#include <stdint.h>
+#include "gb_math.cuh"
+
+namespace gb {
+
+enum { GEOM_ND = 16, BPART_ND = 28, PHI_ND = 20, COLD_ND = 12 };
+enum { B_BMOD1 = 0, B_GB = 1, B_CURLA = 4, B_CURLH = 7, B_GBXH1 = 10, B_GBXCURLA = 13, B_ALP = 14,
+       B_SPALP = 23, B_DTDTAU = 24, B_TOPO = 25 };
+enum { P_PHI1 = 0, P_GPHI = 1, P_GPHIXH1 = 4, P_GPHIXCURLA = 7, P_BET = 8, P_SPBET = 17 };
+enum { C_TETRA_DIST_REF = 0, C_R1 = 1, C_ER_MOD = 2, C_HPHI1 = 3, C_GHPHI = 4, C_APHI1 = 7, C_GAPHI = 8 };
+
+// packed per-face topology: 7 bits per face f (0..3) at bit 7*f:
+//   bits 0-2 neighbour_face+1 (0..5), bits 3-4 perbou_phi+1 (0..2), bits 5-6 perbou_theta+1 (0..2)
+GB_HD int topo_face(uint32_t flags, int f) { return (int)((flags >> (7 * f)) & 7u) - 1; }
+GB_HD int topo_perphi(uint32_t flags, int f) { return (int)((flags >> (7 * f + 3)) & 3u) - 1; }
+GB_HD int topo_pertheta(uint32_t flags, int f) { return (int)((flags >> (7 * f + 5)) & 3u) - 1; }
+
+struct MeshDev {
+  int64_t ntetr;
+  const double *geom;
+  const double *bpart;
+  const double *phi;  // nullptr when the whole Phi group is exactly zero
+  const double *cold;
+  double cm_over_e, particle_mass, particle_charge;
+  double period_phi;   // 2*pi/n_field_periods, formed exactly as the reference does (2.d0*pi/n_field_periods)
+  double period_theta; // 2.d0*pi
+  int32_t sign_sqg, coord_system, grid_size2, boole_guess;
+  // find_tetra
+  int32_t grid_kind, grid_size1, grid_size3, n_field_periods;
+  double Rmin, Rmax, Zmin, Zmax, sfc_s_min;
+};
+
+GB_HD double ldg(const double *p)
+{
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+#if defined(__CUDA_ARCH__)
+GB_HD void ld2(const double *p, double &a, double &b)
+{
+  double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+  a = v.x;
+  b = v.y;
+}
+#else
+GB_HD void ld2(const double *p, double &a, double &b)
+{
+  a = p[0];
+  b = p[1];
+}
+#endif
+
+// One tetrahedron's hot record in registers.
+template <bool PHI>
+struct Rec {
+  double x1[3], dist_ref, an[4][3]; // an[f][i] = anorm(i+1, f+1)
+  double bmod1, gB[3], curlA[3], curlh[3], gBxh1[3], gBxcurlA, alp[9], spalp, dtdtau;
+  double Phi1, gPhi[3], gPhixh1[3], gPhixcurlA, bet[9], spbet;
+  int32_t nb[4];
+  uint32_t flags;
+
+  GB_HD void load(const MeshDev &m, int ind_tetr /*1-based*/)
+  {
+    const int64_t t = (int64_t)ind_tetr - 1;
+    double g[GEOM_ND], b[BPART_ND];
+    const double *pg = m.geom + t * GEOM_ND, *pb = m.bpart + t * BPART_ND;
+#pragma unroll
+    for (int i = 0; i < GEOM_ND; i += 2) ld2(pg + i, g[i], g[i + 1]);
+#pragma unroll
+    for (int i = 0; i < BPART_ND; i += 2) ld2(pb + i, b[i], b[i + 1]);
+    x1[0] = g[0]; x1[1] = g[1]; x1[2] = g[2]; dist_ref = g[3];
+#pragma unroll
+    for (int f = 0; f < 4; f++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) an[f][i] = g[4 + 3 * f + i];
+    bmod1 = b[B_BMOD1];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      gB[i] = b[B_GB + i];
+      curlA[i] = b[B_CURLA + i];
+      curlh[i] = b[B_CURLH + i];
+      gBxh1[i] = b[B_GBXH1 + i];
+    }
+    gBxcurlA = b[B_GBXCURLA];
+#pragma unroll
+    for (int i = 0; i < 9; i++) alp[i] = b[B_ALP + i];
+    spalp = b[B_SPALP];
+    dtdtau = b[B_DTDTAU];
+    {
+      union { double d; int32_t i[2]; } u;
+      u.d = b[B_TOPO]; nb[0] = u.i[0]; nb[1] = u.i[1];
+      u.d = b[B_TOPO + 1]; nb[2] = u.i[0]; nb[3] = u.i[1];
+      u.d = b[B_TOPO + 2]; flags = (uint32_t)u.i[0];
+    }
+    if (PHI) {
+      double p[PHI_ND];
+      const double *pp = m.phi + t * PHI_ND;
+#pragma unroll
+      for (int i = 0; i < 18; i += 2) ld2(pp + i, p[i], p[i + 1]);
+      Phi1 = p[P_PHI1];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        gPhi[i] = p[P_GPHI + i];
+        gPhixh1[i] = p[P_GPHIXH1 + i];
+      }
+      gPhixcurlA = p[P_GPHIXCURLA];
+#pragma unroll
+      for (int i = 0; i < 9; i++) bet[i] = p[P_BET + i];
+      spbet = p[P_SPBET];
+    }
+  }
+};
+
+} // namespace gb

@@ -1,0 +1,689 @@
+// gb_poly.cuh -- polynomial tetrahedron pusher (orders K = 1..4), FP64, one particle per lane.
+//
+// Replaces (reference file:line), for i_precomp = 0, i_time_tracing_option = 1, non-adaptive steps,
+// handover_processing_kind = 1:
+//   initialize_pusher_tetra_poly          SRC/pusher_tetra_poly.f90:125-178
+//   pusher_tetra_poly                     :182-675
+//   check_three_planes / _face_convergence / _velocity / _exit_time   :679-758
+//   prolonged_trajectory                  :762-826
+//   analytic_approx                       :1258-1482
+//   analytic_coeff_without_precomp        :1486-1586
+//   analytic_integration_without_precomp / set_integration_coef_manually   :2047-2113
+//   normal_distance_func / normal_velocity_func / normal_v_func_from_trajectory   :2690-2775
+//   physical_estimate_tau                 :2779-2831
+//   trouble_shooting_polynomial_solver    :2835-2998
+//   pusher_handover2neighbour             SRC/pusher_tetra_func_mod.f90:6-93
+//
+// Design (not a transliteration):
+//   * The ODE matrix is block structured, A = [[a(3x3), c(3)], [0 0 0, s]].  Powers A^2..A^4 are
+//     formed as block products (structural zeros skipped -- adding an exact 0 product never changes
+//     an IEEE sum of finite terms), in the reference's accumulation order, so results are
+//     bit-identical to matmul(amat, amat^k) while costing 39 instead of 112 flops per product.
+//   * push_fast() is the branch-light common case (first attempt succeeds, particle leaves through a
+//     face or stops inside); anything else makes it return false WITHOUT side effects and the caller
+//     re-runs the push through push_full(), the complete fall-back ladder, which is a separate
+//     non-inlined function so that its register/stack footprint does not tax the hot loop.
+//   * The reference's THREADPRIVATE module state is the PolyPusher object; it lives in registers.
+//   * The reference traps on FP exceptions (CMakeLists.txt:24-25); here a non-finite state simply
+//     finds no valid exit time on its next push (every root test 0 < dtau < huge fails for NaN) and
+//     the particle is removed like any unrecoverable push (ind_tetr = -1, iface = -1).
+#pragma once
+#include "gb_mesh.cuh"
+#include "gb_roots.cuh"
+
+namespace gb {
+
+#define GB_CLIGHT 2.9979e10
+#define GB_EPS_TAU 100.0
+
+GB_HD double dot3(const double *a, const double *b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+
+// block matrix [[m, c],[0, s]]
+struct BlockMat {
+  double m[3][3], c[3], s;
+};
+// P = A * B (reference: matmul(A,B), k ascending)
+GB_HD void bm_mul(BlockMat &P, const BlockMat &A, const BlockMat &B)
+{
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) P.m[i][j] = (A.m[i][0] * B.m[0][j] + A.m[i][1] * B.m[1][j]) + A.m[i][2] * B.m[2][j];
+    P.c[i] = ((A.m[i][0] * B.c[0] + A.m[i][1] * B.c[1]) + A.m[i][2] * B.c[2]) + A.c[i] * B.s;
+  }
+  P.s = A.s * B.s;
+}
+GB_HD void bm_vec(double *o, const BlockMat &A, const double *v)
+{
+#pragma unroll
+  for (int i = 0; i < 3; i++) o[i] = ((A.m[i][0] * v[0] + A.m[i][1] * v[1]) + A.m[i][2] * v[2]) + A.c[i] * v[3];
+  o[3] = A.s * v[3];
+}
+
+struct PushOut {
+  double x[3], vpar, z_save[3], t_pass;
+  int32_t ind_tetr, iface;
+  int32_t finished;  // boole_t_finished
+  int32_t z_save_set;
+  int32_t fallback;  // bit0 2nd attempt, bit1 trouble shooting, bit2 prolonged, bit3 finish-outside
+};
+
+template <int K, bool PHI>
+struct PolyPusher {
+  const MeshDev *mp;
+  Rec<PHI> r;
+  double perpinv;
+  int ind_tetr, iface_init, sign_rhs, nsteps, solver_iters, fallback;
+  double dt_dtau_const, bmod0, vmod0, t_remain, z_init[4], k1, k3;
+  BlockMat A;
+  double b[4];
+  double Az[4], Ab[4], A2z[4], A2b[4], A3z[4], A3b[4], A4z[4];
+
+  // ---- :125-178
+  GB_HD void init(int ind_tetr_in, const double *x, int iface, double vpar, double t_remain_in)
+  {
+    t_remain = t_remain_in;
+    ind_tetr = ind_tetr_in;
+    r.load(*mp, ind_tetr);
+    sign_rhs = mp->sign_sqg * (signbit(t_remain) ? -1 : 1);
+#pragma unroll
+    for (int i = 0; i < 3; i++) z_init[i] = x[i] - r.x1[i];
+    z_init[3] = vpar;
+    iface_init = iface;
+    dt_dtau_const = r.dtdtau * (double)sign_rhs;
+    bmod0 = r.bmod1 + dot3(r.gB, z_init);
+    double vperp2 = -2.0 * perpinv * bmod0;
+    double vpar2 = vpar * vpar;
+    vmod0 = sqrt(vpar2 + vperp2);
+    k1 = vperp2 + vpar2 + 2.0 * perpinv * r.bmod1;
+    if (PHI) {
+      double phi_elec = r.Phi1 + dot3(r.gPhi, z_init);
+      k3 = r.Phi1 - phi_elec;
+    } else {
+      k3 = 0.0;
+    }
+    nsteps = 0;
+  }
+
+  // ---- ODE coefficients b, A  (:1503-1530)
+  GB_HD void build_ode()
+  {
+    const double cm = mp->cm_over_e, sg = (double)sign_rhs;
+    const double pc = perpinv * cm;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      double t = (r.curlh[i] * k1 + perpinv * r.gBxh1[i]) * cm;
+      if (PHI) t = t - GB_CLIGHT * (2.0 * k3 * r.curlh[i] + r.gPhixh1[i]);
+      b[i] = t * sg;
+    }
+    {
+      double t = perpinv * r.gBxcurlA;
+      if (PHI) t = t - GB_CLIGHT / cm * r.gPhixcurlA;
+      b[3] = t * sg;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        double t = pc * r.alp[i + 3 * j];
+        if (PHI) t = t - GB_CLIGHT * r.bet[i + 3 * j];
+        A.m[i][j] = t * sg;
+      }
+      A.c[i] = r.curlA[i] * sg;
+    }
+    {
+      double t = pc * r.spalp;
+      if (PHI) t = t - GB_CLIGHT * r.spbet;
+      A.s = t * sg;
+    }
+  }
+
+  // ---- face-distance Taylor coefficients (:1532-1584); cm[n][k] = coef_mat(n+1,k+1)
+  template <int ORD>
+  GB_HD void coeff(unsigned mask, const double *z, double cm[4][5])
+  {
+    build_ode();
+#pragma unroll
+    for (int n = 0; n < 4; n++)
+      if (mask & (1u << n)) cm[n][0] = dot3(r.an[n], z);
+    if (mask & 1u) cm[0][0] = cm[0][0] + r.dist_ref; // coef - dist1, dist1 = -dist_ref
+    if (ORD >= 1) {
+      bm_vec(Az, A, z);
+#pragma unroll
+      for (int n = 0; n < 4; n++)
+        if (mask & (1u << n)) cm[n][1] = dot3(r.an[n], Az) + dot3(r.an[n], b);
+    }
+    if (ORD >= 2) {
+      BlockMat A2;
+      bm_mul(A2, A, A);
+      bm_vec(A2z, A2, z);
+      bm_vec(Ab, A, b);
+#pragma unroll
+      for (int n = 0; n < 4; n++)
+        if (mask & (1u << n)) cm[n][2] = dot3(r.an[n], A2z) + dot3(r.an[n], Ab);
+      if (ORD >= 3) {
+        BlockMat A3;
+        bm_mul(A3, A, A2);
+        bm_vec(A3z, A3, z);
+        bm_vec(A2b, A2, b);
+#pragma unroll
+        for (int n = 0; n < 4; n++)
+          if (mask & (1u << n)) cm[n][3] = dot3(r.an[n], A3z) + dot3(r.an[n], A2b);
+        if (ORD >= 4) {
+          BlockMat A4;
+          bm_mul(A4, A, A3);
+          bm_vec(A4z, A4, z);
+          bm_vec(A3b, A3, b);
+#pragma unroll
+          for (int n = 0; n < 4; n++)
+            if (mask & (1u << n)) cm[n][4] = dot3(r.an[n], A4z) + dot3(r.an[n], A3b);
+        }
+      }
+    }
+  }
+
+  // ---- :2087-2113 (A, b unchanged; matrix powers re-formed, which reproduces the stored ones)
+  GB_HD void set_integration_coef_manually(const double *z0)
+  {
+    if (K >= 1) bm_vec(Az, A, z0);
+    if (K >= 2) {
+      BlockMat A2;
+      bm_mul(A2, A, A);
+      bm_vec(A2z, A2, z0);
+      bm_vec(Ab, A, b);
+      if (K >= 3) {
+        BlockMat A3;
+        bm_mul(A3, A, A2);
+        bm_vec(A3z, A3, z0);
+        bm_vec(A2b, A2, b);
+        if (K >= 4) {
+          BlockMat A4;
+          bm_mul(A4, A, A3);
+          bm_vec(A4z, A4, z0);
+          bm_vec(A3b, A3, b);
+        }
+      }
+    }
+  }
+
+  // ---- one face: order reduction + solver dispatch (:1295-1467)
+  template <int ORD>
+  GB_HD double face_root(const double *c, bool start_face, int i_scaling)
+  {
+    int solver;
+    double qa, qb, qc = 0.0, qd = 0.0, qe = 0.0;
+    const bool reduced = start_face || (c[0] == 0.0);
+    if (ORD == 1) {
+      if (reduced) return 0.0;
+      solver = 1; qa = c[1]; qb = c[0];
+      if (qa == 0.0) return 0.0;
+    } else if (ORD == 2) {
+      if (reduced) {
+        solver = 1; qa = c[2] / 2.0; qb = c[1];
+        if (qa == 0.0) return 0.0;
+      } else {
+        solver = 2; qa = c[2]; qb = c[1]; qc = c[0];
+        if (qa == 0.0) {
+          if (qb != 0.0) { solver = 1; qa = qb; qb = qc; }
+          else return 0.0;
+        }
+      }
+    } else if (ORD == 3) {
+      if (reduced) {
+        solver = 2; qa = c[3] / 3.0; qb = c[2] / 2.0; qc = c[1];
+        if (qa == 0.0) {
+          if (qb != 0.0) { solver = 1; qa = qb; qb = qc; }
+          else return 0.0;
+        }
+      } else {
+        solver = 3; qa = c[3]; qb = c[2]; qc = c[1]; qd = c[0];
+        if (qa == 0.0) {
+          if (qb != 0.0) { solver = 2; qa = qb; qb = qc; qc = qd; }
+          else if (qc != 0.0) { solver = 1; qa = qc; qb = qd; }
+          else return 0.0;
+        }
+      }
+    } else {
+      if (reduced) {
+        solver = 3; qa = c[4] / 4.0; qb = c[3] / 3.0; qc = c[2] / 2.0; qd = c[1];
+        if (qa == 0.0) {
+          if (qb != 0.0) { solver = 2; qa = qb; qb = qc; qc = qd; }
+          else if (qc != 0.0) { solver = 1; qa = qc; qb = qd; }
+          else return 0.0;
+        }
+      } else {
+        solver = 4; qa = c[4]; qb = c[3]; qc = c[2]; qd = c[1]; qe = c[0];
+        if (qa == 0.0) {
+          if (qb != 0.0) { solver = 3; qa = qb; qb = qc; qc = qd; qd = qe; }
+          else if (qc != 0.0) { solver = 2; qa = qc; qb = qd; qc = qe; }
+          else if (qd != 0.0) { solver = 1; qa = qd; qb = qe; }
+          else return 0.0;
+        }
+      }
+    }
+    switch (solver) {
+      case 1: return linear_solver(qa, qb);
+      case 2: return (i_scaling == 0) ? quadratic_solver1(qa, qb, qc) : quadratic_solver2(qa, qb, qc, solver_iters);
+      case 3: return cubic_solver(qa, qb, qc, qd, solver_iters);
+      default: return quartic_solver(i_scaling, qa, qb, qc, qd, qe, solver_iters);
+    }
+  }
+
+  // ---- :1258-1482.  dtau/iface untouched when no valid root exists.
+  template <int ORD>
+  GB_HD bool analytic_approx(unsigned mask, int i_scaling, const double *z, int &iface_inout, double &dtau)
+  {
+    double cm[4][5];
+    coeff<ORD>(mask, z, cm);
+    const int iface = iface_inout;
+    double best = GB_HUGE;
+    int ibest = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (!(mask & (1u << i))) continue;
+      double d = face_root<ORD>(cm[i], (i + 1) == iface, i_scaling);
+      // valid: 0 < d < huge ; minloc keeps the lowest face index on ties
+      if ((d < GB_HUGE) && (d > 0.0) && (ibest == 0 || d < best)) {
+        best = d;
+        ibest = i + 1;
+      }
+    }
+    if (ibest == 0) return false;
+    iface_inout = ibest;
+    dtau = best;
+    return true;
+  }
+
+  // ---- :2047-2083
+  template <int ORD>
+  GB_HD void integrate(double *z, double tau)
+  {
+    nsteps++;
+    if (ORD >= 1) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) z[i] = z[i] + tau * (b[i] + Az[i]);
+    }
+    if (ORD >= 2) {
+      double tau2_half = tau * tau * 0.5;
+#pragma unroll
+      for (int i = 0; i < 4; i++) z[i] = z[i] + tau2_half * (Ab[i] + A2z[i]);
+    }
+    if (ORD >= 3) {
+      double tau3_sixth = (tau * tau) * tau / 6.0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) z[i] = z[i] + tau3_sixth * (A2b[i] + A3z[i]);
+    }
+    if (ORD >= 4) {
+      double t2 = tau * tau;
+      double tau4_24 = (t2 * t2) / 24.0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) z[i] = z[i] + tau4_24 * (A3b[i] + A4z[i]);
+    }
+  }
+
+  GB_HD double normal_distance(const double *z, int iface /*1-based*/) const
+  {
+    double d = dot3(z, r.an[iface - 1]);
+    if (iface == 1) d = d + r.dist_ref;
+    return d;
+  }
+  // ---- :2741-2775
+  GB_HD double normal_v_from_trajectory(int iface, double tau) const
+  {
+    const double *n = r.an[iface - 1];
+    double v = 0.0;
+    if (K >= 1) v = (n[0] * (b[0] + Az[0]) + n[1] * (b[1] + Az[1])) + n[2] * (b[2] + Az[2]);
+    if (K >= 2) v = v + ((n[0] * tau * (Ab[0] + A2z[0]) + n[1] * tau * (Ab[1] + A2z[1])) + n[2] * tau * (Ab[2] + A2z[2]));
+    if (K >= 3) {
+      double h = tau * tau * 0.5;
+      v = v + ((n[0] * h * (A2b[0] + A3z[0]) + n[1] * h * (A2b[1] + A3z[1])) + n[2] * h * (A2b[2] + A3z[2]));
+    }
+    if (K >= 4) {
+      double s = (tau * tau) * tau / 6.0;
+      v = v + ((n[0] * s * (A3b[0] + A4z[0]) + n[1] * s * (A3b[1] + A4z[1])) + n[2] * s * (A3b[2] + A4z[2]));
+    }
+    return v;
+  }
+  // ---- :2709-2739, poly1 quantities (n.alpha, n.beta, n.curlA) formed on the fly
+  GB_HD double normal_velocity(const double *z, int iface) const
+  {
+    const double *n = r.an[iface - 1];
+    const double pc = perpinv * mp->cm_over_e;
+    double t[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double in_alp = dot3(n, &r.alp[3 * j]);
+      if (PHI) {
+        double in_bet = dot3(n, &r.bet[3 * j]);
+        t[j] = (-GB_CLIGHT * in_bet + pc * in_alp) * z[j];
+      } else {
+        t[j] = (pc * in_alp) * z[j];
+      }
+    }
+    double in_betvec = dot3(n, r.curlA);
+    return ((t[0] + t[1]) + t[2] + in_betvec * z[3]) * (double)sign_rhs + dot3(n, b);
+  }
+  GB_HD bool three_planes_ok(const double *z, int iface_new) const
+  {
+    bool ok = true;
+#pragma unroll
+    for (int j = 1; j <= 3; j++) {
+      int k = ((iface_new + j - 1) & 3) + 1;
+      if (normal_distance(z, k) < 0.0) ok = false;
+    }
+    return ok;
+  }
+  GB_HD bool face_converged(const double *z, int iface_new) const
+  {
+    return !(fabs(normal_distance(z, iface_new)) > 1.e-11);
+  }
+  // ---- :2779-2831
+  GB_HD double physical_estimate_tau() const
+  {
+    const double *cold = mp->cold + ((int64_t)ind_tetr - 1) * COLD_ND;
+    double tetra_dist_ref = fabs(ldg(cold + C_TETRA_DIST_REF));
+    double R1 = ldg(cold + C_R1), Er_mod = ldg(cold + C_ER_MOD);
+    double vperp2 = -2.0 * perpinv * bmod0;
+    double vd_ExB = fabs(GB_CLIGHT / bmod0 * Er_mod);
+    double tau_est = fabs(tetra_dist_ref / z_init[3]);
+    if (!(vperp2 == 0.0)) {
+      double c2 = sqrt(tetra_dist_ref * vmod0 * R1 / (vperp2 * (double)mp->grid_size2 * 0.1));
+      if (c2 < tau_est) tau_est = c2;
+    }
+    if (!(vd_ExB == 0.0)) {
+      double c3 = tetra_dist_ref / vd_ExB;
+      if (c3 < tau_est) tau_est = c3;
+    }
+    return fabs(tau_est / dt_dtau_const);
+  }
+
+  // ---- :762-826 ; returns boole_analytical_approx
+  GB_HD bool prolonged_trajectory(int i_scaling, double *z, double &tau, int &iface_new, bool &face_correct)
+  {
+    double tau_save = tau, tau_max = 0.0;
+    int iface_new_save = iface_new;
+    bool approx = true;
+    fallback |= 4;
+    if (K > 2) {
+      approx = analytic_approx<2>(0xFu, i_scaling, z, iface_new, tau);
+      tau_max = tau * GB_EPS_TAU;
+    }
+    iface_new = iface_new_save;
+    approx = analytic_approx<K>(0xFu, i_scaling, z, iface_new, tau);
+    if (!approx) return false;
+    integrate<K>(z, tau);
+    if (K > 2 && tau > tau_max) face_correct = false;
+    if (!three_planes_ok(z, iface_new)) face_correct = false;
+    if (normal_velocity(z, iface_new) > 0.0) face_correct = false;
+    if (!face_converged(z, iface_new)) face_correct = false;
+    tau = tau + tau_save;
+    return true;
+  }
+
+  GB_HD bool ts_checks(const double *z, int iface_new, double tau, double tau_max) const
+  {
+    bool ok = true;
+    if (!three_planes_ok(z, iface_new)) ok = false;
+    if (!face_converged(z, iface_new)) ok = false;
+    if (normal_velocity(z, iface_new) > 0.0) ok = false;
+    if (tau > tau_max) {
+      double tau_max_est = physical_estimate_tau() * GB_EPS_TAU;
+      if (tau > tau_max_est) ok = false;
+    }
+    return ok;
+  }
+  // ---- :2835-2998 ; returns boole_trouble_shooting
+  GB_HD bool trouble_shooting(double *z, double &tau, int &iface_new)
+  {
+    fallback |= 2;
+    bool face_correct = false, approx;
+    iface_new = iface_init;
+#pragma unroll
+    for (int i = 0; i < 4; i++) z[i] = z_init[i];
+    approx = analytic_approx<2>(0xFu, 0, z, iface_new, tau);
+    (void)approx;
+    double tau_max = tau * GB_EPS_TAU;
+    if (K == 4) {
+      for (int i = 1; i <= 6 && !face_correct; i++) {
+        iface_new = iface_init;
+#pragma unroll
+        for (int q = 0; q < 4; q++) z[q] = z_init[q];
+        nsteps = 0;
+        if (!analytic_approx<K>(0xFu, i, z, iface_new, tau)) return false;
+        integrate<K>(z, tau);
+        face_correct = ts_checks(z, iface_new, tau, tau_max);
+      }
+    }
+    if (!face_correct) {
+      iface_new = iface_init;
+#pragma unroll
+      for (int q = 0; q < 4; q++) z[q] = z_init[q];
+      nsteps = 0;
+      if (K == 4) {
+        // order reduced to 3, i_scaling 0; trajectory integrated with the ORIGINAL order (:2961),
+        // using the order-4 terms left over from the loop above (same z_init => same values)
+        if (!analytic_approx<3>(0xFu, 0, z, iface_new, tau)) return false;
+      } else if (K == 1) {
+        // no case(1) in the reference (:2936-2947); keep order, i_scaling = 0
+        if (!analytic_approx<K>(0xFu, 0, z, iface_new, tau)) return false;
+      } else {
+        if (!analytic_approx<K>(0xFu, 1, z, iface_new, tau)) return false;
+      }
+      integrate<K>(z, tau);
+      if (!ts_checks(z, iface_new, tau, tau_max)) return false;
+    }
+    return true;
+  }
+
+  // ---- pusher_handover2neighbour (kind 1)
+  GB_HD void handover(int iface_exit, double *x, int32_t &ind_out, int32_t &iface_out) const
+  {
+    const int f = iface_exit - 1;
+    ind_out = r.nb[f];
+    iface_out = topo_face(r.flags, f);
+    const int iper_phi = topo_perphi(r.flags, f);
+    if (mp->coord_system == 1) {
+      if (iper_phi == 1) x[1] = x[1] - mp->period_phi;
+      else if (iper_phi == -1) x[1] = x[1] + mp->period_phi;
+    } else {
+      const int iper_theta = topo_pertheta(r.flags, f);
+      if (iper_phi == 1) x[2] = x[2] - mp->period_phi;
+      else if (iper_phi == -1) x[2] = x[2] + mp->period_phi;
+      if (iper_theta == 1) x[1] = x[1] - mp->period_theta;
+      else if (iper_theta == -1) x[1] = x[1] + mp->period_theta;
+    }
+  }
+
+  GB_HD void set_removed(PushOut &o) const
+  {
+    o.ind_tetr = -1;
+    o.iface = -1;
+    o.finished = 0;
+    o.t_pass = 0.0;
+    o.z_save_set = 0;
+    o.fallback = fallback;
+  }
+
+  // ---- final processing shared by push_fast / push_full (:459-466, 497-660).
+  // Returns false if (fast mode) the stop-inside case needs the fall-back ladder.
+  template <bool FAST>
+  GB_HD bool finish(double *z, double tau, int iface_new, PushOut &o)
+  {
+    // x, vpar are updated BEFORE the stop-inside test (:459-460); a removal further down keeps them
+#pragma unroll
+    for (int i = 0; i < 3; i++) o.x[i] = z[i] + r.x1[i];
+    o.vpar = z[3];
+    double t_pass = tau * dt_dtau_const;
+    if (fabs(t_pass) >= fabs(t_remain)) {
+      if (FAST && nsteps > 1) return false;
+#pragma unroll
+      for (int i = 0; i < 4; i++) z[i] = z_init[i];
+      if (nsteps > 1) {
+        iface_new = iface_init;
+        set_integration_coef_manually(z);
+      }
+      nsteps = 0;
+      tau = t_remain / dt_dtau_const;
+      integrate<K>(z, tau);
+      bool inside = true;
+#pragma unroll
+      for (int i = 1; i <= 4; i++)
+        if (normal_distance(z, i) < 0.0) inside = false;
+      if (inside) {
+        o.ind_tetr = ind_tetr;
+        o.iface = 0;
+        o.finished = 1;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          o.z_save[i] = z[i];
+          o.x[i] = z[i] + r.x1[i];
+        }
+        o.z_save_set = 1;
+        o.vpar = z[3];
+        o.t_pass = t_remain;
+        o.fallback = fallback;
+        return true;
+      }
+      if (FAST) return false;
+      fallback |= 8;
+      if (!trouble_shooting(z, tau, iface_new)) {
+        set_removed(o);
+        return true;
+      }
+      t_pass = tau * dt_dtau_const;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      o.z_save[i] = z[i];
+      o.x[i] = z[i] + r.x1[i];
+    }
+    o.z_save_set = 1;
+    o.vpar = z[3];
+    o.t_pass = t_pass;
+    o.finished = 0;
+    handover(iface_new, o.x, o.ind_tetr, o.iface);
+    o.fallback = fallback;
+    return true;
+  }
+
+  // ---- common case only; false => nothing decided, call push_full
+  GB_HD bool push_fast(int ind_tetr_in, int iface, const double *x, double vpar, double t_remain_in, PushOut &o)
+  {
+    init(ind_tetr_in, x, iface, vpar, t_remain_in);
+    solver_iters = 0;
+    fallback = 0;
+    double z[4] = {z_init[0], z_init[1], z_init[2], z_init[3]};
+    double tau = 0.0;
+    int iface_new = iface_init;
+    if (!analytic_approx<2>(0xFu, 0, z, iface_new, tau)) return false;
+    const double tau_max = tau * GB_EPS_TAU;
+    if (K > 2) {
+      unsigned mask = mp->boole_guess ? (1u << (iface_new - 1)) : 0xFu;
+      iface_new = iface_init;
+      if (!analytic_approx<K>(mask, 0, z, iface_new, tau)) return false;
+    }
+    integrate<K>(z, tau);
+    if (!three_planes_ok(z, iface_new)) return false;
+    if (!face_converged(z, iface_new)) return false;
+    if (K > 2 && tau > tau_max) return false;
+    if (normal_v_from_trajectory(iface_new, tau) > 0.0) return false;
+    return finish<true>(z, tau, iface_new, o);
+  }
+
+  // ---- the complete ladder (:182-675)
+  GB_HD void push_full(int ind_tetr_in, int iface, const double *x, double vpar, double t_remain_in, PushOut &o)
+  {
+    init(ind_tetr_in, x, iface, vpar, t_remain_in);
+    solver_iters = 0;
+    fallback = 0;
+    double z[4] = {z_init[0], z_init[1], z_init[2], z_init[3]};
+    double tau = 0.0;
+    int iface_new = iface_init;
+    unsigned mask = 0xFu;
+    bool approx = analytic_approx<2>(mask, 0, z, iface_new, tau);
+    const double tau_max = tau * GB_EPS_TAU;
+    if (mp->boole_guess && approx && (K > 2)) mask = 1u << (iface_new - 1);
+    if (K > 2) {
+      iface_new = iface_init;
+      approx = analytic_approx<K>(mask, 0, z, iface_new, tau);
+    }
+    bool face_correct = approx;
+    if (face_correct) {
+      integrate<K>(z, tau);
+      if (!three_planes_ok(z, iface_new)) face_correct = false;
+      if (!face_converged(z, iface_new)) face_correct = false;
+      if (K > 2 && tau > tau_max) face_correct = false;
+      if (face_correct) {
+        if (normal_v_from_trajectory(iface_new, tau) > 0.0) {
+          if (K > 2) {
+            face_correct = false;
+          } else {
+            if (!prolonged_trajectory(0, z, tau, iface_new, face_correct)) {
+              set_removed(o);
+              return;
+            }
+          }
+        }
+      }
+    }
+    if (!face_correct) {
+      fallback |= 1;
+      face_correct = true;
+      iface_new = iface_init;
+#pragma unroll
+      for (int i = 0; i < 4; i++) z[i] = z_init[i];
+      nsteps = 0;
+      approx = analytic_approx<K>(0xFu, (K == 2) ? 1 : 0, z, iface_new, tau);
+      if (!approx) {
+        set_removed(o);
+        return;
+      }
+      integrate<K>(z, tau);
+      if (K > 2 && tau > tau_max) face_correct = false;
+      if (!three_planes_ok(z, iface_new)) face_correct = false;
+      if (!face_converged(z, iface_new)) face_correct = false;
+      if (face_correct) {
+        if (normal_velocity(z, iface_new) > 0.0) {
+          if (!prolonged_trajectory(0, z, tau, iface_new, face_correct)) {
+            set_removed(o);
+            return;
+          }
+        }
+      }
+      if (!face_correct) {
+        if (!trouble_shooting(z, tau, iface_new)) {
+          set_removed(o);
+          return;
+        }
+      }
+    }
+    finish<false>(z, tau, iface_new, o);
+  }
+};
+
+// Non-inlined complete push: by-value in, by-value out, so that no hot-loop variable has its address taken.
+template <int K, bool PHI>
+GB_HD_NOINLINE PushOut push_full_call(const MeshDev *mp, double perpinv, int ind_tetr, int iface, double x0,
+                                      double x1, double x2, double vpar, double t_remain)
+{
+  PolyPusher<K, PHI> P;
+  P.mp = mp;
+  P.perpinv = perpinv;
+  PushOut o;
+  double x[3] = {x0, x1, x2};
+  o.x[0] = x0; o.x[1] = x1; o.x[2] = x2; o.vpar = vpar;
+  o.z_save[0] = o.z_save[1] = o.z_save[2] = 0.0;
+  P.push_full(ind_tetr, iface, x, vpar, t_remain, o);
+  return o;
+}
+
+// ---- small field helpers (SRC/supporting_functions_mod.f90:279-408) on the device layout -------------
+template <bool PHI>
+GB_HD double bmod_at(const MeshDev &m, int ind_tetr, const double *z)
+{
+  const double *pb = m.bpart + ((int64_t)ind_tetr - 1) * BPART_ND;
+  double g[3] = {ldg(pb + B_GB), ldg(pb + B_GB + 1), ldg(pb + B_GB + 2)};
+  return ldg(pb + B_BMOD1) + dot3(g, z);
+}
+
+} // namespace gb

@@ -1,0 +1,560 @@
+// gorilla_b200.cu -- CUDA kernels (sm_100a) and the C ABI of include/gorilla_b200.h.
+//
+// Kernels:
+//   orbit_kernel<K,PHI>   persistent, one particle per lane, lane refill from a global queue:
+//                         the whole `do ... enddo` of orbit_timestep_gorilla (orbit_timestep_gorilla.f90:100-139)
+//                         runs on the device; a lane whose particle finished or got lost immediately pulls
+//                         the next one, so warps stay full until the queue is empty.
+//   find_kernel<PHI>      check_coordinate_domain + find_tetra for not-yet-initialised particles.
+//   invariants_kernel     energy / p_phi / perpinv per particle.
+//   sort keys             radix sort (CUB) of particle indices by tetra index.
+// Compile with --fmad=false: the reference ISA has no FMA and the visited-tetra sequence is only
+// reproducible with separately rounded multiplies and adds.
+#include <cub/device/device_radix_sort.cuh>
+#include <string.h>
+#include <math.h>
+#include <mutex>
+#include <vector>
+#include "gb_internal.cuh"
+
+// ----------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static std::atomic<int64_t> g_launch_count{0};
+namespace gbint {
+void set_error(const char *msg) { g_last_error = msg; }
+void count_launch(int n) { g_launch_count += n; }
+}
+
+static int fail(int code, const char *msg)
+{
+  g_last_error = msg;
+  return code;
+}
+namespace gbhost {
+void set_last_error(const std::string &s) { g_last_error = s; }
+}
+
+// ----------------------------------------------------------------------------------------------------
+template <bool PHI>
+__global__ void __launch_bounds__(128) find_kernel(const __grid_constant__ MeshDev m, const Batch bt)
+{
+  unsigned long long dom_err = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < bt.n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (bt.init && bt.init[i]) continue;
+    double x[3] = {bt.x[3 * i], bt.x[3 * i + 1], bt.x[3 * i + 2]};
+    int32_t it = -1, ifc = -1;
+    if (check_coordinate_domain(m, x, bt.boole_periodic_relocation) != 0) {
+      dom_err++;
+    } else {
+      find_tetra<PHI>(&m, x, bt.vpar[i], bt.vperp[i], it, ifc, bt.sign_t_step);
+      bt.x[3 * i] = x[0];
+      bt.x[3 * i + 1] = x[1];
+      bt.x[3 * i + 2] = x[2];
+    }
+    bt.ind_tetr[i] = it;
+    bt.iface[i] = ifc;
+    if (bt.init && it != -1) bt.init[i] = 1;
+  }
+  if (dom_err) atomicAdd(bt.ctr + CTR_DOMAIN, dom_err);
+}
+
+// ----------------------------------------------------------------------------------------------------
+__global__ void invariants_kernel(const __grid_constant__ MeshDev m, int64_t n, const double *x, const double *vpar,
+                                  const double *vperp, const int32_t *ind_tetr, double *energy, double *p_phi,
+                                  double *perpinv_out)
+{
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t it = ind_tetr[i];
+    double e = NAN, p = NAN, mu = NAN;
+    if (it >= 1) {
+      const double *pg = m.geom + ((int64_t)it - 1) * GEOM_ND;
+      const double *pb = m.bpart + ((int64_t)it - 1) * BPART_ND;
+      const double *pc = m.cold + ((int64_t)it - 1) * COLD_ND;
+      const double z[3] = {x[3 * i] - pg[0], x[3 * i + 1] - pg[1], x[3 * i + 2] - pg[2]};
+      const double gB[3] = {pb[B_GB], pb[B_GB + 1], pb[B_GB + 2]};
+      const double bmod = pb[B_BMOD1] + dot3(gB, z);
+      const double vp = vperp[i], vl = vpar[i];
+      mu = -0.5 * (vp * vp) / bmod;
+      // energy_tot_func (supporting_functions_mod.f90:279-301)
+      const double vperp_e = sqrt(2.0 * fabs(mu) * bmod);
+      double phi = 0.0;
+      if (m.phi) {
+        const double *pp = m.phi + ((int64_t)it - 1) * PHI_ND;
+        const double gP[3] = {pp[P_GPHI], pp[P_GPHI + 1], pp[P_GPHI + 2]};
+        phi = pp[P_PHI1] + dot3(gP, z);
+      }
+      e = m.particle_mass / 2.0 * (vperp_e * vperp_e + vl * vl) + m.particle_charge * phi;
+      // p_phi_func (:377-408)
+      const double gh[3] = {pc[C_GHPHI], pc[C_GHPHI + 1], pc[C_GHPHI + 2]};
+      const double gA[3] = {pc[C_GAPHI], pc[C_GAPHI + 1], pc[C_GAPHI + 2]};
+      p = m.particle_mass * vl * (pc[C_HPHI1] + dot3(gh, z)) +
+          m.particle_mass / m.cm_over_e * (pc[C_APHI1] + dot3(gA, z));
+    }
+    if (energy) energy[i] = e;
+    if (p_phi) p_phi[i] = p;
+    if (perpinv_out) perpinv_out[i] = mu;
+  }
+}
+
+__global__ void sort_keys_kernel(int64_t n, const int32_t *ind_tetr, uint32_t *keys, int64_t *vals)
+{
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t t = ind_tetr[i];
+    keys[i] = t < 1 ? 0xffffffffu : (uint32_t)t;
+    vals[i] = i;
+  }
+}
+
+static int check_settings(const gorilla_settings *s)
+{
+  if (s->ipusher != 2) return fail(GORILLA_ERR_UNSUPPORTED, "ipusher: only 2 (polynomial pusher) is implemented");
+  if (s->poly_order < 1 || s->poly_order > 4) return fail(GORILLA_ERR_ARG, "poly_order must be 1..4");
+  if (s->i_precomp != 0) return fail(GORILLA_ERR_UNSUPPORTED, "i_precomp must be 0");
+  if (s->i_time_tracing_option != 1) return fail(GORILLA_ERR_UNSUPPORTED, "i_time_tracing_option must be 1");
+  if (s->handover_processing_kind != 1) return fail(GORILLA_ERR_UNSUPPORTED, "handover_processing_kind must be 1");
+  if (s->boole_adaptive_time_steps) return fail(GORILLA_ERR_UNSUPPORTED, "boole_adaptive_time_steps must be .false.");
+  if (s->boole_strong_electric_field) return fail(GORILLA_ERR_UNSUPPORTED, "boole_strong_electric_field must be .false.");
+  if (s->boole_pusher_ode45) return fail(GORILLA_ERR_UNSUPPORTED, "boole_pusher_ode45 must be .false.");
+  return GORILLA_OK;
+}
+
+extern "C" const char *gorilla_b200_last_error(void) { return g_last_error.c_str(); }
+extern "C" int64_t gorilla_b200_launch_count(void) { return g_launch_count.load(); }
+
+extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_settings *st, gorilla_b200_handle **out)
+{
+  if (!md || !st || !out || !md->tetra_physics || !md->tetra_grid || md->ntetr < 1)
+    return fail(GORILLA_ERR_ARG, "gorilla_b200_init: null argument or empty mesh");
+  int rc = check_settings(st);
+  if (rc) return rc;
+  if (md->coord_system != 1 && md->coord_system != 2) return fail(GORILLA_ERR_ARG, "coord_system must be 1 or 2");
+  int dev = 0;
+  GB_CUDA(cudaGetDevice(&dev));
+  gorilla_b200_handle *h = new gorilla_b200_handle();
+  h->device = dev;
+  GB_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  h->settings = *st;
+
+  const int64_t nt = md->ntetr;
+  std::vector<double> geom((size_t)nt * GEOM_ND), bpart((size_t)nt * BPART_ND), phi((size_t)nt * PHI_ND, 0.0),
+      cold((size_t)nt * COLD_ND, 0.0);
+  bool has_phi = false;
+  // offsets into type tetrahedron_physics (doubles), tetra_physics_mod.f90:9-83
+  enum { TP_X1 = 0, TP_DIST_REF = 3, TP_TETRA_DIST_REF = 8, TP_ANORM = 9, TP_CURLA = 21, TP_BMOD1 = 24, TP_APHI1 = 26,
+         TP_H2_1 = 28, TP_H3_1 = 29, TP_PHI1 = 30, TP_R1 = 31, TP_ER_MOD = 37, TP_DT_DTAU_CONST = 40, TP_GBXCURLA = 41,
+         TP_GPHIXCURLA = 42, TP_SPALPMAT = 47, TP_SPBETMAT = 48, TP_GBXH1 = 50, TP_GPHIXH1 = 53, TP_GB = 59,
+         TP_GPHI = 62, TP_GAPHI = 77, TP_GH2 = 83, TP_GH3 = 86, TP_CURLH = 89, TP_ALPMAT = 107, TP_BETMAT = 116 };
+  for (int64_t t = 0; t < nt; t++) {
+    const double *r = md->tetra_physics + t * GORILLA_TETRA_PHYSICS_NDOUBLES;
+    const int32_t *g = md->tetra_grid + t * GORILLA_TETRA_GRID_NINTS;
+    double *G = &geom[(size_t)t * GEOM_ND], *B = &bpart[(size_t)t * BPART_ND], *P = &phi[(size_t)t * PHI_ND],
+           *C = &cold[(size_t)t * COLD_ND];
+    for (int i = 0; i < 3; i++) G[i] = r[TP_X1 + i];
+    G[3] = r[TP_DIST_REF];
+    for (int i = 0; i < 12; i++) G[4 + i] = r[TP_ANORM + i];
+    B[B_BMOD1] = r[TP_BMOD1];
+    for (int i = 0; i < 3; i++) {
+      B[B_GB + i] = r[TP_GB + i];
+      B[B_CURLA + i] = r[TP_CURLA + i];
+      B[B_CURLH + i] = r[TP_CURLH + i];
+      B[B_GBXH1 + i] = r[TP_GBXH1 + i];
+    }
+    B[B_GBXCURLA] = r[TP_GBXCURLA];
+    for (int i = 0; i < 9; i++) B[B_ALP + i] = r[TP_ALPMAT + i];
+    B[B_SPALP] = r[TP_SPALPMAT];
+    B[B_DTDTAU] = r[TP_DT_DTAU_CONST];
+    int32_t topo[6] = {g[4], g[5], g[6], g[7], 0, 0};
+    uint32_t flags = 0;
+    for (int f = 0; f < 4; f++) {
+      int nf = g[8 + f], pp = g[12 + f], pt = (md->coord_system == 2) ? g[16 + f] : 0;
+      if (nf < -1 || nf > 4 || pp < -1 || pp > 1 || pt < -1 || pt > 1) {
+        delete h;
+        return fail(GORILLA_ERR_ARG, "tetra_grid: neighbour_face / perbou value out of range");
+      }
+      flags |= ((uint32_t)(nf + 1) | ((uint32_t)(pp + 1) << 3) | ((uint32_t)(pt + 1) << 5)) << (7 * f);
+    }
+    topo[4] = (int32_t)flags;
+    memcpy(&B[B_TOPO], topo, sizeof(topo));
+    P[P_PHI1] = r[TP_PHI1];
+    for (int i = 0; i < 3; i++) {
+      P[P_GPHI + i] = r[TP_GPHI + i];
+      P[P_GPHIXH1 + i] = r[TP_GPHIXH1 + i];
+    }
+    P[P_GPHIXCURLA] = r[TP_GPHIXCURLA];
+    for (int i = 0; i < 9; i++) P[P_BET + i] = r[TP_BETMAT + i];
+    P[P_SPBET] = r[TP_SPBETMAT];
+    for (int i = 0; i < 18; i++)
+      if (P[i] != 0.0) has_phi = true; // NaN counts as "present"
+    C[C_TETRA_DIST_REF] = r[TP_TETRA_DIST_REF];
+    C[C_R1] = r[TP_R1];
+    C[C_ER_MOD] = r[TP_ER_MOD];
+    if (md->coord_system == 1) {
+      C[C_HPHI1] = r[TP_H2_1];
+      for (int i = 0; i < 3; i++) C[C_GHPHI + i] = r[TP_GH2 + i];
+    } else {
+      C[C_HPHI1] = r[TP_H3_1];
+      for (int i = 0; i < 3; i++) C[C_GHPHI + i] = r[TP_GH3 + i];
+    }
+    C[C_APHI1] = r[TP_APHI1];
+    for (int i = 0; i < 3; i++) C[C_GAPHI + i] = r[TP_GAPHI + i];
+  }
+  auto up = [&](double **d, const std::vector<double> &v) -> cudaError_t {
+    cudaError_t e = cudaMalloc((void **)d, v.size() * sizeof(double));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*d, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice);
+  };
+  cudaError_t e;
+  if ((e = up(&h->d_geom, geom)) != cudaSuccess || (e = up(&h->d_bpart, bpart)) != cudaSuccess ||
+      (e = up(&h->d_cold, cold)) != cudaSuccess || (has_phi && (e = up(&h->d_phi, phi)) != cudaSuccess) ||
+      (e = cudaMalloc((void **)&h->d_ctr, CTR_N * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
+      (e = cudaEventCreate(&h->ev2)) != cudaSuccess) {
+    g_last_error = std::string("gorilla_b200_init: ") + cudaGetErrorString(e);
+    gorilla_b200_free(h);
+    return GORILLA_ERR_CUDA;
+  }
+  MeshDev &m = h->mesh;
+  m.ntetr = nt;
+  m.geom = h->d_geom;
+  m.bpart = h->d_bpart;
+  m.phi = has_phi ? h->d_phi : nullptr;
+  m.cold = h->d_cold;
+  m.cm_over_e = md->cm_over_e;
+  m.particle_mass = md->particle_mass;
+  m.particle_charge = md->particle_charge;
+  const double PI = 3.141592653589793238462643383;
+  m.period_phi = 2.0 * PI / md->n_field_periods;
+  m.period_theta = 2.0 * PI;
+  m.sign_sqg = md->sign_sqg;
+  m.coord_system = md->coord_system;
+  m.grid_size1 = md->grid_size[0];
+  m.grid_size2 = md->grid_size[1];
+  m.grid_size3 = md->grid_size[2];
+  m.boole_guess = st->boole_guess;
+  m.grid_kind = md->grid_kind;
+  m.n_field_periods = md->n_field_periods;
+  m.Rmin = md->Rmin;
+  m.Rmax = md->Rmax;
+  m.Zmin = md->Zmin;
+  m.Zmax = md->Zmax;
+  m.sfc_s_min = md->sfc_s_min;
+  *out = h;
+  return GORILLA_OK;
+}
+
+extern "C" void gorilla_b200_free(gorilla_b200_handle *h)
+{
+  if (!h) return;
+  cudaFree(h->d_geom); cudaFree(h->d_bpart); cudaFree(h->d_phi); cudaFree(h->d_cold); cudaFree(h->d_ctr);
+  cudaFree(h->s_x); cudaFree(h->s_vpar); cudaFree(h->s_vperp); cudaFree(h->s_tro); cudaFree(h->s_e);
+  cudaFree(h->s_p); cudaFree(h->s_mu); cudaFree(h->s_init); cudaFree(h->s_ind); cudaFree(h->s_iface);
+  cudaFree(h->s_np); cudaFree(h->s_tr_t); cudaFree(h->s_tr_f); cudaFree(h->sort_tmp);
+  cudaFree(h->sort_keys_in); cudaFree(h->sort_keys_out); cudaFree(h->sort_vals_in);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev2) cudaEventDestroy(h->ev2);
+  delete h;
+}
+
+extern "C" int gorilla_b200_set_launch_config(gorilla_b200_handle *h, int32_t ctas_per_sm, int32_t threads_per_cta)
+{
+  if (!h) return fail(GORILLA_ERR_ARG, "null handle");
+  if (ctas_per_sm > 0) h->ctas_per_sm = ctas_per_sm;
+  if (threads_per_cta > 0) {
+    if (threads_per_cta % 32 || threads_per_cta > 128) return fail(GORILLA_ERR_ARG, "threads_per_cta must be 32..128, multiple of 32");
+    h->threads_per_cta = threads_per_cta;
+  }
+  return GORILLA_OK;
+}
+// test hook (not in the public header): route every push through the complete fall-back ladder
+extern "C" int gorilla_b200_debug_force_full(gorilla_b200_handle *h, int32_t on)
+{
+  if (!h) return GORILLA_ERR_ARG;
+  h->force_full = on;
+  return GORILLA_OK;
+}
+
+// the eight orbit_kernel<K,PHI> instantiations live in gb_orbit_k{1..4}.cu
+#define GB_EXTERN_ORBIT(K) \
+  extern template int launch_orbit_t<K, true>(gorilla_b200_handle *, const Batch &, cudaStream_t); \
+  extern template int launch_orbit_t<K, false>(gorilla_b200_handle *, const Batch &, cudaStream_t);
+GB_EXTERN_ORBIT(1)
+GB_EXTERN_ORBIT(2)
+GB_EXTERN_ORBIT(3)
+GB_EXTERN_ORBIT(4)
+
+template <bool PHI>
+static int launch_orbit_k(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
+{
+  switch (h->settings.poly_order) {
+    case 1: return launch_orbit_t<1, PHI>(h, bt, s);
+    case 2: return launch_orbit_t<2, PHI>(h, bt, s);
+    case 3: return launch_orbit_t<3, PHI>(h, bt, s);
+    default: return launch_orbit_t<4, PHI>(h, bt, s);
+  }
+}
+
+static int run_device(gorilla_b200_handle *h, Batch bt, bool do_find, cudaStream_t s)
+{
+  bt.ctr = h->d_ctr;
+  bt.boole_periodic_relocation = h->settings.boole_periodic_relocation;
+  bt.sign_t_step = signbit(bt.t_step) ? -1 : 1;
+  bt.force_full = h->force_full;
+  GB_CUDA(cudaMemsetAsync(h->d_ctr, 0, CTR_N * sizeof(unsigned long long), s));
+  h->have_find_time = false;
+  h->have_push_time = false;
+  h->last_n = bt.n;
+  h->last_stream = s;
+  if (bt.n == 0) return GORILLA_OK;
+  GB_CUDA(cudaEventRecord(h->ev0, s));
+  if (do_find) {
+    int64_t grid = (bt.n + 127) / 128;
+    if (grid > (int64_t)h->num_sms * 16) grid = (int64_t)h->num_sms * 16;
+    if (h->mesh.phi) find_kernel<true><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
+    else find_kernel<false><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
+    g_launch_count++;
+    GB_CUDA(cudaGetLastError());
+    h->have_find_time = true;
+  }
+  GB_CUDA(cudaEventRecord(h->ev1, s));
+  int rc = h->mesh.phi ? launch_orbit_k<true>(h, bt, s) : launch_orbit_k<false>(h, bt, s);
+  if (rc) return rc;
+  GB_CUDA(cudaEventRecord(h->ev2, s));
+  h->have_push_time = true;
+  return GORILLA_OK;
+}
+
+extern "C" int gorilla_b200_orbit_timestep_dev(gorilla_b200_handle *h, int64_t n, double *x, double *vpar, double *vperp,
+                                               double t_step, int32_t *boole_initialized, int32_t *ind_tetr,
+                                               int32_t *iface, double *t_remain_out, int64_t *n_pushes, void *stream)
+{
+  if (!h || n < 0 || (n > 0 && (!x || !vpar || !vperp || !boole_initialized || !ind_tetr || !iface)))
+    return fail(GORILLA_ERR_ARG, "gorilla_b200_orbit_timestep_dev: null argument");
+  Batch bt{};
+  bt.n = n; bt.x = x; bt.vpar = vpar; bt.vperp = vperp; bt.t_step = t_step; bt.init = boole_initialized;
+  bt.ind_tetr = ind_tetr; bt.iface = iface; bt.t_remain_out = t_remain_out; bt.n_pushes = n_pushes;
+  return run_device(h, bt, true, (cudaStream_t)stream);
+}
+
+static int ensure_scratch(gorilla_b200_handle *h, int64_t n)
+{
+  if (n <= h->cap) return GORILLA_OK;
+  cudaFree(h->s_x); cudaFree(h->s_vpar); cudaFree(h->s_vperp); cudaFree(h->s_tro); cudaFree(h->s_e);
+  cudaFree(h->s_p); cudaFree(h->s_mu); cudaFree(h->s_init); cudaFree(h->s_ind); cudaFree(h->s_iface); cudaFree(h->s_np);
+  h->s_x = h->s_vpar = h->s_vperp = h->s_tro = h->s_e = h->s_p = h->s_mu = nullptr;
+  h->s_init = h->s_ind = h->s_iface = nullptr; h->s_np = nullptr;
+  h->cap = 0;
+  GB_CUDA(cudaMalloc((void **)&h->s_x, (size_t)n * 3 * sizeof(double)));
+  GB_CUDA(cudaMalloc((void **)&h->s_vpar, (size_t)n * sizeof(double)));
+  GB_CUDA(cudaMalloc((void **)&h->s_vperp, (size_t)n * sizeof(double)));
+  GB_CUDA(cudaMalloc((void **)&h->s_tro, (size_t)n * sizeof(double)));
+  GB_CUDA(cudaMalloc((void **)&h->s_e, (size_t)n * sizeof(double)));
+  GB_CUDA(cudaMalloc((void **)&h->s_p, (size_t)n * sizeof(double)));
+  GB_CUDA(cudaMalloc((void **)&h->s_mu, (size_t)n * sizeof(double)));
+  GB_CUDA(cudaMalloc((void **)&h->s_init, (size_t)n * sizeof(int32_t)));
+  GB_CUDA(cudaMalloc((void **)&h->s_ind, (size_t)n * sizeof(int32_t)));
+  GB_CUDA(cudaMalloc((void **)&h->s_iface, (size_t)n * sizeof(int32_t)));
+  GB_CUDA(cudaMalloc((void **)&h->s_np, (size_t)n * sizeof(int64_t)));
+  h->cap = n;
+  return GORILLA_OK;
+}
+
+static int orbit_host(gorilla_b200_handle *h, int64_t n, double *x, double *vpar, double *vperp, double t_step,
+                      int32_t *binit, int32_t *ind_tetr, int32_t *iface, double *tro, int64_t *np, int32_t trace_cap,
+                      int32_t *tr_t, int32_t *tr_f)
+{
+  if (!h || n < 0 || (n > 0 && (!x || !vpar || !vperp || !binit || !ind_tetr || !iface)))
+    return fail(GORILLA_ERR_ARG, "gorilla_b200_orbit_timestep: null argument");
+  if (n == 0) return GORILLA_OK;
+  int rc = ensure_scratch(h, n);
+  if (rc) return rc;
+  cudaStream_t s = nullptr;
+  GB_CUDA(cudaMemcpyAsync(h->s_x, x, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_vpar, vpar, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_vperp, vperp, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_init, binit, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_ind, ind_tetr, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_iface, iface, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  Batch bt{};
+  bt.n = n; bt.x = h->s_x; bt.vpar = h->s_vpar; bt.vperp = h->s_vperp; bt.t_step = t_step; bt.init = h->s_init;
+  bt.ind_tetr = h->s_ind; bt.iface = h->s_iface; bt.t_remain_out = h->s_tro; bt.n_pushes = h->s_np;
+  if (trace_cap > 0) {
+    if (!tr_t || !tr_f) return fail(GORILLA_ERR_ARG, "trace buffers are null");
+    const int64_t elems = n * (int64_t)trace_cap;
+    if (elems > h->trace_cap_elems) {
+      cudaFree(h->s_tr_t); cudaFree(h->s_tr_f);
+      h->s_tr_t = h->s_tr_f = nullptr; h->trace_cap_elems = 0;
+      GB_CUDA(cudaMalloc((void **)&h->s_tr_t, (size_t)elems * sizeof(int32_t)));
+      GB_CUDA(cudaMalloc((void **)&h->s_tr_f, (size_t)elems * sizeof(int32_t)));
+      h->trace_cap_elems = elems;
+    }
+    GB_CUDA(cudaMemsetAsync(h->s_tr_t, 0, (size_t)elems * sizeof(int32_t), s));
+    GB_CUDA(cudaMemsetAsync(h->s_tr_f, 0, (size_t)elems * sizeof(int32_t), s));
+    bt.trace_cap = trace_cap; bt.trace_tetr = h->s_tr_t; bt.trace_face = h->s_tr_f;
+  }
+  rc = run_device(h, bt, true, s);
+  if (rc) return rc;
+  GB_CUDA(cudaMemcpyAsync(x, h->s_x, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaMemcpyAsync(vpar, h->s_vpar, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaMemcpyAsync(vperp, h->s_vperp, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaMemcpyAsync(binit, h->s_init, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaMemcpyAsync(ind_tetr, h->s_ind, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaMemcpyAsync(iface, h->s_iface, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (tro) GB_CUDA(cudaMemcpyAsync(tro, h->s_tro, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (np) GB_CUDA(cudaMemcpyAsync(np, h->s_np, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  if (trace_cap > 0) {
+    GB_CUDA(cudaMemcpyAsync(tr_t, h->s_tr_t, (size_t)n * trace_cap * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    GB_CUDA(cudaMemcpyAsync(tr_f, h->s_tr_f, (size_t)n * trace_cap * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  }
+  GB_CUDA(cudaStreamSynchronize(s));
+  unsigned long long dom = 0;
+  GB_CUDA(cudaMemcpy(&dom, h->d_ctr + CTR_DOMAIN, sizeof(dom), cudaMemcpyDeviceToHost));
+  if (dom) return fail(GORILLA_ERR_DOMAIN, "particle start position outside the computation domain");
+  return GORILLA_OK;
+}
+
+extern "C" int gorilla_b200_orbit_timestep(gorilla_b200_handle *h, int64_t n, double *x, double *vpar, double *vperp,
+                                           double t_step, int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface,
+                                           double *t_remain_out, int64_t *n_pushes)
+{
+  return orbit_host(h, n, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface, t_remain_out, n_pushes, 0, nullptr,
+                    nullptr);
+}
+extern "C" int gorilla_b200_orbit_timestep_trace(gorilla_b200_handle *h, int64_t n, double *x, double *vpar,
+                                                 double *vperp, double t_step, int32_t *boole_initialized,
+                                                 int32_t *ind_tetr, int32_t *iface, double *t_remain_out,
+                                                 int64_t *n_pushes, int32_t trace_cap, int32_t *trace_ind_tetr,
+                                                 int32_t *trace_iface)
+{
+  return orbit_host(h, n, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface, t_remain_out, n_pushes, trace_cap,
+                    trace_ind_tetr, trace_iface);
+}
+
+extern "C" int gorilla_b200_find_tetra(gorilla_b200_handle *h, int64_t n, double *x, const double *vpar,
+                                       const double *vperp, int32_t *ind_tetr, int32_t *iface, int32_t sign_t_step)
+{
+  if (!h || n < 0 || (n > 0 && (!x || !vpar || !vperp || !ind_tetr || !iface)))
+    return fail(GORILLA_ERR_ARG, "gorilla_b200_find_tetra: null argument");
+  if (n == 0) return GORILLA_OK;
+  int rc = ensure_scratch(h, n);
+  if (rc) return rc;
+  cudaStream_t s = nullptr;
+  GB_CUDA(cudaMemcpyAsync(h->s_x, x, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_vpar, vpar, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_vperp, vperp, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemsetAsync(h->d_ctr, 0, CTR_N * sizeof(unsigned long long), s));
+  Batch bt{};
+  bt.n = n; bt.x = h->s_x; bt.vpar = h->s_vpar; bt.vperp = h->s_vperp; bt.init = nullptr; bt.ind_tetr = h->s_ind;
+  bt.iface = h->s_iface; bt.ctr = h->d_ctr; bt.boole_periodic_relocation = h->settings.boole_periodic_relocation;
+  bt.sign_t_step = sign_t_step < 0 ? -1 : 1;
+  int64_t grid = (n + 127) / 128;
+  if (grid > (int64_t)h->num_sms * 16) grid = (int64_t)h->num_sms * 16;
+  if (h->mesh.phi) find_kernel<true><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
+  else find_kernel<false><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
+  g_launch_count++;
+  GB_CUDA(cudaGetLastError());
+  GB_CUDA(cudaMemcpyAsync(x, h->s_x, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaMemcpyAsync(ind_tetr, h->s_ind, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaMemcpyAsync(iface, h->s_iface, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaStreamSynchronize(s));
+  unsigned long long dom = 0;
+  GB_CUDA(cudaMemcpy(&dom, h->d_ctr + CTR_DOMAIN, sizeof(dom), cudaMemcpyDeviceToHost));
+  if (dom) return fail(GORILLA_ERR_DOMAIN, "particle start position outside the computation domain");
+  return GORILLA_OK;
+}
+
+extern "C" int gorilla_b200_invariants_dev(gorilla_b200_handle *h, int64_t n, const double *x, const double *vpar,
+                                           const double *vperp, const int32_t *ind_tetr, double *energy, double *p_phi,
+                                           double *perpinv, void *stream)
+{
+  if (!h || n < 0 || (n > 0 && (!x || !vpar || !vperp || !ind_tetr))) return fail(GORILLA_ERR_ARG, "invariants: null argument");
+  if (n == 0) return GORILLA_OK;
+  int64_t grid = (n + 255) / 256;
+  if (grid > (int64_t)h->num_sms * 8) grid = (int64_t)h->num_sms * 8;
+  invariants_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(h->mesh, n, x, vpar, vperp, ind_tetr, energy, p_phi,
+                                                                       perpinv);
+  g_launch_count++;
+  GB_CUDA(cudaGetLastError());
+  return GORILLA_OK;
+}
+extern "C" int gorilla_b200_invariants(gorilla_b200_handle *h, int64_t n, const double *x, const double *vpar,
+                                       const double *vperp, const int32_t *ind_tetr, double *energy, double *p_phi,
+                                       double *perpinv)
+{
+  if (!h || n < 0 || (n > 0 && (!x || !vpar || !vperp || !ind_tetr))) return fail(GORILLA_ERR_ARG, "invariants: null argument");
+  if (n == 0) return GORILLA_OK;
+  int rc = ensure_scratch(h, n);
+  if (rc) return rc;
+  cudaStream_t s = nullptr;
+  GB_CUDA(cudaMemcpyAsync(h->s_x, x, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_vpar, vpar, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_vperp, vperp, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_ind, ind_tetr, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  rc = gorilla_b200_invariants_dev(h, n, h->s_x, h->s_vpar, h->s_vperp, h->s_ind, h->s_e, h->s_p, h->s_mu, s);
+  if (rc) return rc;
+  if (energy) GB_CUDA(cudaMemcpyAsync(energy, h->s_e, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (p_phi) GB_CUDA(cudaMemcpyAsync(p_phi, h->s_p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (perpinv) GB_CUDA(cudaMemcpyAsync(perpinv, h->s_mu, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaStreamSynchronize(s));
+  return GORILLA_OK;
+}
+
+extern "C" int gorilla_b200_get_counters(gorilla_b200_handle *h, gorilla_counters *out)
+{
+  if (!h || !out) return fail(GORILLA_ERR_ARG, "get_counters: null argument");
+  memset(out, 0, sizeof(*out));
+  GB_CUDA(cudaStreamSynchronize(h->last_stream));
+  unsigned long long c[CTR_N];
+  GB_CUDA(cudaMemcpy(c, h->d_ctr, sizeof(c), cudaMemcpyDeviceToHost));
+  out->n_particles = h->last_n;
+  out->n_pushes = (int64_t)c[CTR_PUSHES];
+  out->n_lost = (int64_t)c[CTR_LOST];
+  out->n_finished = (int64_t)c[CTR_FINISHED];
+  for (int i = 0; i < 4; i++) out->n_fallback[i] = (int64_t)c[CTR_FB0 + i];
+  out->n_domain_errors = (int64_t)c[CTR_DOMAIN];
+  float ms = 0.f;
+  if (h->have_push_time) {
+    GB_CUDA(cudaEventElapsedTime(&ms, h->ev1, h->ev2));
+    out->kernel_ms = ms;
+  }
+  if (h->have_find_time) {
+    GB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    out->find_ms = ms;
+  }
+  return GORILLA_OK;
+}
+
+extern "C" int gorilla_b200_sort_permutation_dev(gorilla_b200_handle *h, int64_t n, const int32_t *ind_tetr, int64_t *perm,
+                                                 void *stream)
+{
+  if (!h || n < 0 || (n > 0 && (!ind_tetr || !perm))) return fail(GORILLA_ERR_ARG, "sort_permutation: null argument");
+  if (n == 0) return GORILLA_OK;
+  if (n > 0x7fffffffLL) return fail(GORILLA_ERR_ARG, "sort_permutation: n too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n > h->sort_cap) {
+    cudaFree(h->sort_keys_in); cudaFree(h->sort_keys_out); cudaFree(h->sort_vals_in); cudaFree(h->sort_tmp);
+    h->sort_keys_in = h->sort_keys_out = nullptr; h->sort_vals_in = nullptr; h->sort_tmp = nullptr; h->sort_cap = 0;
+    GB_CUDA(cudaMalloc((void **)&h->sort_keys_in, (size_t)n * sizeof(uint32_t)));
+    GB_CUDA(cudaMalloc((void **)&h->sort_keys_out, (size_t)n * sizeof(uint32_t)));
+    GB_CUDA(cudaMalloc((void **)&h->sort_vals_in, (size_t)n * sizeof(int64_t)));
+    size_t bytes = 0;
+    GB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->sort_keys_in, h->sort_keys_out, h->sort_vals_in, perm, (int)n,
+                                            0, 32, s));
+    GB_CUDA(cudaMalloc(&h->sort_tmp, bytes));
+    h->sort_tmp_bytes = bytes;
+    h->sort_cap = n;
+  }
+  int64_t grid = (n + 255) / 256;
+  if (grid > (int64_t)h->num_sms * 8) grid = (int64_t)h->num_sms * 8;
+  sort_keys_kernel<<<(unsigned)grid, 256, 0, s>>>(n, ind_tetr, h->sort_keys_in, h->sort_vals_in);
+  g_launch_count++;
+  GB_CUDA(cudaGetLastError());
+  int bits = 1;
+  while (bits < 32 && (1LL << bits) <= h->mesh.ntetr + 1) bits++;
+  bits = 32; // lost particles use key 0xffffffff
+  size_t bytes = h->sort_tmp_bytes;
+  GB_CUDA(cub::DeviceRadixSort::SortPairs(h->sort_tmp, bytes, h->sort_keys_in, h->sort_keys_out, h->sort_vals_in, perm, (int)n,
+                                          0, bits, s));
+  g_launch_count += 4;
+  return GORILLA_OK;
+}

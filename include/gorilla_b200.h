@@ -1,0 +1,198 @@
+/*
+ * gorilla_b200.h -- C ABI of the B200-native GORILLA orbit pusher (libgorilla_b200.so).
+ *
+ * This is the drop-in boundary for the reference's particle-parallel hot path.  GORILLA itself is
+ * Fortran 90 with no C ABI; the entry points below are what its module procedures for this path bind
+ * to through ISO_C_BINDING (see INTEGRATION.md and gorilla_b200/fortran/orbit_timestep_gorilla_b200_mod.f90).
+ * Every function cites the reference interface it replaces (paths relative to the GORILLA tree).
+ *
+ * Conventions (identical to the reference):
+ *   - tetrahedron and face indices are 1-based; iface = 0 means "inside the cell";
+ *     ind_tetr = -1 (and iface = -1) means the particle left the domain / was removed.
+ *   - x is x(3,n) in Fortran order, i.e. C double[n][3]: (R,phi,Z) for coord_system 1, (s,theta,phi) for 2.
+ *   - Gaussian CGS units: cm, s, cm/s, Gauss, statvolt.
+ *   - per-particle logicals are int32 (0 = .false., non-zero = .true.).
+ * All functions return GORILLA_OK (0) or a GORILLA_ERR_* code; nothing calls exit()/stop.
+ * There is no CPU fall-back: every compute entry point runs CUDA kernels on the current device and
+ * returns GORILLA_ERR_CUDA if that is impossible.
+ */
+#ifndef GORILLA_B200_H
+#define GORILLA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  GORILLA_OK = 0,
+  GORILLA_ERR_ARG = 1,          /* null pointer / bad size */
+  GORILLA_ERR_UNSUPPORTED = 2,  /* option of gorilla.inp that this path does not implement (yet) */
+  GORILLA_ERR_CUDA = 3,         /* CUDA runtime failure (gorilla_b200_last_error() has the text) */
+  GORILLA_ERR_DOMAIN = 4,       /* a start position is outside the computation domain
+                                   (reference: print + stop, orbit_timestep_gorilla.f90:299-352) */
+  GORILLA_ERR_IO = 5
+};
+
+#define GORILLA_TETRA_PHYSICS_NDOUBLES 142 /* sizeof(type tetrahedron_physics)/8, tetra_physics_mod.f90:9-83 */
+#define GORILLA_TETRA_GRID_NINTS 20        /* sizeof(type tetrahedron_grid)/4,    tetra_grid_mod.f90:6-15   */
+
+/* The subset of namelist GORILLANML (gorilla_settings_mod.f90:94-105) that the hot path reads. */
+typedef struct gorilla_settings {
+  double eps_Phi;
+  int32_t coord_system;              /* 1 (R,phi,Z) | 2 (s,theta,phi) */
+  int32_t ispecies;                  /* 1 e-, 2 D+, 3 alpha, 4 W74+ (orbit_timestep_gorilla.f90:204-249) */
+  int32_t boole_periodic_relocation;
+  int32_t ipusher;                   /* 1 RK4 | 2 polynomial */
+  int32_t boole_pusher_ode45;        /* must be 0 */
+  int32_t boole_dt_dtau;             /* must be 1 */
+  int32_t boole_newton_precalc;      /* must be 0 */
+  int32_t poly_order;                /* 1..4 */
+  int32_t i_precomp;                 /* must be 0 */
+  int32_t boole_guess;
+  int32_t i_time_tracing_option;     /* must be 1 */
+  int32_t handover_processing_kind;  /* must be 1 */
+  int32_t boole_adaptive_time_steps; /* must be 0 */
+  int32_t boole_strong_electric_field; /* must be 0 (next) */
+  int32_t boole_grid_for_find_tetra; /* ignored: the device scan does not need the box accelerator */
+  int32_t reserved[5];
+} gorilla_settings;
+
+/* Everything initialize_gorilla() (orbit_timestep_gorilla.f90:151-274) leaves in module variables that
+ * the hot path reads afterwards.  A Fortran caller fills it from tetra_physics_mod / tetra_grid_mod /
+ * tetra_grid_settings_mod with c_loc() -- both derived types are `sequence` types of a single kind, so
+ * the arrays are plain [ntetr][142] doubles and [ntetr][20] int32. */
+typedef struct gorilla_mesh_desc {
+  int64_t ntetr;
+  const double *tetra_physics;  /* tetra_physics(1:ntetr)  */
+  const int32_t *tetra_grid;    /* tetra_grid(1:ntetr)     */
+  double cm_over_e;             /* tetra_physics_mod: cm_over_e       */
+  double particle_mass;         /*                    particle_mass   */
+  double particle_charge;       /*                    particle_charge */
+  int32_t sign_sqg;             /* tetra_physics_mod: sign_sqg        */
+  int32_t coord_system;
+  int32_t n_field_periods;      /* tetra_grid_settings_mod */
+  int32_t grid_kind;
+  int32_t grid_size[3];
+  int32_t pad0;
+  double Rmin, Rmax, Zmin, Zmax; /* tetra_grid_mod (rectangular grids; unused otherwise) */
+  double sfc_s_min;              /* tetra_grid_settings_mod */
+} gorilla_mesh_desc;
+
+typedef struct gorilla_b200_handle gorilla_b200_handle;
+
+/* Aggregates of one orbit_timestep call (the reference keeps such counters in gorilla_plot_mod.f90:
+ * counter_tetrahedron_passes :550, lost-particle counter :290-294). */
+typedef struct gorilla_counters {
+  int64_t n_particles;
+  int64_t n_pushes;          /* pusher invocations = "tetra crossings" of the metric */
+  int64_t n_lost;            /* ind_tetr == -1 after the call */
+  int64_t n_finished;        /* boole_t_finished */
+  int64_t n_fallback[4];     /* pushes that needed: 2nd attempt, trouble shooting, prolonged trajectory,
+                                stop-inside landing outside the cell */
+  int64_t n_domain_errors;
+  double kernel_ms;          /* device time of the push kernel (CUDA events on the launch stream) */
+  double find_ms;            /* device time of the localisation kernel, 0 if not run */
+} gorilla_counters;
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+
+/* Uploads the mesh (repacked into sub-record SoA) to the CURRENT CUDA device.
+ * Replaces the "library owns the mesh in module arrays" half of initialize_gorilla. */
+int gorilla_b200_init(const gorilla_mesh_desc *mesh, const gorilla_settings *settings,
+                      gorilla_b200_handle **out);
+void gorilla_b200_free(gorilla_b200_handle *h);
+const char *gorilla_b200_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
+int64_t gorilla_b200_launch_count(void);
+
+/* ---- the hot path ------------------------------------------------------------------------------ */
+
+/* Batched orbit_timestep_gorilla(x,vpar,vperp,t_step,boole_initialized,ind_tetr,iface,t_remain_out)
+ * (orbit_timestep_gorilla.f90:19-147) for n independent particles; HOST pointers, copies included.
+ * t_remain_out and n_pushes may be NULL.  n = 1 is exactly the reference's scalar call. */
+int gorilla_b200_orbit_timestep(gorilla_b200_handle *h, int64_t n, double *x, double *vpar, double *vperp,
+                                double t_step, int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface,
+                                double *t_remain_out, int64_t *n_pushes);
+
+/* Same, all pointers are DEVICE pointers on the handle's device; runs on `stream` (a cudaStream_t,
+ * NULL = default stream) and does not synchronise. */
+int gorilla_b200_orbit_timestep_dev(gorilla_b200_handle *h, int64_t n, double *x, double *vpar, double *vperp,
+                                    double t_step, int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface,
+                                    double *t_remain_out, int64_t *n_pushes, void *stream);
+
+/* As gorilla_b200_orbit_timestep, additionally recording the (ind_tetr, iface) state after each of the
+ * first trace_cap pushes of every particle: trace_* are HOST int32 [n][trace_cap], unused slots = 0.
+ * Used by the parity tests ("visited tetra sequence bit-exact for the first N crossings"). */
+int gorilla_b200_orbit_timestep_trace(gorilla_b200_handle *h, int64_t n, double *x, double *vpar, double *vperp,
+                                      double t_step, int32_t *boole_initialized, int32_t *ind_tetr,
+                                      int32_t *iface, double *t_remain_out, int64_t *n_pushes,
+                                      int32_t trace_cap, int32_t *trace_ind_tetr, int32_t *trace_iface);
+
+/* check_coordinate_domain + find_tetra(x,vpar,vperp,ind_tetr,iface,sign_t_step)
+ * (orbit_timestep_gorilla.f90:278-358, find_tetra_mod.f90:283-600); HOST pointers. x may be modified
+ * (periodic relocation, start points lying on a face). */
+int gorilla_b200_find_tetra(gorilla_b200_handle *h, int64_t n, double *x, const double *vpar, const double *vperp,
+                            int32_t *ind_tetr, int32_t *iface, int32_t sign_t_step);
+
+/* ---- diagnostics ------------------------------------------------------------------------------- */
+
+/* Per-particle invariants, HOST pointers, any output may be NULL:
+ *   energy  = energy_tot_func   (supporting_functions_mod.f90:279-301)
+ *   p_phi   = p_phi_func        (:377-408)
+ *   perpinv = -vperp^2/(2 |B|)  (orbit_timestep_gorilla.f90:77), the conserved magnetic-moment proxy
+ * Particles with ind_tetr < 1 get NaN. */
+int gorilla_b200_invariants(gorilla_b200_handle *h, int64_t n, const double *x, const double *vpar,
+                            const double *vperp, const int32_t *ind_tetr, double *energy, double *p_phi,
+                            double *perpinv);
+int gorilla_b200_invariants_dev(gorilla_b200_handle *h, int64_t n, const double *x, const double *vpar,
+                                const double *vperp, const int32_t *ind_tetr, double *energy, double *p_phi,
+                                double *perpinv, void *stream);
+
+/* Counters of the most recent orbit_timestep* call on this handle (synchronises the launch stream). */
+int gorilla_b200_get_counters(gorilla_b200_handle *h, gorilla_counters *out);
+
+/* Sort keys for periodic particle re-sorting by tetra index: fills perm (DEVICE int64[n]) with the
+ * permutation that orders particles by ind_tetr (lost particles last).  Device pointers. */
+int gorilla_b200_sort_permutation_dev(gorilla_b200_handle *h, int64_t n, const int32_t *ind_tetr, int64_t *perm,
+                                      void *stream);
+
+/* Tuning knobs (0 = keep default): CTAs per SM and threads per CTA of the persistent push kernel. */
+int gorilla_b200_set_launch_config(gorilla_b200_handle *h, int32_t ctas_per_sm, int32_t threads_per_cta);
+
+/* ---- host-side mesh construction (runs once; stays on the host per north_star) ----------------- */
+
+typedef struct gorilla_mesh gorilla_mesh;
+
+/* namelist TETRA_GRID_NML (tetra_grid_settings_mod.f90:70-75) */
+typedef struct gorilla_grid_settings {
+  int32_t grid_kind;             /* 1 rect/EFIT, 2 field-aligned EFIT, 3 field-aligned VMEC, 4 SOLEDGE3X, 5 analytic */
+  int32_t n1, n2, n3;
+  int32_t boole_n_field_periods; /* 1 = take from the equilibrium */
+  int32_t n_field_periods_manual;
+  int32_t i_radial_spacing;
+  int32_t theta_geom_flux;
+  double sfc_s_min;
+  double theta0_at_xpoint;       /* unused for VMEC/analytic */
+  double R0_analytic_circ, a_analytic_circ, B0_analytic_circ, q0_analytic_circ, q1_analytic_circ;
+  const char *g_file_filename;
+  const char *convex_wall_filename;
+  const char *netcdf_filename;
+  const char *knots_SOLEDGE3X_EIRENE_filename;
+  const char *triangles_SOLEDGE3X_EIRENE_filename;
+} gorilla_grid_settings;
+
+/* make_tetra_grid + make_tetra_physics + check_tetra_overlaps of initialize_gorilla
+ * (orbit_timestep_gorilla.f90:151-274; tetra_grid_mod.f90:27-211; tetra_physics_mod.f90:127-1034,1291-1336).
+ * Implemented grid kinds: 5 (analytic circular tokamak, rectangular grid) and 3 (VMEC, field aligned). */
+int gorilla_mesh_build(const gorilla_grid_settings *grid, const gorilla_settings *settings, gorilla_mesh **out);
+int gorilla_mesh_get_desc(const gorilla_mesh *mesh, gorilla_mesh_desc *out);
+/* vertices: nvert, verts_rphiz[nvert][3], verts_sthetaphi[nvert][3] or NULL */
+int gorilla_mesh_get_vertices(const gorilla_mesh *mesh, int64_t *nvert, const double **verts_rphiz,
+                              const double **verts_sthetaphi);
+void gorilla_mesh_free(gorilla_mesh *mesh);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GORILLA_B200_H */

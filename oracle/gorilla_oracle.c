@@ -1,0 +1,1681 @@
+/*
+ * gorilla_oracle.c -- CPU ORACLE (test infrastructure, see gorilla_oracle.h).
+ *
+ * Build: gcc -std=gnu11 -O2 -ffp-contract=off -fcx-fortran-rules -fopenmp -fPIC -shared
+ *   -ffp-contract=off  : the reference ISA (x86-64 baseline) has no FMA (CMakeLists.txt:24-25)
+ *   -fcx-fortran-rules : gfortran's complex * and / lowering (Smith-type division, no NaN recovery)
+ * Mixed real*complex follows Fortran semantics: the real operand is promoted to (r, 0.0) and a
+ * full complex product is formed (this matters for the sign of zero imaginary parts that
+ * csqrt() later branches on).
+ */
+#define _GNU_SOURCE
+#include "gorilla_oracle.h"
+#include <complex.h>
+#include <float.h>
+#include <math.h>
+#include <stdbool.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* SRC/constants_mod.f90:3-8 */
+static const double PI = 3.141592653589793238462643383;
+static const double CLIGHT = 2.9979e10;
+static const double EPS = 1.e-10;
+#define HUGE_D DBL_MAX
+
+typedef double _Complex cplx;
+static inline cplx rc(double r) { return CMPLX(r, 0.0); }               /* real -> complex promotion */
+static inline cplx rmul(double r, cplx z) { return rc(r) * z; }         /* Fortran real*complex */
+static inline bool ceq(cplx a, cplx b) { return creal(a) == creal(b) && cimag(a) == cimag(b); }
+static inline double abs2(cplx p) { return creal(conj(p) * p); }        /* real(conjg(p)*p) */
+
+/* ------------------------------------------------------------------------------------------------
+ * Skowron & Gould solver -- SRC/contrib/cmplx_roots_sg.f90
+ * ---------------------------------------------------------------------------------------------- */
+static const double FRAC_JUMPS[10] = {0.64109297, 0.91577881, 0.25921289, 0.50487203, 0.08177045,
+                                      0.13653241, 0.306162,   0.37794326, 0.04618805, 0.75132137};
+static const double SG_PI = 3.141592653589793;
+static const double FRAC_ERR = 2.0e-15;
+
+static inline cplx frac_jump_phase(int k) /* exp(cmplx(0, FRAC_JUMPS(k+1)*2*pi)) */
+{
+  return cexp(CMPLX(0.0, FRAC_JUMPS[k] * 2 * SG_PI));
+}
+void gor_frac_jump_phase(int k, double out[2])
+{
+  cplx e = frac_jump_phase(k);
+  out[0] = creal(e);
+  out[1] = cimag(e);
+}
+
+/* cmplx_roots_sg.f90:558-731 */
+static void cmplx_laguerre(const cplx *poly, int degree, cplx *root, int *iter, bool *success)
+{
+  const int MAX_ITERS = 200, FRAC_JUMP_EVERY = 10, FRAC_JUMP_LEN = 10;
+  cplx p, dp, d2p_half, denom, denom_sqrt, dx, newroot, fac_netwon = 0, fac_extra, F_half;
+  const cplx c_one = CMPLX(1.0, 0.0), zero = CMPLX(0.0, 0.0);
+  double ek, absroot, abs2p, faq, stopping_crit2;
+  *iter = 0;
+  *success = true;
+  bool good_to_go = false;
+  double one_nth = 1.0 / degree;
+  double n_1_nth = (degree - 1.0) * one_nth;
+  double two_n_div_n_1 = 2.0 / n_1_nth;
+  cplx c_one_nth = CMPLX(one_nth, 0.0);
+
+  for (int i = 1; i <= MAX_ITERS; i++) {
+    ek = cabs(poly[degree]);
+    absroot = cabs(*root);
+    p = poly[degree];
+    dp = zero;
+    d2p_half = zero;
+    for (int k = degree; k >= 1; k--) {
+      d2p_half = dp + d2p_half * (*root);
+      dp = p + dp * (*root);
+      p = poly[k - 1] + p * (*root);
+      ek = absroot * ek + cabs(p);
+    }
+    *iter = *iter + 1;
+    abs2p = abs2(p);
+    if (abs2p == 0.0) return;
+    stopping_crit2 = (FRAC_ERR * ek) * (FRAC_ERR * ek);
+    if (abs2p < stopping_crit2) {
+      if (abs2p < 0.01 * stopping_crit2) return;
+      good_to_go = true;
+    } else {
+      good_to_go = false;
+    }
+    faq = 1.0;
+    denom = zero;
+    if (!ceq(dp, zero)) {
+      fac_netwon = p / dp;
+      fac_extra = d2p_half / dp;
+      F_half = fac_netwon * fac_extra;
+      denom_sqrt = csqrt(c_one - rmul(two_n_div_n_1, F_half));
+      if (creal(denom_sqrt) >= 0.0)
+        denom = c_one_nth + rmul(n_1_nth, denom_sqrt);
+      else
+        denom = c_one_nth - rmul(n_1_nth, denom_sqrt);
+    }
+    if (ceq(denom, zero)) {
+      dx = rmul(absroot + 1.0, frac_jump_phase(i % FRAC_JUMP_LEN));
+    } else {
+      dx = fac_netwon / denom;
+    }
+    newroot = *root - dx;
+    if (ceq(newroot, *root)) return;
+    if (good_to_go) {
+      *root = newroot;
+      return;
+    }
+    if (i % FRAC_JUMP_EVERY == 0) {
+      faq = FRAC_JUMPS[(i / FRAC_JUMP_EVERY - 1) % FRAC_JUMP_LEN];
+      newroot = *root - rmul(faq, dx);
+    }
+    *root = newroot;
+  }
+  *success = false;
+}
+
+/* cmplx_roots_sg.f90:906-1305 */
+static void cmplx_laguerre2newton(const cplx *poly, int degree, cplx *root, int *iter, bool *success,
+                                  int starting_mode)
+{
+  const int MAX_ITERS = 50, FRAC_JUMP_EVERY = 10, FRAC_JUMP_LEN = 10;
+  cplx p, dp, d2p_half, denom, denom_sqrt, dx, newroot, fac_netwon = 0, fac_extra, F_half;
+  const cplx c_one = CMPLX(1.0, 0.0), zero = CMPLX(0.0, 0.0);
+  cplx c_one_nth = zero;
+  double ek, absroot, abs2p, abs2_F_half, faq, stopping_crit2 = 0.0;
+  double one_nth = 0, n_1_nth = 0, two_n_div_n_1 = 0;
+  int i, j = 1, mode = starting_mode;
+  bool good_to_go = false;
+  *iter = 0;
+  *success = true;
+
+  for (;;) {
+    /* ------------------------------------------------ mode 2: Laguerre */
+    if (mode >= 2) {
+      one_nth = 1.0 / degree;
+      n_1_nth = (degree - 1.0) * one_nth;
+      two_n_div_n_1 = 2.0 / n_1_nth;
+      c_one_nth = CMPLX(one_nth, 0.0);
+      for (i = 1; i <= MAX_ITERS; i++) {
+        faq = 1.0;
+        ek = cabs(poly[degree]);
+        absroot = cabs(*root);
+        p = poly[degree];
+        dp = zero;
+        d2p_half = zero;
+        for (int k = degree; k >= 1; k--) {
+          d2p_half = dp + d2p_half * (*root);
+          dp = p + dp * (*root);
+          p = poly[k - 1] + p * (*root);
+          ek = absroot * ek + cabs(p);
+        }
+        abs2p = abs2(p);
+        *iter = *iter + 1;
+        if (abs2p == 0.0) return;
+        stopping_crit2 = (FRAC_ERR * ek) * (FRAC_ERR * ek);
+        if (abs2p < stopping_crit2) {
+          if (abs2p < 0.01 * stopping_crit2) return;
+          good_to_go = true;
+        } else {
+          good_to_go = false;
+        }
+        denom = zero;
+        if (!ceq(dp, zero)) {
+          fac_netwon = p / dp;
+          fac_extra = d2p_half / dp;
+          F_half = fac_netwon * fac_extra;
+          abs2_F_half = abs2(F_half);
+          if (abs2_F_half <= 0.0625) {
+            if (abs2_F_half <= 0.000625)
+              mode = 0;
+            else
+              mode = 1;
+          }
+          denom_sqrt = csqrt(c_one - rmul(two_n_div_n_1, F_half));
+          if (creal(denom_sqrt) >= 0.0)
+            denom = c_one_nth + rmul(n_1_nth, denom_sqrt);
+          else
+            denom = c_one_nth - rmul(n_1_nth, denom_sqrt);
+        }
+        if (ceq(denom, zero)) {
+          dx = rmul(cabs(*root) + 1.0, frac_jump_phase(i % FRAC_JUMP_LEN));
+        } else {
+          dx = fac_netwon / denom;
+        }
+        newroot = *root - dx;
+        if (ceq(newroot, *root)) return;
+        if (good_to_go) {
+          *root = newroot;
+          return;
+        }
+        if (mode != 2) {
+          *root = newroot;
+          j = i + 1;
+          break;
+        }
+        if (i % FRAC_JUMP_EVERY == 0) {
+          faq = FRAC_JUMPS[(i / FRAC_JUMP_EVERY - 1) % FRAC_JUMP_LEN];
+          newroot = *root - rmul(faq, dx);
+        }
+        *root = newroot;
+      }
+      if (i >= MAX_ITERS) {
+        *success = false;
+        return;
+      }
+    }
+    /* ------------------------------------------------ mode 1: SG */
+    if (mode == 1) {
+      for (i = j; i <= MAX_ITERS; i++) {
+        faq = 1.0;
+        p = poly[degree];
+        dp = zero;
+        d2p_half = zero;
+        if ((i - j) % 10 == 0) {
+          ek = cabs(poly[degree]);
+          absroot = cabs(*root);
+          for (int k = degree; k >= 1; k--) {
+            d2p_half = dp + d2p_half * (*root);
+            dp = p + dp * (*root);
+            p = poly[k - 1] + p * (*root);
+            ek = absroot * ek + cabs(p);
+          }
+          stopping_crit2 = (FRAC_ERR * ek) * (FRAC_ERR * ek);
+        } else {
+          for (int k = degree; k >= 1; k--) {
+            d2p_half = dp + d2p_half * (*root);
+            dp = p + dp * (*root);
+            p = poly[k - 1] + p * (*root);
+          }
+        }
+        abs2p = abs2(p);
+        *iter = *iter + 1;
+        if (abs2p == 0.0) return;
+        if (abs2p < stopping_crit2) {
+          if (ceq(dp, zero)) return;
+          if (abs2p < 0.01 * stopping_crit2) return;
+          good_to_go = true;
+        } else {
+          good_to_go = false;
+        }
+        if (ceq(dp, zero)) {
+          dx = rmul(cabs(*root) + 1.0, frac_jump_phase(i % FRAC_JUMP_LEN));
+        } else {
+          fac_netwon = p / dp;
+          fac_extra = d2p_half / dp;
+          F_half = fac_netwon * fac_extra;
+          abs2_F_half = abs2(F_half);
+          if (abs2_F_half <= 0.000625) mode = 0;
+          dx = fac_netwon * (c_one + F_half);
+        }
+        newroot = *root - dx;
+        if (ceq(newroot, *root)) return;
+        if (good_to_go) {
+          *root = newroot;
+          return;
+        }
+        if (mode != 1) {
+          *root = newroot;
+          j = i + 1;
+          break;
+        }
+        if (i % FRAC_JUMP_EVERY == 0) {
+          faq = FRAC_JUMPS[(i / FRAC_JUMP_EVERY - 1) % FRAC_JUMP_LEN];
+          newroot = *root - rmul(faq, dx);
+        }
+        *root = newroot;
+      }
+      if (i >= MAX_ITERS) {
+        *success = false;
+        return;
+      }
+    }
+    /* ------------------------------------------------ mode 0: Newton */
+    if (mode == 0) {
+      for (i = j; i <= j + 10; i++) {
+        faq = 1.0;
+        p = poly[degree];
+        dp = zero;
+        if (i == j) {
+          ek = cabs(poly[degree]);
+          absroot = cabs(*root);
+          for (int k = degree; k >= 1; k--) {
+            dp = p + dp * (*root);
+            p = poly[k - 1] + p * (*root);
+            ek = absroot * ek + cabs(p);
+          }
+          stopping_crit2 = (FRAC_ERR * ek) * (FRAC_ERR * ek);
+        } else {
+          for (int k = degree; k >= 1; k--) {
+            dp = p + dp * (*root);
+            p = poly[k - 1] + p * (*root);
+          }
+        }
+        abs2p = abs2(p);
+        *iter = *iter + 1;
+        if (abs2p == 0.0) return;
+        if (abs2p < stopping_crit2) {
+          if (ceq(dp, zero)) return;
+          if (abs2p < 0.01 * stopping_crit2) return;
+          good_to_go = true;
+        } else {
+          good_to_go = false;
+        }
+        if (ceq(dp, zero)) {
+          dx = rmul(cabs(*root) + 1.0, frac_jump_phase(i % FRAC_JUMP_LEN));
+        } else {
+          dx = p / dp;
+        }
+        newroot = *root - dx;
+        if (ceq(newroot, *root)) return;
+        if (good_to_go) {
+          *root = newroot;
+          return;
+        }
+        *root = newroot;
+      }
+      if (*iter >= MAX_ITERS) {
+        *success = false;
+        return;
+      }
+      mode = 2;
+    }
+  }
+}
+
+/* cmplx_roots_sg.f90:1311-1362 */
+static void solve_quadratic_eq(cplx *x0, cplx *x1, const cplx *poly)
+{
+  cplx a = poly[2], b = poly[1], c = poly[0];
+  cplx b2 = b * b;
+  cplx delta = csqrt(b2 - rmul(4.0, a * c));
+  if (creal(conj(b) * delta) >= 0.0)
+    *x0 = rmul(-0.5, b + delta);
+  else
+    *x0 = rmul(-0.5, b - delta);
+  if (ceq(*x0, CMPLX(0.0, 0.0))) {
+    *x1 = CMPLX(0.0, 0.0);
+  } else {
+    *x1 = c / *x0;
+    *x0 = *x0 / a;
+  }
+}
+
+/* cmplx_roots_sg.f90:83-201 with polish_roots_after=.true., use_roots_as_starting_points=.false. */
+static void cmplx_roots_gen(cplx *roots, const cplx *poly, int degree, gor_trace *tr)
+{
+  cplx poly2[5];
+  const cplx zero = CMPLX(0.0, 0.0);
+  int iter;
+  bool success;
+  cplx coef, prev;
+  for (int i = 0; i <= degree; i++) poly2[i] = poly[i];
+  for (int i = 0; i < degree; i++) roots[i] = zero;
+  if (degree <= 1) {
+    if (degree == 1) roots[0] = -poly[0] / poly[1];
+    return;
+  }
+  for (int n = degree; n >= 3; n--) {
+    cmplx_laguerre2newton(poly2, n, &roots[n - 1], &iter, &success, 2);
+    if (tr) tr->n_solver_iters += iter;
+    if (!success) {
+      roots[n - 1] = zero;
+      cmplx_laguerre(poly2, n, &roots[n - 1], &iter, &success);
+      if (tr) tr->n_solver_iters += iter;
+    }
+    coef = poly2[n];
+    for (int i = n; i >= 1; i--) {
+      prev = poly2[i - 1];
+      poly2[i - 1] = coef;
+      coef = prev + roots[n - 1] * coef;
+    }
+  }
+  cmplx_laguerre2newton(poly2, 2, &roots[1], &iter, &success, 2);
+  if (tr) tr->n_solver_iters += iter;
+  if (!success) {
+    solve_quadratic_eq(&roots[1], &roots[0], poly2);
+  } else {
+    roots[0] = -(roots[1] + poly2[1] / poly2[2]);
+  }
+  for (int n = 0; n < degree; n++) {
+    cmplx_laguerre(poly, degree, &roots[n], &iter, &success);
+    if (tr) tr->n_solver_iters += iter;
+  }
+  if (tr) tr->n_solver_calls += 1;
+}
+
+void gor_cmplx_roots_gen(int degree, const double *poly_re_im, double *roots_re_im)
+{
+  cplx poly[5], roots[4];
+  for (int i = 0; i <= degree; i++) poly[i] = CMPLX(poly_re_im[2 * i], poly_re_im[2 * i + 1]);
+  cmplx_roots_gen(roots, poly, degree, NULL);
+  for (int i = 0; i < degree; i++) {
+    roots_re_im[2 * i] = creal(roots[i]);
+    roots_re_im[2 * i + 1] = cimag(roots[i]);
+  }
+}
+
+/* SRC/contrib/Polynomial234RootSolvers.f90:84-142 ; root is root(n,2) column-major */
+static void pack_roots(const cplx *croots, int n, int *nReal, double *root)
+{
+  const double cmplx_tol = 1.0e-12;
+  double re_part[4], im_part[4];
+  bool is_real[4];
+  int cnt = 0;
+  for (int i = 0; i < n; i++) {
+    re_part[i] = creal(croots[i]);
+    im_part[i] = cimag(croots[i]);
+    double tol_i = cmplx_tol * fmax(1.0, fabs(re_part[i]));
+    is_real[i] = fabs(im_part[i]) <= tol_i;
+    if (is_real[i]) cnt++;
+  }
+  *nReal = cnt;
+  for (int i = 0; i < 2 * n; i++) root[i] = 0.0;
+  int idx = 0;
+  for (int i = 0; i < n; i++)
+    if (is_real[i]) {
+      root[idx] = re_part[i];
+      root[n + idx] = 0.0;
+      idx++;
+    }
+  /* sort_real_descending: insertion sort on the first nReal rows */
+  for (int i = 1; i < cnt; i++) {
+    double tmp_re = root[i], tmp_im = root[n + i];
+    int j = i - 1;
+    while (j >= 0) {
+      if (root[j] >= tmp_re) break;
+      root[j + 1] = root[j];
+      root[n + j + 1] = root[n + j];
+      j--;
+    }
+    root[j + 1] = tmp_re;
+    root[n + j + 1] = tmp_im;
+  }
+  for (int i = 0; i < n; i++)
+    if (!is_real[i]) {
+      root[idx] = re_part[i];
+      root[n + idx] = im_part[i];
+      idx++;
+    }
+}
+
+static void quadraticRoots(double q1, double q0, int *nReal, double *root, gor_trace *tr)
+{
+  cplx poly[3] = {CMPLX(q0, 0.0), CMPLX(q1, 0.0), CMPLX(1.0, 0.0)}, croots[2];
+  cmplx_roots_gen(croots, poly, 2, tr);
+  pack_roots(croots, 2, nReal, root);
+}
+static void cubicRoots(double c2, double c1, double c0, int *nReal, double *root, gor_trace *tr)
+{
+  cplx poly[4] = {CMPLX(c0, 0.0), CMPLX(c1, 0.0), CMPLX(c2, 0.0), CMPLX(1.0, 0.0)}, croots[3];
+  cmplx_roots_gen(croots, poly, 3, tr);
+  pack_roots(croots, 3, nReal, root);
+}
+static void quarticRoots(double q3, double q2, double q1, double q0, int *nReal, double *root,
+                         gor_trace *tr)
+{
+  cplx poly[5] = {CMPLX(q0, 0.0), CMPLX(q1, 0.0), CMPLX(q2, 0.0), CMPLX(q3, 0.0), CMPLX(1.0, 0.0)},
+       croots[4];
+  cmplx_roots_gen(croots, poly, 4, tr);
+  pack_roots(croots, 4, nReal, root);
+}
+void gor_quadratic_roots(double q1, double q0, int *nreal, double root[4])
+{
+  quadraticRoots(q1, q0, nreal, root, NULL);
+}
+void gor_cubic_roots(double c2, double c1, double c0, int *nreal, double root[6])
+{
+  cubicRoots(c2, c1, c0, nreal, root, NULL);
+}
+void gor_quartic_roots(double q3, double q2, double q1, double q0, int *nreal, double root[8])
+{
+  quarticRoots(q3, q2, q1, q0, nreal, root, NULL);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Exit-time solvers -- SRC/pusher_tetra_poly.f90:1767-2021
+ * ---------------------------------------------------------------------------------------------- */
+static double Linear_Solver(double a, double b)
+{
+  if (a == 0.0) return HUGE_D;
+  return -b / a;
+}
+
+/* :1809-1893   f(tau) = a/2 tau^2 + b tau + c */
+static double Quadratic_Solver1(double acoef, double bcoef, double ccoef)
+{
+  double dtau = HUGE_D, discr, dummy;
+  if (ccoef > 0.0) {
+    if (acoef > 0.0) {
+      if (bcoef < 0.0) {
+        discr = bcoef * bcoef - 2.0 * acoef * ccoef;
+        if (discr > 0.0) {
+          dummy = (-bcoef + sqrt(discr));
+          if (fabs(dummy) > EPS)
+            dtau = 2.0 * ccoef / dummy;
+          else
+            dtau = (-sqrt(discr) - bcoef) / acoef;
+        } else if (discr == 0.0) {
+          dtau = -bcoef / acoef;
+        } else {
+          return dtau;
+        }
+      } else {
+        return dtau;
+      }
+    } else if (acoef < 0.0) {
+      discr = bcoef * bcoef - 2.0 * acoef * ccoef;
+      dummy = (-bcoef + sqrt(discr));
+      if (fabs(dummy) > EPS)
+        dtau = 2.0 * ccoef / dummy;
+      else
+        dtau = (-sqrt(discr) - bcoef) / acoef;
+    } else {
+      if (bcoef < 0.0)
+        dtau = -ccoef / bcoef;
+      else
+        return dtau;
+    }
+  } else if (ccoef < 0.0) {
+    if (acoef < 0.0) {
+      if (bcoef > 0.0) {
+        discr = bcoef * bcoef - 2.0 * acoef * ccoef;
+        if (discr > 0.0)
+          dtau = (sqrt(discr) - bcoef) / acoef;
+        else if (discr == 0.0)
+          dtau = -bcoef / acoef;
+        else
+          return dtau;
+      } else {
+        return dtau;
+      }
+    } else if (acoef > 0.0) {
+      discr = bcoef * bcoef - 2.0 * acoef * ccoef;
+      dtau = (sqrt(discr) - bcoef) / acoef;
+    } else {
+      if (bcoef > 0.0)
+        dtau = -ccoef / bcoef;
+      else
+        return dtau;
+    }
+  } else {
+    if (((acoef > 0.0) && (bcoef < 0.0)) || ((acoef < 0.0) && (bcoef > 0.0)))
+      dtau = -2.0 * bcoef / acoef;
+    else
+      return dtau;
+  }
+  return dtau;
+}
+
+/* minval(root(:,1),1,mask) with mask = abs(Im)==0 .and. Re>0 ; empty mask -> huge */
+static double min_positive_real(const double *root, int n, double lambda)
+{
+  double best = HUGE_D;
+  for (int i = 0; i < n; i++) {
+    double re = root[i] / lambda, im = root[n + i] / lambda;
+    if (fabs(im) == 0.0 && re > 0.0)
+      if (re < best) best = re;
+  }
+  return best;
+}
+
+/* :1897-1930 */
+static double Quadratic_Solver2(double a, double b, double c, gor_trace *tr)
+{
+  double root[4], lambda, q0, q1;
+  int nReal;
+  lambda = b / c;
+  q0 = 2.0 * (b * b) / (a * c);
+  q1 = q0;
+  quadraticRoots(q1, q0, &nReal, root, tr);
+  return min_positive_real(root, 2, lambda);
+}
+/* :1934-1967 */
+static double Cubic_Solver(double a, double b, double c, double d, gor_trace *tr)
+{
+  double root[6], lambda, c2, c1, c0;
+  int nReal;
+  lambda = b / (2.0 * c);
+  c2 = 3.0 * lambda * b / a;
+  c1 = 6.0 * c * (lambda * lambda) / a;
+  c0 = 6.0 * d * ((lambda * lambda) * lambda) / a;
+  cubicRoots(c2, c1, c0, &nReal, root, tr);
+  return min_positive_real(root, 3, lambda);
+}
+/* :1971-2021 */
+static double Quartic_Solver(int i_scaling, double a, double b, double c, double d, double e,
+                             gor_trace *tr)
+{
+  double root[8], lambda = 0, q3, q2, q1, q0;
+  int nReal;
+  switch (i_scaling) {
+    case 0: lambda = sqrt(fabs(b / (6.0 * d))); break;
+    case 1: lambda = b / (3.0 * c); break;
+    case 2: lambda = pow(fabs(b / (6.0 * e)), 1.0 / 3.0); break;
+    case 3: lambda = c / (2.0 * d); break;
+    case 4: lambda = sqrt(fabs(c / (2.0 * e))); break;
+    case 5: lambda = d / e; break;
+    case 6: lambda = pow(fabs(a / (24.0 * e)), 1.0 / 4.0); break;
+  }
+  double l2 = lambda * lambda;
+  q3 = 4.0 * b * lambda / a;
+  q2 = 12.0 * c * l2 / a;
+  q1 = 24.0 * d * (l2 * lambda) / a;
+  q0 = 24.0 * e * (l2 * l2) / a;
+  quarticRoots(q3, q2, q1, q0, &nReal, root, tr);
+  return min_positive_real(root, 4, lambda);
+}
+double gor_quadratic_solver1(double a, double b, double c) { return Quadratic_Solver1(a, b, c); }
+double gor_quadratic_solver2(double a, double b, double c) { return Quadratic_Solver2(a, b, c, NULL); }
+double gor_cubic_solver(double a, double b, double c, double d) { return Cubic_Solver(a, b, c, d, NULL); }
+double gor_quartic_solver(int s, double a, double b, double c, double d, double e)
+{
+  return Quartic_Solver(s, a, b, c, d, e, NULL);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * small helpers -- SRC/supporting_functions_mod.f90
+ * ---------------------------------------------------------------------------------------------- */
+static inline const double *rec(const gor_mesh *m, int ind_tetr)
+{
+  return m->tetra_physics + (int64_t)(ind_tetr - 1) * TP_NDOUBLES;
+}
+static inline const int32_t *grd(const gor_mesh *m, int ind_tetr)
+{
+  return m->tetra_grid + (int64_t)(ind_tetr - 1) * TG_NINTS;
+}
+static inline double dot3(const double *a, const double *b) /* sum(a*b), ascending */
+{
+  return ((0.0 + a[0] * b[0]) + a[1] * b[1]) + a[2] * b[2];
+}
+static inline int isign1(double t) { return signbit(t) ? -1 : 1; } /* int(sign(1.d0,t)) */
+
+double gor_bmod(const gor_mesh *m, const double z[3], int32_t ind_tetr) /* :305 */
+{
+  const double *r = rec(m, ind_tetr);
+  return r[TP_BMOD1] + dot3(r + TP_GB, z);
+}
+static double phi_elec_func(const gor_mesh *m, const double z[3], int ind_tetr) /* :342 */
+{
+  const double *r = rec(m, ind_tetr);
+  return r[TP_PHI1] + dot3(r + TP_GPHI, z);
+}
+static double v2_E_mod_func(const gor_mesh *m, const double z[3], int ind_tetr) /* :445 */
+{
+  const double *r = rec(m, ind_tetr);
+  return r[TP_V2EMOD_1] + dot3(z, r + TP_GV2EMOD);
+}
+static double vperp_func(const gor_mesh *m, const double z[3], double perpinv, int ind_tetr) /* :321 */
+{
+  if (perpinv != 0.0) return sqrt(2.0 * fabs(perpinv) * gor_bmod(m, z, ind_tetr));
+  return 0.0;
+}
+double gor_energy_tot(const gor_mesh *m, const double z[4], double perpinv, int32_t ind_tetr) /* :279 */
+{
+  const double *r = rec(m, ind_tetr);
+  double vperp = sqrt(2.0 * fabs(perpinv) * (r[TP_BMOD1] + dot3(r + TP_GB, z)));
+  double e = m->particle_mass / 2.0 * (vperp * vperp + z[3] * z[3]) +
+             m->particle_charge * phi_elec_func(m, z, ind_tetr);
+  if (m->boole_strong_electric_field) e = e + 0.5 * m->particle_mass * v2_E_mod_func(m, z, ind_tetr);
+  return e;
+}
+double gor_p_phi(const gor_mesh *m, double vpar, const double z[3], int32_t ind_tetr) /* :377 */
+{
+  const double *r = rec(m, ind_tetr);
+  double hphi1;
+  const double *ghphi;
+  if (m->coord_system == 1) {
+    hphi1 = r[TP_H2_1];
+    ghphi = r + TP_GH2;
+  } else {
+    hphi1 = r[TP_H3_1];
+    ghphi = r + TP_GH3;
+  }
+  double p = m->particle_mass * vpar * (hphi1 + dot3(ghphi, z)) +
+             m->particle_mass / m->cm_over_e * (r[TP_APHI1] + dot3(r + TP_GAPHI, z));
+  if (m->boole_strong_electric_field) {
+    double vE2 = r[TP_VE2_1] + dot3(z, r + TP_GVE2);
+    p = p + m->particle_mass * vE2;
+  }
+  return p;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * pusher_handover2neighbour -- SRC/pusher_tetra_func_mod.f90:6-93 (handover_processing_kind = 1)
+ * ---------------------------------------------------------------------------------------------- */
+static void handover2neighbour(const gor_mesh *m, int ind_tetr, int *ind_tetr_out, int *iface_inout,
+                               double x[3], int *iper_phi)
+{
+  const int32_t *g = grd(m, ind_tetr);
+  int iface = *iface_inout;
+  *ind_tetr_out = g[TG_NEIGHBOUR_TETR + iface - 1];
+  *iface_inout = g[TG_NEIGHBOUR_FACE + iface - 1];
+  *iper_phi = g[TG_PERBOU_PHI + iface - 1];
+  int iper_theta = g[TG_PERBOU_THETA + iface - 1];
+  if (m->coord_system == 1) {
+    if (*iper_phi == 1)
+      x[1] = x[1] - 2.0 * PI / m->n_field_periods;
+    else if (*iper_phi == -1)
+      x[1] = x[1] + 2.0 * PI / m->n_field_periods;
+  } else {
+    if (*iper_phi == 1)
+      x[2] = x[2] - 2.0 * PI / m->n_field_periods;
+    else if (*iper_phi == -1)
+      x[2] = x[2] + 2.0 * PI / m->n_field_periods;
+    if (iper_theta == 1)
+      x[1] = x[1] - 2.0 * PI;
+    else if (iper_theta == -1)
+      x[1] = x[1] + 2.0 * PI;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * pusher_tetra_poly -- SRC/pusher_tetra_poly.f90
+ * (i_precomp = 0, i_time_tracing_option = 1, boole_adaptive_time_steps = .false.)
+ * The THREADPRIVATE module variables (:6-13,45-61) live in this struct, one per particle.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const gor_mesh *m;
+  const double *r; /* current record */
+  int ind_tetr, iface_init, sign_rhs;
+  double perpinv, perpinv2, vmod0, dt_dtau_const, bmod0, t_remain;
+  double z_init[4], k1, k3;
+  double b[4], amat[4][4], amat2[4][4], amat3[4][4], amat4[4][4]; /* amat[i][j] = amat(i+1,j+1) */
+  double amat_in_z[4], amat2_in_z[4], amat3_in_z[4], amat4_in_z[4];
+  double amat_in_b[4], amat2_in_b[4], amat3_in_b[4];
+  int number_of_integration_steps;
+  gor_trace *tr;
+} poly_state;
+static const double eps_tau = 100.0;
+
+static void matmul44(double c[4][4], double a[4][4], double b[4][4])
+{
+  double t[4][4];
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) {
+      double s = 0.0;
+      for (int k = 0; k < 4; k++) s = s + a[i][k] * b[k][j];
+      t[i][j] = s;
+    }
+  memcpy(c, t, sizeof(t));
+}
+static void matvec4(double c[4], double a[4][4], const double v[4])
+{
+  double t[4];
+  for (int i = 0; i < 4; i++) {
+    double s = 0.0;
+    for (int k = 0; k < 4; k++) s = s + a[i][k] * v[k];
+    t[i] = s;
+  }
+  memcpy(c, t, sizeof(t));
+}
+static inline const double *anorm_col(const poly_state *s, int iface) /* anorm(:,iface) */
+{
+  return s->r + TP_ANORM + 3 * (iface - 1);
+}
+
+/* :125-178 */
+static void initialize_pusher_tetra_poly(poly_state *s, int ind_tetr, const double x[3], int iface,
+                                         double vpar, double t_remain_in)
+{
+  const gor_mesh *m = s->m;
+  s->t_remain = t_remain_in;
+  s->ind_tetr = ind_tetr;
+  s->r = rec(m, ind_tetr);
+  s->sign_rhs = m->sign_sqg * isign1(s->t_remain);
+  for (int i = 0; i < 3; i++) s->z_init[i] = x[i] - s->r[TP_X1 + i];
+  s->z_init[3] = vpar;
+  s->iface_init = iface;
+  s->dt_dtau_const = s->r[TP_DT_DTAU_CONST];
+  s->dt_dtau_const = s->dt_dtau_const * (double)s->sign_rhs;
+  s->bmod0 = gor_bmod(m, s->z_init, ind_tetr);
+  double phi_elec = phi_elec_func(m, s->z_init, ind_tetr);
+  double vperp2 = -2.0 * s->perpinv * s->bmod0;
+  double vpar2 = vpar * vpar;
+  s->vmod0 = sqrt(vpar2 + vperp2);
+  s->k1 = vperp2 + vpar2 + 2.0 * s->perpinv * s->r[TP_BMOD1];
+  if (m->boole_strong_electric_field)
+    s->k1 = s->k1 + (v2_E_mod_func(m, s->z_init, ind_tetr) - s->r[TP_V2EMOD_1]);
+  s->k3 = s->r[TP_PHI1] - phi_elec;
+}
+
+/* :1486-1586 ; coef_mat[n][k] = coef_mat(n+1,k+1) */
+static void analytic_coeff_without_precomp(poly_state *s, int poly_order, const bool boole_faces[4],
+                                           const double z[4], double coef_mat[4][5])
+{
+  const gor_mesh *m = s->m;
+  const double *r = s->r;
+  const double cm_over_e = m->cm_over_e, perpinv = s->perpinv;
+  for (int i = 0; i < 3; i++)
+    s->b[i] = (r[TP_CURLH + i] * (s->k1) + perpinv * r[TP_GBXH1 + i]) * cm_over_e -
+              CLIGHT * (2.0 * (s->k3) * r[TP_CURLH + i] + r[TP_GPHIXH1 + i]);
+  s->b[3] = perpinv * r[TP_GBXCURLA] - CLIGHT / cm_over_e * r[TP_GPHIXCURLA];
+  memset(s->amat, 0, sizeof(s->amat));
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) /* alpmat(i,j) column-major: [i + 3*j] */
+      s->amat[i][j] = perpinv * cm_over_e * r[TP_ALPMAT + i + 3 * j] - CLIGHT * r[TP_BETMAT + i + 3 * j];
+  s->amat[3][3] = perpinv * cm_over_e * r[TP_SPALPMAT] - CLIGHT * r[TP_SPBETMAT];
+  for (int i = 0; i < 3; i++) s->amat[i][3] = r[TP_CURLA + i];
+  if (m->boole_strong_electric_field) {
+    for (int i = 0; i < 3; i++) s->b[i] = s->b[i] - 0.5 * cm_over_e * r[TP_GV2EMODXH1 + i];
+    s->b[3] = s->b[3] + cm_over_e * perpinv * r[TP_GBXCURLVE] - CLIGHT * r[TP_GPHIXCURLVE] -
+              0.5 * cm_over_e * r[TP_GV2EMODXCURLVE] - 0.5 * r[TP_GV2EMODXCURLA];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) s->amat[i][j] = s->amat[i][j] - 0.5 * cm_over_e * r[TP_GAMMAT + i + 3 * j];
+    s->amat[3][3] = s->amat[3][3] - 0.5 * cm_over_e * r[TP_SPGAMMAT];
+    for (int i = 0; i < 3; i++) s->amat[i][3] = s->amat[i][3] + cm_over_e * r[TP_CURLVE + i];
+  }
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) s->amat[i][j] = s->amat[i][j] * (double)s->sign_rhs;
+  for (int i = 0; i < 4; i++) s->b[i] = s->b[i] * (double)s->sign_rhs;
+  double dist1 = -r[TP_DIST_REF];
+
+  for (int n = 0; n < 4; n++) {
+    if (!boole_faces[n]) continue;
+    coef_mat[n][0] = dot3(r + TP_ANORM + 3 * n, z);
+  }
+  coef_mat[0][0] = coef_mat[0][0] - dist1;
+  if (poly_order >= 1) {
+    matvec4(s->amat_in_z, s->amat, z);
+    for (int n = 0; n < 4; n++) {
+      if (!boole_faces[n]) continue;
+      coef_mat[n][1] = dot3(r + TP_ANORM + 3 * n, s->amat_in_z) + dot3(r + TP_ANORM + 3 * n, s->b);
+    }
+  }
+  if (poly_order >= 2) {
+    matmul44(s->amat2, s->amat, s->amat);
+    matvec4(s->amat2_in_z, s->amat2, z);
+    matvec4(s->amat_in_b, s->amat, s->b);
+    for (int n = 0; n < 4; n++) {
+      if (!boole_faces[n]) continue;
+      coef_mat[n][2] = dot3(r + TP_ANORM + 3 * n, s->amat2_in_z) + dot3(r + TP_ANORM + 3 * n, s->amat_in_b);
+    }
+  }
+  if (poly_order >= 3) {
+    matmul44(s->amat3, s->amat, s->amat2);
+    matvec4(s->amat3_in_z, s->amat3, z);
+    matvec4(s->amat2_in_b, s->amat2, s->b);
+    for (int n = 0; n < 4; n++) {
+      if (!boole_faces[n]) continue;
+      coef_mat[n][3] = dot3(r + TP_ANORM + 3 * n, s->amat3_in_z) + dot3(r + TP_ANORM + 3 * n, s->amat2_in_b);
+    }
+  }
+  if (poly_order >= 4) {
+    matmul44(s->amat4, s->amat, s->amat3);
+    matvec4(s->amat4_in_z, s->amat4, z);
+    matvec4(s->amat3_in_b, s->amat3, s->b);
+    for (int n = 0; n < 4; n++) {
+      if (!boole_faces[n]) continue;
+      coef_mat[n][4] = dot3(r + TP_ANORM + 3 * n, s->amat4_in_z) + dot3(r + TP_ANORM + 3 * n, s->amat3_in_b);
+    }
+  }
+}
+
+/* :1258-1482.  dtau is only assigned when a valid root exists (intent(out) left untouched otherwise). */
+static void analytic_approx(poly_state *s, int poly_order, const bool boole_faces[4], int i_scaling,
+                            const double z[4], int *iface_inout, double *dtau, bool *boole_approx)
+{
+  double coef_mat[4][5];
+  double dtau_vec[4] = {HUGE_D, HUGE_D, HUGE_D, HUGE_D};
+  analytic_coeff_without_precomp(s, poly_order, boole_faces, z, coef_mat);
+  int iface = *iface_inout;
+  for (int i = 1; i <= 4; i++) {
+    if (!boole_faces[i - 1]) continue;
+    const double *cm = coef_mat[i - 1];
+    int solver = 0;
+    double qa = 0, qb = 0, qc = 0, qd = 0, qe = 0; /* quart_a.. / cub_a.. / quad_a.. / lin_a.. */
+    bool reduced = (i == iface) || (cm[0] == 0.0);
+    switch (poly_order) {
+      case 1:
+        if (reduced) { dtau_vec[i - 1] = 0.0; continue; }
+        solver = 1; qa = cm[1]; qb = cm[0];
+        if (qa == 0.0) { dtau_vec[i - 1] = 0.0; continue; }
+        break;
+      case 2:
+        if (reduced) {
+          solver = 1; qa = cm[2] / 2.0; qb = cm[1];
+          if (qa == 0.0) { dtau_vec[i - 1] = 0.0; continue; }
+        } else {
+          solver = 2; qa = cm[2]; qb = cm[1]; qc = cm[0];
+          if (qa == 0.0) {
+            if (qb != 0.0) { solver = 1; qa = qb; qb = qc; }
+            else { dtau_vec[i - 1] = 0.0; continue; }
+          }
+        }
+        break;
+      case 3:
+        if (reduced) {
+          solver = 2; qa = cm[3] / 3.0; qb = cm[2] / 2.0; qc = cm[1];
+          if (qa == 0.0) {
+            if (qb != 0.0) { solver = 1; qa = qb; qb = qc; }
+            else { dtau_vec[i - 1] = 0.0; continue; }
+          }
+        } else {
+          solver = 3; qa = cm[3]; qb = cm[2]; qc = cm[1]; qd = cm[0];
+          if (qa == 0.0) {
+            if (qb != 0.0) { solver = 2; qa = qb; qb = qc; qc = qd; }
+            else if (qc != 0.0) { solver = 1; qa = qc; qb = qd; }
+            else { dtau_vec[i - 1] = 0.0; continue; }
+          }
+        }
+        break;
+      case 4:
+        if (reduced) {
+          solver = 3; qa = cm[4] / 4.0; qb = cm[3] / 3.0; qc = cm[2] / 2.0; qd = cm[1];
+          if (qa == 0.0) {
+            if (qb != 0.0) { solver = 2; qa = qb; qb = qc; qc = qd; }
+            else if (qc != 0.0) { solver = 1; qa = qc; qb = qd; }
+            else { dtau_vec[i - 1] = 0.0; continue; }
+          }
+        } else {
+          solver = 4; qa = cm[4]; qb = cm[3]; qc = cm[2]; qd = cm[1]; qe = cm[0];
+          if (qa == 0.0) {
+            if (qb != 0.0) { solver = 3; qa = qb; qb = qc; qc = qd; qd = qe; }
+            else if (qc != 0.0) { solver = 2; qa = qc; qb = qd; qc = qe; }
+            else if (qd != 0.0) { solver = 1; qa = qd; qb = qe; }
+            else { dtau_vec[i - 1] = 0.0; continue; }
+          }
+        }
+        break;
+    }
+    switch (solver) {
+      case 1: dtau_vec[i - 1] = Linear_Solver(qa, qb); break;
+      case 2:
+        dtau_vec[i - 1] = (i_scaling == 0) ? Quadratic_Solver1(qa, qb, qc) : Quadratic_Solver2(qa, qb, qc, s->tr);
+        break;
+      case 3: dtau_vec[i - 1] = Cubic_Solver(qa, qb, qc, qd, s->tr); break;
+      case 4: dtau_vec[i - 1] = Quartic_Solver(i_scaling, qa, qb, qc, qd, qe, s->tr); break;
+    }
+  }
+  int best = -1;
+  for (int i = 0; i < 4; i++) {
+    bool valid = (dtau_vec[i] < HUGE_D) && (dtau_vec[i] > 0.0);
+    if (valid && (best < 0 || dtau_vec[i] < dtau_vec[best])) best = i;
+  }
+  if (best >= 0) {
+    *boole_approx = true;
+    *iface_inout = best + 1;
+    *dtau = dtau_vec[best];
+  } else {
+    *boole_approx = false;
+  }
+}
+
+/* :2047-2083 */
+static void analytic_integration(poly_state *s, int poly_order, double z[4], double tau)
+{
+  s->number_of_integration_steps += 1;
+  if (poly_order >= 1)
+    for (int i = 0; i < 4; i++) z[i] = z[i] + tau * (s->b[i] + s->amat_in_z[i]);
+  if (poly_order >= 2) {
+    double tau2_half = tau * tau * 0.5;
+    for (int i = 0; i < 4; i++) z[i] = z[i] + tau2_half * (s->amat_in_b[i] + s->amat2_in_z[i]);
+  }
+  if (poly_order >= 3) {
+    double tau3_sixth = (tau * tau) * tau / 6.0;
+    for (int i = 0; i < 4; i++) z[i] = z[i] + tau3_sixth * (s->amat2_in_b[i] + s->amat3_in_z[i]);
+  }
+  if (poly_order >= 4) {
+    double t2 = tau * tau;
+    double tau4_twentyfourth = (t2 * t2) / 24.0;
+    for (int i = 0; i < 4; i++) z[i] = z[i] + tau4_twentyfourth * (s->amat3_in_b[i] + s->amat4_in_z[i]);
+  }
+}
+/* :2087-2113 */
+static void set_integration_coef_manually(poly_state *s, int poly_order, const double z0[4])
+{
+  if (poly_order >= 1) matvec4(s->amat_in_z, s->amat, z0);
+  if (poly_order >= 2) {
+    matvec4(s->amat2_in_z, s->amat2, z0);
+    matvec4(s->amat_in_b, s->amat, s->b);
+  }
+  if (poly_order >= 3) {
+    matvec4(s->amat3_in_z, s->amat3, z0);
+    matvec4(s->amat2_in_b, s->amat2, s->b);
+  }
+  if (poly_order >= 4) {
+    matvec4(s->amat4_in_z, s->amat4, z0);
+    matvec4(s->amat3_in_b, s->amat3, s->b);
+  }
+}
+/* :2690-2705 */
+static double normal_distance_func(const poly_state *s, const double z123[3], int iface)
+{
+  double dist1 = -s->r[TP_DIST_REF];
+  double d = dot3(z123, anorm_col(s, iface));
+  if (iface == 1) d = d - dist1;
+  return d;
+}
+/* :2709-2739 (i_precomp = 0 branch; poly1 quantities of tetra_physics_poly_precomp_mod.f90:103-156
+ * formed on the fly with the same matmul(n_vec, mat) accumulation order) */
+static double normal_velocity_func(const poly_state *s, const double z[4], int iface)
+{
+  const gor_mesh *m = s->m;
+  const double *r = s->r, *n = anorm_col(s, iface);
+  double in_alp[3], in_bet[3], in_gam[3];
+  for (int j = 0; j < 3; j++) {
+    in_alp[j] = dot3(n, r + TP_ALPMAT + 3 * j); /* sum_i n(i)*alpmat(i,j) */
+    in_bet[j] = dot3(n, r + TP_BETMAT + 3 * j);
+  }
+  double in_betvec = dot3(n, r + TP_CURLA);
+  double t[3];
+  for (int j = 0; j < 3; j++) t[j] = (-CLIGHT * in_bet[j] + s->perpinv * m->cm_over_e * in_alp[j]) * z[j];
+  double v = (((0.0 + t[0]) + t[1]) + t[2] + in_betvec * z[3]) * (double)s->sign_rhs + dot3(n, s->b);
+  if (m->boole_strong_electric_field) {
+    for (int j = 0; j < 3; j++) in_gam[j] = dot3(n, r + TP_GAMMAT + 3 * j);
+    double in_gamvec = dot3(n, r + TP_CURLVE);
+    for (int j = 0; j < 3; j++) t[j] = -0.5 * m->cm_over_e * in_gam[j] * z[j];
+    v = v + (((0.0 + t[0]) + t[1]) + t[2] + m->cm_over_e * in_gamvec * z[3]) * (double)s->sign_rhs;
+  }
+  return v;
+}
+/* :2741-2775 */
+static double normal_v_func_from_trajectory(const poly_state *s, int poly_order, int iface, double tau)
+{
+  const double *n = anorm_col(s, iface);
+  double v = 0.0, t[3];
+  if (poly_order >= 1) {
+    for (int i = 0; i < 3; i++) t[i] = n[i] * (s->b[i] + s->amat_in_z[i]);
+    v = ((0.0 + t[0]) + t[1]) + t[2];
+  }
+  if (poly_order >= 2) {
+    for (int i = 0; i < 3; i++) t[i] = n[i] * tau * (s->amat_in_b[i] + s->amat2_in_z[i]);
+    v = v + (((0.0 + t[0]) + t[1]) + t[2]);
+  }
+  if (poly_order >= 3) {
+    double tau2_half = tau * tau * 0.5;
+    for (int i = 0; i < 3; i++) t[i] = n[i] * tau2_half * (s->amat2_in_b[i] + s->amat3_in_z[i]);
+    v = v + (((0.0 + t[0]) + t[1]) + t[2]);
+  }
+  if (poly_order >= 4) {
+    double tau3_sixth = (tau * tau) * tau / 6.0;
+    for (int i = 0; i < 3; i++) t[i] = n[i] * tau3_sixth * (s->amat3_in_b[i] + s->amat4_in_z[i]);
+    v = v + (((0.0 + t[0]) + t[1]) + t[2]);
+  }
+  return v;
+}
+/* :679-758 */
+static void check_three_planes(const poly_state *s, const double z[4], int iface_new, bool *ok)
+{
+  for (int j = 1; j <= 3; j++) {
+    int k = ((iface_new + j - 1) % 4) + 1;
+    if (normal_distance_func(s, z, k) < 0.0) *ok = false;
+  }
+}
+static void check_face_convergence(const poly_state *s, const double z[4], int iface_new, bool *ok)
+{
+  if (fabs(normal_distance_func(s, z, iface_new)) > 1.e-11) *ok = false;
+}
+static void check_velocity(const poly_state *s, const double z[4], int iface_new, bool *ok)
+{
+  if (normal_velocity_func(s, z, iface_new) > 0.0) *ok = false;
+}
+static void check_exit_time(double tau, double tau_max, bool *ok, int poly_order)
+{
+  if (poly_order > 2)
+    if (tau > tau_max) *ok = false;
+}
+/* :2779-2831 */
+static double physical_estimate_tau(const poly_state *s)
+{
+  const gor_mesh *m = s->m;
+  const double *r = s->r;
+  const double eps_modulation = 0.1;
+  double tetra_dist_ref = fabs(r[TP_TETRA_DIST_REF]);
+  double vperp2 = -2.0 * s->perpinv * s->bmod0;
+  double vd_ExB;
+  if (m->boole_strong_electric_field)
+    vd_ExB = r[TP_VE_MOD_AVG];
+  else
+    vd_ExB = fabs(CLIGHT / s->bmod0 * r[TP_ER_MOD]);
+  bool boole_vd_ExB = !(vd_ExB == 0.0), boole_vperp = !(vperp2 == 0.0);
+  double c1 = fabs(tetra_dist_ref / s->z_init[3]);
+  double tau_est;
+  if (boole_vperp) {
+    double c2 = sqrt(tetra_dist_ref * s->vmod0 * r[TP_R1] / (vperp2 * m->grid_size[1] * eps_modulation));
+    tau_est = c1;
+    if (c2 < tau_est) tau_est = c2;
+    if (boole_vd_ExB) {
+      double c3 = tetra_dist_ref / vd_ExB;
+      if (c3 < tau_est) tau_est = c3;
+    }
+  } else if (boole_vd_ExB) {
+    double c3 = tetra_dist_ref / vd_ExB;
+    tau_est = c1;
+    if (c3 < tau_est) tau_est = c3;
+  } else {
+    tau_est = c1;
+  }
+  return fabs(tau_est / s->dt_dtau_const);
+}
+
+/* :762-826 ; returns false when the particle has to be removed (ind_tetr=-1, iface=-1) */
+static void prolonged_trajectory(poly_state *s, int poly_order, int i_scaling, double z[4], double *tau,
+                                 int *iface_new, bool *boole_face_correct, bool *boole_analytical_approx)
+{
+  bool boole_faces[4] = {true, true, true, true};
+  double tau_save = *tau, tau_max = 0.0;
+  int iface_new_save = *iface_new;
+  if (poly_order > 2) {
+    analytic_approx(s, 2, boole_faces, i_scaling, z, iface_new, tau, boole_analytical_approx);
+    tau_max = *tau * eps_tau;
+  }
+  *iface_new = iface_new_save;
+  analytic_approx(s, poly_order, boole_faces, i_scaling, z, iface_new, tau, boole_analytical_approx);
+  if (!*boole_analytical_approx) return;
+  analytic_integration(s, poly_order, z, *tau);
+  check_exit_time(*tau, tau_max, boole_face_correct, poly_order);
+  check_three_planes(s, z, *iface_new, boole_face_correct);
+  check_velocity(s, z, *iface_new, boole_face_correct);
+  check_face_convergence(s, z, *iface_new, boole_face_correct);
+  *tau = *tau + tau_save;
+  if (s->tr) s->tr->n_fallback[2]++;
+}
+
+/* :2835-2998 */
+static void trouble_shooting_polynomial_solver(poly_state *s, int poly_order, double z[4], double *tau,
+                                               int *iface_new, bool *boole_trouble_shooting)
+{
+  bool boole_faces[4] = {true, true, true, true};
+  bool boole_analytical_approx, boole_face_correct;
+  int i_scaling = 0, poly_order_new = poly_order;
+  double tau_max, tau_max_est;
+  if (s->tr) s->tr->n_fallback[1]++;
+  *boole_trouble_shooting = true;
+  *iface_new = s->iface_init;
+  memcpy(z, s->z_init, 4 * sizeof(double));
+  analytic_approx(s, 2, boole_faces, i_scaling, z, iface_new, tau, &boole_analytical_approx);
+  tau_max = *tau * eps_tau;
+  boole_face_correct = false;
+  int i = 0;
+  while ((!boole_face_correct) && (poly_order == 4)) {
+    i = i + 1;
+    i_scaling = i;
+    *iface_new = s->iface_init;
+    memcpy(z, s->z_init, 4 * sizeof(double));
+    s->number_of_integration_steps = 0;
+    analytic_approx(s, poly_order, boole_faces, i_scaling, z, iface_new, tau, &boole_analytical_approx);
+    if (!boole_analytical_approx) {
+      *boole_trouble_shooting = false;
+      return;
+    }
+    analytic_integration(s, poly_order, z, *tau);
+    boole_face_correct = true;
+    check_three_planes(s, z, *iface_new, &boole_face_correct);
+    check_face_convergence(s, z, *iface_new, &boole_face_correct);
+    check_velocity(s, z, *iface_new, &boole_face_correct);
+    if (*tau > tau_max) {
+      tau_max_est = physical_estimate_tau(s);
+      tau_max_est = tau_max_est * eps_tau;
+      if (*tau > tau_max_est) boole_face_correct = false;
+    }
+    if (i == 6) break;
+  }
+  if (!boole_face_correct) {
+    *iface_new = s->iface_init;
+    memcpy(z, s->z_init, 4 * sizeof(double));
+    s->number_of_integration_steps = 0;
+    switch (poly_order) {
+      case 2: poly_order_new = 2; i_scaling = 1; break;
+      case 3: poly_order_new = 3; i_scaling = 1; break;
+      case 4: poly_order_new = 3; i_scaling = 0; break;
+      default: /* no case(1) in the reference (:2936-2947): poly_order_new undefined; keep order, i_scaling */
+        poly_order_new = poly_order;
+        break;
+    }
+    analytic_approx(s, poly_order_new, boole_faces, i_scaling, z, iface_new, tau, &boole_analytical_approx);
+    if (!boole_analytical_approx) {
+      *boole_trouble_shooting = false;
+      return;
+    }
+    analytic_integration(s, poly_order, z, *tau); /* original order, :2961 */
+    boole_face_correct = true;
+    check_three_planes(s, z, *iface_new, &boole_face_correct);
+    check_face_convergence(s, z, *iface_new, &boole_face_correct);
+    check_velocity(s, z, *iface_new, &boole_face_correct);
+    if (*tau > tau_max) {
+      tau_max_est = physical_estimate_tau(s);
+      tau_max_est = tau_max_est * eps_tau;
+      if (*tau > tau_max_est) boole_face_correct = false;
+    }
+    if (!boole_face_correct) {
+      *boole_trouble_shooting = false;
+      return;
+    }
+  }
+}
+
+/* :182-675 */
+static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout, int *iface, double x[3],
+                              double *vpar, double z_save[3], double t_remain_in, double *t_pass,
+                              bool *boole_t_finished, int *iper_phi)
+{
+  const gor_mesh *m = s->m;
+  bool boole_faces[4] = {true, true, true, true};
+  bool boole_analytical_approx = false, boole_face_correct, boole_trouble_shooting = true;
+  double z[4], tau = 0.0, tau_max;
+  int iface_new, i_scaling = 0;
+
+  initialize_pusher_tetra_poly(s, *ind_tetr_inout, x, *iface, *vpar, t_remain_in);
+  s->number_of_integration_steps = 0;
+  memcpy(z, s->z_init, sizeof(z));
+  *iper_phi = 0;
+  *boole_t_finished = false;
+  *t_pass = 0.0; /* undefined in the reference on the "remove particle" returns */
+  iface_new = s->iface_init;
+
+  /* ---- first attempt with second order guess (:267-346) */
+  analytic_approx(s, 2, boole_faces, i_scaling, z, &iface_new, &tau, &boole_analytical_approx);
+  tau_max = tau * eps_tau;
+  if (m->boole_guess && boole_analytical_approx && (poly_order > 2)) {
+    for (int i = 0; i < 4; i++) boole_faces[i] = false;
+    boole_faces[iface_new - 1] = true;
+  }
+  if (poly_order > 2) {
+    iface_new = s->iface_init;
+    analytic_approx(s, poly_order, boole_faces, i_scaling, z, &iface_new, &tau, &boole_analytical_approx);
+  }
+  boole_face_correct = true;
+  if (!boole_analytical_approx) boole_face_correct = false;
+  if (boole_face_correct) {
+    analytic_integration(s, poly_order, z, tau);
+    check_three_planes(s, z, iface_new, &boole_face_correct);
+    check_face_convergence(s, z, iface_new, &boole_face_correct);
+    check_exit_time(tau, tau_max, &boole_face_correct, poly_order);
+    if (boole_face_correct) {
+      double nv = normal_v_func_from_trajectory(s, poly_order, iface_new, tau);
+      if (nv > 0.0) {
+        if (poly_order > 2) {
+          boole_face_correct = false;
+        } else {
+          prolonged_trajectory(s, poly_order, i_scaling, z, &tau, &iface_new, &boole_face_correct,
+                               &boole_analytical_approx);
+          if (!boole_analytical_approx) {
+            *ind_tetr_inout = -1;
+            *iface = -1;
+            return;
+          }
+        }
+      }
+    }
+  }
+  /* ---- second attempt without guess (+ rescaling in 2nd order) (:361-418) */
+  if (!boole_face_correct) {
+    if (s->tr) s->tr->n_fallback[0]++;
+    for (int i = 0; i < 4; i++) boole_faces[i] = true;
+    boole_face_correct = true;
+    iface_new = s->iface_init;
+    memcpy(z, s->z_init, sizeof(z));
+    s->number_of_integration_steps = 0;
+    if (poly_order == 2)
+      analytic_approx(s, poly_order, boole_faces, 1, z, &iface_new, &tau, &boole_analytical_approx);
+    else
+      analytic_approx(s, poly_order, boole_faces, i_scaling, z, &iface_new, &tau, &boole_analytical_approx);
+    if (!boole_analytical_approx) {
+      *ind_tetr_inout = -1;
+      *iface = -1;
+      return;
+    }
+    analytic_integration(s, poly_order, z, tau);
+    check_exit_time(tau, tau_max, &boole_face_correct, poly_order);
+    check_three_planes(s, z, iface_new, &boole_face_correct);
+    check_face_convergence(s, z, iface_new, &boole_face_correct);
+    if (boole_face_correct) {
+      if (normal_velocity_func(s, z, iface_new) > 0.0) {
+        prolonged_trajectory(s, poly_order, i_scaling, z, &tau, &iface_new, &boole_face_correct,
+                             &boole_analytical_approx);
+        if (!boole_analytical_approx) {
+          *ind_tetr_inout = -1;
+          *iface = -1;
+          return;
+        }
+      }
+    }
+    /* ---- third attempt: trouble shooting (:429-441) */
+    if (!boole_face_correct) {
+      trouble_shooting_polynomial_solver(s, poly_order, z, &tau, &iface_new, &boole_trouble_shooting);
+      if (!boole_trouble_shooting) {
+        *ind_tetr_inout = -1;
+        *iface = -1;
+        return;
+      }
+    }
+  }
+  /* ---- final processing (:459-466) */
+  for (int i = 0; i < 3; i++) x[i] = z[i] + s->r[TP_X1 + i];
+  *vpar = z[3];
+  *t_pass = tau * s->dt_dtau_const;
+
+  if (fabs(*t_pass) >= fabs(s->t_remain)) {
+    /* ---- fourth attempt: particle stops inside the cell (:497-645) */
+    memcpy(z, s->z_init, sizeof(z));
+    if (s->number_of_integration_steps > 1) {
+      iface_new = s->iface_init;
+      set_integration_coef_manually(s, poly_order, z);
+    }
+    s->number_of_integration_steps = 0;
+    tau = s->t_remain / s->dt_dtau_const;
+    analytic_integration(s, poly_order, z, tau);
+    *ind_tetr_inout = s->ind_tetr;
+    *iface = 0;
+    boole_face_correct = true;
+    for (int i = 1; i <= 4; i++)
+      if (normal_distance_func(s, z, i) < 0.0) boole_face_correct = false;
+    if (boole_face_correct) {
+      *boole_t_finished = true;
+      for (int i = 0; i < 3; i++) z_save[i] = z[i];
+      for (int i = 0; i < 3; i++) x[i] = z[i] + s->r[TP_X1 + i];
+      *vpar = z[3];
+      *t_pass = s->t_remain;
+    } else {
+      if (s->tr) s->tr->n_fallback[3]++;
+      trouble_shooting_polynomial_solver(s, poly_order, z, &tau, &iface_new, &boole_trouble_shooting);
+      if (!boole_trouble_shooting) {
+        *ind_tetr_inout = -1;
+        *iface = -1;
+        return;
+      }
+      for (int i = 0; i < 3; i++) x[i] = z[i] + s->r[TP_X1 + i];
+      *vpar = z[3];
+      *t_pass = tau * s->dt_dtau_const;
+      for (int i = 0; i < 3; i++) z_save[i] = z[i];
+      *iface = iface_new;
+      handover2neighbour(m, s->ind_tetr, ind_tetr_inout, iface, x, iper_phi);
+    }
+  } else {
+    for (int i = 0; i < 3; i++) z_save[i] = z[i];
+    *iface = iface_new;
+    handover2neighbour(m, s->ind_tetr, ind_tetr_inout, iface, x, iper_phi);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * RK-module pieces used by find_tetra -- SRC/pusher_tetra_rk.f90:50-193,810-896,2422-2467
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const gor_mesh *m;
+  const double *r;
+  int ind_tetr, iface_init, sign_rhs, sign_t_step_save;
+  double perpinv, perpinv2, vmod_init, spamat, dt_dtau_const, dist_min, dist1, dist_max, t_remain;
+  double Bvec[3], b[4], z_init[4], amat[3][3], anorm[4][3]; /* anorm[f][i] = anorm(i+1,f+1) */
+  double dtau_ref, dtau_max, dtau_quad;
+} rk_state;
+
+static void initialize_pusher_tetra_rk_mod(rk_state *s, int ind_tetr, const double x[3], int iface,
+                                           double vpar, double t_remain_in)
+{
+  const gor_mesh *m = s->m;
+  const double eps_distmin = 1.e-10, eps_distmax = 10.0, eps_modulation = 0.1, eps_dtau_max = 10.0,
+               eps_dtau_quad = 1.5;
+  s->t_remain = t_remain_in;
+  s->ind_tetr = ind_tetr;
+  const double *r = s->r = rec(m, ind_tetr);
+  s->sign_t_step_save = isign1(s->t_remain);
+  s->sign_rhs = m->sign_sqg * s->sign_t_step_save;
+  for (int i = 0; i < 3; i++) s->z_init[i] = x[i] - r[TP_X1 + i];
+  s->z_init[3] = vpar;
+  s->iface_init = iface;
+  double B0 = r[TP_BMOD1];
+  for (int f = 0; f < 4; f++)
+    for (int i = 0; i < 3; i++) s->anorm[f][i] = r[TP_ANORM + 3 * f + i];
+  s->dt_dtau_const = r[TP_DT_DTAU_CONST];
+  s->dt_dtau_const = s->dt_dtau_const * (double)s->sign_rhs;
+  double bmod = gor_bmod(m, s->z_init, ind_tetr);
+  double phi_elec = phi_elec_func(m, s->z_init, ind_tetr);
+  double vperp2 = -2.0 * s->perpinv * bmod;
+  double vpar2 = vpar * vpar;
+  s->vmod_init = sqrt(vpar2 + vperp2);
+  const double cm_over_e = m->cm_over_e, perpinv = s->perpinv;
+  for (int i = 0; i < 3; i++)
+    s->b[i] = (r[TP_CURLH + i] * (vperp2 + vpar2 + 2.0 * perpinv * B0) + perpinv * r[TP_GBXH1 + i]) * cm_over_e -
+              CLIGHT * (2.0 * (r[TP_PHI1] - phi_elec) * r[TP_CURLH + i] + r[TP_GPHIXH1 + i]);
+  s->b[3] = perpinv * r[TP_GBXCURLA] - CLIGHT / cm_over_e * r[TP_GPHIXCURLA];
+  for (int i = 0; i < 3; i++) s->Bvec[i] = r[TP_CURLA + i];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      s->amat[i][j] = perpinv * cm_over_e * r[TP_ALPMAT + i + 3 * j] - CLIGHT * r[TP_BETMAT + i + 3 * j];
+  s->spamat = perpinv * cm_over_e * r[TP_SPALPMAT] - CLIGHT * r[TP_SPBETMAT];
+  if (m->boole_strong_electric_field) {
+    double dv2 = v2_E_mod_func(m, s->z_init, ind_tetr) - r[TP_V2EMOD_1];
+    for (int i = 0; i < 3; i++)
+      s->b[i] = s->b[i] - 0.5 * cm_over_e * r[TP_GV2EMODXH1 + i] + cm_over_e * r[TP_CURLH + i] * dv2;
+    s->b[3] = s->b[3] + cm_over_e * perpinv * r[TP_GBXCURLVE] - CLIGHT * r[TP_GPHIXCURLVE] -
+              0.5 * cm_over_e * r[TP_GV2EMODXCURLVE] - 0.5 * r[TP_GV2EMODXCURLA];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) s->amat[i][j] = s->amat[i][j] - 0.5 * cm_over_e * r[TP_GAMMAT + i + 3 * j];
+    s->spamat = s->spamat - 0.5 * cm_over_e * r[TP_SPGAMMAT];
+    for (int i = 0; i < 3; i++) s->Bvec[i] = s->Bvec[i] + cm_over_e * r[TP_CURLVE + i];
+  }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) s->amat[i][j] = s->amat[i][j] * (double)s->sign_rhs;
+  for (int i = 0; i < 4; i++) s->b[i] = s->b[i] * (double)s->sign_rhs;
+  for (int i = 0; i < 3; i++) s->Bvec[i] = s->Bvec[i] * (double)s->sign_rhs;
+  s->spamat = s->spamat * (double)s->sign_rhs;
+  s->dist1 = -r[TP_DIST_REF];
+  s->dist_min = eps_distmin * fabs(s->dist1);
+  s->dist_max = eps_distmax * fabs(s->dist1);
+  double tetra_dist_ref = fabs(r[TP_TETRA_DIST_REF]);
+  double vd_ExB;
+  if (m->boole_strong_electric_field)
+    vd_ExB = r[TP_VE_MOD_AVG];
+  else
+    vd_ExB = fabs(CLIGHT / bmod * r[TP_ER_MOD]);
+  bool boole_vd_ExB = !(vd_ExB == 0.0), boole_vperp = !(vperp2 == 0.0);
+  double c1 = fabs(tetra_dist_ref / s->z_init[3]);
+  double dtau_ref = c1;
+  if (boole_vperp) {
+    double c2 = sqrt(tetra_dist_ref * s->vmod_init * r[TP_R1] / (vperp2 * m->grid_size[1] * eps_modulation));
+    if (c2 < dtau_ref) dtau_ref = c2;
+  }
+  if (boole_vd_ExB) {
+    double c3 = tetra_dist_ref / vd_ExB;
+    if (c3 < dtau_ref) dtau_ref = c3;
+  }
+  /* boole_dt_dtau = .true. (default) */
+  dtau_ref = fabs(dtau_ref / s->dt_dtau_const);
+  s->dtau_ref = dtau_ref;
+  s->dtau_max = eps_dtau_max * dtau_ref;
+  s->dtau_quad = eps_dtau_quad * dtau_ref;
+}
+static void rhs_pusher_tetra_rk4(const rk_state *s, const double z[4], double dzdtau[4])
+{
+  for (int i = 0; i < 3; i++) {
+    double mv = ((0.0 + s->amat[i][0] * z[0]) + s->amat[i][1] * z[1]) + s->amat[i][2] * z[2];
+    dzdtau[i] = s->b[i] + mv + s->Bvec[i] * z[3];
+  }
+  dzdtau[3] = s->b[3] + s->spamat * z[3];
+}
+static void rk4_step(const rk_state *s, double y[4], double h, double dzdtau[4])
+{
+  double hh = h * 0.5, h6 = h / 6.0, dydx[4], yt[4], dyt[4], dym[4];
+  rhs_pusher_tetra_rk4(s, y, dydx);
+  for (int i = 0; i < 4; i++) yt[i] = y[i] + hh * dydx[i];
+  rhs_pusher_tetra_rk4(s, yt, dyt);
+  for (int i = 0; i < 4; i++) yt[i] = y[i] + hh * dyt[i];
+  rhs_pusher_tetra_rk4(s, yt, dym);
+  for (int i = 0; i < 4; i++) yt[i] = y[i] + h * dym[i];
+  for (int i = 0; i < 4; i++) dym[i] = dyt[i] + dym[i];
+  rhs_pusher_tetra_rk4(s, yt, dyt);
+  for (int i = 0; i < 4; i++) y[i] = y[i] + h6 * (dydx[i] + dyt[i] + 2.0 * dym[i]);
+  for (int i = 0; i < 4; i++) dzdtau[i] = dyt[i];
+}
+static void rk_normal_distances_func(const rk_state *s, const double z123[3], double out[4])
+{
+  for (int f = 0; f < 4; f++) out[f] = dot3(z123, s->anorm[f]);
+  out[0] = out[0] - s->dist1;
+}
+static double rk_normal_velocity_func(const rk_state *s, int iface, const double dzdtau[4])
+{
+  return dot3(dzdtau, s->anorm[iface - 1]);
+}
+
+/* SRC/tetra_physics_mod.f90:1038-1072 */
+static bool isinside(const gor_mesh *m, int ind_tetr, const double x[3], double cur_dist_value[4])
+{
+  const double *r = rec(m, ind_tetr);
+  double dist_min = EPS * fabs(r[TP_DIST_REF]);
+  double d[3] = {x[0] - r[TP_X1], x[1] - r[TP_X1 + 1], x[2] - r[TP_X1 + 2]};
+  bool all_ok = true;
+  for (int f = 0; f < 4; f++) {
+    double v = dot3(r + TP_ANORM + 3 * f, d);
+    if (f == 0) v = v + r[TP_DIST_REF];
+    cur_dist_value[f] = v;
+    if (!(v >= -dist_min)) all_ok = false;
+  }
+  return all_ok;
+}
+
+/* SRC/find_tetra_mod.f90:283-600 (boole_grid_for_find_tetra = .false.) */
+void gor_find_tetra(const gor_mesh *m, double x[3], double vpar, double vperp, int32_t *ind_tetr_out,
+                    int32_t *iface, int sign_t_step)
+{
+  int64_t indtetr_start = 0, ntetr_searched = 0, ntetr = m->ntetr;
+  int numerical_corr_plus = 0, numerical_corr_minus = 0, nphi = m->grid_size[1];
+  *ind_tetr_out = -1;
+  *iface = -1;
+  if (m->grid_kind == 1 || m->grid_kind == 5) {
+    int nr = m->grid_size[0], nz = m->grid_size[2];
+    double hr = (m->Rmax - m->Rmin) / nr, hphi = (2.0 * PI) / nphi, hz = (m->Zmax - m->Zmin) / nz;
+    int ir = (int)((x[0] - m->Rmin) / hr) + 1, iphi = (int)(x[1] / hphi) + 1,
+        iz = (int)((x[2] - m->Zmin) / hz) + 1;
+    if (ir < 1 || ir > nr || iphi < 1 || iphi > nphi || iz < 1 || iz > nz) return; /* reference: stop */
+    indtetr_start = (int64_t)(((double)iz - 1.0) * 6.0 + 6.0 * (double)nz * ((double)ir - 1.0) +
+                              6.0 * ((double)iphi - 1.0) * (double)nr * (double)nz + 1.0);
+    ntetr_searched = 6;
+  } else {
+    int ind_b = (m->coord_system == 2) ? 2 : 1; /* 0-based slot of phi */
+    int64_t ntetr_in_plane = ntetr / nphi;
+    double q = x[ind_b] * nphi / (2.0 * PI / m->n_field_periods);
+    int ind_plane_tetra_start = (int)q;
+    if (fabs(q - (double)ind_plane_tetra_start) > (1.0 - EPS)) numerical_corr_plus = 1;
+    if (fabs(q - (double)ind_plane_tetra_start) < EPS) numerical_corr_minus = 1;
+    indtetr_start = (int64_t)ind_plane_tetra_start * ntetr_in_plane + 1;
+    ntetr_searched = ntetr_in_plane * (1 + numerical_corr_plus + numerical_corr_minus);
+  }
+  for (int64_t i = 1; i <= ntetr_searched; i++) {
+    int64_t ind_search = indtetr_start + i - 1 - (int64_t)numerical_corr_minus * (ntetr / nphi);
+    if (ind_search > ntetr) ind_search -= ntetr;
+    if (ind_search <= 0) ind_search += ntetr;
+    double cur_dist_value[4];
+    if (isinside(m, (int)ind_search, x, cur_dist_value)) {
+      *ind_tetr_out = (int)ind_search;
+      *iface = 0;
+      const double *r = rec(m, (int)ind_search);
+      bool conv[4];
+      int n_plane_conv = 0;
+      for (int f = 0; f < 4; f++) {
+        conv[f] = fabs(cur_dist_value[f]) <= (EPS * fabs(r[TP_DIST_REF]));
+        if (conv[f]) n_plane_conv++;
+      }
+      if (n_plane_conv > 0) {
+        rk_state rk;
+        memset(&rk, 0, sizeof(rk));
+        rk.m = m;
+        double vperp2 = vperp * vperp, z[4], dzdtau[4];
+        for (int k = 0; k < 3; k++) z[k] = x[k] - r[TP_X1 + k];
+        z[3] = vpar;
+        int iface_new = 1;
+        for (int f = 1; f < 4; f++)
+          if (fabs(cur_dist_value[f]) < fabs(cur_dist_value[iface_new - 1])) iface_new = f + 1;
+        int ind_tetr_tried[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        rk.perpinv = -0.5 * vperp2 / (r[TP_BMOD1] + dot3(r + TP_GB, z));
+        rk.perpinv2 = rk.perpinv * rk.perpinv;
+        for (int i_try = 1; i_try <= 2 * n_plane_conv; i_try++) {
+          if (*ind_tetr_out == -1) break;
+          ind_tetr_tried[i_try - 1] = *ind_tetr_out;
+          const double *rr = rec(m, *ind_tetr_out);
+          for (int k = 0; k < 3; k++) z[k] = x[k] - rr[TP_X1 + k];
+          initialize_pusher_tetra_rk_mod(&rk, *ind_tetr_out, x, iface_new, vpar, (double)sign_t_step);
+          rk_normal_distances_func(&rk, z, cur_dist_value);
+          /* reference stops if any(cur_dist_value < -dist_min); unreachable for isinside-accepted starts */
+          bool conv_t[4];
+          for (int f = 0; f < 4; f++) conv_t[f] = fabs(cur_dist_value[f]) <= (EPS * fabs(rr[TP_DIST_REF]));
+          rk4_step(&rk, z, 0.0, dzdtau);
+          int counter_vnorm_pos = 0;
+          for (int l = 1; l <= 4; l++) {
+            if (!conv_t[l - 1]) continue;
+            if (rk_normal_velocity_func(&rk, l, dzdtau) > 0.0) counter_vnorm_pos++;
+          }
+          if (counter_vnorm_pos == n_plane_conv) {
+            *iface = iface_new;
+            break;
+          } else {
+            int ind_tetr_save = *ind_tetr_out, iface_new_save = iface_new, iper_phi;
+            double x_save[3] = {x[0], x[1], x[2]};
+            for (int l = 1; l <= 4; l++) {
+              if (!conv_t[l - 1]) continue;
+              if (rk_normal_velocity_func(&rk, l, dzdtau) > 0.0) continue;
+              iface_new = l;
+              int out;
+              handover2neighbour(m, ind_tetr_save, &out, &iface_new, x, &iper_phi);
+              *ind_tetr_out = out;
+              bool tried = false;
+              for (int t = 0; t < 2 * n_plane_conv; t++)
+                if (ind_tetr_tried[t] == out) tried = true;
+              if (tried || out == -1) {
+                x[0] = x_save[0]; x[1] = x_save[1]; x[2] = x_save[2];
+                iface_new = iface_new_save;
+              } else {
+                break;
+              }
+            }
+          }
+        }
+      }
+      if (*ind_tetr_out == -1)
+        *iface = -1;
+      else
+        break;
+    } else {
+      *ind_tetr_out = -1;
+      *iface = -1;
+    }
+  }
+}
+
+/* SRC/orbit_timestep_gorilla.f90:278-358 ; Fortran modulo(a,p) = a - floor(a/p)*p */
+static double f_modulo(double a, double p) { return a - floor(a / p) * p; }
+int gor_check_coordinate_domain(const gor_mesh *m, double x[3])
+{
+  double per = 2.0 * PI / m->n_field_periods;
+  if (m->coord_system == 1) {
+    if (m->boole_periodic_relocation)
+      x[1] = f_modulo(x[1], per);
+    else if (x[1] < 0.0 || x[1] > per)
+      return GOR_ERR_DOMAIN;
+  } else {
+    if (x[0] < m->sfc_s_min || x[0] > 1.0) return GOR_ERR_DOMAIN;
+    if (m->boole_periodic_relocation) {
+      x[1] = f_modulo(x[1], 2.0 * PI);
+      x[2] = f_modulo(x[2], per);
+    } else if (x[1] < 0.0 || x[1] > 2.0 * PI || x[2] < 0.0 || x[2] > per) {
+      return GOR_ERR_DOMAIN;
+    }
+  }
+  return GOR_OK;
+}
+
+/* SRC/orbit_timestep_gorilla.f90:19-147 (ipusher = 2) */
+int gor_orbit_timestep(const gor_mesh *m, double x[3], double *vpar, double *vperp, double t_step,
+                       int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface, double *t_remain_out,
+                       gor_trace *tr)
+{
+  if (m->ipusher != 2) return GOR_ERR_CONFIG;
+  if (!*boole_initialized) {
+    int rcd = gor_check_coordinate_domain(m, x);
+    if (rcd != GOR_OK) return rcd;
+    int sign_t_step = isign1(t_step);
+    gor_find_tetra(m, x, *vpar, *vperp, ind_tetr, iface, sign_t_step);
+    if (*ind_tetr == -1) return GOR_OK;
+    *boole_initialized = 1;
+  }
+  if (t_step == 0.0) return GOR_OK;
+  double vperp2 = (*vperp) * (*vperp);
+  double z_save[3];
+  {
+    const double *r = rec(m, *ind_tetr);
+    for (int i = 0; i < 3; i++) z_save[i] = x[i] - r[TP_X1 + i];
+  }
+  poly_state s;
+  memset(&s, 0, sizeof(s));
+  s.m = m;
+  s.tr = tr;
+  s.perpinv = -0.5 * vperp2 / gor_bmod(m, z_save, *ind_tetr);
+  s.perpinv2 = s.perpinv * s.perpinv;
+  double t_remain = t_step, t_pass;
+  bool boole_t_finished = false;
+  int ind_tetr_save = *ind_tetr, iper;
+  for (;;) {
+    if (*ind_tetr == -1) {
+      if (t_remain_out) *t_remain_out = t_remain;
+      break;
+    }
+    ind_tetr_save = *ind_tetr;
+    int it = *ind_tetr, ifc = *iface;
+    pusher_tetra_poly(&s, m->poly_order, &it, &ifc, x, vpar, z_save, t_remain, &t_pass, &boole_t_finished, &iper);
+    *ind_tetr = it;
+    *iface = ifc;
+    if (tr) {
+      if (tr->n_pushes < tr->cap) {
+        tr->ind_tetr[tr->n_pushes] = it;
+        tr->iface[tr->n_pushes] = ifc;
+      }
+      tr->n_pushes++;
+    }
+    t_remain = t_remain - t_pass;
+    if (boole_t_finished) {
+      if (t_remain_out) *t_remain_out = t_remain;
+      break;
+    }
+  }
+  *vperp = vperp_func(m, z_save, s.perpinv, ind_tetr_save);
+  return GOR_OK;
+}
+
+int64_t gor_orbit_timestep_batch(const gor_mesh *m, int64_t n, double *x, double *vpar, double *vperp,
+                                 double t_step, int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface,
+                                 double *t_remain_out, int64_t *n_pushes, int nthreads)
+{
+  int64_t total = 0;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 8) reduction(+ : total)
+  for (int64_t i = 0; i < n; i++) {
+    gor_trace tr;
+    memset(&tr, 0, sizeof(tr));
+    double tro = 0.0;
+    gor_orbit_timestep(m, x + 3 * i, vpar + i, vperp + i, t_step, boole_initialized + i, ind_tetr + i,
+                       iface + i, &tro, &tr);
+    if (t_remain_out) t_remain_out[i] = tro;
+    if (n_pushes) n_pushes[i] = tr.n_pushes;
+    total += tr.n_pushes;
+  }
+  return total;
+}

@@ -1,0 +1,119 @@
+/*
+ * gorilla_oracle.h -- CPU ORACLE for the GORILLA orbit-pusher hot path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The product
+ * (gorilla_b200/) never links, imports or falls back to anything in oracle/.
+ *
+ * It is an op-for-op C99 restatement of the reference Fortran (itpplasma/GORILLA):
+ *   SRC/orbit_timestep_gorilla.f90:19-147,278-358
+ *   SRC/pusher_tetra_poly.f90:125-826,1258-1586,1767-2113,2690-2998
+ *   SRC/pusher_tetra_func_mod.f90:6-93
+ *   SRC/find_tetra_mod.f90:283-600   (+ the RK-module pieces it uses,
+ *                                     SRC/pusher_tetra_rk.f90:50-193,840-896,2422-2467)
+ *   SRC/supporting_functions_mod.f90:279-408
+ *   SRC/contrib/Polynomial234RootSolvers.f90, SRC/contrib/cmplx_roots_sg.f90:83-201,558-731,906-1362
+ *
+ * PARITY STATUS: "parity unpinned".  The reference holds no golden vectors for this path
+ * (both pusher tests are @disable'd, SRC/TESTS/test_orbit_timestep_gorilla.f90:26-42) and it
+ * cannot be compiled in this image (no gfortran / NetCDF-Fortran / LAPACK).  What IS pinned:
+ * the complex-arithmetic lowering (gcc -fcx-fortran-rules, the flag gfortran sets) and the
+ * libm routines gfortran calls (glibc cabs/csqrt/cexp) are the real ones -- this file is
+ * compiled with native `double _Complex` and those flags -- and the solver chain is checked
+ * against constructed-root known-answer tests (tests/test_oracle_*.py).
+ *
+ * Data layout = the reference's own `sequence` derived types, flattened:
+ *   tetra_physics : double [ntetr][142]  (SRC/tetra_physics_mod.f90:9-83)
+ *   tetra_grid    : int32  [ntetr][20]   (SRC/tetra_grid_mod.f90:6-15)
+ * All tetra / face indices are 1-based as in the reference; 0 = inside cell, -1 = lost.
+ */
+#ifndef GORILLA_ORACLE_H
+#define GORILLA_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* offsets (in doubles) into one tetrahedron_physics record */
+enum {
+  TP_X1 = 0, TP_DIST_REF = 3, TP_DIST_REF_VEC = 4, TP_TETRA_DIST_REF = 8, TP_ANORM = 9,
+  TP_CURLA = 21, TP_BMOD1 = 24, TP_ATHETA1 = 25, TP_APHI1 = 26, TP_H1_1 = 27, TP_H2_1 = 28,
+  TP_H3_1 = 29, TP_PHI1 = 30, TP_R1 = 31, TP_Z1 = 32, TP_VE1_1 = 33, TP_VE2_1 = 34, TP_VE3_1 = 35,
+  TP_V2EMOD_1 = 36, TP_ER_MOD = 37, TP_VE_MOD_AVG = 38, TP_SQG1 = 39, TP_DT_DTAU_CONST = 40,
+  TP_GBXCURLA = 41, TP_GPHIXCURLA = 42, TP_GV2EMODXCURLA = 43, TP_GBXCURLVE = 44,
+  TP_GPHIXCURLVE = 45, TP_GV2EMODXCURLVE = 46, TP_SPALPMAT = 47, TP_SPBETMAT = 48,
+  TP_SPGAMMAT = 49, TP_GBXH1 = 50, TP_GPHIXH1 = 53, TP_GV2EMODXH1 = 56, TP_GB = 59, TP_GPHI = 62,
+  TP_GR = 65, TP_GZ = 68, TP_GSQG = 71, TP_GATHETA = 74, TP_GAPHI = 77, TP_GH1 = 80, TP_GH2 = 83,
+  TP_GH3 = 86, TP_CURLH = 89, TP_GVE1 = 92, TP_GVE2 = 95, TP_GVE3 = 98, TP_CURLVE = 101,
+  TP_GV2EMOD = 104, TP_ALPMAT = 107, TP_BETMAT = 116, TP_GAMMAT = 125, TP_ACOEF_PRE = 134,
+  TP_ACOEF_PRE_SE = 138, TP_NDOUBLES = 142
+};
+enum { TG_IND_KNOT = 0, TG_NEIGHBOUR_TETR = 4, TG_NEIGHBOUR_FACE = 8, TG_PERBOU_PHI = 12,
+       TG_PERBOU_THETA = 16, TG_NINTS = 20 };
+
+typedef struct {
+  int64_t ntetr;
+  const double *tetra_physics;   /* [ntetr][142] */
+  const int32_t *tetra_grid;     /* [ntetr][20]  */
+  /* scalars of tetra_physics_mod / tetra_grid_settings_mod / gorilla_settings_mod */
+  double cm_over_e, particle_mass, particle_charge;
+  int32_t sign_sqg, coord_system, n_field_periods, grid_kind;
+  int32_t grid_size[3];
+  double Rmin, Rmax, Zmin, Zmax;          /* rectangular grids only (find_tetra) */
+  double sfc_s_min;
+  int32_t ipusher;                        /* 1 = RK4, 2 = polynomial */
+  int32_t poly_order;                     /* 1..4 */
+  int32_t boole_guess;
+  int32_t boole_strong_electric_field;
+  int32_t boole_periodic_relocation;
+  int32_t boole_dt_dtau;                  /* RK only */
+} gor_mesh;
+
+/* optional per-particle trace of the visited (ind_tetr, iface) sequence */
+typedef struct {
+  int64_t n_pushes;        /* pusher invocations (the metric's "tetra crossings") */
+  int64_t cap;             /* capacity of the arrays below (0 = do not record) */
+  int32_t *ind_tetr;       /* state AFTER push k */
+  int32_t *iface;
+  int64_t n_fallback[4];   /* [0] 2nd attempt, [1] trouble shooting, [2] prolonged, [3] finish-outside */
+  int64_t n_solver_iters;  /* Laguerre/SG/Newton iterations incl. polish */
+  int64_t n_solver_calls;
+} gor_trace;
+
+/* return codes */
+enum { GOR_OK = 0, GOR_ERR_DOMAIN = 1, GOR_ERR_CONFIG = 2 };
+
+int gor_check_coordinate_domain(const gor_mesh *m, double x[3]);
+void gor_find_tetra(const gor_mesh *m, double x[3], double vpar, double vperp,
+                    int32_t *ind_tetr, int32_t *iface, int sign_t_step);
+int gor_orbit_timestep(const gor_mesh *m, double x[3], double *vpar, double *vperp, double t_step,
+                       int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface,
+                       double *t_remain_out, gor_trace *trace);
+/* OpenMP batch driver used as the CPU baseline ("one particle per thread", README.md:181) */
+int64_t gor_orbit_timestep_batch(const gor_mesh *m, int64_t n, double *x /*[n][3]*/, double *vpar,
+                                 double *vperp, double t_step, int32_t *boole_initialized,
+                                 int32_t *ind_tetr, int32_t *iface, double *t_remain_out,
+                                 int64_t *n_pushes /*[n] or NULL*/, int nthreads);
+
+double gor_energy_tot(const gor_mesh *m, const double z[4], double perpinv, int32_t ind_tetr);
+double gor_p_phi(const gor_mesh *m, double vpar, const double z[3], int32_t ind_tetr);
+double gor_bmod(const gor_mesh *m, const double z[3], int32_t ind_tetr);
+
+/* solver chain exposed for known-answer tests; root is [n][2] column-major as in Fortran: root(i,1)=Re */
+void gor_quadratic_roots(double q1, double q0, int *nreal, double root[4]);
+void gor_cubic_roots(double c2, double c1, double c0, int *nreal, double root[6]);
+void gor_quartic_roots(double q3, double q2, double q1, double q0, int *nreal, double root[8]);
+/* raw complex roots (re,im interleaved), same call as cmplx_roots_gen(roots,poly,deg,.true.,.false.) */
+void gor_cmplx_roots_gen(int degree, const double *poly_re_im, double *roots_re_im);
+double gor_quadratic_solver1(double a, double b, double c);
+double gor_quadratic_solver2(double a, double b, double c);
+double gor_cubic_solver(double a, double b, double c, double d);
+double gor_quartic_solver(int i_scaling, double a, double b, double c, double d, double e);
+/* cexp(i*2*pi*FRAC_JUMPS[k]) table entries as glibc computes them (for the device constant table) */
+void gor_frac_jump_phase(int k, double out[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

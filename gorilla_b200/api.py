@@ -1,0 +1,353 @@
+"""Host-side mirror of the reference's public interface for the orbit-pusher hot path.
+
+Reference interface (SRC/orbit_timestep_gorilla.f90:10):
+    use orbit_timestep_gorilla_mod, only: initialize_gorilla, orbit_timestep_gorilla, check_coordinate_domain
+    call orbit_timestep_gorilla(x,vpar,vperp,t_step,boole_initialized,ind_tetr,iface,t_remain_out)
+
+Same names, argument meaning, 1-based indices and in-band loss signalling (ind_tetr = -1) here; the
+arrays are batched (x is [n,3]).  Everything below the ctypes boundary is CUDA: a missing
+libgorilla_b200.so or a missing GPU raises, nothing falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+from .settings import GorillaSettings, TetraGridSettings
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libgorilla_b200.so"
+_lib = None
+
+
+class GorillaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"gorilla_b200 error {code}: {msg}")
+        self.code = code
+
+
+class _Settings(C.Structure):
+    _fields_ = [("eps_Phi", C.c_double)] + [(n, C.c_int32) for n in (
+        "coord_system", "ispecies", "boole_periodic_relocation", "ipusher", "boole_pusher_ode45", "boole_dt_dtau",
+        "boole_newton_precalc", "poly_order", "i_precomp", "boole_guess", "i_time_tracing_option",
+        "handover_processing_kind", "boole_adaptive_time_steps", "boole_strong_electric_field",
+        "boole_grid_for_find_tetra")] + [("reserved", C.c_int32 * 5)]
+
+
+class _MeshDesc(C.Structure):
+    _fields_ = [
+        ("ntetr", C.c_int64), ("tetra_physics", C.POINTER(C.c_double)), ("tetra_grid", C.POINTER(C.c_int32)),
+        ("cm_over_e", C.c_double), ("particle_mass", C.c_double), ("particle_charge", C.c_double),
+        ("sign_sqg", C.c_int32), ("coord_system", C.c_int32), ("n_field_periods", C.c_int32),
+        ("grid_kind", C.c_int32), ("grid_size", C.c_int32 * 3), ("pad0", C.c_int32),
+        ("Rmin", C.c_double), ("Rmax", C.c_double), ("Zmin", C.c_double), ("Zmax", C.c_double),
+        ("sfc_s_min", C.c_double),
+    ]
+
+
+class _GridSettings(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("grid_kind", "n1", "n2", "n3", "boole_n_field_periods",
+                                         "n_field_periods_manual", "i_radial_spacing", "theta_geom_flux")] + \
+               [(n, C.c_double) for n in ("sfc_s_min", "theta0_at_xpoint", "R0_analytic_circ", "a_analytic_circ",
+                                          "B0_analytic_circ", "q0_analytic_circ", "q1_analytic_circ")] + \
+               [(n, C.c_char_p) for n in ("g_file_filename", "convex_wall_filename", "netcdf_filename",
+                                          "knots_SOLEDGE3X_EIRENE_filename", "triangles_SOLEDGE3X_EIRENE_filename")]
+
+
+class _Counters(C.Structure):
+    _fields_ = [("n_particles", C.c_int64), ("n_pushes", C.c_int64), ("n_lost", C.c_int64),
+                ("n_finished", C.c_int64), ("n_fallback", C.c_int64 * 4), ("n_domain_errors", C.c_int64),
+                ("kernel_ms", C.c_double), ("find_ms", C.c_double)]
+
+
+@dataclass
+class Counters:
+    n_particles: int
+    n_pushes: int
+    n_lost: int
+    n_finished: int
+    n_fallback: tuple
+    n_domain_errors: int
+    kernel_ms: float
+    find_ms: float
+
+
+# every symbol include/gorilla_b200.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = (
+    "gorilla_b200_init", "gorilla_b200_free", "gorilla_b200_last_error", "gorilla_b200_launch_count",
+    "gorilla_b200_orbit_timestep", "gorilla_b200_orbit_timestep_dev", "gorilla_b200_orbit_timestep_trace",
+    "gorilla_b200_find_tetra", "gorilla_b200_invariants", "gorilla_b200_invariants_dev",
+    "gorilla_b200_get_counters", "gorilla_b200_sort_permutation_dev", "gorilla_b200_set_launch_config",
+    "gorilla_mesh_build", "gorilla_mesh_get_desc", "gorilla_mesh_get_vertices", "gorilla_mesh_free",
+)
+
+
+def load_library():
+    """dlopen libgorilla_b200.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise ImportError(f"{_LIB_PATH} not found: build it with `python -m gorilla_b200.build` "
+                          "(there is no CPU fall-back for the orbit pusher)")
+    lib = C.CDLL(str(_LIB_PATH))
+    vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+    lib.gorilla_b200_last_error.restype = C.c_char_p
+    lib.gorilla_b200_launch_count.restype = i64
+    lib.gorilla_b200_init.argtypes = [C.POINTER(_MeshDesc), C.POINTER(_Settings), C.POINTER(vp)]
+    lib.gorilla_b200_free.argtypes = [vp]
+    lib.gorilla_b200_free.restype = None
+    lib.gorilla_b200_orbit_timestep.argtypes = [vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp]
+    lib.gorilla_b200_orbit_timestep_dev.argtypes = [vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp]
+    lib.gorilla_b200_orbit_timestep_trace.argtypes = [vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp, i32, vp, vp]
+    lib.gorilla_b200_find_tetra.argtypes = [vp, i64, vp, vp, vp, vp, vp, i32]
+    lib.gorilla_b200_invariants.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp]
+    lib.gorilla_b200_invariants_dev.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.gorilla_b200_get_counters.argtypes = [vp, C.POINTER(_Counters)]
+    lib.gorilla_b200_sort_permutation_dev.argtypes = [vp, i64, vp, vp, vp]
+    lib.gorilla_b200_set_launch_config.argtypes = [vp, i32, i32]
+    lib.gorilla_b200_debug_force_full.argtypes = [vp, i32]
+    lib.gorilla_mesh_build.argtypes = [C.POINTER(_GridSettings), C.POINTER(_Settings), C.POINTER(vp)]
+    lib.gorilla_mesh_get_desc.argtypes = [vp, C.POINTER(_MeshDesc)]
+    lib.gorilla_mesh_get_vertices.argtypes = [vp, C.POINTER(i64), C.POINTER(C.POINTER(dbl)), C.POINTER(C.POINTER(dbl))]
+    lib.gorilla_mesh_free.argtypes = [vp]
+    lib.gorilla_mesh_free.restype = None
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise GorillaError(rc, load_library().gorilla_b200_last_error().decode(errors="replace"))
+
+
+def launch_count() -> int:
+    """Kernels launched by the library in this process (bench.py's gpu_launches)."""
+    return int(load_library().gorilla_b200_launch_count())
+
+
+def _c_settings(s: GorillaSettings) -> _Settings:
+    cs = _Settings()
+    for name, _ in _Settings._fields_:
+        if name == "reserved":
+            continue
+        v = getattr(s, name)
+        setattr(cs, name, float(v) if name == "eps_Phi" else int(v))
+    return cs
+
+
+def _c_grid(g: TetraGridSettings) -> _GridSettings:
+    cg = _GridSettings()
+    for name, typ in _GridSettings._fields_:
+        v = getattr(g, name)
+        if typ is C.c_char_p:
+            setattr(cg, name, str(v).encode() if v else None)
+        elif typ is C.c_double:
+            setattr(cg, name, float(v))
+        else:
+            setattr(cg, name, int(v))
+    return cg
+
+
+class Mesh:
+    """Host mesh in the reference's own AoS layout (tetra_physics [ntetr,142] f64, tetra_grid [ntetr,20] i32).
+
+    Either built by the library (build_mesh: make_tetra_grid + make_tetra_physics + check_tetra_overlaps)
+    or wrapped around arrays that came from elsewhere (from_arrays), e.g. dumped from a Fortran run.
+    """
+
+    def __init__(self):
+        self._handle = None
+        self.tetra_physics: np.ndarray | None = None
+        self.tetra_grid: np.ndarray | None = None
+        self.verts_rphiz: np.ndarray | None = None
+        self.verts_sthetaphi: np.ndarray | None = None
+        self.scalars: dict = {}
+
+    @classmethod
+    def from_arrays(cls, tetra_physics, tetra_grid, **scalars) -> "Mesh":
+        m = cls()
+        m.tetra_physics = np.ascontiguousarray(tetra_physics, dtype=np.float64)
+        m.tetra_grid = np.ascontiguousarray(tetra_grid, dtype=np.int32)
+        assert m.tetra_physics.shape[1] == 142 and m.tetra_grid.shape[1] == 20
+        m.scalars = dict(scalars)
+        return m
+
+    @property
+    def ntetr(self) -> int:
+        return int(self.tetra_physics.shape[0])
+
+    def desc(self) -> _MeshDesc:
+        d = _MeshDesc()
+        d.ntetr = self.ntetr
+        d.tetra_physics = self.tetra_physics.ctypes.data_as(C.POINTER(C.c_double))
+        d.tetra_grid = self.tetra_grid.ctypes.data_as(C.POINTER(C.c_int32))
+        s = self.scalars
+        for k in ("cm_over_e", "particle_mass", "particle_charge", "Rmin", "Rmax", "Zmin", "Zmax", "sfc_s_min"):
+            setattr(d, k, float(s.get(k, 0.0)))
+        for k in ("sign_sqg", "coord_system", "n_field_periods", "grid_kind"):
+            setattr(d, k, int(s[k]))
+        for i in range(3):
+            d.grid_size[i] = int(s["grid_size"][i])
+        return d
+
+    def __del__(self):
+        if self._handle is not None and _lib is not None:
+            _lib.gorilla_mesh_free(self._handle)
+            self._handle = None
+
+
+def build_mesh(grid: TetraGridSettings, settings: GorillaSettings) -> Mesh:
+    """Grid + physics half of initialize_gorilla (host, runs once)."""
+    lib = load_library()
+    h = C.c_void_p()
+    cg, cs = _c_grid(grid), _c_settings(settings)
+    _check(lib.gorilla_mesh_build(C.byref(cg), C.byref(cs), C.byref(h)))
+    d = _MeshDesc()
+    _check(lib.gorilla_mesh_get_desc(h, C.byref(d)))
+    m = Mesh()
+    m._handle = h
+    nt = int(d.ntetr)
+    m.tetra_physics = np.ctypeslib.as_array(d.tetra_physics, shape=(nt, 142))
+    m.tetra_grid = np.ctypeslib.as_array(d.tetra_grid, shape=(nt, 20))
+    nv = C.c_int64()
+    pr, ps = C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
+    _check(lib.gorilla_mesh_get_vertices(h, C.byref(nv), C.byref(pr), C.byref(ps)))
+    m.verts_rphiz = np.ctypeslib.as_array(pr, shape=(nv.value, 3))
+    if ps:
+        m.verts_sthetaphi = np.ctypeslib.as_array(ps, shape=(nv.value, 3))
+    m.scalars = dict(
+        cm_over_e=d.cm_over_e, particle_mass=d.particle_mass, particle_charge=d.particle_charge,
+        sign_sqg=d.sign_sqg, coord_system=d.coord_system, n_field_periods=d.n_field_periods,
+        grid_kind=d.grid_kind, grid_size=tuple(d.grid_size), Rmin=d.Rmin, Rmax=d.Rmax, Zmin=d.Zmin, Zmax=d.Zmax,
+        sfc_s_min=d.sfc_s_min,
+    )
+    return m
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Gorilla:
+    """A mesh resident on one GPU plus the settings: what initialize_gorilla leaves behind."""
+
+    def __init__(self, mesh: Mesh, settings: GorillaSettings):
+        lib = load_library()
+        self.mesh = mesh
+        self.settings = settings
+        self._h = C.c_void_p()
+        d, cs = mesh.desc(), _c_settings(settings)
+        _check(lib.gorilla_b200_init(C.byref(d), C.byref(cs), C.byref(self._h)))
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            load_library().gorilla_b200_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- reference API -------------------------------------------------------------------------
+    def check_coordinate_domain(self, x: np.ndarray) -> None:
+        """check_coordinate_domain (orbit_timestep_gorilla.f90:278-358), in place on x[n,3] (host logic)."""
+        s = self.mesh.scalars
+        per = 2.0 * math.pi / s["n_field_periods"]
+        x = x.reshape(-1, 3)
+        if s["coord_system"] == 1:
+            if self.settings.boole_periodic_relocation:
+                x[:, 1] = x[:, 1] - np.floor(x[:, 1] / per) * per
+            elif np.any((x[:, 1] < 0.0) | (x[:, 1] > per)):
+                raise GorillaError(4, "Particle coordinate phi outside [0, 2 pi/n_field_periods]")
+        else:
+            if np.any((x[:, 0] < s["sfc_s_min"]) | (x[:, 0] > 1.0)):
+                raise GorillaError(4, "Particle flux coordinate s outside [sfc_s_min, 1]")
+            if self.settings.boole_periodic_relocation:
+                x[:, 1] = x[:, 1] - np.floor(x[:, 1] / (2.0 * math.pi)) * (2.0 * math.pi)
+                x[:, 2] = x[:, 2] - np.floor(x[:, 2] / per) * per
+            elif np.any((x[:, 1] < 0) | (x[:, 1] > 2 * math.pi) | (x[:, 2] < 0) | (x[:, 2] > per)):
+                raise GorillaError(4, "Particle coordinate theta/phi outside the domain")
+
+    def find_tetra(self, x, vpar, vperp, sign_t_step: int = 1):
+        """find_tetra (find_tetra_mod.f90:283-600) for a batch; returns (ind_tetr, iface); x may be updated."""
+        n = x.shape[0]
+        ind, ifc = np.empty(n, np.int32), np.empty(n, np.int32)
+        _check(load_library().gorilla_b200_find_tetra(self._h, n, _ptr(x), _ptr(vpar), _ptr(vperp), _ptr(ind),
+                                                      _ptr(ifc), int(sign_t_step)))
+        return ind, ifc
+
+    def orbit_timestep_gorilla(self, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface,
+                               t_remain_out=None, n_pushes=None, trace_cap: int = 0):
+        """Batched orbit_timestep_gorilla; all arrays are updated in place (numpy, C-contiguous):
+        x [n,3] f64, vpar/vperp [n] f64, boole_initialized/ind_tetr/iface [n] i32.
+        Returns (trace_ind_tetr, trace_iface) when trace_cap > 0, else None."""
+        lib = load_library()
+        n = x.shape[0]
+        for a, dt in ((x, np.float64), (vpar, np.float64), (vperp, np.float64), (boole_initialized, np.int32),
+                      (ind_tetr, np.int32), (iface, np.int32)):
+            if a.dtype != dt or not a.flags.c_contiguous:
+                raise TypeError("arrays must be C-contiguous float64 / int32")
+        if trace_cap > 0:
+            tt, tf = np.zeros((n, trace_cap), np.int32), np.zeros((n, trace_cap), np.int32)
+            _check(lib.gorilla_b200_orbit_timestep_trace(self._h, n, _ptr(x), _ptr(vpar), _ptr(vperp), float(t_step),
+                                                         _ptr(boole_initialized), _ptr(ind_tetr), _ptr(iface),
+                                                         _ptr(t_remain_out), _ptr(n_pushes), trace_cap, _ptr(tt),
+                                                         _ptr(tf)))
+            return tt, tf
+        _check(lib.gorilla_b200_orbit_timestep(self._h, n, _ptr(x), _ptr(vpar), _ptr(vperp), float(t_step),
+                                               _ptr(boole_initialized), _ptr(ind_tetr), _ptr(iface),
+                                               _ptr(t_remain_out), _ptr(n_pushes)))
+        return None
+
+    def orbit_timestep_gorilla_dev(self, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface,
+                                   t_remain_out=None, n_pushes=None, stream=None):
+        """Same on torch CUDA tensors already resident in HBM (no copies, no sync)."""
+        def dp(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+        _check(load_library().gorilla_b200_orbit_timestep_dev(
+            self._h, x.shape[0], dp(x), dp(vpar), dp(vperp), float(t_step), dp(boole_initialized), dp(ind_tetr),
+            dp(iface), dp(t_remain_out), dp(n_pushes), C.c_void_p(stream or 0)))
+
+    # ---- diagnostics ---------------------------------------------------------------------------
+    def invariants(self, x, vpar, vperp, ind_tetr):
+        """(energy_tot_func, p_phi_func, perpinv) per particle (supporting_functions_mod.f90:279-408)."""
+        n = x.shape[0]
+        e, p, mu = np.empty(n), np.empty(n), np.empty(n)
+        _check(load_library().gorilla_b200_invariants(self._h, n, _ptr(x), _ptr(vpar), _ptr(vperp), _ptr(ind_tetr),
+                                                      _ptr(e), _ptr(p), _ptr(mu)))
+        return e, p, mu
+
+    def invariants_dev(self, x, vpar, vperp, ind_tetr, energy, p_phi, perpinv, stream=None):
+        def dp(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+        _check(load_library().gorilla_b200_invariants_dev(self._h, x.shape[0], dp(x), dp(vpar), dp(vperp),
+                                                          dp(ind_tetr), dp(energy), dp(p_phi), dp(perpinv),
+                                                          C.c_void_p(stream or 0)))
+
+    def counters(self) -> Counters:
+        c = _Counters()
+        _check(load_library().gorilla_b200_get_counters(self._h, C.byref(c)))
+        return Counters(c.n_particles, c.n_pushes, c.n_lost, c.n_finished, tuple(c.n_fallback), c.n_domain_errors,
+                        c.kernel_ms, c.find_ms)
+
+    def sort_permutation_dev(self, ind_tetr, perm, stream=None):
+        _check(load_library().gorilla_b200_sort_permutation_dev(self._h, ind_tetr.shape[0],
+                                                                C.c_void_p(ind_tetr.data_ptr()),
+                                                                C.c_void_p(perm.data_ptr()), C.c_void_p(stream or 0)))
+
+    def set_launch_config(self, ctas_per_sm: int = 0, threads_per_cta: int = 0):
+        _check(load_library().gorilla_b200_set_launch_config(self._h, ctas_per_sm, threads_per_cta))
+
+    def _debug_force_full(self, on: bool):
+        load_library().gorilla_b200_debug_force_full(self._h, int(on))
+
+
+def initialize_gorilla(grid: TetraGridSettings, settings: GorillaSettings) -> Gorilla:
+    """initialize_gorilla (orbit_timestep_gorilla.f90:151-274): build the mesh on the host, upload it."""
+    return Gorilla(build_mesh(grid, settings), settings)

@@ -499,7 +499,6 @@ struct PolyPusher {
     o.ind_tetr = -1;
     o.iface = -1;
     o.finished = 0;
-    o.t_pass = 0.0;
     o.z_save_set = 0;
     o.fallback = fallback;
   }
@@ -514,6 +513,7 @@ struct PolyPusher {
     for (int i = 0; i < 3; i++) o.x[i] = z[i] + r.x1[i];
     o.vpar = z[3];
     double t_pass = tau * dt_dtau_const;
+    o.t_pass = t_pass; // (:466) assigned before the stop-inside test; kept if the particle is removed below
     if (fabs(t_pass) >= fabs(t_remain)) {
       if (FAST && nsteps > 1) return false;
 #pragma unroll
@@ -673,6 +673,7 @@ GB_HD_NOINLINE PushOut push_full_call(const MeshDev *mp, double perpinv, int ind
   double x[3] = {x0, x1, x2};
   o.x[0] = x0; o.x[1] = x1; o.x[2] = x2; o.vpar = vpar;
   o.z_save[0] = o.z_save[1] = o.z_save[2] = 0.0;
+  o.t_pass = 0.0; // undefined in the reference when the particle is removed in attempts 1-3
   P.push_full(ind_tetr, iface, x, vpar, t_remain, o);
   return o;
 }

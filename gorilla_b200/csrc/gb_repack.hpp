@@ -1,0 +1,79 @@
+// gb_repack.hpp -- host: reference AoS (tetrahedron_physics / tetrahedron_grid) -> device sub-record SoA
+// (layout documented in gb_mesh.cuh).  Pure host code, used by gorilla_b200_init.
+#pragma once
+#include <cstring>
+#include <vector>
+#include "../../include/gorilla_b200.h"
+#include "gb_mesh.cuh"
+
+namespace gb {
+
+inline bool repack_mesh(const gorilla_mesh_desc *md, std::vector<double> &geom, std::vector<double> &bpart,
+                        std::vector<double> &phi, std::vector<double> &cold, bool &has_phi)
+{
+  const int64_t nt = md->ntetr;
+  geom.assign((size_t)nt * GEOM_ND, 0.0);
+  bpart.assign((size_t)nt * BPART_ND, 0.0);
+  phi.assign((size_t)nt * PHI_ND, 0.0);
+  cold.assign((size_t)nt * COLD_ND, 0.0);
+  has_phi = false;
+  // offsets into type tetrahedron_physics (doubles), tetra_physics_mod.f90:9-83
+  enum { TP_X1 = 0, TP_DIST_REF = 3, TP_TETRA_DIST_REF = 8, TP_ANORM = 9, TP_CURLA = 21, TP_BMOD1 = 24, TP_APHI1 = 26,
+         TP_H2_1 = 28, TP_H3_1 = 29, TP_PHI1 = 30, TP_R1 = 31, TP_ER_MOD = 37, TP_DT_DTAU_CONST = 40, TP_GBXCURLA = 41,
+         TP_GPHIXCURLA = 42, TP_SPALPMAT = 47, TP_SPBETMAT = 48, TP_GBXH1 = 50, TP_GPHIXH1 = 53, TP_GB = 59,
+         TP_GPHI = 62, TP_GAPHI = 77, TP_GH2 = 83, TP_GH3 = 86, TP_CURLH = 89, TP_ALPMAT = 107, TP_BETMAT = 116 };
+  for (int64_t t = 0; t < nt; t++) {
+    const double *r = md->tetra_physics + t * GORILLA_TETRA_PHYSICS_NDOUBLES;
+    const int32_t *g = md->tetra_grid + t * GORILLA_TETRA_GRID_NINTS;
+    double *G = &geom[(size_t)t * GEOM_ND], *B = &bpart[(size_t)t * BPART_ND], *P = &phi[(size_t)t * PHI_ND],
+           *C = &cold[(size_t)t * COLD_ND];
+    for (int i = 0; i < 3; i++) G[i] = r[TP_X1 + i];
+    G[3] = r[TP_DIST_REF];
+    for (int i = 0; i < 12; i++) G[4 + i] = r[TP_ANORM + i];
+    B[B_BMOD1] = r[TP_BMOD1];
+    for (int i = 0; i < 3; i++) {
+      B[B_GB + i] = r[TP_GB + i];
+      B[B_CURLA + i] = r[TP_CURLA + i];
+      B[B_CURLH + i] = r[TP_CURLH + i];
+      B[B_GBXH1 + i] = r[TP_GBXH1 + i];
+    }
+    B[B_GBXCURLA] = r[TP_GBXCURLA];
+    for (int i = 0; i < 9; i++) B[B_ALP + i] = r[TP_ALPMAT + i];
+    B[B_SPALP] = r[TP_SPALPMAT];
+    B[B_DTDTAU] = r[TP_DT_DTAU_CONST];
+    int32_t topo[6] = {g[4], g[5], g[6], g[7], 0, 0};
+    uint32_t flags = 0;
+    for (int f = 0; f < 4; f++) {
+      int nf = g[8 + f], pp = g[12 + f], pt = (md->coord_system == 2) ? g[16 + f] : 0;
+      if (nf < -1 || nf > 4 || pp < -1 || pp > 1 || pt < -1 || pt > 1) return false;
+      flags |= ((uint32_t)(nf + 1) | ((uint32_t)(pp + 1) << 3) | ((uint32_t)(pt + 1) << 5)) << (7 * f);
+    }
+    topo[4] = (int32_t)flags;
+    memcpy(&B[B_TOPO], topo, sizeof(topo));
+    P[P_PHI1] = r[TP_PHI1];
+    for (int i = 0; i < 3; i++) {
+      P[P_GPHI + i] = r[TP_GPHI + i];
+      P[P_GPHIXH1 + i] = r[TP_GPHIXH1 + i];
+    }
+    P[P_GPHIXCURLA] = r[TP_GPHIXCURLA];
+    for (int i = 0; i < 9; i++) P[P_BET + i] = r[TP_BETMAT + i];
+    P[P_SPBET] = r[TP_SPBETMAT];
+    for (int i = 0; i < 18; i++)
+      if (P[i] != 0.0) has_phi = true; // NaN counts as "present"
+    C[C_TETRA_DIST_REF] = r[TP_TETRA_DIST_REF];
+    C[C_R1] = r[TP_R1];
+    C[C_ER_MOD] = r[TP_ER_MOD];
+    if (md->coord_system == 1) {
+      C[C_HPHI1] = r[TP_H2_1];
+      for (int i = 0; i < 3; i++) C[C_GHPHI + i] = r[TP_GH2 + i];
+    } else {
+      C[C_HPHI1] = r[TP_H3_1];
+      for (int i = 0; i < 3; i++) C[C_GHPHI + i] = r[TP_GH3 + i];
+    }
+    C[C_APHI1] = r[TP_APHI1];
+    for (int i = 0; i < 3; i++) C[C_GAPHI + i] = r[TP_GAPHI + i];
+  }
+  return true;
+}
+
+} // namespace gb

@@ -1,0 +1,121 @@
+"""Settings of the hot path: the namelists GORILLANML and TETRA_GRID_NML.
+
+Reference: SRC/gorilla_settings_mod.f90:94-150 (namelist + consistency checks),
+SRC/tetra_grid_settings_mod.f90:70-105, blueprint values INPUT/gorilla.inp, INPUT/tetra_grid.inp.
+Only the entries the hot path reads are kept; unknown namelist keys are ignored on load.
+"""
+from __future__ import annotations
+
+import re
+from dataclasses import dataclass, fields
+from pathlib import Path
+
+
+@dataclass
+class GorillaSettings:
+    eps_Phi: float = 0.0
+    coord_system: int = 2
+    ispecies: int = 2
+    boole_periodic_relocation: bool = True
+    ipusher: int = 2
+    boole_pusher_ode45: bool = False
+    boole_dt_dtau: bool = True
+    boole_newton_precalc: bool = False
+    poly_order: int = 2
+    i_precomp: int = 0
+    boole_guess: bool = True
+    i_time_tracing_option: int = 1
+    handover_processing_kind: int = 1
+    boole_adaptive_time_steps: bool = False
+    boole_strong_electric_field: bool = False
+    boole_grid_for_find_tetra: bool = False
+
+
+@dataclass
+class TetraGridSettings:
+    grid_kind: int = 3
+    n1: int = 100
+    n2: int = 40
+    n3: int = 40
+    boole_n_field_periods: bool = True
+    n_field_periods_manual: int = 1
+    i_radial_spacing: int = 0
+    theta_geom_flux: int = 1
+    sfc_s_min: float = 0.1
+    theta0_at_xpoint: float = 0.0
+    R0_analytic_circ: float = 0.0
+    a_analytic_circ: float = 0.0
+    B0_analytic_circ: float = 0.0
+    q0_analytic_circ: float = 1.0
+    q1_analytic_circ: float = 0.0
+    g_file_filename: str = ""
+    convex_wall_filename: str = ""
+    netcdf_filename: str = ""
+    knots_SOLEDGE3X_EIRENE_filename: str = ""
+    triangles_SOLEDGE3X_EIRENE_filename: str = ""
+
+
+_ASSIGN = re.compile(r"^\s*([A-Za-z_][A-Za-z0-9_]*)\s*=\s*(.*?)\s*,?\s*$")
+
+
+def _parse_value(txt: str):
+    t = txt.strip().rstrip(",").strip()
+    if t.lower() in (".true.", "t", ".t."):
+        return True
+    if t.lower() in (".false.", "f", ".f."):
+        return False
+    if (t.startswith("'") and t.endswith("'")) or (t.startswith('"') and t.endswith('"')):
+        return t[1:-1]
+    try:
+        return int(t)
+    except ValueError:
+        pass
+    return float(t.lower().replace("d", "e"))
+
+
+def parse_namelist(path: str | Path, group: str) -> dict:
+    """Minimal Fortran namelist reader (one `key = value ,` per line, `!` comments)."""
+    out: dict = {}
+    inside = False
+    for raw in Path(path).read_text().splitlines():
+        line = raw.split("!")[0].strip()
+        if not line:
+            continue
+        if line.lower().startswith("&" + group.lower()):
+            inside = True
+            continue
+        if inside and line.startswith("/"):
+            break
+        if inside:
+            m = _ASSIGN.match(line)
+            if m:
+                out[m.group(1).lower()] = _parse_value(m.group(2))
+    return out
+
+
+def _fill(cls, values: dict):
+    obj = cls()
+    lut = {f.name.lower(): f for f in fields(cls)}
+    for k, v in values.items():
+        f = lut.get(k)
+        if f is None:
+            continue
+        cur = getattr(obj, f.name)
+        if isinstance(cur, bool):
+            v = bool(v)
+        elif isinstance(cur, int) and not isinstance(v, bool):
+            v = int(v)
+        elif isinstance(cur, float):
+            v = float(v)
+        setattr(obj, f.name, v)
+    return obj
+
+
+def load_gorilla_inp(path: str | Path = "gorilla.inp") -> GorillaSettings:
+    """load_gorilla_inp (gorilla_settings_mod.f90:111-150)."""
+    return _fill(GorillaSettings, parse_namelist(path, "GORILLANML"))
+
+
+def load_tetra_grid_inp(path: str | Path = "tetra_grid.inp") -> TetraGridSettings:
+    """load_tetra_grid_inp (tetra_grid_settings_mod.f90:81-105)."""
+    return _fill(TetraGridSettings, parse_namelist(path, "TETRA_GRID_NML"))

@@ -1679,3 +1679,37 @@ int64_t gor_orbit_timestep_batch(const gor_mesh *m, int64_t n, double *x, double
   }
   return total;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Probes of the real gcc (-fcx-fortran-rules) complex lowering and of glibc cabs/csqrt, used to pin
+ * the device's explicit restatements (gorilla_b200/csrc/gb_math.cuh) bit for bit.
+ * ---------------------------------------------------------------------------------------------- */
+void gor_probe_csqrt(double re, double im, double out[2])
+{
+  cplx r = csqrt(CMPLX(re, im));
+  out[0] = creal(r);
+  out[1] = cimag(r);
+}
+double gor_probe_cabs(double re, double im) { return cabs(CMPLX(re, im)); }
+void gor_probe_cdiv(double ar, double ai, double br, double bi, double out[2])
+{
+  volatile cplx a = CMPLX(ar, ai), b = CMPLX(br, bi);
+  cplx r = a / b;
+  out[0] = creal(r);
+  out[1] = cimag(r);
+}
+void gor_probe_cmul(double ar, double ai, double br, double bi, double out[2])
+{
+  volatile cplx a = CMPLX(ar, ai), b = CMPLX(br, bi);
+  cplx r = a * b;
+  out[0] = creal(r);
+  out[1] = cimag(r);
+}
+void gor_probe_rmul(double r0, double br, double bi, double out[2])
+{
+  volatile double rr = r0;
+  volatile cplx b = CMPLX(br, bi);
+  cplx r = rmul(rr, b);
+  out[0] = creal(r);
+  out[1] = cimag(r);
+}

@@ -113,6 +113,13 @@ double gor_quartic_solver(int i_scaling, double a, double b, double c, double d,
 /* cexp(i*2*pi*FRAC_JUMPS[k]) table entries as glibc computes them (for the device constant table) */
 void gor_frac_jump_phase(int k, double out[2]);
 
+/* probes of gcc -fcx-fortran-rules complex lowering and glibc cabs/csqrt (pin the device restatements) */
+void gor_probe_csqrt(double re, double im, double out[2]);
+double gor_probe_cabs(double re, double im);
+void gor_probe_cdiv(double ar, double ai, double br, double bi, double out[2]);
+void gor_probe_cmul(double ar, double ai, double br, double bi, double out[2]);
+void gor_probe_rmul(double r0, double br, double bi, double out[2]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,150 @@
+// host_mirror.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles the product's device headers (gorilla_b200/csrc/gb_*.cuh) for the HOST with g++
+// (-ffp-contract=off == nvcc --fmad=false) so that the device algorithm can be checked bit-for-bit
+// against the oracle on a machine without a GPU (`pytest -m "not gpu"`).  It is built into
+// tests/_build/ by tests/conftest.py, is never shipped and is never loaded by the product: the
+// product library has no CPU path.  The per-particle loop below restates orbit_kernel's lane logic
+// (gb_internal.cuh) without the warp machinery.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "../../gorilla_b200/csrc/gb_find.cuh"
+#include "../../gorilla_b200/csrc/gb_repack.hpp"
+
+using namespace gb;
+
+struct HostMirror {
+  std::vector<double> geom, bpart, phi, cold;
+  MeshDev m;
+  int poly_order, boole_periodic_relocation;
+};
+
+template <int K, bool PHI>
+static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *vperp_io, double t_step, int32_t *ind_io,
+                         int32_t *iface_io, double *t_remain_out, int64_t *npush_out, int trace_cap, int32_t *tr_t,
+                         int32_t *tr_f, int force_full, int64_t *fallback)
+{
+  int32_t ind_tetr = *ind_io, iface = *iface_io;
+  double vpar = *vpar_io;
+  const double vperp = *vperp_io;
+  const double *pg = m.geom + ((int64_t)ind_tetr - 1) * GEOM_ND;
+  double z_save[3] = {x[0] - pg[0], x[1] - pg[1], x[2] - pg[2]};
+  const double perpinv = -0.5 * (vperp * vperp) / bmod_at<PHI>(m, ind_tetr, z_save);
+  double t_remain = t_step;
+  int32_t ind_save = ind_tetr;
+  int64_t npush = 0;
+  for (;;) {
+    ind_save = ind_tetr;
+    PushOut o;
+    bool done = false;
+    if (!force_full) {
+      PolyPusher<K, PHI> P;
+      P.mp = &m;
+      P.perpinv = perpinv;
+      done = P.push_fast(ind_tetr, iface, x, vpar, t_remain, o);
+    }
+    if (!done) o = push_full_call<K, PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
+    x[0] = o.x[0]; x[1] = o.x[1]; x[2] = o.x[2];
+    vpar = o.vpar;
+    if (o.z_save_set) { z_save[0] = o.z_save[0]; z_save[1] = o.z_save[1]; z_save[2] = o.z_save[2]; }
+    ind_tetr = o.ind_tetr;
+    iface = o.iface;
+    if (trace_cap > 0 && npush < trace_cap) { tr_t[npush] = ind_tetr; tr_f[npush] = iface; }
+    npush++;
+    for (int b = 0; b < 4; b++) if (o.fallback & (1 << b)) fallback[b]++;
+    t_remain = t_remain - o.t_pass;
+    if (o.finished || ind_tetr == -1) break;
+  }
+  double vperp_new = 0.0;
+  if (perpinv != 0.0) vperp_new = sqrt(2.0 * fabs(perpinv) * bmod_at<PHI>(m, ind_save, z_save));
+  *vpar_io = vpar;
+  *vperp_io = vperp_new;
+  *ind_io = ind_tetr;
+  *iface_io = iface;
+  if (t_remain_out) *t_remain_out = t_remain;
+  if (npush_out) *npush_out = npush;
+}
+
+extern "C" {
+
+void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, int boole_periodic_relocation)
+{
+  HostMirror *h = new HostMirror();
+  bool has_phi = false;
+  if (!repack_mesh(md, h->geom, h->bpart, h->phi, h->cold, has_phi)) { delete h; return nullptr; }
+  MeshDev &m = h->m;
+  memset(&m, 0, sizeof(m));
+  m.ntetr = md->ntetr;
+  m.geom = h->geom.data(); m.bpart = h->bpart.data(); m.phi = has_phi ? h->phi.data() : nullptr; m.cold = h->cold.data();
+  m.cm_over_e = md->cm_over_e; m.particle_mass = md->particle_mass; m.particle_charge = md->particle_charge;
+  const double PI = 3.141592653589793238462643383;
+  m.period_phi = 2.0 * PI / md->n_field_periods; m.period_theta = 2.0 * PI;
+  m.sign_sqg = md->sign_sqg; m.coord_system = md->coord_system;
+  m.grid_size1 = md->grid_size[0]; m.grid_size2 = md->grid_size[1]; m.grid_size3 = md->grid_size[2];
+  m.boole_guess = boole_guess; m.grid_kind = md->grid_kind; m.n_field_periods = md->n_field_periods;
+  m.Rmin = md->Rmin; m.Rmax = md->Rmax; m.Zmin = md->Zmin; m.Zmax = md->Zmax; m.sfc_s_min = md->sfc_s_min;
+  h->poly_order = poly_order;
+  h->boole_periodic_relocation = boole_periodic_relocation;
+  return h;
+}
+void hm_free(void *p) { delete (HostMirror *)p; }
+int hm_has_phi(void *p) { return ((HostMirror *)p)->m.phi != nullptr; }
+
+// same contract as gorilla_b200_orbit_timestep_trace; returns number of domain errors
+int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *vperp, double t_step, int32_t *binit,
+                          int32_t *ind_tetr, int32_t *iface, double *t_remain_out, int64_t *n_pushes, int32_t trace_cap,
+                          int32_t *tr_t, int32_t *tr_f, int force_full, int64_t *fallback /*[4]*/)
+{
+  HostMirror *h = (HostMirror *)p;
+  const MeshDev &m = h->m;
+  int64_t dom = 0;
+  const int sign_t = signbit(t_step) ? -1 : 1;
+  for (int64_t i = 0; i < n; i++) {
+    double *xi = x + 3 * i;
+    if (!binit[i]) {
+      int32_t it = -1, ifc = -1;
+      if (check_coordinate_domain(m, xi, h->boole_periodic_relocation) != 0) dom++;
+      else if (m.phi) find_tetra<true>(&m, xi, vpar[i], vperp[i], it, ifc, sign_t);
+      else find_tetra<false>(&m, xi, vpar[i], vperp[i], it, ifc, sign_t);
+      ind_tetr[i] = it; iface[i] = ifc;
+      if (it != -1) binit[i] = 1;
+    }
+    if (n_pushes) n_pushes[i] = 0;
+    if (t_remain_out) t_remain_out[i] = t_step;
+    if (!binit[i] || ind_tetr[i] < 1) continue;
+    if (t_step == 0.0) { if (t_remain_out) t_remain_out[i] = 0.0; continue; }
+    int32_t *tt = trace_cap > 0 ? tr_t + i * trace_cap : nullptr, *tf = trace_cap > 0 ? tr_f + i * trace_cap : nullptr;
+#define HM_RUN(K, PHI) run_particle<K, PHI>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
+      t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, trace_cap, tt, tf, force_full, fallback)
+    if (m.phi) {
+      switch (h->poly_order) { case 1: HM_RUN(1, true); break; case 2: HM_RUN(2, true); break; case 3: HM_RUN(3, true); break; default: HM_RUN(4, true); }
+    } else {
+      switch (h->poly_order) { case 1: HM_RUN(1, false); break; case 2: HM_RUN(2, false); break; case 3: HM_RUN(3, false); break; default: HM_RUN(4, false); }
+    }
+  }
+  return dom;
+}
+
+// device math / solver entry points for bit-level pinning against glibc and the oracle
+void hm_csqrt(double re, double im, double *out) { cd r = csqrt_glibc(mk(re, im)); out[0] = r.re; out[1] = r.im; }
+double hm_hypot(double a, double b) { return hypot_glibc(a, b); }
+void hm_cdiv(double ar, double ai, double br, double bi, double *out) { cd r = cdiv(mk(ar, ai), mk(br, bi)); out[0] = r.re; out[1] = r.im; }
+void hm_cmul(double ar, double ai, double br, double bi, double *out) { cd r = cmul(mk(ar, ai), mk(br, bi)); out[0] = r.re; out[1] = r.im; }
+void hm_rmul(double r0, double br, double bi, double *out) { cd r = rmul(r0, mk(br, bi)); out[0] = r.re; out[1] = r.im; }
+void hm_frac_jump_phase(int k, double *out) { cd r = frac_jump_phase(k); out[0] = r.re; out[1] = r.im; }
+void hm_cmplx_roots_gen(int degree, const double *poly_re_im, double *roots_re_im)
+{
+  cd poly[5], roots[4];
+  int iters = 0;
+  for (int i = 0; i <= degree; i++) poly[i] = mk(poly_re_im[2 * i], poly_re_im[2 * i + 1]);
+  if (degree == 2) cmplx_roots_gen<2>(roots, poly, iters);
+  else if (degree == 3) cmplx_roots_gen<3>(roots, poly, iters);
+  else cmplx_roots_gen<4>(roots, poly, iters);
+  for (int i = 0; i < degree; i++) { roots_re_im[2 * i] = roots[i].re; roots_re_im[2 * i + 1] = roots[i].im; }
+}
+double hm_quadratic_solver1(double a, double b, double c) { return quadratic_solver1(a, b, c); }
+double hm_quadratic_solver2(double a, double b, double c) { int it = 0; return quadratic_solver2(a, b, c, it); }
+double hm_cubic_solver(double a, double b, double c, double d) { int it = 0; return cubic_solver(a, b, c, d, it); }
+double hm_quartic_solver(int s, double a, double b, double c, double d, double e) { int it = 0; return quartic_solver(s, a, b, c, d, e, it); }
+// vectorised comparisons against glibc (returns mismatch count); n random operand pairs supplied by the test
+}

@@ -1,0 +1,78 @@
+"""ctypes binding of tests/_build/libhost_mirror.so (host compile of the device headers; test-only)."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+SRC = HERE / "host_mirror" / "host_mirror.cpp"
+LIB = HERE / "_build" / "libhost_mirror.so"
+CSRC = HERE.parent / "gorilla_b200" / "csrc"
+
+
+def build_host_mirror(force=False) -> Path:
+    LIB.parent.mkdir(exist_ok=True)
+    deps = [SRC] + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.hpp"))
+    if force or not LIB.exists() or LIB.stat().st_mtime < max(p.stat().st_mtime for p in deps):
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", str(LIB),
+                        str(SRC)], check=True, capture_output=True)
+    return LIB
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        build_host_mirror()
+        L = C.CDLL(str(LIB))
+        d, vp = C.c_double, C.c_void_p
+        L.hm_create.restype = vp
+        L.hm_create.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        L.hm_free.argtypes = [vp]
+        L.hm_has_phi.argtypes = [vp]
+        L.hm_orbit_timestep.restype = C.c_int64
+        L.hm_orbit_timestep.argtypes = [vp, C.c_int64, vp, vp, vp, d, vp, vp, vp, vp, vp, C.c_int32, vp, vp, C.c_int, vp]
+        L.hm_hypot.restype = d
+        L.hm_hypot.argtypes = [d, d]
+        L.hm_csqrt.argtypes = [d, d, vp]
+        L.hm_cdiv.argtypes = [d, d, d, d, vp]
+        L.hm_cmul.argtypes = [d, d, d, d, vp]
+        L.hm_rmul.argtypes = [d, d, d, vp]
+        L.hm_frac_jump_phase.argtypes = [C.c_int, vp]
+        L.hm_cmplx_roots_gen.argtypes = [C.c_int, vp, vp]
+        for name, nargs in (("hm_quadratic_solver1", 3), ("hm_quadratic_solver2", 3), ("hm_cubic_solver", 4)):
+            getattr(L, name).argtypes = [d] * nargs
+            getattr(L, name).restype = d
+        L.hm_quartic_solver.argtypes = [C.c_int] + [d] * 5
+        L.hm_quartic_solver.restype = d
+        _lib = L
+    return _lib
+
+
+class HostMirror:
+    def __init__(self, mesh, settings):
+        self.L = load()
+        self.mesh = mesh
+        self._desc = mesh.desc()
+        self.h = self.L.hm_create(C.byref(self._desc), settings.poly_order, int(settings.boole_guess),
+                                  int(settings.boole_periodic_relocation))
+        assert self.h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.hm_free(self.h)
+            self.h = None
+
+    def orbit_timestep(self, x, vpar, vperp, t_step, binit, ind_tetr, iface, trace_cap=0, force_full=False):
+        n = x.shape[0]
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        tt, tf = np.zeros((n, max(trace_cap, 1)), np.int32), np.zeros((n, max(trace_cap, 1)), np.int32)
+        npush, tro, fb = np.zeros(n, np.int64), np.zeros(n), np.zeros(4, np.int64)
+        dom = self.L.hm_orbit_timestep(self.h, n, p(x), p(vpar), p(vperp), float(t_step), p(binit), p(ind_tetr),
+                                       p(iface), p(tro), p(npush), trace_cap, p(tt), p(tf), int(force_full), p(fb))
+        return dict(trace_tetr=tt, trace_face=tf, n_pushes=npush, t_remain=tro, fallback=fb, domain_errors=dom)

@@ -28,6 +28,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
     "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off", "-Xptxas", "-v",
 ]
+NVCC_FLAGS += os.environ.get("GORILLA_NVCC_EXTRA", "").split()
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas"]
 
 CU_SOURCES = ["gorilla_b200.cu", "gb_orbit_k1.cu", "gb_orbit_k2.cu", "gb_orbit_k3.cu", "gb_orbit_k4.cu"]

@@ -46,8 +46,23 @@ struct Batch {
 };
 
 // ----------------------------------------------------------------------------------------------------
+// minimum resident CTAs per SM the compiler must allow for (caps registers per thread); tunable per order
+#ifndef GB_MINB_K1
+#define GB_MINB_K1 2
+#endif
+#ifndef GB_MINB_K2
+#define GB_MINB_K2 2
+#endif
+#ifndef GB_MINB_K3
+#define GB_MINB_K3 2
+#endif
+#ifndef GB_MINB_K4
+#define GB_MINB_K4 2
+#endif
+constexpr int gb_min_blocks(int K) { return K == 1 ? GB_MINB_K1 : K == 2 ? GB_MINB_K2 : K == 3 ? GB_MINB_K3 : GB_MINB_K4; }
+
 template <int K, bool PHI>
-__global__ void __launch_bounds__(128, 1) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
+__global__ void __launch_bounds__(128, gb_min_blocks(K)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
 {
   const unsigned lane = threadIdx.x & 31u;
   bool active = false, exhausted = false;

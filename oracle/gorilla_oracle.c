@@ -1616,6 +1616,12 @@ int gor_orbit_timestep(const gor_mesh *m, double x[3], double *vpar, double *vpe
     *boole_initialized = 1;
   }
   if (t_step == 0.0) return GOR_OK;
+  /* A particle that is already lost (ind_tetr = -1 from an earlier call) is left untouched.  The reference
+   * would index tetra_physics(-1) at :74 (out of bounds; its callers never re-enter with a lost particle). */
+  if (*ind_tetr < 1) {
+    if (t_remain_out) *t_remain_out = t_step;
+    return GOR_OK;
+  }
   double vperp2 = (*vperp) * (*vperp);
   double z_save[3];
   {

@@ -60,7 +60,7 @@ def make_workload(name: str):
     if name == "vmec_qi":
         grid, settings = workloads.vmec_qi(str(vmec_file))
         return dict(name="vmec_qi_alpha_3.5MeV_100x40x40", grid=grid, settings=settings,
-                    particles=workloads.particles_vmec_alpha, n_default=1_000_000, t_step=1.0e-6,
+                    particles=workloads.particles_vmec_alpha, n_default=1_000_000, t_step=1.0e-5,
                     desc="QI stellarator netcdf_file_for_test.nc (VMEC), grid_kind=3 100x40x40, 3.5 MeV alphas, "
                          "s0=0.5, pitch U[-1,1]")
     grid, settings = workloads.analytic_tokamak(40, 80, 40)

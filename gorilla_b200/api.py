@@ -19,7 +19,10 @@ import numpy as np
 
 from .settings import GorillaSettings, TetraGridSettings
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libgorilla_b200.so"
+import os
+
+# GORILLA_B200_LIB selects an alternative build of the same library (tuning experiments); default = in-tree build
+_LIB_PATH = Path(os.environ.get("GORILLA_B200_LIB", Path(__file__).resolve().parent / "lib" / "libgorilla_b200.so"))
 _lib = None
 
 

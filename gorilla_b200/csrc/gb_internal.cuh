@@ -48,10 +48,10 @@ struct Batch {
 // ----------------------------------------------------------------------------------------------------
 // minimum resident CTAs per SM the compiler must allow for (caps registers per thread); tunable per order
 #ifndef GB_MINB_K1
-#define GB_MINB_K1 2
+#define GB_MINB_K1 4
 #endif
 #ifndef GB_MINB_K2
-#define GB_MINB_K2 2
+#define GB_MINB_K2 4
 #endif
 #ifndef GB_MINB_K3
 #define GB_MINB_K3 2

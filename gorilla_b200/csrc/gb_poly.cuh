@@ -269,6 +269,23 @@ struct PolyPusher {
     }
   }
 
+  // ---- one face of an order-2 solve with the closed-form solver (i_scaling = 0): operands of the single
+  // division that yields dtau; false = no valid root on this face (dtau = 0 or huge in the reference)
+  GB_HD bool face_numden_ord2(const double *c, bool start_face, double &num, double &den) const
+  {
+    const bool reduced = start_face || (c[0] == 0.0);
+    // reduced: Linear_Solver(c2/2, c1); degenerate quadratic (c2 == 0): Linear_Solver(c1, c0)
+    const bool lin_deg = !reduced && (c[2] == 0.0);
+    const double la = reduced ? c[2] / 2.0 : c[1];
+    const double lb = reduced ? c[1] : c[0];
+    double qn, qd;
+    const bool qhas = quadratic_solver1_numden(c[2], c[1], c[0], qn, qd);
+    const bool linear = reduced || lin_deg;
+    num = linear ? -lb : qn;
+    den = linear ? la : qd;
+    return linear ? (la != 0.0) : qhas;
+  }
+
   // ---- :1258-1482.  dtau/iface untouched when no valid root exists.
   template <int ORD>
   GB_HD bool analytic_approx(unsigned mask, int i_scaling, const double *z, int &iface_inout, double &dtau)
@@ -281,9 +298,18 @@ struct PolyPusher {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       if (!(mask & (1u << i))) continue;
-      double d = face_root<ORD>(cm[i], (i + 1) == iface, i_scaling);
+      double d;
+      bool ok;
+      if (ORD == 2 && i_scaling == 0) {
+        double num, den;
+        ok = face_numden_ord2(cm[i], (i + 1) == iface, num, den);
+        d = num / den;
+      } else {
+        d = face_root<ORD>(cm[i], (i + 1) == iface, i_scaling);
+        ok = true;
+      }
       // valid: 0 < d < huge ; minloc keeps the lowest face index on ties
-      if ((d < GB_HUGE) && (d > 0.0) && (ibest == 0 || d < best)) {
+      if (ok && (d < GB_HUGE) && (d > 0.0) && (ibest == 0 || d < best)) {
         best = d;
         ibest = i + 1;
       }
@@ -321,16 +347,31 @@ struct PolyPusher {
     }
   }
 
+  // all four normal distances (:2690-2705); static indexing keeps r.an in registers
+  GB_HD void normal_distances(const double *z, double *d) const
+  {
+#pragma unroll
+    for (int f = 0; f < 4; f++) d[f] = dot3(z, r.an[f]);
+    d[0] = d[0] + r.dist_ref;
+  }
   GB_HD double normal_distance(const double *z, int iface /*1-based*/) const
   {
-    double d = dot3(z, r.an[iface - 1]);
-    if (iface == 1) d = d + r.dist_ref;
-    return d;
+    double d[4];
+    normal_distances(z, d);
+    return iface == 1 ? d[0] : iface == 2 ? d[1] : iface == 3 ? d[2] : d[3];
+  }
+  // anorm(:,iface) by selection instead of a dynamically indexed register array
+  GB_HD void face_normal(int iface, double *n) const
+  {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      n[i] = iface == 1 ? r.an[0][i] : iface == 2 ? r.an[1][i] : iface == 3 ? r.an[2][i] : r.an[3][i];
   }
   // ---- :2741-2775
   GB_HD double normal_v_from_trajectory(int iface, double tau) const
   {
-    const double *n = r.an[iface - 1];
+    double n[3];
+    face_normal(iface, n);
     double v = 0.0;
     if (K >= 1) v = (n[0] * (b[0] + Az[0]) + n[1] * (b[1] + Az[1])) + n[2] * (b[2] + Az[2]);
     if (K >= 2) v = v + ((n[0] * tau * (Ab[0] + A2z[0]) + n[1] * tau * (Ab[1] + A2z[1])) + n[2] * tau * (Ab[2] + A2z[2]));
@@ -347,7 +388,8 @@ struct PolyPusher {
   // ---- :2709-2739, poly1 quantities (n.alpha, n.beta, n.curlA) formed on the fly
   GB_HD double normal_velocity(const double *z, int iface) const
   {
-    const double *n = r.an[iface - 1];
+    double n[3];
+    face_normal(iface, n);
     const double pc = perpinv * mp->cm_over_e;
     double t[3];
 #pragma unroll
@@ -363,19 +405,37 @@ struct PolyPusher {
     double in_betvec = dot3(n, r.curlA);
     return ((t[0] + t[1]) + t[2] + in_betvec * z[3]) * (double)sign_rhs + dot3(n, b);
   }
+  // check_three_planes (:679-699): the three faces other than the exit face must have distance >= 0
   GB_HD bool three_planes_ok(const double *z, int iface_new) const
   {
+    double d[4];
+    normal_distances(z, d);
     bool ok = true;
 #pragma unroll
-    for (int j = 1; j <= 3; j++) {
-      int k = ((iface_new + j - 1) & 3) + 1;
-      if (normal_distance(z, k) < 0.0) ok = false;
-    }
+    for (int f = 0; f < 4; f++)
+      if (f + 1 != iface_new && d[f] < 0.0) ok = false;
     return ok;
   }
+  // check_face_convergence (:703-718)
   GB_HD bool face_converged(const double *z, int iface_new) const
   {
     return !(fabs(normal_distance(z, iface_new)) > 1.e-11);
+  }
+  // both of the above from one evaluation of the four distances
+  GB_HD bool exit_point_ok(const double *z, int iface_new) const
+  {
+    double d[4];
+    normal_distances(z, d);
+    bool ok = true;
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      if (f + 1 != iface_new) {
+        if (d[f] < 0.0) ok = false;
+      } else {
+        if (fabs(d[f]) > 1.e-11) ok = false;
+      }
+    }
+    return ok;
   }
   // ---- :2779-2831
   GB_HD double physical_estimate_tau() const
@@ -479,7 +539,7 @@ struct PolyPusher {
   GB_HD void handover(int iface_exit, double *x, int32_t &ind_out, int32_t &iface_out) const
   {
     const int f = iface_exit - 1;
-    ind_out = r.nb[f];
+    ind_out = f == 0 ? r.nb[0] : f == 1 ? r.nb[1] : f == 2 ? r.nb[2] : r.nb[3];
     iface_out = topo_face(r.flags, f);
     const int iper_phi = topo_perphi(r.flags, f);
     if (mp->coord_system == 1) {
@@ -526,9 +586,13 @@ struct PolyPusher {
       tau = t_remain / dt_dtau_const;
       integrate<K>(z, tau);
       bool inside = true;
+      {
+        double d[4];
+        normal_distances(z, d);
 #pragma unroll
-      for (int i = 1; i <= 4; i++)
-        if (normal_distance(z, i) < 0.0) inside = false;
+        for (int f = 0; f < 4; f++)
+          if (d[f] < 0.0) inside = false;
+      }
       if (inside) {
         o.ind_tetr = ind_tetr;
         o.iface = 0;
@@ -583,8 +647,7 @@ struct PolyPusher {
       if (!analytic_approx<K>(mask, 0, z, iface_new, tau)) return false;
     }
     integrate<K>(z, tau);
-    if (!three_planes_ok(z, iface_new)) return false;
-    if (!face_converged(z, iface_new)) return false;
+    if (!exit_point_ok(z, iface_new)) return false;
     if (K > 2 && tau > tau_max) return false;
     if (normal_v_from_trajectory(iface_new, tau) > 0.0) return false;
     return finish<true>(z, tau, iface_new, o);

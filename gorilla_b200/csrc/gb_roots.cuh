@@ -53,247 +53,6 @@ GB_HD double frac_jump(int k)
 
 #define GB_FRAC_ERR 2.0e-15
 
-// Horner evaluation of p, p', p''/2 (+ Adams' error bound) -- the common body of every mode
-template <int DEG, bool WITH_D2, bool WITH_EK>
-GB_HD void horner(const cd *poly, cd root, cd &p, cd &dp, cd &d2p_half, double &ek)
-{
-  double absroot = 0.0;
-  if (WITH_EK) {
-    ek = cabs_glibc(poly[DEG]);
-    absroot = cabs_glibc(root);
-  }
-  p = poly[DEG];
-  dp = mk(0.0, 0.0);
-  d2p_half = mk(0.0, 0.0);
-#pragma unroll
-  for (int k = DEG; k >= 1; k--) {
-    if (WITH_D2) d2p_half = cadd(dp, cmul(d2p_half, root));
-    dp = cadd(p, cmul(dp, root));
-    p = cadd(poly[k - 1], cmul(p, root));
-    if (WITH_EK) ek = absroot * ek + cabs_glibc(p);
-  }
-}
-
-// Laguerre step denominator (shared by cmplx_laguerre and mode 2 of cmplx_laguerre2newton)
-template <int DEG>
-GB_HD cd laguerre_denom(cd F_half)
-{
-  const double one_nth = 1.0 / DEG;
-  const double n_1_nth = (DEG - 1.0) * one_nth;
-  const double two_n_div_n_1 = 2.0 / n_1_nth;
-  const cd c_one = mk(1.0, 0.0), c_one_nth = mk(one_nth, 0.0);
-  cd denom_sqrt = csqrt_glibc(csub(c_one, rmul(two_n_div_n_1, F_half)));
-  if (denom_sqrt.re >= 0.0) return cadd(c_one_nth, rmul(n_1_nth, denom_sqrt));
-  return csub(c_one_nth, rmul(n_1_nth, denom_sqrt));
-}
-
-// cmplx_roots_sg.f90:558-731
-template <int DEG>
-GB_HD_NOINLINE bool cmplx_laguerre(const cd *poly, cd &root, int &iters)
-{
-  const int MAX_ITERS = 200;
-  bool good_to_go = false;
-  for (int i = 1; i <= MAX_ITERS; i++) {
-    cd p, dp, d2p_half, fac_netwon = mk(0.0, 0.0);
-    double ek;
-    double absroot = cabs_glibc(root);
-    horner<DEG, true, true>(poly, root, p, dp, d2p_half, ek);
-    iters++;
-    double abs2p = cabs2(p);
-    if (abs2p == 0.0) return true;
-    double sc = GB_FRAC_ERR * ek;
-    double stopping_crit2 = sc * sc;
-    if (abs2p < stopping_crit2) {
-      if (abs2p < 0.01 * stopping_crit2) return true;
-      good_to_go = true;
-    } else {
-      good_to_go = false;
-    }
-    cd denom = mk(0.0, 0.0);
-    if (!cis0(dp)) {
-      fac_netwon = cdiv(p, dp);
-      cd fac_extra = cdiv(d2p_half, dp);
-      cd F_half = cmul(fac_netwon, fac_extra);
-      denom = laguerre_denom<DEG>(F_half);
-    }
-    cd dx;
-    if (cis0(denom))
-      dx = rmul(absroot + 1.0, frac_jump_phase(i % 10));
-    else
-      dx = cdiv(fac_netwon, denom);
-    cd newroot = csub(root, dx);
-    if (ceq(newroot, root)) return true;
-    if (good_to_go) {
-      root = newroot;
-      return true;
-    }
-    if (i % 10 == 0) {
-      double faq = frac_jump((i / 10 - 1) % 10);
-      newroot = csub(root, rmul(faq, dx));
-    }
-    root = newroot;
-  }
-  return false;
-}
-
-// cmplx_roots_sg.f90:906-1305, starting_mode = 2
-template <int DEG>
-GB_HD_NOINLINE bool cmplx_laguerre2newton(const cd *poly, cd &root, int &iters)
-{
-  const int MAX_ITERS = 50;
-  const cd c_one = mk(1.0, 0.0);
-  int mode = 2, i, j = 1, iter = 0;
-  bool good_to_go = false;
-  double stopping_crit2 = 0.0;
-  for (;;) {
-    if (mode >= 2) {
-      for (i = 1; i <= MAX_ITERS; i++) {
-        cd p, dp, d2p_half, fac_netwon = mk(0.0, 0.0);
-        double ek;
-        horner<DEG, true, true>(poly, root, p, dp, d2p_half, ek);
-        double abs2p = cabs2(p);
-        iter++;
-        if (abs2p == 0.0) { iters += iter; return true; }
-        double sc = GB_FRAC_ERR * ek;
-        stopping_crit2 = sc * sc;
-        if (abs2p < stopping_crit2) {
-          if (abs2p < 0.01 * stopping_crit2) { iters += iter; return true; }
-          good_to_go = true;
-        } else {
-          good_to_go = false;
-        }
-        cd denom = mk(0.0, 0.0);
-        if (!cis0(dp)) {
-          fac_netwon = cdiv(p, dp);
-          cd fac_extra = cdiv(d2p_half, dp);
-          cd F_half = cmul(fac_netwon, fac_extra);
-          double abs2_F_half = cabs2(F_half);
-          if (abs2_F_half <= 0.0625) {
-            if (abs2_F_half <= 0.000625)
-              mode = 0;
-            else
-              mode = 1;
-          }
-          denom = laguerre_denom<DEG>(F_half);
-        }
-        cd dx;
-        if (cis0(denom))
-          dx = rmul(cabs_glibc(root) + 1.0, frac_jump_phase(i % 10));
-        else
-          dx = cdiv(fac_netwon, denom);
-        cd newroot = csub(root, dx);
-        if (ceq(newroot, root)) { iters += iter; return true; }
-        if (good_to_go) {
-          root = newroot;
-          iters += iter;
-          return true;
-        }
-        if (mode != 2) {
-          root = newroot;
-          j = i + 1;
-          break;
-        }
-        if (i % 10 == 0) {
-          double faq = frac_jump((i / 10 - 1) % 10);
-          newroot = csub(root, rmul(faq, dx));
-        }
-        root = newroot;
-      }
-      if (i >= MAX_ITERS) { iters += iter; return false; }
-    }
-    if (mode == 1) {
-      for (i = j; i <= MAX_ITERS; i++) {
-        cd p, dp, d2p_half;
-        double ek;
-        if ((i - j) % 10 == 0) {
-          horner<DEG, true, true>(poly, root, p, dp, d2p_half, ek);
-          double sc = GB_FRAC_ERR * ek;
-          stopping_crit2 = sc * sc;
-        } else {
-          horner<DEG, true, false>(poly, root, p, dp, d2p_half, ek);
-        }
-        double abs2p = cabs2(p);
-        iter++;
-        if (abs2p == 0.0) { iters += iter; return true; }
-        if (abs2p < stopping_crit2) {
-          if (cis0(dp)) { iters += iter; return true; }
-          if (abs2p < 0.01 * stopping_crit2) { iters += iter; return true; }
-          good_to_go = true;
-        } else {
-          good_to_go = false;
-        }
-        cd dx;
-        if (cis0(dp)) {
-          dx = rmul(cabs_glibc(root) + 1.0, frac_jump_phase(i % 10));
-        } else {
-          cd fac_netwon = cdiv(p, dp);
-          cd fac_extra = cdiv(d2p_half, dp);
-          cd F_half = cmul(fac_netwon, fac_extra);
-          double abs2_F_half = cabs2(F_half);
-          if (abs2_F_half <= 0.000625) mode = 0;
-          dx = cmul(fac_netwon, cadd(c_one, F_half));
-        }
-        cd newroot = csub(root, dx);
-        if (ceq(newroot, root)) { iters += iter; return true; }
-        if (good_to_go) {
-          root = newroot;
-          iters += iter;
-          return true;
-        }
-        if (mode != 1) {
-          root = newroot;
-          j = i + 1;
-          break;
-        }
-        if (i % 10 == 0) {
-          double faq = frac_jump((i / 10 - 1) % 10);
-          newroot = csub(root, rmul(faq, dx));
-        }
-        root = newroot;
-      }
-      if (i >= MAX_ITERS) { iters += iter; return false; }
-    }
-    if (mode == 0) {
-      for (i = j; i <= j + 10; i++) {
-        cd p, dp, d2p_half;
-        double ek;
-        if (i == j) {
-          horner<DEG, false, true>(poly, root, p, dp, d2p_half, ek);
-          double sc = GB_FRAC_ERR * ek;
-          stopping_crit2 = sc * sc;
-        } else {
-          horner<DEG, false, false>(poly, root, p, dp, d2p_half, ek);
-        }
-        double abs2p = cabs2(p);
-        iter++;
-        if (abs2p == 0.0) { iters += iter; return true; }
-        if (abs2p < stopping_crit2) {
-          if (cis0(dp)) { iters += iter; return true; }
-          if (abs2p < 0.01 * stopping_crit2) { iters += iter; return true; }
-          good_to_go = true;
-        } else {
-          good_to_go = false;
-        }
-        cd dx;
-        if (cis0(dp))
-          dx = rmul(cabs_glibc(root) + 1.0, frac_jump_phase(i % 10));
-        else
-          dx = cdiv(p, dp);
-        cd newroot = csub(root, dx);
-        if (ceq(newroot, root)) { iters += iter; return true; }
-        if (good_to_go) {
-          root = newroot;
-          iters += iter;
-          return true;
-        }
-        root = newroot;
-      }
-      if (iter >= MAX_ITERS) { iters += iter; return false; }
-      mode = 2;
-    }
-  }
-}
-
 // cmplx_roots_sg.f90:1311-1362
 GB_HD void solve_quadratic_eq(cd &x0, cd &x1, const cd *poly)
 {
@@ -313,73 +72,260 @@ GB_HD void solve_quadratic_eq(cd &x0, cd &x1, const cd *poly)
   }
 }
 
-// One deflation stage: find a root of the degree-N working polynomial, divide it out.
-template <int N>
-GB_HD void find_and_deflate(cd *poly2, cd *roots, int &iters)
+// ----------------------------------------------------------------------------------------------------
+// cmplx_roots_gen(roots, poly, deg, polish=.true., start=.false.) as ONE per-lane state machine.
+//
+// The reference runs, for a degree-d polynomial, d-1 root searches on successively deflated polynomials
+// (cmplx_laguerre2newton: Laguerre -> SG -> Newton modes, with plain Laguerre as a fall-back) and then d
+// Laguerre polishes on the original polynomial (cmplx_roots_sg.f90:146-198).  Written as nested loops, SIMT
+// lanes would wait for each other at the end of every search, every mode and every polish.  Here each lane
+// carries (stage, method, mode, i, j, ...) explicitly and every trip of the single loop below performs one
+// iteration of whatever that lane is doing: all lanes share the same Horner evaluation (degree and
+// coefficients are per-lane data, indexed statically with predicates), so a warp needs max-over-lanes of the
+// TOTAL iteration count instead of the sum over stages of the per-stage maxima.  The arithmetic each lane
+// performs is exactly the reference's sequence of operations (verified bit-for-bit against the oracle).
+// ----------------------------------------------------------------------------------------------------
+struct SgLaguerreConsts {
+  double one_nth, n_1_nth, two_n_div_n_1;
+};
+GB_HD SgLaguerreConsts sg_consts(int degree)
 {
-  roots[N - 1] = mk(0.0, 0.0);
-  if (!cmplx_laguerre2newton<N>(poly2, roots[N - 1], iters)) {
-    roots[N - 1] = mk(0.0, 0.0);
-    cmplx_laguerre<N>(poly2, roots[N - 1], iters);
-  }
-  cd coef = poly2[N];
-#pragma unroll
-  for (int i = N; i >= 1; i--) {
-    cd prev = poly2[i - 1];
-    poly2[i - 1] = coef;
-    coef = cadd(prev, cmul(roots[N - 1], coef));
-  }
+  SgLaguerreConsts c;
+  c.one_nth = 1.0 / degree;
+  c.n_1_nth = (degree - 1.0) * c.one_nth;
+  c.two_n_div_n_1 = 2.0 / c.n_1_nth;
+  return c;
 }
 
-// cmplx_roots_gen(roots, poly, DEG, .true., .false.)   cmplx_roots_sg.f90:83-201
-template <int DEG>
-GB_HD void cmplx_roots_gen(cd *roots, const cd *poly, int &iters)
+// poly: deg+1 coefficients (poly[0] constant term), roots: deg outputs.  deg in {2,3,4}.
+GB_HD void sg_roots(int deg, const cd *poly_in, cd *roots_out, int &iters)
 {
-  cd poly2[DEG + 1];
+  const cd zero = mk(0.0, 0.0), c_one = mk(1.0, 0.0);
+  cd poly[5], work[5], roots[4];
 #pragma unroll
-  for (int i = 0; i <= DEG; i++) poly2[i] = poly[i];
-  if constexpr (DEG >= 4) find_and_deflate<4>(poly2, roots, iters);
-  if constexpr (DEG >= 3) find_and_deflate<3>(poly2, roots, iters);
-  roots[1] = mk(0.0, 0.0);
-  roots[0] = mk(0.0, 0.0);
-  if (!cmplx_laguerre2newton<2>(poly2, roots[1], iters)) {
-    solve_quadratic_eq(roots[1], roots[0], poly2);
-  } else {
-    roots[0] = cneg(cadd(roots[1], cdiv(poly2[1], poly2[2])));
+  for (int k = 0; k < 5; k++) {
+    poly[k] = (k <= deg) ? poly_in[k <= deg ? k : 0] : zero;
+    work[k] = poly[k];
   }
 #pragma unroll
-  for (int n = 0; n < DEG; n++) cmplx_laguerre<DEG>(poly, roots[n], iters);
+  for (int k = 0; k < 4; k++) roots[k] = zero;
+
+  int n = deg;      // degree of the working polynomial during the search stages
+  int phase = 0;    // 0: cmplx_laguerre2newton search, 1: cmplx_laguerre fall-back search, 2: polish
+  int pol = 0;      // root being polished
+  cd root = zero;
+  int mode = 2, i = 1, j = 1, iter = 0;
+  bool good_to_go = false;
+  double stopping_crit2 = 0.0;
+  bool done = false;
+
+  while (!done) {
+    const bool lag = (phase != 0);
+    const int cdeg = (phase == 2) ? deg : n;
+    cd c[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) c[k] = (phase == 2) ? poly[k] : work[k];
+    const int mode0 = mode;  // mode at the start of this iteration
+    const bool need_ek = lag || mode0 == 2 || (mode0 == 1 && ((i - j) % 10 == 0)) || (mode0 == 0 && i == j);
+
+    // ---- Horner: p, p', p''/2 and Adams' bound
+    cd p = (cdeg == 4) ? c[4] : (cdeg == 3) ? c[3] : c[2];
+    cd dp = zero, d2p_half = zero;
+    double ek = 0.0, absroot = 0.0;
+    if (need_ek) {
+      ek = cabs_glibc(p);
+      absroot = cabs_glibc(root);
+    }
+#pragma unroll
+    for (int k = 4; k >= 1; k--) {
+      if (k <= cdeg) {
+        d2p_half = cadd(dp, cmul(d2p_half, root));
+        dp = cadd(p, cmul(dp, root));
+        p = cadd(c[k - 1], cmul(p, root));
+        if (need_ek) ek = absroot * ek + cabs_glibc(p);
+      }
+    }
+    iter++;
+    iters++;
+    int ret = 0;  // 0 continue, 1 routine returns success, 2 routine returns failure
+    const double abs2p = cabs2(p);
+    if (abs2p == 0.0) {
+      ret = 1;
+    } else {
+      if (need_ek) {
+        const double sc = GB_FRAC_ERR * ek;
+        stopping_crit2 = sc * sc;
+      }
+      if (abs2p < stopping_crit2) {
+        if (!lag && mode0 != 2 && cis0(dp)) ret = 1;
+        else if (abs2p < 0.01 * stopping_crit2) ret = 1;
+        else good_to_go = true;
+      } else {
+        good_to_go = false;
+      }
+    }
+    if (ret == 0) {
+      cd dx;
+      const bool dp0 = cis0(dp);
+      if (lag || mode0 == 2) {
+        cd denom = zero, fac_netwon = zero;
+        if (!dp0) {
+          fac_netwon = cdiv(p, dp);
+          const cd fac_extra = cdiv(d2p_half, dp);
+          const cd F_half = cmul(fac_netwon, fac_extra);
+          if (!lag) {
+            const double abs2_F_half = cabs2(F_half);
+            if (abs2_F_half <= 0.0625) mode = (abs2_F_half <= 0.000625) ? 0 : 1;
+          }
+          const SgLaguerreConsts k = sg_consts(cdeg);
+          const cd denom_sqrt = csqrt_glibc(csub(c_one, rmul(k.two_n_div_n_1, F_half)));
+          const cd c_one_nth = mk(k.one_nth, 0.0);
+          if (denom_sqrt.re >= 0.0) denom = cadd(c_one_nth, rmul(k.n_1_nth, denom_sqrt));
+          else denom = csub(c_one_nth, rmul(k.n_1_nth, denom_sqrt));
+        }
+        if (cis0(denom)) dx = rmul(cabs_glibc(root) + 1.0, frac_jump_phase(i % 10));
+        else dx = cdiv(fac_netwon, denom);
+      } else if (mode0 == 1) {
+        if (dp0) {
+          dx = rmul(cabs_glibc(root) + 1.0, frac_jump_phase(i % 10));
+        } else {
+          const cd fac_netwon = cdiv(p, dp);
+          const cd fac_extra = cdiv(d2p_half, dp);
+          const cd F_half = cmul(fac_netwon, fac_extra);
+          if (cabs2(F_half) <= 0.000625) mode = 0;
+          dx = cmul(fac_netwon, cadd(c_one, F_half));
+        }
+      } else {
+        if (dp0) dx = rmul(cabs_glibc(root) + 1.0, frac_jump_phase(i % 10));
+        else dx = cdiv(p, dp);
+      }
+      cd newroot = csub(root, dx);
+      if (ceq(newroot, root)) {
+        ret = 1;
+      } else if (good_to_go) {
+        root = newroot;
+        ret = 1;
+      } else if (lag) {
+        if (i % 10 == 0) newroot = csub(root, rmul(frac_jump((i / 10 - 1) % 10), dx));
+        root = newroot;
+        i++;
+        if (i > 200) ret = 2;
+      } else if (mode0 == 0) {
+        root = newroot;
+        i++;
+        if (i > j + 10) {
+          if (iter >= 50) ret = 2;
+          mode = 2;
+          i = 1;
+        }
+      } else if (mode != mode0) {  // leaving Laguerre (2) or SG (1) for a faster mode
+        root = newroot;
+        j = i + 1;
+        if (i >= 50) ret = 2;
+        i = j;
+      } else {
+        if (i % 10 == 0) newroot = csub(root, rmul(frac_jump((i / 10 - 1) % 10), dx));
+        root = newroot;
+        i++;
+        if (i > 50) ret = 2;
+      }
+    }
+    if (ret != 0) {
+      // ---- the routine this lane was in has returned: advance the stage machine
+      bool start_search = false, start_polish = false;
+      if (phase == 2) {
+        if (pol == 0) roots[0] = root;
+        else if (pol == 1) roots[1] = root;
+        else if (pol == 2) roots[2] = root;
+        else roots[3] = root;
+        pol++;
+        if (pol == deg) done = true;
+        else start_polish = true;
+      } else if (phase == 0 && ret == 2 && n >= 3) {
+        // cmplx_laguerre2newton failed: plain Laguerre from (0,0) on the same polynomial (:163-166)
+        root = zero;
+        phase = 1;
+        i = 1;
+        good_to_go = false;
+      } else if (n >= 3) {
+        // root of the working polynomial found: store, divide it out (:169-176)
+        if (n == 4) roots[3] = root;
+        else roots[2] = root;
+        cd coef = (n == 4) ? work[4] : work[3];
+#pragma unroll
+        for (int k = 4; k >= 1; k--) {
+          if (k <= n) {
+            const cd prev = work[k - 1];
+            work[k - 1] = coef;
+            coef = cadd(prev, cmul(root, coef));
+          }
+        }
+        n--;
+        start_search = true;
+      } else {
+        // n == 2: last search (:184-190)
+        if (ret == 2) {
+          solve_quadratic_eq(roots[1], roots[0], work);
+        } else {
+          roots[1] = root;
+          roots[0] = cneg(cadd(roots[1], cdiv(work[1], work[2])));
+        }
+        pol = 0;
+        start_polish = true;
+      }
+      if (start_search) {
+        phase = 0;
+        root = zero;
+        mode = 2; i = 1; j = 1; iter = 0;
+        good_to_go = false;
+        stopping_crit2 = 0.0;
+      }
+      if (start_polish) {
+        phase = 2;
+        root = (pol == 0) ? roots[0] : (pol == 1) ? roots[1] : (pol == 2) ? roots[2] : roots[3];
+        i = 1;
+        good_to_go = false;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (k < deg) roots_out[k] = roots[k];
 }
 
 // pack_roots + the callers' "smallest positive real root / lambda" reduction, fused:
 // a root counts as real when |Im| <= 1e-12*max(1,|Re|) (then Im := 0 exactly); the callers divide by
 // lambda and take minval over {Im == 0, Re > 0}; empty mask -> huge.  The descending sort of
 // pack_roots does not change a minimum, so it is not materialised.
-template <int DEG>
-GB_HD double min_positive_real_root(const cd *croots, double lambda)
+GB_HD double min_positive_real_root(int deg, const cd *croots, double lambda)
 {
   double best = GB_HUGE;
 #pragma unroll
-  for (int i = 0; i < DEG; i++) {
-    double re = croots[i].re, im = croots[i].im;
-    double tol_i = 1.0e-12 * fmax(1.0, fabs(re));
-    if (fabs(im) <= tol_i) im = 0.0;
-    re = re / lambda;
-    im = im / lambda;
-    if (fabs(im) == 0.0 && re > 0.0 && re < best) best = re;
+  for (int i = 0; i < 4; i++) {
+    if (i < deg) {
+      double re = croots[i].re, im = croots[i].im;
+      const double tol_i = 1.0e-12 * fmax(1.0, fabs(re));
+      if (fabs(im) <= tol_i) im = 0.0;
+      re = re / lambda;
+      im = im / lambda;
+      if (fabs(im) == 0.0 && re > 0.0 && re < best) best = re;
+    }
   }
   return best;
 }
 
-template <int DEG>
-GB_HD double solve_monic_min_positive(const double *q /* q[0]=const .. q[DEG-1] */, double lambda, int &iters)
+// monic real polynomial x^deg + q[deg-1] x^(deg-1) + ... + q[0]; one shared, non-inlined instance
+static GB_HD_NOINLINE double solve_monic_min_positive(int deg, double q0, double q1, double q2, double q3, double lambda,
+                                                      int &iters)
 {
-  cd poly[DEG + 1], roots[DEG];
-#pragma unroll
-  for (int i = 0; i < DEG; i++) poly[i] = mk(q[i], 0.0);
-  poly[DEG] = mk(1.0, 0.0);
-  cmplx_roots_gen<DEG>(roots, poly, iters);
-  return min_positive_real_root<DEG>(roots, lambda);
+  cd poly[5], roots[4];
+  poly[0] = mk(q0, 0.0);
+  poly[1] = mk(deg == 1 ? 1.0 : q1, 0.0);
+  poly[2] = mk(deg == 2 ? 1.0 : q2, 0.0);
+  poly[3] = mk(deg == 3 ? 1.0 : q3, 0.0);
+  poly[4] = mk(1.0, 0.0);
+  sg_roots(deg, poly, roots, iters);
+  return min_positive_real_root(deg, roots, lambda);
 }
 
 // ---- SRC/pusher_tetra_poly.f90:1767-2021 -----------------------------------------------------------
@@ -439,16 +385,65 @@ GB_HD double quadratic_solver1(double acoef, double bcoef, double ccoef)
   return dtau;
 }
 
-static GB_HD_NOINLINE double quadratic_solver2(double a, double b, double c, int &iters)
+// Quadratic_Solver1 rewritten as "choose numerator and denominator, divide once": every branch of the
+// reference's sign-case tree (:1827-1891) ends in exactly one division, so the tree only has to SELECT the
+// operands.  sqrt and the division are then issued unconditionally by all lanes (no divergence, and the four
+// faces of a tetrahedron give four independent chains).  Returns false when no root exists (dtau = huge).
+GB_HD bool quadratic_solver1_numden(double a, double b, double c, double &num, double &den)
+{
+  const double eps = 1.e-10;
+  const double discr = b * b - 2.0 * a * c;
+  const double sq = sqrt(discr);           // NaN when discr < 0: never selected in that case
+  const double dummy = (-b + sq);
+  const bool big = fabs(dummy) > eps;
+  bool has = false;
+  num = 0.0;
+  den = 1.0;
+  if (c > 0.0) {
+    if (a > 0.0) {
+      if (b < 0.0) {
+        if (discr > 0.0) {
+          has = true;
+          num = big ? 2.0 * c : (-sq - b);
+          den = big ? dummy : a;
+        } else if (discr == 0.0) {
+          has = true; num = -b; den = a;
+        }
+      }
+    } else if (a < 0.0) {
+      has = true;
+      num = big ? 2.0 * c : (-sq - b);
+      den = big ? dummy : a;
+    } else {
+      if (b < 0.0) { has = true; num = -c; den = b; }
+    }
+  } else if (c < 0.0) {
+    if (a < 0.0) {
+      if (b > 0.0) {
+        if (discr > 0.0) { has = true; num = sq - b; den = a; }
+        else if (discr == 0.0) { has = true; num = -b; den = a; }
+      }
+    } else if (a > 0.0) {
+      has = true; num = sq - b; den = a;
+    } else {
+      if (b > 0.0) { has = true; num = -c; den = b; }
+    }
+  } else {
+    if (((a > 0.0) && (b < 0.0)) || ((a < 0.0) && (b > 0.0))) { has = true; num = -2.0 * b; den = a; }
+  }
+  return has;
+}
+
+GB_HD double quadratic_solver2(double a, double b, double c, int &iters)
 {
   double lambda = b / c;
   double q[2];
   q[0] = 2.0 * (b * b) / (a * c);
   q[1] = q[0];
-  return solve_monic_min_positive<2>(q, lambda, iters);
+  return solve_monic_min_positive(2, q[0], q[1], 0.0, 0.0, lambda, iters);
 }
 
-static GB_HD_NOINLINE double cubic_solver(double a, double b, double c, double d, int &iters)
+GB_HD double cubic_solver(double a, double b, double c, double d, int &iters)
 {
   double lambda = b / (2.0 * c);
   double l2 = lambda * lambda;
@@ -456,10 +451,10 @@ static GB_HD_NOINLINE double cubic_solver(double a, double b, double c, double d
   q[2] = 3.0 * lambda * b / a;
   q[1] = 6.0 * c * l2 / a;
   q[0] = 6.0 * d * (l2 * lambda) / a;
-  return solve_monic_min_positive<3>(q, lambda, iters);
+  return solve_monic_min_positive(3, q[0], q[1], q[2], 0.0, lambda, iters);
 }
 
-static GB_HD_NOINLINE double quartic_solver(int i_scaling, double a, double b, double c, double d, double e, int &iters)
+GB_HD double quartic_solver(int i_scaling, double a, double b, double c, double d, double e, int &iters)
 {
   double lambda;
   switch (i_scaling) {
@@ -477,7 +472,7 @@ static GB_HD_NOINLINE double quartic_solver(int i_scaling, double a, double b, d
   q[2] = 12.0 * c * l2 / a;
   q[1] = 24.0 * d * (l2 * lambda) / a;
   q[0] = 24.0 * e * (l2 * l2) / a;
-  return solve_monic_min_positive<4>(q, lambda, iters);
+  return solve_monic_min_positive(4, q[0], q[1], q[2], q[3], lambda, iters);
 }
 
 } // namespace gb

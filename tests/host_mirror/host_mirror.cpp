@@ -137,9 +137,7 @@ void hm_cmplx_roots_gen(int degree, const double *poly_re_im, double *roots_re_i
   cd poly[5], roots[4];
   int iters = 0;
   for (int i = 0; i <= degree; i++) poly[i] = mk(poly_re_im[2 * i], poly_re_im[2 * i + 1]);
-  if (degree == 2) cmplx_roots_gen<2>(roots, poly, iters);
-  else if (degree == 3) cmplx_roots_gen<3>(roots, poly, iters);
-  else cmplx_roots_gen<4>(roots, poly, iters);
+  sg_roots(degree, poly, roots, iters);
   for (int i = 0; i < degree; i++) { roots_re_im[2 * i] = roots[i].re; roots_re_im[2 * i + 1] = roots[i].im; }
 }
 double hm_quadratic_solver1(double a, double b, double c) { return quadratic_solver1(a, b, c); }

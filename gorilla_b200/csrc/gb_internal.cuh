@@ -54,10 +54,10 @@ struct Batch {
 #define GB_MINB_K2 4
 #endif
 #ifndef GB_MINB_K3
-#define GB_MINB_K3 2
+#define GB_MINB_K3 4
 #endif
 #ifndef GB_MINB_K4
-#define GB_MINB_K4 2
+#define GB_MINB_K4 4
 #endif
 constexpr int gb_min_blocks(int K) { return K == 1 ? GB_MINB_K1 : K == 2 ? GB_MINB_K2 : K == 3 ? GB_MINB_K3 : GB_MINB_K4; }
 

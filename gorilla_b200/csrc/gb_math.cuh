@@ -43,46 +43,51 @@ GB_HD bool cis0(cd a) { return a.re == 0.0 && a.im == 0.0; }
 // real(conjg(p)*p)
 GB_HD double cabs2(cd p) { return p.re * p.re - (-p.im) * p.im; }
 
-// gcc expand_complex_div_wide (flag_complex_method == 1)
-GB_HD cd cdiv(cd a, cd b)
+// The three routines below are the expensive ones (FP64 divisions and square roots).  They are written
+// branch free -- both variants of every data-dependent case are formed with cheap multiplies and the operands
+// of the single expensive division / square root are SELECTED -- so that lanes whose data fall into different
+// cases still execute the expensive instructions together, and they are compiled as out-of-line functions so
+// that the root-solver loop stays small enough for the instruction cache.
+#if defined(__CUDACC__)
+#define GB_MATH_FN static __host__ __device__ __noinline__
+#else
+#define GB_MATH_FN static inline
+#endif
+
+// gcc expand_complex_div_wide (flag_complex_method == 1): branch on |br| < |bi|
+//   true : ratio = br/bi; div = br*ratio + bi; tr = ar*ratio + ai; ti = ai*ratio - ar
+//   false: ratio = bi/br; div = bi*ratio + br; tr = ai*ratio + ar; ti = ai - ar*ratio
+GB_MATH_FN cd cdiv(cd a, cd b)
 {
+  const bool sw = fabs(b.re) < fabs(b.im);
+  const double num = sw ? b.re : b.im, den = sw ? b.im : b.re;
+  const double ratio = num / den;
+  const double div = (num * ratio) + den;
+  const double u = sw ? a.re : a.im, v = sw ? a.im : a.re;
+  const double tr = (u * ratio) + v;
+  const double w = sw ? a.im : a.re;  // the factor multiplied by ratio in ti
+  const double pw = w * ratio;
+  const double ti = sw ? (pw - a.re) : (a.im - pw);
   cd q;
-  if (fabs(b.re) < fabs(b.im)) {
-    double ratio = b.re / b.im;
-    double div = (b.re * ratio) + b.im;
-    double tr = (a.re * ratio) + a.im;
-    double ti = (a.im * ratio) - a.re;
-    q.re = tr / div;
-    q.im = ti / div;
-  } else {
-    double ratio = b.im / b.re;
-    double div = (b.im * ratio) + b.re;
-    double tr = (a.im * ratio) + a.re;
-    double ti = a.im - (a.re * ratio);
-    q.re = tr / div;
-    q.im = ti / div;
-  }
+  q.re = tr / div;
+  q.im = ti / div;
   return q;
 }
 
-// glibc 2.35+ __hypot, generic (non-FMA) kernel
+// glibc 2.35+ __hypot, generic (non-FMA) kernel:  h = sqrt(ax^2+ay^2) followed by one correction step
 GB_HD double hypot_kernel(double ax, double ay)
 {
-  double t1, t2;
   double h = sqrt(ax * ax + ay * ay);
-  if (h <= 2.0 * ay) {
-    double delta = h - ay;
-    t1 = ax * (2.0 * delta - ax);
-    t2 = (delta - 2.0 * (ax - ay)) * delta;
-  } else {
-    double delta = h - ax;
-    t1 = 2.0 * delta * (ax - 2.0 * ay);
-    t2 = (4.0 * delta - ay) * ay + delta * delta;
-  }
+  const bool near = h <= 2.0 * ay;
+  const double delta = h - (near ? ay : ax);
+  // near: t1 = ax*(2 delta - ax),      t2 = (delta - 2(ax-ay))*delta
+  // far : t1 = 2 delta*(ax - 2 ay),    t2 = (4 delta - ay)*ay + delta*delta
+  const double t1 = near ? ax * (2.0 * delta - ax) : 2.0 * delta * (ax - 2.0 * ay);
+  const double t2 = near ? (delta - 2.0 * (ax - ay)) * delta : (4.0 * delta - ay) * ay + delta * delta;
   h -= (t1 + t2) / (2.0 * h);
   return h;
 }
-GB_HD double hypot_glibc(double x, double y)
+GB_MATH_FN double hypot_glibc(double x, double y)
 {
   const double SCALE = 0x1p-600, LARGE_VAL = 0x1p+511, TINY_VAL = 0x1p-459, HEPS = 0x1p-54;
   if (!(fabs(x) <= DBL_MAX) || !(fabs(y) <= DBL_MAX)) {
@@ -109,40 +114,35 @@ GB_HD double cabs_glibc(cd z) { return hypot_glibc(z.re, z.im); }
 
 // glibc __csqrt for finite arguments with |re|,|im| in [2*DBL_MIN, DBL_MAX/4] (the scaling branches
 // for the extreme ranges are not restated: the reference build traps on overflow long before).
-GB_HD cd csqrt_glibc(cd x)
+GB_MATH_FN cd csqrt_glibc(cd x)
 {
-  cd res;
   if (!(fabs(x.re) <= DBL_MAX) || !(fabs(x.im) <= DBL_MAX)) {
     double n = x.re - x.re + (x.im - x.im); // NaN
     return mk(n, n);
   }
-  if (x.im == 0.0) {
-    if (x.re < 0.0) {
-      res.re = 0.0;
-      res.im = copysign(sqrt(-x.re), x.im);
-    } else {
-      res.re = fabs(sqrt(x.re));
-      res.im = copysign(0.0, x.im);
-    }
-  } else if (x.re == 0.0) {
-    double r;
-    if (fabs(x.im) >= 2.0 * DBL_MIN)
-      r = sqrt(0.5 * fabs(x.im));
-    else
-      r = 0.5 * sqrt(2.0 * fabs(x.im));
+  // glibc distinguishes: Im == 0 (result on an axis), Re == 0, and the general case
+  //   r = sqrt(0.5*(|z| + Re)), s = 0.5*Im/r   (Re > 0)      s = sqrt(0.5*(|z| - Re)), r = |0.5*Im/s|   (Re < 0)
+  // All cases take ONE square root of a selected argument; |z| - Re == |z| + |Re| bit for bit when Re < 0.
+  const bool im0 = x.im == 0.0, re0 = x.re == 0.0;
+  const bool general = !im0 && !re0;
+  const double are = fabs(x.re), aim = fabs(x.im);
+  const bool tiny = aim < 2.0 * DBL_MIN;
+  double d = 0.0;
+  if (general) d = hypot_glibc(x.re, x.im);
+  const double arg = im0 ? are : (re0 ? (tiny ? 2.0 * aim : 0.5 * aim) : 0.5 * (d + are));
+  const double t = sqrt(arg);
+  cd res;
+  if (im0) {
+    res.re = (x.re < 0.0) ? 0.0 : fabs(t);
+    res.im = (x.re < 0.0) ? copysign(t, x.im) : copysign(0.0, x.im);
+  } else if (re0) {
+    const double r = tiny ? 0.5 * t : t;
     res.re = r;
     res.im = copysign(r, x.im);
   } else {
-    double d = hypot_glibc(x.re, x.im), r, s;
-    if (x.re > 0.0) {
-      r = sqrt(0.5 * (d + x.re));
-      s = 0.5 * (x.im / r);
-    } else {
-      s = sqrt(0.5 * (d - x.re));
-      r = fabs(0.5 * (x.im / s));
-    }
-    res.re = r;
-    res.im = copysign(s, x.im);
+    const double u = 0.5 * (x.im / t);
+    res.re = (x.re > 0.0) ? t : fabs(u);
+    res.im = copysign((x.re > 0.0) ? u : t, x.im);
   }
   return res;
 }

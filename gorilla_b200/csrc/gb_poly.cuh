@@ -138,48 +138,49 @@ struct PolyPusher {
     }
   }
 
-  // ---- face-distance Taylor coefficients (:1532-1584); cm[n][k] = coef_mat(n+1,k+1)
+  // ---- ODE coefficients and the Taylor vectors A^k z, A^(k-1) b up to order ORD (:1503-1578, face independent)
   template <int ORD>
-  GB_HD void coeff(unsigned mask, const double *z, double cm[4][5])
+  GB_HD void prepare(const double *z)
   {
     build_ode();
-#pragma unroll
-    for (int n = 0; n < 4; n++)
-      if (mask & (1u << n)) cm[n][0] = dot3(r.an[n], z);
-    if (mask & 1u) cm[0][0] = cm[0][0] + r.dist_ref; // coef - dist1, dist1 = -dist_ref
-    if (ORD >= 1) {
-      bm_vec(Az, A, z);
-#pragma unroll
-      for (int n = 0; n < 4; n++)
-        if (mask & (1u << n)) cm[n][1] = dot3(r.an[n], Az) + dot3(r.an[n], b);
-    }
+    if (ORD >= 1) bm_vec(Az, A, z);
     if (ORD >= 2) {
       BlockMat A2;
       bm_mul(A2, A, A);
       bm_vec(A2z, A2, z);
       bm_vec(Ab, A, b);
-#pragma unroll
-      for (int n = 0; n < 4; n++)
-        if (mask & (1u << n)) cm[n][2] = dot3(r.an[n], A2z) + dot3(r.an[n], Ab);
       if (ORD >= 3) {
         BlockMat A3;
         bm_mul(A3, A, A2);
         bm_vec(A3z, A3, z);
         bm_vec(A2b, A2, b);
-#pragma unroll
-        for (int n = 0; n < 4; n++)
-          if (mask & (1u << n)) cm[n][3] = dot3(r.an[n], A3z) + dot3(r.an[n], A2b);
         if (ORD >= 4) {
           BlockMat A4;
           bm_mul(A4, A, A3);
           bm_vec(A4z, A4, z);
           bm_vec(A3b, A3, b);
-#pragma unroll
-          for (int n = 0; n < 4; n++)
-            if (mask & (1u << n)) cm[n][4] = dot3(r.an[n], A4z) + dot3(r.an[n], A3b);
         }
       }
     }
+  }
+  // ---- face-distance Taylor coefficients of one face with normal n (:1536-1584); c[k] = coef_mat(face,k+1)
+  template <int ORD>
+  GB_HD void face_coeffs(const double *n, bool is_face1, const double *z, double *c) const
+  {
+    c[0] = dot3(n, z);
+    if (is_face1) c[0] = c[0] + r.dist_ref;  // coef - dist1, dist1 = -dist_ref
+    if (ORD >= 1) c[1] = dot3(n, Az) + dot3(n, b);
+    if (ORD >= 2) c[2] = dot3(n, A2z) + dot3(n, Ab);
+    if (ORD >= 3) c[3] = dot3(n, A3z) + dot3(n, A2b);
+    if (ORD >= 4) c[4] = dot3(n, A4z) + dot3(n, A3b);
+  }
+  template <int ORD>
+  GB_HD void coeff(unsigned mask, const double *z, double cm[4][5])
+  {
+    prepare<ORD>(z);
+#pragma unroll
+    for (int f = 0; f < 4; f++)
+      if (mask & (1u << f)) face_coeffs<ORD>(r.an[f], f == 0, z, cm[f]);
   }
 
   // ---- :2087-2113 (A, b unchanged; matrix powers re-formed, which reproduces the stored ones)
@@ -286,37 +287,66 @@ struct PolyPusher {
     return linear ? (la != 0.0) : qhas;
   }
 
-  // ---- :1258-1482.  dtau/iface untouched when no valid root exists.
+  // ---- :1258-1482.  dtau/iface untouched when no valid root exists.  All four faces.
   template <int ORD>
   GB_HD bool analytic_approx(unsigned mask, int i_scaling, const double *z, int &iface_inout, double &dtau)
   {
     double cm[4][5];
     coeff<ORD>(mask, z, cm);
+    return pick_exit<ORD>(cm, mask, i_scaling, iface_inout, dtau);
+  }
+  template <int ORD>
+  GB_HD bool pick_exit(double cm[4][5], unsigned mask, int i_scaling, int &iface_inout, double &dtau)
+  {
     const int iface = iface_inout;
     double best = GB_HUGE;
     int ibest = 0;
+    if (ORD == 2 && i_scaling == 0) {
+      // closed-form solver: branch free, the four faces are four independent instruction streams
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      if (!(mask & (1u << i))) continue;
-      double d;
-      bool ok;
-      if (ORD == 2 && i_scaling == 0) {
+      for (int i = 0; i < 4; i++) {
+        if (!(mask & (1u << i))) continue;
         double num, den;
-        ok = face_numden_ord2(cm[i], (i + 1) == iface, num, den);
-        d = num / den;
-      } else {
-        d = face_root<ORD>(cm[i], (i + 1) == iface, i_scaling);
-        ok = true;
+        const bool ok = face_numden_ord2(cm[i], (i + 1) == iface, num, den);
+        const double d = num / den;
+        if (ok && (d < GB_HUGE) && (d > 0.0) && (ibest == 0 || d < best)) {
+          best = d;
+          ibest = i + 1;
+        }
       }
-      // valid: 0 < d < huge ; minloc keeps the lowest face index on ties
-      if (ok && (d < GB_HUGE) && (d > 0.0) && (ibest == 0 || d < best)) {
-        best = d;
-        ibest = i + 1;
+    } else {
+      // iterative solvers: ONE call site, executed face after face by the whole warp
+#pragma unroll 1
+      for (int i = 0; i < 4; i++) {
+        if (!(mask & (1u << i))) continue;
+        const double d = face_root<ORD>(cm[i], (i + 1) == iface, i_scaling);
+        // valid: 0 < d < huge ; minloc keeps the lowest face index on ties
+        if ((d < GB_HUGE) && (d > 0.0) && (ibest == 0 || d < best)) {
+          best = d;
+          ibest = i + 1;
+        }
       }
     }
     if (ibest == 0) return false;
     iface_inout = ibest;
     dtau = best;
+    return true;
+  }
+  // Same for a single enabled face (boole_faces with only the guessed face set, :281-298).  The face is lane
+  // data: its normal is selected, so that all lanes of a warp run ONE solve together instead of one per face.
+  // `prepared`: prepare<ORD>(z) has already been called for this z.
+  template <int ORD>
+  GB_HD bool analytic_approx_single(int face, int i_scaling, const double *z, int &iface_inout, double &dtau,
+                                    bool prepared)
+  {
+    if (!prepared) prepare<ORD>(z);
+    double n[3], c[5];
+    face_normal(face, n);
+    face_coeffs<ORD>(n, face == 1, z, c);
+    const double d = face_root<ORD>(c, face == iface_inout, i_scaling);
+    if (!((d < GB_HUGE) && (d > 0.0))) return false;
+    iface_inout = face;
+    dtau = d;
     return true;
   }
 
@@ -639,12 +669,26 @@ struct PolyPusher {
     double z[4] = {z_init[0], z_init[1], z_init[2], z_init[3]};
     double tau = 0.0;
     int iface_new = iface_init;
-    if (!analytic_approx<2>(0xFu, 0, z, iface_new, tau)) return false;
+    // b, A and all Taylor vectors up to order K once; the order-2 guess reads the first three coefficients
+    prepare<(K > 2 ? K : 2)>(z);
+    {
+      double cm[4][5];
+#pragma unroll
+      for (int f = 0; f < 4; f++) face_coeffs<2>(r.an[f], f == 0, z, cm[f]);
+      if (!pick_exit<2>(cm, 0xFu, 0, iface_new, tau)) return false;
+    }
     const double tau_max = tau * GB_EPS_TAU;
     if (K > 2) {
-      unsigned mask = mp->boole_guess ? (1u << (iface_new - 1)) : 0xFu;
+      const int guess = iface_new;
       iface_new = iface_init;
-      if (!analytic_approx<K>(mask, 0, z, iface_new, tau)) return false;
+      if (mp->boole_guess) {
+        if (!analytic_approx_single<K>(guess, 0, z, iface_new, tau, true)) return false;
+      } else {
+        double cm[4][5];
+#pragma unroll
+        for (int f = 0; f < 4; f++) face_coeffs<K>(r.an[f], f == 0, z, cm[f]);
+        if (!pick_exit<K>(cm, 0xFu, 0, iface_new, tau)) return false;
+      }
     }
     integrate<K>(z, tau);
     if (!exit_point_ok(z, iface_new)) return false;
@@ -662,13 +706,13 @@ struct PolyPusher {
     double z[4] = {z_init[0], z_init[1], z_init[2], z_init[3]};
     double tau = 0.0;
     int iface_new = iface_init;
-    unsigned mask = 0xFu;
-    bool approx = analytic_approx<2>(mask, 0, z, iface_new, tau);
+    bool approx = analytic_approx<2>(0xFu, 0, z, iface_new, tau);
     const double tau_max = tau * GB_EPS_TAU;
-    if (mp->boole_guess && approx && (K > 2)) mask = 1u << (iface_new - 1);
     if (K > 2) {
+      const int guess = iface_new;
       iface_new = iface_init;
-      approx = analytic_approx<K>(mask, 0, z, iface_new, tau);
+      if (mp->boole_guess && approx) approx = analytic_approx_single<K>(guess, 0, z, iface_new, tau, false);
+      else approx = analytic_approx<K>(0xFu, 0, z, iface_new, tau);
     }
     bool face_correct = approx;
     if (face_correct) {

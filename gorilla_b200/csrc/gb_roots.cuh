@@ -165,40 +165,45 @@ GB_HD void sg_roots(int deg, const cd *poly_in, cd *roots_out, int &iters)
       }
     }
     if (ret == 0) {
+      // The step dx.  All modes divide p by p'; Laguerre and SG also need F/2 = (p/p')(p''/2p'); only
+      // Laguerre takes the complex square root.  The common parts are issued once for the whole warp.
       cd dx;
       const bool dp0 = cis0(dp);
-      if (lag || mode0 == 2) {
-        cd denom = zero, fac_netwon = zero;
-        if (!dp0) {
-          fac_netwon = cdiv(p, dp);
+      const bool laguerre_step = lag || mode0 == 2;
+      cd fac_netwon = zero, F_half = zero;
+      if (!dp0) {
+        fac_netwon = cdiv(p, dp);
+        if (laguerre_step || mode0 == 1) {
           const cd fac_extra = cdiv(d2p_half, dp);
-          const cd F_half = cmul(fac_netwon, fac_extra);
+          F_half = cmul(fac_netwon, fac_extra);
           if (!lag) {
             const double abs2_F_half = cabs2(F_half);
-            if (abs2_F_half <= 0.0625) mode = (abs2_F_half <= 0.000625) ? 0 : 1;
+            if (mode0 == 2) {
+              if (abs2_F_half <= 0.0625) mode = (abs2_F_half <= 0.000625) ? 0 : 1;
+            } else {
+              if (abs2_F_half <= 0.000625) mode = 0;
+            }
           }
+        }
+      }
+      bool jump = dp0;  // random jump of length |root|+1 (denominator vanishes)
+      if (laguerre_step) {
+        cd denom = zero;
+        if (!dp0) {
           const SgLaguerreConsts k = sg_consts(cdeg);
           const cd denom_sqrt = csqrt_glibc(csub(c_one, rmul(k.two_n_div_n_1, F_half)));
           const cd c_one_nth = mk(k.one_nth, 0.0);
           if (denom_sqrt.re >= 0.0) denom = cadd(c_one_nth, rmul(k.n_1_nth, denom_sqrt));
           else denom = csub(c_one_nth, rmul(k.n_1_nth, denom_sqrt));
         }
-        if (cis0(denom)) dx = rmul(cabs_glibc(root) + 1.0, frac_jump_phase(i % 10));
-        else dx = cdiv(fac_netwon, denom);
+        jump = cis0(denom);
+        if (!jump) dx = cdiv(fac_netwon, denom);
       } else if (mode0 == 1) {
-        if (dp0) {
-          dx = rmul(cabs_glibc(root) + 1.0, frac_jump_phase(i % 10));
-        } else {
-          const cd fac_netwon = cdiv(p, dp);
-          const cd fac_extra = cdiv(d2p_half, dp);
-          const cd F_half = cmul(fac_netwon, fac_extra);
-          if (cabs2(F_half) <= 0.000625) mode = 0;
-          dx = cmul(fac_netwon, cadd(c_one, F_half));
-        }
+        if (!jump) dx = cmul(fac_netwon, cadd(c_one, F_half));
       } else {
-        if (dp0) dx = rmul(cabs_glibc(root) + 1.0, frac_jump_phase(i % 10));
-        else dx = cdiv(p, dp);
+        if (!jump) dx = fac_netwon;
       }
+      if (jump) dx = rmul(cabs_glibc(root) + 1.0, frac_jump_phase(i % 10));
       cd newroot = csub(root, dx);
       if (ceq(newroot, root)) {
         ret = 1;

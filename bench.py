@@ -30,6 +30,9 @@ sys.path.insert(0, str(ROOT / "tests"))
 METRIC = "particle_tetra_crossings_per_second"
 UNIT = "crossings/s"
 BYTES_PER_CROSSING = {False: 344.0, True: 488.0}  # hot record (+8 B topology), without/with Phi part
+# FP64 thread-instructions (DADD+DMUL+DFMA) per crossing of the strict build, from the ncu source pages of
+# round 1 (profiles/r01_*): poly order -> count.  Order 3 is interpolated (not yet profiled).
+FP64_INST_PER_CROSSING = {1: 480.0, 2: 484.0, 3: 1900.0, 4: 3530.0}
 
 
 def parse_args():
@@ -164,6 +167,7 @@ def main():
     import torch
     import torch.distributed as dist
     from gorilla_b200 import Gorilla, build_mesh, launch_count
+    from gorilla_b200.api import fp64_peak
     import workloads
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -294,10 +298,26 @@ def main():
         per_rank_pushes = pushes / max(1, args.steps)
         launch_ms = kernel_ms / max(1, args.steps)
         achieved = bytes_per_crossing * per_rank_pushes / (launch_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "kernel": f"orbit_kernel<{settings.poly_order},{'true' if has_phi else 'false'}>",
-                    "algorithmic_bytes_per_crossing": bytes_per_crossing, "launch_ms": launch_ms,
-                    "kernel_share_of_step": kernel_ms / elapsed_ms, "peak_source": peak_src}
+        # the slower of the two per-push limits decides the bound (north_star): HBM gather vs FP64 issue
+        dfma_peak, muladd_peak = fp64_peak()
+        fp64_per = FP64_INST_PER_CROSSING[settings.poly_order]
+        t_hbm, t_fp64 = bytes_per_crossing / (hbm_peak * 1e9), fp64_per / muladd_peak
+        fp64_ach = fp64_per * per_rank_pushes / (launch_ms * 1e-3)
+        fp64 = {"achieved": fp64_ach / 1e12, "peak": muladd_peak / 1e12, "unit": "Tinst/s (thread-level DMUL/DADD)",
+                "frac": fp64_ach / muladd_peak, "inst_per_crossing": fp64_per, "dfma_peak": dfma_peak / 1e12,
+                "peak_source": "measured in this run (gorilla_b200_fp64_peak)"}
+        kern = f"orbit_kernel<{settings.poly_order},{'true' if has_phi else 'false'}>"
+        if t_hbm >= t_fp64:
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved / hbm_peak, "traffic": None, "kernel": kern,
+                        "algorithmic_bytes_per_crossing": bytes_per_crossing, "launch_ms": launch_ms,
+                        "kernel_share_of_step": kernel_ms / elapsed_ms, "peak_source": peak_src, "fp64": fp64}
+        else:
+            roofline = {"bound": "fp64", "achieved": fp64["achieved"], "peak": fp64["peak"], "unit": fp64["unit"],
+                        "frac": fp64["frac"], "traffic": None, "kernel": kern, "launch_ms": launch_ms,
+                        "kernel_share_of_step": kernel_ms / elapsed_ms, "peak_source": fp64["peak_source"],
+                        "hbm": {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                                "algorithmic_bytes_per_crossing": bytes_per_crossing}}
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

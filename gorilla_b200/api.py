@@ -84,6 +84,7 @@ EXPORTED_SYMBOLS = (
     "gorilla_b200_orbit_timestep", "gorilla_b200_orbit_timestep_dev", "gorilla_b200_orbit_timestep_trace",
     "gorilla_b200_find_tetra", "gorilla_b200_invariants", "gorilla_b200_invariants_dev",
     "gorilla_b200_get_counters", "gorilla_b200_sort_permutation_dev", "gorilla_b200_set_launch_config",
+    "gorilla_b200_fp64_peak",
     "gorilla_mesh_build", "gorilla_mesh_get_desc", "gorilla_mesh_get_vertices", "gorilla_mesh_free",
 )
 
@@ -113,6 +114,7 @@ def load_library():
     lib.gorilla_b200_sort_permutation_dev.argtypes = [vp, i64, vp, vp, vp]
     lib.gorilla_b200_set_launch_config.argtypes = [vp, i32, i32]
     lib.gorilla_b200_debug_force_full.argtypes = [vp, i32]
+    lib.gorilla_b200_fp64_peak.argtypes = [C.POINTER(dbl), C.POINTER(dbl)]
     lib.gorilla_mesh_build.argtypes = [C.POINTER(_GridSettings), C.POINTER(_Settings), C.POINTER(vp)]
     lib.gorilla_mesh_get_desc.argtypes = [vp, C.POINTER(_MeshDesc)]
     lib.gorilla_mesh_get_vertices.argtypes = [vp, C.POINTER(i64), C.POINTER(C.POINTER(dbl)), C.POINTER(C.POINTER(dbl))]
@@ -130,6 +132,13 @@ def _check(rc: int):
 def launch_count() -> int:
     """Kernels launched by the library in this process (bench.py's gpu_launches)."""
     return int(load_library().gorilla_b200_launch_count())
+
+
+def fp64_peak() -> tuple[float, float]:
+    """(DFMA, DMUL+DADD) thread-instructions per second of the current device, measured."""
+    a, b = C.c_double(), C.c_double()
+    _check(load_library().gorilla_b200_fp64_peak(C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def _c_settings(s: GorillaSettings) -> _Settings:

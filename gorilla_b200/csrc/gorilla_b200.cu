@@ -60,6 +60,65 @@ __global__ void __launch_bounds__(128) find_kernel(const __grid_constant__ MeshD
 }
 
 // ----------------------------------------------------------------------------------------------------
+// FP64 issue-rate micro-benchmark (roofline denominator for the FP64-bound orders; MEASURED_PEAKS.json has
+// no FP64 figure).  8 independent dependency chains per thread; MODE 0: DFMA, MODE 1: DMUL + DADD pairs
+// (what the strict --fmad=false build issues).
+template <int MODE>
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double seed)
+{
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = seed + 1e-3 * (threadIdx.x + k);
+  const double m = 1.0000001, c = 1e-9;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (MODE == 0) a[k] = __fma_rn(a[k], m, c);
+      else a[k] = __dadd_rn(__dmul_rn(a[k], m), c);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += a[k];
+  if (s == 123.456) out[0] = s;  // keep the chains alive
+}
+
+extern "C" int gorilla_b200_fp64_peak(double *dfma_inst_per_s, double *dmul_dadd_inst_per_s)
+{
+  int dev = 0, sms = 0;
+  GB_CUDA(cudaGetDevice(&dev));
+  GB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double *d_out = nullptr;
+  GB_CUDA(cudaMalloc((void **)&d_out, sizeof(double)));
+  cudaEvent_t e0, e1;
+  GB_CUDA(cudaEventCreate(&e0));
+  GB_CUDA(cudaEventCreate(&e1));
+  const int iters = 1 << 15, grid = sms * 8, block = 256;
+  double best[2] = {0.0, 0.0};
+  for (int mode = 0; mode < 2; mode++) {
+    for (int rep = 0; rep < 4; rep++) {
+      GB_CUDA(cudaEventRecord(e0, 0));
+      if (mode == 0) fp64_peak_kernel<0><<<grid, block>>>(d_out, iters, 1.0 + rep);
+      else fp64_peak_kernel<1><<<grid, block>>>(d_out, iters, 1.0 + rep);
+      g_launch_count++;
+      GB_CUDA(cudaEventRecord(e1, 0));
+      GB_CUDA(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      GB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      const double inst = (double)grid * block * (double)iters * 8.0 * (mode == 0 ? 1.0 : 2.0);
+      const double rate = inst / (ms * 1e-3);
+      if (rep > 0 && rate > best[mode]) best[mode] = rate;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  if (dfma_inst_per_s) *dfma_inst_per_s = best[0];
+  if (dmul_dadd_inst_per_s) *dmul_dadd_inst_per_s = best[1];
+  return GORILLA_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
 __global__ void invariants_kernel(const __grid_constant__ MeshDev m, int64_t n, const double *x, const double *vpar,
                                   const double *vperp, const int32_t *ind_tetr, double *energy, double *p_phi,
                                   double *perpinv_out)

@@ -1,0 +1,185 @@
+!> orbit_timestep_gorilla_b200_mod -- Fortran side of the drop-in boundary (ISO_C_BINDING).
+!!
+!! Batched driver for GORILLA's particle-parallel hot path.  It keeps `orbit_timestep_gorilla` as the entry
+!! point (same argument list as SRC/orbit_timestep_gorilla.f90:19) and adds `orbit_timestep_gorilla_batch`;
+!! both forward to the C ABI of libgorilla_b200.so (include/gorilla_b200.h), whose kernels run on the GPU.
+!!
+!! Usage inside GORILLA (after the usual host initialisation, which stays unchanged):
+!!     call load_tetra_grid_inp(); call load_gorilla_inp(); call initialize_gorilla()
+!!     call initialize_gorilla_b200()                       ! uploads tetra_physics / tetra_grid once
+!!     call orbit_timestep_gorilla_batch(n, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface, ierr)
+!!
+!! NOTE: this image has no Fortran compiler (SURVEY.md F2), so this module is shipped as source and is not
+!! part of the automated build; the C ABI it binds is exercised by the Python ctypes binding in the tests.
+module orbit_timestep_gorilla_b200_mod
+  use, intrinsic :: iso_c_binding
+  implicit none
+  private
+  public :: initialize_gorilla_b200, finalize_gorilla_b200, orbit_timestep_gorilla, orbit_timestep_gorilla_batch, &
+            find_tetra_batch, gorilla_b200_counters_t, get_counters_b200
+
+  !> struct gorilla_settings (include/gorilla_b200.h)
+  type, bind(C) :: gorilla_settings_t
+    real(c_double)  :: eps_Phi
+    integer(c_int32_t) :: coord_system, ispecies, boole_periodic_relocation, ipusher, boole_pusher_ode45, &
+                          boole_dt_dtau, boole_newton_precalc, poly_order, i_precomp, boole_guess, &
+                          i_time_tracing_option, handover_processing_kind, boole_adaptive_time_steps, &
+                          boole_strong_electric_field, boole_grid_for_find_tetra
+    integer(c_int32_t) :: reserved(5)
+  end type
+  !> struct gorilla_mesh_desc
+  type, bind(C) :: gorilla_mesh_desc_t
+    integer(c_int64_t) :: ntetr
+    type(c_ptr)        :: tetra_physics, tetra_grid
+    real(c_double)     :: cm_over_e, particle_mass, particle_charge
+    integer(c_int32_t) :: sign_sqg, coord_system, n_field_periods, grid_kind
+    integer(c_int32_t) :: grid_size(3), pad0
+    real(c_double)     :: Rmin, Rmax, Zmin, Zmax, sfc_s_min
+  end type
+  !> struct gorilla_counters
+  type, bind(C) :: gorilla_b200_counters_t
+    integer(c_int64_t) :: n_particles, n_pushes, n_lost, n_finished, n_fallback(4), n_domain_errors
+    real(c_double)     :: kernel_ms, find_ms
+  end type
+
+  interface
+    integer(c_int) function gorilla_b200_init(mesh, settings, handle) bind(C, name='gorilla_b200_init')
+      import :: c_int, c_ptr, gorilla_mesh_desc_t, gorilla_settings_t
+      type(gorilla_mesh_desc_t), intent(in) :: mesh
+      type(gorilla_settings_t), intent(in)  :: settings
+      type(c_ptr), intent(out)              :: handle
+    end function
+    subroutine gorilla_b200_free(handle) bind(C, name='gorilla_b200_free')
+      import :: c_ptr
+      type(c_ptr), value :: handle
+    end subroutine
+    integer(c_int) function gorilla_b200_orbit_timestep(handle, n, x, vpar, vperp, t_step, boole_initialized, &
+                                                        ind_tetr, iface, t_remain_out, n_pushes) &
+                                                        bind(C, name='gorilla_b200_orbit_timestep')
+      import :: c_int, c_ptr, c_int64_t, c_double, c_int32_t
+      type(c_ptr), value        :: handle
+      integer(c_int64_t), value :: n
+      real(c_double)            :: x(3,*), vpar(*), vperp(*)
+      real(c_double), value     :: t_step
+      integer(c_int32_t)        :: boole_initialized(*), ind_tetr(*), iface(*)
+      type(c_ptr), value        :: t_remain_out, n_pushes      ! c_null_ptr if not wanted
+    end function
+    integer(c_int) function gorilla_b200_find_tetra(handle, n, x, vpar, vperp, ind_tetr, iface, sign_t_step) &
+                                                    bind(C, name='gorilla_b200_find_tetra')
+      import :: c_int, c_ptr, c_int64_t, c_double, c_int32_t
+      type(c_ptr), value        :: handle
+      integer(c_int64_t), value :: n
+      real(c_double)            :: x(3,*)
+      real(c_double), intent(in):: vpar(*), vperp(*)
+      integer(c_int32_t)        :: ind_tetr(*), iface(*)
+      integer(c_int32_t), value :: sign_t_step
+    end function
+    integer(c_int) function gorilla_b200_get_counters(handle, counters) bind(C, name='gorilla_b200_get_counters')
+      import :: c_int, c_ptr, gorilla_b200_counters_t
+      type(c_ptr), value :: handle
+      type(gorilla_b200_counters_t), intent(out) :: counters
+    end function
+  end interface
+
+  type(c_ptr), save :: handle = c_null_ptr
+
+contains
+
+  !> Upload what initialize_gorilla left in the module arrays (orbit_timestep_gorilla.f90:151-274).
+  subroutine initialize_gorilla_b200(ierr)
+    use tetra_physics_mod, only: tetra_physics, cm_over_e, particle_mass, particle_charge, sign_sqg, coord_system
+    use tetra_grid_mod, only: tetra_grid, ntetr, Rmin, Rmax, Zmin, Zmax
+    use tetra_grid_settings_mod, only: grid_kind, grid_size, n_field_periods, sfc_s_min
+    use gorilla_settings_mod
+    integer, intent(out), optional :: ierr
+    type(gorilla_mesh_desc_t) :: md
+    type(gorilla_settings_t)  :: st
+    integer(c_int) :: rc
+    md%ntetr = int(ntetr, c_int64_t)
+    md%tetra_physics = c_loc(tetra_physics(1))   ! sequence type of 142 doubles -> double[ntetr][142]
+    md%tetra_grid    = c_loc(tetra_grid(1))      ! sequence type of 20 integers -> int32[ntetr][20]
+    md%cm_over_e = cm_over_e; md%particle_mass = particle_mass; md%particle_charge = particle_charge
+    md%sign_sqg = sign_sqg; md%coord_system = coord_system; md%n_field_periods = n_field_periods
+    md%grid_kind = grid_kind; md%grid_size = grid_size; md%pad0 = 0
+    md%Rmin = Rmin; md%Rmax = Rmax; md%Zmin = Zmin; md%Zmax = Zmax; md%sfc_s_min = sfc_s_min
+    st%eps_Phi = eps_Phi; st%coord_system = coord_system; st%ispecies = ispecies
+    st%boole_periodic_relocation = merge(1, 0, boole_periodic_relocation)
+    st%ipusher = ipusher; st%boole_pusher_ode45 = merge(1, 0, boole_pusher_ode45)
+    st%boole_dt_dtau = merge(1, 0, boole_dt_dtau); st%boole_newton_precalc = merge(1, 0, boole_newton_precalc)
+    st%poly_order = poly_order; st%i_precomp = i_precomp; st%boole_guess = merge(1, 0, boole_guess)
+    st%i_time_tracing_option = i_time_tracing_option; st%handover_processing_kind = handover_processing_kind
+    st%boole_adaptive_time_steps = merge(1, 0, boole_adaptive_time_steps)
+    st%boole_strong_electric_field = merge(1, 0, boole_strong_electric_field)
+    st%boole_grid_for_find_tetra = merge(1, 0, boole_grid_for_find_tetra); st%reserved = 0
+    rc = gorilla_b200_init(md, st, handle)
+    if (present(ierr)) then
+      ierr = rc
+    else if (rc /= 0) then
+      print *, 'initialize_gorilla_b200: error code ', rc
+      stop
+    end if
+  end subroutine
+
+  subroutine finalize_gorilla_b200()
+    if (c_associated(handle)) call gorilla_b200_free(handle)
+    handle = c_null_ptr
+  end subroutine
+
+  !> Batched orbit_timestep_gorilla: n independent particles, arrays updated in place.
+  subroutine orbit_timestep_gorilla_batch(n, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface, ierr, &
+                                          t_remain_out)
+    integer, intent(in)                      :: n
+    double precision, intent(inout), target  :: x(3,n), vpar(n), vperp(n)
+    double precision, intent(in)             :: t_step
+    logical, intent(inout)                   :: boole_initialized(n)
+    integer, intent(inout)                   :: ind_tetr(n), iface(n)
+    integer, intent(out)                     :: ierr
+    double precision, intent(out), optional, target :: t_remain_out(n)
+    integer(c_int32_t), allocatable :: binit(:)
+    type(c_ptr) :: p_tro
+    allocate(binit(n))
+    binit = merge(1_c_int32_t, 0_c_int32_t, boole_initialized)
+    p_tro = c_null_ptr
+    if (present(t_remain_out)) p_tro = c_loc(t_remain_out(1))
+    ierr = gorilla_b200_orbit_timestep(handle, int(n, c_int64_t), x, vpar, vperp, t_step, binit, ind_tetr, iface, &
+                                       p_tro, c_null_ptr)
+    boole_initialized = binit /= 0
+  end subroutine
+
+  !> The reference's scalar signature (orbit_timestep_gorilla.f90:19), n = 1.
+  subroutine orbit_timestep_gorilla(x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface, t_remain_out)
+    double precision, dimension(3), intent(inout) :: x
+    double precision, intent(inout)               :: vpar, vperp
+    double precision, intent(in)                  :: t_step
+    logical, intent(inout)                        :: boole_initialized
+    integer, intent(inout)                        :: ind_tetr, iface
+    double precision, intent(out), optional       :: t_remain_out
+    double precision :: x1(3,1), vpar1(1), vperp1(1), tro(1)
+    logical :: b1(1)
+    integer :: it1(1), if1(1), ierr
+    x1(:,1) = x; vpar1 = vpar; vperp1 = vperp; b1 = boole_initialized; it1 = ind_tetr; if1 = iface
+    call orbit_timestep_gorilla_batch(1, x1, vpar1, vperp1, t_step, b1, it1, if1, ierr, tro)
+    if (ierr /= 0) then
+      print *, 'orbit_timestep_gorilla (b200): error code ', ierr
+      stop
+    end if
+    x = x1(:,1); vpar = vpar1(1); vperp = vperp1(1); boole_initialized = b1(1); ind_tetr = it1(1); iface = if1(1)
+    if (ind_tetr .eq. -1 .and. boole_initialized) print *, 'WARNING: Particle lost.'
+    if (present(t_remain_out)) t_remain_out = tro(1)
+  end subroutine
+
+  subroutine find_tetra_batch(n, x, vpar, vperp, ind_tetr, iface, sign_t_step, ierr)
+    integer, intent(in)             :: n, sign_t_step
+    double precision, intent(inout) :: x(3,n)
+    double precision, intent(in)    :: vpar(n), vperp(n)
+    integer, intent(out)            :: ind_tetr(n), iface(n), ierr
+    ierr = gorilla_b200_find_tetra(handle, int(n, c_int64_t), x, vpar, vperp, ind_tetr, iface, int(sign_t_step, c_int32_t))
+  end subroutine
+
+  subroutine get_counters_b200(counters, ierr)
+    type(gorilla_b200_counters_t), intent(out) :: counters
+    integer, intent(out) :: ierr
+    ierr = gorilla_b200_get_counters(handle, counters)
+  end subroutine
+
+end module orbit_timestep_gorilla_b200_mod

@@ -157,6 +157,10 @@ int gorilla_b200_get_counters(gorilla_b200_handle *h, gorilla_counters *out);
 int gorilla_b200_sort_permutation_dev(gorilla_b200_handle *h, int64_t n, const int32_t *ind_tetr, int64_t *perm,
                                       void *stream);
 
+/* FP64 issue-rate micro-benchmark on the current device: thread-level instructions per second for DFMA and
+ * for DMUL+DADD pairs (the strict build issues the latter).  Roofline denominator of the FP64-bound orders. */
+int gorilla_b200_fp64_peak(double *dfma_inst_per_s, double *dmul_dadd_inst_per_s);
+
 /* Tuning knobs (0 = keep default): CTAs per SM and threads per CTA of the persistent push kernel. */
 int gorilla_b200_set_launch_config(gorilla_b200_handle *h, int32_t ctas_per_sm, int32_t threads_per_cta);
 

@@ -63,9 +63,9 @@ def make_workload(name: str):
     if name == "vmec_qi":
         grid, settings = workloads.vmec_qi(str(vmec_file))
         return dict(name="vmec_qi_alpha_3.5MeV_100x40x40", grid=grid, settings=settings,
-                    particles=workloads.particles_vmec_alpha, n_default=1_000_000, t_step=1.0e-5,
+                    particles=workloads.particles_vmec_alpha, n_default=1_000_000, t_step=1.0e-4,
                     desc="QI stellarator netcdf_file_for_test.nc (VMEC), grid_kind=3 100x40x40, 3.5 MeV alphas, "
-                         "s0=0.5, pitch U[-1,1]")
+                         "s0=0.5, pitch U[-1,1], time step 1e-4 s (BASELINE config 3: 100 steps of 1e-4 s)")
     grid, settings = workloads.analytic_tokamak(40, 80, 40)
     settings.poly_order = 2
     return dict(name="analytic_tokamak_D_3keV_40x80x40", grid=grid, settings=settings,
@@ -141,7 +141,7 @@ def reference_arm(args):
     t_step = args.t_step or wl["t_step"]
     mesh = build_mesh(wl["grid"], settings)
     cores = os.cpu_count() or 1
-    n_sample = 2000 * cores
+    n_sample = 500 * cores
     value, dt, pushes = cpu_run(wl, mesh, settings, n_sample, t_step, args.steps, args.warmup, cores)
     sample = f"{n_sample} particles x {args.steps} steps of {t_step:g} s ({pushes} pushes, {dt:.1f} s wall)"
     line = {
@@ -321,7 +321,7 @@ def main():
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_s = 2000 * cores
+            n_s = 500 * cores
             v, dt, p = cpu_run(wl, mesh, settings, n_s, t_step, max(1, min(args.steps, 3)), 1, cores)
             cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": f"{n_s} particles x {max(1, min(args.steps, 3))} steps of {t_step:g} s "

@@ -690,6 +690,11 @@ struct PolyPusher {
         if (!pick_exit<K>(cm, 0xFu, 0, iface_new, tau)) return false;
       }
     }
+#ifdef GB_PREFETCH_NEXT
+    // the exit face is known: start pulling the neighbour's record in while this push is finished
+    // (measured on B200: 9.2e9 -> 7.6e9 crossings/s, i.e. harmful -- 16 resident warps already hide the L2 latency)
+    prefetch_record<PHI>(*mp, iface_new == 1 ? r.nb[0] : iface_new == 2 ? r.nb[1] : iface_new == 3 ? r.nb[2] : r.nb[3]);
+#endif
     integrate<K>(z, tau);
     if (!exit_point_ok(z, iface_new)) return false;
     if (K > 2 && tau > tau_max) return false;

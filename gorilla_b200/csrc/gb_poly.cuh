@@ -282,9 +282,10 @@ struct PolyPusher {
     double qn, qd;
     const bool qhas = quadratic_solver1_numden(c[2], c[1], c[0], qn, qd);
     const bool linear = reduced || lin_deg;
-    num = linear ? -lb : qn;
-    den = linear ? la : qd;
-    return linear ? (la != 0.0) : qhas;
+    const bool ok = linear ? (la != 0.0) : qhas;
+    num = !ok ? 1.0 : linear ? -lb : qn;   // lanes without a root divide 1/1: stays on the fast division path
+    den = !ok ? 1.0 : linear ? la : qd;
+    return ok;
   }
 
   // ---- :1258-1482.  dtau/iface untouched when no valid root exists.  All four faces.

@@ -398,44 +398,24 @@ GB_HD bool quadratic_solver1_numden(double a, double b, double c, double &num, d
 {
   const double eps = 1.e-10;
   const double discr = b * b - 2.0 * a * c;
-  const double sq = sqrt(discr);           // NaN when discr < 0: never selected in that case
+  // sqrt of a negative discriminant is never used; feeding 1.0 keeps those lanes on the fast sqrt path
+  const double sq = sqrt(discr >= 0.0 ? discr : 1.0);
   const double dummy = (-b + sq);
   const bool big = fabs(dummy) > eps;
-  bool has = false;
-  num = 0.0;
-  den = 1.0;
-  if (c > 0.0) {
-    if (a > 0.0) {
-      if (b < 0.0) {
-        if (discr > 0.0) {
-          has = true;
-          num = big ? 2.0 * c : (-sq - b);
-          den = big ? dummy : a;
-        } else if (discr == 0.0) {
-          has = true; num = -b; den = a;
-        }
-      }
-    } else if (a < 0.0) {
-      has = true;
-      num = big ? 2.0 * c : (-sq - b);
-      den = big ? dummy : a;
-    } else {
-      if (b < 0.0) { has = true; num = -c; den = b; }
-    }
-  } else if (c < 0.0) {
-    if (a < 0.0) {
-      if (b > 0.0) {
-        if (discr > 0.0) { has = true; num = sq - b; den = a; }
-        else if (discr == 0.0) { has = true; num = -b; den = a; }
-      }
-    } else if (a > 0.0) {
-      has = true; num = sq - b; den = a;
-    } else {
-      if (b > 0.0) { has = true; num = -c; den = b; }
-    }
-  } else {
-    if (((a > 0.0) && (b < 0.0)) || ((a < 0.0) && (b > 0.0))) { has = true; num = -2.0 * b; den = a; }
-  }
+  // the sign-case tree as predicates (else-branches of the reference catch NaN: cz, az are "neither > nor <")
+  const bool cp = c > 0.0, cn = !cp && (c < 0.0), cz = !cp && !cn;
+  const bool ap = a > 0.0, an = !ap && (a < 0.0), az = !ap && !an;
+  const bool bn = b < 0.0, bp = b > 0.0;
+  const bool dpos = discr > 0.0, dzero = !dpos && (discr == 0.0);
+  const bool twoc = (cp && ap && bn && dpos) || (cp && an);          // 2c/dummy or (-sq-b)/a
+  const bool psq = (cn && an && bp && dpos) || (cn && ap);           // (sq-b)/a
+  const bool mb = (cp && ap && bn && dzero) || (cn && an && bp && dzero);  // -b/a
+  const bool mc = (cp && az && bn) || (cn && az && bp);              // -c/b
+  const bool m2b = cz && ((ap && bn) || (an && bp));                 // -2b/a
+  const bool has = twoc || psq || mb || mc || m2b;
+  // operands of the single division; lanes without a root divide 1/1 (fast path, result unused)
+  num = twoc ? (big ? 2.0 * c : (-sq - b)) : psq ? (sq - b) : mb ? -b : mc ? -c : m2b ? -2.0 * b : 1.0;
+  den = twoc ? (big ? dummy : a) : mc ? b : has ? a : 1.0;
   return has;
 }
 

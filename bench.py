@@ -32,7 +32,7 @@ UNIT = "crossings/s"
 BYTES_PER_CROSSING = {False: 344.0, True: 488.0}  # hot record (+8 B topology), without/with Phi part
 # FP64 thread-instructions (DADD+DMUL+DFMA) per crossing of the strict build, from the ncu source pages of
 # round 1 (profiles/r01_*): poly order -> count.  Order 3 is interpolated (not yet profiled).
-FP64_INST_PER_CROSSING = {1: 480.0, 2: 484.0, 3: 1900.0, 4: 3530.0}
+FP64_INST_PER_CROSSING = {1: 480.0, 2: 484.0, 3: 1900.0, 4: 3530.0, "rk4": 800.0}  # rk4: SURVEY estimate
 
 
 def parse_args():
@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--workload", default="auto", choices=["auto", "vmec_qi", "analytic"])
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (0 = workload default)")
     ap.add_argument("--poly-order", type=int, default=0, help="0 = workload default")
+    ap.add_argument("--ipusher", type=int, default=0, help="1 = RK4 pusher, 2 = polynomial pusher (0 = workload default)")
     ap.add_argument("--t-step", type=float, default=0.0, help="physical time per step [s] (0 = workload default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -138,6 +139,8 @@ def reference_arm(args):
     settings = wl["settings"]
     if args.poly_order:
         settings.poly_order = args.poly_order
+    if args.ipusher:
+        settings.ipusher = args.ipusher
     t_step = args.t_step or wl["t_step"]
     mesh = build_mesh(wl["grid"], settings)
     cores = os.cpu_count() or 1
@@ -182,6 +185,8 @@ def main():
     settings = wl["settings"]
     if args.poly_order:
         settings.poly_order = args.poly_order
+    if args.ipusher:
+        settings.ipusher = args.ipusher
     t_step = args.t_step or wl["t_step"]
     n = args.particles or wl["n_default"]
 
@@ -300,13 +305,13 @@ def main():
         achieved = bytes_per_crossing * per_rank_pushes / (launch_ms * 1e-3) / 1e9
         # the slower of the two per-push limits decides the bound (north_star): HBM gather vs FP64 issue
         dfma_peak, muladd_peak = fp64_peak()
-        fp64_per = FP64_INST_PER_CROSSING[settings.poly_order]
+        fp64_per = FP64_INST_PER_CROSSING["rk4" if settings.ipusher == 1 else settings.poly_order]
         t_hbm, t_fp64 = bytes_per_crossing / (hbm_peak * 1e9), fp64_per / muladd_peak
         fp64_ach = fp64_per * per_rank_pushes / (launch_ms * 1e-3)
         fp64 = {"achieved": fp64_ach / 1e12, "peak": muladd_peak / 1e12, "unit": "Tinst/s (thread-level DMUL/DADD)",
                 "frac": fp64_ach / muladd_peak, "inst_per_crossing": fp64_per, "dfma_peak": dfma_peak / 1e12,
                 "peak_source": "measured in this run (gorilla_b200_fp64_peak)"}
-        kern = f"orbit_kernel<{settings.poly_order},{'true' if has_phi else 'false'}>"
+        kern = f"orbit_kernel<{0 if settings.ipusher == 1 else settings.poly_order},{'true' if has_phi else 'false'}>"
         if t_hbm >= t_fp64:
             roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                         "frac": achieved / hbm_peak, "traffic": None, "kernel": kern,
@@ -330,7 +335,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms_max / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["name"], "desc": wl["desc"], "poly_order": settings.poly_order,
+            "config": {"workload": wl["name"], "desc": wl["desc"], "ipusher": settings.ipusher,
+                       "poly_order": settings.poly_order,
                        "particles_per_gpu": n, "t_step_s": t_step, "ntetr": mesh.ntetr,
                        "mesh_hot_bytes": int(mesh.ntetr * (352 + (160 if has_phi else 0))),
                        "l2_policy": "inputs_larger_than_l2 (mesh hot records > 126 MB, gathered at random)",

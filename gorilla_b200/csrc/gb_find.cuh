@@ -13,7 +13,7 @@
 // one lane walks the slice; all lanes of a warp that sit in the same slice read the same 128-byte
 // geometry records, which the L1/L2 serve as broadcasts.
 #pragma once
-#include "gb_poly.cuh"
+#include "gb_rk.cuh"
 
 namespace gb {
 
@@ -58,19 +58,6 @@ GB_HD bool isinside(const MeshDev &m, int64_t ind_tetr, const double *x, double 
     if (!(s >= -dist_min)) all_ok = false;
   }
   return all_ok;
-}
-
-// dz/dtau = b + A z of the RK module (rhs_pusher_tetra_rk4, pusher_tetra_rk.f90:810-836):
-//   (b + matmul(amat, z(1:3))) + Bvec*z(4) ; b4 + spamat*z4
-template <class PP>
-GB_HD void bm_vec_rk(double *o, const PP &P, const double *z)
-{
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    double mv = (P.A.m[i][0] * z[0] + P.A.m[i][1] * z[1]) + P.A.m[i][2] * z[2];
-    o[i] = P.b[i] + mv + P.A.c[i] * z[3];
-  }
-  o[3] = P.b[3] + P.A.s * z[3];
 }
 
 // Start point lies (within tolerance) on >= 1 face: hop through the neighbours until every converged

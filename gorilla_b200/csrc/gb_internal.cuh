@@ -8,6 +8,7 @@
 #include <atomic>
 #include "../../include/gorilla_b200.h"
 #include "gb_find.cuh"
+#include "gb_rk.cuh"
 
 namespace gbint {
 void set_error(const char *msg);
@@ -59,7 +60,10 @@ struct Batch {
 #ifndef GB_MINB_K4
 #define GB_MINB_K4 4
 #endif
-constexpr int gb_min_blocks(int K) { return K == 1 ? GB_MINB_K1 : K == 2 ? GB_MINB_K2 : K == 3 ? GB_MINB_K3 : GB_MINB_K4; }
+#ifndef GB_MINB_RK
+#define GB_MINB_RK 4
+#endif
+constexpr int gb_min_blocks(int K) { return K == 0 ? GB_MINB_RK : K == 1 ? GB_MINB_K1 : K == 2 ? GB_MINB_K2 : K == 3 ? GB_MINB_K3 : GB_MINB_K4; }
 
 template <int K, bool PHI>
 __global__ void __launch_bounds__(128, gb_min_blocks(K)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
@@ -120,13 +124,22 @@ __global__ void __launch_bounds__(128, gb_min_blocks(K)) orbit_kernel(const __gr
       ind_save = ind_tetr;
       PushOut o;
       bool done = false;
-      if (!bt.force_full) {
-        PolyPusher<K, PHI> P;
-        P.mp = &m;
-        P.perpinv = perpinv;
-        done = P.push_fast(ind_tetr, iface, x, vpar, t_remain, o);
+      if constexpr (K == 0) {  // ipusher = 1: RK4 pusher
+        if (!bt.force_full) {
+          RkPusher<PHI> R;
+          R.init(&m, perpinv, ind_tetr, x, iface, vpar, t_remain);
+          done = R.template push<true>(o);
+        }
+        if (!done) o = push_rk_full_call<PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
+      } else {
+        if (!bt.force_full) {
+          PolyPusher<K, PHI> P;
+          P.mp = &m;
+          P.perpinv = perpinv;
+          done = P.push_fast(ind_tetr, iface, x, vpar, t_remain, o);
+        }
+        if (!done) o = push_full_call<K, PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
       }
-      if (!done) o = push_full_call<K, PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
       x[0] = o.x[0];
       x[1] = o.x[1];
       x[2] = o.x[2];

@@ -54,6 +54,17 @@ GB_HD double cabs2(cd p) { return p.re * p.re - (-p.im) * p.im; }
 #define GB_MATH_FN static inline
 #endif
 
+// IEEE division whose zero-numerator case is handled by selection.  Root iterations on the real axis carry
+// exactly-zero imaginary parts, so two of the three divisions of every complex division are 0/x; the GPU's
+// double-precision division takes its slow path for a zero (or subnormal) numerator, which would serialise
+// those lanes.  (+-0)/x = +-0 with the sign product, for finite non-zero x: exactly what is returned here.
+GB_HD double div_z(double num, double den)
+{
+  const bool zero_num = (num == 0.0) && (fabs(den) <= DBL_MAX) && (den != 0.0);
+  const double q = (zero_num ? 1.0 : num) / den;
+  return zero_num ? copysign(0.0, num) * copysign(1.0, den) : q;
+}
+
 // gcc expand_complex_div_wide (flag_complex_method == 1): branch on |br| < |bi|
 //   true : ratio = br/bi; div = br*ratio + bi; tr = ar*ratio + ai; ti = ai*ratio - ar
 //   false: ratio = bi/br; div = bi*ratio + br; tr = ai*ratio + ar; ti = ai - ar*ratio
@@ -61,7 +72,7 @@ GB_MATH_FN cd cdiv(cd a, cd b)
 {
   const bool sw = fabs(b.re) < fabs(b.im);
   const double num = sw ? b.re : b.im, den = sw ? b.im : b.re;
-  const double ratio = num / den;
+  const double ratio = div_z(num, den);
   const double div = (num * ratio) + den;
   const double u = sw ? a.re : a.im, v = sw ? a.im : a.re;
   const double tr = (u * ratio) + v;
@@ -69,8 +80,8 @@ GB_MATH_FN cd cdiv(cd a, cd b)
   const double pw = w * ratio;
   const double ti = sw ? (pw - a.re) : (a.im - pw);
   cd q;
-  q.re = tr / div;
-  q.im = ti / div;
+  q.re = div_z(tr, div);
+  q.im = div_z(ti, div);
   return q;
 }
 
@@ -103,7 +114,7 @@ GB_MATH_FN double hypot_glibc(double x, double y)
     return hypot_kernel(ax * SCALE, ay * SCALE) / SCALE;
   }
   if (ay < TINY_VAL) {
-    if (ax >= ay / HEPS) return ax + ay;
+    if (ax >= ay * 0x1p+54) return ax + ay;  // ay / HEPS, exact (power of two); avoids a 0/x division
     ax = hypot_kernel(ax / SCALE, ay / SCALE) * SCALE;
     return ax;
   }

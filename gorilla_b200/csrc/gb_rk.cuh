@@ -1,0 +1,784 @@
+// gb_rk.cuh -- Runge-Kutta (RK4) tetrahedron pusher, FP64, one particle per lane.
+//
+// Replaces (reference file:line), for boole_pusher_ode45 = .false., boole_dt_dtau = .true.,
+// boole_newton_precalc = .false., handover_processing_kind = 1:
+//   initialize_pusher_tetra_rk_mod        SRC/pusher_tetra_rk.f90:50-193
+//   pusher_tetra_rk                       :197-575
+//   quad_analytic_approx                  :636-809
+//   rhs_pusher_tetra_rk4 / rk4_step       :810-896      (integration_step :2549-2581 is one rk4_step here)
+//   newton_face_convergence(_wrapped)     :914-1188
+//   bisection_face_convergence            :1409-1581
+//   bisection_search_start                :1583-1623    (streamed: the 1000-step history is not materialised)
+//   last_line_defense                     :1696-2071
+//   final_processing                      :2075-2418
+//   normal_distance(s)_func / normal_velocity_func / normal_acceleration_func   :2422-2483
+//
+// Structure: RkPusher::push<FAST> is written once.  With FAST = true every branch that would enter the
+// last-line-of-defence / bisection ladders returns false instead ("not decided"); the kernel then re-runs the
+// push through push_rk_full_call (FAST = false), a non-inlined by-value function, exactly as the polynomial
+// pusher does.  The ODE coefficients b, amat, Bvec, spamat and the step estimate dtau_ref are the polynomial
+// pusher's b, A and physical_estimate_tau (same formulas in the reference, :104-116 vs pusher_tetra_poly.f90
+// :1504-1517 and :170-186 vs :2779-2831), so that object is reused.
+#pragma once
+#include "gb_poly.cuh"
+
+namespace gb {
+
+#define GB_RK_KITER 48
+
+// dz/dtau = b + A z of the RK module (rhs_pusher_tetra_rk4): (b + matmul(amat, z(1:3))) + Bvec*z(4) ; b4 + spamat*z4
+template <class PP>
+GB_HD void bm_vec_rk(double *o, const PP &P, const double *z)
+{
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    double mv = (P.A.m[i][0] * z[0] + P.A.m[i][1] * z[1]) + P.A.m[i][2] * z[2];
+    o[i] = P.b[i] + mv + P.A.c[i] * z[3];
+  }
+  o[3] = P.b[3] + P.A.s * z[3];
+}
+
+template <bool PHI>
+struct RkPusher {
+  PolyPusher<1, PHI> P;  // record, z_init, sign_rhs, dt_dtau_const, b, A (= amat | Bvec | spamat)
+  double dist_min, dist_max, dtau_ref, dtau_max, dtau_quad, t_remain;
+  int iface_init, sign_t_step, fallback;
+
+  GB_HD void init(const MeshDev *mp, double perpinv, int ind_tetr, const double *x, int iface, double vpar, double t_remain_in)
+  {
+    P.mp = mp;
+    P.perpinv = perpinv;
+    P.init(ind_tetr, x, iface, vpar, t_remain_in);
+    P.build_ode();
+    t_remain = t_remain_in;
+    iface_init = iface;
+    sign_t_step = signbit(t_remain_in) ? -1 : 1;
+    const double dist1 = -P.r.dist_ref;
+    dist_min = 1.e-10 * fabs(dist1);
+    dist_max = 10.0 * fabs(dist1);
+    dtau_ref = P.physical_estimate_tau();
+    dtau_max = 10.0 * dtau_ref;
+    dtau_quad = 1.5 * dtau_ref;
+    fallback = 0;
+  }
+
+  GB_HD void distances(const double *z, double *d) const { P.normal_distances(z, d); }
+  GB_HD double distance(const double *z, int iface) const { return P.normal_distance(z, iface); }
+  GB_HD double nvel(int iface, const double *dzdtau) const
+  {
+    double n[3];
+    P.face_normal(iface, n);
+    return dot3(dzdtau, n);
+  }
+  GB_HD double nacc(int iface, const double *dzdtau) const
+  {
+    double n[3], t[3];
+    P.face_normal(iface, n);
+#pragma unroll
+    for (int j = 0; j < 3; j++) t[j] = (n[0] * P.A.m[0][j] + n[1] * P.A.m[1][j]) + n[2] * P.A.m[2][j];
+    return dot3(t, dzdtau) + dot3(n, P.A.c) * dzdtau[3];
+  }
+  GB_HD static bool any_gt(const double *d, double lim) { return d[0] > lim || d[1] > lim || d[2] > lim || d[3] > lim; }
+  GB_HD static int minloc4(const double *d)  // minloc(d,1): first minimum, 1-based
+  {
+    int k = 0;
+    double cur = d[0];
+    if (d[1] < cur) { k = 1; cur = d[1]; }
+    if (d[2] < cur) { k = 2; cur = d[2]; }
+    if (d[3] < cur) { k = 3; }
+    return k + 1;
+  }
+  GB_HD static double sel4(const double *d, int k1) { return k1 == 1 ? d[0] : k1 == 2 ? d[1] : k1 == 3 ? d[2] : d[3]; }
+
+  GB_HD void rk4_step(double *y, double h, double *dzdtau) const
+  {
+    const double hh = h * 0.5, h6 = h / 6.0;
+    double dydx[4], yt[4], dyt[4], dym[4];
+    bm_vec_rk(dydx, P, y);
+#pragma unroll
+    for (int i = 0; i < 4; i++) yt[i] = y[i] + hh * dydx[i];
+    bm_vec_rk(dyt, P, yt);
+#pragma unroll
+    for (int i = 0; i < 4; i++) yt[i] = y[i] + hh * dyt[i];
+    bm_vec_rk(dym, P, yt);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      yt[i] = y[i] + h * dym[i];
+      dym[i] = dyt[i] + dym[i];
+    }
+    bm_vec_rk(dyt, P, yt);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      y[i] = y[i] + h6 * (dydx[i] + dyt[i] + 2.0 * dym[i]);
+      dzdtau[i] = dyt[i];
+    }
+  }
+
+  // :636-809.  allowed: bit f set = face f+1 allowed.  The per-face sign tree is the polynomial pusher's
+  // closed-form quadratic with two differences: the start face uses the reduced (linear) form and the
+  // "c == 0" branch is taken for |c| <= dist_min.
+  GB_HD bool quad_analytic_approx(const double *z, unsigned allowed, int &iface_inout, double &dtau) const
+  {
+    double cc[4];
+    distances(z, cc);
+    const int iface = iface_inout;
+    const double fac = P.b[3] + P.A.s * z[3];
+    double best = 0.0;
+    int ibest = 0;
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      if (!(allowed & (1u << f))) continue;
+      // acoef_pre = matmul(curlA, anorm) re-formed (tetra_physics_mod.f90:857), times sign_rhs
+      const double apre = dot3(P.r.curlA, P.r.an[f]) * (double)P.sign_rhs;
+      const double b = z[3] * apre + dot3(P.b, P.r.an[f]);
+      const double a = apre * fac;
+      const double c = cc[f];
+      double num = 1.0, den = 1.0;
+      bool has;
+      if (iface == f + 1) {
+        has = ((a > 0.0) && (b < 0.0)) || (!(a > 0.0) && (a < 0.0) && (b > 0.0));
+        if (has) { num = -2.0 * b; den = a; }
+      } else if (fabs(c) > dist_min) {
+        has = quadratic_solver1_numden(a, b, c, num, den);
+        // quadratic_solver1's "c == 0" leaf (neither c > 0 nor c < 0) only triggers for NaN here: the reference
+        // stops ('Should not happen'); treat as no root
+        if (!(c > 0.0) && !(c < 0.0)) has = false;
+        if (!has) { num = 1.0; den = 1.0; }
+      } else {
+        has = ((a > 0.0) && (b < 0.0)) || ((a < 0.0) && (b > 0.0));
+        if (has) { num = -2.0 * b; den = a; }
+      }
+      const double d = num / den;
+      if (has && (d < dtau_max) && (d > 0.0) && (ibest == 0 || d < best)) {
+        best = d;
+        ibest = f + 1;
+      }
+    }
+    if (ibest == 0) return false;
+    iface_inout = ibest;
+    dtau = best;
+    return true;
+  }
+
+  // :1000-1188
+  GB_HD bool newton_wrapped(double *z, double &tau, int iface, double *dzdtau, bool start_quadratic)
+  {
+    double z_start[4], dz_start[4], z_save[4], dz_save[4], nd[4];
+    const double tau_start = tau;
+    double dtau = 0.0, tau_save = 0.0, dist_new = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { z_start[i] = z[i]; dz_start[i] = dzdtau[i]; }
+    double dist = distance(z, iface);
+    int k = 0;
+    while (fabs(dist) > dist_min) {
+      k++;
+#pragma unroll
+      for (int i = 0; i < 4; i++) { z_save[i] = z[i]; dz_save[i] = dzdtau[i]; }
+      const double nv = nvel(iface, dzdtau);
+      if (nv != 0.0) dtau = -dist / nv;
+      else return false;
+      tau_save = tau;
+      distances(z, nd);
+      if (any_gt(nd, dist_max)) {
+        dtau = tau + dtau;
+        tau = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
+      }
+      if (fabs(dtau) > dtau_max) {
+        start_quadratic = true;
+      } else {
+        rk4_step(z, dtau, dzdtau);
+        dist_new = distance(z, iface);
+      }
+      if ((fabs(dist_new) >= fabs(dist)) || start_quadratic) {
+        start_quadratic = false;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { z[i] = z_save[i]; dzdtau[i] = dz_save[i]; }
+        tau = tau_save;
+        const double na = 0.5 * nacc(iface, dzdtau);
+        const double discr = nv * nv - 4.0 * na * dist;
+        if (discr > 0.0) {
+          if (na < 0.0) dtau = (-nv - sqrt(discr)) / (2.0 * na);
+          else if (na > 0.0) dtau = (-nv + sqrt(discr)) / (2.0 * na);
+          else dtau = -dist / nv;
+          distances(z, nd);
+          if (any_gt(nd, dist_max)) {
+            dtau = tau + dtau;
+            tau = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
+          }
+          if (fabs(dtau) > dtau_max) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) { z[i] = z_start[i]; dzdtau[i] = dz_start[i]; }
+            tau = tau_start;
+            return false;
+          }
+          rk4_step(z, dtau, dzdtau);
+          tau = tau + dtau;
+          dist = distance(z, iface);
+        } else {
+          return false;
+        }
+      } else {
+        tau = tau + dtau;
+        dist = dist_new;
+      }
+      if (k > GB_RK_KITER) return false;
+    }
+    if (tau <= 0.0) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) { z[i] = z_start[i]; dzdtau[i] = dz_start[i]; }
+      tau = tau_start;
+      return false;
+    }
+    return true;
+  }
+  // :914-996 (RK4 accuracy): state restored when Newton did not converge
+  GB_HD bool newton(double *z, double &tau, int iface, double *dzdtau, bool start_quadratic)
+  {
+    double z_save[4], dz_save[4];
+    const double tau_save = tau;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { z_save[i] = z[i]; dz_save[i] = dzdtau[i]; }
+    const bool ok = newton_wrapped(z, tau, iface, dzdtau, start_quadratic);
+    if (!ok) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) { z[i] = z_save[i]; dzdtau[i] = dz_save[i]; }
+      tau = tau_save;
+    }
+    return ok;
+  }
+
+  // :1583-1623
+  GB_HD void bisection_search_start(double tau_in, int n_steps, double *z_start, double &dtau, double &tau_out)
+  {
+    double zr[4], dz[4], nd[4], tau_run = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { zr[i] = P.z_init[i]; z_start[i] = zr[i]; }
+    dtau = tau_in / (double)n_steps;
+    int last_inside = 0;
+    bool take_next = false;
+    distances(zr, nd);
+    tau_out = 0.0;
+    if (nd[0] > 0.0 && nd[1] > 0.0 && nd[2] > 0.0 && nd[3] > 0.0) { last_inside = 1; take_next = true; }
+    for (int i = 2; i <= n_steps; i++) {
+      rk4_step(zr, dtau, dz);
+      tau_run = tau_run + dtau;
+      distances(zr, nd);
+      if (take_next) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) z_start[q] = zr[q];
+        tau_out = tau_run;
+        take_next = false;
+      }
+      if (nd[0] > 0.0 && nd[1] > 0.0 && nd[2] > 0.0 && nd[3] > 0.0) { last_inside = i; take_next = true; }
+    }
+    if (last_inside == n_steps) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) z_start[q] = zr[q];
+      tau_out = tau_run;
+    }
+  }
+
+  // :1409-1581
+  GB_HD bool bisection(double *z, double &tau_inout, double dtau_in, int &iface, double *dzdtau)
+  {
+    double tau = tau_inout, dtau = dtau_in, z_save[4], nd[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) z_save[i] = z[i];
+    bool converged = false;
+    for (int l = 1; l <= 2 && !converged; l++) {
+      int k = 0;
+      bool stop_all = false;
+      while (!converged) {
+        distances(z, nd);
+        const double mn = sel4(nd, minloc4(nd));
+        if (mn < -dist_min) {
+          dtau = -fabs(dtau / 2.0);
+          if (any_gt(nd, dist_max)) {
+            const double dtau_save = dtau;
+            dtau = tau + dtau;
+            tau = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
+            rk4_step(z, dtau, dzdtau);
+            tau = tau + dtau;
+            dtau = dtau_save;
+          } else {
+            rk4_step(z, dtau, dzdtau);
+            tau = tau + dtau;
+          }
+        } else if (mn > dist_min) {
+          dtau = +fabs(dtau / 2.0);
+          rk4_step(z, dtau, dzdtau);
+          tau = tau + dtau;
+        }
+        distances(z, nd);
+        const int im = minloc4(nd);
+        if (fabs(sel4(nd, im)) < dist_min) {
+          if (nvel(im, dzdtau) > 0.0) {
+            dtau = +fabs(dtau / 2.0);
+            rk4_step(z, dtau, dzdtau);
+            tau = tau + dtau;
+          } else {
+            int j = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+              if (nd[i] < 0.0) j++;
+            if (j <= 1) {
+              iface = im;
+              converged = true;
+            } else {
+              dtau = -fabs(dtau / 2.0);
+              rk4_step(z, dtau, dzdtau);
+              tau = tau + dtau;
+            }
+          }
+        }
+        k++;
+        if (k > GB_RK_KITER) {
+          if (l == 1) {
+            int nfc = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+              if (nd[i] < 0.0 && fabs(nd[i]) < dist_min) nfc++;
+            if (nfc > 1) {
+              dist_min = 2.0 * dist_min;
+              tau = tau_inout;
+              dtau = dtau_in;
+#pragma unroll
+              for (int i = 0; i < 4; i++) z[i] = z_save[i];
+            } else {
+              bisection_search_start(tau_inout, 1000, z, dtau, tau);
+            }
+          } else {
+            stop_all = true;
+          }
+          break;
+        }
+      }
+      if (stop_all) break;
+    }
+    tau_inout = tau;
+    return converged;
+  }
+
+  // :1696-2071 ; z, tau, iface, dzdtau are outputs
+  GB_HD bool last_line_defense(double *z, double &tau, int &iface, double *dzdtau)
+  {
+    fallback |= 2;
+    bool turned_tangential = false, converged = false;
+    double dtau = 0.0, nd[4], z_save[4];
+    int iface_new = iface_init, iface_init_outside = 0, k;
+    tau = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
+    if (iface_init != 0)
+      if (distance(z, iface_init) < 0.0) iface_init_outside = iface_init;
+    if (quad_analytic_approx(z, 0xFu, iface_new, dtau)) {
+      rk4_step(z, dtau, dzdtau);
+      tau = tau + dtau;
+    } else {
+      dtau = dtau_ref;
+      rk4_step(z, dtau, dzdtau);
+      tau = tau + dtau;
+      distances(z, nd);
+      iface_new = minloc4(nd);
+    }
+    k = 0;
+    for (;;) {
+      k++;
+      distances(z, nd);
+      if (any_gt(nd, dist_max)) {
+        dtau = tau - 0.5 * fabs(dtau);
+        tau = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
+        rk4_step(z, dtau, dzdtau);
+        tau = tau + dtau;
+      } else {
+        break;
+      }
+      if (k > GB_RK_KITER) return false;
+    }
+    if (iface_init_outside != 0) {
+      if (distance(z, iface_init_outside) < 0.0) {
+        if (nvel(iface_init_outside, dzdtau) < 0.0) {
+          for (int i = 1; i <= 3; i++) {
+            const int j = ((iface_init_outside + i - 1) & 3) + 1;
+            if (distance(z, j) < 0.0) turned_tangential = true;
+          }
+          iface_new = iface_init_outside;
+          if (fabs(distance(z, iface_new)) < dist_min) converged = true;
+        }
+      }
+    }
+    if (!converged) {
+      if (turned_tangential) {
+        if (!bisection(z, tau, dtau, iface_new, dzdtau)) return false;
+      } else {
+        bool dtau_decreased = false;
+        k = 0;
+        for (;;) {
+          k++;
+          distances(z, nd);
+          int n_out = 0, first_out = 0;
+#pragma unroll
+          for (int i = 3; i >= 0; i--)
+            if (nd[i] < 0.0) { n_out++; first_out = i + 1; }
+          if (n_out == 0) {
+            dtau = dtau_decreased ? 0.5 * fabs(dtau) : 2.0 * fabs(dtau);
+          } else if (n_out == 1) {
+            iface_new = first_out;
+            if (nvel(iface_new, dzdtau) >= 0.0) {
+              if (iface_init_outside != iface_new) {
+                dtau = -0.5 * fabs(dtau);
+                dtau_decreased = true;
+              } else {
+                dtau = dtau_decreased ? 0.5 * fabs(dtau) : 2.0 * fabs(dtau);
+              }
+            } else {
+              break;
+            }
+          } else {
+            int l = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+              if (nd[i] < 0.0 && fabs(nd[i]) < dist_min) l++;
+            if (l == n_out) {
+              int j = 0;
+              for (int i = 0; i < 4; i++) {
+                const double di = sel4(nd, i + 1);
+                if (!(di < 0.0)) continue;
+                if (fabs(di) >= dist_min) continue;
+                if (nvel(i + 1, dzdtau) > 0.0) j++;
+              }
+              if (j > 0) {
+                dtau = 2.0 * fabs(dtau);
+              } else {
+                int best = 0;
+                double bv = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                  if (nd[i] < 0.0 && (best == 0 || fabs(nd[i]) < bv)) { best = i + 1; bv = fabs(nd[i]); }
+                iface_new = best;
+                break;
+              }
+            } else {
+              dtau = -0.5 * fabs(dtau);
+              dtau_decreased = true;
+            }
+          }
+          if (any_gt(nd, dist_max)) {
+            dtau = tau + dtau;
+            tau = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
+          }
+          rk4_step(z, dtau, dzdtau);
+          tau = tau + dtau;
+          if (k > GB_RK_KITER) return false;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) z_save[i] = z[i];
+        const double dtau_save = dtau, tau_save = tau;
+        bool newton_ok = newton(z, tau, iface_new, dzdtau, false);
+        for (int i = 1; i <= 3; i++) {
+          const int j = ((iface_new + i - 1) & 3) + 1;
+          if (distance(z, j) < 0.0) newton_ok = false;
+        }
+        if ((!newton_ok) || (nvel(iface_new, dzdtau) >= 0.0)) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) z[i] = z_save[i];
+          tau = tau_save;
+          dtau = dtau_save;
+          if (!bisection(z, tau, dtau, iface_new, dzdtau)) return false;
+        }
+      }
+    }
+    iface = iface_new;
+    return true;
+  }
+
+  GB_HD void pass_through(const double *z, double tau, int iface_new, bool finished, PushOut &o) const
+  {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      o.x[i] = z[i] + P.r.x1[i];
+      o.z_save[i] = z[i];
+    }
+    o.z_save_set = 1;
+    o.vpar = z[3];
+    o.t_pass = tau * P.dt_dtau_const;
+    o.finished = finished ? 1 : 0;
+    P.handover(iface_new, o.x, o.ind_tetr, o.iface);
+  }
+
+  // 0 = decided and stored in o, 1 = particle removed, 2 = (FAST only) needs the complete path
+  template <bool FAST>
+  GB_HD int final_processing(double *z, double tau, int iface_new, PushOut &o)
+  {
+    double dzdtau[4], nd[4], nd_save[4], z_save[4];
+    const double t_pass0 = tau * P.dt_dtau_const;
+    // x and t_pass are assigned before anything can fail (:2100-2105); a removal further down keeps them
+#pragma unroll
+    for (int i = 0; i < 3; i++) o.x[i] = z[i] + P.r.x1[i];
+    o.t_pass = t_pass0;
+    if (!(fabs(t_remain) < fabs(t_pass0))) {
+      pass_through(z, tau, iface_new, false, o);
+      return 0;
+    }
+    // the orbit stops inside the cell (:2120-2400)
+#pragma unroll
+    for (int i = 0; i < 4; i++) { z[i] = P.z_init[i]; z_save[i] = z[i]; }
+    tau = 0.0;
+    const double dtau = t_remain / P.dt_dtau_const;
+    distances(z, nd_save);
+    rk4_step(z, dtau, dzdtau);
+    if (any_gt(nd_save, dist_max)) {
+      if (FAST) return 2;
+#pragma unroll
+      for (int i = 0; i < 4; i++) z[i] = z_save[i];
+      if (!last_line_defense(z, tau, iface_new, dzdtau)) { /* reference ignores the flag here */ }
+      for (int j = 1; j <= 3; j++) {
+        const int k = ((iface_new + j - 1) & 3) + 1;
+        if (distance(z, k) < 0.0) return 1;
+      }
+      if (nvel(iface_new, dzdtau) > 0.0) return 1;
+#pragma unroll
+      for (int i = 0; i < 3; i++) o.x[i] = z[i] + P.r.x1[i];
+      o.t_pass = tau * P.dt_dtau_const;
+      if (fabs(tau * P.dt_dtau_const) <= fabs(t_remain)) {
+        pass_through(z, tau, iface_new, false, o);
+        return 0;
+      }
+      return 1;
+    }
+    tau = tau + dtau;
+#pragma unroll
+    for (int i = 0; i < 3; i++) o.x[i] = z[i] + P.r.x1[i];
+    o.t_pass = tau * P.dt_dtau_const;
+    distances(z, nd);
+    int n_out = 0, iface_outside = 0;
+    bool any_conv = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (nd[i] < 0.0) { n_out++; iface_outside = i + 1; }
+      if (fabs(nd[i]) < dist_min) any_conv = true;
+    }
+    if (any_conv) {
+      if (n_out == 1) iface_new = iface_outside;
+      else {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          if (fabs(nd[i]) < dist_min) iface_new = i + 1;
+      }
+      if (nvel(iface_new, dzdtau) < 0.0) {
+        pass_through(z, tau, iface_new, true, o);
+      } else {
+        // converged on a face at t_remain but flying inwards: handed to the same tetrahedron again
+#pragma unroll
+        for (int i = 0; i < 3; i++) { o.x[i] = z[i] + P.r.x1[i]; o.z_save[i] = z[i]; }
+        o.z_save_set = 1;
+        o.vpar = z[3];
+        o.t_pass = tau * P.dt_dtau_const;
+        o.finished = 1;
+        o.ind_tetr = P.ind_tetr;
+        o.iface = iface_new;
+      }
+      return 0;
+    }
+    if (n_out != 0) {
+      if (FAST) return 2;
+      fallback |= 8;
+      if (n_out == 1) {
+        iface_new = iface_outside;
+        const double tau_save = tau;
+#pragma unroll
+        for (int i = 0; i < 4; i++) z_save[i] = z[i];
+        bool ok = newton(z, tau, iface_new, dzdtau, true);
+        if (!ok) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) z[i] = z_save[i];
+          tau = tau_save;
+          rk4_step(z, 0.0, dzdtau);
+          ok = newton(z, tau, iface_new, dzdtau, false);
+          if (!ok) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) z[i] = z_save[i];
+            tau = tau_save;
+            if (!bisection(z, tau, tau, iface_new, dzdtau)) return 1;
+          }
+        }
+        if (nvel(iface_new, dzdtau) > 0.0) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) z[i] = z_save[i];
+          tau = tau_save;
+          if (!bisection(z, tau, tau, iface_new, dzdtau)) return 1;
+        }
+      } else {
+        if (!bisection(z, tau, tau, iface_new, dzdtau)) return 1;
+      }
+      pass_through(z, tau, iface_new, false, o);
+      return 0;
+    }
+    // orbit time is finished inside the tetrahedron
+#pragma unroll
+    for (int i = 0; i < 3; i++) { o.x[i] = z[i] + P.r.x1[i]; o.z_save[i] = z[i]; }
+    o.z_save_set = 1;
+    o.vpar = z[3];
+    o.t_pass = tau * P.dt_dtau_const;
+    o.finished = 1;
+    o.ind_tetr = P.ind_tetr;
+    o.iface = 0;
+    return 0;
+  }
+
+  // pusher_tetra_rk (:197-575).  Returns false only with FAST = true ("take the complete path").
+  template <bool FAST>
+  GB_HD bool push(PushOut &o)
+  {
+    unsigned allowed = 0xFu;
+    double z[4], dzdtau[4], nd[4], tau = 0.0, dtau = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
+    int iface_new = iface_init;
+    o.finished = 0;
+    o.z_save_set = 0;
+    o.t_pass = 0.0;
+    bool removed = false, converged = false;
+    if (quad_analytic_approx(z, allowed, iface_new, dtau)) {
+      rk4_step(z, dtau, dzdtau);
+      tau = tau + dtau;
+    } else {
+      if (FAST) return false;
+      dtau = dtau_ref;
+      rk4_step(z, dtau, dzdtau);
+      tau = tau + dtau;
+      distances(z, nd);
+      double ad[4] = {fabs(nd[0]), fabs(nd[1]), fabs(nd[2]), fabs(nd[3])};
+      iface_new = minloc4(ad);
+    }
+    distances(z, nd);
+    if (any_gt(nd, dist_max)) {
+      if (FAST) return false;
+      if (!last_line_defense(z, tau, iface_new, dzdtau)) removed = true;
+    }
+    if (!removed) {
+      for (int it = 1; it <= 5; it++) {
+        converged = true;
+        bool llod = false, requad = false, reset_first = false;
+        if (!newton(z, tau, iface_new, dzdtau, false)) {
+          if (FAST) return false;
+          fallback |= 1;
+          allowed &= ~(1u << (iface_new - 1));
+          if (allowed == 0) llod = true;
+          else requad = true;
+        } else {
+          bool cycled = false;
+          for (int j = 1; j <= 3 && !cycled; j++) {
+            const int k = ((iface_new + j - 1) & 3) + 1;
+            if (distance(z, k) < 0.0) {
+              if (FAST) return false;
+              fallback |= 4;
+              allowed &= ~(1u << (iface_new - 1));
+              if (allowed == 0) llod = true;
+              else if (allowed & (1u << (k - 1))) iface_new = k;
+              else llod = true;
+              converged = false;
+              cycled = true;
+            }
+          }
+          if (!cycled) {
+            if (nvel(iface_new, dzdtau) > 0.0) {
+              if (FAST) return false;
+              fallback |= 8;
+              allowed &= ~(1u << (iface_new - 1));
+              if (allowed == 0) llod = true;
+              else requad = true;
+            } else if (tau <= 0.0) {
+              if (FAST) return false;
+              allowed &= ~(1u << (iface_new - 1));
+#pragma unroll
+              for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
+              tau = 0.0;
+              if (allowed == 0) llod = true;
+              else { requad = true; reset_first = true; }
+            } else {
+              break;  // converged
+            }
+          } else if (!llod) {
+            continue;
+          }
+        }
+        if (llod) {
+          last_line_defense(z, tau, iface_new, dzdtau);  // its flag is not examined in the loop (:358-361)
+          converged = false;
+          continue;
+        }
+        if (requad) {
+          if (!reset_first && tau > dtau_quad) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
+            tau = 0.0;
+          }
+          if (!quad_analytic_approx(z, allowed, iface_new, dtau)) {
+            last_line_defense(z, tau, iface_new, dzdtau);
+            converged = false;
+            continue;
+          }
+          if (!reset_first) {
+            distances(z, nd);
+            if (any_gt(nd, dist_max)) {
+              dtau = tau + dtau;
+              tau = 0.0;
+#pragma unroll
+              for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
+            }
+          }
+          rk4_step(z, dtau, dzdtau);
+          tau = tau + dtau;
+          converged = false;
+          continue;
+        }
+      }
+      if (!converged) removed = true;
+    }
+    if (!removed) {
+      const int rc = final_processing<FAST>(z, tau, iface_new, o);
+      if (rc == 2) return false;
+      if (rc == 1) removed = true;
+    }
+    if (!removed) {
+      if ((fabs(o.t_pass) >= fabs(t_remain)) && !o.finished) removed = true;
+      else if ((o.t_pass * (double)sign_t_step) <= 0.0) removed = true;
+    }
+    if (removed) {
+      // x and vpar keep their input values unless final_processing already wrote them (reference: intent(out))
+      o.ind_tetr = -1;
+      o.iface = -1;
+      o.finished = 0;
+      o.z_save_set = 0;
+    }
+    o.fallback = fallback;
+    return true;
+  }
+};
+
+template <bool PHI>
+GB_HD_NOINLINE PushOut push_rk_full_call(const MeshDev *mp, double perpinv, int ind_tetr, int iface, double x0, double x1,
+                                         double x2, double vpar, double t_remain)
+{
+  RkPusher<PHI> R;
+  PushOut o;
+  const double x[3] = {x0, x1, x2};
+  o.x[0] = x0; o.x[1] = x1; o.x[2] = x2; o.vpar = vpar;
+  o.z_save[0] = o.z_save[1] = o.z_save[2] = 0.0;
+  R.init(mp, perpinv, ind_tetr, x, iface, vpar, t_remain);
+  R.template push<false>(o);
+  return o;
+}
+
+} // namespace gb

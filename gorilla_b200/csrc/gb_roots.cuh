@@ -312,7 +312,7 @@ GB_HD double min_positive_real_root(int deg, const cd *croots, double lambda)
       const double tol_i = 1.0e-12 * fmax(1.0, fabs(re));
       if (fabs(im) <= tol_i) im = 0.0;
       re = re / lambda;
-      im = im / lambda;
+      im = div_z(im, lambda);
       if (fabs(im) == 0.0 && re > 0.0 && re < best) best = re;
     }
   }

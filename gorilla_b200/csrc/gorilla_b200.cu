@@ -167,8 +167,10 @@ __global__ void sort_keys_kernel(int64_t n, const int32_t *ind_tetr, uint32_t *k
 
 static int check_settings(const gorilla_settings *s)
 {
-  if (s->ipusher != 2) return fail(GORILLA_ERR_UNSUPPORTED, "ipusher: only 2 (polynomial pusher) is implemented");
-  if (s->poly_order < 1 || s->poly_order > 4) return fail(GORILLA_ERR_ARG, "poly_order must be 1..4");
+  if (s->ipusher != 1 && s->ipusher != 2) return fail(GORILLA_ERR_ARG, "ipusher must be 1 (RK4) or 2 (polynomial)");
+  if (s->ipusher == 2 && (s->poly_order < 1 || s->poly_order > 4)) return fail(GORILLA_ERR_ARG, "poly_order must be 1..4");
+  if (s->ipusher == 1 && !s->boole_dt_dtau) return fail(GORILLA_ERR_UNSUPPORTED, "ipusher = 1 requires boole_dt_dtau = .true.");
+  if (s->ipusher == 1 && s->boole_newton_precalc) return fail(GORILLA_ERR_UNSUPPORTED, "boole_newton_precalc must be .false.");
   if (s->i_precomp != 0) return fail(GORILLA_ERR_UNSUPPORTED, "i_precomp must be 0");
   if (s->i_time_tracing_option != 1) return fail(GORILLA_ERR_UNSUPPORTED, "i_time_tracing_option must be 1");
   if (s->handover_processing_kind != 1) return fail(GORILLA_ERR_UNSUPPORTED, "handover_processing_kind must be 1");
@@ -282,6 +284,7 @@ extern "C" int gorilla_b200_debug_force_full(gorilla_b200_handle *h, int32_t on)
 #define GB_EXTERN_ORBIT(K) \
   extern template int launch_orbit_t<K, true>(gorilla_b200_handle *, const Batch &, cudaStream_t); \
   extern template int launch_orbit_t<K, false>(gorilla_b200_handle *, const Batch &, cudaStream_t);
+GB_EXTERN_ORBIT(0)
 GB_EXTERN_ORBIT(1)
 GB_EXTERN_ORBIT(2)
 GB_EXTERN_ORBIT(3)
@@ -290,6 +293,7 @@ GB_EXTERN_ORBIT(4)
 template <bool PHI>
 static int launch_orbit_k(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
 {
+  if (h->settings.ipusher == 1) return launch_orbit_t<0, PHI>(h, bt, s);
   switch (h->settings.poly_order) {
     case 1: return launch_orbit_t<1, PHI>(h, bt, s);
     case 2: return launch_orbit_t<2, PHI>(h, bt, s);

@@ -1345,6 +1345,7 @@ typedef struct {
   double perpinv, perpinv2, vmod_init, spamat, dt_dtau_const, dist_min, dist1, dist_max, t_remain;
   double Bvec[3], b[4], z_init[4], amat[3][3], anorm[4][3]; /* anorm[f][i] = anorm(i+1,f+1) */
   double dtau_ref, dtau_max, dtau_quad;
+  int fb; /* per-push fall-back bits: 1 Newton failed, 2 last line of defence, 4 three-planes switch, 8 v_n>0 / stop outside */
 } rk_state;
 
 static void initialize_pusher_tetra_rk_mod(rk_state *s, int ind_tetr, const double x[3], int iface,
@@ -1453,6 +1454,724 @@ static void rk_normal_distances_func(const rk_state *s, const double z123[3], do
 static double rk_normal_velocity_func(const rk_state *s, int iface, const double dzdtau[4])
 {
   return dot3(dzdtau, s->anorm[iface - 1]);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * pusher_tetra_rk -- SRC/pusher_tetra_rk.f90 (RK4 mode: boole_pusher_ode45 = .false., boole_dt_dtau = .true.,
+ * boole_newton_precalc = .false.).  integration_step (:2549-2581) is then a single rk4_step.
+ * ---------------------------------------------------------------------------------------------- */
+#define RK_KITER 48
+static double rk_normal_distance_func(const rk_state *s, const double z123[3], int iface)
+{
+  double d = dot3(z123, s->anorm[iface - 1]);
+  if (iface == 1) d = d - s->dist1;
+  return d;
+}
+/* :2469-2483  sum(matmul(anorm(:,iface),amat)*dzdtau(1:3)) + sum(anorm(:,iface)*Bvec)*dzdtau(4) */
+static double rk_normal_acceleration_func(const rk_state *s, int iface, const double dzdtau[4])
+{
+  const double *n = s->anorm[iface - 1];
+  double t[3];
+  for (int j = 0; j < 3; j++) t[j] = ((0.0 + n[0] * s->amat[0][j]) + n[1] * s->amat[1][j]) + n[2] * s->amat[2][j];
+  return dot3(t, dzdtau) + dot3(n, s->Bvec) * dzdtau[3];
+}
+static bool rk_any_gt(const double d[4], double lim) { return d[0] > lim || d[1] > lim || d[2] > lim || d[3] > lim; }
+static int rk_minloc(const double d[4])
+{
+  int k = 0;
+  for (int i = 1; i < 4; i++)
+    if (d[i] < d[k]) k = i;
+  return k + 1;
+}
+static double rk_minval(const double d[4]) { return d[rk_minloc(d) - 1]; }
+
+/* :636-809 */
+static void quad_analytic_approx(const rk_state *s, const double z[4], const bool allowed_faces[4], int *iface_inout,
+                                 double *dtau, bool *boole_quad_approx)
+{
+  double acoef[4], bcoef[4], ccoef[4], dtau_vec[4], discr, dummy;
+  const double *r = s->r;
+  for (int f = 0; f < 4; f++) acoef[f] = r[TP_ACOEF_PRE + f] * (double)s->sign_rhs;
+  for (int f = 0; f < 4; f++) bcoef[f] = z[3] * acoef[f] + dot3(s->b, s->anorm[f]);
+  for (int f = 0; f < 4; f++) acoef[f] = acoef[f] * (s->b[3] + s->spamat * z[3]);
+  rk_normal_distances_func(s, z, ccoef);
+  const int iface = *iface_inout;
+  for (int f = 0; f < 4; f++) dtau_vec[f] = s->dtau_max;
+  for (int i = 0; i < 4; i++) {
+    if (!allowed_faces[i]) continue;
+    const double a = acoef[i], b = bcoef[i], c = ccoef[i];
+    if (iface == i + 1) {
+      if (a > 0.0) {
+        if (b < 0.0) dtau_vec[i] = -2.0 * b / a;
+      } else if (a < 0.0) {
+        if (b > 0.0) dtau_vec[i] = -2.0 * b / a;
+      }
+    } else if (fabs(c) > s->dist_min) {
+      if (c > 0.0) {
+        if (a > 0.0) {
+          if (b < 0.0) {
+            discr = b * b - 2.0 * a * c;
+            if (discr > 0.0) {
+              dummy = (-b + sqrt(discr));
+              if (fabs(dummy) > EPS) dtau_vec[i] = 2.0 * c / dummy;
+              else dtau_vec[i] = (-sqrt(discr) - b) / a;
+            } else if (discr == 0.0) {
+              dtau_vec[i] = -b / a;
+            }
+          }
+        } else if (a < 0.0) {
+          discr = b * b - 2.0 * a * c;
+          dummy = (-b + sqrt(discr));
+          if (fabs(dummy) > EPS) dtau_vec[i] = 2.0 * c / dummy;
+          else dtau_vec[i] = (-sqrt(discr) - b) / a;
+        } else {
+          if (b < 0.0) dtau_vec[i] = -c / b;
+        }
+      } else if (c < 0.0) {
+        if (a < 0.0) {
+          if (b > 0.0) {
+            discr = b * b - 2.0 * a * c;
+            if (discr > 0.0) dtau_vec[i] = (sqrt(discr) - b) / a;
+            else if (discr == 0.0) dtau_vec[i] = -b / a;
+          }
+        } else if (a > 0.0) {
+          discr = b * b - 2.0 * a * c;
+          dtau_vec[i] = (sqrt(discr) - b) / a;
+        } else {
+          if (b > 0.0) dtau_vec[i] = -c / b;
+        }
+      }
+      /* else (NaN): reference prints 'Should not happen' and stops */
+    } else {
+      if (((a > 0.0) && (b < 0.0)) || ((a < 0.0) && (b > 0.0))) dtau_vec[i] = -2.0 * b / a;
+    }
+  }
+  int best = -1;
+  for (int i = 0; i < 4; i++) {
+    bool valid = (dtau_vec[i] < s->dtau_max) && (dtau_vec[i] > 0.0);
+    if (valid && (best < 0 || dtau_vec[i] < dtau_vec[best])) best = i;
+  }
+  if (best >= 0) {
+    *boole_quad_approx = true;
+    *iface_inout = best + 1;
+    *dtau = dtau_vec[best];
+  } else {
+    *boole_quad_approx = false;
+  }
+}
+
+/* :1000-1188 (newton_face_convergence with RK4 accuracy == newton_face_convergence_wrapped + restore on failure) */
+static void newton_face_convergence_wrapped(rk_state *s, double z[4], double *tau, int iface, double dzdtau[4],
+                                            bool *converged, bool start_quadratic_in)
+{
+  double z_start[4], dzdtau_start[4], z_save[4], dzdtau_save[4];
+  double tau_start = *tau, dtau = 0, tau_save = 0, dist, dist_new = 0.0, discr, nvel, nacc, nd[4];
+  bool start_quadratic = start_quadratic_in;
+  memcpy(z_start, z, sizeof(z_start));
+  memcpy(dzdtau_start, dzdtau, sizeof(dzdtau_start));
+  *converged = false;
+  dist = rk_normal_distance_func(s, z, iface);
+  int k = 0;
+  while (fabs(dist) > s->dist_min) {
+    k++;
+    memcpy(z_save, z, sizeof(z_save));
+    memcpy(dzdtau_save, dzdtau, sizeof(dzdtau_save));
+    nvel = rk_normal_velocity_func(s, iface, dzdtau);
+    if (nvel != 0.0) dtau = -dist / nvel;
+    else return;
+    tau_save = *tau;
+    rk_normal_distances_func(s, z, nd);
+    if (rk_any_gt(nd, s->dist_max)) {
+      dtau = *tau + dtau;
+      *tau = 0.0;
+      memcpy(z, s->z_init, 4 * sizeof(double));
+    }
+    if (fabs(dtau) > s->dtau_max) {
+      start_quadratic = true;
+    } else {
+      rk4_step(s, z, dtau, dzdtau);
+      dist_new = rk_normal_distance_func(s, z, iface);
+    }
+    if ((fabs(dist_new) >= fabs(dist)) || start_quadratic) {
+      start_quadratic = false;
+      memcpy(z, z_save, sizeof(z_save));
+      memcpy(dzdtau, dzdtau_save, sizeof(dzdtau_save));
+      *tau = tau_save;
+      nacc = 0.5 * rk_normal_acceleration_func(s, iface, dzdtau);
+      discr = nvel * nvel - 4.0 * nacc * dist;
+      if (discr > 0.0) {
+        if (nacc < 0.0) dtau = (-nvel - sqrt(discr)) / (2.0 * nacc);
+        else if (nacc > 0.0) dtau = (-nvel + sqrt(discr)) / (2.0 * nacc);
+        else dtau = -dist / nvel;
+        rk_normal_distances_func(s, z, nd);
+        if (rk_any_gt(nd, s->dist_max)) {
+          dtau = *tau + dtau;
+          *tau = 0.0;
+          memcpy(z, s->z_init, 4 * sizeof(double));
+        }
+        if (fabs(dtau) > s->dtau_max) {
+          memcpy(z, z_start, sizeof(z_start));
+          *tau = tau_start;
+          memcpy(dzdtau, dzdtau_start, sizeof(dzdtau_start));
+          return;
+        }
+        rk4_step(s, z, dtau, dzdtau);
+        *tau = *tau + dtau;
+        dist = rk_normal_distance_func(s, z, iface);
+      } else {
+        return;
+      }
+    } else {
+      *tau = *tau + dtau;
+      dist = dist_new;
+    }
+    if (k > RK_KITER) return;
+  }
+  if (*tau <= 0.0) {
+    memcpy(z, z_start, sizeof(z_start));
+    *tau = tau_start;
+    memcpy(dzdtau, dzdtau_start, sizeof(dzdtau_start));
+    return;
+  }
+  *converged = true;
+}
+/* :914-996 */
+static void newton_face_convergence(rk_state *s, double z[4], double *tau, int iface, double dzdtau[4], bool *converged,
+                                    bool start_quadratic)
+{
+  double z_save[4], dzdtau_save[4], tau_save = *tau;
+  memcpy(z_save, z, sizeof(z_save));
+  memcpy(dzdtau_save, dzdtau, sizeof(dzdtau_save));
+  newton_face_convergence_wrapped(s, z, tau, iface, dzdtau, converged, start_quadratic);
+  if (!*converged) {
+    memcpy(z, z_save, sizeof(z_save));
+    *tau = tau_save;
+    memcpy(dzdtau, dzdtau_save, sizeof(dzdtau_save));
+  }
+}
+
+/* :1583-1623 ; streaming form of the 1000-step scan (z_mat/normal_distances_mat are not materialised) */
+static void bisection_search_start(rk_state *s, double tau_in, int n_steps, double z_start[4], double *dtau, double *tau_out)
+{
+  double z_run[4], dzdtau[4], nd[4], tau_run = 0.0;
+  memcpy(z_run, s->z_init, sizeof(z_run));
+  *dtau = tau_in / (double)n_steps;
+  /* start_index = (last index whose point is strictly inside) + 1; 0 + 1 = 1 when none is inside */
+  int last_inside = 0;
+  bool take_next = false;
+  rk_normal_distances_func(s, z_run, nd);
+  memcpy(z_start, z_run, 4 * sizeof(double));
+  *tau_out = 0.0;
+  if (nd[0] > 0.0 && nd[1] > 0.0 && nd[2] > 0.0 && nd[3] > 0.0) { last_inside = 1; take_next = true; }
+  for (int i = 2; i <= n_steps; i++) {
+    rk4_step(s, z_run, *dtau, dzdtau);
+    tau_run = tau_run + *dtau;
+    rk_normal_distances_func(s, z_run, nd);
+    if (take_next) {
+      memcpy(z_start, z_run, 4 * sizeof(double));
+      *tau_out = tau_run;
+      take_next = false;
+    }
+    if (nd[0] > 0.0 && nd[1] > 0.0 && nd[2] > 0.0 && nd[3] > 0.0) { last_inside = i; take_next = true; }
+  }
+  /* last point inside: the reference reads z_mat(:,n_steps+1) (out of bounds); keep the last point instead */
+  if (last_inside == n_steps) {
+    memcpy(z_start, z_run, 4 * sizeof(double));
+    *tau_out = tau_run;
+  }
+}
+
+/* :1409-1581 */
+static void bisection_face_convergence(rk_state *s, double z[4], double *tau_inout, double dtau_in, int *iface,
+                                       double dzdtau[4], bool *converged)
+{
+  double tau = *tau_inout, dtau = dtau_in, z_save[4], nd[4];
+  memcpy(z_save, z, sizeof(z_save));
+  *converged = false;
+  for (int l = 1; l <= 2; l++) {
+    int k = 0;
+    while (!*converged) {
+      rk_normal_distances_func(s, z, nd);
+      double mn = rk_minval(nd);
+      if (mn < -s->dist_min) {
+        dtau = -fabs(dtau / 2.0);
+        if (rk_any_gt(nd, s->dist_max)) {
+          double dtau_save = dtau;
+          dtau = tau + dtau;
+          tau = 0.0;
+          memcpy(z, s->z_init, 4 * sizeof(double));
+          rk4_step(s, z, dtau, dzdtau);
+          tau = tau + dtau;
+          dtau = dtau_save;
+        } else {
+          rk4_step(s, z, dtau, dzdtau);
+          tau = tau + dtau;
+        }
+      } else if (mn > s->dist_min) {
+        dtau = +fabs(dtau / 2.0);
+        rk4_step(s, z, dtau, dzdtau);
+        tau = tau + dtau;
+      }
+      rk_normal_distances_func(s, z, nd);
+      if (fabs(rk_minval(nd)) < s->dist_min) {
+        if (rk_normal_velocity_func(s, rk_minloc(nd), dzdtau) > 0.0) {
+          dtau = +fabs(dtau / 2.0);
+          rk4_step(s, z, dtau, dzdtau);
+          tau = tau + dtau;
+        } else {
+          int j = 0;
+          for (int i = 0; i < 4; i++)
+            if (nd[i] < 0.0) j++;
+          if (j <= 1) {
+            *iface = rk_minloc(nd);
+            *converged = true;
+          } else {
+            dtau = -fabs(dtau / 2.0);
+            rk4_step(s, z, dtau, dzdtau);
+            tau = tau + dtau;
+          }
+        }
+      }
+      k++;
+      if (k > RK_KITER) {
+        if (l == 1) {
+          int nfc = 0;
+          for (int i = 0; i < 4; i++)
+            if (nd[i] < 0.0 && fabs(nd[i]) < s->dist_min) nfc++;
+          if (nfc > 1) {
+            s->dist_min = 2.0 * s->dist_min;
+            tau = *tau_inout;
+            dtau = dtau_in;
+            memcpy(z, z_save, sizeof(z_save));
+          } else {
+            bisection_search_start(s, *tau_inout, 1000, z, &dtau, &tau);
+          }
+          break;
+        } else {
+          goto done;
+        }
+      }
+    }
+    if (*converged) break;
+  }
+done:
+  *tau_inout = tau;
+}
+
+/* :1696-2071 */
+static void last_line_defense(rk_state *s, double z[4], double *tau, int *iface, double dzdtau[4], bool *llod_converged)
+{
+  bool allowed_faces[4] = {true, true, true, true};
+  bool turned_tangential = false, converged = false, distance_bisection = false, quad_ok, bis_ok, newton_ok;
+  double dtau, nd[4], z_save[4], dtau_save, tau_save;
+  int iface_new = s->iface_init, iface_init_outside = 0, k;
+  s->fb |= 2;
+  *llod_converged = true;
+  *tau = 0.0;
+  memcpy(z, s->z_init, 4 * sizeof(double));
+  if (s->iface_init != 0)
+    if (rk_normal_distance_func(s, z, s->iface_init) < 0.0) iface_init_outside = s->iface_init;
+  quad_analytic_approx(s, z, allowed_faces, &iface_new, &dtau, &quad_ok);
+  if (quad_ok) {
+    rk4_step(s, z, dtau, dzdtau);
+    *tau = *tau + dtau;
+  } else {
+    dtau = s->dtau_ref;
+    rk4_step(s, z, dtau, dzdtau);
+    *tau = *tau + dtau;
+    rk_normal_distances_func(s, z, nd);
+    iface_new = rk_minloc(nd);
+  }
+  k = 0;
+  for (;;) {
+    k++;
+    rk_normal_distances_func(s, z, nd);
+    if (rk_any_gt(nd, s->dist_max)) {
+      distance_bisection = true;
+      dtau = *tau - 0.5 * fabs(dtau);
+      *tau = 0.0;
+      memcpy(z, s->z_init, 4 * sizeof(double));
+      rk4_step(s, z, dtau, dzdtau);
+      *tau = *tau + dtau;
+    } else {
+      break; /* RK4 accuracy: both inner branches exit */
+    }
+    if (k > RK_KITER) {
+      *llod_converged = false;
+      return;
+    }
+  }
+  (void)distance_bisection;
+  if (iface_init_outside != 0) {
+    if (rk_normal_distance_func(s, z, iface_init_outside) < 0.0) {
+      if (rk_normal_velocity_func(s, iface_init_outside, dzdtau) < 0.0) {
+        for (int i = 1; i <= 3; i++) {
+          int j = ((iface_init_outside + i - 1) % 4) + 1;
+          if (rk_normal_distance_func(s, z, j) < 0.0) turned_tangential = true;
+        }
+        iface_new = iface_init_outside;
+        if (fabs(rk_normal_distance_func(s, z, iface_new)) < s->dist_min) converged = true;
+      }
+    }
+  }
+  if (!converged) {
+    if (turned_tangential) {
+      bisection_face_convergence(s, z, tau, dtau, &iface_new, dzdtau, &bis_ok);
+      if (!bis_ok) {
+        *llod_converged = false;
+        return;
+      }
+    } else {
+      bool dtau_decreased = false;
+      k = 0;
+      for (;;) {
+        k++;
+        rk_normal_distances_func(s, z, nd);
+        bool out[4];
+        int n_out = 0;
+        for (int i = 0; i < 4; i++) {
+          out[i] = nd[i] < 0.0;
+          if (out[i]) n_out++;
+        }
+        if (n_out == 0) {
+          dtau = dtau_decreased ? 0.5 * fabs(dtau) : 2.0 * fabs(dtau);
+        } else if (n_out == 1) {
+          iface_new = 1;
+          for (int i = 0; i < 4; i++)
+            if (out[i]) { iface_new = i + 1; break; }
+          if (rk_normal_velocity_func(s, iface_new, dzdtau) >= 0.0) {
+            if (iface_init_outside != iface_new) {
+              dtau = -0.5 * fabs(dtau);
+              dtau_decreased = true;
+            } else {
+              dtau = dtau_decreased ? 0.5 * fabs(dtau) : 2.0 * fabs(dtau);
+            }
+          } else {
+            break;
+          }
+        } else {
+          int l = 0;
+          for (int i = 0; i < 4; i++)
+            if (out[i] && fabs(nd[i]) < s->dist_min) l++;
+          if (l == n_out) {
+            int j = 0;
+            for (int i = 0; i < 4; i++) {
+              if (!out[i]) continue;
+              if (fabs(nd[i]) >= s->dist_min) continue;
+              if (rk_normal_velocity_func(s, i + 1, dzdtau) > 0.0) j++;
+            }
+            if (j > 0) {
+              dtau = 2.0 * fabs(dtau);
+            } else {
+              int best = -1;
+              for (int i = 0; i < 4; i++)
+                if (out[i] && (best < 0 || fabs(nd[i]) < fabs(nd[best]))) best = i;
+              iface_new = best + 1;
+              break;
+            }
+          } else {
+            dtau = -0.5 * fabs(dtau);
+            dtau_decreased = true;
+          }
+        }
+        if (rk_any_gt(nd, s->dist_max)) {
+          dtau = *tau + dtau;
+          *tau = 0.0;
+          memcpy(z, s->z_init, 4 * sizeof(double));
+        }
+        rk4_step(s, z, dtau, dzdtau);
+        *tau = *tau + dtau;
+        if (k > RK_KITER) {
+          *llod_converged = false;
+          return;
+        }
+      }
+      memcpy(z_save, z, sizeof(z_save));
+      dtau_save = dtau;
+      tau_save = *tau;
+      newton_face_convergence(s, z, tau, iface_new, dzdtau, &newton_ok, false);
+      for (int i = 1; i <= 3; i++) {
+        int j = ((iface_new + i - 1) % 4) + 1;
+        if (rk_normal_distance_func(s, z, j) < 0.0) newton_ok = false;
+      }
+      if ((!newton_ok) || (rk_normal_velocity_func(s, iface_new, dzdtau) >= 0.0)) {
+        memcpy(z, z_save, sizeof(z_save));
+        *tau = tau_save;
+        dtau = dtau_save;
+        bisection_face_convergence(s, z, tau, dtau, &iface_new, dzdtau, &bis_ok);
+        if (!bis_ok) {
+          *llod_converged = false;
+          return;
+        }
+      }
+    }
+  }
+  *iface = iface_new;
+}
+
+/* :2075-2418 (boole_dt_dtau = .true.) ; returns false when final processing did not converge */
+static bool rk_final_processing(rk_state *s, double z[4], double *tau, int *iface_inout, int *ind_tetr_out, int *iper_phi,
+                                double x[3], double *vpar, double *t_pass, bool *boole_t_finished)
+{
+  const gor_mesh *m = s->m;
+  int iface_new = *iface_inout;
+  double dzdtau[4], nd[4], nd_save[4], z_save[4], dtau, tau_save;
+  bool llod_ok, newton_ok, bis_ok;
+  for (int i = 0; i < 3; i++) x[i] = z[i] + s->r[TP_X1 + i];
+  *t_pass = *tau * s->dt_dtau_const;
+  if (fabs(s->t_remain) < fabs(*t_pass)) {
+    memcpy(z, s->z_init, 4 * sizeof(double));
+    *tau = 0.0;
+    dtau = s->t_remain / s->dt_dtau_const;
+    memcpy(z_save, z, sizeof(z_save));
+    rk_normal_distances_func(s, z, nd_save);
+    rk4_step(s, z, dtau, dzdtau);
+    if (rk_any_gt(nd_save, s->dist_max)) {
+      memcpy(z, z_save, sizeof(z_save));
+      last_line_defense(s, z, tau, &iface_new, dzdtau, &llod_ok);
+      for (int j = 1; j <= 3; j++) {
+        int k = ((iface_new + j - 1) % 4) + 1;
+        if (rk_normal_distance_func(s, z, k) < 0.0) return false;
+      }
+      if (rk_normal_velocity_func(s, iface_new, dzdtau) > 0.0) return false;
+      for (int i = 0; i < 3; i++) x[i] = z[i] + s->r[TP_X1 + i];
+      *t_pass = *tau * s->dt_dtau_const;
+      if (fabs(*t_pass) <= fabs(s->t_remain)) {
+        *boole_t_finished = false;
+        *vpar = z[3];
+        *iface_inout = iface_new;
+        handover2neighbour(m, s->ind_tetr, ind_tetr_out, iface_inout, x, iper_phi);
+        return true; /* `exit` of the loop, then falls to the classification below in the reference: see note */
+      }
+      return false;
+    }
+    *tau = *tau + dtau;
+    for (int i = 0; i < 3; i++) x[i] = z[i] + s->r[TP_X1 + i];
+    rk_normal_distances_func(s, z, nd);
+    *t_pass = *tau * s->dt_dtau_const;
+    int i_outside_plane = 0, iface_outside = 0;
+    for (int i = 0; i < 4; i++)
+      if (nd[i] < 0.0) { i_outside_plane++; iface_outside = i + 1; }
+    bool any_conv = false;
+    for (int i = 0; i < 4; i++)
+      if (fabs(nd[i]) < s->dist_min) any_conv = true;
+    if (any_conv) {
+      if (i_outside_plane == 1) iface_new = iface_outside;
+      else
+        for (int i = 0; i < 4; i++)
+          if (fabs(nd[i]) < s->dist_min) iface_new = i + 1;
+      for (int i = 0; i < 3; i++) x[i] = z[i] + s->r[TP_X1 + i];
+      *t_pass = *tau * s->dt_dtau_const;
+      *boole_t_finished = true;
+      *vpar = z[3];
+      if (rk_normal_velocity_func(s, iface_new, dzdtau) < 0.0) {
+        *iface_inout = iface_new;
+        handover2neighbour(m, s->ind_tetr, ind_tetr_out, iface_inout, x, iper_phi);
+      } else {
+        *ind_tetr_out = s->ind_tetr;
+        *iface_inout = iface_new;
+      }
+    } else if (i_outside_plane != 0) {
+      s->fb |= 8;
+      if (i_outside_plane == 1) {
+        iface_new = iface_outside;
+        tau_save = *tau;
+        memcpy(z_save, z, sizeof(z_save));
+        newton_face_convergence(s, z, tau, iface_new, dzdtau, &newton_ok, true);
+        if (!newton_ok) {
+          memcpy(z, z_save, sizeof(z_save));
+          *tau = tau_save;
+          rk4_step(s, z, 0.0, dzdtau);
+          newton_face_convergence(s, z, tau, iface_new, dzdtau, &newton_ok, false);
+          if (!newton_ok) {
+            memcpy(z, z_save, sizeof(z_save));
+            *tau = tau_save;
+            bisection_face_convergence(s, z, tau, *tau, &iface_new, dzdtau, &bis_ok);
+            if (!bis_ok) return false;
+          }
+        }
+        if (rk_normal_velocity_func(s, iface_new, dzdtau) > 0.0) {
+          memcpy(z, z_save, sizeof(z_save));
+          *tau = tau_save;
+          bisection_face_convergence(s, z, tau, *tau, &iface_new, dzdtau, &bis_ok);
+          if (!bis_ok) return false;
+        }
+      } else {
+        bisection_face_convergence(s, z, tau, *tau, &iface_new, dzdtau, &bis_ok);
+        if (!bis_ok) return false;
+      }
+      for (int i = 0; i < 3; i++) x[i] = z[i] + s->r[TP_X1 + i];
+      *t_pass = *tau * s->dt_dtau_const;
+      *boole_t_finished = false;
+      *vpar = z[3];
+      *iface_inout = iface_new;
+      handover2neighbour(m, s->ind_tetr, ind_tetr_out, iface_inout, x, iper_phi);
+    } else {
+      *vpar = z[3];
+      *boole_t_finished = true;
+      *ind_tetr_out = s->ind_tetr;
+      *iface_inout = 0;
+      *iper_phi = 0;
+    }
+  } else {
+    *boole_t_finished = false;
+    *vpar = z[3];
+    *iface_inout = iface_new;
+    handover2neighbour(m, s->ind_tetr, ind_tetr_out, iface_inout, x, iper_phi);
+  }
+  return true;
+}
+
+/* :197-575 */
+static void pusher_tetra_rk(rk_state *s, int *ind_tetr_inout, int *iface, double x[3], double *vpar, double z_final[3],
+                            double t_remain_in, double *t_pass, bool *boole_t_finished, int *iper_phi, gor_trace *tr)
+{
+  bool allowed_faces[4] = {true, true, true, true};
+  bool quad_ok, newton_ok, llod_ok, boole_converged = false;
+  double z[4], dzdtau[4], tau = 0.0, dtau, nd[4];
+  int iface_new;
+  initialize_pusher_tetra_rk_mod(s, *ind_tetr_inout, x, *iface, *vpar, t_remain_in);
+  s->fb = 0;
+  memcpy(z, s->z_init, sizeof(z));
+  iface_new = *iface;
+  *boole_t_finished = false;
+  *t_pass = 0.0;
+  *iper_phi = 0;
+  quad_analytic_approx(s, z, allowed_faces, &iface_new, &dtau, &quad_ok);
+  if (quad_ok) {
+    rk4_step(s, z, dtau, dzdtau);
+    tau = tau + dtau;
+  } else {
+    dtau = s->dtau_ref;
+    rk4_step(s, z, dtau, dzdtau);
+    tau = tau + dtau;
+    rk_normal_distances_func(s, z, nd);
+    iface_new = 1;
+    for (int i = 1; i < 4; i++)
+      if (fabs(nd[i]) < fabs(nd[iface_new - 1])) iface_new = i + 1;
+  }
+  rk_normal_distances_func(s, z, nd);
+  if (rk_any_gt(nd, s->dist_max)) {
+    last_line_defense(s, z, &tau, &iface_new, dzdtau, &llod_ok);
+    if (!llod_ok) {
+      *ind_tetr_inout = -1;
+      *iface = -1;
+      goto count;
+    }
+  }
+#define RK_LLOD_CYCLE()                                                 \
+  do {                                                                  \
+    last_line_defense(s, z, &tau, &iface_new, dzdtau, &llod_ok);        \
+    boole_converged = false;                                            \
+  } while (0)
+  for (int i = 1; i <= 5; i++) {
+    boole_converged = true;
+    newton_face_convergence(s, z, &tau, iface_new, dzdtau, &newton_ok, false);
+    if (!newton_ok) {
+      s->fb |= 1;
+      allowed_faces[iface_new - 1] = false;
+      if (!allowed_faces[0] && !allowed_faces[1] && !allowed_faces[2] && !allowed_faces[3]) { RK_LLOD_CYCLE(); continue; }
+      if (tau > s->dtau_quad) {
+        memcpy(z, s->z_init, sizeof(z));
+        tau = 0.0;
+      }
+      quad_analytic_approx(s, z, allowed_faces, &iface_new, &dtau, &quad_ok);
+      if (!quad_ok) { RK_LLOD_CYCLE(); continue; }
+      rk_normal_distances_func(s, z, nd);
+      if (rk_any_gt(nd, s->dist_max)) {
+        dtau = tau + dtau;
+        tau = 0.0;
+        memcpy(z, s->z_init, sizeof(z));
+      }
+      rk4_step(s, z, dtau, dzdtau);
+      tau = tau + dtau;
+      boole_converged = false;
+      continue;
+    }
+    bool cycled = false;
+    for (int j = 1; j <= 3; j++) {
+      int k = ((iface_new + j - 1) % 4) + 1;
+      if (rk_normal_distance_func(s, z, k) < 0.0) {
+        s->fb |= 4;
+        allowed_faces[iface_new - 1] = false;
+        if (!allowed_faces[0] && !allowed_faces[1] && !allowed_faces[2] && !allowed_faces[3]) { RK_LLOD_CYCLE(); cycled = true; break; }
+        if (allowed_faces[k - 1]) {
+          iface_new = k;
+          boole_converged = false;
+          cycled = true;
+          break;
+        } else {
+          RK_LLOD_CYCLE();
+          cycled = true;
+          break;
+        }
+      }
+    }
+    if (cycled) continue;
+    if (rk_normal_velocity_func(s, iface_new, dzdtau) > 0.0) {
+      s->fb |= 8;
+      allowed_faces[iface_new - 1] = false;
+      if (!allowed_faces[0] && !allowed_faces[1] && !allowed_faces[2] && !allowed_faces[3]) { RK_LLOD_CYCLE(); continue; }
+      if (tau > s->dtau_quad) {
+        memcpy(z, s->z_init, sizeof(z));
+        tau = 0.0;
+      }
+      quad_analytic_approx(s, z, allowed_faces, &iface_new, &dtau, &quad_ok);
+      if (!quad_ok) { RK_LLOD_CYCLE(); continue; }
+      rk_normal_distances_func(s, z, nd);
+      if (rk_any_gt(nd, s->dist_max)) {
+        dtau = tau + dtau;
+        tau = 0.0;
+        memcpy(z, s->z_init, sizeof(z));
+      }
+      rk4_step(s, z, dtau, dzdtau);
+      tau = tau + dtau;
+      boole_converged = false;
+      continue;
+    }
+    if (tau <= 0.0) {
+      allowed_faces[iface_new - 1] = false;
+      memcpy(z, s->z_init, sizeof(z));
+      tau = 0.0;
+      if (!allowed_faces[0] && !allowed_faces[1] && !allowed_faces[2] && !allowed_faces[3]) { RK_LLOD_CYCLE(); continue; }
+      quad_analytic_approx(s, z, allowed_faces, &iface_new, &dtau, &quad_ok);
+      if (!quad_ok) { RK_LLOD_CYCLE(); continue; }
+      rk4_step(s, z, dtau, dzdtau);
+      tau = tau + dtau;
+      boole_converged = false;
+      continue;
+    }
+    break;
+  }
+#undef RK_LLOD_CYCLE
+  if (!boole_converged) {
+    *ind_tetr_inout = -1;
+    *iface = -1;
+    goto count;
+  }
+  *iface = iface_new;
+  int ind_out = *ind_tetr_inout;
+  if (!rk_final_processing(s, z, &tau, iface, &ind_out, iper_phi, x, vpar, t_pass, boole_t_finished)) {
+    *ind_tetr_inout = -1;
+    *iface = -1;
+    goto count;
+  }
+  *ind_tetr_inout = ind_out;
+  for (int i = 0; i < 3; i++) z_final[i] = z[i];
+  if ((fabs(*t_pass) >= fabs(s->t_remain)) && (!*boole_t_finished)) {
+    *ind_tetr_inout = -1;
+    *iface = -1;
+    goto count;
+  }
+  if ((*t_pass * (double)s->sign_t_step_save) <= 0.0) {
+    *ind_tetr_inout = -1;
+    *iface = -1;
+    goto count;
+  }
+count:
+  if (tr)
+    for (int q = 0; q < 4; q++)
+      if (s->fb & (1 << q)) tr->n_fallback[q]++;
 }
 
 /* SRC/tetra_physics_mod.f90:1038-1072 */
@@ -1606,7 +2325,7 @@ int gor_orbit_timestep(const gor_mesh *m, double x[3], double *vpar, double *vpe
                        int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface, double *t_remain_out,
                        gor_trace *tr)
 {
-  if (m->ipusher != 2) return GOR_ERR_CONFIG;
+  if (m->ipusher != 2 && m->ipusher != 1) return GOR_ERR_CONFIG;
   if (!*boole_initialized) {
     int rcd = gor_check_coordinate_domain(m, x);
     if (rcd != GOR_OK) return rcd;
@@ -1634,6 +2353,11 @@ int gor_orbit_timestep(const gor_mesh *m, double x[3], double *vpar, double *vpe
   s.tr = tr;
   s.perpinv = -0.5 * vperp2 / gor_bmod(m, z_save, *ind_tetr);
   s.perpinv2 = s.perpinv * s.perpinv;
+  rk_state rk;
+  memset(&rk, 0, sizeof(rk));
+  rk.m = m;
+  rk.perpinv = s.perpinv;
+  rk.perpinv2 = s.perpinv2;
   double t_remain = t_step, t_pass;
   bool boole_t_finished = false;
   int ind_tetr_save = *ind_tetr, iper;
@@ -1644,7 +2368,10 @@ int gor_orbit_timestep(const gor_mesh *m, double x[3], double *vpar, double *vpe
     }
     ind_tetr_save = *ind_tetr;
     int it = *ind_tetr, ifc = *iface;
-    pusher_tetra_poly(&s, m->poly_order, &it, &ifc, x, vpar, z_save, t_remain, &t_pass, &boole_t_finished, &iper);
+    if (m->ipusher == 1)
+      pusher_tetra_rk(&rk, &it, &ifc, x, vpar, z_save, t_remain, &t_pass, &boole_t_finished, &iper, tr);
+    else
+      pusher_tetra_poly(&s, m->poly_order, &it, &ifc, x, vpar, z_save, t_remain, &t_pass, &boole_t_finished, &iper);
     *ind_tetr = it;
     *iface = ifc;
     if (tr) {

@@ -16,7 +16,7 @@ using namespace gb;
 struct HostMirror {
   std::vector<double> geom, bpart, phi, cold;
   MeshDev m;
-  int poly_order, boole_periodic_relocation;
+  int poly_order, boole_periodic_relocation, ipusher;
 };
 
 template <int K, bool PHI>
@@ -37,13 +37,22 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
     ind_save = ind_tetr;
     PushOut o;
     bool done = false;
-    if (!force_full) {
-      PolyPusher<K, PHI> P;
-      P.mp = &m;
-      P.perpinv = perpinv;
-      done = P.push_fast(ind_tetr, iface, x, vpar, t_remain, o);
+    if constexpr (K == 0) {
+      if (!force_full) {
+        RkPusher<PHI> R;
+        R.init(&m, perpinv, ind_tetr, x, iface, vpar, t_remain);
+        done = R.template push<true>(o);
+      }
+      if (!done) o = push_rk_full_call<PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
+    } else {
+      if (!force_full) {
+        PolyPusher<K, PHI> P;
+        P.mp = &m;
+        P.perpinv = perpinv;
+        done = P.push_fast(ind_tetr, iface, x, vpar, t_remain, o);
+      }
+      if (!done) o = push_full_call<K, PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
     }
-    if (!done) o = push_full_call<K, PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
     x[0] = o.x[0]; x[1] = o.x[1]; x[2] = o.x[2];
     vpar = o.vpar;
     if (o.z_save_set) { z_save[0] = o.z_save[0]; z_save[1] = o.z_save[1]; z_save[2] = o.z_save[2]; }
@@ -67,7 +76,7 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
 
 extern "C" {
 
-void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, int boole_periodic_relocation)
+void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, int boole_periodic_relocation, int ipusher)
 {
   HostMirror *h = new HostMirror();
   bool has_phi = false;
@@ -83,7 +92,8 @@ void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, in
   m.grid_size1 = md->grid_size[0]; m.grid_size2 = md->grid_size[1]; m.grid_size3 = md->grid_size[2];
   m.boole_guess = boole_guess; m.grid_kind = md->grid_kind; m.n_field_periods = md->n_field_periods;
   m.Rmin = md->Rmin; m.Rmax = md->Rmax; m.Zmin = md->Zmin; m.Zmax = md->Zmax; m.sfc_s_min = md->sfc_s_min;
-  h->poly_order = poly_order;
+  h->poly_order = ipusher == 1 ? 0 : poly_order;
+  h->ipusher = ipusher;
   h->boole_periodic_relocation = boole_periodic_relocation;
   return h;
 }
@@ -117,9 +127,9 @@ int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *v
 #define HM_RUN(K, PHI) run_particle<K, PHI>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
       t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, trace_cap, tt, tf, force_full, fallback)
     if (m.phi) {
-      switch (h->poly_order) { case 1: HM_RUN(1, true); break; case 2: HM_RUN(2, true); break; case 3: HM_RUN(3, true); break; default: HM_RUN(4, true); }
+      switch (h->poly_order) { case 0: HM_RUN(0, true); break; case 1: HM_RUN(1, true); break; case 2: HM_RUN(2, true); break; case 3: HM_RUN(3, true); break; default: HM_RUN(4, true); }
     } else {
-      switch (h->poly_order) { case 1: HM_RUN(1, false); break; case 2: HM_RUN(2, false); break; case 3: HM_RUN(3, false); break; default: HM_RUN(4, false); }
+      switch (h->poly_order) { case 0: HM_RUN(0, false); break; case 1: HM_RUN(1, false); break; case 2: HM_RUN(2, false); break; case 3: HM_RUN(3, false); break; default: HM_RUN(4, false); }
     }
   }
   return dom;

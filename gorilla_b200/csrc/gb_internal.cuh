@@ -61,7 +61,7 @@ struct Batch {
 #define GB_MINB_K4 4
 #endif
 #ifndef GB_MINB_RK
-#define GB_MINB_RK 4
+#define GB_MINB_RK 3
 #endif
 constexpr int gb_min_blocks(int K) { return K == 0 ? GB_MINB_RK : K == 1 ? GB_MINB_K1 : K == 2 ? GB_MINB_K2 : K == 3 ? GB_MINB_K3 : GB_MINB_K4; }
 

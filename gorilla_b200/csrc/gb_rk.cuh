@@ -671,7 +671,6 @@ struct RkPusher {
         converged = true;
         bool llod = false, requad = false, reset_first = false;
         if (!newton(z, tau, iface_new, dzdtau, false)) {
-          if (FAST) return false;
           fallback |= 1;
           allowed &= ~(1u << (iface_new - 1));
           if (allowed == 0) llod = true;
@@ -681,7 +680,6 @@ struct RkPusher {
           for (int j = 1; j <= 3 && !cycled; j++) {
             const int k = ((iface_new + j - 1) & 3) + 1;
             if (distance(z, k) < 0.0) {
-              if (FAST) return false;
               fallback |= 4;
               allowed &= ~(1u << (iface_new - 1));
               if (allowed == 0) llod = true;
@@ -693,13 +691,11 @@ struct RkPusher {
           }
           if (!cycled) {
             if (nvel(iface_new, dzdtau) > 0.0) {
-              if (FAST) return false;
               fallback |= 8;
               allowed &= ~(1u << (iface_new - 1));
               if (allowed == 0) llod = true;
               else requad = true;
             } else if (tau <= 0.0) {
-              if (FAST) return false;
               allowed &= ~(1u << (iface_new - 1));
 #pragma unroll
               for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
@@ -714,6 +710,7 @@ struct RkPusher {
           }
         }
         if (llod) {
+          if (FAST) return false;  // only the last-line-of-defence / bisection ladder is left to the complete path
           last_line_defense(z, tau, iface_new, dzdtau);  // its flag is not examined in the loop (:358-361)
           converged = false;
           continue;
@@ -725,6 +722,7 @@ struct RkPusher {
             tau = 0.0;
           }
           if (!quad_analytic_approx(z, allowed, iface_new, dtau)) {
+            if (FAST) return false;
             last_line_defense(z, tau, iface_new, dzdtau);
             converged = false;
             continue;
@@ -744,7 +742,10 @@ struct RkPusher {
           continue;
         }
       }
-      if (!converged) removed = true;
+      if (!converged) {
+        if (FAST) return false;
+        removed = true;
+      }
     }
     if (!removed) {
       const int rc = final_processing<FAST>(z, tau, iface_new, o);

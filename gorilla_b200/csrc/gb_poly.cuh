@@ -68,6 +68,12 @@ struct PushOut {
   int32_t fallback;  // bit0 2nd attempt, bit1 trouble shooting, bit2 prolonged, bit3 finish-outside
 };
 
+// an exit-time solve that has been set up but not executed (see PolyPusher::face_task)
+struct SolveTask {
+  double q[4], lambda, tau;
+  int deg, kind;
+};
+
 template <int K, bool PHI>
 struct PolyPusher {
   const MeshDev *mp;
@@ -207,26 +213,31 @@ struct PolyPusher {
     }
   }
 
-  // ---- one face: order reduction + solver dispatch (:1295-1467)
+  // ---- one face: order reduction + solver selection (:1295-1467).  The iterative solves are not executed
+  // here: they are described by (deg, q, lambda) so that a kernel can run them from a work queue.
+  // kind 0: dtau = 0 (no valid root), 1: dtau = t.tau (closed form), 2: iterative solve pending.
   template <int ORD>
-  GB_HD double face_root(const double *c, bool start_face, int i_scaling)
+  GB_HD void face_task(const double *c, bool start_face, int i_scaling, SolveTask &t) const
   {
     int solver;
     double qa, qb, qc = 0.0, qd = 0.0, qe = 0.0;
     const bool reduced = start_face || (c[0] == 0.0);
+    t.kind = 0;
+    t.tau = 0.0;
+    t.deg = 0;
     if (ORD == 1) {
-      if (reduced) return 0.0;
+      if (reduced) return;
       solver = 1; qa = c[1]; qb = c[0];
-      if (qa == 0.0) return 0.0;
+      if (qa == 0.0) return;
     } else if (ORD == 2) {
       if (reduced) {
         solver = 1; qa = c[2] / 2.0; qb = c[1];
-        if (qa == 0.0) return 0.0;
+        if (qa == 0.0) return;
       } else {
         solver = 2; qa = c[2]; qb = c[1]; qc = c[0];
         if (qa == 0.0) {
           if (qb != 0.0) { solver = 1; qa = qb; qb = qc; }
-          else return 0.0;
+          else return;
         }
       }
     } else if (ORD == 3) {
@@ -234,14 +245,14 @@ struct PolyPusher {
         solver = 2; qa = c[3] / 3.0; qb = c[2] / 2.0; qc = c[1];
         if (qa == 0.0) {
           if (qb != 0.0) { solver = 1; qa = qb; qb = qc; }
-          else return 0.0;
+          else return;
         }
       } else {
         solver = 3; qa = c[3]; qb = c[2]; qc = c[1]; qd = c[0];
         if (qa == 0.0) {
           if (qb != 0.0) { solver = 2; qa = qb; qb = qc; qc = qd; }
           else if (qc != 0.0) { solver = 1; qa = qc; qb = qd; }
-          else return 0.0;
+          else return;
         }
       }
     } else {
@@ -250,7 +261,7 @@ struct PolyPusher {
         if (qa == 0.0) {
           if (qb != 0.0) { solver = 2; qa = qb; qb = qc; qc = qd; }
           else if (qc != 0.0) { solver = 1; qa = qc; qb = qd; }
-          else return 0.0;
+          else return;
         }
       } else {
         solver = 4; qa = c[4]; qb = c[3]; qc = c[2]; qd = c[1]; qe = c[0];
@@ -258,16 +269,31 @@ struct PolyPusher {
           if (qb != 0.0) { solver = 3; qa = qb; qb = qc; qc = qd; qd = qe; }
           else if (qc != 0.0) { solver = 2; qa = qc; qb = qd; qc = qe; }
           else if (qd != 0.0) { solver = 1; qa = qd; qb = qe; }
-          else return 0.0;
+          else return;
         }
       }
     }
-    switch (solver) {
-      case 1: return linear_solver(qa, qb);
-      case 2: return (i_scaling == 0) ? quadratic_solver1(qa, qb, qc) : quadratic_solver2(qa, qb, qc, solver_iters);
-      case 3: return cubic_solver(qa, qb, qc, qd, solver_iters);
-      default: return quartic_solver(i_scaling, qa, qb, qc, qd, qe, solver_iters);
+    if (solver == 1) {
+      t.kind = 1;
+      t.tau = linear_solver(qa, qb);
+    } else if (solver == 2 && i_scaling == 0) {
+      t.kind = 1;
+      t.tau = quadratic_solver1(qa, qb, qc);
+    } else {
+      t.kind = 2;
+      t.deg = solver;
+      if (solver == 2) quadratic2_prepare(qa, qb, qc, t.q, t.lambda);
+      else if (solver == 3) cubic_prepare(qa, qb, qc, qd, t.q, t.lambda);
+      else quartic_prepare(i_scaling, qa, qb, qc, qd, qe, t.q, t.lambda);
     }
+  }
+  template <int ORD>
+  GB_HD double face_root(const double *c, bool start_face, int i_scaling)
+  {
+    SolveTask t;
+    face_task<ORD>(c, start_face, i_scaling, t);
+    if (t.kind == 2) return solve_monic_min_positive(t.deg, t.q[0], t.q[1], t.q[2], t.q[3], t.lambda, solver_iters);
+    return t.tau;
   }
 
   // ---- one face of an order-2 solve with the closed-form solver (i_scaling = 0): operands of the single
@@ -661,46 +687,77 @@ struct PolyPusher {
     return true;
   }
 
-  // ---- common case only; false => nothing decided, call push_full
-  GB_HD bool push_fast(int ind_tetr_in, int iface, const double *x, double vpar, double t_remain_in, PushOut &o)
+  // ---- common case only; false => nothing decided, call push_full.
+  // push_fast = fast_begin (set-up, order-2 guess, order-K solve described as a task) + the task's solve +
+  // fast_end (integration, checks, hand-over).  Kernels that run the solves from a work queue call the two halves
+  // separately; fast_end re-forms the Taylor vectors when `prepared` is false (bit-identical, same inputs).
+  GB_HD bool fast_begin(int ind_tetr_in, int iface, const double *x, double vpar, double t_remain_in, SolveTask &t,
+                        int &iface_new, double &tau_max)
   {
     init(ind_tetr_in, x, iface, vpar, t_remain_in);
     solver_iters = 0;
     fallback = 0;
-    double z[4] = {z_init[0], z_init[1], z_init[2], z_init[3]};
     double tau = 0.0;
-    int iface_new = iface_init;
+    iface_new = iface_init;
     // b, A and all Taylor vectors up to order K once; the order-2 guess reads the first three coefficients
-    prepare<(K > 2 ? K : 2)>(z);
+    prepare<(K > 2 ? K : 2)>(z_init);
     {
       double cm[4][5];
 #pragma unroll
-      for (int f = 0; f < 4; f++) face_coeffs<2>(r.an[f], f == 0, z, cm[f]);
+      for (int f = 0; f < 4; f++) face_coeffs<2>(r.an[f], f == 0, z_init, cm[f]);
       if (!pick_exit<2>(cm, 0xFu, 0, iface_new, tau)) return false;
     }
-    const double tau_max = tau * GB_EPS_TAU;
+    tau_max = tau * GB_EPS_TAU;
+    t.kind = 1;
+    t.tau = tau;
+    t.deg = 0;
     if (K > 2) {
-      const int guess = iface_new;
-      iface_new = iface_init;
-      if (mp->boole_guess) {
-        if (!analytic_approx_single<K>(guess, 0, z, iface_new, tau, true)) return false;
-      } else {
-        double cm[4][5];
-#pragma unroll
-        for (int f = 0; f < 4; f++) face_coeffs<K>(r.an[f], f == 0, z, cm[f]);
-        if (!pick_exit<K>(cm, 0xFu, 0, iface_new, tau)) return false;
-      }
+      if (!mp->boole_guess) return false;  // all-face order-K solves go through the complete path
+      double n[3], c[5];
+      face_normal(iface_new, n);
+      face_coeffs<K>(n, iface_new == 1, z_init, c);
+      face_task<K>(c, iface_new == iface_init, 0, t);
     }
-#ifdef GB_PREFETCH_NEXT
-    // the exit face is known: start pulling the neighbour's record in while this push is finished
-    // (measured on B200: 9.2e9 -> 7.6e9 crossings/s, i.e. harmful -- 16 resident warps already hide the L2 latency)
-    prefetch_record<PHI>(*mp, iface_new == 1 ? r.nb[0] : iface_new == 2 ? r.nb[1] : iface_new == 3 ? r.nb[2] : r.nb[3]);
-#endif
+    return true;
+  }
+  GB_HD bool fast_end(double tau, int iface_new, double tau_max, bool prepared, PushOut &o)
+  {
+    if (!((tau < GB_HUGE) && (tau > 0.0))) return false;
+    if (!prepared) prepare<(K > 2 ? K : 2)>(z_init);
+    double z[4] = {z_init[0], z_init[1], z_init[2], z_init[3]};
     integrate<K>(z, tau);
     if (!exit_point_ok(z, iface_new)) return false;
     if (K > 2 && tau > tau_max) return false;
     if (normal_v_from_trajectory(iface_new, tau) > 0.0) return false;
     return finish<true>(z, tau, iface_new, o);
+  }
+  GB_HD bool push_fast(int ind_tetr_in, int iface, const double *x, double vpar, double t_remain_in, PushOut &o)
+  {
+    SolveTask t;
+    int iface_new;
+    double tau_max;
+    if (K > 2 && !mp->boole_guess) {
+      // no face guess: order-K roots of all four faces
+      init(ind_tetr_in, x, iface, vpar, t_remain_in);
+      solver_iters = 0;
+      fallback = 0;
+      double z[4] = {z_init[0], z_init[1], z_init[2], z_init[3]}, tau = 0.0;
+      iface_new = iface_init;
+      prepare<K>(z);
+      double cm[4][5];
+#pragma unroll
+      for (int f = 0; f < 4; f++) face_coeffs<K>(r.an[f], f == 0, z, cm[f]);
+      if (!pick_exit<2>(cm, 0xFu, 0, iface_new, tau)) return false;
+      tau_max = tau * GB_EPS_TAU;
+      iface_new = iface_init;
+      if (!pick_exit<K>(cm, 0xFu, 0, iface_new, tau)) return false;
+      return fast_end(tau, iface_new, tau_max, true, o);
+    }
+    if (!fast_begin(ind_tetr_in, iface, x, vpar, t_remain_in, t, iface_new, tau_max)) return false;
+    double tau = t.tau;
+    if (t.kind == 0) return false;
+    if (t.kind == 2) tau = solve_monic_min_positive(t.deg, t.q[0], t.q[1], t.q[2], t.q[3], t.lambda, solver_iters);
+    return fast_end(tau, iface_new, tau_max, true, o);
   }
 
   // ---- the complete ladder (:182-675)

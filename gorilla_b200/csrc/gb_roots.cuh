@@ -97,29 +97,40 @@ GB_HD SgLaguerreConsts sg_consts(int degree)
   return c;
 }
 
-// poly: deg+1 coefficients (poly[0] constant term), roots: deg outputs.  deg in {2,3,4}.
-GB_HD void sg_roots(int deg, const cd *poly_in, cd *roots_out, int &iters)
-{
-  const cd zero = mk(0.0, 0.0), c_one = mk(1.0, 0.0);
-  cd poly[5], work[5], roots[4];
+// One lane's solve as a resumable object: start() loads the polynomial, every step() performs one trip of the
+// loop described above and returns true once all roots are final.  Keeping it resumable lets a kernel hand a lane
+// the next polynomial the moment it finishes one (work queue), so lanes never idle behind slower neighbours.
+struct SgSolver {
+  cd poly[5], work[5], roots[4], root;
+  int deg, n, phase, pol, mode, i, j, iter;
+  bool good_to_go, done;
+  double stopping_crit2;
+
+  // poly_in: deg+1 coefficients (poly_in[0] constant term), deg in {2,3,4}
+  GB_HD void start(int deg_, const cd *poly_in)
+  {
+    const cd zero = mk(0.0, 0.0);
+    deg = deg_;
 #pragma unroll
-  for (int k = 0; k < 5; k++) {
-    poly[k] = (k <= deg) ? poly_in[k <= deg ? k : 0] : zero;
-    work[k] = poly[k];
+    for (int k = 0; k < 5; k++) {
+      poly[k] = (k <= deg) ? poly_in[k <= deg ? k : 0] : zero;
+      work[k] = poly[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) roots[k] = zero;
+    n = deg;      // degree of the working polynomial during the search stages
+    phase = 0;    // 0: cmplx_laguerre2newton search, 1: cmplx_laguerre fall-back search, 2: polish
+    pol = 0;      // root being polished
+    root = zero;
+    mode = 2; i = 1; j = 1; iter = 0;
+    good_to_go = false;
+    stopping_crit2 = 0.0;
+    done = false;
   }
-#pragma unroll
-  for (int k = 0; k < 4; k++) roots[k] = zero;
 
-  int n = deg;      // degree of the working polynomial during the search stages
-  int phase = 0;    // 0: cmplx_laguerre2newton search, 1: cmplx_laguerre fall-back search, 2: polish
-  int pol = 0;      // root being polished
-  cd root = zero;
-  int mode = 2, i = 1, j = 1, iter = 0;
-  bool good_to_go = false;
-  double stopping_crit2 = 0.0;
-  bool done = false;
-
-  while (!done) {
+  GB_HD bool step()
+  {
+    const cd zero = mk(0.0, 0.0), c_one = mk(1.0, 0.0);
     const bool lag = (phase != 0);
     const int cdeg = (phase == 2) ? deg : n;
     cd c[5];
@@ -146,8 +157,7 @@ GB_HD void sg_roots(int deg, const cd *poly_in, cd *roots_out, int &iters)
       }
     }
     iter++;
-    iters++;
-    int ret = 0;  // 0 continue, 1 routine returns success, 2 routine returns failure
+        int ret = 0;  // 0 continue, 1 routine returns success, 2 routine returns failure
     const double abs2p = cabs2(p);
     if (abs2p == 0.0) {
       ret = 1;
@@ -292,10 +302,19 @@ GB_HD void sg_roots(int deg, const cd *poly_in, cd *roots_out, int &iters)
         good_to_go = false;
       }
     }
+    return done;
   }
+};
+
+// poly: deg+1 coefficients (poly[0] constant term), roots: deg outputs.  deg in {2,3,4}.
+GB_HD void sg_roots(int deg, const cd *poly_in, cd *roots_out, int &iters)
+{
+  SgSolver s;
+  s.start(deg, poly_in);
+  while (!s.step()) iters++;
 #pragma unroll
   for (int k = 0; k < 4; k++)
-    if (k < deg) roots_out[k] = roots[k];
+    if (k < deg) roots_out[k] = s.roots[k];
 }
 
 // pack_roots + the callers' "smallest positive real root / lambda" reduction, fused:
@@ -419,29 +438,27 @@ GB_HD bool quadratic_solver1_numden(double a, double b, double c, double &num, d
   return has;
 }
 
-GB_HD double quadratic_solver2(double a, double b, double c, int &iters)
+// Rescaling to a monic polynomial (the part of Quadratic_Solver2 / Cubic_Solver / Quartic_Solver before the root
+// solve): q[0..deg-1] coefficients (constant term first), lambda the scale that the roots are divided by.
+GB_HD void quadratic2_prepare(double a, double b, double c, double *q, double &lambda)
 {
-  double lambda = b / c;
-  double q[2];
+  lambda = b / c;
   q[0] = 2.0 * (b * b) / (a * c);
   q[1] = q[0];
-  return solve_monic_min_positive(2, q[0], q[1], 0.0, 0.0, lambda, iters);
+  q[2] = 0.0;
+  q[3] = 0.0;
 }
-
-GB_HD double cubic_solver(double a, double b, double c, double d, int &iters)
+GB_HD void cubic_prepare(double a, double b, double c, double d, double *q, double &lambda)
 {
-  double lambda = b / (2.0 * c);
-  double l2 = lambda * lambda;
-  double q[3];
+  lambda = b / (2.0 * c);
+  const double l2 = lambda * lambda;
   q[2] = 3.0 * lambda * b / a;
   q[1] = 6.0 * c * l2 / a;
   q[0] = 6.0 * d * (l2 * lambda) / a;
-  return solve_monic_min_positive(3, q[0], q[1], q[2], 0.0, lambda, iters);
+  q[3] = 0.0;
 }
-
-GB_HD double quartic_solver(int i_scaling, double a, double b, double c, double d, double e, int &iters)
+GB_HD void quartic_prepare(int i_scaling, double a, double b, double c, double d, double e, double *q, double &lambda)
 {
-  double lambda;
   switch (i_scaling) {
     case 0: lambda = sqrt(fabs(b / (6.0 * d))); break;
     case 1: lambda = b / (3.0 * c); break;
@@ -451,12 +468,29 @@ GB_HD double quartic_solver(int i_scaling, double a, double b, double c, double 
     case 5: lambda = d / e; break;
     default: lambda = pow(fabs(a / (24.0 * e)), 1.0 / 4.0); break;
   }
-  double l2 = lambda * lambda;
-  double q[4];
+  const double l2 = lambda * lambda;
   q[3] = 4.0 * b * lambda / a;
   q[2] = 12.0 * c * l2 / a;
   q[1] = 24.0 * d * (l2 * lambda) / a;
   q[0] = 24.0 * e * (l2 * l2) / a;
+}
+
+GB_HD double quadratic_solver2(double a, double b, double c, int &iters)
+{
+  double q[4], lambda;
+  quadratic2_prepare(a, b, c, q, lambda);
+  return solve_monic_min_positive(2, q[0], q[1], 0.0, 0.0, lambda, iters);
+}
+GB_HD double cubic_solver(double a, double b, double c, double d, int &iters)
+{
+  double q[4], lambda;
+  cubic_prepare(a, b, c, d, q, lambda);
+  return solve_monic_min_positive(3, q[0], q[1], q[2], 0.0, lambda, iters);
+}
+GB_HD double quartic_solver(int i_scaling, double a, double b, double c, double d, double e, int &iters)
+{
+  double q[4], lambda;
+  quartic_prepare(i_scaling, a, b, c, d, e, q, lambda);
   return solve_monic_min_positive(4, q[0], q[1], q[2], q[3], lambda, iters);
 }
 

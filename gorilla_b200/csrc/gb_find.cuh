@@ -62,7 +62,7 @@ GB_HD bool isinside(const MeshDev &m, int64_t ind_tetr, const double *x, double 
 
 // Start point lies (within tolerance) on >= 1 face: hop through the neighbours until every converged
 // face has inward normal velocity (find_tetra_mod.f90:478-581).
-template <bool PHI>
+template <int PHI>
 GB_HD_NOINLINE void find_tetra_on_face(const MeshDev *mp, double *x, double vpar, double vperp, int32_t &ind_tetr_out,
                                        int32_t &iface, int sign_t_step, const double *dist0, int n_plane_conv)
 {
@@ -84,7 +84,7 @@ GB_HD_NOINLINE void find_tetra_on_face(const MeshDev *mp, double *x, double vpar
     tried[i_try - 1] = ind_tetr_out;
     // ODE coefficients of this tetrahedron (b, amat, Bvec, spamat) for t_remain = sign_t_step
     P.init(ind_tetr_out, x, iface_new, vpar, (double)sign_t_step);
-    P.build_ode();
+    P.template build_ode<true>();
     double z[4] = {P.z_init[0], P.z_init[1], P.z_init[2], vpar};
     double dist[4];
     bool conv[4];
@@ -134,7 +134,7 @@ GB_HD_NOINLINE void find_tetra_on_face(const MeshDev *mp, double *x, double vpar
   }
 }
 
-template <bool PHI>
+template <int PHI>
 GB_HD void find_tetra(const MeshDev *mp, double *x, double vpar, double vperp, int32_t &ind_tetr_out, int32_t &iface,
                       int sign_t_step)
 {

@@ -65,7 +65,7 @@ struct Batch {
 #endif
 constexpr int gb_min_blocks(int K) { return K == 0 ? GB_MINB_RK : K == 1 ? GB_MINB_K1 : K == 2 ? GB_MINB_K2 : K == 3 ? GB_MINB_K3 : GB_MINB_K4; }
 
-template <int K, bool PHI>
+template <int K, int PHI>
 __global__ void __launch_bounds__(128, gb_min_blocks(K)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
 {
   const unsigned lane = threadIdx.x & 31u;
@@ -200,7 +200,7 @@ struct gorilla_b200_handle {
   int num_sms = 0;
   MeshDev mesh{};
   gorilla_settings settings{};
-  double *d_geom = nullptr, *d_bpart = nullptr, *d_phi = nullptr, *d_cold = nullptr;
+  double *d_geom = nullptr, *d_bpart = nullptr, *d_phi = nullptr, *d_cold = nullptr, *d_se = nullptr;
   unsigned long long *d_ctr = nullptr;
   // scratch for the host-pointer entry points
   int64_t cap = 0;
@@ -223,7 +223,7 @@ struct gorilla_b200_handle {
   cudaStream_t last_stream = nullptr;
 };
 
-template <int K, bool PHI>
+template <int K, int PHI>
 int launch_orbit_t(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
 {
   int per_sm = h->ctas_per_sm;

@@ -19,6 +19,10 @@
 //                       dt_dtau_const | neighbour_tetr(4) int32 | packed face/periodic flags  224 B
 //   phi   [ntetr][20] : Phi1 gPhi(3) gPhixh1(3) gPhixcurlA betmat(3,3) spbetmat (2 pad)        160 B
 //   cold  [ntetr][12] : tetra_dist_ref R1 Er_mod h_phi1 gh_phi(3) Aphi1 gAphi(3) (1 pad)        96 B
+//   se    [ntetr][32] : strong-electric-field group (boole_strong_electric_field, cylindrical grids only):
+//                       v2Emod_1 gv2Emod(3) gv2Emodxh1(3) gBxcurlvE gPhixcurlvE gv2EmodxcurlvE gv2EmodxcurlA
+//                       curlvE(3) gammat(3,3) spgammat v_E_mod_average | vE2_1 gvE2(3) (invariants) (3 pad)   256 B
+//                       (hot part = first 26 doubles = 7 sectors)
 // Matrices keep the Fortran column-major order: alpmat(i,j) -> [i + 3*j].
 #pragma once
 #include <stdint.h>
@@ -26,10 +30,13 @@
 
 namespace gb {
 
-enum { GEOM_ND = 16, BPART_ND = 28, PHI_ND = 20, COLD_ND = 12 };
+enum { GEOM_ND = 16, BPART_ND = 28, PHI_ND = 20, COLD_ND = 12, SE_ND = 32 };
 enum { B_BMOD1 = 0, B_GB = 1, B_CURLA = 4, B_CURLH = 7, B_GBXH1 = 10, B_GBXCURLA = 13, B_ALP = 14,
        B_SPALP = 23, B_DTDTAU = 24, B_TOPO = 25 };
 enum { P_PHI1 = 0, P_GPHI = 1, P_GPHIXH1 = 4, P_GPHIXCURLA = 7, P_BET = 8, P_SPBET = 17 };
+enum { S_V2EMOD1 = 0, S_GV2EMOD = 1, S_GV2EMODXH1 = 4, S_GBXCURLVE = 7, S_GPHIXCURLVE = 8, S_GV2EMODXCURLVE = 9,
+       S_GV2EMODXCURLA = 10, S_CURLVE = 11, S_GAMMAT = 14, S_SPGAMMAT = 23, S_VE_MOD_AVG = 24, S_HOT_ND = 26,
+       S_VE2_1 = 26, S_GVE2 = 27 };
 enum { C_TETRA_DIST_REF = 0, C_R1 = 1, C_ER_MOD = 2, C_HPHI1 = 3, C_GHPHI = 4, C_APHI1 = 7, C_GAPHI = 8 };
 
 // packed per-face topology: 7 bits per face f (0..3) at bit 7*f:
@@ -44,6 +51,7 @@ struct MeshDev {
   const double *bpart;
   const double *phi;  // nullptr when the whole Phi group is exactly zero
   const double *cold;
+  const double *se;   // nullptr unless boole_strong_electric_field
   double cm_over_e, particle_mass, particle_charge;
   double period_phi;   // 2*pi/n_field_periods, formed exactly as the reference does (2.d0*pi/n_field_periods)
   double period_theta; // 2.d0*pi
@@ -78,7 +86,7 @@ GB_HD void ld2(const double *p, double &a, double &b)
 
 // Pull the hot record of tetrahedron ind_tetr (1-based) towards the SM while the current push is still being
 // finished: the exit face -- and with it the next tetrahedron -- is known well before the record is needed.
-template <bool PHI>
+template <int PHI>
 GB_HD void prefetch_record(const MeshDev &m, int ind_tetr)
 {
 #if defined(__CUDA_ARCH__)
@@ -100,12 +108,15 @@ GB_HD void prefetch_record(const MeshDev &m, int ind_tetr)
 #endif
 }
 
-// One tetrahedron's hot record in registers.
-template <bool PHI>
+// One tetrahedron's hot record in registers.  PHI: 0 = magnetic part only (Phi group exactly zero), 1 = with the
+// electrostatic group, 2 = electrostatic + strong-electric-field groups.
+template <int PHI>
 struct Rec {
   double x1[3], dist_ref, an[4][3]; // an[f][i] = anorm(i+1, f+1)
   double bmod1, gB[3], curlA[3], curlh[3], gBxh1[3], gBxcurlA, alp[9], spalp, dtdtau;
   double Phi1, gPhi[3], gPhixh1[3], gPhixcurlA, bet[9], spbet;
+  double v2Emod1, gv2Emod[3], gv2Emodxh1[3], gBxcurlvE, gPhixcurlvE, gv2EmodxcurlvE, gv2EmodxcurlA, curlvE[3], gam[9], spgam,
+      vE_mod_avg;
   int32_t nb[4];
   uint32_t flags;
 
@@ -157,6 +168,27 @@ struct Rec {
 #pragma unroll
       for (int i = 0; i < 9; i++) bet[i] = p[P_BET + i];
       spbet = p[P_SPBET];
+    }
+    if (PHI == 2) {
+      double q[S_HOT_ND];
+      const double *ps = m.se + t * SE_ND;
+#pragma unroll
+      for (int i = 0; i < S_HOT_ND; i += 2) ld2(ps + i, q[i], q[i + 1]);
+      v2Emod1 = q[S_V2EMOD1];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        gv2Emod[i] = q[S_GV2EMOD + i];
+        gv2Emodxh1[i] = q[S_GV2EMODXH1 + i];
+        curlvE[i] = q[S_CURLVE + i];
+      }
+      gBxcurlvE = q[S_GBXCURLVE];
+      gPhixcurlvE = q[S_GPHIXCURLVE];
+      gv2EmodxcurlvE = q[S_GV2EMODXCURLVE];
+      gv2EmodxcurlA = q[S_GV2EMODXCURLA];
+#pragma unroll
+      for (int i = 0; i < 9; i++) gam[i] = q[S_GAMMAT + i];
+      spgam = q[S_SPGAMMAT];
+      vE_mod_avg = q[S_VE_MOD_AVG];
     }
   }
 };

@@ -74,13 +74,13 @@ struct SolveTask {
   int deg, kind;
 };
 
-template <int K, bool PHI>
+template <int K, int PHI>
 struct PolyPusher {
   const MeshDev *mp;
   Rec<PHI> r;
   double perpinv;
   int ind_tetr, iface_init, sign_rhs, nsteps, solver_iters, fallback;
-  double dt_dtau_const, bmod0, vmod0, t_remain, z_init[4], k1, k3;
+  double dt_dtau_const, bmod0, vmod0, t_remain, z_init[4], k1, k3, dv2E;
   BlockMat A;
   double b[4];
   double Az[4], Ab[4], A2z[4], A2b[4], A3z[4], A3b[4], A4z[4];
@@ -102,6 +102,9 @@ struct PolyPusher {
     double vpar2 = vpar * vpar;
     vmod0 = sqrt(vpar2 + vperp2);
     k1 = vperp2 + vpar2 + 2.0 * perpinv * r.bmod1;
+    // strong electric field (:175): k1 += v_E^2(z) - v_E^2(x1); kept separately because the RK module adds it to b
+    // as its own term (pusher_tetra_rk.f90:127-128)
+    if (PHI == 2) dv2E = (r.v2Emod1 + dot3(z_init, r.gv2Emod)) - r.v2Emod1;
     if (PHI) {
       double phi_elec = r.Phi1 + dot3(r.gPhi, z_init);
       k3 = r.Phi1 - phi_elec;
@@ -111,20 +114,29 @@ struct PolyPusher {
     nsteps = 0;
   }
 
-  // ---- ODE coefficients b, A  (:1503-1530)
+  // ---- ODE coefficients b, A  (:1503-1530; strong-electric-field terms :1519-1526).  RK = true forms b(1:3) the
+  // way the RK module writes it (pusher_tetra_rk.f90:104-134: k1 spelled out, the v_E^2 part a separate term).
+  template <bool RK = false>
   GB_HD void build_ode()
   {
     const double cm = mp->cm_over_e, sg = (double)sign_rhs;
     const double pc = perpinv * cm;
+    const double k1_eff = (PHI == 2 && !RK) ? k1 + dv2E : k1;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      double t = (r.curlh[i] * k1 + perpinv * r.gBxh1[i]) * cm;
+      double t = (r.curlh[i] * k1_eff + perpinv * r.gBxh1[i]) * cm;
       if (PHI) t = t - GB_CLIGHT * (2.0 * k3 * r.curlh[i] + r.gPhixh1[i]);
+      if (PHI == 2) {
+        if (RK) t = t - 0.5 * cm * r.gv2Emodxh1[i] + cm * r.curlh[i] * dv2E;
+        else t = t - 0.5 * cm * r.gv2Emodxh1[i];
+      }
       b[i] = t * sg;
     }
     {
       double t = perpinv * r.gBxcurlA;
       if (PHI) t = t - GB_CLIGHT / cm * r.gPhixcurlA;
+      if (PHI == 2)
+        t = t + cm * perpinv * r.gBxcurlvE - GB_CLIGHT * r.gPhixcurlvE - 0.5 * cm * r.gv2EmodxcurlvE - 0.5 * r.gv2EmodxcurlA;
       b[3] = t * sg;
     }
 #pragma unroll
@@ -133,13 +145,17 @@ struct PolyPusher {
       for (int j = 0; j < 3; j++) {
         double t = pc * r.alp[i + 3 * j];
         if (PHI) t = t - GB_CLIGHT * r.bet[i + 3 * j];
+        if (PHI == 2) t = t - 0.5 * cm * r.gam[i + 3 * j];
         A.m[i][j] = t * sg;
       }
-      A.c[i] = r.curlA[i] * sg;
+      double c = r.curlA[i];
+      if (PHI == 2) c = c + cm * r.curlvE[i];
+      A.c[i] = c * sg;
     }
     {
       double t = pc * r.spalp;
       if (PHI) t = t - GB_CLIGHT * r.spbet;
+      if (PHI == 2) t = t - 0.5 * cm * r.spgam;
       A.s = t * sg;
     }
   }
@@ -460,7 +476,15 @@ struct PolyPusher {
       }
     }
     double in_betvec = dot3(n, r.curlA);
-    return ((t[0] + t[1]) + t[2] + in_betvec * z[3]) * (double)sign_rhs + dot3(n, b);
+    double v = ((t[0] + t[1]) + t[2] + in_betvec * z[3]) * (double)sign_rhs + dot3(n, b);
+    if (PHI == 2) {  // :2728-2732
+      double g[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) g[j] = -0.5 * mp->cm_over_e * dot3(n, &r.gam[3 * j]) * z[j];
+      const double in_gamvec = dot3(n, r.curlvE);
+      v = v + ((g[0] + g[1]) + g[2] + mp->cm_over_e * in_gamvec * z[3]) * (double)sign_rhs;
+    }
+    return v;
   }
   // check_three_planes (:679-699): the three faces other than the exit face must have distance >= 0
   GB_HD bool three_planes_ok(const double *z, int iface_new) const
@@ -501,7 +525,7 @@ struct PolyPusher {
     double tetra_dist_ref = fabs(ldg(cold + C_TETRA_DIST_REF));
     double R1 = ldg(cold + C_R1), Er_mod = ldg(cold + C_ER_MOD);
     double vperp2 = -2.0 * perpinv * bmod0;
-    double vd_ExB = fabs(GB_CLIGHT / bmod0 * Er_mod);
+    double vd_ExB = (PHI == 2) ? r.vE_mod_avg : fabs(GB_CLIGHT / bmod0 * Er_mod);
     double tau_est = fabs(tetra_dist_ref / z_init[3]);
     if (!(vperp2 == 0.0)) {
       double c2 = sqrt(tetra_dist_ref * vmod0 * R1 / (vperp2 * (double)mp->grid_size2 * 0.1));
@@ -832,7 +856,7 @@ struct PolyPusher {
 };
 
 // Non-inlined complete push: by-value in, by-value out, so that no hot-loop variable has its address taken.
-template <int K, bool PHI>
+template <int K, int PHI>
 GB_HD_NOINLINE PushOut push_full_call(const MeshDev *mp, double perpinv, int ind_tetr, int iface, double x0,
                                       double x1, double x2, double vpar, double t_remain)
 {
@@ -849,7 +873,7 @@ GB_HD_NOINLINE PushOut push_full_call(const MeshDev *mp, double perpinv, int ind
 }
 
 // ---- small field helpers (SRC/supporting_functions_mod.f90:279-408) on the device layout -------------
-template <bool PHI>
+template <int PHI>
 GB_HD double bmod_at(const MeshDev &m, int ind_tetr, const double *z)
 {
   const double *pb = m.bpart + ((int64_t)ind_tetr - 1) * BPART_ND;

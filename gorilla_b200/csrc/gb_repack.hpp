@@ -9,7 +9,7 @@
 namespace gb {
 
 inline bool repack_mesh(const gorilla_mesh_desc *md, std::vector<double> &geom, std::vector<double> &bpart,
-                        std::vector<double> &phi, std::vector<double> &cold, bool &has_phi)
+                        std::vector<double> &phi, std::vector<double> &cold, bool &has_phi, std::vector<double> *se = nullptr)
 {
   const int64_t nt = md->ntetr;
   geom.assign((size_t)nt * GEOM_ND, 0.0);
@@ -17,11 +17,15 @@ inline bool repack_mesh(const gorilla_mesh_desc *md, std::vector<double> &geom, 
   phi.assign((size_t)nt * PHI_ND, 0.0);
   cold.assign((size_t)nt * COLD_ND, 0.0);
   has_phi = false;
+  if (se) se->assign((size_t)nt * SE_ND, 0.0);
   // offsets into type tetrahedron_physics (doubles), tetra_physics_mod.f90:9-83
   enum { TP_X1 = 0, TP_DIST_REF = 3, TP_TETRA_DIST_REF = 8, TP_ANORM = 9, TP_CURLA = 21, TP_BMOD1 = 24, TP_APHI1 = 26,
          TP_H2_1 = 28, TP_H3_1 = 29, TP_PHI1 = 30, TP_R1 = 31, TP_ER_MOD = 37, TP_DT_DTAU_CONST = 40, TP_GBXCURLA = 41,
          TP_GPHIXCURLA = 42, TP_SPALPMAT = 47, TP_SPBETMAT = 48, TP_GBXH1 = 50, TP_GPHIXH1 = 53, TP_GB = 59,
-         TP_GPHI = 62, TP_GAPHI = 77, TP_GH2 = 83, TP_GH3 = 86, TP_CURLH = 89, TP_ALPMAT = 107, TP_BETMAT = 116 };
+         TP_GPHI = 62, TP_GAPHI = 77, TP_GH2 = 83, TP_GH3 = 86, TP_CURLH = 89, TP_ALPMAT = 107, TP_BETMAT = 116,
+         TP_VE2_1 = 34, TP_V2EMOD_1 = 36, TP_VE_MOD_AVG = 38, TP_GV2EMODXCURLA = 43, TP_GBXCURLVE = 44, TP_GPHIXCURLVE = 45,
+         TP_GV2EMODXCURLVE = 46, TP_SPGAMMAT = 49, TP_GV2EMODXH1 = 56, TP_GVE2 = 95, TP_CURLVE = 101, TP_GV2EMOD = 104,
+         TP_GAMMAT = 125 };
   for (int64_t t = 0; t < nt; t++) {
     const double *r = md->tetra_physics + t * GORILLA_TETRA_PHYSICS_NDOUBLES;
     const int32_t *g = md->tetra_grid + t * GORILLA_TETRA_GRID_NINTS;
@@ -72,6 +76,24 @@ inline bool repack_mesh(const gorilla_mesh_desc *md, std::vector<double> &geom, 
     }
     C[C_APHI1] = r[TP_APHI1];
     for (int i = 0; i < 3; i++) C[C_GAPHI + i] = r[TP_GAPHI + i];
+    if (se) {
+      double *S = &(*se)[(size_t)t * SE_ND];
+      S[S_V2EMOD1] = r[TP_V2EMOD_1];
+      for (int i = 0; i < 3; i++) {
+        S[S_GV2EMOD + i] = r[TP_GV2EMOD + i];
+        S[S_GV2EMODXH1 + i] = r[TP_GV2EMODXH1 + i];
+        S[S_CURLVE + i] = r[TP_CURLVE + i];
+        S[S_GVE2 + i] = r[TP_GVE2 + i];
+      }
+      S[S_GBXCURLVE] = r[TP_GBXCURLVE];
+      S[S_GPHIXCURLVE] = r[TP_GPHIXCURLVE];
+      S[S_GV2EMODXCURLVE] = r[TP_GV2EMODXCURLVE];
+      S[S_GV2EMODXCURLA] = r[TP_GV2EMODXCURLA];
+      for (int i = 0; i < 9; i++) S[S_GAMMAT + i] = r[TP_GAMMAT + i];
+      S[S_SPGAMMAT] = r[TP_SPGAMMAT];
+      S[S_VE_MOD_AVG] = r[TP_VE_MOD_AVG];
+      S[S_VE2_1] = r[TP_VE2_1];
+    }
   }
   return true;
 }

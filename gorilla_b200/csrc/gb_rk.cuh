@@ -38,7 +38,7 @@ GB_HD void bm_vec_rk(double *o, const PP &P, const double *z)
   o[3] = P.b[3] + P.A.s * z[3];
 }
 
-template <bool PHI>
+template <int PHI>
 struct RkPusher {
   PolyPusher<1, PHI> P;  // record, z_init, sign_rhs, dt_dtau_const, b, A (= amat | Bvec | spamat)
   double dist_min, dist_max, dtau_ref, dtau_max, dtau_quad, t_remain;
@@ -49,7 +49,7 @@ struct RkPusher {
     P.mp = mp;
     P.perpinv = perpinv;
     P.init(ind_tetr, x, iface, vpar, t_remain_in);
-    P.build_ode();
+    P.template build_ode<true>();
     t_remain = t_remain_in;
     iface_init = iface;
     sign_t_step = signbit(t_remain_in) ? -1 : 1;
@@ -129,7 +129,9 @@ struct RkPusher {
     for (int f = 0; f < 4; f++) {
       if (!(allowed & (1u << f))) continue;
       // acoef_pre = matmul(curlA, anorm) re-formed (tetra_physics_mod.f90:857), times sign_rhs
-      const double apre = dot3(P.r.curlA, P.r.an[f]) * (double)P.sign_rhs;
+      double apre = dot3(P.r.curlA, P.r.an[f]) * (double)P.sign_rhs;
+      // strong electric field (:672): + cm_over_e * matmul(curlvE, anorm) * sign_rhs
+      if (PHI == 2) apre = apre + P.mp->cm_over_e * dot3(P.r.curlvE, P.r.an[f]) * (double)P.sign_rhs;
       const double b = z[3] * apre + dot3(P.b, P.r.an[f]);
       const double a = apre * fac;
       const double c = cc[f];
@@ -768,7 +770,7 @@ struct RkPusher {
   }
 };
 
-template <bool PHI>
+template <int PHI>
 GB_HD_NOINLINE PushOut push_rk_full_call(const MeshDev *mp, double perpinv, int ind_tetr, int iface, double x0, double x1,
                                          double x2, double vpar, double t_remain)
 {

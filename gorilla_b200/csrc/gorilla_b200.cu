@@ -36,7 +36,7 @@ void set_last_error(const std::string &s) { g_last_error = s; }
 }
 
 // ----------------------------------------------------------------------------------------------------
-template <bool PHI>
+template <int PHI>
 __global__ void __launch_bounds__(128) find_kernel(const __grid_constant__ MeshDev m, const Batch bt)
 {
   unsigned long long dom_err = 0;
@@ -144,11 +144,20 @@ __global__ void invariants_kernel(const __grid_constant__ MeshDev m, int64_t n, 
         phi = pp[P_PHI1] + dot3(gP, z);
       }
       e = m.particle_mass / 2.0 * (vperp_e * vperp_e + vl * vl) + m.particle_charge * phi;
+      const double *ps = m.se ? m.se + ((int64_t)it - 1) * SE_ND : nullptr;
+      if (ps) {  // :299
+        const double g2[3] = {ps[S_GV2EMOD], ps[S_GV2EMOD + 1], ps[S_GV2EMOD + 2]};
+        e = e + 0.5 * m.particle_mass * (ps[S_V2EMOD1] + dot3(z, g2));
+      }
       // p_phi_func (:377-408)
       const double gh[3] = {pc[C_GHPHI], pc[C_GHPHI + 1], pc[C_GHPHI + 2]};
       const double gA[3] = {pc[C_GAPHI], pc[C_GAPHI + 1], pc[C_GAPHI + 2]};
       p = m.particle_mass * vl * (pc[C_HPHI1] + dot3(gh, z)) +
           m.particle_mass / m.cm_over_e * (pc[C_APHI1] + dot3(gA, z));
+      if (ps) {  // :402-406 (cylindrical coordinates: phi is the second covariant component)
+        const double gv[3] = {ps[S_GVE2], ps[S_GVE2 + 1], ps[S_GVE2 + 2]};
+        p = p + m.particle_mass * (ps[S_VE2_1] + dot3(z, gv));
+      }
     }
     if (energy) energy[i] = e;
     if (p_phi) p_phi[i] = p;
@@ -175,7 +184,9 @@ static int check_settings(const gorilla_settings *s)
   if (s->i_time_tracing_option != 1) return fail(GORILLA_ERR_UNSUPPORTED, "i_time_tracing_option must be 1");
   if (s->handover_processing_kind != 1) return fail(GORILLA_ERR_UNSUPPORTED, "handover_processing_kind must be 1");
   if (s->boole_adaptive_time_steps) return fail(GORILLA_ERR_UNSUPPORTED, "boole_adaptive_time_steps must be .false.");
-  if (s->boole_strong_electric_field) return fail(GORILLA_ERR_UNSUPPORTED, "boole_strong_electric_field must be .false.");
+  // gorilla_settings_mod.f90:139-144 (coord_system is checked against the mesh in gorilla_b200_init)
+  if (s->boole_strong_electric_field && (s->i_precomp != 0 || s->boole_newton_precalc))
+    return fail(GORILLA_ERR_ARG, "boole_strong_electric_field requires i_precomp = 0 and boole_newton_precalc = .false.");
   if (s->boole_pusher_ode45) return fail(GORILLA_ERR_UNSUPPORTED, "boole_pusher_ode45 must be .false.");
   return GORILLA_OK;
 }
@@ -190,6 +201,8 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
   int rc = check_settings(st);
   if (rc) return rc;
   if (md->coord_system != 1 && md->coord_system != 2) return fail(GORILLA_ERR_ARG, "coord_system must be 1 or 2");
+  if (st->boole_strong_electric_field && md->coord_system != 1)
+    return fail(GORILLA_ERR_ARG, "boole_strong_electric_field requires coord_system = 1 (gorilla_settings_mod.f90:139)");
   int dev = 0;
   GB_CUDA(cudaGetDevice(&dev));
   gorilla_b200_handle *h = new gorilla_b200_handle();
@@ -198,9 +211,10 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
   h->settings = *st;
 
   const int64_t nt = md->ntetr;
-  std::vector<double> geom, bpart, phi, cold;
+  std::vector<double> geom, bpart, phi, cold, se;
   bool has_phi = false;
-  if (!gb::repack_mesh(md, geom, bpart, phi, cold, has_phi)) {
+  const bool strong = st->boole_strong_electric_field != 0;
+  if (!gb::repack_mesh(md, geom, bpart, phi, cold, has_phi, strong ? &se : nullptr)) {
     delete h;
     return fail(GORILLA_ERR_ARG, "tetra_grid: neighbour_face / perbou value out of range");
   }
@@ -211,7 +225,8 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
   };
   cudaError_t e;
   if ((e = up(&h->d_geom, geom)) != cudaSuccess || (e = up(&h->d_bpart, bpart)) != cudaSuccess ||
-      (e = up(&h->d_cold, cold)) != cudaSuccess || (has_phi && (e = up(&h->d_phi, phi)) != cudaSuccess) ||
+      (e = up(&h->d_cold, cold)) != cudaSuccess || ((has_phi || strong) && (e = up(&h->d_phi, phi)) != cudaSuccess) ||
+      (strong && (e = up(&h->d_se, se)) != cudaSuccess) ||
       (e = cudaMalloc((void **)&h->d_ctr, CTR_N * sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
       (e = cudaEventCreate(&h->ev2)) != cudaSuccess) {
@@ -223,7 +238,8 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
   m.ntetr = nt;
   m.geom = h->d_geom;
   m.bpart = h->d_bpart;
-  m.phi = has_phi ? h->d_phi : nullptr;
+  m.phi = (has_phi || strong) ? h->d_phi : nullptr;
+  m.se = strong ? h->d_se : nullptr;
   m.cold = h->d_cold;
   m.cm_over_e = md->cm_over_e;
   m.particle_mass = md->particle_mass;
@@ -251,7 +267,7 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
 extern "C" void gorilla_b200_free(gorilla_b200_handle *h)
 {
   if (!h) return;
-  cudaFree(h->d_geom); cudaFree(h->d_bpart); cudaFree(h->d_phi); cudaFree(h->d_cold); cudaFree(h->d_ctr);
+  cudaFree(h->d_geom); cudaFree(h->d_bpart); cudaFree(h->d_phi); cudaFree(h->d_cold); cudaFree(h->d_se); cudaFree(h->d_ctr);
   cudaFree(h->s_x); cudaFree(h->s_vpar); cudaFree(h->s_vperp); cudaFree(h->s_tro); cudaFree(h->s_e);
   cudaFree(h->s_p); cudaFree(h->s_mu); cudaFree(h->s_init); cudaFree(h->s_ind); cudaFree(h->s_iface);
   cudaFree(h->s_np); cudaFree(h->s_tr_t); cudaFree(h->s_tr_f); cudaFree(h->sort_tmp);
@@ -282,15 +298,16 @@ extern "C" int gorilla_b200_debug_force_full(gorilla_b200_handle *h, int32_t on)
 
 // the eight orbit_kernel<K,PHI> instantiations live in gb_orbit_k{1..4}.cu
 #define GB_EXTERN_ORBIT(K) \
-  extern template int launch_orbit_t<K, true>(gorilla_b200_handle *, const Batch &, cudaStream_t); \
-  extern template int launch_orbit_t<K, false>(gorilla_b200_handle *, const Batch &, cudaStream_t);
+  extern template int launch_orbit_t<K, 0>(gorilla_b200_handle *, const Batch &, cudaStream_t); \
+  extern template int launch_orbit_t<K, 1>(gorilla_b200_handle *, const Batch &, cudaStream_t); \
+  extern template int launch_orbit_t<K, 2>(gorilla_b200_handle *, const Batch &, cudaStream_t);
 GB_EXTERN_ORBIT(0)
 GB_EXTERN_ORBIT(1)
 GB_EXTERN_ORBIT(2)
 GB_EXTERN_ORBIT(3)
 GB_EXTERN_ORBIT(4)
 
-template <bool PHI>
+template <int PHI>
 static int launch_orbit_k(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
 {
   if (h->settings.ipusher == 1) return launch_orbit_t<0, PHI>(h, bt, s);
@@ -318,14 +335,15 @@ static int run_device(gorilla_b200_handle *h, Batch bt, bool do_find, cudaStream
   if (do_find) {
     int64_t grid = (bt.n + 127) / 128;
     if (grid > (int64_t)h->num_sms * 16) grid = (int64_t)h->num_sms * 16;
-    if (h->mesh.phi) find_kernel<true><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
-    else find_kernel<false><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
+    if (h->mesh.se) find_kernel<2><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
+    else if (h->mesh.phi) find_kernel<1><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
+    else find_kernel<0><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
     g_launch_count++;
     GB_CUDA(cudaGetLastError());
     h->have_find_time = true;
   }
   GB_CUDA(cudaEventRecord(h->ev1, s));
-  int rc = h->mesh.phi ? launch_orbit_k<true>(h, bt, s) : launch_orbit_k<false>(h, bt, s);
+  int rc = h->mesh.se ? launch_orbit_k<2>(h, bt, s) : h->mesh.phi ? launch_orbit_k<1>(h, bt, s) : launch_orbit_k<0>(h, bt, s);
   if (rc) return rc;
   GB_CUDA(cudaEventRecord(h->ev2, s));
   h->have_push_time = true;
@@ -457,8 +475,9 @@ extern "C" int gorilla_b200_find_tetra(gorilla_b200_handle *h, int64_t n, double
   bt.sign_t_step = sign_t_step < 0 ? -1 : 1;
   int64_t grid = (n + 127) / 128;
   if (grid > (int64_t)h->num_sms * 16) grid = (int64_t)h->num_sms * 16;
-  if (h->mesh.phi) find_kernel<true><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
-  else find_kernel<false><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
+  if (h->mesh.se) find_kernel<2><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
+  else if (h->mesh.phi) find_kernel<1><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
+  else find_kernel<0><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
   g_launch_count++;
   GB_CUDA(cudaGetLastError());
   GB_CUDA(cudaMemcpyAsync(x, h->s_x, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));

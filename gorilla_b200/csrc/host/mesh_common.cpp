@@ -100,7 +100,8 @@ void linearise_tetrahedra(Mesh &m, const VertexFields &vf)
 {
   const int64_t ntetr = m.ntetr;
   const int gk = m.grid_kind, cs = m.coord_system;
-  const int navec = (gk == 3) ? 11 : 10;
+  const bool strong = vf.strong;  // mutually exclusive with grid_kind 3 (:217-227)
+  const int navec = ((gk == 3) ? 11 : 10) + (strong ? 4 : 0);
   m.tetra_physics.assign((size_t)ntetr * TP_N, 0.0);
   const int64_t last_slice_start = ntetr - ntetr / m.grid_size[1] + 1;
   const double two_pi_nfp = 2.0 * PI / m.n_field_periods;
@@ -109,7 +110,7 @@ void linearise_tetrahedra(Mesh &m, const VertexFields &vf)
   for (int64_t it = 1; it <= ntetr; it++) {
     double *T = &m.tetra_physics[(size_t)(it - 1) * TP_N];
     const int32_t *G = &m.tetra_grid[(size_t)(it - 1) * TG_N];
-    double p1[4], p2[4], p3[4], avec[11][4];
+    double p1[4], p2[4], p3[4], avec[14][4];
     for (int i = 0; i < 4; i++) {
       const int64_t iv = G[TG_KNOT + i] - 1;
       const double *vr = &m.verts_rphiz[3 * iv];
@@ -134,6 +135,9 @@ void linearise_tetrahedra(Mesh &m, const VertexFields &vf)
       avec[6][i] = vf.bmod[iv]; avec[7][i] = vf.phi_elec[iv];
       avec[8][i] = vr[0]; avec[9][i] = vr[2];
       if (gk == 3) avec[10][i] = vf.sqg[iv];
+      if (strong) {  // (:531-536)
+        avec[10][i] = vf.vE_x1[iv]; avec[11][i] = vf.vE_x2[iv]; avec[12][i] = vf.vE_x3[iv]; avec[13][i] = vf.v2E[iv];
+      }
     }
     if (cs == 2) {  // theta = 2pi vertices stored as 0  (:534-540)
       for (int j = 0; j < 4; j++) {
@@ -182,8 +186,11 @@ void linearise_tetrahedra(Mesh &m, const VertexFields &vf)
     T[TP_H1_1] = avec[3][0]; T[TP_H2_1] = avec[4][0]; T[TP_H3_1] = avec[5][0];
     T[TP_PHI1] = avec[7][0];
     if (gk == 3) T[TP_SQG1] = avec[10][0];
+    if (strong) {
+      T[TP_VE1_1] = avec[10][0]; T[TP_VE2_1] = avec[11][0]; T[TP_VE3_1] = avec[12][0]; T[TP_V2EMOD_1] = avec[13][0];
+    }
 
-    double d1[11], d2[11], d3[11];
+    double d1[14], d2[14], d3[14];
     differentiate(p1, p2, p3, navec, &avec[0][0], d1, d2, d3);
     // 0-based quantity index q = Fortran index - 1: A1..A3 = 0..2, h1..h3 = 3..5, B = 6, Phi = 7, R = 8, Z = 9, sqg = 10
     double *curlA = &T[TP_CURLA], *curlh = &T[TP_CURLH];
@@ -225,6 +232,35 @@ void linearise_tetrahedra(Mesh &m, const VertexFields &vf)
         mat[2 + 3 * j] = 2.0 * curlh[2] * grad[j] + d1[q] * dj[4] - d2[q] * dj[3];
       }
     }
+    if (strong) {  // (:708-749, :820-847) quantity indices: vE1..3 = 10..12, v2Emod = 13
+      for (int q = 0; q < 3; q++) {
+        double *g = &T[(q == 0) ? TP_GVE1 : (q == 1) ? TP_GVE2 : TP_GVE3];
+        g[0] = d1[10 + q]; g[1] = d2[10 + q]; g[2] = d3[10 + q];
+      }
+      T[TP_GV2EMOD] = d1[13]; T[TP_GV2EMOD + 1] = d2[13]; T[TP_GV2EMOD + 2] = d3[13];
+      double *cv = &T[TP_CURLVE];
+      cv[0] = d2[12] - d3[11]; cv[1] = d3[10] - d1[12]; cv[2] = d1[11] - d2[10];
+      T[TP_GV2EMODXH1] = d2[13] * h3 - d3[13] * h2;
+      T[TP_GV2EMODXH1 + 1] = d3[13] * h1 - d1[13] * h3;
+      T[TP_GV2EMODXH1 + 2] = d1[13] * h2 - d2[13] * h1;
+      T[TP_GV2EMODXCURLA] = d1[13] * curlA[0] + d2[13] * curlA[1] + d3[13] * curlA[2];
+      T[TP_GBXCURLVE] = d1[6] * cv[0] + d2[6] * cv[1] + d3[6] * cv[2];
+      T[TP_GPHIXCURLVE] = d1[7] * cv[0] + d2[7] * cv[1] + d3[7] * cv[2];
+      T[TP_GV2EMODXCURLVE] = d1[13] * cv[0] + d2[13] * cv[1] + d3[13] * cv[2];
+      const double *grad = &T[TP_GV2EMOD];
+      double *mat = &T[TP_GAMMAT];
+      for (int j = 0; j < 3; j++) {
+        const double *dj = dd[j];
+        mat[0 + 3 * j] = 2.0 * curlh[0] * grad[j] + d2[13] * dj[5] - d3[13] * dj[4];
+        mat[1 + 3 * j] = 2.0 * curlh[1] * grad[j] + d3[13] * dj[3] - d1[13] * dj[5];
+        mat[2 + 3 * j] = 2.0 * curlh[2] * grad[j] + d1[13] * dj[4] - d2[13] * dj[3];
+      }
+      T[TP_SPGAMMAT] = T[TP_GAMMAT] + T[TP_GAMMAT + 4] + T[TP_GAMMAT + 8];
+      for (int f = 0; f < 4; f++) {  // acoef_pre_strong_electric = matmul(curlvE, anorm) (:852-855)
+        const double *an = &T[TP_ANORM + 3 * f];
+        T[TP_ACOEF_PRE_SE + f] = ((0.0 + cv[0] * an[0]) + cv[1] * an[1]) + cv[2] * an[2];
+      }
+    }
     T[TP_SPALPMAT] = T[TP_ALPMAT] + T[TP_ALPMAT + 4] + T[TP_ALPMAT + 8];
     T[TP_SPBETMAT] = T[TP_BETMAT] + T[TP_BETMAT + 4] + T[TP_BETMAT + 8];
     for (int f = 0; f < 4; f++) {  // acoef_pre = matmul(curlA, anorm)
@@ -241,9 +277,13 @@ void linearise_tetrahedra(Mesh &m, const VertexFields &vf)
       dtd = dtd + met_det * avec[6][j];
     }
     T[TP_DT_DTAU_CONST] = dtd / 4.0;
-    // Er_mod (:894-920)
+    // ExB drift scale for the passing-time estimate (:884-920): the mean |v_E| in strong-field mode, else Er_mod
     double er = 0.0;
-    if (cs == 1) {
+    if (strong) {
+      double acc = 0.0;
+      for (int j = 0; j < 4; j++) acc = acc + std::sqrt(avec[13][j]);
+      T[TP_VE_MOD_AVG] = acc / 4.0;
+    } else if (cs == 1) {
       for (int j = 0; j < 4; j++) {
         const double dr = avec[8][j] - m.mag_axis_R0, dz = avec[9][j] - m.mag_axis_Z0;
         const double r_minor = std::sqrt(dr * dr + dz * dz);

@@ -19,10 +19,14 @@ namespace gbhost {
 enum {
   TP_X1 = 0, TP_DIST_REF = 3, TP_DIST_REF_VEC = 4, TP_TETRA_DIST_REF = 8, TP_ANORM = 9, TP_CURLA = 21,
   TP_BMOD1 = 24, TP_ATHETA1 = 25, TP_APHI1 = 26, TP_H1_1 = 27, TP_H2_1 = 28, TP_H3_1 = 29, TP_PHI1 = 30,
-  TP_R1 = 31, TP_Z1 = 32, TP_ER_MOD = 37, TP_SQG1 = 39, TP_DT_DTAU_CONST = 40, TP_GBXCURLA = 41,
+  TP_R1 = 31, TP_Z1 = 32, TP_VE1_1 = 33, TP_VE2_1 = 34, TP_VE3_1 = 35, TP_V2EMOD_1 = 36, TP_ER_MOD = 37, TP_VE_MOD_AVG = 38, TP_SQG1 = 39, TP_DT_DTAU_CONST = 40, TP_GBXCURLA = 41,
   TP_GPHIXCURLA = 42, TP_SPALPMAT = 47, TP_SPBETMAT = 48, TP_GBXH1 = 50, TP_GPHIXH1 = 53, TP_GB = 59,
   TP_GPHI = 62, TP_GR = 65, TP_GZ = 68, TP_GSQG = 71, TP_GATHETA = 74, TP_GAPHI = 77, TP_GH1 = 80, TP_GH2 = 83,
-  TP_GH3 = 86, TP_CURLH = 89, TP_ALPMAT = 107, TP_BETMAT = 116, TP_ACOEF_PRE = 134, TP_N = 142
+  TP_GH3 = 86, TP_CURLH = 89, TP_ALPMAT = 107, TP_BETMAT = 116, TP_ACOEF_PRE = 134, TP_N = 142,
+  // strong electric field (boole_strong_electric_field)
+  TP_GV2EMODXCURLA = 43, TP_GBXCURLVE = 44, TP_GPHIXCURLVE = 45, TP_GV2EMODXCURLVE = 46, TP_SPGAMMAT = 49,
+  TP_GV2EMODXH1 = 56, TP_GVE1 = 92, TP_GVE2 = 95, TP_GVE3 = 98, TP_CURLVE = 101, TP_GV2EMOD = 104, TP_GAMMAT = 125,
+  TP_ACOEF_PRE_SE = 138
 };
 enum { TG_KNOT = 0, TG_NEIGH = 4, TG_NFACE = 8, TG_PERPHI = 12, TG_PERTHETA = 16, TG_N = 20 };
 
@@ -45,12 +49,20 @@ struct Mesh {
 struct VertexFields {
   std::vector<double> A_x1, A_x2, A_x3, h_x1, h_x2, h_x3, bmod, phi_elec;
   std::vector<double> sqg, dR_ds, dZ_ds;  // flux coordinates only (sqg: VMEC only)
+  // strong electric field mode (cylindrical grids): covariant ExB drift v_E and its square, per vertex
+  bool strong = false;
+  std::vector<double> vE_x1, vE_x2, vE_x3, v2E;
   void resize(size_t n, bool flux, bool vmec)
   {
     A_x1.resize(n); A_x2.resize(n); A_x3.resize(n); h_x1.resize(n); h_x2.resize(n); h_x3.resize(n);
     bmod.resize(n); phi_elec.resize(n);
     if (flux) { dR_ds.resize(n); dZ_ds.resize(n); }
     if (vmec) sqg.resize(n);
+  }
+  void resize_strong(size_t n)
+  {
+    strong = true;
+    vE_x1.resize(n); vE_x2.resize(n); vE_x3.resize(n); v2E.resize(n);
   }
 };
 

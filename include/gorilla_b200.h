@@ -53,7 +53,7 @@ typedef struct gorilla_settings {
   int32_t i_time_tracing_option;     /* must be 1 */
   int32_t handover_processing_kind;  /* must be 1 */
   int32_t boole_adaptive_time_steps; /* must be 0 */
-  int32_t boole_strong_electric_field; /* must be 0 (next) */
+  int32_t boole_strong_electric_field; /* ExB-drift terms of order v_E^2; cylindrical grids (coord_system 1) only */
   int32_t boole_grid_for_find_tetra; /* ignored: the device scan does not need the box accelerator */
   int32_t reserved[5];
 } gorilla_settings;

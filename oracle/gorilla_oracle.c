@@ -1492,6 +1492,9 @@ static void quad_analytic_approx(const rk_state *s, const double z[4], const boo
   double acoef[4], bcoef[4], ccoef[4], dtau_vec[4], discr, dummy;
   const double *r = s->r;
   for (int f = 0; f < 4; f++) acoef[f] = r[TP_ACOEF_PRE + f] * (double)s->sign_rhs;
+  if (s->m->boole_strong_electric_field) /* :672 */
+    for (int f = 0; f < 4; f++)
+      acoef[f] = acoef[f] + s->m->cm_over_e * r[TP_ACOEF_PRE_SE + f] * (double)s->sign_rhs;
   for (int f = 0; f < 4; f++) bcoef[f] = z[3] * acoef[f] + dot3(s->b, s->anorm[f]);
   for (int f = 0; f < 4; f++) acoef[f] = acoef[f] * (s->b[3] + s->spamat * z[3]);
   rk_normal_distances_func(s, z, ccoef);

@@ -14,12 +14,12 @@
 using namespace gb;
 
 struct HostMirror {
-  std::vector<double> geom, bpart, phi, cold;
+  std::vector<double> geom, bpart, phi, cold, se;
   MeshDev m;
   int poly_order, boole_periodic_relocation, ipusher;
 };
 
-template <int K, bool PHI>
+template <int K, int PHI>
 static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *vperp_io, double t_step, int32_t *ind_io,
                          int32_t *iface_io, double *t_remain_out, int64_t *npush_out, int trace_cap, int32_t *tr_t,
                          int32_t *tr_f, int force_full, int64_t *fallback)
@@ -76,15 +76,18 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
 
 extern "C" {
 
-void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, int boole_periodic_relocation, int ipusher)
+void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, int boole_periodic_relocation, int ipusher,
+                int boole_strong_electric_field)
 {
   HostMirror *h = new HostMirror();
   bool has_phi = false;
-  if (!repack_mesh(md, h->geom, h->bpart, h->phi, h->cold, has_phi)) { delete h; return nullptr; }
+  const bool strong = boole_strong_electric_field != 0;
+  if (!repack_mesh(md, h->geom, h->bpart, h->phi, h->cold, has_phi, strong ? &h->se : nullptr)) { delete h; return nullptr; }
   MeshDev &m = h->m;
   memset(&m, 0, sizeof(m));
   m.ntetr = md->ntetr;
-  m.geom = h->geom.data(); m.bpart = h->bpart.data(); m.phi = has_phi ? h->phi.data() : nullptr; m.cold = h->cold.data();
+  m.geom = h->geom.data(); m.bpart = h->bpart.data(); m.phi = (has_phi || strong) ? h->phi.data() : nullptr; m.cold = h->cold.data();
+  m.se = strong ? h->se.data() : nullptr;
   m.cm_over_e = md->cm_over_e; m.particle_mass = md->particle_mass; m.particle_charge = md->particle_charge;
   const double PI = 3.141592653589793238462643383;
   m.period_phi = 2.0 * PI / md->n_field_periods; m.period_theta = 2.0 * PI;
@@ -114,8 +117,9 @@ int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *v
     if (!binit[i]) {
       int32_t it = -1, ifc = -1;
       if (check_coordinate_domain(m, xi, h->boole_periodic_relocation) != 0) dom++;
-      else if (m.phi) find_tetra<true>(&m, xi, vpar[i], vperp[i], it, ifc, sign_t);
-      else find_tetra<false>(&m, xi, vpar[i], vperp[i], it, ifc, sign_t);
+      else if (m.se) find_tetra<2>(&m, xi, vpar[i], vperp[i], it, ifc, sign_t);
+      else if (m.phi) find_tetra<1>(&m, xi, vpar[i], vperp[i], it, ifc, sign_t);
+      else find_tetra<0>(&m, xi, vpar[i], vperp[i], it, ifc, sign_t);
       ind_tetr[i] = it; iface[i] = ifc;
       if (it != -1) binit[i] = 1;
     }
@@ -126,10 +130,12 @@ int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *v
     int32_t *tt = trace_cap > 0 ? tr_t + i * trace_cap : nullptr, *tf = trace_cap > 0 ? tr_f + i * trace_cap : nullptr;
 #define HM_RUN(K, PHI) run_particle<K, PHI>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
       t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, trace_cap, tt, tf, force_full, fallback)
-    if (m.phi) {
-      switch (h->poly_order) { case 0: HM_RUN(0, true); break; case 1: HM_RUN(1, true); break; case 2: HM_RUN(2, true); break; case 3: HM_RUN(3, true); break; default: HM_RUN(4, true); }
+    if (m.se) {
+      switch (h->poly_order) { case 0: HM_RUN(0, 2); break; case 1: HM_RUN(1, 2); break; case 2: HM_RUN(2, 2); break; case 3: HM_RUN(3, 2); break; default: HM_RUN(4, 2); }
+    } else if (m.phi) {
+      switch (h->poly_order) { case 0: HM_RUN(0, 1); break; case 1: HM_RUN(1, 1); break; case 2: HM_RUN(2, 1); break; case 3: HM_RUN(3, 1); break; default: HM_RUN(4, 1); }
     } else {
-      switch (h->poly_order) { case 0: HM_RUN(0, false); break; case 1: HM_RUN(1, false); break; case 2: HM_RUN(2, false); break; case 3: HM_RUN(3, false); break; default: HM_RUN(4, false); }
+      switch (h->poly_order) { case 0: HM_RUN(0, 0); break; case 1: HM_RUN(1, 0); break; case 2: HM_RUN(2, 0); break; case 3: HM_RUN(3, 0); break; default: HM_RUN(4, 0); }
     }
   }
   return dom;

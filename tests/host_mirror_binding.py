@@ -32,7 +32,7 @@ def load():
         L = C.CDLL(str(LIB))
         d, vp = C.c_double, C.c_void_p
         L.hm_create.restype = vp
-        L.hm_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.hm_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.hm_free.argtypes = [vp]
         L.hm_has_phi.argtypes = [vp]
         L.hm_orbit_timestep.restype = C.c_int64
@@ -60,7 +60,8 @@ class HostMirror:
         self.mesh = mesh
         self._desc = mesh.desc()
         self.h = self.L.hm_create(C.byref(self._desc), settings.poly_order, int(settings.boole_guess),
-                                  int(settings.boole_periodic_relocation), int(settings.ipusher))
+                                  int(settings.boole_periodic_relocation), int(settings.ipusher),
+                                  int(settings.boole_strong_electric_field))
         assert self.h
 
     def __del__(self):

@@ -68,13 +68,17 @@ GB_HD_NOINLINE void find_tetra_on_face(const MeshDev *mp, double *x, double vpar
 {
   const MeshDev &m = *mp;
   PolyPusher<1, PHI> P; // reuse record loader + ODE coefficient builder (same formulas, :104-116 vs poly :1504-1517)
+  double stash[6];
   P.mp = mp;
+  P.r.set_stash(stash, 1);
   int iface_new = 1;
   for (int f = 1; f < 4; f++)
     if (fabs(dist0[f]) < fabs(dist0[iface_new - 1])) iface_new = f + 1;
   int32_t tried[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   {
     Rec<PHI> r0;
+    double stash0[6];
+    r0.set_stash(stash0, 1);
     r0.load(m, ind_tetr_out);
     double z[3] = {x[0] - r0.x1[0], x[1] - r0.x1[1], x[2] - r0.x1[2]};
     P.perpinv = -0.5 * (vperp * vperp) / (r0.bmod1 + dot3(r0.gB, z));

@@ -65,16 +65,35 @@ struct Batch {
 #endif
 constexpr int gb_min_blocks(int K) { return K == 0 ? GB_MINB_RK : K == 1 ? GB_MINB_K1 : K == 2 ? GB_MINB_K2 : K == 3 ? GB_MINB_K3 : GB_MINB_K4; }
 
+// Loop state of one particle between pushes.  It is only touched at the start and at the end of a push, while the
+// push itself needs every register it can get; left to the compiler it is spilled to local memory, whose reloads
+// miss the L1 (thrashed by the record gathers) and cost an L2 round trip each (ncu: ~10 such waits per push, half of
+// all stall samples).  Shared memory is explicit, conflict free ([field][thread]) and ~30 cycles away.
+#define GB_THREADS 128
+enum { LS_X0 = 0, LS_X1, LS_X2, LS_VPAR, LS_PERPINV, LS_TREM, LS_ZS0, LS_ZS1, LS_ZS2, LS_ND };
+enum { LC_LOST = 0, LC_FIN, LC_FB0, LC_FB1, LC_FB2, LC_FB3, LC_N };
+
 template <int K, int PHI>
-__global__ void __launch_bounds__(128, gb_min_blocks(K)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
+__global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
 {
+  __shared__ double s_d[LS_ND][GB_THREADS], s_stash[6][GB_THREADS];
+  __shared__ long long s_idx[GB_THREADS], s_npush[GB_THREADS];
+  __shared__ unsigned long long s_cpush[GB_THREADS];
+  __shared__ unsigned int s_cnt[LC_N][GB_THREADS];
+  __shared__ int s_ind_save[GB_THREADS];
   const unsigned lane = threadIdx.x & 31u;
+  // all accessors index by threadIdx.x: no address is held in a register across the push
+#define LS(f) (((volatile double *)s_d[f])[threadIdx.x])
+#define LCNT(f) (((volatile unsigned int *)s_cnt[f])[threadIdx.x])
+#define p_idx (((volatile long long *)s_idx) + threadIdx.x)
+#define p_npush (((volatile long long *)s_npush) + threadIdx.x)
+#define p_cpush (((volatile unsigned long long *)s_cpush) + threadIdx.x)
+#define p_ind_save (((volatile int *)s_ind_save) + threadIdx.x)
   bool active = false, exhausted = false;
-  int64_t idx = -1;
-  double x[3] = {0, 0, 0}, vpar = 0, perpinv = 0, t_remain = 0, z_save[3] = {0, 0, 0};
-  int32_t ind_tetr = -1, iface = -1, ind_save = -1;
-  int64_t npush = 0;
-  unsigned long long c_push = 0, c_lost = 0, c_fin = 0, c_fb0 = 0, c_fb1 = 0, c_fb2 = 0, c_fb3 = 0;
+  int32_t ind_tetr = -1, iface = -1;
+  *p_cpush = 0;
+#pragma unroll
+  for (int k = 0; k < LC_N; k++) LCNT(k) = 0;
 
   for (;;) {
     if (!active && !exhausted) {
@@ -84,7 +103,7 @@ __global__ void __launch_bounds__(128, gb_min_blocks(K)) orbit_kernel(const __gr
       unsigned long long base = 0;
       if ((int)lane == leader) base = atomicAdd(bt.ctr + CTR_QUEUE, (unsigned long long)__popc(need));
       base = __shfl_sync(need, base, leader);
-      idx = (int64_t)(base + (unsigned long long)__popc(need & ((1u << lane) - 1u)));
+      const int64_t idx = (int64_t)(base + (unsigned long long)__popc(need & ((1u << lane) - 1u)));
       if (idx >= bt.n) {
         exhausted = true;
       } else {
@@ -96,95 +115,100 @@ __global__ void __launch_bounds__(128, gb_min_blocks(K)) orbit_kernel(const __gr
           // resp. leaves the loop at :103-109 without touching the particle
           if (bt.t_remain_out) bt.t_remain_out[idx] = bt.t_step;
           if (bt.n_pushes) bt.n_pushes[idx] = 0;
-          if (inited && ind_tetr < 1) c_lost++;
+          if (inited && ind_tetr < 1) LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
         } else if (bt.t_step == 0.0) {
           if (bt.t_remain_out) bt.t_remain_out[idx] = 0.0;
           if (bt.n_pushes) bt.n_pushes[idx] = 0;
         } else {
-          x[0] = bt.x[3 * idx];
-          x[1] = bt.x[3 * idx + 1];
-          x[2] = bt.x[3 * idx + 2];
-          vpar = bt.vpar[idx];
+          const double x0 = bt.x[3 * idx], x1 = bt.x[3 * idx + 1], x2 = bt.x[3 * idx + 2];
           const double vperp = bt.vperp[idx];
           // :71-78  z_save = x - x1 ; perpinv = -0.5*vperp**2/bmod_func(z_save, ind_tetr)
           const double *pg = m.geom + ((int64_t)ind_tetr - 1) * GEOM_ND;
-          z_save[0] = x[0] - ldg(pg);
-          z_save[1] = x[1] - ldg(pg + 1);
-          z_save[2] = x[2] - ldg(pg + 2);
-          perpinv = -0.5 * (vperp * vperp) / bmod_at<PHI>(m, ind_tetr, z_save);
-          t_remain = bt.t_step;
-          ind_save = ind_tetr;
-          npush = 0;
+          const double zs[3] = {x0 - ldg(pg), x1 - ldg(pg + 1), x2 - ldg(pg + 2)};
+          LS(LS_X0) = x0; LS(LS_X1) = x1; LS(LS_X2) = x2;
+          LS(LS_VPAR) = bt.vpar[idx];
+          LS(LS_ZS0) = zs[0]; LS(LS_ZS1) = zs[1]; LS(LS_ZS2) = zs[2];
+          LS(LS_PERPINV) = -0.5 * (vperp * vperp) / bmod_at<PHI>(m, ind_tetr, zs);
+          LS(LS_TREM) = bt.t_step;
+          *p_idx = idx;
+          *p_npush = 0;
           active = true;
         }
       }
     }
     if (__all_sync(0xffffffffu, exhausted && !active)) break;
     if (active) {
-      ind_save = ind_tetr;
+      *p_ind_save = ind_tetr;
       PushOut o;
       bool done = false;
+      const double perpinv = LS(LS_PERPINV);
       if constexpr (K == 0) {  // ipusher = 1: RK4 pusher
         if (!bt.force_full) {
+          const double x[3] = {LS(LS_X0), LS(LS_X1), LS(LS_X2)};
           RkPusher<PHI> R;
-          R.init(&m, perpinv, ind_tetr, x, iface, vpar, t_remain);
+          R.P.r.set_stash(&s_stash[0][threadIdx.x], GB_THREADS);
+          R.init(&m, perpinv, ind_tetr, x, iface, LS(LS_VPAR), LS(LS_TREM));
           done = R.template push<true>(o);
         }
-        if (!done) o = push_rk_full_call<PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
+        if (!done)
+          o = push_rk_full_call<PHI>(&m, perpinv, ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2), LS(LS_VPAR), LS(LS_TREM));
       } else {
         if (!bt.force_full) {
+          const double x[3] = {LS(LS_X0), LS(LS_X1), LS(LS_X2)};
           PolyPusher<K, PHI> P;
           P.mp = &m;
           P.perpinv = perpinv;
-          done = P.push_fast(ind_tetr, iface, x, vpar, t_remain, o);
+          P.r.set_stash(&s_stash[0][threadIdx.x], GB_THREADS);
+          done = P.push_fast(ind_tetr, iface, x, LS(LS_VPAR), LS(LS_TREM), o, &LS(LS_TREM));
         }
-        if (!done) o = push_full_call<K, PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
+        if (!done)
+          o = push_full_call<K, PHI>(&m, perpinv, ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2), LS(LS_VPAR), LS(LS_TREM));
       }
-      x[0] = o.x[0];
-      x[1] = o.x[1];
-      x[2] = o.x[2];
-      vpar = o.vpar;
-      if (o.z_save_set) {
-        z_save[0] = o.z_save[0];
-        z_save[1] = o.z_save[1];
-        z_save[2] = o.z_save[2];
-      }
+      LS(LS_X0) = o.x[0]; LS(LS_X1) = o.x[1]; LS(LS_X2) = o.x[2];
+      LS(LS_VPAR) = o.vpar;
+      if (o.z_save_set) { LS(LS_ZS0) = o.z_save[0]; LS(LS_ZS1) = o.z_save[1]; LS(LS_ZS2) = o.z_save[2]; }
       ind_tetr = o.ind_tetr;
       iface = o.iface;
+      const long long npush = *p_npush;
       if (bt.trace_cap > 0 && npush < bt.trace_cap) {
+        const long long idx = *p_idx;
         bt.trace_tetr[idx * bt.trace_cap + npush] = ind_tetr;
         bt.trace_face[idx * bt.trace_cap + npush] = iface;
       }
-      npush++;
-      c_push++;
+      *p_npush = npush + 1;
       if (o.fallback) {
-        if (o.fallback & 1) c_fb0++;
-        if (o.fallback & 2) c_fb1++;
-        if (o.fallback & 4) c_fb2++;
-        if (o.fallback & 8) c_fb3++;
+        if (o.fallback & 1) LCNT(LC_FB0) = LCNT(LC_FB0) + 1;
+        if (o.fallback & 2) LCNT(LC_FB1) = LCNT(LC_FB1) + 1;
+        if (o.fallback & 4) LCNT(LC_FB2) = LCNT(LC_FB2) + 1;
+        if (o.fallback & 8) LCNT(LC_FB3) = LCNT(LC_FB3) + 1;
       }
-      t_remain = t_remain - o.t_pass;
+      const double t_remain = LS(LS_TREM) - o.t_pass;
+      LS(LS_TREM) = t_remain;
       if (o.finished || ind_tetr == -1) {
         // :142  vperp = vperp_func(z_save, perpinv, ind_tetr_save)
+        const long long idx = *p_idx;
+        const double pinv = LS(LS_PERPINV);
+        const double zs[3] = {LS(LS_ZS0), LS(LS_ZS1), LS(LS_ZS2)};
         double vperp_new = 0.0;
-        if (perpinv != 0.0) vperp_new = sqrt(2.0 * fabs(perpinv) * bmod_at<PHI>(m, ind_save, z_save));
-        bt.x[3 * idx] = x[0];
-        bt.x[3 * idx + 1] = x[1];
-        bt.x[3 * idx + 2] = x[2];
-        bt.vpar[idx] = vpar;
+        if (pinv != 0.0) vperp_new = sqrt(2.0 * fabs(pinv) * bmod_at<PHI>(m, *p_ind_save, zs));
+        bt.x[3 * idx] = o.x[0];
+        bt.x[3 * idx + 1] = o.x[1];
+        bt.x[3 * idx + 2] = o.x[2];
+        bt.vpar[idx] = o.vpar;
         bt.vperp[idx] = vperp_new;
         bt.ind_tetr[idx] = ind_tetr;
         bt.iface[idx] = iface;
         if (bt.t_remain_out) bt.t_remain_out[idx] = t_remain;
-        if (bt.n_pushes) bt.n_pushes[idx] = npush;
-        if (o.finished) c_fin++;
-        else c_lost++;
+        if (bt.n_pushes) bt.n_pushes[idx] = npush + 1;
+        *p_cpush = *p_cpush + (unsigned long long)(npush + 1);
+        if (o.finished) LCNT(LC_FIN) = LCNT(LC_FIN) + 1;
+        else LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
         active = false;
       }
     }
   }
   // counters: warp reduce, one atomic per warp and counter
-  unsigned long long v[7] = {c_push, c_lost, c_fin, c_fb0, c_fb1, c_fb2, c_fb3};
+  unsigned long long v[7] = {*p_cpush, LCNT(LC_LOST), LCNT(LC_FIN), LCNT(LC_FB0), LCNT(LC_FB1), LCNT(LC_FB2), LCNT(LC_FB3)};
 #pragma unroll
   for (int k = 0; k < 7; k++) {
     unsigned long long s = v[k];
@@ -192,6 +216,12 @@ __global__ void __launch_bounds__(128, gb_min_blocks(K)) orbit_kernel(const __gr
     for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
     if (lane == 0 && s) atomicAdd(bt.ctr + k, s);
   }
+#undef LS
+#undef LCNT
+#undef p_idx
+#undef p_npush
+#undef p_cpush
+#undef p_ind_save
 }
 
 // ----------------------------------------------------------------------------------------------------

@@ -70,6 +70,8 @@ GB_HD double ldg(const double *p)
 #endif
 }
 #if defined(__CUDA_ARCH__)
+// Gathers allocate in L1 on purpose: particles are sorted by tetrahedron, so neighbouring lanes and warps re-read the
+// same records (measured: ld.global.nc.L1::no_allocate costs 25 % at order 2).
 GB_HD void ld2(const double *p, double &a, double &b)
 {
   double2 v = __ldg(reinterpret_cast<const double2 *>(p));
@@ -117,8 +119,26 @@ struct Rec {
   double Phi1, gPhi[3], gPhixh1[3], gPhixcurlA, bet[9], spbet;
   double v2Emod1, gv2Emod[3], gv2Emodxh1[3], gBxcurlvE, gPhixcurlvE, gv2EmodxcurlvE, gv2EmodxcurlA, curlvE[3], gam[9], spgam,
       vE_mod_avg;
-  int32_t nb[4];
-  uint32_t flags;
+  // The first vertex (for x = z + x1 when the push ends) and the topology (hand-over) are only needed at the END of a
+  // push.  Carried in registers they are spilled to local memory by the 128-register cap and every reload costs an L2
+  // round trip (the L1 is thrashed by the record gathers).  load() therefore parks them in a caller-provided stash
+  // -- shared memory in the kernel, st[k * sts], k = 0..5 -- and x1s()/nb()/flags() read them back from there.
+  volatile double *st;
+  int sts;
+  GB_HD void set_stash(volatile double *p, int stride) { st = p; sts = stride; }
+  GB_HD double x1s(int i) const { return st[i * sts]; }
+  GB_HD int32_t nb(int f) const
+  {
+    union { double d; int32_t i[2]; } u;
+    u.d = st[(3 + (f >> 1)) * sts];
+    return u.i[f & 1];
+  }
+  GB_HD uint32_t flags() const
+  {
+    union { double d; int32_t i[2]; } u;
+    u.d = st[5 * sts];
+    return (uint32_t)u.i[0];
+  }
 
   GB_HD void load(const MeshDev &m, int ind_tetr /*1-based*/)
   {
@@ -147,12 +167,8 @@ struct Rec {
     for (int i = 0; i < 9; i++) alp[i] = b[B_ALP + i];
     spalp = b[B_SPALP];
     dtdtau = b[B_DTDTAU];
-    {
-      union { double d; int32_t i[2]; } u;
-      u.d = b[B_TOPO]; nb[0] = u.i[0]; nb[1] = u.i[1];
-      u.d = b[B_TOPO + 1]; nb[2] = u.i[0]; nb[3] = u.i[1];
-      u.d = b[B_TOPO + 2]; flags = (uint32_t)u.i[0];
-    }
+    st[0] = g[0]; st[sts] = g[1]; st[2 * sts] = g[2];
+    st[3 * sts] = b[B_TOPO]; st[4 * sts] = b[B_TOPO + 1]; st[5 * sts] = b[B_TOPO + 2];
     if (PHI) {
       double p[PHI_ND];
       const double *pp = m.phi + t * PHI_ND;

@@ -620,14 +620,15 @@ struct PolyPusher {
   GB_HD void handover(int iface_exit, double *x, int32_t &ind_out, int32_t &iface_out) const
   {
     const int f = iface_exit - 1;
-    ind_out = f == 0 ? r.nb[0] : f == 1 ? r.nb[1] : f == 2 ? r.nb[2] : r.nb[3];
-    iface_out = topo_face(r.flags, f);
-    const int iper_phi = topo_perphi(r.flags, f);
+    const uint32_t flags = r.flags();
+    ind_out = r.nb(f);
+    iface_out = topo_face(flags, f);
+    const int iper_phi = topo_perphi(flags, f);
     if (mp->coord_system == 1) {
       if (iper_phi == 1) x[1] = x[1] - mp->period_phi;
       else if (iper_phi == -1) x[1] = x[1] + mp->period_phi;
     } else {
-      const int iper_theta = topo_pertheta(r.flags, f);
+      const int iper_theta = topo_pertheta(flags, f);
       if (iper_phi == 1) x[2] = x[2] - mp->period_phi;
       else if (iper_phi == -1) x[2] = x[2] + mp->period_phi;
       if (iper_theta == 1) x[1] = x[1] - mp->period_theta;
@@ -651,7 +652,7 @@ struct PolyPusher {
   {
     // x, vpar are updated BEFORE the stop-inside test (:459-460); a removal further down keeps them
 #pragma unroll
-    for (int i = 0; i < 3; i++) o.x[i] = z[i] + r.x1[i];
+    for (int i = 0; i < 3; i++) o.x[i] = z[i] + r.x1s(i);
     o.vpar = z[3];
     double t_pass = tau * dt_dtau_const;
     o.t_pass = t_pass; // (:466) assigned before the stop-inside test; kept if the particle is removed below
@@ -681,7 +682,7 @@ struct PolyPusher {
 #pragma unroll
         for (int i = 0; i < 3; i++) {
           o.z_save[i] = z[i];
-          o.x[i] = z[i] + r.x1[i];
+          o.x[i] = z[i] + r.x1s(i);
         }
         o.z_save_set = 1;
         o.vpar = z[3];
@@ -700,7 +701,7 @@ struct PolyPusher {
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       o.z_save[i] = z[i];
-      o.x[i] = z[i] + r.x1[i];
+      o.x[i] = z[i] + r.x1s(i);
     }
     o.z_save_set = 1;
     o.vpar = z[3];
@@ -755,7 +756,10 @@ struct PolyPusher {
     if (normal_v_from_trajectory(iface_new, tau) > 0.0) return false;
     return finish<true>(z, tau, iface_new, o);
   }
-  GB_HD bool push_fast(int ind_tetr_in, int iface, const double *x, double vpar, double t_remain_in, PushOut &o)
+  // t_remain_reload (kernel only): where the caller keeps t_remain; re-reading it after the solve -- same value --
+  // ends its register live range at init(), so that it is not carried (spilled) across the solve
+  GB_HD bool push_fast(int ind_tetr_in, int iface, const double *x, double vpar, double t_remain_in, PushOut &o,
+                       const volatile double *t_remain_reload = nullptr)
   {
     SolveTask t;
     int iface_new;
@@ -775,12 +779,14 @@ struct PolyPusher {
       tau_max = tau * GB_EPS_TAU;
       iface_new = iface_init;
       if (!pick_exit<K>(cm, 0xFu, 0, iface_new, tau)) return false;
+      if (t_remain_reload) t_remain = *t_remain_reload;
       return fast_end(tau, iface_new, tau_max, true, o);
     }
     if (!fast_begin(ind_tetr_in, iface, x, vpar, t_remain_in, t, iface_new, tau_max)) return false;
     double tau = t.tau;
     if (t.kind == 0) return false;
     if (t.kind == 2) tau = solve_monic_min_positive(t.deg, t.q[0], t.q[1], t.q[2], t.q[3], t.lambda, solver_iters);
+    if (t_remain_reload) t_remain = *t_remain_reload;
     return fast_end(tau, iface_new, tau_max, true, o);
   }
 
@@ -861,8 +867,10 @@ GB_HD_NOINLINE PushOut push_full_call(const MeshDev *mp, double perpinv, int ind
                                       double x1, double x2, double vpar, double t_remain)
 {
   PolyPusher<K, PHI> P;
+  double stash[6];
   P.mp = mp;
   P.perpinv = perpinv;
+  P.r.set_stash(stash, 1);
   PushOut o;
   double x[3] = {x0, x1, x2};
   o.x[0] = x0; o.x[1] = x1; o.x[2] = x2; o.vpar = vpar;

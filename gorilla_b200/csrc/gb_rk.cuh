@@ -508,7 +508,7 @@ struct RkPusher {
   {
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      o.x[i] = z[i] + P.r.x1[i];
+      o.x[i] = z[i] + P.r.x1s(i);
       o.z_save[i] = z[i];
     }
     o.z_save_set = 1;
@@ -526,7 +526,7 @@ struct RkPusher {
     const double t_pass0 = tau * P.dt_dtau_const;
     // x and t_pass are assigned before anything can fail (:2100-2105); a removal further down keeps them
 #pragma unroll
-    for (int i = 0; i < 3; i++) o.x[i] = z[i] + P.r.x1[i];
+    for (int i = 0; i < 3; i++) o.x[i] = z[i] + P.r.x1s(i);
     o.t_pass = t_pass0;
     if (!(fabs(t_remain) < fabs(t_pass0))) {
       pass_through(z, tau, iface_new, false, o);
@@ -550,7 +550,7 @@ struct RkPusher {
       }
       if (nvel(iface_new, dzdtau) > 0.0) return 1;
 #pragma unroll
-      for (int i = 0; i < 3; i++) o.x[i] = z[i] + P.r.x1[i];
+      for (int i = 0; i < 3; i++) o.x[i] = z[i] + P.r.x1s(i);
       o.t_pass = tau * P.dt_dtau_const;
       if (fabs(tau * P.dt_dtau_const) <= fabs(t_remain)) {
         pass_through(z, tau, iface_new, false, o);
@@ -560,7 +560,7 @@ struct RkPusher {
     }
     tau = tau + dtau;
 #pragma unroll
-    for (int i = 0; i < 3; i++) o.x[i] = z[i] + P.r.x1[i];
+    for (int i = 0; i < 3; i++) o.x[i] = z[i] + P.r.x1s(i);
     o.t_pass = tau * P.dt_dtau_const;
     distances(z, nd);
     int n_out = 0, iface_outside = 0;
@@ -582,7 +582,7 @@ struct RkPusher {
       } else {
         // converged on a face at t_remain but flying inwards: handed to the same tetrahedron again
 #pragma unroll
-        for (int i = 0; i < 3; i++) { o.x[i] = z[i] + P.r.x1[i]; o.z_save[i] = z[i]; }
+        for (int i = 0; i < 3; i++) { o.x[i] = z[i] + P.r.x1s(i); o.z_save[i] = z[i]; }
         o.z_save_set = 1;
         o.vpar = z[3];
         o.t_pass = tau * P.dt_dtau_const;
@@ -628,7 +628,7 @@ struct RkPusher {
     }
     // orbit time is finished inside the tetrahedron
 #pragma unroll
-    for (int i = 0; i < 3; i++) { o.x[i] = z[i] + P.r.x1[i]; o.z_save[i] = z[i]; }
+    for (int i = 0; i < 3; i++) { o.x[i] = z[i] + P.r.x1s(i); o.z_save[i] = z[i]; }
     o.z_save_set = 1;
     o.vpar = z[3];
     o.t_pass = tau * P.dt_dtau_const;
@@ -775,6 +775,8 @@ GB_HD_NOINLINE PushOut push_rk_full_call(const MeshDev *mp, double perpinv, int 
                                          double x2, double vpar, double t_remain)
 {
   RkPusher<PHI> R;
+  double stash[6];
+  R.P.r.set_stash(stash, 1);
   PushOut o;
   const double x[3] = {x0, x1, x2};
   o.x[0] = x0; o.x[1] = x1; o.x[2] = x2; o.vpar = vpar;

@@ -40,6 +40,8 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
     if constexpr (K == 0) {
       if (!force_full) {
         RkPusher<PHI> R;
+        double stash[6];
+        R.P.r.set_stash(stash, 1);
         R.init(&m, perpinv, ind_tetr, x, iface, vpar, t_remain);
         done = R.template push<true>(o);
       }
@@ -47,6 +49,8 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
     } else {
       if (!force_full) {
         PolyPusher<K, PHI> P;
+        double stash[6];
+        P.r.set_stash(stash, 1);
         P.mp = &m;
         P.perpinv = perpinv;
         done = P.push_fast(ind_tetr, iface, x, vpar, t_remain, o);

@@ -70,6 +70,12 @@ constexpr int gb_min_blocks(int K) { return K == 0 ? GB_MINB_RK : K == 1 ? GB_MI
 // miss the L1 (thrashed by the record gathers) and cost an L2 round trip each (ncu: ~10 such waits per push, half of
 // all stall samples).  Shared memory is explicit, conflict free ([field][thread]) and ~30 cycles away.
 #define GB_THREADS 128
+__device__ __forceinline__ unsigned tid_now()
+{
+  unsigned t;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+  return t;
+}
 enum { LS_X0 = 0, LS_X1, LS_X2, LS_VPAR, LS_PERPINV, LS_TREM, LS_ZS0, LS_ZS1, LS_ZS2, LS_ND };
 enum { LC_LOST = 0, LC_FIN, LC_FB0, LC_FB1, LC_FB2, LC_FB3, LC_N };
 
@@ -82,13 +88,14 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
   __shared__ unsigned int s_cnt[LC_N][GB_THREADS];
   __shared__ int s_ind_save[GB_THREADS];
   const unsigned lane = threadIdx.x & 31u;
-  // all accessors index by threadIdx.x: no address is held in a register across the push
-#define LS(f) (((volatile double *)s_d[f])[threadIdx.x])
-#define LCNT(f) (((volatile unsigned int *)s_cnt[f])[threadIdx.x])
-#define p_idx (((volatile long long *)s_idx) + threadIdx.x)
-#define p_npush (((volatile long long *)s_npush) + threadIdx.x)
-#define p_cpush (((volatile unsigned long long *)s_cpush) + threadIdx.x)
-#define p_ind_save (((volatile int *)s_ind_save) + threadIdx.x)
+  // every accessor re-reads %tid.x through a volatile asm: otherwise the compiler forms the slot addresses once,
+  // keeps them live across the push and spills THEM
+#define LS(f) (((volatile double *)s_d[f])[tid_now()])
+#define LCNT(f) (((volatile unsigned int *)s_cnt[f])[tid_now()])
+#define p_idx (((volatile long long *)s_idx) + tid_now())
+#define p_npush (((volatile long long *)s_npush) + tid_now())
+#define p_cpush (((volatile unsigned long long *)s_cpush) + tid_now())
+#define p_ind_save (((volatile int *)s_ind_save) + tid_now())
   bool active = false, exhausted = false;
   int32_t ind_tetr = -1, iface = -1;
   *p_cpush = 0;
@@ -146,7 +153,7 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
         if (!bt.force_full) {
           const double x[3] = {LS(LS_X0), LS(LS_X1), LS(LS_X2)};
           RkPusher<PHI> R;
-          R.P.r.set_stash(&s_stash[0][threadIdx.x], GB_THREADS);
+          R.P.r.set_stash(&s_stash[0][tid_now()], GB_THREADS);
           R.init(&m, perpinv, ind_tetr, x, iface, LS(LS_VPAR), LS(LS_TREM));
           done = R.template push<true>(o);
         }
@@ -158,7 +165,7 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
           PolyPusher<K, PHI> P;
           P.mp = &m;
           P.perpinv = perpinv;
-          P.r.set_stash(&s_stash[0][threadIdx.x], GB_THREADS);
+          P.r.set_stash(&s_stash[0][tid_now()], GB_THREADS);
           done = P.push_fast(ind_tetr, iface, x, LS(LS_VPAR), LS(LS_TREM), o, &LS(LS_TREM));
         }
         if (!done)

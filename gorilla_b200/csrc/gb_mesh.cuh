@@ -127,18 +127,18 @@ struct Rec {
   int sts;
   GB_HD void set_stash(volatile double *p, int stride) { st = p; sts = stride; }
   GB_HD double x1s(int i) const { return st[i * sts]; }
-  GB_HD int32_t nb(int f) const
+  GB_HD static int32_t word_of(double d, int hi)
   {
+#if defined(__CUDA_ARCH__)
+    return hi ? __double2hiint(d) : __double2loint(d);
+#else
     union { double d; int32_t i[2]; } u;
-    u.d = st[(3 + (f >> 1)) * sts];
-    return u.i[f & 1];
+    u.d = d;
+    return u.i[hi];
+#endif
   }
-  GB_HD uint32_t flags() const
-  {
-    union { double d; int32_t i[2]; } u;
-    u.d = st[5 * sts];
-    return (uint32_t)u.i[0];
-  }
+  GB_HD int32_t nb(int f) const { return word_of(st[(3 + (f >> 1)) * sts], f & 1); }
+  GB_HD uint32_t flags() const { return (uint32_t)word_of(st[5 * sts], 0); }
 
   GB_HD void load(const MeshDev &m, int ind_tetr /*1-based*/)
   {

@@ -17,9 +17,12 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
+# GORILLA_VARIANT=name builds lib/libgorilla_b200_name.so from its own object directory (tuning experiments with
+# GORILLA_NVCC_EXTRA; select it at run time with GORILLA_B200_LIB)
+_VARIANT = os.environ.get("GORILLA_VARIANT", "")
 OUT_DIR = ROOT / "lib"
-OBJ_DIR = ROOT / "lib" / "obj"
-LIB = OUT_DIR / "libgorilla_b200.so"
+OBJ_DIR = ROOT / "lib" / ("obj_" + _VARIANT if _VARIANT else "obj")
+LIB = OUT_DIR / ("libgorilla_b200_" + _VARIANT + ".so" if _VARIANT else "libgorilla_b200.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"

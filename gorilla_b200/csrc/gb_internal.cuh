@@ -96,55 +96,60 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
 #define p_npush (((volatile long long *)s_npush) + tid_now())
 #define p_cpush (((volatile unsigned long long *)s_cpush) + tid_now())
 #define p_ind_save (((volatile int *)s_ind_save) + tid_now())
-  bool active = false, exhausted = false;
   int32_t ind_tetr = -1, iface = -1;
   *p_cpush = 0;
 #pragma unroll
   for (int k = 0; k < LC_N; k++) LCNT(k) = 0;
 
-  for (;;) {
-    if (!active && !exhausted) {
-      // warp-aggregated pull from the particle queue
+  // Pull the next particle that actually has to be pushed into this lane's slot; false when the queue is empty.
+  // Warp-aggregated: the lanes that arrive here together take consecutive queue entries with one atomic.
+  auto refill = [&]() -> bool {
+    for (;;) {
       const unsigned need = __activemask();
       const int leader = __ffs(need) - 1;
       unsigned long long base = 0;
       if ((int)lane == leader) base = atomicAdd(bt.ctr + CTR_QUEUE, (unsigned long long)__popc(need));
       base = __shfl_sync(need, base, leader);
       const int64_t idx = (int64_t)(base + (unsigned long long)__popc(need & ((1u << lane) - 1u)));
-      if (idx >= bt.n) {
-        exhausted = true;
-      } else {
-        ind_tetr = bt.ind_tetr[idx];
-        iface = bt.iface[idx];
-        const bool inited = bt.init ? (bt.init[idx] != 0) : true;
-        if (!inited || ind_tetr < 1) {
-          // not localised (find_tetra failed) or already lost: orbit_timestep_gorilla returns at :59-61,
-          // resp. leaves the loop at :103-109 without touching the particle
-          if (bt.t_remain_out) bt.t_remain_out[idx] = bt.t_step;
-          if (bt.n_pushes) bt.n_pushes[idx] = 0;
-          if (inited && ind_tetr < 1) LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
-        } else if (bt.t_step == 0.0) {
-          if (bt.t_remain_out) bt.t_remain_out[idx] = 0.0;
-          if (bt.n_pushes) bt.n_pushes[idx] = 0;
-        } else {
-          const double x0 = bt.x[3 * idx], x1 = bt.x[3 * idx + 1], x2 = bt.x[3 * idx + 2];
-          const double vperp = bt.vperp[idx];
-          // :71-78  z_save = x - x1 ; perpinv = -0.5*vperp**2/bmod_func(z_save, ind_tetr)
-          const double *pg = m.geom + ((int64_t)ind_tetr - 1) * GEOM_ND;
-          const double zs[3] = {x0 - ldg(pg), x1 - ldg(pg + 1), x2 - ldg(pg + 2)};
-          LS(LS_X0) = x0; LS(LS_X1) = x1; LS(LS_X2) = x2;
-          LS(LS_VPAR) = bt.vpar[idx];
-          LS(LS_ZS0) = zs[0]; LS(LS_ZS1) = zs[1]; LS(LS_ZS2) = zs[2];
-          LS(LS_PERPINV) = -0.5 * (vperp * vperp) / bmod_at<PHI>(m, ind_tetr, zs);
-          LS(LS_TREM) = bt.t_step;
-          *p_idx = idx;
-          *p_npush = 0;
-          active = true;
-        }
+      if (idx >= bt.n) return false;
+      ind_tetr = bt.ind_tetr[idx];
+      iface = bt.iface[idx];
+      const bool inited = bt.init ? (bt.init[idx] != 0) : true;
+      if (!inited || ind_tetr < 1) {
+        // not localised (find_tetra failed) or already lost: orbit_timestep_gorilla returns at :59-61,
+        // resp. leaves the loop at :103-109 without touching the particle
+        if (bt.t_remain_out) bt.t_remain_out[idx] = bt.t_step;
+        if (bt.n_pushes) bt.n_pushes[idx] = 0;
+        if (inited && ind_tetr < 1) LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
+        continue;
       }
+      if (bt.t_step == 0.0) {
+        if (bt.t_remain_out) bt.t_remain_out[idx] = 0.0;
+        if (bt.n_pushes) bt.n_pushes[idx] = 0;
+        continue;
+      }
+      const double x0 = bt.x[3 * idx], x1 = bt.x[3 * idx + 1], x2 = bt.x[3 * idx + 2];
+      const double vperp = bt.vperp[idx];
+      // :71-78  z_save = x - x1 ; perpinv = -0.5*vperp**2/bmod_func(z_save, ind_tetr)
+      const double *pg = m.geom + ((int64_t)ind_tetr - 1) * GEOM_ND;
+      const double zs[3] = {x0 - ldg(pg), x1 - ldg(pg + 1), x2 - ldg(pg + 2)};
+      LS(LS_X0) = x0; LS(LS_X1) = x1; LS(LS_X2) = x2;
+      LS(LS_VPAR) = bt.vpar[idx];
+      LS(LS_ZS0) = zs[0]; LS(LS_ZS1) = zs[1]; LS(LS_ZS2) = zs[2];
+      LS(LS_PERPINV) = -0.5 * (vperp * vperp) / bmod_at<PHI>(m, ind_tetr, zs);
+      LS(LS_TREM) = bt.t_step;
+      *p_idx = idx;
+      *p_npush = 0;
+      return true;
     }
-    if (__all_sync(0xffffffffu, exhausted && !active)) break;
-    if (active) {
+  };
+
+  // One lane = one particle at a time.  A lane whose particle is done refills itself at the end of the same loop
+  // body and leaves the loop for good when the queue is empty, so the body has no "is this lane active" region (whose
+  // convergence-barrier register was live, and spilled, across every push).
+  bool active = refill();
+  while (active) {
+    {
       *p_ind_save = ind_tetr;
       PushOut o;
       bool done = false;
@@ -210,10 +215,11 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
         *p_cpush = *p_cpush + (unsigned long long)(npush + 1);
         if (o.finished) LCNT(LC_FIN) = LCNT(LC_FIN) + 1;
         else LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
-        active = false;
+        active = refill();
       }
     }
   }
+  __syncwarp();
   // counters: warp reduce, one atomic per warp and counter
   unsigned long long v[7] = {*p_cpush, LCNT(LC_LOST), LCNT(LC_FIN), LCNT(LC_FB0), LCNT(LC_FB1), LCNT(LC_FB2), LCNT(LC_FB3)};
 #pragma unroll

@@ -30,9 +30,14 @@ sys.path.insert(0, str(ROOT / "tests"))
 METRIC = "particle_tetra_crossings_per_second"
 UNIT = "crossings/s"
 BYTES_PER_CROSSING = {False: 344.0, True: 488.0}  # hot record (+8 B topology), without/with Phi part
-# FP64 thread-instructions (DADD+DMUL+DFMA) per crossing of the strict build, from the ncu source pages of
-# round 1 (profiles/r01_*): poly order -> count.  Order 3 is interpolated (not yet profiled).
-FP64_INST_PER_CROSSING = {1: 480.0, 2: 484.0, 3: 1900.0, 4: 3530.0, "rk4": 800.0}  # rk4: SURVEY estimate
+BYTES_STRONG_E = 192.0  # + 24 doubles of the strong-electric-field group
+# FP64 thread-instructions (DADD+DMUL+DFMA) and DRAM bytes per crossing of the strict build, from one ncu capture per
+# kernel (profiles/r01_ncu_per_crossing.json; order 1 not captured: order-2 figure)
+FP64_INST_PER_CROSSING = {1: 463.0, 2: 463.0, 3: 2026.0, 4: 3349.0, "rk4": 767.0}
+try:
+    _NCU = json.loads((ROOT / "profiles" / "r01_ncu_per_crossing.json").read_text())
+except Exception:  # the table is documentation of a capture; the bench runs without it (traffic: null)
+    _NCU = {}
 
 
 def parse_args():
@@ -197,7 +202,8 @@ def main():
     if args.ctas_per_sm or args.threads:
         g.set_launch_config(args.ctas_per_sm, args.threads)
     has_phi = bool(np.any(mesh.tetra_physics[:, 116:125] != 0.0))
-    bytes_per_crossing = BYTES_PER_CROSSING[has_phi]
+    strong = bool(settings.boole_strong_electric_field)
+    bytes_per_crossing = BYTES_PER_CROSSING[has_phi or strong] + (BYTES_STRONG_E if strong else 0.0)
 
     # particles of this rank (weak scaling: n per GPU fixed); independent streams per rank
     x, vpar, vperp = wl["particles"](n, 1000 + rank)
@@ -305,21 +311,28 @@ def main():
         achieved = bytes_per_crossing * per_rank_pushes / (launch_ms * 1e-3) / 1e9
         # the slower of the two per-push limits decides the bound (north_star): HBM gather vs FP64 issue
         dfma_peak, muladd_peak = fp64_peak()
-        fp64_per = FP64_INST_PER_CROSSING["rk4" if settings.ipusher == 1 else settings.poly_order]
+        kkey = "rk4" if settings.ipusher == 1 else settings.poly_order
+        fp64_per = FP64_INST_PER_CROSSING[kkey]
+        # traffic: DRAM bytes per launch = per-crossing figure of the ncu capture of this kernel x crossings per launch
+        ncu = _NCU.get(str(kkey))
+        traffic = ncu["dram_bytes_per_crossing"] * per_rank_pushes if ncu and not has_phi and not strong else None
+        traffic_src = (f"ncu capture {ncu['capture']}: {ncu['dram_bytes_per_crossing']:.2f} B/crossing x crossings per launch"
+                       if traffic is not None else None)
         t_hbm, t_fp64 = bytes_per_crossing / (hbm_peak * 1e9), fp64_per / muladd_peak
         fp64_ach = fp64_per * per_rank_pushes / (launch_ms * 1e-3)
         fp64 = {"achieved": fp64_ach / 1e12, "peak": muladd_peak / 1e12, "unit": "Tinst/s (thread-level DMUL/DADD)",
                 "frac": fp64_ach / muladd_peak, "inst_per_crossing": fp64_per, "dfma_peak": dfma_peak / 1e12,
                 "peak_source": "measured in this run (gorilla_b200_fp64_peak)"}
-        kern = f"orbit_kernel<{0 if settings.ipusher == 1 else settings.poly_order},{'true' if has_phi else 'false'}>"
+        kern = f"orbit_kernel<{0 if settings.ipusher == 1 else settings.poly_order},{2 if strong else 1 if has_phi else 0}>"
         if t_hbm >= t_fp64:
             roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": achieved / hbm_peak, "traffic": None, "kernel": kern,
+                        "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "kernel": kern,
                         "algorithmic_bytes_per_crossing": bytes_per_crossing, "launch_ms": launch_ms,
                         "kernel_share_of_step": kernel_ms / elapsed_ms, "peak_source": peak_src, "fp64": fp64}
         else:
             roofline = {"bound": "fp64", "achieved": fp64["achieved"], "peak": fp64["peak"], "unit": fp64["unit"],
-                        "frac": fp64["frac"], "traffic": None, "kernel": kern, "launch_ms": launch_ms,
+                        "frac": fp64["frac"], "traffic": traffic, "traffic_source": traffic_src, "kernel": kern,
+                        "launch_ms": launch_ms,
                         "kernel_share_of_step": kernel_ms / elapsed_ms, "peak_source": fp64["peak_source"],
                         "hbm": {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                                 "algorithmic_bytes_per_crossing": bytes_per_crossing}}

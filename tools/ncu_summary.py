@@ -31,9 +31,10 @@ def main():
     r = raw(rep)
     for k in KEYS:
         if k in r: print(f"{k:75s} {r[k][0]:>18s} {r[k][1]}")
-    st = [(float(v[0].replace(",", "")), k) for k, v in r.items() if "warp_issue_stalled" in k and k.endswith("per_warp_active.pct") and v[0] not in ("", "n/a")]
+    st = [(float(v[0].replace(",", "")), k) for k, v in r.items()
+          if "issue_stalled" in k and k.endswith("per_issue_active.ratio") and "not_issued" not in k and v[0] not in ("", "n/a")]
     for v, k in sorted(st, reverse=True)[:10]:
-        print(f"  stall {k.split('issue_stalled_')[1].split('_per_warp')[0]:35s} {v:8.1f}")
+        print(f"  stalled warps per issue: {k.split('issue_stalled_')[1].split('_per_issue')[0]:28s} {v:8.3f}")
     rows = source(rep)
     cols = rows[0].keys()
     c_inst = next(c for c in cols if c.startswith("# Instructions Executed") or c == "Instructions Executed")

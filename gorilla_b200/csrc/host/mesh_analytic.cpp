@@ -69,6 +69,8 @@ struct RectGrid {
   }
 };
 
+}  // namespace
+
 void make_grid_rect(Mesh &m)
 {
   const int nr = m.grid_size[0], nphi = m.grid_size[1], nz = m.grid_size[2];
@@ -155,6 +157,8 @@ void make_grid_rect(Mesh &m)
         }
 }
 
+namespace {
+
 struct AnalyticCirc {
   double R0, a, B0, q0, q1;
   // returns Br, Bp, Bz and psif
@@ -209,40 +213,12 @@ int build_analytic_circ(const gorilla_grid_settings &gs, const gorilla_settings 
     vf.phi_elec[iv] = vf.A_x2[iv] * st.eps_Phi;
   }
   if (st.boole_strong_electric_field) {
-    // strong_electric_field_mod.f90: potential = psif*eps_Phi (option 2), E = -grad(Phi) by central differences with
-    // step 1e-6 * (coordinate extent / points per direction) (:49-85, :215-252), v_E = c ExB/B^2 covariant (:145-165)
-    vf.resize_strong((size_t)m.nvert);
-    double lim[3][2];
-    for (int k = 0; k < 3; k++) { lim[k][0] = INFINITY; lim[k][1] = -INFINITY; }
-    for (int64_t iv = 0; iv < m.nvert; iv++)
-      for (int k = 0; k < 3; k++) {
-        const double v = m.verts_rphiz[3 * iv + k];
-        if (v < lim[k][0]) lim[k][0] = v;
-        if (v > lim[k][1]) lim[k][1] = v;
-      }
-    const double average_2D_n = std::sqrt((double)(m.nvert / gs.n2));
-    const double npts[3] = {average_2D_n, (double)gs.n2, average_2D_n};
-    double dx[3];
-    for (int k = 0; k < 3; k++) dx[k] = std::fabs(lim[k][1] - lim[k][0]) / npts[k] * 1.0e-6;
-    auto potential = [&](double r, double z) {
+    auto psif_at = [&](double r, double z) {
       double Br, Bp, Bz, psif;
       f.field(r, z, Br, Bp, Bz, psif);
-      return psif * st.eps_Phi;
+      return psif;
     };
-#pragma omp parallel for schedule(static)
-    for (int64_t iv = 0; iv < m.nvert; iv++) {
-      const double R = m.verts_rphiz[3 * iv], Z = m.verts_rphiz[3 * iv + 2];
-      const double E1 = -(potential(R + dx[0], Z) - potential(R + -dx[0], Z)) / (2 * dx[0]);
-      const double E2 = -(potential(R, Z) - potential(R, Z)) / (2 * dx[1]);  // axisymmetric potential
-      const double E3 = -(potential(R, Z + dx[2]) - potential(R, Z + -dx[2])) / (2 * dx[2]);
-      vf.phi_elec[iv] = potential(R, Z);
-      const double h1 = vf.h_x1[iv], h2 = vf.h_x2[iv], h3 = vf.h_x3[iv], B = vf.bmod[iv];
-      const double v1 = (E2 * h3 - E3 * h2) / (R * B) * CLIGHT;
-      const double v2 = (E3 * h1 - E1 * h3) / (B)*R * CLIGHT;
-      const double v3 = (E1 * h2 - E2 * h1) / (R * B) * CLIGHT;
-      vf.vE_x1[iv] = v1; vf.vE_x2[iv] = v2; vf.vE_x3[iv] = v3;
-      vf.v2E[iv] = v1 * v1 + v2 * 1 / (R * R) * v2 + v3 * v3;
-    }
+    strong_electric_vertex_fields(m, gs.n2, st.eps_Phi, psif_at, vf);
   }
   linearise_tetrahedra(m, vf);
   check_tetra_overlaps(m);

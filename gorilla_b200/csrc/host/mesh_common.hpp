@@ -9,6 +9,7 @@
 //            species constants   SRC/orbit_timestep_gorilla.f90:204-249.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 #include "../../../include/gorilla_b200.h"
@@ -74,8 +75,18 @@ int set_species(Mesh &m, int ispecies, std::string &err);
 void linearise_tetrahedra(Mesh &m, const VertexFields &vf);
 void check_tetra_overlaps(Mesh &m);
 
+// make_grid_rect (SRC/tetra_grid_mod.f90:344-680): rectangular (R, phi, Z) grid over [Rmin,Rmax] x [Zmin,Zmax], grid_size set
+void make_grid_rect(Mesh &m);
+// strong_electric_field_mod.f90: potential = psif*eps_Phi (option 2), E = -grad(Phi) by central differences with step
+// 1e-6 * (coordinate extent / points per direction) (:49-85, :215-252), v_E = c ExB/B^2 covariant (:145-165).
+// psif_at(R, Z) is the poloidal flux of the equilibrium (axisymmetric); vf.h_*, vf.bmod must be filled.
+void strong_electric_vertex_fields(const Mesh &m, int n2, double eps_Phi, const std::function<double(double, double)> &psif_at,
+                                   VertexFields &vf);
+
 // grid builders (one translation unit each)
 int build_analytic_circ(const gorilla_grid_settings &g, const gorilla_settings &s, Mesh &m, std::string &err);
 int build_vmec(const gorilla_grid_settings &g, const gorilla_settings &s, Mesh &m, std::string &err);
+int build_efit_rect(const gorilla_grid_settings &g, const gorilla_settings &s, Mesh &m, std::string &err);
+int build_soledge3x(const gorilla_grid_settings &g, const gorilla_settings &s, Mesh &m, std::string &err);
 
 } // namespace gbhost

@@ -1,0 +1,114 @@
+"""grid_kind = 1: rectangular (R, phi, Z) grid over an EFIT equilibrium (g-file reader, quintic psi spline, fpol spline,
+convex-wall coordinate stretching; gorilla_b200/csrc/host/mesh_efit.cpp).  The reader and the interpolant are checked
+against an independent Python parse of the same g-file and scipy's quintic spline (different end conditions: compared
+away from the box edge), then the mesh carries orbits through the oracle and the device algorithm."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import workloads
+from gorilla_b200 import GorillaSettings, TetraGridSettings, build_mesh
+from host_mirror_binding import HostMirror
+from oracle_binding import OracleMesh
+
+DATA = Path(__file__).resolve().parent.parent / "data" / "equilibria"
+GFILE = DATA / "g_file_for_test"
+
+
+def parse_gfile(path):
+    lines = path.read_text().splitlines()
+    nw, nh = int(lines[0][52:56]), int(lines[0][56:60])
+    vals = []
+    for ln in lines[1:]:
+        for k in range(0, len(ln), 16):
+            f = ln[k:k + 16]
+            if f.strip():
+                try:
+                    vals.append(float(f))
+                except ValueError:
+                    return nw, nh, np.array(vals)
+    return nw, nh, np.array(vals)
+
+
+@pytest.fixture(scope="module")
+def efit_mesh(product_lib):
+    grid = TetraGridSettings(grid_kind=1, n1=48, n2=12, n3=72, boole_n_field_periods=True,
+                             g_file_filename=str(GFILE), convex_wall_filename=str(DATA / "convex_wall_for_test.dat"))
+    st = GorillaSettings(eps_Phi=0.0, coord_system=1, ispecies=2, boole_periodic_relocation=False, ipusher=2,
+                         poly_order=2, boole_guess=True)
+    return build_mesh(grid, st), grid, st
+
+
+def test_vertex_fields_agree_with_an_independent_spline(efit_mesh):
+    from scipy.interpolate import RectBivariateSpline
+    mesh, grid, _ = efit_mesh
+    nw, nh, v = parse_gfile(GFILE)
+    xdim, zdim, rzero, r1, zmid = v[0:5]
+    psi_axis, psi_sep, bt0 = v[7], v[8], v[9]
+    fpol = v[20:20 + nw]
+    psi = v[20 + 4 * nw:20 + 4 * nw + nw * nh].reshape(nh, nw).T            # psi[i, j] = psiRZ(i+1, j+1)
+    rad = (r1 + np.arange(nw) * (xdim / (nw - 1))) * 1e2
+    zet = (zmid - zdim / 2 + np.arange(nh) * (zdim / (nh - 1))) * 1e2
+    psi_cgs = (psi - psi_axis) * 1e8
+    d = mesh.desc()
+    assert d.Rmin == rad[0] and d.Rmax == rad[-1] and d.Zmin == zet[0] and d.Zmax == zet[-1]
+    spl = RectBivariateSpline(rad, zet, psi_cgs, kx=5, ky=5)
+    tp = mesh.tetra_physics
+    R, Z = tp[:, 0], tp[:, 2]                                                # first vertex x1 = (R, phi, Z)
+    core = (R > 115) & (R < 215) & (Z > -100) & (Z < 100)                    # inside the convex wall: no stretching
+    assert core.sum() > 10000
+    span = psi_cgs.max() - psi_cgs.min()
+    assert np.abs(tp[core, 26] - spl.ev(R[core], Z[core])).max() < 2e-6 * span   # A_phi at the first vertex = psi
+    dpr, dpz = spl.ev(R[core], Z[core], dx=1), spl.ev(R[core], Z[core], dy=1)
+    psihat = np.clip(spl.ev(R[core], Z[core]) / ((psi_sep - psi_axis) * 1e8), 0, None)
+    from scipy.interpolate import CubicSpline
+    F = np.where(psihat > 1, fpol[-1], CubicSpline(np.linspace(0, 1, nw), fpol)(np.minimum(psihat, 1))) * 1e6
+    Bmod = np.sqrt((dpz / R[core]) ** 2 + (dpr / R[core]) ** 2 + (F / R[core]) ** 2)
+    assert np.abs(tp[core, 24] / Bmod - 1).max() < 1e-5
+    # unit vector h: covariant components, |h|^2 = h_R^2 + (h_phi/R)^2 + h_Z^2 = 1
+    h = tp[:, 27:30]
+    assert np.abs(h[:, 0] ** 2 + (h[:, 1] / R) ** 2 + h[:, 2] ** 2 - 1).max() < 1e-12
+    assert mesh.n_overlaps == 0 if hasattr(mesh, "n_overlaps") else True
+
+
+def test_orbits_oracle_vs_device_algorithm_and_invariants(efit_mesh):
+    mesh, _, st = efit_mesh
+    for K in (2, 4):
+        s = type(st)(**{**st.__dict__, "poly_order": K})
+        om, hm = OracleMesh(mesh, s), HostMirror(mesh, s)
+        n = 120
+        xa, va, wa = workloads.particles_cyl(n, 5, R0=165.0, a=40.0)
+        xb, vb, wb = xa.copy(), va.copy(), wa.copy()
+        ia, ta, fa = workloads.fresh_state(n)
+        ib, tb, fb = workloads.fresh_state(n)
+        om.orbit_timestep_batch(xa, va, wa, 0.0, ia, ta, fa)
+        e0, p0, mu0 = om.invariants(xa, va, wa, ta)
+        ra = om.orbit_timestep_trace(xa, va, wa, 2e-5, ia, ta, fa, 256)
+        rb = hm.orbit_timestep(xb, vb, wb, 2e-5, ib, tb, fb, 256)
+        assert (ta > 0).sum() > 110 and ra["n_pushes"].sum() > 3000
+        assert np.array_equal(ra["trace_tetr"], rb["trace_tetr"]) and np.array_equal(ra["trace_face"], rb["trace_face"])
+        assert np.array_equal(xa, xb) and np.array_equal(va, vb) and np.array_equal(wa, wb) and np.array_equal(ta, tb)
+        e1, p1, mu1 = om.invariants(xa, va, wa, ta)
+        ok = ta > 0
+        assert np.abs(mu1 / mu0 - 1)[ok].max() < 1e-13
+        dp = np.abs(p1 - p0)[ok].max() / np.abs(p0[ok]).mean()                 # axisymmetric: p_phi conserved
+        assert dp < (1e-2 if K == 2 else 1e-9), dp     # order 2 on 12 toroidal cells: ~1e-3, as on the analytic grid
+        assert np.abs(e1 / e0 - 1)[ok].max() < (1e-4 if K == 2 else 1e-11)
+
+
+@pytest.mark.gpu
+def test_gpu_parity_on_the_efit_mesh(efit_mesh, cuda_device):
+    from gorilla_b200 import Gorilla
+    mesh, _, st = efit_mesh
+    om, g = OracleMesh(mesh, st), Gorilla(mesh, st)
+    n = 500
+    xa, va, wa = workloads.particles_cyl(n, 6, R0=165.0, a=40.0)
+    xb, vb, wb = xa.copy(), va.copy(), wa.copy()
+    ia, ta, fa = workloads.fresh_state(n)
+    ib, tb, fb = workloads.fresh_state(n)
+    ra = om.orbit_timestep_trace(xa, va, wa, 2e-5, ia, ta, fa, 128)
+    tt, tf = g.orbit_timestep_gorilla(xb, vb, wb, 2e-5, ib, tb, fb, trace_cap=128)
+    assert np.array_equal(ra["trace_tetr"], tt) and np.array_equal(ra["trace_face"], tf)
+    assert np.array_equal(xa, xb) and np.array_equal(va, vb) and np.array_equal(wa, wb) and np.array_equal(ta, tb)
+    g.close()

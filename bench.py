@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "vmec_qi", "analytic"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "vmec_qi", "analytic", "west_soledge3x", "efit_rect"])
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (0 = workload default)")
     ap.add_argument("--poly-order", type=int, default=0, help="0 = workload default")
     ap.add_argument("--ipusher", type=int, default=0, help="1 = RK4 pusher, 2 = polynomial pusher (0 = workload default)")
@@ -72,6 +72,27 @@ def make_workload(name: str):
                     particles=workloads.particles_vmec_alpha, n_default=1_000_000, t_step=1.0e-4,
                     desc="QI stellarator netcdf_file_for_test.nc (VMEC), grid_kind=3 100x40x40, 3.5 MeV alphas, "
                          "s0=0.5, pitch U[-1,1], time step 1e-4 s (BASELINE config 3: 100 steps of 1e-4 s)")
+    data = ROOT / "data" / "equilibria"
+    if name == "west_soledge3x":
+        grid, settings = workloads.west_soledge3x(data, n2=60)
+        return dict(name="west_soledge3x_D_600keV_strongE_rk4", grid=grid, settings=settings,
+                    particles=lambda n, seed: workloads.particles_on_triangles(data, n, seed), n_default=1_000_000,
+                    t_step=2.0e-6,
+                    desc="BASELINE config 4: WEST equilibrium + SOLEDGE3X-EIRENE mesh, grid_kind=4, n2=60 (4 242 060 "
+                         "tetrahedra), strong-electric-field mode eps_Phi=-1.5e-5, 600 keV deuterons uniform over the "
+                         "poloidal mesh, RK4 pusher")
+    if name == "efit_rect":
+        from gorilla_b200 import GorillaSettings, TetraGridSettings
+        grid = TetraGridSettings(grid_kind=1, n1=100, n2=40, n3=160, boole_n_field_periods=True,
+                                 g_file_filename=str(data / "g_file_for_test"),
+                                 convex_wall_filename=str(data / "convex_wall_for_test.dat"))
+        settings = GorillaSettings(eps_Phi=0.0, coord_system=1, ispecies=2, boole_periodic_relocation=True, ipusher=2,
+                                   poly_order=2, boole_guess=True)
+        return dict(name="efit_aug_rect_D_3keV_100x40x160", grid=grid, settings=settings,
+                    particles=lambda n, seed: workloads.particles_cyl(n, seed, R0=165.0, a=45.0), n_default=1_000_000,
+                    t_step=2.0e-5,
+                    desc="BASELINE config 1/2 geometry in cylindrical coordinates: ASDEX Upgrade g_file_for_test, grid_kind=1 "
+                         "100x40x160 (3 840 000 tetrahedra), 3 keV deuterons")
     grid, settings = workloads.analytic_tokamak(40, 80, 40)
     settings.poly_order = 2
     return dict(name="analytic_tokamak_D_3keV_40x80x40", grid=grid, settings=settings,

@@ -35,7 +35,7 @@ NVCC_FLAGS += os.environ.get("GORILLA_NVCC_EXTRA", "").split()
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas"]
 
 CU_SOURCES = ["gorilla_b200.cu", "gb_orbit_k1.cu", "gb_orbit_k2.cu", "gb_orbit_k3.cu", "gb_orbit_k4.cu", "gb_orbit_rk.cu"]
-CPP_SOURCES = ["host/mesh_api.cpp", "host/mesh_common.cpp", "host/mesh_analytic.cpp", "host/mesh_vmec.cpp", "host/mesh_efit.cpp"]
+CPP_SOURCES = ["host/mesh_api.cpp", "host/mesh_common.cpp", "host/mesh_analytic.cpp", "host/mesh_vmec.cpp", "host/mesh_efit.cpp", "host/mesh_soledge3x.cpp"]
 
 
 def _headers_digest() -> str:
@@ -53,7 +53,7 @@ def _compile(src: str, hdr_digest: str, force: bool) -> tuple[Path, str]:
     stamp = obj.with_suffix(".stamp")
     digest = hashlib.sha256(path.read_bytes() + hdr_digest.encode()).hexdigest()
     if not force and obj.exists() and stamp.exists() and stamp.read_text().split("\n")[0] == digest:
-        return obj, ""
+        return obj, None
     if src.endswith(".cu"):
         cmd = [NVCC, *NVCC_FLAGS, "-c", str(path), "-o", str(obj)]
     else:
@@ -72,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         results = list(ex.map(lambda s: _compile(s, hd, force), srcs))
     objs = [str(o) for o, _ in results]
-    rebuilt = any(log for _, log in results) or not LIB.exists()
+    rebuilt = any(log is not None for _, log in results) or not LIB.exists()  # None = object was up to date
     if verbose:
         for _, log in results:
             if log:

@@ -304,8 +304,13 @@ int EfitField::load_convex_wall(const char *path, std::string &err)
     if (ch == 'd' || ch == 'D') ch = 'e';  // Fortran exponent letter
   std::istringstream ss(txt);
   std::vector<double> rw, zw;
-  double r, z;
-  while ((int)rw.size() < 100 && (ss >> r >> z)) { rw.push_back(r); zw.push_back(z); }
+  std::string line;
+  while ((int)rw.size() < 100 && std::getline(ss, line)) {  // list-directed read: two numbers per record, rest ignored
+    std::istringstream ls(line);
+    double r, z;
+    if (!(ls >> r >> z)) break;
+    rw.push_back(r); zw.push_back(z);
+  }
   if (rw.size() < 3) { err = "convex wall: fewer than 3 points"; return GORILLA_ERR_IO; }
   rw.push_back(rw[0]); zw.push_back(zw[0]);
   const int nrz = (int)rw.size();

@@ -63,3 +63,45 @@ def particles_vmec_alpha(n, seed, energy_ev=3.5e6, s0=0.5, nfp=5):
     vpar = lam * vmod
     vperp = np.sqrt(vmod ** 2 - vpar ** 2)
     return x, vpar, vperp
+
+
+def west_soledge3x(data_dir, n2=60, strong=True, ipusher=1, poly_order=2):
+    """BASELINE config 4: WEST equilibrium table + SOLEDGE3X-EIRENE triangle mesh extruded to n2 toroidal
+    slices (4.24 M tetrahedra at n2 = 60), strong-electric-field mode with eps_Phi = -1.5e-5 (MATLAB/example_8.m:42-48),
+    RK4 pusher, cylindrical coordinates."""
+    d = str(data_dir)
+    grid = TetraGridSettings(grid_kind=4, n1=100, n2=n2, n3=60, boole_n_field_periods=True,
+                             g_file_filename=d + "/g_file_for_test_WEST",
+                             convex_wall_filename=d + "/convex_wall_for_test_WEST.dat",
+                             knots_SOLEDGE3X_EIRENE_filename=d + "/MESH_SOLEDGE3X_EIRENE/knots_for_test.dat",
+                             triangles_SOLEDGE3X_EIRENE_filename=d + "/MESH_SOLEDGE3X_EIRENE/triangles_for_test.dat")
+    settings = GorillaSettings(eps_Phi=-1.5e-5 if strong else 0.0, coord_system=1, ispecies=2, boole_periodic_relocation=True,
+                               ipusher=ipusher, poly_order=poly_order, boole_guess=True,
+                               boole_strong_electric_field=bool(strong))
+    return grid, settings
+
+
+def particles_on_triangles(data_dir, n, seed, energy_ev=6.0e5, mass=2.0 * AMP):
+    """Start points uniform over the poloidal mesh area (triangle picked with probability ~ area, uniform barycentric
+    point inside), toroidal angle and pitch uniform."""
+    d = str(data_dir)
+    knots = np.loadtxt(d + "/MESH_SOLEDGE3X_EIRENE/knots_for_test.dat", skiprows=1)
+    tri = np.loadtxt(d + "/MESH_SOLEDGE3X_EIRENE/triangles_for_test.dat", skiprows=1, dtype=np.int64) - 1
+    a, b, c = knots[tri[:, 0]], knots[tri[:, 1]], knots[tri[:, 2]]
+    area = 0.5 * np.abs((b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0]))
+    rng = np.random.Generator(np.random.PCG64(seed))
+    t = rng.choice(len(tri), size=n, p=area / area.sum())
+    u, v = rng.random(n), rng.random(n)
+    flip = u + v > 1
+    u[flip], v[flip] = 1 - u[flip], 1 - v[flip]
+    # keep a little away from the triangle edges so that no start point sits on a cell face
+    u, v = 0.02 + 0.94 * u, 0.02 + 0.94 * v * (1 - 0.0)
+    p = a[t] + u[:, None] * (b[t] - a[t]) + np.minimum(v, 0.98 - u)[:, None] * (c[t] - a[t])
+    x = np.empty((n, 3))
+    x[:, 0], x[:, 2] = p[:, 0], p[:, 1]
+    x[:, 1] = 2 * np.pi * rng.random(n)
+    lam = 2.0 * rng.random(n) - 1.0
+    vmod = np.sqrt(2.0 * energy_ev * EV2ERG / mass)
+    vpar = lam * vmod
+    vperp = np.sqrt(vmod ** 2 - vpar ** 2)
+    return x, vpar, vperp

@@ -75,12 +75,12 @@ def make_workload(name: str):
     data = ROOT / "data" / "equilibria"
     if name == "west_soledge3x":
         grid, settings = workloads.west_soledge3x(data, n2=60)
-        return dict(name="west_soledge3x_D_600keV_strongE_rk4", grid=grid, settings=settings,
+        return dict(name="west_soledge3x_W74_600keV_strongE_rk4", grid=grid, settings=settings,
                     particles=lambda n, seed: workloads.particles_on_triangles(data, n, seed), n_default=1_000_000,
-                    t_step=2.0e-6,
+                    t_step=1.0e-4,
                     desc="BASELINE config 4: WEST equilibrium + SOLEDGE3X-EIRENE mesh, grid_kind=4, n2=60 (4 242 060 "
-                         "tetrahedra), strong-electric-field mode eps_Phi=-1.5e-5, 600 keV deuterons uniform over the "
-                         "poloidal mesh, RK4 pusher")
+                         "tetrahedra), strong-electric-field mode eps_Phi=-1.5e-5, 600 keV W74+ uniform over the "
+                         "poloidal mesh (scrape-off-layer starts are lost in the first steps), RK4 pusher, steps of 1e-4 s")
     if name == "efit_rect":
         from gorilla_b200 import GorillaSettings, TetraGridSettings
         grid = TetraGridSettings(grid_kind=1, n1=100, n2=40, n3=160, boole_n_field_periods=True,

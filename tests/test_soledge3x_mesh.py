@@ -69,8 +69,8 @@ def test_config4_rk4_strong_field_oracle_vs_device_algorithm(west_mesh):
     xb, vb, wb = xa.copy(), va.copy(), wa.copy()
     ia, ta, fa = workloads.fresh_state(n)
     ib, tb, fb = workloads.fresh_state(n)
-    ra = om.orbit_timestep_trace(xa, va, wa, 2e-6, ia, ta, fa, 256)
-    rb = hm.orbit_timestep(xb, vb, wb, 2e-6, ib, tb, fb, 256)
+    ra = om.orbit_timestep_trace(xa, va, wa, 2e-5, ia, ta, fa, 256)
+    rb = hm.orbit_timestep(xb, vb, wb, 2e-5, ib, tb, fb, 256)
     assert ia.all() and ra["n_pushes"].sum() > 3000                    # every start point was located
     assert np.array_equal(ra["trace_tetr"], rb["trace_tetr"]) and np.array_equal(ra["trace_face"], rb["trace_face"])
     assert np.array_equal(xa, xb) and np.array_equal(va, vb) and np.array_equal(wa, wb) and np.array_equal(ta, tb)
@@ -80,10 +80,10 @@ def test_config4_rk4_strong_field_oracle_vs_device_algorithm(west_mesh):
 @pytest.mark.parametrize("K", [2, 4])
 def test_polynomial_pusher_invariants(west_mesh, K):
     mesh, _, st = west_mesh
-    s = type(st)(**{**st.__dict__, "ipusher": 2, "poly_order": K})
+    s = type(st)(**{**st.__dict__, "ipusher": 2, "poly_order": K, "ispecies": 2})
     om = OracleMesh(mesh, s)
     n = 100
-    x, v, w = workloads.particles_on_triangles(DATA, n, 4, energy_ev=3.0e4)
+    x, v, w = workloads.particles_on_triangles(DATA, n, 4, energy_ev=3.0e4, mass=2.0 * workloads.AMP)
     b, t, f = workloads.fresh_state(n)
     om.orbit_timestep_batch(x, v, w, 0.0, b, t, f)
     e0, p0, mu0 = om.invariants(x, v, w, t)
@@ -105,8 +105,8 @@ def test_gpu_parity_config4(west_mesh, cuda_device):
     xb, vb, wb = xa.copy(), va.copy(), wa.copy()
     ia, ta, fa = workloads.fresh_state(n)
     ib, tb, fb = workloads.fresh_state(n)
-    ra = om.orbit_timestep_trace(xa, va, wa, 2e-6, ia, ta, fa, 128)
-    tt, tf = g.orbit_timestep_gorilla(xb, vb, wb, 2e-6, ib, tb, fb, trace_cap=128)
+    ra = om.orbit_timestep_trace(xa, va, wa, 2e-5, ia, ta, fa, 128)
+    tt, tf = g.orbit_timestep_gorilla(xb, vb, wb, 2e-5, ib, tb, fb, trace_cap=128)
     assert np.array_equal(ra["trace_tetr"], tt) and np.array_equal(ra["trace_face"], tf)
     assert np.array_equal(xa, xb) and np.array_equal(va, vb) and np.array_equal(wa, wb) and np.array_equal(ta, tb)
     assert np.array_equal(ia, ib) and np.array_equal(fa, fb)

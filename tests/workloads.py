@@ -68,20 +68,21 @@ def particles_vmec_alpha(n, seed, energy_ev=3.5e6, s0=0.5, nfp=5):
 def west_soledge3x(data_dir, n2=60, strong=True, ipusher=1, poly_order=2):
     """BASELINE config 4: WEST equilibrium table + SOLEDGE3X-EIRENE triangle mesh extruded to n2 toroidal
     slices (4.24 M tetrahedra at n2 = 60), strong-electric-field mode with eps_Phi = -1.5e-5 (MATLAB/example_8.m:42-48),
-    RK4 pusher, cylindrical coordinates."""
+    RK4 pusher, cylindrical coordinates, W74+ (ispecies = 4: the heavy-impurity case the strong-field terms exist for;
+    600 keV deuterons have banana widths of the minor radius in this equilibrium and are lost promptly)."""
     d = str(data_dir)
     grid = TetraGridSettings(grid_kind=4, n1=100, n2=n2, n3=60, boole_n_field_periods=True,
                              g_file_filename=d + "/g_file_for_test_WEST",
                              convex_wall_filename=d + "/convex_wall_for_test_WEST.dat",
                              knots_SOLEDGE3X_EIRENE_filename=d + "/MESH_SOLEDGE3X_EIRENE/knots_for_test.dat",
                              triangles_SOLEDGE3X_EIRENE_filename=d + "/MESH_SOLEDGE3X_EIRENE/triangles_for_test.dat")
-    settings = GorillaSettings(eps_Phi=-1.5e-5 if strong else 0.0, coord_system=1, ispecies=2, boole_periodic_relocation=True,
+    settings = GorillaSettings(eps_Phi=-1.5e-5 if strong else 0.0, coord_system=1, ispecies=4, boole_periodic_relocation=True,
                                ipusher=ipusher, poly_order=poly_order, boole_guess=True,
                                boole_strong_electric_field=bool(strong))
     return grid, settings
 
 
-def particles_on_triangles(data_dir, n, seed, energy_ev=6.0e5, mass=2.0 * AMP):
+def particles_on_triangles(data_dir, n, seed, energy_ev=6.0e5, mass=184.0 * AMP):
     """Start points uniform over the poloidal mesh area (triangle picked with probability ~ area, uniform barycentric
     point inside), toroidal angle and pitch uniform."""
     d = str(data_dir)

@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "vmec_qi", "analytic", "west_soledge3x", "efit_rect"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "vmec_qi", "analytic", "west_soledge3x", "efit_rect", "efit_flux"])
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (0 = workload default)")
     ap.add_argument("--poly-order", type=int, default=0, help="0 = workload default")
     ap.add_argument("--ipusher", type=int, default=0, help="1 = RK4 pusher, 2 = polynomial pusher (0 = workload default)")
@@ -81,6 +81,12 @@ def make_workload(name: str):
                     desc="BASELINE config 4: WEST equilibrium + SOLEDGE3X-EIRENE mesh, grid_kind=4, n2=60 (4 242 060 "
                          "tetrahedra), strong-electric-field mode eps_Phi=-1.5e-5, 600 keV W74+ uniform over the "
                          "poloidal mesh (scrape-off-layer starts are lost in the first steps), RK4 pusher, steps of 1e-4 s")
+    if name == "efit_flux":
+        grid, settings = workloads.efit_flux(data)
+        return dict(name="efit_aug_flux_D_3keV_100x40x40", grid=grid, settings=settings,
+                    particles=lambda n, seed: workloads.particles_flux(n, seed), n_default=1_000_000, t_step=1.0e-4,
+                    desc="BASELINE configs 1/2: ASDEX Upgrade g_file_for_test, grid_kind=2 coord_system=2 field-aligned "
+                         "100x40x40 (960 000 tetrahedra), 3 keV deuterons, s in U[0.2,0.9], steps of 1e-4 s")
     if name == "efit_rect":
         from gorilla_b200 import GorillaSettings, TetraGridSettings
         grid = TetraGridSettings(grid_kind=1, n1=100, n2=40, n3=160, boole_n_field_periods=True,

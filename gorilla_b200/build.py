@@ -35,7 +35,7 @@ NVCC_FLAGS += os.environ.get("GORILLA_NVCC_EXTRA", "").split()
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas"]
 
 CU_SOURCES = ["gorilla_b200.cu", "gb_orbit_k1.cu", "gb_orbit_k2.cu", "gb_orbit_k3.cu", "gb_orbit_k4.cu", "gb_orbit_rk.cu"]
-CPP_SOURCES = ["host/mesh_api.cpp", "host/mesh_common.cpp", "host/mesh_analytic.cpp", "host/mesh_vmec.cpp", "host/mesh_efit.cpp", "host/mesh_soledge3x.cpp"]
+CPP_SOURCES = ["host/mesh_api.cpp", "host/mesh_common.cpp", "host/mesh_analytic.cpp", "host/mesh_vmec.cpp", "host/mesh_efit.cpp", "host/mesh_soledge3x.cpp", "host/mesh_efit_flux.cpp"]
 
 
 def _headers_digest() -> str:

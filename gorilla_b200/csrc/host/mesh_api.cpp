@@ -22,10 +22,11 @@ extern "C" int gorilla_mesh_build(const gorilla_grid_settings *grid, const goril
       case 5: rc = gbhost::build_analytic_circ(*grid, *settings, gm->m, err); break;
       case 3: rc = gbhost::build_vmec(*grid, *settings, gm->m, err); break;
       case 1: rc = gbhost::build_efit_rect(*grid, *settings, gm->m, err); break;
+      case 2: rc = gbhost::build_efit_flux(*grid, *settings, gm->m, err); break;
       case 4: rc = gbhost::build_soledge3x(*grid, *settings, gm->m, err); break;
       default:
-        err = "grid_kind: 1 (EFIT, rectangular), 3 (VMEC, field aligned), 4 (SOLEDGE3X-EIRENE) and 5 (analytic circular "
-              "tokamak) are built by this library; other grids can be passed in through gorilla_mesh_desc";
+        err = "grid_kind must be 1 (EFIT, rectangular), 2 (EFIT, field aligned), 3 (VMEC, field aligned), 4 (SOLEDGE3X-EIRENE) "
+              "or 5 (analytic circular tokamak)";
         rc = GORILLA_ERR_UNSUPPORTED;
     }
   }

@@ -273,7 +273,12 @@ void linearise_tetrahedra(Mesh &m, const VertexFields &vf)
       double met_det;
       if (cs == 1) met_det = p1[j];
       else if (gk == 3) met_det = avec[10][j];
-      else met_det = NAN;  // EFIT flux coordinates: not built by this library yet
+      else {  // EFIT flux coordinates: metric_determinant() of the LINEARISED quantities (:1276-1279)
+        const double dx[3] = {p1[j] - p1[0], p2[j] - p2[0], p3[j] - p3[0]};
+        auto lin = [&](double v1, const double *g) { return v1 + (((0.0 + g[0] * dx[0]) + g[1] * dx[1]) + g[2] * dx[2]); };
+        const double Rl = lin(T[TP_R1], &T[TP_GR]);
+        met_det = (Rl * Rl * m.psitor_max) / (lin(T[TP_H3_1], &T[TP_GH3]) * lin(T[TP_BMOD1], &T[TP_GB]));
+      }
       dtd = dtd + met_det * avec[6][j];
     }
     T[TP_DT_DTAU_CONST] = dtd / 4.0;
@@ -302,7 +307,7 @@ void linearise_tetrahedra(Mesh &m, const VertexFields &vf)
   // sign_sqg = sign(metric_determinant(1, x1(tetra 1)))  (:1019)
   {
     const double *T = &m.tetra_physics[0];
-    double md = (cs == 1) ? T[TP_X1] : T[TP_SQG1];
+    double md = (cs == 1) ? T[TP_X1] : (gk == 3) ? T[TP_SQG1] : (T[TP_R1] * T[TP_R1] * m.psitor_max) / (T[TP_H3_1] * T[TP_BMOD1]);
     m.sign_sqg = std::signbit(md) ? -1 : 1;
   }
 }

@@ -43,6 +43,7 @@ struct Mesh {
   int32_t grid_size[3] = {0, 0, 0};
   double Rmin = 0, Rmax = 0, Zmin = 0, Zmax = 0, sfc_s_min = 0;
   double mag_axis_R0 = 0, mag_axis_Z0 = 0;
+  double psitor_max = 0;  // EFIT flux coordinates (grid_kind 2): toroidal flux at the last surface, A_theta = s*psitor_max
   int64_t n_overlaps = 0;
 };
 
@@ -87,6 +88,7 @@ void strong_electric_vertex_fields(const Mesh &m, int n2, double eps_Phi, const 
 int build_analytic_circ(const gorilla_grid_settings &g, const gorilla_settings &s, Mesh &m, std::string &err);
 int build_vmec(const gorilla_grid_settings &g, const gorilla_settings &s, Mesh &m, std::string &err);
 int build_efit_rect(const gorilla_grid_settings &g, const gorilla_settings &s, Mesh &m, std::string &err);
+int build_efit_flux(const gorilla_grid_settings &g, const gorilla_settings &s, Mesh &m, std::string &err);
 int build_soledge3x(const gorilla_grid_settings &g, const gorilla_settings &s, Mesh &m, std::string &err);
 
 } // namespace gbhost

@@ -375,6 +375,11 @@ void EfitField::field(double r, double z, double &Br, double &Bp, double &Bz, do
 {
   double rm, zm;
   stretch_coords(r, z, rm, zm);
+  field_eq(rm, zm, Br, Bp, Bz, psif);
+}
+
+void EfitField::field_eq(double rm, double zm, double &Br, double &Bp, double &Bz, double &psif) const
+{
   const double rrr = std::max(rad[0], std::min(rad[nrad - 1], rm));
   const double zzz = std::max(zet[0], std::min(zet[nzet - 1], zm));
   double dpdr, dpdz, d2r, d2rz, d2z;

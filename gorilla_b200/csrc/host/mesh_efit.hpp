@@ -34,7 +34,8 @@ struct EfitField {
   int load_west(const char *path, std::string &err);
   int load_convex_wall(const char *path, std::string &err);
   void stretch_coords(double r, double z, double &rm, double &zm) const;
-  void field(double r, double z, double &Br, double &Bp, double &Bz, double &psif) const;
+  void field_eq(double r, double z, double &Br, double &Bp, double &Bz, double &psif) const;  // no stretching
+  void field(double r, double z, double &Br, double &Bp, double &Bz, double &psif) const;     // stretch_coords + field_eq
   void vertex_fields(const Mesh &m, const gorilla_settings &st, int n2, VertexFields &vf) const;
 };
 

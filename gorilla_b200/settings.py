@@ -42,7 +42,7 @@ class TetraGridSettings:
     i_radial_spacing: int = 0
     theta_geom_flux: int = 1
     sfc_s_min: float = 0.1
-    theta0_at_xpoint: float = 0.0
+    theta0_at_xpoint: float = 1.0   # logical in the namelist (.true. = theta = 0 on the axis -> X-point ray)
     R0_analytic_circ: float = 0.0
     a_analytic_circ: float = 0.0
     B0_analytic_circ: float = 0.0

@@ -112,3 +112,100 @@ def test_gpu_parity_on_the_efit_mesh(efit_mesh, cuda_device):
     assert np.array_equal(ra["trace_tetr"], tt) and np.array_equal(ra["trace_face"], tf)
     assert np.array_equal(xa, xb) and np.array_equal(va, vb) and np.array_equal(wa, wb) and np.array_equal(ta, tb)
     g.close()
+
+
+# ---------------------------------------------------------------------------------------------- grid_kind = 2
+@pytest.fixture(scope="module")
+def efit_flux_mesh(product_lib):
+    grid = TetraGridSettings(grid_kind=2, n1=40, n2=8, n3=32, boole_n_field_periods=True, sfc_s_min=0.1,
+                             g_file_filename=str(GFILE), convex_wall_filename=str(DATA / "convex_wall_for_test.dat"))
+    st = GorillaSettings(eps_Phi=0.0, coord_system=2, ispecies=2, boole_periodic_relocation=True, ipusher=2,
+                         poly_order=2, boole_guess=True)
+    return build_mesh(grid, st), grid, st
+
+
+def test_flux_coordinates_reproduce_the_equilibrium(efit_flux_mesh):
+    """The symmetry flux coordinates are constructed by field-line integration.  Independent checks against the g-file:
+    the poloidal flux stored at every vertex equals the psi(R, Z) table at the vertex position, the safety factor
+    q = d(psi_tor)/d(psi_pol) of the constructed surfaces follows the g-file's own q profile, and the poloidal angle is
+    a straight-field-line angle (the Jacobian R^2 psitor_max / (h_phi B) used for dt/dtau is positive and smooth)."""
+    from scipy.interpolate import RectBivariateSpline
+    mesh, grid, _ = efit_flux_mesh
+    nw, nh, v = parse_gfile(GFILE)
+    xdim, zdim, rzero, r1, zmid = v[0:5]
+    psi_axis, psi_sep = v[7], v[8]
+    psi = v[20 + 4 * nw:20 + 4 * nw + nw * nh].reshape(nh, nw).T
+    qpsi = v[20 + 4 * nw + nw * nh:20 + 5 * nw + nw * nh]
+    rad = (r1 + np.arange(nw) * (xdim / (nw - 1))) * 1e2
+    zet = (zmid - zdim / 2 + np.arange(nh) * (zdim / (nh - 1))) * 1e2
+    spl = RectBivariateSpline(rad, zet, (psi - psi_axis) * 1e8, kx=5, ky=5)
+    tp = mesh.tetra_physics
+    s, R, Z, Aphi, Ath = tp[:, 0], tp[:, 31], tp[:, 32], tp[:, 26], tp[:, 25]
+    span = abs(psi_sep - psi_axis) * 1e8
+    # (1) psi at the vertex position; the axis found by field-line averaging is not exactly the table's minimum
+    assert np.abs(Aphi - spl.ev(R, Z)).max() < 2e-4 * span
+    # (2) q profile: ring-to-ring finite difference of A_theta = s psitor_max against A_phi = psi_pol
+    rings = np.unique(np.round(s, 12))
+    a_phi = np.array([Aphi[np.isclose(s, r)].mean() for r in rings])
+    a_th = np.array([Ath[np.isclose(s, r)].mean() for r in rings])
+    q_mesh = np.abs(np.diff(a_th) / np.diff(a_phi))
+    psin_mid = 0.5 * (a_phi[1:] + a_phi[:-1]) / span
+    q_file = np.interp(np.abs(psin_mid), np.linspace(0, 1, nw), np.abs(qpsi))
+    inner = np.abs(psin_mid) < 0.9
+    assert inner.sum() > 20
+    assert np.abs(q_mesh[inner] / q_file[inner] - 1).max() < 0.03
+    # (3) flux surfaces: psi is constant on a ring to interpolation accuracy
+    for r in rings[::5]:
+        sel = np.isclose(s, r)
+        assert np.ptp(Aphi[sel]) < 2e-4 * span
+    assert np.all(tp[:, 40] > 0) and mesh.desc().sign_sqg == 1     # dt/dtau = sqrt(g) B > 0
+
+
+def test_orbits_on_the_field_aligned_efit_mesh(efit_flux_mesh):
+    mesh, grid, st = efit_flux_mesh
+    for K in (2, 4):
+        sK = type(st)(**{**st.__dict__, "poly_order": K})
+        om, hm = OracleMesh(mesh, sK), HostMirror(mesh, sK)
+        n = 120
+        rng = np.random.Generator(np.random.PCG64(9))
+        xa = np.column_stack([0.2 + 0.6 * rng.random(n), 2 * np.pi * rng.random(n), 2 * np.pi * rng.random(n)])
+        lam = 2 * rng.random(n) - 1
+        vmod = np.sqrt(2.0 * 3.0e3 * workloads.EV2ERG / (2.0 * workloads.AMP))
+        va, wa = lam * vmod, vmod * np.sqrt(1 - lam ** 2)
+        xb, vb, wb = xa.copy(), va.copy(), wa.copy()
+        ia, ta, fa = workloads.fresh_state(n)
+        ib, tb, fb = workloads.fresh_state(n)
+        om.orbit_timestep_batch(xa, va, wa, 0.0, ia, ta, fa)
+        hm.orbit_timestep(xb, vb, wb, 0.0, ib, tb, fb, 0)
+        assert ia.all() and np.array_equal(ta, tb)
+        e0, p0, mu0 = om.invariants(xa, va, wa, ta)
+        ra = om.orbit_timestep_trace(xa, va, wa, 2e-5, ia, ta, fa, 256)
+        rb = hm.orbit_timestep(xb, vb, wb, 2e-5, ib, tb, fb, 256)
+        assert ra["n_pushes"].sum() > 2000 and (ta > 0).sum() > 100
+        assert np.array_equal(ra["trace_tetr"], rb["trace_tetr"]) and np.array_equal(ra["trace_face"], rb["trace_face"])
+        assert np.array_equal(xa, xb) and np.array_equal(va, vb) and np.array_equal(wa, wb) and np.array_equal(ta, tb)
+        e1, p1, mu1 = om.invariants(xa, va, wa, ta)
+        ok = ta > 0
+        assert np.abs(mu1 / mu0 - 1)[ok].max() < 1e-13
+        assert np.abs(e1 / e0 - 1)[ok].max() < (1e-4 if K == 2 else 1e-10)
+        dp = np.abs(p1 - p0)[ok].max() / np.abs(p0[ok]).mean()
+        assert dp < (1e-2 if K == 2 else 1e-8), dp
+
+
+@pytest.mark.gpu
+def test_gpu_parity_on_the_field_aligned_efit_mesh(efit_flux_mesh, cuda_device):
+    from gorilla_b200 import Gorilla
+    mesh, _, st = efit_flux_mesh
+    s4 = type(st)(**{**st.__dict__, "poly_order": 4})
+    for s in (st, s4):
+        om, g = OracleMesh(mesh, s), Gorilla(mesh, s)
+        n = 400
+        xa, va, wa = workloads.particles_flux(n, 6)
+        xb, vb, wb = xa.copy(), va.copy(), wa.copy()
+        ia, ta, fa = workloads.fresh_state(n)
+        ib, tb, fb = workloads.fresh_state(n)
+        ra = om.orbit_timestep_trace(xa, va, wa, 2e-5, ia, ta, fa, 128)
+        tt, tf = g.orbit_timestep_gorilla(xb, vb, wb, 2e-5, ib, tb, fb, trace_cap=128)
+        assert np.array_equal(ra["trace_tetr"], tt) and np.array_equal(ra["trace_face"], tf)
+        assert np.array_equal(xa, xb) and np.array_equal(va, vb) and np.array_equal(wa, wb) and np.array_equal(ta, tb)
+        g.close()

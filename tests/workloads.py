@@ -106,3 +106,28 @@ def particles_on_triangles(data_dir, n, seed, energy_ev=6.0e5, mass=184.0 * AMP)
     vpar = lam * vmod
     vperp = np.sqrt(vmod ** 2 - vpar ** 2)
     return x, vpar, vperp
+
+
+def efit_flux(data_dir, n1=100, n2=40, n3=40, poly_order=2):
+    """BASELINE configs 1/2: ASDEX Upgrade g_file_for_test, field-aligned grid in symmetry flux coordinates
+    (grid_kind = 2, coord_system = 2), 100x40x40 = 960 000 tetrahedra, deuterons."""
+    d = str(data_dir)
+    grid = TetraGridSettings(grid_kind=2, n1=n1, n2=n2, n3=n3, boole_n_field_periods=True, sfc_s_min=0.1,
+                             g_file_filename=d + "/g_file_for_test", convex_wall_filename=d + "/convex_wall_for_test.dat")
+    settings = GorillaSettings(eps_Phi=0.0, coord_system=2, ispecies=2, boole_periodic_relocation=True, ipusher=2,
+                               poly_order=poly_order, boole_guess=True)
+    return grid, settings
+
+
+def particles_flux(n, seed, energy_ev=3.0e3, mass=2.0 * AMP, s_lo=0.2, s_hi=0.9, nfp=1):
+    """s uniform in [s_lo, s_hi], theta and phi uniform, pitch uniform in [-1, 1]."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    x = np.empty((n, 3))
+    x[:, 0] = s_lo + (s_hi - s_lo) * rng.random(n)
+    x[:, 1] = 2 * np.pi * rng.random(n)
+    x[:, 2] = 2 * np.pi / nfp * rng.random(n)
+    lam = 2.0 * rng.random(n) - 1.0
+    vmod = np.sqrt(2.0 * energy_ev * EV2ERG / mass)
+    vpar = lam * vmod
+    vperp = np.sqrt(vmod ** 2 - vpar ** 2)
+    return x, vpar, vperp

@@ -78,11 +78,22 @@ GB_HD void ld2(const double *p, double &a, double &b)
   a = v.x;
   b = v.y;
 }
+// 256-bit gather (sm_100): one 32-byte sector per lane and instruction.  The order-2 kernel saturates the L1 data pipe
+// (l1tex__data_pipe_lsu_wavefronts 92 %): lanes hold different records, so every load instruction costs one wavefront
+// per distinct cache line whatever its width -- twice the width, half the wavefronts.  Sub-records are 32-byte aligned.
+GB_HD void ld4(const double *p, double &a, double &b, double &c, double &d)
+{
+  asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
 #else
 GB_HD void ld2(const double *p, double &a, double &b)
 {
   a = p[0];
   b = p[1];
+}
+GB_HD void ld4(const double *p, double &a, double &b, double &c, double &d)
+{
+  a = p[0]; b = p[1]; c = p[2]; d = p[3];
 }
 #endif
 
@@ -146,9 +157,9 @@ struct Rec {
     double g[GEOM_ND], b[BPART_ND];
     const double *pg = m.geom + t * GEOM_ND, *pb = m.bpart + t * BPART_ND;
 #pragma unroll
-    for (int i = 0; i < GEOM_ND; i += 2) ld2(pg + i, g[i], g[i + 1]);
+    for (int i = 0; i < GEOM_ND; i += 4) ld4(pg + i, g[i], g[i + 1], g[i + 2], g[i + 3]);
 #pragma unroll
-    for (int i = 0; i < BPART_ND; i += 2) ld2(pb + i, b[i], b[i + 1]);
+    for (int i = 0; i < BPART_ND; i += 4) ld4(pb + i, b[i], b[i + 1], b[i + 2], b[i + 3]);
     x1[0] = g[0]; x1[1] = g[1]; x1[2] = g[2]; dist_ref = g[3];
 #pragma unroll
     for (int f = 0; f < 4; f++)
@@ -173,7 +184,7 @@ struct Rec {
       double p[PHI_ND];
       const double *pp = m.phi + t * PHI_ND;
 #pragma unroll
-      for (int i = 0; i < 18; i += 2) ld2(pp + i, p[i], p[i + 1]);
+      for (int i = 0; i < PHI_ND; i += 4) ld4(pp + i, p[i], p[i + 1], p[i + 2], p[i + 3]);
       Phi1 = p[P_PHI1];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
@@ -186,10 +197,10 @@ struct Rec {
       spbet = p[P_SPBET];
     }
     if (PHI == 2) {
-      double q[S_HOT_ND];
+      double q[28];  // 26 hot doubles, fetched as seven 32-byte sectors
       const double *ps = m.se + t * SE_ND;
 #pragma unroll
-      for (int i = 0; i < S_HOT_ND; i += 2) ld2(ps + i, q[i], q[i + 1]);
+      for (int i = 0; i < 28; i += 4) ld4(ps + i, q[i], q[i + 1], q[i + 2], q[i + 3]);
       v2Emod1 = q[S_V2EMOD1];
 #pragma unroll
       for (int i = 0; i < 3; i++) {

@@ -168,25 +168,49 @@ GB_HD void find_tetra(const MeshDev *mp, double *x, double vpar, double vperp, i
     indtetr_start = (int64_t)ind_plane * ntetr_in_plane + 1;
     ntetr_searched = ntetr_in_plane * (1 + corr_plus + corr_minus);
   }
+  // one candidate: the reference's loop body.  Returns true when the search is over.
+  auto try_tetra = [&](int64_t ind) -> bool {
+    double dist[4], dist_ref;
+    if (!isinside(m, ind, x, dist, dist_ref)) return false;
+    ind_tetr_out = (int32_t)ind;
+    iface = 0;
+    int n_plane_conv = 0;
+#pragma unroll
+    for (int f = 0; f < 4; f++)
+      if (fabs(dist[f]) <= (GB_EPS * fabs(dist_ref))) n_plane_conv++;
+    if (n_plane_conv > 0)
+      find_tetra_on_face<PHI>(mp, x, vpar, vperp, ind_tetr_out, iface, sign_t_step, dist, n_plane_conv);
+    if (ind_tetr_out == -1) {
+      iface = -1;
+      return false;
+    }
+    return true;
+  };
+  if (m.bin_start && !(m.grid_kind == 1 || m.grid_kind == 5)) {
+    // binned search: same visiting order as the scan below (slice after slice, ascending index inside a slice), but only
+    // the tetrahedra whose 2-D bounding box covers the point
+    const int64_t tps = ntetr / nphi;
+    const int nslices = 1 + corr_plus + corr_minus;
+    // u, v are taken once: a failed start-on-a-face attempt can only leave x shifted by a whole period, which no tetrahedron
+    // contains (isinside below always sees the current x)
+    const double u = x[m.bin_c0], v = x[m.bin_c1];
+    for (int k = 0; k < nslices; k++) {
+      int64_t base = indtetr_start - 1 + (int64_t)(k - corr_minus) * tps;  // 0-based first tetrahedron of the slice
+      if (base >= ntetr) base -= ntetr;
+      if (base < 0) base += ntetr;
+      const int iu = (int)((u - m.bin_u0) * m.bin_du_inv), iv = (int)((v - m.bin_v0) * m.bin_dv_inv);
+      if (u < m.bin_u0 || v < m.bin_v0 || iu >= m.bin_nu || iv >= m.bin_nv) continue;
+      const int b = iv * m.bin_nu + iu;
+      for (int32_t q = m.bin_start[b]; q < m.bin_start[b + 1]; q++)
+        if (try_tetra(base + m.bin_items[q] + 1)) return;
+    }
+    return;
+  }
   for (int64_t i = 1; i <= ntetr_searched; i++) {
     int64_t ind = indtetr_start + i - 1 - (int64_t)corr_minus * (ntetr / nphi);
     if (ind > ntetr) ind -= ntetr;
     if (ind <= 0) ind += ntetr;
-    double dist[4], dist_ref;
-    if (isinside(m, ind, x, dist, dist_ref)) {
-      ind_tetr_out = (int32_t)ind;
-      iface = 0;
-      int n_plane_conv = 0;
-#pragma unroll
-      for (int f = 0; f < 4; f++)
-        if (fabs(dist[f]) <= (GB_EPS * fabs(dist_ref))) n_plane_conv++;
-      if (n_plane_conv > 0)
-        find_tetra_on_face<PHI>(mp, x, vpar, vperp, ind_tetr_out, iface, sign_t_step, dist, n_plane_conv);
-      if (ind_tetr_out == -1)
-        iface = -1;
-      else
-        break;
-    }
+    if (try_tetra(ind)) break;
   }
 }
 

@@ -244,6 +244,7 @@ struct gorilla_b200_handle {
   MeshDev mesh{};
   gorilla_settings settings{};
   double *d_geom = nullptr, *d_bpart = nullptr, *d_phi = nullptr, *d_cold = nullptr, *d_se = nullptr;
+  int32_t *d_bin_start = nullptr, *d_bin_items = nullptr;
   unsigned long long *d_ctr = nullptr;
   // scratch for the host-pointer entry points
   int64_t cap = 0;

@@ -59,6 +59,11 @@ struct MeshDev {
   // find_tetra
   int32_t grid_kind, grid_size1, grid_size3, n_field_periods;
   double Rmin, Rmax, Zmin, Zmax, sfc_s_min;
+  // find_tetra acceleration for the slice-wise grids (kinds 2, 3, 4): the tetrahedra of one phi slice binned on a uniform
+  // 2-D grid over the two non-toroidal coordinates (bin_c0, bin_c1 = coordinate indices); nullptr = scan the whole slice
+  const int32_t *bin_start, *bin_items;
+  int32_t bin_nu, bin_nv, bin_c0, bin_c1;
+  double bin_u0, bin_v0, bin_du_inv, bin_dv_inv;
 };
 
 GB_HD double ldg(const double *p)

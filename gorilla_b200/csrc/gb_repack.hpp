@@ -98,4 +98,89 @@ inline bool repack_mesh(const gorilla_mesh_desc *md, std::vector<double> &geom, 
   return true;
 }
 
+// ---- find_tetra bins --------------------------------------------------------------------------------------------
+// The slice-wise grids repeat the same 2-D cell pattern in every phi slice.  The tetrahedra of slice 0 are binned by
+// the bounding box of their four vertices in the two non-toroidal coordinates; the vertices are reconstructed from the
+// face planes of the record (vertex 1 = x1; vertex j lies on face 1, n1.z = -dist_ref, and on the two faces through x1
+// other than face j), so the bins can be built from the arrays a Fortran caller passes.  Boxes are inflated by 1e-6 of
+// their size: isinside() accepts points up to 1e-10 (relative) outside a face.  Items of a bin are ascending, so walking
+// them visits the tetrahedra in the order of the reference's full scan.
+struct FindBins {
+  std::vector<int32_t> start, items;
+  int32_t nu = 0, nv = 0, c0 = 0, c1 = 2;
+  double u0 = 0, v0 = 0, du_inv = 0, dv_inv = 0;
+};
+
+inline bool build_find_bins(const gorilla_mesh_desc *md, FindBins &fb)
+{
+  if (!(md->grid_kind == 2 || md->grid_kind == 3 || md->grid_kind == 4) || md->grid_size[1] < 1) return false;
+  const int64_t tps = md->ntetr / md->grid_size[1];
+  if (tps < 1 || tps * md->grid_size[1] != md->ntetr) return false;
+  fb.c0 = 0;
+  fb.c1 = (md->coord_system == 2) ? 1 : 2;
+  enum { TP_X1 = 0, TP_DIST_REF = 3, TP_ANORM = 9 };
+  std::vector<double> lo((size_t)tps * 2), hi((size_t)tps * 2);
+  double glo[2] = {1e300, 1e300}, ghi[2] = {-1e300, -1e300};
+  auto solve3 = [](const double *a, const double *b, const double *c, double ra, double rb, double rc, double *z) {
+    const double det = a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
+    if (!(det != 0.0) || !(det == det)) return false;
+    z[0] = (ra * (b[1] * c[2] - b[2] * c[1]) - a[1] * (rb * c[2] - b[2] * rc) + a[2] * (rb * c[1] - b[1] * rc)) / det;
+    z[1] = (a[0] * (rb * c[2] - b[2] * rc) - ra * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * rc - rb * c[0])) / det;
+    z[2] = (a[0] * (b[1] * rc - rb * c[1]) - a[1] * (b[0] * rc - rb * c[0]) + ra * (b[0] * c[1] - b[1] * c[0])) / det;
+    return true;
+  };
+  for (int64_t t = 0; t < tps; t++) {
+    const double *r = md->tetra_physics + t * GORILLA_TETRA_PHYSICS_NDOUBLES;
+    const double *x1 = r + TP_X1, *n = r + TP_ANORM;
+    double l[2] = {x1[fb.c0], x1[fb.c1]}, h[2] = {x1[fb.c0], x1[fb.c1]};
+    for (int j = 1; j < 4; j++) {  // vertex j+1: on face 1 and on the two faces through x1 that are not face j+1
+      int f[2], k = 0;
+      for (int q = 1; q < 4; q++)
+        if (q != j) f[k++] = q;
+      double z[3];
+      if (!solve3(n, n + 3 * f[0], n + 3 * f[1], -r[TP_DIST_REF], 0.0, 0.0, z)) return false;
+      const double p[2] = {x1[fb.c0] + z[fb.c0], x1[fb.c1] + z[fb.c1]};
+      for (int d = 0; d < 2; d++) { l[d] = p[d] < l[d] ? p[d] : l[d]; h[d] = p[d] > h[d] ? p[d] : h[d]; }
+    }
+    for (int d = 0; d < 2; d++) {
+      const double m = 1e-6 * (h[d] - l[d]) + 1e-300;
+      lo[2 * t + d] = l[d] - m; hi[2 * t + d] = h[d] + m;
+      if (!(lo[2 * t + d] == lo[2 * t + d]) || !(hi[2 * t + d] == hi[2 * t + d])) return false;
+      glo[d] = lo[2 * t + d] < glo[d] ? lo[2 * t + d] : glo[d];
+      ghi[d] = hi[2 * t + d] > ghi[d] ? hi[2 * t + d] : ghi[d];
+    }
+  }
+  int nb = 1;
+  while ((int64_t)nb * nb < tps / 3) nb++;
+  fb.nu = fb.nv = nb < 1 ? 1 : nb;
+  fb.u0 = glo[0]; fb.v0 = glo[1];
+  fb.du_inv = fb.nu / (ghi[0] - glo[0]);
+  fb.dv_inv = fb.nv / (ghi[1] - glo[1]);
+  if (!(fb.du_inv > 0.0) || !(fb.dv_inv > 0.0)) return false;
+  auto cell = [&](double v, double v0, double inv, int nn) {
+    int c = (int)((v - v0) * inv);
+    return c < 0 ? 0 : (c >= nn ? nn - 1 : c);
+  };
+  fb.start.assign((size_t)fb.nu * fb.nv + 1, 0);
+  for (int pass = 0; pass < 2; pass++) {
+    std::vector<int32_t> fill;
+    if (pass == 1) {
+      for (size_t i = 1; i < fb.start.size(); i++) fb.start[i] += fb.start[i - 1];
+      fb.items.assign((size_t)fb.start.back(), 0);
+      fill.assign(fb.start.begin(), fb.start.end() - 1);
+    }
+    for (int64_t t = 0; t < tps; t++) {  // ascending t: items of every bin come out ascending
+      const int iu0 = cell(lo[2 * t], fb.u0, fb.du_inv, fb.nu), iu1 = cell(hi[2 * t], fb.u0, fb.du_inv, fb.nu);
+      const int iv0 = cell(lo[2 * t + 1], fb.v0, fb.dv_inv, fb.nv), iv1 = cell(hi[2 * t + 1], fb.v0, fb.dv_inv, fb.nv);
+      for (int iv = iv0; iv <= iv1; iv++)
+        for (int iu = iu0; iu <= iu1; iu++) {
+          const size_t b = (size_t)iv * fb.nu + iu;
+          if (pass == 0) fb.start[b + 1]++;
+          else fb.items[(size_t)fill[b]++] = (int32_t)t;
+        }
+    }
+  }
+  return true;
+}
+
 } // namespace gb

@@ -240,6 +240,24 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
   m.bpart = h->d_bpart;
   m.phi = (has_phi || strong) ? h->d_phi : nullptr;
   m.se = strong ? h->d_se : nullptr;
+  {  // find_tetra bins for the slice-wise grids (kinds 2, 3, 4); without them find_tetra scans the whole slice
+    gb::FindBins fb;
+    m.bin_start = m.bin_items = nullptr;
+    if (gb::build_find_bins(md, fb)) {
+      cudaError_t eb;
+      if ((eb = cudaMalloc((void **)&h->d_bin_start, fb.start.size() * sizeof(int32_t))) != cudaSuccess ||
+          (eb = cudaMalloc((void **)&h->d_bin_items, (fb.items.size() + 1) * sizeof(int32_t))) != cudaSuccess ||
+          (eb = cudaMemcpy(h->d_bin_start, fb.start.data(), fb.start.size() * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess ||
+          (eb = cudaMemcpy(h->d_bin_items, fb.items.data(), fb.items.size() * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        g_last_error = std::string("gorilla_b200_init: ") + cudaGetErrorString(eb);
+        gorilla_b200_free(h);
+        return GORILLA_ERR_CUDA;
+      }
+      m.bin_start = h->d_bin_start; m.bin_items = h->d_bin_items;
+      m.bin_nu = fb.nu; m.bin_nv = fb.nv; m.bin_c0 = fb.c0; m.bin_c1 = fb.c1;
+      m.bin_u0 = fb.u0; m.bin_v0 = fb.v0; m.bin_du_inv = fb.du_inv; m.bin_dv_inv = fb.dv_inv;
+    }
+  }
   m.cold = h->d_cold;
   m.cm_over_e = md->cm_over_e;
   m.particle_mass = md->particle_mass;
@@ -267,7 +285,7 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
 extern "C" void gorilla_b200_free(gorilla_b200_handle *h)
 {
   if (!h) return;
-  cudaFree(h->d_geom); cudaFree(h->d_bpart); cudaFree(h->d_phi); cudaFree(h->d_cold); cudaFree(h->d_se); cudaFree(h->d_ctr);
+  cudaFree(h->d_geom); cudaFree(h->d_bpart); cudaFree(h->d_phi); cudaFree(h->d_cold); cudaFree(h->d_se); cudaFree(h->d_bin_start); cudaFree(h->d_bin_items); cudaFree(h->d_ctr);
   cudaFree(h->s_x); cudaFree(h->s_vpar); cudaFree(h->s_vperp); cudaFree(h->s_tro); cudaFree(h->s_e);
   cudaFree(h->s_p); cudaFree(h->s_mu); cudaFree(h->s_init); cudaFree(h->s_ind); cudaFree(h->s_iface);
   cudaFree(h->s_np); cudaFree(h->s_tr_t); cudaFree(h->s_tr_f); cudaFree(h->sort_tmp);
@@ -286,6 +304,13 @@ extern "C" int gorilla_b200_set_launch_config(gorilla_b200_handle *h, int32_t ct
     if (threads_per_cta % 32 || threads_per_cta > 128) return fail(GORILLA_ERR_ARG, "threads_per_cta must be 32..128, multiple of 32");
     h->threads_per_cta = threads_per_cta;
   }
+  return GORILLA_OK;
+}
+// test hook (not in the public header): 0 = find_tetra scans the whole phi slice like the reference, 1 = binned search
+extern "C" int gorilla_b200_debug_find_bins(gorilla_b200_handle *h, int32_t on)
+{
+  if (!h) return GORILLA_ERR_ARG;
+  h->mesh.bin_start = (on && h->d_bin_start) ? h->d_bin_start : nullptr;
   return GORILLA_OK;
 }
 // test hook (not in the public header): route every push through the complete fall-back ladder

@@ -15,6 +15,7 @@ using namespace gb;
 
 struct HostMirror {
   std::vector<double> geom, bpart, phi, cold, se;
+  gb::FindBins bins;
   MeshDev m;
   int poly_order, boole_periodic_relocation, ipusher;
 };
@@ -92,6 +93,11 @@ void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, in
   m.ntetr = md->ntetr;
   m.geom = h->geom.data(); m.bpart = h->bpart.data(); m.phi = (has_phi || strong) ? h->phi.data() : nullptr; m.cold = h->cold.data();
   m.se = strong ? h->se.data() : nullptr;
+  if (build_find_bins(md, h->bins)) {
+    m.bin_start = h->bins.start.data(); m.bin_items = h->bins.items.data();
+    m.bin_nu = h->bins.nu; m.bin_nv = h->bins.nv; m.bin_c0 = h->bins.c0; m.bin_c1 = h->bins.c1;
+    m.bin_u0 = h->bins.u0; m.bin_v0 = h->bins.v0; m.bin_du_inv = h->bins.du_inv; m.bin_dv_inv = h->bins.dv_inv;
+  }
   m.cm_over_e = md->cm_over_e; m.particle_mass = md->particle_mass; m.particle_charge = md->particle_charge;
   const double PI = 3.141592653589793238462643383;
   m.period_phi = 2.0 * PI / md->n_field_periods; m.period_theta = 2.0 * PI;

@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--sort", type=int, default=1, help="re-sort particles by tetra index before the timed region")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--no-group", action="store_true", help="orders 3/4: 4-warp CTAs instead of the lock-step solver kernel")
     return ap.parse_args()
 
 
@@ -228,6 +229,8 @@ def main():
     g = Gorilla(mesh, settings)
     if args.ctas_per_sm or args.threads:
         g.set_launch_config(args.ctas_per_sm, args.threads)
+    if args.no_group:
+        g._debug_use_group(False)
     has_phi = bool(np.any(mesh.tetra_physics[:, 116:125] != 0.0))
     strong = bool(settings.boole_strong_electric_field)
     bytes_per_crossing = BYTES_PER_CROSSING[has_phi or strong] + (BYTES_STRONG_E if strong else 0.0)

@@ -115,6 +115,7 @@ def load_library():
     lib.gorilla_b200_set_launch_config.argtypes = [vp, i32, i32]
     lib.gorilla_b200_debug_force_full.argtypes = [vp, i32]
     lib.gorilla_b200_debug_find_bins.argtypes = [vp, i32]
+    lib.gorilla_b200_debug_use_group.argtypes = [vp, i32]
     lib.gorilla_b200_fp64_peak.argtypes = [C.POINTER(dbl), C.POINTER(dbl)]
     lib.gorilla_mesh_build.argtypes = [C.POINTER(_GridSettings), C.POINTER(_Settings), C.POINTER(vp)]
     lib.gorilla_mesh_get_desc.argtypes = [vp, C.POINTER(_MeshDesc)]
@@ -359,6 +360,9 @@ class Gorilla:
 
     def _debug_force_full(self, on: bool):
         load_library().gorilla_b200_debug_force_full(self._h, int(on))
+
+    def _debug_use_group(self, on: bool):
+        load_library().gorilla_b200_debug_use_group(self._h, int(on))
 
     def _debug_find_bins(self, on: bool):
         load_library().gorilla_b200_debug_find_bins(self._h, int(on))

@@ -238,6 +238,201 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
 }
 
 // ----------------------------------------------------------------------------------------------------
+// orbit_kernel_g<K,PHI> -- orders 3 and 4 with the iterative exit-time solve run in LOCK STEP by the warps that share an
+// SM sub-partition.
+//
+// ncu: the order-3/4 kernels are instruction-fetch bound (no_instruction = 57 % of all stall samples).  One iteration of
+// the root solver is ~1600 instructions (26 KB) against a 6 KB L0 instruction cache per sub-partition, and with CTAs of
+// four warps the four warps of a sub-partition belong to four CTAs and are at unrelated places in that loop, so every
+// warp streams the whole loop through the L0 on its own.  Here a CTA has 16 warps; warps w, w+4, w+8, w+12 sit on
+// sub-partition w and form a group with its own named barrier.  The group walks the push loop together and executes
+// every solver iteration behind the barrier, so its four warps fetch the same lines at the same time and one L0 fill
+// serves all of them.  Per-particle arithmetic is that of orbit_kernel<K,PHI> (same functions): results are identical.
+#define GBG_THREADS 512
+#define GBG_GROUP 128   // threads per group = 4 warps
+
+// group-wide OR of a per-thread predicate + barrier; must be reached by whole warps of the group in converged state
+__device__ __forceinline__ bool group_any(bool pred, int bar_id)
+{
+  int r;
+  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbarrier.red.or.pred q, %2, %3, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
+               : "=r"(r) : "r"((int)pred), "r"(bar_id), "r"(GBG_GROUP) : "memory");
+  return r != 0;
+}
+
+// monic polynomial solve of every lane that has one (busy), iteration by iteration behind the group barrier
+static __device__ __noinline__ double solve_group(bool busy, int deg, double q0, double q1, double q2, double q3, double lambda,
+                                                  double tau_ready, int bar_id)
+{
+  SgSolver S;
+  cd poly[5];
+  poly[0] = mk(q0, 0.0);
+  poly[1] = mk(deg == 1 ? 1.0 : q1, 0.0);
+  poly[2] = mk(deg == 2 ? 1.0 : q2, 0.0);
+  poly[3] = mk(deg == 3 ? 1.0 : q3, 0.0);
+  poly[4] = mk(1.0, 0.0);
+  S.start(busy ? deg : 2, poly);
+  double tau = tau_ready;
+  for (;;) {
+    if (!group_any(busy, bar_id)) break;
+    if (busy && S.step()) {
+      tau = min_positive_real_root(S.deg, S.roots, lambda);
+      busy = false;
+    }
+  }
+  return tau;
+}
+
+template <int K, int PHI>
+__global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_constant__ MeshDev m, const Batch bt)
+{
+  extern __shared__ __align__(16) unsigned char g_smem[];
+  double (*s_d)[GBG_THREADS] = reinterpret_cast<double (*)[GBG_THREADS]>(g_smem);                       // [LS_ND]
+  double (*s_stash)[GBG_THREADS] = s_d + LS_ND;                                                         // [6]
+  long long *s_idx = reinterpret_cast<long long *>(s_stash + 6), *s_npush = s_idx + GBG_THREADS;
+  unsigned long long *s_cpush = reinterpret_cast<unsigned long long *>(s_npush + GBG_THREADS);
+  unsigned int (*s_cnt)[GBG_THREADS] = reinterpret_cast<unsigned int (*)[GBG_THREADS]>(s_cpush + GBG_THREADS);  // [LC_N]
+  int *s_ind_save = reinterpret_cast<int *>(s_cnt + LC_N);
+  const unsigned lane = threadIdx.x & 31u;
+  const int bar_id = 1 + (int)((threadIdx.x >> 5) & 3u);   // warps w, w+4, w+8, w+12 share sub-partition w
+#define LS(f) (((volatile double *)s_d[f])[tid_now()])
+#define LCNT(f) (((volatile unsigned int *)s_cnt[f])[tid_now()])
+#define p_idx (((volatile long long *)s_idx) + tid_now())
+#define p_npush (((volatile long long *)s_npush) + tid_now())
+#define p_cpush (((volatile unsigned long long *)s_cpush) + tid_now())
+#define p_ind_save (((volatile int *)s_ind_save) + tid_now())
+  int32_t ind_tetr = -1, iface = -1;
+  *p_cpush = 0;
+#pragma unroll
+  for (int k = 0; k < LC_N; k++) LCNT(k) = 0;
+
+  auto refill = [&]() -> bool {
+    for (;;) {
+      const unsigned need = __activemask();
+      const int leader = __ffs(need) - 1;
+      unsigned long long base = 0;
+      if ((int)lane == leader) base = atomicAdd(bt.ctr + CTR_QUEUE, (unsigned long long)__popc(need));
+      base = __shfl_sync(need, base, leader);
+      const int64_t idx = (int64_t)(base + (unsigned long long)__popc(need & ((1u << lane) - 1u)));
+      if (idx >= bt.n) return false;
+      ind_tetr = bt.ind_tetr[idx];
+      iface = bt.iface[idx];
+      const bool inited = bt.init ? (bt.init[idx] != 0) : true;
+      if (!inited || ind_tetr < 1) {
+        if (bt.t_remain_out) bt.t_remain_out[idx] = bt.t_step;
+        if (bt.n_pushes) bt.n_pushes[idx] = 0;
+        if (inited && ind_tetr < 1) LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
+        continue;
+      }
+      if (bt.t_step == 0.0) {
+        if (bt.t_remain_out) bt.t_remain_out[idx] = 0.0;
+        if (bt.n_pushes) bt.n_pushes[idx] = 0;
+        continue;
+      }
+      const double x0 = bt.x[3 * idx], x1 = bt.x[3 * idx + 1], x2 = bt.x[3 * idx + 2];
+      const double vperp = bt.vperp[idx];
+      const double *pg = m.geom + ((int64_t)ind_tetr - 1) * GEOM_ND;
+      const double zs[3] = {x0 - ldg(pg), x1 - ldg(pg + 1), x2 - ldg(pg + 2)};
+      LS(LS_X0) = x0; LS(LS_X1) = x1; LS(LS_X2) = x2;
+      LS(LS_VPAR) = bt.vpar[idx];
+      LS(LS_ZS0) = zs[0]; LS(LS_ZS1) = zs[1]; LS(LS_ZS2) = zs[2];
+      LS(LS_PERPINV) = -0.5 * (vperp * vperp) / bmod_at<PHI>(m, ind_tetr, zs);
+      LS(LS_TREM) = bt.t_step;
+      *p_idx = idx;
+      *p_npush = 0;
+      return true;
+    }
+  };
+
+  bool active = refill();
+  for (;;) {
+    if (!group_any(active, bar_id)) break;   // the group leaves together
+    PushOut o;
+    bool begun = false, done = false;
+    SolveTask t;
+    t.kind = 0; t.deg = 2; t.tau = 0.0; t.lambda = 1.0;
+    t.q[0] = t.q[1] = t.q[2] = t.q[3] = 0.0;
+    int iface_new = 0;
+    double tau_max = 0.0;
+    PolyPusher<K, PHI> P;
+    P.mp = &m;
+    P.r.set_stash(&s_stash[0][tid_now()], GBG_THREADS);
+    if (active && !bt.force_full) {
+      const double x[3] = {LS(LS_X0), LS(LS_X1), LS(LS_X2)};
+      P.perpinv = LS(LS_PERPINV);
+      begun = P.fast_begin(ind_tetr, iface, x, LS(LS_VPAR), LS(LS_TREM), t, iface_new, tau_max) && t.kind != 0;
+    }
+    const double tau = solve_group(begun && t.kind == 2, t.deg, t.q[0], t.q[1], t.q[2], t.q[3], t.lambda, t.tau, bar_id);
+    if (begun) {
+      P.t_remain = LS(LS_TREM);
+      done = P.fast_end(tau, iface_new, tau_max, true, o);
+    }
+    if (active) {
+      *p_ind_save = ind_tetr;
+      if (!done)
+        o = push_full_call<K, PHI>(&m, LS(LS_PERPINV), ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2), LS(LS_VPAR), LS(LS_TREM));
+      LS(LS_X0) = o.x[0]; LS(LS_X1) = o.x[1]; LS(LS_X2) = o.x[2];
+      LS(LS_VPAR) = o.vpar;
+      if (o.z_save_set) { LS(LS_ZS0) = o.z_save[0]; LS(LS_ZS1) = o.z_save[1]; LS(LS_ZS2) = o.z_save[2]; }
+      const int ind_prev = ind_tetr;
+      ind_tetr = o.ind_tetr;
+      iface = o.iface;
+      const long long npush = *p_npush;
+      if (bt.trace_cap > 0 && npush < bt.trace_cap) {
+        const long long idx = *p_idx;
+        bt.trace_tetr[idx * bt.trace_cap + npush] = ind_tetr;
+        bt.trace_face[idx * bt.trace_cap + npush] = iface;
+      }
+      *p_npush = npush + 1;
+      if (o.fallback) {
+        if (o.fallback & 1) LCNT(LC_FB0) = LCNT(LC_FB0) + 1;
+        if (o.fallback & 2) LCNT(LC_FB1) = LCNT(LC_FB1) + 1;
+        if (o.fallback & 4) LCNT(LC_FB2) = LCNT(LC_FB2) + 1;
+        if (o.fallback & 8) LCNT(LC_FB3) = LCNT(LC_FB3) + 1;
+      }
+      const double t_remain = LS(LS_TREM) - o.t_pass;
+      LS(LS_TREM) = t_remain;
+      if (o.finished || ind_tetr == -1) {
+        const long long idx = *p_idx;
+        const double pinv = LS(LS_PERPINV);
+        const double zs[3] = {LS(LS_ZS0), LS(LS_ZS1), LS(LS_ZS2)};
+        double vperp_new = 0.0;
+        if (pinv != 0.0) vperp_new = sqrt(2.0 * fabs(pinv) * bmod_at<PHI>(m, ind_prev, zs));
+        bt.x[3 * idx] = o.x[0];
+        bt.x[3 * idx + 1] = o.x[1];
+        bt.x[3 * idx + 2] = o.x[2];
+        bt.vpar[idx] = o.vpar;
+        bt.vperp[idx] = vperp_new;
+        bt.ind_tetr[idx] = ind_tetr;
+        bt.iface[idx] = iface;
+        if (bt.t_remain_out) bt.t_remain_out[idx] = t_remain;
+        if (bt.n_pushes) bt.n_pushes[idx] = npush + 1;
+        *p_cpush = *p_cpush + (unsigned long long)(npush + 1);
+        if (o.finished) LCNT(LC_FIN) = LCNT(LC_FIN) + 1;
+        else LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
+        active = refill();
+      }
+    }
+  }
+  __syncwarp();
+  unsigned long long v[7] = {*p_cpush, LCNT(LC_LOST), LCNT(LC_FIN), LCNT(LC_FB0), LCNT(LC_FB1), LCNT(LC_FB2), LCNT(LC_FB3)};
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    unsigned long long sacc = v[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, off);
+    if (lane == 0 && sacc) atomicAdd(bt.ctr + k, sacc);
+  }
+#undef LS
+#undef LCNT
+#undef p_idx
+#undef p_npush
+#undef p_cpush
+#undef p_ind_save
+}
+constexpr size_t GBG_SMEM = (size_t)GBG_THREADS * ((LS_ND + 6) * 8 + 3 * 8 + LC_N * 4 + 4);
+
+// ----------------------------------------------------------------------------------------------------
 struct gorilla_b200_handle {
   int device = 0;
   int num_sms = 0;
@@ -264,12 +459,26 @@ struct gorilla_b200_handle {
   int64_t last_n = 0;
   int ctas_per_sm = 0, threads_per_cta = 128;
   int force_full = 0;
+  int use_group = 1;  // orders 3/4: lock-step solver kernel (orbit_kernel_g)
   cudaStream_t last_stream = nullptr;
 };
 
 template <int K, int PHI>
 int launch_orbit_t(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
 {
+  if constexpr (K >= 3) {
+    if (h->use_group) {
+      GB_CUDA(cudaFuncSetAttribute(orbit_kernel_g<K, PHI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GBG_SMEM));
+      int64_t grid_g = h->num_sms;
+      const int64_t need_g = (bt.n + GBG_THREADS - 1) / GBG_THREADS;
+      if (grid_g > need_g) grid_g = need_g;
+      if (grid_g < 1) grid_g = 1;
+      orbit_kernel_g<K, PHI><<<(unsigned)grid_g, GBG_THREADS, GBG_SMEM, s>>>(h->mesh, bt);
+      gbint::count_launch(1);
+      GB_CUDA(cudaGetLastError());
+      return GORILLA_OK;
+    }
+  }
   int per_sm = h->ctas_per_sm;
   if (per_sm <= 0) {
     GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, orbit_kernel<K, PHI>, h->threads_per_cta, 0));

@@ -306,6 +306,13 @@ extern "C" int gorilla_b200_set_launch_config(gorilla_b200_handle *h, int32_t ct
   }
   return GORILLA_OK;
 }
+// test/tuning hook (not in the public header): 0 = one-particle-per-lane kernel of 4-warp CTAs also for orders 3/4
+extern "C" int gorilla_b200_debug_use_group(gorilla_b200_handle *h, int32_t on)
+{
+  if (!h) return GORILLA_ERR_ARG;
+  h->use_group = on;
+  return GORILLA_OK;
+}
 // test hook (not in the public header): 0 = find_tetra scans the whole phi slice like the reference, 1 = binned search
 extern "C" int gorilla_b200_debug_find_bins(gorilla_b200_handle *h, int32_t on)
 {

@@ -177,7 +177,7 @@ def reference_arm(args):
     t_step = args.t_step or wl["t_step"]
     mesh = build_mesh(wl["grid"], settings)
     cores = os.cpu_count() or 1
-    n_sample = 500 * cores
+    n_sample = 2000 * cores   # ~1.5 s of CPU work per step on 16 cores
     value, dt, pushes = cpu_run(wl, mesh, settings, n_sample, t_step, args.steps, args.warmup, cores)
     sample = f"{n_sample} particles x {args.steps} steps of {t_step:g} s ({pushes} pushes, {dt:.1f} s wall)"
     line = {
@@ -369,7 +369,7 @@ def main():
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_s = 500 * cores
+            n_s = 2000 * cores
             v, dt, p = cpu_run(wl, mesh, settings, n_s, t_step, max(1, min(args.steps, 3)), 1, cores)
             cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": f"{n_s} particles x {max(1, min(args.steps, 3))} steps of {t_step:g} s "

@@ -1,5 +1,5 @@
 // gb_internal.cuh -- pieces shared between gorilla_b200.cu and the per-order kernel translation units
-// (gb_orbit_k{1..4}.cu exist only to compile the four polynomial orders in parallel).
+// (gb_orbit_k{1..4}.cu and gb_orbit_rk.cu exist only to compile the pusher variants in parallel).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

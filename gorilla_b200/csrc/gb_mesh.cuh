@@ -102,29 +102,8 @@ GB_HD void ld4(const double *p, double &a, double &b, double &c, double &d)
 }
 #endif
 
-// Pull the hot record of tetrahedron ind_tetr (1-based) towards the SM while the current push is still being
-// finished: the exit face -- and with it the next tetrahedron -- is known well before the record is needed.
-template <int PHI>
-GB_HD void prefetch_record(const MeshDev &m, int ind_tetr)
-{
-#if defined(__CUDA_ARCH__)
-  if (ind_tetr < 1) return;
-  const int64_t t = (int64_t)ind_tetr - 1;
-  const char *pg = reinterpret_cast<const char *>(m.geom + t * GEOM_ND);    // 128 B, 128-byte aligned
-  const char *pb = reinterpret_cast<const char *>(m.bpart + t * BPART_ND);  // 224 B, 32-byte aligned
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(pg));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(pb));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + 128));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + 192));
-  if (PHI) {
-    const char *pp = reinterpret_cast<const char *>(m.phi + t * PHI_ND);    // 160 B
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(pp));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(pp + 128));
-  }
-#else
-  (void)m; (void)ind_tetr;
-#endif
-}
+// (An explicit prefetch of the neighbour's record once the exit face is known -- prefetch.global.L1 or .L2 -- was measured
+// three times on different kernel versions and cost 12-20 % each time; it is not in the code.)
 
 // One tetrahedron's hot record in registers.  PHI: 0 = magnetic part only (Phi group exactly zero), 1 = with the
 // electrostatic group, 2 = electrostatic + strong-electric-field groups.

@@ -748,9 +748,6 @@ struct PolyPusher {
   GB_HD bool fast_end(double tau, int iface_new, double tau_max, bool prepared, PushOut &o)
   {
     if (!((tau < GB_HUGE) && (tau > 0.0))) return false;
-#if defined(GB_PREFETCH_NEXT) && defined(__CUDA_ARCH__)
-    prefetch_record<PHI>(*mp, r.nb(iface_new - 1));  // the exit face is known: start pulling the neighbour's record
-#endif
     if (!prepared) prepare<(K > 2 ? K : 2)>(z_init);
     double z[4] = {z_init[0], z_init[1], z_init[2], z_init[3]};
     integrate<K>(z, tau);

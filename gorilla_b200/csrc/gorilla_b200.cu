@@ -4,8 +4,12 @@
 //   orbit_kernel<K,PHI>   persistent, one particle per lane, lane refill from a global queue:
 //                         the whole `do ... enddo` of orbit_timestep_gorilla (orbit_timestep_gorilla.f90:100-139)
 //                         runs on the device; a lane whose particle finished or got lost immediately pulls
-//                         the next one, so warps stay full until the queue is empty.
-//   find_kernel<PHI>      check_coordinate_domain + find_tetra for not-yet-initialised particles.
+//                         the next one, so warps stay full until the queue is empty.  K = 1, 2: polynomial orders,
+//                         K = 0: RK4; PHI = 0 / 1 / 2: magnetic only / + electrostatic group / + strong-E group.
+//   orbit_kernel_g<K,PHI> orders 3 and 4: the same push in 16-warp CTAs whose sub-partition groups run the root-solver
+//                         iterations in lock step (instruction-cache sharing), see gb_internal.cuh.
+//   find_kernel<PHI>      check_coordinate_domain + find_tetra (binned for the slice-wise grids) for particles that
+//                         are not initialised yet.
 //   invariants_kernel     energy / p_phi / perpinv per particle.
 //   sort keys             radix sort (CUB) of particle indices by tetra index.
 // Compile with --fmad=false: the reference ISA has no FMA and the visited-tetra sequence is only
@@ -328,7 +332,7 @@ extern "C" int gorilla_b200_debug_force_full(gorilla_b200_handle *h, int32_t on)
   return GORILLA_OK;
 }
 
-// the eight orbit_kernel<K,PHI> instantiations live in gb_orbit_k{1..4}.cu
+// the orbit_kernel<K,PHI> / orbit_kernel_g<K,PHI> instantiations live in gb_orbit_k{1..4}.cu and gb_orbit_rk.cu
 #define GB_EXTERN_ORBIT(K) \
   extern template int launch_orbit_t<K, 0>(gorilla_b200_handle *, const Batch &, cudaStream_t); \
   extern template int launch_orbit_t<K, 1>(gorilla_b200_handle *, const Batch &, cudaStream_t); \

@@ -37,7 +37,8 @@ class _Settings(C.Structure):
         "coord_system", "ispecies", "boole_periodic_relocation", "ipusher", "boole_pusher_ode45", "boole_dt_dtau",
         "boole_newton_precalc", "poly_order", "i_precomp", "boole_guess", "i_time_tracing_option",
         "handover_processing_kind", "boole_adaptive_time_steps", "boole_strong_electric_field",
-        "boole_grid_for_find_tetra")] + [("reserved", C.c_int32 * 5)]
+        "boole_grid_for_find_tetra", "boole_time_Hamiltonian", "boole_gyrophase", "boole_vpar_int",
+        "boole_vpar2_int")] + [("reserved", C.c_int32 * 1)]
 
 
 class _MeshDesc(C.Structure):
@@ -82,6 +83,7 @@ class Counters:
 EXPORTED_SYMBOLS = (
     "gorilla_b200_init", "gorilla_b200_free", "gorilla_b200_last_error", "gorilla_b200_launch_count",
     "gorilla_b200_orbit_timestep", "gorilla_b200_orbit_timestep_dev", "gorilla_b200_orbit_timestep_trace",
+    "gorilla_b200_orbit_timestep_optional", "gorilla_b200_orbit_timestep_optional_dev",
     "gorilla_b200_find_tetra", "gorilla_b200_invariants", "gorilla_b200_invariants_dev",
     "gorilla_b200_get_counters", "gorilla_b200_sort_permutation_dev", "gorilla_b200_set_launch_config",
     "gorilla_b200_fp64_peak",
@@ -107,6 +109,10 @@ def load_library():
     lib.gorilla_b200_orbit_timestep.argtypes = [vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp]
     lib.gorilla_b200_orbit_timestep_dev.argtypes = [vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp]
     lib.gorilla_b200_orbit_timestep_trace.argtypes = [vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp, i32, vp, vp]
+    lib.gorilla_b200_orbit_timestep_optional.argtypes = [vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp]
+    lib.gorilla_b200_orbit_timestep_optional_dev.argtypes = [vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp, vp]
+    lib.gorilla_b200_debug_orbit_timestep_trace_optional.argtypes = [vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp, i32, vp,
+                                                                     vp, vp]
     lib.gorilla_b200_find_tetra.argtypes = [vp, i64, vp, vp, vp, vp, vp, i32]
     lib.gorilla_b200_invariants.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.gorilla_b200_invariants_dev.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -297,9 +303,11 @@ class Gorilla:
         return ind, ifc
 
     def orbit_timestep_gorilla(self, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface,
-                               t_remain_out=None, n_pushes=None, trace_cap: int = 0):
+                               t_remain_out=None, n_pushes=None, trace_cap: int = 0, optional_quantities=None):
         """Batched orbit_timestep_gorilla; all arrays are updated in place (numpy, C-contiguous):
         x [n,3] f64, vpar/vperp [n] f64, boole_initialized/ind_tetr/iface [n] i32.
+        optional_quantities: [n,4] f64 output (t_hamiltonian, gyrophase, vpar_int, vpar2_int summed over the pushes of
+        the time step; pusher_tetra_poly's optional_quantities argument, pusher_tetra_poly.f90:204,662-667).
         Returns (trace_ind_tetr, trace_iface) when trace_cap > 0, else None."""
         lib = load_library()
         n = x.shape[0]
@@ -307,6 +315,20 @@ class Gorilla:
                       (ind_tetr, np.int32), (iface, np.int32)):
             if a.dtype != dt or not a.flags.c_contiguous:
                 raise TypeError("arrays must be C-contiguous float64 / int32")
+        if optional_quantities is not None:
+            oq = optional_quantities
+            if oq.dtype != np.float64 or not oq.flags.c_contiguous or oq.shape != (n, 4):
+                raise TypeError("optional_quantities must be a C-contiguous float64 [n,4] array")
+            if trace_cap > 0:
+                tt, tf = np.zeros((n, trace_cap), np.int32), np.zeros((n, trace_cap), np.int32)
+                _check(lib.gorilla_b200_debug_orbit_timestep_trace_optional(
+                    self._h, n, _ptr(x), _ptr(vpar), _ptr(vperp), float(t_step), _ptr(boole_initialized), _ptr(ind_tetr),
+                    _ptr(iface), _ptr(t_remain_out), _ptr(n_pushes), trace_cap, _ptr(tt), _ptr(tf), _ptr(oq)))
+                return tt, tf
+            _check(lib.gorilla_b200_orbit_timestep_optional(self._h, n, _ptr(x), _ptr(vpar), _ptr(vperp), float(t_step),
+                                                            _ptr(boole_initialized), _ptr(ind_tetr), _ptr(iface),
+                                                            _ptr(t_remain_out), _ptr(n_pushes), _ptr(oq)))
+            return None
         if trace_cap > 0:
             tt, tf = np.zeros((n, trace_cap), np.int32), np.zeros((n, trace_cap), np.int32)
             _check(lib.gorilla_b200_orbit_timestep_trace(self._h, n, _ptr(x), _ptr(vpar), _ptr(vperp), float(t_step),
@@ -327,6 +349,15 @@ class Gorilla:
         _check(load_library().gorilla_b200_orbit_timestep_dev(
             self._h, x.shape[0], dp(x), dp(vpar), dp(vperp), float(t_step), dp(boole_initialized), dp(ind_tetr),
             dp(iface), dp(t_remain_out), dp(n_pushes), C.c_void_p(stream or 0)))
+
+    def orbit_timestep_gorilla_optional_dev(self, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface,
+                                            optional_quantities, t_remain_out=None, n_pushes=None, stream=None):
+        """orbit_timestep_gorilla_dev plus the optional quantities ([n,4] f64 CUDA tensor)."""
+        def dp(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+        _check(load_library().gorilla_b200_orbit_timestep_optional_dev(
+            self._h, x.shape[0], dp(x), dp(vpar), dp(vperp), float(t_step), dp(boole_initialized), dp(ind_tetr),
+            dp(iface), dp(t_remain_out), dp(n_pushes), dp(optional_quantities), C.c_void_p(stream or 0)))
 
     # ---- diagnostics ---------------------------------------------------------------------------
     def invariants(self, x, vpar, vperp, ind_tetr):

@@ -34,7 +34,8 @@ NVCC_FLAGS = [
 NVCC_FLAGS += os.environ.get("GORILLA_NVCC_EXTRA", "").split()
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas"]
 
-CU_SOURCES = ["gorilla_b200.cu", "gb_orbit_k1.cu", "gb_orbit_k2.cu", "gb_orbit_k3.cu", "gb_orbit_k4.cu", "gb_orbit_rk.cu"]
+CU_SOURCES = ["gorilla_b200.cu", "gb_orbit_k1.cu", "gb_orbit_k2.cu", "gb_orbit_k3.cu", "gb_orbit_k4.cu", "gb_orbit_rk.cu",
+              "gb_orbit_k4x.cu", "gb_orbit_k3x.cu", "gb_orbit_k2x.cu", "gb_orbit_k1x.cu"]
 CPP_SOURCES = ["host/mesh_api.cpp", "host/mesh_common.cpp", "host/mesh_analytic.cpp", "host/mesh_vmec.cpp", "host/mesh_efit.cpp", "host/mesh_soledge3x.cpp", "host/mesh_efit_flux.cpp"]
 
 
@@ -69,7 +70,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ_DIR.mkdir(parents=True, exist_ok=True)
     hd = _headers_digest()
     srcs = CU_SOURCES + CPP_SOURCES
-    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+    with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(srcs))) as ex:
         results = list(ex.map(lambda s: _compile(s, hd, force), srcs))
     objs = [str(o) for o, _ in results]
     rebuilt = any(log is not None for _, log in results) or not LIB.exists()  # None = object was up to date

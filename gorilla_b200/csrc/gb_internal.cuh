@@ -44,6 +44,10 @@ struct Batch {
   int32_t boole_periodic_relocation;
   int32_t sign_t_step;
   int32_t force_full; // debugging/parity: route every push through the complete ladder
+  // EXT kernels: optional quantities summed over the pushes of the time step, [n][4] = t_hamiltonian, gyrophase,
+  // vpar_int, vpar2_int (nullable); oq_mask bit q set = quantity q requested (boole_array_optional_quantities)
+  double *optq;
+  uint32_t oq_mask;
 };
 
 // ----------------------------------------------------------------------------------------------------
@@ -79,10 +83,24 @@ __device__ __forceinline__ unsigned tid_now()
 enum { LS_X0 = 0, LS_X1, LS_X2, LS_VPAR, LS_PERPINV, LS_TREM, LS_ZS0, LS_ZS1, LS_ZS2, LS_ND };
 enum { LC_LOST = 0, LC_FIN, LC_FB0, LC_FB1, LC_FB2, LC_FB3, LC_N };
 
-template <int K, int PHI>
+// per-lane accumulators of the optional quantities (EXT kernels only)
+template <bool EXT, int NT>
+struct OqSlots {
+  double v[4][NT];
+};
+template <int NT>
+struct OqSlots<false, NT> {
+  double v[1][1];
+};
+
+// EXT = true: i_time_tracing_option 1 or 2 (Hamiltonian time) and the optional quantities of pusher_tetra_poly; the
+// plain variant is the hot path of the default settings and carries none of that code.
+template <int K, int PHI, bool EXT = false>
 __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
 {
   __shared__ double s_d[LS_ND][GB_THREADS], s_stash[6][GB_THREADS];
+  __shared__ OqSlots<EXT, GB_THREADS> s_oq;
+#define LOQ(q) (((volatile double *)s_oq.v[q])[tid_now()])
   __shared__ long long s_idx[GB_THREADS], s_npush[GB_THREADS];
   __shared__ unsigned long long s_cpush[GB_THREADS];
   __shared__ unsigned int s_cnt[LC_N][GB_THREADS];
@@ -120,12 +138,18 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
         // resp. leaves the loop at :103-109 without touching the particle
         if (bt.t_remain_out) bt.t_remain_out[idx] = bt.t_step;
         if (bt.n_pushes) bt.n_pushes[idx] = 0;
+        if constexpr (EXT) {
+          if (bt.optq) { bt.optq[4 * idx] = 0.0; bt.optq[4 * idx + 1] = 0.0; bt.optq[4 * idx + 2] = 0.0; bt.optq[4 * idx + 3] = 0.0; }
+        }
         if (inited && ind_tetr < 1) LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
         continue;
       }
       if (bt.t_step == 0.0) {
         if (bt.t_remain_out) bt.t_remain_out[idx] = 0.0;
         if (bt.n_pushes) bt.n_pushes[idx] = 0;
+        if constexpr (EXT) {
+          if (bt.optq) { bt.optq[4 * idx] = 0.0; bt.optq[4 * idx + 1] = 0.0; bt.optq[4 * idx + 2] = 0.0; bt.optq[4 * idx + 3] = 0.0; }
+        }
         continue;
       }
       const double x0 = bt.x[3 * idx], x1 = bt.x[3 * idx + 1], x2 = bt.x[3 * idx + 2];
@@ -140,6 +164,7 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
       LS(LS_TREM) = bt.t_step;
       *p_idx = idx;
       *p_npush = 0;
+      if constexpr (EXT) { LOQ(0) = 0.0; LOQ(1) = 0.0; LOQ(2) = 0.0; LOQ(3) = 0.0; }
       return true;
     }
   };
@@ -167,14 +192,30 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
       } else {
         if (!bt.force_full) {
           const double x[3] = {LS(LS_X0), LS(LS_X1), LS(LS_X2)};
-          PolyPusher<K, PHI> P;
+          PolyPusher<K, PHI, EXT> P;
           P.mp = &m;
           P.perpinv = perpinv;
+          if constexpr (EXT) P.oq_mask = bt.oq_mask;
           P.r.set_stash(&s_stash[0][tid_now()], GB_THREADS);
           done = P.push_fast(ind_tetr, iface, x, LS(LS_VPAR), LS(LS_TREM), o, &LS(LS_TREM));
+          if constexpr (EXT) {
+            if (done && bt.oq_mask) {
+#pragma unroll
+              for (int q = 0; q < 4; q++) LOQ(q) = LOQ(q) + P.oq[q];
+            }
+          }
         }
-        if (!done)
-          o = push_full_call<K, PHI>(&m, perpinv, ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2), LS(LS_VPAR), LS(LS_TREM));
+        if (!done) {
+          if constexpr (EXT) {
+            const PushOutX ox = push_full_call_x<K, PHI>(&m, perpinv, ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2),
+                                                         LS(LS_VPAR), LS(LS_TREM), bt.oq_mask);
+            o = ox.o;
+#pragma unroll
+            for (int q = 0; q < 4; q++) LOQ(q) = LOQ(q) + ox.oq[q];
+          } else {
+            o = push_full_call<K, PHI>(&m, perpinv, ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2), LS(LS_VPAR), LS(LS_TREM));
+          }
+        }
       }
       LS(LS_X0) = o.x[0]; LS(LS_X1) = o.x[1]; LS(LS_X2) = o.x[2];
       LS(LS_VPAR) = o.vpar;
@@ -212,6 +253,12 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
         bt.iface[idx] = iface;
         if (bt.t_remain_out) bt.t_remain_out[idx] = t_remain;
         if (bt.n_pushes) bt.n_pushes[idx] = npush + 1;
+        if constexpr (EXT) {
+          if (bt.optq) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) bt.optq[4 * idx + q] = LOQ(q);
+          }
+        }
         *p_cpush = *p_cpush + (unsigned long long)(npush + 1);
         if (o.finished) LCNT(LC_FIN) = LCNT(LC_FIN) + 1;
         else LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
@@ -231,6 +278,7 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
   }
 #undef LS
 #undef LCNT
+#undef LOQ
 #undef p_idx
 #undef p_npush
 #undef p_cpush
@@ -283,7 +331,7 @@ static __device__ __noinline__ double solve_group(bool busy, int deg, double q0,
   return tau;
 }
 
-template <int K, int PHI>
+template <int K, int PHI, bool EXT = false>
 __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_constant__ MeshDev m, const Batch bt)
 {
   extern __shared__ __align__(16) unsigned char g_smem[];
@@ -293,6 +341,8 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
   unsigned long long *s_cpush = reinterpret_cast<unsigned long long *>(s_npush + GBG_THREADS);
   unsigned int (*s_cnt)[GBG_THREADS] = reinterpret_cast<unsigned int (*)[GBG_THREADS]>(s_cpush + GBG_THREADS);  // [LC_N]
   int *s_ind_save = reinterpret_cast<int *>(s_cnt + LC_N);
+  double (*s_oq)[GBG_THREADS] = reinterpret_cast<double (*)[GBG_THREADS]>(s_ind_save + GBG_THREADS);   // [4], EXT only
+#define LOQ(q) (((volatile double *)s_oq[q])[tid_now()])
   const unsigned lane = threadIdx.x & 31u;
   const int bar_id = 1 + (int)((threadIdx.x >> 5) & 3u);   // warps w, w+4, w+8, w+12 share sub-partition w
 #define LS(f) (((volatile double *)s_d[f])[tid_now()])
@@ -321,12 +371,18 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
       if (!inited || ind_tetr < 1) {
         if (bt.t_remain_out) bt.t_remain_out[idx] = bt.t_step;
         if (bt.n_pushes) bt.n_pushes[idx] = 0;
+        if constexpr (EXT) {
+          if (bt.optq) { bt.optq[4 * idx] = 0.0; bt.optq[4 * idx + 1] = 0.0; bt.optq[4 * idx + 2] = 0.0; bt.optq[4 * idx + 3] = 0.0; }
+        }
         if (inited && ind_tetr < 1) LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
         continue;
       }
       if (bt.t_step == 0.0) {
         if (bt.t_remain_out) bt.t_remain_out[idx] = 0.0;
         if (bt.n_pushes) bt.n_pushes[idx] = 0;
+        if constexpr (EXT) {
+          if (bt.optq) { bt.optq[4 * idx] = 0.0; bt.optq[4 * idx + 1] = 0.0; bt.optq[4 * idx + 2] = 0.0; bt.optq[4 * idx + 3] = 0.0; }
+        }
         continue;
       }
       const double x0 = bt.x[3 * idx], x1 = bt.x[3 * idx + 1], x2 = bt.x[3 * idx + 2];
@@ -340,6 +396,7 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
       LS(LS_TREM) = bt.t_step;
       *p_idx = idx;
       *p_npush = 0;
+      if constexpr (EXT) { LOQ(0) = 0.0; LOQ(1) = 0.0; LOQ(2) = 0.0; LOQ(3) = 0.0; }
       return true;
     }
   };
@@ -354,8 +411,9 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
     t.q[0] = t.q[1] = t.q[2] = t.q[3] = 0.0;
     int iface_new = 0;
     double tau_max = 0.0;
-    PolyPusher<K, PHI> P;
+    PolyPusher<K, PHI, EXT> P;
     P.mp = &m;
+    if constexpr (EXT) P.oq_mask = bt.oq_mask;
     P.r.set_stash(&s_stash[0][tid_now()], GBG_THREADS);
     if (active && !bt.force_full) {
       const double x[3] = {LS(LS_X0), LS(LS_X1), LS(LS_X2)};
@@ -369,8 +427,23 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
     }
     if (active) {
       *p_ind_save = ind_tetr;
-      if (!done)
-        o = push_full_call<K, PHI>(&m, LS(LS_PERPINV), ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2), LS(LS_VPAR), LS(LS_TREM));
+      if constexpr (EXT) {
+        if (done) {
+          if (bt.oq_mask) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) LOQ(q) = LOQ(q) + P.oq[q];
+          }
+        } else {
+          const PushOutX ox = push_full_call_x<K, PHI>(&m, LS(LS_PERPINV), ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2),
+                                                       LS(LS_VPAR), LS(LS_TREM), bt.oq_mask);
+          o = ox.o;
+#pragma unroll
+          for (int q = 0; q < 4; q++) LOQ(q) = LOQ(q) + ox.oq[q];
+        }
+      } else {
+        if (!done)
+          o = push_full_call<K, PHI>(&m, LS(LS_PERPINV), ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2), LS(LS_VPAR), LS(LS_TREM));
+      }
       LS(LS_X0) = o.x[0]; LS(LS_X1) = o.x[1]; LS(LS_X2) = o.x[2];
       LS(LS_VPAR) = o.vpar;
       if (o.z_save_set) { LS(LS_ZS0) = o.z_save[0]; LS(LS_ZS1) = o.z_save[1]; LS(LS_ZS2) = o.z_save[2]; }
@@ -407,6 +480,12 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
         bt.iface[idx] = iface;
         if (bt.t_remain_out) bt.t_remain_out[idx] = t_remain;
         if (bt.n_pushes) bt.n_pushes[idx] = npush + 1;
+        if constexpr (EXT) {
+          if (bt.optq) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) bt.optq[4 * idx + q] = LOQ(q);
+          }
+        }
         *p_cpush = *p_cpush + (unsigned long long)(npush + 1);
         if (o.finished) LCNT(LC_FIN) = LCNT(LC_FIN) + 1;
         else LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
@@ -425,12 +504,14 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
   }
 #undef LS
 #undef LCNT
+#undef LOQ
 #undef p_idx
 #undef p_npush
 #undef p_cpush
 #undef p_ind_save
 }
 constexpr size_t GBG_SMEM = (size_t)GBG_THREADS * ((LS_ND + 6) * 8 + 3 * 8 + LC_N * 4 + 4);
+constexpr size_t GBG_SMEM_EXT = GBG_SMEM + (size_t)GBG_THREADS * 4 * 8;
 
 // ----------------------------------------------------------------------------------------------------
 struct gorilla_b200_handle {
@@ -438,7 +519,9 @@ struct gorilla_b200_handle {
   int num_sms = 0;
   MeshDev mesh{};
   gorilla_settings settings{};
-  double *d_geom = nullptr, *d_bpart = nullptr, *d_phi = nullptr, *d_cold = nullptr, *d_se = nullptr;
+  double *d_geom = nullptr, *d_bpart = nullptr, *d_phi = nullptr, *d_cold = nullptr, *d_se = nullptr, *d_ham = nullptr;
+  double *s_oq = nullptr;   // [cap][4] scratch for the optional quantities (host-pointer entry point)
+  uint32_t oq_mask = 0;
   int32_t *d_bin_start = nullptr, *d_bin_items = nullptr;
   unsigned long long *d_ctr = nullptr;
   // scratch for the host-pointer entry points
@@ -463,17 +546,18 @@ struct gorilla_b200_handle {
   cudaStream_t last_stream = nullptr;
 };
 
-template <int K, int PHI>
+template <int K, int PHI, bool EXT = false>
 int launch_orbit_t(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
 {
   if constexpr (K >= 3) {
     if (h->use_group) {
-      GB_CUDA(cudaFuncSetAttribute(orbit_kernel_g<K, PHI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GBG_SMEM));
+      constexpr size_t smem_g = EXT ? GBG_SMEM_EXT : GBG_SMEM;
+      GB_CUDA(cudaFuncSetAttribute(orbit_kernel_g<K, PHI, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
       int64_t grid_g = h->num_sms;
       const int64_t need_g = (bt.n + GBG_THREADS - 1) / GBG_THREADS;
       if (grid_g > need_g) grid_g = need_g;
       if (grid_g < 1) grid_g = 1;
-      orbit_kernel_g<K, PHI><<<(unsigned)grid_g, GBG_THREADS, GBG_SMEM, s>>>(h->mesh, bt);
+      orbit_kernel_g<K, PHI, EXT><<<(unsigned)grid_g, GBG_THREADS, smem_g, s>>>(h->mesh, bt);
       gbint::count_launch(1);
       GB_CUDA(cudaGetLastError());
       return GORILLA_OK;
@@ -481,14 +565,14 @@ int launch_orbit_t(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
   }
   int per_sm = h->ctas_per_sm;
   if (per_sm <= 0) {
-    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, orbit_kernel<K, PHI>, h->threads_per_cta, 0));
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, orbit_kernel<K, PHI, EXT>, h->threads_per_cta, 0));
     if (per_sm < 1) per_sm = 1;
   }
   int64_t grid = (int64_t)h->num_sms * per_sm;
   const int64_t need = (bt.n + h->threads_per_cta - 1) / h->threads_per_cta;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  orbit_kernel<K, PHI><<<(unsigned)grid, h->threads_per_cta, 0, s>>>(h->mesh, bt);
+  orbit_kernel<K, PHI, EXT><<<(unsigned)grid, h->threads_per_cta, 0, s>>>(h->mesh, bt);
   gbint::count_launch(1);
   GB_CUDA(cudaGetLastError());
   return GORILLA_OK;

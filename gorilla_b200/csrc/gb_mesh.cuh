@@ -23,6 +23,8 @@
 //                       v2Emod_1 gv2Emod(3) gv2Emodxh1(3) gBxcurlvE gPhixcurlvE gv2EmodxcurlvE gv2EmodxcurlA
 //                       curlvE(3) gammat(3,3) spgammat v_E_mod_average | vE2_1 gvE2(3) (invariants) (3 pad)   256 B
 //                       (hot part = first 26 doubles = 7 sectors)
+//   ham   [ntetr][8]  : type hamiltonian_time_type (tetra_physics_mod.f90:105-114): h1_in_curlA h1_in_curlh
+//                       vec_mismatch_der(3) vec_parcurr_der(3); read at the end of a push by the EXT kernels only       64 B
 // Matrices keep the Fortran column-major order: alpmat(i,j) -> [i + 3*j].
 #pragma once
 #include <stdint.h>
@@ -30,7 +32,7 @@
 
 namespace gb {
 
-enum { GEOM_ND = 16, BPART_ND = 28, PHI_ND = 20, COLD_ND = 12, SE_ND = 32 };
+enum { GEOM_ND = 16, BPART_ND = 28, PHI_ND = 20, COLD_ND = 12, SE_ND = 32, HAM_ND = 8 };
 enum { B_BMOD1 = 0, B_GB = 1, B_CURLA = 4, B_CURLH = 7, B_GBXH1 = 10, B_GBXCURLA = 13, B_ALP = 14,
        B_SPALP = 23, B_DTDTAU = 24, B_TOPO = 25 };
 enum { P_PHI1 = 0, P_GPHI = 1, P_GPHIXH1 = 4, P_GPHIXCURLA = 7, P_BET = 8, P_SPBET = 17 };
@@ -52,6 +54,8 @@ struct MeshDev {
   const double *phi;  // nullptr when the whole Phi group is exactly zero
   const double *cold;
   const double *se;   // nullptr unless boole_strong_electric_field
+  const double *ham;  // hamiltonian_time records (EXT kernels only): h1_in_curlA h1_in_curlh vec_mismatch_der(3) vec_parcurr_der(3)
+  int32_t time_tracing; // i_time_tracing_option: 1 = dt/dtau constant per cell, 2 = Hamiltonian time (EXT kernels)
   double cm_over_e, particle_mass, particle_charge;
   double period_phi;   // 2*pi/n_field_periods, formed exactly as the reference does (2.d0*pi/n_field_periods)
   double period_theta; // 2.d0*pi

@@ -1,7 +1,8 @@
 // gb_poly.cuh -- polynomial tetrahedron pusher (orders K = 1..4), FP64, one particle per lane.
 //
-// Replaces (reference file:line), for i_precomp = 0, i_time_tracing_option = 1, non-adaptive steps,
-// handover_processing_kind = 1:
+// Replaces (reference file:line), for i_precomp = 0, non-adaptive steps, handover_processing_kind = 1;
+// i_time_tracing_option = 1 in the plain variant, 1 or 2 (Hamiltonian time) plus the optional quantities
+// (t_hamiltonian, gyrophase, int v_par dt, int v_par^2 dt) in the EXT variant:
 //   initialize_pusher_tetra_poly          SRC/pusher_tetra_poly.f90:125-178
 //   pusher_tetra_poly                     :182-675
 //   check_three_planes / _face_convergence / _velocity / _exit_time   :679-758
@@ -13,6 +14,9 @@
 //   physical_estimate_tau                 :2779-2831
 //   trouble_shooting_polynomial_solver    :2835-2998
 //   pusher_handover2neighbour             SRC/pusher_tetra_func_mod.f90:6-93
+//   EXT: calc_t_hamiltonian / get_t_hamiltonian_root / calc_optional_quantities / z_series_coef /
+//        poly_multiplication_coef / moment_integration   :2117-2536, 3000-3150 ; hamiltonian_time record
+//        SRC/tetra_physics_mod.f90:105-114, 926-944
 //
 // Design (not a transliteration):
 //   * The ODE matrix is block structured, A = [[a(3x3), c(3)], [0 0 0, s]].  Powers A^2..A^4 are
@@ -74,12 +78,16 @@ struct SolveTask {
   int deg, kind;
 };
 
-template <int K, int PHI>
+template <int K, int PHI, bool EXT = false>
 struct PolyPusher {
   const MeshDev *mp;
   Rec<PHI> r;
   double perpinv;
   int ind_tetr, iface_init, sign_rhs, nsteps, solver_iters, fallback;
+  // EXT: tau_steps_list / intermediate_z0_list (:36-38; two entries in the non-adaptive scheme, :98-104) and the
+  // optional quantities of this push
+  double tau_list[2], z0_list[2][4], oq[4];
+  unsigned oq_mask;  // bit0 boole_time_Hamiltonian, bit1 boole_gyrophase, bit2 boole_vpar_int, bit3 boole_vpar2_int
   double dt_dtau_const, bmod0, vmod0, t_remain, z_init[4], k1, k3, dv2E;
   BlockMat A;
   double b[4];
@@ -112,6 +120,7 @@ struct PolyPusher {
       k3 = 0.0;
     }
     nsteps = 0;
+    if (EXT) oq[0] = oq[1] = oq[2] = oq[3] = 0.0;  // initialise_optional_quantities (:2117-2130)
   }
 
   // ---- ODE coefficients b, A  (:1503-1530; strong-electric-field terms :1519-1526).  RK = true forms b(1:3) the
@@ -398,6 +407,17 @@ struct PolyPusher {
   GB_HD void integrate(double *z, double tau)
   {
     nsteps++;
+    if (EXT) {
+      if (nsteps == 1) {
+        tau_list[0] = tau;
+#pragma unroll
+        for (int i = 0; i < 4; i++) z0_list[0][i] = z[i];
+      } else if (nsteps == 2) {
+        tau_list[1] = tau;
+#pragma unroll
+        for (int i = 0; i < 4; i++) z0_list[1][i] = z[i];
+      }
+    }
     if (ORD >= 1) {
 #pragma unroll
       for (int i = 0; i < 4; i++) z[i] = z[i] + tau * (b[i] + Az[i]);
@@ -418,6 +438,172 @@ struct PolyPusher {
 #pragma unroll
       for (int i = 0; i < 4; i++) z[i] = z[i] + tau4_24 * (A3b[i] + A4z[i]);
     }
+  }
+
+
+  // ==== EXT: Hamiltonian time tracing and optional quantities ===========================================
+  // z_series_coef (:2436-2474): Taylor coefficients of x(tau), vpar(tau) from the current Taylor vectors
+  GB_HD void z_series(const double *z0, double xc[3][5], double vc[5]) const
+  {
+#pragma unroll
+    for (int i = 0; i < 3; i++) xc[i][0] = z0[i];
+    vc[0] = z0[3];
+    if (K >= 1) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) xc[i][1] = b[i] + Az[i];
+      vc[1] = b[3] + Az[3];
+    }
+    if (K >= 2) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) xc[i][2] = 0.5 * (Ab[i] + A2z[i]);
+      vc[2] = 0.5 * (Ab[3] + A2z[3]);
+    }
+    if (K >= 3) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) xc[i][3] = 1.0 / 6.0 * (A2b[i] + A3z[i]);
+      vc[3] = 1.0 / 6.0 * (A2b[3] + A3z[3]);
+    }
+    if (K >= 4) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) xc[i][4] = 1.0 / 24.0 * (A3b[i] + A4z[i]);
+      vc[4] = 1.0 / 24.0 * (A3b[3] + A4z[3]);
+    }
+  }
+  // poly_multiplication_coef (:2478-2520): operands of K+1 coefficients, terms above order K dropped; the
+  // accumulation order (p1 outer, p2 inner, starting from 0) is the reference's
+  GB_HD static void poly_mul(const double *p1, const double *p2, double *res)
+  {
+#pragma unroll
+    for (int i = 0; i <= K; i++) res[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j <= K; j++)
+#pragma unroll
+      for (int k = 0; k <= K; k++)
+        if (j + k <= K) res[j + k] = res[j + k] + p1[j] * p2[k];
+  }
+  // moment_integration, scalar version (:3063-3091); x**3, x**4, x**5 as libgcc __powidf2 forms them
+  GB_HD static double moment(double tau, const double *c)
+  {
+    double m = 0.0;
+    const double t2 = tau * tau;
+    if (K >= 1) m = c[0] * tau + t2 * 0.5 * c[1];
+    if (K >= 2) m = m + (tau * t2) / 3.0 * c[2];
+    if (K >= 3) m = m + (t2 * t2) / 4.0 * c[3];
+    if (K >= 4) m = m + (tau * (t2 * t2)) / 5.0 * c[4];
+    return m;
+  }
+  // hamiltonian_time(ind_tetr): h1_in_curlA, h1_in_curlh, vec_mismatch_der(3), vec_parcurr_der(3) -- two 32-byte sectors
+  GB_HD void load_ham(double *h) const
+  {
+    const double *ph = mp->ham + ((int64_t)ind_tetr - 1) * HAM_ND;
+    ld4(ph, h[0], h[1], h[2], h[3]);
+    ld4(ph + 4, h[4], h[5], h[6], h[7]);
+  }
+  // calc_t_hamiltonian (:2214-2256): Hamiltonian time of one integration step (z0, tau)
+  GB_HD double ham_delta(const double *z0, double tau, bool recompute)
+  {
+    if (recompute) set_integration_coef_manually(z0);
+    double h[8], xc[3][5], vc[5], xv[3][5], mx[3], mxv[3];
+    load_ham(h);
+    z_series(z0, xc, vc);
+#pragma unroll
+    for (int i = 0; i < 3; i++) poly_mul(xc[i], vc, xv[i]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      mx[i] = moment(tau, xc[i]);
+      mxv[i] = moment(tau, xv[i]);
+    }
+    const double cm = mp->cm_over_e;
+    double d = h[0] * tau + cm * h[1] * moment(tau, vc) + dot3(&h[2], mx) + cm * dot3(&h[5], mxv);
+    return d * (double)sign_rhs;
+  }
+  // get_t_hamiltonian_root (:2340-2432): tau at which the Hamiltonian time of the step reaches t_rem (5th order dropped)
+  GB_HD double ham_root(const double *z0, double t_rem)
+  {
+    double h[8], xc[3][5], vc[5], xv[3][5];
+    load_ham(h);
+    z_series(z0, xc, vc);
+#pragma unroll
+    for (int i = 0; i < 3; i++) poly_mul(xc[i], vc, xv[i]);
+    const double cm = mp->cm_over_e, sg = (double)sign_rhs;
+    double co[4] = {0.0, 0.0, 0.0, 0.0};  // e, d, c, b
+#pragma unroll
+    for (int k = 0; k <= (K < 3 ? K : 3); k++) {
+      const double col[3] = {xc[0][k], xc[1][k], xc[2][k]}, colv[3] = {xv[0][k], xv[1][k], xv[2][k]};
+      double t = vc[k] * cm * h[1];
+      if (k == 0) t = h[0] + t;
+      t = t + dot3(col, &h[2]) + cm * dot3(colv, &h[5]);
+      co[k] = k == 0 ? t : k == 1 ? 0.5 * t : k == 2 ? (1.0 / 3.0) * t : (1.0 / 4.0) * t;
+    }
+    if (K >= 1) co[1] = 2.0 * co[1];
+    if (K >= 2) co[2] = 6.0 * co[2];
+    if (K >= 3) co[3] = 24.0 * co[3];
+#pragma unroll
+    for (int k = 0; k <= (K < 3 ? K : 3); k++) co[k] = co[k] * sg;
+    if (K == 1) return quadratic_solver2(co[1], co[0], -t_rem, solver_iters);
+    if (K == 2) return cubic_solver(co[2], co[1], co[0], -t_rem, solver_iters);
+    return quartic_solver(0, co[3], co[2], co[1], co[0], -t_rem, solver_iters);
+  }
+  // calc_optional_quantities (:2134-2210) of one integration step, accumulated into oq[]
+  GB_HD void optional_step(const double *z0, double tau, bool recompute)
+  {
+    if (recompute) set_integration_coef_manually(z0);
+    double h[8], xc[3][5], vc[5], xv[3][5], dtc[5], prod[5];
+    load_ham(h);
+    z_series(z0, xc, vc);
+#pragma unroll
+    for (int i = 0; i < 3; i++) poly_mul(vc, xc[i], xv[i]);
+    const double cm = mp->cm_over_e, sg = (double)sign_rhs;
+#pragma unroll
+    for (int k = 0; k <= K; k++) {
+      const double col[3] = {xc[0][k], xc[1][k], xc[2][k]}, colv[3] = {xv[0][k], xv[1][k], xv[2][k]};
+      dtc[k] = dot3(&h[2], col) + cm * h[1] * vc[k] + cm * dot3(&h[5], colv);
+    }
+    dtc[0] = dtc[0] + h[0];
+    if (oq_mask & 1u) oq[0] = oq[0] + moment(tau, dtc) * sg;
+    if (oq_mask & 2u) {
+      double om[5];
+#pragma unroll
+      for (int k = 0; k <= K; k++) {
+        const double col[3] = {xc[0][k], xc[1][k], xc[2][k]};
+        om[k] = 1.0 / cm * dot3(r.gB, col);
+      }
+      om[0] = om[0] + 1.0 / cm * r.bmod1;
+      poly_mul(dtc, om, prod);
+      oq[1] = oq[1] - sg * moment(tau, prod);
+    }
+    if (oq_mask & 4u) {
+      poly_mul(dtc, vc, prod);
+      oq[2] = oq[2] + sg * moment(tau, prod);
+    }
+    if (oq_mask & 8u) {
+      double v2[5];
+      poly_mul(vc, vc, v2);
+      poly_mul(dtc, v2, prod);
+      oq[3] = oq[3] + sg * moment(tau, prod);
+    }
+  }
+  // the loop over number_of_integration_steps at the end of the pusher (:662-667)
+  GB_HD void optional_all()
+  {
+    if (!EXT || !oq_mask) return;
+    if (nsteps >= 1) optional_step(z0_list[0], tau_list[0], nsteps > 1);
+    if (nsteps >= 2) optional_step(z0_list[1], tau_list[1], true);
+  }
+  // Hamiltonian time summed over the integration steps of the push (:470-486, 621-631); thl = t_hamiltonian_list(2:3)
+  GB_HD double ham_total(double *thl)
+  {
+    double th = 0.0;
+    thl[0] = thl[1] = 0.0;
+    if (nsteps >= 1) {
+      th = th + ham_delta(z0_list[0], tau_list[0], nsteps > 1);
+      thl[0] = th;
+    }
+    if (nsteps >= 2) {
+      th = th + ham_delta(z0_list[1], tau_list[1], true);
+      thl[1] = th;
+    }
+    return th;
   }
 
   // all four normal distances (:2690-2705); static indexing keeps r.an in registers
@@ -645,7 +831,7 @@ struct PolyPusher {
     o.fallback = fallback;
   }
 
-  // ---- final processing shared by push_fast / push_full (:459-466, 497-660).
+  // ---- final processing shared by push_fast / push_full (:459-487, 497-667).
   // Returns false if (fast mode) the stop-inside case needs the fall-back ladder.
   template <bool FAST>
   GB_HD bool finish(double *z, double tau, int iface_new, PushOut &o)
@@ -654,18 +840,37 @@ struct PolyPusher {
 #pragma unroll
     for (int i = 0; i < 3; i++) o.x[i] = z[i] + r.x1s(i);
     o.vpar = z[3];
-    double t_pass = tau * dt_dtau_const;
+    const bool tt2 = EXT && (mp->time_tracing == 2);
+    double thl[2] = {0.0, 0.0};
+    double t_pass;
+    if (tt2) t_pass = ham_total(thl);
+    else t_pass = tau * dt_dtau_const;
     o.t_pass = t_pass; // (:466) assigned before the stop-inside test; kept if the particle is removed below
     if (fabs(t_pass) >= fabs(t_remain)) {
-      if (FAST && nsteps > 1) return false;
+      if (FAST && (tt2 || nsteps > 1)) return false;
+      if (!tt2) {
 #pragma unroll
-      for (int i = 0; i < 4; i++) z[i] = z_init[i];
-      if (nsteps > 1) {
-        iface_new = iface_init;
+        for (int i = 0; i < 4; i++) z[i] = z_init[i];
+        if (nsteps > 1) {
+          iface_new = iface_init;
+          set_integration_coef_manually(z);
+        }
+        nsteps = 0;
+        tau = t_remain / dt_dtau_const;
+      } else {
+        // :523-541  step in which the Hamiltonian time exceeds t_remain (findloc over t_hamiltonian_list; an exact tie,
+        // which the reference does not handle, takes the last step)
+        const bool second = (nsteps > 1) && !(fabs(thl[0]) > fabs(t_remain));
+#pragma unroll
+        for (int i = 0; i < 4; i++) z[i] = second ? z0_list[1][i] : z0_list[0][i];
         set_integration_coef_manually(z);
+        const double tau_step = second ? tau_list[1] : tau_list[0];
+        const double t_remain_new = t_remain - (second ? thl[0] : 0.0);
+        nsteps = second ? 1 : 0;
+        iface_new = iface_init;
+        tau = ham_root(z, t_remain_new);
+        if (tau > tau_step) tau = t_remain_new / dt_dtau_const;
       }
-      nsteps = 0;
-      tau = t_remain / dt_dtau_const;
       integrate<K>(z, tau);
       bool inside = true;
       {
@@ -688,6 +893,7 @@ struct PolyPusher {
         o.vpar = z[3];
         o.t_pass = t_remain;
         o.fallback = fallback;
+        optional_all();
         return true;
       }
       if (FAST) return false;
@@ -696,7 +902,8 @@ struct PolyPusher {
         set_removed(o);
         return true;
       }
-      t_pass = tau * dt_dtau_const;
+      if (tt2) t_pass = ham_total(thl);
+      else t_pass = tau * dt_dtau_const;
     }
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -709,6 +916,7 @@ struct PolyPusher {
     o.finished = 0;
     handover(iface_new, o.x, o.ind_tetr, o.iface);
     o.fallback = fallback;
+    optional_all();
     return true;
   }
 
@@ -878,6 +1086,34 @@ GB_HD_NOINLINE PushOut push_full_call(const MeshDev *mp, double perpinv, int ind
   o.t_pass = 0.0; // undefined in the reference when the particle is removed in attempts 1-3
   P.push_full(ind_tetr, iface, x, vpar, t_remain, o);
   return o;
+}
+
+// EXT variant: the push result plus the optional quantities of the push
+struct PushOutX {
+  PushOut o;
+  double oq[4];
+};
+template <int K, int PHI>
+GB_HD_NOINLINE PushOutX push_full_call_x(const MeshDev *mp, double perpinv, int ind_tetr, int iface, double x0, double x1,
+                                         double x2, double vpar, double t_remain, unsigned oq_mask)
+{
+  PolyPusher<K, PHI, true> P;
+  double stash[6];
+  P.mp = mp;
+  P.perpinv = perpinv;
+  P.oq_mask = oq_mask;
+  P.r.set_stash(stash, 1);
+  PushOutX ox;
+  PushOut &o = ox.o;
+  double x[3] = {x0, x1, x2};
+  o.x[0] = x0; o.x[1] = x1; o.x[2] = x2; o.vpar = vpar;
+  o.z_save[0] = o.z_save[1] = o.z_save[2] = 0.0;
+  o.t_pass = 0.0;
+  P.push_full(ind_tetr, iface, x, vpar, t_remain, o);
+  // a removed particle returns before the optional quantities are formed (:435-441): P.oq is still zero then
+#pragma unroll
+  for (int q = 0; q < 4; q++) ox.oq[q] = P.oq[q];
+  return ox;
 }
 
 // ---- small field helpers (SRC/supporting_functions_mod.f90:279-408) on the device layout -------------

@@ -98,6 +98,27 @@ inline bool repack_mesh(const gorilla_mesh_desc *md, std::vector<double> &geom, 
   return true;
 }
 
+// type hamiltonian_time_type (tetra_physics_mod.f90:105-114), formed from the record exactly as make_tetra_physics does
+// (:926-944): h1_in_curlA = sum(h_1 * curlA), h1_in_curlh = sum(h_1 * curlh), vec_mismatch_der = matmul(mat_gh, curlA),
+// vec_parcurr_der = matmul(mat_gh, curlh) with mat_gh(:,j) = gh_j.
+inline void repack_hamiltonian_time(const gorilla_mesh_desc *md, std::vector<double> &ham)
+{
+  enum { TP_CURLA = 21, TP_H1_1 = 27, TP_GH1 = 80, TP_GH2 = 83, TP_GH3 = 86, TP_CURLH = 89 };
+  const int64_t nt = md->ntetr;
+  ham.assign((size_t)nt * HAM_ND, 0.0);
+  for (int64_t t = 0; t < nt; t++) {
+    const double *r = md->tetra_physics + t * GORILLA_TETRA_PHYSICS_NDOUBLES;
+    double *H = &ham[(size_t)t * HAM_ND];
+    const double *h1 = r + TP_H1_1, *cA = r + TP_CURLA, *ch = r + TP_CURLH;
+    H[0] = (h1[0] * cA[0] + h1[1] * cA[1]) + h1[2] * cA[2];
+    H[1] = (h1[0] * ch[0] + h1[1] * ch[1]) + h1[2] * ch[2];
+    for (int i = 0; i < 3; i++) {
+      H[2 + i] = ((0.0 + r[TP_GH1 + i] * cA[0]) + r[TP_GH2 + i] * cA[1]) + r[TP_GH3 + i] * cA[2];
+      H[5 + i] = ((0.0 + r[TP_GH1 + i] * ch[0]) + r[TP_GH2 + i] * ch[1]) + r[TP_GH3 + i] * ch[2];
+    }
+  }
+}
+
 // ---- find_tetra bins --------------------------------------------------------------------------------------------
 // The slice-wise grids repeat the same 2-D cell pattern in every phi slice.  The tetrahedra of slice 0 are binned by
 // the bounding box of their four vertices in the two non-toroidal coordinates; the vertices are reconstructed from the

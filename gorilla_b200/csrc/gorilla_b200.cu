@@ -185,7 +185,13 @@ static int check_settings(const gorilla_settings *s)
   if (s->ipusher == 1 && !s->boole_dt_dtau) return fail(GORILLA_ERR_UNSUPPORTED, "ipusher = 1 requires boole_dt_dtau = .true.");
   if (s->ipusher == 1 && s->boole_newton_precalc) return fail(GORILLA_ERR_UNSUPPORTED, "boole_newton_precalc must be .false.");
   if (s->i_precomp != 0) return fail(GORILLA_ERR_UNSUPPORTED, "i_precomp must be 0");
-  if (s->i_time_tracing_option != 1) return fail(GORILLA_ERR_UNSUPPORTED, "i_time_tracing_option must be 1");
+  if (s->i_time_tracing_option != 1 && s->i_time_tracing_option != 2)
+    return fail(GORILLA_ERR_ARG, "i_time_tracing_option must be 1 or 2");
+  // gorilla_settings_mod.f90:124-135
+  if (s->i_time_tracing_option == 2 && s->ipusher != 2)
+    return fail(GORILLA_ERR_ARG, "Hamiltonian time tracing (i_time_tracing_option = 2) requires ipusher = 2");
+  if (s->boole_gyrophase && !s->boole_time_Hamiltonian)
+    return fail(GORILLA_ERR_ARG, "boole_gyrophase requires boole_time_Hamiltonian = .true.");
   if (s->handover_processing_kind != 1) return fail(GORILLA_ERR_UNSUPPORTED, "handover_processing_kind must be 1");
   if (s->boole_adaptive_time_steps) return fail(GORILLA_ERR_UNSUPPORTED, "boole_adaptive_time_steps must be .false.");
   // gorilla_settings_mod.f90:139-144 (coord_system is checked against the mesh in gorilla_b200_init)
@@ -238,8 +244,22 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
     gorilla_b200_free(h);
     return GORILLA_ERR_CUDA;
   }
+  // hamiltonian_time records: only the EXT kernels (Hamiltonian time tracing / optional quantities) read them
+  h->oq_mask = (st->boole_time_Hamiltonian ? 1u : 0u) | (st->boole_gyrophase ? 2u : 0u) | (st->boole_vpar_int ? 4u : 0u) |
+               (st->boole_vpar2_int ? 8u : 0u);
+  if (st->ipusher == 2 && (st->i_time_tracing_option == 2 || h->oq_mask)) {
+    std::vector<double> ham;
+    gb::repack_hamiltonian_time(md, ham);
+    if ((e = up(&h->d_ham, ham)) != cudaSuccess) {
+      g_last_error = std::string("gorilla_b200_init: ") + cudaGetErrorString(e);
+      gorilla_b200_free(h);
+      return GORILLA_ERR_CUDA;
+    }
+  }
   MeshDev &m = h->mesh;
   m.ntetr = nt;
+  m.ham = h->d_ham;
+  m.time_tracing = st->i_time_tracing_option;
   m.geom = h->d_geom;
   m.bpart = h->d_bpart;
   m.phi = (has_phi || strong) ? h->d_phi : nullptr;
@@ -289,7 +309,7 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
 extern "C" void gorilla_b200_free(gorilla_b200_handle *h)
 {
   if (!h) return;
-  cudaFree(h->d_geom); cudaFree(h->d_bpart); cudaFree(h->d_phi); cudaFree(h->d_cold); cudaFree(h->d_se); cudaFree(h->d_bin_start); cudaFree(h->d_bin_items); cudaFree(h->d_ctr);
+  cudaFree(h->d_geom); cudaFree(h->d_bpart); cudaFree(h->d_phi); cudaFree(h->d_cold); cudaFree(h->d_se); cudaFree(h->d_ham); cudaFree(h->s_oq); cudaFree(h->d_bin_start); cudaFree(h->d_bin_items); cudaFree(h->d_ctr);
   cudaFree(h->s_x); cudaFree(h->s_vpar); cudaFree(h->s_vperp); cudaFree(h->s_tro); cudaFree(h->s_e);
   cudaFree(h->s_p); cudaFree(h->s_mu); cudaFree(h->s_init); cudaFree(h->s_ind); cudaFree(h->s_iface);
   cudaFree(h->s_np); cudaFree(h->s_tr_t); cudaFree(h->s_tr_f); cudaFree(h->sort_tmp);
@@ -342,11 +362,28 @@ GB_EXTERN_ORBIT(1)
 GB_EXTERN_ORBIT(2)
 GB_EXTERN_ORBIT(3)
 GB_EXTERN_ORBIT(4)
+// EXT variants (Hamiltonian time tracing / optional quantities): gb_orbit_k{1..4}x.cu
+#define GB_EXTERN_ORBIT_X(K) \
+  extern template int launch_orbit_t<K, 0, true>(gorilla_b200_handle *, const Batch &, cudaStream_t); \
+  extern template int launch_orbit_t<K, 1, true>(gorilla_b200_handle *, const Batch &, cudaStream_t); \
+  extern template int launch_orbit_t<K, 2, true>(gorilla_b200_handle *, const Batch &, cudaStream_t);
+GB_EXTERN_ORBIT_X(1)
+GB_EXTERN_ORBIT_X(2)
+GB_EXTERN_ORBIT_X(3)
+GB_EXTERN_ORBIT_X(4)
 
 template <int PHI>
 static int launch_orbit_k(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
 {
   if (h->settings.ipusher == 1) return launch_orbit_t<0, PHI>(h, bt, s);
+  if (h->mesh.time_tracing == 2 || (bt.optq && bt.oq_mask)) {
+    switch (h->settings.poly_order) {
+      case 1: return launch_orbit_t<1, PHI, true>(h, bt, s);
+      case 2: return launch_orbit_t<2, PHI, true>(h, bt, s);
+      case 3: return launch_orbit_t<3, PHI, true>(h, bt, s);
+      default: return launch_orbit_t<4, PHI, true>(h, bt, s);
+    }
+  }
   switch (h->settings.poly_order) {
     case 1: return launch_orbit_t<1, PHI>(h, bt, s);
     case 2: return launch_orbit_t<2, PHI>(h, bt, s);
@@ -361,6 +398,11 @@ static int run_device(gorilla_b200_handle *h, Batch bt, bool do_find, cudaStream
   bt.boole_periodic_relocation = h->settings.boole_periodic_relocation;
   bt.sign_t_step = signbit(bt.t_step) ? -1 : 1;
   bt.force_full = h->force_full;
+  bt.oq_mask = bt.optq ? h->oq_mask : 0u;
+  if (bt.optq && !bt.oq_mask) {  // nothing switched on: all zero, the plain kernel runs
+    GB_CUDA(cudaMemsetAsync(bt.optq, 0, (size_t)bt.n * 4 * sizeof(double), s));
+    bt.optq = nullptr;
+  }
   GB_CUDA(cudaMemsetAsync(h->d_ctr, 0, CTR_N * sizeof(unsigned long long), s));
   h->have_find_time = false;
   h->have_push_time = false;
@@ -398,9 +440,27 @@ extern "C" int gorilla_b200_orbit_timestep_dev(gorilla_b200_handle *h, int64_t n
   return run_device(h, bt, true, (cudaStream_t)stream);
 }
 
+extern "C" int gorilla_b200_orbit_timestep_optional_dev(gorilla_b200_handle *h, int64_t n, double *x, double *vpar,
+                                                        double *vperp, double t_step, int32_t *boole_initialized,
+                                                        int32_t *ind_tetr, int32_t *iface, double *t_remain_out,
+                                                        int64_t *n_pushes, double *optional_quantities, void *stream)
+{
+  if (!h || n < 0 || (n > 0 && (!x || !vpar || !vperp || !boole_initialized || !ind_tetr || !iface || !optional_quantities)))
+    return fail(GORILLA_ERR_ARG, "gorilla_b200_orbit_timestep_optional_dev: null argument");
+  if (h->settings.ipusher != 2)
+    return fail(GORILLA_ERR_UNSUPPORTED, "optional quantities exist for the polynomial pusher only (ipusher = 2)");
+  Batch bt{};
+  bt.n = n; bt.x = x; bt.vpar = vpar; bt.vperp = vperp; bt.t_step = t_step; bt.init = boole_initialized;
+  bt.ind_tetr = ind_tetr; bt.iface = iface; bt.t_remain_out = t_remain_out; bt.n_pushes = n_pushes;
+  bt.optq = optional_quantities;
+  return run_device(h, bt, true, (cudaStream_t)stream);
+}
+
 static int ensure_scratch(gorilla_b200_handle *h, int64_t n)
 {
   if (n <= h->cap) return GORILLA_OK;
+  cudaFree(h->s_oq);
+  h->s_oq = nullptr;
   cudaFree(h->s_x); cudaFree(h->s_vpar); cudaFree(h->s_vperp); cudaFree(h->s_tro); cudaFree(h->s_e);
   cudaFree(h->s_p); cudaFree(h->s_mu); cudaFree(h->s_init); cudaFree(h->s_ind); cudaFree(h->s_iface); cudaFree(h->s_np);
   h->s_x = h->s_vpar = h->s_vperp = h->s_tro = h->s_e = h->s_p = h->s_mu = nullptr;
@@ -417,13 +477,14 @@ static int ensure_scratch(gorilla_b200_handle *h, int64_t n)
   GB_CUDA(cudaMalloc((void **)&h->s_ind, (size_t)n * sizeof(int32_t)));
   GB_CUDA(cudaMalloc((void **)&h->s_iface, (size_t)n * sizeof(int32_t)));
   GB_CUDA(cudaMalloc((void **)&h->s_np, (size_t)n * sizeof(int64_t)));
+  GB_CUDA(cudaMalloc((void **)&h->s_oq, (size_t)n * 4 * sizeof(double)));
   h->cap = n;
   return GORILLA_OK;
 }
 
 static int orbit_host(gorilla_b200_handle *h, int64_t n, double *x, double *vpar, double *vperp, double t_step,
                       int32_t *binit, int32_t *ind_tetr, int32_t *iface, double *tro, int64_t *np, int32_t trace_cap,
-                      int32_t *tr_t, int32_t *tr_f)
+                      int32_t *tr_t, int32_t *tr_f, double *optq = nullptr)
 {
   if (!h || n < 0 || (n > 0 && (!x || !vpar || !vperp || !binit || !ind_tetr || !iface)))
     return fail(GORILLA_ERR_ARG, "gorilla_b200_orbit_timestep: null argument");
@@ -454,8 +515,10 @@ static int orbit_host(gorilla_b200_handle *h, int64_t n, double *x, double *vpar
     GB_CUDA(cudaMemsetAsync(h->s_tr_f, 0, (size_t)elems * sizeof(int32_t), s));
     bt.trace_cap = trace_cap; bt.trace_tetr = h->s_tr_t; bt.trace_face = h->s_tr_f;
   }
+  if (optq) bt.optq = h->s_oq;
   rc = run_device(h, bt, true, s);
   if (rc) return rc;
+  if (optq) GB_CUDA(cudaMemcpyAsync(optq, h->s_oq, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
   GB_CUDA(cudaMemcpyAsync(x, h->s_x, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
   GB_CUDA(cudaMemcpyAsync(vpar, h->s_vpar, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
   GB_CUDA(cudaMemcpyAsync(vperp, h->s_vperp, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -490,6 +553,28 @@ extern "C" int gorilla_b200_orbit_timestep_trace(gorilla_b200_handle *h, int64_t
 {
   return orbit_host(h, n, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface, t_remain_out, n_pushes, trace_cap,
                     trace_ind_tetr, trace_iface);
+}
+
+extern "C" int gorilla_b200_orbit_timestep_optional(gorilla_b200_handle *h, int64_t n, double *x, double *vpar,
+                                                    double *vperp, double t_step, int32_t *boole_initialized,
+                                                    int32_t *ind_tetr, int32_t *iface, double *t_remain_out,
+                                                    int64_t *n_pushes, double *optional_quantities)
+{
+  if (!optional_quantities) return fail(GORILLA_ERR_ARG, "gorilla_b200_orbit_timestep_optional: null argument");
+  if (h && h->settings.ipusher != 2)
+    return fail(GORILLA_ERR_UNSUPPORTED, "optional quantities exist for the polynomial pusher only (ipusher = 2)");
+  return orbit_host(h, n, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface, t_remain_out, n_pushes, 0, nullptr,
+                    nullptr, optional_quantities);
+}
+// test hook (not in the public header): trace + optional quantities in one call
+extern "C" int gorilla_b200_debug_orbit_timestep_trace_optional(gorilla_b200_handle *h, int64_t n, double *x, double *vpar,
+                                                                double *vperp, double t_step, int32_t *boole_initialized,
+                                                                int32_t *ind_tetr, int32_t *iface, double *t_remain_out,
+                                                                int64_t *n_pushes, int32_t trace_cap, int32_t *trace_ind_tetr,
+                                                                int32_t *trace_iface, double *optional_quantities)
+{
+  return orbit_host(h, n, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface, t_remain_out, n_pushes, trace_cap,
+                    trace_ind_tetr, trace_iface, optional_quantities);
 }
 
 extern "C" int gorilla_b200_find_tetra(gorilla_b200_handle *h, int64_t n, double *x, const double *vpar,

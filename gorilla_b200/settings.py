@@ -29,6 +29,11 @@ class GorillaSettings:
     boole_adaptive_time_steps: bool = False
     boole_strong_electric_field: bool = False
     boole_grid_for_find_tetra: bool = False
+    # optional quantities of pusher_tetra_poly (gorilla_settings_mod.f90:51-55, namelist :100)
+    boole_time_Hamiltonian: bool = False
+    boole_gyrophase: bool = False
+    boole_vpar_int: bool = False
+    boole_vpar2_int: bool = False
 
 
 @dataclass

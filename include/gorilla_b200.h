@@ -50,12 +50,19 @@ typedef struct gorilla_settings {
   int32_t poly_order;                /* 1..4 */
   int32_t i_precomp;                 /* must be 0 */
   int32_t boole_guess;
-  int32_t i_time_tracing_option;     /* must be 1 */
+  int32_t i_time_tracing_option;     /* 1 dt/dtau constant per cell | 2 Hamiltonian time (ipusher = 2 only,
+                                        gorilla_settings_mod.f90:124-129) */
   int32_t handover_processing_kind;  /* must be 1 */
   int32_t boole_adaptive_time_steps; /* must be 0 */
   int32_t boole_strong_electric_field; /* ExB-drift terms of order v_E^2; cylindrical grids (coord_system 1) only */
   int32_t boole_grid_for_find_tetra; /* ignored: the device scan does not need the box accelerator */
-  int32_t reserved[5];
+  /* optional quantities of pusher_tetra_poly (gorilla_settings_mod.f90:51-55; ipusher = 2 only); boole_gyrophase
+   * requires boole_time_Hamiltonian (:132-135) */
+  int32_t boole_time_Hamiltonian;
+  int32_t boole_gyrophase;
+  int32_t boole_vpar_int;
+  int32_t boole_vpar2_int;
+  int32_t reserved[1];
 } gorilla_settings;
 
 /* Everything initialize_gorilla() (orbit_timestep_gorilla.f90:151-274) leaves in module variables that
@@ -128,6 +135,22 @@ int gorilla_b200_orbit_timestep_trace(gorilla_b200_handle *h, int64_t n, double 
                                       double t_step, int32_t *boole_initialized, int32_t *ind_tetr,
                                       int32_t *iface, double *t_remain_out, int64_t *n_pushes,
                                       int32_t trace_cap, int32_t *trace_ind_tetr, int32_t *trace_iface);
+
+/* As gorilla_b200_orbit_timestep, additionally returning the optional quantities of pusher_tetra_poly
+ * (type optional_quantities_type, gorilla_settings_mod.f90:9-15; pusher_tetra_poly.f90:204,228-229,662-667,2134-2210):
+ * optional_quantities is HOST double [n][4] = { t_hamiltonian, gyrophase, vpar_int, vpar2_int }, each the SUM over the
+ * pushes of this time step of the value the reference pusher returns per push (what a caller of the pusher accumulates
+ * along the orbit).  Only the quantities switched on in gorilla_settings (boole_time_Hamiltonian, boole_gyrophase,
+ * boole_vpar_int, boole_vpar2_int) are formed, the others are 0.  Polynomial pusher only (GORILLA_ERR_UNSUPPORTED for
+ * ipusher = 1, as in the reference where pusher_tetra_rk has no such argument). */
+int gorilla_b200_orbit_timestep_optional(gorilla_b200_handle *h, int64_t n, double *x, double *vpar, double *vperp,
+                                         double t_step, int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface,
+                                         double *t_remain_out, int64_t *n_pushes, double *optional_quantities);
+/* Same with DEVICE pointers on `stream`, no synchronisation. */
+int gorilla_b200_orbit_timestep_optional_dev(gorilla_b200_handle *h, int64_t n, double *x, double *vpar, double *vperp,
+                                             double t_step, int32_t *boole_initialized, int32_t *ind_tetr,
+                                             int32_t *iface, double *t_remain_out, int64_t *n_pushes,
+                                             double *optional_quantities, void *stream);
 
 /* check_coordinate_domain + find_tetra(x,vpar,vperp,ind_tetr,iface,sign_t_step)
  * (orbit_timestep_gorilla.f90:278-358, find_tetra_mod.f90:283-600); HOST pointers. x may be modified

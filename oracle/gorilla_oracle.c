@@ -717,7 +717,7 @@ static void handover2neighbour(const gor_mesh *m, int ind_tetr, int *ind_tetr_ou
 
 /* ------------------------------------------------------------------------------------------------
  * pusher_tetra_poly -- SRC/pusher_tetra_poly.f90
- * (i_precomp = 0, i_time_tracing_option = 1, boole_adaptive_time_steps = .false.)
+ * (i_precomp = 0, i_time_tracing_option = 1 or 2, boole_adaptive_time_steps = .false.)
  * The THREADPRIVATE module variables (:6-13,45-61) live in this struct, one per particle.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -730,6 +730,8 @@ typedef struct {
   double amat_in_z[4], amat2_in_z[4], amat3_in_z[4], amat4_in_z[4];
   double amat_in_b[4], amat2_in_b[4], amat3_in_b[4];
   int number_of_integration_steps;
+  /* tau_steps_list / intermediate_z0_list (:36-38); non-adaptive scheme: two entries (:98-104) */
+  double tau_steps_list[2], intermediate_z0_list[2][4];
   gor_trace *tr;
 } poly_state;
 static const double eps_tau = 100.0;
@@ -951,6 +953,10 @@ static void analytic_approx(poly_state *s, int poly_order, const bool boole_face
 static void analytic_integration(poly_state *s, int poly_order, double z[4], double tau)
 {
   s->number_of_integration_steps += 1;
+  if (s->number_of_integration_steps <= 2) { /* the reference's lists hold two entries */
+    s->tau_steps_list[s->number_of_integration_steps - 1] = tau;
+    memcpy(s->intermediate_z0_list[s->number_of_integration_steps - 1], z, 4 * sizeof(double));
+  }
   if (poly_order >= 1)
     for (int i = 0; i < 4; i++) z[i] = z[i] + tau * (s->b[i] + s->amat_in_z[i]);
   if (poly_order >= 2) {
@@ -984,6 +990,177 @@ static void set_integration_coef_manually(poly_state *s, int poly_order, const d
     matvec4(s->amat3_in_b, s->amat3, s->b);
   }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Hamiltonian time tracing (i_time_tracing_option = 2) and the optional quantities
+ * (t_hamiltonian, gyrophase, int v_par dt, int v_par^2 dt) -- SRC/pusher_tetra_poly.f90:2117-2536,3000-3150.
+ * type hamiltonian_time_type (SRC/tetra_physics_mod.f90:105-114) is built at :926-944 from fields of the
+ * tetrahedron_physics record; it is re-formed here from the record with the same operations.
+ * Integer powers: gfortran expands only x**2 inline (no -ffast-math in CMakeLists.txt:24); x**3..5 go through
+ * libgcc __powidf2: x**3 = x*(x*x), x**4 = (x*x)*(x*x), x**5 = x*((x*x)*(x*x)).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  double h1_in_curlA, h1_in_curlh, vec_mismatch_der[3], vec_parcurr_der[3];
+} ham_time;
+static void hamiltonian_time_of(const double *r, ham_time *h) /* tetra_physics_mod.f90:926-944 */
+{
+  const double vec_h_1[3] = {r[TP_H1_1], r[TP_H2_1], r[TP_H3_1]};
+  h->h1_in_curlA = dot3(vec_h_1, r + TP_CURLA);
+  h->h1_in_curlh = dot3(vec_h_1, r + TP_CURLH);
+  for (int i = 0; i < 3; i++) { /* matmul(mat_gh, v), mat_gh(:,j) = gh_j */
+    h->vec_mismatch_der[i] = ((0.0 + r[TP_GH1 + i] * r[TP_CURLA]) + r[TP_GH2 + i] * r[TP_CURLA + 1]) + r[TP_GH3 + i] * r[TP_CURLA + 2];
+    h->vec_parcurr_der[i] = ((0.0 + r[TP_GH1 + i] * r[TP_CURLH]) + r[TP_GH2 + i] * r[TP_CURLH + 1]) + r[TP_GH3 + i] * r[TP_CURLH + 2];
+  }
+}
+/* :2436-2474 ; x_coef[i][k] = x_coef(i+1,k+1) */
+static void z_series_coef(const poly_state *s, int poly_order, const double z0[4], double x_coef[3][5], double vpar_coef[5])
+{
+  for (int i = 0; i < 3; i++) x_coef[i][0] = z0[i];
+  vpar_coef[0] = z0[3];
+  if (poly_order >= 1) {
+    for (int i = 0; i < 3; i++) x_coef[i][1] = s->b[i] + s->amat_in_z[i];
+    vpar_coef[1] = s->b[3] + s->amat_in_z[3];
+  }
+  if (poly_order >= 2) {
+    for (int i = 0; i < 3; i++) x_coef[i][2] = 0.5 * (s->amat_in_b[i] + s->amat2_in_z[i]);
+    vpar_coef[2] = 0.5 * (s->amat_in_b[3] + s->amat2_in_z[3]);
+  }
+  if (poly_order >= 3) {
+    for (int i = 0; i < 3; i++) x_coef[i][3] = 1.0 / 6.0 * (s->amat2_in_b[i] + s->amat3_in_z[i]);
+    vpar_coef[3] = 1.0 / 6.0 * (s->amat2_in_b[3] + s->amat3_in_z[3]);
+  }
+  if (poly_order >= 4) {
+    for (int i = 0; i < 3; i++) x_coef[i][4] = 1.0 / 24.0 * (s->amat3_in_b[i] + s->amat4_in_z[i]);
+    vpar_coef[4] = 1.0 / 24.0 * (s->amat3_in_b[4 - 1] + s->amat4_in_z[3]);
+  }
+}
+/* :2478-2520 (both operands of size n; terms of order > n-1 dropped) */
+static void poly_multiplication_coef(const double *p1, const double *p2, int n, double *res)
+{
+  for (int i = 0; i < n; i++) res[i] = 0.0;
+  for (int j = 0; j < n; j++)
+    for (int k = 0; k < n; k++) {
+      int cur_order = j + k;
+      if (cur_order > n - 1) break;
+      res[cur_order] = res[cur_order] + p1[j] * p2[k];
+    }
+}
+/* scalar_integral_without_precomp :3063-3091 (undefined for poly_order = 0) */
+static double moment_integration(int poly_order, double tau, const double *c)
+{
+  double r = 0.0;
+  const double t2 = tau * tau;
+  if (poly_order >= 1) r = c[0] * tau + t2 * 0.5 * c[1];
+  if (poly_order >= 2) r = r + (tau * t2) / 3.0 * c[2];
+  if (poly_order >= 3) r = r + (t2 * t2) / 4.0 * c[3];
+  if (poly_order >= 4) r = r + (tau * (t2 * t2)) / 5.0 * c[4];
+  return r;
+}
+/* :2214-2256 */
+static void calc_t_hamiltonian(poly_state *s, int poly_order, const double z0[4], double tau, double *t_hamiltonian)
+{
+  const double cm_over_e = s->m->cm_over_e;
+  const int n = poly_order + 1;
+  double x_coef[3][5], vpar_coef[5], x_vpar_coef[3][5], mi_x[3], mi_xv[3];
+  ham_time h;
+  hamiltonian_time_of(s->r, &h);
+  if (s->number_of_integration_steps > 1) set_integration_coef_manually(s, poly_order, z0);
+  z_series_coef(s, poly_order, z0, x_coef, vpar_coef);
+  for (int i = 0; i < 3; i++) poly_multiplication_coef(x_coef[i], vpar_coef, n, x_vpar_coef[i]);
+  for (int i = 0; i < 3; i++) {
+    mi_x[i] = moment_integration(poly_order, tau, x_coef[i]);
+    mi_xv[i] = moment_integration(poly_order, tau, x_vpar_coef[i]);
+  }
+  double delta = h.h1_in_curlA * tau + cm_over_e * h.h1_in_curlh * moment_integration(poly_order, tau, vpar_coef) +
+                 dot3(h.vec_mismatch_der, mi_x) + cm_over_e * dot3(h.vec_parcurr_der, mi_xv);
+  delta = delta * (double)s->sign_rhs;
+  *t_hamiltonian = *t_hamiltonian + delta;
+}
+/* :2340-2432 */
+static void get_t_hamiltonian_root(poly_state *s, int poly_order, const double z0[4], double t_remain, double *tau_root)
+{
+  const double cm_over_e = s->m->cm_over_e;
+  const int n = poly_order + 1;
+  double x_coef[3][5], vpar_coef[5], x_vpar_coef[3][5], col[3], colv[3];
+  double b_coef = 0.0, c_coef = 0.0, d_coef = 0.0, e_coef;
+  ham_time h;
+  hamiltonian_time_of(s->r, &h);
+  z_series_coef(s, poly_order, z0, x_coef, vpar_coef);
+  for (int i = 0; i < 3; i++) poly_multiplication_coef(x_coef[i], vpar_coef, n, x_vpar_coef[i]);
+#define COLS(k) for (int i = 0; i < 3; i++) { col[i] = x_coef[i][k]; colv[i] = x_vpar_coef[i][k]; }
+  COLS(0)
+  e_coef = h.h1_in_curlA + vpar_coef[0] * cm_over_e * h.h1_in_curlh + dot3(col, h.vec_mismatch_der) +
+           cm_over_e * dot3(colv, h.vec_parcurr_der);
+  if (poly_order >= 1) {
+    COLS(1)
+    d_coef = 0.5 * (vpar_coef[1] * cm_over_e * h.h1_in_curlh + dot3(col, h.vec_mismatch_der) +
+                    cm_over_e * dot3(colv, h.vec_parcurr_der));
+  }
+  if (poly_order >= 2) {
+    COLS(2)
+    c_coef = (1.0 / 3.0) * (vpar_coef[2] * cm_over_e * h.h1_in_curlh + dot3(col, h.vec_mismatch_der) +
+                            cm_over_e * dot3(colv, h.vec_parcurr_der));
+  }
+  if (poly_order >= 3) {
+    COLS(3)
+    b_coef = (1.0 / 4.0) * (vpar_coef[3] * cm_over_e * h.h1_in_curlh + dot3(col, h.vec_mismatch_der) +
+                            cm_over_e * dot3(colv, h.vec_parcurr_der));
+  }
+#undef COLS
+  if (poly_order >= 1) d_coef = 2.0 * d_coef;
+  if (poly_order >= 2) c_coef = 6.0 * c_coef;
+  if (poly_order >= 3) b_coef = 24.0 * b_coef;
+  e_coef = e_coef * (double)s->sign_rhs;
+  if (poly_order >= 1) d_coef = d_coef * (double)s->sign_rhs;
+  if (poly_order >= 2) c_coef = c_coef * (double)s->sign_rhs;
+  if (poly_order >= 3) b_coef = b_coef * (double)s->sign_rhs;
+  switch (poly_order) {
+    case 1: *tau_root = Quadratic_Solver2(d_coef, e_coef, -t_remain, s->tr); break;
+    case 2: *tau_root = Cubic_Solver(c_coef, d_coef, e_coef, -t_remain, s->tr); break;
+    default: *tau_root = Quartic_Solver(0, b_coef, c_coef, d_coef, e_coef, -t_remain, s->tr); break;
+  }
+}
+/* :2117-2130, 2134-2210 ; optq = {t_hamiltonian, gyrophase, vpar_int, vpar2_int} */
+static void calc_optional_quantities(poly_state *s, int poly_order, const double z0[4], double tau, double optq[4])
+{
+  const gor_mesh *m = s->m;
+  const double cm_over_e = m->cm_over_e;
+  const int n = poly_order + 1;
+  double x_coef[3][5], vpar_coef[5], x_vpar_coef[3][5], dtdtau_coef[5], col[3], colv[3], prod[5], prod2[5];
+  ham_time h;
+  hamiltonian_time_of(s->r, &h);
+  if (s->number_of_integration_steps > 1) set_integration_coef_manually(s, poly_order, z0);
+  z_series_coef(s, poly_order, z0, x_coef, vpar_coef);
+  for (int i = 0; i < 3; i++) poly_multiplication_coef(vpar_coef, x_coef[i], n, x_vpar_coef[i]); /* poly_multiplication(vpar_coef,x_coef) */
+  for (int k = 0; k < n; k++) {
+    for (int i = 0; i < 3; i++) { col[i] = x_coef[i][k]; colv[i] = x_vpar_coef[i][k]; }
+    dtdtau_coef[k] = dot3(h.vec_mismatch_der, col) + cm_over_e * h.h1_in_curlh * vpar_coef[k] +
+                     cm_over_e * dot3(h.vec_parcurr_der, colv);
+  }
+  dtdtau_coef[0] = dtdtau_coef[0] + h.h1_in_curlA;
+  if (m->boole_time_hamiltonian)
+    optq[0] = optq[0] + moment_integration(poly_order, tau, dtdtau_coef) * (double)s->sign_rhs;
+  if (m->boole_gyrophase) {
+    double omega_coef[5];
+    for (int k = 0; k < n; k++) {
+      for (int i = 0; i < 3; i++) col[i] = x_coef[i][k];
+      omega_coef[k] = 1.0 / cm_over_e * dot3(s->r + TP_GB, col);
+    }
+    omega_coef[0] = omega_coef[0] + 1.0 / cm_over_e * s->r[TP_BMOD1];
+    poly_multiplication_coef(dtdtau_coef, omega_coef, n, prod);
+    optq[1] = optq[1] - (double)s->sign_rhs * moment_integration(poly_order, tau, prod);
+  }
+  if (m->boole_vpar_int) {
+    poly_multiplication_coef(dtdtau_coef, vpar_coef, n, prod);
+    optq[2] = optq[2] + (double)s->sign_rhs * moment_integration(poly_order, tau, prod);
+  }
+  if (m->boole_vpar2_int) {
+    poly_multiplication_coef(vpar_coef, vpar_coef, n, prod2);
+    poly_multiplication_coef(dtdtau_coef, prod2, n, prod);
+    optq[3] = optq[3] + (double)s->sign_rhs * moment_integration(poly_order, tau, prod);
+  }
+}
+
 /* :2690-2705 */
 static double normal_distance_func(const poly_state *s, const double z123[3], int iface)
 {
@@ -1194,10 +1371,11 @@ static void trouble_shooting_polynomial_solver(poly_state *s, int poly_order, do
 /* :182-675 */
 static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout, int *iface, double x[3],
                               double *vpar, double z_save[3], double t_remain_in, double *t_pass,
-                              bool *boole_t_finished, int *iper_phi)
+                              bool *boole_t_finished, int *iper_phi, double optq[4] /* intent(out), may be NULL */)
 {
   const gor_mesh *m = s->m;
   bool boole_faces[4] = {true, true, true, true};
+  if (optq) optq[0] = optq[1] = optq[2] = optq[3] = 0.0; /* initialise_optional_quantities :2117-2130 */
   bool boole_analytical_approx = false, boole_face_correct, boole_trouble_shooting = true;
   double z[4], tau = 0.0, tau_max;
   int iface_new, i_scaling = 0;
@@ -1287,20 +1465,51 @@ static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout
       }
     }
   }
-  /* ---- final processing (:459-466) */
+  /* ---- final processing (:459-487) */
+  const bool tt2 = (m->i_time_tracing_option == 2);
+  double t_hamiltonian_list[3] = {0.0, 0.0, 0.0};
   for (int i = 0; i < 3; i++) x[i] = z[i] + s->r[TP_X1 + i];
   *vpar = z[3];
-  *t_pass = tau * s->dt_dtau_const;
+  if (!tt2) {
+    *t_pass = tau * s->dt_dtau_const;
+  } else { /* Hamiltonian time tracing with computation of polynomial (:468-486) */
+    double t_hamiltonian = 0.0;
+    const int nst = s->number_of_integration_steps;
+    for (int i = 1; i <= nst; i++) {
+      calc_t_hamiltonian(s, poly_order, s->intermediate_z0_list[i - 1], s->tau_steps_list[i - 1], &t_hamiltonian);
+      t_hamiltonian_list[i] = t_hamiltonian;
+    }
+    *t_pass = t_hamiltonian;
+  }
 
   if (fabs(*t_pass) >= fabs(s->t_remain)) {
     /* ---- fourth attempt: particle stops inside the cell (:497-645) */
-    memcpy(z, s->z_init, sizeof(z));
-    if (s->number_of_integration_steps > 1) {
-      iface_new = s->iface_init;
+    if (!tt2) {
+      memcpy(z, s->z_init, sizeof(z));
+      if (s->number_of_integration_steps > 1) {
+        iface_new = s->iface_init;
+        set_integration_coef_manually(s, poly_order, z);
+      }
+      s->number_of_integration_steps = 0;
+      tau = s->t_remain / s->dt_dtau_const;
+    } else { /* :523-541 */
+      /* findloc(abs(t_hamiltonian_list) > abs(t_remain)); |t_pass| == |t_remain| exactly finds nothing in the
+       * reference (index 0, out of bounds); the last step is taken here */
+      int i_step_root = 0;
+      for (int i = 1; i <= s->number_of_integration_steps + 1; i++)
+        if (fabs(t_hamiltonian_list[i - 1]) > fabs(s->t_remain)) {
+          i_step_root = i;
+          break;
+        }
+      if (i_step_root == 0) i_step_root = s->number_of_integration_steps + 1;
+      memcpy(z, s->intermediate_z0_list[i_step_root - 2], sizeof(z));
       set_integration_coef_manually(s, poly_order, z);
+      s->number_of_integration_steps = i_step_root - 2;
+      iface_new = s->iface_init;
+      double t_remain_new = s->t_remain - t_hamiltonian_list[i_step_root - 2];
+      get_t_hamiltonian_root(s, poly_order, z, t_remain_new, &tau);
+      if (tau > s->tau_steps_list[i_step_root - 2]) tau = t_remain_new / s->dt_dtau_const;
     }
-    s->number_of_integration_steps = 0;
-    tau = s->t_remain / s->dt_dtau_const;
     analytic_integration(s, poly_order, z, tau);
     *ind_tetr_inout = s->ind_tetr;
     *iface = 0;
@@ -1323,7 +1532,15 @@ static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout
       }
       for (int i = 0; i < 3; i++) x[i] = z[i] + s->r[TP_X1 + i];
       *vpar = z[3];
-      *t_pass = tau * s->dt_dtau_const;
+      if (!tt2) {
+        *t_pass = tau * s->dt_dtau_const;
+      } else { /* :621-631 */
+        double t_hamiltonian = 0.0;
+        const int nst = s->number_of_integration_steps;
+        for (int i = 1; i <= nst; i++)
+          calc_t_hamiltonian(s, poly_order, s->intermediate_z0_list[i - 1], s->tau_steps_list[i - 1], &t_hamiltonian);
+        *t_pass = t_hamiltonian;
+      }
       for (int i = 0; i < 3; i++) z_save[i] = z[i];
       *iface = iface_new;
       handover2neighbour(m, s->ind_tetr, ind_tetr_inout, iface, x, iper_phi);
@@ -1332,6 +1549,12 @@ static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout
     for (int i = 0; i < 3; i++) z_save[i] = z[i];
     *iface = iface_new;
     handover2neighbour(m, s->ind_tetr, ind_tetr_inout, iface, x, iper_phi);
+  }
+  /* optional quantities of this push (:662-667), summed over the pushes of the time step by the caller */
+  if (optq && (m->boole_time_hamiltonian || m->boole_gyrophase || m->boole_vpar_int || m->boole_vpar2_int)) {
+    const int nst = s->number_of_integration_steps;
+    for (int i = 1; i <= nst; i++)
+      calc_optional_quantities(s, poly_order, s->intermediate_z0_list[i - 1], s->tau_steps_list[i - 1], optq);
   }
 }
 
@@ -2374,7 +2597,12 @@ int gor_orbit_timestep(const gor_mesh *m, double x[3], double *vpar, double *vpe
     if (m->ipusher == 1)
       pusher_tetra_rk(&rk, &it, &ifc, x, vpar, z_save, t_remain, &t_pass, &boole_t_finished, &iper, tr);
     else
-      pusher_tetra_poly(&s, m->poly_order, &it, &ifc, x, vpar, z_save, t_remain, &t_pass, &boole_t_finished, &iper);
+    {
+      double optq[4];
+      pusher_tetra_poly(&s, m->poly_order, &it, &ifc, x, vpar, z_save, t_remain, &t_pass, &boole_t_finished, &iper, optq);
+      if (tr) /* a caller of the pusher sums the per-push values along the orbit */
+        for (int q = 0; q < 4; q++) tr->optional_quantities[q] = tr->optional_quantities[q] + optq[q];
+    }
     *ind_tetr = it;
     *iface = ifc;
     if (tr) {
@@ -2398,6 +2626,13 @@ int64_t gor_orbit_timestep_batch(const gor_mesh *m, int64_t n, double *x, double
                                  double t_step, int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface,
                                  double *t_remain_out, int64_t *n_pushes, int nthreads)
 {
+  return gor_orbit_timestep_batch_opt(m, n, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface, t_remain_out,
+                                      n_pushes, NULL, nthreads);
+}
+int64_t gor_orbit_timestep_batch_opt(const gor_mesh *m, int64_t n, double *x, double *vpar, double *vperp,
+                                     double t_step, int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface,
+                                     double *t_remain_out, int64_t *n_pushes, double *optional_quantities, int nthreads)
+{
   int64_t total = 0;
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
@@ -2411,6 +2646,8 @@ int64_t gor_orbit_timestep_batch(const gor_mesh *m, int64_t n, double *x, double
                        iface + i, &tro, &tr);
     if (t_remain_out) t_remain_out[i] = tro;
     if (n_pushes) n_pushes[i] = tr.n_pushes;
+    if (optional_quantities)
+      for (int q = 0; q < 4; q++) optional_quantities[4 * i + q] = tr.optional_quantities[q];
     total += tr.n_pushes;
   }
   return total;

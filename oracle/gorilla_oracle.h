@@ -68,6 +68,9 @@ typedef struct {
   int32_t boole_strong_electric_field;
   int32_t boole_periodic_relocation;
   int32_t boole_dt_dtau;                  /* RK only */
+  int32_t i_time_tracing_option;          /* 1 = dt/dtau constant per cell, 2 = Hamiltonian time (polynomial pusher only) */
+  /* optional quantities of pusher_tetra_poly (gorilla_settings_mod.f90:51-55) */
+  int32_t boole_time_hamiltonian, boole_gyrophase, boole_vpar_int, boole_vpar2_int;
 } gor_mesh;
 
 /* optional per-particle trace of the visited (ind_tetr, iface) sequence */
@@ -79,6 +82,9 @@ typedef struct {
   int64_t n_fallback[4];   /* [0] 2nd attempt, [1] trouble shooting, [2] prolonged, [3] finish-outside */
   int64_t n_solver_iters;  /* Laguerre/SG/Newton iterations incl. polish */
   int64_t n_solver_calls;
+  /* sum over the pushes of the time step of pusher_tetra_poly's optional_quantities
+   * {t_hamiltonian, gyrophase, vpar_int, vpar2_int} (type optional_quantities_type, gorilla_settings_mod.f90:9-15) */
+  double optional_quantities[4];
 } gor_trace;
 
 /* return codes */
@@ -95,6 +101,11 @@ int64_t gor_orbit_timestep_batch(const gor_mesh *m, int64_t n, double *x /*[n][3
                                  double *vperp, double t_step, int32_t *boole_initialized,
                                  int32_t *ind_tetr, int32_t *iface, double *t_remain_out,
                                  int64_t *n_pushes /*[n] or NULL*/, int nthreads);
+/* same, also returning the optional quantities summed along each particle's time step: [n][4] or NULL */
+int64_t gor_orbit_timestep_batch_opt(const gor_mesh *m, int64_t n, double *x, double *vpar, double *vperp,
+                                     double t_step, int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface,
+                                     double *t_remain_out, int64_t *n_pushes, double *optional_quantities,
+                                     int nthreads);
 
 double gor_energy_tot(const gor_mesh *m, const double z[4], double perpinv, int32_t ind_tetr);
 double gor_p_phi(const gor_mesh *m, double vpar, const double z[3], int32_t ind_tetr);

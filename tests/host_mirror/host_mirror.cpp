@@ -14,17 +14,19 @@
 using namespace gb;
 
 struct HostMirror {
-  std::vector<double> geom, bpart, phi, cold, se;
+  std::vector<double> geom, bpart, phi, cold, se, ham;
   gb::FindBins bins;
   MeshDev m;
   int poly_order, boole_periodic_relocation, ipusher;
+  unsigned oq_mask;
 };
 
-template <int K, int PHI>
+template <int K, int PHI, bool EXT = false>
 static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *vperp_io, double t_step, int32_t *ind_io,
                          int32_t *iface_io, double *t_remain_out, int64_t *npush_out, int trace_cap, int32_t *tr_t,
-                         int32_t *tr_f, int force_full, int64_t *fallback)
+                         int32_t *tr_f, int force_full, int64_t *fallback, unsigned oq_mask = 0, double *optq = nullptr)
 {
+  double oq_acc[4] = {0.0, 0.0, 0.0, 0.0};
   int32_t ind_tetr = *ind_io, iface = *iface_io;
   double vpar = *vpar_io;
   const double vperp = *vperp_io;
@@ -49,14 +51,25 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
       if (!done) o = push_rk_full_call<PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
     } else {
       if (!force_full) {
-        PolyPusher<K, PHI> P;
+        PolyPusher<K, PHI, EXT> P;
         double stash[6];
         P.r.set_stash(stash, 1);
         P.mp = &m;
         P.perpinv = perpinv;
+        if (EXT) P.oq_mask = oq_mask;
         done = P.push_fast(ind_tetr, iface, x, vpar, t_remain, o);
+        if (EXT && done && oq_mask)
+          for (int q = 0; q < 4; q++) oq_acc[q] = oq_acc[q] + P.oq[q];
       }
-      if (!done) o = push_full_call<K, PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
+      if (!done) {
+        if constexpr (EXT) {
+          const PushOutX ox = push_full_call_x<K, PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain, oq_mask);
+          o = ox.o;
+          for (int q = 0; q < 4; q++) oq_acc[q] = oq_acc[q] + ox.oq[q];
+        } else {
+          o = push_full_call<K, PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
+        }
+      }
     }
     x[0] = o.x[0]; x[1] = o.x[1]; x[2] = o.x[2];
     vpar = o.vpar;
@@ -77,12 +90,14 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
   *iface_io = iface;
   if (t_remain_out) *t_remain_out = t_remain;
   if (npush_out) *npush_out = npush;
+  if (optq)
+    for (int q = 0; q < 4; q++) optq[q] = oq_acc[q];
 }
 
 extern "C" {
 
 void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, int boole_periodic_relocation, int ipusher,
-                int boole_strong_electric_field)
+                int boole_strong_electric_field, int i_time_tracing_option, int oq_mask)
 {
   HostMirror *h = new HostMirror();
   bool has_phi = false;
@@ -93,6 +108,10 @@ void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, in
   m.ntetr = md->ntetr;
   m.geom = h->geom.data(); m.bpart = h->bpart.data(); m.phi = (has_phi || strong) ? h->phi.data() : nullptr; m.cold = h->cold.data();
   m.se = strong ? h->se.data() : nullptr;
+  repack_hamiltonian_time(md, h->ham);
+  m.ham = h->ham.data();
+  m.time_tracing = i_time_tracing_option;
+  h->oq_mask = (unsigned)oq_mask;
   if (build_find_bins(md, h->bins)) {
     m.bin_start = h->bins.start.data(); m.bin_items = h->bins.items.data();
     m.bin_nu = h->bins.nu; m.bin_nv = h->bins.nv; m.bin_c0 = h->bins.c0; m.bin_c1 = h->bins.c1;
@@ -116,7 +135,7 @@ int hm_has_phi(void *p) { return ((HostMirror *)p)->m.phi != nullptr; }
 // same contract as gorilla_b200_orbit_timestep_trace; returns number of domain errors
 int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *vperp, double t_step, int32_t *binit,
                           int32_t *ind_tetr, int32_t *iface, double *t_remain_out, int64_t *n_pushes, int32_t trace_cap,
-                          int32_t *tr_t, int32_t *tr_f, int force_full, int64_t *fallback /*[4]*/)
+                          int32_t *tr_t, int32_t *tr_f, int force_full, int64_t *fallback /*[4]*/, double *optq /*[n][4] or NULL*/)
 {
   HostMirror *h = (HostMirror *)p;
   const MeshDev &m = h->m;
@@ -135,11 +154,24 @@ int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *v
     }
     if (n_pushes) n_pushes[i] = 0;
     if (t_remain_out) t_remain_out[i] = t_step;
+    if (optq) optq[4 * i] = optq[4 * i + 1] = optq[4 * i + 2] = optq[4 * i + 3] = 0.0;
     if (!binit[i] || ind_tetr[i] < 1) continue;
     if (t_step == 0.0) { if (t_remain_out) t_remain_out[i] = 0.0; continue; }
     int32_t *tt = trace_cap > 0 ? tr_t + i * trace_cap : nullptr, *tf = trace_cap > 0 ? tr_f + i * trace_cap : nullptr;
 #define HM_RUN(K, PHI) run_particle<K, PHI>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
       t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, trace_cap, tt, tf, force_full, fallback)
+#define HM_RUNX(K, PHI) run_particle<K, PHI, true>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
+      t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, trace_cap, tt, tf, force_full, fallback, \
+      optq ? h->oq_mask : 0u, optq ? optq + 4 * i : nullptr)
+    if (h->ipusher == 2 && (m.time_tracing == 2 || (optq && h->oq_mask))) {   // same dispatch as launch_orbit_k
+      if (m.se) {
+        switch (h->poly_order) { case 1: HM_RUNX(1, 2); break; case 2: HM_RUNX(2, 2); break; case 3: HM_RUNX(3, 2); break; default: HM_RUNX(4, 2); }
+      } else if (m.phi) {
+        switch (h->poly_order) { case 1: HM_RUNX(1, 1); break; case 2: HM_RUNX(2, 1); break; case 3: HM_RUNX(3, 1); break; default: HM_RUNX(4, 1); }
+      } else {
+        switch (h->poly_order) { case 1: HM_RUNX(1, 0); break; case 2: HM_RUNX(2, 0); break; case 3: HM_RUNX(3, 0); break; default: HM_RUNX(4, 0); }
+      }
+    } else
     if (m.se) {
       switch (h->poly_order) { case 0: HM_RUN(0, 2); break; case 1: HM_RUN(1, 2); break; case 2: HM_RUN(2, 2); break; case 3: HM_RUN(3, 2); break; default: HM_RUN(4, 2); }
     } else if (m.phi) {

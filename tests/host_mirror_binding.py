@@ -32,11 +32,11 @@ def load():
         L = C.CDLL(str(LIB))
         d, vp = C.c_double, C.c_void_p
         L.hm_create.restype = vp
-        L.hm_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.hm_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.hm_free.argtypes = [vp]
         L.hm_has_phi.argtypes = [vp]
         L.hm_orbit_timestep.restype = C.c_int64
-        L.hm_orbit_timestep.argtypes = [vp, C.c_int64, vp, vp, vp, d, vp, vp, vp, vp, vp, C.c_int32, vp, vp, C.c_int, vp]
+        L.hm_orbit_timestep.argtypes = [vp, C.c_int64, vp, vp, vp, d, vp, vp, vp, vp, vp, C.c_int32, vp, vp, C.c_int, vp, vp]
         L.hm_hypot.restype = d
         L.hm_hypot.argtypes = [d, d]
         L.hm_csqrt.argtypes = [d, d, vp]
@@ -54,6 +54,11 @@ def load():
     return _lib
 
 
+def oq_mask_of(settings) -> int:
+    return (int(bool(settings.boole_time_Hamiltonian)) | 2 * int(bool(settings.boole_gyrophase))
+            | 4 * int(bool(settings.boole_vpar_int)) | 8 * int(bool(settings.boole_vpar2_int)))
+
+
 class HostMirror:
     def __init__(self, mesh, settings):
         self.L = load()
@@ -61,7 +66,8 @@ class HostMirror:
         self._desc = mesh.desc()
         self.h = self.L.hm_create(C.byref(self._desc), settings.poly_order, int(settings.boole_guess),
                                   int(settings.boole_periodic_relocation), int(settings.ipusher),
-                                  int(settings.boole_strong_electric_field))
+                                  int(settings.boole_strong_electric_field), int(settings.i_time_tracing_option),
+                                  oq_mask_of(settings))
         assert self.h
 
     def __del__(self):
@@ -69,11 +75,14 @@ class HostMirror:
             self.L.hm_free(self.h)
             self.h = None
 
-    def orbit_timestep(self, x, vpar, vperp, t_step, binit, ind_tetr, iface, trace_cap=0, force_full=False):
+    def orbit_timestep(self, x, vpar, vperp, t_step, binit, ind_tetr, iface, trace_cap=0, force_full=False,
+                       optional=False):
         n = x.shape[0]
         p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
         tt, tf = np.zeros((n, max(trace_cap, 1)), np.int32), np.zeros((n, max(trace_cap, 1)), np.int32)
         npush, tro, fb = np.zeros(n, np.int64), np.zeros(n), np.zeros(4, np.int64)
+        optq = np.zeros((n, 4)) if optional else None
         dom = self.L.hm_orbit_timestep(self.h, n, p(x), p(vpar), p(vperp), float(t_step), p(binit), p(ind_tetr),
-                                       p(iface), p(tro), p(npush), trace_cap, p(tt), p(tf), int(force_full), p(fb))
-        return dict(trace_tetr=tt, trace_face=tf, n_pushes=npush, t_remain=tro, fallback=fb, domain_errors=dom)
+                                       p(iface), p(tro), p(npush), trace_cap, p(tt), p(tf), int(force_full), p(fb), p(optq))
+        return dict(trace_tetr=tt, trace_face=tf, n_pushes=npush, t_remain=tro, fallback=fb, domain_errors=dom,
+                    optional_quantities=optq)

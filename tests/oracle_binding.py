@@ -22,14 +22,16 @@ class GorMesh(C.Structure):
         ("sfc_s_min", C.c_double),
         ("ipusher", C.c_int32), ("poly_order", C.c_int32), ("boole_guess", C.c_int32),
         ("boole_strong_electric_field", C.c_int32), ("boole_periodic_relocation", C.c_int32),
-        ("boole_dt_dtau", C.c_int32),
+        ("boole_dt_dtau", C.c_int32), ("i_time_tracing_option", C.c_int32),
+        ("boole_time_hamiltonian", C.c_int32), ("boole_gyrophase", C.c_int32), ("boole_vpar_int", C.c_int32),
+        ("boole_vpar2_int", C.c_int32),
     ]
 
 
 class GorTrace(C.Structure):
     _fields_ = [("n_pushes", C.c_int64), ("cap", C.c_int64), ("ind_tetr", C.POINTER(C.c_int32)),
                 ("iface", C.POINTER(C.c_int32)), ("n_fallback", C.c_int64 * 4), ("n_solver_iters", C.c_int64),
-                ("n_solver_calls", C.c_int64)]
+                ("n_solver_calls", C.c_int64), ("optional_quantities", C.c_double * 4)]
 
 
 def build_oracle(force: bool = False) -> Path:
@@ -52,6 +54,10 @@ def load_oracle():
         L.gor_orbit_timestep_batch.argtypes = [C.POINTER(GorMesh), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, d,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.gor_orbit_timestep_batch.restype = C.c_int64
+        L.gor_orbit_timestep_batch_opt.argtypes = [C.POINTER(GorMesh), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, d,
+                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_int]
+        L.gor_orbit_timestep_batch_opt.restype = C.c_int64
         L.gor_find_tetra.argtypes = [C.POINTER(GorMesh), dp, d, d, i32p, i32p, C.c_int]
         L.gor_find_tetra.restype = None
         L.gor_check_coordinate_domain.argtypes = [C.POINTER(GorMesh), dp]
@@ -97,15 +103,20 @@ class OracleMesh:
         m.boole_strong_electric_field = int(settings.boole_strong_electric_field)
         m.boole_periodic_relocation = int(settings.boole_periodic_relocation)
         m.boole_dt_dtau = int(settings.boole_dt_dtau)
+        m.i_time_tracing_option = int(settings.i_time_tracing_option)
+        m.boole_time_hamiltonian = int(settings.boole_time_Hamiltonian)
+        m.boole_gyrophase = int(settings.boole_gyrophase)
+        m.boole_vpar_int = int(settings.boole_vpar_int)
+        m.boole_vpar2_int = int(settings.boole_vpar2_int)
         self.c = m
         self.L = load_oracle()
 
     def orbit_timestep_batch(self, x, vpar, vperp, t_step, binit, ind_tetr, iface, t_remain_out=None, n_pushes=None,
-                             nthreads: int = 0) -> int:
+                             nthreads: int = 0, optional_quantities=None) -> int:
         p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
-        return int(self.L.gor_orbit_timestep_batch(C.byref(self.c), x.shape[0], p(x), p(vpar), p(vperp), float(t_step),
-                                                   p(binit), p(ind_tetr), p(iface), p(t_remain_out), p(n_pushes),
-                                                   int(nthreads)))
+        return int(self.L.gor_orbit_timestep_batch_opt(C.byref(self.c), x.shape[0], p(x), p(vpar), p(vperp),
+                                                       float(t_step), p(binit), p(ind_tetr), p(iface), p(t_remain_out),
+                                                       p(n_pushes), p(optional_quantities), int(nthreads)))
 
     def orbit_timestep_trace(self, x, vpar, vperp, t_step, binit, ind_tetr, iface, trace_cap: int):
         """Per-particle call recording the visited (ind_tetr, iface) sequence; arrays updated in place.
@@ -114,6 +125,7 @@ class OracleMesh:
         tt, tf = np.zeros((n, max(trace_cap, 1)), np.int32), np.zeros((n, max(trace_cap, 1)), np.int32)
         npush, tro = np.zeros(n, np.int64), np.zeros(n)
         fb = np.zeros(4, np.int64)
+        optq = np.zeros((n, 4))
         iters = calls = 0
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         for i in range(n):
@@ -128,11 +140,12 @@ class OracleMesh:
                 ind_tetr[i:i + 1].ctypes.data_as(ip), iface[i:i + 1].ctypes.data_as(ip), C.byref(t_out), C.byref(tr))
             assert rc == 0, rc
             npush[i], tro[i] = tr.n_pushes, t_out.value
+            optq[i] = tr.optional_quantities[:]
             fb += np.array(tr.n_fallback[:], np.int64)
             iters += tr.n_solver_iters
             calls += tr.n_solver_calls
         return dict(trace_tetr=tt, trace_face=tf, n_pushes=npush, t_remain=tro, fallback=fb, solver_iters=iters,
-                    solver_calls=calls)
+                    solver_calls=calls, optional_quantities=optq)
 
     def find_tetra(self, x, vpar, vperp, sign_t_step=1):
         n = x.shape[0]

@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (0 = workload default)")
     ap.add_argument("--poly-order", type=int, default=0, help="0 = workload default")
     ap.add_argument("--ipusher", type=int, default=0, help="1 = RK4 pusher, 2 = polynomial pusher (0 = workload default)")
+    ap.add_argument("--time-tracing", type=int, default=0, choices=[0, 1, 2],
+                    help="i_time_tracing_option: 1 = dt/dtau constant per cell, 2 = Hamiltonian time (0 = workload default)")
     ap.add_argument("--t-step", type=float, default=0.0, help="physical time per step [s] (0 = workload default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -174,6 +176,8 @@ def reference_arm(args):
         settings.poly_order = args.poly_order
     if args.ipusher:
         settings.ipusher = args.ipusher
+    if args.time_tracing:
+        settings.i_time_tracing_option = args.time_tracing
     t_step = args.t_step or wl["t_step"]
     mesh = build_mesh(wl["grid"], settings)
     cores = os.cpu_count() or 1
@@ -220,6 +224,8 @@ def main():
         settings.poly_order = args.poly_order
     if args.ipusher:
         settings.ipusher = args.ipusher
+    if args.time_tracing:
+        settings.i_time_tracing_option = args.time_tracing
     t_step = args.t_step or wl["t_step"]
     n = args.particles or wl["n_default"]
 
@@ -234,6 +240,9 @@ def main():
     has_phi = bool(np.any(mesh.tetra_physics[:, 116:125] != 0.0))
     strong = bool(settings.boole_strong_electric_field)
     bytes_per_crossing = BYTES_PER_CROSSING[has_phi or strong] + (BYTES_STRONG_E if strong else 0.0)
+    ext = settings.ipusher == 2 and settings.i_time_tracing_option == 2
+    if ext:
+        bytes_per_crossing += 64.0   # hamiltonian_time record (8 doubles) read at the end of every push
 
     # particles of this rank (weak scaling: n per GPU fixed); independent streams per rank
     x, vpar, vperp = wl["particles"](n, 1000 + rank)
@@ -345,7 +354,7 @@ def main():
         fp64_per = FP64_INST_PER_CROSSING[kkey]
         # traffic: DRAM bytes per launch = per-crossing figure of the ncu capture of this kernel x crossings per launch
         ncu = _NCU.get(str(kkey))
-        traffic = ncu["dram_bytes_per_crossing"] * per_rank_pushes if ncu and not has_phi and not strong else None
+        traffic = ncu["dram_bytes_per_crossing"] * per_rank_pushes if ncu and not has_phi and not strong and not ext else None
         traffic_src = (f"ncu capture {ncu['capture']}: {ncu['dram_bytes_per_crossing']:.2f} B/crossing x crossings per launch"
                        if traffic is not None else None)
         t_hbm, t_fp64 = bytes_per_crossing / (hbm_peak * 1e9), fp64_per / muladd_peak
@@ -353,7 +362,7 @@ def main():
         fp64 = {"achieved": fp64_ach / 1e12, "peak": muladd_peak / 1e12, "unit": "Tinst/s (thread-level DMUL/DADD)",
                 "frac": fp64_ach / muladd_peak, "inst_per_crossing": fp64_per, "dfma_peak": dfma_peak / 1e12,
                 "peak_source": "measured in this run (gorilla_b200_fp64_peak)"}
-        kern = f"orbit_kernel<{0 if settings.ipusher == 1 else settings.poly_order},{2 if strong else 1 if has_phi else 0}>"
+        kern = f"orbit_kernel<{0 if settings.ipusher == 1 else settings.poly_order},{2 if strong else 1 if has_phi else 0}{',EXT' if ext else ''}>"
         if t_hbm >= t_fp64:
             roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "kernel": kern,
@@ -379,7 +388,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": elapsed_ms_max / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "desc": wl["desc"], "ipusher": settings.ipusher,
-                       "poly_order": settings.poly_order,
+                       "poly_order": settings.poly_order, "i_time_tracing_option": settings.i_time_tracing_option,
                        "particles_per_gpu": n, "t_step_s": t_step, "ntetr": mesh.ntetr,
                        "mesh_hot_bytes": int(mesh.ntetr * (352 + (160 if has_phi else 0))),
                        "l2_policy": "inputs_larger_than_l2 (mesh hot records > 126 MB, gathered at random)",

@@ -67,6 +67,17 @@ class _Counters(C.Structure):
                 ("kernel_ms", C.c_double), ("find_ms", C.c_double)]
 
 
+class _EventSettings(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("boole_poincare_phi_0", "n_skip_phi_0", "boole_poincare_vpar_0", "boole_J_par",
+                                         "n_skip_vpar_0")] + [("reserved", C.c_int32 * 3)]
+
+
+# struct gorilla_event (include/gorilla_b200.h)
+EVENT_DTYPE = np.dtype([("particle", np.int64), ("kind", np.int32), ("counter", np.int32), ("push", np.int64),
+                        ("x", np.float64, 3), ("value", np.float64, 2)])
+EVENT_PHI_0, EVENT_VPAR_0 = 1, 2
+
+
 @dataclass
 class Counters:
     n_particles: int
@@ -84,6 +95,7 @@ EXPORTED_SYMBOLS = (
     "gorilla_b200_init", "gorilla_b200_free", "gorilla_b200_last_error", "gorilla_b200_launch_count",
     "gorilla_b200_orbit_timestep", "gorilla_b200_orbit_timestep_dev", "gorilla_b200_orbit_timestep_trace",
     "gorilla_b200_orbit_timestep_optional", "gorilla_b200_orbit_timestep_optional_dev",
+    "gorilla_b200_orbit_timestep_events", "gorilla_b200_orbit_timestep_events_dev",
     "gorilla_b200_find_tetra", "gorilla_b200_invariants", "gorilla_b200_invariants_dev",
     "gorilla_b200_get_counters", "gorilla_b200_sort_permutation_dev", "gorilla_b200_set_launch_config",
     "gorilla_b200_fp64_peak",
@@ -113,6 +125,10 @@ def load_library():
     lib.gorilla_b200_orbit_timestep_optional_dev.argtypes = [vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp, vp, vp]
     lib.gorilla_b200_debug_orbit_timestep_trace_optional.argtypes = [vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp, i32, vp,
                                                                      vp, vp]
+    lib.gorilla_b200_orbit_timestep_events.argtypes = [vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp,
+                                                       C.POINTER(_EventSettings), vp, vp, vp, vp, i64, C.POINTER(i64)]
+    lib.gorilla_b200_orbit_timestep_events_dev.argtypes = [vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, vp,
+                                                           C.POINTER(_EventSettings), vp, vp, vp, vp, i64, vp, vp]
     lib.gorilla_b200_find_tetra.argtypes = [vp, i64, vp, vp, vp, vp, vp, i32]
     lib.gorilla_b200_invariants.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.gorilla_b200_invariants_dev.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -358,6 +374,26 @@ class Gorilla:
         _check(load_library().gorilla_b200_orbit_timestep_optional_dev(
             self._h, x.shape[0], dp(x), dp(vpar), dp(vperp), float(t_step), dp(boole_initialized), dp(ind_tetr),
             dp(iface), dp(t_remain_out), dp(n_pushes), dp(optional_quantities), C.c_void_p(stream or 0)))
+
+    def orbit_timestep_gorilla_events(self, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface, par_adiab_inv,
+                                      counter_vpar_0, counter_phi_0, event_cap: int, *, boole_poincare_phi_0=True,
+                                      n_skip_phi_0=1, boole_poincare_vpar_0=True, boole_J_par=True, n_skip_vpar_0=1,
+                                      t_remain_out=None, n_pushes=None):
+        """orbit_timestep_gorilla with the event capture of gorilla_plot_orbit_integration (gorilla_plot_mod.f90:585-638):
+        toroidal mappings and banana tips / J_par.  par_adiab_inv [n] f64, counter_vpar_0 / counter_phi_0 [n] i32 carry the
+        per-particle state between calls.  Returns (events, n_events): a structured array (EVENT_DTYPE) sorted by
+        (particle, push, kind) holding min(n_events, event_cap) records."""
+        n = x.shape[0]
+        cfg = _EventSettings(int(boole_poincare_phi_0), int(n_skip_phi_0), int(boole_poincare_vpar_0), int(boole_J_par),
+                             int(n_skip_vpar_0))
+        ev = np.zeros(max(event_cap, 1), EVENT_DTYPE)
+        nev = C.c_int64(0)
+        _check(load_library().gorilla_b200_orbit_timestep_events(
+            self._h, n, _ptr(x), _ptr(vpar), _ptr(vperp), float(t_step), _ptr(boole_initialized), _ptr(ind_tetr),
+            _ptr(iface), _ptr(t_remain_out), _ptr(n_pushes), C.byref(cfg), _ptr(par_adiab_inv), _ptr(counter_vpar_0),
+            _ptr(counter_phi_0), _ptr(ev), int(event_cap), C.byref(nev)))
+        ev = ev[:min(nev.value, event_cap)]
+        return ev[np.lexsort((ev["kind"], ev["push"], ev["particle"]))], nev.value
 
     # ---- diagnostics ---------------------------------------------------------------------------
     def invariants(self, x, vpar, vperp, ind_tetr):

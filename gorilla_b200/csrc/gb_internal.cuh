@@ -48,7 +48,36 @@ struct Batch {
   // vpar_int, vpar2_int (nullable); oq_mask bit q set = quantity q requested (boole_array_optional_quantities)
   double *optq;
   uint32_t oq_mask;
+  // EXT = 2 kernels: orbit events (gorilla_plot_mod.f90:585-638).  ev_flags bit0 boole_poincare_phi_0, bit1
+  // boole_poincare_vpar_0, bit2 boole_J_par; per-particle state in/out; events appended to a global buffer
+  int32_t ev_flags, n_skip_phi_0, n_skip_vpar_0;
+  double *par_adiab_inv;
+  int32_t *counter_vpar_0, *counter_phi_0;
+  gorilla_event *events;
+  long long ev_cap;
+  unsigned long long *ev_count;
 };
+
+// append the events of one push to the global buffer (order between particles is not defined; a record carries the
+// particle and push index); the counter keeps counting past the capacity so that the caller sees the overflow
+__device__ __forceinline__ void emit_events(const Batch &bt, long long particle, long long push, const EvState &es)
+{
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    if (k < es.n) {
+      const unsigned long long slot = atomicAdd(bt.ev_count, 1ull);
+      if ((long long)slot < bt.ev_cap) {
+        gorilla_event *e = bt.events + slot;
+        e->particle = particle;
+        e->kind = es.e[k].kind;
+        e->counter = es.e[k].counter;
+        e->push = push;
+        e->x[0] = es.e[k].x[0]; e->x[1] = es.e[k].x[1]; e->x[2] = es.e[k].x[2];
+        e->value[0] = es.e[k].v[0]; e->value[1] = es.e[k].v[1];
+      }
+    }
+  }
+}
 
 // ----------------------------------------------------------------------------------------------------
 // minimum resident CTAs per SM the compiler must allow for (caps registers per thread); tunable per order
@@ -86,21 +115,25 @@ enum { LC_LOST = 0, LC_FIN, LC_FB0, LC_FB1, LC_FB2, LC_FB3, LC_N };
 // per-lane accumulators of the optional quantities (EXT kernels only)
 template <bool EXT, int NT>
 struct OqSlots {
-  double v[4][NT];
+  double v[5][NT];   // 0..3 optional quantities, 4 par_adiab_inv
+  int c[2][NT];      // counter_banana_mappings, counter_phi_0_mappings
 };
 template <int NT>
 struct OqSlots<false, NT> {
   double v[1][1];
+  int c[1][1];
 };
 
-// EXT = true: i_time_tracing_option 1 or 2 (Hamiltonian time) and the optional quantities of pusher_tetra_poly; the
-// plain variant is the hot path of the default settings and carries none of that code.
-template <int K, int PHI, bool EXT = false>
+// EXT = 1: Hamiltonian time tracing (i_time_tracing_option = 2); EXT = 2: time tracing option read at run time plus the
+// optional quantities of pusher_tetra_poly; the plain variant (EXT = 0) is the hot path of the default settings and
+// carries none of that code (the optional-quantity code alone costs the order-2 kernel ~400 bytes of spills).
+template <int K, int PHI, int EXT = 0>
 __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
 {
   __shared__ double s_d[LS_ND][GB_THREADS], s_stash[6][GB_THREADS];
-  __shared__ OqSlots<EXT, GB_THREADS> s_oq;
+  __shared__ OqSlots<EXT == 2, GB_THREADS> s_oq;
 #define LOQ(q) (((volatile double *)s_oq.v[q])[tid_now()])
+#define LEC(q) (((volatile int *)s_oq.c[q])[tid_now()])
   __shared__ long long s_idx[GB_THREADS], s_npush[GB_THREADS];
   __shared__ unsigned long long s_cpush[GB_THREADS];
   __shared__ unsigned int s_cnt[LC_N][GB_THREADS];
@@ -138,7 +171,7 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
         // resp. leaves the loop at :103-109 without touching the particle
         if (bt.t_remain_out) bt.t_remain_out[idx] = bt.t_step;
         if (bt.n_pushes) bt.n_pushes[idx] = 0;
-        if constexpr (EXT) {
+        if constexpr (EXT == 2) {
           if (bt.optq) { bt.optq[4 * idx] = 0.0; bt.optq[4 * idx + 1] = 0.0; bt.optq[4 * idx + 2] = 0.0; bt.optq[4 * idx + 3] = 0.0; }
         }
         if (inited && ind_tetr < 1) LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
@@ -147,7 +180,7 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
       if (bt.t_step == 0.0) {
         if (bt.t_remain_out) bt.t_remain_out[idx] = 0.0;
         if (bt.n_pushes) bt.n_pushes[idx] = 0;
-        if constexpr (EXT) {
+        if constexpr (EXT == 2) {
           if (bt.optq) { bt.optq[4 * idx] = 0.0; bt.optq[4 * idx + 1] = 0.0; bt.optq[4 * idx + 2] = 0.0; bt.optq[4 * idx + 3] = 0.0; }
         }
         continue;
@@ -164,7 +197,10 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
       LS(LS_TREM) = bt.t_step;
       *p_idx = idx;
       *p_npush = 0;
-      if constexpr (EXT) { LOQ(0) = 0.0; LOQ(1) = 0.0; LOQ(2) = 0.0; LOQ(3) = 0.0; }
+      if constexpr (EXT == 2) {
+        LOQ(0) = 0.0; LOQ(1) = 0.0; LOQ(2) = 0.0; LOQ(3) = 0.0;
+        if (bt.ev_flags) { LOQ(4) = bt.par_adiab_inv[idx]; LEC(0) = bt.counter_vpar_0[idx]; LEC(1) = bt.counter_phi_0[idx]; }
+      }
       return true;
     }
   };
@@ -195,25 +231,40 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
           PolyPusher<K, PHI, EXT> P;
           P.mp = &m;
           P.perpinv = perpinv;
-          if constexpr (EXT) P.oq_mask = bt.oq_mask;
+          if constexpr (EXT == 2) P.oq_mask = bt.oq_mask;
           P.r.set_stash(&s_stash[0][tid_now()], GB_THREADS);
           done = P.push_fast(ind_tetr, iface, x, LS(LS_VPAR), LS(LS_TREM), o, &LS(LS_TREM));
-          if constexpr (EXT) {
+          if constexpr (EXT == 2) {
             if (done && bt.oq_mask) {
 #pragma unroll
               for (int q = 0; q < 4; q++) LOQ(q) = LOQ(q) + P.oq[q];
             }
+            if constexpr (K >= 2) {
+              if (done && bt.ev_flags && !o.finished) {
+                EvState es;
+                es.flags = bt.ev_flags; es.nskip_p = bt.n_skip_phi_0; es.nskip_v = bt.n_skip_vpar_0;
+                es.J = LOQ(4); es.cnt_v = LEC(0); es.cnt_p = LEC(1);
+                P.events_after_push(LS(LS_VPAR), o, es);
+                LOQ(4) = es.J; LEC(0) = es.cnt_v; LEC(1) = es.cnt_p;
+                if (es.n) emit_events(bt, *p_idx, *p_npush, es);
+              }
+            }
           }
         }
         if (!done) {
-          if constexpr (EXT) {
+          if constexpr (EXT == 2) {
             const PushOutX ox = push_full_call_x<K, PHI>(&m, perpinv, ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2),
-                                                         LS(LS_VPAR), LS(LS_TREM), bt.oq_mask);
+                                                         LS(LS_VPAR), LS(LS_TREM), bt.oq_mask, bt.ev_flags, bt.n_skip_phi_0,
+                                                         bt.n_skip_vpar_0, LOQ(4), LEC(0), LEC(1));
             o = ox.o;
 #pragma unroll
             for (int q = 0; q < 4; q++) LOQ(q) = LOQ(q) + ox.oq[q];
+            if (bt.ev_flags) {
+              LOQ(4) = ox.es.J; LEC(0) = ox.es.cnt_v; LEC(1) = ox.es.cnt_p;
+              if (ox.es.n) emit_events(bt, *p_idx, *p_npush, ox.es);
+            }
           } else {
-            o = push_full_call<K, PHI>(&m, perpinv, ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2), LS(LS_VPAR), LS(LS_TREM));
+            o = push_full_call<K, PHI, EXT>(&m, perpinv, ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2), LS(LS_VPAR), LS(LS_TREM));
           }
         }
       }
@@ -253,11 +304,12 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
         bt.iface[idx] = iface;
         if (bt.t_remain_out) bt.t_remain_out[idx] = t_remain;
         if (bt.n_pushes) bt.n_pushes[idx] = npush + 1;
-        if constexpr (EXT) {
+        if constexpr (EXT == 2) {
           if (bt.optq) {
 #pragma unroll
             for (int q = 0; q < 4; q++) bt.optq[4 * idx + q] = LOQ(q);
           }
+          if (bt.ev_flags) { bt.par_adiab_inv[idx] = LOQ(4); bt.counter_vpar_0[idx] = LEC(0); bt.counter_phi_0[idx] = LEC(1); }
         }
         *p_cpush = *p_cpush + (unsigned long long)(npush + 1);
         if (o.finished) LCNT(LC_FIN) = LCNT(LC_FIN) + 1;
@@ -279,6 +331,7 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
 #undef LS
 #undef LCNT
 #undef LOQ
+#undef LEC
 #undef p_idx
 #undef p_npush
 #undef p_cpush
@@ -331,7 +384,7 @@ static __device__ __noinline__ double solve_group(bool busy, int deg, double q0,
   return tau;
 }
 
-template <int K, int PHI, bool EXT = false>
+template <int K, int PHI, int EXT = 0>
 __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_constant__ MeshDev m, const Batch bt)
 {
   extern __shared__ __align__(16) unsigned char g_smem[];
@@ -341,8 +394,10 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
   unsigned long long *s_cpush = reinterpret_cast<unsigned long long *>(s_npush + GBG_THREADS);
   unsigned int (*s_cnt)[GBG_THREADS] = reinterpret_cast<unsigned int (*)[GBG_THREADS]>(s_cpush + GBG_THREADS);  // [LC_N]
   int *s_ind_save = reinterpret_cast<int *>(s_cnt + LC_N);
-  double (*s_oq)[GBG_THREADS] = reinterpret_cast<double (*)[GBG_THREADS]>(s_ind_save + GBG_THREADS);   // [4], EXT only
+  double (*s_oq)[GBG_THREADS] = reinterpret_cast<double (*)[GBG_THREADS]>(s_ind_save + GBG_THREADS);   // [5], EXT = 2 only
+  int (*s_ec)[GBG_THREADS] = reinterpret_cast<int (*)[GBG_THREADS]>(s_oq + 5);                          // [2], EXT = 2 only
 #define LOQ(q) (((volatile double *)s_oq[q])[tid_now()])
+#define LEC(q) (((volatile int *)s_ec[q])[tid_now()])
   const unsigned lane = threadIdx.x & 31u;
   const int bar_id = 1 + (int)((threadIdx.x >> 5) & 3u);   // warps w, w+4, w+8, w+12 share sub-partition w
 #define LS(f) (((volatile double *)s_d[f])[tid_now()])
@@ -371,7 +426,7 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
       if (!inited || ind_tetr < 1) {
         if (bt.t_remain_out) bt.t_remain_out[idx] = bt.t_step;
         if (bt.n_pushes) bt.n_pushes[idx] = 0;
-        if constexpr (EXT) {
+        if constexpr (EXT == 2) {
           if (bt.optq) { bt.optq[4 * idx] = 0.0; bt.optq[4 * idx + 1] = 0.0; bt.optq[4 * idx + 2] = 0.0; bt.optq[4 * idx + 3] = 0.0; }
         }
         if (inited && ind_tetr < 1) LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
@@ -380,7 +435,7 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
       if (bt.t_step == 0.0) {
         if (bt.t_remain_out) bt.t_remain_out[idx] = 0.0;
         if (bt.n_pushes) bt.n_pushes[idx] = 0;
-        if constexpr (EXT) {
+        if constexpr (EXT == 2) {
           if (bt.optq) { bt.optq[4 * idx] = 0.0; bt.optq[4 * idx + 1] = 0.0; bt.optq[4 * idx + 2] = 0.0; bt.optq[4 * idx + 3] = 0.0; }
         }
         continue;
@@ -396,7 +451,10 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
       LS(LS_TREM) = bt.t_step;
       *p_idx = idx;
       *p_npush = 0;
-      if constexpr (EXT) { LOQ(0) = 0.0; LOQ(1) = 0.0; LOQ(2) = 0.0; LOQ(3) = 0.0; }
+      if constexpr (EXT == 2) {
+        LOQ(0) = 0.0; LOQ(1) = 0.0; LOQ(2) = 0.0; LOQ(3) = 0.0;
+        if (bt.ev_flags) { LOQ(4) = bt.par_adiab_inv[idx]; LEC(0) = bt.counter_vpar_0[idx]; LEC(1) = bt.counter_phi_0[idx]; }
+      }
       return true;
     }
   };
@@ -413,7 +471,7 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
     double tau_max = 0.0;
     PolyPusher<K, PHI, EXT> P;
     P.mp = &m;
-    if constexpr (EXT) P.oq_mask = bt.oq_mask;
+    if constexpr (EXT == 2) P.oq_mask = bt.oq_mask;
     P.r.set_stash(&s_stash[0][tid_now()], GBG_THREADS);
     if (active && !bt.force_full) {
       const double x[3] = {LS(LS_X0), LS(LS_X1), LS(LS_X2)};
@@ -427,22 +485,35 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
     }
     if (active) {
       *p_ind_save = ind_tetr;
-      if constexpr (EXT) {
+      if constexpr (EXT == 2) {
         if (done) {
           if (bt.oq_mask) {
 #pragma unroll
             for (int q = 0; q < 4; q++) LOQ(q) = LOQ(q) + P.oq[q];
           }
+          if (bt.ev_flags && !o.finished) {
+            EvState es;
+            es.flags = bt.ev_flags; es.nskip_p = bt.n_skip_phi_0; es.nskip_v = bt.n_skip_vpar_0;
+            es.J = LOQ(4); es.cnt_v = LEC(0); es.cnt_p = LEC(1);
+            P.events_after_push(LS(LS_VPAR), o, es);
+            LOQ(4) = es.J; LEC(0) = es.cnt_v; LEC(1) = es.cnt_p;
+            if (es.n) emit_events(bt, *p_idx, *p_npush, es);
+          }
         } else {
           const PushOutX ox = push_full_call_x<K, PHI>(&m, LS(LS_PERPINV), ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2),
-                                                       LS(LS_VPAR), LS(LS_TREM), bt.oq_mask);
+                                                       LS(LS_VPAR), LS(LS_TREM), bt.oq_mask, bt.ev_flags, bt.n_skip_phi_0,
+                                                       bt.n_skip_vpar_0, LOQ(4), LEC(0), LEC(1));
           o = ox.o;
 #pragma unroll
           for (int q = 0; q < 4; q++) LOQ(q) = LOQ(q) + ox.oq[q];
+          if (bt.ev_flags) {
+            LOQ(4) = ox.es.J; LEC(0) = ox.es.cnt_v; LEC(1) = ox.es.cnt_p;
+            if (ox.es.n) emit_events(bt, *p_idx, *p_npush, ox.es);
+          }
         }
       } else {
         if (!done)
-          o = push_full_call<K, PHI>(&m, LS(LS_PERPINV), ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2), LS(LS_VPAR), LS(LS_TREM));
+          o = push_full_call<K, PHI, EXT>(&m, LS(LS_PERPINV), ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2), LS(LS_VPAR), LS(LS_TREM));
       }
       LS(LS_X0) = o.x[0]; LS(LS_X1) = o.x[1]; LS(LS_X2) = o.x[2];
       LS(LS_VPAR) = o.vpar;
@@ -480,11 +551,12 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
         bt.iface[idx] = iface;
         if (bt.t_remain_out) bt.t_remain_out[idx] = t_remain;
         if (bt.n_pushes) bt.n_pushes[idx] = npush + 1;
-        if constexpr (EXT) {
+        if constexpr (EXT == 2) {
           if (bt.optq) {
 #pragma unroll
             for (int q = 0; q < 4; q++) bt.optq[4 * idx + q] = LOQ(q);
           }
+          if (bt.ev_flags) { bt.par_adiab_inv[idx] = LOQ(4); bt.counter_vpar_0[idx] = LEC(0); bt.counter_phi_0[idx] = LEC(1); }
         }
         *p_cpush = *p_cpush + (unsigned long long)(npush + 1);
         if (o.finished) LCNT(LC_FIN) = LCNT(LC_FIN) + 1;
@@ -505,13 +577,14 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
 #undef LS
 #undef LCNT
 #undef LOQ
+#undef LEC
 #undef p_idx
 #undef p_npush
 #undef p_cpush
 #undef p_ind_save
 }
 constexpr size_t GBG_SMEM = (size_t)GBG_THREADS * ((LS_ND + 6) * 8 + 3 * 8 + LC_N * 4 + 4);
-constexpr size_t GBG_SMEM_EXT = GBG_SMEM + (size_t)GBG_THREADS * 4 * 8;
+constexpr size_t GBG_SMEM_EXT = GBG_SMEM + (size_t)GBG_THREADS * (5 * 8 + 2 * 4);
 
 // ----------------------------------------------------------------------------------------------------
 struct gorilla_b200_handle {
@@ -546,12 +619,12 @@ struct gorilla_b200_handle {
   cudaStream_t last_stream = nullptr;
 };
 
-template <int K, int PHI, bool EXT = false>
+template <int K, int PHI, int EXT = 0>
 int launch_orbit_t(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
 {
   if constexpr (K >= 3) {
     if (h->use_group) {
-      constexpr size_t smem_g = EXT ? GBG_SMEM_EXT : GBG_SMEM;
+      constexpr size_t smem_g = EXT == 2 ? GBG_SMEM_EXT : GBG_SMEM;
       GB_CUDA(cudaFuncSetAttribute(orbit_kernel_g<K, PHI, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
       int64_t grid_g = h->num_sms;
       const int64_t need_g = (bt.n + GBG_THREADS - 1) / GBG_THREADS;

@@ -78,7 +78,23 @@ struct SolveTask {
   int deg, kind;
 };
 
-template <int K, int PHI, bool EXT = false>
+// orbit events of one push (EXT = 2): per-particle state in/out and at most one event of each kind
+struct EvRec {
+  int kind, counter;   // 1 = toroidal mapping (phi = 0), 2 = banana tip (v_par = 0)
+  double x[3], v[2];   // position; {p_phi, e_tot} resp. {J_par, e_tot}
+};
+struct EvState {
+  int flags;           // bit0 boole_poincare_phi_0, bit1 boole_poincare_vpar_0, bit2 boole_J_par
+  int nskip_p, nskip_v;
+  double J;            // par_adiab_inv
+  int cnt_v, cnt_p;    // counter_banana_mappings, counter_phi_0_mappings
+  int n;
+  EvRec e[2];
+};
+
+// EXT: 0 = plain (i_time_tracing_option = 1, no optional quantities); 1 = Hamiltonian time tracing, nothing else;
+// 2 = time tracing option read at run time + optional quantities
+template <int K, int PHI, int EXT = 0>
 struct PolyPusher {
   const MeshDev *mp;
   Rec<PHI> r;
@@ -88,6 +104,8 @@ struct PolyPusher {
   // optional quantities of this push
   double tau_list[2], z0_list[2][4], oq[4];
   unsigned oq_mask;  // bit0 boole_time_Hamiltonian, bit1 boole_gyrophase, bit2 boole_vpar_int, bit3 boole_vpar2_int
+  int iper_phi;      // EXT = 2: toroidal period crossed by the hand-over (+1 / -1 / 0), for the phi = 0 mappings
+  bool removed;      // EXT = 2: the push ended on one of the "remove particle" returns
   double dt_dtau_const, bmod0, vmod0, t_remain, z_init[4], k1, k3, dv2E;
   BlockMat A;
   double b[4];
@@ -120,7 +138,11 @@ struct PolyPusher {
       k3 = 0.0;
     }
     nsteps = 0;
-    if (EXT) oq[0] = oq[1] = oq[2] = oq[3] = 0.0;  // initialise_optional_quantities (:2117-2130)
+    if (EXT == 2) {
+      oq[0] = oq[1] = oq[2] = oq[3] = 0.0;  // initialise_optional_quantities (:2117-2130)
+      iper_phi = 0;
+      removed = false;
+    }
   }
 
   // ---- ODE coefficients b, A  (:1503-1530; strong-electric-field terms :1519-1526).  RK = true forms b(1:3) the
@@ -586,7 +608,8 @@ struct PolyPusher {
   // the loop over number_of_integration_steps at the end of the pusher (:662-667)
   GB_HD void optional_all()
   {
-    if (!EXT || !oq_mask) return;
+    if (EXT != 2) return;
+    if (!oq_mask) return;
     if (nsteps >= 1) optional_step(z0_list[0], tau_list[0], nsteps > 1);
     if (nsteps >= 2) optional_step(z0_list[1], tau_list[1], true);
   }
@@ -604,6 +627,116 @@ struct PolyPusher {
       thl[1] = th;
     }
     return th;
+  }
+
+
+  // ==== EXT = 2: orbit events -- J_par / banana tips / toroidal mappings =================================
+  // module par_adiab_inv_poly_mod (:3156-3429) and the event part of gorilla_plot_orbit_integration
+  // (SRC/gorilla_plot_mod.f90:585-638); events go to a device buffer instead of files.
+  // par_adiab_tau (:3295-3322); a**3, a**4, x**5 as libgcc __powidf2 forms them
+  GB_HD static double par_adiab_tau(double a44, double b4, double tau, double v)
+  {
+    const double t2 = tau * tau, v2 = v * v, a2 = a44 * a44, bb = b4 * b4;
+    const double a3 = a44 * a2, t3 = tau * t2, t4 = t2 * t2;
+    double r = tau * v2 + 0.5 * t2 * (2.0 * b4 * v + 2.0 * a44 * v2);
+    if (K == 4) r = r + 1.0 / 3.0 * t3 * (bb + 3.0 * a44 * b4 * v + 2.0 * a44 * 2.0 * v2);  // (sic) :3316
+    else r = r + 1.0 / 3.0 * t3 * (bb + 3.0 * a44 * b4 * v + 2.0 * a2 * v2);
+    if (K >= 3) r = r + 1.0 / 4.0 * t4 * (a44 * bb + 7.0 / 3.0 * a2 * b4 * v + (4.0 * a3 * v2) / 3.0);
+    if (K >= 4) {
+      const double a4 = a2 * a2, t5 = tau * t4;
+      r = r + 1.0 / 60.0 * t5 * (7.0 * a2 * bb + 15.0 * a3 * b4 * v + 8.0 * a4 * v2);
+    }
+    return r;
+  }
+  // tau_vpar_root (:3326-3374)
+  GB_HD double tau_vpar_root(double a44, double b4, double v)
+  {
+    const double a2 = a44 * a44, a3 = a44 * a2, a4 = a2 * a2;
+    const double c1 = v, c2 = b4 + a44 * v, c3 = a44 * b4 + a2 * v;
+    if (K <= 2) return quadratic_solver2(c3, c2, c1, solver_iters);
+    const double c4 = a2 * b4 + a3 * v;
+    if (K == 3) return cubic_solver(c4, c3, c2, c1, solver_iters);
+    const double c5 = a3 * b4 + a4 * v;
+    return quartic_solver(0, c5, c4, c3, c2, c1, solver_iters);
+  }
+  // energy_tot_func / p_phi_func (SRC/supporting_functions_mod.f90:279-301, 377-408) in the current tetrahedron
+  GB_HD double energy_tot(const double *z /*[4]*/) const
+  {
+    const double vperp = sqrt(2.0 * fabs(perpinv) * (r.bmod1 + dot3(r.gB, z)));
+    double phi = 0.0;
+    if (PHI) phi = r.Phi1 + dot3(r.gPhi, z);
+    double e = mp->particle_mass / 2.0 * (vperp * vperp + z[3] * z[3]) + mp->particle_charge * phi;
+    if (PHI == 2) e = e + 0.5 * mp->particle_mass * (r.v2Emod1 + dot3(z, r.gv2Emod));
+    return e;
+  }
+  GB_HD double p_phi(double vpar, const double *z /*[3]*/) const
+  {
+    const double *pc = mp->cold + ((int64_t)ind_tetr - 1) * COLD_ND;
+    const double gh[3] = {ldg(pc + C_GHPHI), ldg(pc + C_GHPHI + 1), ldg(pc + C_GHPHI + 2)};
+    const double gA[3] = {ldg(pc + C_GAPHI), ldg(pc + C_GAPHI + 1), ldg(pc + C_GAPHI + 2)};
+    double p = mp->particle_mass * vpar * (ldg(pc + C_HPHI1) + dot3(gh, z)) +
+               mp->particle_mass / mp->cm_over_e * (ldg(pc + C_APHI1) + dot3(gA, z));
+    if (PHI == 2) {
+      const double *ps = mp->se + ((int64_t)ind_tetr - 1) * SE_ND;
+      const double gv[3] = {ldg(ps + S_GVE2), ldg(ps + S_GVE2 + 1), ldg(ps + S_GVE2 + 2)};
+      p = p + mp->particle_mass * (ldg(ps + S_VE2_1) + dot3(z, gv));
+    }
+    return p;
+  }
+  // what gorilla_plot_orbit_integration does after a push that did not end the time step (:585-638)
+  GB_HD void events_after_push(double vpar_in, const PushOut &o, EvState &es)
+  {
+    es.n = 0;
+    if ((es.flags & 6) && !removed) {   // par_adiab_inv_tetra_poly (:3173-3291)
+      const double a44 = A.s, b4 = b[3], vpar_end = o.vpar;
+      const double v1 = z0_list[0][3], v2 = z0_list[1][3], tau1 = tau_list[0], tau2 = tau_list[1];
+      if ((vpar_end > 0.0) && (vpar_in < 0.0)) {
+        // turning_index = findloc(z0(4,1:nsteps) > 0) - 1, "not found" -> nsteps (index 0 cannot happen: z0(4,1) = vpar_in < 0)
+        const bool turn2 = (nsteps >= 2) && !(v2 > 0.0);   // the bounce lies in the second integration step
+        const double v_turn = turn2 ? v2 : v1, tau_turn = turn2 ? tau2 : tau1;
+        const double tau_part1 = tau_vpar_root(a44, b4, v_turn);
+        if (turn2) es.J = es.J + par_adiab_tau(a44, b4, tau1, v1) * dt_dtau_const;
+        es.J = es.J + par_adiab_tau(a44, b4, tau_part1, v_turn) * dt_dtau_const;
+        if (es.cnt_v > 1 && (es.cnt_v / es.nskip_v * es.nskip_v == es.cnt_v)) {
+          double z[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) z[i] = turn2 ? z0_list[1][i] : z0_list[0][i];
+          set_integration_coef_manually(z);
+          // analytic_integration_external (:3378-3408) = the arithmetic of integrate(); the step lists are not needed
+          // any more (v1, v2, tau1, tau2 were read above), so its book-keeping is harmless
+          const int keep = nsteps;
+          integrate<K>(z, tau_part1);
+          nsteps = keep;
+          EvRec &e = es.e[es.n++];
+          e.kind = 2;
+          e.counter = es.cnt_v;
+#pragma unroll
+          for (int i = 0; i < 3; i++) e.x[i] = z[i] + r.x1s(i);
+          e.v[0] = es.J;
+          e.v[1] = energy_tot(z);
+        }
+        es.cnt_v = es.cnt_v + 1;
+        es.J = 0.0;
+        es.J = es.J + par_adiab_tau(a44, b4, tau_turn - tau_part1, 0.0) * dt_dtau_const;
+        if (!turn2 && nsteps >= 2) es.J = es.J + par_adiab_tau(a44, b4, tau2, v2) * dt_dtau_const;
+      } else {
+        if (nsteps >= 1) es.J = es.J + par_adiab_tau(a44, b4, tau1, v1) * dt_dtau_const;
+        if (nsteps >= 2) es.J = es.J + par_adiab_tau(a44, b4, tau2, v2) * dt_dtau_const;
+      }
+    }
+    if (iper_phi != 0) {   // toroidal mappings (:601-636)
+      es.cnt_p = es.cnt_p + iper_phi;
+      if ((es.flags & 1) && (es.cnt_p / es.nskip_p * es.nskip_p == es.cnt_p)) {
+        const double zv[4] = {o.z_save[0], o.z_save[1], o.z_save[2], o.vpar};
+        EvRec &e = es.e[es.n++];
+        e.kind = 1;
+        e.counter = es.cnt_p;
+#pragma unroll
+        for (int i = 0; i < 3; i++) e.x[i] = o.x[i];
+        e.v[0] = p_phi(o.vpar, o.z_save);
+        e.v[1] = energy_tot(zv);
+      }
+    }
   }
 
   // all four normal distances (:2690-2705); static indexing keeps r.an in registers
@@ -810,6 +943,7 @@ struct PolyPusher {
     ind_out = r.nb(f);
     iface_out = topo_face(flags, f);
     const int iper_phi = topo_perphi(flags, f);
+    if (EXT == 2) const_cast<PolyPusher *>(this)->iper_phi = iper_phi;
     if (mp->coord_system == 1) {
       if (iper_phi == 1) x[1] = x[1] - mp->period_phi;
       else if (iper_phi == -1) x[1] = x[1] + mp->period_phi;
@@ -824,6 +958,7 @@ struct PolyPusher {
 
   GB_HD void set_removed(PushOut &o) const
   {
+    if (EXT == 2) const_cast<PolyPusher *>(this)->removed = true;
     o.ind_tetr = -1;
     o.iface = -1;
     o.finished = 0;
@@ -840,7 +975,7 @@ struct PolyPusher {
 #pragma unroll
     for (int i = 0; i < 3; i++) o.x[i] = z[i] + r.x1s(i);
     o.vpar = z[3];
-    const bool tt2 = EXT && (mp->time_tracing == 2);
+    const bool tt2 = (EXT == 1) || (EXT == 2 && mp->time_tracing == 2);
     double thl[2] = {0.0, 0.0};
     double t_pass;
     if (tt2) t_pass = ham_total(thl);
@@ -1070,11 +1205,11 @@ struct PolyPusher {
 };
 
 // Non-inlined complete push: by-value in, by-value out, so that no hot-loop variable has its address taken.
-template <int K, int PHI>
+template <int K, int PHI, int EXT = 0>
 GB_HD_NOINLINE PushOut push_full_call(const MeshDev *mp, double perpinv, int ind_tetr, int iface, double x0,
                                       double x1, double x2, double vpar, double t_remain)
 {
-  PolyPusher<K, PHI> P;
+  PolyPusher<K, PHI, EXT> P;
   double stash[6];
   P.mp = mp;
   P.perpinv = perpinv;
@@ -1088,16 +1223,18 @@ GB_HD_NOINLINE PushOut push_full_call(const MeshDev *mp, double perpinv, int ind
   return o;
 }
 
-// EXT variant: the push result plus the optional quantities of the push
+// EXT = 2: the push result plus the optional quantities of the push
 struct PushOutX {
   PushOut o;
   double oq[4];
+  EvState es;
 };
 template <int K, int PHI>
 GB_HD_NOINLINE PushOutX push_full_call_x(const MeshDev *mp, double perpinv, int ind_tetr, int iface, double x0, double x1,
-                                         double x2, double vpar, double t_remain, unsigned oq_mask)
+                                         double x2, double vpar, double t_remain, unsigned oq_mask, int ev_flags,
+                                         int nskip_p, int nskip_v, double J, int cnt_v, int cnt_p)
 {
-  PolyPusher<K, PHI, true> P;
+  PolyPusher<K, PHI, 2> P;
   double stash[6];
   P.mp = mp;
   P.perpinv = perpinv;
@@ -1113,6 +1250,9 @@ GB_HD_NOINLINE PushOutX push_full_call_x(const MeshDev *mp, double perpinv, int 
   // a removed particle returns before the optional quantities are formed (:435-441): P.oq is still zero then
 #pragma unroll
   for (int q = 0; q < 4; q++) ox.oq[q] = P.oq[q];
+  ox.es.flags = ev_flags; ox.es.nskip_p = nskip_p; ox.es.nskip_v = nskip_v;
+  ox.es.J = J; ox.es.cnt_v = cnt_v; ox.es.cnt_p = cnt_p; ox.es.n = 0;
+  if (K >= 2 && ev_flags && !o.finished) P.events_after_push(vpar, o, ox.es);
   return ox;
 }
 

@@ -362,26 +362,38 @@ GB_EXTERN_ORBIT(1)
 GB_EXTERN_ORBIT(2)
 GB_EXTERN_ORBIT(3)
 GB_EXTERN_ORBIT(4)
-// EXT variants (Hamiltonian time tracing / optional quantities): gb_orbit_k{1..4}x.cu
-#define GB_EXTERN_ORBIT_X(K) \
-  extern template int launch_orbit_t<K, 0, true>(gorilla_b200_handle *, const Batch &, cudaStream_t); \
-  extern template int launch_orbit_t<K, 1, true>(gorilla_b200_handle *, const Batch &, cudaStream_t); \
-  extern template int launch_orbit_t<K, 2, true>(gorilla_b200_handle *, const Batch &, cudaStream_t);
-GB_EXTERN_ORBIT_X(1)
-GB_EXTERN_ORBIT_X(2)
-GB_EXTERN_ORBIT_X(3)
-GB_EXTERN_ORBIT_X(4)
+// EXT variants: Hamiltonian time tracing (EXT = 1, gb_orbit_k{1..4}t.cu), + optional quantities (EXT = 2, gb_orbit_k{1..4}x.cu)
+#define GB_EXTERN_ORBIT_X(K, E) \
+  extern template int launch_orbit_t<K, 0, E>(gorilla_b200_handle *, const Batch &, cudaStream_t); \
+  extern template int launch_orbit_t<K, 1, E>(gorilla_b200_handle *, const Batch &, cudaStream_t); \
+  extern template int launch_orbit_t<K, 2, E>(gorilla_b200_handle *, const Batch &, cudaStream_t);
+GB_EXTERN_ORBIT_X(1, 1)
+GB_EXTERN_ORBIT_X(2, 1)
+GB_EXTERN_ORBIT_X(3, 1)
+GB_EXTERN_ORBIT_X(4, 1)
+GB_EXTERN_ORBIT_X(1, 2)
+GB_EXTERN_ORBIT_X(2, 2)
+GB_EXTERN_ORBIT_X(3, 2)
+GB_EXTERN_ORBIT_X(4, 2)
 
 template <int PHI>
 static int launch_orbit_k(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
 {
   if (h->settings.ipusher == 1) return launch_orbit_t<0, PHI>(h, bt, s);
-  if (h->mesh.time_tracing == 2 || (bt.optq && bt.oq_mask)) {
+  if ((bt.optq && bt.oq_mask) || bt.ev_flags) {
     switch (h->settings.poly_order) {
-      case 1: return launch_orbit_t<1, PHI, true>(h, bt, s);
-      case 2: return launch_orbit_t<2, PHI, true>(h, bt, s);
-      case 3: return launch_orbit_t<3, PHI, true>(h, bt, s);
-      default: return launch_orbit_t<4, PHI, true>(h, bt, s);
+      case 1: return launch_orbit_t<1, PHI, 2>(h, bt, s);
+      case 2: return launch_orbit_t<2, PHI, 2>(h, bt, s);
+      case 3: return launch_orbit_t<3, PHI, 2>(h, bt, s);
+      default: return launch_orbit_t<4, PHI, 2>(h, bt, s);
+    }
+  }
+  if (h->mesh.time_tracing == 2) {
+    switch (h->settings.poly_order) {
+      case 1: return launch_orbit_t<1, PHI, 1>(h, bt, s);
+      case 2: return launch_orbit_t<2, PHI, 1>(h, bt, s);
+      case 3: return launch_orbit_t<3, PHI, 1>(h, bt, s);
+      default: return launch_orbit_t<4, PHI, 1>(h, bt, s);
     }
   }
   switch (h->settings.poly_order) {
@@ -454,6 +466,121 @@ extern "C" int gorilla_b200_orbit_timestep_optional_dev(gorilla_b200_handle *h, 
   bt.ind_tetr = ind_tetr; bt.iface = iface; bt.t_remain_out = t_remain_out; bt.n_pushes = n_pushes;
   bt.optq = optional_quantities;
   return run_device(h, bt, true, (cudaStream_t)stream);
+}
+
+static int check_event_args(gorilla_b200_handle *h, const gorilla_event_settings *cfg, int &flags)
+{
+  if (h->settings.ipusher != 2 || h->settings.poly_order < 2)
+    return fail(GORILLA_ERR_UNSUPPORTED, "orbit events need the polynomial pusher of order 2..4 (par_adiab_inv_poly_mod)");
+  flags = (cfg->boole_poincare_phi_0 ? 1 : 0) | (cfg->boole_poincare_vpar_0 ? 2 : 0) | (cfg->boole_J_par ? 4 : 0);
+  if ((flags & 1) && cfg->n_skip_phi_0 < 1) return fail(GORILLA_ERR_ARG, "n_skip_phi_0 must be >= 1");
+  if ((flags & 6) && cfg->n_skip_vpar_0 < 1) return fail(GORILLA_ERR_ARG, "n_skip_vpar_0 must be >= 1");
+  if (!flags) return fail(GORILLA_ERR_ARG, "no event kind switched on");
+  return GORILLA_OK;
+}
+extern "C" int gorilla_b200_orbit_timestep_events_dev(gorilla_b200_handle *h, int64_t n, double *x, double *vpar,
+                                                      double *vperp, double t_step, int32_t *boole_initialized,
+                                                      int32_t *ind_tetr, int32_t *iface, double *t_remain_out,
+                                                      int64_t *n_pushes, const gorilla_event_settings *cfg,
+                                                      double *par_adiab_inv, int32_t *counter_vpar_0,
+                                                      int32_t *counter_phi_0, gorilla_event *events, int64_t event_cap,
+                                                      uint64_t *n_events, void *stream)
+{
+  if (!h || !cfg || n < 0 || event_cap < 0 || !n_events || (event_cap > 0 && !events) ||
+      (n > 0 && (!x || !vpar || !vperp || !boole_initialized || !ind_tetr || !iface || !par_adiab_inv || !counter_vpar_0 ||
+                 !counter_phi_0)))
+    return fail(GORILLA_ERR_ARG, "gorilla_b200_orbit_timestep_events_dev: null argument");
+  int flags = 0;
+  int rc = check_event_args(h, cfg, flags);
+  if (rc) return rc;
+  Batch bt{};
+  bt.n = n; bt.x = x; bt.vpar = vpar; bt.vperp = vperp; bt.t_step = t_step; bt.init = boole_initialized;
+  bt.ind_tetr = ind_tetr; bt.iface = iface; bt.t_remain_out = t_remain_out; bt.n_pushes = n_pushes;
+  bt.ev_flags = flags; bt.n_skip_phi_0 = cfg->n_skip_phi_0 > 0 ? cfg->n_skip_phi_0 : 1;
+  bt.n_skip_vpar_0 = cfg->n_skip_vpar_0 > 0 ? cfg->n_skip_vpar_0 : 1;
+  bt.par_adiab_inv = par_adiab_inv; bt.counter_vpar_0 = counter_vpar_0; bt.counter_phi_0 = counter_phi_0;
+  bt.events = events; bt.ev_cap = event_cap; bt.ev_count = (unsigned long long *)n_events;
+  return run_device(h, bt, true, (cudaStream_t)stream);
+}
+
+extern "C" int gorilla_b200_orbit_timestep_events(gorilla_b200_handle *h, int64_t n, double *x, double *vpar, double *vperp,
+                                                  double t_step, int32_t *boole_initialized, int32_t *ind_tetr,
+                                                  int32_t *iface, double *t_remain_out, int64_t *n_pushes,
+                                                  const gorilla_event_settings *cfg, double *par_adiab_inv,
+                                                  int32_t *counter_vpar_0, int32_t *counter_phi_0, gorilla_event *events,
+                                                  int64_t event_cap, int64_t *n_events)
+{
+  if (!h || !cfg || n < 0 || event_cap < 0 || !n_events || (event_cap > 0 && !events) ||
+      (n > 0 && (!x || !vpar || !vperp || !boole_initialized || !ind_tetr || !iface || !par_adiab_inv || !counter_vpar_0 ||
+                 !counter_phi_0)))
+    return fail(GORILLA_ERR_ARG, "gorilla_b200_orbit_timestep_events: null argument");
+  int flags = 0;
+  int rc = check_event_args(h, cfg, flags);
+  if (rc) return rc;
+  *n_events = 0;
+  if (n == 0) return GORILLA_OK;
+  cudaStream_t s = nullptr;
+  double *d_x = nullptr, *d_vpar = nullptr, *d_vperp = nullptr, *d_tro = nullptr, *d_J = nullptr;
+  int32_t *d_init = nullptr, *d_ind = nullptr, *d_ifc = nullptr, *d_cv = nullptr, *d_cp = nullptr;
+  int64_t *d_np = nullptr;
+  gorilla_event *d_ev = nullptr;
+  uint64_t *d_nev = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_x); cudaFree(d_vpar); cudaFree(d_vperp); cudaFree(d_tro); cudaFree(d_J); cudaFree(d_init); cudaFree(d_ind);
+    cudaFree(d_ifc); cudaFree(d_cv); cudaFree(d_cp); cudaFree(d_np); cudaFree(d_ev); cudaFree(d_nev);
+  };
+#define GB_EV(call)                                                                                       \
+  do {                                                                                                    \
+    cudaError_t e__ = (call);                                                                             \
+    if (e__ != cudaSuccess) {                                                                             \
+      g_last_error = std::string("gorilla_b200_orbit_timestep_events: ") + cudaGetErrorString(e__);       \
+      cleanup();                                                                                          \
+      return GORILLA_ERR_CUDA;                                                                            \
+    }                                                                                                     \
+  } while (0)
+  const size_t nd = (size_t)n * sizeof(double), ni = (size_t)n * sizeof(int32_t);
+  GB_EV(cudaMalloc((void **)&d_x, 3 * nd)); GB_EV(cudaMalloc((void **)&d_vpar, nd)); GB_EV(cudaMalloc((void **)&d_vperp, nd));
+  GB_EV(cudaMalloc((void **)&d_tro, nd)); GB_EV(cudaMalloc((void **)&d_J, nd)); GB_EV(cudaMalloc((void **)&d_init, ni));
+  GB_EV(cudaMalloc((void **)&d_ind, ni)); GB_EV(cudaMalloc((void **)&d_ifc, ni)); GB_EV(cudaMalloc((void **)&d_cv, ni));
+  GB_EV(cudaMalloc((void **)&d_cp, ni)); GB_EV(cudaMalloc((void **)&d_np, (size_t)n * sizeof(int64_t)));
+  GB_EV(cudaMalloc((void **)&d_ev, (size_t)(event_cap > 0 ? event_cap : 1) * sizeof(gorilla_event)));
+  GB_EV(cudaMalloc((void **)&d_nev, sizeof(uint64_t)));
+  GB_EV(cudaMemcpyAsync(d_x, x, 3 * nd, cudaMemcpyHostToDevice, s));
+  GB_EV(cudaMemcpyAsync(d_vpar, vpar, nd, cudaMemcpyHostToDevice, s));
+  GB_EV(cudaMemcpyAsync(d_vperp, vperp, nd, cudaMemcpyHostToDevice, s));
+  GB_EV(cudaMemcpyAsync(d_J, par_adiab_inv, nd, cudaMemcpyHostToDevice, s));
+  GB_EV(cudaMemcpyAsync(d_init, boole_initialized, ni, cudaMemcpyHostToDevice, s));
+  GB_EV(cudaMemcpyAsync(d_ind, ind_tetr, ni, cudaMemcpyHostToDevice, s));
+  GB_EV(cudaMemcpyAsync(d_ifc, iface, ni, cudaMemcpyHostToDevice, s));
+  GB_EV(cudaMemcpyAsync(d_cv, counter_vpar_0, ni, cudaMemcpyHostToDevice, s));
+  GB_EV(cudaMemcpyAsync(d_cp, counter_phi_0, ni, cudaMemcpyHostToDevice, s));
+  GB_EV(cudaMemsetAsync(d_nev, 0, sizeof(uint64_t), s));
+  rc = gorilla_b200_orbit_timestep_events_dev(h, n, d_x, d_vpar, d_vperp, t_step, d_init, d_ind, d_ifc, d_tro, d_np, cfg, d_J,
+                                              d_cv, d_cp, d_ev, event_cap, d_nev, s);
+  if (rc) { cleanup(); return rc; }
+  uint64_t nev = 0;
+  GB_EV(cudaMemcpyAsync(&nev, d_nev, sizeof(nev), cudaMemcpyDeviceToHost, s));
+  GB_EV(cudaMemcpyAsync(x, d_x, 3 * nd, cudaMemcpyDeviceToHost, s));
+  GB_EV(cudaMemcpyAsync(vpar, d_vpar, nd, cudaMemcpyDeviceToHost, s));
+  GB_EV(cudaMemcpyAsync(vperp, d_vperp, nd, cudaMemcpyDeviceToHost, s));
+  GB_EV(cudaMemcpyAsync(par_adiab_inv, d_J, nd, cudaMemcpyDeviceToHost, s));
+  GB_EV(cudaMemcpyAsync(boole_initialized, d_init, ni, cudaMemcpyDeviceToHost, s));
+  GB_EV(cudaMemcpyAsync(ind_tetr, d_ind, ni, cudaMemcpyDeviceToHost, s));
+  GB_EV(cudaMemcpyAsync(iface, d_ifc, ni, cudaMemcpyDeviceToHost, s));
+  GB_EV(cudaMemcpyAsync(counter_vpar_0, d_cv, ni, cudaMemcpyDeviceToHost, s));
+  GB_EV(cudaMemcpyAsync(counter_phi_0, d_cp, ni, cudaMemcpyDeviceToHost, s));
+  if (t_remain_out) GB_EV(cudaMemcpyAsync(t_remain_out, d_tro, nd, cudaMemcpyDeviceToHost, s));
+  if (n_pushes) GB_EV(cudaMemcpyAsync(n_pushes, d_np, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  GB_EV(cudaStreamSynchronize(s));
+  const int64_t stored = (int64_t)nev < event_cap ? (int64_t)nev : event_cap;
+  if (stored > 0) GB_EV(cudaMemcpy(events, d_ev, (size_t)stored * sizeof(gorilla_event), cudaMemcpyDeviceToHost));
+  *n_events = (int64_t)nev;
+  unsigned long long dom = 0;
+  GB_EV(cudaMemcpy(&dom, h->d_ctr + CTR_DOMAIN, sizeof(dom), cudaMemcpyDeviceToHost));
+#undef GB_EV
+  cleanup();
+  if (dom) return fail(GORILLA_ERR_DOMAIN, "particle start position outside the computation domain");
+  return GORILLA_OK;
 }
 
 static int ensure_scratch(gorilla_b200_handle *h, int64_t n)

@@ -152,6 +152,43 @@ int gorilla_b200_orbit_timestep_optional_dev(gorilla_b200_handle *h, int64_t n, 
                                              int32_t *iface, double *t_remain_out, int64_t *n_pushes,
                                              double *optional_quantities, void *stream);
 
+/* ---- orbit events: J_par / banana tips / toroidal mappings ---------------------------------------------
+ * The event capture of gorilla_plot_orbit_integration (gorilla_plot_mod.f90:433-658: after every push that does not end
+ * the time step, par_adiab_inv_tetra_poly :585-596 and the phi = 0 mappings :601-638) with module par_adiab_inv_poly_mod
+ * (pusher_tetra_poly.f90:3156-3429), as a device-side event buffer instead of the reference's text files
+ * (poincare_plot_phi_0 / poincare_plot_vpar_0 / J_par / e_tot / p_phi, gorilla_plot.inp). */
+enum { GORILLA_EVENT_PHI_0 = 1, GORILLA_EVENT_VPAR_0 = 2 };
+typedef struct gorilla_event {
+  int64_t particle;  /* index into the batch */
+  int32_t kind;      /* GORILLA_EVENT_PHI_0: toroidal mapping, value = { p_phi_func, energy_tot_func };
+                        GORILLA_EVENT_VPAR_0: banana tip (v_par = 0), value = { J_par of the completed bounce, energy_tot_func } */
+  int32_t counter;   /* counter_phi_0_mappings resp. counter_banana_mappings at the event */
+  int64_t push;      /* index of the push within this call (0-based) */
+  double x[3];       /* the position the reference writes to poincare_plot_phi_0_* / poincare_plot_vpar_0_* */
+  double value[2];
+} gorilla_event;
+typedef struct gorilla_event_settings { /* namelist GORILLA_PLOT_NML (gorilla_plot_mod.f90) */
+  int32_t boole_poincare_phi_0, n_skip_phi_0;
+  int32_t boole_poincare_vpar_0, boole_J_par, n_skip_vpar_0;
+  int32_t reserved[3];
+} gorilla_event_settings;
+/* As gorilla_b200_orbit_timestep, with event capture.  par_adiab_inv / counter_vpar_0 / counter_phi_0 are HOST [n]
+ * in/out arrays holding the per-particle state of par_adiab_inv_poly_mod and of the mapping counters between calls (zero
+ * them before the first call).  events: HOST buffer of event_cap records, filled in no particular order (sort by
+ * particle, push); *n_events returns the number of events that occurred, which may exceed event_cap (the surplus is
+ * dropped).  Polynomial pusher of order 2..4 only (par_adiab_tau, pusher_tetra_poly.f90:3302-3320, has no other case). */
+int gorilla_b200_orbit_timestep_events(gorilla_b200_handle *h, int64_t n, double *x, double *vpar, double *vperp,
+                                       double t_step, int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface,
+                                       double *t_remain_out, int64_t *n_pushes, const gorilla_event_settings *cfg,
+                                       double *par_adiab_inv, int32_t *counter_vpar_0, int32_t *counter_phi_0,
+                                       gorilla_event *events, int64_t event_cap, int64_t *n_events);
+/* Same with DEVICE pointers (n_events: DEVICE uint64 counter, zeroed by the caller) on `stream`, no synchronisation. */
+int gorilla_b200_orbit_timestep_events_dev(gorilla_b200_handle *h, int64_t n, double *x, double *vpar, double *vperp,
+                                           double t_step, int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface,
+                                           double *t_remain_out, int64_t *n_pushes, const gorilla_event_settings *cfg,
+                                           double *par_adiab_inv, int32_t *counter_vpar_0, int32_t *counter_phi_0,
+                                           gorilla_event *events, int64_t event_cap, uint64_t *n_events, void *stream);
+
 /* check_coordinate_domain + find_tetra(x,vpar,vperp,ind_tetr,iface,sign_t_step)
  * (orbit_timestep_gorilla.f90:278-358, find_tetra_mod.f90:283-600); HOST pointers. x may be modified
  * (periodic relocation, start points lying on a face). */

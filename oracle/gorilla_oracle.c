@@ -732,6 +732,7 @@ typedef struct {
   int number_of_integration_steps;
   /* tau_steps_list / intermediate_z0_list (:36-38); non-adaptive scheme: two entries (:98-104) */
   double tau_steps_list[2], intermediate_z0_list[2][4];
+  bool removed; /* the push ended on one of the 'remove particle' returns */
   gor_trace *tr;
 } poly_state;
 static const double eps_tau = 100.0;
@@ -1381,6 +1382,7 @@ static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout
   int iface_new, i_scaling = 0;
 
   initialize_pusher_tetra_poly(s, *ind_tetr_inout, x, *iface, *vpar, t_remain_in);
+  s->removed = false;
   s->number_of_integration_steps = 0;
   memcpy(z, s->z_init, sizeof(z));
   *iper_phi = 0;
@@ -1417,6 +1419,7 @@ static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout
           if (!boole_analytical_approx) {
             *ind_tetr_inout = -1;
             *iface = -1;
+        s->removed = true;
             return;
           }
         }
@@ -1438,6 +1441,7 @@ static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout
     if (!boole_analytical_approx) {
       *ind_tetr_inout = -1;
       *iface = -1;
+        s->removed = true;
       return;
     }
     analytic_integration(s, poly_order, z, tau);
@@ -1451,6 +1455,7 @@ static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout
         if (!boole_analytical_approx) {
           *ind_tetr_inout = -1;
           *iface = -1;
+        s->removed = true;
           return;
         }
       }
@@ -1461,6 +1466,7 @@ static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout
       if (!boole_trouble_shooting) {
         *ind_tetr_inout = -1;
         *iface = -1;
+        s->removed = true;
         return;
       }
     }
@@ -1528,6 +1534,7 @@ static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout
       if (!boole_trouble_shooting) {
         *ind_tetr_inout = -1;
         *iface = -1;
+        s->removed = true;
         return;
       }
       for (int i = 0; i < 3; i++) x[i] = z[i] + s->r[TP_X1 + i];
@@ -1555,6 +1562,128 @@ static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout
     const int nst = s->number_of_integration_steps;
     for (int i = 1; i <= nst; i++)
       calc_optional_quantities(s, poly_order, s->intermediate_z0_list[i - 1], s->tau_steps_list[i - 1], optq);
+  }
+}
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Orbit events: parallel adiabatic invariant J_par / banana tips (v_par = 0) and toroidal (phi = 0) mappings.
+ * module par_adiab_inv_poly_mod, SRC/pusher_tetra_poly.f90:3156-3429, and the event part of
+ * gorilla_plot_orbit_integration, SRC/gorilla_plot_mod.f90:433-658.  Events go to a buffer instead of files.
+ * Integer powers as libgcc __powidf2 forms them (see above): a**3 = a*(a*a), a**4 = (a*a)*(a*a), x**5 = x*((x*x)*(x*x)).
+ * ---------------------------------------------------------------------------------------------- */
+/* :3295-3322 (no case(1) in the reference: undefined for poly_order = 1, refused by the driver below) */
+static double par_adiab_tau(int poly_order, double a44, double b4, double tau, double vpar_in)
+{
+  const double t2 = tau * tau, v2 = vpar_in * vpar_in, a2 = a44 * a44, bb = b4 * b4;
+  const double a3 = a44 * a2, t3 = tau * t2, t4 = t2 * t2;
+  double r = tau * v2 + 0.5 * t2 * (2.0 * b4 * vpar_in + 2.0 * a44 * v2);
+  if (poly_order == 4) /* (sic) 2.d0*a44*2.d0*vpar_in**2 at :3316 */
+    r = r + 1.0 / 3.0 * t3 * (bb + 3.0 * a44 * b4 * vpar_in + 2.0 * a44 * 2.0 * v2);
+  else
+    r = r + 1.0 / 3.0 * t3 * (bb + 3.0 * a44 * b4 * vpar_in + 2.0 * a2 * v2);
+  if (poly_order >= 3) r = r + 1.0 / 4.0 * t4 * (a44 * bb + 7.0 / 3.0 * a2 * b4 * vpar_in + (4.0 * a3 * v2) / 3.0);
+  if (poly_order >= 4) {
+    const double a4 = a2 * a2, t5 = tau * t4;
+    r = r + 1.0 / 60.0 * t5 * (7.0 * a2 * bb + 15.0 * a3 * b4 * vpar_in + 8.0 * a4 * v2);
+  }
+  return r;
+}
+/* :3326-3374 */
+static double tau_vpar_root(int poly_order, double a44, double b4, double vpar_in, gor_trace *tr)
+{
+  const double a2 = a44 * a44, a3 = a44 * a2, a4 = a2 * a2;
+  double c1 = vpar_in, c2 = b4 + a44 * vpar_in, c3 = a44 * b4 + a2 * vpar_in, c4 = 0.0, c5 = 0.0;
+  if (poly_order >= 3) c4 = a2 * b4 + a3 * vpar_in;
+  if (poly_order >= 4) c5 = a3 * b4 + a4 * vpar_in;
+  switch (poly_order) {
+    case 2: return Quadratic_Solver2(c3, c2, c1, tr);
+    case 3: return Cubic_Solver(c4, c3, c2, c1, tr);
+    default: return Quartic_Solver(0, c5, c4, c3, c2, c1, tr);
+  }
+}
+typedef struct {
+  const gor_event_settings *cfg;
+  double par_adiab_inv;
+  int32_t counter_banana_mappings, counter_phi_0_mappings;
+  int64_t particle, push;
+  gor_event *events;
+  int64_t cap, n_events;
+} event_state;
+static void emit_event(event_state *es, int kind, int counter, const double x[3], double v0, double v1)
+{
+  if (es->n_events < es->cap) {
+    gor_event *e = &es->events[es->n_events];
+    e->particle = es->particle;
+    e->kind = kind;
+    e->counter = counter;
+    e->push = es->push;
+    for (int i = 0; i < 3; i++) e->x[i] = x[i];
+    e->value[0] = v0;
+    e->value[1] = v1;
+  }
+  es->n_events++;
+}
+/* par_adiab_inv_tetra_poly :3173-3291 (uses the pusher's module state after the push) */
+static void par_adiab_inv_tetra_poly(poly_state *s, int poly_order, double vpar_in, double vpar_end, event_state *es)
+{
+  const double a44 = s->amat[3][3], b4 = s->b[3];
+  const int nst = s->number_of_integration_steps;
+  if ((vpar_end > 0.0) && (vpar_in < 0.0)) {
+    int turning_index = -1; /* findloc(intermediate_z0_list(4,1:n) > 0) - 1 */
+    for (int i = 1; i <= nst; i++)
+      if (s->intermediate_z0_list[i - 1][3] > 0.0) {
+        turning_index = i - 1;
+        break;
+      }
+    if (turning_index == 0) return; /* reference: error stop (cannot happen: z0(4,1) = vpar_in < 0) */
+    if (turning_index == -1) turning_index = nst;
+    const double tau_part1 = tau_vpar_root(poly_order, a44, b4, s->intermediate_z0_list[turning_index - 1][3], s->tr);
+    for (int i = 1; i <= turning_index - 1; i++)
+      es->par_adiab_inv = es->par_adiab_inv +
+                          par_adiab_tau(poly_order, a44, b4, s->tau_steps_list[i - 1], s->intermediate_z0_list[i - 1][3]) * s->dt_dtau_const;
+    es->par_adiab_inv = es->par_adiab_inv +
+                        par_adiab_tau(poly_order, a44, b4, tau_part1, s->intermediate_z0_list[turning_index - 1][3]) * s->dt_dtau_const;
+    if (es->counter_banana_mappings > 1) {
+      const int nskip = es->cfg->n_skip_vpar_0;
+      if (es->counter_banana_mappings / nskip * nskip == es->counter_banana_mappings) {
+        double z[4], x[3];
+        memcpy(z, s->intermediate_z0_list[turning_index - 1], sizeof(z));
+        set_integration_coef_manually(s, poly_order, z);
+        { /* analytic_integration_external :3378-3408 */
+          const double tau = tau_part1;
+          if (poly_order >= 1)
+            for (int i = 0; i < 4; i++) z[i] = z[i] + tau * (s->b[i] + s->amat_in_z[i]);
+          if (poly_order >= 2) {
+            double tau2_half = tau * tau * 0.5;
+            for (int i = 0; i < 4; i++) z[i] = z[i] + tau2_half * (s->amat_in_b[i] + s->amat2_in_z[i]);
+          }
+          if (poly_order >= 3) {
+            double tau3_sixth = (tau * tau) * tau / 6.0;
+            for (int i = 0; i < 4; i++) z[i] = z[i] + tau3_sixth * (s->amat2_in_b[i] + s->amat3_in_z[i]);
+          }
+          if (poly_order >= 4) {
+            double t2 = tau * tau;
+            double tau4_twentyfourth = (t2 * t2) / 24.0;
+            for (int i = 0; i < 4; i++) z[i] = z[i] + tau4_twentyfourth * (s->amat3_in_b[i] + s->amat4_in_z[i]);
+          }
+        }
+        for (int i = 0; i < 3; i++) x[i] = z[i] + s->r[TP_X1 + i];
+        emit_event(es, GOR_EVENT_VPAR_0, es->counter_banana_mappings, x, es->par_adiab_inv,
+                   gor_energy_tot(s->m, z, s->perpinv, s->ind_tetr));
+      }
+    }
+    es->counter_banana_mappings = es->counter_banana_mappings + 1;
+    es->par_adiab_inv = 0.0;
+    es->par_adiab_inv = es->par_adiab_inv +
+                        par_adiab_tau(poly_order, a44, b4, s->tau_steps_list[turning_index - 1] - tau_part1, 0.0) * s->dt_dtau_const;
+    for (int i = turning_index + 1; i <= nst; i++)
+      es->par_adiab_inv = es->par_adiab_inv +
+                          par_adiab_tau(poly_order, a44, b4, s->tau_steps_list[i - 1], s->intermediate_z0_list[i - 1][3]) * s->dt_dtau_const;
+  } else {
+    for (int i = 1; i <= nst; i++)
+      es->par_adiab_inv = es->par_adiab_inv +
+                          par_adiab_tau(poly_order, a44, b4, s->tau_steps_list[i - 1], s->intermediate_z0_list[i - 1][3]) * s->dt_dtau_const;
   }
 }
 
@@ -2547,9 +2676,46 @@ int gor_check_coordinate_domain(const gor_mesh *m, double x[3])
 }
 
 /* SRC/orbit_timestep_gorilla.f90:19-147 (ipusher = 2) */
+static int orbit_timestep_core(const gor_mesh *m, double x[3], double *vpar, double *vperp, double t_step,
+                               int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface, double *t_remain_out,
+                               gor_trace *tr, event_state *es);
 int gor_orbit_timestep(const gor_mesh *m, double x[3], double *vpar, double *vperp, double t_step,
                        int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface, double *t_remain_out,
                        gor_trace *tr)
+{
+  return orbit_timestep_core(m, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface, t_remain_out, tr, NULL);
+}
+/* orbit_timestep_gorilla with the event capture of gorilla_plot_orbit_integration (gorilla_plot_mod.f90:520-638):
+ * after every push that does not end the time step, J_par / banana tips (:585-596) and toroidal mappings (:601-638). */
+int gor_orbit_timestep_events(const gor_mesh *m, double x[3], double *vpar, double *vperp, double t_step,
+                              int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface, double *t_remain_out,
+                              gor_trace *tr, const gor_event_settings *cfg, double *par_adiab_inv,
+                              int32_t *counter_vpar_0, int32_t *counter_phi_0, int64_t particle, gor_event *events,
+                              int64_t cap, int64_t *n_events)
+{
+  if (m->ipusher != 2 || m->poly_order < 2) return GOR_ERR_CONFIG; /* polynomial orders 2..4 (par_adiab_tau :3302-3320) */
+  if ((cfg->boole_J_par || cfg->boole_poincare_vpar_0) && cfg->n_skip_vpar_0 < 1) return GOR_ERR_CONFIG;
+  if (cfg->boole_poincare_phi_0 && cfg->n_skip_phi_0 < 1) return GOR_ERR_CONFIG;
+  event_state es;
+  es.cfg = cfg;
+  es.par_adiab_inv = *par_adiab_inv;
+  es.counter_banana_mappings = *counter_vpar_0;
+  es.counter_phi_0_mappings = *counter_phi_0;
+  es.particle = particle;
+  es.push = 0;
+  es.events = events;
+  es.cap = cap;
+  es.n_events = *n_events;
+  int rc = orbit_timestep_core(m, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface, t_remain_out, tr, &es);
+  *par_adiab_inv = es.par_adiab_inv;
+  *counter_vpar_0 = es.counter_banana_mappings;
+  *counter_phi_0 = es.counter_phi_0_mappings;
+  *n_events = es.n_events;
+  return rc;
+}
+static int orbit_timestep_core(const gor_mesh *m, double x[3], double *vpar, double *vperp, double t_step,
+                               int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface, double *t_remain_out,
+                               gor_trace *tr, event_state *es)
 {
   if (m->ipusher != 2 && m->ipusher != 1) return GOR_ERR_CONFIG;
   if (!*boole_initialized) {
@@ -2593,6 +2759,7 @@ int gor_orbit_timestep(const gor_mesh *m, double x[3], double *vpar, double *vpe
       break;
     }
     ind_tetr_save = *ind_tetr;
+    const double vpar_save = *vpar;
     int it = *ind_tetr, ifc = *iface;
     if (m->ipusher == 1)
       pusher_tetra_rk(&rk, &it, &ifc, x, vpar, z_save, t_remain, &t_pass, &boole_t_finished, &iper, tr);
@@ -2616,6 +2783,23 @@ int gor_orbit_timestep(const gor_mesh *m, double x[3], double *vpar, double *vpe
     if (boole_t_finished) {
       if (t_remain_out) *t_remain_out = t_remain;
       break;
+    }
+    if (es) { /* gorilla_plot_mod.f90:585-638 */
+      /* a removed particle (unrecoverable push) is skipped: the reference would evaluate J_par on stale module state */
+      if ((es->cfg->boole_J_par || es->cfg->boole_poincare_vpar_0) && !s.removed)
+        par_adiab_inv_tetra_poly(&s, m->poly_order, vpar_save, *vpar, es);
+      if (iper != 0) {
+        es->counter_phi_0_mappings = es->counter_phi_0_mappings + iper;
+        if (es->cfg->boole_poincare_phi_0) {
+          const int nskip = es->cfg->n_skip_phi_0;
+          if (es->counter_phi_0_mappings / nskip * nskip == es->counter_phi_0_mappings) {
+            double zv[4] = {z_save[0], z_save[1], z_save[2], *vpar};
+            emit_event(es, GOR_EVENT_PHI_0, es->counter_phi_0_mappings, x, gor_p_phi(m, *vpar, z_save, ind_tetr_save),
+                       gor_energy_tot(m, zv, s.perpinv, ind_tetr_save));
+          }
+        }
+      }
+      es->push++;
     }
   }
   *vperp = vperp_func(m, z_save, s.perpinv, ind_tetr_save);

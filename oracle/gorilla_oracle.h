@@ -87,6 +87,20 @@ typedef struct {
   double optional_quantities[4];
 } gor_trace;
 
+/* orbit events (gorilla_plot_mod.f90:585-638, par_adiab_inv_poly_mod pusher_tetra_poly.f90:3156-3429) */
+enum { GOR_EVENT_PHI_0 = 1, GOR_EVENT_VPAR_0 = 2 };
+typedef struct {
+  int64_t particle;   /* index given by the caller */
+  int32_t kind;       /* GOR_EVENT_PHI_0: toroidal mapping, value = {p_phi, e_tot}; GOR_EVENT_VPAR_0: banana tip, value = {J_par, e_tot} */
+  int32_t counter;    /* counter_phi_0_mappings / counter_banana_mappings at the event */
+  int64_t push;       /* index of the push within this call (0-based) */
+  double x[3];        /* position written to poincare_plot_phi_0 / poincare_plot_vpar_0 */
+  double value[2];
+} gor_event;
+typedef struct {
+  int32_t boole_poincare_phi_0, n_skip_phi_0, boole_poincare_vpar_0, boole_J_par, n_skip_vpar_0;
+} gor_event_settings;
+
 /* return codes */
 enum { GOR_OK = 0, GOR_ERR_DOMAIN = 1, GOR_ERR_CONFIG = 2 };
 
@@ -96,6 +110,11 @@ void gor_find_tetra(const gor_mesh *m, double x[3], double vpar, double vperp,
 int gor_orbit_timestep(const gor_mesh *m, double x[3], double *vpar, double *vperp, double t_step,
                        int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface,
                        double *t_remain_out, gor_trace *trace);
+int gor_orbit_timestep_events(const gor_mesh *m, double x[3], double *vpar, double *vperp, double t_step,
+                              int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface, double *t_remain_out,
+                              gor_trace *trace, const gor_event_settings *cfg, double *par_adiab_inv /* inout */,
+                              int32_t *counter_vpar_0 /* inout */, int32_t *counter_phi_0 /* inout */, int64_t particle,
+                              gor_event *events, int64_t cap, int64_t *n_events /* inout: events so far (may exceed cap) */);
 /* OpenMP batch driver used as the CPU baseline ("one particle per thread", README.md:181) */
 int64_t gor_orbit_timestep_batch(const gor_mesh *m, int64_t n, double *x /*[n][3]*/, double *vpar,
                                  double *vperp, double t_step, int32_t *boole_initialized,

@@ -21,10 +21,32 @@ struct HostMirror {
   unsigned oq_mask;
 };
 
-template <int K, int PHI, bool EXT = false>
+// orbit events of one particle (mirrors the Batch event fields + emit_events of gb_internal.cuh)
+struct HmEvents {
+  int flags, nskip_p, nskip_v;
+  double *J;
+  int32_t *cnt_v, *cnt_p;
+  gorilla_event *events;
+  int64_t cap, *n_events, particle;
+};
+static void hm_emit(HmEvents *ev, int64_t push, const EvState &es)
+{
+  for (int k = 0; k < es.n; k++) {
+    const int64_t slot = (*ev->n_events)++;
+    if (slot < ev->cap) {
+      gorilla_event *e = ev->events + slot;
+      e->particle = ev->particle; e->kind = es.e[k].kind; e->counter = es.e[k].counter; e->push = push;
+      for (int i = 0; i < 3; i++) e->x[i] = es.e[k].x[i];
+      e->value[0] = es.e[k].v[0]; e->value[1] = es.e[k].v[1];
+    }
+  }
+}
+
+template <int K, int PHI, int EXT = 0>
 static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *vperp_io, double t_step, int32_t *ind_io,
                          int32_t *iface_io, double *t_remain_out, int64_t *npush_out, int trace_cap, int32_t *tr_t,
-                         int32_t *tr_f, int force_full, int64_t *fallback, unsigned oq_mask = 0, double *optq = nullptr)
+                         int32_t *tr_f, int force_full, int64_t *fallback, unsigned oq_mask = 0, double *optq = nullptr,
+                         HmEvents *ev = nullptr)
 {
   double oq_acc[4] = {0.0, 0.0, 0.0, 0.0};
   int32_t ind_tetr = *ind_io, iface = *iface_io;
@@ -56,18 +78,34 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
         P.r.set_stash(stash, 1);
         P.mp = &m;
         P.perpinv = perpinv;
-        if (EXT) P.oq_mask = oq_mask;
+        if (EXT == 2) P.oq_mask = oq_mask;
         done = P.push_fast(ind_tetr, iface, x, vpar, t_remain, o);
-        if (EXT && done && oq_mask)
+        if (EXT == 2 && done && oq_mask)
           for (int q = 0; q < 4; q++) oq_acc[q] = oq_acc[q] + P.oq[q];
+        if constexpr (EXT == 2 && K >= 2) {
+          if (done && ev && !o.finished) {
+            EvState es;
+            es.flags = ev->flags; es.nskip_p = ev->nskip_p; es.nskip_v = ev->nskip_v;
+            es.J = *ev->J; es.cnt_v = *ev->cnt_v; es.cnt_p = *ev->cnt_p;
+            P.events_after_push(vpar, o, es);
+            *ev->J = es.J; *ev->cnt_v = es.cnt_v; *ev->cnt_p = es.cnt_p;
+            if (es.n) hm_emit(ev, npush, es);
+          }
+        }
       }
       if (!done) {
-        if constexpr (EXT) {
-          const PushOutX ox = push_full_call_x<K, PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain, oq_mask);
+        if constexpr (EXT == 2) {
+          const PushOutX ox = push_full_call_x<K, PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain, oq_mask,
+                                                       ev ? ev->flags : 0, ev ? ev->nskip_p : 1, ev ? ev->nskip_v : 1,
+                                                       ev ? *ev->J : 0.0, ev ? *ev->cnt_v : 0, ev ? *ev->cnt_p : 0);
           o = ox.o;
           for (int q = 0; q < 4; q++) oq_acc[q] = oq_acc[q] + ox.oq[q];
+          if (ev) {
+            *ev->J = ox.es.J; *ev->cnt_v = ox.es.cnt_v; *ev->cnt_p = ox.es.cnt_p;
+            if (ox.es.n) hm_emit(ev, npush, ox.es);
+          }
         } else {
-          o = push_full_call<K, PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
+          o = push_full_call<K, PHI, EXT>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
         }
       }
     }
@@ -160,10 +198,21 @@ int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *v
     int32_t *tt = trace_cap > 0 ? tr_t + i * trace_cap : nullptr, *tf = trace_cap > 0 ? tr_f + i * trace_cap : nullptr;
 #define HM_RUN(K, PHI) run_particle<K, PHI>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
       t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, trace_cap, tt, tf, force_full, fallback)
-#define HM_RUNX(K, PHI) run_particle<K, PHI, true>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
+#define HM_RUNX(K, PHI) run_particle<K, PHI, 2>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
       t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, trace_cap, tt, tf, force_full, fallback, \
       optq ? h->oq_mask : 0u, optq ? optq + 4 * i : nullptr)
-    if (h->ipusher == 2 && (m.time_tracing == 2 || (optq && h->oq_mask))) {   // same dispatch as launch_orbit_k
+#define HM_RUNT(K, PHI) run_particle<K, PHI, 1>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
+      t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, trace_cap, tt, tf, force_full, fallback)
+    if (h->ipusher == 2 && m.time_tracing == 2 && !(optq && h->oq_mask)) {   // same dispatch as launch_orbit_k
+      if (m.se) {
+        switch (h->poly_order) { case 1: HM_RUNT(1, 2); break; case 2: HM_RUNT(2, 2); break; case 3: HM_RUNT(3, 2); break; default: HM_RUNT(4, 2); }
+      } else if (m.phi) {
+        switch (h->poly_order) { case 1: HM_RUNT(1, 1); break; case 2: HM_RUNT(2, 1); break; case 3: HM_RUNT(3, 1); break; default: HM_RUNT(4, 1); }
+      } else {
+        switch (h->poly_order) { case 1: HM_RUNT(1, 0); break; case 2: HM_RUNT(2, 0); break; case 3: HM_RUNT(3, 0); break; default: HM_RUNT(4, 0); }
+      }
+    } else
+    if (h->ipusher == 2 && optq && h->oq_mask) {
       if (m.se) {
         switch (h->poly_order) { case 1: HM_RUNX(1, 2); break; case 2: HM_RUNX(2, 2); break; case 3: HM_RUNX(3, 2); break; default: HM_RUNX(4, 2); }
       } else if (m.phi) {
@@ -181,6 +230,49 @@ int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *v
     }
   }
   return dom;
+}
+
+// same contract as gorilla_b200_orbit_timestep_events (particles must be localised already); returns 0 or -1 (bad config)
+int64_t hm_orbit_timestep_events(void *p, int64_t n, double *x, double *vpar, double *vperp, double t_step, int32_t *binit,
+                                 int32_t *ind_tetr, int32_t *iface, double *t_remain_out, int64_t *n_pushes, int flags,
+                                 int nskip_p, int nskip_v, double *J, int32_t *cnt_v, int32_t *cnt_p, gorilla_event *events,
+                                 int64_t cap, int64_t *n_events, int force_full)
+{
+  HostMirror *h = (HostMirror *)p;
+  const MeshDev &m = h->m;
+  if (h->ipusher != 2 || h->poly_order < 2) return -1;
+  const int sign_t = signbit(t_step) ? -1 : 1;
+  int64_t fallback[4] = {0, 0, 0, 0};
+  *n_events = 0;
+  for (int64_t i = 0; i < n; i++) {
+    double *xi = x + 3 * i;
+    if (!binit[i]) {
+      int32_t it = -1, ifc = -1;
+      if (check_coordinate_domain(m, xi, h->boole_periodic_relocation) == 0) {
+        if (m.se) find_tetra<2>(&m, xi, vpar[i], vperp[i], it, ifc, sign_t);
+        else if (m.phi) find_tetra<1>(&m, xi, vpar[i], vperp[i], it, ifc, sign_t);
+        else find_tetra<0>(&m, xi, vpar[i], vperp[i], it, ifc, sign_t);
+      }
+      ind_tetr[i] = it; iface[i] = ifc;
+      if (it != -1) binit[i] = 1;
+    }
+    if (n_pushes) n_pushes[i] = 0;
+    if (t_remain_out) t_remain_out[i] = t_step;
+    if (!binit[i] || ind_tetr[i] < 1) continue;
+    if (t_step == 0.0) { if (t_remain_out) t_remain_out[i] = 0.0; continue; }
+    HmEvents ev = {flags, nskip_p, nskip_v, J + i, cnt_v + i, cnt_p + i, events, cap, n_events, i};
+#define HM_RUNE(K, PHI) run_particle<K, PHI, 2>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
+      t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, 0, nullptr, nullptr, force_full, fallback, \
+      0u, nullptr, &ev)
+    if (m.se) {
+      switch (h->poly_order) { case 2: HM_RUNE(2, 2); break; case 3: HM_RUNE(3, 2); break; default: HM_RUNE(4, 2); }
+    } else if (m.phi) {
+      switch (h->poly_order) { case 2: HM_RUNE(2, 1); break; case 3: HM_RUNE(3, 1); break; default: HM_RUNE(4, 1); }
+    } else {
+      switch (h->poly_order) { case 2: HM_RUNE(2, 0); break; case 3: HM_RUNE(3, 0); break; default: HM_RUNE(4, 0); }
+    }
+  }
+  return 0;
 }
 
 // device math / solver entry points for bit-level pinning against glibc and the oracle

@@ -34,6 +34,20 @@ class GorTrace(C.Structure):
                 ("n_solver_calls", C.c_int64), ("optional_quantities", C.c_double * 4)]
 
 
+class GorEvent(C.Structure):
+    _fields_ = [("particle", C.c_int64), ("kind", C.c_int32), ("counter", C.c_int32), ("push", C.c_int64),
+                ("x", C.c_double * 3), ("value", C.c_double * 2)]
+
+
+class GorEventSettings(C.Structure):
+    _fields_ = [("boole_poincare_phi_0", C.c_int32), ("n_skip_phi_0", C.c_int32), ("boole_poincare_vpar_0", C.c_int32),
+                ("boole_J_par", C.c_int32), ("n_skip_vpar_0", C.c_int32)]
+
+
+EVENT_DTYPE = np.dtype([("particle", np.int64), ("kind", np.int32), ("counter", np.int32), ("push", np.int64),
+                        ("x", np.float64, 3), ("value", np.float64, 2)])
+
+
 def build_oracle(force: bool = False) -> Path:
     if force or not ORACLE_LIB.exists() or ORACLE_LIB.stat().st_mtime < max(
             (ORACLE_DIR / "gorilla_oracle.c").stat().st_mtime, (ORACLE_DIR / "gorilla_oracle.h").stat().st_mtime):
@@ -58,6 +72,9 @@ def load_oracle():
                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                    C.c_void_p, C.c_int]
         L.gor_orbit_timestep_batch_opt.restype = C.c_int64
+        L.gor_orbit_timestep_events.argtypes = [C.POINTER(GorMesh), dp, dp, dp, d, i32p, i32p, i32p, dp, C.POINTER(GorTrace),
+                                                C.POINTER(GorEventSettings), dp, i32p, i32p, C.c_int64, C.c_void_p,
+                                                C.c_int64, C.POINTER(C.c_int64)]
         L.gor_find_tetra.argtypes = [C.POINTER(GorMesh), dp, d, d, i32p, i32p, C.c_int]
         L.gor_find_tetra.restype = None
         L.gor_check_coordinate_domain.argtypes = [C.POINTER(GorMesh), dp]
@@ -146,6 +163,29 @@ class OracleMesh:
             calls += tr.n_solver_calls
         return dict(trace_tetr=tt, trace_face=tf, n_pushes=npush, t_remain=tro, fallback=fb, solver_iters=iters,
                     solver_calls=calls, optional_quantities=optq)
+
+    def orbit_timestep_events(self, x, vpar, vperp, t_step, binit, ind_tetr, iface, par_adiab_inv, counter_vpar_0,
+                              counter_phi_0, cap, poincare_phi_0=True, n_skip_phi_0=1, poincare_vpar_0=True, J_par=True,
+                              n_skip_vpar_0=1):
+        """Per-particle orbit_timestep with event capture; returns (events[:min(n_events, cap)], n_events, n_pushes)."""
+        n = x.shape[0]
+        cfg = GorEventSettings(int(poincare_phi_0), n_skip_phi_0, int(poincare_vpar_0), int(J_par), n_skip_vpar_0)
+        ev = np.zeros(cap, EVENT_DTYPE)
+        nev = C.c_int64(0)
+        npush = np.zeros(n, np.int64)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        for i in range(n):
+            tr = GorTrace()
+            t_out = C.c_double(0.0)
+            rc = self.L.gor_orbit_timestep_events(
+                C.byref(self.c), x[i].ctypes.data_as(dp), vpar[i:i + 1].ctypes.data_as(dp),
+                vperp[i:i + 1].ctypes.data_as(dp), float(t_step), binit[i:i + 1].ctypes.data_as(ip),
+                ind_tetr[i:i + 1].ctypes.data_as(ip), iface[i:i + 1].ctypes.data_as(ip), C.byref(t_out), C.byref(tr),
+                C.byref(cfg), par_adiab_inv[i:i + 1].ctypes.data_as(dp), counter_vpar_0[i:i + 1].ctypes.data_as(ip),
+                counter_phi_0[i:i + 1].ctypes.data_as(ip), i, ev.ctypes.data_as(C.c_void_p), cap, C.byref(nev))
+            assert rc == 0, rc
+            npush[i] = tr.n_pushes
+        return ev[:min(nev.value, cap)], nev.value, npush
 
     def find_tetra(self, x, vpar, vperp, sign_t_step=1):
         n = x.shape[0]

@@ -1,0 +1,206 @@
+"""Orbit events: toroidal (phi = 0) mappings and banana tips / parallel adiabatic invariant J_par as
+the reference's plotting driver captures them -- gorilla_plot_orbit_integration, gorilla_plot_mod.f90:433-658 (events
+:585-638), module par_adiab_inv_poly_mod, pusher_tetra_poly.f90:3156-3429 -- written to an event buffer instead of files.
+
+CPU: oracle physics + oracle <-> host compile of the device headers, bit for bit.  GPU: C ABI <-> oracle, bit for bit."""
+import numpy as np
+import pytest
+
+import workloads
+from gorilla_b200 import api
+from host_mirror_binding import HostMirror
+from oracle_binding import OracleMesh
+
+
+def _with(settings, **kw):
+    return type(settings)(**{**settings.__dict__, **kw})
+
+
+def _sorted(ev):
+    return ev[np.lexsort((ev["kind"], ev["push"], ev["particle"]))]
+
+
+def _state(n):
+    return np.zeros(n), np.zeros(n, np.int32), np.zeros(n, np.int32)
+
+
+@pytest.mark.parametrize("K", [3, 4])
+def test_j_par_is_conserved_and_mappings_count_toroidal_turns(small_mesh, K):
+    """Trapped deuterons in the axisymmetric test field: J_par of successive complete bounces agrees to the accuracy of the
+    polynomial order; passing particles produce one mapping per toroidal turn, with the sign of the direction."""
+    mesh, _, settings = small_mesh
+    om = OracleMesh(mesh, _with(settings, poly_order=K))
+    n = 60
+    x, vpar, vperp = workloads.particles_cyl(n, 1)
+    v0 = vpar.copy()
+    st = workloads.fresh_state(n)
+    J, cv, cp = _state(n)
+    ev, nev, npush = om.orbit_timestep_events(x, vpar, vperp, 1.2e-3, *st, J, cv, cp, 200000)
+    assert nev == len(ev) and nev > 300
+    tips = ev[ev["kind"] == 2]
+    assert len(tips) > 40
+    checked = 0
+    for p in np.unique(tips["particle"]):
+        j = tips["value"][tips["particle"] == p, 0]
+        if len(j) >= 3:
+            assert np.ptp(j) / np.abs(j).mean() < 2e-4        # J_par of complete bounces
+            e = tips["value"][tips["particle"] == p, 1]
+            assert np.ptp(e) / np.abs(e).mean() < 1e-9       # total energy at the tips
+            checked += 1
+    assert checked >= 5
+    # banana tips: counters are consecutive from 2 (the first two bounces are not reported, :3240), v_par changes sign there
+    for p in np.unique(tips["particle"]):
+        c = tips["counter"][tips["particle"] == p]
+        assert c[0] == 2 and np.all(np.diff(c) == 1) and cv[p] == c[-1] + 1
+    maps = ev[ev["kind"] == 1]
+    passing = [p for p in range(n) if cv[p] == 0 and st[1][p] > 0]
+    assert len(passing) > 10
+    orient = set()
+    for p in passing:
+        c = maps["counter"][maps["particle"] == p]
+        assert len(c) == abs(cp[p]) and np.all(np.abs(np.diff(c)) == 1)
+        if cp[p] != 0:
+            orient.add(int(np.sign(cp[p]) * np.sign(v0[p])))
+    assert len(orient) == 1            # co- and counter-passing particles map in opposite directions
+    # the mapping position is the hand-over point: phi sits on the period boundary (0 after the periodic shift, or 2 pi)
+    ph = maps["x"][:, 1]
+    assert np.all((np.abs(ph) < 1e-9) | (np.abs(ph - 2 * np.pi) < 1e-9))
+
+
+def test_skip_counters_and_switches(small_mesh):
+    mesh, _, settings = small_mesh
+    om = OracleMesh(mesh, _with(settings, poly_order=2))
+    n = 30
+    out = {}
+    for key, kw in (("all", {}), ("skip", dict(n_skip_phi_0=3, n_skip_vpar_0=2)), ("phi_only", dict(poincare_vpar_0=False, J_par=False)),
+                    ("vpar_only", dict(poincare_phi_0=False))):
+        x, vpar, vperp = workloads.particles_cyl(n, 2)
+        st = workloads.fresh_state(n)
+        J, cv, cp = _state(n)
+        ev, nev, _ = om.orbit_timestep_events(x, vpar, vperp, 8e-4, *st, J, cv, cp, 100000, **kw)
+        out[key] = (_sorted(ev), cv.copy(), cp.copy(), x.copy())
+    ev_all = out["all"][0]
+    sk = out["skip"][0]
+    want = ev_all[((ev_all["kind"] == 1) & (ev_all["counter"] % 3 == 0)) | ((ev_all["kind"] == 2) & (ev_all["counter"] % 2 == 0))]
+    assert np.array_equal(sk, want)
+    assert np.array_equal(out["phi_only"][0], ev_all[ev_all["kind"] == 1]) and np.all(out["phi_only"][1] == 0)
+    assert np.array_equal(out["vpar_only"][0], ev_all[ev_all["kind"] == 2])
+    assert np.array_equal(out["vpar_only"][2], out["all"][2])          # the toroidal counter runs regardless (:601-605)
+    for k in out:
+        assert np.array_equal(out[k][3], out["all"][3])                # capturing events never changes the orbit
+
+
+@pytest.mark.parametrize("K", [2, 3, 4])
+@pytest.mark.parametrize("force_full", [False, True])
+def test_host_mirror_parity(small_mesh, K, force_full):
+    mesh, _, settings = small_mesh
+    st = _with(settings, poly_order=K)
+    om, hm = OracleMesh(mesh, st), HostMirror(mesh, st)
+    n = 40
+    xa, va, wa = workloads.particles_cyl(n, 5)
+    xb, vb, wb = xa.copy(), va.copy(), wa.copy()
+    sa, sb = workloads.fresh_state(n), workloads.fresh_state(n)
+    Ja, cva, cpa = _state(n)
+    Jb, cvb, cpb = _state(n)
+    for _ in range(2):   # state carried across two calls
+        eva, nea, npa = om.orbit_timestep_events(xa, va, wa, 5e-4, *sa, Ja, cva, cpa, 100000, n_skip_phi_0=2)
+        evb, neb, npb = hm.orbit_timestep_events(xb, vb, wb, 5e-4, *sb, Jb, cvb, cpb, 100000, n_skip_phi_0=2,
+                                                 force_full=force_full)
+        assert nea == neb and np.array_equal(eva, evb)
+        assert np.array_equal(Ja, Jb) and np.array_equal(cva, cvb) and np.array_equal(cpa, cpb)
+        assert np.array_equal(xa, xb) and np.array_equal(va, vb) and np.array_equal(wa, wb) and np.array_equal(npa, npb)
+    assert (eva["kind"] == 2).sum() > 10 and (eva["kind"] == 1).sum() > 50
+
+
+def test_host_mirror_parity_strong_field_and_backward_time(product_lib):
+    from gorilla_b200 import build_mesh
+    grid, settings = workloads.analytic_tokamak(14, 14, 14)
+    settings.eps_Phi = -1.5e-5
+    settings.boole_strong_electric_field = True
+    mesh = build_mesh(grid, settings)
+    st = _with(settings, poly_order=2)
+    om, hm = OracleMesh(mesh, st), HostMirror(mesh, st)
+    n = 30
+    for t_step in (4e-4, -4e-4):
+        xa, va, wa = workloads.particles_cyl(n, 6)
+        xb, vb, wb = xa.copy(), va.copy(), wa.copy()
+        sa, sb = workloads.fresh_state(n), workloads.fresh_state(n)
+        Ja, cva, cpa = _state(n)
+        Jb, cvb, cpb = _state(n)
+        eva, nea, _ = om.orbit_timestep_events(xa, va, wa, t_step, *sa, Ja, cva, cpa, 100000)
+        evb, neb, _ = hm.orbit_timestep_events(xb, vb, wb, t_step, *sb, Jb, cvb, cpb, 100000)
+        assert nea == neb and nea > 50 and np.array_equal(eva, evb)
+        assert np.array_equal(Ja, Jb) and np.array_equal(cva, cvb) and np.array_equal(cpa, cpb) and np.array_equal(xa, xb)
+
+
+def test_refused_configurations(product_lib, small_mesh):
+    mesh, _, settings = small_mesh
+    om = OracleMesh(mesh, _with(settings, poly_order=1))
+    x, vpar, vperp = workloads.particles_cyl(2, 1)
+    st = workloads.fresh_state(2)
+    J, cv, cp = _state(2)
+    with pytest.raises(AssertionError):     # GOR_ERR_CONFIG: par_adiab_tau has no case(1)
+        om.orbit_timestep_events(x, vpar, vperp, 1e-5, *st, J, cv, cp, 10)
+
+
+# ---------------------------------------------------------------------------------------------- GPU
+def _gpu_pair(mesh, settings, n, seed, t_step, ncalls=2, cap=400000, use_group=True, **kw):
+    from gorilla_b200 import Gorilla
+    om, g = OracleMesh(mesh, settings), Gorilla(mesh, settings)
+    g._debug_use_group(use_group)
+    xa, va, wa = workloads.particles_cyl(n, seed)
+    xb, vb, wb = xa.copy(), va.copy(), wa.copy()
+    sa, sb = workloads.fresh_state(n), workloads.fresh_state(n)
+    Ja, cva, cpa = _state(n)
+    Jb, cvb, cpb = _state(n)
+    total = 0
+    for _ in range(ncalls):
+        eva, nea, npa = om.orbit_timestep_events(xa, va, wa, t_step, *sa, Ja, cva, cpa, cap, **kw)
+        npb = np.zeros(n, np.int64)
+        evb, neb = g.orbit_timestep_gorilla_events(
+            xb, vb, wb, t_step, *sb, Jb, cvb, cpb, cap, n_pushes=npb,
+            **{("boole_" + k if k in ("poincare_phi_0", "poincare_vpar_0", "J_par") else k): v for k, v in kw.items()})
+        assert nea == neb, "number of events differs"
+        assert np.array_equal(_sorted(eva), evb), "events differ"
+        assert np.array_equal(Ja, Jb) and np.array_equal(cva, cvb) and np.array_equal(cpa, cpb)
+        assert np.array_equal(xa, xb) and np.array_equal(va, vb) and np.array_equal(wa, wb) and np.array_equal(npa, npb)
+        assert np.array_equal(sa[1], sb[1]) and np.array_equal(sa[2], sb[2])
+        total += nea
+    g.close()
+    return total, eva
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [2, 3, 4])
+def test_gpu_parity(small_mesh, cuda_device, K):
+    mesh, _, settings = small_mesh
+    total, ev = _gpu_pair(mesh, _with(settings, poly_order=K), 160, 5, 5e-4, n_skip_phi_0=2)
+    assert total > 1000 and (ev["kind"] == 2).sum() > 30
+    if K >= 3:
+        _gpu_pair(mesh, _with(settings, poly_order=K), 64, 7, 3e-4, ncalls=1, use_group=False)
+
+
+@pytest.mark.gpu
+def test_gpu_parity_with_hamiltonian_time_and_phi(small_mesh_phi, cuda_device):
+    mesh, _, settings = small_mesh_phi
+    _gpu_pair(mesh, _with(settings, poly_order=2, i_time_tracing_option=2), 128, 9, 4e-4)
+
+
+@pytest.mark.gpu
+def test_gpu_event_buffer_overflow_and_refusals(small_mesh, cuda_device):
+    from gorilla_b200 import Gorilla
+    mesh, _, settings = small_mesh
+    g = Gorilla(mesh, _with(settings, poly_order=2))
+    n = 200
+    x, vpar, vperp = workloads.particles_cyl(n, 3)
+    st = workloads.fresh_state(n)
+    J, cv, cp = _state(n)
+    ev, nev = g.orbit_timestep_gorilla_events(x, vpar, vperp, 4e-4, *st, J, cv, cp, 64)
+    assert nev > 64 and len(ev) == 64 and np.all(ev["kind"] > 0)       # surplus dropped, count still complete
+    assert nev >= np.abs(cp).sum() * 0 + (cv.clip(2) - 2).sum()        # at least the reported banana tips
+    g.close()
+    for bad in (_with(settings, poly_order=1), _with(settings, ipusher=1)):
+        gb = Gorilla(mesh, bad)
+        with pytest.raises(api.GorillaError):
+            gb.orbit_timestep_gorilla_events(x, vpar, vperp, 1e-5, *workloads.fresh_state(n), *_state(n), 10)
+        gb.close()

@@ -16,7 +16,7 @@ module orbit_timestep_gorilla_b200_mod
   implicit none
   private
   public :: initialize_gorilla_b200, finalize_gorilla_b200, orbit_timestep_gorilla, orbit_timestep_gorilla_batch, &
-            find_tetra_batch, gorilla_b200_counters_t, get_counters_b200
+            orbit_timestep_gorilla_batch_optional, find_tetra_batch, gorilla_b200_counters_t, get_counters_b200
 
   !> struct gorilla_settings (include/gorilla_b200.h)
   type, bind(C) :: gorilla_settings_t
@@ -24,8 +24,9 @@ module orbit_timestep_gorilla_b200_mod
     integer(c_int32_t) :: coord_system, ispecies, boole_periodic_relocation, ipusher, boole_pusher_ode45, &
                           boole_dt_dtau, boole_newton_precalc, poly_order, i_precomp, boole_guess, &
                           i_time_tracing_option, handover_processing_kind, boole_adaptive_time_steps, &
-                          boole_strong_electric_field, boole_grid_for_find_tetra
-    integer(c_int32_t) :: reserved(5)
+                          boole_strong_electric_field, boole_grid_for_find_tetra, &
+                          boole_time_Hamiltonian, boole_gyrophase, boole_vpar_int, boole_vpar2_int
+    integer(c_int32_t) :: reserved(1)
   end type
   !> struct gorilla_mesh_desc
   type, bind(C) :: gorilla_mesh_desc_t
@@ -111,6 +112,8 @@ contains
     st%boole_adaptive_time_steps = merge(1, 0, boole_adaptive_time_steps)
     st%boole_strong_electric_field = merge(1, 0, boole_strong_electric_field)
     st%boole_grid_for_find_tetra = merge(1, 0, boole_grid_for_find_tetra); st%reserved = 0
+    st%boole_time_Hamiltonian = merge(1, 0, boole_time_Hamiltonian); st%boole_gyrophase = merge(1, 0, boole_gyrophase)
+    st%boole_vpar_int = merge(1, 0, boole_vpar_int); st%boole_vpar2_int = merge(1, 0, boole_vpar2_int)
     rc = gorilla_b200_init(md, st, handle)
     if (present(ierr)) then
       ierr = rc
@@ -143,6 +146,39 @@ contains
     if (present(t_remain_out)) p_tro = c_loc(t_remain_out(1))
     ierr = gorilla_b200_orbit_timestep(handle, int(n, c_int64_t), x, vpar, vperp, t_step, binit, ind_tetr, iface, &
                                        p_tro, c_null_ptr)
+    boole_initialized = binit /= 0
+  end subroutine
+
+  !> Batch call that also returns pusher_tetra_poly's optional quantities, summed over the pushes of the time step:
+  !> optional_quantities(1:4,i) = t_hamiltonian, gyrophase, vpar_int, vpar2_int (type optional_quantities_type,
+  !> gorilla_settings_mod.f90:9-15), for the quantities switched on in gorilla.inp.
+  subroutine orbit_timestep_gorilla_batch_optional(n, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface, &
+                                                   optional_quantities, ierr)
+    integer, intent(in)                      :: n
+    double precision, intent(inout), target  :: x(3,n), vpar(n), vperp(n)
+    double precision, intent(in)             :: t_step
+    logical, intent(inout)                   :: boole_initialized(n)
+    integer, intent(inout)                   :: ind_tetr(n), iface(n)
+    double precision, intent(out)            :: optional_quantities(4,n)
+    integer, intent(out)                     :: ierr
+    integer(c_int32_t), allocatable :: binit(:)
+    interface
+      integer(c_int) function gorilla_b200_orbit_timestep_optional(handle, n, x, vpar, vperp, t_step, boole_initialized, &
+                     ind_tetr, iface, t_remain_out, n_pushes, optional_quantities) &
+                     bind(C, name='gorilla_b200_orbit_timestep_optional')
+        import :: c_int, c_ptr, c_int64_t, c_double, c_int32_t
+        type(c_ptr), value :: handle
+        integer(c_int64_t), value :: n
+        real(c_double) :: x(3,*), vpar(*), vperp(*), optional_quantities(4,*)
+        real(c_double), value :: t_step
+        integer(c_int32_t) :: boole_initialized(*), ind_tetr(*), iface(*)
+        type(c_ptr), value :: t_remain_out, n_pushes
+      end function
+    end interface
+    allocate(binit(n))
+    binit = merge(1_c_int32_t, 0_c_int32_t, boole_initialized)
+    ierr = gorilla_b200_orbit_timestep_optional(handle, int(n, c_int64_t), x, vpar, vperp, t_step, binit, ind_tetr, &
+                                                iface, c_null_ptr, c_null_ptr, optional_quantities)
     boole_initialized = binit /= 0
   end subroutine
 

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """BASELINE config 3 end to end: 10^6 alphas of 3.5 MeV on the QI stellarator mesh, 100 steps of 1e-4 s (1e-2 s total).
 Prints the alpha loss fraction with its binomial error, the throughput of the whole run, and checks a sub-sample of the
-same particles against the CPU restatement (identical lost set, identical final state)."""
+same particles against the CPU restatement (identical lost set, identical final state).
+Usage: tools/config3_loss.py [particles [cpu_subsample [i_time_tracing_option]]]"""
 import json
 import sys
 import time
@@ -23,6 +24,7 @@ def main():
     n_sub = int(sys.argv[2]) if len(sys.argv) > 2 else 1500
     nsteps, t_step = 100, 1.0e-4
     grid, st = workloads.vmec_qi(str(ROOT / "data" / "equilibria" / "netcdf_file_for_test.nc"))
+    st.i_time_tracing_option = int(sys.argv[3]) if len(sys.argv) > 3 else 1
     mesh = build_mesh(grid, st)
     g = Gorilla(mesh, st)
     dev = torch.device("cuda", 0)
@@ -50,7 +52,7 @@ def main():
     inv[order] = torch.arange(n, device=dev)
     xg, vg, wg, ig = (a[inv].cpu().numpy() for a in (xd, vd, wd, it))
     p = lost_curve[-1] / n
-    out = {"particles": n, "steps": nsteps, "t_step_s": t_step, "crossings": pushes, "wall_s": wall, "kernel_s": kernel_ms * 1e-3,
+    out = {"i_time_tracing_option": st.i_time_tracing_option, "particles": n, "steps": nsteps, "t_step_s": t_step, "crossings": pushes, "wall_s": wall, "kernel_s": kernel_ms * 1e-3,
            "crossings_per_s_wall": pushes / wall, "crossings_per_s_kernel": pushes / (kernel_ms * 1e-3),
            "loss_fraction": p, "loss_fraction_sigma": float(np.sqrt(p * (1 - p) / n)),
            "lost_after_step": lost_curve[9::10]}

@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--ipusher", type=int, default=0, help="1 = RK4 pusher, 2 = polynomial pusher (0 = workload default)")
     ap.add_argument("--time-tracing", type=int, default=0, choices=[0, 1, 2],
                     help="i_time_tracing_option: 1 = dt/dtau constant per cell, 2 = Hamiltonian time (0 = workload default)")
+    ap.add_argument("--adaptive", type=float, default=0.0,
+                    help="boole_adaptive_time_steps with this desired_delta_energy (max_n_intermediate_steps = 10000)")
     ap.add_argument("--t-step", type=float, default=0.0, help="physical time per step [s] (0 = workload default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -178,6 +180,9 @@ def reference_arm(args):
         settings.ipusher = args.ipusher
     if args.time_tracing:
         settings.i_time_tracing_option = args.time_tracing
+    if args.adaptive > 0.0:
+        settings.boole_adaptive_time_steps = True
+        settings.desired_delta_energy = args.adaptive
     t_step = args.t_step or wl["t_step"]
     mesh = build_mesh(wl["grid"], settings)
     cores = os.cpu_count() or 1
@@ -226,6 +231,9 @@ def main():
         settings.ipusher = args.ipusher
     if args.time_tracing:
         settings.i_time_tracing_option = args.time_tracing
+    if args.adaptive > 0.0:
+        settings.boole_adaptive_time_steps = True
+        settings.desired_delta_energy = args.adaptive
     t_step = args.t_step or wl["t_step"]
     n = args.particles or wl["n_default"]
 
@@ -278,6 +286,7 @@ def main():
     pushes = 0
     kernel_ms = 0.0
     fallback = np.zeros(4, np.int64)
+    n_adaptive = 0
     ev0.record()
     for _ in range(args.steps):
         if args.sort:
@@ -287,6 +296,7 @@ def main():
         pushes += c.n_pushes
         kernel_ms += c.kernel_ms
         fallback += np.array(c.n_fallback)
+        n_adaptive += c.n_adaptive
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -362,7 +372,7 @@ def main():
         fp64 = {"achieved": fp64_ach / 1e12, "peak": muladd_peak / 1e12, "unit": "Tinst/s (thread-level DMUL/DADD)",
                 "frac": fp64_ach / muladd_peak, "inst_per_crossing": fp64_per, "dfma_peak": dfma_peak / 1e12,
                 "peak_source": "measured in this run (gorilla_b200_fp64_peak)"}
-        kern = f"orbit_kernel<{0 if settings.ipusher == 1 else settings.poly_order},{2 if strong else 1 if has_phi else 0}{',EXT' if ext else ''}>"
+        kern = f"orbit_kernel<{0 if settings.ipusher == 1 else settings.poly_order},{2 if strong else 1 if has_phi else 0}{',EXT=1' if ext else ',EXT=3' if settings.boole_adaptive_time_steps else ''}>"
         if t_hbm >= t_fp64:
             roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "kernel": kern,
@@ -389,6 +399,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "desc": wl["desc"], "ipusher": settings.ipusher,
                        "poly_order": settings.poly_order, "i_time_tracing_option": settings.i_time_tracing_option,
+                       "boole_adaptive_time_steps": bool(settings.boole_adaptive_time_steps),
+                       "desired_delta_energy": settings.desired_delta_energy if settings.boole_adaptive_time_steps else None,
                        "particles_per_gpu": n, "t_step_s": t_step, "ntetr": mesh.ntetr,
                        "mesh_hot_bytes": int(mesh.ntetr * (352 + (160 if has_phi else 0))),
                        "l2_policy": "inputs_larger_than_l2 (mesh hot records > 126 MB, gathered at random)",
@@ -397,7 +409,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "clocks": clocks,
             "counters": {"pushes": tot_pushes, "lost": tot_lost, "particles": tot_n,
-                         "fallback_rank0": [int(v) for v in fallback], "located_rank0": n_located,
+                         "fallback_rank0": [int(v) for v in fallback], "adaptive_pushes_rank0": int(n_adaptive), "located_rank0": n_located,
                          "find_tetra_ms_rank0": find_ms, "mesh_build_s_rank0": t_mesh},
         }
         print(json.dumps(line), flush=True)

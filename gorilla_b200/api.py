@@ -38,7 +38,7 @@ class _Settings(C.Structure):
         "boole_newton_precalc", "poly_order", "i_precomp", "boole_guess", "i_time_tracing_option",
         "handover_processing_kind", "boole_adaptive_time_steps", "boole_strong_electric_field",
         "boole_grid_for_find_tetra", "boole_time_Hamiltonian", "boole_gyrophase", "boole_vpar_int",
-        "boole_vpar2_int")] + [("reserved", C.c_int32 * 1)]
+        "boole_vpar2_int", "max_n_intermediate_steps")] + [("desired_delta_energy", C.c_double)]
 
 
 class _MeshDesc(C.Structure):
@@ -64,7 +64,7 @@ class _GridSettings(C.Structure):
 class _Counters(C.Structure):
     _fields_ = [("n_particles", C.c_int64), ("n_pushes", C.c_int64), ("n_lost", C.c_int64),
                 ("n_finished", C.c_int64), ("n_fallback", C.c_int64 * 4), ("n_domain_errors", C.c_int64),
-                ("kernel_ms", C.c_double), ("find_ms", C.c_double)]
+                ("kernel_ms", C.c_double), ("find_ms", C.c_double), ("n_adaptive", C.c_int64)]
 
 
 class _EventSettings(C.Structure):
@@ -88,6 +88,7 @@ class Counters:
     n_domain_errors: int
     kernel_ms: float
     find_ms: float
+    n_adaptive: int = 0
 
 
 # every symbol include/gorilla_b200.h declares (tests check that the library exports all of them)
@@ -167,11 +168,9 @@ def fp64_peak() -> tuple[float, float]:
 
 def _c_settings(s: GorillaSettings) -> _Settings:
     cs = _Settings()
-    for name, _ in _Settings._fields_:
-        if name == "reserved":
-            continue
+    for name, typ in _Settings._fields_:
         v = getattr(s, name)
-        setattr(cs, name, float(v) if name == "eps_Phi" else int(v))
+        setattr(cs, name, float(v) if typ is C.c_double else int(v))
     return cs
 
 
@@ -415,7 +414,7 @@ class Gorilla:
         c = _Counters()
         _check(load_library().gorilla_b200_get_counters(self._h, C.byref(c)))
         return Counters(c.n_particles, c.n_pushes, c.n_lost, c.n_finished, tuple(c.n_fallback), c.n_domain_errors,
-                        c.kernel_ms, c.find_ms)
+                        c.kernel_ms, c.find_ms, c.n_adaptive)
 
     def sort_permutation_dev(self, ind_tetr, perm, stream=None):
         _check(load_library().gorilla_b200_sort_permutation_dev(self._h, ind_tetr.shape[0],

@@ -29,7 +29,7 @@ void count_launch(int n);
 
 using namespace gb;
 
-enum { CTR_PUSHES = 0, CTR_LOST, CTR_FINISHED, CTR_FB0, CTR_FB1, CTR_FB2, CTR_FB3, CTR_DOMAIN, CTR_QUEUE, CTR_N };
+enum { CTR_PUSHES = 0, CTR_LOST, CTR_FINISHED, CTR_FB0, CTR_FB1, CTR_FB2, CTR_FB3, CTR_ADAPT, CTR_DOMAIN, CTR_QUEUE, CTR_N };
 
 struct Batch {
   int64_t n;
@@ -110,7 +110,7 @@ __device__ __forceinline__ unsigned tid_now()
   return t;
 }
 enum { LS_X0 = 0, LS_X1, LS_X2, LS_VPAR, LS_PERPINV, LS_TREM, LS_ZS0, LS_ZS1, LS_ZS2, LS_ND };
-enum { LC_LOST = 0, LC_FIN, LC_FB0, LC_FB1, LC_FB2, LC_FB3, LC_N };
+enum { LC_LOST = 0, LC_FIN, LC_FB0, LC_FB1, LC_FB2, LC_FB3, LC_ADAPT, LC_N };
 
 // per-lane accumulators of the optional quantities (EXT kernels only)
 template <bool EXT, int NT>
@@ -285,6 +285,9 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
         if (o.fallback & 2) LCNT(LC_FB1) = LCNT(LC_FB1) + 1;
         if (o.fallback & 4) LCNT(LC_FB2) = LCNT(LC_FB2) + 1;
         if (o.fallback & 8) LCNT(LC_FB3) = LCNT(LC_FB3) + 1;
+        if constexpr (EXT == 3) {
+          if (o.fallback & 16) LCNT(LC_ADAPT) = LCNT(LC_ADAPT) + 1;
+        }
       }
       const double t_remain = LS(LS_TREM) - o.t_pass;
       LS(LS_TREM) = t_remain;
@@ -320,9 +323,10 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
   }
   __syncwarp();
   // counters: warp reduce, one atomic per warp and counter
-  unsigned long long v[7] = {*p_cpush, LCNT(LC_LOST), LCNT(LC_FIN), LCNT(LC_FB0), LCNT(LC_FB1), LCNT(LC_FB2), LCNT(LC_FB3)};
+  unsigned long long v[8] = {*p_cpush, LCNT(LC_LOST), LCNT(LC_FIN), LCNT(LC_FB0), LCNT(LC_FB1), LCNT(LC_FB2), LCNT(LC_FB3),
+                             LCNT(LC_ADAPT)};
 #pragma unroll
-  for (int k = 0; k < 7; k++) {
+  for (int k = 0; k < 8; k++) {
     unsigned long long s = v[k];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
@@ -533,6 +537,9 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
         if (o.fallback & 2) LCNT(LC_FB1) = LCNT(LC_FB1) + 1;
         if (o.fallback & 4) LCNT(LC_FB2) = LCNT(LC_FB2) + 1;
         if (o.fallback & 8) LCNT(LC_FB3) = LCNT(LC_FB3) + 1;
+        if constexpr (EXT == 3) {
+          if (o.fallback & 16) LCNT(LC_ADAPT) = LCNT(LC_ADAPT) + 1;
+        }
       }
       const double t_remain = LS(LS_TREM) - o.t_pass;
       LS(LS_TREM) = t_remain;
@@ -566,9 +573,10 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
     }
   }
   __syncwarp();
-  unsigned long long v[7] = {*p_cpush, LCNT(LC_LOST), LCNT(LC_FIN), LCNT(LC_FB0), LCNT(LC_FB1), LCNT(LC_FB2), LCNT(LC_FB3)};
+  unsigned long long v[8] = {*p_cpush, LCNT(LC_LOST), LCNT(LC_FIN), LCNT(LC_FB0), LCNT(LC_FB1), LCNT(LC_FB2), LCNT(LC_FB3),
+                             LCNT(LC_ADAPT)};
 #pragma unroll
-  for (int k = 0; k < 7; k++) {
+  for (int k = 0; k < 8; k++) {
     unsigned long long sacc = v[k];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, off);

@@ -55,6 +55,8 @@ struct MeshDev {
   const double *cold;
   const double *se;   // nullptr unless boole_strong_electric_field
   const double *ham;  // hamiltonian_time records (EXT kernels only): h1_in_curlA h1_in_curlh vec_mismatch_der(3) vec_parcurr_der(3)
+  double desired_delta_energy;      // adaptive sub-stepping (EXT = 3 kernels): gorilla_settings_mod.f90:76-77
+  int32_t max_n_intermediate_steps;
   int32_t time_tracing; // i_time_tracing_option: 1 = dt/dtau constant per cell, 2 = Hamiltonian time (EXT kernels)
   double cm_over_e, particle_mass, particle_charge;
   double period_phi;   // 2*pi/n_field_periods, formed exactly as the reference does (2.d0*pi/n_field_periods)

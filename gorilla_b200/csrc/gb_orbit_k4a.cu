@@ -1,0 +1,6 @@
+// gb_orbit_k4a.cu -- EXT = 3 variant of polynomial order 4: adaptive energy-controlled sub-stepping
+// (boole_adaptive_time_steps; see gb_internal.cuh, gb_poly.cuh)
+#include "gb_internal.cuh"
+template int launch_orbit_t<4, 0, 3>(gorilla_b200_handle *, const Batch &, cudaStream_t);
+template int launch_orbit_t<4, 1, 3>(gorilla_b200_handle *, const Batch &, cudaStream_t);
+template int launch_orbit_t<4, 2, 3>(gorilla_b200_handle *, const Batch &, cudaStream_t);

@@ -69,7 +69,7 @@ struct PushOut {
   int32_t ind_tetr, iface;
   int32_t finished;  // boole_t_finished
   int32_t z_save_set;
-  int32_t fallback;  // bit0 2nd attempt, bit1 trouble shooting, bit2 prolonged, bit3 finish-outside
+  int32_t fallback;  // bit0 2nd attempt, bit1 trouble shooting, bit2 prolonged, bit3 finish-outside, bit4 adaptive sub-steps
 };
 
 // an exit-time solve that has been set up but not executed (see PolyPusher::face_task)
@@ -104,6 +104,11 @@ struct PolyPusher {
   // optional quantities of this push
   double tau_list[2], z0_list[2][4], oq[4];
   unsigned oq_mask;  // bit0 boole_time_Hamiltonian, bit1 boole_gyrophase, bit2 boole_vpar_int, bit3 boole_vpar2_int
+  double z0_last[4]; // EXT = 3: intermediate_z0_list(:, number_of_integration_steps), the only list entry the adaptive scheme reads
+  int n_adaptive;    // EXT = 3: segments re-integrated in sub-steps during this push
+  bool main_fc;      // EXT = 3: boole_face_correct of pusher_tetra_poly when the final processing starts: .false. after
+                     // the third attempt (trouble shooting keeps its own copy), which disables the sub-stepping of the
+                     // stop-inside segment (:564-568 with :893)
   int iper_phi;      // EXT = 2: toroidal period crossed by the hand-over (+1 / -1 / 0), for the phi = 0 mappings
   bool removed;      // EXT = 2: the push ended on one of the "remove particle" returns
   double dt_dtau_const, bmod0, vmod0, t_remain, z_init[4], k1, k3, dv2E;
@@ -138,6 +143,10 @@ struct PolyPusher {
       k3 = 0.0;
     }
     nsteps = 0;
+    if (EXT == 3) {
+      n_adaptive = 0;
+      main_fc = true;
+    }
     if (EXT == 2) {
       oq[0] = oq[1] = oq[2] = oq[3] = 0.0;  // initialise_optional_quantities (:2117-2130)
       iper_phi = 0;
@@ -237,20 +246,22 @@ struct PolyPusher {
   }
 
   // ---- :2087-2113 (A, b unchanged; matrix powers re-formed, which reproduces the stored ones)
-  GB_HD void set_integration_coef_manually(const double *z0)
+  GB_HD void set_integration_coef_manually(const double *z0) { set_coef<K>(z0); }
+  template <int ORD>
+  GB_HD void set_coef(const double *z0)
   {
-    if (K >= 1) bm_vec(Az, A, z0);
-    if (K >= 2) {
+    if (ORD >= 1) bm_vec(Az, A, z0);
+    if (ORD >= 2) {
       BlockMat A2;
       bm_mul(A2, A, A);
       bm_vec(A2z, A2, z0);
       bm_vec(Ab, A, b);
-      if (K >= 3) {
+      if (ORD >= 3) {
         BlockMat A3;
         bm_mul(A3, A, A2);
         bm_vec(A3z, A3, z0);
         bm_vec(A2b, A2, b);
-        if (K >= 4) {
+        if (ORD >= 4) {
           BlockMat A4;
           bm_mul(A4, A, A3);
           bm_vec(A4z, A4, z0);
@@ -429,7 +440,10 @@ struct PolyPusher {
   GB_HD void integrate(double *z, double tau)
   {
     nsteps++;
-    if (EXT) {
+    if (EXT == 3) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) z0_last[i] = z[i];
+    } else if (EXT) {
       if (nsteps == 1) {
         tau_list[0] = tau;
 #pragma unroll
@@ -739,6 +753,164 @@ struct PolyPusher {
     }
   }
 
+
+  // ==== EXT = 3: adaptive energy-controlled sub-stepping (boole_adaptive_time_steps, :830-1254) =========
+  // Only the last entry of intermediate_z0_list is read by the scheme (z0_last); the list consumers (Hamiltonian time,
+  // optional quantities, J_par) are not combined with it.  Where the reference reads uninitialised locals:
+  // eta_minimum / tau_minimum start as the unsplit step, iface_out keeps the incoming face if no exit time was solved.
+  // adaptive_time_steps_update_eta (:1167-1213); 1E-15 there is a default-real literal
+  GB_HD void update_eta(int ORD, double delta, int &eta) const
+  {
+    const double min_step_error = (double)1E-15f;
+    const int max_n = mp->max_n_intermediate_steps;
+    double sf = pow(delta / mp->desired_delta_energy, 1.0 / ORD);
+    const double msf = pow(delta / (min_step_error * eta), 1.0 / (ORD + 1));
+    if ((sf > 1.0) && (msf > 1.0)) {
+      sf = sf < msf ? sf : msf;
+      const int c = (int)ceil(eta * sf);
+      eta = c < max_n ? c : max_n;
+    } else if (sf > 1.0) {
+      const int c = (int)ceil(eta * sf);
+      eta = c < max_n ? c : max_n;
+    } else {
+      eta = (int)(eta + 1.0);
+    }
+  }
+  // adaptive_time_steps_exit_time (:1217-1252)
+  template <int ORD>
+  GB_HD bool adaptive_exit_time(int i_scaling, const double *z, bool bga, int &iface, double &tau_exit)
+  {
+    if (bga && ORD > 2) {
+      const bool ok2 = analytic_approx<2>(0xFu, i_scaling, z, iface, tau_exit);
+      const int guess = iface;
+      iface = 0;
+      if (ok2) return analytic_approx_single<ORD>(guess, i_scaling, z, iface, tau_exit, false);
+    }
+    return analytic_approx<ORD>(0xFu, i_scaling, z, iface, tau_exit);
+  }
+  GB_HD bool any_outside(const double *z) const
+  {
+    double d[4];
+    normal_distances(z, d);
+    return (d[0] < 0.0) || (d[1] < 0.0) || (d[2] < 0.0) || (d[3] < 0.0);
+  }
+  // adaptive_time_steps_equidistant (:937-1163)
+  template <int ORD>
+  GB_HD void adaptive_equidistant(int i_scaling, bool bga, bool bp, double delta, int &iface_out, double &tau, double *z,
+                                  bool &bfc)
+  {
+    const int max_n = mp->max_n_intermediate_steps;
+    double z_start[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) z_start[i] = z0_last[i];
+    const int nsteps_start = nsteps - 1;
+    const double energy_start = energy_tot(z_start);
+    int eta = 1, eta_extended = 1, eta_minimum = 1;
+    bool reached_minimum = false;
+    double delta_minimum = delta, tau_minimum = tau, tau_exit = 0.0;
+    int iface_new = iface_out;
+    n_adaptive++;
+    fallback |= 16;
+    // (the partition loop of the reference has no iteration bound and can cycle when two partitions give exactly the same
+    // energy error; it is ended after max_n + 64 partitions here and in the oracle)
+    int n_partitions = 0;
+    while (eta < max_n) {
+      if (++n_partitions > max_n + 64) break;
+      update_eta(ORD, delta, eta);
+      if (reached_minimum) {
+        eta = eta_minimum;
+        tau = tau_minimum;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) z[i] = z_start[i];
+      nsteps = nsteps_start;
+      double tau_prime = tau / eta, tau_collected = 0.0;
+      bfc = true;
+      bool exit_tetra = false;
+      const int eta_limit = bp ? (int)ceil(max_n * 1.1) : eta;
+      for (int i = 1; i <= eta_limit - 1; i++) {
+        set_coef<ORD>(z);
+        integrate<ORD>(z, tau_prime);
+        if (any_outside(z)) {
+          if (i == 1) {
+            bfc = false;
+            return;
+          }
+          // step back to the start of this sub-step (its z0 is the last list entry)
+#pragma unroll
+          for (int q = 0; q < 4; q++) z[q] = z0_last[q];
+          nsteps = nsteps - 1;
+          exit_tetra = true;
+          break;
+        }
+        tau_collected = tau_collected + tau_prime;
+        eta_extended = i;
+        if (!bga) {
+          iface_new = 0;
+          if (!adaptive_exit_time<ORD>(i_scaling, z, false, iface_new, tau_exit)) {
+            bfc = false;
+            return;
+          }
+          if (tau_exit <= tau_prime) {
+            tau_prime = tau_exit;
+            break;
+          }
+        }
+      }
+      if (exit_tetra) {
+        iface_new = 0;
+        if (!adaptive_exit_time<ORD>(i_scaling, z, bga, iface_new, tau_exit)) {
+          bfc = false;
+          return;
+        }
+        tau_prime = tau_exit;
+      } else {
+        set_coef<ORD>(z);
+      }
+      integrate<ORD>(z, tau_prime);
+      tau_collected = tau_collected + tau_prime;
+      delta = fabs(1 - energy_tot(z) / energy_start);
+      const int eta_buffer = eta;
+      const double tau_buffer = tau;
+      eta = eta_extended + 1;
+      tau = tau_collected;
+      if (reached_minimum) {
+        break;
+      } else if (delta < delta_minimum) {
+        delta_minimum = delta;
+        eta_minimum = eta_buffer;
+        tau_minimum = tau_buffer;
+        if (delta <= mp->desired_delta_energy) break;
+      } else if (delta > delta_minimum) {
+        reached_minimum = true;
+      }
+    }
+    iface_out = iface_new;
+  }
+  // the energy test of overhead_adaptive_time_steps (:896-901) for the step that was just integrated from z0_last to z
+  GB_HD double adaptive_delta_energy(const double *z) const
+  {
+    const double energy_start = energy_tot(z0_last), energy_current = energy_tot(z);
+    return fabs(1 - energy_current / energy_start);
+  }
+  // overhead_adaptive_time_steps (:830-933)
+  template <int ORD>
+  GB_HD void overhead_adaptive(int i_scaling, bool bga, bool bp, int &iface, double &tau, double *z, bool &bfc)
+  {
+    if (bp) {
+      if (!three_planes_ok(z, iface)) bfc = false;
+      if (!face_converged(z, iface)) bfc = false;
+    } else {
+      // check_three_planes(z, 0): faces modulo(0 + j - 1, 4) + 1 = 1, 2, 3 -- the fourth face is not looked at (:689-691)
+      double d[4];
+      normal_distances(z, d);
+      if (d[0] < 0.0 || d[1] < 0.0 || d[2] < 0.0) bfc = false;
+    }
+    if (!bfc) return;
+    const double delta = adaptive_delta_energy(z);
+    if (delta > mp->desired_delta_energy) adaptive_equidistant<ORD>(i_scaling, bga, bp, delta, iface, tau, z, bfc);
+  }
+
   // all four normal distances (:2690-2705); static indexing keeps r.an in registers
   GB_HD void normal_distances(const double *z, double *d) const
   {
@@ -872,6 +1044,7 @@ struct PolyPusher {
     approx = analytic_approx<K>(0xFu, i_scaling, z, iface_new, tau);
     if (!approx) return false;
     integrate<K>(z, tau);
+    if (EXT == 3) overhead_adaptive<K>(i_scaling, false, true, iface_new, tau, z, face_correct);  // :811-814
     if (K > 2 && tau > tau_max) face_correct = false;
     if (!three_planes_ok(z, iface_new)) face_correct = false;
     if (normal_velocity(z, iface_new) > 0.0) face_correct = false;
@@ -930,7 +1103,11 @@ struct PolyPusher {
         if (!analytic_approx<K>(0xFu, 1, z, iface_new, tau)) return false;
       }
       integrate<K>(z, tau);
-      if (!ts_checks(z, iface_new, tau, tau_max)) return false;
+      bool fc = true;
+      // :2966-2971, with the REDUCED order and its i_scaling.  (The call inside the loop above, :2897-2902, is made with
+      // boole_face_correct = .false. and returns at once, :893.)
+      if (EXT == 3) overhead_adaptive<(K == 4 ? 3 : K)>((K == 2 || K == 3) ? 1 : 0, false, true, iface_new, tau, z, fc);
+      if (!fc || !ts_checks(z, iface_new, tau, tau_max)) return false;
     }
     return true;
   }
@@ -1007,6 +1184,16 @@ struct PolyPusher {
         if (tau > tau_step) tau = t_remain_new / dt_dtau_const;
       }
       integrate<K>(z, tau);
+      if (EXT == 3) {  // :564-568
+        if (FAST) {
+          double d[4];
+          normal_distances(z, d);
+          if (!(d[0] < 0.0 || d[1] < 0.0 || d[2] < 0.0) && adaptive_delta_energy(z) > mp->desired_delta_energy) return false;
+        } else {
+          bool fc = main_fc;
+          overhead_adaptive<K>(0, false, false, iface_new, tau, z, fc);
+        }
+      }
       bool inside = true;
       {
         double d[4];
@@ -1095,6 +1282,7 @@ struct PolyPusher {
     double z[4] = {z_init[0], z_init[1], z_init[2], z_init[3]};
     integrate<K>(z, tau);
     if (!exit_point_ok(z, iface_new)) return false;
+    if (EXT == 3 && adaptive_delta_energy(z) > mp->desired_delta_energy) return false;  // sub-stepping: complete path
     if (K > 2 && tau > tau_max) return false;
     if (normal_v_from_trajectory(iface_new, tau) > 0.0) return false;
     return finish<true>(z, tau, iface_new, o);
@@ -1153,6 +1341,7 @@ struct PolyPusher {
     bool face_correct = approx;
     if (face_correct) {
       integrate<K>(z, tau);
+      if (EXT == 3) overhead_adaptive<K>(0, mp->boole_guess != 0, true, iface_new, tau, z, face_correct);  // :316-319
       if (!three_planes_ok(z, iface_new)) face_correct = false;
       if (!face_converged(z, iface_new)) face_correct = false;
       if (K > 2 && tau > tau_max) face_correct = false;
@@ -1182,6 +1371,7 @@ struct PolyPusher {
         return;
       }
       integrate<K>(z, tau);
+      if (EXT == 3) overhead_adaptive<K>((K == 2) ? 1 : 0, false, true, iface_new, tau, z, face_correct);  // :391-399
       if (K > 2 && tau > tau_max) face_correct = false;
       if (!three_planes_ok(z, iface_new)) face_correct = false;
       if (!face_converged(z, iface_new)) face_correct = false;
@@ -1194,6 +1384,7 @@ struct PolyPusher {
         }
       }
       if (!face_correct) {
+        if (EXT == 3) main_fc = false;
         if (!trouble_shooting(z, tau, iface_new)) {
           set_removed(o);
           return;

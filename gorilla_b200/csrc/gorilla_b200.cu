@@ -193,7 +193,16 @@ static int check_settings(const gorilla_settings *s)
   if (s->boole_gyrophase && !s->boole_time_Hamiltonian)
     return fail(GORILLA_ERR_ARG, "boole_gyrophase requires boole_time_Hamiltonian = .true.");
   if (s->handover_processing_kind != 1) return fail(GORILLA_ERR_UNSUPPORTED, "handover_processing_kind must be 1");
-  if (s->boole_adaptive_time_steps) return fail(GORILLA_ERR_UNSUPPORTED, "boole_adaptive_time_steps must be .false.");
+  if (s->boole_adaptive_time_steps) {
+    if (s->ipusher != 2) return fail(GORILLA_ERR_ARG, "boole_adaptive_time_steps exists for the polynomial pusher only");
+    // pusher_tetra_poly.f90:868-874
+    if (!(s->desired_delta_energy > 0.0)) return fail(GORILLA_ERR_ARG, "desired_delta_energy must be > 0");
+    if (s->max_n_intermediate_steps < 2) return fail(GORILLA_ERR_ARG, "max_n_intermediate_steps must be >= 2");
+    if (s->i_time_tracing_option != 1 || s->boole_time_Hamiltonian || s->boole_gyrophase || s->boole_vpar_int ||
+        s->boole_vpar2_int)
+      return fail(GORILLA_ERR_UNSUPPORTED,
+                  "boole_adaptive_time_steps is not combined with Hamiltonian time tracing / optional quantities");
+  }
   // gorilla_settings_mod.f90:139-144 (coord_system is checked against the mesh in gorilla_b200_init)
   if (s->boole_strong_electric_field && (s->i_precomp != 0 || s->boole_newton_precalc))
     return fail(GORILLA_ERR_ARG, "boole_strong_electric_field requires i_precomp = 0 and boole_newton_precalc = .false.");
@@ -260,6 +269,8 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
   m.ntetr = nt;
   m.ham = h->d_ham;
   m.time_tracing = st->i_time_tracing_option;
+  m.desired_delta_energy = st->desired_delta_energy;
+  m.max_n_intermediate_steps = st->max_n_intermediate_steps;
   m.geom = h->d_geom;
   m.bpart = h->d_bpart;
   m.phi = (has_phi || strong) ? h->d_phi : nullptr;
@@ -362,7 +373,8 @@ GB_EXTERN_ORBIT(1)
 GB_EXTERN_ORBIT(2)
 GB_EXTERN_ORBIT(3)
 GB_EXTERN_ORBIT(4)
-// EXT variants: Hamiltonian time tracing (EXT = 1, gb_orbit_k{1..4}t.cu), + optional quantities (EXT = 2, gb_orbit_k{1..4}x.cu)
+// EXT variants: Hamiltonian time tracing (EXT = 1, gb_orbit_k{1..4}t.cu), + optional quantities / events (EXT = 2,
+// gb_orbit_k{1..4}x.cu), adaptive sub-stepping (EXT = 3, gb_orbit_k{1..4}a.cu)
 #define GB_EXTERN_ORBIT_X(K, E) \
   extern template int launch_orbit_t<K, 0, E>(gorilla_b200_handle *, const Batch &, cudaStream_t); \
   extern template int launch_orbit_t<K, 1, E>(gorilla_b200_handle *, const Batch &, cudaStream_t); \
@@ -375,17 +387,31 @@ GB_EXTERN_ORBIT_X(1, 2)
 GB_EXTERN_ORBIT_X(2, 2)
 GB_EXTERN_ORBIT_X(3, 2)
 GB_EXTERN_ORBIT_X(4, 2)
+GB_EXTERN_ORBIT_X(1, 3)
+GB_EXTERN_ORBIT_X(2, 3)
+GB_EXTERN_ORBIT_X(3, 3)
+GB_EXTERN_ORBIT_X(4, 3)
 
 template <int PHI>
 static int launch_orbit_k(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
 {
   if (h->settings.ipusher == 1) return launch_orbit_t<0, PHI>(h, bt, s);
+  if (((bt.optq && bt.oq_mask) || bt.ev_flags) && h->settings.boole_adaptive_time_steps)
+    return fail(GORILLA_ERR_UNSUPPORTED, "boole_adaptive_time_steps is not combined with optional quantities / events");
   if ((bt.optq && bt.oq_mask) || bt.ev_flags) {
     switch (h->settings.poly_order) {
       case 1: return launch_orbit_t<1, PHI, 2>(h, bt, s);
       case 2: return launch_orbit_t<2, PHI, 2>(h, bt, s);
       case 3: return launch_orbit_t<3, PHI, 2>(h, bt, s);
       default: return launch_orbit_t<4, PHI, 2>(h, bt, s);
+    }
+  }
+  if (h->settings.boole_adaptive_time_steps) {   // adaptive sub-stepping (gb_orbit_k{1..4}a.cu)
+    switch (h->settings.poly_order) {
+      case 1: return launch_orbit_t<1, PHI, 3>(h, bt, s);
+      case 2: return launch_orbit_t<2, PHI, 3>(h, bt, s);
+      case 3: return launch_orbit_t<3, PHI, 3>(h, bt, s);
+      default: return launch_orbit_t<4, PHI, 3>(h, bt, s);
     }
   }
   if (h->mesh.time_tracing == 2) {
@@ -787,6 +813,7 @@ extern "C" int gorilla_b200_get_counters(gorilla_b200_handle *h, gorilla_counter
   out->n_finished = (int64_t)c[CTR_FINISHED];
   for (int i = 0; i < 4; i++) out->n_fallback[i] = (int64_t)c[CTR_FB0 + i];
   out->n_domain_errors = (int64_t)c[CTR_DOMAIN];
+  out->n_adaptive = (int64_t)c[CTR_ADAPT];
   float ms = 0.f;
   if (h->have_push_time) {
     GB_CUDA(cudaEventElapsedTime(&ms, h->ev1, h->ev2));

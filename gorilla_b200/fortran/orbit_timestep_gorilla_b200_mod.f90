@@ -25,8 +25,9 @@ module orbit_timestep_gorilla_b200_mod
                           boole_dt_dtau, boole_newton_precalc, poly_order, i_precomp, boole_guess, &
                           i_time_tracing_option, handover_processing_kind, boole_adaptive_time_steps, &
                           boole_strong_electric_field, boole_grid_for_find_tetra, &
-                          boole_time_Hamiltonian, boole_gyrophase, boole_vpar_int, boole_vpar2_int
-    integer(c_int32_t) :: reserved(1)
+                          boole_time_Hamiltonian, boole_gyrophase, boole_vpar_int, boole_vpar2_int, &
+                          max_n_intermediate_steps
+    real(c_double)  :: desired_delta_energy
   end type
   !> struct gorilla_mesh_desc
   type, bind(C) :: gorilla_mesh_desc_t
@@ -41,6 +42,7 @@ module orbit_timestep_gorilla_b200_mod
   type, bind(C) :: gorilla_b200_counters_t
     integer(c_int64_t) :: n_particles, n_pushes, n_lost, n_finished, n_fallback(4), n_domain_errors
     real(c_double)     :: kernel_ms, find_ms
+    integer(c_int64_t) :: n_adaptive
   end type
 
   interface
@@ -111,7 +113,8 @@ contains
     st%i_time_tracing_option = i_time_tracing_option; st%handover_processing_kind = handover_processing_kind
     st%boole_adaptive_time_steps = merge(1, 0, boole_adaptive_time_steps)
     st%boole_strong_electric_field = merge(1, 0, boole_strong_electric_field)
-    st%boole_grid_for_find_tetra = merge(1, 0, boole_grid_for_find_tetra); st%reserved = 0
+    st%boole_grid_for_find_tetra = merge(1, 0, boole_grid_for_find_tetra)
+    st%max_n_intermediate_steps = max_n_intermediate_steps; st%desired_delta_energy = desired_delta_energy
     st%boole_time_Hamiltonian = merge(1, 0, boole_time_Hamiltonian); st%boole_gyrophase = merge(1, 0, boole_gyrophase)
     st%boole_vpar_int = merge(1, 0, boole_vpar_int); st%boole_vpar2_int = merge(1, 0, boole_vpar2_int)
     rc = gorilla_b200_init(md, st, handle)

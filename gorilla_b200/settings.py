@@ -27,6 +27,8 @@ class GorillaSettings:
     i_time_tracing_option: int = 1
     handover_processing_kind: int = 1
     boole_adaptive_time_steps: bool = False
+    desired_delta_energy: float = 1.0e-10      # INPUT/gorilla.inp:147
+    max_n_intermediate_steps: int = 10000      # INPUT/gorilla.inp:151
     boole_strong_electric_field: bool = False
     boole_grid_for_find_tetra: bool = False
     # optional quantities of pusher_tetra_poly (gorilla_settings_mod.f90:51-55, namelist :100)

@@ -53,7 +53,8 @@ typedef struct gorilla_settings {
   int32_t i_time_tracing_option;     /* 1 dt/dtau constant per cell | 2 Hamiltonian time (ipusher = 2 only,
                                         gorilla_settings_mod.f90:124-129) */
   int32_t handover_processing_kind;  /* must be 1 */
-  int32_t boole_adaptive_time_steps; /* must be 0 */
+  int32_t boole_adaptive_time_steps; /* energy-controlled sub-stepping (pusher_tetra_poly.f90:830-1254); polynomial pusher,
+                                        i_time_tracing_option = 1, not combined with optional quantities / events */
   int32_t boole_strong_electric_field; /* ExB-drift terms of order v_E^2; cylindrical grids (coord_system 1) only */
   int32_t boole_grid_for_find_tetra; /* ignored: the device scan does not need the box accelerator */
   /* optional quantities of pusher_tetra_poly (gorilla_settings_mod.f90:51-55; ipusher = 2 only); boole_gyrophase
@@ -62,7 +63,8 @@ typedef struct gorilla_settings {
   int32_t boole_gyrophase;
   int32_t boole_vpar_int;
   int32_t boole_vpar2_int;
-  int32_t reserved[1];
+  int32_t max_n_intermediate_steps;  /* adaptive scheme: >= 2 (INPUT/gorilla.inp:151) */
+  double desired_delta_energy;       /* adaptive scheme: > 0, relative energy error per tetrahedron (gorilla.inp:147) */
 } gorilla_settings;
 
 /* Everything initialize_gorilla() (orbit_timestep_gorilla.f90:151-274) leaves in module variables that
@@ -100,6 +102,7 @@ typedef struct gorilla_counters {
   int64_t n_domain_errors;
   double kernel_ms;          /* device time of the push kernel (CUDA events on the launch stream) */
   double find_ms;            /* device time of the localisation kernel, 0 if not run */
+  int64_t n_adaptive;        /* pushes in which the adaptive scheme re-integrated a segment in sub-steps */
 } gorilla_counters;
 
 /* ---- lifetime ---------------------------------------------------------------------------------- */

@@ -731,7 +731,9 @@ typedef struct {
   double amat_in_b[4], amat2_in_b[4], amat3_in_b[4];
   int number_of_integration_steps;
   /* tau_steps_list / intermediate_z0_list (:36-38); non-adaptive scheme: two entries (:98-104) */
-  double tau_steps_list[2], intermediate_z0_list[2][4];
+  double *tau_steps_list, (*intermediate_z0_list)[4];
+  int list_cap; /* 2, or 3*max_n_intermediate_steps with the adaptive scheme (:98-104) */
+  double list_tau_static[2], list_z0_static[2][4];
   bool removed; /* the push ended on one of the 'remove particle' returns */
   gor_trace *tr;
 } poly_state;
@@ -954,7 +956,7 @@ static void analytic_approx(poly_state *s, int poly_order, const bool boole_face
 static void analytic_integration(poly_state *s, int poly_order, double z[4], double tau)
 {
   s->number_of_integration_steps += 1;
-  if (s->number_of_integration_steps <= 2) { /* the reference's lists hold two entries */
+  if (s->number_of_integration_steps <= s->list_cap) { /* the reference's lists hold list_cap entries */
     s->tau_steps_list[s->number_of_integration_steps - 1] = tau;
     memcpy(s->intermediate_z0_list[s->number_of_integration_steps - 1], z, 4 * sizeof(double));
   }
@@ -1273,6 +1275,180 @@ static double physical_estimate_tau(const poly_state *s)
   return fabs(tau_est / s->dt_dtau_const);
 }
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Adaptive energy-controlled sub-stepping (boole_adaptive_time_steps) -- SRC/pusher_tetra_poly.f90:830-1254.
+ * Where the reference reads uninitialised locals the restatement defines: eta_minimum / tau_minimum start as the unsplit
+ * step (1, tau), and iface_out_adaptive keeps the incoming face when no exit-time solve was made.
+ * ---------------------------------------------------------------------------------------------- */
+static void analytic_approx(poly_state *s, int poly_order, const bool boole_faces[4], int i_scaling,
+                            const double z[4], int *iface_inout, double *dtau, bool *boole_approx);
+/* :1167-1213 */
+static void adaptive_time_steps_update_eta(const gor_mesh *m, int poly_order, double delta_energy_current, int *eta)
+{
+  const double threshold = 1.0, min_step_error = (double)1E-15f, additive_increase = 1.0; /* 1E-15 is a default-real literal */
+  double scale_factor = pow(delta_energy_current / m->desired_delta_energy, 1.0 / poly_order);
+  double max_scale_factor = pow(delta_energy_current / (min_step_error * *eta), 1.0 / (poly_order + 1));
+  if ((scale_factor > threshold) && (max_scale_factor > threshold)) {
+    scale_factor = scale_factor < max_scale_factor ? scale_factor : max_scale_factor;
+    int c = (int)ceil(*eta * scale_factor);
+    *eta = c < m->max_n_intermediate_steps ? c : m->max_n_intermediate_steps;
+  } else if (scale_factor > threshold) {
+    int c = (int)ceil(*eta * scale_factor);
+    *eta = c < m->max_n_intermediate_steps ? c : m->max_n_intermediate_steps;
+  } else {
+    *eta = (int)(*eta + additive_increase);
+  }
+}
+/* :1217-1252 */
+static void adaptive_time_steps_exit_time(poly_state *s, int poly_order, int i_scaling, const double z[4],
+                                          bool boole_guess_adaptive, int *iface_new_adaptive, double *tau_exit,
+                                          bool *boole_analytical_approx)
+{
+  bool boole_faces[4] = {true, true, true, true};
+  if (boole_guess_adaptive && (poly_order > 2)) {
+    analytic_approx(s, 2, boole_faces, i_scaling, z, iface_new_adaptive, tau_exit, boole_analytical_approx);
+    if (*boole_analytical_approx) {
+      for (int i = 0; i < 4; i++) boole_faces[i] = false;
+      boole_faces[*iface_new_adaptive - 1] = true;
+    }
+    *iface_new_adaptive = 0;
+  }
+  analytic_approx(s, poly_order, boole_faces, i_scaling, z, iface_new_adaptive, tau_exit, boole_analytical_approx);
+}
+/* :937-1163 */
+static void adaptive_time_steps_equidistant(poly_state *s, int poly_order, int i_scaling, bool boole_guess_adaptive,
+                                            bool boole_passing, double *delta_energy_current, int *iface_out_adaptive,
+                                            double *tau, double z[4], bool *boole_face_correct)
+{
+  const gor_mesh *m = s->m;
+  const int max_n = m->max_n_intermediate_steps;
+  double z_start_adaptive[4];
+  memcpy(z_start_adaptive, s->intermediate_z0_list[s->number_of_integration_steps - 1], sizeof(z_start_adaptive));
+  const int number_of_integration_steps_start_adaptive = s->number_of_integration_steps - 1;
+  const double energy_start_adaptive = gor_energy_tot(m, z_start_adaptive, s->perpinv, s->ind_tetr);
+  int eta = 1, eta_extended = 1, eta_limit, eta_minimum = 1, eta_buffer;
+  bool boole_reached_minimum = false, boole_energy_check = false, boole_exit_tetrahedron, boole_analytical_approx;
+  double delta_energy_minimum = *delta_energy_current;
+  double tau_prime, tau_collected, tau_exit = 0.0, tau_minimum = *tau, tau_buffer, energy_current;
+  int iface_new_adaptive = *iface_out_adaptive;
+  /* Safety: the reference's loop has no iteration bound; when two partitions give EXACTLY the same energy error (it is a
+   * multiple of 2^-53) neither branch below fires, eta is reset to the steps actually taken and the loop can cycle for
+   * ever.  The restatement ends the loop after max_n + 64 partitions, keeping the last one. */
+  int n_partitions = 0;
+  while (eta < max_n) { /* PARTITION */
+    if (++n_partitions > max_n + 64) break;
+    adaptive_time_steps_update_eta(m, poly_order, *delta_energy_current, &eta);
+    if (boole_reached_minimum) {
+      eta = eta_minimum;
+      *tau = tau_minimum;
+    }
+    memcpy(z, z_start_adaptive, 4 * sizeof(double));
+    s->number_of_integration_steps = number_of_integration_steps_start_adaptive;
+    tau_prime = *tau / eta;
+    tau_collected = 0;
+    *boole_face_correct = true;
+    boole_exit_tetrahedron = false;
+    boole_energy_check = false;
+    if (boole_passing)
+      eta_limit = (int)ceil(max_n * 1.1);
+    else
+      eta_limit = eta;
+    for (int i = 1; i <= eta_limit - 1; i++) { /* STEPWISE */
+      set_integration_coef_manually(s, poly_order, z);
+      analytic_integration(s, poly_order, z, tau_prime);
+      bool left = false;
+      for (int k = 1; k <= 4; k++)
+        if (normal_distance_func(s, z, k) < 0.0) {
+          left = true;
+          break;
+        }
+      if (left) {
+        if (i == 1) {
+          *boole_face_correct = false;
+          return;
+        }
+        memcpy(z, s->intermediate_z0_list[s->number_of_integration_steps - 1], 4 * sizeof(double));
+        s->number_of_integration_steps = s->number_of_integration_steps - 1;
+        boole_exit_tetrahedron = true;
+        break;
+      }
+      tau_collected = tau_collected + tau_prime;
+      eta_extended = i;
+      if (!boole_guess_adaptive) {
+        iface_new_adaptive = 0;
+        adaptive_time_steps_exit_time(s, poly_order, i_scaling, z, false, &iface_new_adaptive, &tau_exit,
+                                      &boole_analytical_approx);
+        if (!boole_analytical_approx) {
+          *boole_face_correct = false;
+          return;
+        }
+        if (tau_exit <= tau_prime) {
+          tau_prime = tau_exit;
+          break;
+        }
+      }
+    }
+    if (boole_exit_tetrahedron) {
+      iface_new_adaptive = 0;
+      adaptive_time_steps_exit_time(s, poly_order, i_scaling, z, boole_guess_adaptive, &iface_new_adaptive, &tau_exit,
+                                    &boole_analytical_approx);
+      if (!boole_analytical_approx) {
+        *boole_face_correct = false;
+        return;
+      }
+      tau_prime = tau_exit;
+    } else {
+      set_integration_coef_manually(s, poly_order, z);
+    }
+    analytic_integration(s, poly_order, z, tau_prime);
+    tau_collected = tau_collected + tau_prime;
+    energy_current = gor_energy_tot(m, z, s->perpinv, s->ind_tetr);
+    *delta_energy_current = fabs(1 - energy_current / energy_start_adaptive);
+    eta_buffer = eta;
+    tau_buffer = *tau;
+    eta = eta_extended + 1;
+    *tau = tau_collected;
+    if (boole_reached_minimum) {
+      break;
+    } else if (*delta_energy_current < delta_energy_minimum) {
+      delta_energy_minimum = *delta_energy_current;
+      eta_minimum = eta_buffer;
+      tau_minimum = tau_buffer;
+      if (*delta_energy_current <= m->desired_delta_energy) {
+        boole_energy_check = true;
+        break;
+      }
+    } else if (*delta_energy_current > delta_energy_minimum) {
+      boole_reached_minimum = true;
+      continue;
+    }
+  }
+  *iface_out_adaptive = iface_new_adaptive;
+  (void)boole_energy_check; /* the reference only prints a message when the energy goal was not met */
+  if (s->tr) s->tr->n_adaptive++;
+}
+/* :830-933 */
+static void overhead_adaptive_time_steps(poly_state *s, int poly_order, int i_scaling, bool boole_guess_adaptive,
+                                         bool boole_passing, int *iface_inout_adaptive, double *tau, double z[4],
+                                         bool *boole_face_correct)
+{
+  if (boole_passing) {
+    check_three_planes(s, z, *iface_inout_adaptive, boole_face_correct);
+    check_face_convergence(s, z, *iface_inout_adaptive, boole_face_correct);
+  } else {
+    check_three_planes(s, z, 0, boole_face_correct);
+  }
+  if (!*boole_face_correct) return;
+  const double *z0 = s->intermediate_z0_list[s->number_of_integration_steps - 1];
+  double energy_start = gor_energy_tot(s->m, z0, s->perpinv, s->ind_tetr);
+  double energy_current = gor_energy_tot(s->m, z, s->perpinv, s->ind_tetr);
+  double delta_energy_current = fabs(1 - energy_current / energy_start);
+  if (delta_energy_current > s->m->desired_delta_energy)
+    adaptive_time_steps_equidistant(s, poly_order, i_scaling, boole_guess_adaptive, boole_passing, &delta_energy_current,
+                                    iface_inout_adaptive, tau, z, boole_face_correct);
+}
+
 /* :762-826 ; returns false when the particle has to be removed (ind_tetr=-1, iface=-1) */
 static void prolonged_trajectory(poly_state *s, int poly_order, int i_scaling, double z[4], double *tau,
                                  int *iface_new, bool *boole_face_correct, bool *boole_analytical_approx)
@@ -1288,6 +1464,8 @@ static void prolonged_trajectory(poly_state *s, int poly_order, int i_scaling, d
   analytic_approx(s, poly_order, boole_faces, i_scaling, z, iface_new, tau, boole_analytical_approx);
   if (!*boole_analytical_approx) return;
   analytic_integration(s, poly_order, z, *tau);
+  if (s->m->boole_adaptive_time_steps) /* :811-814 */
+    overhead_adaptive_time_steps(s, poly_order, i_scaling, false, true, iface_new, tau, z, boole_face_correct);
   check_exit_time(*tau, tau_max, boole_face_correct, poly_order);
   check_three_planes(s, z, *iface_new, boole_face_correct);
   check_velocity(s, z, *iface_new, boole_face_correct);
@@ -1324,6 +1502,9 @@ static void trouble_shooting_polynomial_solver(poly_state *s, int poly_order, do
       return;
     }
     analytic_integration(s, poly_order, z, *tau);
+    /* :2897-2902 -- called BEFORE boole_face_correct is reset, i.e. with .false.: it returns at once (:893) */
+    if (s->m->boole_adaptive_time_steps)
+      overhead_adaptive_time_steps(s, poly_order, i_scaling, false, true, iface_new, tau, z, &boole_face_correct);
     boole_face_correct = true;
     check_three_planes(s, z, *iface_new, &boole_face_correct);
     check_face_convergence(s, z, *iface_new, &boole_face_correct);
@@ -1354,6 +1535,8 @@ static void trouble_shooting_polynomial_solver(poly_state *s, int poly_order, do
     }
     analytic_integration(s, poly_order, z, *tau); /* original order, :2961 */
     boole_face_correct = true;
+    if (s->m->boole_adaptive_time_steps) /* :2966-2971, with the REDUCED order */
+      overhead_adaptive_time_steps(s, poly_order_new, i_scaling, false, true, iface_new, tau, z, &boole_face_correct);
     check_three_planes(s, z, *iface_new, &boole_face_correct);
     check_face_convergence(s, z, *iface_new, &boole_face_correct);
     check_velocity(s, z, *iface_new, &boole_face_correct);
@@ -1405,6 +1588,8 @@ static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout
   if (!boole_analytical_approx) boole_face_correct = false;
   if (boole_face_correct) {
     analytic_integration(s, poly_order, z, tau);
+    if (m->boole_adaptive_time_steps) /* :316-319 */
+      overhead_adaptive_time_steps(s, poly_order, i_scaling, m->boole_guess != 0, true, &iface_new, &tau, z, &boole_face_correct);
     check_three_planes(s, z, iface_new, &boole_face_correct);
     check_face_convergence(s, z, iface_new, &boole_face_correct);
     check_exit_time(tau, tau_max, &boole_face_correct, poly_order);
@@ -1445,6 +1630,9 @@ static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout
       return;
     }
     analytic_integration(s, poly_order, z, tau);
+    if (m->boole_adaptive_time_steps) /* :391-399 */
+      overhead_adaptive_time_steps(s, poly_order, poly_order == 2 ? 1 : i_scaling, false, true, &iface_new, &tau, z,
+                                   &boole_face_correct);
     check_exit_time(tau, tau_max, &boole_face_correct, poly_order);
     check_three_planes(s, z, iface_new, &boole_face_correct);
     check_face_convergence(s, z, iface_new, &boole_face_correct);
@@ -1517,6 +1705,8 @@ static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout
       if (tau > s->tau_steps_list[i_step_root - 2]) tau = t_remain_new / s->dt_dtau_const;
     }
     analytic_integration(s, poly_order, z, tau);
+    if (m->boole_adaptive_time_steps) /* :564-568 */
+      overhead_adaptive_time_steps(s, poly_order, i_scaling, false, false, &iface_new, &tau, z, &boole_face_correct);
     *ind_tetr_inout = s->ind_tetr;
     *iface = 0;
     boole_face_correct = true;
@@ -2743,6 +2933,17 @@ static int orbit_timestep_core(const gor_mesh *m, double x[3], double *vpar, dou
   memset(&s, 0, sizeof(s));
   s.m = m;
   s.tr = tr;
+  s.tau_steps_list = s.list_tau_static;
+  s.intermediate_z0_list = s.list_z0_static;
+  s.list_cap = 2;
+  void *list_heap = NULL;
+  if (m->boole_adaptive_time_steps && m->ipusher == 2) { /* manage_intermediate_steps_arrays :98-101 */
+    if (m->desired_delta_energy <= 0.0 || m->max_n_intermediate_steps < 2) return GOR_ERR_CONFIG; /* :868-874 */
+    s.list_cap = 3 * m->max_n_intermediate_steps;
+    list_heap = malloc((size_t)s.list_cap * 5 * sizeof(double));
+    s.tau_steps_list = (double *)list_heap;
+    s.intermediate_z0_list = (double(*)[4])((double *)list_heap + s.list_cap);
+  }
   s.perpinv = -0.5 * vperp2 / gor_bmod(m, z_save, *ind_tetr);
   s.perpinv2 = s.perpinv * s.perpinv;
   rk_state rk;
@@ -2803,6 +3004,7 @@ static int orbit_timestep_core(const gor_mesh *m, double x[3], double *vpar, dou
     }
   }
   *vperp = vperp_func(m, z_save, s.perpinv, ind_tetr_save);
+  free(list_heap);
   return GOR_OK;
 }
 

@@ -71,6 +71,9 @@ typedef struct {
   int32_t i_time_tracing_option;          /* 1 = dt/dtau constant per cell, 2 = Hamiltonian time (polynomial pusher only) */
   /* optional quantities of pusher_tetra_poly (gorilla_settings_mod.f90:51-55) */
   int32_t boole_time_hamiltonian, boole_gyrophase, boole_vpar_int, boole_vpar2_int;
+  /* adaptive energy-controlled sub-stepping (gorilla_settings_mod.f90:75-77) */
+  int32_t boole_adaptive_time_steps, max_n_intermediate_steps;
+  double desired_delta_energy;
 } gor_mesh;
 
 /* optional per-particle trace of the visited (ind_tetr, iface) sequence */
@@ -85,6 +88,7 @@ typedef struct {
   /* sum over the pushes of the time step of pusher_tetra_poly's optional_quantities
    * {t_hamiltonian, gyrophase, vpar_int, vpar2_int} (type optional_quantities_type, gorilla_settings_mod.f90:9-15) */
   double optional_quantities[4];
+  int64_t n_adaptive;      /* pushes / segments that were re-integrated in sub-steps (adaptive scheme) */
 } gor_trace;
 
 /* orbit events (gorilla_plot_mod.f90:585-638, par_adiab_inv_poly_mod pusher_tetra_poly.f90:3156-3429) */

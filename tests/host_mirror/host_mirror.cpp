@@ -17,7 +17,7 @@ struct HostMirror {
   std::vector<double> geom, bpart, phi, cold, se, ham;
   gb::FindBins bins;
   MeshDev m;
-  int poly_order, boole_periodic_relocation, ipusher;
+  int poly_order, boole_periodic_relocation, ipusher, adaptive;
   unsigned oq_mask;
 };
 
@@ -116,7 +116,7 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
     iface = o.iface;
     if (trace_cap > 0 && npush < trace_cap) { tr_t[npush] = ind_tetr; tr_f[npush] = iface; }
     npush++;
-    for (int b = 0; b < 4; b++) if (o.fallback & (1 << b)) fallback[b]++;
+    for (int b = 0; b < 5; b++) if (o.fallback & (1 << b)) fallback[b]++;
     t_remain = t_remain - o.t_pass;
     if (o.finished || ind_tetr == -1) break;
   }
@@ -135,7 +135,8 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
 extern "C" {
 
 void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, int boole_periodic_relocation, int ipusher,
-                int boole_strong_electric_field, int i_time_tracing_option, int oq_mask)
+                int boole_strong_electric_field, int i_time_tracing_option, int oq_mask, int boole_adaptive_time_steps,
+                double desired_delta_energy, int max_n_intermediate_steps)
 {
   HostMirror *h = new HostMirror();
   bool has_phi = false;
@@ -150,6 +151,9 @@ void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, in
   m.ham = h->ham.data();
   m.time_tracing = i_time_tracing_option;
   h->oq_mask = (unsigned)oq_mask;
+  h->adaptive = boole_adaptive_time_steps;
+  m.desired_delta_energy = desired_delta_energy;
+  m.max_n_intermediate_steps = max_n_intermediate_steps;
   if (build_find_bins(md, h->bins)) {
     m.bin_start = h->bins.start.data(); m.bin_items = h->bins.items.data();
     m.bin_nu = h->bins.nu; m.bin_nv = h->bins.nv; m.bin_c0 = h->bins.c0; m.bin_c1 = h->bins.c1;
@@ -201,6 +205,17 @@ int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *v
 #define HM_RUNX(K, PHI) run_particle<K, PHI, 2>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
       t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, trace_cap, tt, tf, force_full, fallback, \
       optq ? h->oq_mask : 0u, optq ? optq + 4 * i : nullptr)
+#define HM_RUNA(K, PHI) run_particle<K, PHI, 3>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
+      t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, trace_cap, tt, tf, force_full, fallback)
+    if (h->ipusher == 2 && h->adaptive) {
+      if (m.se) {
+        switch (h->poly_order) { case 1: HM_RUNA(1, 2); break; case 2: HM_RUNA(2, 2); break; case 3: HM_RUNA(3, 2); break; default: HM_RUNA(4, 2); }
+      } else if (m.phi) {
+        switch (h->poly_order) { case 1: HM_RUNA(1, 1); break; case 2: HM_RUNA(2, 1); break; case 3: HM_RUNA(3, 1); break; default: HM_RUNA(4, 1); }
+      } else {
+        switch (h->poly_order) { case 1: HM_RUNA(1, 0); break; case 2: HM_RUNA(2, 0); break; case 3: HM_RUNA(3, 0); break; default: HM_RUNA(4, 0); }
+      }
+    } else
 #define HM_RUNT(K, PHI) run_particle<K, PHI, 1>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
       t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, trace_cap, tt, tf, force_full, fallback)
     if (h->ipusher == 2 && m.time_tracing == 2 && !(optq && h->oq_mask)) {   // same dispatch as launch_orbit_k
@@ -242,7 +257,7 @@ int64_t hm_orbit_timestep_events(void *p, int64_t n, double *x, double *vpar, do
   const MeshDev &m = h->m;
   if (h->ipusher != 2 || h->poly_order < 2) return -1;
   const int sign_t = signbit(t_step) ? -1 : 1;
-  int64_t fallback[4] = {0, 0, 0, 0};
+  int64_t fallback[5] = {0, 0, 0, 0, 0};
   *n_events = 0;
   for (int64_t i = 0; i < n; i++) {
     double *xi = x + 3 * i;

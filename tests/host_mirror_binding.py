@@ -32,7 +32,7 @@ def load():
         L = C.CDLL(str(LIB))
         d, vp = C.c_double, C.c_void_p
         L.hm_create.restype = vp
-        L.hm_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.hm_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, d, C.c_int]
         L.hm_free.argtypes = [vp]
         L.hm_has_phi.argtypes = [vp]
         L.hm_orbit_timestep.restype = C.c_int64
@@ -74,7 +74,8 @@ class HostMirror:
         self.h = self.L.hm_create(C.byref(self._desc), settings.poly_order, int(settings.boole_guess),
                                   int(settings.boole_periodic_relocation), int(settings.ipusher),
                                   int(settings.boole_strong_electric_field), int(settings.i_time_tracing_option),
-                                  oq_mask_of(settings))
+                                  oq_mask_of(settings), int(settings.boole_adaptive_time_steps),
+                                  float(settings.desired_delta_energy), int(settings.max_n_intermediate_steps))
         assert self.h
 
     def __del__(self):
@@ -87,12 +88,12 @@ class HostMirror:
         n = x.shape[0]
         p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
         tt, tf = np.zeros((n, max(trace_cap, 1)), np.int32), np.zeros((n, max(trace_cap, 1)), np.int32)
-        npush, tro, fb = np.zeros(n, np.int64), np.zeros(n), np.zeros(4, np.int64)
+        npush, tro, fb = np.zeros(n, np.int64), np.zeros(n), np.zeros(5, np.int64)
         optq = np.zeros((n, 4)) if optional else None
         dom = self.L.hm_orbit_timestep(self.h, n, p(x), p(vpar), p(vperp), float(t_step), p(binit), p(ind_tetr),
                                        p(iface), p(tro), p(npush), trace_cap, p(tt), p(tf), int(force_full), p(fb), p(optq))
-        return dict(trace_tetr=tt, trace_face=tf, n_pushes=npush, t_remain=tro, fallback=fb, domain_errors=dom,
-                    optional_quantities=optq)
+        return dict(trace_tetr=tt, trace_face=tf, n_pushes=npush, t_remain=tro, fallback=fb[:4], domain_errors=dom,
+                    optional_quantities=optq, n_adaptive=int(fb[4]))
 
     def orbit_timestep_events(self, x, vpar, vperp, t_step, binit, ind_tetr, iface, par_adiab_inv, counter_vpar_0,
                               counter_phi_0, cap, poincare_phi_0=True, n_skip_phi_0=1, poincare_vpar_0=True, J_par=True,

@@ -24,14 +24,15 @@ class GorMesh(C.Structure):
         ("boole_strong_electric_field", C.c_int32), ("boole_periodic_relocation", C.c_int32),
         ("boole_dt_dtau", C.c_int32), ("i_time_tracing_option", C.c_int32),
         ("boole_time_hamiltonian", C.c_int32), ("boole_gyrophase", C.c_int32), ("boole_vpar_int", C.c_int32),
-        ("boole_vpar2_int", C.c_int32),
+        ("boole_vpar2_int", C.c_int32), ("boole_adaptive_time_steps", C.c_int32), ("max_n_intermediate_steps", C.c_int32),
+        ("desired_delta_energy", C.c_double),
     ]
 
 
 class GorTrace(C.Structure):
     _fields_ = [("n_pushes", C.c_int64), ("cap", C.c_int64), ("ind_tetr", C.POINTER(C.c_int32)),
                 ("iface", C.POINTER(C.c_int32)), ("n_fallback", C.c_int64 * 4), ("n_solver_iters", C.c_int64),
-                ("n_solver_calls", C.c_int64), ("optional_quantities", C.c_double * 4)]
+                ("n_solver_calls", C.c_int64), ("optional_quantities", C.c_double * 4), ("n_adaptive", C.c_int64)]
 
 
 class GorEvent(C.Structure):
@@ -125,6 +126,9 @@ class OracleMesh:
         m.boole_gyrophase = int(settings.boole_gyrophase)
         m.boole_vpar_int = int(settings.boole_vpar_int)
         m.boole_vpar2_int = int(settings.boole_vpar2_int)
+        m.boole_adaptive_time_steps = int(settings.boole_adaptive_time_steps)
+        m.max_n_intermediate_steps = int(settings.max_n_intermediate_steps)
+        m.desired_delta_energy = float(settings.desired_delta_energy)
         self.c = m
         self.L = load_oracle()
 
@@ -143,7 +147,7 @@ class OracleMesh:
         npush, tro = np.zeros(n, np.int64), np.zeros(n)
         fb = np.zeros(4, np.int64)
         optq = np.zeros((n, 4))
-        iters = calls = 0
+        iters = calls = nadapt = 0
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         for i in range(n):
             tr = GorTrace()
@@ -158,11 +162,12 @@ class OracleMesh:
             assert rc == 0, rc
             npush[i], tro[i] = tr.n_pushes, t_out.value
             optq[i] = tr.optional_quantities[:]
+            nadapt += tr.n_adaptive
             fb += np.array(tr.n_fallback[:], np.int64)
             iters += tr.n_solver_iters
             calls += tr.n_solver_calls
         return dict(trace_tetr=tt, trace_face=tf, n_pushes=npush, t_remain=tro, fallback=fb, solver_iters=iters,
-                    solver_calls=calls, optional_quantities=optq)
+                    solver_calls=calls, optional_quantities=optq, n_adaptive=nadapt)
 
     def orbit_timestep_events(self, x, vpar, vperp, t_step, binit, ind_tetr, iface, par_adiab_inv, counter_vpar_0,
                               counter_phi_0, cap, poincare_phi_0=True, n_skip_phi_0=1, poincare_vpar_0=True, J_par=True,

@@ -36,6 +36,46 @@ CASES = [  # name, settings overrides, t_step, seed
 ]
 
 
+# second file (orbits_v2.npz): Hamiltonian time tracing + optional quantities, adaptive sub-stepping, orbit events
+_OQ = dict(boole_time_Hamiltonian=True, boole_gyrophase=True, boole_vpar_int=True, boole_vpar2_int=True)
+CASES_V2 = [  # name, settings overrides, t_step, seed, kind
+    ("k2_hamiltonian_optq", dict(poly_order=2, i_time_tracing_option=2, **_OQ), 2.0e-5, 31, "optq"),
+    ("k4_hamiltonian_optq", dict(poly_order=4, i_time_tracing_option=2, **_OQ), 2.0e-5, 32, "optq"),
+    ("k3_optq_backward", dict(poly_order=3, boole_vpar_int=True, boole_vpar2_int=True), -1.0e-5, 33, "optq"),
+    ("k2_adaptive", dict(poly_order=2, boole_adaptive_time_steps=True, desired_delta_energy=1e-11,
+                         max_n_intermediate_steps=30), 2.0e-5, 34, "plain"),
+    ("k3_adaptive", dict(poly_order=3, boole_adaptive_time_steps=True, desired_delta_energy=1e-14,
+                         max_n_intermediate_steps=30), 2.0e-5, 35, "plain"),
+    ("k2_events", dict(poly_order=2), 6.0e-4, 36, "events"),
+    ("k4_events", dict(poly_order=4), 6.0e-4, 37, "events"),
+]
+N_EV, EV_CAP = 24, 20000
+
+
+def run_case_v2(over, t_step, seed, kind):
+    grid, st = workloads.analytic_tokamak(10, 10, 10)
+    st = type(st)(**{**st.__dict__, **over})
+    mesh = build_mesh(grid, st)
+    om = OracleMesh(mesh, st)
+    n = N_EV if kind == "events" else N
+    x, vpar, vperp = workloads.particles_cyl(n, seed)
+    binit, ind, ifc = workloads.fresh_state(n)
+    if kind == "events":
+        J, cv, cp = np.zeros(n), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        ev, nev, npush = om.orbit_timestep_events(x, vpar, vperp, t_step, binit, ind, ifc, J, cv, cp, EV_CAP, n_skip_phi_0=2)
+        assert nev <= EV_CAP
+        ev = ev[np.lexsort((ev["kind"], ev["push"], ev["particle"]))]
+        return dict(x=x, vpar=vpar, vperp=vperp, ind_tetr=ind, iface=ifc, n_pushes=npush, par_adiab_inv=J, counter_vpar_0=cv,
+                    counter_phi_0=cp, ev_particle=ev["particle"], ev_kind=ev["kind"], ev_counter=ev["counter"],
+                    ev_push=ev["push"], ev_x=ev["x"], ev_value=ev["value"])
+    r = om.orbit_timestep_trace(x, vpar, vperp, t_step, binit, ind, ifc, CAP)
+    out = dict(x=x, vpar=vpar, vperp=vperp, ind_tetr=ind, iface=ifc, trace_tetr=r["trace_tetr"].astype(np.int32),
+               trace_face=r["trace_face"].astype(np.int8), n_pushes=r["n_pushes"].astype(np.int64), t_remain=r["t_remain"])
+    if kind == "optq":
+        out["optional_quantities"] = r["optional_quantities"]
+    return out
+
+
 def run_case(over, t_step, seed):
     grid, st = workloads.analytic_tokamak(10, 10, 10)
     st = type(st)(**{**st.__dict__, **over})
@@ -56,6 +96,12 @@ def main():
             out[f"{name}/{k}"] = v
     np.savez_compressed(Path(__file__).with_name("orbits_v1.npz"), **out)
     print("wrote", len(out), "arrays")
+    out = {}
+    for name, over, t_step, seed, kind in CASES_V2:
+        for k, v in run_case_v2(over, t_step, seed, kind).items():
+            out[f"{name}/{k}"] = v
+    np.savez_compressed(Path(__file__).with_name("orbits_v2.npz"), **out)
+    print("wrote", len(out), "arrays (v2)")
 
 
 if __name__ == "__main__":

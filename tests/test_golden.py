@@ -1,4 +1,5 @@
-"""Committed golden vectors (tests/golden/orbits_v1.npz, made by tests/golden/make_golden.py from the CPU oracle): eleven
+"""Committed golden vectors (tests/golden/orbits_v1.npz and orbits_v2.npz -- the latter: Hamiltonian time tracing with the
+optional quantities, adaptive sub-stepping, orbit events -- made by tests/golden/make_golden.py from the CPU oracle): eleven
 small cases -- polynomial orders 1-4, backward time, no face guess, RK4, electrostatic potential, strong electric field --
 with final phase-space state, visited-tetra trace and push counts.  CPU: the oracle still reproduces them bit for bit;
 GPU: the CUDA path reproduces them WITHOUT the oracle in the loop."""
@@ -12,9 +13,10 @@ import workloads
 from gorilla_b200 import build_mesh
 
 sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
-from make_golden import CAP, CASES, N  # noqa: E402
+from make_golden import CAP, CASES, CASES_V2, EV_CAP, N, N_EV, run_case_v2  # noqa: E402
 
 GOLD = np.load(Path(__file__).resolve().parent / "golden" / "orbits_v1.npz")
+GOLD2 = np.load(Path(__file__).resolve().parent / "golden" / "orbits_v2.npz")
 
 
 def same(a, b):
@@ -57,5 +59,56 @@ def test_cuda_reproduces_golden(cuda_device, product_lib, case):
     g = lambda k: GOLD[f"{name}/{k}"]  # noqa: E731
     assert same(tt, g("trace_tetr")) and same(tf, g("trace_face")), "visited tetra sequence differs from the golden vector"
     assert same(npu, g("n_pushes")) and same(tro, g("t_remain"))
+    assert same(x, g("x")) and same(vpar, g("vpar")) and same(vperp, g("vperp"))
+    assert same(ind, g("ind_tetr")) and same(ifc, g("iface"))
+
+
+# ---- orbits_v2.npz: Hamiltonian time + optional quantities, adaptive sub-stepping, orbit events -------------------
+@pytest.mark.parametrize("case", CASES_V2, ids=[c[0] for c in CASES_V2])
+def test_oracle_reproduces_golden_v2(product_lib, case):
+    name, over, t_step, seed, kind = case
+    r = run_case_v2(over, t_step, seed, kind)
+    keys = [k.split("/", 1)[1] for k in GOLD2.files if k.startswith(name + "/")]
+    assert sorted(keys) == sorted(r.keys())
+    for k in keys:
+        assert same(r[k], GOLD2[f"{name}/{k}"]), k
+    assert int(GOLD2[f"{name}/n_pushes"].sum()) > 500
+    if kind == "events":
+        assert (GOLD2[f"{name}/ev_kind"] == 2).sum() > 5 and (GOLD2[f"{name}/ev_kind"] == 1).sum() > 20
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES_V2, ids=[c[0] for c in CASES_V2])
+def test_cuda_reproduces_golden_v2(cuda_device, product_lib, case):
+    from gorilla_b200 import Gorilla
+    name, over, t_step, seed, kind = case
+    n = N_EV if kind == "events" else N
+    grid, st = workloads.analytic_tokamak(10, 10, 10)
+    st = type(st)(**{**st.__dict__, **over})
+    mesh = build_mesh(grid, st)
+    x, vpar, vperp = workloads.particles_cyl(n, seed)
+    binit, ind, ifc = workloads.fresh_state(n)
+    gk = Gorilla(mesh, st)
+    g = lambda k: GOLD2[f"{name}/{k}"]  # noqa: E731
+    npu = np.zeros(n, np.int64)
+    if kind == "events":
+        J, cv, cp = np.zeros(n), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        ev, nev = gk.orbit_timestep_gorilla_events(x, vpar, vperp, t_step, binit, ind, ifc, J, cv, cp, EV_CAP, n_skip_phi_0=2,
+                                                   n_pushes=npu)
+        assert nev == len(g("ev_kind"))
+        for k in ("particle", "kind", "counter", "push", "x", "value"):
+            assert same(ev[k], g("ev_" + k)), k
+        assert same(J, g("par_adiab_inv")) and same(cv, g("counter_vpar_0")) and same(cp, g("counter_phi_0"))
+    else:
+        tro = np.zeros(n)
+        oq = np.zeros((n, 4)) if kind == "optq" else None
+        tt, tf = gk.orbit_timestep_gorilla(x, vpar, vperp, t_step, binit, ind, ifc, t_remain_out=tro, n_pushes=npu,
+                                           trace_cap=CAP, optional_quantities=oq)
+        assert same(tt, g("trace_tetr")) and same(tf, g("trace_face")), "visited tetra sequence differs from the golden vector"
+        assert same(tro, g("t_remain"))
+        if oq is not None:
+            assert same(oq, g("optional_quantities"))
+    gk.close()
+    assert same(npu, g("n_pushes"))
     assert same(x, g("x")) and same(vpar, g("vpar")) and same(vperp, g("vperp"))
     assert same(ind, g("ind_tetr")) and same(ifc, g("iface"))

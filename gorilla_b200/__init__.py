@@ -12,11 +12,12 @@ from .api import (  # noqa: F401
     GorillaError,
     Mesh,
     build_mesh,
+    load_mesh,
     initialize_gorilla,
     launch_count,
 )
 
 __all__ = [
-    "Gorilla", "GorillaError", "Mesh", "build_mesh", "initialize_gorilla", "launch_count",
+    "Gorilla", "GorillaError", "Mesh", "build_mesh", "load_mesh", "initialize_gorilla", "launch_count",
     "GorillaSettings", "TetraGridSettings", "load_gorilla_inp", "load_tetra_grid_inp",
 ]

@@ -101,6 +101,7 @@ EXPORTED_SYMBOLS = (
     "gorilla_b200_get_counters", "gorilla_b200_sort_permutation_dev", "gorilla_b200_set_launch_config",
     "gorilla_b200_fp64_peak",
     "gorilla_mesh_build", "gorilla_mesh_get_desc", "gorilla_mesh_get_vertices", "gorilla_mesh_free",
+    "gorilla_mesh_save", "gorilla_mesh_load",
 )
 
 
@@ -145,6 +146,8 @@ def load_library():
     lib.gorilla_mesh_get_vertices.argtypes = [vp, C.POINTER(i64), C.POINTER(C.POINTER(dbl)), C.POINTER(C.POINTER(dbl))]
     lib.gorilla_mesh_free.argtypes = [vp]
     lib.gorilla_mesh_free.restype = None
+    lib.gorilla_mesh_save.argtypes = [C.POINTER(_MeshDesc), i64, vp, vp, C.c_char_p]
+    lib.gorilla_mesh_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     _lib = lib
     return lib
 
@@ -229,10 +232,50 @@ class Mesh:
             d.grid_size[i] = int(s["grid_size"][i])
         return d
 
+    def save(self, path) -> None:
+        """Write the mesh as a versioned .gmesh file (gorilla_mesh_save)."""
+        d = self.desc()
+        nv = 0 if self.verts_rphiz is None else int(self.verts_rphiz.shape[0])
+        _check(load_library().gorilla_mesh_save(C.byref(d), nv, _ptr(self.verts_rphiz) if nv else None,
+                                                _ptr(self.verts_sthetaphi) if nv and self.verts_sthetaphi is not None else None,
+                                                str(path).encode()))
+
     def __del__(self):
         if self._handle is not None and _lib is not None:
             _lib.gorilla_mesh_free(self._handle)
             self._handle = None
+
+
+def _mesh_from_handle(h) -> Mesh:
+    lib = load_library()
+    d = _MeshDesc()
+    _check(lib.gorilla_mesh_get_desc(h, C.byref(d)))
+    m = Mesh()
+    m._handle = h
+    nt = int(d.ntetr)
+    m.tetra_physics = np.ctypeslib.as_array(d.tetra_physics, shape=(nt, 142))
+    m.tetra_grid = np.ctypeslib.as_array(d.tetra_grid, shape=(nt, 20))
+    nv = C.c_int64()
+    pr, ps = C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
+    _check(lib.gorilla_mesh_get_vertices(h, C.byref(nv), C.byref(pr), C.byref(ps)))
+    if nv.value > 0:
+        m.verts_rphiz = np.ctypeslib.as_array(pr, shape=(nv.value, 3))
+        if ps:
+            m.verts_sthetaphi = np.ctypeslib.as_array(ps, shape=(nv.value, 3))
+    m.scalars = dict(
+        cm_over_e=d.cm_over_e, particle_mass=d.particle_mass, particle_charge=d.particle_charge,
+        sign_sqg=d.sign_sqg, coord_system=d.coord_system, n_field_periods=d.n_field_periods,
+        grid_kind=d.grid_kind, grid_size=tuple(d.grid_size), Rmin=d.Rmin, Rmax=d.Rmax, Zmin=d.Zmin, Zmax=d.Zmax,
+        sfc_s_min=d.sfc_s_min,
+    )
+    return m
+
+
+def load_mesh(path) -> Mesh:
+    """Read a .gmesh file written by Mesh.save / gorilla_mesh_save (raises GorillaError on a bad or corrupted file)."""
+    h = C.c_void_p()
+    _check(load_library().gorilla_mesh_load(str(path).encode(), C.byref(h)))
+    return _mesh_from_handle(h)
 
 
 def build_mesh(grid: TetraGridSettings, settings: GorillaSettings) -> Mesh:

@@ -261,6 +261,16 @@ int gorilla_mesh_get_vertices(const gorilla_mesh *mesh, int64_t *nvert, const do
                               const double **verts_sthetaphi);
 void gorilla_mesh_free(gorilla_mesh *mesh);
 
+/* .gmesh: versioned on-disk form of a host mesh (header with magic, format version, byte-order tag, record sizes, sizes,
+ * the module scalars of gorilla_mesh_desc and an FNV-1a checksum; payload = tetra_physics, tetra_grid, vertex tables as
+ * they sit in memory).  The reference has no mesh file -- initialize_gorilla rebuilds the mesh in every run
+ * (orbit_timestep_gorilla.f90:151-274); a Fortran caller can dump its own arrays through gorilla_mesh_save and any later
+ * run can start from gorilla_mesh_load + gorilla_mesh_get_desc + gorilla_b200_init.  verts_* may be NULL (nvert = 0).
+ * Wrong magic / version / byte order / sizes, truncation and corruption give GORILLA_ERR_IO. */
+int gorilla_mesh_save(const gorilla_mesh_desc *mesh, int64_t nvert, const double *verts_rphiz,
+                      const double *verts_sthetaphi, const char *path);
+int gorilla_mesh_load(const char *path, gorilla_mesh **out);
+
 #ifdef __cplusplus
 }
 #endif

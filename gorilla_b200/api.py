@@ -48,7 +48,7 @@ class _MeshDesc(C.Structure):
         ("sign_sqg", C.c_int32), ("coord_system", C.c_int32), ("n_field_periods", C.c_int32),
         ("grid_kind", C.c_int32), ("grid_size", C.c_int32 * 3), ("pad0", C.c_int32),
         ("Rmin", C.c_double), ("Rmax", C.c_double), ("Zmin", C.c_double), ("Zmax", C.c_double),
-        ("sfc_s_min", C.c_double),
+        ("sfc_s_min", C.c_double), ("tetra_skew_coord", C.POINTER(C.c_double)),
     ]
 
 
@@ -203,6 +203,7 @@ class Mesh:
         self.tetra_grid: np.ndarray | None = None
         self.verts_rphiz: np.ndarray | None = None
         self.verts_sthetaphi: np.ndarray | None = None
+        self.tetra_skew_coord: np.ndarray | None = None   # [ntetr,168], handover_processing_kind = 2 only
         self.scalars: dict = {}
 
     @classmethod
@@ -230,6 +231,8 @@ class Mesh:
             setattr(d, k, int(s[k]))
         for i in range(3):
             d.grid_size[i] = int(s["grid_size"][i])
+        if self.tetra_skew_coord is not None:
+            d.tetra_skew_coord = self.tetra_skew_coord.ctypes.data_as(C.POINTER(C.c_double))
         return d
 
     def save(self, path) -> None:
@@ -255,6 +258,8 @@ def _mesh_from_handle(h) -> Mesh:
     nt = int(d.ntetr)
     m.tetra_physics = np.ctypeslib.as_array(d.tetra_physics, shape=(nt, 142))
     m.tetra_grid = np.ctypeslib.as_array(d.tetra_grid, shape=(nt, 20))
+    if d.tetra_skew_coord:
+        m.tetra_skew_coord = np.ctypeslib.as_array(d.tetra_skew_coord, shape=(nt, 168))
     nv = C.c_int64()
     pr, ps = C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
     _check(lib.gorilla_mesh_get_vertices(h, C.byref(nv), C.byref(pr), C.byref(ps)))
@@ -291,6 +296,8 @@ def build_mesh(grid: TetraGridSettings, settings: GorillaSettings) -> Mesh:
     nt = int(d.ntetr)
     m.tetra_physics = np.ctypeslib.as_array(d.tetra_physics, shape=(nt, 142))
     m.tetra_grid = np.ctypeslib.as_array(d.tetra_grid, shape=(nt, 20))
+    if d.tetra_skew_coord:
+        m.tetra_skew_coord = np.ctypeslib.as_array(d.tetra_skew_coord, shape=(nt, 168))
     nv = C.c_int64()
     pr, ps = C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
     _check(lib.gorilla_mesh_get_vertices(h, C.byref(nv), C.byref(pr), C.byref(ps)))

@@ -600,7 +600,7 @@ struct gorilla_b200_handle {
   int num_sms = 0;
   MeshDev mesh{};
   gorilla_settings settings{};
-  double *d_geom = nullptr, *d_bpart = nullptr, *d_phi = nullptr, *d_cold = nullptr, *d_se = nullptr, *d_ham = nullptr;
+  double *d_geom = nullptr, *d_bpart = nullptr, *d_phi = nullptr, *d_cold = nullptr, *d_se = nullptr, *d_ham = nullptr, *d_skew = nullptr;
   double *s_oq = nullptr;   // [cap][4] scratch for the optional quantities (host-pointer entry point)
   uint32_t oq_mask = 0;
   int32_t *d_bin_start = nullptr, *d_bin_items = nullptr;

@@ -32,7 +32,7 @@
 
 namespace gb {
 
-enum { GEOM_ND = 16, BPART_ND = 28, PHI_ND = 20, COLD_ND = 12, SE_ND = 32, HAM_ND = 8 };
+enum { GEOM_ND = 16, BPART_ND = 28, PHI_ND = 20, COLD_ND = 12, SE_ND = 32, HAM_ND = 8, SKEW_ND = 192 };
 enum { B_BMOD1 = 0, B_GB = 1, B_CURLA = 4, B_CURLH = 7, B_GBXH1 = 10, B_GBXCURLA = 13, B_ALP = 14,
        B_SPALP = 23, B_DTDTAU = 24, B_TOPO = 25 };
 enum { P_PHI1 = 0, P_GPHI = 1, P_GPHIXH1 = 4, P_GPHIXCURLA = 7, P_BET = 8, P_SPBET = 17 };
@@ -54,6 +54,10 @@ struct MeshDev {
   const double *phi;  // nullptr when the whole Phi group is exactly zero
   const double *cold;
   const double *se;   // nullptr unless boole_strong_electric_field
+  // handover_processing_kind = 2 (EXT = 2 kernels): per tetrahedron and face 48 doubles = two 192-byte blocks,
+  //   leave: skew_ref_x1x2x3(3) inv_skew_coord_x1x2x3(3,3) skew_coord_xyz(3,3) skew_ref_xyz(3)
+  //   enter: skew_ref_xyz(3) inv_skew_coord_xyz(3,3) skew_coord_x1x2x3(3,3) skew_ref_x1x2x3(3)      (matrices column-major)
+  const double *skew;
   const double *ham;  // hamiltonian_time records (EXT kernels only): h1_in_curlA h1_in_curlh vec_mismatch_der(3) vec_parcurr_der(3)
   double desired_delta_energy;      // adaptive sub-stepping (EXT = 3 kernels): gorilla_settings_mod.f90:76-77
   int32_t max_n_intermediate_steps;

@@ -1121,6 +1121,31 @@ struct PolyPusher {
     iface_out = topo_face(flags, f);
     const int iper_phi = topo_perphi(flags, f);
     if (EXT == 2) const_cast<PolyPusher *>(this)->iper_phi = iper_phi;
+    if (EXT == 2 && mp->skew != nullptr) {
+      // handover_processing_kind = 2: position exchange via Cartesian skew coordinates (pusher_tetra_func_mod.f90:59-89).
+      // A particle leaving the domain keeps its exit position (the reference indexes tetra_skew_coord(-1) there).
+      if (ind_out < 1) return;
+      double blk[24], bv[3], tv[3], xc[3];
+      const double *pl = mp->skew + ((int64_t)ind_tetr - 1) * SKEW_ND + 48 * f;
+#pragma unroll
+      for (int i = 0; i < 24; i += 4) ld4(pl + i, blk[i], blk[i + 1], blk[i + 2], blk[i + 3]);
+#pragma unroll
+      for (int i = 0; i < 3; i++) bv[i] = x[i] - blk[i];
+#pragma unroll
+      for (int i = 0; i < 3; i++) tv[i] = ((0.0 + blk[3 + i] * bv[0]) + blk[6 + i] * bv[1]) + blk[9 + i] * bv[2];
+#pragma unroll
+      for (int i = 0; i < 3; i++) xc[i] = (((0.0 + blk[12 + i] * tv[0]) + blk[15 + i] * tv[1]) + blk[18 + i] * tv[2]) + blk[21 + i];
+      const double *pe = mp->skew + ((int64_t)ind_out - 1) * SKEW_ND + 48 * (iface_out - 1) + 24;
+#pragma unroll
+      for (int i = 0; i < 24; i += 4) ld4(pe + i, blk[i], blk[i + 1], blk[i + 2], blk[i + 3]);
+#pragma unroll
+      for (int i = 0; i < 3; i++) bv[i] = xc[i] - blk[i];
+#pragma unroll
+      for (int i = 0; i < 3; i++) tv[i] = ((0.0 + blk[3 + i] * bv[0]) + blk[6 + i] * bv[1]) + blk[9 + i] * bv[2];
+#pragma unroll
+      for (int i = 0; i < 3; i++) x[i] = (((0.0 + blk[12 + i] * tv[0]) + blk[15 + i] * tv[1]) + blk[18 + i] * tv[2]) + blk[21 + i];
+      return;
+    }
     if (mp->coord_system == 1) {
       if (iper_phi == 1) x[1] = x[1] - mp->period_phi;
       else if (iper_phi == -1) x[1] = x[1] + mp->period_phi;

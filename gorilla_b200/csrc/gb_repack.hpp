@@ -119,6 +119,31 @@ inline void repack_hamiltonian_time(const gorilla_mesh_desc *md, std::vector<dou
   }
 }
 
+// type tetrahedron_skew_coord (168 doubles) -> per (tetrahedron, face) a "leave" and an "enter" block (gb_mesh.cuh)
+inline void repack_skew(const gorilla_mesh_desc *md, std::vector<double> &skew)
+{
+  const int64_t nt = md->ntetr;
+  skew.assign((size_t)nt * SKEW_ND, 0.0);
+  for (int64_t t = 0; t < nt; t++) {
+    const double *S = md->tetra_skew_coord + t * GORILLA_TETRA_SKEW_NDOUBLES;
+    for (int k = 0; k < 4; k++) {
+      double *L = &skew[(size_t)t * SKEW_ND + 48 * k], *E = L + 24;
+      for (int i = 0; i < 3; i++) {
+        L[i] = S[144 + 3 * k + i];
+        L[21 + i] = S[156 + 3 * k + i];
+        E[i] = S[156 + 3 * k + i];
+        E[21 + i] = S[144 + 3 * k + i];
+      }
+      for (int q = 0; q < 9; q++) {
+        L[3 + q] = S[72 + 9 * k + q];
+        L[12 + q] = S[36 + 9 * k + q];
+        E[3 + q] = S[108 + 9 * k + q];
+        E[12 + q] = S[9 * k + q];
+      }
+    }
+  }
+}
+
 // ---- find_tetra bins --------------------------------------------------------------------------------------------
 // The slice-wise grids repeat the same 2-D cell pattern in every phi slice.  The tetrahedra of slice 0 are binned by
 // the bounding box of their four vertices in the two non-toroidal coordinates; the vertices are reconstructed from the

@@ -192,7 +192,11 @@ static int check_settings(const gorilla_settings *s)
     return fail(GORILLA_ERR_ARG, "Hamiltonian time tracing (i_time_tracing_option = 2) requires ipusher = 2");
   if (s->boole_gyrophase && !s->boole_time_Hamiltonian)
     return fail(GORILLA_ERR_ARG, "boole_gyrophase requires boole_time_Hamiltonian = .true.");
-  if (s->handover_processing_kind != 1) return fail(GORILLA_ERR_UNSUPPORTED, "handover_processing_kind must be 1");
+  if (s->handover_processing_kind != 1 && s->handover_processing_kind != 2)
+    return fail(GORILLA_ERR_ARG, "handover_processing_kind must be 1 or 2");
+  if (s->handover_processing_kind == 2 && (s->ipusher != 2 || s->boole_adaptive_time_steps))
+    return fail(GORILLA_ERR_UNSUPPORTED,
+                "handover_processing_kind = 2 is built for the polynomial pusher without adaptive sub-stepping");
   if (s->boole_adaptive_time_steps) {
     if (s->ipusher != 2) return fail(GORILLA_ERR_ARG, "boole_adaptive_time_steps exists for the polynomial pusher only");
     // pusher_tetra_poly.f90:868-874
@@ -222,6 +226,8 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
   if (md->coord_system != 1 && md->coord_system != 2) return fail(GORILLA_ERR_ARG, "coord_system must be 1 or 2");
   if (st->boole_strong_electric_field && md->coord_system != 1)
     return fail(GORILLA_ERR_ARG, "boole_strong_electric_field requires coord_system = 1 (gorilla_settings_mod.f90:139)");
+  if (st->handover_processing_kind == 2 && !md->tetra_skew_coord)
+    return fail(GORILLA_ERR_ARG, "handover_processing_kind = 2 needs gorilla_mesh_desc.tetra_skew_coord");
   int dev = 0;
   GB_CUDA(cudaGetDevice(&dev));
   gorilla_b200_handle *h = new gorilla_b200_handle();
@@ -265,8 +271,18 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
       return GORILLA_ERR_CUDA;
     }
   }
+  if (st->handover_processing_kind == 2) {
+    std::vector<double> skew;
+    gb::repack_skew(md, skew);
+    if ((e = up(&h->d_skew, skew)) != cudaSuccess) {
+      g_last_error = std::string("gorilla_b200_init: ") + cudaGetErrorString(e);
+      gorilla_b200_free(h);
+      return GORILLA_ERR_CUDA;
+    }
+  }
   MeshDev &m = h->mesh;
   m.ntetr = nt;
+  m.skew = h->d_skew;
   m.ham = h->d_ham;
   m.time_tracing = st->i_time_tracing_option;
   m.desired_delta_energy = st->desired_delta_energy;
@@ -320,7 +336,7 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
 extern "C" void gorilla_b200_free(gorilla_b200_handle *h)
 {
   if (!h) return;
-  cudaFree(h->d_geom); cudaFree(h->d_bpart); cudaFree(h->d_phi); cudaFree(h->d_cold); cudaFree(h->d_se); cudaFree(h->d_ham); cudaFree(h->s_oq); cudaFree(h->d_bin_start); cudaFree(h->d_bin_items); cudaFree(h->d_ctr);
+  cudaFree(h->d_geom); cudaFree(h->d_bpart); cudaFree(h->d_phi); cudaFree(h->d_cold); cudaFree(h->d_se); cudaFree(h->d_ham); cudaFree(h->d_skew); cudaFree(h->s_oq); cudaFree(h->d_bin_start); cudaFree(h->d_bin_items); cudaFree(h->d_ctr);
   cudaFree(h->s_x); cudaFree(h->s_vpar); cudaFree(h->s_vperp); cudaFree(h->s_tro); cudaFree(h->s_e);
   cudaFree(h->s_p); cudaFree(h->s_mu); cudaFree(h->s_init); cudaFree(h->s_ind); cudaFree(h->s_iface);
   cudaFree(h->s_np); cudaFree(h->s_tr_t); cudaFree(h->s_tr_f); cudaFree(h->sort_tmp);
@@ -398,7 +414,7 @@ static int launch_orbit_k(gorilla_b200_handle *h, const Batch &bt, cudaStream_t 
   if (h->settings.ipusher == 1) return launch_orbit_t<0, PHI>(h, bt, s);
   if (((bt.optq && bt.oq_mask) || bt.ev_flags) && h->settings.boole_adaptive_time_steps)
     return fail(GORILLA_ERR_UNSUPPORTED, "boole_adaptive_time_steps is not combined with optional quantities / events");
-  if ((bt.optq && bt.oq_mask) || bt.ev_flags) {
+  if ((bt.optq && bt.oq_mask) || bt.ev_flags || h->mesh.skew) {   // handover kind 2 lives in the EXT = 2 kernels
     switch (h->settings.poly_order) {
       case 1: return launch_orbit_t<1, PHI, 2>(h, bt, s);
       case 2: return launch_orbit_t<2, PHI, 2>(h, bt, s);

@@ -18,6 +18,7 @@ extern "C" int gorilla_mesh_build(const gorilla_grid_settings *grid, const goril
   gorilla_mesh *gm = new (std::nothrow) gorilla_mesh();
   if (!gm) return GORILLA_ERR_ARG;
   std::string err;
+  gm->m.handover_processing_kind = settings->handover_processing_kind;
   int rc = gbhost::set_species(gm->m, settings->ispecies, err);
   if (rc == GORILLA_OK) {
     switch (grid->grid_kind) {
@@ -59,6 +60,7 @@ extern "C" int gorilla_mesh_get_desc(const gorilla_mesh *mesh, gorilla_mesh_desc
   d->pad0 = 0;
   d->Rmin = m.Rmin; d->Rmax = m.Rmax; d->Zmin = m.Zmin; d->Zmax = m.Zmax;
   d->sfc_s_min = m.sfc_s_min;
+  d->tetra_skew_coord = m.tetra_skew_coord.empty() ? nullptr : m.tetra_skew_coord.data();
   return GORILLA_OK;
 }
 

@@ -103,6 +103,8 @@ void linearise_tetrahedra(Mesh &m, const VertexFields &vf)
   const bool strong = vf.strong;  // mutually exclusive with grid_kind 3 (:217-227)
   const int navec = ((gk == 3) ? 11 : 10) + (strong ? 4 : 0);
   m.tetra_physics.assign((size_t)ntetr * TP_N, 0.0);
+  const bool skew = m.handover_processing_kind == 2;
+  if (skew) m.tetra_skew_coord.assign((size_t)ntetr * 168, 0.0);
   const int64_t last_slice_start = ntetr - ntetr / m.grid_size[1] + 1;
   const double two_pi_nfp = 2.0 * PI / m.n_field_periods;
 
@@ -303,6 +305,54 @@ void linearise_tetrahedra(Mesh &m, const VertexFields &vf)
     }
     T[TP_ER_MOD] = std::fabs(er / 4.0);
     T[TP_TETRA_DIST_REF] = 2.0 * PI / m.n_field_periods * T[TP_R1] / m.grid_size[1];
+
+    if (skew) {  // matrices for the position exchange via Cartesian coordinates (tetra_physics_mod.f90:946-1011)
+      // type tetrahedron_skew_coord: skew_coord_x1x2x3(3,3,4) skew_coord_xyz(3,3,4) inv_skew_coord_x1x2x3(3,3,4)
+      // inv_skew_coord_xyz(3,3,4) skew_ref_x1x2x3(3,4) skew_ref_xyz(3,4), column-major
+      double *S = &m.tetra_skew_coord[(size_t)(it - 1) * 168];
+      double xyz[4][3];
+      for (int i = 0; i < 4; i++) {  // verts_xyz (tetra_grid_mod.f90:155-160)
+        const double *vr = &m.verts_rphiz[3 * (size_t)(G[TG_KNOT + i] - 1)];
+        xyz[i][0] = vr[0] * cos(vr[1]); xyz[i][1] = vr[0] * sin(vr[1]); xyz[i][2] = vr[2];
+      }
+      auto inv3 = [](const double *A, double *B) {  // dmatinv3 (various_functions_mod.f90:6-40), A(i,j) = A[i + 3*j]
+        auto a = [&](int i, int j) { return A[(i - 1) + 3 * (j - 1)]; };
+        double detinv = (a(1, 1) * a(2, 2) * a(3, 3) - a(1, 1) * a(2, 3) * a(3, 2) - a(1, 2) * a(2, 1) * a(3, 3) +
+                         a(1, 2) * a(2, 3) * a(3, 1) + a(1, 3) * a(2, 1) * a(3, 2) - a(1, 3) * a(2, 2) * a(3, 1));
+        if (detinv == 0.0) {
+          for (int q = 0; q < 9; q++) B[q] = 0.0;
+          return;
+        }
+        detinv = 1 / detinv;
+        auto b = [&](int i, int j) -> double & { return B[(i - 1) + 3 * (j - 1)]; };
+        b(1, 1) = +detinv * (a(2, 2) * a(3, 3) - a(2, 3) * a(3, 2));
+        b(2, 1) = -detinv * (a(2, 1) * a(3, 3) - a(2, 3) * a(3, 1));
+        b(3, 1) = +detinv * (a(2, 1) * a(3, 2) - a(2, 2) * a(3, 1));
+        b(1, 2) = -detinv * (a(1, 2) * a(3, 3) - a(1, 3) * a(3, 2));
+        b(2, 2) = +detinv * (a(1, 1) * a(3, 3) - a(1, 3) * a(3, 1));
+        b(3, 2) = -detinv * (a(1, 1) * a(3, 2) - a(1, 2) * a(3, 1));
+        b(1, 3) = +detinv * (a(1, 2) * a(2, 3) - a(1, 3) * a(2, 2));
+        b(2, 3) = -detinv * (a(1, 1) * a(2, 3) - a(1, 3) * a(2, 1));
+        b(3, 3) = +detinv * (a(1, 1) * a(2, 2) - a(1, 2) * a(2, 1));
+      };
+      for (int k = 1; k <= 4; k++) {
+        int vi[4];
+        for (int l = 1; l <= 4; l++) vi[l - 1] = ((k + l - 1) % 4);  // modulo(k+l-1,4)+1, 0-based
+        double *cx = S + 9 * (k - 1), *cc = S + 36 + 9 * (k - 1), *icx = S + 72 + 9 * (k - 1), *icc = S + 108 + 9 * (k - 1);
+        double *rx = S + 144 + 3 * (k - 1), *rc = S + 156 + 3 * (k - 1);
+        const double *pp[3] = {p1, p2, p3};
+        for (int i = 0; i < 3; i++) {
+          rx[i] = pp[i][vi[0]];
+          rc[i] = xyz[vi[0]][i];
+          for (int j = 0; j < 3; j++) {
+            cx[i + 3 * j] = pp[i][vi[j + 1]] - pp[i][vi[0]];
+            cc[i + 3 * j] = xyz[vi[j + 1]][i] - xyz[vi[0]][i];
+          }
+        }
+        inv3(cx, icx);
+        inv3(cc, icc);
+      }
+    }
   }
   // sign_sqg = sign(metric_determinant(1, x1(tetra 1)))  (:1019)
   {

@@ -38,6 +38,9 @@ struct Mesh {
   std::vector<double> verts_rphiz;    // [nvert][3]
   std::vector<double> verts_sthetaphi;  // [nvert][3] (flux-coordinate grids)
   std::vector<double> verts_theta_vmec; // [nvert]
+  // handover_processing_kind = 2: type tetrahedron_skew_coord (tetra_physics_mod.f90:89-99), [ntetr][168]
+  int32_t handover_processing_kind = 1;
+  std::vector<double> tetra_skew_coord;
   double cm_over_e = 0, particle_mass = 0, particle_charge = 0;
   int32_t sign_sqg = 1, coord_system = 1, n_field_periods = 1, grid_kind = 0;
   int32_t grid_size[3] = {0, 0, 0};

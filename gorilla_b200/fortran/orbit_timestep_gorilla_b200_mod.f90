@@ -37,6 +37,7 @@ module orbit_timestep_gorilla_b200_mod
     integer(c_int32_t) :: sign_sqg, coord_system, n_field_periods, grid_kind
     integer(c_int32_t) :: grid_size(3), pad0
     real(c_double)     :: Rmin, Rmax, Zmin, Zmax, sfc_s_min
+    type(c_ptr)        :: tetra_skew_coord   ! c_loc(tetra_skew_coord(1)) if handover_processing_kind = 2, else c_null_ptr
   end type
   !> struct gorilla_counters
   type, bind(C) :: gorilla_b200_counters_t
@@ -90,7 +91,7 @@ contains
 
   !> Upload what initialize_gorilla left in the module arrays (orbit_timestep_gorilla.f90:151-274).
   subroutine initialize_gorilla_b200(ierr)
-    use tetra_physics_mod, only: tetra_physics, cm_over_e, particle_mass, particle_charge, sign_sqg, coord_system
+    use tetra_physics_mod, only: tetra_skew_coord, tetra_physics, cm_over_e, particle_mass, particle_charge, sign_sqg, coord_system
     use tetra_grid_mod, only: tetra_grid, ntetr, Rmin, Rmax, Zmin, Zmax
     use tetra_grid_settings_mod, only: grid_kind, grid_size, n_field_periods, sfc_s_min
     use gorilla_settings_mod
@@ -105,6 +106,8 @@ contains
     md%sign_sqg = sign_sqg; md%coord_system = coord_system; md%n_field_periods = n_field_periods
     md%grid_kind = grid_kind; md%grid_size = grid_size; md%pad0 = 0
     md%Rmin = Rmin; md%Rmax = Rmax; md%Zmin = Zmin; md%Zmax = Zmax; md%sfc_s_min = sfc_s_min
+    md%tetra_skew_coord = c_null_ptr
+    if (handover_processing_kind == 2) md%tetra_skew_coord = c_loc(tetra_skew_coord(1))   ! sequence type, 168 doubles
     st%eps_Phi = eps_Phi; st%coord_system = coord_system; st%ispecies = ispecies
     st%boole_periodic_relocation = merge(1, 0, boole_periodic_relocation)
     st%ipusher = ipusher; st%boole_pusher_ode45 = merge(1, 0, boole_pusher_ode45)

@@ -36,6 +36,7 @@ enum {
 
 #define GORILLA_TETRA_PHYSICS_NDOUBLES 142 /* sizeof(type tetrahedron_physics)/8, tetra_physics_mod.f90:9-83 */
 #define GORILLA_TETRA_GRID_NINTS 20        /* sizeof(type tetrahedron_grid)/4,    tetra_grid_mod.f90:6-15   */
+#define GORILLA_TETRA_SKEW_NDOUBLES 168     /* sizeof(type tetrahedron_skew_coord)/8, tetra_physics_mod.f90:89-99 */
 
 /* The subset of namelist GORILLANML (gorilla_settings_mod.f90:94-105) that the hot path reads. */
 typedef struct gorilla_settings {
@@ -52,7 +53,8 @@ typedef struct gorilla_settings {
   int32_t boole_guess;
   int32_t i_time_tracing_option;     /* 1 dt/dtau constant per cell | 2 Hamiltonian time (ipusher = 2 only,
                                         gorilla_settings_mod.f90:124-129) */
-  int32_t handover_processing_kind;  /* must be 1 */
+  int32_t handover_processing_kind;  /* 1 periodic shifts | 2 position exchange via Cartesian skew coordinates
+                                        (pusher_tetra_func_mod.f90:59-89; polynomial pusher, needs tetra_skew_coord) */
   int32_t boole_adaptive_time_steps; /* energy-controlled sub-stepping (pusher_tetra_poly.f90:830-1254); polynomial pusher,
                                         i_time_tracing_option = 1, not combined with optional quantities / events */
   int32_t boole_strong_electric_field; /* ExB-drift terms of order v_E^2; cylindrical grids (coord_system 1) only */
@@ -86,6 +88,8 @@ typedef struct gorilla_mesh_desc {
   int32_t pad0;
   double Rmin, Rmax, Zmin, Zmax; /* tetra_grid_mod (rectangular grids; unused otherwise) */
   double sfc_s_min;              /* tetra_grid_settings_mod */
+  const double *tetra_skew_coord; /* tetra_skew_coord(1:ntetr) (`sequence` type, 168 doubles, tetra_physics_mod.f90:89-99);
+                                     NULL unless handover_processing_kind = 2 */
 } gorilla_mesh_desc;
 
 typedef struct gorilla_b200_handle gorilla_b200_handle;

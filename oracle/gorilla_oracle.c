@@ -698,6 +698,41 @@ static void handover2neighbour(const gor_mesh *m, int ind_tetr, int *ind_tetr_ou
   *iface_inout = g[TG_NEIGHBOUR_FACE + iface - 1];
   *iper_phi = g[TG_PERBOU_PHI + iface - 1];
   int iper_theta = g[TG_PERBOU_THETA + iface - 1];
+  if (m->handover_processing_kind == 2) { /* position exchange via Cartesian variables (skew coordinates), :59-89 */
+    /* type tetrahedron_skew_coord, column-major: skew_coord_x1x2x3(3,3,4) @0, skew_coord_xyz @36, inv_skew_coord_x1x2x3 @72,
+     * inv_skew_coord_xyz @108, skew_ref_x1x2x3(3,4) @144, skew_ref_xyz(3,4) @156.  A particle that leaves the domain
+     * (neighbour -1) keeps its exit position: the reference indexes tetra_skew_coord(-1) there. */
+    const int iface_out = *iface_inout;
+    if (*ind_tetr_out < 1) return;
+    const double *A = m->tetra_skew_coord + (int64_t)(ind_tetr - 1) * 168, *B = m->tetra_skew_coord + (int64_t)(*ind_tetr_out - 1) * 168;
+    const int k = iface - 1, g = iface_out - 1;
+    double b[3], t[3], x_lin_cart[3];
+    for (int i = 0; i < 3; i++) b[i] = x[i] - A[144 + 3 * k + i];
+    for (int i = 0; i < 3; i++) { /* matmul(inv_skew_coord_x1x2x3(:,:,iface), b) */
+      double acc = 0.0;
+      for (int j = 0; j < 3; j++) acc = acc + A[72 + 9 * k + i + 3 * j] * b[j];
+      t[i] = acc;
+    }
+    for (int i = 0; i < 3; i++) { /* matmul(skew_coord_xyz(:,:,iface), .) */
+      double acc = 0.0;
+      for (int j = 0; j < 3; j++) acc = acc + A[36 + 9 * k + i + 3 * j] * t[j];
+      x_lin_cart[i] = acc;
+    }
+    for (int i = 0; i < 3; i++) x_lin_cart[i] = x_lin_cart[i] + A[156 + 3 * k + i];
+    for (int i = 0; i < 3; i++) b[i] = x_lin_cart[i] - B[156 + 3 * g + i];
+    for (int i = 0; i < 3; i++) { /* matmul(inv_skew_coord_xyz(:,:,iface_out), b) */
+      double acc = 0.0;
+      for (int j = 0; j < 3; j++) acc = acc + B[108 + 9 * g + i + 3 * j] * b[j];
+      t[i] = acc;
+    }
+    for (int i = 0; i < 3; i++) { /* matmul(skew_coord_x1x2x3(:,:,iface_out), .) */
+      double acc = 0.0;
+      for (int j = 0; j < 3; j++) acc = acc + B[9 * g + i + 3 * j] * t[j];
+      x[i] = acc;
+    }
+    for (int i = 0; i < 3; i++) x[i] = x[i] + B[144 + 3 * g + i];
+    return;
+  }
   if (m->coord_system == 1) {
     if (*iper_phi == 1)
       x[1] = x[1] - 2.0 * PI / m->n_field_periods;

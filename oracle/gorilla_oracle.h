@@ -74,6 +74,9 @@ typedef struct {
   /* adaptive energy-controlled sub-stepping (gorilla_settings_mod.f90:75-77) */
   int32_t boole_adaptive_time_steps, max_n_intermediate_steps;
   double desired_delta_energy;
+  /* handover_processing_kind = 2: tetra_skew_coord [ntetr][168] (tetra_physics_mod.f90:89-99), else NULL / 1 */
+  const double *tetra_skew_coord;
+  int32_t handover_processing_kind;
 } gor_mesh;
 
 /* optional per-particle trace of the visited (ind_tetr, iface) sequence */

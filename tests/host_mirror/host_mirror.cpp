@@ -14,7 +14,7 @@
 using namespace gb;
 
 struct HostMirror {
-  std::vector<double> geom, bpart, phi, cold, se, ham;
+  std::vector<double> geom, bpart, phi, cold, se, ham, skew;
   gb::FindBins bins;
   MeshDev m;
   int poly_order, boole_periodic_relocation, ipusher, adaptive;
@@ -136,7 +136,7 @@ extern "C" {
 
 void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, int boole_periodic_relocation, int ipusher,
                 int boole_strong_electric_field, int i_time_tracing_option, int oq_mask, int boole_adaptive_time_steps,
-                double desired_delta_energy, int max_n_intermediate_steps)
+                double desired_delta_energy, int max_n_intermediate_steps, int handover_processing_kind)
 {
   HostMirror *h = new HostMirror();
   bool has_phi = false;
@@ -152,6 +152,10 @@ void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, in
   m.time_tracing = i_time_tracing_option;
   h->oq_mask = (unsigned)oq_mask;
   h->adaptive = boole_adaptive_time_steps;
+  if (handover_processing_kind == 2 && md->tetra_skew_coord) {
+    repack_skew(md, h->skew);
+    m.skew = h->skew.data();
+  }
   m.desired_delta_energy = desired_delta_energy;
   m.max_n_intermediate_steps = max_n_intermediate_steps;
   if (build_find_bins(md, h->bins)) {
@@ -218,7 +222,7 @@ int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *v
     } else
 #define HM_RUNT(K, PHI) run_particle<K, PHI, 1>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
       t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, trace_cap, tt, tf, force_full, fallback)
-    if (h->ipusher == 2 && m.time_tracing == 2 && !(optq && h->oq_mask)) {   // same dispatch as launch_orbit_k
+    if (h->ipusher == 2 && m.time_tracing == 2 && !(optq && h->oq_mask) && !m.skew) {   // same dispatch as launch_orbit_k
       if (m.se) {
         switch (h->poly_order) { case 1: HM_RUNT(1, 2); break; case 2: HM_RUNT(2, 2); break; case 3: HM_RUNT(3, 2); break; default: HM_RUNT(4, 2); }
       } else if (m.phi) {
@@ -227,7 +231,7 @@ int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *v
         switch (h->poly_order) { case 1: HM_RUNT(1, 0); break; case 2: HM_RUNT(2, 0); break; case 3: HM_RUNT(3, 0); break; default: HM_RUNT(4, 0); }
       }
     } else
-    if (h->ipusher == 2 && optq && h->oq_mask) {
+    if (h->ipusher == 2 && ((optq && h->oq_mask) || m.skew)) {
       if (m.se) {
         switch (h->poly_order) { case 1: HM_RUNX(1, 2); break; case 2: HM_RUNX(2, 2); break; case 3: HM_RUNX(3, 2); break; default: HM_RUNX(4, 2); }
       } else if (m.phi) {

@@ -25,7 +25,8 @@ class GorMesh(C.Structure):
         ("boole_dt_dtau", C.c_int32), ("i_time_tracing_option", C.c_int32),
         ("boole_time_hamiltonian", C.c_int32), ("boole_gyrophase", C.c_int32), ("boole_vpar_int", C.c_int32),
         ("boole_vpar2_int", C.c_int32), ("boole_adaptive_time_steps", C.c_int32), ("max_n_intermediate_steps", C.c_int32),
-        ("desired_delta_energy", C.c_double),
+        ("desired_delta_energy", C.c_double), ("tetra_skew_coord", C.POINTER(C.c_double)),
+        ("handover_processing_kind", C.c_int32),
     ]
 
 
@@ -129,6 +130,9 @@ class OracleMesh:
         m.boole_adaptive_time_steps = int(settings.boole_adaptive_time_steps)
         m.max_n_intermediate_steps = int(settings.max_n_intermediate_steps)
         m.desired_delta_energy = float(settings.desired_delta_energy)
+        m.handover_processing_kind = int(settings.handover_processing_kind)
+        if settings.handover_processing_kind == 2:
+            m.tetra_skew_coord = mesh.tetra_skew_coord.ctypes.data_as(C.POINTER(C.c_double))
         self.c = m
         self.L = load_oracle()
 

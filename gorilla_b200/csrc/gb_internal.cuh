@@ -218,13 +218,13 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K)) orbit_kernel(con
       if constexpr (K == 0) {  // ipusher = 1: RK4 pusher
         if (!bt.force_full) {
           const double x[3] = {LS(LS_X0), LS(LS_X1), LS(LS_X2)};
-          RkPusher<PHI> R;
+          RkPusher<PHI, (EXT == 2 ? 2 : 0)> R;
           R.P.r.set_stash(&s_stash[0][tid_now()], GB_THREADS);
           R.init(&m, perpinv, ind_tetr, x, iface, LS(LS_VPAR), LS(LS_TREM));
           done = R.template push<true>(o);
         }
         if (!done)
-          o = push_rk_full_call<PHI>(&m, perpinv, ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2), LS(LS_VPAR), LS(LS_TREM));
+          o = push_rk_full_call<PHI, (EXT == 2 ? 2 : 0)>(&m, perpinv, ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2), LS(LS_VPAR), LS(LS_TREM));
       } else {
         if (!bt.force_full) {
           const double x[3] = {LS(LS_X0), LS(LS_X1), LS(LS_X2)};

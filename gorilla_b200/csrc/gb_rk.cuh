@@ -1,7 +1,7 @@
 // gb_rk.cuh -- Runge-Kutta (RK4) tetrahedron pusher, FP64, one particle per lane.
 //
 // Replaces (reference file:line), for boole_pusher_ode45 = .false., boole_dt_dtau = .true.,
-// boole_newton_precalc = .false., handover_processing_kind = 1:
+// boole_newton_precalc = .false., handover_processing_kind = 1 (2 in the EXT = 2 variant):
 //   initialize_pusher_tetra_rk_mod        SRC/pusher_tetra_rk.f90:50-193
 //   pusher_tetra_rk                       :197-575
 //   quad_analytic_approx                  :636-809
@@ -38,9 +38,10 @@ GB_HD void bm_vec_rk(double *o, const PP &P, const double *z)
   o[3] = P.b[3] + P.A.s * z[3];
 }
 
-template <int PHI>
+// EXT = 2: hand-over via Cartesian skew coordinates when the mesh carries them (handover_processing_kind = 2)
+template <int PHI, int EXT = 0>
 struct RkPusher {
-  PolyPusher<1, PHI> P;  // record, z_init, sign_rhs, dt_dtau_const, b, A (= amat | Bvec | spamat)
+  PolyPusher<1, PHI, EXT> P;  // record, z_init, sign_rhs, dt_dtau_const, b, A (= amat | Bvec | spamat)
   double dist_min, dist_max, dtau_ref, dtau_max, dtau_quad, t_remain;
   int iface_init, sign_t_step, fallback;
 
@@ -770,11 +771,11 @@ struct RkPusher {
   }
 };
 
-template <int PHI>
+template <int PHI, int EXT = 0>
 GB_HD_NOINLINE PushOut push_rk_full_call(const MeshDev *mp, double perpinv, int ind_tetr, int iface, double x0, double x1,
                                          double x2, double vpar, double t_remain)
 {
-  RkPusher<PHI> R;
+  RkPusher<PHI, EXT> R;
   double stash[6];
   R.P.r.set_stash(stash, 1);
   PushOut o;

@@ -194,9 +194,8 @@ static int check_settings(const gorilla_settings *s)
     return fail(GORILLA_ERR_ARG, "boole_gyrophase requires boole_time_Hamiltonian = .true.");
   if (s->handover_processing_kind != 1 && s->handover_processing_kind != 2)
     return fail(GORILLA_ERR_ARG, "handover_processing_kind must be 1 or 2");
-  if (s->handover_processing_kind == 2 && (s->ipusher != 2 || s->boole_adaptive_time_steps))
-    return fail(GORILLA_ERR_UNSUPPORTED,
-                "handover_processing_kind = 2 is built for the polynomial pusher without adaptive sub-stepping");
+  if (s->handover_processing_kind == 2 && s->boole_adaptive_time_steps)
+    return fail(GORILLA_ERR_UNSUPPORTED, "handover_processing_kind = 2 is not combined with adaptive sub-stepping");
   if (s->boole_adaptive_time_steps) {
     if (s->ipusher != 2) return fail(GORILLA_ERR_ARG, "boole_adaptive_time_steps exists for the polynomial pusher only");
     // pusher_tetra_poly.f90:868-874
@@ -403,6 +402,7 @@ GB_EXTERN_ORBIT_X(1, 2)
 GB_EXTERN_ORBIT_X(2, 2)
 GB_EXTERN_ORBIT_X(3, 2)
 GB_EXTERN_ORBIT_X(4, 2)
+GB_EXTERN_ORBIT_X(0, 2)   // RK4 with handover_processing_kind = 2 (gb_orbit_rkx.cu)
 GB_EXTERN_ORBIT_X(1, 3)
 GB_EXTERN_ORBIT_X(2, 3)
 GB_EXTERN_ORBIT_X(3, 3)
@@ -411,7 +411,7 @@ GB_EXTERN_ORBIT_X(4, 3)
 template <int PHI>
 static int launch_orbit_k(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
 {
-  if (h->settings.ipusher == 1) return launch_orbit_t<0, PHI>(h, bt, s);
+  if (h->settings.ipusher == 1) return h->mesh.skew ? launch_orbit_t<0, PHI, 2>(h, bt, s) : launch_orbit_t<0, PHI>(h, bt, s);
   if (((bt.optq && bt.oq_mask) || bt.ev_flags) && h->settings.boole_adaptive_time_steps)
     return fail(GORILLA_ERR_UNSUPPORTED, "boole_adaptive_time_steps is not combined with optional quantities / events");
   if ((bt.optq && bt.oq_mask) || bt.ev_flags || h->mesh.skew) {   // handover kind 2 lives in the EXT = 2 kernels

@@ -54,7 +54,7 @@ typedef struct gorilla_settings {
   int32_t i_time_tracing_option;     /* 1 dt/dtau constant per cell | 2 Hamiltonian time (ipusher = 2 only,
                                         gorilla_settings_mod.f90:124-129) */
   int32_t handover_processing_kind;  /* 1 periodic shifts | 2 position exchange via Cartesian skew coordinates
-                                        (pusher_tetra_func_mod.f90:59-89; polynomial pusher, needs tetra_skew_coord) */
+                                        (pusher_tetra_func_mod.f90:59-89; needs gorilla_mesh_desc.tetra_skew_coord) */
   int32_t boole_adaptive_time_steps; /* energy-controlled sub-stepping (pusher_tetra_poly.f90:830-1254); polynomial pusher,
                                         i_time_tracing_option = 1, not combined with optional quantities / events */
   int32_t boole_strong_electric_field; /* ExB-drift terms of order v_E^2; cylindrical grids (coord_system 1) only */

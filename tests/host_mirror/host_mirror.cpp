@@ -64,13 +64,13 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
     bool done = false;
     if constexpr (K == 0) {
       if (!force_full) {
-        RkPusher<PHI> R;
+        RkPusher<PHI, (EXT == 2 ? 2 : 0)> R;
         double stash[6];
         R.P.r.set_stash(stash, 1);
         R.init(&m, perpinv, ind_tetr, x, iface, vpar, t_remain);
         done = R.template push<true>(o);
       }
-      if (!done) o = push_rk_full_call<PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
+      if (!done) o = push_rk_full_call<PHI, (EXT == 2 ? 2 : 0)>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
     } else {
       if (!force_full) {
         PolyPusher<K, PHI, EXT> P;
@@ -230,6 +230,9 @@ int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *v
       } else {
         switch (h->poly_order) { case 1: HM_RUNT(1, 0); break; case 2: HM_RUNT(2, 0); break; case 3: HM_RUNT(3, 0); break; default: HM_RUNT(4, 0); }
       }
+    } else
+    if (h->ipusher == 1 && m.skew) {
+      if (m.se) HM_RUNX(0, 2); else if (m.phi) HM_RUNX(0, 1); else HM_RUNX(0, 0);
     } else
     if (h->ipusher == 2 && ((optq && h->oq_mask) || m.skew)) {
       if (m.se) {

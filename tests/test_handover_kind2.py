@@ -65,11 +65,15 @@ def test_same_orbits_as_kind_1(skew_mesh):
     assert same(out[1][2]["trace_tetr"][ok], out[2][2]["trace_tetr"][ok])
 
 
-@pytest.mark.parametrize("K", [1, 2, 3, 4])
+@pytest.mark.parametrize("K", [0, 1, 2, 3, 4])
 def test_host_mirror_parity(skew_mesh, K):
     mesh, _, settings = skew_mesh
-    for st, ff, t in ((_with(settings, poly_order=K), False, 5e-6),
-                      (_with(settings, poly_order=K, i_time_tracing_option=2, boole_time_Hamiltonian=True), True, -4e-6)):
+    if K == 0:      # RK4 pusher
+        cases = ((_with(settings, ipusher=1), False, 5e-6), (_with(settings, ipusher=1), True, -4e-6))
+    else:
+        cases = ((_with(settings, poly_order=K), False, 5e-6),
+                 (_with(settings, poly_order=K, i_time_tracing_option=2, boole_time_Hamiltonian=True), True, -4e-6))
+    for st, ff, t in cases:
         om, hm = OracleMesh(mesh, st), HostMirror(mesh, st)
         xa, va, wa = workloads.particles_cyl(120, 4)
         xb, vb, wb = xa.copy(), va.copy(), wa.copy()
@@ -87,8 +91,7 @@ def test_host_mirror_parity(skew_mesh, K):
 
 def test_settings_rules(product_lib, skew_mesh, small_mesh):
     mesh, _, settings = skew_mesh
-    for bad, code in ((_with(settings, ipusher=1), 2),
-                      (_with(settings, boole_adaptive_time_steps=True, desired_delta_energy=1e-10, max_n_intermediate_steps=10), 2),
+    for bad, code in ((_with(settings, boole_adaptive_time_steps=True, desired_delta_energy=1e-10, max_n_intermediate_steps=10), 2),
                       (_with(settings, handover_processing_kind=3), 1)):
         with pytest.raises(api.GorillaError) as ei:
             api.Gorilla(mesh, bad)
@@ -100,11 +103,11 @@ def test_settings_rules(product_lib, skew_mesh, small_mesh):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("K", [2, 4])
+@pytest.mark.parametrize("K", [0, 2, 4])
 def test_gpu_parity(skew_mesh, cuda_device, K):
     from gorilla_b200 import Gorilla
     mesh, _, settings = skew_mesh
-    st = _with(settings, poly_order=K)
+    st = _with(settings, ipusher=1) if K == 0 else _with(settings, poly_order=K)
     om, g = OracleMesh(mesh, st), Gorilla(mesh, st)
     n = 500
     xa, va, wa = workloads.particles_cyl(n, 4)

@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--ipusher", type=int, default=0, help="1 = RK4 pusher, 2 = polynomial pusher (0 = workload default)")
     ap.add_argument("--time-tracing", type=int, default=0, choices=[0, 1, 2],
                     help="i_time_tracing_option: 1 = dt/dtau constant per cell, 2 = Hamiltonian time (0 = workload default)")
+    ap.add_argument("--optional-quantities", action="store_true",
+                    help="also form pusher_tetra_poly's optional quantities (t_hamiltonian, gyrophase, vpar_int, vpar2_int)")
     ap.add_argument("--adaptive", type=float, default=0.0,
                     help="boole_adaptive_time_steps with this desired_delta_energy (max_n_intermediate_steps = 10000)")
     ap.add_argument("--t-step", type=float, default=0.0, help="physical time per step [s] (0 = workload default)")
@@ -183,6 +185,8 @@ def reference_arm(args):
     if args.adaptive > 0.0:
         settings.boole_adaptive_time_steps = True
         settings.desired_delta_energy = args.adaptive
+    if getattr(args, "optional_quantities", False):
+        settings.boole_time_Hamiltonian = settings.boole_gyrophase = settings.boole_vpar_int = settings.boole_vpar2_int = True
     t_step = args.t_step or wl["t_step"]
     mesh = build_mesh(wl["grid"], settings)
     cores = os.cpu_count() or 1
@@ -234,6 +238,8 @@ def main():
     if args.adaptive > 0.0:
         settings.boole_adaptive_time_steps = True
         settings.desired_delta_energy = args.adaptive
+    if getattr(args, "optional_quantities", False):
+        settings.boole_time_Hamiltonian = settings.boole_gyrophase = settings.boole_vpar_int = settings.boole_vpar2_int = True
     t_step = args.t_step or wl["t_step"]
     n = args.particles or wl["n_default"]
 
@@ -249,7 +255,7 @@ def main():
     strong = bool(settings.boole_strong_electric_field)
     bytes_per_crossing = BYTES_PER_CROSSING[has_phi or strong] + (BYTES_STRONG_E if strong else 0.0)
     ext = settings.ipusher == 2 and settings.i_time_tracing_option == 2
-    if ext:
+    if ext or args.optional_quantities:
         bytes_per_crossing += 64.0   # hamiltonian_time record (8 doubles) read at the end of every push
 
     # particles of this rank (weak scaling: n per GPU fixed); independent streams per rank
@@ -263,6 +269,14 @@ def main():
     find_ms = g.counters().find_ms
     n_located = int((it > 0).sum())
 
+    oqd = torch.zeros((n, 4), dtype=torch.float64, device=dev) if args.optional_quantities else None
+
+    def step_dev():
+        if oqd is not None:
+            g.orbit_timestep_gorilla_optional_dev(xd, vd, wd, t_step, bd, it, fd, oqd, n_pushes=npd, stream=stream)
+        else:
+            g.orbit_timestep_gorilla_dev(xd, vd, wd, t_step, bd, it, fd, n_pushes=npd, stream=stream)
+
     def resort():
         perm = torch.empty(n, dtype=torch.int64, device=dev)
         g.sort_permutation_dev(it, perm, stream=stream)
@@ -271,7 +285,7 @@ def main():
     for _ in range(args.warmup):
         if args.sort:
             xd, vd, wd, bd, it, fd = resort()
-        g.orbit_timestep_gorilla_dev(xd, vd, wd, t_step, bd, it, fd, n_pushes=npd, stream=stream)
+        step_dev()
     torch.cuda.synchronize()
 
     # ---- timed region: K steps, device time via CUDA events on the launch stream, max over ranks
@@ -291,7 +305,7 @@ def main():
     for _ in range(args.steps):
         if args.sort:
             xd, vd, wd, bd, it, fd = resort()
-        g.orbit_timestep_gorilla_dev(xd, vd, wd, t_step, bd, it, fd, n_pushes=npd, stream=stream)
+        step_dev()
         c = g.counters()           # synchronises the stream; reads the device counters of this step
         pushes += c.n_pushes
         kernel_ms += c.kernel_ms
@@ -372,7 +386,7 @@ def main():
         fp64 = {"achieved": fp64_ach / 1e12, "peak": muladd_peak / 1e12, "unit": "Tinst/s (thread-level DMUL/DADD)",
                 "frac": fp64_ach / muladd_peak, "inst_per_crossing": fp64_per, "dfma_peak": dfma_peak / 1e12,
                 "peak_source": "measured in this run (gorilla_b200_fp64_peak)"}
-        kern = f"orbit_kernel<{0 if settings.ipusher == 1 else settings.poly_order},{2 if strong else 1 if has_phi else 0}{',EXT=1' if ext else ',EXT=3' if settings.boole_adaptive_time_steps else ''}>"
+        kern = f"orbit_kernel<{0 if settings.ipusher == 1 else settings.poly_order},{2 if strong else 1 if has_phi else 0}{',EXT=2' if args.optional_quantities else ',EXT=1' if ext else ',EXT=3' if settings.boole_adaptive_time_steps else ''}>"
         if t_hbm >= t_fp64:
             roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "kernel": kern,
@@ -400,6 +414,7 @@ def main():
             "config": {"workload": wl["name"], "desc": wl["desc"], "ipusher": settings.ipusher,
                        "poly_order": settings.poly_order, "i_time_tracing_option": settings.i_time_tracing_option,
                        "boole_adaptive_time_steps": bool(settings.boole_adaptive_time_steps),
+                       "optional_quantities": bool(args.optional_quantities),
                        "desired_delta_energy": settings.desired_delta_energy if settings.boole_adaptive_time_steps else None,
                        "particles_per_gpu": n, "t_step_s": t_step, "ntetr": mesh.ntetr,
                        "mesh_hot_bytes": int(mesh.ntetr * (352 + (160 if has_phi else 0))),

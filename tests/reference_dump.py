@@ -8,7 +8,8 @@ particles the state after one orbit_timestep_gorilla call (SRC/orbit_timestep_go
 Fortran file; `write_dump` here produces the same bytes so that the reader and the check are tested without
 gfortran (tests/test_reference_dump.py).
 
-Test infrastructure: `check_oracle` runs the C oracle, `check_device` the CUDA path through the C ABI.
+Test infrastructure: `check_oracle` runs the C oracle, `check_host_mirror` the device headers compiled for the host,
+`check_device` the CUDA path through the C ABI.
 
     python tests/reference_dump.py particles OUT.bin --n 2000 --trace-cap 64 --t-step 1e-5 --kind cyl|flux ...
     python tests/reference_dump.py check gorilla_reference_dump.bin [--device] [--gmesh OUT.gmesh]
@@ -173,6 +174,10 @@ def _compare(d: ReferenceDump, got: dict) -> dict:
     for k in _STATE_KEYS:
         a, b = d.results[k], got[k]
         neq = ~((a == b) | ((a != a) & (b != b))) if a.dtype.kind == "f" else (a != b)
+        if k == "t_remain":
+            # a particle find_tetra could not place returns before t_remain_out is assigned (orbit_timestep_gorilla.f90:57-59):
+            # the value is undefined in the reference (the dump program writes 0 there), so it is not compared
+            neq = neq & (d.results["boole_initialized"] != 0)
         cnt = int(np.count_nonzero(neq.reshape(neq.shape[0], -1).any(axis=1))) if neq.size else 0
         if cnt:
             bad[k] = cnt
@@ -201,6 +206,21 @@ def run_device(d: ReferenceDump) -> dict:
     g.close()
     return dict(x=x, vpar=vpar, vperp=vperp, t_remain=t_rem, boole_initialized=binit, ind_tetr=ind, iface=ifc,
                 n_pushes=npush.astype(np.int32), trace_ind_tetr=tt, trace_iface=tf)
+
+
+def run_host_mirror(d: ReferenceDump) -> dict:
+    """The device headers compiled for the host (tests/host_mirror): the kernels' algorithm without a GPU."""
+    from host_mirror_binding import HostMirror
+    mesh, st = mesh_and_settings(d)
+    hm = HostMirror(mesh, st)
+    x, vpar, vperp, binit, ind, ifc = _fresh(d)
+    r = hm.orbit_timestep(x, vpar, vperp, d.t_step, binit, ind, ifc, d.trace_cap)
+    return dict(x=x, vpar=vpar, vperp=vperp, t_remain=r["t_remain"], boole_initialized=binit, ind_tetr=ind, iface=ifc,
+                n_pushes=r["n_pushes"].astype(np.int32), trace_ind_tetr=r["trace_tetr"], trace_iface=r["trace_face"])
+
+
+def check_host_mirror(d: ReferenceDump) -> dict:
+    return _compare(d, run_host_mirror(d))
 
 
 def check_oracle(d: ReferenceDump) -> dict:
@@ -255,6 +275,9 @@ def _cli():
         mesh_and_settings(d)[0].save(a.gmesh)
     bad = check_oracle(d)
     print("oracle vs reference:", "bit-identical" if not bad else f"DIFFERS {bad}")
+    bh = check_host_mirror(d)
+    print("device headers on the host vs reference:", "bit-identical" if not bh else f"DIFFERS {bh}")
+    bad.update({"host_mirror_" + k: v for k, v in bh.items()})
     if a.device:
         bd = check_device(d)
         print("CUDA path vs reference:", "bit-identical" if not bd else f"DIFFERS {bd}")

@@ -59,6 +59,7 @@ def test_dump_format_round_trip_and_oracle_check(tmp_path, small_mesh, small_mes
     assert d.results["n_pushes"].sum() > 1000
     # the check: oracle on the dumped mesh reproduces the dumped results
     assert rd.check_oracle(d) == {}
+    assert rd.check_host_mirror(d) == {}   # the kernels' algorithm (device headers compiled for the host)
     # ... and a dump whose reference results differ in one bit / one cell is caught
     d.results["vpar"][5] = np.nextafter(d.results["vpar"][5], np.inf)
     d.results["trace_ind_tetr"][7, 3] += 1
@@ -114,8 +115,10 @@ def test_particle_file_layout(tmp_path):
 
 @pytest.mark.skipif(not REAL_DUMPS, reason="no dump of the gfortran build committed yet: parity unpinned (DESIGN.md section 4)")
 @pytest.mark.parametrize("path", REAL_DUMPS, ids=lambda p: p.name)
-def test_committed_reference_dumps_pin_the_oracle(path, product_lib, oracle_lib):
-    assert rd.check_oracle(rd.read_dump(path)) == {}
+def test_committed_reference_dumps_pin_the_oracle(path, product_lib, oracle_lib, host_mirror_lib):
+    d = rd.read_dump(path)
+    assert rd.check_oracle(d) == {}
+    assert rd.check_host_mirror(d) == {}
 
 
 @pytest.mark.gpu

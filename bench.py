@@ -29,6 +29,10 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 METRIC = "particle_tetra_crossings_per_second"
 UNIT = "crossings/s"
+# the shipped library is the strict build; GORILLA_B200_LIB=.../libgorilla_b200_fma.so (GORILLA_VARIANT=fma
+# GORILLA_NVCC_EXTRA=--fmad=true python -m gorilla_b200.build) is a measurement-only variant that is NOT bit-exact
+FP_MODE = ("fma (--fmad=true, measurement-only variant, not bit-exact)" if "_fma" in os.environ.get("GORILLA_B200_LIB", "")
+           else "strict (--fmad=false, bit-exact vs oracle)")
 BYTES_PER_CROSSING = {False: 344.0, True: 488.0}  # hot record (+8 B topology), without/with Phi part
 BYTES_STRONG_E = 192.0  # + 24 doubles of the strong-electric-field group
 # FP64 thread-instructions (DADD+DMUL+DFMA) and DRAM bytes per crossing of the strict build, from one ncu capture per
@@ -420,7 +424,7 @@ def main():
                        "mesh_hot_bytes": int(mesh.ntetr * (352 + (160 if has_phi else 0))),
                        "l2_policy": "inputs_larger_than_l2 (mesh hot records > 126 MB, gathered at random)",
                        "parallelism": f"particles sharded over {world} GPU(s), mesh replicated",
-                       "sort_by_tetra_each_step": bool(args.sort), "fp_mode": "strict (--fmad=false, bit-exact vs oracle)"},
+                       "sort_by_tetra_each_step": bool(args.sort), "fp_mode": FP_MODE},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "clocks": clocks,
             "counters": {"pushes": tot_pushes, "lost": tot_lost, "particles": tot_n,

@@ -31,7 +31,10 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
     "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off", "-Xptxas", "-v",
 ]
-NVCC_FLAGS += os.environ.get("GORILLA_NVCC_EXTRA", "").split()
+_EXTRA = os.environ.get("GORILLA_NVCC_EXTRA", "").split()
+if any(f.startswith("--fmad") for f in _EXTRA):   # a variant that allows contraction (measurement only: not bit-exact)
+    NVCC_FLAGS = [f for f in NVCC_FLAGS if not f.startswith("--fmad")]
+NVCC_FLAGS += _EXTRA
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas"]
 
 # longest compiles first (order 4 takes ~2 min per unit)

@@ -45,7 +45,10 @@
 !!   int32    trace_ind_tetr [n][trace_cap], trace_iface [n][trace_cap]        (unused slots 0)
 program gorilla_reference_dump
   use tetra_grid_settings_mod, only: load_tetra_grid_inp, grid_kind, grid_size, n_field_periods, sfc_s_min
-  use gorilla_settings_mod
+  use gorilla_settings_mod, only: load_gorilla_inp, eps_Phi, ispecies, boole_periodic_relocation, ipusher, boole_pusher_ode45, &
+                                  boole_dt_dtau, boole_newton_precalc, poly_order, i_precomp, boole_guess, &
+                                  i_time_tracing_option, handover_processing_kind, boole_adaptive_time_steps, &
+                                  desired_delta_energy, max_n_intermediate_steps, boole_strong_electric_field
   use orbit_timestep_gorilla_mod, only: initialize_gorilla, orbit_timestep_gorilla, check_coordinate_domain
   use tetra_physics_mod, only: tetra_physics, tetra_skew_coord, cm_over_e, particle_mass, particle_charge, sign_sqg, &
                                cs_phys => coord_system

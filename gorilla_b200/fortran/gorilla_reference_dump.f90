@@ -99,7 +99,10 @@ program gorilla_reference_dump
   print *, 'gorilla_reference_dump: particles = ', n, ' n_mismatch (traced loop vs orbit_timestep_gorilla) = ', n_mismatch
 
   ! ---- file ------------------------------------------------------------------------------------------------
-  has_sthetaphi = merge(1, 0, allocated(verts_sthetaphi))
+  has_sthetaphi = 0     ! only the field-aligned grids allocate it (create_points)
+  if (allocated(verts_sthetaphi)) then
+    if (size(verts_sthetaphi, 2) >= nvert) has_sthetaphi = 1
+  end if
   has_skew = merge(1, 0, handover_processing_kind == 2)
   open(newunit=u, file='gorilla_reference_dump.bin', access='stream', form='unformatted', status='replace', action='write')
   write(u) 'GREFDMP1'

@@ -100,14 +100,14 @@ contains
     type(gorilla_settings_t)  :: st
     integer(c_int) :: rc
     md%ntetr = int(ntetr, c_int64_t)
-    md%tetra_physics = c_loc(tetra_physics(1))   ! sequence type of 142 doubles -> double[ntetr][142]
-    md%tetra_grid    = c_loc(tetra_grid(1))      ! sequence type of 20 integers -> int32[ntetr][20]
+    md%tetra_physics = addr_tetra_physics(tetra_physics)   ! sequence type of 142 doubles -> double[ntetr][142]
+    md%tetra_grid    = addr_tetra_grid(tetra_grid)         ! sequence type of 20 integers -> int32[ntetr][20]
     md%cm_over_e = cm_over_e; md%particle_mass = particle_mass; md%particle_charge = particle_charge
     md%sign_sqg = sign_sqg; md%coord_system = coord_system; md%n_field_periods = n_field_periods
     md%grid_kind = grid_kind; md%grid_size = grid_size; md%pad0 = 0
     md%Rmin = Rmin; md%Rmax = Rmax; md%Zmin = Zmin; md%Zmax = Zmax; md%sfc_s_min = sfc_s_min
     md%tetra_skew_coord = c_null_ptr
-    if (handover_processing_kind == 2) md%tetra_skew_coord = c_loc(tetra_skew_coord(1))   ! sequence type, 168 doubles
+    if (handover_processing_kind == 2) md%tetra_skew_coord = addr_tetra_skew(tetra_skew_coord)   ! sequence type, 168 doubles
     st%eps_Phi = eps_Phi; st%coord_system = coord_system; st%ispecies = ispecies
     st%boole_periodic_relocation = merge(1, 0, boole_periodic_relocation)
     st%ipusher = ipusher; st%boole_pusher_ode45 = merge(1, 0, boole_pusher_ode45)
@@ -223,5 +223,28 @@ contains
     integer, intent(out) :: ierr
     ierr = gorilla_b200_get_counters(handle, counters)
   end subroutine
+
+  ! Addresses of GORILLA's module arrays.  They are declared `allocatable, public, protected` WITHOUT the target attribute
+  ! (tetra_physics_mod.f90:85,101; tetra_grid_mod.f90:17), so c_loc() cannot be applied to them directly; they are passed to
+  ! an assumed-size dummy that has it.  The arrays are contiguous (no copy-in) and stay allocated until GORILLA deallocates
+  ! them, and the library copies them during gorilla_b200_init, so the address is only used inside that call.
+  function addr_tetra_physics(a) result(p)
+    use tetra_physics_mod, only: tetrahedron_physics
+    type(tetrahedron_physics), intent(in), target :: a(*)
+    type(c_ptr) :: p
+    p = c_loc(a(1))
+  end function
+  function addr_tetra_grid(a) result(p)
+    use tetra_grid_mod, only: tetrahedron_grid
+    type(tetrahedron_grid), intent(in), target :: a(*)
+    type(c_ptr) :: p
+    p = c_loc(a(1))
+  end function
+  function addr_tetra_skew(a) result(p)
+    use tetra_physics_mod, only: tetrahedron_skew_coord
+    type(tetrahedron_skew_coord), intent(in), target :: a(*)
+    type(c_ptr) :: p
+    p = c_loc(a(1))
+  end function
 
 end module orbit_timestep_gorilla_b200_mod

@@ -91,7 +91,10 @@ contains
 
   !> Upload what initialize_gorilla left in the module arrays (orbit_timestep_gorilla.f90:151-274).
   subroutine initialize_gorilla_b200(ierr)
-    use tetra_physics_mod, only: tetra_skew_coord, tetra_physics, cm_over_e, particle_mass, particle_charge, sign_sqg, coord_system
+    ! coord_system exists in tetra_physics_mod (the value the mesh was built with) and in gorilla_settings_mod (the namelist
+    ! entry); both are needed, so the first one is renamed
+    use tetra_physics_mod, only: tetra_skew_coord, tetra_physics, cm_over_e, particle_mass, particle_charge, sign_sqg, &
+                                 coord_system_mesh => coord_system
     use tetra_grid_mod, only: tetra_grid, ntetr, Rmin, Rmax, Zmin, Zmax
     use tetra_grid_settings_mod, only: grid_kind, grid_size, n_field_periods, sfc_s_min
     use gorilla_settings_mod
@@ -103,7 +106,7 @@ contains
     md%tetra_physics = addr_tetra_physics(tetra_physics)   ! sequence type of 142 doubles -> double[ntetr][142]
     md%tetra_grid    = addr_tetra_grid(tetra_grid)         ! sequence type of 20 integers -> int32[ntetr][20]
     md%cm_over_e = cm_over_e; md%particle_mass = particle_mass; md%particle_charge = particle_charge
-    md%sign_sqg = sign_sqg; md%coord_system = coord_system; md%n_field_periods = n_field_periods
+    md%sign_sqg = sign_sqg; md%coord_system = coord_system_mesh; md%n_field_periods = n_field_periods
     md%grid_kind = grid_kind; md%grid_size = grid_size; md%pad0 = 0
     md%Rmin = Rmin; md%Rmax = Rmax; md%Zmin = Zmin; md%Zmax = Zmax; md%sfc_s_min = sfc_s_min
     md%tetra_skew_coord = c_null_ptr

@@ -13,6 +13,7 @@ Test infrastructure: `check_oracle` runs the C oracle, `check_host_mirror` the d
 
     python tests/reference_dump.py particles OUT.bin --n 2000 --trace-cap 64 --t-step 1e-5 --kind cyl|flux ...
     python tests/reference_dump.py check gorilla_reference_dump.bin [--device] [--gmesh OUT.gmesh]
+    python tests/reference_dump.py mesh-diff gorilla_reference_dump.bin --tetra-grid-inp tetra_grid.inp --gorilla-inp gorilla.inp
 """
 from __future__ import annotations
 
@@ -231,6 +232,40 @@ def check_device(d: ReferenceDump) -> dict:
     return _compare(d, run_device(d))
 
 
+# first column of the named members of type tetrahedron_physics (tetra_physics_mod.f90:9-83) inside the 142-double record, as
+# the repack reads them (gorilla_b200/csrc/gb_repack.hpp); a range ends where the next named member starts
+_TP_OFFSETS = dict(x1=0, dist_ref=3, tetra_dist_ref=8, anorm=9, curlA=21, bmod1=24, Aphi1=26, h1_1=27, h2_1=28, h3_1=29, Phi1=30,
+                   R1=31, vE2_1=34, v2Emod_1=36, Er_mod=37, v_E_mod_average=38, dt_dtau_const=40, gBxcurlA=41, gPhixcurlA=42,
+                   gv2EmodxcurlA=43, gBxcurlvE=44, gPhixcurlvE=45, gv2EmodxcurlvE=46, spalpmat=47, spbetmat=48, spgammat=49,
+                   gBxh1=50, gPhixh1=53, gv2Emodxh1=56, gB=59, gPhi=62, gAphi=77, gh1=80, gh2=83, gh3=86, curlh=89, gvE2=95,
+                   curlvE=101, gv2Emod=104, alpmat=107, betmat=116, gammat=125)
+
+
+def mesh_diff(d: ReferenceDump, mesh) -> dict:
+    """Deviation of a mesh built by this library's host builders from the mesh the reference built (same namelists).
+    The host builders restate ~6 k lines of spline / mesh Fortran; bit equality with the Fortran is not claimed for them
+    (SURVEY.md H6), so this reports, per member of tetrahedron_physics, the largest deviation relative to the member's
+    largest magnitude, and for tetra_grid (vertex indices, neighbours, faces, periodic-boundary flags) the share of
+    identical records.  The push itself is pinned on the DUMPED mesh (check_oracle / check_device)."""
+    out = {"ntetr_reference": int(d.head["ntetr"]), "ntetr_built": int(mesh.ntetr)}
+    if d.head["ntetr"] != mesh.ntetr:
+        return out
+    out["tetra_grid_identical_records"] = float(np.mean(np.all(d.tetra_grid == mesh.tetra_grid, axis=1)))
+    names = sorted(_TP_OFFSETS, key=_TP_OFFSETS.get)
+    dev = {}
+    for k, name in enumerate(names):
+        lo = _TP_OFFSETS[name]
+        hi = _TP_OFFSETS[names[k + 1]] if k + 1 < len(names) else 134
+        a, b = d.tetra_physics[:, lo:hi], mesh.tetra_physics[:, lo:hi]
+        scale = float(np.max(np.abs(a)))
+        dev[name] = 0.0 if scale == 0.0 and not np.any(b) else float(np.max(np.abs(a - b)) / (scale or 1.0))
+    out["tetra_physics_max_dev_rel_to_member_scale"] = dev
+    out["tetra_physics_identical_records"] = float(np.mean(np.all(d.tetra_physics == mesh.tetra_physics, axis=1)))
+    for k in ("cm_over_e", "particle_mass", "particle_charge", "sign_sqg", "n_field_periods"):
+        out[k + "_equal"] = bool(d.scalars[k] == mesh.scalars[k])
+    return out
+
+
 def _cli():
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -251,6 +286,10 @@ def _cli():
     c.add_argument("dump")
     c.add_argument("--device", action="store_true")
     c.add_argument("--gmesh", default="", help="also save the dumped mesh as a .gmesh file")
+    m = sub.add_parser("mesh-diff", help="build the mesh of the same namelists with this library and compare it with the dumped one")
+    m.add_argument("dump")
+    m.add_argument("--tetra-grid-inp", required=True)
+    m.add_argument("--gorilla-inp", required=True)
     a = ap.parse_args()
     sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
     sys.path.insert(0, str(Path(__file__).resolve().parent))
@@ -266,6 +305,12 @@ def _cli():
         vpar = (2.0 * rng.random(a.n) - 1.0) * vmod
         write_particles(a.out, x, vpar, np.sqrt(vmod ** 2 - vpar ** 2), a.t_step, a.trace_cap)
         print(f"wrote {a.out}: {a.n} particles, trace_cap {a.trace_cap}, t_step {a.t_step}")
+        return 0
+    if a.cmd == "mesh-diff":
+        import json
+        from gorilla_b200 import build_mesh, load_gorilla_inp, load_tetra_grid_inp
+        built = build_mesh(load_tetra_grid_inp(a.tetra_grid_inp), load_gorilla_inp(a.gorilla_inp))
+        print(json.dumps(mesh_diff(read_dump(a.dump), built), indent=1))
         return 0
     d = read_dump(a.dump)
     print(f"{a.dump}: ntetr {d.head['ntetr']}, grid_kind {d.head['grid_kind']}, ipusher {d.settings['ipusher']}, "

@@ -81,6 +81,24 @@ def test_dumped_mesh_to_gmesh(tmp_path, small_mesh):
     assert m2.scalars["cm_over_e"] == mesh.scalars["cm_over_e"] and m2.scalars["grid_kind"] == 5
 
 
+def test_mesh_diff_of_builder_against_dump(tmp_path, small_mesh):
+    """mesh-diff: a mesh built by the host builders against a dumped one -- identical here (same builder), and a perturbed
+    member / a changed neighbour entry show up under the right name."""
+    mesh, _, settings = small_mesh
+    p = tmp_path / "d.bin"
+    _synthetic_dump(p, mesh, dataclasses.replace(settings, poly_order=2), n=8, cap=4)
+    d = rd.read_dump(p)
+    r = rd.mesh_diff(d, mesh)
+    assert r["tetra_grid_identical_records"] == 1.0 and r["tetra_physics_identical_records"] == 1.0
+    assert set(r["tetra_physics_max_dev_rel_to_member_scale"].values()) == {0.0} and r["cm_over_e_equal"]
+    d.tetra_physics[17, 24] *= 1.0 + 1e-9     # bmod1 of one tetrahedron
+    d.tetra_grid[5, 7] += 1
+    r = rd.mesh_diff(d, mesh)
+    dev = r["tetra_physics_max_dev_rel_to_member_scale"]
+    assert 1e-10 < dev["bmod1"] < 1e-8 and all(v == 0.0 for k, v in dev.items() if k != "bmod1")
+    assert r["tetra_grid_identical_records"] == 1.0 - 1.0 / mesh.ntetr
+
+
 def test_bad_dumps_are_rejected(tmp_path, small_mesh):
     mesh, _, settings = small_mesh
     p = tmp_path / "d.bin"

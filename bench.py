@@ -23,6 +23,17 @@ from pathlib import Path
 
 import numpy as np
 
+
+def _claim_stdout():
+    """stdout carries exactly ONE line, the JSON result.  Libraries write there too (NCCL prints its version banner to
+    stdout at NCCL_DEBUG=VERSION and ignores NCCL_DEBUG_FILE at that level), so the process keeps a private copy of the
+    original stdout for the result and points file descriptor 1 at stderr for everything else."""
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return out
+
+
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
@@ -208,7 +219,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -431,11 +442,14 @@ def main():
                          "fallback_rank0": [int(v) for v in fallback], "adaptive_pushes_rank0": int(n_adaptive), "located_rank0": n_located,
                          "find_tetra_ms_rank0": find_ms, "mesh_build_s_rank0": t_mesh},
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
     g.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+RESULT_OUT = sys.stdout
+
 if __name__ == "__main__":
+    RESULT_OUT = _claim_stdout()
     main()

@@ -4,8 +4,9 @@
 !! and writes, for the settings of the gorilla.inp / tetra_grid.inp in the working directory,
 !!   (1) the mesh the reference built:  tetra_physics(1:ntetr), tetra_grid(1:ntetr), the vertex tables and the
 !!       module scalars the hot path reads (what `gorilla_mesh_desc` of include/gorilla_b200.h carries), and
-!!   (2) for the particles of `dump_particles.bin`: the state after ONE orbit_timestep_gorilla call and the
-!!       (ind_tetr, iface) pair after each of the first trace_cap pusher calls,
+!!   (2) for the particles of `dump_particles.bin`: the state after n_steps successive orbit_timestep_gorilla calls (the
+!!       first one locates the particle, the later ones start from ind_tetr / iface) and the (ind_tetr, iface) pair after
+!!       each of the first trace_cap pusher calls,
 !! into one little-endian stream file `gorilla_reference_dump.bin` (layout below = tests/reference_dump.py, which
 !! reads it back, turns it into a .gmesh + golden vectors and checks the C oracle and the CUDA path against it).
 !! This is what turns "parity unpinned" into "pinned against the gfortran binary".
@@ -38,10 +39,12 @@
 !!   real64   tetra_physics  [ntetr][142]        int32 tetra_grid [ntetr][20]
 !!   real64   verts_rphiz [nvert][3]             real64 verts_sthetaphi [nvert][3]   (if has_sthetaphi)
 !!   real64   tetra_skew_coord [ntetr][168]      (if has_skew)
-!!   int32    n_particles, trace_cap             real64 t_step
+!!   int32    n_particles, trace_cap, n_steps    real64 t_step
 !!   real64   x0 [n][3], vpar0 [n], vperp0 [n]                     (the inputs, echoed)
-!!   real64   x [n][3], vpar [n], vperp [n], t_remain [n]          (after the call)
-!!   int32    boole_initialized [n], ind_tetr [n], iface [n], n_pushes [n]
+!!   real64   x [n][3], vpar [n], vperp [n], t_remain [n]          (after the last call made for the particle; a particle
+!!                                                                  that was not placed or has left the domain is not
+!!                                                                  passed to orbit_timestep_gorilla again)
+!!   int32    boole_initialized [n], ind_tetr [n], iface [n], n_pushes [n]   (n_pushes: sum over the calls)
 !!   int32    trace_ind_tetr [n][trace_cap], trace_iface [n][trace_cap]        (unused slots 0)
 program gorilla_reference_dump
   use tetra_grid_settings_mod, only: load_tetra_grid_inp, grid_kind, grid_size, n_field_periods, sfc_s_min
@@ -60,8 +63,8 @@ program gorilla_reference_dump
   use, intrinsic :: iso_fortran_env, only: int32, real64
   implicit none
 
-  integer :: u, n, cap, i, n_mismatch
-  integer(int32) :: n32, cap32, has_sthetaphi, has_skew
+  integer :: u, n, cap, i, k, n_steps, n_mismatch
+  integer(int32) :: n32, cap32, nsteps32, np1, has_sthetaphi, has_skew
   real(real64) :: t_step
   real(real64), allocatable :: x0(:,:), vpar0(:), vperp0(:), x(:,:), vpar(:), vperp(:), t_rem(:)
   integer(int32), allocatable :: binit(:), itetr(:), ifc(:), npush(:), tr_tetr(:,:), tr_face(:,:)
@@ -76,8 +79,8 @@ program gorilla_reference_dump
 
   ! ---- particles -------------------------------------------------------------------------------------------
   open(newunit=u, file='dump_particles.bin', access='stream', form='unformatted', status='old', action='read')
-  read(u) n32, cap32, t_step
-  n = n32; cap = max(int(cap32), 1)
+  read(u) n32, cap32, nsteps32, t_step
+  n = n32; cap = max(int(cap32), 1); n_steps = max(int(nsteps32), 1)
   allocate(x0(3,n), vpar0(n), vperp0(n), x(3,n), vpar(n), vperp(n), t_rem(n))
   allocate(binit(n), itetr(n), ifc(n), npush(n), tr_tetr(cap,n), tr_face(cap,n))
   read(u) x0, vpar0, vperp0
@@ -89,10 +92,17 @@ program gorilla_reference_dump
   ! the dump does not depend on the OpenMP schedule.
   n_mismatch = 0
   do i = 1, n
-    call traced_timestep(x(:,i), vpar(i), vperp(i), t_step, binit(i), itetr(i), ifc(i), t_rem(i), npush(i), &
-                         tr_tetr(:,i), tr_face(:,i))
+    do k = 1, n_steps
+      call traced_timestep(x(:,i), vpar(i), vperp(i), t_step, binit(i), itetr(i), ifc(i), t_rem(i), np1, npush(i), &
+                           tr_tetr(:,i), tr_face(:,i))
+      npush(i) = npush(i) + np1
+      if (binit(i) == 0 .or. itetr(i) == -1) exit     ! not placed / left the domain: no further calls
+    end do
     xc = x0(:,i); vparc = vpar0(i); vperpc = vperp0(i); binitc = .false.; itetrc = -1; ifcc = -1
-    call orbit_timestep_gorilla(xc, vparc, vperpc, t_step, binitc, itetrc, ifcc)
+    do k = 1, n_steps
+      call orbit_timestep_gorilla(xc, vparc, vperpc, t_step, binitc, itetrc, ifcc)
+      if (.not. binitc .or. itetrc == -1) exit
+    end do
     if (any(xc /= x(:,i)) .or. vparc /= vpar(i) .or. vperpc /= vperp(i) .or. itetrc /= itetr(i) .or. ifcc /= ifc(i)) &
       n_mismatch = n_mismatch + 1
   end do
@@ -119,7 +129,7 @@ program gorilla_reference_dump
   write(u) verts_rphiz(:, 1:nvert)
   if (has_sthetaphi == 1) write(u) verts_sthetaphi(:, 1:nvert)
   if (has_skew == 1) write(u) tetra_skew_coord(1:ntetr)
-  write(u) n32, int(cap, int32), t_step
+  write(u) n32, int(cap, int32), int(n_steps, int32), t_step
   write(u) x0, vpar0, vperp0
   write(u) x, vpar, vperp, t_rem
   write(u) binit, itetr, ifc, npush
@@ -135,13 +145,15 @@ contains
     l2i = merge(1_int32, 0_int32, b)
   end function
 
-  !> One orbit_timestep_gorilla call for a not yet located particle, recording the cell/face after every push.
-  subroutine traced_timestep(xp, vparp, vperpp, dt, binit_p, ind, face, t_remain, n_push, trace_t, trace_f)
+  !> One orbit_timestep_gorilla call, recording the cell/face after every push: push number n_before + j of the particle
+  !> goes to slot n_before + j of the trace (n_before = pushes of its earlier calls).
+  subroutine traced_timestep(xp, vparp, vperpp, dt, binit_p, ind, face, t_remain, n_push, n_before, trace_t, trace_f)
     real(real64), intent(inout) :: xp(3), vparp, vperpp
     real(real64), intent(in) :: dt
     integer(int32), intent(inout) :: binit_p, ind, face
     real(real64), intent(out) :: t_remain
     integer(int32), intent(out) :: n_push
+    integer(int32), intent(in) :: n_before
     integer(int32), intent(inout) :: trace_t(:), trace_f(:)
     real(real64) :: z_save(3), perpinv, perpinv2, t_pass
     logical :: finished
@@ -178,8 +190,8 @@ contains
         call pusher_tetra_poly(poly_order, ind_l, face_l, xp, vparp, z_save, t_remain, t_pass, finished, iper)
       end if
       n_push = n_push + 1
-      if (n_push <= size(trace_t)) then
-        trace_t(n_push) = ind_l; trace_f(n_push) = face_l
+      if (n_before + n_push <= size(trace_t)) then
+        trace_t(n_before + n_push) = ind_l; trace_f(n_before + n_push) = face_l
       end if
       t_remain = t_remain - t_pass
       if (finished) exit

@@ -47,6 +47,7 @@ class ReferenceDump:
     tetra_skew_coord: np.ndarray | None
     t_step: float = 0.0
     trace_cap: int = 0
+    n_steps: int = 1                 # successive orbit_timestep_gorilla calls of t_step each
     inputs: dict = field(default_factory=dict)    # x0 [n,3], vpar0, vperp0
     results: dict = field(default_factory=dict)   # x, vpar, vperp, t_remain, boole_initialized, ind_tetr, iface, n_pushes,
     #                                               trace_ind_tetr [n,cap], trace_iface [n,cap]
@@ -91,7 +92,7 @@ def read_dump(path) -> ReferenceDump:
     vr = c.take("<f8", nv * 3, (nv, 3))
     vs = c.take("<f8", nv * 3, (nv, 3)) if head["has_sthetaphi"] else None
     sk = c.take("<f8", nt * 168, (nt, 168)) if head["has_skew"] else None
-    n, cap = map(int, c.take("<i4", 2))
+    n, cap, n_steps = map(int, c.take("<i4", 3))
     t_step = float(c.take("<f8", 1)[0])
     inputs = dict(x0=c.take("<f8", n * 3, (n, 3)), vpar0=c.take("<f8", n), vperp0=c.take("<f8", n))
     results = dict(x=c.take("<f8", n * 3, (n, 3)), vpar=c.take("<f8", n), vperp=c.take("<f8", n), t_remain=c.take("<f8", n))
@@ -101,10 +102,10 @@ def read_dump(path) -> ReferenceDump:
     results["trace_iface"] = c.take("<i4", n * cap, (n, cap))
     if c.pos != len(buf):
         raise ValueError(f"{path}: {len(buf) - c.pos} trailing bytes after the last array")
-    return ReferenceDump(head, settings, scalars, tp, tg, vr, vs, sk, t_step, cap, inputs, results)
+    return ReferenceDump(head, settings, scalars, tp, tg, vr, vs, sk, t_step, cap, n_steps, inputs, results)
 
 
-def write_dump(path, mesh, settings, t_step, trace_cap, inputs, results) -> None:
+def write_dump(path, mesh, settings, t_step, trace_cap, inputs, results, n_steps=1) -> None:
     """The bytes gorilla_reference_dump.f90 writes, from a gorilla_b200.Mesh + GorillaSettings + result arrays."""
     s = mesh.scalars
     nt = mesh.ntetr
@@ -127,7 +128,7 @@ def write_dump(path, mesh, settings, t_step, trace_cap, inputs, results) -> None
             f.write(np.ascontiguousarray(mesh.verts_sthetaphi, "<f8").tobytes())
         if has_k:
             f.write(np.ascontiguousarray(mesh.tetra_skew_coord, "<f8").tobytes())
-        f.write(np.asarray([n, trace_cap], "<i4").tobytes())
+        f.write(np.asarray([n, trace_cap, n_steps], "<i4").tobytes())
         f.write(np.asarray([t_step], "<f8").tobytes())
         for k in ("x0", "vpar0", "vperp0"):
             f.write(np.ascontiguousarray(inputs[k], "<f8").tobytes())
@@ -137,10 +138,12 @@ def write_dump(path, mesh, settings, t_step, trace_cap, inputs, results) -> None
             f.write(np.ascontiguousarray(results[k], "<i4").tobytes())
 
 
-def write_particles(path, x0, vpar0, vperp0, t_step, trace_cap) -> None:
-    """dump_particles.bin, the input of gorilla_reference_dump.f90: int32 n, trace_cap; f64 t_step; x0[n][3], vpar0, vperp0."""
+def write_particles(path, x0, vpar0, vperp0, t_step, trace_cap, n_steps=1) -> None:
+    """dump_particles.bin, the input of gorilla_reference_dump.f90: int32 n, trace_cap, n_steps; f64 t_step; x0[n][3], vpar0,
+    vperp0."""
+    assert trace_cap >= 1 and n_steps >= 1
     with open(path, "wb") as f:
-        f.write(np.asarray([x0.shape[0], trace_cap], "<i4").tobytes())
+        f.write(np.asarray([x0.shape[0], trace_cap, n_steps], "<i4").tobytes())
         f.write(np.asarray([t_step], "<f8").tobytes())
         for a in (x0, vpar0, vperp0):
             f.write(np.ascontiguousarray(a, "<f8").tobytes())
@@ -185,28 +188,61 @@ def _compare(d: ReferenceDump, got: dict) -> dict:
     return bad
 
 
+def _run_steps(d: ReferenceDump, step) -> dict:
+    """d.n_steps successive orbit_timestep_gorilla calls, as the dump program makes them.  `step(x, vpar, vperp, binit, ind, ifc,
+    cap)` performs ONE batched call in place and returns (t_remain [m], n_pushes [m], trace_ind_tetr [m,cap], trace_iface [m,cap]).
+    A particle that was not placed by find_tetra or has left the domain is not passed on to the next call (the reference would
+    index tetra_physics(-1)); n_pushes adds up over the calls, the traces hold the first trace_cap pushes of all calls together,
+    t_remain is that of the last call made for the particle."""
+    x, vpar, vperp, binit, ind, ifc = _fresh(d)
+    n, cap = x.shape[0], max(d.trace_cap, 1)
+    t_rem, npush = np.zeros(n), np.zeros(n, np.int64)
+    tt, tf = np.zeros((n, cap), np.int32), np.zeros((n, cap), np.int32)
+    act = np.arange(n)
+    for _ in range(d.n_steps):
+        if act.size == 0:
+            break
+        sub = [np.ascontiguousarray(a[act]) for a in (x, vpar, vperp, binit, ind, ifc)]
+        tr, np1, t1, f1 = step(*sub, cap)
+        for a, b in zip((x, vpar, vperp, binit, ind, ifc), sub):
+            a[act] = b
+        t_rem[act] = tr
+        before = npush[act]
+        for j in np.nonzero((before < cap) & (np1 > 0))[0]:
+            m = int(min(cap - before[j], np1[j]))
+            tt[act[j], before[j]:before[j] + m] = t1[j, :m]
+            tf[act[j], before[j]:before[j] + m] = f1[j, :m]
+        npush[act] += np1
+        act = act[(sub[4] != -1) & (sub[3] != 0)]
+    return dict(x=x, vpar=vpar, vperp=vperp, t_remain=t_rem, boole_initialized=binit, ind_tetr=ind, iface=ifc,
+                n_pushes=npush.astype(np.int32), trace_ind_tetr=tt, trace_iface=tf)
+
+
 def run_oracle(d: ReferenceDump) -> dict:
     from oracle_binding import OracleMesh
     mesh, st = mesh_and_settings(d)
     om = OracleMesh(mesh, st)
-    x, vpar, vperp, binit, ind, ifc = _fresh(d)
-    r = om.orbit_timestep_trace(x, vpar, vperp, d.t_step, binit, ind, ifc, d.trace_cap)
-    return dict(x=x, vpar=vpar, vperp=vperp, t_remain=r["t_remain"], boole_initialized=binit, ind_tetr=ind, iface=ifc,
-                n_pushes=r["n_pushes"].astype(np.int32), trace_ind_tetr=r["trace_tetr"], trace_iface=r["trace_face"])
+
+    def step(x, vpar, vperp, binit, ind, ifc, cap):
+        r = om.orbit_timestep_trace(x, vpar, vperp, d.t_step, binit, ind, ifc, cap)
+        return r["t_remain"], r["n_pushes"], r["trace_tetr"], r["trace_face"]
+    return _run_steps(d, step)
 
 
 def run_device(d: ReferenceDump) -> dict:
     from gorilla_b200 import Gorilla
     mesh, st = mesh_and_settings(d)
     g = Gorilla(mesh, st)
-    x, vpar, vperp, binit, ind, ifc = _fresh(d)
-    n = x.shape[0]
-    t_rem, npush = np.zeros(n), np.zeros(n, np.int64)
-    tt, tf = g.orbit_timestep_gorilla(x, vpar, vperp, d.t_step, binit, ind, ifc, t_remain_out=t_rem, n_pushes=npush,
-                                      trace_cap=d.trace_cap)
-    g.close()
-    return dict(x=x, vpar=vpar, vperp=vperp, t_remain=t_rem, boole_initialized=binit, ind_tetr=ind, iface=ifc,
-                n_pushes=npush.astype(np.int32), trace_ind_tetr=tt, trace_iface=tf)
+
+    def step(x, vpar, vperp, binit, ind, ifc, cap):
+        t_rem, npush = np.zeros(x.shape[0]), np.zeros(x.shape[0], np.int64)
+        tt, tf = g.orbit_timestep_gorilla(x, vpar, vperp, d.t_step, binit, ind, ifc, t_remain_out=t_rem, n_pushes=npush,
+                                          trace_cap=cap)
+        return t_rem, npush, tt, tf
+    try:
+        return _run_steps(d, step)
+    finally:
+        g.close()
 
 
 def run_host_mirror(d: ReferenceDump) -> dict:
@@ -214,10 +250,11 @@ def run_host_mirror(d: ReferenceDump) -> dict:
     from host_mirror_binding import HostMirror
     mesh, st = mesh_and_settings(d)
     hm = HostMirror(mesh, st)
-    x, vpar, vperp, binit, ind, ifc = _fresh(d)
-    r = hm.orbit_timestep(x, vpar, vperp, d.t_step, binit, ind, ifc, d.trace_cap)
-    return dict(x=x, vpar=vpar, vperp=vperp, t_remain=r["t_remain"], boole_initialized=binit, ind_tetr=ind, iface=ifc,
-                n_pushes=r["n_pushes"].astype(np.int32), trace_ind_tetr=r["trace_tetr"], trace_iface=r["trace_face"])
+
+    def step(x, vpar, vperp, binit, ind, ifc, cap):
+        r = hm.orbit_timestep(x, vpar, vperp, d.t_step, binit, ind, ifc, cap)
+        return r["t_remain"], r["n_pushes"], r["trace_tetr"], r["trace_face"]
+    return _run_steps(d, step)
 
 
 def check_host_mirror(d: ReferenceDump) -> dict:
@@ -274,6 +311,7 @@ def _cli():
     p.add_argument("--n", type=int, default=2000)
     p.add_argument("--trace-cap", type=int, default=64)
     p.add_argument("--t-step", type=float, default=1e-5)
+    p.add_argument("--n-steps", type=int, default=3, help="successive orbit_timestep_gorilla calls per particle")
     p.add_argument("--seed", type=int, default=2024)
     p.add_argument("--kind", choices=["cyl", "flux"], default="cyl",
                    help="cyl: (R,phi,Z) around --R0/--a (coord_system 1); flux: (s,theta,phi) with s in [0.2,0.9] (coord_system 2)")
@@ -303,8 +341,8 @@ def _cli():
             x[:, 0], x[:, 1], x[:, 2] = 0.2 + 0.7 * rng.random(a.n), 2 * np.pi * rng.random(a.n), 2 * np.pi / a.nfp * rng.random(a.n)
         vmod = np.sqrt(2.0 * a.energy_ev * 1.6022e-12 / (a.mass_amu * 1.6726e-24))
         vpar = (2.0 * rng.random(a.n) - 1.0) * vmod
-        write_particles(a.out, x, vpar, np.sqrt(vmod ** 2 - vpar ** 2), a.t_step, a.trace_cap)
-        print(f"wrote {a.out}: {a.n} particles, trace_cap {a.trace_cap}, t_step {a.t_step}")
+        write_particles(a.out, x, vpar, np.sqrt(vmod ** 2 - vpar ** 2), a.t_step, a.trace_cap, a.n_steps)
+        print(f"wrote {a.out}: {a.n} particles, trace_cap {a.trace_cap}, {a.n_steps} steps of {a.t_step} s")
         return 0
     if a.cmd == "mesh-diff":
         import json
@@ -314,7 +352,7 @@ def _cli():
         return 0
     d = read_dump(a.dump)
     print(f"{a.dump}: ntetr {d.head['ntetr']}, grid_kind {d.head['grid_kind']}, ipusher {d.settings['ipusher']}, "
-          f"poly_order {d.settings['poly_order']}, {d.inputs['x0'].shape[0]} particles, "
+          f"poly_order {d.settings['poly_order']}, {d.inputs['x0'].shape[0]} particles x {d.n_steps} steps, "
           f"{int(d.results['n_pushes'].sum())} pushes")
     if a.gmesh:
         mesh_and_settings(d)[0].save(a.gmesh)

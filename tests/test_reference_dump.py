@@ -21,17 +21,16 @@ DUMP_DIR = Path(__file__).resolve().parent / "golden" / "reference_dumps"
 REAL_DUMPS = sorted(DUMP_DIR.glob("*.bin")) if DUMP_DIR.is_dir() else []
 
 
-def _synthetic_dump(path, mesh, settings, n=120, seed=11, t_step=1.5e-5, cap=48):
+def _synthetic_dump(path, mesh, settings, n=120, seed=11, t_step=1.5e-5, cap=48, n_steps=1):
     """A dump in the Fortran program's layout whose results come from the oracle (stand-in for the gfortran run)."""
-    from oracle_binding import OracleMesh
     x0, vpar0, vperp0 = workloads.particles_cyl(n, seed)
     x0[0, 0] = 1.0e4   # one particle outside the grid: find_tetra gives ind_tetr = -1, state untouched
-    x, vpar, vperp = x0.copy(), vpar0.copy(), vperp0.copy()
-    binit, ind, ifc = workloads.fresh_state(n)
-    r = OracleMesh(mesh, settings).orbit_timestep_trace(x, vpar, vperp, t_step, binit, ind, ifc, cap)
-    results = dict(x=x, vpar=vpar, vperp=vperp, t_remain=r["t_remain"], boole_initialized=binit, ind_tetr=ind, iface=ifc,
-                   n_pushes=r["n_pushes"], trace_ind_tetr=r["trace_tetr"], trace_iface=r["trace_face"])
-    rd.write_dump(path, mesh, settings, t_step, cap, dict(x0=x0, vpar0=vpar0, vperp0=vperp0), results)
+    inputs = dict(x0=x0, vpar0=vpar0, vperp0=vperp0)
+    skeleton = rd.ReferenceDump({}, {k: getattr(settings, k) for k in rd._SETTING_INTS + ("eps_Phi", "desired_delta_energy", "coord_system")},
+                                dict(mesh.scalars), mesh.tetra_physics, mesh.tetra_grid, mesh.verts_rphiz, mesh.verts_sthetaphi,
+                                mesh.tetra_skew_coord, t_step, cap, n_steps, inputs, {})
+    results = rd.run_oracle(skeleton)
+    rd.write_dump(path, mesh, settings, t_step, cap, inputs, results, n_steps)
     return results
 
 
@@ -65,6 +64,40 @@ def test_dump_format_round_trip_and_oracle_check(tmp_path, small_mesh, small_mes
     d.results["trace_ind_tetr"][7, 3] += 1
     bad = rd.check_oracle(d)
     assert bad == {"vpar": 1, "trace_ind_tetr": 1}
+
+
+def test_multi_step_dump(tmp_path, small_mesh):
+    """n_steps successive calls: the first locates the particle, the later ones start from (ind_tetr, iface); pushes add up,
+    the traces run on across the calls, particles that left the domain are not pushed again."""
+    from oracle_binding import OracleMesh
+    mesh, _, settings = small_mesh
+    st = dataclasses.replace(settings, poly_order=3)
+    p = tmp_path / "d.bin"
+    n, t_step, cap = 150, 4e-6, 40
+    _synthetic_dump(p, mesh, st, n=n, t_step=t_step, cap=cap, n_steps=3, seed=5)
+    d = rd.read_dump(p)
+    assert d.n_steps == 3
+    assert rd.check_oracle(d) == {} and rd.check_host_mirror(d) == {}
+    # independent of _run_steps: three plain batched calls on all particles that stay inside
+    x, vpar, vperp = d.inputs["x0"].copy(), d.inputs["vpar0"].copy(), d.inputs["vperp0"].copy()
+    binit, ind, ifc = workloads.fresh_state(n)
+    om = OracleMesh(mesh, st)
+    total = np.zeros(n, np.int64)
+    first = None
+    for k in range(3):
+        r = om.orbit_timestep_trace(x, vpar, vperp, t_step, binit, ind, ifc, cap)
+        total += r["n_pushes"]
+        first = r if first is None else first
+    inside = (ind > 0) & (d.results["ind_tetr"] > 0)
+    assert inside.sum() > n // 2
+    assert np.array_equal(d.results["x"][inside], x[inside]) and np.array_equal(d.results["vpar"][inside], vpar[inside])
+    assert np.array_equal(d.results["n_pushes"][inside], total[inside])
+    # the trace continues over the call boundary: a particle with fewer than cap pushes in call 1 has later slots filled by call 2
+    short = inside & (first["n_pushes"] < cap) & (total > first["n_pushes"])
+    assert short.any()
+    j = int(np.nonzero(short)[0][0])
+    k1 = int(first["n_pushes"][j])
+    assert np.array_equal(d.results["trace_ind_tetr"][j, :k1], first["trace_tetr"][j, :k1]) and d.results["trace_ind_tetr"][j, k1] > 0
 
 
 def test_dumped_mesh_to_gmesh(tmp_path, small_mesh):
@@ -121,14 +154,14 @@ def test_bad_dumps_are_rejected(tmp_path, small_mesh):
 
 
 def test_particle_file_layout(tmp_path):
-    """dump_particles.bin as the Fortran program reads it: int32 n, cap; f64 t_step; x0[n][3], vpar0[n], vperp0[n]."""
+    """dump_particles.bin as the Fortran program reads it: int32 n, cap, n_steps; f64 t_step; x0[n][3], vpar0[n], vperp0[n]."""
     x, vpar, vperp = workloads.particles_cyl(5, 1)
-    rd.write_particles(tmp_path / "p.bin", x, vpar, vperp, 2e-5, 16)
+    rd.write_particles(tmp_path / "p.bin", x, vpar, vperp, 2e-5, 16, 3)
     raw = (tmp_path / "p.bin").read_bytes()
-    assert len(raw) == 8 + 8 + 5 * 5 * 8
-    assert tuple(np.frombuffer(raw, "<i4", 2)) == (5, 16) and np.frombuffer(raw, "<f8", 1, 8)[0] == 2e-5
-    assert np.array_equal(np.frombuffer(raw, "<f8", 15, 16).reshape(5, 3), x)
-    assert np.array_equal(np.frombuffer(raw, "<f8", 5, 16 + 15 * 8 + 40), vperp)
+    assert len(raw) == 12 + 8 + 5 * 5 * 8
+    assert tuple(np.frombuffer(raw, "<i4", 3)) == (5, 16, 3) and np.frombuffer(raw, "<f8", 1, 12)[0] == 2e-5
+    assert np.array_equal(np.frombuffer(raw, "<f8", 15, 20).reshape(5, 3), x)
+    assert np.array_equal(np.frombuffer(raw, "<f8", 5, 20 + 15 * 8 + 40), vperp)
 
 
 @pytest.mark.skipif(not REAL_DUMPS, reason="no dump of the gfortran build committed yet: parity unpinned (DESIGN.md section 4)")

@@ -64,7 +64,19 @@ class _GridSettings(C.Structure):
 class _Counters(C.Structure):
     _fields_ = [("n_particles", C.c_int64), ("n_pushes", C.c_int64), ("n_lost", C.c_int64),
                 ("n_finished", C.c_int64), ("n_fallback", C.c_int64 * 4), ("n_domain_errors", C.c_int64),
-                ("kernel_ms", C.c_double), ("find_ms", C.c_double), ("n_adaptive", C.c_int64)]
+                ("kernel_ms", C.c_double), ("find_ms", C.c_double), ("n_adaptive", C.c_int64),
+                ("n_lost_inner", C.c_int64), ("n_failed", C.c_int64)]
+
+
+class _Diag(C.Structure):   # struct gorilla_diag
+    _fields_ = [(n, C.c_int64) for n in ("n_particles", "n_pushes", "n_lost", "n_lost_outer", "n_lost_inner", "n_failed",
+                                         "n_finished")] + [("n_fallback", C.c_int64 * 4), ("n_adaptive", C.c_int64),
+                                                           ("n_sampled", C.c_int64)] + \
+               [(n, C.c_double) for n in ("max_delta_energy", "rms_delta_energy", "max_delta_perpinv", "rms_delta_perpinv",
+                                          "max_delta_p_phi", "rms_delta_p_phi")] + [("nranks", C.c_int32), ("reserved", C.c_int32)]
+
+
+COMM_ID_BYTES = 128
 
 
 class _EventSettings(C.Structure):
@@ -89,6 +101,30 @@ class Counters:
     kernel_ms: float
     find_ms: float
     n_adaptive: int = 0
+    n_lost_inner: int = 0
+    n_failed: int = 0
+
+
+@dataclass
+class Diag:
+    """struct gorilla_diag: counters since diag_reset and conservation statistics, reduced over all ranks."""
+    n_particles: int
+    n_pushes: int
+    n_lost: int
+    n_lost_outer: int
+    n_lost_inner: int
+    n_failed: int
+    n_finished: int
+    n_fallback: tuple
+    n_adaptive: int
+    n_sampled: int
+    max_delta_energy: float
+    rms_delta_energy: float
+    max_delta_perpinv: float
+    rms_delta_perpinv: float
+    max_delta_p_phi: float
+    rms_delta_p_phi: float
+    nranks: int
 
 
 # every symbol include/gorilla_b200.h declares (tests check that the library exports all of them)
@@ -98,8 +134,10 @@ EXPORTED_SYMBOLS = (
     "gorilla_b200_orbit_timestep_optional", "gorilla_b200_orbit_timestep_optional_dev",
     "gorilla_b200_orbit_timestep_events", "gorilla_b200_orbit_timestep_events_dev",
     "gorilla_b200_find_tetra", "gorilla_b200_invariants", "gorilla_b200_invariants_dev",
-    "gorilla_b200_get_counters", "gorilla_b200_sort_permutation_dev", "gorilla_b200_set_launch_config",
-    "gorilla_b200_fp64_peak",
+    "gorilla_b200_get_counters", "gorilla_b200_sort_permutation_dev", "gorilla_b200_resort_dev",
+    "gorilla_b200_set_host_resort", "gorilla_b200_set_launch_config", "gorilla_b200_fp64_peak",
+    "gorilla_b200_comm_unique_id", "gorilla_b200_comm_init", "gorilla_b200_comm_free", "gorilla_b200_comm_allreduce_f64",
+    "gorilla_b200_shard_range", "gorilla_b200_diag_reset", "gorilla_b200_diag_reduce_dev",
     "gorilla_mesh_build", "gorilla_mesh_get_desc", "gorilla_mesh_get_vertices", "gorilla_mesh_free",
     "gorilla_mesh_save", "gorilla_mesh_load",
 )
@@ -136,6 +174,15 @@ def load_library():
     lib.gorilla_b200_invariants_dev.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.gorilla_b200_get_counters.argtypes = [vp, C.POINTER(_Counters)]
     lib.gorilla_b200_sort_permutation_dev.argtypes = [vp, i64, vp, vp, vp]
+    lib.gorilla_b200_resort_dev.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, i32, C.POINTER(vp), vp, vp]
+    lib.gorilla_b200_set_host_resort.argtypes = [vp, i32]
+    lib.gorilla_b200_comm_unique_id.argtypes = [vp]
+    lib.gorilla_b200_comm_init.argtypes = [vp, vp, i32, i32]
+    lib.gorilla_b200_comm_free.argtypes = [vp]
+    lib.gorilla_b200_comm_allreduce_f64.argtypes = [vp, vp, i64, i32, vp]
+    lib.gorilla_b200_shard_range.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+    lib.gorilla_b200_diag_reset.argtypes = [vp, vp]
+    lib.gorilla_b200_diag_reduce_dev.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(_Diag), vp]
     lib.gorilla_b200_set_launch_config.argtypes = [vp, i32, i32]
     lib.gorilla_b200_debug_force_full.argtypes = [vp, i32]
     lib.gorilla_b200_debug_find_bins.argtypes = [vp, i32]
@@ -167,6 +214,34 @@ def fp64_peak() -> tuple[float, float]:
     a, b = C.c_double(), C.c_double()
     _check(load_library().gorilla_b200_fp64_peak(C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0); hand the bytes to the other ranks."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(load_library().gorilla_b200_comm_unique_id(buf))
+    return buf.raw
+
+
+def shard_range(n_total: int, rank: int, nranks: int) -> tuple[int, int]:
+    """(first, count) of the contiguous shard [r N/G, (r+1) N/G) (gorilla_b200_shard_range)."""
+    a, b = C.c_int64(), C.c_int64()
+    _check(load_library().gorilla_b200_shard_range(int(n_total), int(rank), int(nranks), C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def _require(a, dtype, shape=None, name="array", allow_none=False):
+    """Every array that crosses the C ABI as a raw pointer: right dtype, C-contiguous, right shape -- or a TypeError
+    instead of a silent overflow."""
+    if a is None:
+        if allow_none:
+            return None
+        raise TypeError(f"{name} must not be None")
+    if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dtype) or not a.flags.c_contiguous:
+        raise TypeError(f"{name} must be a C-contiguous numpy array of {np.dtype(dtype).name}")
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise TypeError(f"{name} must have shape {tuple(shape)}, not {tuple(a.shape)}")
+    return a
 
 
 def _c_settings(s: GorillaSettings) -> _Settings:
@@ -243,10 +318,34 @@ class Mesh:
                                                 _ptr(self.verts_sthetaphi) if nv and self.verts_sthetaphi is not None else None,
                                                 str(path).encode()))
 
+
+
+class _MeshOwner:
+    """Owns the C-side gorilla_mesh.  The numpy views handed out by _mesh_from_handle keep a reference to it (through
+    their base), so the backing memory outlives every view, not only the Mesh object."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
     def __del__(self):
-        if self._handle is not None and _lib is not None:
-            _lib.gorilla_mesh_free(self._handle)
-            self._handle = None
+        if self.handle is not None and _lib is not None:
+            _lib.gorilla_mesh_free(self.handle)
+            self.handle = None
+
+
+class _View(np.ndarray):
+    """ndarray view that carries a reference to the owner of its memory."""
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self._owner = getattr(obj, "_owner", None)
+
+
+def _owned_view(ptr, shape, owner):
+    v = np.ctypeslib.as_array(ptr, shape=shape).view(_View)
+    v._owner = owner
+    return v
 
 
 def _mesh_from_handle(h) -> Mesh:
@@ -254,19 +353,20 @@ def _mesh_from_handle(h) -> Mesh:
     d = _MeshDesc()
     _check(lib.gorilla_mesh_get_desc(h, C.byref(d)))
     m = Mesh()
-    m._handle = h
+    owner = _MeshOwner(h)
+    m._handle = owner
     nt = int(d.ntetr)
-    m.tetra_physics = np.ctypeslib.as_array(d.tetra_physics, shape=(nt, 142))
-    m.tetra_grid = np.ctypeslib.as_array(d.tetra_grid, shape=(nt, 20))
+    m.tetra_physics = _owned_view(d.tetra_physics, (nt, 142), owner)
+    m.tetra_grid = _owned_view(d.tetra_grid, (nt, 20), owner)
     if d.tetra_skew_coord:
-        m.tetra_skew_coord = np.ctypeslib.as_array(d.tetra_skew_coord, shape=(nt, 168))
+        m.tetra_skew_coord = _owned_view(d.tetra_skew_coord, (nt, 168), owner)
     nv = C.c_int64()
     pr, ps = C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
     _check(lib.gorilla_mesh_get_vertices(h, C.byref(nv), C.byref(pr), C.byref(ps)))
     if nv.value > 0:
-        m.verts_rphiz = np.ctypeslib.as_array(pr, shape=(nv.value, 3))
+        m.verts_rphiz = _owned_view(pr, (nv.value, 3), owner)
         if ps:
-            m.verts_sthetaphi = np.ctypeslib.as_array(ps, shape=(nv.value, 3))
+            m.verts_sthetaphi = _owned_view(ps, (nv.value, 3), owner)
     m.scalars = dict(
         cm_over_e=d.cm_over_e, particle_mass=d.particle_mass, particle_charge=d.particle_charge,
         sign_sqg=d.sign_sqg, coord_system=d.coord_system, n_field_periods=d.n_field_periods,
@@ -289,28 +389,7 @@ def build_mesh(grid: TetraGridSettings, settings: GorillaSettings) -> Mesh:
     h = C.c_void_p()
     cg, cs = _c_grid(grid), _c_settings(settings)
     _check(lib.gorilla_mesh_build(C.byref(cg), C.byref(cs), C.byref(h)))
-    d = _MeshDesc()
-    _check(lib.gorilla_mesh_get_desc(h, C.byref(d)))
-    m = Mesh()
-    m._handle = h
-    nt = int(d.ntetr)
-    m.tetra_physics = np.ctypeslib.as_array(d.tetra_physics, shape=(nt, 142))
-    m.tetra_grid = np.ctypeslib.as_array(d.tetra_grid, shape=(nt, 20))
-    if d.tetra_skew_coord:
-        m.tetra_skew_coord = np.ctypeslib.as_array(d.tetra_skew_coord, shape=(nt, 168))
-    nv = C.c_int64()
-    pr, ps = C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
-    _check(lib.gorilla_mesh_get_vertices(h, C.byref(nv), C.byref(pr), C.byref(ps)))
-    m.verts_rphiz = np.ctypeslib.as_array(pr, shape=(nv.value, 3))
-    if ps:
-        m.verts_sthetaphi = np.ctypeslib.as_array(ps, shape=(nv.value, 3))
-    m.scalars = dict(
-        cm_over_e=d.cm_over_e, particle_mass=d.particle_mass, particle_charge=d.particle_charge,
-        sign_sqg=d.sign_sqg, coord_system=d.coord_system, n_field_periods=d.n_field_periods,
-        grid_kind=d.grid_kind, grid_size=tuple(d.grid_size), Rmin=d.Rmin, Rmax=d.Rmax, Zmin=d.Zmin, Zmax=d.Zmax,
-        sfc_s_min=d.sfc_s_min,
-    )
-    return m
+    return _mesh_from_handle(h)
 
 
 def _ptr(a):
@@ -345,27 +424,44 @@ class Gorilla:
         s = self.mesh.scalars
         per = 2.0 * math.pi / s["n_field_periods"]
         x = x.reshape(-1, 3)
+
+        def modulo(a, p):   # Fortran MODULO for reals as gfortran expands it: fmod (exact) + sign fix
+            r = np.fmod(a, p)
+            r = np.where((r != 0.0) & ((r < 0.0) != (p < 0.0)), r + p, r)
+            return np.where(r == 0.0, math.copysign(0.0, p), r)
         if s["coord_system"] == 1:
             if self.settings.boole_periodic_relocation:
-                x[:, 1] = x[:, 1] - np.floor(x[:, 1] / per) * per
+                x[:, 1] = modulo(x[:, 1], per)
             elif np.any((x[:, 1] < 0.0) | (x[:, 1] > per)):
                 raise GorillaError(4, "Particle coordinate phi outside [0, 2 pi/n_field_periods]")
         else:
             if np.any((x[:, 0] < s["sfc_s_min"]) | (x[:, 0] > 1.0)):
                 raise GorillaError(4, "Particle flux coordinate s outside [sfc_s_min, 1]")
             if self.settings.boole_periodic_relocation:
-                x[:, 1] = x[:, 1] - np.floor(x[:, 1] / (2.0 * math.pi)) * (2.0 * math.pi)
-                x[:, 2] = x[:, 2] - np.floor(x[:, 2] / per) * per
+                x[:, 1] = modulo(x[:, 1], 2.0 * math.pi)
+                x[:, 2] = modulo(x[:, 2], per)
             elif np.any((x[:, 1] < 0) | (x[:, 1] > 2 * math.pi) | (x[:, 2] < 0) | (x[:, 2] > per)):
                 raise GorillaError(4, "Particle coordinate theta/phi outside the domain")
 
     def find_tetra(self, x, vpar, vperp, sign_t_step: int = 1):
         """find_tetra (find_tetra_mod.f90:283-600) for a batch; returns (ind_tetr, iface); x may be updated."""
         n = x.shape[0]
+        _require(x, np.float64, (n, 3), "x"); _require(vpar, np.float64, (n,), "vpar"); _require(vperp, np.float64, (n,), "vperp")
         ind, ifc = np.empty(n, np.int32), np.empty(n, np.int32)
         _check(load_library().gorilla_b200_find_tetra(self._h, n, _ptr(x), _ptr(vpar), _ptr(vperp), _ptr(ind),
                                                       _ptr(ifc), int(sign_t_step)))
         return ind, ifc
+
+    @staticmethod
+    def _require_state(n, x, vpar, vperp, boole_initialized, ind_tetr, iface, t_remain_out=None, n_pushes=None):
+        _require(x, np.float64, (n, 3), "x")
+        _require(vpar, np.float64, (n,), "vpar")
+        _require(vperp, np.float64, (n,), "vperp")
+        _require(boole_initialized, np.int32, (n,), "boole_initialized")
+        _require(ind_tetr, np.int32, (n,), "ind_tetr")
+        _require(iface, np.int32, (n,), "iface")
+        _require(t_remain_out, np.float64, (n,), "t_remain_out", allow_none=True)
+        _require(n_pushes, np.int64, (n,), "n_pushes", allow_none=True)
 
     def orbit_timestep_gorilla(self, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface,
                                t_remain_out=None, n_pushes=None, trace_cap: int = 0, optional_quantities=None):
@@ -376,10 +472,7 @@ class Gorilla:
         Returns (trace_ind_tetr, trace_iface) when trace_cap > 0, else None."""
         lib = load_library()
         n = x.shape[0]
-        for a, dt in ((x, np.float64), (vpar, np.float64), (vperp, np.float64), (boole_initialized, np.int32),
-                      (ind_tetr, np.int32), (iface, np.int32)):
-            if a.dtype != dt or not a.flags.c_contiguous:
-                raise TypeError("arrays must be C-contiguous float64 / int32")
+        self._require_state(n, x, vpar, vperp, boole_initialized, ind_tetr, iface, t_remain_out, n_pushes)
         if optional_quantities is not None:
             oq = optional_quantities
             if oq.dtype != np.float64 or not oq.flags.c_contiguous or oq.shape != (n, 4):
@@ -433,6 +526,10 @@ class Gorilla:
         per-particle state between calls.  Returns (events, n_events): a structured array (EVENT_DTYPE) sorted by
         (particle, push, kind) holding min(n_events, event_cap) records."""
         n = x.shape[0]
+        self._require_state(n, x, vpar, vperp, boole_initialized, ind_tetr, iface, t_remain_out, n_pushes)
+        _require(par_adiab_inv, np.float64, (n,), "par_adiab_inv")
+        _require(counter_vpar_0, np.int32, (n,), "counter_vpar_0")
+        _require(counter_phi_0, np.int32, (n,), "counter_phi_0")
         cfg = _EventSettings(int(boole_poincare_phi_0), int(n_skip_phi_0), int(boole_poincare_vpar_0), int(boole_J_par),
                              int(n_skip_vpar_0))
         ev = np.zeros(max(event_cap, 1), EVENT_DTYPE)
@@ -448,6 +545,8 @@ class Gorilla:
     def invariants(self, x, vpar, vperp, ind_tetr):
         """(energy_tot_func, p_phi_func, perpinv) per particle (supporting_functions_mod.f90:279-408)."""
         n = x.shape[0]
+        _require(x, np.float64, (n, 3), "x"); _require(vpar, np.float64, (n,), "vpar"); _require(vperp, np.float64, (n,), "vperp")
+        _require(ind_tetr, np.int32, (n,), "ind_tetr")
         e, p, mu = np.empty(n), np.empty(n), np.empty(n)
         _check(load_library().gorilla_b200_invariants(self._h, n, _ptr(x), _ptr(vpar), _ptr(vperp), _ptr(ind_tetr),
                                                       _ptr(e), _ptr(p), _ptr(mu)))
@@ -464,12 +563,58 @@ class Gorilla:
         c = _Counters()
         _check(load_library().gorilla_b200_get_counters(self._h, C.byref(c)))
         return Counters(c.n_particles, c.n_pushes, c.n_lost, c.n_finished, tuple(c.n_fallback), c.n_domain_errors,
-                        c.kernel_ms, c.find_ms, c.n_adaptive)
+                        c.kernel_ms, c.find_ms, c.n_adaptive, c.n_lost_inner, c.n_failed)
 
     def sort_permutation_dev(self, ind_tetr, perm, stream=None):
         _check(load_library().gorilla_b200_sort_permutation_dev(self._h, ind_tetr.shape[0],
                                                                 C.c_void_p(ind_tetr.data_ptr()),
                                                                 C.c_void_p(perm.data_ptr()), C.c_void_p(stream or 0)))
+
+    def resort_dev(self, x, vpar, vperp, boole_initialized, ind_tetr, iface, extra=(), perm_out=None, stream=None):
+        """Re-sort a resident batch (torch CUDA tensors) by tetrahedron index in place (gorilla_b200_resort_dev); `extra`:
+        further float64 [n] tensors permuted alongside."""
+        def dp(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+        ex = (C.c_void_p * max(1, len(extra)))(*[t.data_ptr() for t in extra])
+        _check(load_library().gorilla_b200_resort_dev(self._h, x.shape[0], dp(x), dp(vpar), dp(vperp), dp(boole_initialized),
+                                                      dp(ind_tetr), dp(iface), len(extra), ex, dp(perm_out),
+                                                      C.c_void_p(stream or 0)))
+
+    def set_host_resort(self, on: bool):
+        """Host-pointer orbit_timestep_gorilla: sort each uploaded batch by tetrahedron before the push (caller's order is
+        restored before the download)."""
+        _check(load_library().gorilla_b200_set_host_resort(self._h, int(on)))
+
+    # ---- multi-GPU + diagnostics reduction -----------------------------------------------------
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        """Join the NCCL communicator of the job (one handle per GPU); unique_id from comm_unique_id() on rank 0."""
+        assert len(unique_id) == COMM_ID_BYTES
+        _check(load_library().gorilla_b200_comm_init(self._h, C.c_char_p(unique_id), int(rank), int(nranks)))
+
+    def comm_free(self):
+        _check(load_library().gorilla_b200_comm_free(self._h))
+
+    def comm_allreduce_f64(self, buf, op: str = "sum", stream=None):
+        """In-place all-reduce of a small float64 CUDA tensor over the handle's communicator (no-op on one GPU)."""
+        _check(load_library().gorilla_b200_comm_allreduce_f64(self._h, C.c_void_p(buf.data_ptr()), buf.numel(),
+                                                              {"sum": 0, "max": 1, "min": 2}[op], C.c_void_p(stream or 0)))
+
+    def diag_reset(self, stream=None):
+        _check(load_library().gorilla_b200_diag_reset(self._h, C.c_void_p(stream or 0)))
+
+    def diag_reduce_dev(self, x, vpar, vperp, ind_tetr, energy_ref=None, p_phi_ref=None, perpinv_ref=None,
+                        stream=None) -> Diag:
+        """gorilla_b200_diag_reduce_dev: counters since diag_reset + max/rms drift of E, perpinv, p_phi against the given
+        reference values, reduced over all ranks of the communicator (collective)."""
+        def dp(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+        d = _Diag()
+        _check(load_library().gorilla_b200_diag_reduce_dev(self._h, x.shape[0], dp(x), dp(vpar), dp(vperp), dp(ind_tetr),
+                                                           dp(energy_ref), dp(p_phi_ref), dp(perpinv_ref), C.byref(d),
+                                                           C.c_void_p(stream or 0)))
+        return Diag(d.n_particles, d.n_pushes, d.n_lost, d.n_lost_outer, d.n_lost_inner, d.n_failed, d.n_finished,
+                    tuple(d.n_fallback), d.n_adaptive, d.n_sampled, d.max_delta_energy, d.rms_delta_energy,
+                    d.max_delta_perpinv, d.rms_delta_perpinv, d.max_delta_p_phi, d.rms_delta_p_phi, d.nranks)
 
     def set_launch_config(self, ctas_per_sm: int = 0, threads_per_cta: int = 0):
         _check(load_library().gorilla_b200_set_launch_config(self._h, ctas_per_sm, threads_per_cta))

@@ -39,7 +39,7 @@ CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wa
 
 # longest compiles first (order 4 takes ~2 min per unit)
 CU_SOURCES = ["gb_orbit_k4x.cu", "gb_orbit_k4a.cu", "gb_orbit_k4t.cu", "gb_orbit_k4.cu", "gb_orbit_k3x.cu", "gb_orbit_k3a.cu",
-              "gb_orbit_k3t.cu", "gb_orbit_k3.cu", "gorilla_b200.cu", "gb_orbit_rk.cu", "gb_orbit_rkx.cu", "gb_orbit_k2x.cu", "gb_orbit_k2a.cu",
+              "gb_orbit_k3t.cu", "gb_orbit_k3.cu", "gorilla_b200.cu", "gb_diag.cu", "gb_orbit_rk.cu", "gb_orbit_rkx.cu", "gb_orbit_k2x.cu", "gb_orbit_k2a.cu",
               "gb_orbit_k2t.cu", "gb_orbit_k2.cu", "gb_orbit_k1x.cu", "gb_orbit_k1a.cu", "gb_orbit_k1t.cu", "gb_orbit_k1.cu"]
 CPP_SOURCES = ["host/mesh_api.cpp", "host/mesh_common.cpp", "host/mesh_analytic.cpp", "host/mesh_vmec.cpp", "host/mesh_efit.cpp", "host/mesh_soledge3x.cpp", "host/mesh_efit_flux.cpp"]
 
@@ -85,7 +85,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
                 sys.stderr.write(log)
     if rebuilt or force:
         cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", HOST_CXX,
-               "-Xcompiler", "-fPIC,-fopenmp", "-o", str(LIB), *objs, "-lgomp"]
+               "-Xcompiler", "-fPIC,-fopenmp", "-o", str(LIB), *objs, "-lgomp", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed: {' '.join(cmd)}\n{r.stdout}\n{r.stderr}")

@@ -19,8 +19,16 @@ namespace gb {
 
 #define GB_EPS 1.e-10
 
-// Fortran modulo(a,p) for p > 0
-GB_HD double f_modulo(double a, double p) { return a - floor(a / p) * p; }
+// Fortran modulo(a,p) for reals as gfortran expands it (trans-intrinsic.cc, gfc_conv_intrinsic_mod): r = fmod(a,p), which is
+// exact; r += p when r != 0 and its sign differs from p's; a zero result takes the sign of p.  (a - floor(a/p)*p rounds k*p
+// and differs in the last bits once |a| >= 2p.)
+GB_HD double f_modulo(double a, double p)
+{
+  double r = fmod(a, p);
+  if (r != 0.0 && ((r < 0.0) != (p < 0.0))) r += p;
+  if (r == 0.0) r = copysign(0.0, p);
+  return r;
+}
 
 // returns 0 ok, 1 outside the computation domain (reference: print + stop)
 GB_HD int check_coordinate_domain(const MeshDev &m, double *x, int boole_periodic_relocation)
@@ -67,7 +75,9 @@ GB_HD_NOINLINE void find_tetra_on_face(const MeshDev *mp, double *x, double vpar
                                        int32_t &iface, int sign_t_step, const double *dist0, int n_plane_conv)
 {
   const MeshDev &m = *mp;
-  PolyPusher<1, PHI> P; // reuse record loader + ODE coefficient builder (same formulas, :104-116 vs poly :1504-1517)
+  // reuse record loader + ODE coefficient builder (same formulas, :104-116 vs poly :1504-1517); EXT = 2 carries the
+  // run-time hand-over kind (pusher_handover2neighbour honours handover_processing_kind = 2 here too, find_tetra_mod.f90:558)
+  PolyPusher<1, PHI, 2> P;
   double stash[6];
   P.mp = mp;
   P.r.set_stash(stash, 1);

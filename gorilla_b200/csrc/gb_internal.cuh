@@ -10,9 +10,17 @@
 #include "gb_find.cuh"
 #include "gb_rk.cuh"
 
+struct gorilla_b200_handle;
 namespace gbint {
 void set_error(const char *msg);
 void count_launch(int n);
+int fail(int code, const char *msg);
+// gb_diag.cu: particle re-sorting through the handle's scratch
+int sort_permutation(gorilla_b200_handle *h, int64_t n, const int32_t *ind_tetr, int64_t *perm, cudaStream_t s);
+int permute_state_inplace(gorilla_b200_handle *h, int64_t n, const int64_t *perm, bool inverse, double *x, double *vpar,
+                          double *vperp, int32_t *init, int32_t *ind, int32_t *iface, cudaStream_t s);
+template <typename T>
+int permute_one_inplace(gorilla_b200_handle *h, int64_t n, const int64_t *perm, bool inverse, T *a, cudaStream_t s);
 }
 
 #define GB_CUDA(call)                                                                              \
@@ -29,7 +37,8 @@ void count_launch(int n);
 
 using namespace gb;
 
-enum { CTR_PUSHES = 0, CTR_LOST, CTR_FINISHED, CTR_FB0, CTR_FB1, CTR_FB2, CTR_FB3, CTR_ADAPT, CTR_DOMAIN, CTR_QUEUE, CTR_N };
+enum { CTR_PUSHES = 0, CTR_LOST, CTR_FINISHED, CTR_FB0, CTR_FB1, CTR_FB2, CTR_FB3, CTR_ADAPT, CTR_DOMAIN, CTR_QUEUE, CTR_LOST_INNER,
+       CTR_FAILED, CTR_LOST_PREV, CTR_N };
 
 struct Batch {
   int64_t n;
@@ -117,19 +126,231 @@ __device__ __forceinline__ unsigned tid_now()
   return t;
 }
 enum { LS_X0 = 0, LS_X1, LS_X2, LS_VPAR, LS_PERPINV, LS_TREM, LS_ZS0, LS_ZS1, LS_ZS2, LS_ND };
-enum { LC_LOST = 0, LC_FIN, LC_FB0, LC_FB1, LC_FB2, LC_FB3, LC_ADAPT, LC_N };
+enum { LC_LOST = 0, LC_FIN, LC_FB0, LC_FB1, LC_FB2, LC_FB3, LC_ADAPT, LC_LOST_INNER, LC_FAILED, LC_LOST_PREV, LC_N };
 
-// per-lane accumulators of the optional quantities (EXT kernels only)
-template <bool EXT, int NT>
-struct OqSlots {
-  double v[5][NT];   // 0..3 optional quantities, 4 par_adiab_inv
-  int c[2][NT];      // counter_banana_mappings, counter_phi_0_mappings
-};
+// The per-lane slots of a CTA of NT threads ([field][thread], conflict free), shared by both kernel shapes: the 4-warp
+// kernel places them in static shared memory, the 16-warp lock-step kernel in dynamic shared memory.  Every accessor
+// re-reads %tid.x through a volatile asm: otherwise the compiler forms the slot addresses once, keeps them live across the
+// push and spills THEM.
 template <int NT>
-struct OqSlots<false, NT> {
-  double v[1][1];
-  int c[1][1];
+struct LaneSlots {
+  double (*d)[NT];        // [LS_ND] loop state
+  double (*stash)[NT];    // [6] first vertex + topology words of the current record (Rec::load)
+  long long *idx, *npush;
+  unsigned long long *cpush;
+  unsigned int (*cnt)[NT];  // [LC_N]
+  int *ind_save;
+  double (*oq)[NT];       // [5] EXT = 2: optional quantities 0..3, par_adiab_inv
+  int (*ec)[NT];          // [2] EXT = 2: counter_banana_mappings, counter_phi_0_mappings
+  static constexpr size_t BYTES = (size_t)NT * ((LS_ND + 6) * 8 + 3 * 8 + LC_N * 4 + 4 + 4 /*pad to 8*/);
+  static constexpr size_t BYTES_EXT2 = BYTES + (size_t)NT * (5 * 8 + 2 * 4);
+  __device__ __forceinline__ void carve(unsigned char *base, bool ext2)
+  {
+    d = reinterpret_cast<double (*)[NT]>(base);
+    stash = d + LS_ND;
+    idx = reinterpret_cast<long long *>(stash + 6);
+    npush = idx + NT;
+    cpush = reinterpret_cast<unsigned long long *>(npush + NT);
+    cnt = reinterpret_cast<unsigned int (*)[NT]>(cpush + NT);
+    ind_save = reinterpret_cast<int *>(cnt + LC_N);
+    oq = reinterpret_cast<double (*)[NT]>(ind_save + 2 * NT);
+    ec = reinterpret_cast<int (*)[NT]>(oq + 5);
+    (void)ext2;
+  }
+  __device__ __forceinline__ volatile double &D(int f) const { return ((volatile double *)d[f])[tid_now()]; }
+  __device__ __forceinline__ volatile unsigned int &C(int f) const { return ((volatile unsigned int *)cnt[f])[tid_now()]; }
+  __device__ __forceinline__ volatile double &OQ(int q) const { return ((volatile double *)oq[q])[tid_now()]; }
+  __device__ __forceinline__ volatile int &EC(int q) const { return ((volatile int *)ec[q])[tid_now()]; }
+  __device__ __forceinline__ volatile long long &Idx() const { return ((volatile long long *)idx)[tid_now()]; }
+  __device__ __forceinline__ volatile long long &Npush() const { return ((volatile long long *)npush)[tid_now()]; }
+  __device__ __forceinline__ volatile unsigned long long &Cpush() const { return ((volatile unsigned long long *)cpush)[tid_now()]; }
+  __device__ __forceinline__ volatile int &IndSave() const { return ((volatile int *)ind_save)[tid_now()]; }
+  __device__ __forceinline__ volatile double *Stash() const { return &stash[0][tid_now()]; }
+  __device__ __forceinline__ void zero_counters() const
+  {
+    Cpush() = 0;
+#pragma unroll
+    for (int k = 0; k < LC_N; k++) C(k) = 0;
+  }
 };
+
+// Pull the next particle that actually has to be pushed into this lane's slot; false when the queue is empty.
+// Warp-aggregated: the lanes that arrive here together take consecutive queue entries with one atomic.
+template <int PHI, int EXT, int NT>
+__device__ __forceinline__ bool lane_refill(const MeshDev &m, const Batch &bt, const LaneSlots<NT> &S, unsigned lane,
+                                            int32_t &ind_tetr, int32_t &iface)
+{
+  for (;;) {
+    const unsigned need = __activemask();
+    const int leader = __ffs(need) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(bt.ctr + CTR_QUEUE, (unsigned long long)__popc(need));
+    base = __shfl_sync(need, base, leader);
+    const int64_t idx = (int64_t)(base + (unsigned long long)__popc(need & ((1u << lane) - 1u)));
+    if (idx >= bt.n) return false;
+    ind_tetr = bt.ind_tetr[idx];
+    iface = bt.iface[idx];
+    const bool inited = bt.init ? (bt.init[idx] != 0) : true;
+    if (!inited || ind_tetr < 1) {
+      // not localised (find_tetra failed) or already lost: orbit_timestep_gorilla returns at :59-61,
+      // resp. leaves the loop at :103-109 without touching the particle
+      if (bt.t_remain_out) bt.t_remain_out[idx] = bt.t_step;
+      if (bt.n_pushes) bt.n_pushes[idx] = 0;
+      if constexpr (EXT == 2) {
+        if (bt.optq) { bt.optq[4 * idx] = 0.0; bt.optq[4 * idx + 1] = 0.0; bt.optq[4 * idx + 2] = 0.0; bt.optq[4 * idx + 3] = 0.0; }
+      }
+      if (inited && ind_tetr < 1) S.C(LC_LOST_PREV) = S.C(LC_LOST_PREV) + 1;   // lost in an earlier call
+      continue;
+    }
+    if (bt.t_step == 0.0) {
+      if (bt.t_remain_out) bt.t_remain_out[idx] = 0.0;
+      if (bt.n_pushes) bt.n_pushes[idx] = 0;
+      if constexpr (EXT == 2) {
+        if (bt.optq) { bt.optq[4 * idx] = 0.0; bt.optq[4 * idx + 1] = 0.0; bt.optq[4 * idx + 2] = 0.0; bt.optq[4 * idx + 3] = 0.0; }
+      }
+      continue;
+    }
+    const double x0 = bt.x[3 * idx], x1 = bt.x[3 * idx + 1], x2 = bt.x[3 * idx + 2];
+    const double vperp = bt.vperp[idx];
+    // :71-78  z_save = x - x1 ; perpinv = -0.5*vperp**2/bmod_func(z_save, ind_tetr)
+    const double *pg = m.geom + ((int64_t)ind_tetr - 1) * GEOM_ND;
+    const double zs[3] = {x0 - ldg(pg), x1 - ldg(pg + 1), x2 - ldg(pg + 2)};
+    S.D(LS_X0) = x0; S.D(LS_X1) = x1; S.D(LS_X2) = x2;
+    S.D(LS_VPAR) = bt.vpar[idx];
+    S.D(LS_ZS0) = zs[0]; S.D(LS_ZS1) = zs[1]; S.D(LS_ZS2) = zs[2];
+    S.D(LS_PERPINV) = -0.5 * (vperp * vperp) / bmod_at<PHI>(m, ind_tetr, zs);
+    S.D(LS_TREM) = bt.t_step;
+    S.Idx() = idx;
+    S.Npush() = 0;
+    if constexpr (EXT == 2) {
+      S.OQ(0) = 0.0; S.OQ(1) = 0.0; S.OQ(2) = 0.0; S.OQ(3) = 0.0;
+      if (bt.ev_flags) { S.OQ(4) = bt.par_adiab_inv[idx]; S.EC(0) = bt.counter_vpar_0[idx]; S.EC(1) = bt.counter_phi_0[idx]; }
+    }
+    return true;
+  }
+}
+
+// EXT = 2: optional quantities and orbit events of a push that the fast path completed
+template <int K, int PHI, int NT>
+__device__ __forceinline__ void lane_ext2_after_fast(const Batch &bt, const LaneSlots<NT> &S, PolyPusher<K, PHI, 2> &P,
+                                                     const PushOut &o)
+{
+  if (bt.oq_mask) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) S.OQ(q) = S.OQ(q) + P.oq[q];
+  }
+  if constexpr (K >= 2) {
+    if (bt.ev_flags && !o.finished) {
+      EvState es;
+      es.flags = bt.ev_flags; es.nskip_p = bt.n_skip_phi_0; es.nskip_v = bt.n_skip_vpar_0;
+      es.J = S.OQ(4); es.cnt_v = S.EC(0); es.cnt_p = S.EC(1);
+      P.events_after_push(S.D(LS_VPAR), o, es);
+      S.OQ(4) = es.J; S.EC(0) = es.cnt_v; S.EC(1) = es.cnt_p;
+      if (es.n) emit_events(bt, S.Idx(), S.Npush(), es);
+    }
+  }
+}
+// EXT = 2: the complete ladder with optional quantities and events
+template <int K, int PHI, int NT>
+__device__ __forceinline__ PushOut lane_ext2_full(const MeshDev &m, const Batch &bt, const LaneSlots<NT> &S, int32_t ind_tetr,
+                                                  int32_t iface)
+{
+  const PushOutX ox = push_full_call_x<K, PHI>(&m, S.D(LS_PERPINV), ind_tetr, iface, S.D(LS_X0), S.D(LS_X1), S.D(LS_X2),
+                                               S.D(LS_VPAR), S.D(LS_TREM), bt.oq_mask, bt.ev_flags, bt.n_skip_phi_0,
+                                               bt.n_skip_vpar_0, S.OQ(4), S.EC(0), S.EC(1));
+#pragma unroll
+  for (int q = 0; q < 4; q++) S.OQ(q) = S.OQ(q) + ox.oq[q];
+  if (bt.ev_flags) {
+    S.OQ(4) = ox.es.J; S.EC(0) = ox.es.cnt_v; S.EC(1) = ox.es.cnt_p;
+    if (ox.es.n) emit_events(bt, S.Idx(), S.Npush(), ox.es);
+  }
+  return ox.o;
+}
+
+// Book-keeping after a push (orbit_timestep_gorilla.f90:129-142): loop state, trace, counters; when the particle has
+// finished its time step or is lost, its state goes back to the caller's arrays.  Returns true in that case (the lane
+// needs a new particle).  ind_prev = the tetrahedron the push started in (ind_tetr_save of the reference).
+template <int PHI, int EXT, int NT>
+__device__ __forceinline__ bool lane_after_push(const MeshDev &m, const Batch &bt, const LaneSlots<NT> &S, const PushOut &o,
+                                                int ind_prev, int32_t &ind_tetr, int32_t &iface)
+{
+  S.D(LS_X0) = o.x[0]; S.D(LS_X1) = o.x[1]; S.D(LS_X2) = o.x[2];
+  S.D(LS_VPAR) = o.vpar;
+  if (o.z_save_set) { S.D(LS_ZS0) = o.z_save[0]; S.D(LS_ZS1) = o.z_save[1]; S.D(LS_ZS2) = o.z_save[2]; }
+  ind_tetr = o.ind_tetr;
+  iface = o.iface;
+  const long long npush = S.Npush();
+  if (bt.trace_cap > 0 && npush < bt.trace_cap) {
+    const long long idx = S.Idx();
+    bt.trace_tetr[idx * bt.trace_cap + npush] = ind_tetr;
+    bt.trace_face[idx * bt.trace_cap + npush] = iface;
+  }
+  S.Npush() = npush + 1;
+  if (o.fallback) {
+    if (o.fallback & 1) S.C(LC_FB0) = S.C(LC_FB0) + 1;
+    if (o.fallback & 2) S.C(LC_FB1) = S.C(LC_FB1) + 1;
+    if (o.fallback & 4) S.C(LC_FB2) = S.C(LC_FB2) + 1;
+    if (o.fallback & 8) S.C(LC_FB3) = S.C(LC_FB3) + 1;
+    if constexpr (EXT == 3) {
+      if (o.fallback & 16) S.C(LC_ADAPT) = S.C(LC_ADAPT) + 1;
+    }
+  }
+  const double t_remain = S.D(LS_TREM) - o.t_pass;
+  S.D(LS_TREM) = t_remain;
+  if (!(o.finished || ind_tetr == -1)) return false;
+  // :142  vperp = vperp_func(z_save, perpinv, ind_tetr_save)
+  const long long idx = S.Idx();
+  const double pinv = S.D(LS_PERPINV);
+  const double zs[3] = {S.D(LS_ZS0), S.D(LS_ZS1), S.D(LS_ZS2)};
+  double vperp_new = 0.0;
+  if (pinv != 0.0) vperp_new = sqrt(2.0 * fabs(pinv) * bmod_at<PHI>(m, ind_prev, zs));
+  bt.x[3 * idx] = o.x[0];
+  bt.x[3 * idx + 1] = o.x[1];
+  bt.x[3 * idx + 2] = o.x[2];
+  bt.vpar[idx] = o.vpar;
+  bt.vperp[idx] = vperp_new;
+  bt.ind_tetr[idx] = ind_tetr;
+  bt.iface[idx] = iface;
+  if (bt.t_remain_out) bt.t_remain_out[idx] = t_remain;
+  if (bt.n_pushes) bt.n_pushes[idx] = npush + 1;
+  if constexpr (EXT == 2) {
+    if (bt.optq) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) bt.optq[4 * idx + q] = S.OQ(q);
+    }
+    if (bt.ev_flags) { bt.par_adiab_inv[idx] = S.OQ(4); bt.counter_vpar_0[idx] = S.EC(0); bt.counter_phi_0[idx] = S.EC(1); }
+  }
+  S.Cpush() = S.Cpush() + (unsigned long long)(npush + 1);
+  if (o.finished) {
+    S.C(LC_FIN) = S.C(LC_FIN) + 1;
+  } else {
+    // lost: through a boundary face (hand-over to neighbour -1; the position is the exit point) or removed by the pusher
+    // (no valid exit time / trouble shooting failed: z_save not set).  Flux-coordinate grids have two boundaries: the inner
+    // annulus edge s = sfc_s_min and the outer surface s = 1 (SURVEY 8d config 3 reports them separately).
+    S.C(LC_LOST) = S.C(LC_LOST) + 1;
+    if (!o.z_save_set) S.C(LC_FAILED) = S.C(LC_FAILED) + 1;
+    else if (m.coord_system == 2 && o.x[0] < 0.5 * (m.sfc_s_min + 1.0)) S.C(LC_LOST_INNER) = S.C(LC_LOST_INNER) + 1;
+  }
+  return true;
+}
+
+// counters: warp reduce, one atomic per warp and counter
+template <int NT>
+__device__ __forceinline__ void lane_reduce_counters(const Batch &bt, const LaneSlots<NT> &S, unsigned lane)
+{
+  __syncwarp();
+  unsigned long long v[11] = {S.Cpush(), S.C(LC_LOST), S.C(LC_FIN), S.C(LC_FB0), S.C(LC_FB1), S.C(LC_FB2), S.C(LC_FB3),
+                              S.C(LC_ADAPT), S.C(LC_LOST_INNER), S.C(LC_FAILED), S.C(LC_LOST_PREV)};
+  const int slot[11] = {CTR_PUSHES, CTR_LOST, CTR_FINISHED, CTR_FB0, CTR_FB1, CTR_FB2, CTR_FB3, CTR_ADAPT, CTR_LOST_INNER,
+                        CTR_FAILED, CTR_LOST_PREV};
+#pragma unroll
+  for (int k = 0; k < 11; k++) {
+    unsigned long long s = v[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    if (lane == 0 && s) atomicAdd(bt.ctr + slot[k], s);
+  }
+}
 
 // EXT = 1: Hamiltonian time tracing (i_time_tracing_option = 2); EXT = 2: time tracing option read at run time plus the
 // optional quantities of pusher_tetra_poly; the plain variant (EXT = 0) is the hot path of the default settings and
@@ -137,216 +358,58 @@ struct OqSlots<false, NT> {
 template <int K, int PHI, int EXT = 0>
 __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K, EXT)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
 {
-  __shared__ double s_d[LS_ND][GB_THREADS], s_stash[6][GB_THREADS];
-  __shared__ OqSlots<EXT == 2, GB_THREADS> s_oq;
-#define LOQ(q) (((volatile double *)s_oq.v[q])[tid_now()])
-#define LEC(q) (((volatile int *)s_oq.c[q])[tid_now()])
-  __shared__ long long s_idx[GB_THREADS], s_npush[GB_THREADS];
-  __shared__ unsigned long long s_cpush[GB_THREADS];
-  __shared__ unsigned int s_cnt[LC_N][GB_THREADS];
-  __shared__ int s_ind_save[GB_THREADS];
+  __shared__ __align__(16) unsigned char s_raw[EXT == 2 ? LaneSlots<GB_THREADS>::BYTES_EXT2 : LaneSlots<GB_THREADS>::BYTES];
+  LaneSlots<GB_THREADS> S;
+  S.carve(s_raw, EXT == 2);
   const unsigned lane = threadIdx.x & 31u;
-  // every accessor re-reads %tid.x through a volatile asm: otherwise the compiler forms the slot addresses once,
-  // keeps them live across the push and spills THEM
-#define LS(f) (((volatile double *)s_d[f])[tid_now()])
-#define LCNT(f) (((volatile unsigned int *)s_cnt[f])[tid_now()])
-#define p_idx (((volatile long long *)s_idx) + tid_now())
-#define p_npush (((volatile long long *)s_npush) + tid_now())
-#define p_cpush (((volatile unsigned long long *)s_cpush) + tid_now())
-#define p_ind_save (((volatile int *)s_ind_save) + tid_now())
   int32_t ind_tetr = -1, iface = -1;
-  *p_cpush = 0;
-#pragma unroll
-  for (int k = 0; k < LC_N; k++) LCNT(k) = 0;
-
-  // Pull the next particle that actually has to be pushed into this lane's slot; false when the queue is empty.
-  // Warp-aggregated: the lanes that arrive here together take consecutive queue entries with one atomic.
-  auto refill = [&]() -> bool {
-    for (;;) {
-      const unsigned need = __activemask();
-      const int leader = __ffs(need) - 1;
-      unsigned long long base = 0;
-      if ((int)lane == leader) base = atomicAdd(bt.ctr + CTR_QUEUE, (unsigned long long)__popc(need));
-      base = __shfl_sync(need, base, leader);
-      const int64_t idx = (int64_t)(base + (unsigned long long)__popc(need & ((1u << lane) - 1u)));
-      if (idx >= bt.n) return false;
-      ind_tetr = bt.ind_tetr[idx];
-      iface = bt.iface[idx];
-      const bool inited = bt.init ? (bt.init[idx] != 0) : true;
-      if (!inited || ind_tetr < 1) {
-        // not localised (find_tetra failed) or already lost: orbit_timestep_gorilla returns at :59-61,
-        // resp. leaves the loop at :103-109 without touching the particle
-        if (bt.t_remain_out) bt.t_remain_out[idx] = bt.t_step;
-        if (bt.n_pushes) bt.n_pushes[idx] = 0;
-        if constexpr (EXT == 2) {
-          if (bt.optq) { bt.optq[4 * idx] = 0.0; bt.optq[4 * idx + 1] = 0.0; bt.optq[4 * idx + 2] = 0.0; bt.optq[4 * idx + 3] = 0.0; }
-        }
-        if (inited && ind_tetr < 1) LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
-        continue;
-      }
-      if (bt.t_step == 0.0) {
-        if (bt.t_remain_out) bt.t_remain_out[idx] = 0.0;
-        if (bt.n_pushes) bt.n_pushes[idx] = 0;
-        if constexpr (EXT == 2) {
-          if (bt.optq) { bt.optq[4 * idx] = 0.0; bt.optq[4 * idx + 1] = 0.0; bt.optq[4 * idx + 2] = 0.0; bt.optq[4 * idx + 3] = 0.0; }
-        }
-        continue;
-      }
-      const double x0 = bt.x[3 * idx], x1 = bt.x[3 * idx + 1], x2 = bt.x[3 * idx + 2];
-      const double vperp = bt.vperp[idx];
-      // :71-78  z_save = x - x1 ; perpinv = -0.5*vperp**2/bmod_func(z_save, ind_tetr)
-      const double *pg = m.geom + ((int64_t)ind_tetr - 1) * GEOM_ND;
-      const double zs[3] = {x0 - ldg(pg), x1 - ldg(pg + 1), x2 - ldg(pg + 2)};
-      LS(LS_X0) = x0; LS(LS_X1) = x1; LS(LS_X2) = x2;
-      LS(LS_VPAR) = bt.vpar[idx];
-      LS(LS_ZS0) = zs[0]; LS(LS_ZS1) = zs[1]; LS(LS_ZS2) = zs[2];
-      LS(LS_PERPINV) = -0.5 * (vperp * vperp) / bmod_at<PHI>(m, ind_tetr, zs);
-      LS(LS_TREM) = bt.t_step;
-      *p_idx = idx;
-      *p_npush = 0;
-      if constexpr (EXT == 2) {
-        LOQ(0) = 0.0; LOQ(1) = 0.0; LOQ(2) = 0.0; LOQ(3) = 0.0;
-        if (bt.ev_flags) { LOQ(4) = bt.par_adiab_inv[idx]; LEC(0) = bt.counter_vpar_0[idx]; LEC(1) = bt.counter_phi_0[idx]; }
-      }
-      return true;
-    }
-  };
+  S.zero_counters();
 
   // One lane = one particle at a time.  A lane whose particle is done refills itself at the end of the same loop
   // body and leaves the loop for good when the queue is empty, so the body has no "is this lane active" region (whose
   // convergence-barrier register was live, and spilled, across every push).
-  bool active = refill();
+  bool active = lane_refill<PHI, EXT>(m, bt, S, lane, ind_tetr, iface);
   while (active) {
-    {
-      *p_ind_save = ind_tetr;
-      PushOut o;
-      bool done = false;
-      const double perpinv = LS(LS_PERPINV);
-      if constexpr (K == 0) {  // ipusher = 1: RK4 pusher
-        if (!bt.force_full) {
-          const double x[3] = {LS(LS_X0), LS(LS_X1), LS(LS_X2)};
-          RkPusher<PHI, (EXT == 2 ? 2 : 0)> R;
-          R.P.r.set_stash(&s_stash[0][tid_now()], GB_THREADS);
-          R.init(&m, perpinv, ind_tetr, x, iface, LS(LS_VPAR), LS(LS_TREM));
-          done = R.template push<true>(o);
-        }
-        if (!done)
-          o = push_rk_full_call<PHI, (EXT == 2 ? 2 : 0)>(&m, perpinv, ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2), LS(LS_VPAR), LS(LS_TREM));
-      } else {
-        if (!bt.force_full) {
-          const double x[3] = {LS(LS_X0), LS(LS_X1), LS(LS_X2)};
-          PolyPusher<K, PHI, EXT> P;
-          P.mp = &m;
-          P.perpinv = perpinv;
-          if constexpr (EXT == 2) P.oq_mask = bt.oq_mask;
-          P.r.set_stash(&s_stash[0][tid_now()], GB_THREADS);
-          done = P.push_fast(ind_tetr, iface, x, LS(LS_VPAR), LS(LS_TREM), o, &LS(LS_TREM));
-          if constexpr (EXT == 2) {
-            if (done && bt.oq_mask) {
-#pragma unroll
-              for (int q = 0; q < 4; q++) LOQ(q) = LOQ(q) + P.oq[q];
-            }
-            if constexpr (K >= 2) {
-              if (done && bt.ev_flags && !o.finished) {
-                EvState es;
-                es.flags = bt.ev_flags; es.nskip_p = bt.n_skip_phi_0; es.nskip_v = bt.n_skip_vpar_0;
-                es.J = LOQ(4); es.cnt_v = LEC(0); es.cnt_p = LEC(1);
-                P.events_after_push(LS(LS_VPAR), o, es);
-                LOQ(4) = es.J; LEC(0) = es.cnt_v; LEC(1) = es.cnt_p;
-                if (es.n) emit_events(bt, *p_idx, *p_npush, es);
-              }
-            }
-          }
-        }
-        if (!done) {
-          if constexpr (EXT == 2) {
-            const PushOutX ox = push_full_call_x<K, PHI>(&m, perpinv, ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2),
-                                                         LS(LS_VPAR), LS(LS_TREM), bt.oq_mask, bt.ev_flags, bt.n_skip_phi_0,
-                                                         bt.n_skip_vpar_0, LOQ(4), LEC(0), LEC(1));
-            o = ox.o;
-#pragma unroll
-            for (int q = 0; q < 4; q++) LOQ(q) = LOQ(q) + ox.oq[q];
-            if (bt.ev_flags) {
-              LOQ(4) = ox.es.J; LEC(0) = ox.es.cnt_v; LEC(1) = ox.es.cnt_p;
-              if (ox.es.n) emit_events(bt, *p_idx, *p_npush, ox.es);
-            }
-          } else {
-            o = push_full_call<K, PHI, EXT>(&m, perpinv, ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2), LS(LS_VPAR), LS(LS_TREM));
-          }
-        }
+    S.IndSave() = ind_tetr;
+    PushOut o;
+    bool done = false;
+    const double perpinv = S.D(LS_PERPINV);
+    if constexpr (K == 0) {  // ipusher = 1: RK4 pusher
+      if (!bt.force_full) {
+        const double x[3] = {S.D(LS_X0), S.D(LS_X1), S.D(LS_X2)};
+        RkPusher<PHI, (EXT == 2 ? 2 : 0)> R;
+        R.P.r.set_stash(S.Stash(), GB_THREADS);
+        R.init(&m, perpinv, ind_tetr, x, iface, S.D(LS_VPAR), S.D(LS_TREM));
+        done = R.template push<true>(o);
       }
-      LS(LS_X0) = o.x[0]; LS(LS_X1) = o.x[1]; LS(LS_X2) = o.x[2];
-      LS(LS_VPAR) = o.vpar;
-      if (o.z_save_set) { LS(LS_ZS0) = o.z_save[0]; LS(LS_ZS1) = o.z_save[1]; LS(LS_ZS2) = o.z_save[2]; }
-      ind_tetr = o.ind_tetr;
-      iface = o.iface;
-      const long long npush = *p_npush;
-      if (bt.trace_cap > 0 && npush < bt.trace_cap) {
-        const long long idx = *p_idx;
-        bt.trace_tetr[idx * bt.trace_cap + npush] = ind_tetr;
-        bt.trace_face[idx * bt.trace_cap + npush] = iface;
-      }
-      *p_npush = npush + 1;
-      if (o.fallback) {
-        if (o.fallback & 1) LCNT(LC_FB0) = LCNT(LC_FB0) + 1;
-        if (o.fallback & 2) LCNT(LC_FB1) = LCNT(LC_FB1) + 1;
-        if (o.fallback & 4) LCNT(LC_FB2) = LCNT(LC_FB2) + 1;
-        if (o.fallback & 8) LCNT(LC_FB3) = LCNT(LC_FB3) + 1;
-        if constexpr (EXT == 3) {
-          if (o.fallback & 16) LCNT(LC_ADAPT) = LCNT(LC_ADAPT) + 1;
-        }
-      }
-      const double t_remain = LS(LS_TREM) - o.t_pass;
-      LS(LS_TREM) = t_remain;
-      if (o.finished || ind_tetr == -1) {
-        // :142  vperp = vperp_func(z_save, perpinv, ind_tetr_save)
-        const long long idx = *p_idx;
-        const double pinv = LS(LS_PERPINV);
-        const double zs[3] = {LS(LS_ZS0), LS(LS_ZS1), LS(LS_ZS2)};
-        double vperp_new = 0.0;
-        if (pinv != 0.0) vperp_new = sqrt(2.0 * fabs(pinv) * bmod_at<PHI>(m, *p_ind_save, zs));
-        bt.x[3 * idx] = o.x[0];
-        bt.x[3 * idx + 1] = o.x[1];
-        bt.x[3 * idx + 2] = o.x[2];
-        bt.vpar[idx] = o.vpar;
-        bt.vperp[idx] = vperp_new;
-        bt.ind_tetr[idx] = ind_tetr;
-        bt.iface[idx] = iface;
-        if (bt.t_remain_out) bt.t_remain_out[idx] = t_remain;
-        if (bt.n_pushes) bt.n_pushes[idx] = npush + 1;
+      if (!done)
+        o = push_rk_full_call<PHI, (EXT == 2 ? 2 : 0)>(&m, perpinv, ind_tetr, iface, S.D(LS_X0), S.D(LS_X1), S.D(LS_X2),
+                                                        S.D(LS_VPAR), S.D(LS_TREM));
+    } else {
+      if (!bt.force_full) {
+        const double x[3] = {S.D(LS_X0), S.D(LS_X1), S.D(LS_X2)};
+        PolyPusher<K, PHI, EXT> P;
+        P.mp = &m;
+        P.perpinv = perpinv;
+        if constexpr (EXT == 2) P.oq_mask = bt.oq_mask;
+        P.r.set_stash(S.Stash(), GB_THREADS);
+        done = P.push_fast(ind_tetr, iface, x, S.D(LS_VPAR), S.D(LS_TREM), o, &S.D(LS_TREM));
         if constexpr (EXT == 2) {
-          if (bt.optq) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) bt.optq[4 * idx + q] = LOQ(q);
-          }
-          if (bt.ev_flags) { bt.par_adiab_inv[idx] = LOQ(4); bt.counter_vpar_0[idx] = LEC(0); bt.counter_phi_0[idx] = LEC(1); }
+          if (done) lane_ext2_after_fast<K, PHI>(bt, S, P, o);
         }
-        *p_cpush = *p_cpush + (unsigned long long)(npush + 1);
-        if (o.finished) LCNT(LC_FIN) = LCNT(LC_FIN) + 1;
-        else LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
-        active = refill();
+      }
+      if (!done) {
+        if constexpr (EXT == 2)
+          o = lane_ext2_full<K, PHI>(m, bt, S, ind_tetr, iface);
+        else
+          o = push_full_call<K, PHI, EXT>(&m, perpinv, ind_tetr, iface, S.D(LS_X0), S.D(LS_X1), S.D(LS_X2), S.D(LS_VPAR),
+                                          S.D(LS_TREM));
       }
     }
+    if (lane_after_push<PHI, EXT>(m, bt, S, o, S.IndSave(), ind_tetr, iface))
+      active = lane_refill<PHI, EXT>(m, bt, S, lane, ind_tetr, iface);
   }
-  __syncwarp();
-  // counters: warp reduce, one atomic per warp and counter
-  unsigned long long v[8] = {*p_cpush, LCNT(LC_LOST), LCNT(LC_FIN), LCNT(LC_FB0), LCNT(LC_FB1), LCNT(LC_FB2), LCNT(LC_FB3),
-                             LCNT(LC_ADAPT)};
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    unsigned long long s = v[k];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
-    if (lane == 0 && s) atomicAdd(bt.ctr + k, s);
-  }
-#undef LS
-#undef LCNT
-#undef LOQ
-#undef LEC
-#undef p_idx
-#undef p_npush
-#undef p_cpush
-#undef p_ind_save
+  lane_reduce_counters(bt, S, lane);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -399,78 +462,14 @@ template <int K, int PHI, int EXT = 0>
 __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_constant__ MeshDev m, const Batch bt)
 {
   extern __shared__ __align__(16) unsigned char g_smem[];
-  double (*s_d)[GBG_THREADS] = reinterpret_cast<double (*)[GBG_THREADS]>(g_smem);                       // [LS_ND]
-  double (*s_stash)[GBG_THREADS] = s_d + LS_ND;                                                         // [6]
-  long long *s_idx = reinterpret_cast<long long *>(s_stash + 6), *s_npush = s_idx + GBG_THREADS;
-  unsigned long long *s_cpush = reinterpret_cast<unsigned long long *>(s_npush + GBG_THREADS);
-  unsigned int (*s_cnt)[GBG_THREADS] = reinterpret_cast<unsigned int (*)[GBG_THREADS]>(s_cpush + GBG_THREADS);  // [LC_N]
-  int *s_ind_save = reinterpret_cast<int *>(s_cnt + LC_N);
-  double (*s_oq)[GBG_THREADS] = reinterpret_cast<double (*)[GBG_THREADS]>(s_ind_save + GBG_THREADS);   // [5], EXT = 2 only
-  int (*s_ec)[GBG_THREADS] = reinterpret_cast<int (*)[GBG_THREADS]>(s_oq + 5);                          // [2], EXT = 2 only
-#define LOQ(q) (((volatile double *)s_oq[q])[tid_now()])
-#define LEC(q) (((volatile int *)s_ec[q])[tid_now()])
+  LaneSlots<GBG_THREADS> S;
+  S.carve(g_smem, EXT == 2);
   const unsigned lane = threadIdx.x & 31u;
   const int bar_id = 1 + (int)((threadIdx.x >> 5) & 3u);   // warps w, w+4, w+8, w+12 share sub-partition w
-#define LS(f) (((volatile double *)s_d[f])[tid_now()])
-#define LCNT(f) (((volatile unsigned int *)s_cnt[f])[tid_now()])
-#define p_idx (((volatile long long *)s_idx) + tid_now())
-#define p_npush (((volatile long long *)s_npush) + tid_now())
-#define p_cpush (((volatile unsigned long long *)s_cpush) + tid_now())
-#define p_ind_save (((volatile int *)s_ind_save) + tid_now())
   int32_t ind_tetr = -1, iface = -1;
-  *p_cpush = 0;
-#pragma unroll
-  for (int k = 0; k < LC_N; k++) LCNT(k) = 0;
+  S.zero_counters();
 
-  auto refill = [&]() -> bool {
-    for (;;) {
-      const unsigned need = __activemask();
-      const int leader = __ffs(need) - 1;
-      unsigned long long base = 0;
-      if ((int)lane == leader) base = atomicAdd(bt.ctr + CTR_QUEUE, (unsigned long long)__popc(need));
-      base = __shfl_sync(need, base, leader);
-      const int64_t idx = (int64_t)(base + (unsigned long long)__popc(need & ((1u << lane) - 1u)));
-      if (idx >= bt.n) return false;
-      ind_tetr = bt.ind_tetr[idx];
-      iface = bt.iface[idx];
-      const bool inited = bt.init ? (bt.init[idx] != 0) : true;
-      if (!inited || ind_tetr < 1) {
-        if (bt.t_remain_out) bt.t_remain_out[idx] = bt.t_step;
-        if (bt.n_pushes) bt.n_pushes[idx] = 0;
-        if constexpr (EXT == 2) {
-          if (bt.optq) { bt.optq[4 * idx] = 0.0; bt.optq[4 * idx + 1] = 0.0; bt.optq[4 * idx + 2] = 0.0; bt.optq[4 * idx + 3] = 0.0; }
-        }
-        if (inited && ind_tetr < 1) LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
-        continue;
-      }
-      if (bt.t_step == 0.0) {
-        if (bt.t_remain_out) bt.t_remain_out[idx] = 0.0;
-        if (bt.n_pushes) bt.n_pushes[idx] = 0;
-        if constexpr (EXT == 2) {
-          if (bt.optq) { bt.optq[4 * idx] = 0.0; bt.optq[4 * idx + 1] = 0.0; bt.optq[4 * idx + 2] = 0.0; bt.optq[4 * idx + 3] = 0.0; }
-        }
-        continue;
-      }
-      const double x0 = bt.x[3 * idx], x1 = bt.x[3 * idx + 1], x2 = bt.x[3 * idx + 2];
-      const double vperp = bt.vperp[idx];
-      const double *pg = m.geom + ((int64_t)ind_tetr - 1) * GEOM_ND;
-      const double zs[3] = {x0 - ldg(pg), x1 - ldg(pg + 1), x2 - ldg(pg + 2)};
-      LS(LS_X0) = x0; LS(LS_X1) = x1; LS(LS_X2) = x2;
-      LS(LS_VPAR) = bt.vpar[idx];
-      LS(LS_ZS0) = zs[0]; LS(LS_ZS1) = zs[1]; LS(LS_ZS2) = zs[2];
-      LS(LS_PERPINV) = -0.5 * (vperp * vperp) / bmod_at<PHI>(m, ind_tetr, zs);
-      LS(LS_TREM) = bt.t_step;
-      *p_idx = idx;
-      *p_npush = 0;
-      if constexpr (EXT == 2) {
-        LOQ(0) = 0.0; LOQ(1) = 0.0; LOQ(2) = 0.0; LOQ(3) = 0.0;
-        if (bt.ev_flags) { LOQ(4) = bt.par_adiab_inv[idx]; LEC(0) = bt.counter_vpar_0[idx]; LEC(1) = bt.counter_phi_0[idx]; }
-      }
-      return true;
-    }
-  };
-
-  bool active = refill();
+  bool active = lane_refill<PHI, EXT>(m, bt, S, lane, ind_tetr, iface);
   for (;;) {
     if (!group_any(active, bar_id)) break;   // the group leaves together
     PushOut o;
@@ -483,125 +482,85 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
     PolyPusher<K, PHI, EXT> P;
     P.mp = &m;
     if constexpr (EXT == 2) P.oq_mask = bt.oq_mask;
-    P.r.set_stash(&s_stash[0][tid_now()], GBG_THREADS);
+    P.r.set_stash(S.Stash(), GBG_THREADS);
     if (active && !bt.force_full) {
-      const double x[3] = {LS(LS_X0), LS(LS_X1), LS(LS_X2)};
-      P.perpinv = LS(LS_PERPINV);
-      begun = P.fast_begin(ind_tetr, iface, x, LS(LS_VPAR), LS(LS_TREM), t, iface_new, tau_max) && t.kind != 0;
+      const double x[3] = {S.D(LS_X0), S.D(LS_X1), S.D(LS_X2)};
+      P.perpinv = S.D(LS_PERPINV);
+      begun = P.fast_begin(ind_tetr, iface, x, S.D(LS_VPAR), S.D(LS_TREM), t, iface_new, tau_max) && t.kind != 0;
     }
     const double tau = solve_group(begun && t.kind == 2, t.deg, t.q[0], t.q[1], t.q[2], t.q[3], t.lambda, t.tau, bar_id);
     if (begun) {
-      P.t_remain = LS(LS_TREM);
+      P.t_remain = S.D(LS_TREM);
       done = P.fast_end(tau, iface_new, tau_max, true, o);
     }
     if (active) {
-      *p_ind_save = ind_tetr;
       if constexpr (EXT == 2) {
-        if (done) {
-          if (bt.oq_mask) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) LOQ(q) = LOQ(q) + P.oq[q];
-          }
-          if (bt.ev_flags && !o.finished) {
-            EvState es;
-            es.flags = bt.ev_flags; es.nskip_p = bt.n_skip_phi_0; es.nskip_v = bt.n_skip_vpar_0;
-            es.J = LOQ(4); es.cnt_v = LEC(0); es.cnt_p = LEC(1);
-            P.events_after_push(LS(LS_VPAR), o, es);
-            LOQ(4) = es.J; LEC(0) = es.cnt_v; LEC(1) = es.cnt_p;
-            if (es.n) emit_events(bt, *p_idx, *p_npush, es);
-          }
-        } else {
-          const PushOutX ox = push_full_call_x<K, PHI>(&m, LS(LS_PERPINV), ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2),
-                                                       LS(LS_VPAR), LS(LS_TREM), bt.oq_mask, bt.ev_flags, bt.n_skip_phi_0,
-                                                       bt.n_skip_vpar_0, LOQ(4), LEC(0), LEC(1));
-          o = ox.o;
-#pragma unroll
-          for (int q = 0; q < 4; q++) LOQ(q) = LOQ(q) + ox.oq[q];
-          if (bt.ev_flags) {
-            LOQ(4) = ox.es.J; LEC(0) = ox.es.cnt_v; LEC(1) = ox.es.cnt_p;
-            if (ox.es.n) emit_events(bt, *p_idx, *p_npush, ox.es);
-          }
-        }
+        if (done) lane_ext2_after_fast<K, PHI>(bt, S, P, o);
+        else o = lane_ext2_full<K, PHI>(m, bt, S, ind_tetr, iface);
       } else {
         if (!done)
-          o = push_full_call<K, PHI, EXT>(&m, LS(LS_PERPINV), ind_tetr, iface, LS(LS_X0), LS(LS_X1), LS(LS_X2), LS(LS_VPAR), LS(LS_TREM));
+          o = push_full_call<K, PHI, EXT>(&m, S.D(LS_PERPINV), ind_tetr, iface, S.D(LS_X0), S.D(LS_X1), S.D(LS_X2),
+                                          S.D(LS_VPAR), S.D(LS_TREM));
       }
-      LS(LS_X0) = o.x[0]; LS(LS_X1) = o.x[1]; LS(LS_X2) = o.x[2];
-      LS(LS_VPAR) = o.vpar;
-      if (o.z_save_set) { LS(LS_ZS0) = o.z_save[0]; LS(LS_ZS1) = o.z_save[1]; LS(LS_ZS2) = o.z_save[2]; }
-      const int ind_prev = ind_tetr;
-      ind_tetr = o.ind_tetr;
-      iface = o.iface;
-      const long long npush = *p_npush;
-      if (bt.trace_cap > 0 && npush < bt.trace_cap) {
-        const long long idx = *p_idx;
-        bt.trace_tetr[idx * bt.trace_cap + npush] = ind_tetr;
-        bt.trace_face[idx * bt.trace_cap + npush] = iface;
-      }
-      *p_npush = npush + 1;
-      if (o.fallback) {
-        if (o.fallback & 1) LCNT(LC_FB0) = LCNT(LC_FB0) + 1;
-        if (o.fallback & 2) LCNT(LC_FB1) = LCNT(LC_FB1) + 1;
-        if (o.fallback & 4) LCNT(LC_FB2) = LCNT(LC_FB2) + 1;
-        if (o.fallback & 8) LCNT(LC_FB3) = LCNT(LC_FB3) + 1;
-        if constexpr (EXT == 3) {
-          if (o.fallback & 16) LCNT(LC_ADAPT) = LCNT(LC_ADAPT) + 1;
-        }
-      }
-      const double t_remain = LS(LS_TREM) - o.t_pass;
-      LS(LS_TREM) = t_remain;
-      if (o.finished || ind_tetr == -1) {
-        const long long idx = *p_idx;
-        const double pinv = LS(LS_PERPINV);
-        const double zs[3] = {LS(LS_ZS0), LS(LS_ZS1), LS(LS_ZS2)};
-        double vperp_new = 0.0;
-        if (pinv != 0.0) vperp_new = sqrt(2.0 * fabs(pinv) * bmod_at<PHI>(m, ind_prev, zs));
-        bt.x[3 * idx] = o.x[0];
-        bt.x[3 * idx + 1] = o.x[1];
-        bt.x[3 * idx + 2] = o.x[2];
-        bt.vpar[idx] = o.vpar;
-        bt.vperp[idx] = vperp_new;
-        bt.ind_tetr[idx] = ind_tetr;
-        bt.iface[idx] = iface;
-        if (bt.t_remain_out) bt.t_remain_out[idx] = t_remain;
-        if (bt.n_pushes) bt.n_pushes[idx] = npush + 1;
-        if constexpr (EXT == 2) {
-          if (bt.optq) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) bt.optq[4 * idx + q] = LOQ(q);
-          }
-          if (bt.ev_flags) { bt.par_adiab_inv[idx] = LOQ(4); bt.counter_vpar_0[idx] = LEC(0); bt.counter_phi_0[idx] = LEC(1); }
-        }
-        *p_cpush = *p_cpush + (unsigned long long)(npush + 1);
-        if (o.finished) LCNT(LC_FIN) = LCNT(LC_FIN) + 1;
-        else LCNT(LC_LOST) = LCNT(LC_LOST) + 1;
-        active = refill();
-      }
+      if (lane_after_push<PHI, EXT>(m, bt, S, o, ind_tetr, ind_tetr, iface))
+        active = lane_refill<PHI, EXT>(m, bt, S, lane, ind_tetr, iface);
     }
   }
-  __syncwarp();
-  unsigned long long v[8] = {*p_cpush, LCNT(LC_LOST), LCNT(LC_FIN), LCNT(LC_FB0), LCNT(LC_FB1), LCNT(LC_FB2), LCNT(LC_FB3),
-                             LCNT(LC_ADAPT)};
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    unsigned long long sacc = v[k];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, off);
-    if (lane == 0 && sacc) atomicAdd(bt.ctr + k, sacc);
-  }
-#undef LS
-#undef LCNT
-#undef LOQ
-#undef LEC
-#undef p_idx
-#undef p_npush
-#undef p_cpush
-#undef p_ind_save
+  lane_reduce_counters(bt, S, lane);
 }
-constexpr size_t GBG_SMEM = (size_t)GBG_THREADS * ((LS_ND + 6) * 8 + 3 * 8 + LC_N * 4 + 4);
-constexpr size_t GBG_SMEM_EXT = GBG_SMEM + (size_t)GBG_THREADS * (5 * 8 + 2 * 4);
+constexpr size_t GBG_SMEM = LaneSlots<GBG_THREADS>::BYTES;
+constexpr size_t GBG_SMEM_EXT = LaneSlots<GBG_THREADS>::BYTES_EXT2;
 
 // ----------------------------------------------------------------------------------------------------
+// energy_tot_func, p_phi_func (SRC/supporting_functions_mod.f90:279-301, 377-408) and perpinv = -vperp^2/(2|B|)
+// (SRC/orbit_timestep_gorilla.f90:77) of one particle in tetrahedron it (1-based)
+__device__ __forceinline__ void particle_invariants(const MeshDev &m, int32_t it, const double *x, double vl, double vp,
+                                                    double &e, double &p, double &mu)
+{
+  const double *pg = m.geom + ((int64_t)it - 1) * GEOM_ND;
+  const double *pb = m.bpart + ((int64_t)it - 1) * BPART_ND;
+  const double *pc = m.cold + ((int64_t)it - 1) * COLD_ND;
+  const double z[3] = {x[0] - pg[0], x[1] - pg[1], x[2] - pg[2]};
+  const double gB[3] = {pb[B_GB], pb[B_GB + 1], pb[B_GB + 2]};
+  const double bmod = pb[B_BMOD1] + dot3(gB, z);
+  mu = -0.5 * (vp * vp) / bmod;
+  const double vperp_e = sqrt(2.0 * fabs(mu) * bmod);
+  double phi = 0.0;
+  if (m.phi) {
+    const double *pp = m.phi + ((int64_t)it - 1) * PHI_ND;
+    const double gP[3] = {pp[P_GPHI], pp[P_GPHI + 1], pp[P_GPHI + 2]};
+    phi = pp[P_PHI1] + dot3(gP, z);
+  }
+  e = m.particle_mass / 2.0 * (vperp_e * vperp_e + vl * vl) + m.particle_charge * phi;
+  const double *ps = m.se ? m.se + ((int64_t)it - 1) * SE_ND : nullptr;
+  if (ps) {  // :299
+    const double g2[3] = {ps[S_GV2EMOD], ps[S_GV2EMOD + 1], ps[S_GV2EMOD + 2]};
+    e = e + 0.5 * m.particle_mass * (ps[S_V2EMOD1] + dot3(z, g2));
+  }
+  const double gh[3] = {pc[C_GHPHI], pc[C_GHPHI + 1], pc[C_GHPHI + 2]};
+  const double gA[3] = {pc[C_GAPHI], pc[C_GAPHI + 1], pc[C_GAPHI + 2]};
+  p = m.particle_mass * vl * (pc[C_HPHI1] + dot3(gh, z)) + m.particle_mass / m.cm_over_e * (pc[C_APHI1] + dot3(gA, z));
+  if (ps) {  // :402-406 (cylindrical coordinates: phi is the second covariant component)
+    const double gv[3] = {ps[S_GVE2], ps[S_GVE2 + 1], ps[S_GVE2 + 2]};
+    p = p + m.particle_mass * (ps[S_VE2_1] + dot3(z, gv));
+  }
+}
+
+// device partials of one diagnostics reduction: [0..2] max |E/E0-1|, |mu/mu0-1|, |p_phi/p_phi0-1| ; [3..5] the sums of their
+// squares ; then as int64: [6] particles sampled, [7] particles in the batch, [8..] the accumulated counters (CTR_N)
+enum { DG_MAX = 0, DG_SUM = 3, DG_NSAMP = 6, DG_NPART = 7, DG_CTR = 8, GB_DIAG_ND = DG_CTR + CTR_N };
+
+// One orbit_timestep* call in flight: its own device counter block (incl. the work-queue cursor) and timing events, so that
+// calls issued on different streams of one handle do not share a cursor.  The handle keeps a small ring; a slot is reused
+// only after the call that used it last has completed on the device.
+#define GB_NSLOTS 8
+struct CallSlot {
+  unsigned long long *d_ctr = nullptr;   // [CTR_N]
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, done = nullptr;
+  bool used = false, have_find_time = false, have_push_time = false;
+  int64_t n = 0;
+};
+
 struct gorilla_b200_handle {
   int device = 0;
   int num_sms = 0;
@@ -611,7 +570,9 @@ struct gorilla_b200_handle {
   double *s_oq = nullptr;   // [cap][4] scratch for the optional quantities (host-pointer entry point)
   uint32_t oq_mask = 0;
   int32_t *d_bin_start = nullptr, *d_bin_items = nullptr;
-  unsigned long long *d_ctr = nullptr;
+  CallSlot slots[GB_NSLOTS];
+  int cur_slot = -1;                     // slot of the most recent orbit_timestep* call
+  unsigned long long *d_acc = nullptr;   // [CTR_N] counters accumulated over all calls since gorilla_b200_diag_reset
   // scratch for the host-pointer entry points
   int64_t cap = 0;
   double *s_x = nullptr, *s_vpar = nullptr, *s_vperp = nullptr, *s_tro = nullptr, *s_e = nullptr, *s_p = nullptr, *s_mu = nullptr;
@@ -619,20 +580,54 @@ struct gorilla_b200_handle {
   int64_t *s_np = nullptr;
   int64_t trace_cap_elems = 0;
   int32_t *s_tr_t = nullptr, *s_tr_f = nullptr;
-  // sort scratch
+  // host-pointer event capture: per-particle state, event buffer, event counter
+  int64_t ev_state_cap = 0, ev_cap = 0;
+  double *s_J = nullptr;
+  int32_t *s_cv = nullptr, *s_cp = nullptr;
+  gorilla_event *s_ev = nullptr;
+  uint64_t *s_nev = nullptr;
+  // sort scratch (one sort at a time per handle: a sort on another stream waits for the previous one, sort_done)
   size_t sort_tmp_bytes = 0;
   void *sort_tmp = nullptr;
   int64_t sort_cap = 0;
   uint32_t *sort_keys_in = nullptr, *sort_keys_out = nullptr;
-  int64_t *sort_vals_in = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
-  bool have_find_time = false, have_push_time = false;
-  int64_t last_n = 0;
+  int64_t *sort_vals_in = nullptr, *sort_perm = nullptr;
+  cudaEvent_t sort_done = nullptr;
+  bool sort_used = false;
+  // gorilla_b200_resort_dev / in-library re-sort of the host-pointer path: gather scratch
+  int64_t gather_cap = 0;
+  double *g_d = nullptr;     // [gather_cap][3]
+  int32_t *g_i = nullptr;    // [gather_cap]
+  int32_t host_resort = 0;   // gorilla_b200_set_host_resort
+  // diagnostics reduction (gorilla_b200_diag_reduce*): device partials + pinned host copy
+  double *d_diag = nullptr;  // [GB_DIAG_ND]
+  void *h_diag = nullptr;    // pinned
+  // multi-GPU (gorilla_b200_comm_*): NCCL communicator of this rank, loaded at run time
+  void *comm = nullptr;
+  int32_t rank = 0, nranks = 1;
   int ctas_per_sm = 0, threads_per_cta = 128;
   int force_full = 0;
   int use_group = 1;  // orders 3/4: lock-step solver kernel (orbit_kernel_g)
-  cudaStream_t last_stream = nullptr;
 };
+
+// makes the handle's device current for the duration of an entry point (a handle belongs to the device it was created on)
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev)
+  {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) { ok = false; return; }
+    if (cur != dev) {
+      ok = cudaSetDevice(dev) == cudaSuccess;
+      if (ok) prev = cur;
+    }
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define GB_ENTER(h)                                                                                          \
+  DeviceGuard dg__((h)->device);                                                                             \
+  if (!dg__.ok) { gbint::set_error("cannot make the handle's CUDA device current"); return GORILLA_ERR_CUDA; }
 
 template <int K, int PHI, int EXT = 0>
 int launch_orbit_t(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)

@@ -14,7 +14,6 @@
 //   sort keys             radix sort (CUB) of particle indices by tetra index.
 // Compile with --fmad=false: the reference ISA has no FMA and the visited-tetra sequence is only
 // reproducible with separately rounded multiplies and adds.
-#include <cub/device/device_radix_sort.cuh>
 #include <string.h>
 #include <math.h>
 #include <mutex>
@@ -28,13 +27,13 @@ static std::atomic<int64_t> g_launch_count{0};
 namespace gbint {
 void set_error(const char *msg) { g_last_error = msg; }
 void count_launch(int n) { g_launch_count += n; }
-}
-
-static int fail(int code, const char *msg)
+int fail(int code, const char *msg)
 {
   g_last_error = msg;
   return code;
 }
+}
+using gbint::fail;
 namespace gbhost {
 void set_last_error(const std::string &s) { g_last_error = s; }
 }
@@ -130,52 +129,18 @@ __global__ void invariants_kernel(const __grid_constant__ MeshDev m, int64_t n, 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t it = ind_tetr[i];
     double e = NAN, p = NAN, mu = NAN;
-    if (it >= 1) {
-      const double *pg = m.geom + ((int64_t)it - 1) * GEOM_ND;
-      const double *pb = m.bpart + ((int64_t)it - 1) * BPART_ND;
-      const double *pc = m.cold + ((int64_t)it - 1) * COLD_ND;
-      const double z[3] = {x[3 * i] - pg[0], x[3 * i + 1] - pg[1], x[3 * i + 2] - pg[2]};
-      const double gB[3] = {pb[B_GB], pb[B_GB + 1], pb[B_GB + 2]};
-      const double bmod = pb[B_BMOD1] + dot3(gB, z);
-      const double vp = vperp[i], vl = vpar[i];
-      mu = -0.5 * (vp * vp) / bmod;
-      // energy_tot_func (supporting_functions_mod.f90:279-301)
-      const double vperp_e = sqrt(2.0 * fabs(mu) * bmod);
-      double phi = 0.0;
-      if (m.phi) {
-        const double *pp = m.phi + ((int64_t)it - 1) * PHI_ND;
-        const double gP[3] = {pp[P_GPHI], pp[P_GPHI + 1], pp[P_GPHI + 2]};
-        phi = pp[P_PHI1] + dot3(gP, z);
-      }
-      e = m.particle_mass / 2.0 * (vperp_e * vperp_e + vl * vl) + m.particle_charge * phi;
-      const double *ps = m.se ? m.se + ((int64_t)it - 1) * SE_ND : nullptr;
-      if (ps) {  // :299
-        const double g2[3] = {ps[S_GV2EMOD], ps[S_GV2EMOD + 1], ps[S_GV2EMOD + 2]};
-        e = e + 0.5 * m.particle_mass * (ps[S_V2EMOD1] + dot3(z, g2));
-      }
-      // p_phi_func (:377-408)
-      const double gh[3] = {pc[C_GHPHI], pc[C_GHPHI + 1], pc[C_GHPHI + 2]};
-      const double gA[3] = {pc[C_GAPHI], pc[C_GAPHI + 1], pc[C_GAPHI + 2]};
-      p = m.particle_mass * vl * (pc[C_HPHI1] + dot3(gh, z)) +
-          m.particle_mass / m.cm_over_e * (pc[C_APHI1] + dot3(gA, z));
-      if (ps) {  // :402-406 (cylindrical coordinates: phi is the second covariant component)
-        const double gv[3] = {ps[S_GVE2], ps[S_GVE2 + 1], ps[S_GVE2 + 2]};
-        p = p + m.particle_mass * (ps[S_VE2_1] + dot3(z, gv));
-      }
-    }
+    if (it >= 1) particle_invariants(m, it, &x[3 * i], vpar[i], vperp[i], e, p, mu);
     if (energy) energy[i] = e;
     if (p_phi) p_phi[i] = p;
     if (perpinv_out) perpinv_out[i] = mu;
   }
 }
 
-__global__ void sort_keys_kernel(int64_t n, const int32_t *ind_tetr, uint32_t *keys, int64_t *vals)
+// adds the counters of a finished call to the handle's accumulators (gorilla_b200_diag_reduce_dev)
+__global__ void accumulate_counters_kernel(const unsigned long long *ctr, unsigned long long *acc)
 {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int32_t t = ind_tetr[i];
-    keys[i] = t < 1 ? 0xffffffffu : (uint32_t)t;
-    vals[i] = i;
-  }
+  const int k = threadIdx.x;
+  if (k < CTR_N && k != CTR_QUEUE) acc[k] += ctr[k];
 }
 
 static int check_settings(const gorilla_settings *s)
@@ -210,6 +175,32 @@ static int check_settings(const gorilla_settings *s)
   if (s->boole_strong_electric_field && (s->i_precomp != 0 || s->boole_newton_precalc))
     return fail(GORILLA_ERR_ARG, "boole_strong_electric_field requires i_precomp = 0 and boole_newton_precalc = .false.");
   if (s->boole_pusher_ode45) return fail(GORILLA_ERR_UNSUPPORTED, "boole_pusher_ode45 must be .false.");
+  return GORILLA_OK;
+}
+
+static cudaError_t init_slots(gorilla_b200_handle *h)
+{
+  cudaError_t e;
+  for (int k = 0; k < GB_NSLOTS; k++) {
+    CallSlot &c = h->slots[k];
+    if ((e = cudaMalloc((void **)&c.d_ctr, CTR_N * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaEventCreate(&c.ev0)) != cudaSuccess || (e = cudaEventCreate(&c.ev1)) != cudaSuccess ||
+        (e = cudaEventCreate(&c.ev2)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming)) != cudaSuccess)
+      return e;
+  }
+  return cudaSuccess;
+}
+// the next call slot of the ring; waits if the call that used it last is still running
+static int acquire_slot(gorilla_b200_handle *h, CallSlot **out)
+{
+  const int k = (h->cur_slot + 1) % GB_NSLOTS;
+  CallSlot &c = h->slots[k];
+  if (c.used) GB_CUDA(cudaEventSynchronize(c.done));
+  c.used = true;
+  c.have_find_time = c.have_push_time = false;
+  h->cur_slot = k;
+  *out = &c;
   return GORILLA_OK;
 }
 
@@ -251,9 +242,12 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
   if ((e = up(&h->d_geom, geom)) != cudaSuccess || (e = up(&h->d_bpart, bpart)) != cudaSuccess ||
       (e = up(&h->d_cold, cold)) != cudaSuccess || ((has_phi || strong) && (e = up(&h->d_phi, phi)) != cudaSuccess) ||
       (strong && (e = up(&h->d_se, se)) != cudaSuccess) ||
-      (e = cudaMalloc((void **)&h->d_ctr, CTR_N * sizeof(unsigned long long))) != cudaSuccess ||
-      (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
-      (e = cudaEventCreate(&h->ev2)) != cudaSuccess) {
+      (e = cudaMalloc((void **)&h->d_acc, CTR_N * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMemset(h->d_acc, 0, CTR_N * sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMalloc((void **)&h->d_diag, GB_DIAG_ND * sizeof(double))) != cudaSuccess ||
+      (e = cudaMallocHost(&h->h_diag, GB_DIAG_ND * sizeof(double))) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->sort_done, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = init_slots(h)) != cudaSuccess) {
     g_last_error = std::string("gorilla_b200_init: ") + cudaGetErrorString(e);
     gorilla_b200_free(h);
     return GORILLA_ERR_CUDA;
@@ -335,14 +329,26 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
 extern "C" void gorilla_b200_free(gorilla_b200_handle *h)
 {
   if (!h) return;
-  cudaFree(h->d_geom); cudaFree(h->d_bpart); cudaFree(h->d_phi); cudaFree(h->d_cold); cudaFree(h->d_se); cudaFree(h->d_ham); cudaFree(h->d_skew); cudaFree(h->s_oq); cudaFree(h->d_bin_start); cudaFree(h->d_bin_items); cudaFree(h->d_ctr);
+  DeviceGuard dg(h->device);
+  gorilla_b200_comm_free(h);
+  cudaDeviceSynchronize();
+  cudaFree(h->d_geom); cudaFree(h->d_bpart); cudaFree(h->d_phi); cudaFree(h->d_cold); cudaFree(h->d_se); cudaFree(h->d_ham); cudaFree(h->d_skew); cudaFree(h->s_oq); cudaFree(h->d_bin_start); cudaFree(h->d_bin_items);
+  cudaFree(h->d_acc); cudaFree(h->d_diag); cudaFree(h->g_d); cudaFree(h->g_i); cudaFree(h->sort_perm);
+  cudaFree(h->s_J); cudaFree(h->s_cv); cudaFree(h->s_cp); cudaFree(h->s_ev); cudaFree(h->s_nev);
+  if (h->h_diag) cudaFreeHost(h->h_diag);
+  if (h->sort_done) cudaEventDestroy(h->sort_done);
+  for (int k = 0; k < GB_NSLOTS; k++) {
+    CallSlot &c = h->slots[k];
+    cudaFree(c.d_ctr);
+    if (c.ev0) cudaEventDestroy(c.ev0);
+    if (c.ev1) cudaEventDestroy(c.ev1);
+    if (c.ev2) cudaEventDestroy(c.ev2);
+    if (c.done) cudaEventDestroy(c.done);
+  }
   cudaFree(h->s_x); cudaFree(h->s_vpar); cudaFree(h->s_vperp); cudaFree(h->s_tro); cudaFree(h->s_e);
   cudaFree(h->s_p); cudaFree(h->s_mu); cudaFree(h->s_init); cudaFree(h->s_ind); cudaFree(h->s_iface);
   cudaFree(h->s_np); cudaFree(h->s_tr_t); cudaFree(h->s_tr_f); cudaFree(h->sort_tmp);
   cudaFree(h->sort_keys_in); cudaFree(h->sort_keys_out); cudaFree(h->sort_vals_in);
-  if (h->ev0) cudaEventDestroy(h->ev0);
-  if (h->ev1) cudaEventDestroy(h->ev1);
-  if (h->ev2) cudaEventDestroy(h->ev2);
   delete h;
 }
 
@@ -446,9 +452,27 @@ static int launch_orbit_k(gorilla_b200_handle *h, const Batch &bt, cudaStream_t 
   }
 }
 
-static int run_device(gorilla_b200_handle *h, Batch bt, bool do_find, cudaStream_t s)
+static int launch_find(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
 {
-  bt.ctr = h->d_ctr;
+  int64_t grid = (bt.n + 127) / 128;
+  if (grid > (int64_t)h->num_sms * 16) grid = (int64_t)h->num_sms * 16;
+  if (h->mesh.se) find_kernel<2><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
+  else if (h->mesh.phi) find_kernel<1><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
+  else find_kernel<0><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
+  g_launch_count++;
+  GB_CUDA(cudaGetLastError());
+  return GORILLA_OK;
+}
+
+// One batched call on stream s: [find_tetra of the particles that are not localised yet] -> [optional re-sort by
+// tetrahedron: resort_perm != nullptr gathers the six state arrays through a fresh permutation before the push and
+// scatters them (and t_remain_out / n_pushes) back afterwards] -> push kernel -> counters into the accumulators.
+static int run_device(gorilla_b200_handle *h, Batch bt, bool do_find, cudaStream_t s, bool resort = false)
+{
+  CallSlot *slot = nullptr;
+  int rc = acquire_slot(h, &slot);
+  if (rc) return rc;
+  bt.ctr = slot->d_ctr;
   bt.boole_periodic_relocation = h->settings.boole_periodic_relocation;
   bt.sign_t_step = signbit(bt.t_step) ? -1 : 1;
   bt.force_full = h->force_full;
@@ -457,28 +481,38 @@ static int run_device(gorilla_b200_handle *h, Batch bt, bool do_find, cudaStream
     GB_CUDA(cudaMemsetAsync(bt.optq, 0, (size_t)bt.n * 4 * sizeof(double), s));
     bt.optq = nullptr;
   }
-  GB_CUDA(cudaMemsetAsync(h->d_ctr, 0, CTR_N * sizeof(unsigned long long), s));
-  h->have_find_time = false;
-  h->have_push_time = false;
-  h->last_n = bt.n;
-  h->last_stream = s;
-  if (bt.n == 0) return GORILLA_OK;
-  GB_CUDA(cudaEventRecord(h->ev0, s));
-  if (do_find) {
-    int64_t grid = (bt.n + 127) / 128;
-    if (grid > (int64_t)h->num_sms * 16) grid = (int64_t)h->num_sms * 16;
-    if (h->mesh.se) find_kernel<2><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
-    else if (h->mesh.phi) find_kernel<1><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
-    else find_kernel<0><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
-    g_launch_count++;
-    GB_CUDA(cudaGetLastError());
-    h->have_find_time = true;
+  GB_CUDA(cudaMemsetAsync(slot->d_ctr, 0, CTR_N * sizeof(unsigned long long), s));
+  slot->n = bt.n;
+  if (bt.n == 0) {
+    GB_CUDA(cudaEventRecord(slot->done, s));
+    return GORILLA_OK;
   }
-  GB_CUDA(cudaEventRecord(h->ev1, s));
-  int rc = h->mesh.se ? launch_orbit_k<2>(h, bt, s) : h->mesh.phi ? launch_orbit_k<1>(h, bt, s) : launch_orbit_k<0>(h, bt, s);
+  GB_CUDA(cudaEventRecord(slot->ev0, s));
+  if (do_find) {
+    rc = launch_find(h, bt, s);
+    if (rc) return rc;
+    slot->have_find_time = true;
+  }
+  if (resort) {
+    rc = gbint::sort_permutation(h, bt.n, bt.ind_tetr, nullptr, s);
+    if (!rc) rc = gbint::permute_state_inplace(h, bt.n, h->sort_perm, false, bt.x, bt.vpar, bt.vperp, bt.init, bt.ind_tetr, bt.iface, s);
+    if (rc) return rc;
+  }
+  GB_CUDA(cudaEventRecord(slot->ev1, s));
+  rc = h->mesh.se ? launch_orbit_k<2>(h, bt, s) : h->mesh.phi ? launch_orbit_k<1>(h, bt, s) : launch_orbit_k<0>(h, bt, s);
   if (rc) return rc;
-  GB_CUDA(cudaEventRecord(h->ev2, s));
-  h->have_push_time = true;
+  GB_CUDA(cudaEventRecord(slot->ev2, s));
+  slot->have_push_time = true;
+  if (resort) {
+    rc = gbint::permute_state_inplace(h, bt.n, h->sort_perm, true, bt.x, bt.vpar, bt.vperp, bt.init, bt.ind_tetr, bt.iface, s);
+    if (!rc && bt.t_remain_out) rc = gbint::permute_one_inplace<double>(h, bt.n, h->sort_perm, true, bt.t_remain_out, s);
+    if (!rc && bt.n_pushes) rc = gbint::permute_one_inplace<int64_t>(h, bt.n, h->sort_perm, true, bt.n_pushes, s);
+    if (rc) return rc;
+  }
+  accumulate_counters_kernel<<<1, 32, 0, s>>>(slot->d_ctr, h->d_acc);
+  g_launch_count++;
+  GB_CUDA(cudaGetLastError());
+  GB_CUDA(cudaEventRecord(slot->done, s));
   return GORILLA_OK;
 }
 
@@ -488,6 +522,7 @@ extern "C" int gorilla_b200_orbit_timestep_dev(gorilla_b200_handle *h, int64_t n
 {
   if (!h || n < 0 || (n > 0 && (!x || !vpar || !vperp || !boole_initialized || !ind_tetr || !iface)))
     return fail(GORILLA_ERR_ARG, "gorilla_b200_orbit_timestep_dev: null argument");
+  GB_ENTER(h);
   Batch bt{};
   bt.n = n; bt.x = x; bt.vpar = vpar; bt.vperp = vperp; bt.t_step = t_step; bt.init = boole_initialized;
   bt.ind_tetr = ind_tetr; bt.iface = iface; bt.t_remain_out = t_remain_out; bt.n_pushes = n_pushes;
@@ -503,6 +538,7 @@ extern "C" int gorilla_b200_orbit_timestep_optional_dev(gorilla_b200_handle *h, 
     return fail(GORILLA_ERR_ARG, "gorilla_b200_orbit_timestep_optional_dev: null argument");
   if (h->settings.ipusher != 2)
     return fail(GORILLA_ERR_UNSUPPORTED, "optional quantities exist for the polynomial pusher only (ipusher = 2)");
+  GB_ENTER(h);
   Batch bt{};
   bt.n = n; bt.x = x; bt.vpar = vpar; bt.vperp = vperp; bt.t_step = t_step; bt.init = boole_initialized;
   bt.ind_tetr = ind_tetr; bt.iface = iface; bt.t_remain_out = t_remain_out; bt.n_pushes = n_pushes;
@@ -510,6 +546,7 @@ extern "C" int gorilla_b200_orbit_timestep_optional_dev(gorilla_b200_handle *h, 
   return run_device(h, bt, true, (cudaStream_t)stream);
 }
 
+static int ensure_scratch(gorilla_b200_handle *h, int64_t n);
 static int check_event_args(gorilla_b200_handle *h, const gorilla_event_settings *cfg, int &flags)
 {
   if (h->settings.ipusher != 2 || h->settings.poly_order < 2)
@@ -535,6 +572,7 @@ extern "C" int gorilla_b200_orbit_timestep_events_dev(gorilla_b200_handle *h, in
   int flags = 0;
   int rc = check_event_args(h, cfg, flags);
   if (rc) return rc;
+  GB_ENTER(h);
   Batch bt{};
   bt.n = n; bt.x = x; bt.vpar = vpar; bt.vperp = vperp; bt.t_step = t_step; bt.init = boole_initialized;
   bt.ind_tetr = ind_tetr; bt.iface = iface; bt.t_remain_out = t_remain_out; bt.n_pushes = n_pushes;
@@ -561,66 +599,59 @@ extern "C" int gorilla_b200_orbit_timestep_events(gorilla_b200_handle *h, int64_
   if (rc) return rc;
   *n_events = 0;
   if (n == 0) return GORILLA_OK;
+  GB_ENTER(h);
+  // persistent scratch on the handle (grown on demand), no allocation per call
+  rc = ensure_scratch(h, n);
+  if (rc) return rc;
+  if (n > h->ev_state_cap) {
+    cudaFree(h->s_J); cudaFree(h->s_cv); cudaFree(h->s_cp);
+    h->s_J = nullptr; h->s_cv = h->s_cp = nullptr; h->ev_state_cap = 0;
+    GB_CUDA(cudaMalloc((void **)&h->s_J, (size_t)n * sizeof(double)));
+    GB_CUDA(cudaMalloc((void **)&h->s_cv, (size_t)n * sizeof(int32_t)));
+    GB_CUDA(cudaMalloc((void **)&h->s_cp, (size_t)n * sizeof(int32_t)));
+    h->ev_state_cap = n;
+  }
+  if (event_cap > h->ev_cap || !h->s_ev) {
+    cudaFree(h->s_ev);
+    h->s_ev = nullptr; h->ev_cap = 0;
+    GB_CUDA(cudaMalloc((void **)&h->s_ev, (size_t)(event_cap > 0 ? event_cap : 1) * sizeof(gorilla_event)));
+    h->ev_cap = event_cap > 0 ? event_cap : 1;
+  }
+  if (!h->s_nev) GB_CUDA(cudaMalloc((void **)&h->s_nev, sizeof(uint64_t)));
   cudaStream_t s = nullptr;
-  double *d_x = nullptr, *d_vpar = nullptr, *d_vperp = nullptr, *d_tro = nullptr, *d_J = nullptr;
-  int32_t *d_init = nullptr, *d_ind = nullptr, *d_ifc = nullptr, *d_cv = nullptr, *d_cp = nullptr;
-  int64_t *d_np = nullptr;
-  gorilla_event *d_ev = nullptr;
-  uint64_t *d_nev = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(d_x); cudaFree(d_vpar); cudaFree(d_vperp); cudaFree(d_tro); cudaFree(d_J); cudaFree(d_init); cudaFree(d_ind);
-    cudaFree(d_ifc); cudaFree(d_cv); cudaFree(d_cp); cudaFree(d_np); cudaFree(d_ev); cudaFree(d_nev);
-  };
-#define GB_EV(call)                                                                                       \
-  do {                                                                                                    \
-    cudaError_t e__ = (call);                                                                             \
-    if (e__ != cudaSuccess) {                                                                             \
-      g_last_error = std::string("gorilla_b200_orbit_timestep_events: ") + cudaGetErrorString(e__);       \
-      cleanup();                                                                                          \
-      return GORILLA_ERR_CUDA;                                                                            \
-    }                                                                                                     \
-  } while (0)
   const size_t nd = (size_t)n * sizeof(double), ni = (size_t)n * sizeof(int32_t);
-  GB_EV(cudaMalloc((void **)&d_x, 3 * nd)); GB_EV(cudaMalloc((void **)&d_vpar, nd)); GB_EV(cudaMalloc((void **)&d_vperp, nd));
-  GB_EV(cudaMalloc((void **)&d_tro, nd)); GB_EV(cudaMalloc((void **)&d_J, nd)); GB_EV(cudaMalloc((void **)&d_init, ni));
-  GB_EV(cudaMalloc((void **)&d_ind, ni)); GB_EV(cudaMalloc((void **)&d_ifc, ni)); GB_EV(cudaMalloc((void **)&d_cv, ni));
-  GB_EV(cudaMalloc((void **)&d_cp, ni)); GB_EV(cudaMalloc((void **)&d_np, (size_t)n * sizeof(int64_t)));
-  GB_EV(cudaMalloc((void **)&d_ev, (size_t)(event_cap > 0 ? event_cap : 1) * sizeof(gorilla_event)));
-  GB_EV(cudaMalloc((void **)&d_nev, sizeof(uint64_t)));
-  GB_EV(cudaMemcpyAsync(d_x, x, 3 * nd, cudaMemcpyHostToDevice, s));
-  GB_EV(cudaMemcpyAsync(d_vpar, vpar, nd, cudaMemcpyHostToDevice, s));
-  GB_EV(cudaMemcpyAsync(d_vperp, vperp, nd, cudaMemcpyHostToDevice, s));
-  GB_EV(cudaMemcpyAsync(d_J, par_adiab_inv, nd, cudaMemcpyHostToDevice, s));
-  GB_EV(cudaMemcpyAsync(d_init, boole_initialized, ni, cudaMemcpyHostToDevice, s));
-  GB_EV(cudaMemcpyAsync(d_ind, ind_tetr, ni, cudaMemcpyHostToDevice, s));
-  GB_EV(cudaMemcpyAsync(d_ifc, iface, ni, cudaMemcpyHostToDevice, s));
-  GB_EV(cudaMemcpyAsync(d_cv, counter_vpar_0, ni, cudaMemcpyHostToDevice, s));
-  GB_EV(cudaMemcpyAsync(d_cp, counter_phi_0, ni, cudaMemcpyHostToDevice, s));
-  GB_EV(cudaMemsetAsync(d_nev, 0, sizeof(uint64_t), s));
-  rc = gorilla_b200_orbit_timestep_events_dev(h, n, d_x, d_vpar, d_vperp, t_step, d_init, d_ind, d_ifc, d_tro, d_np, cfg, d_J,
-                                              d_cv, d_cp, d_ev, event_cap, d_nev, s);
-  if (rc) { cleanup(); return rc; }
+  GB_CUDA(cudaMemcpyAsync(h->s_x, x, 3 * nd, cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_vpar, vpar, nd, cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_vperp, vperp, nd, cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_J, par_adiab_inv, nd, cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_init, boole_initialized, ni, cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_ind, ind_tetr, ni, cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_iface, iface, ni, cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_cv, counter_vpar_0, ni, cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemcpyAsync(h->s_cp, counter_phi_0, ni, cudaMemcpyHostToDevice, s));
+  GB_CUDA(cudaMemsetAsync(h->s_nev, 0, sizeof(uint64_t), s));
+  rc = gorilla_b200_orbit_timestep_events_dev(h, n, h->s_x, h->s_vpar, h->s_vperp, t_step, h->s_init, h->s_ind, h->s_iface,
+                                              h->s_tro, h->s_np, cfg, h->s_J, h->s_cv, h->s_cp, h->s_ev, event_cap, h->s_nev, s);
+  if (rc) return rc;
   uint64_t nev = 0;
-  GB_EV(cudaMemcpyAsync(&nev, d_nev, sizeof(nev), cudaMemcpyDeviceToHost, s));
-  GB_EV(cudaMemcpyAsync(x, d_x, 3 * nd, cudaMemcpyDeviceToHost, s));
-  GB_EV(cudaMemcpyAsync(vpar, d_vpar, nd, cudaMemcpyDeviceToHost, s));
-  GB_EV(cudaMemcpyAsync(vperp, d_vperp, nd, cudaMemcpyDeviceToHost, s));
-  GB_EV(cudaMemcpyAsync(par_adiab_inv, d_J, nd, cudaMemcpyDeviceToHost, s));
-  GB_EV(cudaMemcpyAsync(boole_initialized, d_init, ni, cudaMemcpyDeviceToHost, s));
-  GB_EV(cudaMemcpyAsync(ind_tetr, d_ind, ni, cudaMemcpyDeviceToHost, s));
-  GB_EV(cudaMemcpyAsync(iface, d_ifc, ni, cudaMemcpyDeviceToHost, s));
-  GB_EV(cudaMemcpyAsync(counter_vpar_0, d_cv, ni, cudaMemcpyDeviceToHost, s));
-  GB_EV(cudaMemcpyAsync(counter_phi_0, d_cp, ni, cudaMemcpyDeviceToHost, s));
-  if (t_remain_out) GB_EV(cudaMemcpyAsync(t_remain_out, d_tro, nd, cudaMemcpyDeviceToHost, s));
-  if (n_pushes) GB_EV(cudaMemcpyAsync(n_pushes, d_np, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  GB_EV(cudaStreamSynchronize(s));
+  GB_CUDA(cudaMemcpyAsync(&nev, h->s_nev, sizeof(nev), cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaMemcpyAsync(x, h->s_x, 3 * nd, cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaMemcpyAsync(vpar, h->s_vpar, nd, cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaMemcpyAsync(vperp, h->s_vperp, nd, cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaMemcpyAsync(par_adiab_inv, h->s_J, nd, cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaMemcpyAsync(boole_initialized, h->s_init, ni, cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaMemcpyAsync(ind_tetr, h->s_ind, ni, cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaMemcpyAsync(iface, h->s_iface, ni, cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaMemcpyAsync(counter_vpar_0, h->s_cv, ni, cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaMemcpyAsync(counter_phi_0, h->s_cp, ni, cudaMemcpyDeviceToHost, s));
+  if (t_remain_out) GB_CUDA(cudaMemcpyAsync(t_remain_out, h->s_tro, nd, cudaMemcpyDeviceToHost, s));
+  if (n_pushes) GB_CUDA(cudaMemcpyAsync(n_pushes, h->s_np, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  GB_CUDA(cudaStreamSynchronize(s));
   const int64_t stored = (int64_t)nev < event_cap ? (int64_t)nev : event_cap;
-  if (stored > 0) GB_EV(cudaMemcpy(events, d_ev, (size_t)stored * sizeof(gorilla_event), cudaMemcpyDeviceToHost));
+  if (stored > 0) GB_CUDA(cudaMemcpy(events, h->s_ev, (size_t)stored * sizeof(gorilla_event), cudaMemcpyDeviceToHost));
   *n_events = (int64_t)nev;
   unsigned long long dom = 0;
-  GB_EV(cudaMemcpy(&dom, h->d_ctr + CTR_DOMAIN, sizeof(dom), cudaMemcpyDeviceToHost));
-#undef GB_EV
-  cleanup();
+  GB_CUDA(cudaMemcpy(&dom, h->slots[h->cur_slot].d_ctr + CTR_DOMAIN, sizeof(dom), cudaMemcpyDeviceToHost));
   if (dom) return fail(GORILLA_ERR_DOMAIN, "particle start position outside the computation domain");
   return GORILLA_OK;
 }
@@ -658,6 +689,7 @@ static int orbit_host(gorilla_b200_handle *h, int64_t n, double *x, double *vpar
   if (!h || n < 0 || (n > 0 && (!x || !vpar || !vperp || !binit || !ind_tetr || !iface)))
     return fail(GORILLA_ERR_ARG, "gorilla_b200_orbit_timestep: null argument");
   if (n == 0) return GORILLA_OK;
+  GB_ENTER(h);
   int rc = ensure_scratch(h, n);
   if (rc) return rc;
   cudaStream_t s = nullptr;
@@ -685,7 +717,9 @@ static int orbit_host(gorilla_b200_handle *h, int64_t n, double *x, double *vpar
     bt.trace_cap = trace_cap; bt.trace_tetr = h->s_tr_t; bt.trace_face = h->s_tr_f;
   }
   if (optq) bt.optq = h->s_oq;
-  rc = run_device(h, bt, true, s);
+  // in-library re-sort (gorilla_b200_set_host_resort): gather locality for callers that only have host arrays
+  const bool resort = h->host_resort && trace_cap <= 0 && !optq && t_step != 0.0 && n >= 4096;
+  rc = run_device(h, bt, true, s, resort);
   if (rc) return rc;
   if (optq) GB_CUDA(cudaMemcpyAsync(optq, h->s_oq, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
   GB_CUDA(cudaMemcpyAsync(x, h->s_x, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -702,7 +736,7 @@ static int orbit_host(gorilla_b200_handle *h, int64_t n, double *x, double *vpar
   }
   GB_CUDA(cudaStreamSynchronize(s));
   unsigned long long dom = 0;
-  GB_CUDA(cudaMemcpy(&dom, h->d_ctr + CTR_DOMAIN, sizeof(dom), cudaMemcpyDeviceToHost));
+  GB_CUDA(cudaMemcpy(&dom, h->slots[h->cur_slot].d_ctr + CTR_DOMAIN, sizeof(dom), cudaMemcpyDeviceToHost));
   if (dom) return fail(GORILLA_ERR_DOMAIN, "particle start position outside the computation domain");
   return GORILLA_OK;
 }
@@ -752,30 +786,31 @@ extern "C" int gorilla_b200_find_tetra(gorilla_b200_handle *h, int64_t n, double
   if (!h || n < 0 || (n > 0 && (!x || !vpar || !vperp || !ind_tetr || !iface)))
     return fail(GORILLA_ERR_ARG, "gorilla_b200_find_tetra: null argument");
   if (n == 0) return GORILLA_OK;
+  GB_ENTER(h);
   int rc = ensure_scratch(h, n);
   if (rc) return rc;
   cudaStream_t s = nullptr;
+  CallSlot *slot = nullptr;
+  rc = acquire_slot(h, &slot);
+  if (rc) return rc;
+  slot->n = n;
   GB_CUDA(cudaMemcpyAsync(h->s_x, x, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
   GB_CUDA(cudaMemcpyAsync(h->s_vpar, vpar, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
   GB_CUDA(cudaMemcpyAsync(h->s_vperp, vperp, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
-  GB_CUDA(cudaMemsetAsync(h->d_ctr, 0, CTR_N * sizeof(unsigned long long), s));
+  GB_CUDA(cudaMemsetAsync(slot->d_ctr, 0, CTR_N * sizeof(unsigned long long), s));
   Batch bt{};
   bt.n = n; bt.x = h->s_x; bt.vpar = h->s_vpar; bt.vperp = h->s_vperp; bt.init = nullptr; bt.ind_tetr = h->s_ind;
-  bt.iface = h->s_iface; bt.ctr = h->d_ctr; bt.boole_periodic_relocation = h->settings.boole_periodic_relocation;
+  bt.iface = h->s_iface; bt.ctr = slot->d_ctr; bt.boole_periodic_relocation = h->settings.boole_periodic_relocation;
   bt.sign_t_step = sign_t_step < 0 ? -1 : 1;
-  int64_t grid = (n + 127) / 128;
-  if (grid > (int64_t)h->num_sms * 16) grid = (int64_t)h->num_sms * 16;
-  if (h->mesh.se) find_kernel<2><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
-  else if (h->mesh.phi) find_kernel<1><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
-  else find_kernel<0><<<(unsigned)grid, 128, 0, s>>>(h->mesh, bt);
-  g_launch_count++;
-  GB_CUDA(cudaGetLastError());
+  rc = launch_find(h, bt, s);
+  if (rc) return rc;
+  GB_CUDA(cudaEventRecord(slot->done, s));
   GB_CUDA(cudaMemcpyAsync(x, h->s_x, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
   GB_CUDA(cudaMemcpyAsync(ind_tetr, h->s_ind, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   GB_CUDA(cudaMemcpyAsync(iface, h->s_iface, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   GB_CUDA(cudaStreamSynchronize(s));
   unsigned long long dom = 0;
-  GB_CUDA(cudaMemcpy(&dom, h->d_ctr + CTR_DOMAIN, sizeof(dom), cudaMemcpyDeviceToHost));
+  GB_CUDA(cudaMemcpy(&dom, slot->d_ctr + CTR_DOMAIN, sizeof(dom), cudaMemcpyDeviceToHost));
   if (dom) return fail(GORILLA_ERR_DOMAIN, "particle start position outside the computation domain");
   return GORILLA_OK;
 }
@@ -786,6 +821,7 @@ extern "C" int gorilla_b200_invariants_dev(gorilla_b200_handle *h, int64_t n, co
 {
   if (!h || n < 0 || (n > 0 && (!x || !vpar || !vperp || !ind_tetr))) return fail(GORILLA_ERR_ARG, "invariants: null argument");
   if (n == 0) return GORILLA_OK;
+  GB_ENTER(h);
   int64_t grid = (n + 255) / 256;
   if (grid > (int64_t)h->num_sms * 8) grid = (int64_t)h->num_sms * 8;
   invariants_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(h->mesh, n, x, vpar, vperp, ind_tetr, energy, p_phi,
@@ -800,6 +836,7 @@ extern "C" int gorilla_b200_invariants(gorilla_b200_handle *h, int64_t n, const 
 {
   if (!h || n < 0 || (n > 0 && (!x || !vpar || !vperp || !ind_tetr))) return fail(GORILLA_ERR_ARG, "invariants: null argument");
   if (n == 0) return GORILLA_OK;
+  GB_ENTER(h);
   int rc = ensure_scratch(h, n);
   if (rc) return rc;
   cudaStream_t s = nullptr;
@@ -820,59 +857,29 @@ extern "C" int gorilla_b200_get_counters(gorilla_b200_handle *h, gorilla_counter
 {
   if (!h || !out) return fail(GORILLA_ERR_ARG, "get_counters: null argument");
   memset(out, 0, sizeof(*out));
-  GB_CUDA(cudaStreamSynchronize(h->last_stream));
+  if (h->cur_slot < 0) return GORILLA_OK;
+  GB_ENTER(h);
+  CallSlot &slot = h->slots[h->cur_slot];
+  GB_CUDA(cudaEventSynchronize(slot.done));
   unsigned long long c[CTR_N];
-  GB_CUDA(cudaMemcpy(c, h->d_ctr, sizeof(c), cudaMemcpyDeviceToHost));
-  out->n_particles = h->last_n;
+  GB_CUDA(cudaMemcpy(c, slot.d_ctr, sizeof(c), cudaMemcpyDeviceToHost));
+  out->n_particles = slot.n;
   out->n_pushes = (int64_t)c[CTR_PUSHES];
-  out->n_lost = (int64_t)c[CTR_LOST];
+  out->n_lost = (int64_t)(c[CTR_LOST] + c[CTR_LOST_PREV]);   // ind_tetr == -1 after the call: lost in it or before it
   out->n_finished = (int64_t)c[CTR_FINISHED];
   for (int i = 0; i < 4; i++) out->n_fallback[i] = (int64_t)c[CTR_FB0 + i];
   out->n_domain_errors = (int64_t)c[CTR_DOMAIN];
   out->n_adaptive = (int64_t)c[CTR_ADAPT];
+  out->n_lost_inner = (int64_t)c[CTR_LOST_INNER];
+  out->n_failed = (int64_t)c[CTR_FAILED];
   float ms = 0.f;
-  if (h->have_push_time) {
-    GB_CUDA(cudaEventElapsedTime(&ms, h->ev1, h->ev2));
+  if (slot.have_push_time) {
+    GB_CUDA(cudaEventElapsedTime(&ms, slot.ev1, slot.ev2));
     out->kernel_ms = ms;
   }
-  if (h->have_find_time) {
-    GB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (slot.have_find_time) {
+    GB_CUDA(cudaEventElapsedTime(&ms, slot.ev0, slot.ev1));
     out->find_ms = ms;
   }
-  return GORILLA_OK;
-}
-
-extern "C" int gorilla_b200_sort_permutation_dev(gorilla_b200_handle *h, int64_t n, const int32_t *ind_tetr, int64_t *perm,
-                                                 void *stream)
-{
-  if (!h || n < 0 || (n > 0 && (!ind_tetr || !perm))) return fail(GORILLA_ERR_ARG, "sort_permutation: null argument");
-  if (n == 0) return GORILLA_OK;
-  if (n > 0x7fffffffLL) return fail(GORILLA_ERR_ARG, "sort_permutation: n too large");
-  cudaStream_t s = (cudaStream_t)stream;
-  if (n > h->sort_cap) {
-    cudaFree(h->sort_keys_in); cudaFree(h->sort_keys_out); cudaFree(h->sort_vals_in); cudaFree(h->sort_tmp);
-    h->sort_keys_in = h->sort_keys_out = nullptr; h->sort_vals_in = nullptr; h->sort_tmp = nullptr; h->sort_cap = 0;
-    GB_CUDA(cudaMalloc((void **)&h->sort_keys_in, (size_t)n * sizeof(uint32_t)));
-    GB_CUDA(cudaMalloc((void **)&h->sort_keys_out, (size_t)n * sizeof(uint32_t)));
-    GB_CUDA(cudaMalloc((void **)&h->sort_vals_in, (size_t)n * sizeof(int64_t)));
-    size_t bytes = 0;
-    GB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->sort_keys_in, h->sort_keys_out, h->sort_vals_in, perm, (int)n,
-                                            0, 32, s));
-    GB_CUDA(cudaMalloc(&h->sort_tmp, bytes));
-    h->sort_tmp_bytes = bytes;
-    h->sort_cap = n;
-  }
-  int64_t grid = (n + 255) / 256;
-  if (grid > (int64_t)h->num_sms * 8) grid = (int64_t)h->num_sms * 8;
-  sort_keys_kernel<<<(unsigned)grid, 256, 0, s>>>(n, ind_tetr, h->sort_keys_in, h->sort_vals_in);
-  g_launch_count++;
-  GB_CUDA(cudaGetLastError());
-  int bits = 1;
-  while (bits < 32 && (1LL << bits) <= h->mesh.ntetr + 1) bits++;
-  bits = 32; // lost particles use key 0xffffffff
-  size_t bytes = h->sort_tmp_bytes;
-  GB_CUDA(cub::DeviceRadixSort::SortPairs(h->sort_tmp, bytes, h->sort_keys_in, h->sort_keys_out, h->sort_vals_in, perm, (int)n,
-                                          0, bits, s));
-  g_launch_count += 4;
   return GORILLA_OK;
 }

@@ -81,12 +81,15 @@ extern "C" void gorilla_mesh_free(gorilla_mesh *mesh) { delete mesh; }
 // those two arrays as they sit in memory (the `sequence` derived types, [ntetr][142] doubles and [ntetr][20] int32), the
 // vertex tables and the module scalars the hot path reads, behind a fixed little-endian header:
 //   magic "GMESHB2\0" | u32 version | u32 endian tag 0x01020304 | u32 ndoubles per record (142) | u32 nints (20)
-//   | i64 ntetr | i64 nvert | i32 has_sthetaphi | i32 sign_sqg, coord_system, n_field_periods, grid_kind, grid_size[3]
+//   | i64 ntetr | i64 nvert | i32 flags | i32 sign_sqg, coord_system, n_field_periods, grid_kind, grid_size[3]
 //   | f64 cm_over_e, particle_mass, particle_charge, Rmin, Rmax, Zmin, Zmax, sfc_s_min | u64 FNV-1a of the payload
-// followed by the payload: tetra_physics, tetra_grid, verts_rphiz, [verts_sthetaphi].
+// followed by the payload: tetra_physics, tetra_grid, verts_rphiz, [verts_sthetaphi], [tetra_skew_coord].
+// flags: bit 0 = verts_sthetaphi present, bit 1 (version 2) = tetra_skew_coord present ([ntetr][168] doubles, the records
+// of handover_processing_kind = 2).  Version 1 files (no skew records) are still read.
 namespace {
 const char GMESH_MAGIC[8] = {'G', 'M', 'E', 'S', 'H', 'B', '2', '\0'};
-const uint32_t GMESH_VERSION = 1, GMESH_ENDIAN = 0x01020304u;
+const uint32_t GMESH_VERSION = 2, GMESH_ENDIAN = 0x01020304u;
+const int32_t GMESH_F_STHETAPHI = 1, GMESH_F_SKEW = 2;
 struct GmeshHeader {
   char magic[8];
   uint32_t version, endian, ndoubles, nints;
@@ -124,24 +127,29 @@ extern "C" int gorilla_mesh_save(const gorilla_mesh_desc *d, int64_t nvert, cons
   memcpy(h.magic, GMESH_MAGIC, 8);
   h.version = GMESH_VERSION; h.endian = GMESH_ENDIAN;
   h.ndoubles = GORILLA_TETRA_PHYSICS_NDOUBLES; h.nints = GORILLA_TETRA_GRID_NINTS;
-  h.ntetr = d->ntetr; h.nvert = nvert; h.has_sthetaphi = (verts_sthetaphi && nvert > 0) ? 1 : 0;
+  h.ntetr = d->ntetr; h.nvert = nvert;
+  const bool has_sth = verts_sthetaphi && nvert > 0, has_skew = d->tetra_skew_coord != nullptr;
+  h.has_sthetaphi = (has_sth ? GMESH_F_STHETAPHI : 0) | (has_skew ? GMESH_F_SKEW : 0);
   h.sign_sqg = d->sign_sqg; h.coord_system = d->coord_system; h.n_field_periods = d->n_field_periods; h.grid_kind = d->grid_kind;
   for (int i = 0; i < 3; i++) h.grid_size[i] = d->grid_size[i];
   h.cm_over_e = d->cm_over_e; h.particle_mass = d->particle_mass; h.particle_charge = d->particle_charge;
   h.Rmin = d->Rmin; h.Rmax = d->Rmax; h.Zmin = d->Zmin; h.Zmax = d->Zmax; h.sfc_s_min = d->sfc_s_min;
   const size_t n_tp = (size_t)d->ntetr * h.ndoubles * sizeof(double), n_tg = (size_t)d->ntetr * h.nints * sizeof(int32_t),
-               n_v = (size_t)nvert * 3 * sizeof(double);
+               n_v = (size_t)nvert * 3 * sizeof(double),
+               n_sk = (size_t)d->ntetr * GORILLA_TETRA_SKEW_NDOUBLES * sizeof(double);
   uint64_t c = 14695981039346656037ull;
   c = fnv1a(c, d->tetra_physics, n_tp);
   c = fnv1a(c, d->tetra_grid, n_tg);
   if (nvert > 0) c = fnv1a(c, verts_rphiz, n_v);
-  if (h.has_sthetaphi) c = fnv1a(c, verts_sthetaphi, n_v);
+  if (has_sth) c = fnv1a(c, verts_sthetaphi, n_v);
+  if (has_skew) c = fnv1a(c, d->tetra_skew_coord, n_sk);
   h.checksum = c;
   FILE *f = fopen(path, "wb");
   if (!f) return io_fail(std::string("gorilla_mesh_save: cannot open ") + path);
   bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(d->tetra_physics, 1, n_tp, f) == n_tp &&
             fwrite(d->tetra_grid, 1, n_tg, f) == n_tg && (nvert == 0 || fwrite(verts_rphiz, 1, n_v, f) == n_v) &&
-            (!h.has_sthetaphi || fwrite(verts_sthetaphi, 1, n_v, f) == n_v);
+            (!has_sth || fwrite(verts_sthetaphi, 1, n_v, f) == n_v) &&
+            (!has_skew || fwrite(d->tetra_skew_coord, 1, n_sk, f) == n_sk);
   if (fclose(f) != 0) ok = false;
   if (!ok) return io_fail(std::string("gorilla_mesh_save: short write to ") + path);
   return GORILLA_OK;
@@ -156,7 +164,7 @@ extern "C" int gorilla_mesh_load(const char *path, gorilla_mesh **out)
   if (fread(&h, sizeof(h), 1, f) != 1) return io_fail("gorilla_mesh_load: file shorter than the .gmesh header", f);
   if (memcmp(h.magic, GMESH_MAGIC, 8) != 0) return io_fail("gorilla_mesh_load: not a .gmesh file (bad magic)", f);
   if (h.endian != GMESH_ENDIAN) return io_fail("gorilla_mesh_load: file written with the other byte order", f);
-  if (h.version != GMESH_VERSION)
+  if (h.version != GMESH_VERSION && h.version != 1)
     return io_fail("gorilla_mesh_load: unsupported .gmesh version " + std::to_string(h.version) + " (this build reads version " +
                    std::to_string(GMESH_VERSION) + ")", f);
   if (h.ndoubles != GORILLA_TETRA_PHYSICS_NDOUBLES || h.nints != GORILLA_TETRA_GRID_NINTS)
@@ -172,19 +180,28 @@ extern "C" int gorilla_mesh_load(const char *path, gorilla_mesh **out)
   m.cm_over_e = h.cm_over_e; m.particle_mass = h.particle_mass; m.particle_charge = h.particle_charge;
   m.Rmin = h.Rmin; m.Rmax = h.Rmax; m.Zmin = h.Zmin; m.Zmax = h.Zmax; m.sfc_s_min = h.sfc_s_min;
   bool ok = true;
+  const bool has_sth = (h.has_sthetaphi & GMESH_F_STHETAPHI) != 0;
+  const bool has_skew = h.version >= 2 && (h.has_sthetaphi & GMESH_F_SKEW) != 0;
+  if (h.has_sthetaphi & ~(h.version >= 2 ? (GMESH_F_STHETAPHI | GMESH_F_SKEW) : GMESH_F_STHETAPHI)) {
+    delete gm;
+    return io_fail("gorilla_mesh_load: unknown payload flags in the header", f);
+  }
+  m.handover_processing_kind = has_skew ? 2 : 1;
   try {
     m.tetra_physics.resize((size_t)h.ntetr * h.ndoubles);
     m.tetra_grid.resize((size_t)h.ntetr * h.nints);
     m.verts_rphiz.resize((size_t)h.nvert * 3);
-    if (h.has_sthetaphi) m.verts_sthetaphi.resize((size_t)h.nvert * 3);
+    if (has_sth) m.verts_sthetaphi.resize((size_t)h.nvert * 3);
+    if (has_skew) m.tetra_skew_coord.resize((size_t)h.ntetr * GORILLA_TETRA_SKEW_NDOUBLES);
   } catch (...) {
     ok = false;
   }
   const size_t n_tp = m.tetra_physics.size() * sizeof(double), n_tg = m.tetra_grid.size() * sizeof(int32_t),
-               n_v = m.verts_rphiz.size() * sizeof(double);
+               n_v = m.verts_rphiz.size() * sizeof(double), n_sk = m.tetra_skew_coord.size() * sizeof(double);
   ok = ok && fread(m.tetra_physics.data(), 1, n_tp, f) == n_tp && fread(m.tetra_grid.data(), 1, n_tg, f) == n_tg &&
        (n_v == 0 || fread(m.verts_rphiz.data(), 1, n_v, f) == n_v) &&
-       (!h.has_sthetaphi || fread(m.verts_sthetaphi.data(), 1, n_v, f) == n_v);
+       (!has_sth || fread(m.verts_sthetaphi.data(), 1, n_v, f) == n_v) &&
+       (!has_skew || fread(m.tetra_skew_coord.data(), 1, n_sk, f) == n_sk);
   const bool at_end = ok && fgetc(f) == EOF;
   fclose(f);
   if (!ok || !at_end) {
@@ -195,7 +212,8 @@ extern "C" int gorilla_mesh_load(const char *path, gorilla_mesh **out)
   c = fnv1a(c, m.tetra_physics.data(), n_tp);
   c = fnv1a(c, m.tetra_grid.data(), n_tg);
   if (n_v) c = fnv1a(c, m.verts_rphiz.data(), n_v);
-  if (h.has_sthetaphi) c = fnv1a(c, m.verts_sthetaphi.data(), n_v);
+  if (has_sth) c = fnv1a(c, m.verts_sthetaphi.data(), n_v);
+  if (has_skew) c = fnv1a(c, m.tetra_skew_coord.data(), n_sk);
   if (c != h.checksum) {
     delete gm;
     return io_fail("gorilla_mesh_load: checksum mismatch (file is corrupted)");

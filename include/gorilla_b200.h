@@ -107,6 +107,9 @@ typedef struct gorilla_counters {
   double kernel_ms;          /* device time of the push kernel (CUDA events on the launch stream) */
   double find_ms;            /* device time of the localisation kernel, 0 if not run */
   int64_t n_adaptive;        /* pushes in which the adaptive scheme re-integrated a segment in sub-steps */
+  int64_t n_lost_inner;      /* lost IN this call through the inner boundary s = sfc_s_min (flux-coordinate grids) */
+  int64_t n_failed;          /* lost IN this call: removed by the pusher inside the domain (no valid exit time / trouble shooting
+                                failed, pusher_tetra_poly.f90:434-440,609-615) */
 } gorilla_counters;
 
 /* ---- lifetime ---------------------------------------------------------------------------------- */
@@ -130,7 +133,9 @@ int gorilla_b200_orbit_timestep(gorilla_b200_handle *h, int64_t n, double *x, do
                                 double *t_remain_out, int64_t *n_pushes);
 
 /* Same, all pointers are DEVICE pointers on the handle's device; runs on `stream` (a cudaStream_t,
- * NULL = default stream) and does not synchronise. */
+ * NULL = default stream) and does not synchronise.  Every call gets its own device counter block and work queue (a ring of
+ * 8 per handle; a 9th call in flight waits for the oldest), so calls on different streams of one handle do not interfere.
+ * The handle's device is made current for the duration of every entry point. */
 int gorilla_b200_orbit_timestep_dev(gorilla_b200_handle *h, int64_t n, double *x, double *vpar, double *vperp,
                                     double t_step, int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface,
                                     double *t_remain_out, int64_t *n_pushes, void *stream);
@@ -216,13 +221,72 @@ int gorilla_b200_invariants_dev(gorilla_b200_handle *h, int64_t n, const double 
                                 const double *vperp, const int32_t *ind_tetr, double *energy, double *p_phi,
                                 double *perpinv, void *stream);
 
-/* Counters of the most recent orbit_timestep* call on this handle (synchronises the launch stream). */
+/* Counters of the most recent orbit_timestep* call on this handle (waits for that call to complete). */
 int gorilla_b200_get_counters(gorilla_b200_handle *h, gorilla_counters *out);
 
-/* Sort keys for periodic particle re-sorting by tetra index: fills perm (DEVICE int64[n]) with the
- * permutation that orders particles by ind_tetr (lost particles last).  Device pointers. */
+/* ---- periodic particle re-sorting by tetrahedron index (gather locality; north_star) -------------------------- */
+
+/* Fills perm (DEVICE int64[n]) with the permutation that orders particles by ind_tetr (lost particles last). */
 int gorilla_b200_sort_permutation_dev(gorilla_b200_handle *h, int64_t n, const int32_t *ind_tetr, int64_t *perm,
                                       void *stream);
+/* Re-sorts a resident batch in place: computes that permutation and applies it to the six state arrays (DEVICE pointers;
+ * boole_initialized may be NULL) and to n_extra further DEVICE double[n] arrays the caller keeps per particle (e.g. the
+ * reference invariants of gorilla_b200_diag_reduce_dev); perm_out (DEVICE int64[n], may be NULL) receives the permutation,
+ * new[i] = old[perm[i]].  One pass over the data per array; does not synchronise. */
+int gorilla_b200_resort_dev(gorilla_b200_handle *h, int64_t n, double *x, double *vpar, double *vperp,
+                            int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface, int32_t n_extra,
+                            double *const *extra, int64_t *perm_out, void *stream);
+/* on != 0: the HOST-pointer entry point gorilla_b200_orbit_timestep sorts each uploaded batch by tetrahedron on the device
+ * before the push and restores the caller's order before the download (results are identical: particles are independent).
+ * Off by default; ignored by the trace / optional-quantity / event variants. */
+int gorilla_b200_set_host_resort(gorilla_b200_handle *h, int32_t on);
+
+/* ---- diagnostics reduction and multi-GPU ---------------------------------------------------------------------
+ * The reference is one OpenMP process; its counters live in gorilla_plot_mod (counter_tetrahedron_passes :550, lost
+ * particles :290-294,488-491) and it writes E_tot / p_phi per time step for the user to compare (:603).  Here particles shard
+ * over the GPUs of one box with the mesh replicated on each (one process and one handle per GPU); the only exchange of the
+ * path is the reduction below.  NCCL is loaded at run time (libnccl.so.2; GORILLA_B200_NCCL_LIB overrides the name). */
+typedef struct gorilla_diag {
+  int64_t n_particles;       /* particles in the reduced batches, all ranks */
+  int64_t n_pushes;          /* tetra crossings since gorilla_b200_diag_reset (or init), all ranks */
+  int64_t n_lost;            /* particles lost since the reset = n_lost_outer + n_lost_inner + n_failed */
+  int64_t n_lost_outer;      /* left through the outer boundary (flux grids: s = 1; cylindrical grids: any boundary face) */
+  int64_t n_lost_inner;      /* left through the inner boundary s = sfc_s_min (flux-coordinate grids) */
+  int64_t n_failed;          /* removed by the pusher inside the domain */
+  int64_t n_finished;        /* completed time steps (boole_t_finished) */
+  int64_t n_fallback[4];     /* as gorilla_counters */
+  int64_t n_adaptive;
+  int64_t n_sampled;         /* particles that entered the drift statistics (still in the domain, finite reference) */
+  /* conservation since the reference values were taken: max and rms over the sampled particles of
+   * |E/E_ref - 1| (energy_tot_func), |perpinv/perpinv_ref - 1| (magnetic moment) and |p_phi/p_phi_ref - 1| (p_phi_func) */
+  double max_delta_energy, rms_delta_energy;
+  double max_delta_perpinv, rms_delta_perpinv;
+  double max_delta_p_phi, rms_delta_p_phi;
+  int32_t nranks, reserved;
+} gorilla_diag;
+
+#define GORILLA_COMM_ID_BYTES 128 /* sizeof(ncclUniqueId) */
+/* Rank 0 creates the id (ncclGetUniqueId) and hands the bytes to the other ranks by whatever means the host program has
+ * (MPI_Bcast, a file, torch.distributed); then every rank joins with its handle (ncclCommInitRank on the handle's device). */
+int gorilla_b200_comm_unique_id(void *id_out /* GORILLA_COMM_ID_BYTES */);
+int gorilla_b200_comm_init(gorilla_b200_handle *h, const void *id, int32_t rank, int32_t nranks);
+int gorilla_b200_comm_free(gorilla_b200_handle *h);
+/* In-place all-reduce of a small DEVICE double buffer over the handle's communicator (op: 0 sum, 1 max, 2 min); a handle
+ * without communicator (single GPU) leaves the buffer as it is.  For what a driver reduces besides the diagnostics (timings). */
+int gorilla_b200_comm_allreduce_f64(gorilla_b200_handle *h, double *buf, int64_t count, int32_t op, void *stream);
+/* The contiguous shard [first, first+count) of n_total particles that belongs to `rank` of `nranks`
+ * ([r N/G, (r+1) N/G), BASELINE config 5). */
+int gorilla_b200_shard_range(int64_t n_total, int32_t rank, int32_t nranks, int64_t *first, int64_t *count);
+
+/* Zeroes the counters that the orbit_timestep* calls of this handle accumulate for gorilla_b200_diag_reduce_dev. */
+int gorilla_b200_diag_reset(gorilla_b200_handle *h, void *stream);
+/* One device reduction kernel over the batch (DEVICE pointers) + one grouped NCCL all-reduce when the handle has a
+ * communicator; *out (HOST) is complete on return (synchronises `stream`).  energy_ref / p_phi_ref / perpinv_ref: DEVICE
+ * double[n] reference values per particle as gorilla_b200_invariants_dev returned them earlier (each may be NULL: that drift
+ * is then reported as 0).  Collective: every rank of the communicator must call it. */
+int gorilla_b200_diag_reduce_dev(gorilla_b200_handle *h, int64_t n, const double *x, const double *vpar,
+                                 const double *vperp, const int32_t *ind_tetr, const double *energy_ref,
+                                 const double *p_phi_ref, const double *perpinv_ref, gorilla_diag *out, void *stream);
 
 /* FP64 issue-rate micro-benchmark on the current device: thread-level instructions per second for DFMA and
  * for DMUL+DADD pairs (the strict build issues the latter).  Roofline denominator of the FP64-bound orders. */

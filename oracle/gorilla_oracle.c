@@ -2878,8 +2878,16 @@ void gor_find_tetra(const gor_mesh *m, double x[3], double vpar, double vperp, i
   }
 }
 
-/* SRC/orbit_timestep_gorilla.f90:278-358 ; Fortran modulo(a,p) = a - floor(a/p)*p */
-static double f_modulo(double a, double p) { return a - floor(a / p) * p; }
+/* SRC/orbit_timestep_gorilla.f90:278-358 ; Fortran modulo(a,p) for reals as gfortran expands it (trans-intrinsic.cc,
+ * gfc_conv_intrinsic_mod): r = fmod(a,p) -- exact --, r += p when r != 0 and its sign differs from p's, and a zero result
+ * takes the sign of p.  (a - floor(a/p)*p rounds k*p and differs in the last bits once |a| >= 2p.) */
+static double f_modulo(double a, double p)
+{
+  double r = fmod(a, p);
+  if (r != 0.0 && ((r < 0.0) != (p < 0.0))) r += p;
+  if (r == 0.0) r = copysign(0.0, p);
+  return r;
+}
 int gor_check_coordinate_domain(const gor_mesh *m, double x[3])
 {
   double per = 2.0 * PI / m->n_field_periods;

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import workloads
-from gorilla_b200 import GorillaError, Mesh, load_mesh
+from gorilla_b200 import GorillaError, Mesh, build_mesh, load_mesh
 from oracle_binding import OracleMesh
 
 HEADER_BYTES = 8 + 4 * 4 + 2 * 8 + 8 * 4 + 8 * 8 + 8
@@ -59,8 +59,13 @@ def test_bad_files_are_refused(small_mesh, tmp_path):
 
     refused(b"not a mesh file at all" * 20, "magic")
     refused(raw[:40], "header")
-    v2 = bytearray(raw); v2[8:12] = struct.pack("<I", 2)
-    refused(v2, "version 2")
+    v3 = bytearray(raw); v3[8:12] = struct.pack("<I", 3)
+    refused(v3, "version 3")
+    fl = bytearray(raw); fl[40:44] = struct.pack("<i", 4)
+    refused(fl, "flags")
+    v1 = bytearray(raw); v1[8:12] = struct.pack("<I", 1)     # version-1 files (no skew records) are still read
+    (tmp_path / "v1.gmesh").write_bytes(bytes(v1))
+    assert load_mesh(tmp_path / "v1.gmesh").ntetr == 200
     sw = bytearray(raw); sw[12:16] = struct.pack(">I", 0x01020304)
     refused(sw, "byte order")
     rs = bytearray(raw); rs[16:20] = struct.pack("<I", 141)
@@ -71,6 +76,38 @@ def test_bad_files_are_refused(small_mesh, tmp_path):
     refused(flip, "checksum")
     with pytest.raises(GorillaError):
         load_mesh(tmp_path / "does_not_exist.gmesh")
+
+
+def test_kind2_mesh_keeps_its_skew_records(product_lib, tmp_path):
+    """a mesh built (or dumped) with handover_processing_kind = 2 carries tetra_skew_coord ([ntetr][168],
+    tetra_physics_mod.f90:89-99); the file is the complete resume state, so the records travel with it and are covered by the
+    checksum."""
+    grid, settings = workloads.analytic_tokamak(8, 8, 8)
+    settings.handover_processing_kind = 2
+    settings.poly_order = 2
+    mesh = build_mesh(grid, settings)
+    assert mesh.tetra_skew_coord is not None
+    path = tmp_path / "skew.gmesh"
+    mesh.save(path)
+    assert path.stat().st_size == HEADER_BYTES + mesh.ntetr * (142 * 8 + 20 * 4 + 168 * 8) + mesh.verts_rphiz.size * 8
+    back = load_mesh(path)
+    assert back.tetra_skew_coord is not None and np.array_equal(back.tetra_skew_coord, mesh.tetra_skew_coord)
+    assert np.array_equal(back.tetra_physics, mesh.tetra_physics)
+    res = []
+    for m in (mesh, back):
+        om = OracleMesh(m, settings)
+        x, vpar, vperp = workloads.particles_cyl(30, 5)
+        s = workloads.fresh_state(30)
+        r = om.orbit_timestep_trace(x, vpar, vperp, 1e-5, *s, 24)
+        res.append((x, vpar, r["trace_tetr"]))
+    assert all(np.array_equal(a, b) for a, b in zip(res[0], res[1]))
+    raw = bytearray(path.read_bytes())
+    raw[-100] ^= 0x01                      # inside the skew payload (last in the file)
+    bad = tmp_path / "bad.gmesh"
+    bad.write_bytes(bytes(raw))
+    with pytest.raises(GorillaError) as ei:
+        load_mesh(bad)
+    assert "checksum" in str(ei.value)
 
 
 @pytest.mark.gpu

@@ -135,7 +135,7 @@ EXPORTED_SYMBOLS = (
     "gorilla_b200_orbit_timestep_events", "gorilla_b200_orbit_timestep_events_dev",
     "gorilla_b200_find_tetra", "gorilla_b200_invariants", "gorilla_b200_invariants_dev",
     "gorilla_b200_get_counters", "gorilla_b200_sort_permutation_dev", "gorilla_b200_resort_dev",
-    "gorilla_b200_set_host_resort", "gorilla_b200_set_launch_config", "gorilla_b200_fp64_peak",
+    "gorilla_b200_set_host_resort", "gorilla_b200_set_launch_config", "gorilla_b200_fp64_peak", "gorilla_b200_set_prefetch", "gorilla_b200_set_gather",
     "gorilla_b200_comm_unique_id", "gorilla_b200_comm_init", "gorilla_b200_comm_free", "gorilla_b200_comm_allreduce_f64",
     "gorilla_b200_shard_range", "gorilla_b200_diag_reset", "gorilla_b200_diag_reduce_dev",
     "gorilla_mesh_build", "gorilla_mesh_get_desc", "gorilla_mesh_get_vertices", "gorilla_mesh_free",
@@ -184,6 +184,8 @@ def load_library():
     lib.gorilla_b200_diag_reset.argtypes = [vp, vp]
     lib.gorilla_b200_diag_reduce_dev.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(_Diag), vp]
     lib.gorilla_b200_set_launch_config.argtypes = [vp, i32, i32]
+    lib.gorilla_b200_set_prefetch.argtypes = [vp, i32]
+    lib.gorilla_b200_set_gather.argtypes = [vp, i32]
     lib.gorilla_b200_debug_force_full.argtypes = [vp, i32]
     lib.gorilla_b200_debug_find_bins.argtypes = [vp, i32]
     lib.gorilla_b200_debug_use_group.argtypes = [vp, i32]
@@ -615,6 +617,14 @@ class Gorilla:
         return Diag(d.n_particles, d.n_pushes, d.n_lost, d.n_lost_outer, d.n_lost_inner, d.n_failed, d.n_finished,
                     tuple(d.n_fallback), d.n_adaptive, d.n_sampled, d.max_delta_energy, d.rms_delta_energy,
                     d.max_delta_perpinv, d.rms_delta_perpinv, d.max_delta_p_phi, d.rms_delta_p_phi, d.nranks)
+
+    def set_prefetch(self, mode: int):
+        """Neighbour-record prefetch of the push kernels: 1 on, 0 off, -1 auto (gorilla_b200_set_prefetch)."""
+        _check(load_library().gorilla_b200_set_prefetch(self._h, int(mode)))
+
+    def set_gather(self, mode: int):
+        """Record gather of the order-1/2 and RK4 kernels: 0 vector loads, 1 bulk copies one push ahead, -1 auto."""
+        _check(load_library().gorilla_b200_set_gather(self._h, int(mode)))
 
     def set_launch_config(self, ctas_per_sm: int = 0, threads_per_cta: int = 0):
         _check(load_library().gorilla_b200_set_launch_config(self._h, ctas_per_sm, threads_per_cta))

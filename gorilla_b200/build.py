@@ -38,7 +38,7 @@ NVCC_FLAGS += _EXTRA
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas"]
 
 # longest compiles first (order 4 takes ~2 min per unit)
-CU_SOURCES = ["gb_orbit_k4x.cu", "gb_orbit_k4a.cu", "gb_orbit_k4t.cu", "gb_orbit_k4.cu", "gb_orbit_k3x.cu", "gb_orbit_k3a.cu",
+CU_SOURCES = ["gb_orbit_k4x.cu", "gb_orbit_k4a.cu", "gb_orbit_k4t.cu", "gb_orbit_k4.cu", "gb_orbit_k4p.cu", "gb_orbit_k3p.cu", "gb_orbit_k2p.cu", "gb_orbit_k3x.cu", "gb_orbit_k3a.cu",
               "gb_orbit_k3t.cu", "gb_orbit_k3.cu", "gorilla_b200.cu", "gb_diag.cu", "gb_orbit_rk.cu", "gb_orbit_rkx.cu", "gb_orbit_k2x.cu", "gb_orbit_k2a.cu",
               "gb_orbit_k2t.cu", "gb_orbit_k2.cu", "gb_orbit_k1x.cu", "gb_orbit_k1a.cu", "gb_orbit_k1t.cu", "gb_orbit_k1.cu"]
 CPP_SOURCES = ["host/mesh_api.cpp", "host/mesh_common.cpp", "host/mesh_analytic.cpp", "host/mesh_vmec.cpp", "host/mesh_efit.cpp", "host/mesh_soledge3x.cpp", "host/mesh_efit_flux.cpp"]
@@ -75,9 +75,20 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ_DIR.mkdir(parents=True, exist_ok=True)
     hd = _headers_digest()
     srcs = CU_SOURCES + CPP_SOURCES
+    # GORILLA_VARIANT_UNITS=a.cu,b.cu (with GORILLA_VARIANT): only these units are compiled with the variant's flags, every
+    # other object is taken from the main build (tuning experiments on one kernel need not recompile all twenty units)
+    only = [u for u in os.environ.get("GORILLA_VARIANT_UNITS", "").split(",") if u]
+    borrowed = []
+    if _VARIANT and only:
+        main_obj = ROOT / "lib" / "obj"
+        borrowed = [str(main_obj / (s.replace("/", "_") + ".o")) for s in srcs if s not in only]
+        missing = [b for b in borrowed if not Path(b).exists()]
+        if missing:
+            raise RuntimeError(f"GORILLA_VARIANT_UNITS needs the main build first (missing {missing[0]})")
+        srcs = [s for s in srcs if s in only]
     with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(srcs))) as ex:
         results = list(ex.map(lambda s: _compile(s, hd, force), srcs))
-    objs = [str(o) for o, _ in results]
+    objs = [str(o) for o, _ in results] + borrowed
     rebuilt = any(log is not None for _, log in results) or not LIB.exists()  # None = object was up to date
     if verbose:
         for _, log in results:

@@ -355,8 +355,11 @@ __device__ __forceinline__ void lane_reduce_counters(const Batch &bt, const Lane
 // EXT = 1: Hamiltonian time tracing (i_time_tracing_option = 2); EXT = 2: time tracing option read at run time plus the
 // optional quantities of pusher_tetra_poly; the plain variant (EXT = 0) is the hot path of the default settings and
 // carries none of that code (the optional-quantity code alone costs the order-2 kernel ~400 bytes of spills).
-template <int K, int PHI, int EXT = 0>
-__global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K, EXT)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
+// BULK = true: the geom / bpart sub-records reach the lane through the bulk-copy engine and a shared-memory slot, prefetched
+// one push ahead (gb_mesh.cuh); 48 KB of dynamic shared memory per CTA on top of the lane slots => three CTAs per SM.
+#define GB_BULK_SMEM ((size_t)GB_THREADS * (GB_BULK_STRIDE + 16))
+template <int K, int PHI, int EXT = 0, bool BULK = false>
+__global__ void __launch_bounds__(GB_THREADS, BULK ? 3 : gb_min_blocks(K, EXT)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
 {
   __shared__ __align__(16) unsigned char s_raw[EXT == 2 ? LaneSlots<GB_THREADS>::BYTES_EXT2 : LaneSlots<GB_THREADS>::BYTES];
   LaneSlots<GB_THREADS> S;
@@ -364,6 +367,7 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K, EXT)) orbit_kerne
   const unsigned lane = threadIdx.x & 31u;
   int32_t ind_tetr = -1, iface = -1;
   S.zero_counters();
+  if constexpr (BULK) bulk_init();
 
   // One lane = one particle at a time.  A lane whose particle is done refills itself at the end of the same loop
   // body and leaves the loop for good when the queue is empty, so the body has no "is this lane active" region (whose
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K, EXT)) orbit_kerne
       if (!bt.force_full) {
         const double x[3] = {S.D(LS_X0), S.D(LS_X1), S.D(LS_X2)};
         RkPusher<PHI, (EXT == 2 ? 2 : 0)> R;
-        R.P.r.set_stash(S.Stash(), GB_THREADS);
+        R.P.r.set_stash(S.Stash(), GB_THREADS, BULK);
         R.init(&m, perpinv, ind_tetr, x, iface, S.D(LS_VPAR), S.D(LS_TREM));
         done = R.template push<true>(o);
       }
@@ -392,7 +396,7 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K, EXT)) orbit_kerne
         P.mp = &m;
         P.perpinv = perpinv;
         if constexpr (EXT == 2) P.oq_mask = bt.oq_mask;
-        P.r.set_stash(S.Stash(), GB_THREADS);
+        P.r.set_stash(S.Stash(), GB_THREADS, BULK);
         done = P.push_fast(ind_tetr, iface, x, S.D(LS_VPAR), S.D(LS_TREM), o, &S.D(LS_TREM));
         if constexpr (EXT == 2) {
           if (done) lane_ext2_after_fast<K, PHI>(bt, S, P, o);
@@ -409,6 +413,7 @@ __global__ void __launch_bounds__(GB_THREADS, gb_min_blocks(K, EXT)) orbit_kerne
     if (lane_after_push<PHI, EXT>(m, bt, S, o, S.IndSave(), ind_tetr, iface))
       active = lane_refill<PHI, EXT>(m, bt, S, lane, ind_tetr, iface);
   }
+  if constexpr (BULK) bulk_wait();   // no copy may still be on its way to this CTA's shared memory when it exits
   lane_reduce_counters(bt, S, lane);
 }
 
@@ -567,6 +572,8 @@ struct gorilla_b200_handle {
   MeshDev mesh{};
   gorilla_settings settings{};
   double *d_geom = nullptr, *d_bpart = nullptr, *d_phi = nullptr, *d_cold = nullptr, *d_se = nullptr, *d_ham = nullptr, *d_skew = nullptr;
+  double *d_poly4 = nullptr;   // tetra_physics_poly4 records (i_precomp = 1, 2)
+  double *d_rec44 = nullptr;   // geom + bpart as one contiguous record per tetrahedron (bulk-copy gather only)
   double *s_oq = nullptr;   // [cap][4] scratch for the optional quantities (host-pointer entry point)
   uint32_t oq_mask = 0;
   int32_t *d_bin_start = nullptr, *d_bin_items = nullptr;
@@ -605,6 +612,8 @@ struct gorilla_b200_handle {
   // multi-GPU (gorilla_b200_comm_*): NCCL communicator of this rank, loaded at run time
   void *comm = nullptr;
   int32_t rank = 0, nranks = 1;
+  int64_t l2_bytes = 0, hot_bytes = 0;   // L2 capacity of the device, bytes of hot records of the mesh
+  int32_t bulk_gather = 0;               // gorilla_b200_set_gather: records through the bulk-copy engine (orders 1, 2 / RK4, EXT = 0)
   int ctas_per_sm = 0, threads_per_cta = 128;
   int force_full = 0;
   int use_group = 1;  // orders 3/4: lock-step solver kernel (orbit_kernel_g)
@@ -641,6 +650,24 @@ int launch_orbit_t(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
       if (grid_g > need_g) grid_g = need_g;
       if (grid_g < 1) grid_g = 1;
       orbit_kernel_g<K, PHI, EXT><<<(unsigned)grid_g, GBG_THREADS, smem_g, s>>>(h->mesh, bt);
+      gbint::count_launch(1);
+      GB_CUDA(cudaGetLastError());
+      return GORILLA_OK;
+    }
+  }
+  if constexpr (EXT == 0 && (K == 0 || K == 2)) {
+    if (h->bulk_gather && h->threads_per_cta == GB_THREADS) {
+      GB_CUDA(cudaFuncSetAttribute(orbit_kernel<K, PHI, EXT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB_BULK_SMEM));
+      int per_sm_b = h->ctas_per_sm;
+      if (per_sm_b <= 0) {
+        GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, orbit_kernel<K, PHI, EXT, true>, GB_THREADS, GB_BULK_SMEM));
+        if (per_sm_b < 1) per_sm_b = 1;
+      }
+      int64_t grid_b = (int64_t)h->num_sms * per_sm_b;
+      const int64_t need_b = (bt.n + GB_THREADS - 1) / GB_THREADS;
+      if (grid_b > need_b) grid_b = need_b;
+      if (grid_b < 1) grid_b = 1;
+      orbit_kernel<K, PHI, EXT, true><<<(unsigned)grid_b, GB_THREADS, GB_BULK_SMEM, s>>>(h->mesh, bt);
       gbint::count_launch(1);
       GB_CUDA(cudaGetLastError());
       return GORILLA_OK;

@@ -39,6 +39,12 @@ enum { P_PHI1 = 0, P_GPHI = 1, P_GPHIXH1 = 4, P_GPHIXCURLA = 7, P_BET = 8, P_SPB
 enum { S_V2EMOD1 = 0, S_GV2EMOD = 1, S_GV2EMODXH1 = 4, S_GBXCURLVE = 7, S_GPHIXCURLVE = 8, S_GV2EMODXCURLVE = 9,
        S_GV2EMODXCURLA = 10, S_CURLVE = 11, S_GAMMAT = 14, S_SPGAMMAT = 23, S_VE_MOD_AVG = 24, S_HOT_ND = 26,
        S_VE2_1 = 26, S_GVE2 = 27 };
+// type tetrahedron_physics_precomp_poly4 (SRC/tetra_physics_poly_precomp_mod.f90:21-45), 544 doubles, kept in the reference's
+// own order (4x4 matrices column-major: M(i,j) at [i-1 + 4*(j-1)]; anorm_in_amat*(:,n) is column n); offsets in doubles
+enum { P4_AMAT = 0,        // amat1_0 amat1_1 | amat2_0..2 | amat3_0..3 | amat4_0..4 : 14 matrices of 16
+       P4_AN_AMAT = 224,   // anorm_in_amat*, same 14
+       P4_B0 = 448, P4_B1 = 452, P4_B2 = 456, P4_B3 = 460, P4_A10_B0 = 464, P4_A11_B0 = 480, P4_AN_B0 = 496,
+       P4_AN_A10_B0 = 512, P4_AN_A11_B0 = 528, P4_ND = 544 };
 enum { C_TETRA_DIST_REF = 0, C_R1 = 1, C_ER_MOD = 2, C_HPHI1 = 3, C_GHPHI = 4, C_APHI1 = 7, C_GAPHI = 8 };
 
 // packed per-face topology: 7 bits per face f (0..3) at bit 7*f:
@@ -58,7 +64,17 @@ struct MeshDev {
   //   leave: skew_ref_x1x2x3(3) inv_skew_coord_x1x2x3(3,3) skew_coord_xyz(3,3) skew_ref_xyz(3)
   //   enter: skew_ref_xyz(3) inv_skew_coord_xyz(3,3) skew_coord_x1x2x3(3,3) skew_ref_x1x2x3(3)      (matrices column-major)
   const double *skew;
+  // bulk-copy gather: geom(16) + bpart(28) of a tetrahedron as ONE contiguous 352-byte record (a second copy of those two
+  // arrays, made when the bulk gather is switched on), so that a lane needs one bulk copy per push instead of two
+  const double *rec44;
+  // precomputed-coefficient modes (EXT = 4 kernels): tetra_physics_poly4 records as the reference stores them, built by the
+  // library at init from the tetra_physics records (make_precomp_poly4); i_precomp = 1 or 2
+  const double *poly4;
+  int32_t i_precomp, pad_precomp;
   const double *ham;  // hamiltonian_time records (EXT kernels only): h1_in_curlA h1_in_curlh vec_mismatch_der(3) vec_parcurr_der(3)
+  int32_t prefetch;    // 1: once the exit face of a push is known, prefetch the neighbour's records into the L2 (pays when
+                       // the records a batch touches do not fit the L2; costs 12-20 % when they do -- host decides)
+  int32_t pad_prefetch;
   double desired_delta_energy;      // adaptive sub-stepping (EXT = 3 kernels): gorilla_settings_mod.f90:76-77
   int32_t max_n_intermediate_steps;
   int32_t time_tracing; // i_time_tracing_option: 1 = dt/dtau constant per cell, 2 = Hamiltonian time (EXT kernels)
@@ -112,8 +128,115 @@ GB_HD void ld4(const double *p, double &a, double &b, double &c, double &d)
 }
 #endif
 
-// (An explicit prefetch of the neighbour's record once the exit face is known -- prefetch.global.L1 or .L2 -- was measured
-// three times on different kernel versions and cost 12-20 % each time; it is not in the code.)
+// An explicit prefetch of the neighbour's record once the exit face is known was measured three times in round 1 on the
+// L2-resident VMEC workload and cost 12-20 % each time.  Where the gather misses the L2 (3.8 M / 4.2 M-tetrahedron meshes) the
+// push is latency bound instead (ncu: long_scoreboard 9.5 stalled warps per issue, DRAM at 9 % of peak), so the prefetch is
+// a RUN-TIME option of the mesh handle (MeshDev::prefetch).
+GB_HD void prefetch_l2(const void *p)
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+// the 128-byte lines of the hot sub-records of tetrahedron t (1-based)
+template <int PHI>
+GB_HD void prefetch_record(const MeshDev &m, int ind_tetr)
+{
+  if (ind_tetr < 1) return;
+  const int64_t t = (int64_t)ind_tetr - 1;
+  const char *pg = reinterpret_cast<const char *>(m.geom + t * GEOM_ND);
+  const char *pb = reinterpret_cast<const char *>(m.bpart + t * BPART_ND);
+  prefetch_l2(pg);                    // 128 bytes, line aligned
+  prefetch_l2(pb);
+  prefetch_l2(pb + 128);
+  prefetch_l2(pb + 8 * BPART_ND - 32);  // last sector: a third line when the record straddles two boundaries
+  if (PHI) {
+    const char *pp = reinterpret_cast<const char *>(m.phi + t * PHI_ND);
+    prefetch_l2(pp);
+    prefetch_l2(pp + 8 * PHI_ND - 32);
+  }
+  if (PHI == 2) {
+    const char *ps = reinterpret_cast<const char *>(m.se + t * SE_ND);
+    prefetch_l2(ps);
+    prefetch_l2(ps + 128);
+  }
+}
+
+// ---- bulk-copy gather (kernels launched with the BULK flag) --------------------------------------------------------------
+// ncu on the meshes whose records do not fit the L2 (3.8 M / 4.2 M tetrahedra): the gather is latency bound with only ~180
+// sectors in flight per SM (long_scoreboard 9.5 stalled warps per issue, DRAM at 9 % of peak), and neither more resident warps
+// nor an L2 prefetch change that -- the per-lane LDGs queue in the L1's miss path.  The bulk-copy engine (TMA,
+// cp.async.bulk global -> shared, completion on an mbarrier) does not go through the L1: every lane owns a 368-byte slot of
+// dynamic shared memory and an mbarrier; the geom (128 B) and bpart (224 B) sub-records of a tetrahedron are fetched with two
+// bulk copies, issued for the NEIGHBOUR as soon as the exit face of the running push is known, and unpacked from shared
+// memory (LDS.128, conflict free with the 16-byte pad) at the start of the next push.
+#define GB_BULK_STRIDE 368
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned gb_tid_now()
+{
+  unsigned t;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+  return t;
+}
+// dynamic shared memory of a BULK kernel of NT threads: [NT][368] slots | [NT] u64 mbarrier | [NT] i32 tetrahedron in the slot
+// | [NT] i32 flags (bit 0 copy pending, bit 1 mbarrier phase parity)
+__device__ __forceinline__ unsigned bulk_base()
+{
+  extern __shared__ __align__(16) unsigned char gb_dyn_smem[];
+  return (unsigned)__cvta_generic_to_shared(gb_dyn_smem);
+}
+__device__ __forceinline__ unsigned bulk_slot() { return bulk_base() + gb_tid_now() * GB_BULK_STRIDE; }
+__device__ __forceinline__ unsigned bulk_bar() { return bulk_base() + blockDim.x * GB_BULK_STRIDE + gb_tid_now() * 8u; }
+__device__ __forceinline__ unsigned bulk_tet() { return bulk_base() + blockDim.x * (GB_BULK_STRIDE + 8u) + gb_tid_now() * 4u; }
+__device__ __forceinline__ unsigned bulk_flg() { return bulk_base() + blockDim.x * (GB_BULK_STRIDE + 12u) + gb_tid_now() * 4u; }
+__device__ __forceinline__ int lds_i32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_i32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void bulk_init()
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bulk_bar()) : "memory");
+  sts_i32(bulk_tet(), 0);
+  sts_i32(bulk_flg(), 0);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait()
+{
+  const int f = lds_i32(bulk_flg());
+  if (f & 1) {
+    const unsigned bar = bulk_bar(), parity = (unsigned)(f >> 1) & 1u;
+    asm volatile("{\n\t.reg .pred p;\n\tGB_BULK_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra GB_BULK_WAIT;\n\t}"
+                 ::"r"(bar), "r"(parity) : "memory");
+    sts_i32(bulk_flg(), (f ^ 2) & ~1);   // phase flips, nothing pending
+  }
+}
+__device__ __forceinline__ void bulk_issue(const double *rec44, int ind_tetr)
+{
+  const unsigned bar = bulk_bar(), slot = bulk_slot();
+  const double *pr = rec44 + ((int64_t)ind_tetr - 1) * 44;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot's last reads (generic proxy) come first
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 352;" ::"r"(bar) : "memory");
+  // (the instruction takes its addresses from uniform registers: the compiler serialises the lanes of the warp around it)
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 352, [%2];"
+               ::"r"(slot), "l"(pr), "r"(bar) : "memory");
+  sts_i32(bulk_tet(), ind_tetr);
+  sts_i32(bulk_flg(), lds_i32(bulk_flg()) | 1);
+}
+// make the slot hold the record of ind_tetr
+__device__ __forceinline__ void bulk_acquire(const double *rec44, int ind_tetr)
+{
+  bulk_wait();
+  if (lds_i32(bulk_tet()) != ind_tetr) {
+    bulk_issue(rec44, ind_tetr);
+    bulk_wait();
+  }
+}
+__device__ __forceinline__ void lds2(unsigned a, double &x, double &y)
+{
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+#endif
 
 // One tetrahedron's hot record in registers.  PHI: 0 = magnetic part only (Phi group exactly zero), 1 = with the
 // electrostatic group, 2 = electrostatic + strong-electric-field groups.
@@ -130,7 +253,17 @@ struct Rec {
   // -- shared memory in the kernel, st[k * sts], k = 0..5 -- and x1s()/nb()/flags() read them back from there.
   volatile double *st;
   int sts;
-  GB_HD void set_stash(volatile double *p, int stride) { st = p; sts = stride; }
+  bool bulk;   // this lane's geom / bpart sub-records arrive by bulk copy into its shared-memory slot (BULK kernels)
+  GB_HD void set_stash(volatile double *p, int stride, bool bulk_gather = false) { st = p; sts = stride; bulk = bulk_gather; }
+  // ask for the record of the tetrahedron behind the exit face while the push is still running
+  GB_HD void prefetch_next(const MeshDev &m, int ind_next)
+  {
+#if defined(__CUDA_ARCH__)
+    if (bulk && ind_next >= 1) bulk_issue(m.rec44, ind_next);
+#else
+    (void)m; (void)ind_next;
+#endif
+  }
   GB_HD double x1s(int i) const { return st[i * sts]; }
   GB_HD static int32_t word_of(double d, int hi)
   {
@@ -150,10 +283,22 @@ struct Rec {
     const int64_t t = (int64_t)ind_tetr - 1;
     double g[GEOM_ND], b[BPART_ND];
     const double *pg = m.geom + t * GEOM_ND, *pb = m.bpart + t * BPART_ND;
+#if defined(__CUDA_ARCH__)
+    if (bulk) {
+      bulk_acquire(m.rec44, ind_tetr);
+      const unsigned slot = bulk_slot();
 #pragma unroll
-    for (int i = 0; i < GEOM_ND; i += 4) ld4(pg + i, g[i], g[i + 1], g[i + 2], g[i + 3]);
+      for (int i = 0; i < GEOM_ND; i += 2) lds2(slot + 8u * i, g[i], g[i + 1]);
 #pragma unroll
-    for (int i = 0; i < BPART_ND; i += 4) ld4(pb + i, b[i], b[i + 1], b[i + 2], b[i + 3]);
+      for (int i = 0; i < BPART_ND; i += 2) lds2(slot + 128u + 8u * i, b[i], b[i + 1]);
+    } else
+#endif
+    {
+#pragma unroll
+      for (int i = 0; i < GEOM_ND; i += 4) ld4(pg + i, g[i], g[i + 1], g[i + 2], g[i + 3]);
+#pragma unroll
+      for (int i = 0; i < BPART_ND; i += 4) ld4(pb + i, b[i], b[i + 1], b[i + 2], b[i + 3]);
+    }
     x1[0] = g[0]; x1[1] = g[1]; x1[2] = g[2]; dist_ref = g[3];
 #pragma unroll
     for (int f = 0; f < 4; f++)

@@ -1,0 +1,5 @@
+// gb_orbit_k2p.cu -- EXT = 4 variant of polynomial order 2: precomputed coefficients, i_precomp = 1, 2
+// (tetra_physics_poly4 records; see gb_poly.cuh)
+#include "gb_internal.cuh"
+template int launch_orbit_t<2, 0, 4>(gorilla_b200_handle *, const Batch &, cudaStream_t);
+template int launch_orbit_t<2, 1, 4>(gorilla_b200_handle *, const Batch &, cudaStream_t);

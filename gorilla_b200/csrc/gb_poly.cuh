@@ -152,6 +152,135 @@ struct PolyPusher {
       iper_phi = 0;
       removed = false;
     }
+    if (EXT == 4) {
+      // i_precomp = 2 never assigns the module variable b (it is only read by normal_velocity_func): it stays the
+      // zero-initialised static it is in the reference build
+      b[0] = b[1] = b[2] = b[3] = 0.0;
+    }
+  }
+
+  // ==== EXT = 4: precomputed coefficients, i_precomp = 1, 2 (analytic_coeff_with_precomp :1590-1725,
+  // analytic_integration_with_precomp :2530-2650, normal_velocity_func :2734-2738; record tetra_physics_poly4) ============
+  GB_HD const double *p4() const { return mp->poly4 + ((int64_t)ind_tetr - 1) * P4_ND; }
+  // index of the first of the ORD+1 matrices of order ORD among the 14: amat1_* 0, amat2_* 2, amat3_* 5, amat4_* 9
+  GB_HD static constexpr int p4_first(int ord) { return ord == 1 ? 0 : ord == 2 ? 2 : ord == 3 ? 5 : 9; }
+  // sum_i (M_0 + p M_1 + p^2 M_2 + ...)(i, n) * v(i) over the anorm_in_amat<ORD>_* columns of face n (ascending powers, :1633-1715)
+  template <int ORD>
+  GB_HD double p4_face_dot(const double *q, int n, const double *fac, const double *v) const
+  {
+    const double *base = q + P4_AN_AMAT + 16 * p4_first(ORD) + 4 * n;
+    double sacc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      double e = ldg(base + i);
+#pragma unroll
+      for (int k = 1; k <= ORD; k++) e = e + fac[k] * ldg(base + 16 * k + i);
+      sacc = sacc + e * v[i];
+    }
+    return sacc;
+  }
+  // element (i,j) of p^ORD amat<ORD>_<ORD> + ... + p amat<ORD>_1 + amat<ORD>_0 (DESCENDING powers, :2558-2640)
+  template <int ORD>
+  GB_HD double p4_op_elem(const double *q, int i, int j, const double *fac) const
+  {
+    const double *base = q + P4_AMAT + 16 * p4_first(ORD) + i + 4 * j;
+    double e = fac[ORD] * ldg(base + 16 * ORD);
+#pragma unroll
+    for (int k = ORD - 1; k >= 1; k--) e = e + fac[k] * ldg(base + 16 * k);
+    return e + ldg(base);
+  }
+  GB_HD void p4_factors(double *fac) const
+  {
+    const double perpinv2 = perpinv * perpinv;
+    fac[0] = 1.0; fac[1] = perpinv; fac[2] = perpinv2; fac[3] = perpinv2 * perpinv; fac[4] = perpinv2 * perpinv2;
+  }
+  template <int ORD>
+  GB_HD void face_coeffs_precomp(int n /*0-based face*/, const double *z, double *c) const
+  {
+    const double *q = p4();
+    double fac[5];
+    p4_factors(fac);
+    {
+      double nn[3];
+      face_normal(n + 1, nn);
+      c[0] = dot3(nn, z);
+      if (n == 0) c[0] = c[0] + r.dist_ref;
+      const bool one = mp->i_precomp == 1;
+      if (ORD >= 1) {
+        const double sz = p4_face_dot<1>(q, n, fac, z);
+        if (one) c[1] = sz + dot3(nn, b);
+        else c[1] = sz + ldg(q + P4_AN_B0 + n) + k1 * ldg(q + P4_AN_B0 + 4 + n) + perpinv * ldg(q + P4_AN_B0 + 8 + n) +
+                    k3 * ldg(q + P4_AN_B0 + 12 + n);
+      }
+      if (ORD >= 2) {
+        const double sz = p4_face_dot<2>(q, n, fac, z);
+        if (one) {
+          c[2] = sz + p4_face_dot<1>(q, n, fac, b);
+        } else {
+          const double *a0 = q + P4_AN_A10_B0 + n, *a1 = q + P4_AN_A11_B0 + n;   // [.. + 4 k]: b0..b3
+          c[2] = sz + ldg(a0) + perpinv * ldg(a1) + k1 * (ldg(a0 + 4) + perpinv * ldg(a1 + 4)) +
+                 perpinv * (ldg(a0 + 8) + perpinv * ldg(a1 + 8)) + k3 * (ldg(a0 + 12) + perpinv * ldg(a1 + 12));
+        }
+      }
+      if (ORD >= 3) c[3] = p4_face_dot<3>(q, n, fac, z) + p4_face_dot<2>(q, n, fac, b);
+      if (ORD >= 4) c[4] = p4_face_dot<4>(q, n, fac, z) + p4_face_dot<3>(q, n, fac, b);
+    }
+  }
+  template <int ORD>
+  GB_HD void integrate_precomp(double *z, double tau) const
+  {
+    if (ORD < 2) return;                       // no case(1) in the reference: z unchanged
+    const bool one = mp->i_precomp == 1;
+    if (!one && ORD != 2) return;              // i_precomp = 2 has the order-2 case only
+    const double *q = p4();
+    double fac[5];
+    p4_factors(fac);
+    const double tau2_half = tau * tau * 0.5, tau3_sixth = (tau * tau) * tau / 6.0;
+    const double t2 = tau * tau, tau4_24 = (t2 * t2) / 24.0;
+    double oz[4], ob[4];
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+      double sz = 0.0, sb = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double c1 = p4_op_elem<1>(q, i, j, fac), c2 = p4_op_elem<2>(q, i, j, fac);
+        double e = tau * c1 + tau2_half * c2;
+        double f = tau * (i == j ? 1.0 : 0.0) + tau2_half * c1;
+        if (ORD >= 3) {
+          const double c3 = p4_op_elem<(ORD >= 3 ? 3 : 1)>(q, i, j, fac);
+          e = e + tau3_sixth * c3;
+          f = f + tau3_sixth * c2;
+          if (ORD >= 4) {
+            e = e + tau4_24 * p4_op_elem<(ORD >= 4 ? 4 : 1)>(q, i, j, fac);
+            f = f + tau4_24 * c3;
+          }
+        }
+        sz = sz + e * z[j];
+        sb = sb + f * b[j];
+      }
+      oz[i] = sz;
+      ob[i] = sb;
+    }
+    if (!one) {   // operator_b_in_b (:2578-2587)
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const double *a0 = q + P4_A10_B0 + i, *a1 = q + P4_A11_B0 + i;
+        ob[i] = tau * (ldg(q + P4_B0 + i) + k1 * ldg(q + P4_B1 + i) + perpinv * ldg(q + P4_B2 + i) + k3 * ldg(q + P4_B3 + i)) +
+                tau2_half * ((ldg(a0) + perpinv * ldg(a1)) + k1 * (ldg(a0 + 4) + perpinv * ldg(a1 + 4)) +
+                             perpinv * (ldg(a0 + 8) + perpinv * ldg(a1 + 8)) + k3 * (ldg(a0 + 12) + perpinv * ldg(a1 + 12)));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) z[i] = z[i] + ob[i] + oz[i];
+  }
+  GB_HD double normal_velocity_precomp(const double *z, int iface) const
+  {
+    const double *q = p4() + P4_AN_AMAT + 4 * (iface - 1);
+    double n[3], sacc = 0.0;
+    face_normal(iface, n);
+#pragma unroll
+    for (int i = 0; i < 4; i++) sacc = sacc + (ldg(q + i) + perpinv * ldg(q + 16 + i)) * z[i];
+    return sacc * (double)sign_rhs + dot3(n, b);
   }
 
   // ---- ODE coefficients b, A  (:1503-1530; strong-electric-field terms :1519-1526).  RK = true forms b(1:3) the
@@ -204,6 +333,23 @@ struct PolyPusher {
   template <int ORD>
   GB_HD void prepare(const double *z)
   {
+    if (EXT == 4) {
+      if (mp->i_precomp == 1) {   // b WITHOUT sign_rhs (:1607-1614); no matrix, no Taylor vectors
+        const double cm = mp->cm_over_e;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          double t = (r.curlh[i] * k1 + perpinv * r.gBxh1[i]) * cm;
+          if (PHI) t = t - GB_CLIGHT * (2.0 * k3 * r.curlh[i] + r.gPhixh1[i]);
+          else t = t - GB_CLIGHT * (2.0 * k3 * r.curlh[i] + 0.0);
+          b[i] = t;
+        }
+        double t = perpinv * r.gBxcurlA;
+        if (PHI) t = t - GB_CLIGHT / cm * r.gPhixcurlA;
+        else t = t - GB_CLIGHT / cm * 0.0;
+        b[3] = t;
+      }
+      return;
+    }
     build_ode();
     if (ORD >= 1) bm_vec(Az, A, z);
     if (ORD >= 2) {
@@ -227,8 +373,12 @@ struct PolyPusher {
   }
   // ---- face-distance Taylor coefficients of one face with normal n (:1536-1584); c[k] = coef_mat(face,k+1)
   template <int ORD>
-  GB_HD void face_coeffs(const double *n, bool is_face1, const double *z, double *c) const
+  GB_HD void face_coeffs(const double *n, bool is_face1, const double *z, double *c, int face0 = 0) const
   {
+    if (EXT == 4) {
+      face_coeffs_precomp<ORD>(face0, z, c);
+      return;
+    }
     c[0] = dot3(n, z);
     if (is_face1) c[0] = c[0] + r.dist_ref;  // coef - dist1, dist1 = -dist_ref
     if (ORD >= 1) c[1] = dot3(n, Az) + dot3(n, b);
@@ -242,7 +392,7 @@ struct PolyPusher {
     prepare<ORD>(z);
 #pragma unroll
     for (int f = 0; f < 4; f++)
-      if (mask & (1u << f)) face_coeffs<ORD>(r.an[f], f == 0, z, cm[f]);
+      if (mask & (1u << f)) face_coeffs<ORD>(r.an[f], f == 0, z, cm[f], f);
   }
 
   // ---- :2087-2113 (A, b unchanged; matrix powers re-formed, which reproduces the stored ones)
@@ -250,6 +400,7 @@ struct PolyPusher {
   template <int ORD>
   GB_HD void set_coef(const double *z0)
   {
+    if (EXT == 4) return;   // the precomputed-coefficient integration reads nothing of this
     if (ORD >= 1) bm_vec(Az, A, z0);
     if (ORD >= 2) {
       BlockMat A2;
@@ -427,7 +578,7 @@ struct PolyPusher {
     if (!prepared) prepare<ORD>(z);
     double n[3], c[5];
     face_normal(face, n);
-    face_coeffs<ORD>(n, face == 1, z, c);
+    face_coeffs<ORD>(n, face == 1, z, c, face - 1);
     const double d = face_root<ORD>(c, face == iface_inout, i_scaling);
     if (!((d < GB_HUGE) && (d > 0.0))) return false;
     iface_inout = face;
@@ -439,6 +590,10 @@ struct PolyPusher {
   template <int ORD>
   GB_HD void integrate(double *z, double tau)
   {
+    if (EXT == 4) {   // analytic_integration dispatches (:2034-2039); the step book-keeping is in the other branch only
+      integrate_precomp<ORD>(z, tau);
+      return;
+    }
     nsteps++;
     if (EXT == 3) {
 #pragma unroll
@@ -952,6 +1107,7 @@ struct PolyPusher {
   // ---- :2709-2739, poly1 quantities (n.alpha, n.beta, n.curlA) formed on the fly
   GB_HD double normal_velocity(const double *z, int iface) const
   {
+    if (EXT == 4) return normal_velocity_precomp(z, iface);
     double n[3];
     face_normal(iface, n);
     const double pc = perpinv * mp->cm_over_e;
@@ -1035,7 +1191,6 @@ struct PolyPusher {
     double tau_save = tau, tau_max = 0.0;
     int iface_new_save = iface_new;
     bool approx = true;
-    fallback |= 4;
     if (K > 2) {
       approx = analytic_approx<2>(0xFu, i_scaling, z, iface_new, tau);
       tau_max = tau * GB_EPS_TAU;
@@ -1050,6 +1205,7 @@ struct PolyPusher {
     if (normal_velocity(z, iface_new) > 0.0) face_correct = false;
     if (!face_converged(z, iface_new)) face_correct = false;
     tau = tau + tau_save;
+    fallback |= 4;   // counted when the second segment was actually integrated
     return true;
   }
 
@@ -1284,10 +1440,12 @@ struct PolyPusher {
     {
       double cm[4][5];
 #pragma unroll
-      for (int f = 0; f < 4; f++) face_coeffs<2>(r.an[f], f == 0, z_init, cm[f]);
+      for (int f = 0; f < 4; f++) face_coeffs<2>(r.an[f], f == 0, z_init, cm[f], f);
       if (!pick_exit<2>(cm, 0xFu, 0, iface_new, tau)) return false;
     }
     tau_max = tau * GB_EPS_TAU;
+    if (mp->prefetch) prefetch_record<PHI>(*mp, r.nb(iface_new - 1));   // the exit face is (almost always) this one
+    r.prefetch_next(*mp, r.nb(iface_new - 1));                          // BULK kernels: neighbour's record -> shared memory
     t.kind = 1;
     t.tau = tau;
     t.deg = 0;
@@ -1295,7 +1453,7 @@ struct PolyPusher {
       if (!mp->boole_guess) return false;  // all-face order-K solves go through the complete path
       double n[3], c[5];
       face_normal(iface_new, n);
-      face_coeffs<K>(n, iface_new == 1, z_init, c);
+      face_coeffs<K>(n, iface_new == 1, z_init, c, iface_new - 1);
       face_task<K>(c, iface_new == iface_init, 0, t);
     }
     return true;
@@ -1309,7 +1467,7 @@ struct PolyPusher {
     if (!exit_point_ok(z, iface_new)) return false;
     if (EXT == 3 && adaptive_delta_energy(z) > mp->desired_delta_energy) return false;  // sub-stepping: complete path
     if (K > 2 && tau > tau_max) return false;
-    if (normal_v_from_trajectory(iface_new, tau) > 0.0) return false;
+    if ((EXT == 4 ? normal_velocity(z, iface_new) : normal_v_from_trajectory(iface_new, tau)) > 0.0) return false;   // :328-332
     return finish<true>(z, tau, iface_new, o);
   }
   // t_remain_reload (kernel only): where the caller keeps t_remain; re-reading it after the solve -- same value --
@@ -1330,7 +1488,7 @@ struct PolyPusher {
       prepare<K>(z);
       double cm[4][5];
 #pragma unroll
-      for (int f = 0; f < 4; f++) face_coeffs<K>(r.an[f], f == 0, z, cm[f]);
+      for (int f = 0; f < 4; f++) face_coeffs<K>(r.an[f], f == 0, z, cm[f], f);
       if (!pick_exit<2>(cm, 0xFu, 0, iface_new, tau)) return false;
       tau_max = tau * GB_EPS_TAU;
       iface_new = iface_init;
@@ -1371,7 +1529,7 @@ struct PolyPusher {
       if (!face_converged(z, iface_new)) face_correct = false;
       if (K > 2 && tau > tau_max) face_correct = false;
       if (face_correct) {
-        if (normal_v_from_trajectory(iface_new, tau) > 0.0) {
+        if ((EXT == 4 ? normal_velocity(z, iface_new) : normal_v_from_trajectory(iface_new, tau)) > 0.0) {
           if (K > 2) {
             face_correct = false;
           } else {

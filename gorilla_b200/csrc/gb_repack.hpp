@@ -119,6 +119,105 @@ inline void repack_hamiltonian_time(const gorilla_mesh_desc *md, std::vector<dou
   }
 }
 
+// make_precomp_poly4 (SRC/tetra_physics_poly_precomp_mod.f90:160-476): the tetra_physics_poly4 records, [ntetr][544] in the
+// reference's own member order (offsets P4_* of gb_mesh.cuh), formed from the tetra_physics records with the reference's
+// operations: 4x4 matmul / matmul(n_vec, M) / sum() accumulate in ascending index order starting from 0, the sums of products
+// of alpha and beta chains are added left to right as written.
+inline void make_precomp_poly4(const gorilla_mesh_desc *md, std::vector<double> &poly4)
+{
+  enum { TP_ANORM = 9, TP_CURLA = 21, TP_GBXCURLA = 41, TP_GPHIXCURLA = 42, TP_SPALPMAT = 47, TP_SPBETMAT = 48, TP_GBXH1 = 50,
+         TP_GPHIXH1 = 53, TP_CURLH = 89, TP_ALPMAT = 107, TP_BETMAT = 116 };
+  const double CLIGHT = 2.9979e10;
+  const int64_t nt = md->ntetr;
+  const double cm = md->cm_over_e;
+  poly4.assign((size_t)nt * P4_ND, 0.0);
+  struct M4 { double a[4][4]; };
+  auto mul = [](const M4 &A, const M4 &B) {
+    M4 C;
+    for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 4; j++) {
+        double s = 0.0;
+        for (int k = 0; k < 4; k++) s = s + A.a[i][k] * B.a[k][j];
+        C.a[i][j] = s;
+      }
+    return C;
+  };
+  auto add = [](const M4 &A, const M4 &B) {
+    M4 C;
+    for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 4; j++) C.a[i][j] = A.a[i][j] + B.a[i][j];
+    return C;
+  };
+#pragma omp parallel for schedule(static)
+  for (int64_t t = 0; t < nt; t++) {
+    const double *r = md->tetra_physics + t * GORILLA_TETRA_PHYSICS_NDOUBLES;
+    double *o = &poly4[(size_t)t * P4_ND];
+    M4 alp{}, bet{};
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        alp.a[i][j] = cm * r[TP_ALPMAT + i + 3 * j];
+        bet.a[i][j] = -(CLIGHT * r[TP_BETMAT + i + 3 * j]);
+      }
+    alp.a[3][3] = cm * r[TP_SPALPMAT];
+    for (int i = 0; i < 3; i++) bet.a[i][3] = r[TP_CURLA + i];
+    bet.a[3][3] = -(CLIGHT * r[TP_SPBETMAT]);
+    const M4 aa = mul(alp, alp), ab = mul(alp, bet), bb = mul(bet, bet), ba = mul(bet, alp);
+    const M4 aaa = mul(alp, aa), aab = mul(alp, ab), aba = mul(alp, ba), abb = mul(alp, bb);
+    const M4 baa = mul(bet, aa), bab = mul(bet, ab), bba = mul(bet, ba), bbb = mul(bet, bb);
+    const M4 aaaa = mul(alp, aaa), aaab = mul(alp, aab), aaba = mul(alp, aba), aabb = mul(alp, abb);
+    const M4 abaa = mul(alp, baa), abab = mul(alp, bab), abba = mul(alp, bba), abbb = mul(alp, bbb);
+    const M4 baaa = mul(bet, aaa), baab = mul(bet, aab), baba = mul(bet, aba), babb = mul(bet, abb);
+    const M4 bbaa = mul(bet, baa), bbab = mul(bet, bab), bbba = mul(bet, bba), bbbb = mul(bet, bbb);
+    const M4 mats[14] = {
+        bet, alp,                                                                  // amat1_0, amat1_1
+        bb, add(ba, ab), aa,                                                       // amat2_0..2
+        bbb, add(add(bba, bab), abb), add(add(baa, aba), aab), aaa,                // amat3_0..3
+        bbbb, add(add(add(bbba, bbab), babb), abbb),                               // amat4_0, amat4_1
+        add(add(add(add(add(bbaa, baba), baab), abba), abab), aabb),               // amat4_2
+        add(add(add(abaa, aaba), aaab), baaa), aaaa};                              // amat4_3, amat4_4
+    for (int k = 0; k < 14; k++) {
+      for (int j = 0; j < 4; j++)
+        for (int i = 0; i < 4; i++) o[P4_AMAT + 16 * k + i + 4 * j] = mats[k].a[i][j];
+      for (int n = 0; n < 4; n++) {   // anorm_in_amat(:,n) = matmul(n_vec, amat), n_vec = (anorm(:,n), 0)
+        const double nv[4] = {r[TP_ANORM + 3 * n], r[TP_ANORM + 3 * n + 1], r[TP_ANORM + 3 * n + 2], 0.0};
+        for (int j = 0; j < 4; j++) {
+          double s = 0.0;
+          for (int i = 0; i < 4; i++) s = s + nv[i] * mats[k].a[i][j];
+          o[P4_AN_AMAT + 16 * k + j + 4 * n] = s;
+        }
+      }
+    }
+    for (int i = 0; i < 3; i++) {
+      o[P4_B0 + i] = -CLIGHT * r[TP_GPHIXH1 + i];
+      o[P4_B1 + i] = cm * r[TP_CURLH + i];
+      o[P4_B2 + i] = cm * r[TP_GBXH1 + i];
+      o[P4_B3 + i] = -2.0 * CLIGHT * r[TP_CURLH + i];
+    }
+    o[P4_B0 + 3] = -CLIGHT / cm * r[TP_GPHIXCURLA];
+    o[P4_B1 + 3] = 0.0;
+    o[P4_B2 + 3] = r[TP_GBXCURLA];
+    o[P4_B3 + 3] = 0.0;
+    for (int q = 0; q < 2; q++)      // amat1_q in b_k
+      for (int k = 0; k < 4; k++)
+        for (int i = 0; i < 4; i++) {
+          double s = 0.0;
+          for (int j = 0; j < 4; j++) s = s + mats[q].a[i][j] * o[P4_B0 + 4 * k + j];
+          o[(q == 0 ? P4_A10_B0 : P4_A11_B0) + 4 * k + i] = s;
+        }
+    for (int k = 0; k < 4; k++)
+      for (int n = 0; n < 4; n++) {
+        const double *an = r + TP_ANORM + 3 * n, *bk = o + P4_B0 + 4 * k;
+        o[P4_AN_B0 + 4 * k + n] = ((0.0 + an[0] * bk[0]) + an[1] * bk[1]) + an[2] * bk[2];
+        for (int q = 0; q < 2; q++) {
+          const double *col = o + P4_AN_AMAT + 16 * q + 4 * n;
+          double s = 0.0;
+          for (int i = 0; i < 4; i++) s = s + col[i] * bk[i];
+          o[(q == 0 ? P4_AN_A10_B0 : P4_AN_A11_B0) + 4 * k + n] = s;
+        }
+      }
+  }
+}
+
 // type tetrahedron_skew_coord (168 doubles) -> per (tetrahedron, face) a "leave" and an "enter" block (gb_mesh.cuh)
 inline void repack_skew(const gorilla_mesh_desc *md, std::vector<double> &skew)
 {

@@ -653,6 +653,8 @@ struct RkPusher {
     o.t_pass = 0.0;
     bool removed = false, converged = false;
     if (quad_analytic_approx(z, allowed, iface_new, dtau)) {
+      if (FAST && P.mp->prefetch) prefetch_record<PHI>(*P.mp, P.r.nb(iface_new - 1));   // quadratic guess of the exit face
+      if (FAST) P.r.prefetch_next(*P.mp, P.r.nb(iface_new - 1));
       rk4_step(z, dtau, dzdtau);
       tau = tau + dtau;
     } else {

@@ -9,6 +9,14 @@
 !!     call initialize_gorilla_b200()                       ! uploads tetra_physics / tetra_grid once
 !!     call orbit_timestep_gorilla_batch(n, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface, ierr)
 !!
+!! Multi-GPU (one process per GPU, particles sharded, mesh replicated on every GPU):
+!!     if (rank == 0) call comm_unique_id_b200(id)          ! 128 bytes
+!!     call MPI_Bcast(id, 128, MPI_BYTE, 0, comm, ierr)     ! or any other way to hand them to the ranks
+!!     call comm_init_b200(id, rank, nranks, ierr)
+!!     call shard_range_b200(n_total, rank, nranks, first, count)      ! this rank pushes particles first+1 .. first+count
+!!     ... time steps ...
+!!     call diag_reduce_b200(n, x, vpar, vperp, ind_tetr, e0, pphi0, perpinv0, diag, ierr)   ! counters + conservation, all ranks
+!!
 !! NOTE: this image has no Fortran compiler (SURVEY.md F2), so this module is shipped as source and is not
 !! part of the automated build; the C ABI it binds is exercised by the Python ctypes binding in the tests.
 module orbit_timestep_gorilla_b200_mod
@@ -16,7 +24,10 @@ module orbit_timestep_gorilla_b200_mod
   implicit none
   private
   public :: initialize_gorilla_b200, finalize_gorilla_b200, orbit_timestep_gorilla, orbit_timestep_gorilla_batch, &
-            orbit_timestep_gorilla_batch_optional, find_tetra_batch, gorilla_b200_counters_t, get_counters_b200
+            orbit_timestep_gorilla_batch_optional, orbit_timestep_gorilla_batch_events, find_tetra_batch, &
+            gorilla_b200_counters_t, get_counters_b200, invariants_b200, set_host_resort_b200, &
+            gorilla_b200_diag_t, gorilla_b200_event_t, gorilla_b200_event_settings_t, &
+            comm_unique_id_b200, comm_init_b200, comm_free_b200, shard_range_b200, diag_reset_b200, diag_reduce_b200
 
   !> struct gorilla_settings (include/gorilla_b200.h)
   type, bind(C) :: gorilla_settings_t
@@ -43,7 +54,26 @@ module orbit_timestep_gorilla_b200_mod
   type, bind(C) :: gorilla_b200_counters_t
     integer(c_int64_t) :: n_particles, n_pushes, n_lost, n_finished, n_fallback(4), n_domain_errors
     real(c_double)     :: kernel_ms, find_ms
-    integer(c_int64_t) :: n_adaptive
+    integer(c_int64_t) :: n_adaptive, n_lost_inner, n_failed
+  end type
+  !> struct gorilla_diag: counters since diag_reset_b200 and conservation statistics, reduced over all ranks
+  type, bind(C) :: gorilla_b200_diag_t
+    integer(c_int64_t) :: n_particles, n_pushes, n_lost, n_lost_outer, n_lost_inner, n_failed, n_finished
+    integer(c_int64_t) :: n_fallback(4), n_adaptive, n_sampled
+    real(c_double)     :: max_delta_energy, rms_delta_energy, max_delta_perpinv, rms_delta_perpinv
+    real(c_double)     :: max_delta_p_phi, rms_delta_p_phi
+    integer(c_int32_t) :: nranks, reserved
+  end type
+  !> struct gorilla_event / gorilla_event_settings (banana tips with J_par, toroidal mappings; gorilla_plot_mod.f90:585-638)
+  type, bind(C) :: gorilla_b200_event_t
+    integer(c_int64_t) :: particle
+    integer(c_int32_t) :: kind, counter
+    integer(c_int64_t) :: push
+    real(c_double)     :: x(3), value(2)
+  end type
+  type, bind(C) :: gorilla_b200_event_settings_t
+    integer(c_int32_t) :: boole_poincare_phi_0, n_skip_phi_0, boole_poincare_vpar_0, boole_J_par, n_skip_vpar_0
+    integer(c_int32_t) :: reserved(3)
   end type
 
   interface
@@ -82,6 +112,69 @@ module orbit_timestep_gorilla_b200_mod
       import :: c_int, c_ptr, gorilla_b200_counters_t
       type(c_ptr), value :: handle
       type(gorilla_b200_counters_t), intent(out) :: counters
+    end function
+    integer(c_int) function gorilla_b200_orbit_timestep_events(handle, n, x, vpar, vperp, t_step, boole_initialized, &
+                   ind_tetr, iface, t_remain_out, n_pushes, cfg, par_adiab_inv, counter_vpar_0, counter_phi_0, events, &
+                   event_cap, n_events) bind(C, name='gorilla_b200_orbit_timestep_events')
+      import :: c_int, c_ptr, c_int64_t, c_double, c_int32_t, gorilla_b200_event_settings_t, gorilla_b200_event_t
+      type(c_ptr), value        :: handle
+      integer(c_int64_t), value :: n, event_cap
+      real(c_double)            :: x(3,*), vpar(*), vperp(*), par_adiab_inv(*)
+      real(c_double), value     :: t_step
+      integer(c_int32_t)        :: boole_initialized(*), ind_tetr(*), iface(*), counter_vpar_0(*), counter_phi_0(*)
+      type(c_ptr), value        :: t_remain_out, n_pushes
+      type(gorilla_b200_event_settings_t), intent(in) :: cfg
+      type(gorilla_b200_event_t) :: events(*)
+      integer(c_int64_t), intent(out) :: n_events
+    end function
+    integer(c_int) function gorilla_b200_invariants(handle, n, x, vpar, vperp, ind_tetr, energy, p_phi, perpinv) &
+                   bind(C, name='gorilla_b200_invariants')
+      import :: c_int, c_ptr, c_int64_t, c_double, c_int32_t
+      type(c_ptr), value        :: handle
+      integer(c_int64_t), value :: n
+      real(c_double), intent(in):: x(3,*), vpar(*), vperp(*)
+      integer(c_int32_t), intent(in) :: ind_tetr(*)
+      real(c_double)            :: energy(*), p_phi(*), perpinv(*)
+    end function
+    integer(c_int) function gorilla_b200_set_host_resort(handle, on) bind(C, name='gorilla_b200_set_host_resort')
+      import :: c_int, c_ptr, c_int32_t
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: on
+    end function
+    integer(c_int) function gorilla_b200_comm_unique_id(id) bind(C, name='gorilla_b200_comm_unique_id')
+      import :: c_int, c_char
+      character(kind=c_char) :: id(128)
+    end function
+    integer(c_int) function gorilla_b200_comm_init(handle, id, rank, nranks) bind(C, name='gorilla_b200_comm_init')
+      import :: c_int, c_ptr, c_char, c_int32_t
+      type(c_ptr), value :: handle
+      character(kind=c_char), intent(in) :: id(128)
+      integer(c_int32_t), value :: rank, nranks
+    end function
+    integer(c_int) function gorilla_b200_comm_free(handle) bind(C, name='gorilla_b200_comm_free')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle
+    end function
+    integer(c_int) function gorilla_b200_shard_range(n_total, rank, nranks, first, count) &
+                   bind(C, name='gorilla_b200_shard_range')
+      import :: c_int, c_int64_t, c_int32_t
+      integer(c_int64_t), value :: n_total
+      integer(c_int32_t), value :: rank, nranks
+      integer(c_int64_t), intent(out) :: first, count
+    end function
+    integer(c_int) function gorilla_b200_diag_reset(handle, stream) bind(C, name='gorilla_b200_diag_reset')
+      import :: c_int, c_ptr
+      type(c_ptr), value :: handle, stream
+    end function
+    integer(c_int) function gorilla_b200_diag_reduce(handle, n, x, vpar, vperp, ind_tetr, energy_ref, p_phi_ref, &
+                   perpinv_ref, diag) bind(C, name='gorilla_b200_diag_reduce')
+      import :: c_int, c_ptr, c_int64_t, c_double, c_int32_t, gorilla_b200_diag_t
+      type(c_ptr), value        :: handle
+      integer(c_int64_t), value :: n
+      real(c_double), intent(in):: x(3,*), vpar(*), vperp(*)
+      integer(c_int32_t), intent(in) :: ind_tetr(*)
+      type(c_ptr), value        :: energy_ref, p_phi_ref, perpinv_ref     ! c_null_ptr: that drift is not formed
+      type(gorilla_b200_diag_t), intent(out) :: diag
     end function
   end interface
 
@@ -219,6 +312,88 @@ contains
     double precision, intent(in)    :: vpar(n), vperp(n)
     integer, intent(out)            :: ind_tetr(n), iface(n), ierr
     ierr = gorilla_b200_find_tetra(handle, int(n, c_int64_t), x, vpar, vperp, ind_tetr, iface, int(sign_t_step, c_int32_t))
+  end subroutine
+
+  !> Batch call with the event capture of gorilla_plot_orbit_integration (gorilla_plot_mod.f90:585-638): banana tips with
+  !> J_par and toroidal mappings go to `events` (event_cap records; n_events may exceed it, the surplus is dropped).
+  !> par_adiab_inv / counter_vpar_0 / counter_phi_0 carry the per-particle state between calls (zero them first).
+  subroutine orbit_timestep_gorilla_batch_events(n, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface, cfg, &
+                                                 par_adiab_inv, counter_vpar_0, counter_phi_0, events, n_events, ierr)
+    integer, intent(in)             :: n
+    double precision, intent(inout) :: x(3,n), vpar(n), vperp(n), par_adiab_inv(n)
+    double precision, intent(in)    :: t_step
+    logical, intent(inout)          :: boole_initialized(n)
+    integer, intent(inout)          :: ind_tetr(n), iface(n), counter_vpar_0(n), counter_phi_0(n)
+    type(gorilla_b200_event_settings_t), intent(in) :: cfg
+    type(gorilla_b200_event_t), intent(out) :: events(:)
+    integer(c_int64_t), intent(out) :: n_events
+    integer, intent(out)            :: ierr
+    integer(c_int32_t), allocatable :: binit(:)
+    allocate(binit(n))
+    binit = merge(1_c_int32_t, 0_c_int32_t, boole_initialized)
+    ierr = gorilla_b200_orbit_timestep_events(handle, int(n, c_int64_t), x, vpar, vperp, t_step, binit, ind_tetr, iface, &
+                                              c_null_ptr, c_null_ptr, cfg, par_adiab_inv, counter_vpar_0, counter_phi_0, &
+                                              events, int(size(events), c_int64_t), n_events)
+    boole_initialized = binit /= 0
+  end subroutine
+
+  !> energy_tot_func, p_phi_func and perpinv of every particle (supporting_functions_mod.f90:279-301, 377-408)
+  subroutine invariants_b200(n, x, vpar, vperp, ind_tetr, energy, p_phi, perpinv, ierr)
+    integer, intent(in)           :: n
+    double precision, intent(in)  :: x(3,n), vpar(n), vperp(n)
+    integer, intent(in)           :: ind_tetr(n)
+    double precision, intent(out) :: energy(n), p_phi(n), perpinv(n)
+    integer, intent(out)          :: ierr
+    ierr = gorilla_b200_invariants(handle, int(n, c_int64_t), x, vpar, vperp, ind_tetr, energy, p_phi, perpinv)
+  end subroutine
+
+  !> .true.: every batch of orbit_timestep_gorilla_batch is sorted by tetrahedron on the device before the push (gather
+  !> locality); the caller's particle order is restored before the arrays come back.
+  subroutine set_host_resort_b200(on, ierr)
+    logical, intent(in)  :: on
+    integer, intent(out) :: ierr
+    ierr = gorilla_b200_set_host_resort(handle, merge(1_c_int32_t, 0_c_int32_t, on))
+  end subroutine
+
+  !> Multi-GPU: rank 0 creates the id, every rank joins with its own handle (one process per GPU).
+  subroutine comm_unique_id_b200(id, ierr)
+    character(kind=c_char), intent(out) :: id(128)
+    integer, intent(out) :: ierr
+    ierr = gorilla_b200_comm_unique_id(id)
+  end subroutine
+  subroutine comm_init_b200(id, rank, nranks, ierr)
+    character(kind=c_char), intent(in) :: id(128)
+    integer, intent(in)  :: rank, nranks
+    integer, intent(out) :: ierr
+    ierr = gorilla_b200_comm_init(handle, id, int(rank, c_int32_t), int(nranks, c_int32_t))
+  end subroutine
+  subroutine comm_free_b200(ierr)
+    integer, intent(out) :: ierr
+    ierr = gorilla_b200_comm_free(handle)
+  end subroutine
+  !> Contiguous shard of n_total particles owned by `rank`: particles first+1 .. first+count (1-based).
+  subroutine shard_range_b200(n_total, rank, nranks, first, count)
+    integer(c_int64_t), intent(in)  :: n_total
+    integer, intent(in)             :: rank, nranks
+    integer(c_int64_t), intent(out) :: first, count
+    integer(c_int) :: rc
+    rc = gorilla_b200_shard_range(n_total, int(rank, c_int32_t), int(nranks, c_int32_t), first, count)
+  end subroutine
+  subroutine diag_reset_b200(ierr)
+    integer, intent(out) :: ierr
+    ierr = gorilla_b200_diag_reset(handle, c_null_ptr)
+  end subroutine
+  !> Counters accumulated since diag_reset_b200 and max / rms drift of energy, perpinv, p_phi against the reference values
+  !> (from invariants_b200 at the start), reduced over all ranks of the communicator (collective call).
+  subroutine diag_reduce_b200(n, x, vpar, vperp, ind_tetr, energy_ref, p_phi_ref, perpinv_ref, diag, ierr)
+    integer, intent(in)                  :: n
+    double precision, intent(in)         :: x(3,n), vpar(n), vperp(n)
+    integer, intent(in)                  :: ind_tetr(n)
+    double precision, intent(in), target :: energy_ref(n), p_phi_ref(n), perpinv_ref(n)
+    type(gorilla_b200_diag_t), intent(out) :: diag
+    integer, intent(out)                 :: ierr
+    ierr = gorilla_b200_diag_reduce(handle, int(n, c_int64_t), x, vpar, vperp, ind_tetr, c_loc(energy_ref(1)), &
+                                    c_loc(p_phi_ref(1)), c_loc(perpinv_ref(1)), diag)
   end subroutine
 
   subroutine get_counters_b200(counters, ierr)

@@ -47,9 +47,12 @@ typedef struct gorilla_settings {
   int32_t ipusher;                   /* 1 RK4 | 2 polynomial */
   int32_t boole_pusher_ode45;        /* must be 0 */
   int32_t boole_dt_dtau;             /* must be 1 */
-  int32_t boole_newton_precalc;      /* must be 0 */
+  int32_t boole_newton_precalc;      /* must be 0 (RK pusher with tetra_physics_poly4 normal velocities) */
   int32_t poly_order;                /* 1..4 */
-  int32_t i_precomp;                 /* must be 0 */
+  int32_t i_precomp;                 /* 0 | 1 (poly_order 2..4) | 2 (poly_order 2): precomputed coefficients, the library
+                                        forms the tetra_physics_poly4 records (tetra_physics_poly_precomp_mod.f90:160-476,
+                                        4352 bytes per tetrahedron) itself at init; polynomial pusher, not combined with
+                                        Hamiltonian time / optional quantities / adaptive steps / strong E / hand-over kind 2 */
   int32_t boole_guess;
   int32_t i_time_tracing_option;     /* 1 dt/dtau constant per cell | 2 Hamiltonian time (ipusher = 2 only,
                                         gorilla_settings_mod.f90:124-129) */
@@ -291,6 +294,18 @@ int gorilla_b200_diag_reduce_dev(gorilla_b200_handle *h, int64_t n, const double
 /* FP64 issue-rate micro-benchmark on the current device: thread-level instructions per second for DFMA and
  * for DMUL+DADD pairs (the strict build issues the latter).  Roofline denominator of the FP64-bound orders. */
 int gorilla_b200_fp64_peak(double *dfma_inst_per_s, double *dmul_dadd_inst_per_s);
+
+/* Neighbour-record prefetch of the push kernels: once the exit face of a push is known the records of the tetrahedron
+ * behind it are requested into the L2, overlapping the gather latency with the rest of the push.  It pays when the records
+ * a batch touches do not fit the L2 and costs when they do, so it is a run-time option: mode 1 on, 0 off, -1 auto (on when
+ * the hot records of the mesh are more than four times the L2 capacity; the default after gorilla_b200_init).  Results are
+ * identical either way. */
+int gorilla_b200_set_prefetch(gorilla_b200_handle *h, int32_t mode);
+
+/* How the push kernels of orders 1, 2 and of the RK4 pusher gather the geometry / magnetic sub-records: 0 = per-lane vector
+ * loads through the L1 (best when the records a batch touches are L2 resident), 1 = per-lane bulk copies (cp.async.bulk into a
+ * shared-memory slot, issued one push ahead; best when they are not), -1 = auto by mesh size.  Results are identical. */
+int gorilla_b200_set_gather(gorilla_b200_handle *h, int32_t mode);
 
 /* Tuning knobs (0 = keep default): CTAs per SM and threads per CTA of the persistent push kernel. */
 int gorilla_b200_set_launch_config(gorilla_b200_handle *h, int32_t ctas_per_sm, int32_t threads_per_cta);

@@ -897,13 +897,234 @@ static void analytic_coeff_without_precomp(poly_state *s, int poly_order, const 
   }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Precomputed-coefficient modes: type tetrahedron_physics_precomp_poly4 and make_precomp_poly4
+ * (SRC/tetra_physics_poly_precomp_mod.f90:21-45,160-476).  Matrices are handled as m[i][j] = M(i+1,j+1) and stored in the
+ * record in Fortran order (P4_* offsets, gorilla_oracle.h).  matmul / sum accumulate in ascending index order from 0.
+ * ---------------------------------------------------------------------------------------------- */
+static void p4_store(double *rec4, int off, double a[4][4])
+{
+  for (int j = 0; j < 4; j++)
+    for (int i = 0; i < 4; i++) rec4[off + i + 4 * j] = a[i][j];
+}
+static void p4_load(const double *rec4, int off, double a[4][4])
+{
+  for (int j = 0; j < 4; j++)
+    for (int i = 0; i < 4; i++) a[i][j] = rec4[off + i + 4 * j];
+}
+static void add44(double c[4][4], double a[4][4], double b[4][4])
+{
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) c[i][j] = a[i][j] + b[i][j];
+}
+static void make_precomp_poly4_one(const gor_mesh *m, int ind_tetr, double *o)
+{
+  const double *r = rec(m, ind_tetr);
+  const double cm = m->cm_over_e;
+  double alp[4][4], bet[4][4];
+  memset(alp, 0, sizeof(alp));
+  memset(bet, 0, sizeof(bet));
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      alp[i][j] = cm * r[TP_ALPMAT + i + 3 * j];
+      bet[i][j] = -(CLIGHT * r[TP_BETMAT + i + 3 * j]);
+    }
+  alp[3][3] = cm * r[TP_SPALPMAT];
+  for (int i = 0; i < 3; i++) bet[i][3] = r[TP_CURLA + i];
+  bet[3][3] = -(CLIGHT * r[TP_SPBETMAT]);
+  double aa[4][4], ab[4][4], bb[4][4], ba[4][4];
+  matmul44(aa, alp, alp); matmul44(ab, alp, bet); matmul44(bb, bet, bet); matmul44(ba, bet, alp);
+  double aaa[4][4], aab[4][4], aba[4][4], abb[4][4], baa[4][4], bab[4][4], bba[4][4], bbb[4][4];
+  matmul44(aaa, alp, aa); matmul44(aab, alp, ab); matmul44(aba, alp, ba); matmul44(abb, alp, bb);
+  matmul44(baa, bet, aa); matmul44(bab, bet, ab); matmul44(bba, bet, ba); matmul44(bbb, bet, bb);
+  double aaaa[4][4], aaab[4][4], aaba[4][4], aabb[4][4], abaa[4][4], abab[4][4], abba[4][4], abbb[4][4];
+  double baaa[4][4], baab[4][4], baba[4][4], babb[4][4], bbaa[4][4], bbab[4][4], bbba[4][4], bbbb[4][4];
+  matmul44(aaaa, alp, aaa); matmul44(aaab, alp, aab); matmul44(aaba, alp, aba); matmul44(aabb, alp, abb);
+  matmul44(abaa, alp, baa); matmul44(abab, alp, bab); matmul44(abba, alp, bba); matmul44(abbb, alp, bbb);
+  matmul44(baaa, bet, aaa); matmul44(baab, bet, aab); matmul44(baba, bet, aba); matmul44(babb, bet, abb);
+  matmul44(bbaa, bet, baa); matmul44(bbab, bet, bab); matmul44(bbba, bet, bba); matmul44(bbbb, bet, bbb);
+  double t[4][4];
+  p4_store(o, P4_AMAT1_0, bet);
+  p4_store(o, P4_AMAT1_1, alp);
+  p4_store(o, P4_AMAT2_0, bb);
+  add44(t, ba, ab); p4_store(o, P4_AMAT2_1, t);                               /* bet_alp + alp_bet */
+  p4_store(o, P4_AMAT2_2, aa);
+  p4_store(o, P4_AMAT3_0, bbb);
+  add44(t, bba, bab); add44(t, t, abb); p4_store(o, P4_AMAT3_1, t);           /* bet_bet_alp + bet_alp_bet + alp_bet_bet */
+  add44(t, baa, aba); add44(t, t, aab); p4_store(o, P4_AMAT3_2, t);           /* bet_alp_alp + alp_bet_alp + alp_alp_bet */
+  p4_store(o, P4_AMAT3_3, aaa);
+  p4_store(o, P4_AMAT4_0, bbbb);
+  add44(t, bbba, bbab); add44(t, t, babb); add44(t, t, abbb); p4_store(o, P4_AMAT4_1, t);
+  add44(t, bbaa, baba); add44(t, t, baab); add44(t, t, abba); add44(t, t, abab); add44(t, t, aabb);
+  p4_store(o, P4_AMAT4_2, t);
+  add44(t, abaa, aaba); add44(t, t, aaab); add44(t, t, baaa); p4_store(o, P4_AMAT4_3, t);
+  p4_store(o, P4_AMAT4_4, aaaa);
+  /* n in a^k: anorm_in_amatK(:,n) = matmul(n_vec, amatK), n_vec = (anorm(:,n), 0) */
+  for (int k = 0; k < 14; k++) {
+    double a[4][4];
+    p4_load(o, 16 * k, a);
+    for (int n = 0; n < 4; n++) {
+      const double nv[4] = {r[TP_ANORM + 3 * n], r[TP_ANORM + 3 * n + 1], r[TP_ANORM + 3 * n + 2], 0.0};
+      for (int j = 0; j < 4; j++) {
+        double sacc = 0.0;
+        for (int i = 0; i < 4; i++) sacc = sacc + nv[i] * a[i][j];
+        o[P4_AN_AMAT1_0 + 16 * k + j + 4 * n] = sacc;
+      }
+    }
+  }
+  /* factorised b-vector */
+  for (int i = 0; i < 3; i++) {
+    o[P4_B0 + i] = -CLIGHT * r[TP_GPHIXH1 + i];
+    o[P4_B1 + i] = cm * r[TP_CURLH + i];
+    o[P4_B2 + i] = cm * r[TP_GBXH1 + i];
+    o[P4_B3 + i] = -2.0 * CLIGHT * r[TP_CURLH + i];
+  }
+  o[P4_B0 + 3] = -CLIGHT / cm * r[TP_GPHIXCURLA];
+  o[P4_B1 + 3] = 0.0;
+  o[P4_B2 + 3] = r[TP_GBXCURLA];
+  o[P4_B3 + 3] = 0.0;
+  for (int q = 0; q < 2; q++) {    /* amat1_0, amat1_1 in b0..b3 */
+    double a[4][4];
+    p4_load(o, q == 0 ? P4_AMAT1_0 : P4_AMAT1_1, a);
+    for (int k = 0; k < 4; k++) matvec4(o + (q == 0 ? P4_A10_B0 : P4_A11_B0) + 4 * k, a, o + P4_B0 + 4 * k);
+  }
+  for (int k = 0; k < 4; k++)
+    for (int n = 0; n < 4; n++) {
+      o[P4_AN_B0 + 4 * k + n] = dot3(r + TP_ANORM + 3 * n, o + P4_B0 + 4 * k);
+      for (int q = 0; q < 2; q++) {
+        const double *col = o + (q == 0 ? P4_AN_AMAT1_0 : P4_AN_AMAT1_1) + 4 * n, *bk = o + P4_B0 + 4 * k;
+        double sacc = 0.0;
+        for (int i = 0; i < 4; i++) sacc = sacc + col[i] * bk[i];
+        o[(q == 0 ? P4_AN_A10_B0 : P4_AN_A11_B0) + 4 * k + n] = sacc;
+      }
+    }
+}
+void gor_make_precomp_poly4(const gor_mesh *m, double *out)
+{
+#pragma omp parallel for schedule(static)
+  for (int64_t t = 1; t <= m->ntetr; t++) make_precomp_poly4_one(m, (int)t, out + (t - 1) * P4_NDOUBLES);
+}
+static inline const double *p4rec(const poly_state *s)
+{
+  return s->m->tetra_physics_poly4 + ((int64_t)s->ind_tetr - 1) * P4_NDOUBLES;
+}
+/* sum over the four components of (c0 + f1*c1 + f2*c2 + ...)(:) * v(:): the shape of every precomputed coefficient */
+static double p4_combo_dot(const double *p4, const int *off, const double *fac, int nterms, int n, const double v[4])
+{
+  double sacc = 0.0;
+  for (int i = 0; i < 4; i++) {
+    double e = p4[off[0] + i + 4 * n];
+    for (int k = 1; k < nterms; k++) e = e + fac[k] * p4[off[k] + i + 4 * n];
+    sacc = sacc + e * v[i];
+  }
+  return sacc;
+}
+/* analytic_coeff_with_precomp (:1590-1725); i_precomp = 2 exists for orders <= 2 only (the reference leaves the higher
+ * coefficients unassigned) */
+static void analytic_coeff_with_precomp(poly_state *s, int poly_order, int i_precomp, const bool boole_faces[4],
+                                        const double z[4], double coef_mat[4][5])
+{
+  const gor_mesh *m = s->m;
+  const double *r = s->r, *p4 = p4rec(s);
+  const double cm_over_e = m->cm_over_e, perpinv = s->perpinv, perpinv2 = s->perpinv2;
+  if (i_precomp == 1) { /* b without sign_rhs (:1607-1614) */
+    for (int i = 0; i < 3; i++)
+      s->b[i] = (r[TP_CURLH + i] * (s->k1) + perpinv * r[TP_GBXH1 + i]) * cm_over_e -
+                CLIGHT * (2.0 * (s->k3) * r[TP_CURLH + i] + r[TP_GPHIXH1 + i]);
+    s->b[3] = perpinv * r[TP_GBXCURLA] - CLIGHT / cm_over_e * r[TP_GPHIXCURLA];
+  }
+  const double dist1 = -r[TP_DIST_REF];
+  const double perpinv3 = perpinv2 * perpinv, perpinv4 = perpinv2 * perpinv2;
+  const double fac[5] = {1.0, perpinv, perpinv2, perpinv3, perpinv4};
+  static const int A1[2] = {P4_AN_AMAT1_0, P4_AN_AMAT1_1}, A2[3] = {P4_AN_AMAT2_0, P4_AN_AMAT2_1, P4_AN_AMAT2_2},
+                   A3[4] = {P4_AN_AMAT3_0, P4_AN_AMAT3_1, P4_AN_AMAT3_2, P4_AN_AMAT3_3},
+                   A4[5] = {P4_AN_AMAT4_0, P4_AN_AMAT4_1, P4_AN_AMAT4_2, P4_AN_AMAT4_3, P4_AN_AMAT4_4};
+  for (int n = 0; n < 4; n++) {
+    if (!boole_faces[n]) continue;
+    coef_mat[n][0] = dot3(r + TP_ANORM + 3 * n, z);
+  }
+  coef_mat[0][0] = coef_mat[0][0] - dist1;
+  for (int n = 0; n < 4; n++) {
+    if (!boole_faces[n]) continue;
+    if (poly_order >= 1) {
+      const double sz = p4_combo_dot(p4, A1, fac, 2, n, z);
+      if (i_precomp == 1)
+        coef_mat[n][1] = sz + dot3(r + TP_ANORM + 3 * n, s->b);
+      else
+        coef_mat[n][1] = sz + p4[P4_AN_B0 + n] + s->k1 * p4[P4_AN_B1 + n] + perpinv * p4[P4_AN_B2 + n] + s->k3 * p4[P4_AN_B3 + n];
+    }
+    if (poly_order >= 2) {
+      const double sz = p4_combo_dot(p4, A2, fac, 3, n, z);
+      if (i_precomp == 1)
+        coef_mat[n][2] = sz + p4_combo_dot(p4, A1, fac, 2, n, s->b);
+      else
+        coef_mat[n][2] = sz + p4[P4_AN_A10_B0 + n] + perpinv * p4[P4_AN_A11_B0 + n] +
+                         s->k1 * (p4[P4_AN_A10_B1 + n] + perpinv * p4[P4_AN_A11_B1 + n]) +
+                         perpinv * (p4[P4_AN_A10_B2 + n] + perpinv * p4[P4_AN_A11_B2 + n]) +
+                         s->k3 * (p4[P4_AN_A10_B3 + n] + perpinv * p4[P4_AN_A11_B3 + n]);
+    }
+    if (poly_order >= 3) coef_mat[n][3] = p4_combo_dot(p4, A3, fac, 4, n, z) + p4_combo_dot(p4, A2, fac, 3, n, s->b);
+    if (poly_order >= 4) coef_mat[n][4] = p4_combo_dot(p4, A4, fac, 5, n, z) + p4_combo_dot(p4, A3, fac, 4, n, s->b);
+  }
+}
+/* one element of (f_hi*M_hi + ... + f_1*M_1 + M_0): the operators of analytic_integration_with_precomp are written with the
+ * HIGHEST power of perpinv first (:2558-2660) */
+static double p4_combo_desc(const double *p4, const int *off, const double *fac, int nterms, int i, int j)
+{
+  double e = fac[nterms - 1] * p4[off[nterms - 1] + i + 4 * j];
+  for (int k = nterms - 2; k >= 1; k--) e = e + fac[k] * p4[off[k] + i + 4 * j];
+  return e + p4[off[0] + i + 4 * j];
+}
+/* analytic_integration_with_precomp (:2530-2650).  Does not touch number_of_integration_steps or the step lists (that
+ * book-keeping lives in analytic_integration_without_precomp only); poly_order = 1 has no case: z is left unchanged. */
+static void analytic_integration_with_precomp(poly_state *s, int poly_order, int i_precomp, double z[4], double tau)
+{
+  const double *p4 = p4rec(s);
+  const double perpinv = s->perpinv, perpinv2 = s->perpinv2;
+  const double perpinv3 = perpinv2 * perpinv, perpinv4 = perpinv2 * perpinv2;
+  const double fac[5] = {1.0, perpinv, perpinv2, perpinv3, perpinv4};
+  static const int M1[2] = {P4_AMAT1_0, P4_AMAT1_1}, M2[3] = {P4_AMAT2_0, P4_AMAT2_1, P4_AMAT2_2},
+                   M3[4] = {P4_AMAT3_0, P4_AMAT3_1, P4_AMAT3_2, P4_AMAT3_3},
+                   M4[5] = {P4_AMAT4_0, P4_AMAT4_1, P4_AMAT4_2, P4_AMAT4_3, P4_AMAT4_4};
+  if (poly_order < 2 || poly_order > 4) return;
+  if (i_precomp == 2 && poly_order != 2) return;
+  const double tau2_half = tau * tau * 0.5, tau3_sixth = (tau * tau) * tau / 6.0;
+  const double t2 = tau * tau, tau4_twentyfourth = (t2 * t2) / 24.0;
+  double op_z[4][4], op_b[4][4];
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) {
+      double e = tau * p4_combo_desc(p4, M1, fac, 2, i, j) + tau2_half * p4_combo_desc(p4, M2, fac, 3, i, j);
+      if (poly_order >= 3) e = e + tau3_sixth * p4_combo_desc(p4, M3, fac, 4, i, j);
+      if (poly_order >= 4) e = e + tau4_twentyfourth * p4_combo_desc(p4, M4, fac, 5, i, j);
+      op_z[i][j] = e;
+      double f = tau * (i == j ? 1.0 : 0.0) + tau2_half * p4_combo_desc(p4, M1, fac, 2, i, j);
+      if (poly_order >= 3) f = f + tau3_sixth * p4_combo_desc(p4, M2, fac, 3, i, j);
+      if (poly_order >= 4) f = f + tau4_twentyfourth * p4_combo_desc(p4, M3, fac, 4, i, j);
+      op_b[i][j] = f;
+    }
+  double oz[4], ob[4];
+  matvec4(oz, op_z, z);
+  if (i_precomp == 1) {
+    matvec4(ob, op_b, s->b);
+  } else { /* operator_b_in_b (:2578-2587) */
+    for (int i = 0; i < 4; i++)
+      ob[i] = tau * (p4[P4_B0 + i] + s->k1 * p4[P4_B1 + i] + perpinv * p4[P4_B2 + i] + s->k3 * p4[P4_B3 + i]) +
+              tau2_half * ((p4[P4_A10_B0 + i] + perpinv * p4[P4_A11_B0 + i]) +
+                           s->k1 * (p4[P4_A10_B1 + i] + perpinv * p4[P4_A11_B1 + i]) +
+                           perpinv * (p4[P4_A10_B2 + i] + perpinv * p4[P4_A11_B2 + i]) +
+                           s->k3 * (p4[P4_A10_B3 + i] + perpinv * p4[P4_A11_B3 + i]));
+  }
+  for (int i = 0; i < 4; i++) z[i] = z[i] + ob[i] + oz[i];
+}
+
 /* :1258-1482.  dtau is only assigned when a valid root exists (intent(out) left untouched otherwise). */
 static void analytic_approx(poly_state *s, int poly_order, const bool boole_faces[4], int i_scaling,
                             const double z[4], int *iface_inout, double *dtau, bool *boole_approx)
 {
   double coef_mat[4][5];
   double dtau_vec[4] = {HUGE_D, HUGE_D, HUGE_D, HUGE_D};
-  analytic_coeff_without_precomp(s, poly_order, boole_faces, z, coef_mat);
+  if (s->m->i_precomp == 0) analytic_coeff_without_precomp(s, poly_order, boole_faces, z, coef_mat);
+  else analytic_coeff_with_precomp(s, poly_order, s->m->i_precomp, boole_faces, z, coef_mat);
   int iface = *iface_inout;
   for (int i = 1; i <= 4; i++) {
     if (!boole_faces[i - 1]) continue;
@@ -990,6 +1211,10 @@ static void analytic_approx(poly_state *s, int poly_order, const bool boole_face
 /* :2047-2083 */
 static void analytic_integration(poly_state *s, int poly_order, double z[4], double tau)
 {
+  if (s->m->i_precomp != 0) { /* :2034-2039 */
+    analytic_integration_with_precomp(s, poly_order, s->m->i_precomp, z, tau);
+    return;
+  }
   s->number_of_integration_steps += 1;
   if (s->number_of_integration_steps <= s->list_cap) { /* the reference's lists hold list_cap entries */
     s->tau_steps_list[s->number_of_integration_steps - 1] = tau;
@@ -1213,6 +1438,13 @@ static double normal_velocity_func(const poly_state *s, const double z[4], int i
 {
   const gor_mesh *m = s->m;
   const double *r = s->r, *n = anorm_col(s, iface);
+  if (m->i_precomp != 0) { /* :2734-2738; b is the module variable: set by i_precomp = 1, never by i_precomp = 2 (zero) */
+    const double *p4 = p4rec(s);
+    double sacc = 0.0;
+    for (int i = 0; i < 4; i++)
+      sacc = sacc + (p4[P4_AN_AMAT1_0 + i + 4 * (iface - 1)] + s->perpinv * p4[P4_AN_AMAT1_1 + i + 4 * (iface - 1)]) * z[i];
+    return sacc * (double)s->sign_rhs + dot3(n, s->b);
+  }
   double in_alp[3], in_bet[3], in_gam[3];
   for (int j = 0; j < 3; j++) {
     in_alp[j] = dot3(n, r + TP_ALPMAT + 3 * j); /* sum_i n(i)*alpmat(i,j) */
@@ -1629,7 +1861,8 @@ static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout
     check_face_convergence(s, z, iface_new, &boole_face_correct);
     check_exit_time(tau, tau_max, &boole_face_correct, poly_order);
     if (boole_face_correct) {
-      double nv = normal_v_func_from_trajectory(s, poly_order, iface_new, tau);
+      double nv = (m->i_precomp == 0) ? normal_v_func_from_trajectory(s, poly_order, iface_new, tau)
+                                      : normal_velocity_func(s, z, iface_new); /* :328-332 */
       if (nv > 0.0) {
         if (poly_order > 2) {
           boole_face_correct = false;

@@ -49,6 +49,19 @@ enum {
   TP_GV2EMOD = 104, TP_ALPMAT = 107, TP_BETMAT = 116, TP_GAMMAT = 125, TP_ACOEF_PRE = 134,
   TP_ACOEF_PRE_SE = 138, TP_NDOUBLES = 142
 };
+/* offsets (in doubles) into one tetrahedron_physics_precomp_poly4 record (SRC/tetra_physics_poly_precomp_mod.f90:21-45);
+ * 4x4 matrices in Fortran column-major order, amat(i,j) at [i-1 + 4*(j-1)]; anorm_in_amat*(:,n) is column n */
+enum {
+  P4_AMAT1_0 = 0, P4_AMAT1_1 = 16, P4_AMAT2_0 = 32, P4_AMAT2_1 = 48, P4_AMAT2_2 = 64, P4_AMAT3_0 = 80, P4_AMAT3_1 = 96,
+  P4_AMAT3_2 = 112, P4_AMAT3_3 = 128, P4_AMAT4_0 = 144, P4_AMAT4_1 = 160, P4_AMAT4_2 = 176, P4_AMAT4_3 = 192,
+  P4_AMAT4_4 = 208, P4_AN_AMAT1_0 = 224, P4_AN_AMAT1_1 = 240, P4_AN_AMAT2_0 = 256, P4_AN_AMAT2_1 = 272,
+  P4_AN_AMAT2_2 = 288, P4_AN_AMAT3_0 = 304, P4_AN_AMAT3_1 = 320, P4_AN_AMAT3_2 = 336, P4_AN_AMAT3_3 = 352,
+  P4_AN_AMAT4_0 = 368, P4_AN_AMAT4_1 = 384, P4_AN_AMAT4_2 = 400, P4_AN_AMAT4_3 = 416, P4_AN_AMAT4_4 = 432,
+  P4_B0 = 448, P4_B1 = 452, P4_B2 = 456, P4_B3 = 460, P4_A10_B0 = 464, P4_A10_B1 = 468, P4_A10_B2 = 472, P4_A10_B3 = 476,
+  P4_A11_B0 = 480, P4_A11_B1 = 484, P4_A11_B2 = 488, P4_A11_B3 = 492, P4_AN_B0 = 496, P4_AN_B1 = 500, P4_AN_B2 = 504,
+  P4_AN_B3 = 508, P4_AN_A10_B0 = 512, P4_AN_A10_B1 = 516, P4_AN_A10_B2 = 520, P4_AN_A10_B3 = 524, P4_AN_A11_B0 = 528,
+  P4_AN_A11_B1 = 532, P4_AN_A11_B2 = 536, P4_AN_A11_B3 = 540, P4_NDOUBLES = 544
+};
 enum { TG_IND_KNOT = 0, TG_NEIGHBOUR_TETR = 4, TG_NEIGHBOUR_FACE = 8, TG_PERBOU_PHI = 12,
        TG_PERBOU_THETA = 16, TG_NINTS = 20 };
 
@@ -77,7 +90,14 @@ typedef struct {
   /* handover_processing_kind = 2: tetra_skew_coord [ntetr][168] (tetra_physics_mod.f90:89-99), else NULL / 1 */
   const double *tetra_skew_coord;
   int32_t handover_processing_kind;
+  /* precomputed-coefficient modes (SRC/tetra_physics_poly_precomp_mod.f90:160-476): i_precomp = 1, 2 of the polynomial
+   * pusher, boole_newton_precalc of the RK pusher; tetra_physics_poly4 [ntetr][544] from gor_make_precomp_poly4 */
+  int32_t i_precomp, boole_newton_precalc;
+  const double *tetra_physics_poly4;
 } gor_mesh;
+
+/* make_precomp_poly4 (SRC/tetra_physics_poly_precomp_mod.f90:160-476): out = [ntetr][544] */
+void gor_make_precomp_poly4(const gor_mesh *m, double *out);
 
 /* optional per-particle trace of the visited (ind_tetr, iface) sequence */
 typedef struct {

@@ -14,7 +14,7 @@
 using namespace gb;
 
 struct HostMirror {
-  std::vector<double> geom, bpart, phi, cold, se, ham, skew;
+  std::vector<double> geom, bpart, phi, cold, se, ham, skew, poly4;
   gb::FindBins bins;
   MeshDev m;
   int poly_order, boole_periodic_relocation, ipusher, adaptive;
@@ -136,7 +136,7 @@ extern "C" {
 
 void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, int boole_periodic_relocation, int ipusher,
                 int boole_strong_electric_field, int i_time_tracing_option, int oq_mask, int boole_adaptive_time_steps,
-                double desired_delta_energy, int max_n_intermediate_steps, int handover_processing_kind)
+                double desired_delta_energy, int max_n_intermediate_steps, int handover_processing_kind, int i_precomp)
 {
   HostMirror *h = new HostMirror();
   bool has_phi = false;
@@ -158,6 +158,11 @@ void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, in
   }
   m.desired_delta_energy = desired_delta_energy;
   m.max_n_intermediate_steps = max_n_intermediate_steps;
+  if (ipusher == 2 && i_precomp != 0) {
+    make_precomp_poly4(md, h->poly4);
+    m.poly4 = h->poly4.data();
+    m.i_precomp = i_precomp;
+  }
   if (build_find_bins(md, h->bins)) {
     m.bin_start = h->bins.start.data(); m.bin_items = h->bins.items.data();
     m.bin_nu = h->bins.nu; m.bin_nv = h->bins.nv; m.bin_c0 = h->bins.c0; m.bin_c1 = h->bins.c1;
@@ -211,6 +216,15 @@ int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *v
       optq ? h->oq_mask : 0u, optq ? optq + 4 * i : nullptr)
 #define HM_RUNA(K, PHI) run_particle<K, PHI, 3>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
       t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, trace_cap, tt, tf, force_full, fallback)
+#define HM_RUNP(K, PHI) run_particle<K, PHI, 4>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
+      t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, trace_cap, tt, tf, force_full, fallback)
+    if (h->ipusher == 2 && m.i_precomp != 0) {   // precomputed coefficients (no strong-E variant)
+      if (m.phi) {
+        switch (h->poly_order) { case 2: HM_RUNP(2, 1); break; case 3: HM_RUNP(3, 1); break; default: HM_RUNP(4, 1); }
+      } else {
+        switch (h->poly_order) { case 2: HM_RUNP(2, 0); break; case 3: HM_RUNP(3, 0); break; default: HM_RUNP(4, 0); }
+      }
+    } else
     if (h->ipusher == 2 && h->adaptive) {
       if (m.se) {
         switch (h->poly_order) { case 1: HM_RUNA(1, 2); break; case 2: HM_RUNA(2, 2); break; case 3: HM_RUNA(3, 2); break; default: HM_RUNA(4, 2); }

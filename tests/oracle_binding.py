@@ -27,6 +27,7 @@ class GorMesh(C.Structure):
         ("boole_vpar2_int", C.c_int32), ("boole_adaptive_time_steps", C.c_int32), ("max_n_intermediate_steps", C.c_int32),
         ("desired_delta_energy", C.c_double), ("tetra_skew_coord", C.POINTER(C.c_double)),
         ("handover_processing_kind", C.c_int32),
+        ("i_precomp", C.c_int32), ("boole_newton_precalc", C.c_int32), ("tetra_physics_poly4", C.POINTER(C.c_double)),
     ]
 
 
@@ -77,6 +78,8 @@ def load_oracle():
         L.gor_orbit_timestep_events.argtypes = [C.POINTER(GorMesh), dp, dp, dp, d, i32p, i32p, i32p, dp, C.POINTER(GorTrace),
                                                 C.POINTER(GorEventSettings), dp, i32p, i32p, C.c_int64, C.c_void_p,
                                                 C.c_int64, C.POINTER(C.c_int64)]
+        L.gor_make_precomp_poly4.argtypes = [C.POINTER(GorMesh), dp]
+        L.gor_make_precomp_poly4.restype = None
         L.gor_find_tetra.argtypes = [C.POINTER(GorMesh), dp, d, d, i32p, i32p, C.c_int]
         L.gor_find_tetra.restype = None
         L.gor_check_coordinate_domain.argtypes = [C.POINTER(GorMesh), dp]
@@ -133,8 +136,17 @@ class OracleMesh:
         m.handover_processing_kind = int(settings.handover_processing_kind)
         if settings.handover_processing_kind == 2:
             m.tetra_skew_coord = mesh.tetra_skew_coord.ctypes.data_as(C.POINTER(C.c_double))
-        self.c = m
+        m.i_precomp = int(getattr(settings, "i_precomp", 0))
+        m.boole_newton_precalc = int(getattr(settings, "boole_newton_precalc", False))
         self.L = load_oracle()
+        self.poly4 = None
+        if m.i_precomp != 0 or m.boole_newton_precalc:
+            # make_precomp_poly4 (tetra_physics_poly_precomp_mod.f90:160-476): [ntetr][544], built by the oracle itself
+            self.poly4 = np.empty((mesh.ntetr, 544))
+            self.c = m
+            self.L.gor_make_precomp_poly4(C.byref(m), self.poly4.ctypes.data_as(C.POINTER(C.c_double)))
+            m.tetra_physics_poly4 = self.poly4.ctypes.data_as(C.POINTER(C.c_double))
+        self.c = m
 
     def orbit_timestep_batch(self, x, vpar, vperp, t_step, binit, ind_tetr, iface, t_remain_out=None, n_pushes=None,
                              nthreads: int = 0, optional_quantities=None) -> int:

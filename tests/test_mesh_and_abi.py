@@ -29,7 +29,7 @@ def test_struct_layouts_match_header_sizes():
 
 def test_unsupported_settings_are_refused_without_touching_the_gpu(product_lib, small_mesh):
     mesh, _, settings = small_mesh
-    for field, value in (("i_precomp", 1),
+    for field, value in (("i_precomp", 3),
                          ("boole_pusher_ode45", True)):
         bad = type(settings)(**{**settings.__dict__, field: value})
         with pytest.raises(api.GorillaError) as ei:

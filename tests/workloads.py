@@ -65,6 +65,15 @@ def particles_vmec_alpha(n, seed, energy_ev=3.5e6, s0=0.5, nfp=5):
     return x, vpar, vperp
 
 
+def particles_vmec_alpha_spread(n, seed, s_lo=0.15, s_hi=0.95, **kw):
+    """As particles_vmec_alpha, started uniformly in s over [s_lo, s_hi] instead of on one flux surface: the batch then
+    touches (nearly) every record of the mesh in every step, which does not fit the L2."""
+    x, vpar, vperp = particles_vmec_alpha(n, seed, **kw)
+    rng = np.random.Generator(np.random.PCG64(seed + 7919))
+    x[:, 0] = s_lo + (s_hi - s_lo) * rng.random(n)
+    return x, vpar, vperp
+
+
 def west_soledge3x(data_dir, n2=60, strong=True, ipusher=1, poly_order=2):
     """BASELINE config 4: WEST equilibrium table + SOLEDGE3X-EIRENE triangle mesh extruded to n2 toroidal
     slices (4.24 M tetrahedra at n2 = 60), strong-electric-field mode with eps_Phi = -1.5e-5 (MATLAB/example_8.m:42-48),

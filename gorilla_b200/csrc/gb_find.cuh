@@ -119,6 +119,12 @@ GB_HD_NOINLINE void find_tetra_on_face(const MeshDev *mp, double *x, double vpar
     double vn[4];
     for (int l = 0; l < 4; l++) {
       vn[l] = dot3(dyt, P.r.an[l]);
+      if (m.newton_precalc) {   // normal_velocity_func of the RK module with boole_newton_precalc (pusher_tetra_rk.f90:2487-2505)
+        const double *q = P.p4() + P4_AN_AMAT + 4 * l;
+        double sacc = 0.0;
+        for (int i = 0; i < 4; i++) sacc = sacc + (ldg(q + i) + P.perpinv * ldg(q + 16 + i)) * z[i];
+        vn[l] = sacc * (double)P.sign_rhs + dot3(P.r.an[l], P.b);
+      }
       if (conv[l] && vn[l] > 0.0) counter_vnorm_pos++;
     }
     if (counter_vnorm_pos == n_plane_conv) {

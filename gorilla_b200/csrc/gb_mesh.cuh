@@ -70,7 +70,8 @@ struct MeshDev {
   // precomputed-coefficient modes (EXT = 4 kernels): tetra_physics_poly4 records as the reference stores them, built by the
   // library at init from the tetra_physics records (make_precomp_poly4); i_precomp = 1 or 2
   const double *poly4;
-  int32_t i_precomp, pad_precomp;
+  int32_t i_precomp;
+  int32_t newton_precalc;   // RK pusher: normal velocity / acceleration / quadratic start guess from poly4 (EXT = 2 kernels)
   const double *ham;  // hamiltonian_time records (EXT kernels only): h1_in_curlA h1_in_curlh vec_mismatch_der(3) vec_parcurr_der(3)
   int32_t prefetch;    // 1: once the exit face of a push is known, prefetch the neighbour's records into the L2 (pays when
                        // the records a batch touches do not fit the L2; costs 12-20 % when they do -- host decides)
@@ -171,7 +172,8 @@ GB_HD void prefetch_record(const MeshDev &m, int ind_tetr)
 // cp.async.bulk global -> shared, completion on an mbarrier) does not go through the L1: every lane owns a 368-byte slot of
 // dynamic shared memory and an mbarrier; the geom (128 B) and bpart (224 B) sub-records of a tetrahedron are fetched with two
 // bulk copies, issued for the NEIGHBOUR as soon as the exit face of the running push is known, and unpacked from shared
-// memory (LDS.128, conflict free with the 16-byte pad) at the start of the next push.
+// memory (LDS.128, conflict free with the 16-byte pad) at the start of the next push.  (Filling the same slot with 22 per-lane
+// 16-byte cp.async copies instead -- LDGSTS, through the L1 again -- was measured at a third of the bulk-copy rate.)
 #define GB_BULK_STRIDE 368
 #if defined(__CUDACC__)
 __device__ __forceinline__ unsigned gb_tid_now()

@@ -65,14 +65,33 @@ struct RkPusher {
 
   GB_HD void distances(const double *z, double *d) const { P.normal_distances(z, d); }
   GB_HD double distance(const double *z, int iface) const { return P.normal_distance(z, iface); }
-  GB_HD double nvel(int iface, const double *dzdtau) const
+  // boole_newton_precalc (EXT = 2 kernels): sum((anorm_in_amat<k>_0 + perpinv*..._1 [+ perpinv^2*..._2])(:,iface) * v)
+  GB_HD double p4_dot(int order, int iface, const double *v) const
+  {
+    const double *q = P.p4() + P4_AN_AMAT + (order == 1 ? 0 : 32) + 4 * (iface - 1);
+    const double perpinv2 = P.perpinv * P.perpinv;   // analytic_coeff / initialize_const_motion_rk
+    double sacc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      double e = ldg(q + i) + P.perpinv * ldg(q + 16 + i);
+      if (order == 2) e = e + perpinv2 * ldg(q + 32 + i);
+      sacc = sacc + e * v[i];
+    }
+    return sacc;
+  }
+  GB_HD bool precalc() const { return EXT == 2 && P.mp->newton_precalc; }
+  // normal_velocity_func (:2451-2467) / normal_velocity_analytic (:2487-2505)
+  GB_HD double nvel(int iface, const double *dzdtau, const double *z) const
   {
     double n[3];
     P.face_normal(iface, n);
+    if (precalc()) return p4_dot(1, iface, z) * (double)P.sign_rhs + dot3(n, P.b);
     return dot3(dzdtau, n);
   }
-  GB_HD double nacc(int iface, const double *dzdtau) const
+  // normal_acceleration_func (:2469-2483) / normal_acceleration_analytic (:2507-2527)
+  GB_HD double nacc(int iface, const double *dzdtau, const double *z) const
   {
+    if (precalc()) return p4_dot(2, iface, z) + p4_dot(1, iface, P.b) * (double)P.sign_rhs;
     double n[3], t[3];
     P.face_normal(iface, n);
 #pragma unroll
@@ -133,9 +152,15 @@ struct RkPusher {
       double apre = dot3(P.r.curlA, P.r.an[f]) * (double)P.sign_rhs;
       // strong electric field (:672): + cm_over_e * matmul(curlvE, anorm) * sign_rhs
       if (PHI == 2) apre = apre + P.mp->cm_over_e * dot3(P.r.curlvE, P.r.an[f]) * (double)P.sign_rhs;
-      const double b = z[3] * apre + dot3(P.b, P.r.an[f]);
-      const double a = apre * fac;
-      const double c = cc[f];
+      double b = z[3] * apre + dot3(P.b, P.r.an[f]);
+      double a = apre * fac;
+      double c = cc[f];
+      if (precalc()) {   // analytic_coeff(2, z, coef_mat) (:579-632): all three coefficients from the poly4 record
+        c = dot3(z, P.r.an[f]);
+        if (f == 0) c = c + P.r.dist_ref;
+        b = p4_dot(1, f + 1, z) * (double)P.sign_rhs + dot3(P.r.an[f], P.b);
+        a = p4_dot(2, f + 1, z) + p4_dot(1, f + 1, P.b) * (double)P.sign_rhs;
+      }
       double num = 1.0, den = 1.0;
       bool has;
       if (iface == f + 1) {
@@ -177,7 +202,7 @@ struct RkPusher {
       k++;
 #pragma unroll
       for (int i = 0; i < 4; i++) { z_save[i] = z[i]; dz_save[i] = dzdtau[i]; }
-      const double nv = nvel(iface, dzdtau);
+      const double nv = nvel(iface, dzdtau, z);
       if (nv != 0.0) dtau = -dist / nv;
       else return false;
       tau_save = tau;
@@ -199,7 +224,7 @@ struct RkPusher {
 #pragma unroll
         for (int i = 0; i < 4; i++) { z[i] = z_save[i]; dzdtau[i] = dz_save[i]; }
         tau = tau_save;
-        const double na = 0.5 * nacc(iface, dzdtau);
+        const double na = 0.5 * nacc(iface, dzdtau, z);
         const double discr = nv * nv - 4.0 * na * dist;
         if (discr > 0.0) {
           if (na < 0.0) dtau = (-nv - sqrt(discr)) / (2.0 * na);
@@ -321,7 +346,7 @@ struct RkPusher {
         distances(z, nd);
         const int im = minloc4(nd);
         if (fabs(sel4(nd, im)) < dist_min) {
-          if (nvel(im, dzdtau) > 0.0) {
+          if (nvel(im, dzdtau, z) > 0.0) {
             dtau = +fabs(dtau / 2.0);
             rk4_step(z, dtau, dzdtau);
             tau = tau + dtau;
@@ -408,7 +433,7 @@ struct RkPusher {
     }
     if (iface_init_outside != 0) {
       if (distance(z, iface_init_outside) < 0.0) {
-        if (nvel(iface_init_outside, dzdtau) < 0.0) {
+        if (nvel(iface_init_outside, dzdtau, z) < 0.0) {
           for (int i = 1; i <= 3; i++) {
             const int j = ((iface_init_outside + i - 1) & 3) + 1;
             if (distance(z, j) < 0.0) turned_tangential = true;
@@ -435,7 +460,7 @@ struct RkPusher {
             dtau = dtau_decreased ? 0.5 * fabs(dtau) : 2.0 * fabs(dtau);
           } else if (n_out == 1) {
             iface_new = first_out;
-            if (nvel(iface_new, dzdtau) >= 0.0) {
+            if (nvel(iface_new, dzdtau, z) >= 0.0) {
               if (iface_init_outside != iface_new) {
                 dtau = -0.5 * fabs(dtau);
                 dtau_decreased = true;
@@ -456,7 +481,7 @@ struct RkPusher {
                 const double di = sel4(nd, i + 1);
                 if (!(di < 0.0)) continue;
                 if (fabs(di) >= dist_min) continue;
-                if (nvel(i + 1, dzdtau) > 0.0) j++;
+                if (nvel(i + 1, dzdtau, z) > 0.0) j++;
               }
               if (j > 0) {
                 dtau = 2.0 * fabs(dtau);
@@ -492,7 +517,7 @@ struct RkPusher {
           const int j = ((iface_new + i - 1) & 3) + 1;
           if (distance(z, j) < 0.0) newton_ok = false;
         }
-        if ((!newton_ok) || (nvel(iface_new, dzdtau) >= 0.0)) {
+        if ((!newton_ok) || (nvel(iface_new, dzdtau, z) >= 0.0)) {
 #pragma unroll
           for (int i = 0; i < 4; i++) z[i] = z_save[i];
           tau = tau_save;
@@ -549,7 +574,7 @@ struct RkPusher {
         const int k = ((iface_new + j - 1) & 3) + 1;
         if (distance(z, k) < 0.0) return 1;
       }
-      if (nvel(iface_new, dzdtau) > 0.0) return 1;
+      if (nvel(iface_new, dzdtau, z) > 0.0) return 1;
 #pragma unroll
       for (int i = 0; i < 3; i++) o.x[i] = z[i] + P.r.x1s(i);
       o.t_pass = tau * P.dt_dtau_const;
@@ -578,7 +603,7 @@ struct RkPusher {
         for (int i = 0; i < 4; i++)
           if (fabs(nd[i]) < dist_min) iface_new = i + 1;
       }
-      if (nvel(iface_new, dzdtau) < 0.0) {
+      if (nvel(iface_new, dzdtau, z) < 0.0) {
         pass_through(z, tau, iface_new, true, o);
       } else {
         // converged on a face at t_remain but flying inwards: handed to the same tetrahedron again
@@ -615,7 +640,7 @@ struct RkPusher {
             if (!bisection(z, tau, tau, iface_new, dzdtau)) return 1;
           }
         }
-        if (nvel(iface_new, dzdtau) > 0.0) {
+        if (nvel(iface_new, dzdtau, z) > 0.0) {
 #pragma unroll
           for (int i = 0; i < 4; i++) z[i] = z_save[i];
           tau = tau_save;
@@ -695,7 +720,7 @@ struct RkPusher {
             }
           }
           if (!cycled) {
-            if (nvel(iface_new, dzdtau) > 0.0) {
+            if (nvel(iface_new, dzdtau, z) > 0.0) {
               fallback |= 8;
               allowed &= ~(1u << (iface_new - 1));
               if (allowed == 0) llod = true;

@@ -148,7 +148,6 @@ static int check_settings(const gorilla_settings *s)
   if (s->ipusher != 1 && s->ipusher != 2) return fail(GORILLA_ERR_ARG, "ipusher must be 1 (RK4) or 2 (polynomial)");
   if (s->ipusher == 2 && (s->poly_order < 1 || s->poly_order > 4)) return fail(GORILLA_ERR_ARG, "poly_order must be 1..4");
   if (s->ipusher == 1 && !s->boole_dt_dtau) return fail(GORILLA_ERR_UNSUPPORTED, "ipusher = 1 requires boole_dt_dtau = .true.");
-  if (s->ipusher == 1 && s->boole_newton_precalc) return fail(GORILLA_ERR_UNSUPPORTED, "boole_newton_precalc must be .false.");
   if (s->i_precomp < 0 || s->i_precomp > 2) return fail(GORILLA_ERR_UNSUPPORTED, "i_precomp must be 0, 1 or 2 (3 is not implemented in the reference either)");
   if (s->i_precomp != 0 && s->ipusher == 2) {
     // analytic_integration_with_precomp has no case(1); i_precomp = 2 assigns the coefficients of orders <= 2 only
@@ -280,7 +279,7 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
       return GORILLA_ERR_CUDA;
     }
   }
-  if (st->ipusher == 2 && st->i_precomp != 0) {
+  if ((st->ipusher == 2 && st->i_precomp != 0) || (st->ipusher == 1 && st->boole_newton_precalc)) {
     std::vector<double> p4;
     gb::make_precomp_poly4(md, p4);
     if ((e = up(&h->d_poly4, p4)) != cudaSuccess) {
@@ -308,7 +307,7 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
   m.poly4 = h->d_poly4;
   m.rec44 = nullptr;   // made by gorilla_b200_set_gather
   m.i_precomp = (st->ipusher == 2) ? st->i_precomp : 0;
-  m.pad_precomp = 0;
+  m.newton_precalc = (st->ipusher == 1 && st->boole_newton_precalc) ? 1 : 0;
   m.time_tracing = st->i_time_tracing_option;
   m.desired_delta_energy = st->desired_delta_energy;
   m.max_n_intermediate_steps = st->max_n_intermediate_steps;
@@ -491,7 +490,9 @@ GB_EXTERN_ORBIT_P(4)
 template <int PHI>
 static int launch_orbit_k(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
 {
-  if (h->settings.ipusher == 1) return h->mesh.skew ? launch_orbit_t<0, PHI, 2>(h, bt, s) : launch_orbit_t<0, PHI>(h, bt, s);
+  // RK4: the kernel with the run-time options carries hand-over kind 2 and boole_newton_precalc
+  if (h->settings.ipusher == 1)
+    return (h->mesh.skew || h->mesh.newton_precalc) ? launch_orbit_t<0, PHI, 2>(h, bt, s) : launch_orbit_t<0, PHI>(h, bt, s);
   if (((bt.optq && bt.oq_mask) || bt.ev_flags) && h->settings.boole_adaptive_time_steps)
     return fail(GORILLA_ERR_UNSUPPORTED, "boole_adaptive_time_steps is not combined with optional quantities / events");
   if ((bt.optq && bt.oq_mask) || bt.ev_flags || h->mesh.skew) {   // handover kind 2 lives in the EXT = 2 kernels

@@ -47,7 +47,8 @@ typedef struct gorilla_settings {
   int32_t ipusher;                   /* 1 RK4 | 2 polynomial */
   int32_t boole_pusher_ode45;        /* must be 0 */
   int32_t boole_dt_dtau;             /* must be 1 */
-  int32_t boole_newton_precalc;      /* must be 0 (RK pusher with tetra_physics_poly4 normal velocities) */
+  int32_t boole_newton_precalc;      /* ipusher = 1: normal velocity / acceleration and the quadratic start guess from the
+                                        tetra_physics_poly4 records (pusher_tetra_rk.f90:579-632, 2487-2527) */
   int32_t poly_order;                /* 1..4 */
   int32_t i_precomp;                 /* 0 | 1 (poly_order 2..4) | 2 (poly_order 2): precomputed coefficients, the library
                                         forms the tetra_physics_poly4 records (tetra_physics_poly_precomp_mod.f90:160-476,

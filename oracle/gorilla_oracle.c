@@ -2261,8 +2261,28 @@ static void rk_normal_distances_func(const rk_state *s, const double z123[3], do
   for (int f = 0; f < 4; f++) out[f] = dot3(z123, s->anorm[f]);
   out[0] = out[0] - s->dist1;
 }
-static double rk_normal_velocity_func(const rk_state *s, int iface, const double dzdtau[4])
+/* the tetra_physics_poly4 record of the current tetrahedron (boole_newton_precalc) */
+static inline const double *rk_p4rec(const rk_state *s)
 {
+  return s->m->tetra_physics_poly4 + ((int64_t)s->ind_tetr - 1) * P4_NDOUBLES;
+}
+/* sum((anorm_in_amat<k>_0 + perpinv*..._1 [+ perpinv2*..._2])(:,iface) * v) */
+static double rk_p4_dot(const rk_state *s, int order, int iface, const double v[4])
+{
+  const double *p4 = rk_p4rec(s);
+  const int base = order == 1 ? P4_AN_AMAT1_0 : P4_AN_AMAT2_0;
+  double sacc = 0.0;
+  for (int i = 0; i < 4; i++) {
+    double e = p4[base + i + 4 * (iface - 1)] + s->perpinv * p4[base + 16 + i + 4 * (iface - 1)];
+    if (order == 2) e = e + s->perpinv2 * p4[base + 32 + i + 4 * (iface - 1)];
+    sacc = sacc + e * v[i];
+  }
+  return sacc;
+}
+/* :2451-2467 ; boole_newton_precalc: normal_velocity_analytic (:2487-2505) from the current position z */
+static double rk_normal_velocity_func(const rk_state *s, int iface, const double dzdtau[4], const double z[4])
+{
+  if (s->m->boole_newton_precalc) return rk_p4_dot(s, 1, iface, z) * (double)s->sign_rhs + dot3(s->anorm[iface - 1], s->b);
   return dot3(dzdtau, s->anorm[iface - 1]);
 }
 
@@ -2278,9 +2298,11 @@ static double rk_normal_distance_func(const rk_state *s, const double z123[3], i
   return d;
 }
 /* :2469-2483  sum(matmul(anorm(:,iface),amat)*dzdtau(1:3)) + sum(anorm(:,iface)*Bvec)*dzdtau(4) */
-static double rk_normal_acceleration_func(const rk_state *s, int iface, const double dzdtau[4])
+static double rk_normal_acceleration_func(const rk_state *s, int iface, const double dzdtau[4], const double z[4])
 {
   const double *n = s->anorm[iface - 1];
+  if (s->m->boole_newton_precalc) /* normal_acceleration_analytic (:2507-2527) */
+    return rk_p4_dot(s, 2, iface, z) + rk_p4_dot(s, 1, iface, s->b) * (double)s->sign_rhs;
   double t[3];
   for (int j = 0; j < 3; j++) t[j] = ((0.0 + n[0] * s->amat[0][j]) + n[1] * s->amat[1][j]) + n[2] * s->amat[2][j];
   return dot3(t, dzdtau) + dot3(n, s->Bvec) * dzdtau[3];
@@ -2301,6 +2323,14 @@ static void quad_analytic_approx(const rk_state *s, const double z[4], const boo
 {
   double acoef[4], bcoef[4], ccoef[4], dtau_vec[4], discr, dummy;
   const double *r = s->r;
+  if (s->m->boole_newton_precalc) { /* analytic_coeff(2, z, coef_mat) (:579-632) */
+    for (int f = 0; f < 4; f++) {
+      ccoef[f] = dot3(z, s->anorm[f]);
+      bcoef[f] = rk_p4_dot(s, 1, f + 1, z) * (double)s->sign_rhs + dot3(s->anorm[f], s->b);
+      acoef[f] = rk_p4_dot(s, 2, f + 1, z) + rk_p4_dot(s, 1, f + 1, s->b) * (double)s->sign_rhs;
+    }
+    ccoef[0] = ccoef[0] - s->dist1;
+  } else {
   for (int f = 0; f < 4; f++) acoef[f] = r[TP_ACOEF_PRE + f] * (double)s->sign_rhs;
   if (s->m->boole_strong_electric_field) /* :672 */
     for (int f = 0; f < 4; f++)
@@ -2308,6 +2338,7 @@ static void quad_analytic_approx(const rk_state *s, const double z[4], const boo
   for (int f = 0; f < 4; f++) bcoef[f] = z[3] * acoef[f] + dot3(s->b, s->anorm[f]);
   for (int f = 0; f < 4; f++) acoef[f] = acoef[f] * (s->b[3] + s->spamat * z[3]);
   rk_normal_distances_func(s, z, ccoef);
+  }
   const int iface = *iface_inout;
   for (int f = 0; f < 4; f++) dtau_vec[f] = s->dtau_max;
   for (int i = 0; i < 4; i++) {
@@ -2389,7 +2420,7 @@ static void newton_face_convergence_wrapped(rk_state *s, double z[4], double *ta
     k++;
     memcpy(z_save, z, sizeof(z_save));
     memcpy(dzdtau_save, dzdtau, sizeof(dzdtau_save));
-    nvel = rk_normal_velocity_func(s, iface, dzdtau);
+    nvel = rk_normal_velocity_func(s, iface, dzdtau, z);
     if (nvel != 0.0) dtau = -dist / nvel;
     else return;
     tau_save = *tau;
@@ -2410,7 +2441,7 @@ static void newton_face_convergence_wrapped(rk_state *s, double z[4], double *ta
       memcpy(z, z_save, sizeof(z_save));
       memcpy(dzdtau, dzdtau_save, sizeof(dzdtau_save));
       *tau = tau_save;
-      nacc = 0.5 * rk_normal_acceleration_func(s, iface, dzdtau);
+      nacc = 0.5 * rk_normal_acceleration_func(s, iface, dzdtau, z);
       discr = nvel * nvel - 4.0 * nacc * dist;
       if (discr > 0.0) {
         if (nacc < 0.0) dtau = (-nvel - sqrt(discr)) / (2.0 * nacc);
@@ -2527,7 +2558,7 @@ static void bisection_face_convergence(rk_state *s, double z[4], double *tau_ino
       }
       rk_normal_distances_func(s, z, nd);
       if (fabs(rk_minval(nd)) < s->dist_min) {
-        if (rk_normal_velocity_func(s, rk_minloc(nd), dzdtau) > 0.0) {
+        if (rk_normal_velocity_func(s, rk_minloc(nd), dzdtau, z) > 0.0) {
           dtau = +fabs(dtau / 2.0);
           rk4_step(s, z, dtau, dzdtau);
           tau = tau + dtau;
@@ -2617,7 +2648,7 @@ static void last_line_defense(rk_state *s, double z[4], double *tau, int *iface,
   (void)distance_bisection;
   if (iface_init_outside != 0) {
     if (rk_normal_distance_func(s, z, iface_init_outside) < 0.0) {
-      if (rk_normal_velocity_func(s, iface_init_outside, dzdtau) < 0.0) {
+      if (rk_normal_velocity_func(s, iface_init_outside, dzdtau, z) < 0.0) {
         for (int i = 1; i <= 3; i++) {
           int j = ((iface_init_outside + i - 1) % 4) + 1;
           if (rk_normal_distance_func(s, z, j) < 0.0) turned_tangential = true;
@@ -2652,7 +2683,7 @@ static void last_line_defense(rk_state *s, double z[4], double *tau, int *iface,
           iface_new = 1;
           for (int i = 0; i < 4; i++)
             if (out[i]) { iface_new = i + 1; break; }
-          if (rk_normal_velocity_func(s, iface_new, dzdtau) >= 0.0) {
+          if (rk_normal_velocity_func(s, iface_new, dzdtau, z) >= 0.0) {
             if (iface_init_outside != iface_new) {
               dtau = -0.5 * fabs(dtau);
               dtau_decreased = true;
@@ -2671,7 +2702,7 @@ static void last_line_defense(rk_state *s, double z[4], double *tau, int *iface,
             for (int i = 0; i < 4; i++) {
               if (!out[i]) continue;
               if (fabs(nd[i]) >= s->dist_min) continue;
-              if (rk_normal_velocity_func(s, i + 1, dzdtau) > 0.0) j++;
+              if (rk_normal_velocity_func(s, i + 1, dzdtau, z) > 0.0) j++;
             }
             if (j > 0) {
               dtau = 2.0 * fabs(dtau);
@@ -2707,7 +2738,7 @@ static void last_line_defense(rk_state *s, double z[4], double *tau, int *iface,
         int j = ((iface_new + i - 1) % 4) + 1;
         if (rk_normal_distance_func(s, z, j) < 0.0) newton_ok = false;
       }
-      if ((!newton_ok) || (rk_normal_velocity_func(s, iface_new, dzdtau) >= 0.0)) {
+      if ((!newton_ok) || (rk_normal_velocity_func(s, iface_new, dzdtau, z) >= 0.0)) {
         memcpy(z, z_save, sizeof(z_save));
         *tau = tau_save;
         dtau = dtau_save;
@@ -2746,7 +2777,7 @@ static bool rk_final_processing(rk_state *s, double z[4], double *tau, int *ifac
         int k = ((iface_new + j - 1) % 4) + 1;
         if (rk_normal_distance_func(s, z, k) < 0.0) return false;
       }
-      if (rk_normal_velocity_func(s, iface_new, dzdtau) > 0.0) return false;
+      if (rk_normal_velocity_func(s, iface_new, dzdtau, z) > 0.0) return false;
       for (int i = 0; i < 3; i++) x[i] = z[i] + s->r[TP_X1 + i];
       *t_pass = *tau * s->dt_dtau_const;
       if (fabs(*t_pass) <= fabs(s->t_remain)) {
@@ -2777,7 +2808,7 @@ static bool rk_final_processing(rk_state *s, double z[4], double *tau, int *ifac
       *t_pass = *tau * s->dt_dtau_const;
       *boole_t_finished = true;
       *vpar = z[3];
-      if (rk_normal_velocity_func(s, iface_new, dzdtau) < 0.0) {
+      if (rk_normal_velocity_func(s, iface_new, dzdtau, z) < 0.0) {
         *iface_inout = iface_new;
         handover2neighbour(m, s->ind_tetr, ind_tetr_out, iface_inout, x, iper_phi);
       } else {
@@ -2803,7 +2834,7 @@ static bool rk_final_processing(rk_state *s, double z[4], double *tau, int *ifac
             if (!bis_ok) return false;
           }
         }
-        if (rk_normal_velocity_func(s, iface_new, dzdtau) > 0.0) {
+        if (rk_normal_velocity_func(s, iface_new, dzdtau, z) > 0.0) {
           memcpy(z, z_save, sizeof(z_save));
           *tau = tau_save;
           bisection_face_convergence(s, z, tau, *tau, &iface_new, dzdtau, &bis_ok);
@@ -2921,7 +2952,7 @@ static void pusher_tetra_rk(rk_state *s, int *ind_tetr_inout, int *iface, double
       }
     }
     if (cycled) continue;
-    if (rk_normal_velocity_func(s, iface_new, dzdtau) > 0.0) {
+    if (rk_normal_velocity_func(s, iface_new, dzdtau, z) > 0.0) {
       s->fb |= 8;
       allowed_faces[iface_new - 1] = false;
       if (!allowed_faces[0] && !allowed_faces[1] && !allowed_faces[2] && !allowed_faces[3]) { RK_LLOD_CYCLE(); continue; }
@@ -3072,7 +3103,7 @@ void gor_find_tetra(const gor_mesh *m, double x[3], double vpar, double vperp, i
           int counter_vnorm_pos = 0;
           for (int l = 1; l <= 4; l++) {
             if (!conv_t[l - 1]) continue;
-            if (rk_normal_velocity_func(&rk, l, dzdtau) > 0.0) counter_vnorm_pos++;
+            if (rk_normal_velocity_func(&rk, l, dzdtau, z) > 0.0) counter_vnorm_pos++;
           }
           if (counter_vnorm_pos == n_plane_conv) {
             *iface = iface_new;
@@ -3082,7 +3113,7 @@ void gor_find_tetra(const gor_mesh *m, double x[3], double vpar, double vperp, i
             double x_save[3] = {x[0], x[1], x[2]};
             for (int l = 1; l <= 4; l++) {
               if (!conv_t[l - 1]) continue;
-              if (rk_normal_velocity_func(&rk, l, dzdtau) > 0.0) continue;
+              if (rk_normal_velocity_func(&rk, l, dzdtau, z) > 0.0) continue;
               iface_new = l;
               int out;
               handover2neighbour(m, ind_tetr_save, &out, &iface_new, x, &iper_phi);

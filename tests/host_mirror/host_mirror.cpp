@@ -136,7 +136,8 @@ extern "C" {
 
 void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, int boole_periodic_relocation, int ipusher,
                 int boole_strong_electric_field, int i_time_tracing_option, int oq_mask, int boole_adaptive_time_steps,
-                double desired_delta_energy, int max_n_intermediate_steps, int handover_processing_kind, int i_precomp)
+                double desired_delta_energy, int max_n_intermediate_steps, int handover_processing_kind, int i_precomp,
+                int boole_newton_precalc)
 {
   HostMirror *h = new HostMirror();
   bool has_phi = false;
@@ -158,10 +159,11 @@ void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, in
   }
   m.desired_delta_energy = desired_delta_energy;
   m.max_n_intermediate_steps = max_n_intermediate_steps;
-  if (ipusher == 2 && i_precomp != 0) {
+  if ((ipusher == 2 && i_precomp != 0) || (ipusher == 1 && boole_newton_precalc)) {
     make_precomp_poly4(md, h->poly4);
     m.poly4 = h->poly4.data();
-    m.i_precomp = i_precomp;
+    m.i_precomp = ipusher == 2 ? i_precomp : 0;
+    m.newton_precalc = ipusher == 1 ? 1 : 0;
   }
   if (build_find_bins(md, h->bins)) {
     m.bin_start = h->bins.start.data(); m.bin_items = h->bins.items.data();
@@ -245,7 +247,7 @@ int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *v
         switch (h->poly_order) { case 1: HM_RUNT(1, 0); break; case 2: HM_RUNT(2, 0); break; case 3: HM_RUNT(3, 0); break; default: HM_RUNT(4, 0); }
       }
     } else
-    if (h->ipusher == 1 && m.skew) {
+    if (h->ipusher == 1 && (m.skew || m.newton_precalc)) {
       if (m.se) HM_RUNX(0, 2); else if (m.phi) HM_RUNX(0, 1); else HM_RUNX(0, 0);
     } else
     if (h->ipusher == 2 && ((optq && h->oq_mask) || m.skew)) {

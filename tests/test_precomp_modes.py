@@ -131,3 +131,56 @@ def test_cuda_precomp_bit_exact(small_mesh, small_mesh_phi, cuda_device, K, ip):
                 assert fa[:2] == c.n_fallback[:2] and fa[3] == c.n_fallback[3] and fa[2] >= c.n_fallback[2]
                 assert c.n_pushes == int(npu.sum())
             g.close()
+
+
+# ---- boole_newton_precalc: the RK pusher takes normal velocity / acceleration and the quadratic start guess from the
+# tetra_physics_poly4 records (SRC/pusher_tetra_rk.f90:579-632, 2451-2527)
+def _rk_pair(run_b, mesh, st, n, seed, t_step, cap, nsteps=2, **pk):
+    om = OracleMesh(mesh, st)
+    xa, va, wa = workloads.particles_cyl(n, seed, **pk)
+    xb, vb, wb = xa.copy(), va.copy(), wa.copy()
+    sa, sb = workloads.fresh_state(n), workloads.fresh_state(n)
+    for _ in range(nsteps):
+        ra = om.orbit_timestep_trace(xa, va, wa, t_step, *sa, cap)
+        tt, tf, npu, tro, fb = run_b(xb, vb, wb, t_step, sb, cap)
+        assert same(ra["trace_tetr"], tt) and same(ra["trace_face"], tf)
+        assert same(xa, xb) and same(va, vb) and same(wa, wb) and same(ra["t_remain"], tro)
+        assert same(sa[1], sb[1]) and same(sa[2], sb[2]) and same(ra["n_pushes"], npu)
+        assert tuple(int(v) for v in ra["fallback"]) == tuple(int(v) for v in fb)
+    return xa, va, sa[1]
+
+
+def test_newton_precalc_host_mirror_bit_exact_and_consistent(small_mesh, small_mesh_phi, oracle_lib, host_mirror_lib):
+    for mesh, _, settings in (small_mesh, small_mesh_phi):
+        res = {}
+        for pre in (False, True):
+            st = dataclasses.replace(settings, ipusher=1, boole_newton_precalc=pre)
+            hm = HostMirror(mesh, st)
+
+            def run_b(x, v, w, t, s, cap):
+                r = hm.orbit_timestep(x, v, w, t, *s, trace_cap=cap)
+                return r["trace_tetr"], r["trace_face"], r["n_pushes"], r["t_remain"], r["fallback"]
+            for t_step in (1e-5, -7e-6):
+                res[(pre, t_step)] = _rk_pair(run_b, mesh, st, 200, 17, t_step, 64, rmax_frac=0.97)
+        # the analytic normal velocity equals n . dz/dtau for sign_rhs = +1: same orbits to the Newton tolerance
+        (x0, v0, i0), (x1, v1, i1) = res[(False, 1e-5)], res[(True, 1e-5)]
+        ok = (i0 == i1) & (i0 > 0)
+        assert ok.mean() > 0.97 and np.abs(x0[ok] - x1[ok]).max() < 1e-6
+
+
+@pytest.mark.gpu
+def test_newton_precalc_cuda_bit_exact(small_mesh, small_mesh_phi, cuda_device):
+    from gorilla_b200 import Gorilla
+    for mesh, _, settings in (small_mesh, small_mesh_phi):
+        st = dataclasses.replace(settings, ipusher=1, boole_newton_precalc=True)
+        for t_step, force_full in ((2e-5, False), (1e-5, True), (-7e-6, False)):
+            g = Gorilla(mesh, st)
+            g._debug_force_full(force_full)
+
+            def run_b(x, v, w, t, s, cap):
+                n = x.shape[0]
+                tro, npu = np.zeros(n), np.zeros(n, np.int64)
+                tt, tf = g.orbit_timestep_gorilla(x, v, w, t, *s, t_remain_out=tro, n_pushes=npu, trace_cap=cap)
+                return tt, tf, npu, tro, g.counters().n_fallback
+            _rk_pair(run_b, mesh, st, 800, 19, t_step, 96, rmax_frac=0.97)
+            g.close()

@@ -38,7 +38,7 @@ class _Settings(C.Structure):
         "boole_newton_precalc", "poly_order", "i_precomp", "boole_guess", "i_time_tracing_option",
         "handover_processing_kind", "boole_adaptive_time_steps", "boole_strong_electric_field",
         "boole_grid_for_find_tetra", "boole_time_Hamiltonian", "boole_gyrophase", "boole_vpar_int",
-        "boole_vpar2_int", "max_n_intermediate_steps")] + [("desired_delta_energy", C.c_double)]
+        "boole_vpar2_int", "max_n_intermediate_steps")] + [("desired_delta_energy", C.c_double), ("rel_err_ode45", C.c_double)]
 
 
 class _MeshDesc(C.Structure):

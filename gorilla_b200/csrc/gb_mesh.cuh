@@ -72,6 +72,8 @@ struct MeshDev {
   const double *poly4;
   int32_t i_precomp;
   int32_t newton_precalc;   // RK pusher: normal velocity / acceleration / quadratic start guess from poly4 (EXT = 2 kernels)
+  int32_t ode45, pad_ode45; // RK pusher: boole_pusher_ode45 (EXT = 2 kernels)
+  double rel_err_ode45;
   const double *ham;  // hamiltonian_time records (EXT kernels only): h1_in_curlA h1_in_curlh vec_mismatch_der(3) vec_parcurr_der(3)
   int32_t prefetch;    // 1: once the exit face of a push is known, prefetch the neighbour's records into the L2 (pays when
                        // the records a batch touches do not fit the L2; costs 12-20 % when they do -- host decides)

@@ -38,12 +38,204 @@ GB_HD void bm_vec_rk(double *o, const PP &P, const double *z)
   o[3] = P.b[3] + P.A.s * z[3];
 }
 
+// ---- boole_pusher_ode45 (EXT = 2 kernels of the RK pusher): r8_fehl / r8_rkf45 (SRC/contrib/rkf45.f90:776-923, 925-1578) for the four
+// equations dz/dtau = b + a z + Bvec v_par, and odeint_allroutines (SRC/odeint_rkf45.f90).  Only the paths reachable from
+// odeint_allroutines are restated (first call with flag = 1, continuation with flag = 2 after a return of 6 or 7).
+// x**0.2 is pow() of the platform's libm: the CUDA one on the device, which is not glibc's to the last bit -- the one
+// place where this mode can leave the oracle's rounding (parity of this mode is asserted at 1e-10, not bit for bit).
+struct Rkf45 {
+  double abserr_save, h, relerr_save, f1[4], f2[4], f3[4], f4[4], f5[4];
+  int flag_save, init, kflag, kop, nfe;
+};
+// the linear right-hand side of one tetrahedron, by value: b, A = (amat | Bvec | spamat)
+struct OdeLin {
+double b[4];
+BlockMat A;
+};
+GB_HD void ode_rhs(const OdeLin &L, const double *z, double *dz) { bm_vec_rk(dz, L, z); }
+GB_HD void rkf45_fehl(const OdeLin &L, const double *y, double h, const double *yp, Rkf45 &q)
+{
+  double ch = h / 4.0, t1[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) q.f5[i] = y[i] + ch * yp[i];
+  ode_rhs(L, q.f5, q.f1);
+  ch = 3.0 * h / 32.0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) q.f5[i] = y[i] + ch * (yp[i] + 3.0 * q.f1[i]);
+  ode_rhs(L, q.f5, q.f2);
+  ch = h / 2197.0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) q.f5[i] = y[i] + ch * (1932.0 * yp[i] + (7296.0 * q.f2[i] - 7200.0 * q.f1[i]));
+  ode_rhs(L, q.f5, q.f3);
+  ch = h / 4104.0;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    q.f5[i] = y[i] + ch * ((8341.0 * yp[i] - 845.0 * q.f3[i]) + (29440.0 * q.f2[i] - 32832.0 * q.f1[i]));
+  ode_rhs(L, q.f5, q.f4);
+  ch = h / 20520.0;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    t1[i] = y[i] + ch * ((-6080.0 * yp[i] + (9295.0 * q.f3[i] - 5643.0 * q.f4[i])) + (41040.0 * q.f1[i] - 28352.0 * q.f2[i]));
+#pragma unroll
+  for (int i = 0; i < 4; i++) q.f1[i] = t1[i];
+  ode_rhs(L, q.f1, q.f5);
+  ch = h / 7618050.0;
+#pragma unroll
+  for (int i = 0; i < 4; i++)   // the solution estimate goes to f1 (the caller passes f1 as s)
+    q.f1[i] = y[i] + ch * ((902880.0 * yp[i] + (3855735.0 * q.f3[i] - 1371249.0 * q.f4[i])) +
+                           (3953664.0 * q.f2[i] + 277020.0 * q.f5[i]));
+}
+GB_HD int rkf45_run(const OdeLin &L, Rkf45 &q, double *y, double *yp, double &t, double tout, double &relerr, double abserr, int flag)
+{
+  const double remin = 1.0e-12, eps = DBL_EPSILON;
+  const int maxnfe = 3000;
+  if (relerr < 0.0 || abserr < 0.0) return 8;
+  if (flag == 0 || 8 < flag || flag < -2) return 8;
+  int mflag = flag < 0 ? -flag : flag;
+  if (mflag != 1) {
+    if (t == tout && q.kflag != 3) return 8;
+    if (mflag == 2) {
+      if (q.kflag == 3) { flag = q.flag_save; mflag = flag < 0 ? -flag : flag; }
+      else if (q.init == 0) flag = q.flag_save;
+      else if (q.kflag == 4) q.nfe = 0;
+      else if (q.kflag == 5 && abserr == 0.0) return 8;
+      else if (q.kflag == 6 && relerr <= q.relerr_save && abserr <= q.abserr_save) return 8;
+    } else {
+      return 8;
+    }
+  }
+  q.flag_save = flag;
+  q.kflag = 0;
+  q.relerr_save = relerr;
+  q.abserr_save = abserr;
+  const double relerr_min = 2.0 * DBL_EPSILON + remin;
+  if (relerr < relerr_min) {
+    relerr = relerr_min;
+    q.kflag = 3;
+    return 3;
+  }
+  double dt = tout - t;
+  if (mflag == 1) {
+    q.init = 0;
+    q.kop = 0;
+    ode_rhs(L, y, yp);
+    q.nfe = 1;
+    if (t == tout) return 2;
+  }
+  if (q.init == 0) {
+    q.init = 1;
+    q.h = fabs(dt);
+    double toln = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const double tol = relerr * fabs(y[k]) + abserr;
+      if (0.0 < tol) {
+        toln = tol;
+        const double ypk = fabs(yp[k]);
+        const double h2 = q.h * q.h;
+        if (tol < ypk * (q.h * (h2 * h2))) q.h = pow(tol / ypk, 0.2);
+      }
+    }
+    if (toln <= 0.0) q.h = 0.0;
+    q.h = fmax(q.h, 26.0 * eps * fmax(fabs(t), fabs(dt)));
+    q.flag_save = flag < 0 ? -2 : 2;
+  }
+  q.h = copysign(q.h, dt);
+  if (2.0 * fabs(dt) <= fabs(q.h)) q.kop = q.kop + 1;
+  if (q.kop == 10000) {
+    q.kop = 0;
+    return 7;
+  }
+  if (fabs(dt) <= 26.0 * eps * fabs(t)) {
+    t = tout;
+#pragma unroll
+    for (int i = 0; i < 4; i++) y[i] = y[i] + dt * yp[i];
+    ode_rhs(L, y, yp);
+    q.nfe = q.nfe + 1;
+    return 2;
+  }
+  bool output = false;
+  const double scale = 2.0 / relerr, ae = scale * abserr;
+  for (;;) {
+    bool hfaild = false;
+    const double hmin = 26.0 * eps * fabs(t);
+    dt = tout - t;
+    if (!(2.0 * fabs(q.h) <= fabs(dt))) {
+      if (fabs(dt) <= fabs(q.h)) { output = true; q.h = dt; }
+      else q.h = 0.5 * dt;
+    }
+    double esttol;
+    for (;;) {
+      if (maxnfe < q.nfe) { q.kflag = 4; return 4; }
+      rkf45_fehl(L, y, q.h, yp, q);
+      q.nfe = q.nfe + 5;
+      double eeoet = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const double et = fabs(y[k]) + fabs(q.f1[k]) + ae;
+        if (et <= 0.0) return 5;
+        const double ee = fabs((-2090.0 * yp[k] + (21970.0 * q.f3[k] - 15048.0 * q.f4[k])) +
+                               (22528.0 * q.f2[k] - 27360.0 * q.f5[k]));
+        eeoet = fmax(eeoet, ee / et);
+      }
+      esttol = fabs(q.h) * eeoet * scale / 752400.0;
+      if (esttol <= 1.0) break;
+      hfaild = true;
+      output = false;
+      double sf;
+      if (esttol < 59049.0) sf = 0.9 / pow(esttol, 0.2);
+      else sf = 0.1;
+      q.h = sf * q.h;
+      if (fabs(q.h) < hmin) { q.kflag = 6; return 6; }
+    }
+    t = t + q.h;
+#pragma unroll
+    for (int i = 0; i < 4; i++) y[i] = q.f1[i];
+    ode_rhs(L, y, yp);
+    q.nfe = q.nfe + 1;
+    double sf;
+    if (0.0001889568 < esttol) sf = 0.9 / pow(esttol, 0.2);
+    else sf = 5.0;
+    if (hfaild) sf = fmin(sf, 1.0);
+    q.h = copysign(fmax(sf * fabs(q.h), hmin), q.h);
+    if (output) {
+      t = tout;
+      return 2;
+    }
+    if (flag <= 0) break;
+  }
+  return -2;
+}
+struct Vec4 {
+double v[4];
+};
+// odeint_allroutines(y, 4, 0, x2, eps, rhs) (SRC/odeint_rkf45.f90).  One shared, non-inlined instance: the RK pusher calls
+// it from more than a dozen integration_step sites.
+static GB_HD_NOINLINE Vec4 odeint_rkf45(OdeLin L, Vec4 y0, double x2, double eps_rel)
+{
+Rkf45 q;
+q.abserr_save = q.h = q.relerr_save = 0.0;
+q.flag_save = q.init = q.kflag = q.kop = q.nfe = 0;
+double yp[4], epsrel = eps_rel, epsabs = 1e-31, x1in = 0.0;
+double *y = y0.v;
+int flag = rkf45_run(L, q, y, yp, x1in, x2, epsrel, epsabs, 1);
+if (flag == 6) {
+  epsrel = 10 * epsrel;
+  epsabs = 10 * epsabs;
+  rkf45_run(L, q, y, yp, x1in, x2, epsrel, epsabs, 2);
+} else if (flag == 7) {
+  rkf45_run(L, q, y, yp, x1in, x2, epsrel, epsabs, 2);
+}
+return y0;
+}
+
 // EXT = 2: hand-over via Cartesian skew coordinates when the mesh carries them (handover_processing_kind = 2)
 template <int PHI, int EXT = 0>
 struct RkPusher {
   PolyPusher<1, PHI, EXT> P;  // record, z_init, sign_rhs, dt_dtau_const, b, A (= amat | Bvec | spamat)
   double dist_min, dist_max, dtau_ref, dtau_max, dtau_quad, t_remain;
   int iface_init, sign_t_step, fallback;
+  bool acc;   // boole_accuracy_ode45 of the routine that is running (EXT = 2 kernels; = boole_pusher_ode45 except in the Newton wrapper)
 
   GB_HD void init(const MeshDev *mp, double perpinv, int ind_tetr, const double *x, int iface, double vpar, double t_remain_in)
   {
@@ -61,6 +253,7 @@ struct RkPusher {
     dtau_max = 10.0 * dtau_ref;
     dtau_quad = 1.5 * dtau_ref;
     fallback = 0;
+    acc = (EXT == 2) && (mp->ode45 != 0);   // :261
   }
 
   GB_HD void distances(const double *z, double *d) const { P.normal_distances(z, d); }
@@ -131,6 +324,24 @@ struct RkPusher {
     for (int i = 0; i < 4; i++) {
       y[i] = y[i] + h6 * (dydx[i] + dyt[i] + 2.0 * dym[i]);
       dzdtau[i] = dyt[i];
+    }
+  }
+
+  // integration_step (:2549-2581)
+  GB_HD void integration_step(double *z, double dtau, double *dzdtau) const
+  {
+    if (EXT == 2 && acc) {
+      OdeLin L;
+      Vec4 y;
+#pragma unroll
+      for (int i = 0; i < 4; i++) { L.b[i] = P.b[i]; y.v[i] = z[i]; }
+      L.A = P.A;
+      y = odeint_rkf45(L, y, dtau, P.mp->rel_err_ode45);
+#pragma unroll
+      for (int i = 0; i < 4; i++) z[i] = y.v[i];
+      rk4_step(z, 0.0, dzdtau);
+    } else {
+      rk4_step(z, dtau, dzdtau);
     }
   }
 
@@ -216,7 +427,7 @@ struct RkPusher {
       if (fabs(dtau) > dtau_max) {
         start_quadratic = true;
       } else {
-        rk4_step(z, dtau, dzdtau);
+        integration_step(z, dtau, dzdtau);
         dist_new = distance(z, iface);
       }
       if ((fabs(dist_new) >= fabs(dist)) || start_quadratic) {
@@ -243,7 +454,7 @@ struct RkPusher {
             tau = tau_start;
             return false;
           }
-          rk4_step(z, dtau, dzdtau);
+          integration_step(z, dtau, dzdtau);
           tau = tau + dtau;
           dist = distance(z, iface);
         } else {
@@ -270,11 +481,22 @@ struct RkPusher {
     const double tau_save = tau;
 #pragma unroll
     for (int i = 0; i < 4; i++) { z_save[i] = z[i]; dz_save[i] = dzdtau[i]; }
-    const bool ok = newton_wrapped(z, tau, iface, dzdtau, start_quadratic);
+    const bool acc_in = acc;   // boole_accuracy_ode45_in
+    acc = false;               // Newton with the RK4 method first (:938-941)
+    bool ok = newton_wrapped(z, tau, iface, dzdtau, start_quadratic);
+    acc = acc_in;
     if (!ok) {
 #pragma unroll
       for (int i = 0; i < 4; i++) { z[i] = z_save[i]; dzdtau[i] = dz_save[i]; }
       tau = tau_save;
+      return false;
+    }
+    if (EXT == 2 && acc_in) {   // repeat the RK4-Newton step with ODE45, then converge with the ODE45-Newton (:950-979)
+#pragma unroll
+      for (int i = 0; i < 4; i++) z[i] = z_save[i];
+      const double dtau = tau - tau_save;
+      integration_step(z, dtau, dzdtau);
+      ok = newton_wrapped(z, tau, iface, dzdtau, false);
     }
     return ok;
   }
@@ -292,7 +514,7 @@ struct RkPusher {
     tau_out = 0.0;
     if (nd[0] > 0.0 && nd[1] > 0.0 && nd[2] > 0.0 && nd[3] > 0.0) { last_inside = 1; take_next = true; }
     for (int i = 2; i <= n_steps; i++) {
-      rk4_step(zr, dtau, dz);
+      integration_step(zr, dtau, dz);
       tau_run = tau_run + dtau;
       distances(zr, nd);
       if (take_next) {
@@ -331,16 +553,16 @@ struct RkPusher {
             tau = 0.0;
 #pragma unroll
             for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
-            rk4_step(z, dtau, dzdtau);
+            integration_step(z, dtau, dzdtau);
             tau = tau + dtau;
             dtau = dtau_save;
           } else {
-            rk4_step(z, dtau, dzdtau);
+            integration_step(z, dtau, dzdtau);
             tau = tau + dtau;
           }
         } else if (mn > dist_min) {
           dtau = +fabs(dtau / 2.0);
-          rk4_step(z, dtau, dzdtau);
+          integration_step(z, dtau, dzdtau);
           tau = tau + dtau;
         }
         distances(z, nd);
@@ -348,7 +570,7 @@ struct RkPusher {
         if (fabs(sel4(nd, im)) < dist_min) {
           if (nvel(im, dzdtau, z) > 0.0) {
             dtau = +fabs(dtau / 2.0);
-            rk4_step(z, dtau, dzdtau);
+            integration_step(z, dtau, dzdtau);
             tau = tau + dtau;
           } else {
             int j = 0;
@@ -360,7 +582,7 @@ struct RkPusher {
               converged = true;
             } else {
               dtau = -fabs(dtau / 2.0);
-              rk4_step(z, dtau, dzdtau);
+              integration_step(z, dtau, dzdtau);
               tau = tau + dtau;
             }
           }
@@ -406,28 +628,38 @@ struct RkPusher {
     if (iface_init != 0)
       if (distance(z, iface_init) < 0.0) iface_init_outside = iface_init;
     if (quad_analytic_approx(z, 0xFu, iface_new, dtau)) {
-      rk4_step(z, dtau, dzdtau);
+      integration_step(z, dtau, dzdtau);
       tau = tau + dtau;
     } else {
       dtau = dtau_ref;
-      rk4_step(z, dtau, dzdtau);
+      integration_step(z, dtau, dzdtau);
       tau = tau + dtau;
       distances(z, nd);
       iface_new = minloc4(nd);
     }
     k = 0;
+    bool distance_bisection = false;
     for (;;) {
       k++;
       distances(z, nd);
       if (any_gt(nd, dist_max)) {
+        distance_bisection = true;
         dtau = tau - 0.5 * fabs(dtau);
         tau = 0.0;
 #pragma unroll
         for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
-        rk4_step(z, dtau, dzdtau);
+        rk4_step(z, dtau, dzdtau);   // integration_step(..., .false.): "Set accuracy to FALSE, always!" (:1798)
         tau = tau + dtau;
       } else {
-        break;
+        if (EXT == 2 && distance_bisection && acc) {   // :1802-1808
+#pragma unroll
+          for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
+          dtau = tau;
+          integration_step(z, dtau, dzdtau);
+          distance_bisection = false;
+        } else {
+          break;
+        }
       }
       if (k > GB_RK_KITER) return false;
     }
@@ -505,7 +737,7 @@ struct RkPusher {
 #pragma unroll
             for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
           }
-          rk4_step(z, dtau, dzdtau);
+          integration_step(z, dtau, dzdtau);
           tau = tau + dtau;
           if (k > GB_RK_KITER) return false;
         }
@@ -564,7 +796,7 @@ struct RkPusher {
     tau = 0.0;
     const double dtau = t_remain / P.dt_dtau_const;
     distances(z, nd_save);
-    rk4_step(z, dtau, dzdtau);
+    integration_step(z, dtau, dzdtau);
     if (any_gt(nd_save, dist_max)) {
       if (FAST) return 2;
 #pragma unroll
@@ -680,12 +912,12 @@ struct RkPusher {
     if (quad_analytic_approx(z, allowed, iface_new, dtau)) {
       if (FAST && P.mp->prefetch) prefetch_record<PHI>(*P.mp, P.r.nb(iface_new - 1));   // quadratic guess of the exit face
       if (FAST) P.r.prefetch_next(*P.mp, P.r.nb(iface_new - 1));
-      rk4_step(z, dtau, dzdtau);
+      integration_step(z, dtau, dzdtau);
       tau = tau + dtau;
     } else {
       if (FAST) return false;
       dtau = dtau_ref;
-      rk4_step(z, dtau, dzdtau);
+      rk4_step(z, dtau, dzdtau);   // a plain rk4_step in the reference (:315)
       tau = tau + dtau;
       distances(z, nd);
       double ad[4] = {fabs(nd[0]), fabs(nd[1]), fabs(nd[2]), fabs(nd[3])};
@@ -766,7 +998,7 @@ struct RkPusher {
               for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
             }
           }
-          rk4_step(z, dtau, dzdtau);
+          integration_step(z, dtau, dzdtau);
           tau = tau + dtau;
           converged = false;
           continue;

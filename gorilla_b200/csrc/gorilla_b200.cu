@@ -184,7 +184,8 @@ static int check_settings(const gorilla_settings *s)
   // gorilla_settings_mod.f90:139-144 (coord_system is checked against the mesh in gorilla_b200_init)
   if (s->boole_strong_electric_field && (s->i_precomp != 0 || s->boole_newton_precalc))
     return fail(GORILLA_ERR_ARG, "boole_strong_electric_field requires i_precomp = 0 and boole_newton_precalc = .false.");
-  if (s->boole_pusher_ode45) return fail(GORILLA_ERR_UNSUPPORTED, "boole_pusher_ode45 must be .false.");
+  if (s->boole_pusher_ode45 && s->ipusher == 1 && !(s->rel_err_ode45 >= 0.0))
+    return fail(GORILLA_ERR_ARG, "rel_err_ode45 must be >= 0");
   return GORILLA_OK;
 }
 
@@ -308,6 +309,9 @@ extern "C" int gorilla_b200_init(const gorilla_mesh_desc *md, const gorilla_sett
   m.rec44 = nullptr;   // made by gorilla_b200_set_gather
   m.i_precomp = (st->ipusher == 2) ? st->i_precomp : 0;
   m.newton_precalc = (st->ipusher == 1 && st->boole_newton_precalc) ? 1 : 0;
+  m.ode45 = (st->ipusher == 1 && st->boole_pusher_ode45) ? 1 : 0;
+  m.pad_ode45 = 0;
+  m.rel_err_ode45 = st->rel_err_ode45;
   m.time_tracing = st->i_time_tracing_option;
   m.desired_delta_energy = st->desired_delta_energy;
   m.max_n_intermediate_steps = st->max_n_intermediate_steps;
@@ -492,7 +496,8 @@ static int launch_orbit_k(gorilla_b200_handle *h, const Batch &bt, cudaStream_t 
 {
   // RK4: the kernel with the run-time options carries hand-over kind 2 and boole_newton_precalc
   if (h->settings.ipusher == 1)
-    return (h->mesh.skew || h->mesh.newton_precalc) ? launch_orbit_t<0, PHI, 2>(h, bt, s) : launch_orbit_t<0, PHI>(h, bt, s);
+    return (h->mesh.skew || h->mesh.newton_precalc || h->mesh.ode45) ? launch_orbit_t<0, PHI, 2>(h, bt, s)
+                                                                      : launch_orbit_t<0, PHI>(h, bt, s);
   if (((bt.optq && bt.oq_mask) || bt.ev_flags) && h->settings.boole_adaptive_time_steps)
     return fail(GORILLA_ERR_UNSUPPORTED, "boole_adaptive_time_steps is not combined with optional quantities / events");
   if ((bt.optq && bt.oq_mask) || bt.ev_flags || h->mesh.skew) {   // handover kind 2 lives in the EXT = 2 kernels

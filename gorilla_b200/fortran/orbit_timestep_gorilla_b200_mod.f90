@@ -38,7 +38,7 @@ module orbit_timestep_gorilla_b200_mod
                           boole_strong_electric_field, boole_grid_for_find_tetra, &
                           boole_time_Hamiltonian, boole_gyrophase, boole_vpar_int, boole_vpar2_int, &
                           max_n_intermediate_steps
-    real(c_double)  :: desired_delta_energy
+    real(c_double)  :: desired_delta_energy, rel_err_ode45
   end type
   !> struct gorilla_mesh_desc
   type, bind(C) :: gorilla_mesh_desc_t
@@ -214,6 +214,7 @@ contains
     st%boole_strong_electric_field = merge(1, 0, boole_strong_electric_field)
     st%boole_grid_for_find_tetra = merge(1, 0, boole_grid_for_find_tetra)
     st%max_n_intermediate_steps = max_n_intermediate_steps; st%desired_delta_energy = desired_delta_energy
+    st%rel_err_ode45 = rel_err_ode45
     st%boole_time_Hamiltonian = merge(1, 0, boole_time_Hamiltonian); st%boole_gyrophase = merge(1, 0, boole_gyrophase)
     st%boole_vpar_int = merge(1, 0, boole_vpar_int); st%boole_vpar2_int = merge(1, 0, boole_vpar2_int)
     rc = gorilla_b200_init(md, st, handle)

@@ -19,6 +19,7 @@ class GorillaSettings:
     boole_periodic_relocation: bool = True
     ipusher: int = 2
     boole_pusher_ode45: bool = False
+    rel_err_ode45: float = 1.0e-8              # INPUT/gorilla.inp:36
     boole_dt_dtau: bool = True
     boole_newton_precalc: bool = False
     poly_order: int = 2

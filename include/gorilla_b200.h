@@ -45,7 +45,8 @@ typedef struct gorilla_settings {
   int32_t ispecies;                  /* 1 e-, 2 D+, 3 alpha, 4 W74+ (orbit_timestep_gorilla.f90:204-249) */
   int32_t boole_periodic_relocation;
   int32_t ipusher;                   /* 1 RK4 | 2 polynomial */
-  int32_t boole_pusher_ode45;        /* must be 0 */
+  int32_t boole_pusher_ode45;        /* ipusher = 1: every integration step with the adaptive RKF45 integrator (rel_err_ode45)
+                                        instead of one RK4 step (pusher_tetra_rk.f90:2549-2581, contrib/rkf45.f90) */
   int32_t boole_dt_dtau;             /* must be 1 */
   int32_t boole_newton_precalc;      /* ipusher = 1: normal velocity / acceleration and the quadratic start guess from the
                                         tetra_physics_poly4 records (pusher_tetra_rk.f90:579-632, 2487-2527) */
@@ -71,6 +72,7 @@ typedef struct gorilla_settings {
   int32_t boole_vpar2_int;
   int32_t max_n_intermediate_steps;  /* adaptive scheme: >= 2 (INPUT/gorilla.inp:151) */
   double desired_delta_energy;       /* adaptive scheme: > 0, relative energy error per tetrahedron (gorilla.inp:147) */
+  double rel_err_ode45;              /* boole_pusher_ode45: relative error of the RKF45 integrator (gorilla.inp:43, 1e-8) */
 } gorilla_settings;
 
 /* Everything initialize_gorilla() (orbit_timestep_gorilla.f90:151-274) leaves in module variables that

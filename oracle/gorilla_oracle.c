@@ -2156,6 +2156,7 @@ typedef struct {
   double Bvec[3], b[4], z_init[4], amat[3][3], anorm[4][3]; /* anorm[f][i] = anorm(i+1,f+1) */
   double dtau_ref, dtau_max, dtau_quad;
   int fb; /* per-push fall-back bits: 1 Newton failed, 2 last line of defence, 4 three-planes switch, 8 v_n>0 / stop outside */
+  bool acc; /* boole_accuracy_ode45 of the routine that is running (= boole_pusher_ode45 except inside the Newton wrapper) */
 } rk_state;
 
 static void initialize_pusher_tetra_rk_mod(rk_state *s, int ind_tetr, const double x[3], int iface,
@@ -2255,6 +2256,186 @@ static void rk4_step(const rk_state *s, double y[4], double h, double dzdtau[4])
   rhs_pusher_tetra_rk4(s, yt, dyt);
   for (int i = 0; i < 4; i++) y[i] = y[i] + h6 * (dydx[i] + dyt[i] + 2.0 * dym[i]);
   for (int i = 0; i < 4; i++) dzdtau[i] = dyt[i];
+}
+/* ------------------------------------------------------------------------------------------------
+ * r8_fehl / r8_rkf45 (SRC/contrib/rkf45.f90:776-923, 925-1578) for neqn = 4 and the right-hand side
+ * rhs_pusher_tetra_rk45 (SRC/pusher_tetra_rk.f90:900-910, the same as the RK4 one), and odeint_allroutines
+ * (SRC/odeint_rkf45.f90).  The routine's SAVEd variables are the struct; x**0.2 is libm pow as gfortran calls it.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  double abserr_save, h, relerr_save, f1[4], f2[4], f3[4], f4[4], f5[4];
+  int flag_save, init, kflag, kop, nfe;
+} rkf45_state;
+static void r8_fehl(const rk_state *s, const double y[4], double h, const double yp[4], double f1[4], double f2[4],
+                    double f3[4], double f4[4], double f5[4], double sout[4])
+{
+  double ch = h / 4.0, t1[4];
+  for (int i = 0; i < 4; i++) f5[i] = y[i] + ch * yp[i];
+  rhs_pusher_tetra_rk4(s, f5, f1);
+  ch = 3.0 * h / 32.0;
+  for (int i = 0; i < 4; i++) f5[i] = y[i] + ch * (yp[i] + 3.0 * f1[i]);
+  rhs_pusher_tetra_rk4(s, f5, f2);
+  ch = h / 2197.0;
+  for (int i = 0; i < 4; i++) f5[i] = y[i] + ch * (1932.0 * yp[i] + (7296.0 * f2[i] - 7200.0 * f1[i]));
+  rhs_pusher_tetra_rk4(s, f5, f3);
+  ch = h / 4104.0;
+  for (int i = 0; i < 4; i++)
+    f5[i] = y[i] + ch * ((8341.0 * yp[i] - 845.0 * f3[i]) + (29440.0 * f2[i] - 32832.0 * f1[i]));
+  rhs_pusher_tetra_rk4(s, f5, f4);
+  ch = h / 20520.0;
+  for (int i = 0; i < 4; i++)
+    t1[i] = y[i] + ch * ((-6080.0 * yp[i] + (9295.0 * f3[i] - 5643.0 * f4[i])) + (41040.0 * f1[i] - 28352.0 * f2[i]));
+  memcpy(f1, t1, sizeof(t1));
+  rhs_pusher_tetra_rk4(s, f1, f5);
+  ch = h / 7618050.0;
+  /* the caller passes f1 as the output array s as well (call r8_fehl(..., f1, f2, f3, f4, f5, f1)) */
+  for (int i = 0; i < 4; i++)
+    sout[i] = y[i] + ch * ((902880.0 * yp[i] + (3855735.0 * f3[i] - 1371249.0 * f4[i])) + (3953664.0 * f2[i] + 277020.0 * f5[i]));
+}
+/* returns the flag; only the branches reachable from odeint_allroutines are restated (flag = 1 first call, flag = 2 after a
+ * return with 6 or 7); a fatal stop of the reference returns 8 */
+static int r8_rkf45(const rk_state *s, rkf45_state *q, double y[4], double yp[4], double *t, double tout, double *relerr,
+                    double abserr, int flag)
+{
+  const double remin = 1.0e-12, eps = DBL_EPSILON;
+  const int maxnfe = 3000;
+  if (*relerr < 0.0 || abserr < 0.0) return 8;
+  if (flag == 0 || 8 < flag || flag < -2) return 8;
+  int mflag = abs(flag);
+  if (mflag != 1) {
+    if (*t == tout && q->kflag != 3) return 8;
+    if (mflag == 2) {
+      if (q->kflag == 3) { flag = q->flag_save; mflag = abs(flag); }
+      else if (q->init == 0) flag = q->flag_save;
+      else if (q->kflag == 4) q->nfe = 0;
+      else if (q->kflag == 5 && abserr == 0.0) return 8;
+      else if (q->kflag == 6 && *relerr <= q->relerr_save && abserr <= q->abserr_save) return 8;
+    } else {
+      return 8;
+    }
+  }
+  q->flag_save = flag;
+  q->kflag = 0;
+  q->relerr_save = *relerr;
+  q->abserr_save = abserr;
+  const double relerr_min = 2.0 * DBL_EPSILON + remin;
+  if (*relerr < relerr_min) {
+    *relerr = relerr_min;
+    q->kflag = 3;
+    return 3;
+  }
+  double dt = tout - *t;
+  if (mflag == 1) {
+    q->init = 0;
+    q->kop = 0;
+    rhs_pusher_tetra_rk4(s, y, yp);
+    q->nfe = 1;
+    if (*t == tout) return 2;
+  }
+  if (q->init == 0) {
+    q->init = 1;
+    q->h = fabs(dt);
+    double toln = 0.0;
+    for (int k = 0; k < 4; k++) {
+      const double tol = *relerr * fabs(y[k]) + abserr;
+      if (0.0 < tol) {
+        toln = tol;
+        const double ypk = fabs(yp[k]);
+        const double h2 = q->h * q->h;
+        if (tol < ypk * (q->h * (h2 * h2))) q->h = pow(tol / ypk, 0.2); /* h**5 = h*((h*h)*(h*h)) (__powidf2) */
+      }
+    }
+    if (toln <= 0.0) q->h = 0.0;
+    q->h = fmax(q->h, 26.0 * eps * fmax(fabs(*t), fabs(dt)));
+    q->flag_save = flag < 0 ? -2 : 2;
+  }
+  q->h = copysign(q->h, dt);
+  if (2.0 * fabs(dt) <= fabs(q->h)) q->kop = q->kop + 1;
+  if (q->kop == 10000) {
+    q->kop = 0;
+    return 7;
+  }
+  if (fabs(dt) <= 26.0 * eps * fabs(*t)) {
+    *t = tout;
+    for (int i = 0; i < 4; i++) y[i] = y[i] + dt * yp[i];
+    rhs_pusher_tetra_rk4(s, y, yp);
+    q->nfe = q->nfe + 1;
+    return 2;
+  }
+  bool output = false;
+  const double scale = 2.0 / *relerr, ae = scale * abserr;
+  for (;;) {
+    bool hfaild = false;
+    const double hmin = 26.0 * eps * fabs(*t);
+    dt = tout - *t;
+    if (!(2.0 * fabs(q->h) <= fabs(dt))) {
+      if (fabs(dt) <= fabs(q->h)) { output = true; q->h = dt; }
+      else q->h = 0.5 * dt;
+    }
+    double esttol;
+    for (;;) {
+      if (maxnfe < q->nfe) { q->kflag = 4; return 4; }
+      r8_fehl(s, y, q->h, yp, q->f1, q->f2, q->f3, q->f4, q->f5, q->f1);
+      q->nfe = q->nfe + 5;
+      double eeoet = 0.0;
+      for (int k = 0; k < 4; k++) {
+        const double et = fabs(y[k]) + fabs(q->f1[k]) + ae;
+        if (et <= 0.0) return 5;
+        const double ee = fabs((-2090.0 * yp[k] + (21970.0 * q->f3[k] - 15048.0 * q->f4[k])) +
+                               (22528.0 * q->f2[k] - 27360.0 * q->f5[k]));
+        eeoet = fmax(eeoet, ee / et);
+      }
+      esttol = fabs(q->h) * eeoet * scale / 752400.0;
+      if (esttol <= 1.0) break;
+      hfaild = true;
+      output = false;
+      double sf;
+      if (esttol < 59049.0) sf = 0.9 / pow(esttol, 0.2);
+      else sf = 0.1;
+      q->h = sf * q->h;
+      if (fabs(q->h) < hmin) { q->kflag = 6; return 6; }
+    }
+    *t = *t + q->h;
+    memcpy(y, q->f1, 4 * sizeof(double));
+    rhs_pusher_tetra_rk4(s, y, yp);
+    q->nfe = q->nfe + 1;
+    double sf;
+    if (0.0001889568 < esttol) sf = 0.9 / pow(esttol, 0.2);
+    else sf = 5.0;
+    if (hfaild) sf = fmin(sf, 1.0);
+    q->h = copysign(fmax(sf * fabs(q->h), hmin), q->h);
+    if (output) {
+      *t = tout;
+      return 2;
+    }
+    if (flag <= 0) break;
+  }
+  return -2;
+}
+/* odeint_allroutines(y, 4, 0, x2, eps, rhs) (SRC/odeint_rkf45.f90) */
+static void odeint_allroutines(const rk_state *s, double y[4], double x2, double eps_rel)
+{
+  rkf45_state q;
+  memset(&q, 0, sizeof(q));
+  double yp[4], epsrel = eps_rel, epsabs = 1e-31, x1in = 0.0;
+  int flag = r8_rkf45(s, &q, y, yp, &x1in, x2, &epsrel, epsabs, 1);
+  if (flag == 6) {
+    epsrel = 10 * epsrel;
+    epsabs = 10 * epsabs;
+    r8_rkf45(s, &q, y, yp, &x1in, x2, &epsrel, epsabs, 2);
+  } else if (flag == 7) {
+    r8_rkf45(s, &q, y, yp, &x1in, x2, &epsrel, epsabs, 2);
+  }
+}
+/* integration_step (:2549-2581): adaptive ODE45 over [0, dtau] followed by a zero-length RK4 step for dz/dtau, or one RK4 step */
+static void integration_step(const rk_state *s, double z[4], double dtau, double dzdtau[4], bool boole_accuracy)
+{
+  if (boole_accuracy) {
+    odeint_allroutines(s, z, dtau, s->m->rel_err_ode45);
+    rk4_step(s, z, 0.0, dzdtau);
+  } else {
+    rk4_step(s, z, dtau, dzdtau);
+  }
 }
 static void rk_normal_distances_func(const rk_state *s, const double z123[3], double out[4])
 {
@@ -2433,7 +2614,7 @@ static void newton_face_convergence_wrapped(rk_state *s, double z[4], double *ta
     if (fabs(dtau) > s->dtau_max) {
       start_quadratic = true;
     } else {
-      rk4_step(s, z, dtau, dzdtau);
+      integration_step(s, z, dtau, dzdtau, s->acc);
       dist_new = rk_normal_distance_func(s, z, iface);
     }
     if ((fabs(dist_new) >= fabs(dist)) || start_quadratic) {
@@ -2459,7 +2640,7 @@ static void newton_face_convergence_wrapped(rk_state *s, double z[4], double *ta
           memcpy(dzdtau, dzdtau_start, sizeof(dzdtau_start));
           return;
         }
-        rk4_step(s, z, dtau, dzdtau);
+        integration_step(s, z, dtau, dzdtau, s->acc);
         *tau = *tau + dtau;
         dist = rk_normal_distance_func(s, z, iface);
       } else {
@@ -2484,13 +2665,23 @@ static void newton_face_convergence(rk_state *s, double z[4], double *tau, int i
                                     bool start_quadratic)
 {
   double z_save[4], dzdtau_save[4], tau_save = *tau;
+  const bool acc_in = s->acc; /* boole_accuracy_ode45_in */
   memcpy(z_save, z, sizeof(z_save));
   memcpy(dzdtau_save, dzdtau, sizeof(dzdtau_save));
+  s->acc = false; /* Newton with the RK4 method first (:938-941) */
   newton_face_convergence_wrapped(s, z, tau, iface, dzdtau, converged, start_quadratic);
+  s->acc = acc_in;
   if (!*converged) {
     memcpy(z, z_save, sizeof(z_save));
     *tau = tau_save;
     memcpy(dzdtau, dzdtau_save, sizeof(dzdtau_save));
+    return;
+  }
+  if (acc_in) { /* repeat the RK4-Newton step with ODE45 and converge with the ODE45-Newton (:950-979) */
+    memcpy(z, z_save, sizeof(z_save));
+    const double dtau = *tau - tau_save;
+    integration_step(s, z, dtau, dzdtau, acc_in);
+    newton_face_convergence_wrapped(s, z, tau, iface, dzdtau, converged, false);
   }
 }
 
@@ -2508,7 +2699,7 @@ static void bisection_search_start(rk_state *s, double tau_in, int n_steps, doub
   *tau_out = 0.0;
   if (nd[0] > 0.0 && nd[1] > 0.0 && nd[2] > 0.0 && nd[3] > 0.0) { last_inside = 1; take_next = true; }
   for (int i = 2; i <= n_steps; i++) {
-    rk4_step(s, z_run, *dtau, dzdtau);
+    integration_step(s, z_run, *dtau, dzdtau, s->acc);
     tau_run = tau_run + *dtau;
     rk_normal_distances_func(s, z_run, nd);
     if (take_next) {
@@ -2544,23 +2735,23 @@ static void bisection_face_convergence(rk_state *s, double z[4], double *tau_ino
           dtau = tau + dtau;
           tau = 0.0;
           memcpy(z, s->z_init, 4 * sizeof(double));
-          rk4_step(s, z, dtau, dzdtau);
+          integration_step(s, z, dtau, dzdtau, s->acc);
           tau = tau + dtau;
           dtau = dtau_save;
         } else {
-          rk4_step(s, z, dtau, dzdtau);
+          integration_step(s, z, dtau, dzdtau, s->acc);
           tau = tau + dtau;
         }
       } else if (mn > s->dist_min) {
         dtau = +fabs(dtau / 2.0);
-        rk4_step(s, z, dtau, dzdtau);
+        integration_step(s, z, dtau, dzdtau, s->acc);
         tau = tau + dtau;
       }
       rk_normal_distances_func(s, z, nd);
       if (fabs(rk_minval(nd)) < s->dist_min) {
         if (rk_normal_velocity_func(s, rk_minloc(nd), dzdtau, z) > 0.0) {
           dtau = +fabs(dtau / 2.0);
-          rk4_step(s, z, dtau, dzdtau);
+          integration_step(s, z, dtau, dzdtau, s->acc);
           tau = tau + dtau;
         } else {
           int j = 0;
@@ -2571,7 +2762,7 @@ static void bisection_face_convergence(rk_state *s, double z[4], double *tau_ino
             *converged = true;
           } else {
             dtau = -fabs(dtau / 2.0);
-            rk4_step(s, z, dtau, dzdtau);
+            integration_step(s, z, dtau, dzdtau, s->acc);
             tau = tau + dtau;
           }
         }
@@ -2617,11 +2808,11 @@ static void last_line_defense(rk_state *s, double z[4], double *tau, int *iface,
     if (rk_normal_distance_func(s, z, s->iface_init) < 0.0) iface_init_outside = s->iface_init;
   quad_analytic_approx(s, z, allowed_faces, &iface_new, &dtau, &quad_ok);
   if (quad_ok) {
-    rk4_step(s, z, dtau, dzdtau);
+    integration_step(s, z, dtau, dzdtau, s->acc);
     *tau = *tau + dtau;
   } else {
     dtau = s->dtau_ref;
-    rk4_step(s, z, dtau, dzdtau);
+    integration_step(s, z, dtau, dzdtau, s->acc);
     *tau = *tau + dtau;
     rk_normal_distances_func(s, z, nd);
     iface_new = rk_minloc(nd);
@@ -2635,10 +2826,17 @@ static void last_line_defense(rk_state *s, double z[4], double *tau, int *iface,
       dtau = *tau - 0.5 * fabs(dtau);
       *tau = 0.0;
       memcpy(z, s->z_init, 4 * sizeof(double));
-      rk4_step(s, z, dtau, dzdtau);
+      rk4_step(s, z, dtau, dzdtau); /* integration_step(..., .false.): "Set accuracy to FALSE, always!" (:1798) */
       *tau = *tau + dtau;
     } else {
-      break; /* RK4 accuracy: both inner branches exit */
+      if (distance_bisection && s->acc) { /* :1802-1808 */
+        memcpy(z, s->z_init, 4 * sizeof(double));
+        dtau = *tau;
+        integration_step(s, z, dtau, dzdtau, s->acc);
+        distance_bisection = false;
+      } else {
+        break;
+      }
     }
     if (k > RK_KITER) {
       *llod_converged = false;
@@ -2723,7 +2921,7 @@ static void last_line_defense(rk_state *s, double z[4], double *tau, int *iface,
           *tau = 0.0;
           memcpy(z, s->z_init, 4 * sizeof(double));
         }
-        rk4_step(s, z, dtau, dzdtau);
+        integration_step(s, z, dtau, dzdtau, s->acc);
         *tau = *tau + dtau;
         if (k > RK_KITER) {
           *llod_converged = false;
@@ -2769,7 +2967,7 @@ static bool rk_final_processing(rk_state *s, double z[4], double *tau, int *ifac
     dtau = s->t_remain / s->dt_dtau_const;
     memcpy(z_save, z, sizeof(z_save));
     rk_normal_distances_func(s, z, nd_save);
-    rk4_step(s, z, dtau, dzdtau);
+    integration_step(s, z, dtau, dzdtau, s->acc);
     if (rk_any_gt(nd_save, s->dist_max)) {
       memcpy(z, z_save, sizeof(z_save));
       last_line_defense(s, z, tau, &iface_new, dzdtau, &llod_ok);
@@ -2881,13 +3079,14 @@ static void pusher_tetra_rk(rk_state *s, int *ind_tetr_inout, int *iface, double
   *boole_t_finished = false;
   *t_pass = 0.0;
   *iper_phi = 0;
+  s->acc = s->m->boole_pusher_ode45 != 0; /* :261 */
   quad_analytic_approx(s, z, allowed_faces, &iface_new, &dtau, &quad_ok);
   if (quad_ok) {
-    rk4_step(s, z, dtau, dzdtau);
+    integration_step(s, z, dtau, dzdtau, s->acc);
     tau = tau + dtau;
   } else {
     dtau = s->dtau_ref;
-    rk4_step(s, z, dtau, dzdtau);
+    rk4_step(s, z, dtau, dzdtau); /* a plain rk4_step in the reference (:315) */
     tau = tau + dtau;
     rk_normal_distances_func(s, z, nd);
     iface_new = 1;
@@ -2927,7 +3126,7 @@ static void pusher_tetra_rk(rk_state *s, int *ind_tetr_inout, int *iface, double
         tau = 0.0;
         memcpy(z, s->z_init, sizeof(z));
       }
-      rk4_step(s, z, dtau, dzdtau);
+      integration_step(s, z, dtau, dzdtau, s->acc);
       tau = tau + dtau;
       boole_converged = false;
       continue;
@@ -2968,7 +3167,7 @@ static void pusher_tetra_rk(rk_state *s, int *ind_tetr_inout, int *iface, double
         tau = 0.0;
         memcpy(z, s->z_init, sizeof(z));
       }
-      rk4_step(s, z, dtau, dzdtau);
+      integration_step(s, z, dtau, dzdtau, s->acc);
       tau = tau + dtau;
       boole_converged = false;
       continue;
@@ -2980,7 +3179,7 @@ static void pusher_tetra_rk(rk_state *s, int *ind_tetr_inout, int *iface, double
       if (!allowed_faces[0] && !allowed_faces[1] && !allowed_faces[2] && !allowed_faces[3]) { RK_LLOD_CYCLE(); continue; }
       quad_analytic_approx(s, z, allowed_faces, &iface_new, &dtau, &quad_ok);
       if (!quad_ok) { RK_LLOD_CYCLE(); continue; }
-      rk4_step(s, z, dtau, dzdtau);
+      integration_step(s, z, dtau, dzdtau, s->acc);
       tau = tau + dtau;
       boole_converged = false;
       continue;

@@ -94,6 +94,10 @@ typedef struct {
    * pusher, boole_newton_precalc of the RK pusher; tetra_physics_poly4 [ntetr][544] from gor_make_precomp_poly4 */
   int32_t i_precomp, boole_newton_precalc;
   const double *tetra_physics_poly4;
+  /* RK pusher with adaptive RKF45 steps (boole_pusher_ode45, rel_err_ode45; SRC/pusher_tetra_rk.f90:2549-2581,
+   * SRC/odeint_rkf45.f90, SRC/contrib/rkf45.f90) */
+  int32_t boole_pusher_ode45, pad_ode45;
+  double rel_err_ode45;
 } gor_mesh;
 
 /* make_precomp_poly4 (SRC/tetra_physics_poly_precomp_mod.f90:160-476): out = [ntetr][544] */

@@ -137,7 +137,7 @@ extern "C" {
 void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, int boole_periodic_relocation, int ipusher,
                 int boole_strong_electric_field, int i_time_tracing_option, int oq_mask, int boole_adaptive_time_steps,
                 double desired_delta_energy, int max_n_intermediate_steps, int handover_processing_kind, int i_precomp,
-                int boole_newton_precalc)
+                int boole_newton_precalc, int boole_pusher_ode45, double rel_err_ode45)
 {
   HostMirror *h = new HostMirror();
   bool has_phi = false;
@@ -165,6 +165,8 @@ void *hm_create(const gorilla_mesh_desc *md, int poly_order, int boole_guess, in
     m.i_precomp = ipusher == 2 ? i_precomp : 0;
     m.newton_precalc = ipusher == 1 ? 1 : 0;
   }
+  m.ode45 = (ipusher == 1 && boole_pusher_ode45) ? 1 : 0;
+  m.rel_err_ode45 = rel_err_ode45;
   if (build_find_bins(md, h->bins)) {
     m.bin_start = h->bins.start.data(); m.bin_items = h->bins.items.data();
     m.bin_nu = h->bins.nu; m.bin_nv = h->bins.nv; m.bin_c0 = h->bins.c0; m.bin_c1 = h->bins.c1;
@@ -247,7 +249,7 @@ int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *v
         switch (h->poly_order) { case 1: HM_RUNT(1, 0); break; case 2: HM_RUNT(2, 0); break; case 3: HM_RUNT(3, 0); break; default: HM_RUNT(4, 0); }
       }
     } else
-    if (h->ipusher == 1 && (m.skew || m.newton_precalc)) {
+    if (h->ipusher == 1 && (m.skew || m.newton_precalc || m.ode45)) {
       if (m.se) HM_RUNX(0, 2); else if (m.phi) HM_RUNX(0, 1); else HM_RUNX(0, 0);
     } else
     if (h->ipusher == 2 && ((optq && h->oq_mask) || m.skew)) {

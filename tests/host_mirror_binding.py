@@ -33,7 +33,7 @@ def load():
         d, vp = C.c_double, C.c_void_p
         L.hm_create.restype = vp
         L.hm_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, d, C.c_int, C.c_int,
-                                C.c_int, C.c_int]
+                                C.c_int, C.c_int, C.c_int, d]
         L.hm_free.argtypes = [vp]
         L.hm_has_phi.argtypes = [vp]
         L.hm_orbit_timestep.restype = C.c_int64
@@ -78,7 +78,8 @@ class HostMirror:
                                   oq_mask_of(settings), int(settings.boole_adaptive_time_steps),
                                   float(settings.desired_delta_energy), int(settings.max_n_intermediate_steps),
                                   int(settings.handover_processing_kind), int(settings.i_precomp),
-                                  int(settings.boole_newton_precalc))
+                                  int(settings.boole_newton_precalc), int(settings.boole_pusher_ode45),
+                                  float(settings.rel_err_ode45))
         assert self.h
 
     def __del__(self):

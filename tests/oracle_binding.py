@@ -28,6 +28,7 @@ class GorMesh(C.Structure):
         ("desired_delta_energy", C.c_double), ("tetra_skew_coord", C.POINTER(C.c_double)),
         ("handover_processing_kind", C.c_int32),
         ("i_precomp", C.c_int32), ("boole_newton_precalc", C.c_int32), ("tetra_physics_poly4", C.POINTER(C.c_double)),
+        ("boole_pusher_ode45", C.c_int32), ("pad_ode45", C.c_int32), ("rel_err_ode45", C.c_double),
     ]
 
 
@@ -136,6 +137,8 @@ class OracleMesh:
         m.handover_processing_kind = int(settings.handover_processing_kind)
         if settings.handover_processing_kind == 2:
             m.tetra_skew_coord = mesh.tetra_skew_coord.ctypes.data_as(C.POINTER(C.c_double))
+        m.boole_pusher_ode45 = int(getattr(settings, "boole_pusher_ode45", False))
+        m.rel_err_ode45 = float(getattr(settings, "rel_err_ode45", 1.0e-8))
         m.i_precomp = int(getattr(settings, "i_precomp", 0))
         m.boole_newton_precalc = int(getattr(settings, "boole_newton_precalc", False))
         self.L = load_oracle()

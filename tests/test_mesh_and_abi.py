@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(product_lib):
 
 
 def test_struct_layouts_match_header_sizes():
-    assert C.sizeof(api._Settings) == 8 + 4 * 20 + 8
+    assert C.sizeof(api._Settings) == 8 + 4 * 20 + 8 + 8
     assert C.sizeof(api._Counters) == 8 * 9 + 16 + 8 + 16
     assert C.sizeof(api._Diag) == 8 * 7 + 8 * 4 + 8 * 2 + 8 * 6 + 8
     assert api._MeshDesc.tetra_physics.offset == 8 and api._MeshDesc.Rmin.offset % 8 == 0
@@ -29,8 +29,7 @@ def test_struct_layouts_match_header_sizes():
 
 def test_unsupported_settings_are_refused_without_touching_the_gpu(product_lib, small_mesh):
     mesh, _, settings = small_mesh
-    for field, value in (("i_precomp", 3),
-                         ("boole_pusher_ode45", True)):
+    for field, value in (("i_precomp", 3),):
         bad = type(settings)(**{**settings.__dict__, field: value})
         with pytest.raises(api.GorillaError) as ei:
             api.Gorilla(mesh, bad)

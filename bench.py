@@ -91,8 +91,8 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --particles per GPU; strong: --total-particles sharded contiguously [rN/G,(r+1)N/G) (BASELINE config 5)")
     ap.add_argument("--total-particles", type=int, default=10_000_000, help="strong scaling: particles of the whole job")
-    ap.add_argument("--prefetch", type=int, default=-1, choices=[-1, 0, 1], help="neighbour-record prefetch: -1 auto, 0 off, 1 on")
-    ap.add_argument("--gather", type=int, default=0, choices=[-1, 0, 1], help="record gather: 0 vector loads, 1 bulk copies (TMA), -1 auto")
+    ap.add_argument("--prefetch", type=int, default=-1, choices=[-1, 0, 1], help="neighbour-record L2 prefetch: -1 library default (off), 0 off, 1 on")
+    ap.add_argument("--gather", type=int, default=-1, choices=[-1, 0, 1], help="record gather: -1 library default (bulk copies when the mesh is > 4x the L2), 0 vector loads, 1 bulk copies (TMA)")
     ap.add_argument("--start", default="default", choices=["default", "spread"],
                     help="vmec_qi: 'spread' starts s in U[0.15, 0.95] instead of on s = 0.5 (records touched exceed the L2)")
     ap.add_argument("--no-variants", action="store_true", help="skip the short K=4 / RK4 / spread-start variant runs")
@@ -100,6 +100,7 @@ def parse_args():
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-group", action="store_true", help="orders 3/4: 4-warp CTAs instead of the lock-step solver kernel")
+    ap.add_argument("--rebin", type=int, default=-1, choices=[-1, 0, 1], help="orders 3/4: re-bin the root solves by solver mode (-1 = library default)")
     return ap.parse_args()
 
 
@@ -423,7 +424,9 @@ def main():
     if args.ctas_per_sm or args.threads:
         g.set_launch_config(args.ctas_per_sm, args.threads)
     if args.no_group:
-        g._debug_use_group(False)
+        g._debug_use_group(0)
+    elif args.rebin >= 0:
+        g._debug_use_group(2 if args.rebin else 1)
     if world > 1:
         # the library's own communicator: rank 0 creates the NCCL id, torch.distributed only carries the 128 bytes
         idt = torch.zeros(COMM_ID_BYTES, dtype=torch.uint8, device=dev)

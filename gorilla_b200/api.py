@@ -137,7 +137,7 @@ EXPORTED_SYMBOLS = (
     "gorilla_b200_get_counters", "gorilla_b200_sort_permutation_dev", "gorilla_b200_resort_dev",
     "gorilla_b200_set_host_resort", "gorilla_b200_set_launch_config", "gorilla_b200_fp64_peak", "gorilla_b200_set_prefetch", "gorilla_b200_set_gather",
     "gorilla_b200_comm_unique_id", "gorilla_b200_comm_init", "gorilla_b200_comm_free", "gorilla_b200_comm_allreduce_f64",
-    "gorilla_b200_shard_range", "gorilla_b200_diag_reset", "gorilla_b200_diag_reduce_dev",
+    "gorilla_b200_shard_range", "gorilla_b200_diag_reset", "gorilla_b200_diag_reduce_dev", "gorilla_b200_diag_reduce",
     "gorilla_mesh_build", "gorilla_mesh_get_desc", "gorilla_mesh_get_vertices", "gorilla_mesh_free",
     "gorilla_mesh_save", "gorilla_mesh_load",
 )
@@ -183,6 +183,7 @@ def load_library():
     lib.gorilla_b200_shard_range.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
     lib.gorilla_b200_diag_reset.argtypes = [vp, vp]
     lib.gorilla_b200_diag_reduce_dev.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(_Diag), vp]
+    lib.gorilla_b200_diag_reduce.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(_Diag)]
     lib.gorilla_b200_set_launch_config.argtypes = [vp, i32, i32]
     lib.gorilla_b200_set_prefetch.argtypes = [vp, i32]
     lib.gorilla_b200_set_gather.argtypes = [vp, i32]
@@ -626,14 +627,29 @@ class Gorilla:
         """Record gather of the order-1/2 and RK4 kernels: 0 vector loads, 1 bulk copies one push ahead, -1 auto."""
         _check(load_library().gorilla_b200_set_gather(self._h, int(mode)))
 
+    def diag_reduce(self, x, vpar, vperp, ind_tetr, energy_ref=None, p_phi_ref=None, perpinv_ref=None) -> Diag:
+        """gorilla_b200_diag_reduce: the same reduction from numpy arrays on the host (collective over the communicator)."""
+        n = x.shape[0]
+        _require(x, np.float64, (n, 3), "x"); _require(vpar, np.float64, (n,), "vpar"); _require(vperp, np.float64, (n,), "vperp")
+        _require(ind_tetr, np.int32, (n,), "ind_tetr")
+        for a, nm in ((energy_ref, "energy_ref"), (p_phi_ref, "p_phi_ref"), (perpinv_ref, "perpinv_ref")):
+            _require(a, np.float64, (n,), nm, allow_none=True)
+        d = _Diag()
+        _check(load_library().gorilla_b200_diag_reduce(self._h, n, _ptr(x), _ptr(vpar), _ptr(vperp), _ptr(ind_tetr),
+                                                       _ptr(energy_ref), _ptr(p_phi_ref), _ptr(perpinv_ref), C.byref(d)))
+        return Diag(d.n_particles, d.n_pushes, d.n_lost, d.n_lost_outer, d.n_lost_inner, d.n_failed, d.n_finished,
+                    tuple(d.n_fallback), d.n_adaptive, d.n_sampled, d.max_delta_energy, d.rms_delta_energy,
+                    d.max_delta_perpinv, d.rms_delta_perpinv, d.max_delta_p_phi, d.rms_delta_p_phi, d.nranks)
+
     def set_launch_config(self, ctas_per_sm: int = 0, threads_per_cta: int = 0):
         _check(load_library().gorilla_b200_set_launch_config(self._h, ctas_per_sm, threads_per_cta))
 
     def _debug_force_full(self, on: bool):
         load_library().gorilla_b200_debug_force_full(self._h, int(on))
 
-    def _debug_use_group(self, on: bool):
-        load_library().gorilla_b200_debug_use_group(self._h, int(on))
+    def _debug_use_group(self, mode: int):
+        """orders 3/4: 0 = 4-warp CTAs, 1 = lock-step solver kernel, 2 = lock-step kernel with the solves re-binned by mode"""
+        load_library().gorilla_b200_debug_use_group(self._h, int(mode))
 
     def _debug_find_bins(self, on: bool):
         load_library().gorilla_b200_debug_find_bins(self._h, int(on))

@@ -452,3 +452,28 @@ extern "C" int gorilla_b200_diag_reduce_dev(gorilla_b200_handle *h, int64_t n, c
   out->rms_delta_p_phi = sqrt(d[DG_SUM + 2] / ns);
   return GORILLA_OK;
 }
+
+// HOST-pointer variant (what a Fortran caller has): uploads the batch and the reference values into the handle's scratch.
+extern "C" int gorilla_b200_diag_reduce(gorilla_b200_handle *h, int64_t n, const double *x, const double *vpar,
+                                        const double *vperp, const int32_t *ind_tetr, const double *energy_ref,
+                                        const double *p_phi_ref, const double *perpinv_ref, gorilla_diag *out)
+{
+  if (!h || !out || n < 0 || (n > 0 && (!x || !vpar || !vperp || !ind_tetr)))
+    return fail(GORILLA_ERR_ARG, "gorilla_b200_diag_reduce: null argument");
+  GB_ENTER(h);
+  cudaStream_t s = nullptr;
+  if (n > 0) {
+    int rc = gbint::ensure_host_scratch(h, n);
+    if (rc) return rc;
+    const size_t nd = (size_t)n * sizeof(double);
+    GB_CUDA(cudaMemcpyAsync(h->s_x, x, 3 * nd, cudaMemcpyHostToDevice, s));
+    GB_CUDA(cudaMemcpyAsync(h->s_vpar, vpar, nd, cudaMemcpyHostToDevice, s));
+    GB_CUDA(cudaMemcpyAsync(h->s_vperp, vperp, nd, cudaMemcpyHostToDevice, s));
+    GB_CUDA(cudaMemcpyAsync(h->s_ind, ind_tetr, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (energy_ref) GB_CUDA(cudaMemcpyAsync(h->s_e, energy_ref, nd, cudaMemcpyHostToDevice, s));
+    if (p_phi_ref) GB_CUDA(cudaMemcpyAsync(h->s_p, p_phi_ref, nd, cudaMemcpyHostToDevice, s));
+    if (perpinv_ref) GB_CUDA(cudaMemcpyAsync(h->s_mu, perpinv_ref, nd, cudaMemcpyHostToDevice, s));
+  }
+  return gorilla_b200_diag_reduce_dev(h, n, h->s_x, h->s_vpar, h->s_vperp, h->s_ind, energy_ref ? h->s_e : nullptr,
+                                      p_phi_ref ? h->s_p : nullptr, perpinv_ref ? h->s_mu : nullptr, out, s);
+}

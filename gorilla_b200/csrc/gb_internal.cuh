@@ -21,6 +21,7 @@ int permute_state_inplace(gorilla_b200_handle *h, int64_t n, const int64_t *perm
                           double *vperp, int32_t *init, int32_t *ind, int32_t *iface, cudaStream_t s);
 template <typename T>
 int permute_one_inplace(gorilla_b200_handle *h, int64_t n, const int64_t *perm, bool inverse, T *a, cudaStream_t s);
+int ensure_host_scratch(gorilla_b200_handle *h, int64_t n);   // the s_* arrays of the host-pointer entry points
 }
 
 #define GB_CUDA(call)                                                                              \
@@ -53,6 +54,7 @@ struct Batch {
   int32_t boole_periodic_relocation;
   int32_t sign_t_step;
   int32_t force_full; // debugging/parity: route every push through the complete ladder
+  int32_t rebin;      // orders 3/4 (orbit_kernel_g): re-bin the root solves of a group by solver mode between iterations
   // EXT kernels: optional quantities summed over the pushes of the time step, [n][4] = t_hamiltonian, gyrophase,
   // vpar_int, vpar2_int (nullable); oq_mask bit q set = quantity q requested (boole_array_optional_quantities)
   double *optq;
@@ -463,12 +465,146 @@ static __device__ __noinline__ double solve_group(bool busy, int deg, double q0,
   return tau;
 }
 
+// ---- the same solves, RE-BINNED between iterations ---------------------------------------------------------------------
+// ncu on the lock-step kernel: 10 of 32 lanes are active per instruction inside the solver.  Two causes: (1) the lanes of a
+// warp are in different solver modes (a Laguerre iteration with its square root and Adams bound costs ~3x a Newton iteration,
+// and the warp pays the most expensive mode present), (2) the 128 solves of a group finish after 15..40 iterations and the
+// group waits for the last one with ever emptier warps.  Here the state of every solve lives in shared memory (24 doubles + 3
+// words), and before every iteration the solves that are still running are counting-sorted by mode and handed out densely:
+// warp 0 of the group takes the first 32, warp 1 the next 32, ...; a warp without work skips the iteration, a warp with work
+// runs (almost) one mode.  The arithmetic of an iteration is SgSolver::step() as before, so results are identical.
+#define GBR_ND 24   // q0..q3 | lambda | work[0..3] | roots[0..3] | root | stopping_crit2 ; field 0 holds tau once done
+struct RebinSlots {
+  double (*d)[GBG_THREADS];   // [GBR_ND][slot]
+  int (*w)[GBG_THREADS];      // [3][slot]: packed state, i | j << 16, iter
+  int *order;                 // [slot]
+  int *wcnt;                  // [16 warps][4]
+  static constexpr size_t BYTES = (size_t)GBG_THREADS * (GBR_ND * 8 + 3 * 4 + 4) + 16 * 4 * 4;
+  __device__ __forceinline__ void carve(unsigned char *base)
+  {
+    d = reinterpret_cast<double (*)[GBG_THREADS]>(base);
+    w = reinterpret_cast<int (*)[GBG_THREADS]>(d + GBR_ND);
+    order = reinterpret_cast<int *>(w + 3);
+    wcnt = order + GBG_THREADS;
+  }
+};
+enum { GBR_DONE_BIT = 1 << 14 };
+__device__ __forceinline__ void rebin_pack(const RebinSlots &R, int s, const SgSolver &S, bool all)
+{
+  R.w[0][s] = S.deg | (S.n << 3) | (S.phase << 6) | (S.pol << 8) | (S.mode << 11) | ((int)S.good_to_go << 13) |
+              (S.done ? GBR_DONE_BIT : 0);
+  R.w[1][s] = S.i | (S.j << 16);
+  R.w[2][s] = S.iter;
+  R.d[21][s] = S.root.re; R.d[22][s] = S.root.im; R.d[23][s] = S.stopping_crit2;
+  if (all) {   // work / roots only change when a search or a polish ends
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      R.d[5 + 2 * k][s] = S.work[k].re; R.d[6 + 2 * k][s] = S.work[k].im;
+      R.d[13 + 2 * k][s] = S.roots[k].re; R.d[14 + 2 * k][s] = S.roots[k].im;
+    }
+  }
+}
+__device__ __forceinline__ void rebin_unpack(const RebinSlots &R, int s, SgSolver &S)
+{
+  const int w0 = R.w[0][s], w1 = R.w[1][s];
+  S.deg = w0 & 7; S.n = (w0 >> 3) & 7; S.phase = (w0 >> 6) & 3; S.pol = (w0 >> 8) & 7; S.mode = (w0 >> 11) & 3;
+  S.good_to_go = (w0 >> 13) & 1; S.done = false;
+  S.i = w1 & 0xffff; S.j = (w1 >> 16) & 0xffff; S.iter = R.w[2][s];
+  const cd zero = mk(0.0, 0.0), one = mk(1.0, 0.0);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    // the polynomial is real and monic: poly[k] = (q_k, 0) below the degree, (1, 0) at it, 0 above (SgSolver::start)
+    S.poly[k] = (k < S.deg) ? mk(R.d[k][s], 0.0) : (k == S.deg) ? one : zero;
+    S.work[k] = mk(R.d[5 + 2 * k][s], R.d[6 + 2 * k][s]);
+    S.roots[k] = mk(R.d[13 + 2 * k][s], R.d[14 + 2 * k][s]);
+  }
+  S.poly[4] = (S.deg == 4) ? one : zero;
+  S.work[4] = (S.deg == 4) ? one : zero;   // only read while n = 4, where it is the leading (1, 0)
+  S.root = mk(R.d[21][s], R.d[22][s]);
+  S.stopping_crit2 = R.d[23][s];
+}
+// mode class of a running solve: 0 Laguerre-type iteration (search in mode 2, fall-back search, polish), 1 SG, 2 Newton
+__device__ __forceinline__ int rebin_class(int w0)
+{
+  if (w0 & GBR_DONE_BIT) return 3;
+  const int phase = (w0 >> 6) & 3, mode = (w0 >> 11) & 3;
+  return (phase != 0 || mode == 2) ? 0 : (mode == 1 ? 1 : 2);
+}
+__device__ __forceinline__ void group_sync(int bar_id)
+{
+  asm volatile("barrier.sync %0, %1;" ::"r"(bar_id), "r"(GBG_GROUP) : "memory");
+}
+static __device__ __noinline__ double solve_group_rebin(bool busy, int deg, double q0, double q1, double q2, double q3,
+                                                        double lambda, double tau_ready, int bar_id, RebinSlots R)
+{
+  const unsigned lane = threadIdx.x & 31u;
+  const int w = (int)(threadIdx.x >> 5), grp = w & 3, wig = w >> 2;   // warps grp, grp+4, grp+8, grp+12 form the group
+  const int gl = wig * 32 + (int)lane, gbase = grp * GBG_GROUP, own = gbase + gl;
+  if (busy) {
+    SgSolver S;
+    cd poly[5];
+    poly[0] = mk(q0, 0.0);
+    poly[1] = mk(deg == 1 ? 1.0 : q1, 0.0);
+    poly[2] = mk(deg == 2 ? 1.0 : q2, 0.0);
+    poly[3] = mk(deg == 3 ? 1.0 : q3, 0.0);
+    poly[4] = mk(1.0, 0.0);
+    S.start(deg, poly);
+    R.d[0][own] = q0; R.d[1][own] = q1; R.d[2][own] = q2; R.d[3][own] = q3; R.d[4][own] = lambda;
+    rebin_pack(R, own, S, true);
+  } else {
+    R.w[0][own] = GBR_DONE_BIT;
+    R.d[0][own] = tau_ready;
+  }
+  group_sync(bar_id);
+  for (;;) {
+    const int c = rebin_class(R.w[0][own]);
+    const unsigned b0 = __ballot_sync(0xffffffffu, c == 0), b1 = __ballot_sync(0xffffffffu, c == 1),
+                   b2 = __ballot_sync(0xffffffffu, c == 2);
+    if (lane == 0) {
+      R.wcnt[w * 4 + 0] = __popc(b0); R.wcnt[w * 4 + 1] = __popc(b1); R.wcnt[w * 4 + 2] = __popc(b2);
+    }
+    group_sync(bar_id);
+    int tot[3] = {0, 0, 0}, before[3] = {0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int v = R.wcnt[(grp + 4 * q) * 4 + k];
+        tot[k] += v;
+        if (q < wig) before[k] += v;
+      }
+    }
+    const int total = tot[0] + tot[1] + tot[2];
+    if (total == 0) break;   // the same for every thread of the group
+    if (c < 3) {
+      const unsigned mine = c == 0 ? b0 : c == 1 ? b1 : b2;
+      const int off = (c == 0 ? 0 : c == 1 ? tot[0] : tot[0] + tot[1]) + (c == 0 ? before[0] : c == 1 ? before[1] : before[2]) +
+                      __popc(mine & ((1u << lane) - 1u));
+      R.order[gbase + off] = own;
+    }
+    group_sync(bar_id);
+    if (gl < total) {
+      const int s = R.order[gbase + gl];
+      SgSolver S;
+      rebin_unpack(R, s, S);
+      const int n0 = S.n, ph0 = S.phase, pol0 = S.pol;
+      const bool fin = S.step();
+      rebin_pack(R, s, S, fin || S.n != n0 || S.phase != ph0 || S.pol != pol0);
+      if (fin) R.d[0][s] = min_positive_real_root(S.deg, S.roots, R.d[4][s]);
+    }
+    group_sync(bar_id);
+  }
+  return R.d[0][own];
+}
+
 template <int K, int PHI, int EXT = 0>
 __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_constant__ MeshDev m, const Batch bt)
 {
   extern __shared__ __align__(16) unsigned char g_smem[];
   LaneSlots<GBG_THREADS> S;
   S.carve(g_smem, EXT == 2);
+  RebinSlots RB;
+  RB.carve(g_smem + (EXT == 2 ? LaneSlots<GBG_THREADS>::BYTES_EXT2 : LaneSlots<GBG_THREADS>::BYTES));
   const unsigned lane = threadIdx.x & 31u;
   const int bar_id = 1 + (int)((threadIdx.x >> 5) & 3u);   // warps w, w+4, w+8, w+12 share sub-partition w
   int32_t ind_tetr = -1, iface = -1;
@@ -493,7 +629,11 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
       P.perpinv = S.D(LS_PERPINV);
       begun = P.fast_begin(ind_tetr, iface, x, S.D(LS_VPAR), S.D(LS_TREM), t, iface_new, tau_max) && t.kind != 0;
     }
-    const double tau = solve_group(begun && t.kind == 2, t.deg, t.q[0], t.q[1], t.q[2], t.q[3], t.lambda, t.tau, bar_id);
+    double tau;
+    if (EXT != 2 && bt.rebin)
+      tau = solve_group_rebin(begun && t.kind == 2, t.deg, t.q[0], t.q[1], t.q[2], t.q[3], t.lambda, t.tau, bar_id, RB);
+    else
+      tau = solve_group(begun && t.kind == 2, t.deg, t.q[0], t.q[1], t.q[2], t.q[3], t.lambda, t.tau, bar_id);
     if (begun) {
       P.t_remain = S.D(LS_TREM);
       done = P.fast_end(tau, iface_new, tau_max, true, o);
@@ -616,7 +756,7 @@ struct gorilla_b200_handle {
   int32_t bulk_gather = 0;               // gorilla_b200_set_gather: records through the bulk-copy engine (orders 1, 2 / RK4, EXT = 0)
   int ctas_per_sm = 0, threads_per_cta = 128;
   int force_full = 0;
-  int use_group = 1;  // orders 3/4: lock-step solver kernel (orbit_kernel_g)
+  int use_group = 1;  // orders 3/4: lock-step solver kernel (orbit_kernel_g); 2 = with the solves re-binned by mode
 };
 
 // makes the handle's device current for the duration of an entry point (a handle belongs to the device it was created on)
@@ -643,7 +783,7 @@ int launch_orbit_t(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
 {
   if constexpr (K >= 3) {
     if (h->use_group) {
-      constexpr size_t smem_g = EXT == 2 ? GBG_SMEM_EXT : GBG_SMEM;
+      const size_t smem_g = EXT == 2 ? GBG_SMEM_EXT : (bt.rebin ? GBG_SMEM + RebinSlots::BYTES : GBG_SMEM);
       GB_CUDA(cudaFuncSetAttribute(orbit_kernel_g<K, PHI, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
       int64_t grid_g = h->num_sms;
       const int64_t need_g = (bt.n + GBG_THREADS - 1) / GBG_THREADS;

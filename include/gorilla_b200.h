@@ -293,6 +293,10 @@ int gorilla_b200_diag_reset(gorilla_b200_handle *h, void *stream);
 int gorilla_b200_diag_reduce_dev(gorilla_b200_handle *h, int64_t n, const double *x, const double *vpar,
                                  const double *vperp, const int32_t *ind_tetr, const double *energy_ref,
                                  const double *p_phi_ref, const double *perpinv_ref, gorilla_diag *out, void *stream);
+/* Same with HOST pointers (copies included), for callers whose particle arrays live on the host. */
+int gorilla_b200_diag_reduce(gorilla_b200_handle *h, int64_t n, const double *x, const double *vpar, const double *vperp,
+                             const int32_t *ind_tetr, const double *energy_ref, const double *p_phi_ref,
+                             const double *perpinv_ref, gorilla_diag *out);
 
 /* FP64 issue-rate micro-benchmark on the current device: thread-level instructions per second for DFMA and
  * for DMUL+DADD pairs (the strict build issues the latter).  Roofline denominator of the FP64-bound orders. */

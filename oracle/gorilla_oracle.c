@@ -2263,42 +2263,48 @@ static void rk4_step(const rk_state *s, double y[4], double h, double dzdtau[4])
  * (SRC/odeint_rkf45.f90).  The routine's SAVEd variables are the struct; x**0.2 is libm pow as gfortran calls it.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
-  double abserr_save, h, relerr_save, f1[4], f2[4], f3[4], f4[4], f5[4];
+  double abserr_save, h, relerr_save, f1[5], f2[5], f3[5], f4[5], f5[5];
   int flag_save, init, kflag, kop, nfe;
+  int neqn; /* 4: rhs_pusher_tetra_rk45 ; 5: rhs_par_adiab_ode45 (:2779-2790), z(5) = integral of v_par^2 */
 } rkf45_state;
-static void r8_fehl(const rk_state *s, const double y[4], double h, const double yp[4], double f1[4], double f2[4],
-                    double f3[4], double f4[4], double f5[4], double sout[4])
+static void rkf45_rhs(const rk_state *s, int neqn, const double *z, double *dz)
 {
-  double ch = h / 4.0, t1[4];
-  for (int i = 0; i < 4; i++) f5[i] = y[i] + ch * yp[i];
-  rhs_pusher_tetra_rk4(s, f5, f1);
+  rhs_pusher_tetra_rk4(s, z, dz);
+  if (neqn == 5) dz[4] = z[3] * z[3];
+}
+static void r8_fehl(const rk_state *s, int neqn, const double *y, double h, const double *yp, double *f1, double *f2,
+                    double *f3, double *f4, double *f5, double *sout)
+{
+  double ch = h / 4.0, t1[5];
+  for (int i = 0; i < neqn; i++) f5[i] = y[i] + ch * yp[i];
+  rkf45_rhs(s, neqn, f5, f1);
   ch = 3.0 * h / 32.0;
-  for (int i = 0; i < 4; i++) f5[i] = y[i] + ch * (yp[i] + 3.0 * f1[i]);
-  rhs_pusher_tetra_rk4(s, f5, f2);
+  for (int i = 0; i < neqn; i++) f5[i] = y[i] + ch * (yp[i] + 3.0 * f1[i]);
+  rkf45_rhs(s, neqn, f5, f2);
   ch = h / 2197.0;
-  for (int i = 0; i < 4; i++) f5[i] = y[i] + ch * (1932.0 * yp[i] + (7296.0 * f2[i] - 7200.0 * f1[i]));
-  rhs_pusher_tetra_rk4(s, f5, f3);
+  for (int i = 0; i < neqn; i++) f5[i] = y[i] + ch * (1932.0 * yp[i] + (7296.0 * f2[i] - 7200.0 * f1[i]));
+  rkf45_rhs(s, neqn, f5, f3);
   ch = h / 4104.0;
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < neqn; i++)
     f5[i] = y[i] + ch * ((8341.0 * yp[i] - 845.0 * f3[i]) + (29440.0 * f2[i] - 32832.0 * f1[i]));
-  rhs_pusher_tetra_rk4(s, f5, f4);
+  rkf45_rhs(s, neqn, f5, f4);
   ch = h / 20520.0;
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < neqn; i++)
     t1[i] = y[i] + ch * ((-6080.0 * yp[i] + (9295.0 * f3[i] - 5643.0 * f4[i])) + (41040.0 * f1[i] - 28352.0 * f2[i]));
-  memcpy(f1, t1, sizeof(t1));
-  rhs_pusher_tetra_rk4(s, f1, f5);
+  memcpy(f1, t1, (size_t)neqn * sizeof(double));
+  rkf45_rhs(s, neqn, f1, f5);
   ch = h / 7618050.0;
   /* the caller passes f1 as the output array s as well (call r8_fehl(..., f1, f2, f3, f4, f5, f1)) */
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < neqn; i++)
     sout[i] = y[i] + ch * ((902880.0 * yp[i] + (3855735.0 * f3[i] - 1371249.0 * f4[i])) + (3953664.0 * f2[i] + 277020.0 * f5[i]));
 }
 /* returns the flag; only the branches reachable from odeint_allroutines are restated (flag = 1 first call, flag = 2 after a
  * return with 6 or 7); a fatal stop of the reference returns 8 */
-static int r8_rkf45(const rk_state *s, rkf45_state *q, double y[4], double yp[4], double *t, double tout, double *relerr,
+static int r8_rkf45(const rk_state *s, rkf45_state *q, double *y, double *yp, double *t, double tout, double *relerr,
                     double abserr, int flag)
 {
   const double remin = 1.0e-12, eps = DBL_EPSILON;
-  const int maxnfe = 3000;
+  const int maxnfe = 3000, neqn = q->neqn;
   if (*relerr < 0.0 || abserr < 0.0) return 8;
   if (flag == 0 || 8 < flag || flag < -2) return 8;
   int mflag = abs(flag);
@@ -2328,7 +2334,7 @@ static int r8_rkf45(const rk_state *s, rkf45_state *q, double y[4], double yp[4]
   if (mflag == 1) {
     q->init = 0;
     q->kop = 0;
-    rhs_pusher_tetra_rk4(s, y, yp);
+    rkf45_rhs(s, neqn, y, yp);
     q->nfe = 1;
     if (*t == tout) return 2;
   }
@@ -2336,7 +2342,7 @@ static int r8_rkf45(const rk_state *s, rkf45_state *q, double y[4], double yp[4]
     q->init = 1;
     q->h = fabs(dt);
     double toln = 0.0;
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < neqn; k++) {
       const double tol = *relerr * fabs(y[k]) + abserr;
       if (0.0 < tol) {
         toln = tol;
@@ -2357,8 +2363,8 @@ static int r8_rkf45(const rk_state *s, rkf45_state *q, double y[4], double yp[4]
   }
   if (fabs(dt) <= 26.0 * eps * fabs(*t)) {
     *t = tout;
-    for (int i = 0; i < 4; i++) y[i] = y[i] + dt * yp[i];
-    rhs_pusher_tetra_rk4(s, y, yp);
+    for (int i = 0; i < neqn; i++) y[i] = y[i] + dt * yp[i];
+    rkf45_rhs(s, neqn, y, yp);
     q->nfe = q->nfe + 1;
     return 2;
   }
@@ -2375,10 +2381,10 @@ static int r8_rkf45(const rk_state *s, rkf45_state *q, double y[4], double yp[4]
     double esttol;
     for (;;) {
       if (maxnfe < q->nfe) { q->kflag = 4; return 4; }
-      r8_fehl(s, y, q->h, yp, q->f1, q->f2, q->f3, q->f4, q->f5, q->f1);
+      r8_fehl(s, neqn, y, q->h, yp, q->f1, q->f2, q->f3, q->f4, q->f5, q->f1);
       q->nfe = q->nfe + 5;
       double eeoet = 0.0;
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < neqn; k++) {
         const double et = fabs(y[k]) + fabs(q->f1[k]) + ae;
         if (et <= 0.0) return 5;
         const double ee = fabs((-2090.0 * yp[k] + (21970.0 * q->f3[k] - 15048.0 * q->f4[k])) +
@@ -2396,8 +2402,8 @@ static int r8_rkf45(const rk_state *s, rkf45_state *q, double y[4], double yp[4]
       if (fabs(q->h) < hmin) { q->kflag = 6; return 6; }
     }
     *t = *t + q->h;
-    memcpy(y, q->f1, 4 * sizeof(double));
-    rhs_pusher_tetra_rk4(s, y, yp);
+    memcpy(y, q->f1, (size_t)neqn * sizeof(double));
+    rkf45_rhs(s, neqn, y, yp);
     q->nfe = q->nfe + 1;
     double sf;
     if (0.0001889568 < esttol) sf = 0.9 / pow(esttol, 0.2);
@@ -2412,12 +2418,13 @@ static int r8_rkf45(const rk_state *s, rkf45_state *q, double y[4], double yp[4]
   }
   return -2;
 }
-/* odeint_allroutines(y, 4, 0, x2, eps, rhs) (SRC/odeint_rkf45.f90) */
-static void odeint_allroutines(const rk_state *s, double y[4], double x2, double eps_rel)
+/* odeint_allroutines(y, nvar, 0, x2, eps, rhs) (SRC/odeint_rkf45.f90) */
+static void odeint_allroutines_n(const rk_state *s, double *y, int neqn, double x2, double eps_rel)
 {
   rkf45_state q;
   memset(&q, 0, sizeof(q));
-  double yp[4], epsrel = eps_rel, epsabs = 1e-31, x1in = 0.0;
+  q.neqn = neqn;
+  double yp[5], epsrel = eps_rel, epsabs = 1e-31, x1in = 0.0;
   int flag = r8_rkf45(s, &q, y, yp, &x1in, x2, &epsrel, epsabs, 1);
   if (flag == 6) {
     epsrel = 10 * epsrel;
@@ -2426,6 +2433,10 @@ static void odeint_allroutines(const rk_state *s, double y[4], double x2, double
   } else if (flag == 7) {
     r8_rkf45(s, &q, y, yp, &x1in, x2, &epsrel, epsabs, 2);
   }
+}
+static void odeint_allroutines(const rk_state *s, double y[4], double x2, double eps_rel)
+{
+  odeint_allroutines_n(s, y, 4, x2, eps_rel);
 }
 /* integration_step (:2549-2581): adaptive ODE45 over [0, dtau] followed by a zero-length RK4 step for dz/dtau, or one RK4 step */
 static void integration_step(const rk_state *s, double z[4], double dtau, double dzdtau[4], bool boole_accuracy)
@@ -3383,13 +3394,74 @@ int gor_orbit_timestep(const gor_mesh *m, double x[3], double *vpar, double *vpe
 }
 /* orbit_timestep_gorilla with the event capture of gorilla_plot_orbit_integration (gorilla_plot_mod.f90:520-638):
  * after every push that does not end the time step, J_par / banana tips (:585-596) and toroidal mappings (:601-638). */
+/* ------------------------------------------------------------------------------------------------
+ * module par_adiab_inv_rk_mod (SRC/pusher_tetra_rk.f90:2589-2798): J_par and banana tips for the RK pusher.  v_par^2 is
+ * integrated along the orbit as a fifth equation of the RKF45 integration from z_init over tau = t_pass / dt_dtau_const; the
+ * bounce point is bracketed by halving the step with alternating sign until |v_par| <= 10 cm/s.
+ * ---------------------------------------------------------------------------------------------- */
+static void calc_par_adiab_tau(const rk_state *s, double dtau, double z_inout[4], double *par_adiab_tau)
+{
+  double z[5] = {z_inout[0], z_inout[1], z_inout[2], z_inout[3], 0.0};
+  odeint_allroutines_n(s, z, 5, dtau, s->m->rel_err_ode45);
+  *par_adiab_tau = z[4];
+  memcpy(z_inout, z, 4 * sizeof(double));
+}
+static void calc_par_adiab_until_root(const rk_state *s, double tau_in, double z_inout[4], double *par_adiab_tau, double *tau_out)
+{
+  double z[5] = {z_inout[0], z_inout[1], z_inout[2], z_inout[3], 0.0};
+  const double vpar_min = 1.e1;
+  double dtau = tau_in;
+  *tau_out = 0.0;
+  int i = 0;
+  while (fabs(z[3]) > vpar_min) {
+    i++;
+    const double vpar_save = z[3];
+    odeint_allroutines_n(s, z, 5, dtau, s->m->rel_err_ode45);
+    *tau_out = *tau_out + dtau;
+    /* same sign of v_par as before the step: keep the direction, else turn around; half the length either way */
+    const bool same_side = (vpar_save > 0.0) == (z[3] > 0.0);
+    if (same_side) dtau = (dtau > 0.0) ? fabs(dtau / 2) : -fabs(dtau / 2);
+    else dtau = (dtau > 0.0) ? -fabs(dtau / 2) : fabs(dtau / 2);
+    if (i > 100) break; /* reference: print + stop */
+  }
+  *par_adiab_tau = z[4];
+  memcpy(z_inout, z, 4 * sizeof(double));
+}
+static void par_adiab_inv_tetra_rk(const rk_state *s, double t_pass, double vpar_in, double vpar_end, event_state *es)
+{
+  const double tau = t_pass / s->dt_dtau_const;
+  double z[4], par_adiab_tau, tau_part1;
+  memcpy(z, s->z_init, sizeof(z));
+  if ((vpar_end > 0.0) && (vpar_in < 0.0)) {
+    calc_par_adiab_until_root(s, tau, z, &par_adiab_tau, &tau_part1);
+    es->par_adiab_inv = es->par_adiab_inv + par_adiab_tau * s->dt_dtau_const;
+    if (es->counter_banana_mappings > 1) {
+      const int nskip = es->cfg->n_skip_vpar_0;
+      if (es->counter_banana_mappings / nskip * nskip == es->counter_banana_mappings) {
+        double x[3];
+        for (int i = 0; i < 3; i++) x[i] = z[i] + s->r[TP_X1 + i];
+        emit_event(es, GOR_EVENT_VPAR_0, es->counter_banana_mappings, x, es->par_adiab_inv,
+                   gor_energy_tot(s->m, z, s->perpinv, s->ind_tetr));
+      }
+    }
+    es->counter_banana_mappings = es->counter_banana_mappings + 1;
+    es->par_adiab_inv = 0.0;
+    calc_par_adiab_tau(s, tau - tau_part1, z, &par_adiab_tau);
+    es->par_adiab_inv = es->par_adiab_inv + par_adiab_tau * s->dt_dtau_const;
+  } else {
+    calc_par_adiab_tau(s, tau, z, &par_adiab_tau);
+    es->par_adiab_inv = es->par_adiab_inv + par_adiab_tau * s->dt_dtau_const;
+  }
+}
+
 int gor_orbit_timestep_events(const gor_mesh *m, double x[3], double *vpar, double *vperp, double t_step,
                               int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface, double *t_remain_out,
                               gor_trace *tr, const gor_event_settings *cfg, double *par_adiab_inv,
                               int32_t *counter_vpar_0, int32_t *counter_phi_0, int64_t particle, gor_event *events,
                               int64_t cap, int64_t *n_events)
 {
-  if (m->ipusher != 2 || m->poly_order < 2) return GOR_ERR_CONFIG; /* polynomial orders 2..4 (par_adiab_tau :3302-3320) */
+  /* polynomial orders 2..4 (par_adiab_tau :3302-3320) or the RK pusher (par_adiab_inv_rk_mod) */
+  if (m->ipusher == 2 && m->poly_order < 2) return GOR_ERR_CONFIG;
   if ((cfg->boole_J_par || cfg->boole_poincare_vpar_0) && cfg->n_skip_vpar_0 < 1) return GOR_ERR_CONFIG;
   if (cfg->boole_poincare_phi_0 && cfg->n_skip_phi_0 < 1) return GOR_ERR_CONFIG;
   event_state es;
@@ -3493,8 +3565,10 @@ static int orbit_timestep_core(const gor_mesh *m, double x[3], double *vpar, dou
     }
     if (es) { /* gorilla_plot_mod.f90:585-638 */
       /* a removed particle (unrecoverable push) is skipped: the reference would evaluate J_par on stale module state */
-      if ((es->cfg->boole_J_par || es->cfg->boole_poincare_vpar_0) && !s.removed)
-        par_adiab_inv_tetra_poly(&s, m->poly_order, vpar_save, *vpar, es);
+      if (es->cfg->boole_J_par || es->cfg->boole_poincare_vpar_0) {
+        if (m->ipusher == 1) par_adiab_inv_tetra_rk(&rk, t_pass, vpar_save, *vpar, es);
+        else if (!s.removed) par_adiab_inv_tetra_poly(&s, m->poly_order, vpar_save, *vpar, es);
+      }
       if (iper != 0) {
         es->counter_phi_0_mappings = es->counter_phi_0_mappings + iper;
         if (es->cfg->boole_poincare_phi_0) {

@@ -176,6 +176,16 @@ def test_diag_reduce_matches_numpy_and_splits_losses(cuda_device, product_lib):
         assert abs(rms - np.sqrt((dd ** 2).sum() / alive.sum())) <= 1e-12 * max(rms, 1e-300) + 1e-30
     assert d.n_sampled == int(alive.sum())
     assert d.max_delta_energy < 0.1 and d.max_delta_perpinv < 1e-12      # order 2 on a coarse mesh; mu round-trips through vperp
+    # the host-pointer variant gives the same numbers
+    dh = g.diag_reduce(xd.cpu().numpy(), vd.cpu().numpy(), wd.cpu().numpy(), ind, e0.cpu().numpy(), p0.cpu().numpy(),
+                       m0.cpu().numpy())
+    import dataclasses as _dc
+    for f in _dc.fields(d):
+        a, b = getattr(d, f.name), getattr(dh, f.name)
+        if f.name.startswith("rms_"):       # sums of squares are accumulated with atomics: order, hence last bits, may differ
+            assert abs(a - b) <= 1e-12 * max(abs(a), 1e-300)
+        else:
+            assert a == b, f.name
     # a reset really resets
     g.diag_reset()
     assert g.diag_reduce_dev(xd, vd, wd, it).n_pushes == 0

@@ -241,3 +241,29 @@ def test_vmec_flux_coordinates_bit_exact(cuda_device, product_lib, K):
         assert same(xa, xb) and same(va, vb) and same(wa, wb) and same(sa[1], sb[1]) and same(sa[2], sb[2])
     assert g.counters().n_pushes > 10000
     g.close()
+
+
+@pytest.mark.parametrize("K", [3, 4])
+def test_rebinned_solver_kernel_bit_exact(small_mesh, small_mesh_phi, cuda_device, K):
+    """orbit_kernel_g with the root solves of a group re-binned by solver mode between iterations (solver state in shared
+    memory, counting sort, dense hand-out): the arithmetic of an iteration is unchanged, so every result is identical to the
+    oracle's -- incl. lanes without a solve, pushes that fall back to the complete ladder, losses and queue refills."""
+    for mesh, _, settings in (small_mesh, small_mesh_phi):
+        st = type(settings)(**{**settings.__dict__, "poly_order": K})
+        om, g = OracleMesh(mesh, st), _gorilla(mesh, st)
+        g._debug_use_group(2)
+        n = 3000     # more particles than one CTA holds, not a multiple of the group size
+        xa, va, wa = workloads.particles_cyl(n, 41, rmax_frac=0.97, energy_ev=2.0e4)
+        xb, vb, wb = xa.copy(), va.copy(), wa.copy()
+        sa, sb = workloads.fresh_state(n), workloads.fresh_state(n)
+        for t_step in (1.5e-5, -1.0e-5):
+            ra = om.orbit_timestep_trace(xa, va, wa, t_step, *sa, 64)
+            tro, npu = np.zeros(n), np.zeros(n, np.int64)
+            tt, tf = g.orbit_timestep_gorilla(xb, vb, wb, t_step, *sb, t_remain_out=tro, n_pushes=npu, trace_cap=64)
+            c = g.counters()
+            assert same(ra["trace_tetr"], tt) and same(ra["trace_face"], tf)
+            assert same(xa, xb) and same(va, vb) and same(wa, wb) and same(ra["t_remain"], tro)
+            assert same(sa[1], sb[1]) and same(sa[2], sb[2]) and same(ra["n_pushes"], npu)
+            assert tuple(int(v) for v in ra["fallback"]) == c.n_fallback
+        assert (sa[1] == -1).sum() > 0
+        g.close()

@@ -391,6 +391,17 @@ __global__ void __launch_bounds__(GB_THREADS, BULK ? 3 : gb_min_blocks(K, EXT)) 
       if (!done)
         o = push_rk_full_call<PHI, (EXT == 2 ? 2 : 0)>(&m, perpinv, ind_tetr, iface, S.D(LS_X0), S.D(LS_X1), S.D(LS_X2),
                                                         S.D(LS_VPAR), S.D(LS_TREM));
+      if constexpr (EXT == 2) {
+        if (bt.ev_flags && !o.finished) {   // J_par / banana tips / toroidal mappings (par_adiab_inv_rk_mod)
+          EvState es;
+          es.flags = bt.ev_flags; es.nskip_p = bt.n_skip_phi_0; es.nskip_v = bt.n_skip_vpar_0;
+          es.J = S.OQ(4); es.cnt_v = S.EC(0); es.cnt_p = S.EC(1); es.n = 0;
+          es = rk_events_call<PHI>(&m, perpinv, ind_tetr, iface, S.D(LS_X0), S.D(LS_X1), S.D(LS_X2), S.D(LS_VPAR), S.D(LS_TREM),
+                                   o, es);
+          S.OQ(4) = es.J; S.EC(0) = es.cnt_v; S.EC(1) = es.cnt_p;
+          if (es.n) emit_events(bt, S.Idx(), S.Npush(), es);
+        }
+      }
     } else {
       if (!bt.force_full) {
         const double x[3] = {S.D(LS_X0), S.D(LS_X1), S.D(LS_X2)};

@@ -43,8 +43,10 @@ GB_HD void bm_vec_rk(double *o, const PP &P, const double *z)
 // odeint_allroutines are restated (first call with flag = 1, continuation with flag = 2 after a return of 6 or 7).
 // x**0.2 is pow() of the platform's libm: the CUDA one on the device, which is not glibc's to the last bit -- the one
 // place where this mode can leave the oracle's rounding (parity of this mode is asserted at 1e-10, not bit for bit).
-struct Rkf45 {
-  double abserr_save, h, relerr_save, f1[4], f2[4], f3[4], f4[4], f5[4];
+// NEQ = 4: the orbit (rhs_pusher_tetra_rk45); NEQ = 5: orbit + integral of v_par^2 (rhs_par_adiab_ode45, :2779-2790)
+template <int NEQ>
+struct Rkf45T {
+  double abserr_save, h, relerr_save, f1[NEQ], f2[NEQ], f3[NEQ], f4[NEQ], f5[NEQ];
   int flag_save, init, kflag, kop, nfe;
 };
 // the linear right-hand side of one tetrahedron, by value: b, A = (amat | Bvec | spamat)
@@ -52,40 +54,47 @@ struct OdeLin {
 double b[4];
 BlockMat A;
 };
-GB_HD void ode_rhs(const OdeLin &L, const double *z, double *dz) { bm_vec_rk(dz, L, z); }
-GB_HD void rkf45_fehl(const OdeLin &L, const double *y, double h, const double *yp, Rkf45 &q)
+template <int NEQ>
+GB_HD void ode_rhs(const OdeLin &L, const double *z, double *dz)
 {
-  double ch = h / 4.0, t1[4];
+  bm_vec_rk(dz, L, z);
+  if (NEQ == 5) dz[4] = z[3] * z[3];
+}
+template <int NEQ>
+GB_HD void rkf45_fehl(const OdeLin &L, const double *y, double h, const double *yp, Rkf45T<NEQ> &q)
+{
+  double ch = h / 4.0, t1[NEQ];
 #pragma unroll
-  for (int i = 0; i < 4; i++) q.f5[i] = y[i] + ch * yp[i];
-  ode_rhs(L, q.f5, q.f1);
+  for (int i = 0; i < NEQ; i++) q.f5[i] = y[i] + ch * yp[i];
+  ode_rhs<NEQ>(L, q.f5, q.f1);
   ch = 3.0 * h / 32.0;
 #pragma unroll
-  for (int i = 0; i < 4; i++) q.f5[i] = y[i] + ch * (yp[i] + 3.0 * q.f1[i]);
-  ode_rhs(L, q.f5, q.f2);
+  for (int i = 0; i < NEQ; i++) q.f5[i] = y[i] + ch * (yp[i] + 3.0 * q.f1[i]);
+  ode_rhs<NEQ>(L, q.f5, q.f2);
   ch = h / 2197.0;
 #pragma unroll
-  for (int i = 0; i < 4; i++) q.f5[i] = y[i] + ch * (1932.0 * yp[i] + (7296.0 * q.f2[i] - 7200.0 * q.f1[i]));
-  ode_rhs(L, q.f5, q.f3);
+  for (int i = 0; i < NEQ; i++) q.f5[i] = y[i] + ch * (1932.0 * yp[i] + (7296.0 * q.f2[i] - 7200.0 * q.f1[i]));
+  ode_rhs<NEQ>(L, q.f5, q.f3);
   ch = h / 4104.0;
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < NEQ; i++)
     q.f5[i] = y[i] + ch * ((8341.0 * yp[i] - 845.0 * q.f3[i]) + (29440.0 * q.f2[i] - 32832.0 * q.f1[i]));
-  ode_rhs(L, q.f5, q.f4);
+  ode_rhs<NEQ>(L, q.f5, q.f4);
   ch = h / 20520.0;
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < NEQ; i++)
     t1[i] = y[i] + ch * ((-6080.0 * yp[i] + (9295.0 * q.f3[i] - 5643.0 * q.f4[i])) + (41040.0 * q.f1[i] - 28352.0 * q.f2[i]));
 #pragma unroll
-  for (int i = 0; i < 4; i++) q.f1[i] = t1[i];
-  ode_rhs(L, q.f1, q.f5);
+  for (int i = 0; i < NEQ; i++) q.f1[i] = t1[i];
+  ode_rhs<NEQ>(L, q.f1, q.f5);
   ch = h / 7618050.0;
 #pragma unroll
-  for (int i = 0; i < 4; i++)   // the solution estimate goes to f1 (the caller passes f1 as s)
+  for (int i = 0; i < NEQ; i++)   // the solution estimate goes to f1 (the caller passes f1 as s)
     q.f1[i] = y[i] + ch * ((902880.0 * yp[i] + (3855735.0 * q.f3[i] - 1371249.0 * q.f4[i])) +
                            (3953664.0 * q.f2[i] + 277020.0 * q.f5[i]));
 }
-GB_HD int rkf45_run(const OdeLin &L, Rkf45 &q, double *y, double *yp, double &t, double tout, double &relerr, double abserr, int flag)
+template <int NEQ>
+GB_HD int rkf45_run(const OdeLin &L, Rkf45T<NEQ> &q, double *y, double *yp, double &t, double tout, double &relerr, double abserr, int flag)
 {
   const double remin = 1.0e-12, eps = DBL_EPSILON;
   const int maxnfe = 3000;
@@ -118,7 +127,7 @@ GB_HD int rkf45_run(const OdeLin &L, Rkf45 &q, double *y, double *yp, double &t,
   if (mflag == 1) {
     q.init = 0;
     q.kop = 0;
-    ode_rhs(L, y, yp);
+    ode_rhs<NEQ>(L, y, yp);
     q.nfe = 1;
     if (t == tout) return 2;
   }
@@ -127,7 +136,7 @@ GB_HD int rkf45_run(const OdeLin &L, Rkf45 &q, double *y, double *yp, double &t,
     q.h = fabs(dt);
     double toln = 0.0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < NEQ; k++) {
       const double tol = relerr * fabs(y[k]) + abserr;
       if (0.0 < tol) {
         toln = tol;
@@ -149,8 +158,8 @@ GB_HD int rkf45_run(const OdeLin &L, Rkf45 &q, double *y, double *yp, double &t,
   if (fabs(dt) <= 26.0 * eps * fabs(t)) {
     t = tout;
 #pragma unroll
-    for (int i = 0; i < 4; i++) y[i] = y[i] + dt * yp[i];
-    ode_rhs(L, y, yp);
+    for (int i = 0; i < NEQ; i++) y[i] = y[i] + dt * yp[i];
+    ode_rhs<NEQ>(L, y, yp);
     q.nfe = q.nfe + 1;
     return 2;
   }
@@ -167,11 +176,11 @@ GB_HD int rkf45_run(const OdeLin &L, Rkf45 &q, double *y, double *yp, double &t,
     double esttol;
     for (;;) {
       if (maxnfe < q.nfe) { q.kflag = 4; return 4; }
-      rkf45_fehl(L, y, q.h, yp, q);
+      rkf45_fehl<NEQ>(L, y, q.h, yp, q);
       q.nfe = q.nfe + 5;
       double eeoet = 0.0;
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < NEQ; k++) {
         const double et = fabs(y[k]) + fabs(q.f1[k]) + ae;
         if (et <= 0.0) return 5;
         const double ee = fabs((-2090.0 * yp[k] + (21970.0 * q.f3[k] - 15048.0 * q.f4[k])) +
@@ -190,8 +199,8 @@ GB_HD int rkf45_run(const OdeLin &L, Rkf45 &q, double *y, double *yp, double &t,
     }
     t = t + q.h;
 #pragma unroll
-    for (int i = 0; i < 4; i++) y[i] = q.f1[i];
-    ode_rhs(L, y, yp);
+    for (int i = 0; i < NEQ; i++) y[i] = q.f1[i];
+    ode_rhs<NEQ>(L, y, yp);
     q.nfe = q.nfe + 1;
     double sf;
     if (0.0001889568 < esttol) sf = 0.9 / pow(esttol, 0.2);
@@ -206,28 +215,32 @@ GB_HD int rkf45_run(const OdeLin &L, Rkf45 &q, double *y, double *yp, double &t,
   }
   return -2;
 }
-struct Vec4 {
-double v[4];
+template <int NEQ>
+struct VecN {
+double v[NEQ];
 };
+typedef VecN<4> Vec4;
 // odeint_allroutines(y, 4, 0, x2, eps, rhs) (SRC/odeint_rkf45.f90).  One shared, non-inlined instance: the RK pusher calls
 // it from more than a dozen integration_step sites.
-static GB_HD_NOINLINE Vec4 odeint_rkf45(OdeLin L, Vec4 y0, double x2, double eps_rel)
+template <int NEQ>
+GB_HD_NOINLINE VecN<NEQ> odeint_rkf45_n(OdeLin L, VecN<NEQ> y0, double x2, double eps_rel)
 {
-Rkf45 q;
+Rkf45T<NEQ> q;
 q.abserr_save = q.h = q.relerr_save = 0.0;
 q.flag_save = q.init = q.kflag = q.kop = q.nfe = 0;
-double yp[4], epsrel = eps_rel, epsabs = 1e-31, x1in = 0.0;
+double yp[NEQ], epsrel = eps_rel, epsabs = 1e-31, x1in = 0.0;
 double *y = y0.v;
-int flag = rkf45_run(L, q, y, yp, x1in, x2, epsrel, epsabs, 1);
+int flag = rkf45_run<NEQ>(L, q, y, yp, x1in, x2, epsrel, epsabs, 1);
 if (flag == 6) {
   epsrel = 10 * epsrel;
   epsabs = 10 * epsabs;
-  rkf45_run(L, q, y, yp, x1in, x2, epsrel, epsabs, 2);
+  rkf45_run<NEQ>(L, q, y, yp, x1in, x2, epsrel, epsabs, 2);
 } else if (flag == 7) {
-  rkf45_run(L, q, y, yp, x1in, x2, epsrel, epsabs, 2);
+  rkf45_run<NEQ>(L, q, y, yp, x1in, x2, epsrel, epsabs, 2);
 }
 return y0;
 }
+GB_HD Vec4 odeint_rkf45(const OdeLin &L, const Vec4 &y0, double x2, double eps_rel) { return odeint_rkf45_n<4>(L, y0, x2, eps_rel); }
 
 // EXT = 2: hand-over via Cartesian skew coordinates when the mesh carries them (handover_processing_kind = 2)
 template <int PHI, int EXT = 0>
@@ -896,6 +909,88 @@ struct RkPusher {
     return 0;
   }
 
+  // ==== EXT = 2: orbit events for the RK pusher ==========================================================================
+  // module par_adiab_inv_rk_mod (:2589-2798): v_par^2 is integrated along the orbit as a fifth equation of the RKF45
+  // integration (relative error rel_err_ode45) from z_init over tau = t_pass / dt_dtau_const; at a bounce (v_par from < 0
+  // to > 0) the turning point is approached by steps of alternating sign and halving length until |v_par| <= 10 cm/s.
+  // Followed by the toroidal mappings of gorilla_plot_orbit_integration (SRC/gorilla_plot_mod.f90:601-636).
+  GB_HD void par_adiab_tau(const OdeLin &L, double dtau, double *z, double &J_tau) const
+  {
+    VecN<5> y;
+#pragma unroll
+    for (int i = 0; i < 4; i++) y.v[i] = z[i];
+    y.v[4] = 0.0;
+    y = odeint_rkf45_n<5>(L, y, dtau, P.mp->rel_err_ode45);
+#pragma unroll
+    for (int i = 0; i < 4; i++) z[i] = y.v[i];
+    J_tau = y.v[4];
+  }
+  GB_HD void events_after_push(double vpar_in, const PushOut &o, int iper_phi, EvState &es)
+  {
+    es.n = 0;
+    if (es.flags & 6) {
+      OdeLin L;
+#pragma unroll
+      for (int i = 0; i < 4; i++) L.b[i] = P.b[i];
+      L.A = P.A;
+      const double tau = o.t_pass / P.dt_dtau_const;
+      double z[4], J_tau;
+#pragma unroll
+      for (int i = 0; i < 4; i++) z[i] = P.z_init[i];
+      if ((o.vpar > 0.0) && (vpar_in < 0.0)) {
+        // calc_par_adiab_until_root (:2703-2760)
+        VecN<5> y;
+#pragma unroll
+        for (int i = 0; i < 4; i++) y.v[i] = z[i];
+        y.v[4] = 0.0;
+        double dtau = tau, tau_part1 = 0.0;
+        int it = 0;
+        while (fabs(y.v[3]) > 1.e1) {
+          it++;
+          const double vpar_save = y.v[3];
+          y = odeint_rkf45_n<5>(L, y, dtau, P.mp->rel_err_ode45);
+          tau_part1 = tau_part1 + dtau;
+          const bool same_side = (vpar_save > 0.0) == (y.v[3] > 0.0);
+          if (same_side) dtau = (dtau > 0.0) ? fabs(dtau / 2) : -fabs(dtau / 2);
+          else dtau = (dtau > 0.0) ? -fabs(dtau / 2) : fabs(dtau / 2);
+          if (it > 100) break;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) z[i] = y.v[i];
+        es.J = es.J + y.v[4] * P.dt_dtau_const;
+        if (es.cnt_v > 1 && (es.cnt_v / es.nskip_v * es.nskip_v == es.cnt_v)) {
+          EvRec &e = es.e[es.n++];
+          e.kind = 2;
+          e.counter = es.cnt_v;
+#pragma unroll
+          for (int i = 0; i < 3; i++) e.x[i] = z[i] + P.r.x1s(i);
+          e.v[0] = es.J;
+          e.v[1] = P.energy_tot(z);
+        }
+        es.cnt_v = es.cnt_v + 1;
+        es.J = 0.0;
+        par_adiab_tau(L, tau - tau_part1, z, J_tau);
+        es.J = es.J + J_tau * P.dt_dtau_const;
+      } else {
+        par_adiab_tau(L, tau, z, J_tau);
+        es.J = es.J + J_tau * P.dt_dtau_const;
+      }
+    }
+    if (iper_phi != 0) {
+      es.cnt_p = es.cnt_p + iper_phi;
+      if ((es.flags & 1) && (es.cnt_p / es.nskip_p * es.nskip_p == es.cnt_p)) {
+        const double zv[4] = {o.z_save[0], o.z_save[1], o.z_save[2], o.vpar};
+        EvRec &e = es.e[es.n++];
+        e.kind = 1;
+        e.counter = es.cnt_p;
+#pragma unroll
+        for (int i = 0; i < 3; i++) e.x[i] = o.x[i];
+        e.v[0] = P.p_phi(o.vpar, o.z_save);
+        e.v[1] = P.energy_tot(zv);
+      }
+    }
+  }
+
   // pusher_tetra_rk (:197-575).  Returns false only with FAST = true ("take the complete path").
   template <bool FAST>
   GB_HD bool push(PushOut &o)
@@ -1026,6 +1121,8 @@ struct RkPusher {
       o.z_save_set = 0;
     }
     o.fallback = fallback;
+    // EXT = 2: the toroidal period the hand-over crossed travels in bits 8/9 (read by rk_events_call only)
+    if (EXT == 2) o.fallback |= (P.iper_phi == 1) ? 256 : (P.iper_phi == -1) ? 512 : 0;
     return true;
   }
 };
@@ -1044,6 +1141,22 @@ GB_HD_NOINLINE PushOut push_rk_full_call(const MeshDev *mp, double perpinv, int 
   R.init(mp, perpinv, ind_tetr, x, iface, vpar, t_remain);
   R.template push<false>(o);
   return o;
+}
+
+// events of one RK push, out of line: the pusher state is set up again from the push's inputs (init is deterministic), so
+// the orbit loop carries nothing extra for a feature that is off in production runs
+template <int PHI>
+GB_HD_NOINLINE EvState rk_events_call(const MeshDev *mp, double perpinv, int ind_tetr, int iface, double x0, double x1, double x2,
+                                      double vpar_in, double t_remain, PushOut o, EvState es)
+{
+  RkPusher<PHI, 2> R;
+  double stash[6];
+  R.P.r.set_stash(stash, 1);
+  const double x[3] = {x0, x1, x2};
+  R.init(mp, perpinv, ind_tetr, x, iface, vpar_in, t_remain);
+  const int iper_phi = (o.fallback & 256) ? 1 : (o.fallback & 512) ? -1 : 0;
+  R.events_after_push(vpar_in, o, iper_phi, es);
+  return es;
 }
 
 } // namespace gb

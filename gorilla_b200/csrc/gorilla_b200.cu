@@ -500,9 +500,9 @@ GB_EXTERN_ORBIT_P(4)
 template <int PHI>
 static int launch_orbit_k(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
 {
-  // RK4: the kernel with the run-time options carries hand-over kind 2 and boole_newton_precalc
+  // RK4: the kernel with the run-time options carries hand-over kind 2, boole_newton_precalc, ODE45 and the orbit events
   if (h->settings.ipusher == 1)
-    return (h->mesh.skew || h->mesh.newton_precalc || h->mesh.ode45) ? launch_orbit_t<0, PHI, 2>(h, bt, s)
+    return (h->mesh.skew || h->mesh.newton_precalc || h->mesh.ode45 || bt.ev_flags) ? launch_orbit_t<0, PHI, 2>(h, bt, s)
                                                                       : launch_orbit_t<0, PHI>(h, bt, s);
   if (((bt.optq && bt.oq_mask) || bt.ev_flags) && h->settings.boole_adaptive_time_steps)
     return fail(GORILLA_ERR_UNSUPPORTED, "boole_adaptive_time_steps is not combined with optional quantities / events");
@@ -651,8 +651,8 @@ int ensure_host_scratch(gorilla_b200_handle *h, int64_t n) { return ensure_scrat
 }
 static int check_event_args(gorilla_b200_handle *h, const gorilla_event_settings *cfg, int &flags)
 {
-  if (h->settings.ipusher != 2 || h->settings.poly_order < 2)
-    return fail(GORILLA_ERR_UNSUPPORTED, "orbit events need the polynomial pusher of order 2..4 (par_adiab_inv_poly_mod)");
+  if (h->settings.ipusher == 2 && h->settings.poly_order < 2)
+    return fail(GORILLA_ERR_UNSUPPORTED, "orbit events need the polynomial pusher of order 2..4 (par_adiab_inv_poly_mod) or the RK pusher (par_adiab_inv_rk_mod)");
   flags = (cfg->boole_poincare_phi_0 ? 1 : 0) | (cfg->boole_poincare_vpar_0 ? 2 : 0) | (cfg->boole_J_par ? 4 : 0);
   if ((flags & 1) && cfg->n_skip_phi_0 < 1) return fail(GORILLA_ERR_ARG, "n_skip_phi_0 must be >= 1");
   if ((flags & 6) && cfg->n_skip_vpar_0 < 1) return fail(GORILLA_ERR_ARG, "n_skip_vpar_0 must be >= 1");

@@ -194,7 +194,9 @@ typedef struct gorilla_event_settings { /* namelist GORILLA_PLOT_NML (gorilla_pl
  * in/out arrays holding the per-particle state of par_adiab_inv_poly_mod and of the mapping counters between calls (zero
  * them before the first call).  events: HOST buffer of event_cap records, filled in no particular order (sort by
  * particle, push); *n_events returns the number of events that occurred, which may exceed event_cap (the surplus is
- * dropped).  Polynomial pusher of order 2..4 only (par_adiab_tau, pusher_tetra_poly.f90:3302-3320, has no other case). */
+ * dropped).  Polynomial pusher of order 2..4 (par_adiab_tau, pusher_tetra_poly.f90:3302-3320, has no case for order 1) or
+ * the RK pusher (module par_adiab_inv_rk_mod, pusher_tetra_rk.f90:2589-2798: J_par as a fifth RKF45 equation integrated
+ * with rel_err_ode45). */
 int gorilla_b200_orbit_timestep_events(gorilla_b200_handle *h, int64_t n, double *x, double *vpar, double *vperp,
                                        double t_step, int32_t *boole_initialized, int32_t *ind_tetr, int32_t *iface,
                                        double *t_remain_out, int64_t *n_pushes, const gorilla_event_settings *cfg,

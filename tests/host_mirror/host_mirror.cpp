@@ -71,6 +71,16 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
         done = R.template push<true>(o);
       }
       if (!done) o = push_rk_full_call<PHI, (EXT == 2 ? 2 : 0)>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
+      if constexpr (EXT == 2) {
+        if (ev && !o.finished) {
+          EvState es;
+          es.flags = ev->flags; es.nskip_p = ev->nskip_p; es.nskip_v = ev->nskip_v;
+          es.J = *ev->J; es.cnt_v = *ev->cnt_v; es.cnt_p = *ev->cnt_p; es.n = 0;
+          es = rk_events_call<PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain, o, es);
+          *ev->J = es.J; *ev->cnt_v = es.cnt_v; *ev->cnt_p = es.cnt_p;
+          if (es.n) hm_emit(ev, npush, es);
+        }
+      }
     } else {
       if (!force_full) {
         PolyPusher<K, PHI, EXT> P;
@@ -280,7 +290,7 @@ int64_t hm_orbit_timestep_events(void *p, int64_t n, double *x, double *vpar, do
 {
   HostMirror *h = (HostMirror *)p;
   const MeshDev &m = h->m;
-  if (h->ipusher != 2 || h->poly_order < 2) return -1;
+  if (h->ipusher == 2 && h->poly_order < 2) return -1;
   const int sign_t = signbit(t_step) ? -1 : 1;
   int64_t fallback[5] = {0, 0, 0, 0, 0};
   *n_events = 0;
@@ -304,7 +314,9 @@ int64_t hm_orbit_timestep_events(void *p, int64_t n, double *x, double *vpar, do
 #define HM_RUNE(K, PHI) run_particle<K, PHI, 2>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
       t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, 0, nullptr, nullptr, force_full, fallback, \
       0u, nullptr, &ev)
-    if (m.se) {
+    if (h->ipusher == 1) {
+      if (m.se) HM_RUNE(0, 2); else if (m.phi) HM_RUNE(0, 1); else HM_RUNE(0, 0);
+    } else if (m.se) {
       switch (h->poly_order) { case 2: HM_RUNE(2, 2); break; case 3: HM_RUNE(3, 2); break; default: HM_RUNE(4, 2); }
     } else if (m.phi) {
       switch (h->poly_order) { case 2: HM_RUNE(2, 1); break; case 3: HM_RUNE(3, 1); break; default: HM_RUNE(4, 1); }

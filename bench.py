@@ -85,6 +85,9 @@ def parse_args():
     ap.add_argument("--adaptive", type=float, default=0.0,
                     help="boole_adaptive_time_steps with this desired_delta_energy (max_n_intermediate_steps = 10000)")
     ap.add_argument("--t-step", type=float, default=0.0, help="physical time per step [s] (0 = workload default)")
+    ap.add_argument("--i-precomp", type=int, default=0, choices=[0, 1, 2], help="polynomial pusher: coefficients from the precomputed poly4 record")
+    ap.add_argument("--newton-precalc", action="store_true", help="RK pusher: boole_newton_precalc")
+    ap.add_argument("--ode45", action="store_true", help="RK pusher: boole_pusher_ode45 (RKF45 instead of RK4)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sort", type=int, default=1, help="re-sort particles by tetra index before every step")
@@ -222,6 +225,12 @@ def apply_args(settings, args):
     if args.adaptive > 0.0:
         settings.boole_adaptive_time_steps = True
         settings.desired_delta_energy = args.adaptive
+    if getattr(args, "i_precomp", 0):
+        settings.i_precomp = args.i_precomp
+    if getattr(args, "newton_precalc", False):
+        settings.boole_newton_precalc = True
+    if getattr(args, "ode45", False):
+        settings.boole_pusher_ode45 = True
     if getattr(args, "optional_quantities", False):
         settings.boole_time_Hamiltonian = settings.boole_gyrophase = settings.boole_vpar_int = settings.boole_vpar2_int = True
     return settings
@@ -236,7 +245,8 @@ def make_config(wl, settings, args, world, n, t_step, mesh):
     return {"workload": wl["name"], "desc": wl["desc"], "ipusher": settings.ipusher,
             "poly_order": settings.poly_order, "i_time_tracing_option": settings.i_time_tracing_option,
             "boole_adaptive_time_steps": bool(settings.boole_adaptive_time_steps),
-            "optional_quantities": bool(args.optional_quantities),
+            "optional_quantities": bool(args.optional_quantities), "i_precomp": int(settings.i_precomp),
+            "boole_newton_precalc": bool(settings.boole_newton_precalc), "boole_pusher_ode45": bool(settings.boole_pusher_ode45),
             "desired_delta_energy": settings.desired_delta_energy if settings.boole_adaptive_time_steps else None,
             "particles_per_gpu": None if strong else n, "total_particles": args.total_particles if strong else n * world,
             "t_step_s": t_step, "ntetr": mesh.ntetr, "mesh_hot_bytes": int(mesh.ntetr * hot_rec),

@@ -415,9 +415,10 @@ extern "C" int gorilla_b200_set_gather(gorilla_b200_handle *h, int32_t mode)
 {
   if (!h || mode < -1 || mode > 1) return fail(GORILLA_ERR_ARG, "gorilla_b200_set_gather: mode must be -1 (auto), 0 (loads) or 1 (bulk copy)");
   GB_ENTER(h);
-  // auto: bulk copies for the polynomial pusher when the hot records of the mesh exceed the L2 by a wide margin (measured:
-  // +34 % / +58 % on the 3.8 M / 4.2 M-tetrahedron meshes, -40 % on the L2-resident 0.96 M-tetrahedron one)
-  const int want = mode >= 0 ? mode : ((h->hot_bytes > 4 * h->l2_bytes && h->settings.ipusher == 2) ? 1 : 0);
+  // auto: bulk copies when the hot records of the mesh exceed the L2 by a wide margin (measured, order 2: +46 % / +69 % on the
+  // 3.8 M / 4.2 M-tetrahedron meshes, -34 % on the L2-resident 0.96 M-tetrahedron one; RK4: +12 % / -2 % on the two big meshes)
+  const bool has_bulk_kernel = h->settings.ipusher == 1 || h->settings.poly_order == 2;   // launch_orbit_t: EXT = 0, K = 2 or RK4
+  const int want = mode >= 0 ? mode : ((h->hot_bytes > 4 * h->l2_bytes && has_bulk_kernel) ? 1 : 0);
   if (want && !h->d_rec44) {
     GB_CUDA(cudaMalloc((void **)&h->d_rec44, (size_t)h->mesh.ntetr * 44 * sizeof(double)));
     interleave_rec44_kernel<<<h->num_sms * 8, 256>>>(h->mesh.ntetr, h->d_geom, h->d_bpart, h->d_rec44);

@@ -38,8 +38,8 @@ NVCC_FLAGS += _EXTRA
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas"]
 
 # longest compiles first (order 4 takes ~2 min per unit)
-CU_SOURCES = ["gb_orbit_k4x.cu", "gb_orbit_k4a.cu", "gb_orbit_k4t.cu", "gb_orbit_k4.cu", "gb_orbit_k4p.cu", "gb_orbit_k3p.cu", "gb_orbit_k2p.cu", "gb_orbit_k3x.cu", "gb_orbit_k3a.cu",
-              "gb_orbit_k3t.cu", "gb_orbit_k3.cu", "gorilla_b200.cu", "gb_diag.cu", "gb_orbit_rk.cu", "gb_orbit_rkx.cu", "gb_orbit_k2x.cu", "gb_orbit_k2a.cu",
+CU_SOURCES = ["gb_orbit_k4ax.cu", "gb_orbit_k3ax.cu", "gb_orbit_k4x.cu", "gb_orbit_k4a.cu", "gb_orbit_k4t.cu", "gb_orbit_k4.cu", "gb_orbit_k4p.cu", "gb_orbit_k3p.cu", "gb_orbit_k2p.cu", "gb_orbit_k3x.cu", "gb_orbit_k3a.cu",
+              "gb_orbit_k3t.cu", "gb_orbit_k3.cu", "gorilla_b200.cu", "gb_diag.cu", "gb_orbit_rk.cu", "gb_orbit_rkx.cu", "gb_orbit_k2ax.cu", "gb_orbit_k1ax.cu", "gb_orbit_k2x.cu", "gb_orbit_k2a.cu",
               "gb_orbit_k2t.cu", "gb_orbit_k2.cu", "gb_orbit_k1x.cu", "gb_orbit_k1a.cu", "gb_orbit_k1t.cu", "gb_orbit_k1.cu"]
 CPP_SOURCES = ["host/mesh_api.cpp", "host/mesh_common.cpp", "host/mesh_analytic.cpp", "host/mesh_vmec.cpp", "host/mesh_efit.cpp", "host/mesh_soledge3x.cpp", "host/mesh_efit_flux.cpp"]
 

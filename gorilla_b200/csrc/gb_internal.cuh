@@ -67,6 +67,9 @@ struct Batch {
   gorilla_event *events;
   long long ev_cap;
   unsigned long long *ev_count;
+  // EXT = 5 kernels (adaptive sub-stepping + list consumers): per-thread step lists, [thread][lst_cap][5]
+  double *lst;
+  int32_t lst_cap;
 };
 
 // append the events of one push to the global buffer (order between particles is not defined; a record carries the
@@ -112,7 +115,7 @@ __device__ __forceinline__ void emit_events(const Batch &bt, long long particle,
 #endif
 constexpr int gb_min_blocks(int K, int EXT = 0)
 {
-  return (EXT == 2 && K != 0 && GB_MINB_X2 > 0) ? GB_MINB_X2
+  return ((EXT == 2 || EXT == 5) && K != 0 && GB_MINB_X2 > 0) ? GB_MINB_X2
          : K == 0 ? GB_MINB_RK : K == 1 ? GB_MINB_K1 : K == 2 ? GB_MINB_K2 : K == 3 ? GB_MINB_K3 : GB_MINB_K4;
 }
 
@@ -198,7 +201,7 @@ __device__ __forceinline__ bool lane_refill(const MeshDev &m, const Batch &bt, c
       // resp. leaves the loop at :103-109 without touching the particle
       if (bt.t_remain_out) bt.t_remain_out[idx] = bt.t_step;
       if (bt.n_pushes) bt.n_pushes[idx] = 0;
-      if constexpr (EXT == 2) {
+      if constexpr (EXT == 2 || EXT == 5) {
         if (bt.optq) { bt.optq[4 * idx] = 0.0; bt.optq[4 * idx + 1] = 0.0; bt.optq[4 * idx + 2] = 0.0; bt.optq[4 * idx + 3] = 0.0; }
       }
       if (inited && ind_tetr < 1) S.C(LC_LOST_PREV) = S.C(LC_LOST_PREV) + 1;   // lost in an earlier call
@@ -207,7 +210,7 @@ __device__ __forceinline__ bool lane_refill(const MeshDev &m, const Batch &bt, c
     if (bt.t_step == 0.0) {
       if (bt.t_remain_out) bt.t_remain_out[idx] = 0.0;
       if (bt.n_pushes) bt.n_pushes[idx] = 0;
-      if constexpr (EXT == 2) {
+      if constexpr (EXT == 2 || EXT == 5) {
         if (bt.optq) { bt.optq[4 * idx] = 0.0; bt.optq[4 * idx + 1] = 0.0; bt.optq[4 * idx + 2] = 0.0; bt.optq[4 * idx + 3] = 0.0; }
       }
       continue;
@@ -224,7 +227,7 @@ __device__ __forceinline__ bool lane_refill(const MeshDev &m, const Batch &bt, c
     S.D(LS_TREM) = bt.t_step;
     S.Idx() = idx;
     S.Npush() = 0;
-    if constexpr (EXT == 2) {
+    if constexpr (EXT == 2 || EXT == 5) {
       S.OQ(0) = 0.0; S.OQ(1) = 0.0; S.OQ(2) = 0.0; S.OQ(3) = 0.0;
       if (bt.ev_flags) { S.OQ(4) = bt.par_adiab_inv[idx]; S.EC(0) = bt.counter_vpar_0[idx]; S.EC(1) = bt.counter_phi_0[idx]; }
     }
@@ -253,13 +256,15 @@ __device__ __forceinline__ void lane_ext2_after_fast(const Batch &bt, const Lane
   }
 }
 // EXT = 2: the complete ladder with optional quantities and events
-template <int K, int PHI, int NT>
+template <int K, int PHI, int NT, int EXT = 2>
 __device__ __forceinline__ PushOut lane_ext2_full(const MeshDev &m, const Batch &bt, const LaneSlots<NT> &S, int32_t ind_tetr,
                                                   int32_t iface)
 {
-  const PushOutX ox = push_full_call_x<K, PHI>(&m, S.D(LS_PERPINV), ind_tetr, iface, S.D(LS_X0), S.D(LS_X1), S.D(LS_X2),
-                                               S.D(LS_VPAR), S.D(LS_TREM), bt.oq_mask, bt.ev_flags, bt.n_skip_phi_0,
-                                               bt.n_skip_vpar_0, S.OQ(4), S.EC(0), S.EC(1));
+  double *lst = nullptr;
+  if constexpr (EXT == 5) lst = bt.lst + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * (size_t)bt.lst_cap * 5;
+  const PushOutX ox = push_full_call_x<K, PHI, EXT>(&m, S.D(LS_PERPINV), ind_tetr, iface, S.D(LS_X0), S.D(LS_X1), S.D(LS_X2),
+                                                    S.D(LS_VPAR), S.D(LS_TREM), bt.oq_mask, bt.ev_flags, bt.n_skip_phi_0,
+                                                    bt.n_skip_vpar_0, S.OQ(4), S.EC(0), S.EC(1), lst, bt.lst_cap);
 #pragma unroll
   for (int q = 0; q < 4; q++) S.OQ(q) = S.OQ(q) + ox.oq[q];
   if (bt.ev_flags) {
@@ -293,7 +298,7 @@ __device__ __forceinline__ bool lane_after_push(const MeshDev &m, const Batch &b
     if (o.fallback & 2) S.C(LC_FB1) = S.C(LC_FB1) + 1;
     if (o.fallback & 4) S.C(LC_FB2) = S.C(LC_FB2) + 1;
     if (o.fallback & 8) S.C(LC_FB3) = S.C(LC_FB3) + 1;
-    if constexpr (EXT == 3) {
+    if constexpr (EXT == 3 || EXT == 5) {
       if (o.fallback & 16) S.C(LC_ADAPT) = S.C(LC_ADAPT) + 1;
     }
   }
@@ -315,7 +320,7 @@ __device__ __forceinline__ bool lane_after_push(const MeshDev &m, const Batch &b
   bt.iface[idx] = iface;
   if (bt.t_remain_out) bt.t_remain_out[idx] = t_remain;
   if (bt.n_pushes) bt.n_pushes[idx] = npush + 1;
-  if constexpr (EXT == 2) {
+  if constexpr (EXT == 2 || EXT == 5) {
     if (bt.optq) {
 #pragma unroll
       for (int q = 0; q < 4; q++) bt.optq[4 * idx + q] = S.OQ(q);
@@ -363,9 +368,9 @@ __device__ __forceinline__ void lane_reduce_counters(const Batch &bt, const Lane
 template <int K, int PHI, int EXT = 0, bool BULK = false>
 __global__ void __launch_bounds__(GB_THREADS, BULK ? 3 : gb_min_blocks(K, EXT)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
 {
-  __shared__ __align__(16) unsigned char s_raw[EXT == 2 ? LaneSlots<GB_THREADS>::BYTES_EXT2 : LaneSlots<GB_THREADS>::BYTES];
+  __shared__ __align__(16) unsigned char s_raw[(EXT == 2 || EXT == 5) ? LaneSlots<GB_THREADS>::BYTES_EXT2 : LaneSlots<GB_THREADS>::BYTES];
   LaneSlots<GB_THREADS> S;
-  S.carve(s_raw, EXT == 2);
+  S.carve(s_raw, EXT == 2 || EXT == 5);
   const unsigned lane = threadIdx.x & 31u;
   int32_t ind_tetr = -1, iface = -1;
   S.zero_counters();
@@ -402,6 +407,9 @@ __global__ void __launch_bounds__(GB_THREADS, BULK ? 3 : gb_min_blocks(K, EXT)) 
           if (es.n) emit_events(bt, S.Idx(), S.Npush(), es);
         }
       }
+    } else if constexpr (EXT == 5) {
+      // adaptive sub-stepping with the list consumers: every push takes the complete path (the step lists live in global memory)
+      o = lane_ext2_full<K, PHI, GB_THREADS, 5>(m, bt, S, ind_tetr, iface);
     } else {
       if (!bt.force_full) {
         const double x[3] = {S.D(LS_X0), S.D(LS_X1), S.D(LS_X2)};
@@ -725,6 +733,8 @@ struct gorilla_b200_handle {
   double *d_geom = nullptr, *d_bpart = nullptr, *d_phi = nullptr, *d_cold = nullptr, *d_se = nullptr, *d_ham = nullptr, *d_skew = nullptr;
   double *d_poly4 = nullptr;   // tetra_physics_poly4 records (i_precomp = 1, 2)
   double *d_rec44 = nullptr;   // geom + bpart as one contiguous record per tetrahedron (bulk-copy gather only)
+  double *d_lst = nullptr;     // EXT = 5 kernels: per-thread step lists
+  size_t lst_bytes = 0;
   double *s_oq = nullptr;   // [cap][4] scratch for the optional quantities (host-pointer entry point)
   uint32_t oq_mask = 0;
   int32_t *d_bin_start = nullptr, *d_bin_items = nullptr;
@@ -792,6 +802,33 @@ struct DeviceGuard {
 template <int K, int PHI, int EXT = 0>
 int launch_orbit_t(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
 {
+  if constexpr (EXT == 5) {
+    // one CTA per SM: each thread owns a step list of 3 * max_n_intermediate_steps entries (manage_intermediate_steps_arrays,
+    // pusher_tetra_poly.f90:98-101) of 40 bytes in global scratch
+    int64_t grid5 = h->num_sms;
+    const int64_t need5 = (bt.n + GB_THREADS - 1) / GB_THREADS;
+    if (grid5 > need5) grid5 = need5;
+    if (grid5 < 1) grid5 = 1;
+    const int32_t cap = 3 * h->settings.max_n_intermediate_steps;
+    const size_t bytes = (size_t)grid5 * GB_THREADS * (size_t)cap * 5 * sizeof(double);
+    if (bytes > ((size_t)64 << 30))
+      return gbint::fail(GORILLA_ERR_UNSUPPORTED, "adaptive sub-stepping with Hamiltonian time / optional quantities / events: the step lists "
+                                                  "(threads x 3 max_n_intermediate_steps x 40 B) exceed 64 GB; lower max_n_intermediate_steps");
+    if (bytes > h->lst_bytes) {
+      GB_CUDA(cudaStreamSynchronize(s));
+      if (h->d_lst) GB_CUDA(cudaFree(h->d_lst));
+      h->d_lst = nullptr; h->lst_bytes = 0;
+      GB_CUDA(cudaMalloc((void **)&h->d_lst, bytes));
+      h->lst_bytes = bytes;
+    }
+    Batch b5 = bt;
+    b5.lst = h->d_lst;
+    b5.lst_cap = cap;
+    orbit_kernel<K, PHI, 5><<<(unsigned)grid5, GB_THREADS, 0, s>>>(h->mesh, b5);
+    gbint::count_launch(1);
+    GB_CUDA(cudaGetLastError());
+    return GORILLA_OK;
+  } else {
   if constexpr (K >= 3) {
     if (h->use_group) {
       const size_t smem_g = EXT == 2 ? GBG_SMEM_EXT : (bt.rebin ? GBG_SMEM + RebinSlots::BYTES : GBG_SMEM);
@@ -837,4 +874,5 @@ int launch_orbit_t(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
   gbint::count_launch(1);
   GB_CUDA(cudaGetLastError());
   return GORILLA_OK;
+  }
 }

@@ -109,6 +109,14 @@ struct PolyPusher {
   bool main_fc;      // EXT = 3: boole_face_correct of pusher_tetra_poly when the final processing starts: .false. after
                      // the third attempt (trouble shooting keeps its own copy), which disables the sub-stepping of the
                      // stop-inside segment (:564-568 with :893)
+  // EXT = 5 = adaptive sub-stepping combined with the list consumers (Hamiltonian time, optional quantities, J_par): the
+  // kernels of EXT = 2 and EXT = 3 in one, with tau_steps_list / intermediate_z0_list kept in full (3 * max_n_intermediate_steps
+  // entries, :98-101) in a per-thread global scratch region
+  static constexpr bool OPT = (EXT == 2 || EXT == 5);     // run-time options: optional quantities, events, hand-over kind 2
+  static constexpr bool ADAPT = (EXT == 3 || EXT == 5);   // boole_adaptive_time_steps
+  static constexpr bool LONG = (EXT == 5);
+  double *lst;       // EXT = 5: [entry][5] = tau_steps_list(i), intermediate_z0_list(1:4, i)
+  int lst_cap;
   int iper_phi;      // EXT = 2: toroidal period crossed by the hand-over (+1 / -1 / 0), for the phi = 0 mappings
   bool removed;      // EXT = 2: the push ended on one of the "remove particle" returns
   double dt_dtau_const, bmod0, vmod0, t_remain, z_init[4], k1, k3, dv2E;
@@ -143,11 +151,11 @@ struct PolyPusher {
       k3 = 0.0;
     }
     nsteps = 0;
-    if (EXT == 3) {
+    if (ADAPT) {
       n_adaptive = 0;
       main_fc = true;
     }
-    if (EXT == 2) {
+    if (OPT) {
       oq[0] = oq[1] = oq[2] = oq[3] = 0.0;  // initialise_optional_quantities (:2117-2130)
       iper_phi = 0;
       removed = false;
@@ -595,10 +603,18 @@ struct PolyPusher {
       return;
     }
     nsteps++;
-    if (EXT == 3) {
+    if (ADAPT) {
 #pragma unroll
       for (int i = 0; i < 4; i++) z0_last[i] = z[i];
-    } else if (EXT) {
+    }
+    if (LONG) {
+      if (nsteps <= lst_cap) {   // the reference's arrays hold 3 * max_n_intermediate_steps entries
+        double *e = lst + 5 * (size_t)(nsteps - 1);
+        e[0] = tau;
+#pragma unroll
+        for (int i = 0; i < 4; i++) e[1 + i] = z[i];
+      }
+    } else if (EXT && EXT != 3) {
       if (nsteps == 1) {
         tau_list[0] = tau;
 #pragma unroll
@@ -777,12 +793,42 @@ struct PolyPusher {
   // the loop over number_of_integration_steps at the end of the pusher (:662-667)
   GB_HD void optional_all()
   {
-    if (EXT != 2) return;
+    if (!OPT) return;
     if (!oq_mask) return;
+    if (LONG) {
+      const int nst = nsteps < lst_cap ? nsteps : lst_cap;
+      for (int i = 0; i < nst; i++) {
+        const double *e = lst + 5 * (size_t)i;
+        const double z0[4] = {e[1], e[2], e[3], e[4]};
+        optional_step(z0, e[0], nsteps > 1);
+      }
+      return;
+    }
     if (nsteps >= 1) optional_step(z0_list[0], tau_list[0], nsteps > 1);
     if (nsteps >= 2) optional_step(z0_list[1], tau_list[1], true);
   }
   // Hamiltonian time summed over the integration steps of the push (:470-486, 621-631); thl = t_hamiltonian_list(2:3)
+  // EXT = 5: the same over the long lists; i_root = the first step after which |t_hamiltonian| > |t_lim| (0: none),
+  // th_before = t_hamiltonian_list(i_root) = the sum before that step, th_before_last = the sum before the last step
+  GB_HD double ham_total_long(double t_lim, int &i_root, double &th_before, double &th_before_last)
+  {
+    double th = 0.0;
+    i_root = 0;
+    th_before = th_before_last = 0.0;
+    const int nst = nsteps < lst_cap ? nsteps : lst_cap;
+    for (int i = 0; i < nst; i++) {
+      const double *e = lst + 5 * (size_t)i;
+      const double z0[4] = {e[1], e[2], e[3], e[4]};
+      const double prev = th;
+      th = th + ham_delta(z0, e[0], nsteps > 1);
+      th_before_last = prev;
+      if (i_root == 0 && fabs(th) > fabs(t_lim)) {
+        i_root = i + 1;
+        th_before = prev;
+      }
+    }
+    return th;
+  }
   GB_HD double ham_total(double *thl)
   {
     double th = 0.0;
@@ -856,7 +902,57 @@ struct PolyPusher {
   GB_HD void events_after_push(double vpar_in, const PushOut &o, EvState &es)
   {
     es.n = 0;
-    if ((es.flags & 6) && !removed) {   // par_adiab_inv_tetra_poly (:3173-3291)
+    if (LONG && (es.flags & 6) && !removed) {   // par_adiab_inv_tetra_poly (:3173-3291) over the long lists
+      const double a44 = A.s, b4 = b[3], vpar_end = o.vpar;
+      const int nst = nsteps < lst_cap ? nsteps : lst_cap;
+      if ((vpar_end > 0.0) && (vpar_in < 0.0)) {
+        int turning_index = -1;   // findloc(intermediate_z0_list(4, 1:n) > 0) - 1
+        for (int i = 1; i <= nst; i++)
+          if (lst[5 * (size_t)(i - 1) + 4] > 0.0) {
+            turning_index = i - 1;
+            break;
+          }
+        if (turning_index != 0) {   // 0: reference stops with an error (cannot happen: z0(4,1) = vpar_in < 0)
+          if (turning_index == -1) turning_index = nst;
+          const double *et = lst + 5 * (size_t)(turning_index - 1);
+          const double tau_part1 = tau_vpar_root(a44, b4, et[4]);
+          for (int i = 1; i <= turning_index - 1; i++) {
+            const double *e = lst + 5 * (size_t)(i - 1);
+            es.J = es.J + par_adiab_tau(a44, b4, e[0], e[4]) * dt_dtau_const;
+          }
+          es.J = es.J + par_adiab_tau(a44, b4, tau_part1, et[4]) * dt_dtau_const;
+          if (es.cnt_v > 1 && (es.cnt_v / es.nskip_v * es.nskip_v == es.cnt_v)) {
+            double z[4] = {et[1], et[2], et[3], et[4]};
+            set_integration_coef_manually(z);
+            const int keep = nsteps;
+            const double k0 = lst[0], k1z = lst[1], k2z = lst[2], k3z = lst[3], k4z = lst[4];
+            nsteps = 0;                   // analytic_integration_external (:3378-3408) has no step book-keeping:
+            integrate<K>(z, tau_part1);   // entry 1 of the list is overwritten by integrate() and restored
+            lst[0] = k0; lst[1] = k1z; lst[2] = k2z; lst[3] = k3z; lst[4] = k4z;
+            nsteps = keep;
+            EvRec &e = es.e[es.n++];
+            e.kind = 2;
+            e.counter = es.cnt_v;
+#pragma unroll
+            for (int i = 0; i < 3; i++) e.x[i] = z[i] + r.x1s(i);
+            e.v[0] = es.J;
+            e.v[1] = energy_tot(z);
+          }
+          es.cnt_v = es.cnt_v + 1;
+          es.J = 0.0;
+          es.J = es.J + par_adiab_tau(a44, b4, et[0] - tau_part1, 0.0) * dt_dtau_const;
+          for (int i = turning_index + 1; i <= nst; i++) {
+            const double *e = lst + 5 * (size_t)(i - 1);
+            es.J = es.J + par_adiab_tau(a44, b4, e[0], e[4]) * dt_dtau_const;
+          }
+        }
+      } else {
+        for (int i = 1; i <= nst; i++) {
+          const double *e = lst + 5 * (size_t)(i - 1);
+          es.J = es.J + par_adiab_tau(a44, b4, e[0], e[4]) * dt_dtau_const;
+        }
+      }
+    } else if ((es.flags & 6) && !removed) {   // par_adiab_inv_tetra_poly (:3173-3291)
       const double a44 = A.s, b4 = b[3], vpar_end = o.vpar;
       const double v1 = z0_list[0][3], v2 = z0_list[1][3], tau1 = tau_list[0], tau2 = tau_list[1];
       if ((vpar_end > 0.0) && (vpar_in < 0.0)) {
@@ -1199,7 +1295,7 @@ struct PolyPusher {
     approx = analytic_approx<K>(0xFu, i_scaling, z, iface_new, tau);
     if (!approx) return false;
     integrate<K>(z, tau);
-    if (EXT == 3) overhead_adaptive<K>(i_scaling, false, true, iface_new, tau, z, face_correct);  // :811-814
+    if (ADAPT) overhead_adaptive<K>(i_scaling, false, true, iface_new, tau, z, face_correct);  // :811-814
     if (K > 2 && tau > tau_max) face_correct = false;
     if (!three_planes_ok(z, iface_new)) face_correct = false;
     if (normal_velocity(z, iface_new) > 0.0) face_correct = false;
@@ -1262,7 +1358,7 @@ struct PolyPusher {
       bool fc = true;
       // :2966-2971, with the REDUCED order and its i_scaling.  (The call inside the loop above, :2897-2902, is made with
       // boole_face_correct = .false. and returns at once, :893.)
-      if (EXT == 3) overhead_adaptive<(K == 4 ? 3 : K)>((K == 2 || K == 3) ? 1 : 0, false, true, iface_new, tau, z, fc);
+      if (ADAPT) overhead_adaptive<(K == 4 ? 3 : K)>((K == 2 || K == 3) ? 1 : 0, false, true, iface_new, tau, z, fc);
       if (!fc || !ts_checks(z, iface_new, tau, tau_max)) return false;
     }
     return true;
@@ -1276,8 +1372,8 @@ struct PolyPusher {
     ind_out = r.nb(f);
     iface_out = topo_face(flags, f);
     const int iper_phi = topo_perphi(flags, f);
-    if (EXT == 2) const_cast<PolyPusher *>(this)->iper_phi = iper_phi;
-    if (EXT == 2 && mp->skew != nullptr) {
+    if (OPT) const_cast<PolyPusher *>(this)->iper_phi = iper_phi;
+    if (OPT && mp->skew != nullptr) {
       // handover_processing_kind = 2: position exchange via Cartesian skew coordinates (pusher_tetra_func_mod.f90:59-89).
       // A particle leaving the domain keeps its exit position (the reference indexes tetra_skew_coord(-1) there).
       if (ind_out < 1) return;
@@ -1316,7 +1412,7 @@ struct PolyPusher {
 
   GB_HD void set_removed(PushOut &o) const
   {
-    if (EXT == 2) const_cast<PolyPusher *>(this)->removed = true;
+    if (OPT) const_cast<PolyPusher *>(this)->removed = true;
     o.ind_tetr = -1;
     o.iface = -1;
     o.finished = 0;
@@ -1333,10 +1429,12 @@ struct PolyPusher {
 #pragma unroll
     for (int i = 0; i < 3; i++) o.x[i] = z[i] + r.x1s(i);
     o.vpar = z[3];
-    const bool tt2 = (EXT == 1) || (EXT == 2 && mp->time_tracing == 2);
+    const bool tt2 = (EXT == 1) || (OPT && mp->time_tracing == 2);
     double thl[2] = {0.0, 0.0};
+    int i_root = 0;                              // EXT = 5 (long lists)
+    double th_before = 0.0, th_before_last = 0.0;
     double t_pass;
-    if (tt2) t_pass = ham_total(thl);
+    if (tt2) t_pass = LONG ? ham_total_long(t_remain, i_root, th_before, th_before_last) : ham_total(thl);
     else t_pass = tau * dt_dtau_const;
     o.t_pass = t_pass; // (:466) assigned before the stop-inside test; kept if the particle is removed below
     if (fabs(t_pass) >= fabs(t_remain)) {
@@ -1350,6 +1448,23 @@ struct PolyPusher {
         }
         nsteps = 0;
         tau = t_remain / dt_dtau_const;
+      } else if (LONG) {
+        // :523-541 over the long lists
+        const int nst = nsteps < lst_cap ? nsteps : lst_cap;
+        if (i_root == 0) {
+          i_root = nst;
+          th_before = th_before_last;
+        }
+        const double *e = lst + 5 * (size_t)(i_root - 1);
+#pragma unroll
+        for (int i = 0; i < 4; i++) z[i] = e[1 + i];
+        set_integration_coef_manually(z);
+        const double tau_step = e[0];
+        const double t_remain_new = t_remain - th_before;
+        nsteps = i_root - 1;
+        iface_new = iface_init;
+        tau = ham_root(z, t_remain_new);
+        if (tau > tau_step) tau = t_remain_new / dt_dtau_const;
       } else {
         // :523-541  step in which the Hamiltonian time exceeds t_remain (findloc over t_hamiltonian_list; an exact tie,
         // which the reference does not handle, takes the last step)
@@ -1365,7 +1480,7 @@ struct PolyPusher {
         if (tau > tau_step) tau = t_remain_new / dt_dtau_const;
       }
       integrate<K>(z, tau);
-      if (EXT == 3) {  // :564-568
+      if (ADAPT) {  // :564-568
         if (FAST) {
           double d[4];
           normal_distances(z, d);
@@ -1405,7 +1520,7 @@ struct PolyPusher {
         set_removed(o);
         return true;
       }
-      if (tt2) t_pass = ham_total(thl);
+      if (tt2) t_pass = LONG ? ham_total_long(t_remain, i_root, th_before, th_before_last) : ham_total(thl);
       else t_pass = tau * dt_dtau_const;
     }
 #pragma unroll
@@ -1465,7 +1580,7 @@ struct PolyPusher {
     double z[4] = {z_init[0], z_init[1], z_init[2], z_init[3]};
     integrate<K>(z, tau);
     if (!exit_point_ok(z, iface_new)) return false;
-    if (EXT == 3 && adaptive_delta_energy(z) > mp->desired_delta_energy) return false;  // sub-stepping: complete path
+    if (ADAPT && adaptive_delta_energy(z) > mp->desired_delta_energy) return false;  // sub-stepping: complete path
     if (K > 2 && tau > tau_max) return false;
     if ((EXT == 4 ? normal_velocity(z, iface_new) : normal_v_from_trajectory(iface_new, tau)) > 0.0) return false;   // :328-332
     return finish<true>(z, tau, iface_new, o);
@@ -1524,7 +1639,7 @@ struct PolyPusher {
     bool face_correct = approx;
     if (face_correct) {
       integrate<K>(z, tau);
-      if (EXT == 3) overhead_adaptive<K>(0, mp->boole_guess != 0, true, iface_new, tau, z, face_correct);  // :316-319
+      if (ADAPT) overhead_adaptive<K>(0, mp->boole_guess != 0, true, iface_new, tau, z, face_correct);  // :316-319
       if (!three_planes_ok(z, iface_new)) face_correct = false;
       if (!face_converged(z, iface_new)) face_correct = false;
       if (K > 2 && tau > tau_max) face_correct = false;
@@ -1554,7 +1669,7 @@ struct PolyPusher {
         return;
       }
       integrate<K>(z, tau);
-      if (EXT == 3) overhead_adaptive<K>((K == 2) ? 1 : 0, false, true, iface_new, tau, z, face_correct);  // :391-399
+      if (ADAPT) overhead_adaptive<K>((K == 2) ? 1 : 0, false, true, iface_new, tau, z, face_correct);  // :391-399
       if (K > 2 && tau > tau_max) face_correct = false;
       if (!three_planes_ok(z, iface_new)) face_correct = false;
       if (!face_converged(z, iface_new)) face_correct = false;
@@ -1567,7 +1682,7 @@ struct PolyPusher {
         }
       }
       if (!face_correct) {
-        if (EXT == 3) main_fc = false;
+        if (ADAPT) main_fc = false;
         if (!trouble_shooting(z, tau, iface_new)) {
           set_removed(o);
           return;
@@ -1603,16 +1718,19 @@ struct PushOutX {
   double oq[4];
   EvState es;
 };
-template <int K, int PHI>
+template <int K, int PHI, int EXT = 2>
 GB_HD_NOINLINE PushOutX push_full_call_x(const MeshDev *mp, double perpinv, int ind_tetr, int iface, double x0, double x1,
                                          double x2, double vpar, double t_remain, unsigned oq_mask, int ev_flags,
-                                         int nskip_p, int nskip_v, double J, int cnt_v, int cnt_p)
+                                         int nskip_p, int nskip_v, double J, int cnt_v, int cnt_p, double *lst = nullptr,
+                                         int lst_cap = 0)
 {
-  PolyPusher<K, PHI, 2> P;
+  PolyPusher<K, PHI, EXT> P;
   double stash[6];
   P.mp = mp;
   P.perpinv = perpinv;
   P.oq_mask = oq_mask;
+  P.lst = lst;
+  P.lst_cap = lst_cap;
   P.r.set_stash(stash, 1);
   PushOutX ox;
   PushOut &o = ox.o;

@@ -176,10 +176,7 @@ static int check_settings(const gorilla_settings *s)
     // pusher_tetra_poly.f90:868-874
     if (!(s->desired_delta_energy > 0.0)) return fail(GORILLA_ERR_ARG, "desired_delta_energy must be > 0");
     if (s->max_n_intermediate_steps < 2) return fail(GORILLA_ERR_ARG, "max_n_intermediate_steps must be >= 2");
-    if (s->i_time_tracing_option != 1 || s->boole_time_Hamiltonian || s->boole_gyrophase || s->boole_vpar_int ||
-        s->boole_vpar2_int)
-      return fail(GORILLA_ERR_UNSUPPORTED,
-                  "boole_adaptive_time_steps is not combined with Hamiltonian time tracing / optional quantities");
+    // with Hamiltonian time tracing / optional quantities / events the step lists are kept in full (EXT = 5 kernels)
   }
   // gorilla_settings_mod.f90:139-144 (coord_system is checked against the mesh in gorilla_b200_init)
   if (s->boole_strong_electric_field && (s->i_precomp != 0 || s->boole_newton_precalc))
@@ -372,7 +369,7 @@ extern "C" void gorilla_b200_free(gorilla_b200_handle *h)
   gorilla_b200_comm_free(h);
   cudaDeviceSynchronize();
   cudaFree(h->d_geom); cudaFree(h->d_bpart); cudaFree(h->d_phi); cudaFree(h->d_cold); cudaFree(h->d_se); cudaFree(h->d_ham); cudaFree(h->d_skew); cudaFree(h->s_oq); cudaFree(h->d_bin_start); cudaFree(h->d_bin_items);
-  cudaFree(h->d_poly4); cudaFree(h->d_rec44);
+  cudaFree(h->d_poly4); cudaFree(h->d_rec44); cudaFree(h->d_lst);
   cudaFree(h->d_acc); cudaFree(h->d_diag); cudaFree(h->g_d); cudaFree(h->g_i); cudaFree(h->sort_perm);
   cudaFree(h->s_J); cudaFree(h->s_cv); cudaFree(h->s_cp); cudaFree(h->s_ev); cudaFree(h->s_nev);
   if (h->h_diag) cudaFreeHost(h->h_diag);
@@ -490,6 +487,10 @@ GB_EXTERN_ORBIT_X(1, 3)
 GB_EXTERN_ORBIT_X(2, 3)
 GB_EXTERN_ORBIT_X(3, 3)
 GB_EXTERN_ORBIT_X(4, 3)
+GB_EXTERN_ORBIT_X(1, 5)   // adaptive sub-stepping + list consumers (gb_orbit_k{1..4}ax.cu)
+GB_EXTERN_ORBIT_X(2, 5)
+GB_EXTERN_ORBIT_X(3, 5)
+GB_EXTERN_ORBIT_X(4, 5)
 // precomputed-coefficient modes i_precomp = 1, 2 (EXT = 4, gb_orbit_k{2..4}p.cu; no strong-electric-field variant)
 #define GB_EXTERN_ORBIT_P(K) \
   extern template int launch_orbit_t<K, 0, 4>(gorilla_b200_handle *, const Batch &, cudaStream_t); \
@@ -505,8 +506,16 @@ static int launch_orbit_k(gorilla_b200_handle *h, const Batch &bt, cudaStream_t 
   if (h->settings.ipusher == 1)
     return (h->mesh.skew || h->mesh.newton_precalc || h->mesh.ode45 || bt.ev_flags) ? launch_orbit_t<0, PHI, 2>(h, bt, s)
                                                                       : launch_orbit_t<0, PHI>(h, bt, s);
-  if (((bt.optq && bt.oq_mask) || bt.ev_flags) && h->settings.boole_adaptive_time_steps)
-    return fail(GORILLA_ERR_UNSUPPORTED, "boole_adaptive_time_steps is not combined with optional quantities / events");
+  if (h->settings.boole_adaptive_time_steps && ((bt.optq && bt.oq_mask) || bt.ev_flags || h->mesh.time_tracing == 2)) {
+    // the list consumers with the long step lists of the adaptive scheme (hand-over kind 2 and i_precomp stay separate)
+    if (h->mesh.skew) return fail(GORILLA_ERR_UNSUPPORTED, "boole_adaptive_time_steps with handover_processing_kind = 2 is not combined with Hamiltonian time / optional quantities / events");
+    switch (h->settings.poly_order) {
+      case 1: return launch_orbit_t<1, PHI, 5>(h, bt, s);
+      case 2: return launch_orbit_t<2, PHI, 5>(h, bt, s);
+      case 3: return launch_orbit_t<3, PHI, 5>(h, bt, s);
+      default: return launch_orbit_t<4, PHI, 5>(h, bt, s);
+    }
+  }
   if ((bt.optq && bt.oq_mask) || bt.ev_flags || h->mesh.skew) {   // handover kind 2 lives in the EXT = 2 kernels
     switch (h->settings.poly_order) {
       case 1: return launch_orbit_t<1, PHI, 2>(h, bt, s);

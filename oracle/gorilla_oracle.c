@@ -769,6 +769,7 @@ typedef struct {
   double *tau_steps_list, (*intermediate_z0_list)[4];
   int list_cap; /* 2, or 3*max_n_intermediate_steps with the adaptive scheme (:98-104) */
   double list_tau_static[2], list_z0_static[2][4];
+  double *thl_heap; /* t_hamiltonian_list (:471) when the lists are the long ones of the adaptive scheme: list_cap + 1 entries */
   bool removed; /* the push ended on one of the 'remove particle' returns */
   gor_trace *tr;
 } poly_state;
@@ -1929,7 +1930,9 @@ static void pusher_tetra_poly(poly_state *s, int poly_order, int *ind_tetr_inout
   }
   /* ---- final processing (:459-487) */
   const bool tt2 = (m->i_time_tracing_option == 2);
-  double t_hamiltonian_list[3] = {0.0, 0.0, 0.0};
+  double thl_static[3] = {0.0, 0.0, 0.0};
+  double *t_hamiltonian_list = s->thl_heap ? s->thl_heap : thl_static; /* allocate(t_hamiltonian_list(number_of_integration_steps+1)) :471 */
+  t_hamiltonian_list[0] = 0.0;
   for (int i = 0; i < 3; i++) x[i] = z[i] + s->r[TP_X1 + i];
   *vpar = z[3];
   if (!tt2) {
@@ -3518,9 +3521,10 @@ static int orbit_timestep_core(const gor_mesh *m, double x[3], double *vpar, dou
   if (m->boole_adaptive_time_steps && m->ipusher == 2) { /* manage_intermediate_steps_arrays :98-101 */
     if (m->desired_delta_energy <= 0.0 || m->max_n_intermediate_steps < 2) return GOR_ERR_CONFIG; /* :868-874 */
     s.list_cap = 3 * m->max_n_intermediate_steps;
-    list_heap = malloc((size_t)s.list_cap * 5 * sizeof(double));
+    list_heap = malloc(((size_t)s.list_cap * 6 + 1) * sizeof(double));
     s.tau_steps_list = (double *)list_heap;
     s.intermediate_z0_list = (double(*)[4])((double *)list_heap + s.list_cap);
+    s.thl_heap = (double *)list_heap + (size_t)s.list_cap * 5;
   }
   s.perpinv = -0.5 * vperp2 / gor_bmod(m, z_save, *ind_tetr);
   s.perpinv2 = s.perpinv * s.perpinv;

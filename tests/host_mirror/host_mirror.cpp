@@ -82,6 +82,7 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
         }
       }
     } else {
+      if constexpr (EXT != 5) {   // EXT = 5 (adaptive steps + list consumers) always takes the complete path
       if (!force_full) {
         PolyPusher<K, PHI, EXT> P;
         double stash[6];
@@ -103,11 +104,16 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
           }
         }
       }
+      }
       if (!done) {
-        if constexpr (EXT == 2) {
-          const PushOutX ox = push_full_call_x<K, PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain, oq_mask,
-                                                       ev ? ev->flags : 0, ev ? ev->nskip_p : 1, ev ? ev->nskip_v : 1,
-                                                       ev ? *ev->J : 0.0, ev ? *ev->cnt_v : 0, ev ? *ev->cnt_p : 0);
+        if constexpr (EXT == 2 || EXT == 5) {
+          static thread_local std::vector<double> lst;
+          const int lst_cap = EXT == 5 ? 3 * m.max_n_intermediate_steps : 0;
+          if (EXT == 5 && lst.size() < (size_t)lst_cap * 5) lst.resize((size_t)lst_cap * 5);
+          const PushOutX ox = push_full_call_x<K, PHI, EXT>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain, oq_mask,
+                                                            ev ? ev->flags : 0, ev ? ev->nskip_p : 1, ev ? ev->nskip_v : 1,
+                                                            ev ? *ev->J : 0.0, ev ? *ev->cnt_v : 0, ev ? *ev->cnt_p : 0,
+                                                            EXT == 5 ? lst.data() : nullptr, lst_cap);
           o = ox.o;
           for (int q = 0; q < 4; q++) oq_acc[q] = oq_acc[q] + ox.oq[q];
           if (ev) {
@@ -239,6 +245,18 @@ int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *v
         switch (h->poly_order) { case 2: HM_RUNP(2, 0); break; case 3: HM_RUNP(3, 0); break; default: HM_RUNP(4, 0); }
       }
     } else
+#define HM_RUN5(K, PHI) run_particle<K, PHI, 5>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
+      t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, trace_cap, tt, tf, force_full, fallback, \
+      optq ? h->oq_mask : 0u, optq ? optq + 4 * i : nullptr)
+    if (h->ipusher == 2 && h->adaptive && ((optq && h->oq_mask) || m.time_tracing == 2)) {   // same dispatch as launch_orbit_k
+      if (m.se) {
+        switch (h->poly_order) { case 1: HM_RUN5(1, 2); break; case 2: HM_RUN5(2, 2); break; case 3: HM_RUN5(3, 2); break; default: HM_RUN5(4, 2); }
+      } else if (m.phi) {
+        switch (h->poly_order) { case 1: HM_RUN5(1, 1); break; case 2: HM_RUN5(2, 1); break; case 3: HM_RUN5(3, 1); break; default: HM_RUN5(4, 1); }
+      } else {
+        switch (h->poly_order) { case 1: HM_RUN5(1, 0); break; case 2: HM_RUN5(2, 0); break; case 3: HM_RUN5(3, 0); break; default: HM_RUN5(4, 0); }
+      }
+    } else
     if (h->ipusher == 2 && h->adaptive) {
       if (m.se) {
         switch (h->poly_order) { case 1: HM_RUNA(1, 2); break; case 2: HM_RUNA(2, 2); break; case 3: HM_RUNA(3, 2); break; default: HM_RUNA(4, 2); }
@@ -314,8 +332,19 @@ int64_t hm_orbit_timestep_events(void *p, int64_t n, double *x, double *vpar, do
 #define HM_RUNE(K, PHI) run_particle<K, PHI, 2>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
       t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, 0, nullptr, nullptr, force_full, fallback, \
       0u, nullptr, &ev)
+#define HM_RUNE5(K, PHI) run_particle<K, PHI, 5>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
+      t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, 0, nullptr, nullptr, force_full, fallback, \
+      0u, nullptr, &ev)
     if (h->ipusher == 1) {
       if (m.se) HM_RUNE(0, 2); else if (m.phi) HM_RUNE(0, 1); else HM_RUNE(0, 0);
+    } else if (h->adaptive) {
+      if (m.se) {
+        switch (h->poly_order) { case 2: HM_RUNE5(2, 2); break; case 3: HM_RUNE5(3, 2); break; default: HM_RUNE5(4, 2); }
+      } else if (m.phi) {
+        switch (h->poly_order) { case 2: HM_RUNE5(2, 1); break; case 3: HM_RUNE5(3, 1); break; default: HM_RUNE5(4, 1); }
+      } else {
+        switch (h->poly_order) { case 2: HM_RUNE5(2, 0); break; case 3: HM_RUNE5(3, 0); break; default: HM_RUNE5(4, 0); }
+      }
     } else if (m.se) {
       switch (h->poly_order) { case 2: HM_RUNE(2, 2); break; case 3: HM_RUNE(3, 2); break; default: HM_RUNE(4, 2); }
     } else if (m.phi) {

@@ -67,8 +67,7 @@ def test_settings_rules(product_lib, small_mesh):
     mesh, _, settings = small_mesh
     good = _adaptive(settings, 2, 1e-10)
     for bad, code in ((_with(good, desired_delta_energy=0.0), 1), (_with(good, max_n_intermediate_steps=1), 1),
-                      (_with(good, ipusher=1), 1), (_with(good, i_time_tracing_option=2), 2),
-                      (_with(good, boole_vpar_int=True), 2)):
+                      (_with(good, ipusher=1), 1), (_with(good, handover_processing_kind=2), 2)):
         with pytest.raises(api.GorillaError) as ei:
             api.Gorilla(mesh, bad)
         assert ei.value.code == code

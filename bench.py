@@ -386,8 +386,11 @@ def roofline_of(settings, wl_name, bytes_per_crossing, per_rank_pushes, launch_m
             "frac": fp64_ach / muladd_peak, "inst_per_crossing": fp64_per, "dfma_peak": dfma_peak / 1e12,
             "peak_source": "measured in this run (gorilla_b200_fp64_peak)"}
     phi = 2 if strong_e else 1 if has_phi else 0
-    tag = ",EXT=2" if args.optional_quantities else ",EXT=1" if ext else ",EXT=3" if settings.boole_adaptive_time_steps else ""
-    kern = f"orbit_kernel{'_g' if settings.ipusher == 2 and settings.poly_order >= 3 else ''}<{0 if settings.ipusher == 1 else settings.poly_order},{phi}{tag}>"
+    tag = (",EXT=5" if settings.boole_adaptive_time_steps and (args.optional_quantities or ext) else
+           ",EXT=2" if args.optional_quantities else ",EXT=1" if ext else ",EXT=3" if settings.boole_adaptive_time_steps else
+           ",EXT=4" if settings.ipusher == 2 and settings.i_precomp else
+           ",EXT=2" if settings.ipusher == 1 and (settings.boole_newton_precalc or settings.boole_pusher_ode45) else "")
+    kern = f"orbit_kernel{'_g' if settings.ipusher == 2 and settings.poly_order >= 3 and 'EXT=5' not in tag else ''}<{0 if settings.ipusher == 1 else settings.poly_order},{phi}{tag}>"
     common = {"traffic": traffic, "traffic_source": traffic_src, "dram_frac": dram_frac, "kernel": kern,
               "launch_ms": launch_ms, "kernel_share_of_step": kernel_share,
               "note": "frac = ALGORITHMIC bytes (or FP64 instructions) per second against the peak; dram_frac = DRAM bytes "

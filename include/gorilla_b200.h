@@ -60,8 +60,10 @@ typedef struct gorilla_settings {
                                         gorilla_settings_mod.f90:124-129) */
   int32_t handover_processing_kind;  /* 1 periodic shifts | 2 position exchange via Cartesian skew coordinates
                                         (pusher_tetra_func_mod.f90:59-89; needs gorilla_mesh_desc.tetra_skew_coord) */
-  int32_t boole_adaptive_time_steps; /* energy-controlled sub-stepping (pusher_tetra_poly.f90:830-1254); polynomial pusher,
-                                        i_time_tracing_option = 1, not combined with optional quantities / events */
+  int32_t boole_adaptive_time_steps; /* energy-controlled sub-stepping (pusher_tetra_poly.f90:830-1254); polynomial pusher.
+                                        Combined with Hamiltonian time tracing / optional quantities / events the step
+                                        lists are kept in full (3 * max_n_intermediate_steps entries of 40 bytes per
+                                        device thread, allocated on first use; refused above 64 GB) */
   int32_t boole_strong_electric_field; /* ExB-drift terms of order v_E^2; cylindrical grids (coord_system 1) only */
   int32_t boole_grid_for_find_tetra; /* ignored: the device scan does not need the box accelerator */
   /* optional quantities of pusher_tetra_poly (gorilla_settings_mod.f90:51-55; ipusher = 2 only); boole_gyrophase

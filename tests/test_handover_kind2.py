@@ -89,6 +89,48 @@ def test_host_mirror_parity(skew_mesh, K):
         assert ra["n_pushes"].sum() > 500
 
 
+def _face_starts(grid, n, seed):
+    """start points of which three in five lie exactly on a cell face (R, Z or phi plane of the vertex grid)"""
+    xa, va, wa = workloads.particles_cyl(n, seed, rmin_frac=0.05, rmax_frac=0.95)
+    hr, hz, hphi = 100.0 / grid.n1, 100.0 / grid.n3, 2 * np.pi / grid.n2
+    xa[0::5, 0] = 120.0 + hr * np.round((xa[0::5, 0] - 120.0) / hr)
+    xa[1::5, 2] = -50.0 + hz * np.round((xa[1::5, 2] + 50.0) / hz)
+    xa[2::5, 1] = hphi * np.floor(xa[2::5, 1] / hphi)
+    return xa, va, wa
+
+
+def test_start_on_a_face_is_handed_over_with_skew_coordinates(skew_mesh):
+    """find_tetra's neighbour hop for a start point on a face goes through pusher_handover2neighbour, which
+    honours handover_processing_kind = 2 (find_tetra_mod.f90:283-600); oracle <-> host compile of the device headers."""
+    mesh, grid, settings = skew_mesh
+    st = _with(settings, poly_order=2)
+    om, hm = OracleMesh(mesh, st), HostMirror(mesh, st)
+    n = 1500
+    xa, va, wa = _face_starts(grid, n, 17)
+    xb, vb, wb = xa.copy(), va.copy(), wa.copy()
+    sa, sb = workloads.fresh_state(n), workloads.fresh_state(n)
+    ra = om.orbit_timestep_trace(xa, va, wa, 2e-6, *sa, 16)
+    rb = hm.orbit_timestep(xb, vb, wb, 2e-6, *sb, trace_cap=16)
+    assert same(ra["trace_tetr"], rb["trace_tetr"]) and same(ra["trace_face"], rb["trace_face"])
+    assert same(xa, xb) and same(va, vb) and same(wa, wb) and same(sa[1], sb[1]) and same(sa[2], sb[2])
+    assert (sa[1] > 0).sum() > 0.9 * n
+
+
+@pytest.mark.gpu
+def test_gpu_start_on_a_face(skew_mesh, cuda_device):
+    from gorilla_b200 import Gorilla
+    mesh, grid, settings = skew_mesh
+    st = _with(settings, poly_order=2)
+    om, g = OracleMesh(mesh, st), Gorilla(mesh, st)
+    n = 3000
+    xa, va, wa = _face_starts(grid, n, 19)
+    xb = xa.copy()
+    ta, fa = om.find_tetra(xa, va, wa)
+    tb, fb = g.find_tetra(xb, va, wa)
+    assert same(ta, tb) and same(fa, fb) and same(xa, xb) and (fa > 0).sum() > 100
+    g.close()
+
+
 def test_settings_rules(product_lib, skew_mesh, small_mesh):
     mesh, _, settings = skew_mesh
     for bad, code in ((_with(settings, boole_adaptive_time_steps=True, desired_delta_energy=1e-10, max_n_intermediate_steps=10), 2),

@@ -735,6 +735,8 @@ struct gorilla_b200_handle {
   double *d_rec44 = nullptr;   // geom + bpart as one contiguous record per tetrahedron (bulk-copy gather only)
   double *d_lst = nullptr;     // EXT = 5 kernels: per-thread step lists
   size_t lst_bytes = 0;
+  cudaEvent_t lst_done = nullptr;
+  bool lst_used = false;
   double *s_oq = nullptr;   // [cap][4] scratch for the optional quantities (host-pointer entry point)
   uint32_t oq_mask = 0;
   int32_t *d_bin_start = nullptr, *d_bin_items = nullptr;
@@ -814,8 +816,9 @@ int launch_orbit_t(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
     if (bytes > ((size_t)64 << 30))
       return gbint::fail(GORILLA_ERR_UNSUPPORTED, "adaptive sub-stepping with Hamiltonian time / optional quantities / events: the step lists "
                                                   "(threads x 3 max_n_intermediate_steps x 40 B) exceed 64 GB; lower max_n_intermediate_steps");
+    if (!h->lst_done) GB_CUDA(cudaEventCreateWithFlags(&h->lst_done, cudaEventDisableTiming));
     if (bytes > h->lst_bytes) {
-      GB_CUDA(cudaStreamSynchronize(s));
+      GB_CUDA(cudaDeviceSynchronize());   // a launch on another stream may still be using the old region
       if (h->d_lst) GB_CUDA(cudaFree(h->d_lst));
       h->d_lst = nullptr; h->lst_bytes = 0;
       GB_CUDA(cudaMalloc((void **)&h->d_lst, bytes));
@@ -824,9 +827,13 @@ int launch_orbit_t(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
     Batch b5 = bt;
     b5.lst = h->d_lst;
     b5.lst_cap = cap;
+    // one scratch region per handle: a launch on another stream waits for the previous one to finish with it
+    if (h->lst_used) GB_CUDA(cudaStreamWaitEvent(s, h->lst_done, 0));
     orbit_kernel<K, PHI, 5><<<(unsigned)grid5, GB_THREADS, 0, s>>>(h->mesh, b5);
     gbint::count_launch(1);
     GB_CUDA(cudaGetLastError());
+    GB_CUDA(cudaEventRecord(h->lst_done, s));
+    h->lst_used = true;
     return GORILLA_OK;
   } else {
   if constexpr (K >= 3) {

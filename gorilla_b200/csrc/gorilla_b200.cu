@@ -374,6 +374,7 @@ extern "C" void gorilla_b200_free(gorilla_b200_handle *h)
   cudaFree(h->s_J); cudaFree(h->s_cv); cudaFree(h->s_cp); cudaFree(h->s_ev); cudaFree(h->s_nev);
   if (h->h_diag) cudaFreeHost(h->h_diag);
   if (h->sort_done) cudaEventDestroy(h->sort_done);
+  if (h->lst_done) cudaEventDestroy(h->lst_done);
   for (int k = 0; k < GB_NSLOTS; k++) {
     CallSlot &c = h->slots[k];
     cudaFree(c.d_ctr);

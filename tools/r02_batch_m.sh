@@ -12,5 +12,7 @@ $B --poly-order 3 --particles 300000 > $O/r02m_bench_analytic_k3.json 2>> $O/r02
 $B --poly-order 3 --particles 300000 --i-precomp 1 > $O/r02m_bench_analytic_k3_precomp1.json 2>> $O/r02m_err.log
 $B --ipusher 1 > $O/r02m_bench_analytic_rk4.json 2>> $O/r02m_err.log
 $B --ipusher 1 --newton-precalc > $O/r02m_bench_analytic_rk4_newton_precalc.json 2>> $O/r02m_err.log
-for f in $O/r02m_bench_*.json; do echo $f; cut -c1-120 $f; done; tail -5 $O/r02m_err.log
+(time timeout 900 python tools/config2_conservation.py 100000 300 4) > $O/r02m_config2_conservation.json 2> $O/r02m_config2.err
+(time timeout 900 python tools/config3_loss.py 1000000 500) > $O/r02m_config3_full_run.json 2> $O/r02m_config3.err
+for f in $O/r02m_bench_*.json; do echo $f; cut -c1-120 $f; done; tail -5 $O/r02m_err.log; cut -c1-600 $O/r02m_config2_conservation.json; tail -3 $O/r02m_config2.err; cut -c1-600 $O/r02m_config3_full_run.json
 bash tools/r02_batch_l.sh

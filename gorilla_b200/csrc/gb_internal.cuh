@@ -452,9 +452,12 @@ __global__ void __launch_bounds__(GB_THREADS, BULK ? 3 : gb_min_blocks(K, EXT)) 
 #define GBG_THREADS 512
 #define GBG_GROUP 128   // threads per group = 4 warps
 
-// group-wide OR of a per-thread predicate + barrier; must be reached by whole warps of the group in converged state
+// group-wide OR of a per-thread predicate + barrier.  Every lane of the group's four warps reaches it (lanes never leave the
+// push loop on their own); __syncwarp() re-converges a warp whose lanes come out of divergent code first, so that the barrier
+// is executed by whole warps (compute-sanitizer synccheck flagged divergent arrivals at the loop top).
 __device__ __forceinline__ bool group_any(bool pred, int bar_id)
 {
+  __syncwarp();
   int r;
   asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbarrier.red.or.pred q, %2, %3, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
                : "=r"(r) : "r"((int)pred), "r"(bar_id), "r"(GBG_GROUP) : "memory");
@@ -551,6 +554,7 @@ __device__ __forceinline__ int rebin_class(int w0)
 }
 __device__ __forceinline__ void group_sync(int bar_id)
 {
+  __syncwarp();
   asm volatile("barrier.sync %0, %1;" ::"r"(bar_id), "r"(GBG_GROUP) : "memory");
 }
 static __device__ __noinline__ double solve_group_rebin(bool busy, int deg, double q0, double q1, double q2, double q3,

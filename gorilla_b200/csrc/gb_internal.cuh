@@ -453,15 +453,36 @@ __global__ void __launch_bounds__(GB_THREADS, BULK ? 3 : gb_min_blocks(K, EXT)) 
 #define GBG_GROUP 128   // threads per group = 4 warps
 
 // group-wide OR of a per-thread predicate + barrier.  Every lane of the group's four warps reaches it (lanes never leave the
-// push loop on their own); __syncwarp() re-converges a warp whose lanes come out of divergent code first, so that the barrier
-// is executed by whole warps (compute-sanitizer synccheck flagged divergent arrivals at the loop top).
+// push loop on their own); __syncwarp() re-converges a warp whose lanes come out of divergent code first.  The OR goes
+// through shared memory -- one ballot word per warp, double-buffered by a per-warp phase so that one barrier per call is
+// enough: a warp can only overwrite its word of phase p two calls later, i.e. after a barrier that every reader of the old
+// value has passed -- and the barrier is a plain named barrier.sync with a thread count (what compute-sanitizer's synccheck
+// models; the earlier barrier.red.or form was reported as block-divergent by the tool).
+__device__ __forceinline__ volatile unsigned *group_flags()
+{
+  __shared__ unsigned f[48];   // [phase][warp] ballot words, then the phase of every warp
+  return f;
+}
+__device__ __forceinline__ void group_init()
+{
+  if ((threadIdx.x & 31u) == 0) group_flags()[32 + (threadIdx.x >> 5)] = 0u;
+  __syncwarp();
+}
 __device__ __forceinline__ bool group_any(bool pred, int bar_id)
 {
+  volatile unsigned *f = group_flags();
+  const unsigned w = threadIdx.x >> 5, grp = w & 3u;
   __syncwarp();
-  int r;
-  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbarrier.red.or.pred q, %2, %3, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
-               : "=r"(r) : "r"((int)pred), "r"(bar_id), "r"(GBG_GROUP) : "memory");
-  return r != 0;
+  const unsigned b = __ballot_sync(0xffffffffu, pred);
+  const unsigned ph = f[32 + w];
+  __syncwarp();   // every lane has read the phase before lane 0 flips it
+  if ((threadIdx.x & 31u) == 0) {
+    f[ph * 16 + w] = b;
+    f[32 + w] = ph ^ 1u;
+  }
+  asm volatile("barrier.sync %0, %1;" ::"r"(bar_id), "r"(GBG_GROUP) : "memory");
+  const unsigned r = f[ph * 16 + grp] | f[ph * 16 + grp + 4] | f[ph * 16 + grp + 8] | f[ph * 16 + grp + 12];
+  return r != 0u;
 }
 
 // monic polynomial solve of every lane that has one (busy), iteration by iteration behind the group barrier
@@ -632,6 +653,7 @@ __global__ void __launch_bounds__(GBG_THREADS, 1) orbit_kernel_g(const __grid_co
   const int bar_id = 1 + (int)((threadIdx.x >> 5) & 3u);   // warps w, w+4, w+8, w+12 share sub-partition w
   int32_t ind_tetr = -1, iface = -1;
   S.zero_counters();
+  group_init();
 
   bool active = lane_refill<PHI, EXT>(m, bt, S, lane, ind_tetr, iface);
   for (;;) {

@@ -453,11 +453,17 @@ __global__ void __launch_bounds__(GB_THREADS, BULK ? 3 : gb_min_blocks(K, EXT)) 
 #define GBG_GROUP 128   // threads per group = 4 warps
 
 // group-wide OR of a per-thread predicate + barrier.  Every lane of the group's four warps reaches it (lanes never leave the
-// push loop on their own); __syncwarp() re-converges a warp whose lanes come out of divergent code first.  The OR goes
-// through shared memory -- one ballot word per warp, double-buffered by a per-warp phase so that one barrier per call is
-// enough: a warp can only overwrite its word of phase p two calls later, i.e. after a barrier that every reader of the old
-// value has passed -- and the barrier is a plain named barrier.sync with a thread count (what compute-sanitizer's synccheck
-// models; the earlier barrier.red.or form was reported as block-divergent by the tool).
+// push loop on their own); __syncwarp() re-converges a warp whose lanes come out of divergent code first.
+// Two forms.  Shipped: one barrier.red.or with a thread count (one instruction).  compute-sanitizer's synccheck reports that
+// form as "divergent thread(s) in block" -- it is the partial-count barrier.red it objects to: with GB_GROUP_BARRIER_SMEM=1
+// the OR goes through shared memory (one ballot word per warp, double-buffered by a per-warp phase so that one barrier per
+// call is enough: a warp can only overwrite its word of phase p two calls later, i.e. after a barrier that every reader of
+// the old value has passed) behind a plain named barrier.sync, the same tests pass under synccheck, results are identical,
+// and orders 3/4 run 3-11 % slower (profiles/r02_compute_sanitizer.txt).
+#ifndef GB_GROUP_BARRIER_SMEM
+#define GB_GROUP_BARRIER_SMEM 0
+#endif
+#if GB_GROUP_BARRIER_SMEM
 __device__ __forceinline__ volatile unsigned *group_flags()
 {
   __shared__ unsigned f[48];   // [phase][warp] ballot words, then the phase of every warp
@@ -484,6 +490,17 @@ __device__ __forceinline__ bool group_any(bool pred, int bar_id)
   const unsigned r = f[ph * 16 + grp] | f[ph * 16 + grp + 4] | f[ph * 16 + grp + 8] | f[ph * 16 + grp + 12];
   return r != 0u;
 }
+#else
+__device__ __forceinline__ void group_init() {}
+__device__ __forceinline__ bool group_any(bool pred, int bar_id)
+{
+  __syncwarp();
+  int r;
+  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbarrier.red.or.pred q, %2, %3, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
+               : "=r"(r) : "r"((int)pred), "r"(bar_id), "r"(GBG_GROUP) : "memory");
+  return r != 0;
+}
+#endif
 
 // monic polynomial solve of every lane that has one (busy), iteration by iteration behind the group barrier
 static __device__ __noinline__ double solve_group(bool busy, int deg, double q0, double q1, double q2, double q3, double lambda,

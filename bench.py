@@ -95,7 +95,7 @@ def parse_args():
                     help="weak: --particles per GPU; strong: --total-particles sharded contiguously [rN/G,(r+1)N/G) (BASELINE config 5)")
     ap.add_argument("--total-particles", type=int, default=10_000_000, help="strong scaling: particles of the whole job")
     ap.add_argument("--prefetch", type=int, default=-1, choices=[-1, 0, 1], help="neighbour-record L2 prefetch: -1 library default (off), 0 off, 1 on")
-    ap.add_argument("--gather", type=int, default=-1, choices=[-1, 0, 1], help="record gather: -1 library default (bulk copies when the mesh is > 4x the L2), 0 vector loads, 1 bulk copies (TMA)")
+    ap.add_argument("--gather", type=int, default=-1, choices=[-1, 0, 1, 2], help="record gather: -1 library default, 0 vector loads, 1 per-lane bulk copies (TMA), 2 warp-cooperative cp.async copies")
     ap.add_argument("--start", default="default", choices=["default", "spread"],
                     help="vmec_qi: 'spread' starts s in U[0.15, 0.95] instead of on s = 0.5 (records touched exceed the L2)")
     ap.add_argument("--no-variants", action="store_true", help="skip the short K=4 / RK4 / spread-start variant runs")
@@ -369,7 +369,7 @@ def timed_steps(res, t_step, steps, warmup, sort, flush_buf, barrier=None, sampl
 
 
 def roofline_of(settings, wl_name, bytes_per_crossing, per_rank_pushes, launch_ms, hbm_peak, peak_src, muladd_peak, dfma_peak,
-                kernel_share, has_phi, strong_e, ext, args):
+                kernel_share, has_phi, strong_e, ext, args, gather_mode=0):
     """north_star: the slower of the two per-push limits decides the bound -- HBM gather vs FP64 issue."""
     achieved = bytes_per_crossing * per_rank_pushes / (launch_ms * 1e-3) / 1e9
     kkey = "rk4" if settings.ipusher == 1 else settings.poly_order
@@ -391,7 +391,11 @@ def roofline_of(settings, wl_name, bytes_per_crossing, per_rank_pushes, launch_m
            ",EXT=4" if settings.ipusher == 2 and settings.i_precomp else
            ",EXT=2" if settings.ipusher == 1 and (settings.boole_newton_precalc or settings.boole_pusher_ode45) else "")
     kern = f"orbit_kernel{'_g' if settings.ipusher == 2 and settings.poly_order >= 3 and 'EXT=5' not in tag else ''}<{0 if settings.ipusher == 1 else settings.poly_order},{phi}{tag}>"
+    if gather_mode and not tag and (settings.ipusher == 1 or settings.poly_order == 2):   # the library's launch rule
+        kern = kern[:-1] + f",0,GATHER={gather_mode}>"
     common = {"traffic": traffic, "traffic_source": traffic_src, "dram_frac": dram_frac, "kernel": kern,
+              "gather": {0: "per-lane vector loads", 1: "per-lane bulk copies (TMA) one push ahead",
+                         2: "warp-cooperative cp.async copies one push ahead"}[int(gather_mode)],
               "launch_ms": launch_ms, "kernel_share_of_step": kernel_share,
               "note": "frac = ALGORITHMIC bytes (or FP64 instructions) per second against the peak; dram_frac = DRAM bytes "
                       "actually moved (ncu capture of this kernel on this workload) against the same peak -- a dram_frac far "
@@ -553,7 +557,7 @@ def main():
             dv = rv.diag()
             lm = mv["kernel_ms"] / 2
             rf = roofline_of(st, wname, bytes_per_crossing, mv["pushes"] / 2, lm, hbm_peak, peak_src, muladd_peak, dfma_peak,
-                             mv["kernel_ms"] / mv["elapsed_ms"], has_phi, strong_e, False, args)
+                             mv["kernel_ms"] / mv["elapsed_ms"], has_phi, strong_e, False, args, gv.get_gather())
             variants.append({"variant": label, "workload": wname, "particles": nv_, "steps": 2, "warmup": 3,
                              "value": mv["pushes"] / (mv["elapsed_ms"] * 1e-3), "unit": UNIT,
                              "ms_per_step": mv["elapsed_ms"] / 2, "kernel": rf["kernel"], "bound": rf["bound"],
@@ -567,7 +571,8 @@ def main():
         per_rank_pushes = m["pushes"] / max(1, args.steps)
         launch_ms = m["kernel_ms"] / max(1, args.steps)
         roofline = roofline_of(settings, wl["name"], bytes_per_crossing, per_rank_pushes, launch_ms, hbm_peak, peak_src,
-                               muladd_peak, dfma_peak, m["kernel_ms"] / m["elapsed_ms"], has_phi, strong_e, ext, args)
+                               muladd_peak, dfma_peak, m["kernel_ms"] / m["elapsed_ms"], has_phi, strong_e, ext, args,
+                               g.get_gather())
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

@@ -135,7 +135,7 @@ EXPORTED_SYMBOLS = (
     "gorilla_b200_orbit_timestep_events", "gorilla_b200_orbit_timestep_events_dev",
     "gorilla_b200_find_tetra", "gorilla_b200_invariants", "gorilla_b200_invariants_dev",
     "gorilla_b200_get_counters", "gorilla_b200_sort_permutation_dev", "gorilla_b200_resort_dev",
-    "gorilla_b200_set_host_resort", "gorilla_b200_set_launch_config", "gorilla_b200_fp64_peak", "gorilla_b200_set_prefetch", "gorilla_b200_set_gather",
+    "gorilla_b200_set_host_resort", "gorilla_b200_set_launch_config", "gorilla_b200_fp64_peak", "gorilla_b200_set_prefetch", "gorilla_b200_set_gather", "gorilla_b200_get_gather",
     "gorilla_b200_comm_unique_id", "gorilla_b200_comm_init", "gorilla_b200_comm_free", "gorilla_b200_comm_allreduce_f64",
     "gorilla_b200_shard_range", "gorilla_b200_diag_reset", "gorilla_b200_diag_reduce_dev", "gorilla_b200_diag_reduce",
     "gorilla_mesh_build", "gorilla_mesh_get_desc", "gorilla_mesh_get_vertices", "gorilla_mesh_free",
@@ -187,6 +187,7 @@ def load_library():
     lib.gorilla_b200_set_launch_config.argtypes = [vp, i32, i32]
     lib.gorilla_b200_set_prefetch.argtypes = [vp, i32]
     lib.gorilla_b200_set_gather.argtypes = [vp, i32]
+    lib.gorilla_b200_get_gather.argtypes = [vp, C.POINTER(C.c_int32)]
     lib.gorilla_b200_debug_force_full.argtypes = [vp, i32]
     lib.gorilla_b200_debug_find_bins.argtypes = [vp, i32]
     lib.gorilla_b200_debug_use_group.argtypes = [vp, i32]
@@ -624,8 +625,15 @@ class Gorilla:
         _check(load_library().gorilla_b200_set_prefetch(self._h, int(mode)))
 
     def set_gather(self, mode: int):
-        """Record gather of the order-1/2 and RK4 kernels: 0 vector loads, 1 bulk copies one push ahead, -1 auto."""
+        """Record gather of the order-2 and RK4 kernels: 0 vector loads, 1 per-lane bulk copies (TMA) one push ahead,
+        2 warp-cooperative cp.async copies one push ahead, -1 auto."""
         _check(load_library().gorilla_b200_set_gather(self._h, int(mode)))
+
+    def get_gather(self) -> int:
+        """The gather mode in effect (what -1 resolved to)."""
+        m = C.c_int32(0)
+        _check(load_library().gorilla_b200_get_gather(self._h, C.byref(m)))
+        return int(m.value)
 
     def diag_reduce(self, x, vpar, vperp, ind_tetr, energy_ref=None, p_phi_ref=None, perpinv_ref=None) -> Diag:
         """gorilla_b200_diag_reduce: the same reduction from numpy arrays on the host (collective over the communicator)."""

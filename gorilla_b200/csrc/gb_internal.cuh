@@ -362,11 +362,17 @@ __device__ __forceinline__ void lane_reduce_counters(const Batch &bt, const Lane
 // EXT = 1: Hamiltonian time tracing (i_time_tracing_option = 2); EXT = 2: time tracing option read at run time plus the
 // optional quantities of pusher_tetra_poly; the plain variant (EXT = 0) is the hot path of the default settings and
 // carries none of that code (the optional-quantity code alone costs the order-2 kernel ~400 bytes of spills).
-// BULK = true: the geom / bpart sub-records reach the lane through the bulk-copy engine and a shared-memory slot, prefetched
+// GATHER = 1: the geom / bpart sub-records reach the lane through the bulk-copy engine and a shared-memory slot, prefetched
 // one push ahead (gb_mesh.cuh); 48 KB of dynamic shared memory per CTA on top of the lane slots => three CTAs per SM.
+// GATHER = 2: the same slots filled by the warp-cooperative cp.async gather (gb_mesh.cuh).
 #define GB_BULK_SMEM ((size_t)GB_THREADS * (GB_BULK_STRIDE + 16))
-template <int K, int PHI, int EXT = 0, bool BULK = false>
-__global__ void __launch_bounds__(GB_THREADS, BULK ? 3 : gb_min_blocks(K, EXT)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
+#define GB_COOP_SMEM ((size_t)GB_THREADS * GB_COOP_SMEM_PER_THREAD)
+#ifndef GB_COOP_MINB
+#define GB_COOP_MINB 3   // CTAs per SM of the cooperative-gather kernels (4 needs GB_COOP_CHUNKS <= 15: shared memory)
+#endif
+constexpr size_t gb_gather_smem(int gather) { return gather == 1 ? GB_BULK_SMEM : gather == 2 ? GB_COOP_SMEM : 0; }
+template <int K, int PHI, int EXT = 0, int BULK = 0>
+__global__ void __launch_bounds__(GB_THREADS, BULK == 2 ? GB_COOP_MINB : BULK ? 3 : gb_min_blocks(K, EXT)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
 {
   __shared__ __align__(16) unsigned char s_raw[(EXT == 2 || EXT == 5) ? LaneSlots<GB_THREADS>::BYTES_EXT2 : LaneSlots<GB_THREADS>::BYTES];
   LaneSlots<GB_THREADS> S;
@@ -374,13 +380,17 @@ __global__ void __launch_bounds__(GB_THREADS, BULK ? 3 : gb_min_blocks(K, EXT)) 
   const unsigned lane = threadIdx.x & 31u;
   int32_t ind_tetr = -1, iface = -1;
   S.zero_counters();
-  if constexpr (BULK) bulk_init();
+  if constexpr (BULK == 1) bulk_init();
+  if constexpr (BULK == 2) coop_init();
+  unsigned wmask = 0xffffffffu;   // GATHER = 2: the lanes of this warp that are still in the push loop
 
   // One lane = one particle at a time.  A lane whose particle is done refills itself at the end of the same loop
   // body and leaves the loop for good when the queue is empty, so the body has no "is this lane active" region (whose
   // convergence-barrier register was live, and spilled, across every push).
   bool active = lane_refill<PHI, EXT>(m, bt, S, lane, ind_tetr, iface);
+  if constexpr (BULK == 2) wmask = __ballot_sync(0xffffffffu, active);
   while (active) {
+    if constexpr (BULK == 2) coop_wait(wmask);   // the records requested during the previous push are in the slots
     S.IndSave() = ind_tetr;
     PushOut o;
     bool done = false;
@@ -389,7 +399,7 @@ __global__ void __launch_bounds__(GB_THREADS, BULK ? 3 : gb_min_blocks(K, EXT)) 
       if (!bt.force_full) {
         const double x[3] = {S.D(LS_X0), S.D(LS_X1), S.D(LS_X2)};
         RkPusher<PHI, (EXT == 2 ? 2 : 0)> R;
-        R.P.r.set_stash(S.Stash(), GB_THREADS, BULK);
+        R.P.r.set_stash(S.Stash(), GB_THREADS, BULK, wmask);
         R.init(&m, perpinv, ind_tetr, x, iface, S.D(LS_VPAR), S.D(LS_TREM));
         done = R.template push<true>(o);
       }
@@ -417,7 +427,7 @@ __global__ void __launch_bounds__(GB_THREADS, BULK ? 3 : gb_min_blocks(K, EXT)) 
         P.mp = &m;
         P.perpinv = perpinv;
         if constexpr (EXT == 2) P.oq_mask = bt.oq_mask;
-        P.r.set_stash(S.Stash(), GB_THREADS, BULK);
+        P.r.set_stash(S.Stash(), GB_THREADS, BULK, wmask);
         done = P.push_fast(ind_tetr, iface, x, S.D(LS_VPAR), S.D(LS_TREM), o, &S.D(LS_TREM));
         if constexpr (EXT == 2) {
           if (done) lane_ext2_after_fast<K, PHI>(bt, S, P, o);
@@ -433,8 +443,11 @@ __global__ void __launch_bounds__(GB_THREADS, BULK ? 3 : gb_min_blocks(K, EXT)) 
     }
     if (lane_after_push<PHI, EXT>(m, bt, S, o, S.IndSave(), ind_tetr, iface))
       active = lane_refill<PHI, EXT>(m, bt, S, lane, ind_tetr, iface);
+    if constexpr (BULK == 2) wmask = __ballot_sync(wmask, active);   // lanes that leave the loop drop out of the warp's gather
   }
-  if constexpr (BULK) bulk_wait();   // no copy may still be on its way to this CTA's shared memory when it exits
+  // no copy may still be on its way to this CTA's shared memory when it exits
+  if constexpr (BULK == 1) bulk_wait();
+  if constexpr (BULK == 2) asm volatile("cp.async.wait_all;" ::: "memory");
   lane_reduce_counters(bt, S, lane);
 }
 
@@ -775,7 +788,8 @@ struct gorilla_b200_handle {
   gorilla_settings settings{};
   double *d_geom = nullptr, *d_bpart = nullptr, *d_phi = nullptr, *d_cold = nullptr, *d_se = nullptr, *d_ham = nullptr, *d_skew = nullptr;
   double *d_poly4 = nullptr;   // tetra_physics_poly4 records (i_precomp = 1, 2)
-  double *d_rec44 = nullptr;   // geom + bpart as one contiguous record per tetrahedron (bulk-copy gather only)
+  double *d_rec44 = nullptr;   // geom + bpart as one contiguous record per tetrahedron (bulk-copy / cooperative gather only)
+  int rec_nd = 0;              // doubles per record in d_rec44: 44 (bulk copy) or GB_COOP_ND (cooperative gather)
   double *d_lst = nullptr;     // EXT = 5 kernels: per-thread step lists
   size_t lst_bytes = 0;
   cudaEvent_t lst_done = nullptr;
@@ -894,21 +908,27 @@ int launch_orbit_t(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
     }
   }
   if constexpr (EXT == 0 && (K == 0 || K == 2)) {
-    if (h->bulk_gather && h->threads_per_cta == GB_THREADS) {
-      GB_CUDA(cudaFuncSetAttribute(orbit_kernel<K, PHI, EXT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB_BULK_SMEM));
-      int per_sm_b = h->ctas_per_sm;
-      if (per_sm_b <= 0) {
-        GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, orbit_kernel<K, PHI, EXT, true>, GB_THREADS, GB_BULK_SMEM));
-        if (per_sm_b < 1) per_sm_b = 1;
-      }
-      int64_t grid_b = (int64_t)h->num_sms * per_sm_b;
-      const int64_t need_b = (bt.n + GB_THREADS - 1) / GB_THREADS;
-      if (grid_b > need_b) grid_b = need_b;
-      if (grid_b < 1) grid_b = 1;
-      orbit_kernel<K, PHI, EXT, true><<<(unsigned)grid_b, GB_THREADS, GB_BULK_SMEM, s>>>(h->mesh, bt);
-      gbint::count_launch(1);
-      GB_CUDA(cudaGetLastError());
-      return GORILLA_OK;
+    // force_full (test hook) never reaches the warp-level gather call of the fast path: those launches use the plain kernel
+    if (h->bulk_gather && h->threads_per_cta == GB_THREADS && !(h->bulk_gather == 2 && bt.force_full)) {
+      auto launch_gather = [&](auto kernel, size_t smem) -> int {
+        GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        int per_sm_b = h->ctas_per_sm;
+        if (per_sm_b <= 0) {
+          GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, kernel, GB_THREADS, smem));
+          if (per_sm_b < 1) per_sm_b = 1;
+        }
+        int64_t grid_b = (int64_t)h->num_sms * per_sm_b;
+        const int64_t need_b = (bt.n + GB_THREADS - 1) / GB_THREADS;
+        if (grid_b > need_b) grid_b = need_b;
+        if (grid_b < 1) grid_b = 1;
+        kernel<<<(unsigned)grid_b, GB_THREADS, smem, s>>>(h->mesh, bt);
+        gbint::count_launch(1);
+        GB_CUDA(cudaGetLastError());
+        return GORILLA_OK;
+      };
+      if (h->bulk_gather == 2) return launch_gather(orbit_kernel<K, PHI, EXT, 2>, GB_COOP_SMEM);
+      return launch_gather(orbit_kernel<K, PHI, EXT, 1>, GB_BULK_SMEM);
     }
   }
   int per_sm = h->ctas_per_sm;

@@ -240,6 +240,69 @@ __device__ __forceinline__ void lds2(unsigned a, double &x, double &y)
 {
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
 }
+
+// ---- warp-cooperative gather (kernels launched with GATHER = 2) -----------------------------------------------------------
+// The per-lane gathers cost the L1 one wavefront per lane and instruction: every lane holds a different record, so the 11
+// 256-bit loads of a push are 352 wavefronts per warp (ncu: the first uses of the record carry ~30 % of all stall samples of
+// the order-2 kernel although 94 % of the sectors hit the L2).  Here the WARP copies the 32 records its lanes need next:
+// once the exit faces are known every lane hands the tetrahedron behind its face to the warp (shuffle), and the records are
+// fetched with 16-byte cp.async copies (LDGSTS, no registers), eight consecutive lanes taking one 128-byte line of one record:
+// an instruction touches 4 lines instead of 32, 24 instructions move the 32 records (stored with a stride of 384 bytes =
+// three lines for this purpose, MeshDev::rec44 with GB_COOP_ND doubles per tetrahedron) straight into the lanes'
+// shared-memory slots, without the lane-by-lane serialisation the bulk-copy instruction needs (its operands are
+// warp-uniform).  The copies overlap the rest of the push; the lanes wait (cp.async.wait_all + __syncwarp) at the top of the
+// next push and read their slot with LDS.128.  A lane whose slot does not hold the record it needs (new particle, push
+// redone by the complete path, warp no longer complete at the end of the queue) falls back to the per-lane loads.
+// dynamic shared memory of such a kernel of NT threads: [NT][368] slots | [NT] i32 tetrahedron in the slot
+#define GB_COOP_ND 48
+// GB_COOP_CHUNKS 16-byte pieces of the record are staged (22 = all of it; fewer = the rest of bpart is loaded per lane at the
+// start of the push, which buys shared memory for a fourth CTA per SM).  Slot stride: conflict free for LDS.128 when the
+// number of 16-byte pieces per slot is odd.
+#ifndef GB_COOP_CHUNKS
+#define GB_COOP_CHUNKS 22
+#endif
+#define GB_COOP_STRIDE (16 * (GB_COOP_CHUNKS | 1))
+#define GB_COOP_SMEM_PER_THREAD (GB_COOP_STRIDE + 4)
+__device__ __forceinline__ unsigned coop_slot() { return bulk_base() + gb_tid_now() * GB_COOP_STRIDE; }
+__device__ __forceinline__ unsigned coop_tag(unsigned t) { return bulk_base() + blockDim.x * GB_COOP_STRIDE + t * 4u; }
+__device__ __forceinline__ void coop_init() { sts_i32(coop_tag(gb_tid_now()), 0); }
+// every copy into the slots of this warp has landed (called by all lanes of wmask together)
+__device__ __forceinline__ void coop_wait(unsigned wmask)
+{
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncwarp(wmask);
+}
+// called by all lanes of wmask together; ind_next < 1 = this lane has nothing to fetch
+__device__ __forceinline__ void coop_issue(const double *rec, int ind_next, unsigned wmask)
+{
+  const unsigned tid = gb_tid_now(), lane = tid & 31u;
+  const bool full = (wmask == 0xffffffffu);
+  const int want = ind_next >= 1 ? ind_next : 0;
+  sts_i32(coop_tag(tid), full ? want : 0);
+  if (full) {
+    // lanes 8 sub .. 8 sub + 7 copy the record of lane 4 g + sub (g = 0..7), lane q of them piece q of every 128-byte line
+    const unsigned sub = lane >> 3, q = lane & 7u;
+    const char *srcl = reinterpret_cast<const char *>(rec) - 8 * GB_COOP_ND + q * 16u;
+    const unsigned dstl = bulk_base() + ((tid & ~31u) + sub) * GB_COOP_STRIDE + q * 16u;
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+      // a lane with nothing to fetch gets the first record (its tag says "empty"): no branch in the copy sequence
+      const unsigned t = (unsigned)max(__shfl_sync(0xffffffffu, want, 4 * g + (int)sub), 1);
+      const char *src = srcl + (uint64_t)t * (8 * GB_COOP_ND);
+      const unsigned dst = dstl + (unsigned)g * 4u * GB_COOP_STRIDE;
+      // line j of the record: pieces 8 j .. 8 j + 7, the last line up to piece GB_COOP_CHUNKS - 1
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      if (GB_COOP_CHUNKS >= 16)
+        asm volatile("cp.async.cg.shared.global [%0+128], [%1+128], 16;" ::"r"(dst), "l"(src) : "memory");
+      else
+        asm volatile("{\n\t.reg .pred pq;\n\tsetp.lt.u32 pq, %2, %3;\n\t@pq cp.async.cg.shared.global [%0+128], [%1+128], 16;\n\t}"
+                     ::"r"(dst), "l"(src), "r"(q), "n"(GB_COOP_CHUNKS - 8) : "memory");
+      if (GB_COOP_CHUNKS > 16)
+        asm volatile("{\n\t.reg .pred pq;\n\tsetp.lt.u32 pq, %2, %3;\n\t@pq cp.async.cg.shared.global [%0+256], [%1+256], 16;\n\t}"
+                     ::"r"(dst), "l"(src), "r"(q), "n"(GB_COOP_CHUNKS - 16) : "memory");
+    }
+  }
+}
 #endif
 
 // One tetrahedron's hot record in registers.  PHI: 0 = magnetic part only (Phi group exactly zero), 1 = with the
@@ -257,13 +320,20 @@ struct Rec {
   // -- shared memory in the kernel, st[k * sts], k = 0..5 -- and x1s()/nb()/flags() read them back from there.
   volatile double *st;
   int sts;
-  bool bulk;   // this lane's geom / bpart sub-records arrive by bulk copy into its shared-memory slot (BULK kernels)
-  GB_HD void set_stash(volatile double *p, int stride, bool bulk_gather = false) { st = p; sts = stride; bulk = bulk_gather; }
-  // ask for the record of the tetrahedron behind the exit face while the push is still running
+  int gmode;       // how this lane's geom / bpart sub-records arrive: 0 per-lane loads, 1 bulk copy into its shared-memory slot
+                   // (GATHER = 1 kernels), 2 warp-cooperative cp.async into the slot (GATHER = 2 kernels)
+  unsigned wmask;  // gmode 2: the lanes of this warp that are still in the push loop
+  GB_HD void set_stash(volatile double *p, int stride, int gather = 0, unsigned warp_mask = 0u)
+  {
+    st = p; sts = stride; gmode = gather; wmask = warp_mask;
+  }
+  // ask for the record of the tetrahedron behind the exit face while the push is still running (ind_next < 1: nothing to
+  // fetch).  gmode 2: a warp-level operation, every lane of wmask has to call it.
   GB_HD void prefetch_next(const MeshDev &m, int ind_next)
   {
 #if defined(__CUDA_ARCH__)
-    if (bulk && ind_next >= 1) bulk_issue(m.rec44, ind_next);
+    if (gmode == 1 && ind_next >= 1) bulk_issue(m.rec44, ind_next);
+    if (gmode == 2) coop_issue(m.rec44, ind_next, wmask);
 #else
     (void)m; (void)ind_next;
 #endif
@@ -288,13 +358,34 @@ struct Rec {
     double g[GEOM_ND], b[BPART_ND];
     const double *pg = m.geom + t * GEOM_ND, *pb = m.bpart + t * BPART_ND;
 #if defined(__CUDA_ARCH__)
-    if (bulk) {
+    bool from_slot = false;
+    if (gmode == 1) {
       bulk_acquire(m.rec44, ind_tetr);
-      const unsigned slot = bulk_slot();
+      from_slot = true;
+    } else if (gmode == 2) {
+      from_slot = lds_i32(coop_tag(gb_tid_now())) == ind_tetr;   // the kernel has called coop_wait at the top of the push
+    }
+    if (from_slot) {
+      const unsigned slot = gmode == 2 ? coop_slot() : bulk_slot();
+      // doubles of bpart that are staged in the slot (all of them with the bulk copy)
+      constexpr int NB = GB_COOP_CHUNKS >= 22 ? BPART_ND : 2 * (GB_COOP_CHUNKS - 8);
+      const int nb = gmode == 2 ? NB : BPART_ND;
 #pragma unroll
       for (int i = 0; i < GEOM_ND; i += 2) lds2(slot + 8u * i, g[i], g[i + 1]);
 #pragma unroll
-      for (int i = 0; i < BPART_ND; i += 2) lds2(slot + 128u + 8u * i, b[i], b[i + 1]);
+      for (int i = 0; i < BPART_ND; i += 2)
+        if (i < nb) lds2(slot + 128u + 8u * i, b[i], b[i + 1]);
+      if (nb < BPART_ND) {   // the rest of bpart: per-lane sector loads (the sector that straddles the boundary is read whole)
+#pragma unroll
+        for (int i = (NB / 4) * 4; i < BPART_ND; i += 4) {
+          double t0, t1, t2, t3;
+          ld4(pb + i, t0, t1, t2, t3);
+          if (i >= NB) b[i] = t0;
+          if (i + 1 >= NB) b[i + 1] = t1;
+          if (i + 2 >= NB) b[i + 2] = t2;
+          if (i + 3 >= NB) b[i + 3] = t3;
+        }
+      }
     } else
 #endif
     {

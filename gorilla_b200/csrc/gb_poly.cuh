@@ -1556,11 +1556,13 @@ struct PolyPusher {
       double cm[4][5];
 #pragma unroll
       for (int f = 0; f < 4; f++) face_coeffs<2>(r.an[f], f == 0, z_init, cm[f], f);
-      if (!pick_exit<2>(cm, 0xFu, 0, iface_new, tau)) return false;
+      const bool have_exit = pick_exit<2>(cm, 0xFu, 0, iface_new, tau);
+      // GATHER kernels: neighbour's record -> shared memory.  Called by every lane (the cooperative form is a warp operation)
+      r.prefetch_next(*mp, have_exit ? r.nb(iface_new - 1) : 0);
+      if (!have_exit) return false;
     }
     tau_max = tau * GB_EPS_TAU;
     if (mp->prefetch) prefetch_record<PHI>(*mp, r.nb(iface_new - 1));   // the exit face is (almost always) this one
-    r.prefetch_next(*mp, r.nb(iface_new - 1));                          // BULK kernels: neighbour's record -> shared memory
     t.kind = 1;
     t.tau = tau;
     t.deg = 0;

@@ -1004,9 +1004,12 @@ struct RkPusher {
     o.z_save_set = 0;
     o.t_pass = 0.0;
     bool removed = false, converged = false;
-    if (quad_analytic_approx(z, allowed, iface_new, dtau)) {
+    const bool have_guess = quad_analytic_approx(z, allowed, iface_new, dtau);
+    // GATHER kernels: the record behind the quadratic guess of the exit face -> shared memory (every lane calls it: the
+    // cooperative form is a warp operation)
+    if (FAST) P.r.prefetch_next(*P.mp, have_guess ? P.r.nb(iface_new - 1) : 0);
+    if (have_guess) {
       if (FAST && P.mp->prefetch) prefetch_record<PHI>(*P.mp, P.r.nb(iface_new - 1));   // quadratic guess of the exit face
-      if (FAST) P.r.prefetch_next(*P.mp, P.r.nb(iface_new - 1));
       integration_step(z, dtau, dzdtau);
       tau = tau + dtau;
     } else {

@@ -400,32 +400,50 @@ extern "C" int gorilla_b200_set_launch_config(gorilla_b200_handle *h, int32_t ct
   }
   return GORILLA_OK;
 }
-// geom[t][16] + bpart[t][28] -> rec44[t][44]
-__global__ void interleave_rec44_kernel(int64_t ntetr, const double *geom, const double *bpart, double *rec44)
+// geom[t][16] + bpart[t][28] -> rec[t][nd]: nd = 44 (bulk-copy gather) or GB_COOP_ND = 48 (warp-cooperative gather: records
+// of three 128-byte lines, the last four doubles are padding)
+__global__ void interleave_rec44_kernel(int64_t ntetr, const double *geom, const double *bpart, double *rec, int nd)
 {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ntetr * 44; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t t = i / 44;
-    const int k = (int)(i - t * 44);
-    rec44[i] = k < GEOM_ND ? geom[t * GEOM_ND + k] : bpart[t * BPART_ND + (k - GEOM_ND)];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ntetr * nd; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / nd;
+    const int k = (int)(i - t * nd);
+    rec[i] = k < GEOM_ND ? geom[t * GEOM_ND + k] : k < GEOM_ND + BPART_ND ? bpart[t * BPART_ND + (k - GEOM_ND)] : 0.0;
   }
 }
 extern "C" int gorilla_b200_set_gather(gorilla_b200_handle *h, int32_t mode)
 {
-  if (!h || mode < -1 || mode > 1) return fail(GORILLA_ERR_ARG, "gorilla_b200_set_gather: mode must be -1 (auto), 0 (loads) or 1 (bulk copy)");
+  if (!h || mode < -1 || mode > 2)
+    return fail(GORILLA_ERR_ARG, "gorilla_b200_set_gather: mode must be -1 (auto), 0 (loads), 1 (bulk copy) or 2 (warp-cooperative copy)");
   GB_ENTER(h);
-  // auto: bulk copies when the hot records of the mesh exceed the L2 by a wide margin (measured, order 2: +46 % / +69 % on the
-  // 3.8 M / 4.2 M-tetrahedron meshes, -34 % on the L2-resident 0.96 M-tetrahedron one; RK4: +12 % / -2 % on the two big meshes)
+  // auto: records staged in shared memory one push ahead when the hot records of the mesh exceed the L2 by a wide margin.
+  // Measured, order 2, 3.84 M-tetrahedron EFIT mesh: vector loads 5.56e9, per-lane bulk copies 8.24e9, warp-cooperative copies
+  // 1.19e10 crossings/s (RK4: 3.95e9 bulk, 4.23e9 cooperative); on the L2-resident 0.96 M-tetrahedron meshes the vector loads stay
+  // ahead (VMEC order 2: 1.42e10 against 1.38e10 cooperative / 0.94e10 bulk).  With the electrostatic / strong-E sub-records
+  // (which no staged form covers) the bulk copies are the better companion of the remaining per-lane loads: they do not share
+  // the L1 with them (WEST, strong E, order 2: 3.83e9 bulk, 3.39e9 cooperative).
   const bool has_bulk_kernel = h->settings.ipusher == 1 || h->settings.poly_order == 2;   // launch_orbit_t: EXT = 0, K = 2 or RK4
-  const int want = mode >= 0 ? mode : ((h->hot_bytes > 4 * h->l2_bytes && has_bulk_kernel) ? 1 : 0);
-  if (want && !h->d_rec44) {
-    GB_CUDA(cudaMalloc((void **)&h->d_rec44, (size_t)h->mesh.ntetr * 44 * sizeof(double)));
-    interleave_rec44_kernel<<<h->num_sms * 8, 256>>>(h->mesh.ntetr, h->d_geom, h->d_bpart, h->d_rec44);
+  const int want = mode >= 0 ? mode : ((h->hot_bytes > 4 * h->l2_bytes && has_bulk_kernel) ? (h->mesh.phi ? 1 : 2) : 0);
+  const int nd = want == 2 ? GB_COOP_ND : 44;
+  if (want && (!h->d_rec44 || h->rec_nd != nd)) {
+    GB_CUDA(cudaDeviceSynchronize());   // a launch may still be reading the other layout
+    if (h->d_rec44) GB_CUDA(cudaFree(h->d_rec44));
+    h->d_rec44 = nullptr;
+    h->mesh.rec44 = nullptr;
+    GB_CUDA(cudaMalloc((void **)&h->d_rec44, (size_t)h->mesh.ntetr * nd * sizeof(double)));
+    interleave_rec44_kernel<<<h->num_sms * 8, 256>>>(h->mesh.ntetr, h->d_geom, h->d_bpart, h->d_rec44, nd);
     g_launch_count++;
     GB_CUDA(cudaGetLastError());
     GB_CUDA(cudaDeviceSynchronize());
     h->mesh.rec44 = h->d_rec44;
+    h->rec_nd = nd;
   }
   h->bulk_gather = want;
+  return GORILLA_OK;
+}
+extern "C" int gorilla_b200_get_gather(gorilla_b200_handle *h, int32_t *mode)
+{
+  if (!h || !mode) return fail(GORILLA_ERR_ARG, "gorilla_b200_get_gather: null argument");
+  *mode = h->bulk_gather;
   return GORILLA_OK;
 }
 extern "C" int gorilla_b200_set_prefetch(gorilla_b200_handle *h, int32_t mode)

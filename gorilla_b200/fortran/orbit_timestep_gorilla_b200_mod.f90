@@ -25,7 +25,7 @@ module orbit_timestep_gorilla_b200_mod
   private
   public :: initialize_gorilla_b200, finalize_gorilla_b200, orbit_timestep_gorilla, orbit_timestep_gorilla_batch, &
             orbit_timestep_gorilla_batch_optional, orbit_timestep_gorilla_batch_events, find_tetra_batch, &
-            gorilla_b200_counters_t, get_counters_b200, invariants_b200, set_host_resort_b200, &
+            gorilla_b200_counters_t, get_counters_b200, invariants_b200, set_host_resort_b200, set_gather_b200, &
             gorilla_b200_diag_t, gorilla_b200_event_t, gorilla_b200_event_settings_t, &
             comm_unique_id_b200, comm_init_b200, comm_free_b200, shard_range_b200, diag_reset_b200, diag_reduce_b200
 
@@ -140,6 +140,11 @@ module orbit_timestep_gorilla_b200_mod
       import :: c_int, c_ptr, c_int32_t
       type(c_ptr), value :: handle
       integer(c_int32_t), value :: on
+    end function
+    integer(c_int) function gorilla_b200_set_gather(handle, mode) bind(C, name='gorilla_b200_set_gather')
+      import :: c_int, c_ptr, c_int32_t
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: mode
     end function
     integer(c_int) function gorilla_b200_comm_unique_id(id) bind(C, name='gorilla_b200_comm_unique_id')
       import :: c_int, c_char
@@ -354,6 +359,14 @@ contains
     logical, intent(in)  :: on
     integer, intent(out) :: ierr
     ierr = gorilla_b200_set_host_resort(handle, merge(1_c_int32_t, 0_c_int32_t, on))
+  end subroutine
+
+  !> How the order-2 / RK4 kernels gather the tetrahedron records: -1 library default (by mesh size and field content),
+  !> 0 per-lane vector loads, 1 per-lane bulk copies, 2 warp-cooperative copies one push ahead.  Results are identical.
+  subroutine set_gather_b200(mode, ierr)
+    integer, intent(in)  :: mode
+    integer, intent(out) :: ierr
+    ierr = gorilla_b200_set_gather(handle, int(mode, c_int32_t))
   end subroutine
 
   !> Multi-GPU: rank 0 creates the id, every rank joins with its own handle (one process per GPU).

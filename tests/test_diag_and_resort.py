@@ -280,14 +280,14 @@ def test_periodic_relocation_many_periods_away(cuda_device, product_lib):
 @pytest.mark.gpu
 @pytest.mark.parametrize("pusher", ["poly2", "rk4"])
 def test_gather_and_prefetch_modes_give_identical_results(small_mesh, small_mesh_phi, cuda_device, pusher):
-    """gorilla_b200_set_gather (vector loads vs per-lane bulk copies one push ahead) and gorilla_b200_set_prefetch only change
+    """gorilla_b200_set_gather (vector loads, per-lane bulk copies or warp-cooperative copies one push ahead) and gorilla_b200_set_prefetch only change
     how a record reaches the lane: every particle, trace and counter is identical -- including lanes whose predicted exit
     face was wrong (fall-back pushes), lost particles and refills."""
     import dataclasses
     for mesh, _, settings in (small_mesh, small_mesh_phi):
         st = dataclasses.replace(settings, ipusher=1) if pusher == "rk4" else dataclasses.replace(settings, ipusher=2, poly_order=2)
         out = []
-        for gather, prefetch in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        for gather, prefetch in ((0, 0), (1, 0), (0, 1), (1, 1), (2, 0), (2, 1)):
             g = Gorilla(mesh, st)
             g.set_gather(gather)
             g.set_prefetch(prefetch)

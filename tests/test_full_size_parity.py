@@ -32,12 +32,15 @@ def _with(settings, **kw):
     return type(settings)(**{**settings.__dict__, **kw})
 
 
-def cross_check(mesh, settings, particles, t_step, n_calls, n_traced):
+def cross_check(mesh, settings, particles, t_step, n_calls, n_traced, gather=None):
     """n_calls successive calls on all particles; the first call records the trace of the first n_traced particles (oracle:
     one particle at a time), the other particles and calls go through the oracle's batched entry point (OpenMP)."""
     x, vpar, vperp = particles
     n = x.shape[0]
     om, g = OracleMesh(mesh, settings), Gorilla(mesh, settings)
+    if gather is not None:
+        g.set_gather(gather)
+        assert g.get_gather() == gather
     xa, va, wa = x.copy(), vpar.copy(), vperp.copy()
     xb, vb, wb = x.copy(), vpar.copy(), vperp.copy()
     ia, ta, fa = workloads.fresh_state(n)
@@ -92,6 +95,19 @@ def test_config3_vmec_alphas(vmec_full, cuda_device, K):
     assert mesh.ntetr == 960_000
     r = cross_check(mesh, _with(settings, poly_order=K), workloads.particles_vmec_alpha(600, 31), 1.0e-4, 3, 600)
     assert r["pushes"] > 600 * 3 * 1500
+
+
+@pytest.mark.parametrize("pusher", ["poly2", "rk4"])
+@pytest.mark.parametrize("gather", [1, 2])
+def test_config3_vmec_alphas_staged_gathers(vmec_full, cuda_device, pusher, gather):
+    """The same workload with the records staged in shared memory one push ahead -- per-lane bulk copies (1) and the
+    warp-cooperative cp.async gather (2), which the library selects by itself only on meshes much larger than the L2 -- against
+    the oracle: 2048 particles = 64 full warps, so the warp-level copy path, its per-lane fall-back (refills, pushes redone by
+    the complete ladder, warps that empty towards the end of the queue) and the hand-over between them are all exercised."""
+    mesh, settings = vmec_full
+    st = _with(settings, ipusher=1) if pusher == "rk4" else _with(settings, ipusher=2, poly_order=2)
+    r = cross_check(mesh, st, workloads.particles_vmec_alpha(2048, 37), 1.0e-4, 2, 256, gather=gather)
+    assert r["pushes"] > 2048 * 2 * 1500
 
 
 def test_config1_efit_flux_deuterons(efit_flux_full, cuda_device):

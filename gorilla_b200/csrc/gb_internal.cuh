@@ -137,8 +137,11 @@ enum { LC_LOST = 0, LC_FIN, LC_FB0, LC_FB1, LC_FB2, LC_FB3, LC_ADAPT, LC_LOST_IN
 // kernel places them in static shared memory, the 16-warp lock-step kernel in dynamic shared memory.  Every accessor
 // re-reads %tid.x through a volatile asm: otherwise the compiler forms the slot addresses once, keeps them live across the
 // push and spills THEM.
-template <int NT>
+// STASH = false (cooperative-gather kernels that stage the whole record, PHI = 2): no stash in shared memory, the kernel
+// keeps those six doubles in local memory.
+template <int NT, bool STASH = true>
 struct LaneSlots {
+  static constexpr int NSTASH = STASH ? 6 : 0;
   double (*d)[NT];        // [LS_ND] loop state
   double (*stash)[NT];    // [6] first vertex + topology words of the current record (Rec::load)
   long long *idx, *npush;
@@ -147,13 +150,13 @@ struct LaneSlots {
   int *ind_save;
   double (*oq)[NT];       // [5] EXT = 2: optional quantities 0..3, par_adiab_inv
   int (*ec)[NT];          // [2] EXT = 2: counter_banana_mappings, counter_phi_0_mappings
-  static constexpr size_t BYTES = (size_t)NT * ((LS_ND + 6) * 8 + 3 * 8 + LC_N * 4 + 4 + 4 /*pad to 8*/);
+  static constexpr size_t BYTES = (size_t)NT * ((LS_ND + NSTASH) * 8 + 3 * 8 + LC_N * 4 + 4 + 4 /*pad to 8*/);
   static constexpr size_t BYTES_EXT2 = BYTES + (size_t)NT * (5 * 8 + 2 * 4);
   __device__ __forceinline__ void carve(unsigned char *base, bool ext2)
   {
     d = reinterpret_cast<double (*)[NT]>(base);
     stash = d + LS_ND;
-    idx = reinterpret_cast<long long *>(stash + 6);
+    idx = reinterpret_cast<long long *>(stash + NSTASH);
     npush = idx + NT;
     cpush = reinterpret_cast<unsigned long long *>(npush + NT);
     cnt = reinterpret_cast<unsigned int (*)[NT]>(cpush + NT);
@@ -181,8 +184,8 @@ struct LaneSlots {
 
 // Pull the next particle that actually has to be pushed into this lane's slot; false when the queue is empty.
 // Warp-aggregated: the lanes that arrive here together take consecutive queue entries with one atomic.
-template <int PHI, int EXT, int NT>
-__device__ __forceinline__ bool lane_refill(const MeshDev &m, const Batch &bt, const LaneSlots<NT> &S, unsigned lane,
+template <int PHI, int EXT, int NT, bool ST>
+__device__ __forceinline__ bool lane_refill(const MeshDev &m, const Batch &bt, const LaneSlots<NT, ST> &S, unsigned lane,
                                             int32_t &ind_tetr, int32_t &iface)
 {
   for (;;) {
@@ -277,8 +280,8 @@ __device__ __forceinline__ PushOut lane_ext2_full(const MeshDev &m, const Batch 
 // Book-keeping after a push (orbit_timestep_gorilla.f90:129-142): loop state, trace, counters; when the particle has
 // finished its time step or is lost, its state goes back to the caller's arrays.  Returns true in that case (the lane
 // needs a new particle).  ind_prev = the tetrahedron the push started in (ind_tetr_save of the reference).
-template <int PHI, int EXT, int NT>
-__device__ __forceinline__ bool lane_after_push(const MeshDev &m, const Batch &bt, const LaneSlots<NT> &S, const PushOut &o,
+template <int PHI, int EXT, int NT, bool ST>
+__device__ __forceinline__ bool lane_after_push(const MeshDev &m, const Batch &bt, const LaneSlots<NT, ST> &S, const PushOut &o,
                                                 int ind_prev, int32_t &ind_tetr, int32_t &iface)
 {
   S.D(LS_X0) = o.x[0]; S.D(LS_X1) = o.x[1]; S.D(LS_X2) = o.x[2];
@@ -342,8 +345,8 @@ __device__ __forceinline__ bool lane_after_push(const MeshDev &m, const Batch &b
 }
 
 // counters: warp reduce, one atomic per warp and counter
-template <int NT>
-__device__ __forceinline__ void lane_reduce_counters(const Batch &bt, const LaneSlots<NT> &S, unsigned lane)
+template <int NT, bool ST>
+__device__ __forceinline__ void lane_reduce_counters(const Batch &bt, const LaneSlots<NT, ST> &S, unsigned lane)
 {
   __syncwarp();
   unsigned long long v[11] = {S.Cpush(), S.C(LC_LOST), S.C(LC_FIN), S.C(LC_FB0), S.C(LC_FB1), S.C(LC_FB2), S.C(LC_FB3),
@@ -366,22 +369,26 @@ __device__ __forceinline__ void lane_reduce_counters(const Batch &bt, const Lane
 // one push ahead (gb_mesh.cuh); 48 KB of dynamic shared memory per CTA on top of the lane slots => three CTAs per SM.
 // GATHER = 2: the same slots filled by the warp-cooperative cp.async gather (gb_mesh.cuh).
 #define GB_BULK_SMEM ((size_t)GB_THREADS * (GB_BULK_STRIDE + 16))
-#define GB_COOP_SMEM ((size_t)GB_THREADS * GB_COOP_SMEM_PER_THREAD)
-#ifndef GB_COOP_MINB
-#define GB_COOP_MINB 3   // CTAs per SM of the cooperative-gather kernels (4 needs GB_COOP_CHUNKS <= 15: shared memory)
-#endif
-constexpr size_t gb_gather_smem(int gather) { return gather == 1 ? GB_BULK_SMEM : gather == 2 ? GB_COOP_SMEM : 0; }
-template <int K, int PHI, int EXT = 0, int BULK = 0>
-__global__ void __launch_bounds__(GB_THREADS, BULK == 2 ? GB_COOP_MINB : BULK ? 3 : gb_min_blocks(K, EXT)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
+constexpr size_t gb_gather_smem(int gather, int phi)
 {
-  __shared__ __align__(16) unsigned char s_raw[(EXT == 2 || EXT == 5) ? LaneSlots<GB_THREADS>::BYTES_EXT2 : LaneSlots<GB_THREADS>::BYTES];
-  LaneSlots<GB_THREADS> S;
+  return gather == 1 ? GB_BULK_SMEM : gather == 2 ? (size_t)GB_THREADS * coop_smem_per_thread(phi) : 0;
+}
+// CTAs per SM: what the shared memory holds (GATHER = 2 with PHI = 2 stages 724 bytes per lane)
+constexpr int gb_gather_min_blocks(int gather, int phi) { return gather == 2 && phi == 2 ? 2 : 3; }
+template <int K, int PHI, int EXT = 0, int BULK = 0>
+__global__ void __launch_bounds__(GB_THREADS, BULK ? gb_gather_min_blocks(BULK, PHI) : gb_min_blocks(K, EXT)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
+{
+  constexpr bool ALL_STAGED = (BULK == 2 && PHI == 2);   // no shared-memory stash (see LaneSlots)
+  using Slots = LaneSlots<GB_THREADS, !ALL_STAGED>;
+  __shared__ __align__(16) unsigned char s_raw[(EXT == 2 || EXT == 5) ? Slots::BYTES_EXT2 : Slots::BYTES];
+  Slots S;
   S.carve(s_raw, EXT == 2 || EXT == 5);
+  double local_stash[6];
   const unsigned lane = threadIdx.x & 31u;
   int32_t ind_tetr = -1, iface = -1;
   S.zero_counters();
   if constexpr (BULK == 1) bulk_init();
-  if constexpr (BULK == 2) coop_init();
+  if constexpr (BULK == 2) coop_init<PHI>();
   unsigned wmask = 0xffffffffu;   // GATHER = 2: the lanes of this warp that are still in the push loop
 
   // One lane = one particle at a time.  A lane whose particle is done refills itself at the end of the same loop
@@ -399,7 +406,7 @@ __global__ void __launch_bounds__(GB_THREADS, BULK == 2 ? GB_COOP_MINB : BULK ? 
       if (!bt.force_full) {
         const double x[3] = {S.D(LS_X0), S.D(LS_X1), S.D(LS_X2)};
         RkPusher<PHI, (EXT == 2 ? 2 : 0)> R;
-        R.P.r.set_stash(S.Stash(), GB_THREADS, BULK, wmask);
+        R.P.r.set_stash(ALL_STAGED ? local_stash : S.Stash(), ALL_STAGED ? 1 : GB_THREADS, BULK, wmask);
         R.init(&m, perpinv, ind_tetr, x, iface, S.D(LS_VPAR), S.D(LS_TREM));
         done = R.template push<true>(o);
       }
@@ -427,7 +434,7 @@ __global__ void __launch_bounds__(GB_THREADS, BULK == 2 ? GB_COOP_MINB : BULK ? 
         P.mp = &m;
         P.perpinv = perpinv;
         if constexpr (EXT == 2) P.oq_mask = bt.oq_mask;
-        P.r.set_stash(S.Stash(), GB_THREADS, BULK, wmask);
+        P.r.set_stash(ALL_STAGED ? local_stash : S.Stash(), ALL_STAGED ? 1 : GB_THREADS, BULK, wmask);
         done = P.push_fast(ind_tetr, iface, x, S.D(LS_VPAR), S.D(LS_TREM), o, &S.D(LS_TREM));
         if constexpr (EXT == 2) {
           if (done) lane_ext2_after_fast<K, PHI>(bt, S, P, o);
@@ -789,7 +796,7 @@ struct gorilla_b200_handle {
   double *d_geom = nullptr, *d_bpart = nullptr, *d_phi = nullptr, *d_cold = nullptr, *d_se = nullptr, *d_ham = nullptr, *d_skew = nullptr;
   double *d_poly4 = nullptr;   // tetra_physics_poly4 records (i_precomp = 1, 2)
   double *d_rec44 = nullptr;   // geom + bpart as one contiguous record per tetrahedron (bulk-copy / cooperative gather only)
-  int rec_nd = 0;              // doubles per record in d_rec44: 44 (bulk copy) or GB_COOP_ND (cooperative gather)
+  int rec_nd = 0;              // doubles per record in d_rec44: 44 (bulk copy) or coop_nd(PHI) = 48 / 96 (cooperative gather)
   double *d_lst = nullptr;     // EXT = 5 kernels: per-thread step lists
   size_t lst_bytes = 0;
   cudaEvent_t lst_done = nullptr;
@@ -927,7 +934,7 @@ int launch_orbit_t(gorilla_b200_handle *h, const Batch &bt, cudaStream_t s)
         GB_CUDA(cudaGetLastError());
         return GORILLA_OK;
       };
-      if (h->bulk_gather == 2) return launch_gather(orbit_kernel<K, PHI, EXT, 2>, GB_COOP_SMEM);
+      if (h->bulk_gather == 2) return launch_gather(orbit_kernel<K, PHI, EXT, 2>, gb_gather_smem(2, PHI));
       return launch_gather(orbit_kernel<K, PHI, EXT, 1>, GB_BULK_SMEM);
     }
   }

@@ -144,17 +144,21 @@ GB_HD void prefetch_l2(const void *p)
 #endif
 }
 // the 128-byte lines of the hot sub-records of tetrahedron t (1-based)
+// staged: geom / bpart of that tetrahedron are already on their way to shared memory (GATHER kernels); only the sub-records
+// that stay per-lane loads (Phi, strong E) are requested
 template <int PHI>
-GB_HD void prefetch_record(const MeshDev &m, int ind_tetr)
+GB_HD void prefetch_record(const MeshDev &m, int ind_tetr, bool staged = false)
 {
   if (ind_tetr < 1) return;
   const int64_t t = (int64_t)ind_tetr - 1;
-  const char *pg = reinterpret_cast<const char *>(m.geom + t * GEOM_ND);
-  const char *pb = reinterpret_cast<const char *>(m.bpart + t * BPART_ND);
-  prefetch_l2(pg);                    // 128 bytes, line aligned
-  prefetch_l2(pb);
-  prefetch_l2(pb + 128);
-  prefetch_l2(pb + 8 * BPART_ND - 32);  // last sector: a third line when the record straddles two boundaries
+  if (!staged) {
+    const char *pg = reinterpret_cast<const char *>(m.geom + t * GEOM_ND);
+    const char *pb = reinterpret_cast<const char *>(m.bpart + t * BPART_ND);
+    prefetch_l2(pg);                    // 128 bytes, line aligned
+    prefetch_l2(pb);
+    prefetch_l2(pb + 128);
+    prefetch_l2(pb + 8 * BPART_ND - 32);  // last sector: a third line when the record straddles two boundaries
+  }
   if (PHI) {
     const char *pp = reinterpret_cast<const char *>(m.phi + t * PHI_ND);
     prefetch_l2(pp);
@@ -254,18 +258,22 @@ __device__ __forceinline__ void lds2(unsigned a, double &x, double &y)
 // next push and read their slot with LDS.128.  A lane whose slot does not hold the record it needs (new particle, push
 // redone by the complete path, warp no longer complete at the end of the queue) falls back to the per-lane loads.
 // dynamic shared memory of such a kernel of NT threads: [NT][368] slots | [NT] i32 tetrahedron in the slot
-#define GB_COOP_ND 48
-// GB_COOP_CHUNKS 16-byte pieces of the record are staged (22 = all of it; fewer = the rest of bpart is loaded per lane at the
-// start of the push, which buys shared memory for a fourth CTA per SM).  Slot stride: conflict free for LDS.128 when the
-// number of 16-byte pieces per slot is odd.
-#ifndef GB_COOP_CHUNKS
-#define GB_COOP_CHUNKS 22
-#endif
-#define GB_COOP_STRIDE (16 * (GB_COOP_CHUNKS | 1))
-#define GB_COOP_SMEM_PER_THREAD (GB_COOP_STRIDE + 4)
-__device__ __forceinline__ unsigned coop_slot() { return bulk_base() + gb_tid_now() * GB_COOP_STRIDE; }
-__device__ __forceinline__ unsigned coop_tag(unsigned t) { return bulk_base() + blockDim.x * GB_COOP_STRIDE + t * 4u; }
-__device__ __forceinline__ void coop_init() { sts_i32(coop_tag(gb_tid_now()), 0); }
+// What is staged depends on the field content of the mesh (kernel template PHI): the magnetic record alone (PHI = 0, 1: geom +
+// bpart = 22 16-byte pieces, stored with a stride of 48 doubles = three 128-byte lines; with PHI = 1 the Phi sub-record stays a
+// per-lane load) or, with the strong-electric-field terms (PHI = 2), everything a push reads: geom + bpart + phi + the 26 hot
+// doubles of se = 45 pieces, stored with a stride of 96 doubles = six lines.  The PHI = 2 kernels run two CTAs per SM (the
+// 724-byte slots are what the shared memory holds) and keep the six end-of-push doubles of Rec in local memory instead of a
+// shared-memory stash.  Slot stride: an odd number of 16-byte pieces, conflict free for LDS.128.
+__host__ __device__ constexpr int coop_chunks(int phi) { return phi == 2 ? (GEOM_ND + BPART_ND + PHI_ND + S_HOT_ND) / 2 : (GEOM_ND + BPART_ND) / 2; }
+__host__ __device__ constexpr int coop_nd(int phi) { return phi == 2 ? 96 : 48; }
+__host__ __device__ constexpr unsigned coop_stride(int phi) { return 16u * (unsigned)(coop_chunks(phi) | 1); }
+__host__ __device__ constexpr size_t coop_smem_per_thread(int phi) { return coop_stride(phi) + 4; }
+template <int PHI>
+__device__ __forceinline__ unsigned coop_slot() { return bulk_base() + gb_tid_now() * coop_stride(PHI); }
+template <int PHI>
+__device__ __forceinline__ unsigned coop_tag(unsigned t) { return bulk_base() + blockDim.x * coop_stride(PHI) + t * 4u; }
+template <int PHI>
+__device__ __forceinline__ void coop_init() { sts_i32(coop_tag<PHI>(gb_tid_now()), 0); }
 // every copy into the slots of this warp has landed (called by all lanes of wmask together)
 __device__ __forceinline__ void coop_wait(unsigned wmask)
 {
@@ -273,33 +281,35 @@ __device__ __forceinline__ void coop_wait(unsigned wmask)
   __syncwarp(wmask);
 }
 // called by all lanes of wmask together; ind_next < 1 = this lane has nothing to fetch
+template <int PHI>
 __device__ __forceinline__ void coop_issue(const double *rec, int ind_next, unsigned wmask)
 {
+  constexpr int NCH = coop_chunks(PHI), ND = coop_nd(PHI);
+  constexpr unsigned STRIDE = coop_stride(PHI);
   const unsigned tid = gb_tid_now(), lane = tid & 31u;
   const bool full = (wmask == 0xffffffffu);
   const int want = ind_next >= 1 ? ind_next : 0;
-  sts_i32(coop_tag(tid), full ? want : 0);
+  sts_i32(coop_tag<PHI>(tid), full ? want : 0);
   if (full) {
     // lanes 8 sub .. 8 sub + 7 copy the record of lane 4 g + sub (g = 0..7), lane q of them piece q of every 128-byte line
     const unsigned sub = lane >> 3, q = lane & 7u;
-    const char *srcl = reinterpret_cast<const char *>(rec) - 8 * GB_COOP_ND + q * 16u;
-    const unsigned dstl = bulk_base() + ((tid & ~31u) + sub) * GB_COOP_STRIDE + q * 16u;
+    const char *srcl = reinterpret_cast<const char *>(rec) - 8 * ND + q * 16u;
+    const unsigned dstl = bulk_base() + ((tid & ~31u) + sub) * STRIDE + q * 16u;
 #pragma unroll
     for (int g = 0; g < 8; g++) {
       // a lane with nothing to fetch gets the first record (its tag says "empty"): no branch in the copy sequence
       const unsigned t = (unsigned)max(__shfl_sync(0xffffffffu, want, 4 * g + (int)sub), 1);
-      const char *src = srcl + (uint64_t)t * (8 * GB_COOP_ND);
-      const unsigned dst = dstl + (unsigned)g * 4u * GB_COOP_STRIDE;
-      // line j of the record: pieces 8 j .. 8 j + 7, the last line up to piece GB_COOP_CHUNKS - 1
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-      if (GB_COOP_CHUNKS >= 16)
-        asm volatile("cp.async.cg.shared.global [%0+128], [%1+128], 16;" ::"r"(dst), "l"(src) : "memory");
-      else
-        asm volatile("{\n\t.reg .pred pq;\n\tsetp.lt.u32 pq, %2, %3;\n\t@pq cp.async.cg.shared.global [%0+128], [%1+128], 16;\n\t}"
-                     ::"r"(dst), "l"(src), "r"(q), "n"(GB_COOP_CHUNKS - 8) : "memory");
-      if (GB_COOP_CHUNKS > 16)
-        asm volatile("{\n\t.reg .pred pq;\n\tsetp.lt.u32 pq, %2, %3;\n\t@pq cp.async.cg.shared.global [%0+256], [%1+256], 16;\n\t}"
-                     ::"r"(dst), "l"(src), "r"(q), "n"(GB_COOP_CHUNKS - 16) : "memory");
+      const char *src = srcl + (uint64_t)t * (8 * ND);
+      const unsigned dst = dstl + (unsigned)g * 4u * STRIDE;
+      // line j of the record: pieces 8 j .. 8 j + 7, the last line up to piece NCH - 1
+#pragma unroll
+      for (int j = 0; j < (NCH + 7) / 8; j++) {
+        if (8 * j + 8 <= NCH)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 128u * j), "l"(src + 128 * j) : "memory");
+        else
+          asm volatile("{\n\t.reg .pred pq;\n\tsetp.lt.u32 pq, %2, %3;\n\t@pq cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                       ::"r"(dst + 128u * j), "l"(src + 128 * j), "r"(q), "n"(NCH % 8) : "memory");
+      }
     }
   }
 }
@@ -333,7 +343,7 @@ struct Rec {
   {
 #if defined(__CUDA_ARCH__)
     if (gmode == 1 && ind_next >= 1) bulk_issue(m.rec44, ind_next);
-    if (gmode == 2) coop_issue(m.rec44, ind_next, wmask);
+    if (gmode == 2) coop_issue<PHI>(m.rec44, ind_next, wmask);
 #else
     (void)m; (void)ind_next;
 #endif
@@ -363,29 +373,15 @@ struct Rec {
       bulk_acquire(m.rec44, ind_tetr);
       from_slot = true;
     } else if (gmode == 2) {
-      from_slot = lds_i32(coop_tag(gb_tid_now())) == ind_tetr;   // the kernel has called coop_wait at the top of the push
+      from_slot = lds_i32(coop_tag<PHI>(gb_tid_now())) == ind_tetr;   // the kernel has called coop_wait at the top of the push
     }
+    const unsigned slot = gmode == 2 ? coop_slot<PHI>() : bulk_slot();
+    const bool all_staged = from_slot && gmode == 2 && PHI == 2;   // Phi and strong-E sub-records are in the slot as well
     if (from_slot) {
-      const unsigned slot = gmode == 2 ? coop_slot() : bulk_slot();
-      // doubles of bpart that are staged in the slot (all of them with the bulk copy)
-      constexpr int NB = GB_COOP_CHUNKS >= 22 ? BPART_ND : 2 * (GB_COOP_CHUNKS - 8);
-      const int nb = gmode == 2 ? NB : BPART_ND;
 #pragma unroll
       for (int i = 0; i < GEOM_ND; i += 2) lds2(slot + 8u * i, g[i], g[i + 1]);
 #pragma unroll
-      for (int i = 0; i < BPART_ND; i += 2)
-        if (i < nb) lds2(slot + 128u + 8u * i, b[i], b[i + 1]);
-      if (nb < BPART_ND) {   // the rest of bpart: per-lane sector loads (the sector that straddles the boundary is read whole)
-#pragma unroll
-        for (int i = (NB / 4) * 4; i < BPART_ND; i += 4) {
-          double t0, t1, t2, t3;
-          ld4(pb + i, t0, t1, t2, t3);
-          if (i >= NB) b[i] = t0;
-          if (i + 1 >= NB) b[i + 1] = t1;
-          if (i + 2 >= NB) b[i + 2] = t2;
-          if (i + 3 >= NB) b[i + 3] = t3;
-        }
-      }
+      for (int i = 0; i < BPART_ND; i += 2) lds2(slot + 128u + 8u * i, b[i], b[i + 1]);
     } else
 #endif
     {
@@ -417,8 +413,16 @@ struct Rec {
     if (PHI) {
       double p[PHI_ND];
       const double *pp = m.phi + t * PHI_ND;
+#if defined(__CUDA_ARCH__)
+      if (all_staged) {
 #pragma unroll
-      for (int i = 0; i < PHI_ND; i += 4) ld4(pp + i, p[i], p[i + 1], p[i + 2], p[i + 3]);
+        for (int i = 0; i < PHI_ND; i += 2) lds2(slot + 8u * (GEOM_ND + BPART_ND + i), p[i], p[i + 1]);
+      } else
+#endif
+      {
+#pragma unroll
+        for (int i = 0; i < PHI_ND; i += 4) ld4(pp + i, p[i], p[i + 1], p[i + 2], p[i + 3]);
+      }
       Phi1 = p[P_PHI1];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
@@ -433,8 +437,16 @@ struct Rec {
     if (PHI == 2) {
       double q[28];  // 26 hot doubles, fetched as seven 32-byte sectors
       const double *ps = m.se + t * SE_ND;
+#if defined(__CUDA_ARCH__)
+      if (all_staged) {
 #pragma unroll
-      for (int i = 0; i < 28; i += 4) ld4(ps + i, q[i], q[i + 1], q[i + 2], q[i + 3]);
+        for (int i = 0; i < S_HOT_ND; i += 2) lds2(slot + 8u * (GEOM_ND + BPART_ND + PHI_ND + i), q[i], q[i + 1]);
+      } else
+#endif
+      {
+#pragma unroll
+        for (int i = 0; i < 28; i += 4) ld4(ps + i, q[i], q[i + 1], q[i + 2], q[i + 3]);
+      }
       v2Emod1 = q[S_V2EMOD1];
 #pragma unroll
       for (int i = 0; i < 3; i++) {

@@ -1562,7 +1562,7 @@ struct PolyPusher {
       if (!have_exit) return false;
     }
     tau_max = tau * GB_EPS_TAU;
-    if (mp->prefetch) prefetch_record<PHI>(*mp, r.nb(iface_new - 1));   // the exit face is (almost always) this one
+    if (mp->prefetch) prefetch_record<PHI>(*mp, r.nb(iface_new - 1), r.gmode != 0);   // the exit face is (almost always) this one
     t.kind = 1;
     t.tau = tau;
     t.deg = 0;

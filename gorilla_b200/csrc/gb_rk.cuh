@@ -1009,7 +1009,7 @@ struct RkPusher {
     // cooperative form is a warp operation)
     if (FAST) P.r.prefetch_next(*P.mp, have_guess ? P.r.nb(iface_new - 1) : 0);
     if (have_guess) {
-      if (FAST && P.mp->prefetch) prefetch_record<PHI>(*P.mp, P.r.nb(iface_new - 1));   // quadratic guess of the exit face
+      if (FAST && P.mp->prefetch) prefetch_record<PHI>(*P.mp, P.r.nb(iface_new - 1), P.r.gmode != 0);   // quadratic guess of the exit face
       integration_step(z, dtau, dzdtau);
       tau = tau + dtau;
     } else {

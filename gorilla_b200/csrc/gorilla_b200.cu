@@ -400,14 +400,21 @@ extern "C" int gorilla_b200_set_launch_config(gorilla_b200_handle *h, int32_t ct
   }
   return GORILLA_OK;
 }
-// geom[t][16] + bpart[t][28] -> rec[t][nd]: nd = 44 (bulk-copy gather) or GB_COOP_ND = 48 (warp-cooperative gather: records
-// of three 128-byte lines, the last four doubles are padding)
-__global__ void interleave_rec44_kernel(int64_t ntetr, const double *geom, const double *bpart, double *rec, int nd)
+// geom[t][16] + bpart[t][28] (+ phi[t][20] + the hot doubles of se[t][32]) -> rec[t][nd]: nd = 44 (bulk-copy gather), 48
+// (warp-cooperative gather: records of three 128-byte lines) or 96 (warp-cooperative gather with the strong-electric-field
+// terms: everything a push reads, six lines); the doubles behind the last sub-record are padding
+__global__ void interleave_rec44_kernel(int64_t ntetr, const double *geom, const double *bpart, const double *phi, const double *se,
+                                        double *rec, int nd)
 {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ntetr * nd; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t t = i / nd;
-    const int k = (int)(i - t * nd);
-    rec[i] = k < GEOM_ND ? geom[t * GEOM_ND + k] : k < GEOM_ND + BPART_ND ? bpart[t * BPART_ND + (k - GEOM_ND)] : 0.0;
+    int k = (int)(i - t * nd);
+    double v = 0.0;
+    if (k < GEOM_ND) v = geom[t * GEOM_ND + k];
+    else if ((k -= GEOM_ND) < BPART_ND) v = bpart[t * BPART_ND + k];
+    else if (nd == 96 && (k -= BPART_ND) < PHI_ND) v = phi[t * PHI_ND + k];
+    else if (nd == 96 && (k -= PHI_ND) < S_HOT_ND) v = se[t * SE_ND + k];
+    rec[i] = v;
   }
 }
 extern "C" int gorilla_b200_set_gather(gorilla_b200_handle *h, int32_t mode)
@@ -417,20 +424,22 @@ extern "C" int gorilla_b200_set_gather(gorilla_b200_handle *h, int32_t mode)
   GB_ENTER(h);
   // auto: records staged in shared memory one push ahead when the hot records of the mesh exceed the L2 by a wide margin.
   // Measured, order 2, 3.84 M-tetrahedron EFIT mesh: vector loads 5.56e9, per-lane bulk copies 8.24e9, warp-cooperative copies
-  // 1.19e10 crossings/s (RK4: 3.95e9 bulk, 4.23e9 cooperative); on the L2-resident 0.96 M-tetrahedron meshes the vector loads stay
-  // ahead (VMEC order 2: 1.42e10 against 1.38e10 cooperative / 0.94e10 bulk).  With the electrostatic / strong-E sub-records
-  // (which no staged form covers) the bulk copies are the better companion of the remaining per-lane loads: they do not share
-  // the L1 with them (WEST, strong E, order 2: 3.83e9 bulk, 3.39e9 cooperative).
+  // 1.19e10 crossings/s (RK4: 3.95e9 bulk, 4.23e9 cooperative); 4.24 M-tetrahedron WEST mesh with strong E (the cooperative form
+  // stages the Phi / strong-E sub-records as well): order 2 3.88e9 bulk, 5.37e9 cooperative, RK4 2.37e9 / 2.71e9.  On the
+  // L2-resident 0.96 M-tetrahedron meshes the vector loads stay ahead (VMEC order 2: 1.42e10 against 1.38e10 cooperative /
+  // 0.94e10 bulk).  With Phi but without strong E the cooperative form stages the magnetic record only and shares the L1 with
+  // the per-lane loads of the Phi sub-record; the bulk copies do not, so they stay the choice there.
   const bool has_bulk_kernel = h->settings.ipusher == 1 || h->settings.poly_order == 2;   // launch_orbit_t: EXT = 0, K = 2 or RK4
-  const int want = mode >= 0 ? mode : ((h->hot_bytes > 4 * h->l2_bytes && has_bulk_kernel) ? (h->mesh.phi ? 1 : 2) : 0);
-  const int nd = want == 2 ? GB_COOP_ND : 44;
+  const int phi_kind = h->mesh.se ? 2 : h->mesh.phi ? 1 : 0;
+  const int want = mode >= 0 ? mode : ((h->hot_bytes > 4 * h->l2_bytes && has_bulk_kernel) ? (phi_kind == 1 ? 1 : 2) : 0);
+  const int nd = want == 2 ? coop_nd(phi_kind) : 44;   // phi_kind = the launcher's PHI
   if (want && (!h->d_rec44 || h->rec_nd != nd)) {
     GB_CUDA(cudaDeviceSynchronize());   // a launch may still be reading the other layout
     if (h->d_rec44) GB_CUDA(cudaFree(h->d_rec44));
     h->d_rec44 = nullptr;
     h->mesh.rec44 = nullptr;
     GB_CUDA(cudaMalloc((void **)&h->d_rec44, (size_t)h->mesh.ntetr * nd * sizeof(double)));
-    interleave_rec44_kernel<<<h->num_sms * 8, 256>>>(h->mesh.ntetr, h->d_geom, h->d_bpart, h->d_rec44, nd);
+    interleave_rec44_kernel<<<h->num_sms * 8, 256>>>(h->mesh.ntetr, h->d_geom, h->d_bpart, h->d_phi, h->d_se, h->d_rec44, nd);
     g_launch_count++;
     GB_CUDA(cudaGetLastError());
     GB_CUDA(cudaDeviceSynchronize());

@@ -140,10 +140,13 @@ def test_strong_terms_change_the_orbit_and_conserve_the_extended_energy(strong_m
 
 
 # ---------------------------------------------------------------------------------------------- GPU
-def _gpu_pair(mesh, settings, n, seed, t_step, cap, force_full=False):
+def _gpu_pair(mesh, settings, n, seed, t_step, cap, force_full=False, gather=None):
     from gorilla_b200 import Gorilla
     om, g = OracleMesh(mesh, settings), Gorilla(mesh, settings)
     g._debug_force_full(force_full)
+    if gather is not None:
+        g.set_gather(gather)
+        assert g.get_gather() == gather
     xa, va, wa = workloads.particles_cyl(n, seed)
     xb, vb, wb = xa.copy(), va.copy(), wa.copy()
     ia, ta, fa = workloads.fresh_state(n)
@@ -178,3 +181,18 @@ def test_gpu_parity_rk4(strong_mesh, cuda_device):
     mesh, _, settings = strong_mesh
     _gpu_pair(mesh, _with(settings, ipusher=1), 600, 4, 2e-5, 128)
     _gpu_pair(mesh, _with(settings, ipusher=1), 200, 6, -1e-5, 64, force_full=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gather", [1, 2])
+@pytest.mark.parametrize("pusher", ["poly2", "rk4"])
+def test_gpu_parity_staged_gathers(strong_mesh, cuda_device, pusher, gather):
+    """Strong-E kernels with the records staged in shared memory one push ahead: per-lane bulk copies of the magnetic record
+    (1; Phi / strong-E sub-records stay per-lane loads) and the warp-cooperative gather (2), which for these kernels stages
+    everything a push reads -- geom, bpart, phi and the hot part of se, 45 16-byte pieces per lane -- at two CTAs per SM.
+    2048 particles = 64 full warps; forward and backward time."""
+    mesh, _, settings = strong_mesh
+    st = _with(settings, ipusher=1) if pusher == "rk4" else _with(settings, poly_order=2)
+    c = _gpu_pair(mesh, st, 2048, 11, 2e-5, 64, gather=gather)
+    assert c.n_pushes > 50000
+    _gpu_pair(mesh, st, 700, 12, -1e-5, 64, gather=gather)

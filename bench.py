@@ -89,6 +89,7 @@ def parse_args():
     ap.add_argument("--newton-precalc", action="store_true", help="RK pusher: boole_newton_precalc")
     ap.add_argument("--ode45", action="store_true", help="RK pusher: boole_pusher_ode45 (RKF45 instead of RK4)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--eps-phi", type=float, default=None, help="electrostatic potential strength eps_Phi of the mesh (PHI = 1 kernels); default: the workload's")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sort", type=int, default=1, help="re-sort particles by tetra index before every step")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -231,6 +232,8 @@ def apply_args(settings, args):
         settings.boole_newton_precalc = True
     if getattr(args, "ode45", False):
         settings.boole_pusher_ode45 = True
+    if getattr(args, "eps_phi", None) is not None:
+        settings.eps_Phi = args.eps_phi
     if getattr(args, "optional_quantities", False):
         settings.boole_time_Hamiltonian = settings.boole_gyrophase = settings.boole_vpar_int = settings.boole_vpar2_int = True
     return settings
@@ -243,7 +246,8 @@ def make_config(wl, settings, args, world, n, t_step, mesh):
     strong_e = bool(settings.boole_strong_electric_field)
     hot_rec = 352 + (160 if has_phi or strong_e else 0) + (256 if strong_e else 0)
     return {"workload": wl["name"], "desc": wl["desc"], "ipusher": settings.ipusher,
-            "poly_order": settings.poly_order, "i_time_tracing_option": settings.i_time_tracing_option,
+            "poly_order": settings.poly_order, "eps_Phi": float(settings.eps_Phi),
+            "i_time_tracing_option": settings.i_time_tracing_option,
             "boole_adaptive_time_steps": bool(settings.boole_adaptive_time_steps),
             "optional_quantities": bool(args.optional_quantities), "i_precomp": int(settings.i_precomp),
             "boole_newton_precalc": bool(settings.boole_newton_precalc), "boole_pusher_ode45": bool(settings.boole_pusher_ode45),

@@ -137,7 +137,7 @@ enum { LC_LOST = 0, LC_FIN, LC_FB0, LC_FB1, LC_FB2, LC_FB3, LC_ADAPT, LC_LOST_IN
 // kernel places them in static shared memory, the 16-warp lock-step kernel in dynamic shared memory.  Every accessor
 // re-reads %tid.x through a volatile asm: otherwise the compiler forms the slot addresses once, keeps them live across the
 // push and spills THEM.
-// STASH = false (cooperative-gather kernels that stage the whole record, PHI = 2): no stash in shared memory, the kernel
+// STASH = false (cooperative-gather kernels that stage the whole record, PHI >= 1): no stash in shared memory, the kernel
 // keeps those six doubles in local memory.
 template <int NT, bool STASH = true>
 struct LaneSlots {
@@ -373,12 +373,12 @@ constexpr size_t gb_gather_smem(int gather, int phi)
 {
   return gather == 1 ? GB_BULK_SMEM : gather == 2 ? (size_t)GB_THREADS * coop_smem_per_thread(phi) : 0;
 }
-// CTAs per SM: what the shared memory holds (GATHER = 2 with PHI = 2 stages 724 bytes per lane)
-constexpr int gb_gather_min_blocks(int gather, int phi) { return gather == 2 && phi == 2 ? 2 : 3; }
+// CTAs per SM: what the shared memory holds (GATHER = 2 with PHI = 1 / 2 stages 532 / 724 bytes per lane)
+constexpr int gb_gather_min_blocks(int gather, int phi) { return gather == 2 && phi >= 1 ? 2 : 3; }
 template <int K, int PHI, int EXT = 0, int BULK = 0>
 __global__ void __launch_bounds__(GB_THREADS, BULK ? gb_gather_min_blocks(BULK, PHI) : gb_min_blocks(K, EXT)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
 {
-  constexpr bool ALL_STAGED = (BULK == 2 && PHI == 2);   // no shared-memory stash (see LaneSlots)
+  constexpr bool ALL_STAGED = (BULK == 2 && PHI >= 1);   // no shared-memory stash (see LaneSlots)
   using Slots = LaneSlots<GB_THREADS, !ALL_STAGED>;
   __shared__ __align__(16) unsigned char s_raw[(EXT == 2 || EXT == 5) ? Slots::BYTES_EXT2 : Slots::BYTES];
   Slots S;

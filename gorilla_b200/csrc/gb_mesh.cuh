@@ -258,14 +258,18 @@ __device__ __forceinline__ void lds2(unsigned a, double &x, double &y)
 // next push and read their slot with LDS.128.  A lane whose slot does not hold the record it needs (new particle, push
 // redone by the complete path, warp no longer complete at the end of the queue) falls back to the per-lane loads.
 // dynamic shared memory of such a kernel of NT threads: [NT][368] slots | [NT] i32 tetrahedron in the slot
-// What is staged depends on the field content of the mesh (kernel template PHI): the magnetic record alone (PHI = 0, 1: geom +
-// bpart = 22 16-byte pieces, stored with a stride of 48 doubles = three 128-byte lines; with PHI = 1 the Phi sub-record stays a
-// per-lane load) or, with the strong-electric-field terms (PHI = 2), everything a push reads: geom + bpart + phi + the 26 hot
-// doubles of se = 45 pieces, stored with a stride of 96 doubles = six lines.  The PHI = 2 kernels run two CTAs per SM (the
-// 724-byte slots are what the shared memory holds) and keep the six end-of-push doubles of Rec in local memory instead of a
-// shared-memory stash.  Slot stride: an odd number of 16-byte pieces, conflict free for LDS.128.
-__host__ __device__ constexpr int coop_chunks(int phi) { return phi == 2 ? (GEOM_ND + BPART_ND + PHI_ND + S_HOT_ND) / 2 : (GEOM_ND + BPART_ND) / 2; }
-__host__ __device__ constexpr int coop_nd(int phi) { return phi == 2 ? 96 : 48; }
+// What is staged depends on the field content of the mesh (kernel template PHI): the magnetic record alone (PHI = 0: geom +
+// bpart = 22 16-byte pieces, stored with a stride of 48 doubles = three 128-byte lines) or everything a push reads: with the
+// electrostatic group (PHI = 1) geom + bpart + phi = 32 pieces in records of 64 doubles = four lines, with the
+// strong-electric-field terms (PHI = 2) geom + bpart + phi + the 26 hot doubles of se = 45 pieces in records of 96 doubles =
+// six lines.  The PHI >= 1 kernels run two CTAs per SM (the 532- / 724-byte slots are what the shared memory holds) and keep
+// the six end-of-push doubles of Rec in local memory instead of a shared-memory stash.  Slot stride: an odd number of 16-byte
+// pieces, conflict free for LDS.128.
+__host__ __device__ constexpr int coop_chunks(int phi)
+{
+  return (GEOM_ND + BPART_ND + (phi >= 1 ? PHI_ND : 0) + (phi == 2 ? S_HOT_ND : 0)) / 2;
+}
+__host__ __device__ constexpr int coop_nd(int phi) { return phi == 2 ? 96 : phi == 1 ? 64 : 48; }
 __host__ __device__ constexpr unsigned coop_stride(int phi) { return 16u * (unsigned)(coop_chunks(phi) | 1); }
 __host__ __device__ constexpr size_t coop_smem_per_thread(int phi) { return coop_stride(phi) + 4; }
 template <int PHI>
@@ -376,7 +380,7 @@ struct Rec {
       from_slot = lds_i32(coop_tag<PHI>(gb_tid_now())) == ind_tetr;   // the kernel has called coop_wait at the top of the push
     }
     const unsigned slot = gmode == 2 ? coop_slot<PHI>() : bulk_slot();
-    const bool all_staged = from_slot && gmode == 2 && PHI == 2;   // Phi and strong-E sub-records are in the slot as well
+    const bool all_staged = from_slot && gmode == 2 && PHI >= 1;   // Phi (and strong-E) sub-records are in the slot as well
     if (from_slot) {
 #pragma unroll
       for (int i = 0; i < GEOM_ND; i += 2) lds2(slot + 8u * i, g[i], g[i + 1]);

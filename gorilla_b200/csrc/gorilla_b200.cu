@@ -400,9 +400,9 @@ extern "C" int gorilla_b200_set_launch_config(gorilla_b200_handle *h, int32_t ct
   }
   return GORILLA_OK;
 }
-// geom[t][16] + bpart[t][28] (+ phi[t][20] + the hot doubles of se[t][32]) -> rec[t][nd]: nd = 44 (bulk-copy gather), 48
-// (warp-cooperative gather: records of three 128-byte lines) or 96 (warp-cooperative gather with the strong-electric-field
-// terms: everything a push reads, six lines); the doubles behind the last sub-record are padding
+// geom[t][16] + bpart[t][28] (+ phi[t][20] (+ the hot doubles of se[t][32])) -> rec[t][nd]: nd = 44 (bulk-copy gather), 48
+// (warp-cooperative gather: records of three 128-byte lines), 64 (with Phi: four lines) or 96 (with the strong-electric-field
+// terms: six lines) -- everything a push reads; the doubles behind the last sub-record are padding
 __global__ void interleave_rec44_kernel(int64_t ntetr, const double *geom, const double *bpart, const double *phi, const double *se,
                                         double *rec, int nd)
 {
@@ -412,7 +412,7 @@ __global__ void interleave_rec44_kernel(int64_t ntetr, const double *geom, const
     double v = 0.0;
     if (k < GEOM_ND) v = geom[t * GEOM_ND + k];
     else if ((k -= GEOM_ND) < BPART_ND) v = bpart[t * BPART_ND + k];
-    else if (nd == 96 && (k -= BPART_ND) < PHI_ND) v = phi[t * PHI_ND + k];
+    else if (nd >= 64 && (k -= BPART_ND) < PHI_ND) v = phi[t * PHI_ND + k];
     else if (nd == 96 && (k -= PHI_ND) < S_HOT_ND) v = se[t * SE_ND + k];
     rec[i] = v;
   }
@@ -427,11 +427,12 @@ extern "C" int gorilla_b200_set_gather(gorilla_b200_handle *h, int32_t mode)
   // 1.19e10 crossings/s (RK4: 3.95e9 bulk, 4.23e9 cooperative); 4.24 M-tetrahedron WEST mesh with strong E (the cooperative form
   // stages the Phi / strong-E sub-records as well): order 2 3.88e9 bulk, 5.37e9 cooperative, RK4 2.37e9 / 2.71e9.  On the
   // L2-resident 0.96 M-tetrahedron meshes the vector loads stay ahead (VMEC order 2: 1.42e10 against 1.38e10 cooperative /
-  // 0.94e10 bulk).  With Phi but without strong E the cooperative form stages the magnetic record only and shares the L1 with
-  // the per-lane loads of the Phi sub-record; the bulk copies do not, so they stay the choice there.
+  // 0.94e10 bulk).  With Phi alone (whole record staged as well, two CTAs per SM): EFIT mesh, order 2 4.03e9 loads / 7.30e9 bulk /
+  // 8.35e9 cooperative, RK4 3.49e9 bulk / 3.42e9 cooperative -- the one case where the bulk copies stay the choice.
   const bool has_bulk_kernel = h->settings.ipusher == 1 || h->settings.poly_order == 2;   // launch_orbit_t: EXT = 0, K = 2 or RK4
   const int phi_kind = h->mesh.se ? 2 : h->mesh.phi ? 1 : 0;
-  const int want = mode >= 0 ? mode : ((h->hot_bytes > 4 * h->l2_bytes && has_bulk_kernel) ? (phi_kind == 1 ? 1 : 2) : 0);
+  const int staged = (phi_kind == 1 && h->settings.ipusher == 1) ? 1 : 2;
+  const int want = mode >= 0 ? mode : ((h->hot_bytes > 4 * h->l2_bytes && has_bulk_kernel) ? staged : 0);
   const int nd = want == 2 ? coop_nd(phi_kind) : 44;   // phi_kind = the launcher's PHI
   if (want && (!h->d_rec44 || h->rec_nd != nd)) {
     GB_CUDA(cudaDeviceSynchronize());   // a launch may still be reading the other layout

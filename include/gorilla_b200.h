@@ -313,11 +313,12 @@ int gorilla_b200_fp64_peak(double *dfma_inst_per_s, double *dmul_dadd_inst_per_s
  * identical either way. */
 int gorilla_b200_set_prefetch(gorilla_b200_handle *h, int32_t mode);
 
-/* How the push kernels of order 2 and of the RK4 pusher gather the geometry / magnetic sub-records: 0 = per-lane vector
- * loads through the L1 (best when the records a batch touches are L2 resident), 1 = per-lane bulk copies (cp.async.bulk into a
- * shared-memory slot, issued one push ahead), 2 = warp-cooperative cp.async copies of the 32 records a warp needs next into
- * the same slots (24 instructions per warp, four cache lines each; best on meshes much larger than the L2), -1 = auto by mesh
- * size and field content (the default after gorilla_b200_init).  Results are identical in every mode. */
+/* How the push kernels of order 2 and of the RK4 pusher gather the tetrahedron records: 0 = per-lane vector loads through
+ * the L1 (best when the records a batch touches are L2 resident), 1 = per-lane bulk copies of the geometry / magnetic
+ * sub-records (cp.async.bulk into a shared-memory slot, issued one push ahead), 2 = warp-cooperative cp.async copies of the 32
+ * records a warp needs next into the same kind of slots (four cache lines per instruction; with Phi / strong E the whole
+ * record is staged; best on meshes much larger than the L2), -1 = auto by mesh size, field content and pusher (the default
+ * after gorilla_b200_init).  Results are identical in every mode. */
 int gorilla_b200_set_gather(gorilla_b200_handle *h, int32_t mode);
 /* The gather mode in effect (0, 1 or 2; what -1 resolved to). */
 int gorilla_b200_get_gather(gorilla_b200_handle *h, int32_t *mode);

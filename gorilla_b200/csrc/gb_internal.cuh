@@ -375,10 +375,10 @@ constexpr size_t gb_gather_smem(int gather, int phi)
 }
 // CTAs per SM: what the shared memory holds (GATHER = 2 with PHI = 1 / 2 stages 532 / 724 bytes per lane)
 constexpr int gb_gather_min_blocks(int gather, int phi) { return gather == 2 && phi >= 1 ? 2 : 3; }
-template <int K, int PHI, int EXT = 0, int BULK = 0>
-__global__ void __launch_bounds__(GB_THREADS, BULK ? gb_gather_min_blocks(BULK, PHI) : gb_min_blocks(K, EXT)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
+template <int K, int PHI, int EXT = 0, int GATHER = 0>
+__global__ void __launch_bounds__(GB_THREADS, GATHER ? gb_gather_min_blocks(GATHER, PHI) : gb_min_blocks(K, EXT)) orbit_kernel(const __grid_constant__ MeshDev m, const Batch bt)
 {
-  constexpr bool ALL_STAGED = (BULK == 2 && PHI >= 1);   // no shared-memory stash (see LaneSlots)
+  constexpr bool ALL_STAGED = (GATHER == 2 && PHI >= 1);   // no shared-memory stash (see LaneSlots)
   using Slots = LaneSlots<GB_THREADS, !ALL_STAGED>;
   __shared__ __align__(16) unsigned char s_raw[(EXT == 2 || EXT == 5) ? Slots::BYTES_EXT2 : Slots::BYTES];
   Slots S;
@@ -387,17 +387,17 @@ __global__ void __launch_bounds__(GB_THREADS, BULK ? gb_gather_min_blocks(BULK, 
   const unsigned lane = threadIdx.x & 31u;
   int32_t ind_tetr = -1, iface = -1;
   S.zero_counters();
-  if constexpr (BULK == 1) bulk_init();
-  if constexpr (BULK == 2) coop_init<PHI>();
+  if constexpr (GATHER == 1) bulk_init();
+  if constexpr (GATHER == 2) coop_init<PHI>();
   unsigned wmask = 0xffffffffu;   // GATHER = 2: the lanes of this warp that are still in the push loop
 
   // One lane = one particle at a time.  A lane whose particle is done refills itself at the end of the same loop
   // body and leaves the loop for good when the queue is empty, so the body has no "is this lane active" region (whose
   // convergence-barrier register was live, and spilled, across every push).
   bool active = lane_refill<PHI, EXT>(m, bt, S, lane, ind_tetr, iface);
-  if constexpr (BULK == 2) wmask = __ballot_sync(0xffffffffu, active);
+  if constexpr (GATHER == 2) wmask = __ballot_sync(0xffffffffu, active);
   while (active) {
-    if constexpr (BULK == 2) coop_wait(wmask);   // the records requested during the previous push are in the slots
+    if constexpr (GATHER == 2) coop_wait(wmask);   // the records requested during the previous push are in the slots
     S.IndSave() = ind_tetr;
     PushOut o;
     bool done = false;
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(GB_THREADS, BULK ? gb_gather_min_blocks(BULK, 
       if (!bt.force_full) {
         const double x[3] = {S.D(LS_X0), S.D(LS_X1), S.D(LS_X2)};
         RkPusher<PHI, (EXT == 2 ? 2 : 0)> R;
-        R.P.r.set_stash(ALL_STAGED ? local_stash : S.Stash(), ALL_STAGED ? 1 : GB_THREADS, BULK, wmask);
+        R.P.r.set_stash(ALL_STAGED ? local_stash : S.Stash(), ALL_STAGED ? 1 : GB_THREADS, GATHER, wmask);
         R.init(&m, perpinv, ind_tetr, x, iface, S.D(LS_VPAR), S.D(LS_TREM));
         done = R.template push<true>(o);
       }
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(GB_THREADS, BULK ? gb_gather_min_blocks(BULK, 
         P.mp = &m;
         P.perpinv = perpinv;
         if constexpr (EXT == 2) P.oq_mask = bt.oq_mask;
-        P.r.set_stash(ALL_STAGED ? local_stash : S.Stash(), ALL_STAGED ? 1 : GB_THREADS, BULK, wmask);
+        P.r.set_stash(ALL_STAGED ? local_stash : S.Stash(), ALL_STAGED ? 1 : GB_THREADS, GATHER, wmask);
         done = P.push_fast(ind_tetr, iface, x, S.D(LS_VPAR), S.D(LS_TREM), o, &S.D(LS_TREM));
         if constexpr (EXT == 2) {
           if (done) lane_ext2_after_fast<K, PHI>(bt, S, P, o);
@@ -450,11 +450,11 @@ __global__ void __launch_bounds__(GB_THREADS, BULK ? gb_gather_min_blocks(BULK, 
     }
     if (lane_after_push<PHI, EXT>(m, bt, S, o, S.IndSave(), ind_tetr, iface))
       active = lane_refill<PHI, EXT>(m, bt, S, lane, ind_tetr, iface);
-    if constexpr (BULK == 2) wmask = __ballot_sync(wmask, active);   // lanes that leave the loop drop out of the warp's gather
+    if constexpr (GATHER == 2) wmask = __ballot_sync(wmask, active);   // lanes that leave the loop drop out of the warp's gather
   }
   // no copy may still be on its way to this CTA's shared memory when it exits
-  if constexpr (BULK == 1) bulk_wait();
-  if constexpr (BULK == 2) asm volatile("cp.async.wait_all;" ::: "memory");
+  if constexpr (GATHER == 1) bulk_wait();
+  if constexpr (GATHER == 2) asm volatile("cp.async.wait_all;" ::: "memory");
   lane_reduce_counters(bt, S, lane);
 }
 

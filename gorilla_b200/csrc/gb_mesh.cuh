@@ -171,7 +171,7 @@ GB_HD void prefetch_record(const MeshDev &m, int ind_tetr, bool staged = false)
   }
 }
 
-// ---- bulk-copy gather (kernels launched with the BULK flag) --------------------------------------------------------------
+// ---- bulk-copy gather (kernels launched with GATHER = 1) --------------------------------------------------------------
 // ncu on the meshes whose records do not fit the L2 (3.8 M / 4.2 M tetrahedra): the gather is latency bound with only ~180
 // sectors in flight per SM (long_scoreboard 9.5 stalled warps per issue, DRAM at 9 % of peak), and neither more resident warps
 // nor an L2 prefetch change that -- the per-lane LDGs queue in the L1's miss path.  The bulk-copy engine (TMA,
@@ -188,7 +188,7 @@ __device__ __forceinline__ unsigned gb_tid_now()
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
   return t;
 }
-// dynamic shared memory of a BULK kernel of NT threads: [NT][368] slots | [NT] u64 mbarrier | [NT] i32 tetrahedron in the slot
+// dynamic shared memory of a GATHER = 1 kernel of NT threads: [NT][368] slots | [NT] u64 mbarrier | [NT] i32 tetrahedron in the slot
 // | [NT] i32 flags (bit 0 copy pending, bit 1 mbarrier phase parity)
 __device__ __forceinline__ unsigned bulk_base()
 {

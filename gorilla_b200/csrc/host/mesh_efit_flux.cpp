@@ -17,7 +17,8 @@
 // Dormand-Prince 5(4) pair instead of RKF45, the last closed surface is found by bisection instead of a linear scan of
 // nsurfmax start points, and nothing is written to / re-read from files (box_size_axis.dat, flux_functions.dat,
 // twodim_functions.dat round the numbers through list-directed formatting in the reference).
-// theta_geom_flux = 1 (poloidal grid equidistant in the flux angle) only.
+// theta_geom_flux = 1: poloidal grid equidistant in the flux angle; 2: equidistant in the geometrical angle around the
+// magnetic axis (theta_geom2theta_flux, SRC/points_2d.f90:254-373), see geom_to_flux_angles below.
 #include "mesh_efit.hpp"
 #include <algorithm>
 #include <cmath>
@@ -194,6 +195,60 @@ struct FluxCoords {
     }
   }
 };
+
+// theta_geom2theta_flux (SRC/points_2d.f90:254-373): the symmetry-flux angles at which the surface `s` has the geometrical
+// poloidal angles theta_geom[0..n) around the magnetic axis (measured from the axis -> X-point ray when theta0_at_xpoint).
+// The geometrical angle is sampled at ntheta_interp = 500 equidistant flux angles (+ nplag/2 wrapped samples either side),
+// made monotonic across the 2 pi cut and inverted with nplag = 10 point Lagrange interpolation.
+// One deviation: the geometrical angle 0 maps to the flux angle 0 exactly (both are the axis -> X-point ray, resp. the
+// outboard horizontal ray, by construction; the reference carries this shortcut commented out, :323-326), so that the first
+// vertex of every ring keeps the "theta = 0 is also theta = 2 pi" vertex convention of make_tetra_physics
+// (SRC/tetra_physics_mod.f90:534-540) whatever the integrator tolerance (1e-9) left in the last digits.
+int geom_to_flux_angles(const FluxCoords &F, bool theta0_at_xpoint, double s, const double *theta_geom, int n,
+                        double *theta_flux, std::string &err)
+{
+  constexpr int NI = 500, NP = 10, NT = NI + NP;
+  const double twopi = 2.0 * PI_T;  // points_2d.f90:4
+  auto modulo = [](double a, double p) { double r = std::fmod(a, p); if (r != 0.0 && ((r < 0.0) != (p < 0.0))) r += p; return r; };
+  double tf[NT], tg[NT];
+  for (int i = 0; i < NT; i++) tf[i] = (double)(i - NP / 2) / (double)NI * twopi;
+  for (int i = 0; i < NT; i++) {
+    double psi, q, sqrtg, bmod, R, dR_ds, dR_dt, Z, dZ_ds, dZ_dt;
+    F.eval(s, modulo(tf[i], twopi), psi, q, sqrtg, bmod, R, dR_ds, dR_dt, Z, dZ_ds, dZ_dt);
+    const double a = std::atan2(Z - F.zaxis, R - F.raxis);
+    tg[i] = modulo(theta0_at_xpoint ? a - F.theta0 : a, twopi) - twopi;
+    if (i > 0) {
+      if (tg[i] < tg[i - 1]) tg[i] = tg[i] + twopi * std::ceil((tg[i - 1] - tg[i]) / twopi);
+      if (tg[i] - tg[i - 1] > PI_T) {
+        err = "theta_geom2theta_flux: big jump in the geometrical angle (the map flux angle -> geometrical angle is not monotonic)";
+        return GORILLA_ERR_DOMAIN;
+      }
+    }
+  }
+  for (int k = 0; k < n; k++) {
+    double th = theta_geom[k];
+    if (th == 0.0) { theta_flux[k] = 0.0; continue; }
+    if (th < tg[NP / 2]) th = th + twopi;
+    else if (th > tg[NI + NP / 2 - 1]) th = th - twopi;
+    // binsrc(theta_geom_interp(nplag/2+1 : ntheta_interp+nplag/2), 1, ntheta_interp, theta, i)
+    const double *p = &tg[NP / 2] - 1;  // 1-based view
+    int imin = 1, imax = NI, i = 0;
+    for (int it = 1; it <= NI - 1; it++) {
+      i = (imax - imin) / 2 + imin;
+      if (p[i] > th) imax = i;
+      else imin = i;
+      if (imax == imin + 1) break;
+    }
+    const int ig = imax + NP / 2;            // 1-based index into the full sample arrays
+    const int first = ig - NP / 2 - 1;       // 0-based start of the nplag nodes
+    double c[NP];
+    lagrange(NP, th, &tg[first], c, nullptr);
+    double sum = 0.0;
+    for (int j = 0; j < NP; j++) sum += c[j] * tf[first + j];
+    theta_flux[k] = modulo(sum, twopi);
+  }
+  return GORILLA_OK;
+}
 
 int build_flux_coords(const EfitField &f, bool theta0_at_xpoint, FluxCoords &F, std::string &err)
 {
@@ -392,7 +447,7 @@ int build_flux_coords(const EfitField &f, bool theta0_at_xpoint, FluxCoords &F, 
 int build_efit_flux(const gorilla_grid_settings &gs, const gorilla_settings &st, Mesh &m, std::string &err)
 {
   if (st.coord_system != 2) { err = "grid_kind 2 with coord_system 1 is not built by this library (use coord_system = 2)"; return GORILLA_ERR_UNSUPPORTED; }
-  if (gs.theta_geom_flux != 1) { err = "grid_kind 2: only theta_geom_flux = 1 is implemented"; return GORILLA_ERR_UNSUPPORTED; }
+  if (gs.theta_geom_flux != 1 && gs.theta_geom_flux != 2) { err = "grid_kind 2: theta_geom_flux must be 1 (flux angle) or 2 (geometrical angle)"; return GORILLA_ERR_ARG; }
   if (gs.n1 < 1 || gs.n2 < 3 || gs.n3 < 3) { err = "field-aligned grid needs n1 >= 1, n2 >= 3, n3 >= 3"; return GORILLA_ERR_ARG; }
   if (!(gs.sfc_s_min > 0.0 && gs.sfc_s_min < 1.0)) { err = "sfc_s_min must be in (0, 1)"; return GORILLA_ERR_ARG; }
   EfitField f;
@@ -431,6 +486,27 @@ int build_efit_flux(const gorilla_grid_settings &gs, const gorilla_settings &st,
   for (int i = 1; i <= n_extra; i++)
     r_frac[i] = std::exp(std::log(s_min) + (double)i * (std::log(r_frac[n_extra + 1]) - std::log(s_min)) / (double)(n_extra + 1));
 
+  // poloidal angles of the vertices of each ring (create_points_2d, SRC/points_2d.f90:135-149)
+  std::vector<double> ring_theta((size_t)(n1 + 1) * n3);
+  {
+    std::vector<double> frac(n3);
+    for (int j = 0; j < n3; j++) frac[j] = ((double)j / (double)n3) * 2.0 * PI_T;
+    bool bad = false;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int ring = 0; ring <= n1; ring++) {
+      double *out = &ring_theta[(size_t)ring * n3];
+      if (gs.theta_geom_flux == 1) {
+        for (int j = 0; j < n3; j++) out[j] = frac[j];
+      } else {
+        std::string e;
+        if (geom_to_flux_angles(F, gs.theta0_at_xpoint != 0.0, ring == 0 ? s_min : r_frac[ring], frac.data(), n3, out, e)) {
+#pragma omp critical
+          { bad = true; err = e; }
+        }
+      }
+    }
+    if (bad) return GORILLA_ERR_DOMAIN;
+  }
   const int64_t vps = (int64_t)(n1 + 1) * n3;
   m.verts_sthetaphi.assign((size_t)m.nvert * 3, 0.0);
   m.verts_rphiz.assign((size_t)m.nvert * 3, 0.0);
@@ -440,7 +516,7 @@ int build_efit_flux(const gorilla_grid_settings &gs, const gorilla_settings &st,
   for (int64_t iv = 0; iv < m.nvert; iv++) {
     const int slice = (int)(iv / vps), ring = (int)((iv % vps) / n3), j = (int)(iv % n3);
     const double s = (ring == 0) ? s_min : r_frac[ring];
-    const double theta = ((double)j / (double)n3) * 2.0 * PI_T;
+    const double theta = ring_theta[(size_t)ring * n3 + j];
     const double phi = slice == 0 ? 0.0 : (2.0 * PI_T / m.n_field_periods * slice) / n2;
     double psi, q, sqrtg, b1, R, dR_ds, dR_dt, Z, dZ_ds, dZ_dt;
     F.eval(s, theta, psi, q, sqrtg, b1, R, dR_ds, dR_dt, Z, dZ_ds, dZ_dt);

@@ -48,7 +48,7 @@ class TetraGridSettings:
     boole_n_field_periods: bool = True
     n_field_periods_manual: int = 1
     i_radial_spacing: int = 0
-    theta_geom_flux: int = 1
+    theta_geom_flux: int = 1          # grid_kind 2: poloidal grid equidistant in 1 the flux angle | 2 the geometrical angle
     sfc_s_min: float = 0.1
     theta0_at_xpoint: float = 1.0   # logical in the namelist (.true. = theta = 0 on the axis -> X-point ray)
     R0_analytic_circ: float = 0.0

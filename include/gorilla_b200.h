@@ -351,7 +351,7 @@ typedef struct gorilla_grid_settings {
 /* make_tetra_grid + make_tetra_physics + check_tetra_overlaps of initialize_gorilla
  * (orbit_timestep_gorilla.f90:151-274; tetra_grid_mod.f90:27-211; tetra_physics_mod.f90:127-1034,1291-1336).
  * Implemented grid kinds: 1 (EFIT g-file, rectangular grid), 2 (EFIT g-file, field aligned, symmetry flux coordinates
- * constructed by field-line integration; theta_geom_flux = 1 only), 3 (VMEC, field aligned), 4 (SOLEDGE3X-EIRENE triangle mesh
+ * constructed by field-line integration; theta_geom_flux = 1 flux angle | 2 geometrical angle, points_2d.f90:139-149), 3 (VMEC, field aligned), 4 (SOLEDGE3X-EIRENE triangle mesh
  * extruded toroidally, WEST equilibrium table), 5 (analytic circular tokamak, rectangular grid). */
 int gorilla_mesh_build(const gorilla_grid_settings *grid, const gorilla_settings *settings, gorilla_mesh **out);
 int gorilla_mesh_get_desc(const gorilla_mesh *mesh, gorilla_mesh_desc *out);

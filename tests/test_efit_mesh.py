@@ -209,3 +209,100 @@ def test_gpu_parity_on_the_field_aligned_efit_mesh(efit_flux_mesh, cuda_device):
         assert np.array_equal(ra["trace_tetr"], tt) and np.array_equal(ra["trace_face"], tf)
         assert np.array_equal(xa, xb) and np.array_equal(va, vb) and np.array_equal(wa, wb) and np.array_equal(ta, tb)
         g.close()
+
+
+# ------------------------------------------------------------- grid_kind = 2, theta_geom_flux = 2 (points_2d.f90:139-149)
+@pytest.fixture(scope="module")
+def efit_flux_geom_mesh(product_lib):
+    grid = TetraGridSettings(grid_kind=2, n1=24, n2=6, n3=32, boole_n_field_periods=True, sfc_s_min=0.1, theta_geom_flux=2,
+                             g_file_filename=str(GFILE), convex_wall_filename=str(DATA / "convex_wall_for_test.dat"))
+    st = GorillaSettings(eps_Phi=0.0, coord_system=2, ispecies=2, boole_periodic_relocation=True, ipusher=2,
+                         poly_order=2, boole_guess=True)
+    return build_mesh(grid, st), grid, st
+
+
+def test_theta_geom_flux_2_places_the_vertices_at_equidistant_geometrical_angles(efit_flux_geom_mesh, efit_flux_mesh):
+    """theta_geom2theta_flux (SRC/points_2d.f90:254-373): with theta_geom_flux = 2 the n3 vertices of every ring sit at
+    equidistant GEOMETRICAL poloidal angles around the magnetic axis, measured from the axis -> X-point ray; their flux
+    angles (verts_sthetaphi) are what the inversion returned.  Independent check from the vertex positions alone."""
+    mesh, grid, _ = efit_flux_geom_mesh
+    n1 = mesh.desc().grid_size[0]
+    n3 = grid.n3
+    vr, vs = mesh.verts_rphiz[:(n1 + 1) * n3], mesh.verts_sthetaphi[:(n1 + 1) * n3]     # first phi slice
+    # the magnetic axis is the ONE centre around which every ring is equidistant in the geometrical angle: fit it on three
+    # rings, then check all of them
+    from scipy.optimize import least_squares
+
+    def steps(c, ring):
+        R, Z = vr[ring * n3:(ring + 1) * n3, 0], vr[ring * n3:(ring + 1) * n3, 2]
+        ang = np.unwrap(np.arctan2(Z - c[1], R - c[0]))
+        return np.diff(np.append(ang, ang[0] + np.sign(ang[1] - ang[0]) * 2 * np.pi))
+
+    fit = least_squares(lambda c: np.concatenate([np.abs(steps(c, r)) - 2 * np.pi / n3 for r in (2, n1 // 2, n1)]),
+                        x0=[vr[:n3, 0].mean(), vr[:n3, 2].mean()], xtol=1e-14, ftol=1e-14)
+    assert abs(fit.x[0] - vr[:n3, 0].mean()) < 1.0 and abs(fit.x[1] - vr[:n3, 2].mean()) < 1.0      # [cm]
+    for ring in range(n1 + 1):
+        th = vs[ring * n3:(ring + 1) * n3, 1]
+        step = steps(fit.x, ring)
+        assert np.all(step > 0) or np.all(step < 0)
+        assert np.abs(np.abs(step) - 2 * np.pi / n3).max() < 2e-5, (ring, np.abs(np.abs(step) - 2 * np.pi / n3).max())
+        # the flux angles are a monotonic re-parametrisation that starts at exactly 0 and is NOT equidistant
+        assert th[0] == 0.0 and np.all(np.diff(th) > 0) and th[-1] < 2 * np.pi
+    outer = vs[n1 * n3:(n1 + 1) * n3, 1]
+    assert np.abs(np.diff(outer) - 2 * np.pi / n3).max() > 0.02
+    # same surfaces as the flux-angle grid: s of the rings, psi on them
+    m1 = efit_flux_mesh[0]
+    assert np.array_equal(np.unique(mesh.verts_sthetaphi[:, 2]).size, grid.n2)
+    tp = mesh.tetra_physics
+    s, Aphi = tp[:, 0], tp[:, 26]
+    span = np.abs(m1.tetra_physics[:, 26]).max()
+    for r in np.unique(np.round(s, 12))[::4]:
+        sel = np.isclose(s, r)
+        assert np.ptp(Aphi[sel]) < 2e-4 * span
+    assert np.all(tp[:, 40] > 0)
+
+
+def test_orbits_on_the_geometrical_angle_grid(efit_flux_geom_mesh):
+    """Oracle and device algorithm (host compile) carry the same orbits over the theta_geom_flux = 2 mesh bit for bit, the
+    particles cross the theta = 0 / 2 pi seam, and the invariants hold as on the flux-angle grid."""
+    mesh, grid, st = efit_flux_geom_mesh
+    om, hm = OracleMesh(mesh, st), HostMirror(mesh, st)
+    n = 120
+    rng = np.random.Generator(np.random.PCG64(19))
+    xa = np.column_stack([0.25 + 0.5 * rng.random(n), 2 * np.pi * rng.random(n), 2 * np.pi * rng.random(n)])
+    lam = 2 * rng.random(n) - 1
+    vmod = np.sqrt(2.0 * 3.0e3 * workloads.EV2ERG / (2.0 * workloads.AMP))
+    va, wa = lam * vmod, vmod * np.sqrt(1 - lam ** 2)
+    xb, vb, wb = xa.copy(), va.copy(), wa.copy()
+    ia, ta, fa = workloads.fresh_state(n)
+    ib, tb, fb = workloads.fresh_state(n)
+    om.orbit_timestep_batch(xa, va, wa, 0.0, ia, ta, fa)
+    hm.orbit_timestep(xb, vb, wb, 0.0, ib, tb, fb, 0)
+    assert ia.all() and np.array_equal(ta, tb) and (ta > 0).all()
+    e0, p0, mu0 = om.invariants(xa, va, wa, ta)
+    ra = om.orbit_timestep_trace(xa, va, wa, 4e-5, ia, ta, fa, 256)
+    rb = hm.orbit_timestep(xb, vb, wb, 4e-5, ib, tb, fb, 256)
+    assert ra["n_pushes"].sum() > 2000 and (ta > 0).sum() > 100
+    assert np.array_equal(ra["trace_tetr"], rb["trace_tetr"]) and np.array_equal(ra["trace_face"], rb["trace_face"])
+    assert np.array_equal(xa, xb) and np.array_equal(va, vb) and np.array_equal(wa, wb) and np.array_equal(ta, tb)
+    e1, p1, mu1 = om.invariants(xa, va, wa, ta)
+    ok = ta > 0
+    assert np.abs(mu1 / mu0 - 1)[ok].max() < 1e-13
+    assert np.abs(e1 / e0 - 1)[ok].max() < 1e-4
+    assert np.abs(p1 - p0)[ok].max() / np.abs(p0[ok]).mean() < 1e-2
+
+
+@pytest.mark.gpu
+def test_gpu_parity_on_the_geometrical_angle_grid(efit_flux_geom_mesh, cuda_device):
+    from gorilla_b200 import Gorilla
+    mesh, _, st = efit_flux_geom_mesh
+    g, om = Gorilla(mesh, st), OracleMesh(mesh, st)
+    n = 400
+    xa, va, wa = workloads.particles_flux(n, 23)
+    xb, vb, wb = xa.copy(), va.copy(), wa.copy()
+    sa, sb = workloads.fresh_state(n), workloads.fresh_state(n)
+    ra = om.orbit_timestep_trace(xa, va, wa, 2e-5, *sa, 128)
+    tt, tf = g.orbit_timestep_gorilla(xb, vb, wb, 2e-5, *sb, trace_cap=128)
+    assert np.array_equal(ra["trace_tetr"], tt) and np.array_equal(ra["trace_face"], tf)
+    assert np.array_equal(xa, xb) and np.array_equal(va, vb) and np.array_equal(wa, wb) and np.array_equal(sa[1], sb[1])
+    g.close()

@@ -38,7 +38,10 @@ class _Settings(C.Structure):
         "boole_newton_precalc", "poly_order", "i_precomp", "boole_guess", "i_time_tracing_option",
         "handover_processing_kind", "boole_adaptive_time_steps", "boole_strong_electric_field",
         "boole_grid_for_find_tetra", "boole_time_Hamiltonian", "boole_gyrophase", "boole_vpar_int",
-        "boole_vpar2_int", "max_n_intermediate_steps")] + [("desired_delta_energy", C.c_double), ("rel_err_ode45", C.c_double)]
+        "boole_vpar2_int", "max_n_intermediate_steps")] + [("desired_delta_energy", C.c_double), ("rel_err_ode45", C.c_double),
+                                                        ("helical_pert_eps_Aphi", C.c_double), ("boole_helical_pert", C.c_int32),
+                                                        ("helical_pert_m_fourier", C.c_int32),
+                                                        ("helical_pert_n_fourier", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class _MeshDesc(C.Structure):
@@ -58,7 +61,8 @@ class _GridSettings(C.Structure):
                [(n, C.c_double) for n in ("sfc_s_min", "theta0_at_xpoint", "R0_analytic_circ", "a_analytic_circ",
                                           "B0_analytic_circ", "q0_analytic_circ", "q1_analytic_circ")] + \
                [(n, C.c_char_p) for n in ("g_file_filename", "convex_wall_filename", "netcdf_filename",
-                                          "knots_SOLEDGE3X_EIRENE_filename", "triangles_SOLEDGE3X_EIRENE_filename")]
+                                          "knots_SOLEDGE3X_EIRENE_filename", "triangles_SOLEDGE3X_EIRENE_filename")] + \
+               [("bmod_multiplier", C.c_double), ("nwindow_r", C.c_int32), ("nwindow_z", C.c_int32)]
 
 
 class _Counters(C.Structure):
@@ -81,13 +85,13 @@ COMM_ID_BYTES = 128
 
 class _EventSettings(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("boole_poincare_phi_0", "n_skip_phi_0", "boole_poincare_vpar_0", "boole_J_par",
-                                         "n_skip_vpar_0")] + [("reserved", C.c_int32 * 3)]
+                                         "n_skip_vpar_0", "boole_full_orbit", "n_skip_full_orbit", "reserved")]
 
 
 # struct gorilla_event (include/gorilla_b200.h)
 EVENT_DTYPE = np.dtype([("particle", np.int64), ("kind", np.int32), ("counter", np.int32), ("push", np.int64),
-                        ("x", np.float64, 3), ("value", np.float64, 2)])
-EVENT_PHI_0, EVENT_VPAR_0 = 1, 2
+                        ("x", np.float64, 3), ("value", np.float64, 2), ("t", np.float64)])
+EVENT_PHI_0, EVENT_VPAR_0, EVENT_FULL_ORBIT = 1, 2, 3
 
 
 @dataclass
@@ -139,7 +143,7 @@ EXPORTED_SYMBOLS = (
     "gorilla_b200_comm_unique_id", "gorilla_b200_comm_init", "gorilla_b200_comm_free", "gorilla_b200_comm_allreduce_f64",
     "gorilla_b200_shard_range", "gorilla_b200_diag_reset", "gorilla_b200_diag_reduce_dev", "gorilla_b200_diag_reduce",
     "gorilla_mesh_build", "gorilla_mesh_get_desc", "gorilla_mesh_get_vertices", "gorilla_mesh_free",
-    "gorilla_mesh_save", "gorilla_mesh_load",
+    "gorilla_mesh_save", "gorilla_mesh_load", "gorilla_b200_abi_struct_sizes",
 )
 
 
@@ -199,6 +203,16 @@ def load_library():
     lib.gorilla_mesh_free.restype = None
     lib.gorilla_mesh_save.argtypes = [C.POINTER(_MeshDesc), i64, vp, vp, C.c_char_p]
     lib.gorilla_mesh_load.argtypes = [C.c_char_p, C.POINTER(vp)]
+    # the ctypes mirrors above against the layout the library was compiled with
+    sizes = (i64 * 7)()
+    lib.gorilla_b200_abi_struct_sizes.argtypes = [C.POINTER(i64)]
+    if lib.gorilla_b200_abi_struct_sizes(sizes) != 0:
+        raise ImportError("gorilla_b200_abi_struct_sizes failed")
+    mine = (C.sizeof(_Settings), C.sizeof(_MeshDesc), C.sizeof(_Counters), C.sizeof(_Diag), C.sizeof(_GridSettings),
+            EVENT_DTYPE.itemsize, C.sizeof(_EventSettings))
+    if tuple(sizes) != mine:
+        raise ImportError(f"struct layouts of {_LIB_PATH.name} {tuple(sizes)} differ from this binding's {mine}: "
+                          "rebuild the library (python -m gorilla_b200.build)")
     _lib = lib
     return lib
 
@@ -251,7 +265,7 @@ def _require(a, dtype, shape=None, name="array", allow_none=False):
 def _c_settings(s: GorillaSettings) -> _Settings:
     cs = _Settings()
     for name, typ in _Settings._fields_:
-        v = getattr(s, name)
+        v = getattr(s, name, 0)
         setattr(cs, name, float(v) if typ is C.c_double else int(v))
     return cs
 
@@ -524,9 +538,10 @@ class Gorilla:
     def orbit_timestep_gorilla_events(self, x, vpar, vperp, t_step, boole_initialized, ind_tetr, iface, par_adiab_inv,
                                       counter_vpar_0, counter_phi_0, event_cap: int, *, boole_poincare_phi_0=True,
                                       n_skip_phi_0=1, boole_poincare_vpar_0=True, boole_J_par=True, n_skip_vpar_0=1,
-                                      t_remain_out=None, n_pushes=None):
-        """orbit_timestep_gorilla with the event capture of gorilla_plot_orbit_integration (gorilla_plot_mod.f90:585-638):
-        toroidal mappings and banana tips / J_par.  par_adiab_inv [n] f64, counter_vpar_0 / counter_phi_0 [n] i32 carry the
+                                      t_remain_out=None, n_pushes=None, boole_full_orbit=False, n_skip_full_orbit=1):
+        """orbit_timestep_gorilla with the event capture of gorilla_plot_orbit_integration (gorilla_plot_mod.f90:553-638):
+        toroidal mappings, banana tips / J_par and (boole_full_orbit) the orbit point, p_phi and E_tot after every
+        n_skip_full_orbit-th push.  par_adiab_inv [n] f64, counter_vpar_0 / counter_phi_0 [n] i32 carry the
         per-particle state between calls.  Returns (events, n_events): a structured array (EVENT_DTYPE) sorted by
         (particle, push, kind) holding min(n_events, event_cap) records."""
         n = x.shape[0]
@@ -535,7 +550,7 @@ class Gorilla:
         _require(counter_vpar_0, np.int32, (n,), "counter_vpar_0")
         _require(counter_phi_0, np.int32, (n,), "counter_phi_0")
         cfg = _EventSettings(int(boole_poincare_phi_0), int(n_skip_phi_0), int(boole_poincare_vpar_0), int(boole_J_par),
-                             int(n_skip_vpar_0))
+                             int(n_skip_vpar_0), int(boole_full_orbit), int(n_skip_full_orbit), 0)
         ev = np.zeros(max(event_cap, 1), EVENT_DTYPE)
         nev = C.c_int64(0)
         _check(load_library().gorilla_b200_orbit_timestep_events(

@@ -230,4 +230,36 @@ GB_HD void find_tetra(const MeshDev *mp, double *x, double vpar, double vperp, i
   }
 }
 
+// boole_full_orbit (SRC/gorilla_plot_mod.f90:553-579): what the reference writes next to the orbit point after a push,
+// p_phi_func(vpar, z_save, ind_tetr_save) and energy_tot_func([z_save, vpar], perpinv, ind_tetr_save)
+// (SRC/supporting_functions_mod.f90:377-408, 279-301), z = z_save relative to the first vertex of tetrahedron it (1-based)
+GB_HD void orbit_point_invariants(const MeshDev &m, int32_t it, const double *z, double vpar, double perpinv, double &p_phi,
+                                  double &e_tot)
+{
+  const double *pb = m.bpart + ((int64_t)it - 1) * BPART_ND;
+  const double *pc = m.cold + ((int64_t)it - 1) * COLD_ND;
+  const double gB[3] = {pb[B_GB], pb[B_GB + 1], pb[B_GB + 2]};
+  double vperp = 0.0;  // vperp_func :321-338
+  if (perpinv != 0.0) vperp = sqrt(2.0 * fabs(perpinv) * (pb[B_BMOD1] + dot3(gB, z)));
+  double phi = 0.0;
+  if (m.phi) {
+    const double *pp = m.phi + ((int64_t)it - 1) * PHI_ND;
+    const double gP[3] = {pp[P_GPHI], pp[P_GPHI + 1], pp[P_GPHI + 2]};
+    phi = pp[P_PHI1] + dot3(gP, z);
+  }
+  e_tot = m.particle_mass / 2.0 * (vperp * vperp + vpar * vpar) + m.particle_charge * phi;
+  const double *ps = m.se ? m.se + ((int64_t)it - 1) * SE_ND : nullptr;
+  if (ps) {
+    const double g2[3] = {ps[S_GV2EMOD], ps[S_GV2EMOD + 1], ps[S_GV2EMOD + 2]};
+    e_tot = e_tot + 0.5 * m.particle_mass * (ps[S_V2EMOD1] + dot3(z, g2));
+  }
+  const double gh[3] = {pc[C_GHPHI], pc[C_GHPHI + 1], pc[C_GHPHI + 2]};
+  const double gA[3] = {pc[C_GAPHI], pc[C_GAPHI + 1], pc[C_GAPHI + 2]};
+  p_phi = m.particle_mass * vpar * (pc[C_HPHI1] + dot3(gh, z)) + m.particle_mass / m.cm_over_e * (pc[C_APHI1] + dot3(gA, z));
+  if (ps) {
+    const double gv[3] = {ps[S_GVE2], ps[S_GVE2 + 1], ps[S_GVE2 + 2]};
+    p_phi = p_phi + m.particle_mass * (ps[S_VE2_1] + dot3(z, gv));
+  }
+}
+
 } // namespace gb

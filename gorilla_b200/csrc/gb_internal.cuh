@@ -61,7 +61,8 @@ struct Batch {
   uint32_t oq_mask;
   // EXT = 2 kernels: orbit events (gorilla_plot_mod.f90:585-638).  ev_flags bit0 boole_poincare_phi_0, bit1
   // boole_poincare_vpar_0, bit2 boole_J_par; per-particle state in/out; events appended to a global buffer
-  int32_t ev_flags, n_skip_phi_0, n_skip_vpar_0;
+  int32_t ev_flags, n_skip_phi_0, n_skip_vpar_0;   // ev_flags bit3: boole_full_orbit (:553-579)
+  int32_t n_skip_full_orbit;
   double *par_adiab_inv;
   int32_t *counter_vpar_0, *counter_phi_0;
   gorilla_event *events;
@@ -74,7 +75,7 @@ struct Batch {
 
 // append the events of one push to the global buffer (order between particles is not defined; a record carries the
 // particle and push index); the counter keeps counting past the capacity so that the caller sees the overflow
-__device__ __forceinline__ void emit_events(const Batch &bt, long long particle, long long push, const EvState &es)
+__device__ __forceinline__ void emit_events(const Batch &bt, long long particle, long long push, const EvState &es, double t)
 {
 #pragma unroll
   for (int k = 0; k < 2; k++) {
@@ -88,6 +89,7 @@ __device__ __forceinline__ void emit_events(const Batch &bt, long long particle,
         e->push = push;
         e->x[0] = es.e[k].x[0]; e->x[1] = es.e[k].x[1]; e->x[2] = es.e[k].x[2];
         e->value[0] = es.e[k].v[0]; e->value[1] = es.e[k].v[1];
+        e->t = t;
       }
     }
   }
@@ -254,7 +256,7 @@ __device__ __forceinline__ void lane_ext2_after_fast(const Batch &bt, const Lane
       es.J = S.OQ(4); es.cnt_v = S.EC(0); es.cnt_p = S.EC(1);
       P.events_after_push(S.D(LS_VPAR), o, es);
       S.OQ(4) = es.J; S.EC(0) = es.cnt_v; S.EC(1) = es.cnt_p;
-      if (es.n) emit_events(bt, S.Idx(), S.Npush(), es);
+      if (es.n) emit_events(bt, S.Idx(), S.Npush(), es, bt.t_step - (S.D(LS_TREM) - o.t_pass));
     }
   }
 }
@@ -272,7 +274,7 @@ __device__ __forceinline__ PushOut lane_ext2_full(const MeshDev &m, const Batch 
   for (int q = 0; q < 4; q++) S.OQ(q) = S.OQ(q) + ox.oq[q];
   if (bt.ev_flags) {
     S.OQ(4) = ox.es.J; S.EC(0) = ox.es.cnt_v; S.EC(1) = ox.es.cnt_p;
-    if (ox.es.n) emit_events(bt, S.Idx(), S.Npush(), ox.es);
+    if (ox.es.n) emit_events(bt, S.Idx(), S.Npush(), ox.es, bt.t_step - (S.D(LS_TREM) - ox.o.t_pass));
   }
   return ox.o;
 }
@@ -307,6 +309,25 @@ __device__ __forceinline__ bool lane_after_push(const MeshDev &m, const Batch &b
   }
   const double t_remain = S.D(LS_TREM) - o.t_pass;
   S.D(LS_TREM) = t_remain;
+  if constexpr (EXT == 2 || EXT == 5) {
+    if (bt.ev_flags & 8) {   // boole_full_orbit: the orbit point after every n_skip_full_orbit-th push (gorilla_plot_mod.f90:553-579)
+      const long long cnt = npush + 1;   // counter_tetrahedron_passes
+      if (cnt / bt.n_skip_full_orbit * bt.n_skip_full_orbit == cnt) {
+        const unsigned long long slot = atomicAdd(bt.ev_count, 1ull);
+        if ((long long)slot < bt.ev_cap) {
+          const double zs[3] = {S.D(LS_ZS0), S.D(LS_ZS1), S.D(LS_ZS2)};
+          gorilla_event *e = bt.events + slot;
+          e->particle = S.Idx();
+          e->kind = GORILLA_EVENT_FULL_ORBIT;
+          e->counter = (int32_t)cnt;
+          e->push = npush;
+          e->x[0] = o.x[0]; e->x[1] = o.x[1]; e->x[2] = o.x[2];
+          orbit_point_invariants(m, ind_prev, zs, o.vpar, S.D(LS_PERPINV), e->value[0], e->value[1]);
+          e->t = bt.t_step - t_remain;
+        }
+      }
+    }
+  }
   if (!(o.finished || ind_tetr == -1)) return false;
   // :142  vperp = vperp_func(z_save, perpinv, ind_tetr_save)
   const long long idx = S.Idx();
@@ -421,7 +442,7 @@ __global__ void __launch_bounds__(GB_THREADS, GATHER ? gb_gather_min_blocks(GATH
           es = rk_events_call<PHI>(&m, perpinv, ind_tetr, iface, S.D(LS_X0), S.D(LS_X1), S.D(LS_X2), S.D(LS_VPAR), S.D(LS_TREM),
                                    o, es);
           S.OQ(4) = es.J; S.EC(0) = es.cnt_v; S.EC(1) = es.cnt_p;
-          if (es.n) emit_events(bt, S.Idx(), S.Npush(), es);
+          if (es.n) emit_events(bt, S.Idx(), S.Npush(), es, bt.t_step - (S.D(LS_TREM) - o.t_pass));
         }
       }
     } else if constexpr (EXT == 5) {

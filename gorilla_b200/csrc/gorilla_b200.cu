@@ -692,7 +692,9 @@ static int check_event_args(gorilla_b200_handle *h, const gorilla_event_settings
 {
   if (h->settings.ipusher == 2 && h->settings.poly_order < 2)
     return fail(GORILLA_ERR_UNSUPPORTED, "orbit events need the polynomial pusher of order 2..4 (par_adiab_inv_poly_mod) or the RK pusher (par_adiab_inv_rk_mod)");
-  flags = (cfg->boole_poincare_phi_0 ? 1 : 0) | (cfg->boole_poincare_vpar_0 ? 2 : 0) | (cfg->boole_J_par ? 4 : 0);
+  flags = (cfg->boole_poincare_phi_0 ? 1 : 0) | (cfg->boole_poincare_vpar_0 ? 2 : 0) | (cfg->boole_J_par ? 4 : 0) |
+          (cfg->boole_full_orbit ? 8 : 0);
+  if ((flags & 8) && cfg->n_skip_full_orbit < 1) return fail(GORILLA_ERR_ARG, "n_skip_full_orbit must be >= 1");
   if ((flags & 1) && cfg->n_skip_phi_0 < 1) return fail(GORILLA_ERR_ARG, "n_skip_phi_0 must be >= 1");
   if ((flags & 6) && cfg->n_skip_vpar_0 < 1) return fail(GORILLA_ERR_ARG, "n_skip_vpar_0 must be >= 1");
   if (!flags) return fail(GORILLA_ERR_ARG, "no event kind switched on");
@@ -719,6 +721,7 @@ extern "C" int gorilla_b200_orbit_timestep_events_dev(gorilla_b200_handle *h, in
   bt.ind_tetr = ind_tetr; bt.iface = iface; bt.t_remain_out = t_remain_out; bt.n_pushes = n_pushes;
   bt.ev_flags = flags; bt.n_skip_phi_0 = cfg->n_skip_phi_0 > 0 ? cfg->n_skip_phi_0 : 1;
   bt.n_skip_vpar_0 = cfg->n_skip_vpar_0 > 0 ? cfg->n_skip_vpar_0 : 1;
+  bt.n_skip_full_orbit = cfg->n_skip_full_orbit > 0 ? cfg->n_skip_full_orbit : 1;
   bt.par_adiab_inv = par_adiab_inv; bt.counter_vpar_0 = counter_vpar_0; bt.counter_phi_0 = counter_phi_0;
   bt.events = events; bt.ev_cap = event_cap; bt.ev_count = (unsigned long long *)n_events;
   return run_device(h, bt, true, (cudaStream_t)stream);

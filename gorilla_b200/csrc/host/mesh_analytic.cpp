@@ -202,7 +202,7 @@ int build_analytic_circ(const gorilla_grid_settings &gs, const gorilla_settings 
     const double r = m.verts_rphiz[3 * iv], z = m.verts_rphiz[3 * iv + 2];
     double Br, Bp, Bz, psif;
     f.field(r, z, Br, Bp, Bz, psif);
-    const double bmod = std::sqrt(Br * Br + Bp * Bp + Bz * Bz) * 1.0;  // bmod_multiplier = 1
+    const double bmod = std::sqrt(Br * Br + Bp * Bp + Bz * Bz) * m.bmod_multiplier;
     vf.A_x1[iv] = 0.0;
     vf.A_x2[iv] = psif;
     vf.A_x3[iv] = -rtf * btf * std::log(r);

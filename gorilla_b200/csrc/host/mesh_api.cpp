@@ -19,6 +19,7 @@ extern "C" int gorilla_mesh_build(const gorilla_grid_settings *grid, const goril
   if (!gm) return GORILLA_ERR_ARG;
   std::string err;
   gm->m.handover_processing_kind = settings->handover_processing_kind;
+  gm->m.bmod_multiplier = grid->bmod_multiplier != 0.0 ? grid->bmod_multiplier : 1.0;
   int rc = gbhost::set_species(gm->m, settings->ispecies, err);
   if (rc == GORILLA_OK) {
     switch (grid->grid_kind) {
@@ -39,6 +40,16 @@ extern "C" int gorilla_mesh_build(const gorilla_grid_settings *grid, const goril
     return rc;
   }
   *out = gm;
+  return GORILLA_OK;
+}
+
+extern "C" int gorilla_b200_abi_struct_sizes(int64_t sizes_out[GORILLA_ABI_N_STRUCTS])
+{
+  if (!sizes_out) return GORILLA_ERR_ARG;
+  const size_t sz[GORILLA_ABI_N_STRUCTS] = {sizeof(gorilla_settings), sizeof(gorilla_mesh_desc), sizeof(gorilla_counters),
+                                            sizeof(gorilla_diag), sizeof(gorilla_grid_settings), sizeof(gorilla_event),
+                                            sizeof(gorilla_event_settings)};
+  for (int i = 0; i < GORILLA_ABI_N_STRUCTS; i++) sizes_out[i] = (int64_t)sz[i];
   return GORILLA_OK;
 }
 

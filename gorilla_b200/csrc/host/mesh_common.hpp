@@ -48,6 +48,7 @@ struct Mesh {
   double mag_axis_R0 = 0, mag_axis_Z0 = 0;
   double psitor_max = 0;  // EFIT flux coordinates (grid_kind 2): toroidal flux at the last surface, A_theta = s*psitor_max
   int64_t n_overlaps = 0;
+  double bmod_multiplier = 1.0;  // make_tetra_physics' optional argument (tetra_physics_mod.f90:281-286), set by gorilla_mesh_build
 };
 
 // values of the field at the vertices, as gathered in make_tetra_physics :330-446

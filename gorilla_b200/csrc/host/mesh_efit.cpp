@@ -9,8 +9,8 @@
 //            vector_potential_rphiz        SRC/tetra_physics_mod.f90:1076-1109
 //            make_tetra_grid case(1)       SRC/tetra_grid_mod.f90:73-95
 // Restated, not transcribed: same interpolant (end conditions, sweep order) so that vertex fields agree with
-// the reference to round-off; the hot path never sees this code.  nwindow_r = nwindow_z = 0 (no psi filtering), as
-// in every field_divB0.inp the reference ships.
+// the reference to round-off; the hot path never sees this code.  The moving-average psi filter of field_divB0.inp
+// (nwindow_r, nwindow_z) is applied to the raw table as in the reference; every input the reference ships sets 0 0.
 #include "mesh_efit.hpp"
 #include <algorithm>
 #include <cmath>
@@ -198,6 +198,28 @@ struct FixedReader {
 };
 }  // namespace
 
+// window_filter (utils_bdivfree.f90:859-872): centred moving average, the window shrinks towards the ends of the row
+void EfitField::filter_psi(std::vector<double> &psi) const
+{
+  if (nwindow_r <= 0 && nwindow_z <= 0) return;  // windows of 0: sum of one element / 1, the identity
+  std::vector<double> psi0(psi.size());
+  const int nwr = std::max(nwindow_r, 0), nwz = std::max(nwindow_z, 0);
+  for (int iz = 0; iz < nzet; iz++)
+    for (int i = 1; i <= nrad; i++) {
+      const int nwa = std::min(nwr, std::min(i - 1, nrad - i));
+      double s = 0.0;
+      for (int k = i - nwa; k <= i + nwa; k++) s += psi[(k - 1) + (size_t)nrad * iz];
+      psi0[(i - 1) + (size_t)nrad * iz] = s / (double)(2 * nwa + 1);
+    }
+  for (int ir = 0; ir < nrad; ir++)
+    for (int i = 1; i <= nzet; i++) {
+      const int nwa = std::min(nwz, std::min(i - 1, nzet - i));
+      double s = 0.0;
+      for (int k = i - nwa; k <= i + nwa; k++) s += psi0[ir + (size_t)nrad * (k - 1)];
+      psi[ir + (size_t)nrad * (i - 1)] = s / (double)(2 * nwa + 1);
+    }
+}
+
 int EfitField::load_efit(const char *path, std::string &err)
 {
   std::string txt;
@@ -252,6 +274,7 @@ int EfitField::load_efit(const char *path, std::string &err)
       s[0] = a[i]; s[1] = b[i]; s[2] = c[i]; s[3] = d[i]; s[4] = e[i]; s[5] = f[i];
     }
   }
+  filter_psi(psi_in);
   for (auto &x : rad) x = x * 1.0e2;
   for (auto &x : zet) x = x * 1.0e2;
   rtf = rtf * 1.0e2;
@@ -283,6 +306,7 @@ int EfitField::load_west(const char *path, std::string &err)
   use_fpol = false;
   rtf = 0.5 * (rad[0] + rad[nrad - 1]);
   btf = b / rtf;
+  filter_psi(psi_in);
   for (auto &x : rad) x = x * 1.0e2;
   for (auto &x : zet) x = x * 1.0e2;
   rtf = rtf * 1.0e2;
@@ -414,7 +438,7 @@ void EfitField::vertex_fields(const Mesh &m, const gorilla_settings &st, int n2,
     const double r = m.verts_rphiz[3 * iv], z = m.verts_rphiz[3 * iv + 2];
     double Br, Bp, Bz, psif;
     field(r, z, Br, Bp, Bz, psif);
-    const double bmod = std::sqrt(Br * Br + Bp * Bp + Bz * Bz) * 1.0;  // bmod_multiplier = 1
+    const double bmod = std::sqrt(Br * Br + Bp * Bp + Bz * Bz) * m.bmod_multiplier;
     vf.A_x1[iv] = 0.0;
     vf.A_x2[iv] = psif;
     vf.A_x3[iv] = -rtf * btf * std::log(r);
@@ -443,6 +467,7 @@ int build_efit_rect(const gorilla_grid_settings &gs, const gorilla_settings &st,
   }
   if (gs.n1 < 1 || gs.n2 < 1 || gs.n3 < 1) { err = "n1,n2,n3 must be positive"; return GORILLA_ERR_ARG; }
   EfitField f;
+  f.nwindow_r = gs.nwindow_r; f.nwindow_z = gs.nwindow_z;
   int rc = f.load_efit(gs.g_file_filename, err);
   if (rc) return rc;
   if (gs.convex_wall_filename && gs.convex_wall_filename[0]) {

@@ -30,6 +30,8 @@ struct EfitField {
   double wall_R0 = 0, wall_htht = 0;
   std::vector<double> rho_wall, tht_wall;
 
+  int nwindow_r = 0, nwindow_z = 0;  // field_divB0.inp: psi filter windows, set before load_*
+  void filter_psi(std::vector<double> &psi) const;  // window_filter over R, then over Z (bdivfree.f90:1144-1164)
   int load_efit(const char *path, std::string &err);
   int load_west(const char *path, std::string &err);
   int load_convex_wall(const char *path, std::string &err);

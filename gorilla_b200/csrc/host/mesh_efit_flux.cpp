@@ -451,6 +451,7 @@ int build_efit_flux(const gorilla_grid_settings &gs, const gorilla_settings &st,
   if (gs.n1 < 1 || gs.n2 < 3 || gs.n3 < 3) { err = "field-aligned grid needs n1 >= 1, n2 >= 3, n3 >= 3"; return GORILLA_ERR_ARG; }
   if (!(gs.sfc_s_min > 0.0 && gs.sfc_s_min < 1.0)) { err = "sfc_s_min must be in (0, 1)"; return GORILLA_ERR_ARG; }
   EfitField f;
+  f.nwindow_r = gs.nwindow_r; f.nwindow_z = gs.nwindow_z;
   int rc = f.load_efit(gs.g_file_filename, err);
   if (rc) return rc;
   if (gs.convex_wall_filename && gs.convex_wall_filename[0]) {
@@ -525,10 +526,12 @@ int build_efit_flux(const gorilla_grid_settings &gs, const gorilla_settings &st,
     vr[0] = R; vr[1] = phi; vr[2] = Z;
     double Br, Bp, Bz, psif;
     f.field(R, Z, Br, Bp, Bz, psif);
-    const double bmod = std::sqrt(Br * Br + Bp * Bp + Bz * Bz) * 1.0;
+    const double bmod = std::sqrt(Br * Br + Bp * Bp + Bz * Bz) * m.bmod_multiplier;
     vf.A_x1[iv] = 0.0;
     vf.A_x2[iv] = s * F.psitor_max;
     vf.A_x3[iv] = psi;
+    if (st.boole_helical_pert)  // analytical perturbation (tetra_physics_mod.f90:1158-1161)
+      vf.A_x3[iv] = psi + psi * st.helical_pert_eps_Aphi * std::cos(st.helical_pert_m_fourier * theta + st.helical_pert_n_fourier * phi);
     vf.bmod[iv] = bmod;
     vf.h_x1[iv] = (Br * dR_ds + Bz * dZ_ds) / bmod;
     vf.h_x2[iv] = (Br * dR_dt + Bz * dZ_dt) / bmod;

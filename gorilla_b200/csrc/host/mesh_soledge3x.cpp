@@ -106,6 +106,7 @@ int build_soledge3x(const gorilla_grid_settings &gs, const gorilla_settings &st,
   const int n_slices = gs.n2;
   if (n_slices < 3) { err = "grid_kind 4: n2 (toroidal slices) must be >= 3"; return GORILLA_ERR_ARG; }
   EfitField fld;
+  fld.nwindow_r = gs.nwindow_r; fld.nwindow_z = gs.nwindow_z;
   int rc = fld.load_west(gs.g_file_filename, err);
   if (rc) return rc;
   if (gs.convex_wall_filename && gs.convex_wall_filename[0]) {

@@ -314,7 +314,8 @@ double theta_vmec_of(const Vmec &V, double s, double vartheta, double phi)
 }
 
 // vmec_field (splint_vmec_data.f90:161-207) + vector_potential_sthetaphi_vmec (tetra_physics_mod.f90:1167-1210)
-void vertex_field(const Vmec &V, double s, double theta_vmec, double phi, double out[10] /*A1 A2 A3 h1 h2 h3 B sqg dRds dZds*/)
+void vertex_field(const Vmec &V, double s, double theta_vmec, double phi, double bmod_multiplier,
+                  double out[10] /*A1 A2 A3 h1 h2 h3 B sqg dRds dZds*/)
 {
   Vmec::Point P;
   V.eval(s, theta_vmec, phi, P);
@@ -344,7 +345,7 @@ void vertex_field(const Vmec &V, double s, double theta_vmec, double phi, double
   const double Bcov_r = g[0][1] * Bt + g[0][2] * Bp;
   const double Bcov_t = g[1][1] * Bt + g[1][2] * Bp;
   const double Bcov_p = g[2][1] * Bt + g[2][2] * Bp;
-  const double bmod = std::sqrt(Bt * Bcov_t + Bp * Bcov_p);
+  const double bmod = std::sqrt(Bt * Bcov_t + Bp * Bcov_p) * bmod_multiplier;
   out[0] = 0.0; out[1] = P.A_theta; out[2] = P.A_phi;
   out[3] = Bcov_r / bmod; out[4] = Bcov_t / bmod; out[5] = Bcov_p / bmod;
   out[6] = bmod; out[7] = sqg; out[8] = P.dR_ds; out[9] = P.dZ_ds;
@@ -480,7 +481,7 @@ int build_vmec(const gorilla_grid_settings &gs, const gorilla_settings &st, Mesh
     const double thv = theta_vmec_of(V, s, theta, phi);
     m.verts_theta_vmec[iv] = thv;
     double f[10];
-    vertex_field(V, s, thv, phi, f);
+    vertex_field(V, s, thv, phi, m.bmod_multiplier, f);
     Vmec::Point P;
     V.eval(s, thv, phi, P);
     double *vr = &m.verts_rphiz[3 * iv];

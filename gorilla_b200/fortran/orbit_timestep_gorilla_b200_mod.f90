@@ -39,6 +39,9 @@ module orbit_timestep_gorilla_b200_mod
                           boole_time_Hamiltonian, boole_gyrophase, boole_vpar_int, boole_vpar2_int, &
                           max_n_intermediate_steps
     real(c_double)  :: desired_delta_energy, rel_err_ode45
+    ! read by gorilla_mesh_build only (a Fortran caller's make_tetra_physics has already applied the perturbation)
+    real(c_double)  :: helical_pert_eps_Aphi = 0.d0
+    integer(c_int32_t) :: boole_helical_pert = 0, helical_pert_m_fourier = 0, helical_pert_n_fourier = 0, reserved0 = 0
   end type
   !> struct gorilla_mesh_desc
   type, bind(C) :: gorilla_mesh_desc_t
@@ -70,10 +73,12 @@ module orbit_timestep_gorilla_b200_mod
     integer(c_int32_t) :: kind, counter
     integer(c_int64_t) :: push
     real(c_double)     :: x(3), value(2)
+    real(c_double)     :: t   ! t_step - t_remain after the push of the event
   end type
   type, bind(C) :: gorilla_b200_event_settings_t
     integer(c_int32_t) :: boole_poincare_phi_0, n_skip_phi_0, boole_poincare_vpar_0, boole_J_par, n_skip_vpar_0
-    integer(c_int32_t) :: reserved(3)
+    integer(c_int32_t) :: boole_full_orbit = 0, n_skip_full_orbit = 1   ! kind 3 events: the full_orbit_plot / p_phi / e_tot files
+    integer(c_int32_t) :: reserved = 0
   end type
 
   interface
@@ -181,6 +186,10 @@ module orbit_timestep_gorilla_b200_mod
       type(c_ptr), value        :: energy_ref, p_phi_ref, perpinv_ref     ! c_null_ptr: that drift is not formed
       type(gorilla_b200_diag_t), intent(out) :: diag
     end function
+    integer(c_int) function gorilla_b200_abi_struct_sizes(sizes) bind(C, name='gorilla_b200_abi_struct_sizes')
+      import :: c_int, c_int64_t
+      integer(c_int64_t), intent(out) :: sizes(7)
+    end function
   end interface
 
   type(c_ptr), save :: handle = c_null_ptr
@@ -199,9 +208,25 @@ contains
     integer, intent(out), optional :: ierr
     type(gorilla_mesh_desc_t) :: md
     type(gorilla_settings_t)  :: st
+    type(gorilla_b200_counters_t) :: ct
+    type(gorilla_b200_diag_t) :: dg
+    type(gorilla_b200_event_t) :: evt
+    type(gorilla_b200_event_settings_t) :: evs
+    integer(c_int64_t) :: abi(7)
     integer(c_int) :: rc
     md%ntetr = int(ntetr, c_int64_t)
     md%tetra_physics = addr_tetra_physics(tetra_physics)   ! sequence type of 142 doubles -> double[ntetr][142]
+    ! the bind(C) types of this module against the layout the library was compiled with
+    rc = gorilla_b200_abi_struct_sizes(abi)
+    if (rc /= 0 .or. abi(1) /= c_sizeof(st) .or. abi(2) /= c_sizeof(md) .or. abi(3) /= c_sizeof(ct) .or. &
+        abi(4) /= c_sizeof(dg) .or. abi(6) /= c_sizeof(evt) .or. abi(7) /= c_sizeof(evs)) then
+      print *, 'initialize_gorilla_b200: struct layouts of libgorilla_b200 differ from this module (rebuild both)'
+      if (present(ierr)) then
+        ierr = 1
+        return
+      end if
+      stop
+    end if
     md%tetra_grid    = addr_tetra_grid(tetra_grid)         ! sequence type of 20 integers -> int32[ntetr][20]
     md%cm_over_e = cm_over_e; md%particle_mass = particle_mass; md%particle_charge = particle_charge
     md%sign_sqg = sign_sqg; md%coord_system = coord_system_mesh; md%n_field_periods = n_field_periods

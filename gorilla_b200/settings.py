@@ -37,6 +37,12 @@ class GorillaSettings:
     boole_gyrophase: bool = False
     boole_vpar_int: bool = False
     boole_vpar2_int: bool = False
+    # analytical helical perturbation of A_phi at the vertices of a grid_kind 2 mesh (INPUT/gorilla.inp:118-125,
+    # tetra_physics_mod.f90:1158-1161); read by build_mesh
+    boole_helical_pert: bool = False
+    helical_pert_eps_Aphi: float = 1.0e-1
+    helical_pert_m_fourier: int = 2
+    helical_pert_n_fourier: int = 2
 
 
 @dataclass
@@ -61,6 +67,11 @@ class TetraGridSettings:
     netcdf_filename: str = ""
     knots_SOLEDGE3X_EIRENE_filename: str = ""
     triangles_SOLEDGE3X_EIRENE_filename: str = ""
+    # not a namelist entry: the optional argument bmod_multiplier of initialize_gorilla (orbit_timestep_gorilla.f90:151)
+    bmod_multiplier: float = 1.0
+    # field_divB0.inp lines 11-12: moving-average filter windows of the psi(R, Z) table (bdivfree.f90:1144-1164)
+    nwindow_r: int = 0
+    nwindow_z: int = 0
 
 
 _ASSIGN = re.compile(r"^\s*([A-Za-z_][A-Za-z0-9_]*)\s*=\s*(.*?)\s*,?\s*$")

@@ -75,6 +75,14 @@ typedef struct gorilla_settings {
   int32_t max_n_intermediate_steps;  /* adaptive scheme: >= 2 (INPUT/gorilla.inp:151) */
   double desired_delta_energy;       /* adaptive scheme: > 0, relative energy error per tetrahedron (gorilla.inp:147) */
   double rel_err_ode45;              /* boole_pusher_ode45: relative error of the RKF45 integrator (gorilla.inp:43, 1e-8) */
+  /* analytical helical perturbation of the equilibrium (gorilla.inp:118-125; vector_potential_sthetaphi,
+   * tetra_physics_mod.f90:1158-1161): A_phi += A_phi * eps * cos(m * theta + n * phi) at the vertices.  Read by
+   * gorilla_mesh_build for grid_kind 2 only (as in the reference); ignored by gorilla_b200_init (the records carry it). */
+  double helical_pert_eps_Aphi;
+  int32_t boole_helical_pert;
+  int32_t helical_pert_m_fourier;
+  int32_t helical_pert_n_fourier;
+  int32_t reserved0;
 } gorilla_settings;
 
 /* Everything initialize_gorilla() (orbit_timestep_gorilla.f90:151-274) leaves in module variables that
@@ -177,20 +185,28 @@ int gorilla_b200_orbit_timestep_optional_dev(gorilla_b200_handle *h, int64_t n, 
  * the time step, par_adiab_inv_tetra_poly :585-596 and the phi = 0 mappings :601-638) with module par_adiab_inv_poly_mod
  * (pusher_tetra_poly.f90:3156-3429), as a device-side event buffer instead of the reference's text files
  * (poincare_plot_phi_0 / poincare_plot_vpar_0 / J_par / e_tot / p_phi, gorilla_plot.inp). */
-enum { GORILLA_EVENT_PHI_0 = 1, GORILLA_EVENT_VPAR_0 = 2 };
+enum { GORILLA_EVENT_PHI_0 = 1, GORILLA_EVENT_VPAR_0 = 2, GORILLA_EVENT_FULL_ORBIT = 3 };
 typedef struct gorilla_event {
   int64_t particle;  /* index into the batch */
   int32_t kind;      /* GORILLA_EVENT_PHI_0: toroidal mapping, value = { p_phi_func, energy_tot_func };
-                        GORILLA_EVENT_VPAR_0: banana tip (v_par = 0), value = { J_par of the completed bounce, energy_tot_func } */
-  int32_t counter;   /* counter_phi_0_mappings resp. counter_banana_mappings at the event */
+                        GORILLA_EVENT_VPAR_0: banana tip (v_par = 0), value = { J_par of the completed bounce, energy_tot_func };
+                        GORILLA_EVENT_FULL_ORBIT: the orbit point after a push (boole_full_orbit, gorilla_plot_mod.f90:553-579:
+                        the full_orbit_plot / p_phi / e_tot files), value = { p_phi_func, energy_tot_func } in the tetrahedron
+                        the push ran in */
+  int32_t counter;   /* counter_phi_0_mappings resp. counter_banana_mappings at the event; full orbit: the number of pushes of
+                        this call so far (counter_tetrahedron_passes), a multiple of n_skip_full_orbit */
   int64_t push;      /* index of the push within this call (0-based) */
   double x[3];       /* the position the reference writes to poincare_plot_phi_0_* / poincare_plot_vpar_0_* */
   double value[2];
+  double t;          /* elapsed part of the time step after this push, t_step - t_remain (what the reference writes next to
+                        p_phi / e_tot); set for every kind */
 } gorilla_event;
 typedef struct gorilla_event_settings { /* namelist GORILLA_PLOT_NML (gorilla_plot_mod.f90) */
   int32_t boole_poincare_phi_0, n_skip_phi_0;
   int32_t boole_poincare_vpar_0, boole_J_par, n_skip_vpar_0;
-  int32_t reserved[3];
+  int32_t boole_full_orbit, n_skip_full_orbit; /* one GORILLA_EVENT_FULL_ORBIT record after every n_skip_full_orbit-th push,
+                                                  the one that ends the time step included (:553-556) */
+  int32_t reserved;
 } gorilla_event_settings;
 /* As gorilla_b200_orbit_timestep, with event capture.  par_adiab_inv / counter_vpar_0 / counter_phi_0 are HOST [n]
  * in/out arrays holding the per-particle state of par_adiab_inv_poly_mod and of the mapping counters between calls (zero
@@ -346,6 +362,12 @@ typedef struct gorilla_grid_settings {
   const char *netcdf_filename;
   const char *knots_SOLEDGE3X_EIRENE_filename;
   const char *triangles_SOLEDGE3X_EIRENE_filename;
+  double bmod_multiplier;        /* optional argument of initialize_gorilla / make_tetra_physics (orbit_timestep_gorilla.f90:151,
+                                    tetra_physics_mod.f90:281-286): |B| at the vertices is multiplied by it before h = B / |B| and
+                                    the records are formed (large values give field-line following); 0 = not given = 1 */
+  int32_t nwindow_r, nwindow_z;  /* field_divB0.inp: half-widths of the moving-average filter of the psi(R, Z) table over R and
+                                    over Z before it is splined (bdivfree.f90:1144-1164, window_filter
+                                    utils_bdivfree.f90:859-872); 0 0 = no filtering, as in every input the reference ships */
 } gorilla_grid_settings;
 
 /* make_tetra_grid + make_tetra_physics + check_tetra_overlaps of initialize_gorilla
@@ -354,6 +376,12 @@ typedef struct gorilla_grid_settings {
  * constructed by field-line integration; theta_geom_flux = 1 flux angle | 2 geometrical angle, points_2d.f90:139-149), 3 (VMEC, field aligned), 4 (SOLEDGE3X-EIRENE triangle mesh
  * extruded toroidally, WEST equilibrium table), 5 (analytic circular tokamak, rectangular grid). */
 int gorilla_mesh_build(const gorilla_grid_settings *grid, const gorilla_settings *settings, gorilla_mesh **out);
+/* sizeof of the structs of this header as the library was compiled, in the order gorilla_settings, gorilla_mesh_desc,
+ * gorilla_counters, gorilla_diag, gorilla_grid_settings, gorilla_event, gorilla_event_settings: a binding in another
+ * language (the bind(C) types of the Fortran module, a ctypes mirror) checks its own layout against it once at start-up
+ * instead of finding out through a corrupted field. */
+#define GORILLA_ABI_N_STRUCTS 7
+int gorilla_b200_abi_struct_sizes(int64_t sizes_out[GORILLA_ABI_N_STRUCTS]);
 int gorilla_mesh_get_desc(const gorilla_mesh *mesh, gorilla_mesh_desc *out);
 /* vertices: nvert, verts_rphiz[nvert][3], verts_sthetaphi[nvert][3] or NULL */
 int gorilla_mesh_get_vertices(const gorilla_mesh *mesh, int64_t *nvert, const double **verts_rphiz,

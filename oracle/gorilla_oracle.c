@@ -2070,6 +2070,7 @@ typedef struct {
   int64_t particle, push;
   gor_event *events;
   int64_t cap, n_events;
+  double t; /* t_step - t_remain after the current push */
 } event_state;
 static void emit_event(event_state *es, int kind, int counter, const double x[3], double v0, double v1)
 {
@@ -2082,6 +2083,7 @@ static void emit_event(event_state *es, int kind, int counter, const double x[3]
     for (int i = 0; i < 3; i++) e->x[i] = x[i];
     e->value[0] = v0;
     e->value[1] = v1;
+    e->t = es->t;
   }
   es->n_events++;
 }
@@ -3467,6 +3469,7 @@ int gor_orbit_timestep_events(const gor_mesh *m, double x[3], double *vpar, doub
   if (m->ipusher == 2 && m->poly_order < 2) return GOR_ERR_CONFIG;
   if ((cfg->boole_J_par || cfg->boole_poincare_vpar_0) && cfg->n_skip_vpar_0 < 1) return GOR_ERR_CONFIG;
   if (cfg->boole_poincare_phi_0 && cfg->n_skip_phi_0 < 1) return GOR_ERR_CONFIG;
+  if (cfg->boole_full_orbit && cfg->n_skip_full_orbit < 1) return GOR_ERR_CONFIG;
   event_state es;
   es.cfg = cfg;
   es.par_adiab_inv = *par_adiab_inv;
@@ -3474,6 +3477,7 @@ int gor_orbit_timestep_events(const gor_mesh *m, double x[3], double *vpar, doub
   es.counter_phi_0_mappings = *counter_phi_0;
   es.particle = particle;
   es.push = 0;
+  es.t = 0.0;
   es.events = events;
   es.cap = cap;
   es.n_events = *n_events;
@@ -3563,6 +3567,17 @@ static int orbit_timestep_core(const gor_mesh *m, double x[3], double *vpar, dou
       tr->n_pushes++;
     }
     t_remain = t_remain - t_pass;
+    if (es) {
+      es->t = t_step - t_remain;
+      if (es->cfg->boole_full_orbit) { /* gorilla_plot_mod.f90:553-579, before the exit on boole_t_finished */
+        const int64_t cnt = es->push + 1, nskip = es->cfg->n_skip_full_orbit; /* counter_tetrahedron_passes */
+        if (cnt / nskip * nskip == cnt) {
+          double zv[4] = {z_save[0], z_save[1], z_save[2], *vpar};
+          emit_event(es, GOR_EVENT_FULL_ORBIT, (int)cnt, x, gor_p_phi(m, *vpar, z_save, ind_tetr_save),
+                     gor_energy_tot(m, zv, s.perpinv, ind_tetr_save));
+        }
+      }
+    }
     if (boole_t_finished) {
       if (t_remain_out) *t_remain_out = t_remain;
       break;

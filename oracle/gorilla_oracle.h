@@ -119,7 +119,7 @@ typedef struct {
 } gor_trace;
 
 /* orbit events (gorilla_plot_mod.f90:585-638, par_adiab_inv_poly_mod pusher_tetra_poly.f90:3156-3429) */
-enum { GOR_EVENT_PHI_0 = 1, GOR_EVENT_VPAR_0 = 2 };
+enum { GOR_EVENT_PHI_0 = 1, GOR_EVENT_VPAR_0 = 2, GOR_EVENT_FULL_ORBIT = 3 };
 typedef struct {
   int64_t particle;   /* index given by the caller */
   int32_t kind;       /* GOR_EVENT_PHI_0: toroidal mapping, value = {p_phi, e_tot}; GOR_EVENT_VPAR_0: banana tip, value = {J_par, e_tot} */
@@ -127,9 +127,12 @@ typedef struct {
   int64_t push;       /* index of the push within this call (0-based) */
   double x[3];        /* position written to poincare_plot_phi_0 / poincare_plot_vpar_0 */
   double value[2];
+  double t;           /* t_step - t_remain after the push of the event (gorilla_plot_mod.f90:564,572) */
 } gor_event;
 typedef struct {
   int32_t boole_poincare_phi_0, n_skip_phi_0, boole_poincare_vpar_0, boole_J_par, n_skip_vpar_0;
+  /* boole_full_orbit (gorilla_plot_mod.f90:553-579): position, p_phi and E_tot after every n_skip_full_orbit-th push */
+  int32_t boole_full_orbit, n_skip_full_orbit, reserved;
 } gor_event_settings;
 
 /* return codes */

@@ -28,8 +28,10 @@ struct HmEvents {
   int32_t *cnt_v, *cnt_p;
   gorilla_event *events;
   int64_t cap, *n_events, particle;
+  int nskip_f;     // flags bit3: boole_full_orbit, every nskip_f-th push
+  double t_step;
 };
-static void hm_emit(HmEvents *ev, int64_t push, const EvState &es)
+static void hm_emit(HmEvents *ev, int64_t push, const EvState &es, double t)
 {
   for (int k = 0; k < es.n; k++) {
     const int64_t slot = (*ev->n_events)++;
@@ -38,6 +40,7 @@ static void hm_emit(HmEvents *ev, int64_t push, const EvState &es)
       e->particle = ev->particle; e->kind = es.e[k].kind; e->counter = es.e[k].counter; e->push = push;
       for (int i = 0; i < 3; i++) e->x[i] = es.e[k].x[i];
       e->value[0] = es.e[k].v[0]; e->value[1] = es.e[k].v[1];
+      e->t = t;
     }
   }
 }
@@ -78,7 +81,7 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
           es.J = *ev->J; es.cnt_v = *ev->cnt_v; es.cnt_p = *ev->cnt_p; es.n = 0;
           es = rk_events_call<PHI>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain, o, es);
           *ev->J = es.J; *ev->cnt_v = es.cnt_v; *ev->cnt_p = es.cnt_p;
-          if (es.n) hm_emit(ev, npush, es);
+          if (es.n) hm_emit(ev, npush, es, ev->t_step - (t_remain - o.t_pass));
         }
       }
     } else {
@@ -100,7 +103,7 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
             es.J = *ev->J; es.cnt_v = *ev->cnt_v; es.cnt_p = *ev->cnt_p;
             P.events_after_push(vpar, o, es);
             *ev->J = es.J; *ev->cnt_v = es.cnt_v; *ev->cnt_p = es.cnt_p;
-            if (es.n) hm_emit(ev, npush, es);
+            if (es.n) hm_emit(ev, npush, es, ev->t_step - (t_remain - o.t_pass));
           }
         }
       }
@@ -118,7 +121,7 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
           for (int q = 0; q < 4; q++) oq_acc[q] = oq_acc[q] + ox.oq[q];
           if (ev) {
             *ev->J = ox.es.J; *ev->cnt_v = ox.es.cnt_v; *ev->cnt_p = ox.es.cnt_p;
-            if (ox.es.n) hm_emit(ev, npush, ox.es);
+            if (ox.es.n) hm_emit(ev, npush, ox.es, ev->t_step - (t_remain - o.t_pass));
           }
         } else {
           o = push_full_call<K, PHI, EXT>(&m, perpinv, ind_tetr, iface, x[0], x[1], x[2], vpar, t_remain);
@@ -134,6 +137,19 @@ static void run_particle(const MeshDev &m, double *x, double *vpar_io, double *v
     npush++;
     for (int b = 0; b < 5; b++) if (o.fallback & (1 << b)) fallback[b]++;
     t_remain = t_remain - o.t_pass;
+    if (ev && (ev->flags & 8)) {   // as lane_after_push (gb_internal.cuh): boole_full_orbit
+      const long long cnt = npush;   // already incremented: counter_tetrahedron_passes
+      if (cnt / ev->nskip_f * ev->nskip_f == cnt) {
+        const int64_t slot = (*ev->n_events)++;
+        if (slot < ev->cap) {
+          gorilla_event *e = ev->events + slot;
+          e->particle = ev->particle; e->kind = GORILLA_EVENT_FULL_ORBIT; e->counter = (int32_t)cnt; e->push = npush - 1;
+          e->x[0] = o.x[0]; e->x[1] = o.x[1]; e->x[2] = o.x[2];
+          orbit_point_invariants(m, ind_save, z_save, o.vpar, perpinv, e->value[0], e->value[1]);
+          e->t = ev->t_step - t_remain;
+        }
+      }
+    }
     if (o.finished || ind_tetr == -1) break;
   }
   double vperp_new = 0.0;
@@ -304,7 +320,7 @@ int64_t hm_orbit_timestep(void *p, int64_t n, double *x, double *vpar, double *v
 int64_t hm_orbit_timestep_events(void *p, int64_t n, double *x, double *vpar, double *vperp, double t_step, int32_t *binit,
                                  int32_t *ind_tetr, int32_t *iface, double *t_remain_out, int64_t *n_pushes, int flags,
                                  int nskip_p, int nskip_v, double *J, int32_t *cnt_v, int32_t *cnt_p, gorilla_event *events,
-                                 int64_t cap, int64_t *n_events, int force_full)
+                                 int64_t cap, int64_t *n_events, int force_full, int nskip_f)
 {
   HostMirror *h = (HostMirror *)p;
   const MeshDev &m = h->m;
@@ -328,7 +344,7 @@ int64_t hm_orbit_timestep_events(void *p, int64_t n, double *x, double *vpar, do
     if (t_remain_out) t_remain_out[i] = t_step;
     if (!binit[i] || ind_tetr[i] < 1) continue;
     if (t_step == 0.0) { if (t_remain_out) t_remain_out[i] = 0.0; continue; }
-    HmEvents ev = {flags, nskip_p, nskip_v, J + i, cnt_v + i, cnt_p + i, events, cap, n_events, i};
+    HmEvents ev = {flags, nskip_p, nskip_v, J + i, cnt_v + i, cnt_p + i, events, cap, n_events, i, nskip_f > 0 ? nskip_f : 1, t_step};
 #define HM_RUNE(K, PHI) run_particle<K, PHI, 2>(m, xi, vpar + i, vperp + i, t_step, ind_tetr + i, iface + i, \
       t_remain_out ? t_remain_out + i : nullptr, n_pushes ? n_pushes + i : nullptr, 0, nullptr, nullptr, force_full, fallback, \
       0u, nullptr, &ev)

@@ -40,7 +40,7 @@ def load():
         L.hm_orbit_timestep.argtypes = [vp, C.c_int64, vp, vp, vp, d, vp, vp, vp, vp, vp, C.c_int32, vp, vp, C.c_int, vp, vp]
         L.hm_orbit_timestep_events.restype = C.c_int64
         L.hm_orbit_timestep_events.argtypes = [vp, C.c_int64, vp, vp, vp, d, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int,
-                                               vp, vp, vp, vp, C.c_int64, vp, C.c_int]
+                                               vp, vp, vp, vp, C.c_int64, vp, C.c_int, C.c_int]
         L.hm_hypot.restype = d
         L.hm_hypot.argtypes = [d, d]
         L.hm_csqrt.argtypes = [d, d, vp]
@@ -59,7 +59,7 @@ def load():
 
 
 EVENT_DTYPE = np.dtype([("particle", np.int64), ("kind", np.int32), ("counter", np.int32), ("push", np.int64),
-                        ("x", np.float64, 3), ("value", np.float64, 2)])
+                        ("x", np.float64, 3), ("value", np.float64, 2), ("t", np.float64)])
 
 
 def oq_mask_of(settings) -> int:
@@ -101,16 +101,16 @@ class HostMirror:
 
     def orbit_timestep_events(self, x, vpar, vperp, t_step, binit, ind_tetr, iface, par_adiab_inv, counter_vpar_0,
                               counter_phi_0, cap, poincare_phi_0=True, n_skip_phi_0=1, poincare_vpar_0=True, J_par=True,
-                              n_skip_vpar_0=1, force_full=False):
+                              n_skip_vpar_0=1, force_full=False, full_orbit=False, n_skip_full_orbit=1):
         n = x.shape[0]
         p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
         ev = np.zeros(max(cap, 1), EVENT_DTYPE)
         nev = np.zeros(1, np.int64)
         npush, tro = np.zeros(n, np.int64), np.zeros(n)
-        flags = int(poincare_phi_0) | 2 * int(poincare_vpar_0) | 4 * int(J_par)
+        flags = int(poincare_phi_0) | 2 * int(poincare_vpar_0) | 4 * int(J_par) | 8 * int(full_orbit)
         rc = self.L.hm_orbit_timestep_events(self.h, n, p(x), p(vpar), p(vperp), float(t_step), p(binit), p(ind_tetr),
                                              p(iface), p(tro), p(npush), flags, n_skip_phi_0, n_skip_vpar_0,
                                              p(par_adiab_inv), p(counter_vpar_0), p(counter_phi_0), p(ev), cap, p(nev),
-                                             int(force_full))
+                                             int(force_full), int(n_skip_full_orbit))
         assert rc == 0
         return ev[:min(int(nev[0]), cap)], int(nev[0]), npush

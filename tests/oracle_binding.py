@@ -45,11 +45,12 @@ class GorEvent(C.Structure):
 
 class GorEventSettings(C.Structure):
     _fields_ = [("boole_poincare_phi_0", C.c_int32), ("n_skip_phi_0", C.c_int32), ("boole_poincare_vpar_0", C.c_int32),
-                ("boole_J_par", C.c_int32), ("n_skip_vpar_0", C.c_int32)]
+                ("boole_J_par", C.c_int32), ("n_skip_vpar_0", C.c_int32), ("boole_full_orbit", C.c_int32),
+                ("n_skip_full_orbit", C.c_int32), ("reserved", C.c_int32)]
 
 
 EVENT_DTYPE = np.dtype([("particle", np.int64), ("kind", np.int32), ("counter", np.int32), ("push", np.int64),
-                        ("x", np.float64, 3), ("value", np.float64, 2)])
+                        ("x", np.float64, 3), ("value", np.float64, 2), ("t", np.float64)])
 
 
 def build_oracle(force: bool = False) -> Path:
@@ -190,10 +191,11 @@ class OracleMesh:
 
     def orbit_timestep_events(self, x, vpar, vperp, t_step, binit, ind_tetr, iface, par_adiab_inv, counter_vpar_0,
                               counter_phi_0, cap, poincare_phi_0=True, n_skip_phi_0=1, poincare_vpar_0=True, J_par=True,
-                              n_skip_vpar_0=1):
+                              n_skip_vpar_0=1, full_orbit=False, n_skip_full_orbit=1):
         """Per-particle orbit_timestep with event capture; returns (events[:min(n_events, cap)], n_events, n_pushes)."""
         n = x.shape[0]
-        cfg = GorEventSettings(int(poincare_phi_0), n_skip_phi_0, int(poincare_vpar_0), int(J_par), n_skip_vpar_0)
+        cfg = GorEventSettings(int(poincare_phi_0), n_skip_phi_0, int(poincare_vpar_0), int(J_par), n_skip_vpar_0,
+                               int(full_orbit), n_skip_full_orbit, 0)
         ev = np.zeros(cap, EVENT_DTYPE)
         nev = C.c_int64(0)
         npush = np.zeros(n, np.int64)

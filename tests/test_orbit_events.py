@@ -244,7 +244,7 @@ def _gpu_pair(mesh, settings, n, seed, t_step, ncalls=2, cap=400000, use_group=T
         npb = np.zeros(n, np.int64)
         evb, neb = g.orbit_timestep_gorilla_events(
             xb, vb, wb, t_step, *sb, Jb, cvb, cpb, cap, n_pushes=npb,
-            **{("boole_" + k if k in ("poincare_phi_0", "poincare_vpar_0", "J_par") else k): v for k, v in kw.items()})
+            **{("boole_" + k if k in ("poincare_phi_0", "poincare_vpar_0", "J_par", "full_orbit") else k): v for k, v in kw.items()})
         assert nea == neb, "number of events differs"
         assert np.array_equal(_sorted(eva), evb), "events differ"
         assert np.array_equal(Ja, Jb) and np.array_equal(cva, cvb) and np.array_equal(cpa, cpb)
@@ -289,3 +289,68 @@ def test_gpu_event_buffer_overflow_and_refusals(small_mesh, cuda_device):
         with pytest.raises(api.GorillaError):
             gb.orbit_timestep_gorilla_events(x, vpar, vperp, 1e-5, *workloads.fresh_state(n), *_state(n), 10)
         gb.close()
+
+
+# ------------------------------------------------ boole_full_orbit (gorilla_plot_mod.f90:553-579): kind 3 events
+@pytest.mark.parametrize("pusher,K,force_full", [(2, 2, False), (2, 2, True), (2, 4, False), (1, 4, False), (1, 4, True)])
+def test_full_orbit_events(small_mesh, pusher, K, force_full):
+    """The orbit point, p_phi and E_tot after every n_skip_full_orbit-th push (the reference's full_orbit_plot / p_phi /
+    e_tot files), the push that ends the time step included: oracle <-> host compile of the device headers bit for bit,
+    alone and together with the other event kinds, and the records against what the call itself returns."""
+    mesh, _, settings = small_mesh
+    st = _with(settings, ipusher=pusher, poly_order=K)
+    om, hm = OracleMesh(mesh, st), HostMirror(mesh, st)
+    n, t_step = 24, 2e-4
+    for kw in (dict(poincare_phi_0=False, poincare_vpar_0=False, J_par=False, full_orbit=True, n_skip_full_orbit=1),
+               dict(full_orbit=True, n_skip_full_orbit=3, n_skip_phi_0=2)):
+        xa, va, wa = workloads.particles_cyl(n, 11)
+        xb, vb, wb = xa.copy(), va.copy(), wa.copy()
+        sa, sb = workloads.fresh_state(n), workloads.fresh_state(n)
+        om.orbit_timestep_batch(xa, va, wa, 0.0, *sa)
+        hm.orbit_timestep(xb, vb, wb, 0.0, *sb, 0)
+        e0, p0, _ = om.invariants(xa, va, wa, sa[1])
+        Ja, cva, cpa = _state(n)
+        Jb, cvb, cpb = _state(n)
+        eva, nea, npa = om.orbit_timestep_events(xa, va, wa, t_step, *sa, Ja, cva, cpa, 200000, **kw)
+        evb, neb, npb = hm.orbit_timestep_events(xb, vb, wb, t_step, *sb, Jb, cvb, cpb, 200000, force_full=force_full, **kw)
+        assert nea == neb and np.array_equal(_sorted(eva), _sorted(evb))
+        assert np.array_equal(xa, xb) and np.array_equal(va, vb) and np.array_equal(npa, npb)
+        assert np.array_equal(Ja, Jb) and np.array_equal(cva, cvb) and np.array_equal(cpa, cpb)
+        fo = _sorted(eva[eva["kind"] == api.EVENT_FULL_ORBIT])
+        nskip = kw["n_skip_full_orbit"]
+        assert len(fo) == (npa // nskip).sum() and len(fo) > 500
+        if kw.get("J_par", True):
+            assert (eva["kind"] == api.EVENT_PHI_0).sum() > 0
+        else:
+            assert len(fo) == nea
+        for i in range(n):
+            f = fo[fo["particle"] == i]
+            assert np.array_equal(f["counter"], nskip * np.arange(1, len(f) + 1)) and np.array_equal(f["push"], f["counter"] - 1)
+            assert np.all(np.diff(f["t"]) > 0) and f["t"][-1] <= t_step
+            if nskip == 1 and sa[1][i] > 0:        # the last record is the state the call returns
+                assert np.array_equal(f["x"][-1], xa[i]) and f["t"][-1] == t_step
+            if sa[1][i] > 0:                       # axisymmetric field, no potential: both invariants hold along the orbit
+                assert np.abs(f["value"][:, 1] / e0[i] - 1).max() < (2e-3 if K == 2 and pusher == 2 else 1e-6)
+                assert np.abs(f["value"][:, 0] - p0[i]).max() < 2e-2 * abs(p0).mean()
+
+
+def test_full_orbit_refusals(small_mesh):
+    mesh, _, settings = small_mesh
+    om = OracleMesh(mesh, settings)
+    n = 2
+    x, v, w = workloads.particles_cyl(n, 1)
+    with pytest.raises(AssertionError):
+        om.orbit_timestep_events(x, v, w, 1e-5, *workloads.fresh_state(n), *_state(n), 10, full_orbit=True, n_skip_full_orbit=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pusher,K", [(2, 2), (2, 4), (1, 4)])
+def test_gpu_parity_full_orbit(small_mesh, cuda_device, pusher, K):
+    mesh, _, settings = small_mesh
+    st = _with(settings, ipusher=pusher, poly_order=K)
+    # RK pusher: J_par goes through RKF45's pow() (not bit-identical on the GPU, see test_rk_pusher_gpu_parity): keep to the
+    # kinds that come from the orbit itself
+    extra = dict(poincare_vpar_0=False, J_par=False) if pusher == 1 else {}
+    total, ev = _gpu_pair(mesh, st, 128, 13, 2e-4, ncalls=2, full_orbit=True, n_skip_full_orbit=2, n_skip_phi_0=2, **extra)
+    assert (ev["kind"] == api.EVENT_FULL_ORBIT).sum() > 2000
+    _gpu_pair(mesh, st, 64, 14, 1e-4, ncalls=1, poincare_phi_0=False, poincare_vpar_0=False, J_par=False, full_orbit=True)

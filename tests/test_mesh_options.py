@@ -172,3 +172,23 @@ def test_psi_window_filter_of_field_divB0_inp(product_lib):
     assert np.abs(filt[core, APHI1] - spl.ev(R[core], Z[core])).max() < 2e-6 * span
     # and the filter did something: the smoothed flux differs from the raw one by much more than that
     assert np.abs(filt[core, APHI1] - base[core, APHI1]).max() > 1e-4 * span
+
+
+def test_invalid_mesh_options_are_refused(product_lib):
+    from gorilla_b200 import api
+    with pytest.raises(api.GorillaError) as ei:
+        build_mesh(flux_grid(theta_geom_flux=3), flux_settings())
+    assert ei.value.code == 1 and "theta_geom_flux" in str(ei.value)
+
+
+def test_binding_checks_its_struct_layouts_against_the_library(product_lib):
+    """gorilla_b200_abi_struct_sizes: sizeof of every struct of the header as compiled; load_library() compares them with the
+    ctypes mirrors (and the Fortran module with its bind(C) types) so that a stale binding fails at start-up."""
+    import ctypes as C
+    from gorilla_b200 import api
+    sizes = (C.c_int64 * 7)()
+    assert product_lib.gorilla_b200_abi_struct_sizes(sizes) == 0
+    assert tuple(sizes) == (C.sizeof(api._Settings), C.sizeof(api._MeshDesc), C.sizeof(api._Counters), C.sizeof(api._Diag),
+                            C.sizeof(api._GridSettings), api.EVENT_DTYPE.itemsize, C.sizeof(api._EventSettings))
+    assert api.EVENT_DTYPE.itemsize == 72 and C.sizeof(api._EventSettings) == 32
+    assert product_lib.gorilla_b200_abi_struct_sizes(None) == 1

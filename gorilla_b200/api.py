@@ -41,7 +41,12 @@ class _Settings(C.Structure):
         "boole_vpar2_int", "max_n_intermediate_steps")] + [("desired_delta_energy", C.c_double), ("rel_err_ode45", C.c_double),
                                                         ("helical_pert_eps_Aphi", C.c_double), ("boole_helical_pert", C.c_int32),
                                                         ("helical_pert_m_fourier", C.c_int32),
-                                                        ("helical_pert_n_fourier", C.c_int32), ("reserved0", C.c_int32)]
+                                                        ("helical_pert_n_fourier", C.c_int32), ("reserved0", C.c_int32),
+                                                        ("axi_noise_eps_A", C.c_double), ("axi_noise_eps_Phi", C.c_double),
+                                                        ("non_axi_noise_eps_A", C.c_double),
+                                                        ("boole_axi_noise_vector_pot", C.c_int32),
+                                                        ("boole_axi_noise_elec_pot", C.c_int32),
+                                                        ("boole_non_axi_noise_vector_pot", C.c_int32), ("noise_seed", C.c_int32)]
 
 
 class _MeshDesc(C.Structure):

@@ -220,6 +220,7 @@ int build_analytic_circ(const gorilla_grid_settings &gs, const gorilla_settings 
     };
     strong_electric_vertex_fields(m, gs.n2, st.eps_Phi, psif_at, vf);
   }
+  apply_vertex_noise(m, st, vf);
   linearise_tetrahedra(m, vf);
   check_tetra_overlaps(m);
   return GORILLA_OK;

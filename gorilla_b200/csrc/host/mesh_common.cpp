@@ -96,6 +96,60 @@ static void differentiate(const double x[4], const double y[4], const double z[4
   }
 }
 
+namespace {
+struct Xoshiro256ss {  // xoshiro256** (Blackman, Vigna), state from splitmix64
+  uint64_t s[4];
+  explicit Xoshiro256ss(uint64_t seed)
+  {
+    for (auto &w : s) {
+      seed += 0x9e3779b97f4a7c15ull;
+      uint64_t z = seed;
+      z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+      z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+      w = z ^ (z >> 31);
+    }
+  }
+  static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+  double next()  // uniform in [0, 1), 53 bits
+  {
+    const uint64_t r = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
+    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45);
+    return (double)(r >> 11) * 0x1.0p-53;
+  }
+};
+}  // namespace
+
+void apply_vertex_noise(const Mesh &m, const gorilla_settings &st, VertexFields &vf)
+{
+  const bool axiA = st.boole_axi_noise_vector_pot != 0, axiP = st.boole_axi_noise_elec_pot != 0,
+             nonA = st.boole_non_axi_noise_vector_pot != 0;
+  if (!axiA && !axiP && !nonA) return;
+  Xoshiro256ss rng(st.noise_seed ? (uint64_t)(uint32_t)st.noise_seed : 0x60121aull);
+  const int64_t per_plane = m.nvert / m.grid_size[1];  // nvert / grid_size(2)
+  std::vector<double> rnd_axi;
+  if (axiA || axiP) {  // :256-261
+    rnd_axi.resize((size_t)per_plane);
+    for (auto &r : rnd_axi) r = rng.next();
+  }
+  for (int64_t iv = 0; iv < m.nvert; iv++) {  // in vertex order, as the reference's serial loop draws
+    if (axiA) {  // :400-405
+      const double r = rnd_axi[(size_t)(iv % per_plane)];
+      vf.A_x1[iv] = vf.A_x1[iv] + vf.A_x1[iv] * st.axi_noise_eps_A * r;
+      vf.A_x2[iv] = vf.A_x2[iv] + vf.A_x2[iv] * st.axi_noise_eps_A * r;
+      vf.A_x3[iv] = vf.A_x3[iv] + vf.A_x3[iv] * st.axi_noise_eps_A * r;
+    }
+    if (nonA) {  // :407-415
+      const double r1 = rng.next(), r2 = rng.next(), r3 = rng.next();
+      vf.A_x1[iv] = vf.A_x1[iv] + vf.A_x1[iv] * st.non_axi_noise_eps_A * r1;
+      vf.A_x2[iv] = vf.A_x2[iv] + vf.A_x2[iv] * st.non_axi_noise_eps_A * r2;
+      vf.A_x3[iv] = vf.A_x3[iv] + vf.A_x3[iv] * st.non_axi_noise_eps_A * r3;
+    }
+    // :425-439 the electrostatic potential follows the (noisy) vector potential unless the strong-field mode set it
+    if (!vf.strong && (axiA || nonA)) vf.phi_elec[iv] = vf.A_x2[iv] * st.eps_Phi;
+    if (axiP) vf.phi_elec[iv] = vf.phi_elec[iv] + vf.phi_elec[iv] * st.axi_noise_eps_Phi * rnd_axi[(size_t)(iv % per_plane)];  // :441-444
+  }
+}
+
 void linearise_tetrahedra(Mesh &m, const VertexFields &vf)
 {
   const int64_t ntetr = m.ntetr;

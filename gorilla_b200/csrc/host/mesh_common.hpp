@@ -78,6 +78,9 @@ extern const double CLIGHT, ECHARGE, AMP, AME;
 int set_species(Mesh &m, int ispecies, std::string &err);
 // per-tetra block of make_tetra_physics; m.tetra_grid, m.verts_* and m.grid_size must be filled
 void linearise_tetrahedra(Mesh &m, const VertexFields &vf);
+// optional random noise on the vertex potentials (make_tetra_physics :256-261, :400-415, :441-444); call after the vertex
+// fields are complete and before linearise_tetrahedra
+void apply_vertex_noise(const Mesh &m, const gorilla_settings &st, VertexFields &vf);
 void check_tetra_overlaps(Mesh &m);
 
 // make_grid_rect (SRC/tetra_grid_mod.f90:344-680): rectangular (R, phi, Z) grid over [Rmin,Rmax] x [Zmin,Zmax], grid_size set

@@ -486,6 +486,7 @@ int build_efit_rect(const gorilla_grid_settings &gs, const gorilla_settings &st,
   make_grid_rect(m);
   VertexFields vf;
   f.vertex_fields(m, st, gs.n2, vf);
+  apply_vertex_noise(m, st, vf);
   linearise_tetrahedra(m, vf);
   check_tetra_overlaps(m);
   return GORILLA_OK;

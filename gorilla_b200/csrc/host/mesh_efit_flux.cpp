@@ -544,6 +544,7 @@ int build_efit_flux(const gorilla_grid_settings &gs, const gorilla_settings &st,
     F.eval(0.0, 2.706, psi, q, sqrtg, b1, m.mag_axis_R0, dR_ds, dR_dt, m.mag_axis_Z0, dZ_ds, dZ_dt);
   }
   m.Rmin = m.Rmax = m.Zmin = m.Zmax = 0.0;
+  apply_vertex_noise(m, st, vf);
   linearise_tetrahedra(m, vf);
   check_tetra_overlaps(m);
   return GORILLA_OK;

@@ -287,6 +287,7 @@ int build_soledge3x(const gorilla_grid_settings &gs, const gorilla_settings &st,
 
   VertexFields vf;
   fld.vertex_fields(m, st, gs.n2, vf);
+  apply_vertex_noise(m, st, vf);
   linearise_tetrahedra(m, vf);
   check_tetra_overlaps(m);
   return GORILLA_OK;

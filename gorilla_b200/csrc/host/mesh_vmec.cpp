@@ -499,6 +499,7 @@ int build_vmec(const gorilla_grid_settings &gs, const gorilla_settings &st, Mesh
     m.mag_axis_Z0 = P.Z;
   }
   m.Rmin = m.Rmax = m.Zmin = m.Zmax = 0.0;
+  apply_vertex_noise(m, st, vf);
   linearise_tetrahedra(m, vf);
   check_tetra_overlaps(m);
   return GORILLA_OK;

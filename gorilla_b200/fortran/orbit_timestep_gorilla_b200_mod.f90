@@ -42,6 +42,9 @@ module orbit_timestep_gorilla_b200_mod
     ! read by gorilla_mesh_build only (a Fortran caller's make_tetra_physics has already applied the perturbation)
     real(c_double)  :: helical_pert_eps_Aphi = 0.d0
     integer(c_int32_t) :: boole_helical_pert = 0, helical_pert_m_fourier = 0, helical_pert_n_fourier = 0, reserved0 = 0
+    real(c_double)  :: axi_noise_eps_A = 0.d0, axi_noise_eps_Phi = 0.d0, non_axi_noise_eps_A = 0.d0
+    integer(c_int32_t) :: boole_axi_noise_vector_pot = 0, boole_axi_noise_elec_pot = 0, boole_non_axi_noise_vector_pot = 0, &
+                          noise_seed = 0
   end type
   !> struct gorilla_mesh_desc
   type, bind(C) :: gorilla_mesh_desc_t

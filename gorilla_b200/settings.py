@@ -43,6 +43,15 @@ class GorillaSettings:
     helical_pert_eps_Aphi: float = 1.0e-1
     helical_pert_m_fourier: int = 2
     helical_pert_n_fourier: int = 2
+    # random noise on the vertex potentials of a built mesh (INPUT/gorilla.inp:84-109, tetra_physics_mod.f90:400-444); the
+    # stream is the library's own (noise_seed; 0 = fixed default), not gfortran's random_number
+    boole_axi_noise_vector_pot: bool = False
+    axi_noise_eps_A: float = 1.0e-1
+    boole_axi_noise_elec_pot: bool = False
+    axi_noise_eps_Phi: float = 3.0e-1
+    boole_non_axi_noise_vector_pot: bool = False
+    non_axi_noise_eps_A: float = 1.0e-4
+    noise_seed: int = 0
 
 
 @dataclass

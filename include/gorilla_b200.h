@@ -83,6 +83,15 @@ typedef struct gorilla_settings {
   int32_t helical_pert_m_fourier;
   int32_t helical_pert_n_fourier;
   int32_t reserved0;
+  /* random noise on the vertex values of a built mesh, for testing how the integrator copes with a rough field
+   * (gorilla.inp:84-109; tetra_physics_mod.f90:256-261,400-415,441-444): A_k += A_k * eps * r with r uniform in [0, 1) --
+   * one r per vertex of a poloidal plane repeated in every plane (axisymmetric, vector potential and / or electrostatic
+   * potential) or three fresh r per vertex (non-axisymmetric, vector potential).  Read by gorilla_mesh_build, all grid kinds.
+   * The reference draws from gfortran's random_number; this library from its own xoshiro256** stream seeded with noise_seed
+   * (0 = a fixed default): the same noise statistically, not the same numbers. */
+  double axi_noise_eps_A, axi_noise_eps_Phi, non_axi_noise_eps_A;
+  int32_t boole_axi_noise_vector_pot, boole_axi_noise_elec_pot, boole_non_axi_noise_vector_pot;
+  int32_t noise_seed;
 } gorilla_settings;
 
 /* Everything initialize_gorilla() (orbit_timestep_gorilla.f90:151-274) leaves in module variables that

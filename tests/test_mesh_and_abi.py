@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(product_lib):
 
 
 def test_struct_layouts_match_header_sizes():
-    assert C.sizeof(api._Settings) == 8 + 4 * 20 + 8 + 8 + 8 + 4 * 4
+    assert C.sizeof(api._Settings) == 8 + 4 * 20 + 8 + 8 + 8 + 4 * 4 + 3 * 8 + 4 * 4
     assert C.sizeof(api._Counters) == 8 * 9 + 16 + 8 + 16
     assert C.sizeof(api._Diag) == 8 * 7 + 8 * 4 + 8 * 2 + 8 * 6 + 8
     assert api._MeshDesc.tetra_physics.offset == 8 and api._MeshDesc.Rmin.offset % 8 == 0

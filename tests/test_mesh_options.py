@@ -192,3 +192,73 @@ def test_binding_checks_its_struct_layouts_against_the_library(product_lib):
                             C.sizeof(api._GridSettings), api.EVENT_DTYPE.itemsize, C.sizeof(api._EventSettings))
     assert api.EVENT_DTYPE.itemsize == 72 and C.sizeof(api._EventSettings) == 32
     assert product_lib.gorilla_b200_abi_struct_sizes(None) == 1
+
+
+def test_vertex_noise_options(product_lib):
+    """boole_axi_noise_vector_pot / boole_non_axi_noise_vector_pot / boole_axi_noise_elec_pot (gorilla.inp:84-109;
+    tetra_physics_mod.f90:256-261,400-415,441-444): A_k += A_k eps r with r uniform in [0, 1), the same r in every poloidal
+    plane (axisymmetric) or fresh per vertex and component; the electrostatic potential follows the noisy A_2 and can get
+    its own axisymmetric noise.  The stream is the library's own (deterministic per noise_seed).  On a field-aligned grid,
+    where nvert / grid_size(2) is the number of vertices of a poloidal plane (on the rectangular grid, with its n2 + 1
+    planes, the reference's index arithmetic does not repeat plane by plane; the library follows the same arithmetic)."""
+    grid, st0 = flux_grid(), dataclasses.replace(flux_settings(), eps_Phi=-1e-5)
+    base = build_mesh(grid, st0)
+    tp0, tg = base.tetra_physics, base.tetra_grid
+    # poloidal position of the first vertex of every tetrahedron -> group index (the same (R, Z) in every phi plane)
+    rz = np.round(np.column_stack([tp0[:, 31], tp0[:, 32]]), 7)
+    _, group = np.unique(rz, axis=0, return_inverse=True)
+    group = group.ravel()
+
+    def spread_within_groups(v):
+        lo = np.full(group.max() + 1, np.inf); hi = np.full(group.max() + 1, -np.inf)
+        np.minimum.at(lo, group, v); np.maximum.at(hi, group, v)
+        return (hi - lo).max()
+
+    sel = np.abs(tp0[:, APHI1]) > 1e-3 * np.abs(tp0[:, APHI1]).max()
+
+    def ratio(tp):   # (A_3' / A_3 - 1) at the first vertex of every tetrahedron, A_3 = A_phi = psi_pol in flux coordinates
+        return tp[sel, APHI1] / tp0[sel, APHI1] - 1
+
+    eps = 0.05
+    axi = build_mesh(grid, dataclasses.replace(st0, boole_axi_noise_vector_pot=True, axi_noise_eps_A=eps)).tetra_physics
+    r = ratio(axi) / eps
+    assert r.min() >= -1e-12 and r.max() < 1 and 0.3 < r.mean() < 0.7 and r.std() > 0.2
+    # axisymmetric: the same factor at corresponding tetrahedra of every phi slice
+    full = axi[:, APHI1] / np.where(tp0[:, APHI1] == 0, 1, tp0[:, APHI1])
+    assert np.bincount(group).min() >= grid.n2 and spread_within_groups(full) < 1e-13
+    # the potential follows: Phi_1 = A_2 eps_Phi at the first vertex (TP_PHI1 = 30)
+    assert np.allclose(axi[sel, 30], axi[sel, ATHETA1] * -1e-5, rtol=1e-13, atol=0)
+    # deterministic, and a different seed gives different numbers
+    again = build_mesh(grid, dataclasses.replace(st0, boole_axi_noise_vector_pot=True, axi_noise_eps_A=eps)).tetra_physics
+    other = build_mesh(grid, dataclasses.replace(st0, boole_axi_noise_vector_pot=True, axi_noise_eps_A=eps, noise_seed=7)).tetra_physics
+    assert np.array_equal(axi, again) and not np.array_equal(axi, other)
+    # non-axisymmetric: differs between slices
+    non = build_mesh(grid, dataclasses.replace(st0, boole_non_axi_noise_vector_pot=True, non_axi_noise_eps_A=eps)).tetra_physics
+    r = ratio(non) / eps
+    assert r.min() >= -1e-12 and r.max() < 1 and 0.3 < r.mean() < 0.7
+    fulln = non[:, APHI1] / np.where(tp0[:, APHI1] == 0, 1, tp0[:, APHI1])
+    assert spread_within_groups(fulln) > 0.3 * eps
+    # noise on the electrostatic potential alone leaves A untouched
+    pot = build_mesh(grid, dataclasses.replace(st0, boole_axi_noise_elec_pot=True, axi_noise_eps_Phi=0.3)).tetra_physics
+    assert np.array_equal(pot[:, APHI1], tp0[:, APHI1]) and np.array_equal(pot[:, BMOD1], tp0[:, BMOD1])
+    rp = (pot[sel, 30] / tp0[sel, 30] - 1) / 0.3
+    assert rp.min() >= -1e-12 and rp.max() < 1 and rp.std() > 0.2
+    assert np.array_equal(tg, build_mesh(grid, dataclasses.replace(st0, boole_axi_noise_elec_pot=True)).tetra_grid)
+
+
+def test_orbits_on_a_noisy_mesh(product_lib):
+    """What the options are for: a rough field.  Oracle and device algorithm (host compile) stay bit-identical on it."""
+    grid, st0 = workloads.analytic_tokamak(10, 10, 10)
+    st = dataclasses.replace(st0, boole_non_axi_noise_vector_pot=True, non_axi_noise_eps_A=1e-4)
+    mesh = build_mesh(grid, st)
+    om, hm = OracleMesh(mesh, st), HostMirror(mesh, st)
+    n = 100
+    xa, va, wa = workloads.particles_cyl(n, 3)
+    xb, vb, wb = xa.copy(), va.copy(), wa.copy()
+    ia, ta, fa = workloads.fresh_state(n)
+    ib, tb, fb = workloads.fresh_state(n)
+    ra = om.orbit_timestep_trace(xa, va, wa, 1e-4, ia, ta, fa, 256)
+    rb = hm.orbit_timestep(xb, vb, wb, 1e-4, ib, tb, fb, 256)
+    assert ra["n_pushes"].sum() > 8000
+    assert np.array_equal(ra["trace_tetr"], rb["trace_tetr"]) and np.array_equal(ra["trace_face"], rb["trace_face"])
+    assert np.array_equal(xa, xb) and np.array_equal(va, vb) and np.array_equal(wa, wb) and np.array_equal(ta, tb)

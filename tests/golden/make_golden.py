@@ -1,4 +1,4 @@
-"""Regenerates tests/golden/orbits_v1.npz from the CPU oracle (oracle/gorilla_oracle.c).
+"""Regenerates tests/golden/orbits_v1.npz, orbits_v2.npz and orbits_v3.npz from the CPU oracle (oracle/gorilla_oracle.c).
 
 The reference ships no golden vectors for this path and cannot be compiled in this image (no gfortran), so these
 vectors do NOT pin the oracle to the Fortran binary ("parity unpinned").  What they pin is the oracle
@@ -76,6 +76,31 @@ def run_case_v2(over, t_step, seed, kind):
     return out
 
 
+# third file (orbits_v3.npz): full-orbit output (event kind 3, with the elapsed time of every event) for both pushers
+CASES_V3 = [  # name, settings overrides, t_step, seed, event switches
+    ("k2_full_orbit", dict(poly_order=2), 2.0e-4, 41, dict(full_orbit=True, n_skip_full_orbit=3, n_skip_phi_0=2)),
+    ("k4_full_orbit_only", dict(poly_order=4), 1.0e-4, 42,
+     dict(poincare_phi_0=False, poincare_vpar_0=False, J_par=False, full_orbit=True, n_skip_full_orbit=1)),
+    ("rk4_full_orbit", dict(ipusher=1), 2.0e-4, 43, dict(full_orbit=True, n_skip_full_orbit=2)),
+]
+
+
+def run_case_v3(over, t_step, seed, switches):
+    grid, st = workloads.analytic_tokamak(10, 10, 10)
+    st = type(st)(**{**st.__dict__, **over})
+    om = OracleMesh(build_mesh(grid, st), st)
+    n = N_EV
+    x, vpar, vperp = workloads.particles_cyl(n, seed)
+    binit, ind, ifc = workloads.fresh_state(n)
+    J, cv, cp = np.zeros(n), np.zeros(n, np.int32), np.zeros(n, np.int32)
+    ev, nev, npush = om.orbit_timestep_events(x, vpar, vperp, t_step, binit, ind, ifc, J, cv, cp, EV_CAP, **switches)
+    assert nev <= EV_CAP
+    ev = ev[np.lexsort((ev["kind"], ev["push"], ev["particle"]))]
+    return dict(x=x, vpar=vpar, vperp=vperp, ind_tetr=ind, iface=ifc, n_pushes=npush, par_adiab_inv=J, counter_vpar_0=cv,
+                counter_phi_0=cp, ev_particle=ev["particle"], ev_kind=ev["kind"], ev_counter=ev["counter"],
+                ev_push=ev["push"], ev_x=ev["x"], ev_value=ev["value"], ev_t=ev["t"])
+
+
 def run_case(over, t_step, seed):
     grid, st = workloads.analytic_tokamak(10, 10, 10)
     st = type(st)(**{**st.__dict__, **over})
@@ -102,6 +127,12 @@ def main():
             out[f"{name}/{k}"] = v
     np.savez_compressed(Path(__file__).with_name("orbits_v2.npz"), **out)
     print("wrote", len(out), "arrays (v2)")
+    out = {}
+    for name, over, t_step, seed, switches in CASES_V3:
+        for k, v in run_case_v3(over, t_step, seed, switches).items():
+            out[f"{name}/{k}"] = v
+    np.savez_compressed(Path(__file__).with_name("orbits_v3.npz"), **out)
+    print("wrote", len(out), "arrays (v3)")
 
 
 if __name__ == "__main__":
